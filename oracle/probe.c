@@ -1,0 +1,359 @@
+/* oracle/probe.c -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Compiled *into* oracle/_ref/liboracle_{scalar,simd}.so next to the unmodified
+ * reference objects.  It contains no reference code: it only *observes* the
+ * reference through `ld --wrap=<symbol>` (see oracle/build_ref.sh), copying the
+ * arguments/results of hot-path functions and a snapshot of the reference's
+ * global state (atmos, geometry, spectrum: pyrh_compute1dray.c:47-53) into an
+ * in-memory record log that tests/golden generators read through ctypes.
+ *
+ * Wrapped reference functions (file:line of the real definition):
+ *   rlk_opacity              rh/kurucz.c:511
+ *   writeBackground          rh/readj.c:284
+ *   Piece_Stokes_Bezier3_1D  rh/rhf1d/bezier_1D.c:52
+ *   Piecewise_Bezier3_1D     rh/rhf1d/bezier_1D.c:306
+ *   Feautrier                rh/rhf1d/feautrier.c:56
+ *   Formal                   rh/rhf1d/formal.c:44
+ *   Opacity                  rh/opacity.c:64
+ *   addtoGamma / addtoRates  rh/fillgamma.c:82 / :375
+ *   statEquil                rh/statequil.c:40
+ *   Accelerate               rh/accelerate.c:68
+ */
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+
+#include "rh.h"
+#include "atom.h"
+#include "atmos.h"
+#include "rhf1d/geometry.h"
+#include "spectrum.h"
+#include "background.h"
+#include "inputs.h"
+#include "accelerate.h"
+
+extern Atmosphere atmos;
+extern Geometry geometry;
+extern Spectrum spectrum;
+extern InputData input;
+
+/* ------------------------------------------------------------------ log */
+
+typedef struct {
+  char    tag[24];
+  int     meta[8];
+  long    n;
+  double *data;
+} ProbeRec;
+
+static ProbeRec *recs = NULL;
+static long nrec = 0, cap = 0;
+static unsigned probe_mask = 0;   /* bit field, see PROBE_* below */
+static int snapshot_done = 0;
+
+enum { PROBE_RLK = 1, PROBE_BG = 2, PROBE_DELO = 4, PROBE_SNAP = 8,
+       PROBE_BEZ = 16, PROBE_FEAU = 32, PROBE_NLTE = 64, PROBE_FORMAL = 128 };
+
+void probe_enable(unsigned mask) { probe_mask = mask; }
+
+void probe_reset(void)
+{
+  for (long i = 0; i < nrec; i++) free(recs[i].data);
+  nrec = 0;
+  snapshot_done = 0;
+}
+long      probe_count(void)       { return nrec; }
+ProbeRec *probe_get(long i)       { return (i >= 0 && i < nrec) ? &recs[i] : NULL; }
+
+static double *rec_new(const char *tag, long n, int m0, int m1, int m2, int m3,
+                       int m4, int m5)
+{
+  if (nrec == cap) {
+    cap = cap ? 2*cap : 1024;
+    recs = (ProbeRec *) realloc(recs, cap * sizeof(ProbeRec));
+  }
+  ProbeRec *r = &recs[nrec++];
+  memset(r, 0, sizeof(*r));
+  strncpy(r->tag, tag, sizeof(r->tag)-1);
+  r->meta[0] = m0; r->meta[1] = m1; r->meta[2] = m2; r->meta[3] = m3;
+  r->meta[4] = m4; r->meta[5] = m5;
+  r->n = n;
+  r->data = (double *) malloc((n > 0 ? n : 1) * sizeof(double));
+  return r->data;
+}
+
+static void rec_copy(const char *tag, const double *src, long n,
+                     int m0, int m1, int m2, int m3)
+{
+  double *d = rec_new(tag, n, m0, m1, m2, m3, 0, 0);
+  if (src) memcpy(d, src, n*sizeof(double)); else memset(d, 0, n*sizeof(double));
+}
+
+/* ------------------------------------------------------------ snapshot */
+
+static void snapshot(void)
+{
+  int N = atmos.Nspace, i, n, k;
+  if (snapshot_done) return;
+  snapshot_done = 1;
+
+  rec_copy("T", atmos.T, N, 0,0,0,0);
+  rec_copy("ne", atmos.ne, N, 0,0,0,0);
+  rec_copy("vturb", atmos.vturb, N, 0,0,0,0);
+  rec_copy("vel", geometry.vel, N, 0,0,0,0);
+  rec_copy("nHtot", atmos.nHtot, N, 0,0,0,0);
+  rec_copy("height", geometry.height, N, 0,0,0,0);
+  rec_copy("tau_ref", geometry.tau_ref, N, 0,0,0,0);
+  rec_copy("cmass", geometry.cmass, N, 0,0,0,0);
+  if (atmos.Stokes && atmos.B) {
+    rec_copy("B", atmos.B, N, 0,0,0,0);
+    rec_copy("gamma_B", atmos.gamma_B, N, 0,0,0,0);
+    rec_copy("chi_B", atmos.chi_B, N, 0,0,0,0);
+    for (i = 0; i < atmos.Nrays; i++) {
+      rec_copy("cos_gamma", atmos.cos_gamma[i], N, i,0,0,0);
+      rec_copy("cos_2chi",  atmos.cos_2chi[i],  N, i,0,0,0);
+      rec_copy("sin_2chi",  atmos.sin_2chi[i],  N, i,0,0,0);
+    }
+  }
+  rec_copy("np", atmos.H->n[atmos.H->Nlevel-1], N, 0,0,0,0);
+  rec_copy("muz", geometry.muz, geometry.Nrays, 0,0,0,0);
+  rec_copy("wmu", geometry.wmu, geometry.Nrays, 0,0,0,0);
+  rec_copy("lambda", spectrum.lambda, spectrum.Nspect, 0,0,0,0);
+  {
+    double *d = rec_new("flags", 16, 0,0,0,0,0,0);
+    d[0] = atmos.moving; d[1] = atmos.Stokes; d[2] = input.magneto_optical;
+    d[3] = input.rlkscatter; d[4] = geometry.vboundary[TOP];
+    d[5] = geometry.vboundary[BOTTOM]; d[6] = atmos.vmicro_char;
+    d[7] = atmos.lambda_ref; d[8] = input.StokesMode; d[9] = input.solve_NLTE;
+    d[10] = atmos.Nrays; d[11] = atmos.Nrlk; d[12] = input.S_interpolation;
+    d[13] = input.S_interpolation_stokes; d[14] = atmos.H_LTE; d[15] = input.LS_Lande;
+  }
+  {
+    double *d = rec_new("backgrflags", 2*spectrum.Nspect, 0,0,0,0,0,0);
+    for (n = 0; n < spectrum.Nspect; n++) {
+      d[2*n]   = atmos.backgrflags[n].hasline;
+      d[2*n+1] = atmos.backgrflags[n].ispolarized;
+    }
+  }
+  if (atmos.Npf > 0 && atmos.Tpf) rec_copy("Tpf", atmos.Tpf, atmos.Npf, 0,0,0,0);
+
+  /* Kurucz lines (sorted, as used by rlk_opacity) + the element tables they need */
+  for (n = 0; n < atmos.Nrlk; n++) {
+    RLK_Line *r = &atmos.rlk_lines[n];
+    int Nc = r->zm ? r->zm->Ncomponent : 0;
+    double *d = rec_new("rlk_line", 32 + 3*Nc, n, Nc, 0,0,0,0);
+    d[0] = r->lambda0; d[1] = r->gi; d[2] = r->gj; d[3] = r->Ei; d[4] = r->Ej;
+    d[5] = r->Bji; d[6] = r->Aji; d[7] = r->Bij; d[8] = r->Si; d[9] = r->Sj;
+    d[10] = r->Grad; d[11] = r->GStark; d[12] = r->GvdWaals;
+    d[13] = r->hyperfine_frac; d[14] = r->isotope_frac; d[15] = r->gL_i;
+    d[16] = r->gL_j; d[17] = r->cross; d[18] = r->alpha; d[19] = r->polarizable;
+    d[20] = r->vdwaals; d[21] = r->pt_index; d[22] = r->stage; d[23] = r->Li;
+    d[24] = r->Lj; d[25] = Nc; d[26] = r->li; d[27] = r->lj;
+    d[28] = r->get_loggf_rf; d[29] = r->loggf_rf_ind; d[30] = 0; d[31] = 0;
+    for (i = 0; i < Nc; i++) {
+      d[32+3*i]   = r->zm->q[i];
+      d[32+3*i+1] = r->zm->shift[i];
+      d[32+3*i+2] = r->zm->strength[i];
+    }
+    Element *e = &atmos.elements[r->pt_index - 1];
+    {
+      double *h = rec_new("elem", 8 + e->Nstage, r->pt_index, e->Nstage, 0,0,0,0);
+      h[0] = e->weight; h[1] = e->abund; h[2] = e->abundance_set;
+      h[3] = (e->model != NULL); h[4] = e->Nstage; h[5] = h[6] = h[7] = 0;
+      for (i = 0; i < e->Nstage; i++)
+        h[8+i] = (i < e->Nstage-1 && e->ionpot) ? e->ionpot[i] : 0.0;
+    }
+    if (e->pf)
+      for (i = 0; i < e->Nstage; i++)
+        rec_copy("elem_pf", e->pf[i], atmos.Npf, r->pt_index, i, 0,0);
+    if (e->n)
+      for (i = 0; i < e->Nstage; i++)
+        rec_copy("elem_n", e->n[i], N, r->pt_index, i, 0,0);
+  }
+  (void) k;
+}
+
+void probe_snapshot(void) { snapshot_done = 0; snapshot(); }
+
+/* ------------------------------------------------------------ wrappers */
+
+flags __real_rlk_opacity(double lambda, int nspect, int mu, bool_t to_obs,
+                         double *chi, double *eta, double *scatt, double *chip);
+flags __wrap_rlk_opacity(double lambda, int nspect, int mu, bool_t to_obs,
+                         double *chi, double *eta, double *scatt, double *chip)
+{
+  flags f = __real_rlk_opacity(lambda, nspect, mu, to_obs, chi, eta, scatt, chip);
+  if (probe_mask & PROBE_RLK) {
+    int N = atmos.Nspace, ns = atmos.Stokes ? 4 : 1;
+    double *d = rec_new("rlk", 2*ns*N, nspect, mu, to_obs, f.hasline,
+                        f.ispolarized, ns);
+    if (f.hasline) {
+      memcpy(d, chi, ns*N*sizeof(double));
+      memcpy(d + ns*N, eta, ns*N*sizeof(double));
+    } else
+      memset(d, 0, 2*ns*N*sizeof(double));
+  }
+  return f;
+}
+
+int __real_writeBackground(int nspect, int mu, bool_t to_obs, double *chi_c,
+                           double *eta_c, double *sca_c, double *chip_c);
+int __wrap_writeBackground(int nspect, int mu, bool_t to_obs, double *chi_c,
+                           double *eta_c, double *sca_c, double *chip_c)
+{
+  if (probe_mask & PROBE_BG) {
+    int N = atmos.Nspace;
+    int ns = atmos.backgrflags[nspect].ispolarized ? 4 : 1;
+    double *d = rec_new("bg", (2*ns+1)*N, nspect, mu, to_obs, ns, 0, 0);
+    memcpy(d, chi_c, ns*N*sizeof(double));
+    memcpy(d + ns*N, eta_c, ns*N*sizeof(double));
+    memcpy(d + 2*ns*N, sca_c, N*sizeof(double));
+  }
+  return __real_writeBackground(nspect, mu, to_obs, chi_c, eta_c, sca_c, chip_c);
+}
+
+void __real_Piece_Stokes_Bezier3_1D(int nspect, int mu, bool_t to_obs,
+                                    double *chi, double **S, double **I, double *Psi);
+void __wrap_Piece_Stokes_Bezier3_1D(int nspect, int mu, bool_t to_obs,
+                                    double *chi, double **S, double **I, double *Psi)
+{
+  __real_Piece_Stokes_Bezier3_1D(nspect, mu, to_obs, chi, S, I, Psi);
+  if (probe_mask & PROBE_DELO) {
+    int N = atmos.Nspace, n;
+    ActiveSet *as = &spectrum.as[nspect];
+    /* layout: chi[N], S[4][N], I[4][N], Psi[N], chiQUV_total[3][N] */
+    double *d = rec_new("delo", 13*N, nspect, mu, to_obs, Psi != NULL, 0, 0);
+    memcpy(d, chi, N*sizeof(double));
+    for (n = 0; n < 4; n++) memcpy(d + (1+n)*N, S[n], N*sizeof(double));
+    for (n = 0; n < 4; n++) memcpy(d + (5+n)*N, I[n], N*sizeof(double));
+    if (Psi) memcpy(d + 9*N, Psi, N*sizeof(double));
+    else memset(d + 9*N, 0, N*sizeof(double));
+    for (n = 0; n < 3*N; n++) {
+      double v = 0.0;
+      if (containsPolarized(as)) v += as->chi[N + n];
+      if (atmos.backgrflags[nspect].ispolarized) v += as->chi_c[N + n];
+      d[10*N + n] = v;
+    }
+  }
+}
+
+void __real_Piecewise_Bezier3_1D(int nspect, int mu, bool_t to_obs, double *chi,
+                                 double *S, double *I, double *Psi, double **dI);
+void __wrap_Piecewise_Bezier3_1D(int nspect, int mu, bool_t to_obs, double *chi,
+                                 double *S, double *I, double *Psi, double **dI)
+{
+  __real_Piecewise_Bezier3_1D(nspect, mu, to_obs, chi, S, I, Psi, dI);
+  if (probe_mask & PROBE_BEZ) {
+    int N = atmos.Nspace;
+    double *d = rec_new("bez", 4*N, nspect, mu, to_obs, Psi != NULL, 0, 0);
+    memcpy(d, chi, N*sizeof(double));
+    memcpy(d + N, S, N*sizeof(double));
+    memcpy(d + 2*N, I, N*sizeof(double));
+    if (Psi) memcpy(d + 3*N, Psi, N*sizeof(double));
+    else memset(d + 3*N, 0, N*sizeof(double));
+  }
+}
+
+double __real_Feautrier(int nspect, int mu, double *chi, double *S,
+                        enum FeautrierOrder order, double *P, double *Psi);
+double __wrap_Feautrier(int nspect, int mu, double *chi, double *S,
+                        enum FeautrierOrder order, double *P, double *Psi)
+{
+  double Iem = __real_Feautrier(nspect, mu, chi, S, order, P, Psi);
+  if (probe_mask & PROBE_FEAU) {
+    int N = atmos.Nspace;
+    double *d = rec_new("feau", 4*N + 1, nspect, mu, order, Psi != NULL, 0, 0);
+    memcpy(d, chi, N*sizeof(double));
+    memcpy(d + N, S, N*sizeof(double));
+    memcpy(d + 2*N, P, N*sizeof(double));
+    if (Psi) memcpy(d + 3*N, Psi, N*sizeof(double));
+    else memset(d + 3*N, 0, N*sizeof(double));
+    d[4*N] = Iem;
+  }
+  return Iem;
+}
+
+double __real_Formal(int nspect, bool_t eval_operator, bool_t redistribute);
+double __wrap_Formal(int nspect, bool_t eval_operator, bool_t redistribute)
+{
+  if (probe_mask & PROBE_SNAP) snapshot();
+  double dJ = __real_Formal(nspect, eval_operator, redistribute);
+  if (probe_mask & PROBE_FORMAL) {
+    int N = atmos.Nspace;
+    double *d = rec_new("formal", N + 1, nspect, eval_operator, redistribute, 0,0,0);
+    memcpy(d, spectrum.J[nspect], N*sizeof(double));
+    d[N] = dJ;
+  }
+  return dJ;
+}
+
+/* --- NLTE observers: record inputs/outputs of the rate machinery -------- */
+
+void __real_Opacity(int nspect, int mu, bool_t to_obs, bool_t initialize);
+void __wrap_Opacity(int nspect, int mu, bool_t to_obs, bool_t initialize)
+{
+  __real_Opacity(nspect, mu, to_obs, initialize);
+  if (probe_mask & PROBE_NLTE) {
+    int N = atmos.Nspace;
+    ActiveSet *as = &spectrum.as[nspect];
+    double *d = rec_new("opac", 2*N, nspect, mu, to_obs, initialize, 0, 0);
+    memcpy(d, as->chi, N*sizeof(double));
+    memcpy(d + N, as->eta, N*sizeof(double));
+  }
+}
+
+void __real_addtoGamma(int nspect, double wmu, double *P, double *Psi);
+void __wrap_addtoGamma(int nspect, double wmu, double *P, double *Psi)
+{
+  if (probe_mask & PROBE_NLTE) {
+    int N = atmos.Nspace;
+    double *d = rec_new("gam_in", 2*N + 1, nspect, 0,0,0,0,0);
+    memcpy(d, P, N*sizeof(double));
+    memcpy(d + N, Psi, N*sizeof(double));
+    d[2*N] = wmu;
+  }
+  __real_addtoGamma(nspect, wmu, P, Psi);
+}
+
+void __real_addtoRates(int nspect, int mu, bool_t to_obs, double wmu, double *I,
+                       bool_t redistribute);
+void __wrap_addtoRates(int nspect, int mu, bool_t to_obs, double wmu, double *I,
+                       bool_t redistribute)
+{
+  __real_addtoRates(nspect, mu, to_obs, wmu, I, redistribute);
+}
+
+void __real_statEquil(Atom *atom, int isum);
+void __wrap_statEquil(Atom *atom, int isum)
+{
+  int N = atmos.Nspace, Nl = atom->Nlevel;
+  if (probe_mask & PROBE_NLTE) {
+    double *d = rec_new("se_in", (long)(Nl*Nl + 2*Nl)*N + N, Nl, isum, 0,0,0,0);
+    memcpy(d, atom->Gamma[0], (long)Nl*Nl*N*sizeof(double));
+    memcpy(d + (long)Nl*Nl*N, atom->n[0], (long)Nl*N*sizeof(double));
+    memcpy(d + (long)(Nl*Nl+Nl)*N, atom->nstar[0], (long)Nl*N*sizeof(double));
+    memcpy(d + (long)(Nl*Nl+2*Nl)*N, atom->ntotal, N*sizeof(double));
+  }
+  __real_statEquil(atom, isum);
+  if (probe_mask & PROBE_NLTE) {
+    double *d = rec_new("se_out", (long)Nl*N, Nl, isum, 0,0,0,0);
+    memcpy(d, atom->n[0], (long)Nl*N*sizeof(double));
+  }
+}
+
+bool_t __real_Accelerate(struct Ng *Ngs, double *solution);
+bool_t __wrap_Accelerate(struct Ng *Ngs, double *solution)
+{
+  long N = Ngs->N;
+  if (probe_mask & PROBE_NLTE) {
+    double *d = rec_new("ng_in", N, Ngs->Norder, Ngs->Ndelay, Ngs->Nperiod,
+                        Ngs->count, 0, 0);
+    memcpy(d, solution, N*sizeof(double));
+  }
+  bool_t acc = __real_Accelerate(Ngs, solution);
+  if (probe_mask & PROBE_NLTE) {
+    double *d = rec_new("ng_out", N, Ngs->Norder, acc, 0,0,0,0);
+    memcpy(d, solution, N*sizeof(double));
+  }
+  return acc;
+}
