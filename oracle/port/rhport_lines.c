@@ -1,0 +1,279 @@
+/* oracle/port/rhport_lines.c -- TEST INFRASTRUCTURE ONLY (see rhport.h).
+ *
+ * CPU restatement of the reference's LTE Kurucz-line opacity:
+ *   Voigt/Faraday-Voigt (Humlicek 1982)   rh/voigt.c:381-419, rh/humlicek.c:28-117,
+ *                                         rh/complex.c:27-155
+ *   Linear / Hunt                          rh/linear.c:22-58, rh/hunt.c:17-78
+ *   LTEpops_elem (Saha)                    rh/ltepops.c:116-159
+ *   RLKProfile                             rh/kurucz.c:729-828
+ *   rlk_opacity                            rh/kurucz.c:511-725
+ * Arithmetic order follows the reference expression by expression; compile
+ * with -O2 -ffp-contract=off (the reference x86-64 build has no FMA).
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include "rhport.h"
+
+/* ---- complex helpers, same operation order as complex.c ---------------- */
+typedef struct { double r, i; } cplx;
+
+static inline cplx c_mul(cplx a, cplx b)        /* complex.c:53-64 */
+{ cplx c; c.r = a.r*b.r - a.i*b.i; c.i = a.r*b.i + a.i*b.r; return c; }
+static inline cplx c_scl(double a, cplx b)      /* complex.c:69-79 */
+{ cplx c; c.r = a*b.r; c.i = a*b.i; return c; }
+static inline cplx c_div(cplx a, cplx b)        /* complex.c:84-99 */
+{ cplx c; double d = b.r*b.r + b.i*b.i;
+  c.r = (a.r*b.r + a.i*b.i) / d; c.i = (a.i*b.r - a.r*b.i) / d; return c; }
+static inline cplx c_addr(cplx a, double b)     /* complex.c:128-138 */
+{ cplx c; c.r = a.r + b; c.i = a.i; return c; }
+
+int rp_humlicek_region(double a, double v)      /* voigt.c:404-413 */
+{
+  double s = fabs(v) + a;
+  if (s >= 15.0) return 1;
+  if (s >= 5.5)  return 2;
+  if (a >= 0.195*fabs(v) - 0.176) return 3;
+  return 4;
+}
+
+double rp_voigt_humlicek(double a, double v, double *F)
+{
+  cplx z = { a, -v }, W, z1, z2, u;
+  int n;
+  switch (rp_humlicek_region(a, v)) {
+  case 1:                                       /* humlicek.c:28-38 */
+    z1 = c_scl(0.5641896, z);
+    z2 = c_addr(c_mul(z, z), 0.5);
+    W  = c_div(z1, z2);
+    break;
+  case 2:                                       /* humlicek.c:43-55 */
+    u  = c_mul(z, z);
+    z1 = c_scl(0.5641896, u);
+    z1 = c_mul(z, c_addr(z1, 1.410474));
+    z2 = c_mul(u, c_addr(u, 3.0));
+    z2 = c_addr(z2, 0.75);
+    W  = c_div(z1, z2);
+    break;
+  case 3: {                                     /* humlicek.c:62-83 */
+    static const double A[5] = {0.5642236, 3.778987, 11.96482, 20.20933, 16.4955};
+    static const double B[5] = {6.699398, 21.69274,  39.27121, 38.82363, 16.4955};
+    z1.r = A[0]; z1.i = 0.0;
+    z2 = c_addr(z, B[0]);
+    for (n = 1; n < 5; n++) {
+      z1 = c_addr(c_mul(z1, z), A[n]);
+      z2 = c_addr(c_mul(z2, z), B[n]);
+    }
+    W = c_div(z1, z2);
+    break;
+  }
+  default: {                                    /* humlicek.c:90-117 */
+    static const double A[7] =
+      {0.56419, 1.320522, 35.7668, 219.031, 1540.787, 3321.99, 36183.31};
+    static const double B[7] =
+      {1.841439, 61.57037, 364.2191, 2186.181, 9022.228, 24322.84, 32066.6};
+    cplx mu_, e, q;
+    u = c_mul(z, c_scl(-1.0, z));
+    z1.r = A[0]; z1.i = 0.0;
+    z2 = c_addr(u, B[0]);
+    for (n = 1; n < 7; n++) {
+      z1 = c_addr(c_mul(u, z1), A[n]);
+      z2 = c_addr(c_mul(u, z2), B[n]);
+    }
+    mu_ = c_scl(-1.0, u);
+    { cplx cs; cs.r = cos(mu_.i); cs.i = sin(mu_.i);       /* complex.c:104-109 */
+      e = c_scl(exp(mu_.r), cs); }
+    q = c_div(c_mul(z, z1), z2);
+    W.r = e.r - q.r; W.i = e.i - q.i;
+  }
+  }
+  if (F) *F = W.i;
+  return W.r;
+}
+
+/* ---- Linear() with hunt=TRUE; for xmin < x < xmax Hunt() returns the unique
+        bracket j with xt[j] <= x < xt[j+1], found here by bisection
+        (linear.c:22-58, hunt.c:59-68; ascending tables only: Tpf is) ------- */
+void rp_linear(int Ntable, const double *xt, const double *yt, int N,
+               const double *x, double *y)
+{
+  double xmin = xt[0], xmax = xt[Ntable-1];
+  for (int n = 0; n < N; n++) {
+    if (x[n] <= xmin) y[n] = yt[0];
+    else if (x[n] >= xmax) y[n] = yt[Ntable-1];
+    else {
+      int lo = 0, hi = Ntable;
+      while (hi - lo > 1) {
+        int mid = (hi + lo) >> 1;
+        if (x[n] >= xt[mid]) lo = mid; else hi = mid;
+      }
+      double fx = (xt[lo+1] - x[n]) / (xt[lo+1] - xt[lo]);
+      y[n] = fx*yt[lo] + (1 - fx)*yt[lo+1];
+    }
+  }
+}
+
+/* ---- LTEpops_elem, ltepops.c:116-159 ------------------------------------ */
+void rp_ltepops_elem(const rp_linetable *lt, int ielem, const rp_column *col, double *n)
+{
+  const double *e = lt->elems + (long) ielem * RE_NFIELD;
+  int Nst = (int) e[RE_NSTAGE], pfrow = (int) e[RE_PFROW], N = col->Ndep, k, i;
+  double C1 = (RP_HPLANCK/(2.0*RP_PI*RP_M_ELECTRON)) * (RP_HPLANCK/RP_KBOLTZMANN);
+  double *sum = malloc(N*sizeof(double)), *CT_ne = malloc(N*sizeof(double)),
+         *Uk = malloc(N*sizeof(double)), *Ukp1 = malloc(N*sizeof(double)), *tmp;
+
+  for (k = 0; k < N; k++) {
+    CT_ne[k] = 2.0 * pow(C1/col->T[k], -1.5) / col->ne[k];
+    sum[k] = 1.0;
+    n[k] = 1.0;
+  }
+  rp_linear(lt->npf, lt->Tpf, lt->pf + (long) pfrow*lt->npf, N, col->T, Uk);
+  for (i = 1; i < Nst; i++) {
+    rp_linear(lt->npf, lt->Tpf, lt->pf + (long)(pfrow+i)*lt->npf, N, col->T, Ukp1);
+    for (k = 0; k < N; k++) {
+      n[i*N+k] = n[(i-1)*N+k] * CT_ne[k] *
+        exp(Ukp1[k] - Uk[k] - e[RE_IONPOT0 + i-1]/(RP_KBOLTZMANN*col->T[k]));
+      sum[k] += n[i*N+k];
+    }
+    tmp = Uk; Uk = Ukp1; Ukp1 = tmp;
+  }
+  for (k = 0; k < N; k++) n[k] = e[RE_ABUND] * col->nHtot[k] / sum[k];
+  for (i = 1; i < Nst; i++)
+    for (k = 0; k < N; k++) n[i*N+k] *= n[k];
+  free(sum); free(CT_ne); free(Uk); free(Ukp1);
+}
+
+/* ---- RLKProfile, kurucz.c:729-828 (magneto_optical = FALSE) ------------- */
+static double rlk_profile(const rp_linetable *lt, const double *L, const rp_column *c,
+                          int k, int to_obs, double lambda,
+                          double *phi_Q, double *phi_U, double *phi_V)
+{
+  const double *el = lt->elems + (long)((int) L[RL_ELEM]) * RE_NFIELD;
+  double vtherm = 2.0*RP_KBOLTZMANN/(RP_AMU * el[RE_WEIGHT]);
+  double vbroad = sqrt(vtherm*c->T[k] + c->vturb[k]*c->vturb[k]);
+  double v, sv, GvdW, adamp, phi;
+
+  v = (lambda/L[RL_LAMBDA0] - 1.0) * RP_CLIGHT/vbroad;
+  if (c->moving) {
+    if (to_obs) v += (c->muz * c->vel[k]) / vbroad;     /* vproject(), project.c:28-36 */
+    else        v -= (c->muz * c->vel[k]) / vbroad;
+  }
+  sv = 1.0 / (RP_SQRTPI * vbroad);
+
+  if (L[RL_GRAD]) {
+    switch ((int) L[RL_VDWAALS]) {
+    case RP_UNSOLD:  GvdW = L[RL_CROSS] * pow(c->T[k], 0.3); break;
+    case RP_BARKLEM: GvdW = L[RL_CROSS] * pow(c->T[k], (1.0 - L[RL_ALPHA])/2.0); break;
+    default:         GvdW = L[RL_GVDW]; break;
+    }
+    adamp = (L[RL_GRAD] + L[RL_GSTARK] * c->ne[k] +
+             GvdW * (c->nHtot[k] - c->np[k])) *
+      (L[RL_LAMBDA0] * RP_NM_TO_M) / (4.0*RP_PI * vbroad);
+  } else {
+    phi = (fabs(v) <= RP_MAX_GAUSS_DOPPLER) ? exp(-v*v) : 0.0;
+    return phi * sv;
+  }
+
+  if (L[RL_POLARIZABLE]) {
+    double sin2_gamma = 1.0 - c->cos_gamma[k]*c->cos_gamma[k];
+    double vB = (RP_LARMOR * L[RL_LAMBDA0]) * c->B[k] / vbroad;
+    double sign = to_obs ? 1.0 : -1.0;
+    double phi_sm = 0.0, phi_pi = 0.0, phi_sp = 0.0, H, F, phi_sigma, phi_delta;
+    int zoff = (int) L[RL_ZOFF], nc = (int) L[RL_NCOMP], nz;
+
+    for (nz = 0; nz < nc; nz++) {
+      H = rp_voigt_humlicek(adamp, v - lt->zshift[zoff+nz]*vB, &F);
+      switch (lt->zq[zoff+nz]) {
+      case -1: phi_sm += lt->zstrength[zoff+nz] * H; break;
+      case  0: phi_pi += lt->zstrength[zoff+nz] * H; break;
+      case  1: phi_sp += lt->zstrength[zoff+nz] * H; break;
+      }
+    }
+    phi_sigma = phi_sp + phi_sm;
+    phi_delta = 0.5*phi_pi - 0.25*phi_sigma;
+    phi = (phi_delta*sin2_gamma + 0.5*phi_sigma) * sv;
+    *phi_Q = sign * phi_delta * sin2_gamma * c->cos_2chi[k] * sv;
+    *phi_U = phi_delta * sin2_gamma * c->sin_2chi[k] * sv;
+    *phi_V = sign * 0.5*(phi_sp - phi_sm) * c->cos_gamma[k] * sv;
+    return phi;
+  }
+  /* non-polarizable lines use VoigtArmstrong in the reference (kurucz.c:824);
+     not restated here: every line of the pinned configurations is polarizable */
+  return NAN;
+}
+
+/* ---- rlk_opacity, kurucz.c:511-725 (rlkscatter = FALSE, no model-atom veto:
+        callers pass only lines whose element has no overlapping explicit
+        AtomicLine, kurucz.c:616-631) ------------------------------------- */
+int rp_rlk_opacity(const rp_linetable *lt, const rp_column *col, const double *elem_n,
+                   double lambda, int to_obs, double *chi, double *eta)
+{
+  int N = col->Ndep, nl = lt->nline, flags = 0, n, k, Nwhite, Nblue, Nred;
+  const double *LT = lt->lines;
+  double dlamb_char = lambda * RP_Q_WING * (lt->vmicro_char / RP_CLIGHT);
+  double hc = RP_HPLANCK * RP_CLIGHT, fourPI = 4.0 * RP_PI, hc_4PI = hc / fourPI;
+  double *pf;
+
+  if (nl == 0) return 0;
+  if (lambda < LT[RL_LAMBDA0] - dlamb_char ||
+      lambda > LT[(long)(nl-1)*RL_NFIELD + RL_LAMBDA0] + dlamb_char) return 0;
+
+  /* rlk_locate (kurucz.c:453-507) with *low = 0 is a plain bisection */
+  { int lo = 0, hi = nl;
+    while (hi - lo > 1) {
+      int mid = (hi + lo) >> 1;
+      if (lambda >= LT[(long)mid*RL_NFIELD + RL_LAMBDA0]) lo = mid; else hi = mid;
+    }
+    Nwhite = lo; }
+  Nblue = Nwhite;
+  while (LT[(long)Nblue*RL_NFIELD + RL_LAMBDA0] + dlamb_char > lambda && Nblue > 0) Nblue--;
+  Nred = Nwhite;
+  while (LT[(long)Nred*RL_NFIELD + RL_LAMBDA0] - dlamb_char < lambda && Nred < nl-1) Nred++;
+
+  if (Nred >= Nblue)
+    for (k = 0; k < 4*N; k++) { chi[k] = 0.0; eta[k] = 0.0; }
+
+  pf = malloc(N * sizeof(double));
+  for (n = Nblue; n <= Nred; n++) {
+    const double *L = LT + (long) n*RL_NFIELD;
+    if (fabs(L[RL_LAMBDA0] - lambda) <= dlamb_char) {
+      int ie = (int) L[RL_ELEM], st = (int) L[RL_STAGE];
+      const double *el = lt->elems + (long) ie*RE_NFIELD;
+      if (!(st < (int) el[RE_NSTAGE] - 1)) continue;
+      {
+        double hc_la      = (RP_HPLANCK * RP_CLIGHT) / (L[RL_LAMBDA0] * RP_NM_TO_M);
+        double Bijhc_4PI  = hc_4PI * L[RL_BIJ] * L[RL_ISO_FRAC] * L[RL_HFS_FRAC] * L[RL_GI];
+        double twohnu3_c2 = L[RL_AJI] / L[RL_BJI];
+        const double *nst = elem_n + ((long) ie*RE_MAXSTAGE + st) * N;
+
+        flags |= 1;
+        if (L[RL_POLARIZABLE]) flags |= 2;
+        rp_linear(lt->npf, lt->Tpf, lt->pf + (long)((int) el[RE_PFROW] + st)*lt->npf,
+                  N, col->T, pf);
+        for (k = 0; k < N; k++) {
+          double phi_Q = 0, phi_U = 0, phi_V = 0;
+          double phi = rlk_profile(lt, L, col, k, to_obs, lambda, &phi_Q, &phi_U, &phi_V);
+          if (phi) {
+            double kT    = 1.0 / (RP_KBOLTZMANN * col->T[k]);
+            double ni_gi = nst[k] * exp(-L[RL_EI]*kT - pf[k]);
+            double nj_gj = ni_gi * exp(-hc_la * kT);
+            double chi_l = Bijhc_4PI * (ni_gi - nj_gj);
+            double eta_l = Bijhc_4PI * twohnu3_c2 * nj_gj;
+            chi[k] += chi_l * phi;
+            eta[k] += eta_l * phi;
+            if (L[RL_POLARIZABLE] && L[RL_GRAD]) {
+              chi[N+k]   += chi_l * phi_Q;
+              chi[2*N+k] += chi_l * phi_U;
+              chi[3*N+k] += chi_l * phi_V;
+              eta[N+k]   += eta_l * phi_Q;
+              eta[2*N+k] += eta_l * phi_U;
+              eta[3*N+k] += eta_l * phi_V;
+            }
+          }
+        }
+      }
+    }
+  }
+  free(pf);
+  return flags;
+}

@@ -1,0 +1,156 @@
+"""oracle/portdriver.py -- TEST INFRASTRUCTURE ONLY.
+
+ctypes bindings for our plain-C restatement of the reference hot path
+(oracle/port/*.c -> oracle/_build/liboracle_port.so).  Used by tests/ as the
+checker for the CUDA path, by __graft_entry__.smoke(), and by bench.py's
+cpu_baseline leg.  Never imported by pyrh_b200.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+LIB = HERE / "_build" / "liboracle_port.so"
+
+RL_NFIELD, RE_NFIELD, RE_MAXSTAGE = 24, 16, 12
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int)
+
+
+class RpLineTable(C.Structure):
+    _fields_ = [("nline", C.c_int), ("nelem", C.c_int), ("npf", C.c_int), ("matinv_simd", C.c_int),
+                ("lines", dp), ("zq", ip), ("zshift", dp), ("zstrength", dp),
+                ("elems", dp), ("pf", dp), ("Tpf", dp),
+                ("vmicro_char", C.c_double), ("magneto_optical", C.c_int)]
+
+
+class RpColumn(C.Structure):
+    _fields_ = [("Ndep", C.c_int)] + [(n, dp) for n in (
+        "T", "ne", "vturb", "vel", "B", "cos_gamma", "cos_2chi", "sin_2chi",
+        "nHtot", "np", "height")] + [("muz", C.c_double), ("moving", C.c_int)]
+
+
+def build(force: bool = False):
+    if force or not LIB.exists():
+        subprocess.check_call(["make", "-C", str(HERE), "port"], stdout=subprocess.DEVNULL)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(str(LIB))
+        _lib.rp_voigt_humlicek.restype = C.c_double
+        _lib.rp_voigt_humlicek.argtypes = [C.c_double, C.c_double, dp]
+        _lib.rp_humlicek_region.argtypes = [C.c_double, C.c_double]
+        _lib.rp_planck.restype = C.c_double
+        _lib.rp_planck.argtypes = [C.c_double, C.c_double]
+        _lib.rp_cent_deriv.restype = C.c_double
+        _lib.rp_cent_deriv.argtypes = [C.c_double] * 5
+        _lib.rp_rlk_opacity.restype = C.c_int
+    return _lib
+
+
+def _d(a):
+    return a.ctypes.data_as(dp)
+
+
+class PortTables:
+    """Keeps numpy arrays alive behind an rp_linetable."""
+
+    def __init__(self, lt, matinv_simd=False):
+        # lt: pyrh_b200.linelist.LineTable-like (attributes lines, zq, zshift, zstrength, elems, pf, Tpf, vmicro_char)
+        self.a = dict(lines=np.ascontiguousarray(lt.lines, np.float64),
+                      zq=np.ascontiguousarray(lt.zq, np.int32),
+                      zshift=np.ascontiguousarray(lt.zshift, np.float64),
+                      zstrength=np.ascontiguousarray(lt.zstrength, np.float64),
+                      elems=np.ascontiguousarray(lt.elems, np.float64),
+                      pf=np.ascontiguousarray(lt.pf, np.float64),
+                      Tpf=np.ascontiguousarray(lt.Tpf, np.float64))
+        a = self.a
+        self.c = RpLineTable(a["lines"].shape[0], a["elems"].shape[0], a["Tpf"].shape[0],
+                             int(matinv_simd), _d(a["lines"]), a["zq"].ctypes.data_as(ip),
+                             _d(a["zshift"]), _d(a["zstrength"]), _d(a["elems"]), _d(a["pf"]),
+                             _d(a["Tpf"]), float(lt.vmicro_char), 0)
+
+
+class PortColumn:
+    FIELDS = ("T", "ne", "vturb", "vel", "B", "cos_gamma", "cos_2chi", "sin_2chi",
+              "nHtot", "np", "height")
+
+    def __init__(self, muz=1.0, moving=True, **arrs):
+        self.a = {k: np.ascontiguousarray(arrs[k], np.float64) for k in self.FIELDS}
+        n = self.a["T"].shape[0]
+        self.c = RpColumn(n, *[_d(self.a[k]) for k in self.FIELDS], float(muz), int(moving))
+        self.Ndep = n
+
+
+def ltepops_elem(tab: PortTables, col: PortColumn, ielem: int) -> np.ndarray:
+    nst = int(tab.a["elems"][ielem, 2])
+    out = np.zeros((nst, col.Ndep))
+    lib().rp_ltepops_elem(C.byref(tab.c), ielem, C.byref(col.c), _d(out))
+    return out
+
+
+def elem_pops(tab: PortTables, col: PortColumn) -> np.ndarray:
+    ne = tab.a["elems"].shape[0]
+    out = np.zeros((ne, RE_MAXSTAGE, col.Ndep))
+    for ie in range(ne):
+        n = ltepops_elem(tab, col, ie)
+        out[ie, : n.shape[0]] = n
+    return out
+
+
+def rlk_opacity(tab: PortTables, col: PortColumn, elem_n: np.ndarray, lam: float, to_obs: int = 1):
+    chi = np.zeros((4, col.Ndep))
+    eta = np.zeros((4, col.Ndep))
+    elem_n = np.ascontiguousarray(elem_n)
+    fl = lib().rp_rlk_opacity(C.byref(tab.c), C.byref(col.c), _d(elem_n), C.c_double(lam),
+                              int(to_obs), _d(chi), _d(eta))
+    return fl, chi, eta
+
+
+def stokes_bezier3(height, muz, to_obs, chi, S, chiQUV, T, lam, bc_top=1, bc_bottom=2,
+                   matinv_simd=False, want_psi=False):
+    n = len(chi)
+    arr = [np.ascontiguousarray(x, np.float64) for x in (height, chi, S, chiQUV, T)]
+    I = np.zeros((4, n))
+    Psi = np.zeros(n)
+    lib().rp_stokes_bezier3(n, _d(arr[0]), C.c_double(muz), int(to_obs), _d(arr[1]), _d(arr[2]),
+                            _d(arr[3]), _d(arr[4]), C.c_double(lam), int(bc_top), int(bc_bottom),
+                            int(matinv_simd), _d(I), _d(Psi) if want_psi else None)
+    return (I, Psi) if want_psi else I
+
+
+def bezier3_scalar(height, muz, to_obs, chi, S, T, lam, bc_top=1, bc_bottom=2, want_psi=False):
+    n = len(chi)
+    arr = [np.ascontiguousarray(x, np.float64) for x in (height, chi, S, T)]
+    I = np.zeros(n)
+    Psi = np.zeros(n)
+    lib().rp_bezier3_scalar(n, _d(arr[0]), C.c_double(muz), int(to_obs), _d(arr[1]), _d(arr[2]),
+                            _d(arr[3]), C.c_double(lam), int(bc_top), int(bc_bottom), _d(I),
+                            _d(Psi) if want_psi else None)
+    return (I, Psi) if want_psi else I
+
+
+def lte_stokes_column(tab: PortTables, col: PortColumn, lam, chi_ai, eta_ai, bc_top=1, bc_bottom=2):
+    lam = np.ascontiguousarray(lam, np.float64)
+    chi_ai = np.ascontiguousarray(chi_ai, np.float64)
+    eta_ai = np.ascontiguousarray(eta_ai, np.float64)
+    out = np.zeros((4, len(lam)))
+    lib().rp_lte_stokes_column(C.byref(tab.c), C.byref(col.c), len(lam), _d(lam), _d(chi_ai),
+                               _d(eta_ai), int(bc_top), int(bc_bottom), _d(out))
+    return out
+
+
+def voigt(a, v):
+    F = C.c_double()
+    H = lib().rp_voigt_humlicek(float(a), float(v), C.byref(F))
+    return H, F.value

@@ -89,7 +89,7 @@ def load(variant: str = "scalar") -> C.CDLL:
 
 def make_workdir(kind: str = "benchmark", keywords: dict | None = None,
                  atoms_active: tuple = (), kurucz_lines: str | None = None,
-                 root: str | None = None) -> str:
+                 no_kurucz: bool = False, root: str | None = None) -> str:
     """Stage a cwd for rhf1d(): the reference's own input set (`benchmark/` or
     `tests/`) with optional keyword overrides (``KEY = value`` lines replaced or
     appended) and optional ACTIVE atoms."""
@@ -124,6 +124,9 @@ def make_workdir(kind: str = "benchmark", keywords: dict | None = None,
     if kurucz_lines is not None:
         (Path(d) / "kurucz_lines.dat").write_text(kurucz_lines)
         (Path(d) / "kurucz.input").write_text("kurucz_lines.dat\n")
+    if no_kurucz:
+        # an empty list of line files: readKuruczLines() (kurucz.c:159) reads nothing, Nrlk stays 0
+        (Path(d) / "kurucz.input").write_text("# no Kurucz line files\n")
     return d
 
 
