@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- formal-solution ray-points/s of the LTE polarised hot path on B200.
+
+Workload (BASELINE.json configs[1]): a batch of 16 384 perturbed FAL-C columns (70 depths,
+B field), LTE FULL_STOKES DELO-Bezier3 synthesis of the Hinode Fe I 6301/6302 window
+(301 wavelengths, 2 Kurucz lines, mu = 1), column-sharded: every rank gets its own 16 384
+columns ("weak" scaling, no data-path collective).
+
+One step = one pass of the hot path (prep + line opacity + DELO-Bezier3) over the rank's batch.
+  value : ray-points/s (ncol x nlambda x ndep useful up-ray depth steps per step, summed over
+          ranks) with inputs resident in HBM, timed with CUDA events on the launching stream.
+  e2e   : the same through rhb200_lte_stokes_batch() with pinned HOST buffers (H2D of the
+          atmosphere + background opacities and D2H of the spectra inside the timed region).
+  --impl reference : the unmodified reference rhf1d() (oracle/_ref) on the host cores
+          (fork farm over all cores: the only parallel mode the reference supports).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "formal-solution ray-points/s"
+NCOL_DEFAULT, NDEP, NLAMBDA = 16384, 70, 301
+
+# algorithmic FP64 work per ray-point (SURVEY.md 8(d) counting rule)
+FLOP_DELO = 1170.0
+FLOP_OPACITY = 16 * 32.8 + 2 * 45.0 + 30.0     # 16 Humlicek evals (measured region mix) + 2 line preambles + combine
+BYTES_DELO = 64.0                              # chi, K'(3), S(4) read per ray-point
+
+
+# ------------------------------------------------------------------ synthetic inputs
+def smooth_noise(rng, n, ndep, sigma_pts=7.0):
+    x = rng.standard_normal((n, ndep))
+    d = (np.arange(ndep)[:, None] - np.arange(ndep)[None, :]) / sigma_pts
+    w = np.exp(-0.5 * d * d)
+    w /= w.sum(axis=1, keepdims=True)
+    y = x @ w.T
+    return y / np.sqrt((w * w).sum(axis=1))[None, :]
+
+
+def synth_inputs(ncol, rank=0, pinned=True):
+    """Per-column inputs of the hot path.  The three golden 70-depth columns (whose background
+    opacities, proton densities and heights were produced by the reference's own host code)
+    are tiled and perturbed: T, ne, nH and the background by smooth +-1-2 % factors, and every
+    column gets its own B (0-2500 G), inclination, azimuth, v_los (sigma 1.5 km/s) and v_mic."""
+    from pyrh_b200 import api
+    rng = np.random.default_rng(20261017 + 1000 * rank)
+    gs = [dict(np.load(ROOT / "tests" / "golden" / f"synth70_c{c}.npz")) for c in range(3)]
+    k = gs[0]["lam_keep"]
+    lam = gs[0]["lam_spect"][k]
+    A = api.AT
+    base_at = np.zeros((3, len(A), NDEP))
+    for j, g in enumerate(gs):
+        for f, i in A.items():
+            base_at[j, i] = g["col_" + f]
+    base_chi = np.stack([g["chi_ai"][k] for g in gs])
+    base_eta = np.stack([g["eta_ai"][k] for g in gs])
+    alloc = api.pinned_empty if pinned else (lambda s: np.empty(s))
+    at = alloc((ncol, len(A), NDEP))
+    chi = alloc((ncol, NLAMBDA, NDEP))
+    eta = alloc((ncol, NLAMBDA, NDEP))
+    sel = np.arange(ncol) % 3
+    blk = 1024
+    for c0 in range(0, ncol, blk):
+        s = slice(c0, min(ncol, c0 + blk))
+        n = s.stop - s.start
+        j = sel[s]
+        a = base_at[j].copy()
+        fT = 1.0 + 0.01 * smooth_noise(rng, n, NDEP)
+        a[:, A["T"]] *= fT
+        a[:, A["ne"]] /= fT
+        a[:, A["nHtot"]] /= fT
+        a[:, A["np"]] /= fT
+        a[:, A["vel"]] = 1.5e3 * smooth_noise(rng, n, NDEP)
+        a[:, A["vturb"]] = np.clip(1.0 + 0.5 * smooth_noise(rng, n, NDEP), 0.2, 3.0) * 1e3
+        a[:, A["B"]] = np.maximum(rng.uniform(0, 2500, (n, 1)) * (1 + 0.2 * smooth_noise(rng, n, NDEP)), 0) / 1e4
+        gam = rng.uniform(0, np.pi, (n, 1)) + 0.1 * smooth_noise(rng, n, NDEP)
+        azi = rng.uniform(0, np.pi, (n, 1)) + 0.1 * smooth_noise(rng, n, NDEP)
+        a[:, A["cos_gamma"]] = np.cos(gam)
+        a[:, A["cos_2chi"]] = np.cos(2 * azi)
+        a[:, A["sin_2chi"]] = np.sin(2 * azi)
+        at[s] = a
+        fc = (1.0 + 0.02 * smooth_noise(rng, n, NDEP))[:, None, :]
+        np.multiply(base_chi[j], fc, out=chi[s])
+        np.multiply(base_eta[j], fc, out=eta[s])
+    return gs[0], lam, at, chi, eta
+
+
+# ------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.idx, self.p = gpu_index, None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+            out, _ = self.p.communicate()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        load = [s for s in sm if s > 0.5 * max(mx)] if sm and mx else sm
+        return {"sm_mhz": statistics.median(load or sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "power_w_max": max(pw) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------- reference arm
+def _ref_worker(args):
+    first, n, ndep = args
+    from oracle import refdriver as rd
+    from pyrh_b200 import synthetic
+    base = np.load(ROOT / "tests" / "golden" / "falc_base.npy")
+    wave = rd.hinode_wave(NLAMBDA)
+    cwd = rd.make_workdir("benchmark")
+    atms = synthetic.perturbed_batch(base, n, ndep=ndep, first=first)
+    rd.rhf1d(atms[0], wave, cwd)           # warm-up: page in the library and the atomic data
+    t0 = time.perf_counter()
+    for a in atms:
+        rd.rhf1d(a, wave, cwd)
+    return time.perf_counter() - t0
+
+
+def reference_throughput(cols_per_proc=4, procs=None, variant="scalar"):
+    """rhf1d() of the unmodified reference (oracle/_ref) on `procs` host cores, one process per
+    core; returns (ray-points/s, spectra/s, procs, ncolumns, wall)."""
+    import multiprocessing as mp
+    from oracle import refdriver as rd
+    if not rd.available(variant):
+        raise RuntimeError("oracle/_ref is not built (make -C oracle ref where /root/reference exists)")
+    procs = procs or os.cpu_count() or 1
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(procs) as pool:
+        pool.map(_ref_worker, [(1000 + p * cols_per_proc, cols_per_proc, NDEP) for p in range(procs)])
+    wall_all = time.perf_counter() - t0
+    # second pass, timed: pools are warm only per process, so time inside the workers and
+    # use the slowest worker (all run concurrently)
+    with ctx.Pool(procs) as pool:
+        t = pool.map(_ref_worker, [(2000 + p * cols_per_proc, cols_per_proc, NDEP) for p in range(procs)])
+    wall = max(t)
+    ncols = procs * cols_per_proc
+    return ncols * NLAMBDA * NDEP / wall, ncols / wall, procs, ncols, wall, wall_all
+
+
+# ------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ncol", type=int, default=NCOL_DEFAULT)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-cols-per-proc", type=int, default=4)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    config = {"workload": f"configs[1]: {args.ncol} perturbed FAL-C columns/GPU x {NDEP} depths x {NLAMBDA} "
+                          "wavelengths (Hinode Fe I 6301/6302, 2 Kurucz lines, 16 Zeeman components), LTE "
+                          "FULL_STOKES DELO-Bezier3, mu=1",
+              "ncol_per_gpu": args.ncol, "ndep": NDEP, "nlambda": NLAMBDA, "parallelism": f"columns x{world}",
+              "l2": "inputs (5.5 GB) and ray-point workspace (>5 GB) far larger than the 126 MB L2"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        rps, sps, procs, ncols, wall, _ = reference_throughput(args.ref_cols_per_proc)
+        line = {"impl": "reference", "metric": METRIC, "value": rps, "unit": "ray-points/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": config, "spectra_per_s": sps,
+                "cpu_baseline": {"value": rps, "unit": "ray-points/s", "cores": procs, "kind": "reference",
+                                 "sample": f"{ncols} perturbed FAL-C columns ({args.ref_cols_per_proc}/process), full rhf1d() "
+                                           "per column incl. input parsing + continuum (the reference has no way to "
+                                           "run the hot path alone)"},
+                "e2e": {"value": rps, "unit": "ray-points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from pyrh_b200 import api
+    from pyrh_b200.linelist import LineTable
+    ctx = api.Context(local_rank)
+    g0, lam, at, chi, eta = synth_inputs(args.ncol, rank)
+    ctx.set_lines(LineTable.from_npz(g0))
+    ctx.set_wavelengths(lam)
+    ncol = args.ncol
+    stokes = api.pinned_empty((ncol, 4, NLAMBDA))
+    units = ncol * NLAMBDA * NDEP
+
+    def barrier():
+        ctx.synchronize()
+        if dist is not None:
+            dist.barrier()
+        ctx.synchronize()
+
+    def maxreduce(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident arm
+    d_at, d_chi, d_eta, d_st = (ctx.dev_alloc(x.nbytes) for x in (at, chi, eta, stokes))
+    ctx.h2d(d_at, at); ctx.h2d(d_chi, chi); ctx.h2d(d_eta, eta)
+    for _ in range(args.warmup):
+        ctx.lte_stokes_batch_dev(ncol, NDEP, d_at, d_chi, d_eta, d_st)
+    ctx.timing(False)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ctx.timer_begin()
+    for _ in range(args.steps):
+        ctx.lte_stokes_batch_dev(ncol, NDEP, d_at, d_chi, d_eta, d_st)
+    ms_dev = ctx.timer_end()
+    launches = sum(v[1] for v in ctx.timing_get().values())
+    barrier()
+    clocks = sampler.stop()
+    ms_dev = maxreduce(ms_dev)
+    dev_out = np.empty((ncol, 4, NLAMBDA))
+    ctx.d2h(dev_out, d_st)
+
+    # ---- per-kernel durations (CUDA events around every launch; serialising, so separate pass)
+    ctx.timing(True)
+    for _ in range(max(1, min(args.steps, 3))):
+        ctx.lte_stokes_batch_dev(ncol, NDEP, d_at, d_chi, d_eta, d_st)
+    kt = {n: (ms / max(cnt, 1), cnt) for n, (ms, cnt) in ctx.timing_get().items() if cnt}
+    ctx.timing(False)
+    nlaunch_pass = {n: v[1] // max(1, min(args.steps, 3)) for n, v in kt.items()}
+    for p in (d_at, d_chi, d_eta, d_st):
+        ctx.dev_free(p)
+
+    # ---- end-to-end arm: host (pinned) buffers through the C ABI
+    for _ in range(max(1, args.warmup - 1)):
+        ctx.lte_stokes_batch(at, chi, eta, out=stokes)
+    barrier()
+    t0 = time.perf_counter()
+    ctx.timer_begin()
+    for _ in range(args.steps):
+        ctx.lte_stokes_batch(at, chi, eta, out=stokes)
+    ms_e2e_dev = ctx.timer_end()
+    ms_e2e = max(ms_e2e_dev, 1e3 * (time.perf_counter() - t0))
+    barrier()
+    ms_e2e = maxreduce(ms_e2e)
+    same = bool(np.array_equal(dev_out, stokes))
+
+    fma_tf, nofma_tf = ctx.fp64_peak()
+
+    if rank != 0:
+        ctx.close()
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except OSError:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    value = world * units * args.steps / (ms_dev * 1e-3)
+    e2e_val = world * units * args.steps / (ms_e2e * 1e-3)
+    # dominant kernel
+    dom = max(kt, key=lambda n: kt[n][0] * nlaunch_pass[n])
+    dom_ms = kt[dom][0]
+    cols_per_launch = ncol / max(1, nlaunch_pass[dom])
+    pts_per_launch = cols_per_launch * NLAMBDA * NDEP
+    flop_pt = {"delo": FLOP_DELO, "opacity": FLOP_OPACITY}.get(dom, 0.0)
+    achieved_tf = pts_per_launch * flop_pt / (dom_ms * 1e-3) / 1e12
+    roofline = {"kernel": {"delo": "delo_raypts_kernel", "opacity": "opacity_fused_kernel",
+                           "prep": "prep_kernel"}.get(dom, dom),
+                "bound": "fp64", "achieved": achieved_tf, "peak": fma_tf, "unit": "TFLOP/s",
+                "frac": achieved_tf / fma_tf if fma_tf else None, "traffic": None,
+                "peak_source": "rhb200_fp64_peak(): DFMA micro-benchmark run in this process (2 flop/FMA); "
+                               f"non-FMA FP64 issue rate {nofma_tf:.1f} Tinst/s",
+                "algorithmic_flop_per_raypoint": flop_pt, "ms_per_launch": dom_ms,
+                "hbm": {"achieved": pts_per_launch * (BYTES_DELO if dom == "delo" else 80.0) / (dom_ms * 1e-3) / 1e9,
+                        "peak": hbm_peak, "unit": "GB/s",
+                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"},
+                "kernels_ms_per_launch": {n: v[0] for n, v in kt.items()},
+                "kernel_launches_per_step": nlaunch_pass}
+    line = {"metric": METRIC, "value": value, "unit": "ray-points/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "spectra_per_s": world * ncol * args.steps / (ms_dev * 1e-3),
+            "e2e": {"value": e2e_val, "unit": "ray-points/s",
+                    "h2d_bytes_per_step": int(at.nbytes + chi.nbytes + eta.nbytes),
+                    "d2h_bytes_per_step": int(stokes.nbytes), "ms_per_step": ms_e2e / args.steps,
+                    "spectra_per_s": world * ncol * args.steps / (ms_e2e * 1e-3),
+                    "bitwise_equal_to_device_resident_run": same},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            rps, sps, procs, ncols, wall, _ = reference_throughput(args.ref_cols_per_proc)
+            line["cpu_baseline"] = {"value": rps, "unit": "ray-points/s", "cores": procs, "kind": "reference",
+                                    "spectra_per_s": sps,
+                                    "sample": f"{ncols} perturbed FAL-C columns (70 depths, 301 wavelengths), one rhf1d() "
+                                              f"process per core x {procs} cores, {wall:.1f} s; whole call (parsing + "
+                                              "continuum + line opacity + formal solution)"}
+        except Exception as e:          # noqa: BLE001
+            line["cpu_baseline"] = {"value": None, "unit": "ray-points/s", "cores": 0, "kind": "reference",
+                                    "sample": f"unavailable: {e}"}
+    print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,214 @@
+/* include/rhb200.h -- C ABI of librhb200.so, the B200 (sm_100a) hot path of RH / pyrh.
+ *
+ * Plain C: pointers and sizes only.  This is the boundary the RH host library
+ * (reference: /root/reference/rh) binds to; every entry point names the
+ * reference interface it replaces (file:line relative to the reference root).
+ * The reference-side stubs a maintainer would add are shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - all floating point data is IEEE double, SI units, exactly the values the
+ *     reference holds in `atmos`, `geometry`, `spectrum` when Formal() starts
+ *     (i.e. after the in-place conversion in pyrh_compute1dray.c:263-270);
+ *   - "ray" = one (column, wavelength) pair at the single LTE angle mu;
+ *   - every function returns 0 on success, a negative RHB200_E* code otherwise,
+ *     and rhb200_last_error() describes the failure.  The library never calls
+ *     exit() (the reference's Error(ERROR_LEVEL_2) does: rh/error.c:45-60);
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     point fails with RHB200_ENODEV.
+ */
+#ifndef RHB200_H
+#define RHB200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RHB200_VERSION 100
+
+enum {
+  RHB200_OK = 0,
+  RHB200_ENODEV = -1,   /* no CUDA device / driver */
+  RHB200_ECUDA = -2,    /* CUDA runtime error (message in rhb200_last_error) */
+  RHB200_EINVAL = -3,   /* bad argument */
+  RHB200_ESTATE = -4,   /* tables / wavelengths not set */
+  RHB200_ENOMEM = -5,
+  RHB200_EUNSUPPORTED = -6   /* keyword combination outside the implemented path */
+};
+
+/* ---- line-table row layout: the numeric fields of RLK_Line, rh/atom.h:156-167,
+        as filled by readKuruczLines (rh/kurucz.c:121-431) and sorted by
+        qsort(rlk_ascend) (rh/background.c:292-294).  One row of doubles per line. */
+enum {
+  RHB200_RL_LAMBDA0 = 0, /* nm, vacuum */
+  RHB200_RL_GI, RHB200_RL_GJ,
+  RHB200_RL_EI, RHB200_RL_EJ,                 /* J */
+  RHB200_RL_BJI, RHB200_RL_AJI, RHB200_RL_BIJ,
+  RHB200_RL_GRAD, RHB200_RL_GSTARK, RHB200_RL_GVDW,
+  RHB200_RL_HFS_FRAC, RHB200_RL_ISO_FRAC,
+  RHB200_RL_CROSS, RHB200_RL_ALPHA,
+  RHB200_RL_POLARIZABLE,                      /* 0/1 */
+  RHB200_RL_VDWAALS,                          /* enum vdWaals, rh/atom.h:32 */
+  RHB200_RL_ELEM,                             /* row index into the element table */
+  RHB200_RL_STAGE,
+  RHB200_RL_ZOFF, RHB200_RL_NCOMP,            /* slice of the Zeeman component arrays */
+  RHB200_RL_NFIELD = 24
+};
+/* ---- element-table row layout: Element, rh/atom.h:139-145 */
+enum {
+  RHB200_RE_WEIGHT = 0, RHB200_RE_ABUND, RHB200_RE_NSTAGE,
+  RHB200_RE_PFROW,                            /* first row of this element in pf[][] */
+  RHB200_RE_IONPOT0,                          /* ionpot[0 .. NSTAGE-2], J */
+  RHB200_RE_MAXSTAGE = 12,
+  RHB200_RE_NFIELD = RHB200_RE_IONPOT0 + RHB200_RE_MAXSTAGE
+};
+/* ---- per-column atmosphere rows [RHB200_AT_NFIELD][Ndep] (atmos.h:55-79, geometry.h:19-25) */
+enum {
+  RHB200_AT_T = 0, RHB200_AT_NE, RHB200_AT_VTURB, RHB200_AT_VEL, RHB200_AT_B,
+  RHB200_AT_COS_GAMMA, RHB200_AT_COS_2CHI, RHB200_AT_SIN_2CHI,   /* Bproject(), rhf1d/project.c:38 */
+  RHB200_AT_NHTOT, RHB200_AT_NP,              /* np = atmos.H->n[Nlevel-1] (kurucz.c:772) */
+  RHB200_AT_HEIGHT,
+  RHB200_AT_NFIELD
+};
+enum { RHB200_BC_IRRADIATED = 0, RHB200_BC_ZERO = 1, RHB200_BC_THERMALIZED = 2 };  /* geometry.h:13 */
+
+typedef struct rhb200_ctx rhb200_ctx;
+
+/* ---- library / device ------------------------------------------------ */
+int         rhb200_version(void);
+const char *rhb200_last_error(void);
+int         rhb200_device_count(void);
+/* device name, SM count, memory; any pointer may be NULL */
+int         rhb200_device_info(int device, char *name, int name_len, int *sm_count,
+                               size_t *mem_bytes, int *cc_major, int *cc_minor);
+
+/* ---- context: one per (process, GPU); owns a stream pair, the device copies
+        of the shared tables and a reusable workspace.  Replaces the reference's
+        process-global structs (pyrh_compute1dray.c:47-53). */
+rhb200_ctx *rhb200_open(int device);
+void        rhb200_close(rhb200_ctx *ctx);
+
+/* Shared read-only tables.  Replaces atmos.rlk_lines / atmos.elements / atmos.Tpf
+   as set up by readKuruczLines (kurucz.c:121), RLKZeeman (kurucz.c:832) and
+   readAbundance + pf_Kurucz.input (abundance.c:72-203).
+   vmicro_char: keyword VMICRO_CHAR in m/s.  magneto_optical, rlkscatter: keywords
+   MAGNETO_OPTICAL, RLK_SCATTER (both must be 0: RHB200_EUNSUPPORTED otherwise). */
+int rhb200_set_lines(rhb200_ctx *ctx,
+                     int nline, const double *lines /* [nline][RHB200_RL_NFIELD] */,
+                     int ncomp, const int *zq, const double *zshift, const double *zstrength,
+                     int nelem, const double *elems /* [nelem][RHB200_RE_NFIELD] */,
+                     int npf_rows, int npf, const double *pf /* [npf_rows][npf] */,
+                     const double *Tpf /* [npf] */,
+                     double vmicro_char, int magneto_optical, int rlkscatter);
+
+/* Wavelengths [nm, vacuum] at which Stokes spectra are wanted (spectrum.lambda
+   minus lambda_ref, pyrh_solveray.c:130-150).  Builds the per-wavelength line
+   windows of rlk_opacity (kurucz.c:538-566,608) on the host: integer work,
+   bit-exact. */
+int rhb200_set_wavelengths(rhb200_ctx *ctx, int nlambda, const double *lambda);
+/* read back the window table: for wavelength i the lines first[i] .. first[i]+count[i]-1
+   of the *contributing* list idx[] (test hook for the integer part) */
+int rhb200_get_line_windows(rhb200_ctx *ctx, int *first /*[nlambda]*/, int *count /*[nlambda]*/,
+                            int *idx /*[cap]*/, int cap, int *nidx);
+
+/* ---- the hot path ------------------------------------------------------
+   LTE FULL_STOKES synthesis of `ncol` independent columns.  Replaces, per column,
+     Background(): rlk_opacity() for every (lambda, mu, to_obs)   background.c:519-546, kurucz.c:511-828
+     Iterate() -> solveSpectrum() -> Formal() -> Piece_Stokes_Bezier3_1D
+                                                   iterate.c:48, formal.c:157-275, bezier_1D.c:52-300
+     _solveray() packing                                          pyrh_solveray.c:130-150
+   of the reference's rhf1d() (pyrh_compute1dray.c:112-389) for the case
+   solve_NLTE = FALSE (no ACTIVE atom), STOKES_MODE = FULL_STOKES,
+   S_INTERPOLATION_STOKES = DELO_BEZIER3, Nrays = 1.
+
+   atmos   [ncol][RHB200_AT_NFIELD][ndep]   SI
+   chi_ai, eta_ai [ncol][nlambda][ndep]     angle-independent background (chi_ai/eta_ai of
+                                            background.c:343-465 incl. passive_bb), reference layout
+   stokes  [ncol][4][nlambda]               emergent I,Q,U,V at mu (W m^-2 Hz^-1 sr^-1)
+   moving: atmos.moving (pyrh_compute1dray.c:261-278); bc_*: geometry.vboundary (getBoundary)
+   All pointers are HOST pointers; H2D/D2H copies are part of the call. */
+int rhb200_lte_stokes_batch(rhb200_ctx *ctx, int ncol, int ndep, double muz, int moving,
+                            int bc_top, int bc_bottom,
+                            const double *atmos, const double *chi_ai, const double *eta_ai,
+                            double *stokes);
+/* same, with DEVICE pointers (inputs already resident in HBM; no copies) */
+int rhb200_lte_stokes_batch_dev(rhb200_ctx *ctx, int ncol, int ndep, double muz, int moving,
+                                int bc_top, int bc_bottom,
+                                const double *d_atmos, const double *d_chi_ai,
+                                const double *d_eta_ai, double *d_stokes);
+
+/* ---- function-level entry points (each mirrors one reference function; used by
+        the parity tests and by hosts that keep the rest of Formal() on the CPU).
+        HOST pointers. ---------------------------------------------------- */
+
+/* LTEpops_elem (ltepops.c:116-159) for every element row: n [ncol][nelem][RHB200_RE_MAXSTAGE][ndep] */
+int rhb200_ltepops_elem_batch(rhb200_ctx *ctx, int ncol, int ndep, const double *atmos, double *n);
+
+/* rlk_opacity (kurucz.c:511-725) at every set wavelength, direction to_obs:
+   chi, eta [ncol][nlambda][4][ndep] (line part only, accumulated from 0 in line order),
+   flags [nlambda] bit0 hasline bit1 ispolarized (may be NULL) */
+int rhb200_rlk_opacity_batch(rhb200_ctx *ctx, int ncol, int ndep, double muz, int moving,
+                             int to_obs, const double *atmos, double *chi, double *eta, int *flags);
+
+/* Piece_Stokes_Bezier3_1D (bezier_1D.c:52-300) + StokesK (stokesopac.c:28-87) for nray rays.
+   ray_col[nray] selects the column (height, T) of each ray, ray_lambda[nray] its wavelength [nm].
+   chi [nray][ndep], S [nray][4][ndep], chiQUV [nray][3][ndep] (numerators of K', un-divided),
+   out I [nray][4][ndep], Psi [nray][ndep] or NULL.  height,T: [ncol][ndep]. */
+int rhb200_stokes_bezier3_batch(rhb200_ctx *ctx, int nray, int ncol, int ndep, double muz, int to_obs,
+                                int bc_top, int bc_bottom,
+                                const int *ray_col, const double *ray_lambda,
+                                const double *height, const double *T,
+                                const double *chi, const double *S, const double *chiQUV,
+                                double *I, double *Psi);
+
+/* Piecewise_Bezier3_1D (bezier_1D.c:306-541, without the log gf response function):
+   chi, S [nray][ndep]; out I, Psi [nray][ndep] (Psi may be NULL) */
+int rhb200_bezier3_batch(rhb200_ctx *ctx, int nray, int ncol, int ndep, double muz, int to_obs,
+                         int bc_top, int bc_bottom,
+                         const int *ray_col, const double *ray_lambda,
+                         const double *height, const double *T,
+                         const double *chi, const double *S, double *I, double *Psi);
+
+/* Voigt(a, v, &F, HUMLICEK) (voigt.c:381-419, humlicek.c): H, F for n (a, v) pairs;
+   region[n] (1..4) may be NULL */
+int rhb200_voigt_humlicek(rhb200_ctx *ctx, int n, const double *a, const double *v,
+                          double *H, double *F, int *region);
+
+/* exp / pow / sin / cos exactly as the device code evaluates them (test hook for
+   the glibc-equivalence of the device math) */
+int rhb200_math_probe(rhb200_ctx *ctx, int n, int func /*0 exp 1 sin 2 cos 3 pow*/,
+                      const double *x, const double *y, double *out);
+
+/* ---- device memory helpers (for callers that keep inputs resident) -------- */
+int rhb200_dev_alloc(rhb200_ctx *ctx, size_t bytes, void **dptr);
+int rhb200_dev_free(rhb200_ctx *ctx, void *dptr);
+int rhb200_host_alloc_pinned(size_t bytes, void **hptr);
+int rhb200_host_free_pinned(void *hptr);
+int rhb200_memcpy_h2d(rhb200_ctx *ctx, void *dst, const void *src, size_t bytes);
+int rhb200_memcpy_d2h(rhb200_ctx *ctx, void *dst, const void *src, size_t bytes);
+int rhb200_synchronize(rhb200_ctx *ctx);
+/* write `bytes` of a scratch buffer (> L2) to evict L2 between timed iterations */
+int rhb200_flush_l2(rhb200_ctx *ctx);
+
+/* ---- instrumentation ------------------------------------------------------
+   CUDA-event time (ms) and launch count per kernel family accumulated since the
+   last rhb200_timing_reset(); which: 0 prep, 1 line opacity, 2 DELO-Bezier3,
+   3 scalar Bezier3, 4 other.  Mirrors the getCPU() labels the reference stubs
+   out (rh/getcpu.c:60). */
+enum { RHB200_K_PREP = 0, RHB200_K_OPACITY, RHB200_K_DELO, RHB200_K_BEZIER, RHB200_K_OTHER,
+       RHB200_K_COUNT };
+int rhb200_timing_enable(rhb200_ctx *ctx, int on);
+int rhb200_timing_reset(rhb200_ctx *ctx);
+int rhb200_timing_get(rhb200_ctx *ctx, int which, double *ms, long *launches);
+/* CUDA-event stopwatch on the context's compute stream (bench.py times K steps with it) */
+int rhb200_timer_begin(rhb200_ctx *ctx);
+int rhb200_timer_end(rhb200_ctx *ctx, double *ms);
+/* FP64 pipe micro-benchmark: runs a dependent-free DFMA kernel, returns TFLOP/s
+   (2 flop per FMA).  Used by bench.py as the measured FP64 roofline denominator. */
+int rhb200_fp64_peak(rhb200_ctx *ctx, double *tflops_fma, double *tflops_nofma);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RHB200_H */

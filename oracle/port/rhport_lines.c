@@ -277,3 +277,37 @@ int rp_rlk_opacity(const rp_linetable *lt, const rp_column *col, const double *e
   free(pf);
   return flags;
 }
+
+/* ---- bookkeeping helper for DESIGN.md / bench.py: histogram of the Humlicek region taken
+        by every Voigt evaluation of rlk_opacity over a wavelength grid (hist[1..4]) and the
+        number of (line, depth, wavelength) profile evaluations (hist[0]) ---------------- */
+void rp_region_hist(const rp_linetable *lt, const rp_column *c, int Nlambda,
+                    const double *lambda, int to_obs, long *hist)
+{
+  for (int i = 0; i < 5; i++) hist[i] = 0;
+  for (int nl = 0; nl < Nlambda; nl++) {
+    double dlamb_char = lambda[nl] * RP_Q_WING * (lt->vmicro_char / RP_CLIGHT);
+    for (int n = 0; n < lt->nline; n++) {
+      const double *L = lt->lines + (long) n*RL_NFIELD;
+      if (fabs(L[RL_LAMBDA0] - lambda[nl]) > dlamb_char) continue;
+      const double *el = lt->elems + (long)((int) L[RL_ELEM]) * RE_NFIELD;
+      double vtherm = 2.0*RP_KBOLTZMANN/(RP_AMU * el[RE_WEIGHT]);
+      for (int k = 0; k < c->Ndep; k++) {
+        double vbroad = sqrt(vtherm*c->T[k] + c->vturb[k]*c->vturb[k]);
+        double v = (lambda[nl]/L[RL_LAMBDA0] - 1.0) * RP_CLIGHT/vbroad, GvdW, adamp, vB;
+        if (c->moving) v += (to_obs ? 1.0 : -1.0) * (c->muz * c->vel[k]) / vbroad;
+        switch ((int) L[RL_VDWAALS]) {
+        case RP_UNSOLD:  GvdW = L[RL_CROSS] * pow(c->T[k], 0.3); break;
+        case RP_BARKLEM: GvdW = L[RL_CROSS] * pow(c->T[k], (1.0 - L[RL_ALPHA])/2.0); break;
+        default:         GvdW = L[RL_GVDW]; break;
+        }
+        adamp = (L[RL_GRAD] + L[RL_GSTARK] * c->ne[k] + GvdW * (c->nHtot[k] - c->np[k])) *
+          (L[RL_LAMBDA0] * RP_NM_TO_M) / (4.0*RP_PI * vbroad);
+        vB = (RP_LARMOR * L[RL_LAMBDA0]) * c->B[k] / vbroad;
+        hist[0]++;
+        for (int nz = 0; nz < (int) L[RL_NCOMP]; nz++)
+          hist[rp_humlicek_region(adamp, v - lt->zshift[(int) L[RL_ZOFF]+nz]*vB)]++;
+      }
+    }
+  }
+}

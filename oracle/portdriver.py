@@ -154,3 +154,10 @@ def voigt(a, v):
     F = C.c_double()
     H = lib().rp_voigt_humlicek(float(a), float(v), C.byref(F))
     return H, F.value
+
+
+def region_hist(tab: PortTables, col: PortColumn, lam, to_obs: int = 1):
+    lam = np.ascontiguousarray(lam, np.float64)
+    h = (C.c_long * 5)()
+    lib().rp_region_hist(C.byref(tab.c), C.byref(col.c), len(lam), _d(lam), int(to_obs), h)
+    return np.array(list(h))

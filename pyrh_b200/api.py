@@ -1,0 +1,282 @@
+"""Host-side mirror of the reference's operator interface for the LTE Stokes path.
+
+Reference call stack being replaced: ``pyrh.compute1d`` (pyrh.pyx:537-668)
+-> ``rhf1d`` (rh/rhf1d/pyrh_compute1dray.c:112-389) -> Background/rlk_opacity -> Iterate ->
+Formal -> Piece_Stokes_Bezier3_1D -> _solveray.  The RH host keeps everything that is not
+on the hot path (input parsing, LTE/chemical equilibrium, continuum opacities, tau->height):
+it hands this module the per-column arrays it already holds when ``Formal`` starts, and gets
+the emergent Stokes spectra back.  Argument meaning and units follow ``compute1d``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+from .linelist import LineTable
+
+KM_TO_M = 1.0E+03
+CM_TO_M = 1.0E-02
+_CUBE_CM_TO_M = (CM_TO_M * CM_TO_M) * CM_TO_M         # CUBE(CM_TO_M), rh.h:48
+
+AT = dict(T=0, ne=1, vturb=2, vel=3, B=4, cos_gamma=5, cos_2chi=6, sin_2chi=7, nHtot=8, np=9, height=10)
+
+
+def _dp(a: np.ndarray):
+    return a.ctypes.data_as(_lib.dp)
+
+
+def _vp(a: np.ndarray):
+    return C.c_void_p(a.ctypes.data)
+
+
+_cos = np.frompyfunc(math.cos, 1, 1)     # glibc libm, like the reference's Bproject()
+_sin = np.frompyfunc(math.sin, 1, 1)
+
+
+def atmos_rows_from_pyrh(atmosphere: np.ndarray, np_: np.ndarray, height: np.ndarray,
+                         mu: float = 1.0) -> np.ndarray:
+    """pyrh-unit atmosphere(s) ``[..., 9+, Ndep]`` (pyrh.pyx:621-625) -> device rows
+    ``[..., RHB200_AT_NFIELD, Ndep]`` in SI, applying exactly the in-place conversion of
+    pyrh_compute1dray.c:263-270 and ``Bproject`` for mu = 1 (rhf1d/project.c:52-58).
+    ``np_`` [m^-3] and ``height`` [m] come from the RH host (LTE populations of hydrogen,
+    convertScales)."""
+    a = np.asarray(atmosphere, dtype=np.float64)
+    if mu != 1.0:
+        raise NotImplementedError("Bproject for mu != 1 (project.c:60-77) stays on the RH host: "
+                                  "pass cos_gamma/cos_2chi/sin_2chi rows directly")
+    out = np.empty(a.shape[:-2] + (_lib.AT_NFIELD, a.shape[-1]))
+    out[..., AT["T"], :] = a[..., 1, :]
+    out[..., AT["ne"], :] = a[..., 2, :] / _CUBE_CM_TO_M
+    out[..., AT["vel"], :] = a[..., 3, :] * KM_TO_M
+    out[..., AT["vturb"], :] = a[..., 4, :] * KM_TO_M
+    out[..., AT["B"], :] = a[..., 5, :] / 1e4
+    out[..., AT["cos_gamma"], :] = _cos(a[..., 6, :]).astype(np.float64)
+    out[..., AT["cos_2chi"], :] = _cos(2.0 * a[..., 7, :]).astype(np.float64)
+    out[..., AT["sin_2chi"], :] = _sin(2.0 * a[..., 7, :]).astype(np.float64)
+    out[..., AT["nHtot"], :] = a[..., 8, :] / _CUBE_CM_TO_M
+    out[..., AT["np"], :] = np_
+    out[..., AT["height"], :] = height
+    return out
+
+
+def is_moving(atmosphere: np.ndarray, vmacro_tresh: float = 0.0) -> bool:
+    """atmos.moving, pyrh_compute1dray.c:261-278 (per column)."""
+    return bool(np.any(np.abs(np.asarray(atmosphere)[..., 3, :] * KM_TO_M) >= vmacro_tresh))
+
+
+class Context:
+    """One GPU context (``rhb200_open``): shared line tables + wavelength grid."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        if self.lib.rhb200_device_count() <= 0:
+            raise _lib.RHB200Error("no CUDA device visible: pyrh_b200 has no CPU fallback")
+        self.h = self.lib.rhb200_open(int(device))
+        if not self.h:
+            raise _lib.RHB200Error(self.lib.rhb200_last_error().decode())
+        self.device = device
+        self.nlambda = 0
+        self.lt: LineTable | None = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rhb200_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- tables ------------------------------------------------------------
+    def set_lines(self, lt: LineTable, magneto_optical: bool = False, rlkscatter: bool = False):
+        lt.validate()
+        lines = np.ascontiguousarray(lt.lines, np.float64)
+        zq = np.ascontiguousarray(lt.zq, np.int32)
+        zs = np.ascontiguousarray(lt.zshift, np.float64)
+        zt = np.ascontiguousarray(lt.zstrength, np.float64)
+        el = np.ascontiguousarray(lt.elems, np.float64)
+        pf = np.ascontiguousarray(lt.pf, np.float64)
+        tp = np.ascontiguousarray(lt.Tpf, np.float64)
+        _lib.check(self.lib.rhb200_set_lines(self.h, lines.shape[0], _dp(lines), len(zq),
+                                             zq.ctypes.data_as(_lib.ip), _dp(zs), _dp(zt),
+                                             el.shape[0], _dp(el), pf.shape[0], pf.shape[1], _dp(pf),
+                                             _dp(tp), float(lt.vmicro_char), int(magneto_optical),
+                                             int(rlkscatter)))
+        self.lt = lt
+        self.nlambda = 0
+
+    def set_wavelengths(self, lam):
+        lam = np.ascontiguousarray(lam, np.float64)
+        _lib.check(self.lib.rhb200_set_wavelengths(self.h, len(lam), _dp(lam)))
+        self.nlambda = len(lam)
+        self.lam = lam
+
+    def line_windows(self):
+        first = np.zeros(self.nlambda, np.int32)
+        count = np.zeros(self.nlambda, np.int32)
+        n = C.c_int()
+        _lib.check(self.lib.rhb200_get_line_windows(self.h, first.ctypes.data_as(_lib.ip),
+                                                    count.ctypes.data_as(_lib.ip), None, 0, C.byref(n)))
+        idx = np.zeros(max(n.value, 1), np.int32)
+        _lib.check(self.lib.rhb200_get_line_windows(self.h, None, None, idx.ctypes.data_as(_lib.ip),
+                                                    len(idx), C.byref(n)))
+        return first, count, idx[: n.value]
+
+    # -- the hot path --------------------------------------------------------
+    def lte_stokes_batch(self, atmos_rows, chi_ai, eta_ai, mu=1.0, moving=True,
+                         bc_top=_lib.BC_ZERO, bc_bottom=_lib.BC_THERMALIZED, out=None):
+        """atmos_rows [ncol, AT_NFIELD, ndep], chi_ai/eta_ai [ncol, nlambda, ndep] (host arrays)
+        -> stokes [ncol, 4, nlambda]."""
+        at = np.ascontiguousarray(atmos_rows, np.float64)
+        ca = np.ascontiguousarray(chi_ai, np.float64)
+        ea = np.ascontiguousarray(eta_ai, np.float64)
+        ncol, nf, ndep = at.shape
+        assert nf == _lib.AT_NFIELD
+        assert ca.shape == (ncol, self.nlambda, ndep) and ea.shape == ca.shape
+        if out is None:
+            out = np.empty((ncol, 4, self.nlambda))
+        _lib.check(self.lib.rhb200_lte_stokes_batch(self.h, ncol, ndep, float(mu), int(moving),
+                                                    int(bc_top), int(bc_bottom), _vp(at), _vp(ca),
+                                                    _vp(ea), _vp(out)))
+        return out
+
+    def lte_stokes_batch_dev(self, ncol, ndep, d_atmos, d_chi_ai, d_eta_ai, d_stokes, mu=1.0,
+                             moving=True, bc_top=_lib.BC_ZERO, bc_bottom=_lib.BC_THERMALIZED):
+        _lib.check(self.lib.rhb200_lte_stokes_batch_dev(self.h, int(ncol), int(ndep), float(mu),
+                                                        int(moving), int(bc_top), int(bc_bottom),
+                                                        d_atmos, d_chi_ai, d_eta_ai, d_stokes))
+
+    # -- function-level entry points -------------------------------------------
+    def ltepops_elem(self, atmos_rows):
+        at = np.ascontiguousarray(atmos_rows, np.float64)
+        ncol, _, ndep = at.shape
+        n = np.zeros((ncol, self.lt.nelem, _lib.RE_MAXSTAGE, ndep))
+        _lib.check(self.lib.rhb200_ltepops_elem_batch(self.h, ncol, ndep, _dp(at), _dp(n)))
+        return n
+
+    def rlk_opacity(self, atmos_rows, mu=1.0, moving=True, to_obs=True):
+        at = np.ascontiguousarray(atmos_rows, np.float64)
+        ncol, _, ndep = at.shape
+        chi = np.zeros((ncol, self.nlambda, 4, ndep))
+        eta = np.zeros_like(chi)
+        flags = np.zeros(self.nlambda, np.int32)
+        _lib.check(self.lib.rhb200_rlk_opacity_batch(self.h, ncol, ndep, float(mu), int(moving),
+                                                     int(to_obs), _dp(at), _dp(chi), _dp(eta),
+                                                     flags.ctypes.data_as(_lib.ip)))
+        return chi, eta, flags
+
+    def stokes_bezier3(self, ray_col, ray_lambda, height, T, chi, S, chiQUV, mu=1.0, to_obs=True,
+                       bc_top=_lib.BC_ZERO, bc_bottom=_lib.BC_THERMALIZED, want_psi=False):
+        rc = np.ascontiguousarray(ray_col, np.int32)
+        rl = np.ascontiguousarray(ray_lambda, np.float64)
+        h = np.ascontiguousarray(np.atleast_2d(height), np.float64)
+        t = np.ascontiguousarray(np.atleast_2d(T), np.float64)
+        chi = np.ascontiguousarray(chi, np.float64)
+        S = np.ascontiguousarray(S, np.float64)
+        q = np.ascontiguousarray(chiQUV, np.float64)
+        nray, ndep = chi.shape
+        I = np.zeros((nray, 4, ndep))
+        Psi = np.zeros((nray, ndep)) if want_psi else None
+        _lib.check(self.lib.rhb200_stokes_bezier3_batch(
+            self.h, nray, h.shape[0], ndep, float(mu), int(to_obs), int(bc_top), int(bc_bottom),
+            rc.ctypes.data_as(_lib.ip), _dp(rl), _dp(h), _dp(t), _dp(chi), _dp(S), _dp(q), _dp(I),
+            _dp(Psi) if want_psi else None))
+        return (I, Psi) if want_psi else I
+
+    def bezier3(self, ray_col, ray_lambda, height, T, chi, S, mu=1.0, to_obs=True,
+                bc_top=_lib.BC_ZERO, bc_bottom=_lib.BC_THERMALIZED, want_psi=False):
+        rc = np.ascontiguousarray(ray_col, np.int32)
+        rl = np.ascontiguousarray(ray_lambda, np.float64)
+        h = np.ascontiguousarray(np.atleast_2d(height), np.float64)
+        t = np.ascontiguousarray(np.atleast_2d(T), np.float64)
+        chi = np.ascontiguousarray(chi, np.float64)
+        S = np.ascontiguousarray(S, np.float64)
+        nray, ndep = chi.shape
+        I = np.zeros((nray, ndep))
+        Psi = np.zeros((nray, ndep)) if want_psi else None
+        _lib.check(self.lib.rhb200_bezier3_batch(
+            self.h, nray, h.shape[0], ndep, float(mu), int(to_obs), int(bc_top), int(bc_bottom),
+            rc.ctypes.data_as(_lib.ip), _dp(rl), _dp(h), _dp(t), _dp(chi), _dp(S), _dp(I),
+            _dp(Psi) if want_psi else None))
+        return (I, Psi) if want_psi else I
+
+    def voigt(self, a, v):
+        a = np.ascontiguousarray(a, np.float64)
+        v = np.ascontiguousarray(v, np.float64)
+        H, F = np.zeros_like(a), np.zeros_like(a)
+        reg = np.zeros(a.shape, np.int32)
+        _lib.check(self.lib.rhb200_voigt_humlicek(self.h, a.size, _dp(a), _dp(v), _dp(H), _dp(F),
+                                                  reg.ctypes.data_as(_lib.ip)))
+        return H, F, reg
+
+    def math_probe(self, func: str, x, y=None):
+        code = dict(exp=0, sin=1, cos=2, pow=3)[func]
+        x = np.ascontiguousarray(x, np.float64)
+        out = np.zeros_like(x)
+        yy = np.ascontiguousarray(y, np.float64) if y is not None else None
+        _lib.check(self.lib.rhb200_math_probe(self.h, x.size, code, _dp(x),
+                                              _dp(yy) if yy is not None else None, _dp(out)))
+        return out
+
+    # -- device memory / instrumentation ------------------------------------------
+    def dev_alloc(self, nbytes: int) -> C.c_void_p:
+        p = C.c_void_p()
+        _lib.check(self.lib.rhb200_dev_alloc(self.h, int(nbytes), C.byref(p)))
+        return p
+
+    def dev_free(self, p):
+        _lib.check(self.lib.rhb200_dev_free(self.h, p))
+
+    def h2d(self, dptr, arr: np.ndarray):
+        arr = np.ascontiguousarray(arr)
+        _lib.check(self.lib.rhb200_memcpy_h2d(self.h, dptr, _vp(arr), arr.nbytes))
+
+    def d2h(self, arr: np.ndarray, dptr):
+        _lib.check(self.lib.rhb200_memcpy_d2h(self.h, _vp(arr), dptr, arr.nbytes))
+
+    def synchronize(self):
+        _lib.check(self.lib.rhb200_synchronize(self.h))
+
+    def flush_l2(self):
+        _lib.check(self.lib.rhb200_flush_l2(self.h))
+
+    def timing(self, on=True):
+        _lib.check(self.lib.rhb200_timing_enable(self.h, int(on)))
+        _lib.check(self.lib.rhb200_timing_reset(self.h))
+
+    def timing_get(self):
+        out = {}
+        for name, k in (("prep", 0), ("opacity", 1), ("delo", 2), ("bezier", 3), ("other", 4)):
+            ms, n = C.c_double(), C.c_long()
+            _lib.check(self.lib.rhb200_timing_get(self.h, k, C.byref(ms), C.byref(n)))
+            out[name] = (ms.value, n.value)
+        return out
+
+    def timer_begin(self):
+        _lib.check(self.lib.rhb200_timer_begin(self.h))
+
+    def timer_end(self) -> float:
+        ms = C.c_double()
+        _lib.check(self.lib.rhb200_timer_end(self.h, C.byref(ms)))
+        return ms.value
+
+    def fp64_peak(self):
+        a, b = C.c_double(), C.c_double()
+        _lib.check(self.lib.rhb200_fp64_peak(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+
+def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+    """numpy view over page-locked host memory (cudaHostAlloc) for overlapped H2D/D2H."""
+    lib = _lib.load()
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    _lib.check(lib.rhb200_host_alloc_pinned(n, C.byref(p)))
+    buf = (C.c_char * n).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    return arr

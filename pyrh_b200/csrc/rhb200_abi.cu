@@ -1,0 +1,593 @@
+// rhb200_abi.cu -- the C ABI of librhb200.so (include/rhb200.h): context management,
+// shared tables, the batched LTE Stokes pipeline and the function-level entry points.
+#include <cstdarg>
+#include <cmath>
+#include <algorithm>
+#include <mutex>
+#include "rhb200_common.cuh"
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_err[1024] = "";
+
+void rhb200_set_error(const char *fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char *rhb200_last_error(void) { return g_err; }
+extern "C" int rhb200_version(void) { return RHB200_VERSION; }
+
+extern "C" int rhb200_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+extern "C" int rhb200_device_info(int device, char *name, int name_len, int *sm_count,
+                                  size_t *mem_bytes, int *cc_major, int *cc_minor)
+{
+  cudaDeviceProp p;
+  RH_CUDA(cudaGetDeviceProperties(&p, device));
+  if (name && name_len > 0) { strncpy(name, p.name, name_len-1); name[name_len-1] = 0; }
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (mem_bytes) *mem_bytes = p.totalGlobalMem;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  return RHB200_OK;
+}
+
+// ----------------------------------------------------------------- context
+extern "C" rhb200_ctx *rhb200_open(int device)
+{
+  int n = rhb200_device_count();
+  if (n <= 0) { rhb200_set_error("no CUDA device visible (librhb200 has no CPU fallback)"); return nullptr; }
+  if (device < 0 || device >= n) { rhb200_set_error("device %d out of range (%d visible)", device, n); return nullptr; }
+  if (cudaSetDevice(device) != cudaSuccess) { rhb200_set_error("cudaSetDevice(%d) failed", device); return nullptr; }
+  rhb200_ctx *c = new rhb200_ctx();
+  c->device = device;
+  cudaDeviceProp p;
+  cudaGetDeviceProperties(&p, device);
+  c->sm_count = p.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+    rhb200_set_error("stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    delete c;
+    return nullptr;
+  }
+  return c;
+}
+
+static void free_tables(rhb200_ctx *c)
+{
+  DevTables &t = c->tab;
+  cudaFree(t.lines); cudaFree(t.zshift); cudaFree(t.zstrength); cudaFree(t.elems);
+  cudaFree(t.pf); cudaFree(t.Tpf); cudaFree(t.zq);
+  t = DevTables();
+}
+static void free_wave(rhb200_ctx *c)
+{
+  DevWave &w = c->wav;
+  cudaFree(w.lambda); cudaFree(w.first); cudaFree(w.count); cudaFree(w.idx); cudaFree(w.flags);
+  w = DevWave();
+}
+
+extern "C" void rhb200_close(rhb200_ctx *c)
+{
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  free_tables(c); free_wave(c);
+  cudaFree(c->ws); cudaFree(c->flush);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  delete c;
+}
+
+int rh_ws_reserve(rhb200_ctx *c, size_t bytes)
+{
+  if (bytes <= c->ws_bytes) return RHB200_OK;
+  if (c->ws) { RH_CUDA(cudaFree(c->ws)); c->ws = nullptr; c->ws_bytes = 0; }
+  cudaError_t e = cudaMalloc(&c->ws, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    rhb200_set_error("workspace cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    return RHB200_ENOMEM;
+  }
+  c->ws_bytes = bytes;
+  return RHB200_OK;
+}
+
+template <class T>
+static int upload(T **dptr, const T *h, size_t n)
+{
+  *dptr = nullptr;
+  if (n == 0) return RHB200_OK;
+  RH_CUDA(cudaMalloc((void **) dptr, n * sizeof(T)));
+  RH_CUDA(cudaMemcpy(*dptr, h, n * sizeof(T), cudaMemcpyHostToDevice));
+  return RHB200_OK;
+}
+
+#define RH_CHECK(expr) do { int rc__ = (expr); if (rc__ != RHB200_OK) return rc__; } while (0)
+#define RH_NEED_CTX(c) do { if (!(c)) { rhb200_set_error("null context"); return RHB200_EINVAL; } \
+                            RH_CUDA(cudaSetDevice((c)->device)); } while (0)
+
+extern "C" int rhb200_set_lines(rhb200_ctx *c, int nline, const double *lines, int ncomp,
+                                const int *zq, const double *zshift, const double *zstrength,
+                                int nelem, const double *elems, int npf_rows, int npf,
+                                const double *pf, const double *Tpf, double vmicro_char,
+                                int magneto_optical, int rlkscatter)
+{
+  RH_NEED_CTX(c);
+  if (magneto_optical) { rhb200_set_error("MAGNETO_OPTICAL = TRUE is not implemented (the reference overflows chip_c there, readj.c:328)"); return RHB200_EUNSUPPORTED; }
+  if (rlkscatter) { rhb200_set_error("RLK_SCATTER = TRUE is not implemented"); return RHB200_EUNSUPPORTED; }
+  if (nline < 0 || nelem < 0 || npf < 2 || (nline > 0 && (!lines || !elems || !pf || !Tpf))) {
+    rhb200_set_error("rhb200_set_lines: bad arguments"); return RHB200_EINVAL;
+  }
+  for (int n = 0; n < nline; n++) {
+    const double *L = lines + (size_t) n * RHB200_RL_NFIELD;
+    if (n > 0 && L[RHB200_RL_LAMBDA0] < L[RHB200_RL_LAMBDA0 - RHB200_RL_NFIELD]) {
+      rhb200_set_error("line table not sorted by lambda0 at row %d (background.c:292-294)", n); return RHB200_EINVAL;
+    }
+    const int ie = (int) L[RHB200_RL_ELEM];
+    if (ie < 0 || ie >= nelem) { rhb200_set_error("line %d: element row %d out of range", n, ie); return RHB200_EINVAL; }
+    const int zo = (int) L[RHB200_RL_ZOFF], nc = (int) L[RHB200_RL_NCOMP];
+    if (zo < 0 || nc < 0 || zo + nc > ncomp) { rhb200_set_error("line %d: Zeeman slice out of range", n); return RHB200_EINVAL; }
+    if (L[RHB200_RL_GRAD] != 0.0 && L[RHB200_RL_POLARIZABLE] == 0.0) {
+      rhb200_set_error("line %d is not polarizable: the VoigtArmstrong branch (kurucz.c:824) is not implemented", n);
+      return RHB200_EUNSUPPORTED;
+    }
+  }
+  for (int e = 0; e < nelem; e++) {
+    const double *E = elems + (size_t) e * RHB200_RE_NFIELD;
+    const int nst = (int) E[RHB200_RE_NSTAGE], row = (int) E[RHB200_RE_PFROW];
+    if (nst < 1 || nst > RHB200_RE_MAXSTAGE || row < 0 || row + nst > npf_rows) {
+      rhb200_set_error("element row %d: Nstage/pf rows out of range", e); return RHB200_EINVAL;
+    }
+  }
+  if (Tpf && !(Tpf[1] > Tpf[0])) { rhb200_set_error("Tpf must ascend"); return RHB200_EINVAL; }
+  free_tables(c);
+  DevTables &t = c->tab;
+  t.nline = nline; t.ncomp = ncomp; t.nelem = nelem; t.npf_rows = npf_rows; t.npf = npf;
+  t.vmicro_char = vmicro_char;
+  RH_CHECK(upload(&t.lines, lines, (size_t) nline * RHB200_RL_NFIELD));
+  RH_CHECK(upload(&t.zq, zq, (size_t) ncomp));
+  RH_CHECK(upload(&t.zshift, zshift, (size_t) ncomp));
+  RH_CHECK(upload(&t.zstrength, zstrength, (size_t) ncomp));
+  RH_CHECK(upload(&t.elems, elems, (size_t) nelem * RHB200_RE_NFIELD));
+  RH_CHECK(upload(&t.pf, pf, (size_t) npf_rows * npf));
+  RH_CHECK(upload(&t.Tpf, Tpf, (size_t) npf));
+  c->h_lines.assign(lines, lines + (size_t) nline * RHB200_RL_NFIELD);
+  c->h_elems.assign(elems, elems + (size_t) nelem * RHB200_RE_NFIELD);
+  free_wave(c);     // windows depend on the line table
+  return RHB200_OK;
+}
+
+// Per-wavelength line window: the integer part of rlk_opacity (kurucz.c:538-566, 605-634),
+// evaluated once on the host with the reference's own comparisons.
+extern "C" int rhb200_set_wavelengths(rhb200_ctx *c, int nlambda, const double *lambda)
+{
+  RH_NEED_CTX(c);
+  if (nlambda <= 0 || !lambda) { rhb200_set_error("rhb200_set_wavelengths: bad arguments"); return RHB200_EINVAL; }
+  const int N = c->tab.nline;
+  const double *LT = c->h_lines.data();
+  auto lam0 = [&](int n) { return LT[(size_t) n * RHB200_RL_NFIELD + RHB200_RL_LAMBDA0]; };
+  c->h_lambda.assign(lambda, lambda + nlambda);
+  c->h_first.assign(nlambda, 0); c->h_count.assign(nlambda, 0); c->h_flags.assign(nlambda, 0);
+  c->h_idx.clear();
+  for (int l = 0; l < nlambda; l++) {
+    const double lam = lambda[l];
+    c->h_first[l] = (int) c->h_idx.size();
+    if (N == 0) continue;
+    const double dlamb_char = lam * RH_Q_WING * (c->tab.vmicro_char / RH_CLIGHT);
+    if (lam < lam0(0) - dlamb_char || lam > lam0(N-1) + dlamb_char) continue;
+    int lo = 0, hi = N;                              // rlk_locate with *low = 0: plain bisection
+    while (hi - lo > 1) { const int mid = (hi + lo) >> 1; if (lam >= lam0(mid)) lo = mid; else hi = mid; }
+    int Nblue = lo, Nred = lo;
+    while (lam0(Nblue) + dlamb_char > lam && Nblue > 0) Nblue--;
+    while (lam0(Nred) - dlamb_char < lam && Nred < N-1) Nred++;
+    for (int n = Nblue; n <= Nred; n++) {
+      if (std::fabs(lam0(n) - lam) <= dlamb_char) {
+        const double *L = LT + (size_t) n * RHB200_RL_NFIELD;
+        const double *E = c->h_elems.data() + (size_t) ((int) L[RHB200_RL_ELEM]) * RHB200_RE_NFIELD;
+        if ((int) L[RHB200_RL_STAGE] < (int) E[RHB200_RE_NSTAGE] - 1) {   // kurucz.c:614
+          c->h_idx.push_back(n);
+          c->h_flags[l] |= 1;
+          if (L[RHB200_RL_POLARIZABLE] != 0.0) c->h_flags[l] |= 2;
+        }
+      }
+    }
+    c->h_count[l] = (int) c->h_idx.size() - c->h_first[l];
+  }
+  free_wave(c);
+  DevWave &w = c->wav;
+  w.nlambda = nlambda; w.nidx = (int) c->h_idx.size();
+  RH_CHECK(upload(&w.lambda, lambda, (size_t) nlambda));
+  RH_CHECK(upload(&w.first, c->h_first.data(), (size_t) nlambda));
+  RH_CHECK(upload(&w.count, c->h_count.data(), (size_t) nlambda));
+  RH_CHECK(upload(&w.flags, c->h_flags.data(), (size_t) nlambda));
+  if (w.nidx) RH_CHECK(upload(&w.idx, c->h_idx.data(), (size_t) w.nidx));
+  else RH_CUDA(cudaMalloc((void **) &w.idx, sizeof(int)));
+  return RHB200_OK;
+}
+
+extern "C" int rhb200_get_line_windows(rhb200_ctx *c, int *first, int *count, int *idx, int cap, int *nidx)
+{
+  if (!c || c->wav.nlambda == 0) { rhb200_set_error("wavelengths not set"); return RHB200_ESTATE; }
+  if (first) memcpy(first, c->h_first.data(), c->h_first.size()*sizeof(int));
+  if (count) memcpy(count, c->h_count.data(), c->h_count.size()*sizeof(int));
+  if (nidx) *nidx = (int) c->h_idx.size();
+  if (idx) memcpy(idx, c->h_idx.data(), std::min((size_t) cap, c->h_idx.size())*sizeof(int));
+  return RHB200_OK;
+}
+
+static int need_state(rhb200_ctx *c, bool wave)
+{
+  if (c->tab.nelem == 0 && c->tab.nline == 0 && c->tab.Tpf == nullptr) {
+    rhb200_set_error("rhb200_set_lines() has not been called"); return RHB200_ESTATE;
+  }
+  if (wave && c->wav.nlambda == 0) { rhb200_set_error("rhb200_set_wavelengths() has not been called"); return RHB200_ESTATE; }
+  return RHB200_OK;
+}
+
+// ------------------------------------------------------- batched LTE Stokes
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t) 255; }
+
+struct ChunkLayout {
+  size_t elem_n, lineprep, raypts, total;
+  ChunkLayout(const rhb200_ctx *c, int cc, int ndep) {
+    elem_n   = align_up((size_t) cc * std::max(1, c->tab.nelem) * RHB200_RE_MAXSTAGE * ndep * sizeof(double));
+    lineprep = align_up((size_t) cc * std::max(1, c->tab.nline) * ndep * LP_NFIELD * sizeof(double));
+    raypts   = align_up((size_t) cc * c->wav.nlambda * ndep * RP_NFIELD * sizeof(double));
+    total = elem_n + lineprep + raypts;
+  }
+};
+
+static int chunk_columns(const rhb200_ctx *c, int ncol, int ndep, int nslots)
+{
+  size_t budget = (size_t) 8 << 30;
+  if (const char *e = getenv("RHB200_WS_GB")) { double g = atof(e); if (g > 0.01) budget = (size_t) (g * (double) ((size_t) 1 << 30)); }
+  ChunkLayout one(c, 1, ndep);
+  size_t per = one.total + (size_t) (RHB200_AT_NFIELD * ndep + 2 * c->wav.nlambda * ndep + 4 * c->wav.nlambda) * sizeof(double);
+  size_t cc = budget / ((size_t) nslots * per);
+  if (cc < 1) cc = 1;
+  if (const char *e = getenv("RHB200_CHUNK_COLS")) { int v = atoi(e); if (v > 0) cc = (size_t) v; }
+  return (int) std::min((size_t) ncol, cc);
+}
+
+static int run_chunk_dev(rhb200_ctx *c, int cc, int ndep, double muz, int moving, int bc_top, int bc_bottom,
+                         const double *d_atmos, const double *d_chi_ai, const double *d_eta_ai,
+                         double *d_stokes, char *ws)
+{
+  ChunkLayout L(c, cc, ndep);
+  double *d_elem_n = (double *) ws, *d_lineprep = (double *) (ws + L.elem_n),
+         *d_raypts = (double *) (ws + L.elem_n + L.lineprep);
+  RH_CHECK(rh_launch_prep(c, cc, ndep, muz, moving, d_atmos, d_elem_n, d_lineprep));
+  RH_CHECK(rh_launch_opacity_fused(c, cc, ndep, 1, d_atmos, d_lineprep, d_chi_ai, d_eta_ai, d_raypts));
+  RH_CHECK(rh_launch_delo_raypts(c, cc, ndep, muz, bc_top, bc_bottom, d_atmos, d_raypts, d_stokes));
+  return RHB200_OK;
+}
+
+static int check_batch_args(rhb200_ctx *c, int ncol, int ndep, double muz, int bc_top, int bc_bottom)
+{
+  RH_CHECK(need_state(c, true));
+  if (ncol < 0 || ndep < 3 || !(muz > 0.0 && muz <= 1.0)) { rhb200_set_error("bad ncol/ndep/muz (%d, %d, %g)", ncol, ndep, muz); return RHB200_EINVAL; }
+  if (bc_top != RHB200_BC_ZERO) { rhb200_set_error("top boundary: only ZERO is implemented"); return RHB200_EUNSUPPORTED; }
+  if (bc_bottom != RHB200_BC_THERMALIZED && bc_bottom != RHB200_BC_ZERO) { rhb200_set_error("bottom boundary: only THERMALIZED / ZERO are implemented"); return RHB200_EUNSUPPORTED; }
+  return RHB200_OK;
+}
+
+extern "C" int rhb200_lte_stokes_batch_dev(rhb200_ctx *c, int ncol, int ndep, double muz, int moving,
+                                           int bc_top, int bc_bottom, const double *d_atmos,
+                                           const double *d_chi_ai, const double *d_eta_ai, double *d_stokes)
+{
+  RH_NEED_CTX(c);
+  RH_CHECK(check_batch_args(c, ncol, ndep, muz, bc_top, bc_bottom));
+  if (ncol == 0) return RHB200_OK;
+  const int nl = c->wav.nlambda;
+  const int cc = chunk_columns(c, ncol, ndep, 1);
+  ChunkLayout L(c, cc, ndep);
+  RH_CHECK(rh_ws_reserve(c, L.total));
+  for (int c0 = 0; c0 < ncol; c0 += cc) {
+    const int n = std::min(cc, ncol - c0);
+    RH_CHECK(run_chunk_dev(c, n, ndep, muz, moving, bc_top, bc_bottom,
+                           d_atmos + (size_t) c0 * RHB200_AT_NFIELD * ndep,
+                           d_chi_ai + (size_t) c0 * nl * ndep, d_eta_ai + (size_t) c0 * nl * ndep,
+                           d_stokes + (size_t) c0 * 4 * nl, (char *) c->ws));
+  }
+  RH_CUDA(cudaStreamSynchronize(c->stream));
+  return RHB200_OK;
+}
+
+// HOST pointers.  Two slots (device input/output buffers + workspace), each driven by its own
+// stream: the H2D copy of chunk i+1 overlaps the kernels of chunk i when the host buffers are
+// pinned (rhb200_host_alloc_pinned); pageable memory still works, just without overlap.
+extern "C" int rhb200_lte_stokes_batch(rhb200_ctx *c, int ncol, int ndep, double muz, int moving,
+                                       int bc_top, int bc_bottom, const double *atmos,
+                                       const double *chi_ai, const double *eta_ai, double *stokes)
+{
+  RH_NEED_CTX(c);
+  RH_CHECK(check_batch_args(c, ncol, ndep, muz, bc_top, bc_bottom));
+  if (ncol == 0) return RHB200_OK;
+  if (!atmos || !chi_ai || !eta_ai || !stokes) { rhb200_set_error("null buffer"); return RHB200_EINVAL; }
+  const int nl = c->wav.nlambda;
+  const int nslots = 2;
+  const int cc = chunk_columns(c, ncol, ndep, nslots);
+  ChunkLayout L(c, cc, ndep);
+  const size_t b_at = align_up((size_t) cc * RHB200_AT_NFIELD * ndep * sizeof(double));
+  const size_t b_op = align_up((size_t) cc * nl * ndep * sizeof(double));
+  const size_t b_st = align_up((size_t) cc * 4 * nl * sizeof(double));
+  const size_t slot = L.total + b_at + 2*b_op + b_st;
+  RH_CHECK(rh_ws_reserve(c, nslots * slot));
+  cudaStream_t streams[2] = {c->stream, c->copy_stream};
+  cudaStream_t saved = c->stream;
+  int rc = RHB200_OK, i = 0;
+  for (int c0 = 0; c0 < ncol && rc == RHB200_OK; c0 += cc, i++) {
+    const int n = std::min(cc, ncol - c0);
+    char *base = (char *) c->ws + (size_t) (i % nslots) * slot;
+    double *d_at = (double *) base, *d_chi = (double *) (base + b_at), *d_eta = (double *) (base + b_at + b_op),
+           *d_st = (double *) (base + b_at + 2*b_op);
+    char *ws = base + b_at + 2*b_op + b_st;
+    cudaStream_t st = streams[i % nslots];
+    c->stream = st;
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(d_at, atmos + (size_t) c0 * RHB200_AT_NFIELD * ndep,
+                             (size_t) n * RHB200_AT_NFIELD * ndep * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(d_chi, chi_ai + (size_t) c0 * nl * ndep, (size_t) n * nl * ndep * sizeof(double),
+                             cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(d_eta, eta_ai + (size_t) c0 * nl * ndep, (size_t) n * nl * ndep * sizeof(double),
+                             cudaMemcpyHostToDevice, st)) != cudaSuccess) {
+      rhb200_set_error("H2D copy failed: %s", cudaGetErrorString(e)); rc = RHB200_ECUDA; break;
+    }
+    rc = run_chunk_dev(c, n, ndep, muz, moving, bc_top, bc_bottom, d_at, d_chi, d_eta, d_st, ws);
+    if (rc != RHB200_OK) break;
+    if ((e = cudaMemcpyAsync(stokes + (size_t) c0 * 4 * nl, d_st, (size_t) n * 4 * nl * sizeof(double),
+                             cudaMemcpyDeviceToHost, st)) != cudaSuccess) {
+      rhb200_set_error("D2H copy failed: %s", cudaGetErrorString(e)); rc = RHB200_ECUDA; break;
+    }
+  }
+  c->stream = saved;
+  cudaError_t e1 = cudaStreamSynchronize(streams[0]), e2 = cudaStreamSynchronize(streams[1]);
+  if (rc == RHB200_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) {
+    rhb200_set_error("kernel execution failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    rc = RHB200_ECUDA;
+  }
+  return rc;
+}
+
+// ------------------------------------------------ function-level entry points
+struct DevBuf {
+  void *p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  int alloc(size_t bytes) {
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(bytes, 8));
+    if (e != cudaSuccess) { cudaGetLastError(); rhb200_set_error("cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); return RHB200_ENOMEM; }
+    return RHB200_OK;
+  }
+  int from_host(const void *h, size_t bytes) {
+    RH_CHECK(alloc(bytes));
+    if (bytes) RH_CUDA(cudaMemcpy(p, h, bytes, cudaMemcpyHostToDevice));
+    return RHB200_OK;
+  }
+  template <class T> T *as() { return (T *) p; }
+};
+static int to_host(void *h, const void *d, size_t bytes)
+{
+  if (bytes) RH_CUDA(cudaMemcpy(h, d, bytes, cudaMemcpyDeviceToHost));
+  return RHB200_OK;
+}
+
+extern "C" int rhb200_ltepops_elem_batch(rhb200_ctx *c, int ncol, int ndep, const double *atmos, double *n)
+{
+  RH_NEED_CTX(c);
+  RH_CHECK(need_state(c, false));
+  if (ncol <= 0 || ndep <= 0 || !atmos || !n) { rhb200_set_error("bad arguments"); return RHB200_EINVAL; }
+  DevBuf at, en, lp;
+  const size_t nb = (size_t) ncol * c->tab.nelem * RHB200_RE_MAXSTAGE * ndep * sizeof(double);
+  RH_CHECK(at.from_host(atmos, (size_t) ncol * RHB200_AT_NFIELD * ndep * sizeof(double)));
+  RH_CHECK(en.alloc(nb));
+  RH_CUDA(cudaMemset(en.p, 0, std::max<size_t>(nb, 8)));
+  RH_CHECK(lp.alloc((size_t) ncol * std::max(1, c->tab.nline) * ndep * LP_NFIELD * sizeof(double)));
+  RH_CHECK(rh_launch_prep(c, ncol, ndep, 1.0, 1, at.as<double>(), en.as<double>(), lp.as<double>()));
+  RH_CUDA(cudaStreamSynchronize(c->stream));
+  return to_host(n, en.p, nb);
+}
+
+extern "C" int rhb200_rlk_opacity_batch(rhb200_ctx *c, int ncol, int ndep, double muz, int moving,
+                                        int to_obs, const double *atmos, double *chi, double *eta, int *flags)
+{
+  RH_NEED_CTX(c);
+  RH_CHECK(need_state(c, true));
+  if (ncol <= 0 || ndep <= 0 || !atmos || !chi || !eta) { rhb200_set_error("bad arguments"); return RHB200_EINVAL; }
+  const int nl = c->wav.nlambda;
+  DevBuf at, en, lp, dchi, deta;
+  const size_t ob = (size_t) ncol * nl * 4 * ndep * sizeof(double);
+  RH_CHECK(at.from_host(atmos, (size_t) ncol * RHB200_AT_NFIELD * ndep * sizeof(double)));
+  RH_CHECK(en.alloc((size_t) ncol * std::max(1, c->tab.nelem) * RHB200_RE_MAXSTAGE * ndep * sizeof(double)));
+  RH_CHECK(lp.alloc((size_t) ncol * std::max(1, c->tab.nline) * ndep * LP_NFIELD * sizeof(double)));
+  RH_CHECK(dchi.alloc(ob)); RH_CHECK(deta.alloc(ob));
+  RH_CHECK(rh_launch_prep(c, ncol, ndep, muz, moving, at.as<double>(), en.as<double>(), lp.as<double>()));
+  RH_CHECK(rh_launch_opacity_raw(c, ncol, ndep, to_obs, at.as<double>(), lp.as<double>(),
+                                 dchi.as<double>(), deta.as<double>()));
+  RH_CUDA(cudaStreamSynchronize(c->stream));
+  RH_CHECK(to_host(chi, dchi.p, ob));
+  RH_CHECK(to_host(eta, deta.p, ob));
+  if (flags) memcpy(flags, c->h_flags.data(), (size_t) nl * sizeof(int));
+  return RHB200_OK;
+}
+
+extern "C" int rhb200_stokes_bezier3_batch(rhb200_ctx *c, int nray, int ncol, int ndep, double muz, int to_obs,
+                                           int bc_top, int bc_bottom, const int *ray_col,
+                                           const double *ray_lambda, const double *height, const double *T,
+                                           const double *chi, const double *S, const double *chiQUV,
+                                           double *I, double *Psi)
+{
+  RH_NEED_CTX(c);
+  if (nray <= 0 || ncol <= 0 || ndep < 3 || !ray_col || !ray_lambda || !height || !T || !chi || !S || !chiQUV || !I) {
+    rhb200_set_error("bad arguments"); return RHB200_EINVAL;
+  }
+  for (int r = 0; r < nray; r++) if (ray_col[r] < 0 || ray_col[r] >= ncol) { rhb200_set_error("ray_col[%d] out of range", r); return RHB200_EINVAL; }
+  DevBuf rc, rl, h, t, dchi, dS, dq, dI, dP;
+  const size_t rb = (size_t) nray * ndep * sizeof(double);
+  RH_CHECK(rc.from_host(ray_col, (size_t) nray * sizeof(int)));
+  RH_CHECK(rl.from_host(ray_lambda, (size_t) nray * sizeof(double)));
+  RH_CHECK(h.from_host(height, (size_t) ncol * ndep * sizeof(double)));
+  RH_CHECK(t.from_host(T, (size_t) ncol * ndep * sizeof(double)));
+  RH_CHECK(dchi.from_host(chi, rb)); RH_CHECK(dS.from_host(S, 4*rb)); RH_CHECK(dq.from_host(chiQUV, 3*rb));
+  RH_CHECK(dI.alloc(4*rb));
+  if (Psi) RH_CHECK(dP.alloc(rb));
+  RH_CHECK(rh_launch_delo_generic(c, nray, ndep, muz, to_obs, bc_top, bc_bottom, rc.as<int>(), rl.as<double>(),
+                                  h.as<double>(), t.as<double>(), dchi.as<double>(), dS.as<double>(),
+                                  dq.as<double>(), dI.as<double>(), Psi ? dP.as<double>() : nullptr));
+  RH_CUDA(cudaStreamSynchronize(c->stream));
+  RH_CHECK(to_host(I, dI.p, 4*rb));
+  if (Psi) RH_CHECK(to_host(Psi, dP.p, rb));
+  return RHB200_OK;
+}
+
+extern "C" int rhb200_bezier3_batch(rhb200_ctx *c, int nray, int ncol, int ndep, double muz, int to_obs,
+                                    int bc_top, int bc_bottom, const int *ray_col, const double *ray_lambda,
+                                    const double *height, const double *T, const double *chi, const double *S,
+                                    double *I, double *Psi)
+{
+  RH_NEED_CTX(c);
+  if (nray <= 0 || ncol <= 0 || ndep < 3 || !ray_col || !ray_lambda || !height || !T || !chi || !S || !I) {
+    rhb200_set_error("bad arguments"); return RHB200_EINVAL;
+  }
+  for (int r = 0; r < nray; r++) if (ray_col[r] < 0 || ray_col[r] >= ncol) { rhb200_set_error("ray_col[%d] out of range", r); return RHB200_EINVAL; }
+  DevBuf rc, rl, h, t, dchi, dS, dI, dP;
+  const size_t rb = (size_t) nray * ndep * sizeof(double);
+  RH_CHECK(rc.from_host(ray_col, (size_t) nray * sizeof(int)));
+  RH_CHECK(rl.from_host(ray_lambda, (size_t) nray * sizeof(double)));
+  RH_CHECK(h.from_host(height, (size_t) ncol * ndep * sizeof(double)));
+  RH_CHECK(t.from_host(T, (size_t) ncol * ndep * sizeof(double)));
+  RH_CHECK(dchi.from_host(chi, rb)); RH_CHECK(dS.from_host(S, rb));
+  RH_CHECK(dI.alloc(rb));
+  if (Psi) RH_CHECK(dP.alloc(rb));
+  RH_CHECK(rh_launch_bezier3(c, nray, ndep, muz, to_obs, bc_top, bc_bottom, rc.as<int>(), rl.as<double>(),
+                             h.as<double>(), t.as<double>(), dchi.as<double>(), dS.as<double>(),
+                             dI.as<double>(), Psi ? dP.as<double>() : nullptr));
+  RH_CUDA(cudaStreamSynchronize(c->stream));
+  RH_CHECK(to_host(I, dI.p, rb));
+  if (Psi) RH_CHECK(to_host(Psi, dP.p, rb));
+  return RHB200_OK;
+}
+
+extern "C" int rhb200_voigt_humlicek(rhb200_ctx *c, int n, const double *a, const double *v,
+                                     double *H, double *F, int *region)
+{
+  RH_NEED_CTX(c);
+  if (n <= 0 || !a || !v || !H || !F) { rhb200_set_error("bad arguments"); return RHB200_EINVAL; }
+  DevBuf da, dv, dH, dF, dR;
+  const size_t b = (size_t) n * sizeof(double);
+  RH_CHECK(da.from_host(a, b)); RH_CHECK(dv.from_host(v, b));
+  RH_CHECK(dH.alloc(b)); RH_CHECK(dF.alloc(b));
+  if (region) RH_CHECK(dR.alloc((size_t) n * sizeof(int)));
+  RH_CHECK(rh_launch_voigt(c, n, da.as<double>(), dv.as<double>(), dH.as<double>(), dF.as<double>(),
+                           region ? dR.as<int>() : nullptr));
+  RH_CUDA(cudaStreamSynchronize(c->stream));
+  RH_CHECK(to_host(H, dH.p, b)); RH_CHECK(to_host(F, dF.p, b));
+  if (region) RH_CHECK(to_host(region, dR.p, (size_t) n * sizeof(int)));
+  return RHB200_OK;
+}
+
+extern "C" int rhb200_math_probe(rhb200_ctx *c, int n, int func, const double *x, const double *y, double *out)
+{
+  RH_NEED_CTX(c);
+  if (n <= 0 || !x || !out || func < 0 || func > 3 || (func == 3 && !y)) { rhb200_set_error("bad arguments"); return RHB200_EINVAL; }
+  DevBuf dx, dy, dout;
+  const size_t b = (size_t) n * sizeof(double);
+  RH_CHECK(dx.from_host(x, b));
+  if (y) RH_CHECK(dy.from_host(y, b)); else RH_CHECK(dy.alloc(8));
+  RH_CHECK(dout.alloc(b));
+  RH_CHECK(rh_launch_math_probe(c, n, func, dx.as<double>(), dy.as<double>(), dout.as<double>()));
+  RH_CUDA(cudaStreamSynchronize(c->stream));
+  return to_host(out, dout.p, b);
+}
+
+// -------------------------------------------------------- memory helpers
+extern "C" int rhb200_dev_alloc(rhb200_ctx *c, size_t bytes, void **dptr)
+{
+  RH_NEED_CTX(c);
+  if (!dptr) { rhb200_set_error("null dptr"); return RHB200_EINVAL; }
+  cudaError_t e = cudaMalloc(dptr, std::max<size_t>(bytes, 8));
+  if (e != cudaSuccess) { cudaGetLastError(); rhb200_set_error("cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); return RHB200_ENOMEM; }
+  return RHB200_OK;
+}
+extern "C" int rhb200_dev_free(rhb200_ctx *c, void *dptr) { RH_NEED_CTX(c); RH_CUDA(cudaFree(dptr)); return RHB200_OK; }
+extern "C" int rhb200_host_alloc_pinned(size_t bytes, void **hptr)
+{
+  if (!hptr) { rhb200_set_error("null hptr"); return RHB200_EINVAL; }
+  cudaError_t e = cudaHostAlloc(hptr, std::max<size_t>(bytes, 8), cudaHostAllocDefault);
+  if (e != cudaSuccess) { cudaGetLastError(); rhb200_set_error("cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e)); return RHB200_ENOMEM; }
+  return RHB200_OK;
+}
+extern "C" int rhb200_host_free_pinned(void *hptr) { RH_CUDA(cudaFreeHost(hptr)); return RHB200_OK; }
+extern "C" int rhb200_memcpy_h2d(rhb200_ctx *c, void *dst, const void *src, size_t bytes)
+{ RH_NEED_CTX(c); RH_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice)); return RHB200_OK; }
+extern "C" int rhb200_memcpy_d2h(rhb200_ctx *c, void *dst, const void *src, size_t bytes)
+{ RH_NEED_CTX(c); RH_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost)); return RHB200_OK; }
+extern "C" int rhb200_synchronize(rhb200_ctx *c) { RH_NEED_CTX(c); RH_CUDA(cudaDeviceSynchronize()); return RHB200_OK; }
+
+extern "C" int rhb200_flush_l2(rhb200_ctx *c)
+{
+  RH_NEED_CTX(c);
+  const size_t bytes = (size_t) 256 << 20;      // 256 MiB > 126 MB L2
+  if (!c->flush) {
+    cudaError_t e = cudaMalloc(&c->flush, bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); rhb200_set_error("flush buffer: %s", cudaGetErrorString(e)); return RHB200_ENOMEM; }
+    c->flush_bytes = bytes;
+  }
+  static int v = 0;
+  RH_CUDA(cudaMemsetAsync(c->flush, (++v) & 0xff, c->flush_bytes, c->stream));
+  RH_CUDA(cudaStreamSynchronize(c->stream));
+  return RHB200_OK;
+}
+
+// --------------------------------------------------------- instrumentation
+extern "C" int rhb200_timing_enable(rhb200_ctx *c, int on) { if (!c) return RHB200_EINVAL; c->timing = on != 0; return RHB200_OK; }
+extern "C" int rhb200_timing_reset(rhb200_ctx *c)
+{
+  if (!c) return RHB200_EINVAL;
+  for (int i = 0; i < RHB200_K_COUNT; i++) { c->k_ms[i] = 0.0; c->k_launch[i] = 0; }
+  return RHB200_OK;
+}
+extern "C" int rhb200_timing_get(rhb200_ctx *c, int which, double *ms, long *launches)
+{
+  if (!c || which < 0 || which >= RHB200_K_COUNT) return RHB200_EINVAL;
+  if (ms) *ms = c->k_ms[which];
+  if (launches) *launches = c->k_launch[which];
+  return RHB200_OK;
+}
+static cudaEvent_t g_t0 = nullptr, g_t1 = nullptr;
+extern "C" int rhb200_timer_begin(rhb200_ctx *c)
+{
+  RH_NEED_CTX(c);
+  if (!g_t0) { RH_CUDA(cudaEventCreate(&g_t0)); RH_CUDA(cudaEventCreate(&g_t1)); }
+  RH_CUDA(cudaDeviceSynchronize());
+  RH_CUDA(cudaEventRecord(g_t0, c->stream));
+  return RHB200_OK;
+}
+extern "C" int rhb200_timer_end(rhb200_ctx *c, double *ms)
+{
+  RH_NEED_CTX(c);
+  if (!g_t0 || !ms) { rhb200_set_error("timer not started"); return RHB200_EINVAL; }
+  RH_CUDA(cudaEventRecord(g_t1, c->stream));
+  RH_CUDA(cudaEventSynchronize(g_t1));
+  RH_CUDA(cudaDeviceSynchronize());
+  float f = 0.f;
+  RH_CUDA(cudaEventElapsedTime(&f, g_t0, g_t1));
+  *ms = f;
+  return RHB200_OK;
+}
+extern "C" int rhb200_fp64_peak(rhb200_ctx *c, double *tf_fma, double *tf_nofma)
+{
+  RH_NEED_CTX(c);
+  return rh_fp64_peak(c, tf_fma, tf_nofma);
+}

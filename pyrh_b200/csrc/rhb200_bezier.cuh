@@ -1,0 +1,85 @@
+// rhb200_bezier.cuh -- scalar cubic-Bezier short-characteristics ray (unpolarised).
+// Reference: Piecewise_Bezier3_1D rh/rhf1d/bezier_1D.c:306-541 (the log gf response-function
+// branch, :416-428/:477-490/:509-516, is not part of this kernel).
+#pragma once
+#include "rhb200_delo.cuh"
+
+namespace rhz {
+
+__device__ __forceinline__ void bezier3_ray(const int ndep, const double *__restrict__ z, const double muz,
+                                            const int to_obs, const int bc_top, const int bc_bottom,
+                                            const double *__restrict__ T, const double lambda,
+                                            const double *__restrict__ chi, const double *__restrict__ S,
+                                            double *__restrict__ I, double *__restrict__ Psi)
+{
+  using namespace rhd;
+  const double zmu = 1.0 / muz;
+  const int dk = to_obs ? -1 : 1;
+  const int ks = to_obs ? ndep-1 : 0, ke = to_obs ? 0 : ndep-1;
+
+  double dtau_uw = 0.5 * zmu * (chi[ks] + chi[ks+dk]) * fabs(z[ks] - z[ks+dk]);
+  double I_upw = 0.0;                                   // bezier_1D.c:352-386
+  if (to_obs) {
+    if (bc_bottom == RHB200_BC_THERMALIZED) {
+      const double B0 = planck(T[ndep-2], lambda), B1 = planck(T[ndep-1], lambda);
+      I_upw = B1 - (B0 - B1) / dtau_uw;
+    }
+  } else if (bc_top == RHB200_BC_THERMALIZED) {
+    const double B0 = planck(T[0], lambda), B1 = planck(T[1], lambda);
+    I_upw = B0 - (B1 - B0) / dtau_uw;
+  }
+  I[ks] = I_upw;
+  if (Psi) Psi[ks] = 0.0;
+
+  int k = ks + dk;
+  double dsup = fabs(z[k] - z[k-dk]) * zmu;
+  double dsdn = fabs(z[k+dk] - z[k]) * zmu;
+  double dchi_up = (chi[k] - chi[k-dk]) / dsup;
+  double fchi = (chi[k+dk] - chi[k]) / dsdn;
+  double dchi_c = fb_deriv(dchi_up, fchi, fb_alpha(dsup, dsdn));
+  {
+    const double c1 = RH_MAX0(chi[k]    - (dsup/3.0) * dchi_c);
+    const double c2 = RH_MAX0(chi[k-dk] + (dsup/3.0) * dchi_up);
+    dtau_uw = dsup * (chi[k] + chi[k-dk] + c1 + c2) * 0.25;
+  }
+  double dS_up = (S[k] - S[k-dk]) / dtau_uw;
+  double fS = dS_up, dtau_dw = 0.0, dchi_dn = 0.0, dS_c = 0.0;
+
+  for (; k != ke + dk; k += dk) {
+    if (k != ke) {
+      dsdn = fabs(z[k+dk] - z[k]) * zmu;
+      double fnext = fchi;
+      if (abs(k - ke) > 1) {
+        const double dsdn2 = fabs(z[k+2*dk] - z[k+dk]) * zmu;
+        fnext = (chi[k+2*dk] - chi[k+dk]) / dsdn2;
+        dchi_dn = fb_deriv(fchi, fnext, fb_alpha(dsdn, dsdn2));
+      } else
+        dchi_dn = fchi;
+      double c1 = RH_MAX0(chi[k]    + (dsdn/3.0) * dchi_c);
+      double c2 = RH_MAX0(chi[k+dk] - (dsdn/3.0) * dchi_dn);
+      dtau_dw = dsdn * (chi[k] + chi[k+dk] + c1 + c2) * 0.25;
+      const double dt03 = dtau_uw / 3.0;
+      double alpha, beta, gamma, theta, eps;
+      bezier3_coeffs(dtau_uw, alpha, beta, gamma, theta, eps);
+      const double fi = (S[k+dk] - S[k]) / dtau_dw;
+      dS_c = fb_deriv(fS, fi, fb_alpha(dtau_uw, dtau_dw));
+      fS = fi;
+      c1 = RH_MAX0(S[k]    - dt03 * dS_c);
+      c2 = RH_MAX0(S[k-dk] + dt03 * dS_up);
+      I[k] = I_upw*eps + alpha*S[k] + beta*S[k-dk] + gamma * c1 + theta * c2;
+      if (Psi) Psi[k] = alpha + gamma;
+      fchi = fnext;
+    } else {
+      dtau_uw = 0.5 * zmu * (chi[k] + chi[k-dk]) * fabs(z[k] - z[k-dk]);
+      const double dS_uw = -(S[k] - S[k-dk]) / dtau_uw;
+      double w0, w1;
+      w3(dtau_uw, w0, w1);
+      I[k] = (1.0 - w0)*I_upw + w0*S[k] + w1*dS_uw;
+      if (Psi) Psi[k] = w0 - w1 / dtau_uw;
+    }
+    I_upw = I[k];
+    dsup = dsdn; dchi_up = dchi_c; dchi_c = dchi_dn; dtau_uw = dtau_dw; dS_up = dS_c;
+  }
+}
+
+}  // namespace rhz

@@ -1,0 +1,129 @@
+// rhb200_common.cuh -- shared declarations of librhb200.so (sm_100a).
+// All device arithmetic is compiled with -fmad=false: the reference x86-64
+// build has no FMA contraction, and parity is bit-for-bit where the reference
+// is IEEE-deterministic (see DESIGN.md "Arithmetic contract").
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/rhb200.h"
+
+// physical constants: rh/constant.h:28-73 (same literals, same expressions)
+#define RH_CLIGHT      2.99792458E+08
+#define RH_HPLANCK     6.6260755E-34
+#define RH_KBOLTZMANN  1.380658E-23
+#define RH_AMU         1.6605402E-27
+#define RH_M_ELECTRON  9.1093897E-31
+#define RH_Q_ELECTRON  1.60217733E-19
+#define RH_NM_TO_M     1.0E-09
+#define RH_PI          3.14159265358979
+#define RH_SQRTPI      1.77245385090551
+// constant.h:68 -- the macro has no outer parentheses in the reference: keep it so
+#define RH_LARMOR      (RH_Q_ELECTRON / (4.0*RH_PI*RH_M_ELECTRON)) * RH_NM_TO_M
+#define RH_Q_WING            20.0   // kurucz.c:89
+#define RH_MAX_GAUSS_DOPPLER 7.0    // kurucz.c:92
+
+void rhb200_set_error(const char *fmt, ...);
+
+#define RH_CUDA(call)                                                          \
+  do {                                                                         \
+    cudaError_t e__ = (call);                                                  \
+    if (e__ != cudaSuccess) {                                                  \
+      rhb200_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call,            \
+                       cudaGetErrorString(e__));                               \
+      return RHB200_ECUDA;                                                     \
+    }                                                                          \
+  } while (0)
+
+// per-(column, line, depth) quantities that do not depend on wavelength
+// (hoisted out of RLKProfile / rlk_opacity, kurucz.c:669-691,744-783)
+enum { LP_VBROAD = 0, LP_ADAMP, LP_VB, LP_W, LP_SV, LP_CHIL, LP_ETAL, LP_NFIELD = 8 };
+// ray-point record handed from the opacity kernel to the DELO kernel
+enum { RP_CHI = 0, RP_KQ, RP_KU, RP_KV, RP_SI, RP_SQ, RP_SU, RP_SV, RP_NFIELD };
+
+struct DevTables {
+  int nline = 0, ncomp = 0, nelem = 0, npf_rows = 0, npf = 0;
+  double *lines = nullptr, *zshift = nullptr, *zstrength = nullptr, *elems = nullptr,
+         *pf = nullptr, *Tpf = nullptr;
+  int *zq = nullptr;
+  double vmicro_char = 0.0;
+};
+
+struct DevWave {
+  int nlambda = 0, nidx = 0;
+  double *lambda = nullptr;   // [nlambda]
+  int *first = nullptr, *count = nullptr, *idx = nullptr, *flags = nullptr;
+};
+
+struct KTimer {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+};
+
+struct rhb200_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  DevTables tab;
+  DevWave wav;
+  std::vector<double> h_lines, h_elems, h_lambda;
+  std::vector<int> h_first, h_count, h_idx, h_flags;
+  // workspace (grown on demand)
+  void *ws = nullptr; size_t ws_bytes = 0;
+  void *flush = nullptr; size_t flush_bytes = 0;
+  // instrumentation
+  bool timing = false;
+  double k_ms[RHB200_K_COUNT] = {0};
+  long k_launch[RHB200_K_COUNT] = {0};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+// timed launch helper: records CUDA events around the launch on ctx->stream when
+// instrumentation is on (synchronising: only used for measurement runs)
+struct ScopedKernelTimer {
+  rhb200_ctx *c; int which;
+  ScopedKernelTimer(rhb200_ctx *ctx, int w) : c(ctx), which(w) {
+    if (c->timing) cudaEventRecord(c->ev0, c->stream);
+  }
+  ~ScopedKernelTimer() {
+    c->k_launch[which] += 1;
+    if (c->timing) {
+      cudaEventRecord(c->ev1, c->stream);
+      cudaEventSynchronize(c->ev1);
+      float ms = 0.f; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+      c->k_ms[which] += ms;
+    }
+  }
+};
+
+int rh_ws_reserve(rhb200_ctx *ctx, size_t bytes);
+
+// launchers implemented in the .cu files (device pointers)
+int rh_launch_prep(rhb200_ctx *ctx, int ncol, int ndep, double muz, int moving,
+                   const double *d_atmos, double *d_elem_n, double *d_lineprep);
+int rh_launch_opacity_fused(rhb200_ctx *ctx, int ncol, int ndep, int to_obs,
+                            const double *d_atmos, const double *d_lineprep,
+                            const double *d_chi_ai, const double *d_eta_ai,
+                            double *d_raypts /* [ndep][RP_NFIELD][nray] */);
+int rh_launch_opacity_raw(rhb200_ctx *ctx, int ncol, int ndep, int to_obs,
+                          const double *d_atmos, const double *d_lineprep,
+                          double *d_chi, double *d_eta /* [ncol][nlambda][4][ndep] */);
+int rh_launch_delo_raypts(rhb200_ctx *ctx, int ncol, int ndep, double muz, int bc_top, int bc_bottom,
+                          const double *d_atmos, const double *d_raypts,
+                          double *d_stokes /* [ncol][4][nlambda] */);
+int rh_launch_delo_generic(rhb200_ctx *ctx, int nray, int ndep, double muz, int to_obs,
+                           int bc_top, int bc_bottom, const int *d_ray_col,
+                           const double *d_ray_lambda, const double *d_height, const double *d_T,
+                           const double *d_chi, const double *d_S, const double *d_chiQUV,
+                           double *d_I, double *d_Psi);
+int rh_launch_bezier3(rhb200_ctx *ctx, int nray, int ndep, double muz, int to_obs,
+                      int bc_top, int bc_bottom, const int *d_ray_col,
+                      const double *d_ray_lambda, const double *d_height, const double *d_T,
+                      const double *d_chi, const double *d_S, double *d_I, double *d_Psi);
+int rh_launch_voigt(rhb200_ctx *ctx, int n, const double *d_a, const double *d_v,
+                    double *d_H, double *d_F, int *d_region);
+int rh_launch_math_probe(rhb200_ctx *ctx, int n, int func, const double *d_x, const double *d_y,
+                         double *d_out);
+int rh_fp64_peak(rhb200_ctx *ctx, double *tf_fma, double *tf_nofma);

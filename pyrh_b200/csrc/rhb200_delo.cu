@@ -1,0 +1,153 @@
+// rhb200_delo.cu -- kernels + launchers for the polarised DELO-Bezier3 solver and the
+// scalar cubic-Bezier short-characteristics solver (one thread per ray, depth sequential).
+#include "rhb200_delo.cuh"
+#include "rhb200_bezier.cuh"
+
+namespace {
+
+// ---- IO policy: ray-point records written by the fused opacity kernel,
+//      layout [depth][RP_NFIELD][nray]: consecutive rays (= consecutive wavelengths of a
+//      column) are consecutive in memory, so every warp load is one 256-byte run.
+struct RayPtsIO {
+  const double *__restrict__ rp;   // already offset by ray index
+  size_t nray;
+  double *out;                     // stokes + col*4*nlambda + l, stride nlambda between I,Q,U,V
+  int nlambda, kout;
+  __device__ __forceinline__ double chi(int k) const { return __ldg(rp + ((size_t)k*RP_NFIELD + RP_CHI)*nray); }
+  __device__ __forceinline__ void K(int k, double x[3]) const {
+    x[0] = __ldg(rp + ((size_t)k*RP_NFIELD + RP_KQ)*nray);
+    x[1] = __ldg(rp + ((size_t)k*RP_NFIELD + RP_KU)*nray);
+    x[2] = __ldg(rp + ((size_t)k*RP_NFIELD + RP_KV)*nray);
+  }
+  __device__ __forceinline__ void S(int k, double s[4]) const {
+    s[0] = __ldg(rp + ((size_t)k*RP_NFIELD + RP_SI)*nray);
+    s[1] = __ldg(rp + ((size_t)k*RP_NFIELD + RP_SQ)*nray);
+    s[2] = __ldg(rp + ((size_t)k*RP_NFIELD + RP_SU)*nray);
+    s[3] = __ldg(rp + ((size_t)k*RP_NFIELD + RP_SV)*nray);
+  }
+  __device__ __forceinline__ void storeI(int k, const double I[4]) {
+    if (k == kout) {
+      out[0] = I[0]; out[nlambda] = I[1]; out[2*(size_t)nlambda] = I[2]; out[3*(size_t)nlambda] = I[3];
+    }
+  }
+  __device__ __forceinline__ void storePsi(int, double) {}
+};
+
+// ---- IO policy: reference layouts chi[nray][ndep], S[nray][4][ndep], chiQUV[nray][3][ndep]
+struct GenericIO {
+  const double *__restrict__ chi_, *__restrict__ S_, *__restrict__ q_;
+  double *I_, *Psi_;
+  int ndep;
+  __device__ __forceinline__ double chi(int k) const { return chi_[k]; }
+  __device__ __forceinline__ void K(int k, double x[3]) const {   // StokesK, stokesopac.c:72-77
+    const double c = chi_[k];
+    x[0] = q_[k] / c; x[1] = q_[ndep + k] / c; x[2] = q_[2*ndep + k] / c;
+  }
+  __device__ __forceinline__ void S(int k, double s[4]) const {
+    s[0] = S_[k]; s[1] = S_[ndep+k]; s[2] = S_[2*ndep+k]; s[3] = S_[3*ndep+k];
+  }
+  __device__ __forceinline__ void storeI(int k, const double I[4]) {
+    I_[k] = I[0]; I_[ndep+k] = I[1]; I_[2*ndep+k] = I[2]; I_[3*ndep+k] = I[3];
+  }
+  __device__ __forceinline__ void storePsi(int k, double p) { if (Psi_) Psi_[k] = p; }
+};
+
+__global__ void __launch_bounds__(128)
+delo_raypts_kernel(int ncol, int nlambda, int ndep, double muz, int bc_top, int bc_bottom,
+                   const double *__restrict__ atmos, const double *__restrict__ lambda,
+                   const double *__restrict__ raypts, double *__restrict__ stokes)
+{
+  const size_t nray = (size_t) ncol * nlambda;
+  const size_t r = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nray) return;
+  const int col = (int) (r / nlambda), l = (int) (r - (size_t) col * nlambda);
+  const double *at = atmos + (size_t) col * RHB200_AT_NFIELD * ndep;
+  RayPtsIO io{raypts + r, nray, stokes + (size_t) col * 4 * nlambda + l, nlambda, 0};
+  rhd::delo_bezier3_ray(io, ndep, at + RHB200_AT_HEIGHT * ndep, muz, 1, bc_top, bc_bottom,
+                        at + RHB200_AT_T * ndep, __ldg(lambda + l));
+}
+
+__global__ void __launch_bounds__(128)
+delo_generic_kernel(int nray, int ndep, double muz, int to_obs, int bc_top, int bc_bottom,
+                    const int *__restrict__ ray_col, const double *__restrict__ ray_lambda,
+                    const double *__restrict__ height, const double *__restrict__ T,
+                    const double *__restrict__ chi, const double *__restrict__ S,
+                    const double *__restrict__ chiQUV, double *__restrict__ I, double *__restrict__ Psi)
+{
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nray) return;
+  const int col = ray_col[r];
+  GenericIO io{chi + (size_t) r*ndep, S + (size_t) r*4*ndep, chiQUV + (size_t) r*3*ndep,
+               I + (size_t) r*4*ndep, Psi ? Psi + (size_t) r*ndep : nullptr, ndep};
+  rhd::delo_bezier3_ray(io, ndep, height + (size_t) col*ndep, muz, to_obs, bc_top, bc_bottom,
+                        T + (size_t) col*ndep, ray_lambda[r]);
+}
+
+__global__ void __launch_bounds__(128)
+bezier3_kernel(int nray, int ndep, double muz, int to_obs, int bc_top, int bc_bottom,
+               const int *__restrict__ ray_col, const double *__restrict__ ray_lambda,
+               const double *__restrict__ height, const double *__restrict__ T,
+               const double *__restrict__ chi, const double *__restrict__ S,
+               double *__restrict__ I, double *__restrict__ Psi)
+{
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nray) return;
+  const int col = ray_col[r];
+  rhz::bezier3_ray(ndep, height + (size_t) col*ndep, muz, to_obs, bc_top, bc_bottom,
+                   T + (size_t) col*ndep, ray_lambda[r], chi + (size_t) r*ndep, S + (size_t) r*ndep,
+                   I + (size_t) r*ndep, Psi ? Psi + (size_t) r*ndep : nullptr);
+}
+
+}  // namespace
+
+int rh_launch_delo_raypts(rhb200_ctx *ctx, int ncol, int ndep, double muz, int bc_top, int bc_bottom,
+                          const double *d_atmos, const double *d_raypts, double *d_stokes)
+{
+  const size_t nray = (size_t) ncol * ctx->wav.nlambda;
+  if (nray == 0) return RHB200_OK;
+  const int threads = 128;
+  const unsigned blocks = (unsigned) ((nray + threads - 1) / threads);
+  {
+    ScopedKernelTimer t(ctx, RHB200_K_DELO);
+    delo_raypts_kernel<<<blocks, threads, 0, ctx->stream>>>(ncol, ctx->wav.nlambda, ndep, muz, bc_top,
+                                                             bc_bottom, d_atmos, ctx->wav.lambda,
+                                                             d_raypts, d_stokes);
+  }
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}
+
+int rh_launch_delo_generic(rhb200_ctx *ctx, int nray, int ndep, double muz, int to_obs,
+                           int bc_top, int bc_bottom, const int *d_ray_col,
+                           const double *d_ray_lambda, const double *d_height, const double *d_T,
+                           const double *d_chi, const double *d_S, const double *d_chiQUV,
+                           double *d_I, double *d_Psi)
+{
+  if (nray == 0) return RHB200_OK;
+  const int threads = 128, blocks = (nray + threads - 1) / threads;
+  {
+    ScopedKernelTimer t(ctx, RHB200_K_DELO);
+    delo_generic_kernel<<<blocks, threads, 0, ctx->stream>>>(nray, ndep, muz, to_obs, bc_top, bc_bottom,
+                                                              d_ray_col, d_ray_lambda, d_height, d_T,
+                                                              d_chi, d_S, d_chiQUV, d_I, d_Psi);
+  }
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}
+
+int rh_launch_bezier3(rhb200_ctx *ctx, int nray, int ndep, double muz, int to_obs,
+                      int bc_top, int bc_bottom, const int *d_ray_col,
+                      const double *d_ray_lambda, const double *d_height, const double *d_T,
+                      const double *d_chi, const double *d_S, double *d_I, double *d_Psi)
+{
+  if (nray == 0) return RHB200_OK;
+  const int threads = 128, blocks = (nray + threads - 1) / threads;
+  {
+    ScopedKernelTimer t(ctx, RHB200_K_BEZIER);
+    bezier3_kernel<<<blocks, threads, 0, ctx->stream>>>(nray, ndep, muz, to_obs, bc_top, bc_bottom,
+                                                         d_ray_col, d_ray_lambda, d_height, d_T,
+                                                         d_chi, d_S, d_I, d_Psi);
+  }
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}

@@ -1,0 +1,364 @@
+// rhb200_lines.cu -- LTE Kurucz-line opacity on the device.
+//
+// Reference:
+//   LTEpops_elem   rh/ltepops.c:116-159     Saha chain per element
+//   Linear / Hunt  rh/linear.c:22-58, rh/hunt.c:17-78
+//   RLKProfile     rh/kurucz.c:729-828      Voigt-Faraday x Zeeman pattern
+//   rlk_opacity    rh/kurucz.c:511-725      chi/eta (I,Q,U,V) of all lines in the window
+//   Background     rh/background.c:476-537  chi_c = chi_ai + lines
+//   Formal         rh/rhf1d/formal.c:178-208  S = eta/chi ; StokesK stokesopac.c:72-77
+//
+// B200 design.  The reference evaluates rlk_opacity once per
+// (wavelength, mu, direction) and inside it recomputes, for every depth, quantities that do
+// not depend on wavelength at all (Doppler width, damping, Saha-Boltzmann populations: two
+// pow(), two exp(), one sqrt per line and depth).  Here a tiny "prep" kernel evaluates them once
+// per (column, line, depth) with the *same expressions*, and the opacity kernel -- one thread
+// per ray-point, wavelengths of a column along the warp -- only does the wavelength-dependent
+// part: the Zeeman-component loop of Humlicek W(z) evaluations.  Warps see one (column, depth)
+// at a time, so the prep record is a broadcast load and the Humlicek region branch is nearly
+// uniform (neighbouring wavelengths fall in the same region).
+#include "rhb200_common.cuh"
+#include "rhb200_voigt.cuh"
+
+namespace {
+
+// Linear(), linear.c:22-58 with hunt=TRUE: for xmin < x < xmax the bracket returned by Hunt
+// (hunt.c) is the unique j with xt[j] <= x < xt[j+1]; found by the same bisection (hunt.c:59-68)
+__device__ __forceinline__ double linear_interp(int nt, const double *__restrict__ xt,
+                                                const double *__restrict__ yt, double x)
+{
+  if (x <= xt[0]) return yt[0];
+  if (x >= xt[nt-1]) return yt[nt-1];
+  int lo = 0, hi = nt;
+  while (hi - lo > 1) {
+    const int mid = (hi + lo) >> 1;
+    if (x >= xt[mid]) lo = mid; else hi = mid;
+  }
+  const double fx = (xt[lo+1] - x) / (xt[lo+1] - xt[lo]);
+  return fx*yt[lo] + (1 - fx)*yt[lo+1];
+}
+
+// one thread per (column, depth)
+__global__ void __launch_bounds__(128)
+prep_kernel(int ncol, int ndep, double muz, int moving,
+            int nline, int nelem, int npf,
+            const double *__restrict__ lines, const double *__restrict__ elems,
+            const double *__restrict__ pf, const double *__restrict__ Tpf,
+            const double *__restrict__ atmos,
+            double *__restrict__ elem_n,      // [ncol][nelem][MAXSTAGE][ndep]
+            double *__restrict__ lineprep)    // [ncol][nline][ndep][LP_NFIELD]
+{
+  const size_t idx = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t) ncol * ndep) return;
+  const int col = (int) (idx / ndep), k = (int) (idx - (size_t) col * ndep);
+  const double *at = atmos + (size_t) col * RHB200_AT_NFIELD * ndep;
+  const double T = at[RHB200_AT_T*ndep + k], ne = at[RHB200_AT_NE*ndep + k];
+  const double vturb = at[RHB200_AT_VTURB*ndep + k], vel = at[RHB200_AT_VEL*ndep + k];
+  const double B = at[RHB200_AT_B*ndep + k], nHtot = at[RHB200_AT_NHTOT*ndep + k];
+  const double np = at[RHB200_AT_NP*ndep + k];
+
+  // ---- LTEpops_elem, ltepops.c:116-159
+  const double C1 = (RH_HPLANCK/(2.0*RH_PI*RH_M_ELECTRON)) * (RH_HPLANCK/RH_KBOLTZMANN);
+  const double CT_ne = 2.0 * rhm::rh_pow(C1/T, -1.5) / ne;
+  for (int ie = 0; ie < nelem; ie++) {
+    const double *e = elems + (size_t) ie * RHB200_RE_NFIELD;
+    const int nst = (int) e[RHB200_RE_NSTAGE], pfrow = (int) e[RHB200_RE_PFROW];
+    double *n = elem_n + (((size_t) col*nelem + ie) * RHB200_RE_MAXSTAGE) * ndep + k;
+    double sum = 1.0, nprev = 1.0;
+    double Uk = linear_interp(npf, Tpf, pf + (size_t) pfrow*npf, T);
+    n[0] = 1.0;
+    for (int i = 1; i < nst; i++) {
+      const double Ukp1 = linear_interp(npf, Tpf, pf + (size_t)(pfrow+i)*npf, T);
+      const double ni = nprev * CT_ne *
+        rhm::rh_exp(Ukp1 - Uk - e[RHB200_RE_IONPOT0 + i-1]/(RH_KBOLTZMANN*T));
+      n[(size_t) i*ndep] = ni;
+      sum += ni;
+      nprev = ni;
+      Uk = Ukp1;
+    }
+    const double n0 = e[RHB200_RE_ABUND] * nHtot / sum;
+    n[0] = n0;
+    for (int i = 1; i < nst; i++) n[(size_t) i*ndep] *= n0;
+  }
+
+  // ---- wavelength-independent part of RLKProfile / rlk_opacity per line
+  const double hc = RH_HPLANCK * RH_CLIGHT, fourPI = 4.0 * RH_PI, hc_4PI = hc / fourPI;
+  for (int nl = 0; nl < nline; nl++) {
+    const double *L = lines + (size_t) nl * RHB200_RL_NFIELD;
+    const int ie = (int) L[RHB200_RL_ELEM], st = (int) L[RHB200_RL_STAGE];
+    const double *e = elems + (size_t) ie * RHB200_RE_NFIELD;
+    const double lambda0 = L[RHB200_RL_LAMBDA0];
+    double *out = lineprep + (((size_t) col*nline + nl) * ndep + k) * LP_NFIELD;
+
+    const double vtherm = 2.0*RH_KBOLTZMANN/(RH_AMU * e[RHB200_RE_WEIGHT]);     // kurucz.c:745-746
+    const double vbroad = sqrt(vtherm*T + vturb*vturb);
+    const double w = moving ? (muz * vel) / vbroad : 0.0;                        // kurucz.c:749-754
+    const double sv = 1.0 / (RH_SQRTPI * vbroad);
+    double adamp = 0.0;
+    if (L[RHB200_RL_GRAD] != 0.0) {                                              // kurucz.c:758-775
+      double GvdW;
+      const int vdw = (int) L[RHB200_RL_VDWAALS];
+      if (vdw == 0)      GvdW = L[RHB200_RL_CROSS] * rhm::rh_pow(T, 0.3);
+      else if (vdw == 2) GvdW = L[RHB200_RL_CROSS] * rhm::rh_pow(T, (1.0 - L[RHB200_RL_ALPHA])/2.0);
+      else               GvdW = L[RHB200_RL_GVDW];
+      adamp = (L[RHB200_RL_GRAD] + L[RHB200_RL_GSTARK] * ne + GvdW * (nHtot - np)) *
+        (lambda0 * RH_NM_TO_M) / (4.0*RH_PI * vbroad);
+    }
+    const double vB = (RH_LARMOR * lambda0) * B / vbroad;                        // kurucz.c:783
+
+    // Boltzmann factors, kurucz.c:638-640,666,675-680
+    const double hc_la      = (RH_HPLANCK * RH_CLIGHT) / (lambda0 * RH_NM_TO_M);
+    const double Bijhc_4PI  = hc_4PI * L[RHB200_RL_BIJ] * L[RHB200_RL_ISO_FRAC] *
+                              L[RHB200_RL_HFS_FRAC] * L[RHB200_RL_GI];
+    const double twohnu3_c2 = L[RHB200_RL_AJI] / L[RHB200_RL_BJI];
+    const double pfk = linear_interp(npf, Tpf, pf + (size_t)((int) e[RHB200_RE_PFROW] + st)*npf, T);
+    const double kT = 1.0 / (RH_KBOLTZMANN * T);
+    const double nstage = elem_n[(((size_t) col*nelem + ie) * RHB200_RE_MAXSTAGE + st) * ndep + k];
+    const double ni_gi = nstage * rhm::rh_exp(-L[RHB200_RL_EI]*kT - pfk);
+    const double nj_gj = ni_gi * rhm::rh_exp(-hc_la * kT);
+    out[LP_VBROAD] = vbroad;
+    out[LP_ADAMP]  = adamp;
+    out[LP_VB]     = vB;
+    out[LP_W]      = w;
+    out[LP_SV]     = sv;
+    out[LP_CHIL]   = Bijhc_4PI * (ni_gi - nj_gj);
+    out[LP_ETAL]   = Bijhc_4PI * twohnu3_c2 * nj_gj;
+    out[7]         = 0.0;
+  }
+}
+
+struct LineSums { double chi[4], eta[4]; };
+
+// Sum of all contributing lines at one (column, depth, wavelength): the body of the
+// n-loop of rlk_opacity (kurucz.c:605-720) with RLKProfile (kurucz.c:729-828) inlined.
+__device__ __forceinline__ void line_sums(LineSums &s, const double lambda, const int to_obs,
+                                          const int first, const int count,
+                                          const int *__restrict__ widx,
+                                          const double *__restrict__ lines,
+                                          const int *__restrict__ zq, const double *__restrict__ zshift,
+                                          const double *__restrict__ zstrength,
+                                          const double *__restrict__ lp_colk,   // lineprep + (col*nline*ndep + k)*LP, stride ndep*LP per line
+                                          const size_t lp_stride,
+                                          const double cos_gamma, const double cos_2chi,
+                                          const double sin_2chi)
+{
+#pragma unroll
+  for (int i = 0; i < 4; i++) { s.chi[i] = 0.0; s.eta[i] = 0.0; }
+  const double sign = to_obs ? 1.0 : -1.0;
+  for (int j = 0; j < count; j++) {
+    const int nl = __ldg(widx + first + j);
+    const double *L = lines + (size_t) nl * RHB200_RL_NFIELD;
+    const double *P = lp_colk + (size_t) nl * lp_stride;
+    const double vbroad = __ldg(P + LP_VBROAD), sv = __ldg(P + LP_SV);
+    double v = (lambda/__ldg(L + RHB200_RL_LAMBDA0) - 1.0) * RH_CLIGHT/vbroad;
+    if (to_obs) v += __ldg(P + LP_W); else v -= __ldg(P + LP_W);
+
+    double phi, phi_Q = 0.0, phi_U = 0.0, phi_V = 0.0;
+    const bool has_grad = (__ldg(L + RHB200_RL_GRAD) != 0.0);
+    const bool polarizable = (__ldg(L + RHB200_RL_POLARIZABLE) != 0.0);
+    if (!has_grad) {
+      phi = ((fabs(v) <= RH_MAX_GAUSS_DOPPLER) ? rhm::rh_exp(-v*v) : 0.0) * sv;   // kurucz.c:777-778
+    } else {
+      const double adamp = __ldg(P + LP_ADAMP), vB = __ldg(P + LP_VB);
+      const double sin2_gamma = 1.0 - cos_gamma*cos_gamma;
+      double phi_sm = 0.0, phi_pi = 0.0, phi_sp = 0.0;
+      const int zoff = (int) __ldg(L + RHB200_RL_ZOFF), nc = (int) __ldg(L + RHB200_RL_NCOMP);
+      for (int nz = 0; nz < nc; nz++) {
+        double F;
+        const double H = rhv::humlicek(adamp, v - __ldg(zshift + zoff + nz)*vB, &F);
+        const int q = __ldg(zq + zoff + nz);
+        const double st = __ldg(zstrength + zoff + nz);
+        if (q == -1)     phi_sm += st * H;
+        else if (q == 0) phi_pi += st * H;
+        else if (q == 1) phi_sp += st * H;
+      }
+      const double phi_sigma = phi_sp + phi_sm;
+      const double phi_delta = 0.5*phi_pi - 0.25*phi_sigma;
+      phi   = (phi_delta*sin2_gamma + 0.5*phi_sigma) * sv;
+      phi_Q = sign * phi_delta * sin2_gamma * cos_2chi * sv;
+      phi_U = phi_delta * sin2_gamma * sin_2chi * sv;
+      phi_V = sign * 0.5*(phi_sp - phi_sm) * cos_gamma * sv;
+    }
+    if (phi != 0.0) {                                   // kurucz.c:674
+      const double chi_l = __ldg(P + LP_CHIL), eta_l = __ldg(P + LP_ETAL);
+      s.chi[0] += chi_l * phi;
+      s.eta[0] += eta_l * phi;
+      if (polarizable && has_grad) {                    // kurucz.c:701-708
+        s.chi[1] += chi_l * phi_Q;  s.chi[2] += chi_l * phi_U;  s.chi[3] += chi_l * phi_V;
+        s.eta[1] += eta_l * phi_Q;  s.eta[2] += eta_l * phi_U;  s.eta[3] += eta_l * phi_V;
+      }
+    }
+  }
+}
+
+// FUSED: total opacity + source vector + reduced propagation matrix per ray-point,
+// written in the DELO kernel's layout [depth][RP_NFIELD][nray].
+// block = (32 rays) x (4 depths); grid = (ceil(nray/32), ceil(ndep/4))
+__global__ void __launch_bounds__(128)
+opacity_fused_kernel(int ncol, int nlambda, int ndep, int to_obs, int nline,
+                     const double *__restrict__ lambda, const int *__restrict__ wfirst,
+                     const int *__restrict__ wcount, const int *__restrict__ widx,
+                     const double *__restrict__ lines, const int *__restrict__ zq,
+                     const double *__restrict__ zshift, const double *__restrict__ zstrength,
+                     const double *__restrict__ atmos, const double *__restrict__ lineprep,
+                     const double *__restrict__ chi_ai, const double *__restrict__ eta_ai,
+                     double *__restrict__ raypts)
+{
+  const size_t nray = (size_t) ncol * nlambda;
+  const size_t r = (size_t) blockIdx.x * 32 + threadIdx.x;
+  const int k = blockIdx.y * blockDim.y + threadIdx.y;
+  if (r >= nray || k >= ndep) return;
+  const int col = (int) (r / nlambda), l = (int) (r - (size_t) col * nlambda);
+  const double *at = atmos + (size_t) col * RHB200_AT_NFIELD * ndep;
+
+  LineSums s;
+  line_sums(s, __ldg(lambda + l), to_obs, __ldg(wfirst + l), __ldg(wcount + l), widx, lines,
+            zq, zshift, zstrength,
+            lineprep + ((size_t) col*nline*ndep + k) * LP_NFIELD, (size_t) ndep * LP_NFIELD,
+            __ldg(at + RHB200_AT_COS_GAMMA*ndep + k), __ldg(at + RHB200_AT_COS_2CHI*ndep + k),
+            __ldg(at + RHB200_AT_SIN_2CHI*ndep + k));
+
+  // background.c:476-537: chi_c = chi_ai + chi_lines (I), 0 + lines (Q,U,V);
+  // formal.c:178-208: chi = 0 + chi_c, S = (0 + eta_c)/chi; stokesopac.c:72-77: K' = chi_QUV/chi_I
+  const double chi = __ldg(chi_ai + r*ndep + k) + s.chi[0];
+  double *o = raypts + (size_t) k * RP_NFIELD * nray + r;
+  o[(size_t) RP_CHI*nray] = chi;
+  o[(size_t) RP_KQ*nray]  = s.chi[1] / chi;
+  o[(size_t) RP_KU*nray]  = s.chi[2] / chi;
+  o[(size_t) RP_KV*nray]  = s.chi[3] / chi;
+  o[(size_t) RP_SI*nray]  = (__ldg(eta_ai + r*ndep + k) + s.eta[0]) / chi;
+  o[(size_t) RP_SQ*nray]  = s.eta[1] / chi;
+  o[(size_t) RP_SU*nray]  = s.eta[2] / chi;
+  o[(size_t) RP_SV*nray]  = s.eta[3] / chi;
+}
+
+// RAW: exactly the output of rlk_opacity(), chi/eta [ncol][nlambda][4][ndep]
+__global__ void __launch_bounds__(128)
+opacity_raw_kernel(int ncol, int nlambda, int ndep, int to_obs, int nline,
+                   const double *__restrict__ lambda, const int *__restrict__ wfirst,
+                   const int *__restrict__ wcount, const int *__restrict__ widx,
+                   const double *__restrict__ lines, const int *__restrict__ zq,
+                   const double *__restrict__ zshift, const double *__restrict__ zstrength,
+                   const double *__restrict__ atmos, const double *__restrict__ lineprep,
+                   double *__restrict__ chi, double *__restrict__ eta)
+{
+  const size_t nray = (size_t) ncol * nlambda;
+  const size_t r = (size_t) blockIdx.x * 32 + threadIdx.x;
+  const int k = blockIdx.y * blockDim.y + threadIdx.y;
+  if (r >= nray || k >= ndep) return;
+  const int col = (int) (r / nlambda), l = (int) (r - (size_t) col * nlambda);
+  const double *at = atmos + (size_t) col * RHB200_AT_NFIELD * ndep;
+  LineSums s;
+  line_sums(s, __ldg(lambda + l), to_obs, __ldg(wfirst + l), __ldg(wcount + l), widx, lines,
+            zq, zshift, zstrength,
+            lineprep + ((size_t) col*nline*ndep + k) * LP_NFIELD, (size_t) ndep * LP_NFIELD,
+            __ldg(at + RHB200_AT_COS_GAMMA*ndep + k), __ldg(at + RHB200_AT_COS_2CHI*ndep + k),
+            __ldg(at + RHB200_AT_SIN_2CHI*ndep + k));
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    chi[(r*4 + i)*ndep + k] = s.chi[i];
+    eta[(r*4 + i)*ndep + k] = s.eta[i];
+  }
+}
+
+__global__ void voigt_kernel(int n, const double *__restrict__ a, const double *__restrict__ v,
+                             double *__restrict__ H, double *__restrict__ F, int *__restrict__ region)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double f;
+  H[i] = rhv::humlicek(a[i], v[i], &f);
+  F[i] = f;
+  if (region) region[i] = rhv::humlicek_region(a[i], v[i]);
+}
+
+__global__ void math_probe_kernel(int n, int func, const double *__restrict__ x,
+                                  const double *__restrict__ y, double *__restrict__ out)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double r;
+  switch (func) {
+  case 0: r = rhm::rh_exp(x[i]); break;
+  case 1: r = rhm::rh_sin(x[i]); break;
+  case 2: r = rhm::rh_cos(x[i]); break;
+  default: r = rhm::rh_pow(x[i], y[i]); break;
+  }
+  out[i] = r;
+}
+
+}  // namespace
+
+int rh_launch_prep(rhb200_ctx *ctx, int ncol, int ndep, double muz, int moving,
+                   const double *d_atmos, double *d_elem_n, double *d_lineprep)
+{
+  const size_t n = (size_t) ncol * ndep;
+  if (n == 0) return RHB200_OK;
+  const int threads = 128;
+  const unsigned blocks = (unsigned) ((n + threads - 1) / threads);
+  {
+    ScopedKernelTimer t(ctx, RHB200_K_PREP);
+    prep_kernel<<<blocks, threads, 0, ctx->stream>>>(ncol, ndep, muz, moving, ctx->tab.nline,
+        ctx->tab.nelem, ctx->tab.npf, ctx->tab.lines, ctx->tab.elems, ctx->tab.pf, ctx->tab.Tpf,
+        d_atmos, d_elem_n, d_lineprep);
+  }
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}
+
+int rh_launch_opacity_fused(rhb200_ctx *ctx, int ncol, int ndep, int to_obs,
+                            const double *d_atmos, const double *d_lineprep,
+                            const double *d_chi_ai, const double *d_eta_ai, double *d_raypts)
+{
+  const size_t nray = (size_t) ncol * ctx->wav.nlambda;
+  if (nray == 0) return RHB200_OK;
+  dim3 block(32, 4), grid((unsigned) ((nray + 31) / 32), (unsigned) ((ndep + 3) / 4));
+  {
+    ScopedKernelTimer t(ctx, RHB200_K_OPACITY);
+    opacity_fused_kernel<<<grid, block, 0, ctx->stream>>>(ncol, ctx->wav.nlambda, ndep, to_obs,
+        ctx->tab.nline, ctx->wav.lambda, ctx->wav.first, ctx->wav.count, ctx->wav.idx,
+        ctx->tab.lines, ctx->tab.zq, ctx->tab.zshift, ctx->tab.zstrength, d_atmos, d_lineprep,
+        d_chi_ai, d_eta_ai, d_raypts);
+  }
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}
+
+int rh_launch_opacity_raw(rhb200_ctx *ctx, int ncol, int ndep, int to_obs,
+                          const double *d_atmos, const double *d_lineprep,
+                          double *d_chi, double *d_eta)
+{
+  const size_t nray = (size_t) ncol * ctx->wav.nlambda;
+  if (nray == 0) return RHB200_OK;
+  dim3 block(32, 4), grid((unsigned) ((nray + 31) / 32), (unsigned) ((ndep + 3) / 4));
+  {
+    ScopedKernelTimer t(ctx, RHB200_K_OPACITY);
+    opacity_raw_kernel<<<grid, block, 0, ctx->stream>>>(ncol, ctx->wav.nlambda, ndep, to_obs,
+        ctx->tab.nline, ctx->wav.lambda, ctx->wav.first, ctx->wav.count, ctx->wav.idx,
+        ctx->tab.lines, ctx->tab.zq, ctx->tab.zshift, ctx->tab.zstrength, d_atmos, d_lineprep,
+        d_chi, d_eta);
+  }
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}
+
+int rh_launch_voigt(rhb200_ctx *ctx, int n, const double *d_a, const double *d_v,
+                    double *d_H, double *d_F, int *d_region)
+{
+  if (n == 0) return RHB200_OK;
+  {
+    ScopedKernelTimer t(ctx, RHB200_K_OTHER);
+    voigt_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(n, d_a, d_v, d_H, d_F, d_region);
+  }
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}
+
+int rh_launch_math_probe(rhb200_ctx *ctx, int n, int func, const double *d_x, const double *d_y,
+                         double *d_out)
+{
+  if (n == 0) return RHB200_OK;
+  math_probe_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(n, func, d_x, d_y, d_out);
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}

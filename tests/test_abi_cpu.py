@@ -1,0 +1,68 @@
+"""CPU tests of the boundary: the C-ABI library loads, exports every symbol that
+include/rhb200.h declares, and refuses to compute without a GPU (no CPU fallback)."""
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from pyrh_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def test_header_symbols_all_exported(lib):
+    hdr = (ROOT / "include" / "rhb200.h").read_text()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(rhb200_[a-z0-9_]+)\s*\(", hdr))
+    from pyrh_b200 import _lib
+    bound = {s[0] for s in _lib.SYMBOLS}
+    assert declared == bound, (declared - bound, bound - declared)
+    for name in declared:
+        assert hasattr(lib, name)
+
+
+def test_version_and_no_device_fails_loudly(lib):
+    assert lib.rhb200_version() == 100
+    if lib.rhb200_device_count() == 0:
+        from pyrh_b200 import _lib
+        from pyrh_b200.api import Context
+        with pytest.raises(_lib.RHB200Error):
+            Context()
+        assert lib.rhb200_open(0) is None
+        assert b"no CUDA device" in lib.rhb200_last_error()
+
+
+def test_product_never_imports_oracle():
+    for p in (ROOT / "pyrh_b200").rglob("*"):
+        if p.suffix in (".py", ".cu", ".cuh", ".h"):
+            txt = p.read_text()
+            assert "oracle" not in txt.replace("oracle/", "").lower() or "import" not in txt or \
+                not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), p
+            assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), p
+            assert "rhport" not in txt, p
+
+
+def test_unit_conversion_and_bproject_match_reference(golden):
+    """pyrh-unit rows -> SI rows, bit-exact against what the reference held in Formal()."""
+    name, g = golden
+    from pyrh_b200 import api
+    rows = api.atmos_rows_from_pyrh(g["atmosphere"], g["col_np"], g["col_height"])
+    for f, i in api.AT.items():
+        assert np.array_equal(rows[i], g["col_" + f]), f
+
+
+def test_synthetic_generator_is_deterministic():
+    from pyrh_b200 import synthetic
+    base = np.load(ROOT / "tests" / "golden" / "falc_base.npy")
+    a = synthetic.perturbed_batch(base, 3)
+    b = synthetic.perturbed_batch(base, 2, first=1)
+    assert a.shape == (3, 9, 70)
+    assert np.array_equal(a[1:], b)
+    g = np.load(ROOT / "tests" / "golden" / "synth70_c1.npz")
+    assert np.array_equal(g["atmosphere"], a[1])
