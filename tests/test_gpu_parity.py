@@ -232,3 +232,48 @@ def test_error_paths(ctx, golden_falc):
     with pytest.raises(_lib.RHB200Error):                 # wavelengths not set
         c2.rlk_opacity(rows_of(g)[None])
     c2.close()
+
+
+def test_device_math_bit_identical_to_glibc(ctx):
+    """exp/pow/sin/cos on the device vs this host's glibc (math.* calls libm) -- only meaningful
+    on a glibc 2.39 + FMA host, which is what the golden vectors were generated on."""
+    import math
+    rng = np.random.default_rng(3)
+    n = 200000
+    cases = {
+        "exp": np.concatenate([rng.uniform(-60, 5, n // 2), rng.uniform(-745, 700, n // 2)]),
+        "sin": np.concatenate([rng.uniform(-12, 12, n // 2), rng.uniform(-1e4, 1e4, n // 2)]),
+        "cos": np.concatenate([rng.uniform(-12, 12, n // 2), rng.uniform(-1e4, 1e4, n // 2)]),
+    }
+    for f, x in cases.items():
+        got = ctx.math_probe(f, x)
+        ref = np.array([getattr(math, f)(v) for v in x])
+        REPORT[f"math_{f}_mismatch"] = int(np.sum(got != ref))
+        assert np.array_equal(got, ref), f
+    x = 10 ** rng.uniform(-2, 6, n)
+    for y in (0.3, 0.38, -1.5):
+        got = ctx.math_probe("pow", x, np.full(n, y))
+        ref = np.array([math.pow(v, y) for v in x])
+        REPORT[f"math_pow_{y}_mismatch"] = int(np.sum(got != ref))
+        assert np.array_equal(got, ref), y
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_bit_exact_against_reference(ctx, case):
+    """Stronger than north_star's tolerances: with glibc-identical device math and the
+    reference's operation order, every stage reproduces the reference bit for bit."""
+    g = dict(np.load(GOLD / f"{case}.npz"))
+    setup_ctx(ctx, g)
+    assert np.array_equal(ctx.ltepops_elem(rows_of(g)[None])[0], g["elem_n"])
+    k = g["lam_keep"]
+    st = ctx.lte_stokes_batch(rows_of(g)[None], g["chi_ai"][k][None], g["eta_ai"][k][None],
+                              mu=float(g["muz"][0]), moving=bool(g["flags"][0]))[0]
+    assert np.array_equal(st, g["stokes_scalar"])
+    setup_ctx(ctx, g, lam=g["lam_spect"][g["sub"]])
+    chi, eta, _ = ctx.rlk_opacity(rows_of(g)[None], moving=bool(g["flags"][0]))
+    assert np.array_equal(chi[0], g["rlk_chi"]) and np.array_equal(eta[0], g["rlk_eta"])
+    d = g["delo"]
+    I, Psi = ctx.stokes_bezier3(np.zeros(d.shape[0], np.int32), g["lam_spect"][g["sub"]],
+                                g["col_height"], g["col_T"], d[:, 0], d[:, 1:5], d[:, 10:13],
+                                want_psi=True)
+    assert np.array_equal(I, d[:, 5:9]) and np.array_equal(Psi, d[:, 9])
