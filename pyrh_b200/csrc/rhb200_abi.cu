@@ -165,6 +165,7 @@ extern "C" int rhb200_set_lines(rhb200_ctx *c, int nline, const double *lines, i
   RH_CHECK(upload(&t.Tpf, Tpf, (size_t) npf));
   c->h_lines.assign(lines, lines + (size_t) nline * RHB200_RL_NFIELD);
   c->h_elems.assign(elems, elems + (size_t) nelem * RHB200_RE_NFIELD);
+  c->h_zq.assign(zq, zq + ncomp); c->h_zshift.assign(zshift, zshift + ncomp); c->h_zstrength.assign(zstrength, zstrength + ncomp);
   free_wave(c);     // windows depend on the line table
   return RHB200_OK;
 }

@@ -68,7 +68,8 @@ struct rhb200_ctx {
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   DevTables tab;
   DevWave wav;
-  std::vector<double> h_lines, h_elems, h_lambda;
+  std::vector<double> h_lines, h_elems, h_lambda, h_zshift, h_zstrength;
+  std::vector<int> h_zq;
   std::vector<int> h_first, h_count, h_idx, h_flags;
   // workspace (grown on demand)
   void *ws = nullptr; size_t ws_bytes = 0;
@@ -106,7 +107,7 @@ int rh_launch_prep(rhb200_ctx *ctx, int ncol, int ndep, double muz, int moving,
 int rh_launch_opacity_fused(rhb200_ctx *ctx, int ncol, int ndep, int to_obs,
                             const double *d_atmos, const double *d_lineprep,
                             const double *d_chi_ai, const double *d_eta_ai,
-                            double *d_raypts /* [ndep][RP_NFIELD][nray] */);
+                            double *d_raypts /* [nray][ndep][RP_NFIELD] */);
 int rh_launch_opacity_raw(rhb200_ctx *ctx, int ncol, int ndep, int to_obs,
                           const double *d_atmos, const double *d_lineprep,
                           double *d_chi, double *d_eta /* [ncol][nlambda][4][ndep] */);

@@ -5,25 +5,21 @@
 
 namespace {
 
-// ---- IO policy: ray-point records written by the fused opacity kernel,
-//      layout [depth][RP_NFIELD][nray]: consecutive rays (= consecutive wavelengths of a
-//      column) are consecutive in memory, so every warp load is one 256-byte run.
+// ---- IO policy: ray-point records written by the fused opacity kernel, raypts[ray][k] =
+//      {chi_I, K'_Q, K'_U, K'_V, S_I, S_Q, S_U, S_V}: one thread owns one ray and walks its own
+//      64-byte records with four 128-bit loads per depth (every fetched sector is fully used).
 struct RayPtsIO {
-  const double *__restrict__ rp;   // already offset by ray index
-  size_t nray;
+  const double2 *__restrict__ rp;  // this ray's records, 4 x double2 per depth
   double *out;                     // stokes + col*4*nlambda + l, stride nlambda between I,Q,U,V
   int nlambda, kout;
-  __device__ __forceinline__ double chi(int k) const { return __ldg(rp + ((size_t)k*RP_NFIELD + RP_CHI)*nray); }
+  __device__ __forceinline__ double chi(int k) const { return __ldg(reinterpret_cast<const double *>(rp + 4*(size_t)k)); }
   __device__ __forceinline__ void K(int k, double x[3]) const {
-    x[0] = __ldg(rp + ((size_t)k*RP_NFIELD + RP_KQ)*nray);
-    x[1] = __ldg(rp + ((size_t)k*RP_NFIELD + RP_KU)*nray);
-    x[2] = __ldg(rp + ((size_t)k*RP_NFIELD + RP_KV)*nray);
+    const double2 a = __ldg(rp + 4*(size_t)k), b = __ldg(rp + 4*(size_t)k + 1);
+    x[0] = a.y; x[1] = b.x; x[2] = b.y;
   }
   __device__ __forceinline__ void S(int k, double s[4]) const {
-    s[0] = __ldg(rp + ((size_t)k*RP_NFIELD + RP_SI)*nray);
-    s[1] = __ldg(rp + ((size_t)k*RP_NFIELD + RP_SQ)*nray);
-    s[2] = __ldg(rp + ((size_t)k*RP_NFIELD + RP_SU)*nray);
-    s[3] = __ldg(rp + ((size_t)k*RP_NFIELD + RP_SV)*nray);
+    const double2 a = __ldg(rp + 4*(size_t)k + 2), b = __ldg(rp + 4*(size_t)k + 3);
+    s[0] = a.x; s[1] = a.y; s[2] = b.x; s[3] = b.y;
   }
   __device__ __forceinline__ void storeI(int k, const double I[4]) {
     if (k == kout) {
@@ -62,7 +58,8 @@ delo_raypts_kernel(int ncol, int nlambda, int ndep, double muz, int bc_top, int 
   if (r >= nray) return;
   const int col = (int) (r / nlambda), l = (int) (r - (size_t) col * nlambda);
   const double *at = atmos + (size_t) col * RHB200_AT_NFIELD * ndep;
-  RayPtsIO io{raypts + r, nray, stokes + (size_t) col * 4 * nlambda + l, nlambda, 0};
+  RayPtsIO io{reinterpret_cast<const double2 *>(raypts + r * (size_t) ndep * RP_NFIELD),
+              stokes + (size_t) col * 4 * nlambda + l, nlambda, 0};
   rhd::delo_bezier3_ray(io, ndep, at + RHB200_AT_HEIGHT * ndep, muz, 1, bc_top, bc_bottom,
                         at + RHB200_AT_T * ndep, __ldg(lambda + l));
 }

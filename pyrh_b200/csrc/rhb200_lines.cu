@@ -13,10 +13,8 @@
 // not depend on wavelength at all (Doppler width, damping, Saha-Boltzmann populations: two
 // pow(), two exp(), one sqrt per line and depth).  Here a tiny "prep" kernel evaluates them once
 // per (column, line, depth) with the *same expressions*, and the opacity kernel -- one thread
-// per ray-point, wavelengths of a column along the warp -- only does the wavelength-dependent
-// part: the Zeeman-component loop of Humlicek W(z) evaluations.  Warps see one (column, depth)
-// at a time, so the prep record is a broadcast load and the Humlicek region branch is nearly
-// uniform (neighbouring wavelengths fall in the same region).
+// per ray-point, consecutive DEPTHS of one wavelength along the warp -- only does the
+// wavelength-dependent part: the Zeeman-component loop of Humlicek W(z) evaluations.
 #include "rhb200_common.cuh"
 #include "rhb200_voigt.cuh"
 
@@ -46,7 +44,7 @@ prep_kernel(int ncol, int ndep, double muz, int moving,
             const double *__restrict__ pf, const double *__restrict__ Tpf,
             const double *__restrict__ atmos,
             double *__restrict__ elem_n,      // [ncol][nelem][MAXSTAGE][ndep]
-            double *__restrict__ lineprep)    // [ncol][nline][ndep][LP_NFIELD]
+            double *__restrict__ lineprep)    // [ncol][nline][LP_NFIELD][ndep]
 {
   const size_t idx = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t) ncol * ndep) return;
@@ -88,7 +86,7 @@ prep_kernel(int ncol, int ndep, double muz, int moving,
     const int ie = (int) L[RHB200_RL_ELEM], st = (int) L[RHB200_RL_STAGE];
     const double *e = elems + (size_t) ie * RHB200_RE_NFIELD;
     const double lambda0 = L[RHB200_RL_LAMBDA0];
-    double *out = lineprep + (((size_t) col*nline + nl) * ndep + k) * LP_NFIELD;
+    double *out = lineprep + ((size_t) col*nline + nl) * LP_NFIELD * ndep + k;
 
     const double vtherm = 2.0*RH_KBOLTZMANN/(RH_AMU * e[RHB200_RE_WEIGHT]);     // kurucz.c:745-746
     const double vbroad = sqrt(vtherm*T + vturb*vturb);
@@ -116,29 +114,43 @@ prep_kernel(int ncol, int ndep, double muz, int moving,
     const double nstage = elem_n[(((size_t) col*nelem + ie) * RHB200_RE_MAXSTAGE + st) * ndep + k];
     const double ni_gi = nstage * rhm::rh_exp(-L[RHB200_RL_EI]*kT - pfk);
     const double nj_gj = ni_gi * rhm::rh_exp(-hc_la * kT);
-    out[LP_VBROAD] = vbroad;
-    out[LP_ADAMP]  = adamp;
-    out[LP_VB]     = vB;
-    out[LP_W]      = w;
-    out[LP_SV]     = sv;
-    out[LP_CHIL]   = Bijhc_4PI * (ni_gi - nj_gj);
-    out[LP_ETAL]   = Bijhc_4PI * twohnu3_c2 * nj_gj;
-    out[7]         = 0.0;
+    out[(size_t) LP_VBROAD*ndep] = vbroad;
+    out[(size_t) LP_ADAMP*ndep]  = adamp;
+    out[(size_t) LP_VB*ndep]     = vB;
+    out[(size_t) LP_W*ndep]      = w;
+    out[(size_t) LP_SV*ndep]     = sv;
+    out[(size_t) LP_CHIL*ndep]   = Bijhc_4PI * (ni_gi - nj_gj);
+    out[(size_t) LP_ETAL*ndep]   = Bijhc_4PI * twohnu3_c2 * nj_gj;
   }
 }
 
 struct LineSums { double chi[4], eta[4]; };
 
+// Zeeman components are read with a warp-uniform index.  Small line lists pass them BY VALUE in
+// the kernel parameter block (constant bank: one broadcast LDC per read, no L1 traffic);
+// larger ones fall back to global memory.
+#define RH_ZPARAM_MAX 160
+struct ZeemanParam {
+  double shift[RH_ZPARAM_MAX], strength[RH_ZPARAM_MAX];
+  signed char q[RH_ZPARAM_MAX];
+};
+struct ZeemanGlobal { const int *q; const double *shift, *strength; };
+__device__ __forceinline__ int    zq_of(const ZeemanParam &z, int i) { return z.q[i]; }
+__device__ __forceinline__ double zshift_of(const ZeemanParam &z, int i) { return z.shift[i]; }
+__device__ __forceinline__ double zstrength_of(const ZeemanParam &z, int i) { return z.strength[i]; }
+__device__ __forceinline__ int    zq_of(const ZeemanGlobal &z, int i) { return __ldg(z.q + i); }
+__device__ __forceinline__ double zshift_of(const ZeemanGlobal &z, int i) { return __ldg(z.shift + i); }
+__device__ __forceinline__ double zstrength_of(const ZeemanGlobal &z, int i) { return __ldg(z.strength + i); }
+
 // Sum of all contributing lines at one (column, depth, wavelength): the body of the
 // n-loop of rlk_opacity (kurucz.c:605-720) with RLKProfile (kurucz.c:729-828) inlined.
+// lp_colk points at lineprep[col][0][0][k]; line nl / field f is at lp_colk[(nl*LP_NFIELD + f)*ndep].
+template <class ZT>
 __device__ __forceinline__ void line_sums(LineSums &s, const double lambda, const int to_obs,
                                           const int first, const int count,
                                           const int *__restrict__ widx,
-                                          const double *__restrict__ lines,
-                                          const int *__restrict__ zq, const double *__restrict__ zshift,
-                                          const double *__restrict__ zstrength,
-                                          const double *__restrict__ lp_colk,   // lineprep + (col*nline*ndep + k)*LP, stride ndep*LP per line
-                                          const size_t lp_stride,
+                                          const double *__restrict__ lines, const ZT &zee,
+                                          const double *__restrict__ lp_colk, const int ndep,
                                           const double cos_gamma, const double cos_2chi,
                                           const double sin_2chi)
 {
@@ -148,10 +160,10 @@ __device__ __forceinline__ void line_sums(LineSums &s, const double lambda, cons
   for (int j = 0; j < count; j++) {
     const int nl = __ldg(widx + first + j);
     const double *L = lines + (size_t) nl * RHB200_RL_NFIELD;
-    const double *P = lp_colk + (size_t) nl * lp_stride;
-    const double vbroad = __ldg(P + LP_VBROAD), sv = __ldg(P + LP_SV);
+    const double *P = lp_colk + (size_t) nl * LP_NFIELD * ndep;
+    const double vbroad = __ldg(P + (size_t) LP_VBROAD*ndep), sv = __ldg(P + (size_t) LP_SV*ndep);
     double v = (lambda/__ldg(L + RHB200_RL_LAMBDA0) - 1.0) * RH_CLIGHT/vbroad;
-    if (to_obs) v += __ldg(P + LP_W); else v -= __ldg(P + LP_W);
+    if (to_obs) v += __ldg(P + (size_t) LP_W*ndep); else v -= __ldg(P + (size_t) LP_W*ndep);
 
     double phi, phi_Q = 0.0, phi_U = 0.0, phi_V = 0.0;
     const bool has_grad = (__ldg(L + RHB200_RL_GRAD) != 0.0);
@@ -159,15 +171,14 @@ __device__ __forceinline__ void line_sums(LineSums &s, const double lambda, cons
     if (!has_grad) {
       phi = ((fabs(v) <= RH_MAX_GAUSS_DOPPLER) ? rhm::rh_exp(-v*v) : 0.0) * sv;   // kurucz.c:777-778
     } else {
-      const double adamp = __ldg(P + LP_ADAMP), vB = __ldg(P + LP_VB);
+      const double adamp = __ldg(P + (size_t) LP_ADAMP*ndep), vB = __ldg(P + (size_t) LP_VB*ndep);
       const double sin2_gamma = 1.0 - cos_gamma*cos_gamma;
       double phi_sm = 0.0, phi_pi = 0.0, phi_sp = 0.0;
       const int zoff = (int) __ldg(L + RHB200_RL_ZOFF), nc = (int) __ldg(L + RHB200_RL_NCOMP);
       for (int nz = 0; nz < nc; nz++) {
-        double F;
-        const double H = rhv::humlicek(adamp, v - __ldg(zshift + zoff + nz)*vB, &F);
-        const int q = __ldg(zq + zoff + nz);
-        const double st = __ldg(zstrength + zoff + nz);
+        const double H = rhv::humlicek_H(adamp, v - zshift_of(zee, zoff + nz)*vB);
+        const int q = zq_of(zee, zoff + nz);
+        const double st = zstrength_of(zee, zoff + nz);
         if (q == -1)     phi_sm += st * H;
         else if (q == 0) phi_pi += st * H;
         else if (q == 1) phi_sp += st * H;
@@ -180,7 +191,7 @@ __device__ __forceinline__ void line_sums(LineSums &s, const double lambda, cons
       phi_V = sign * 0.5*(phi_sp - phi_sm) * cos_gamma * sv;
     }
     if (phi != 0.0) {                                   // kurucz.c:674
-      const double chi_l = __ldg(P + LP_CHIL), eta_l = __ldg(P + LP_ETAL);
+      const double chi_l = __ldg(P + (size_t) LP_CHIL*ndep), eta_l = __ldg(P + (size_t) LP_ETAL*ndep);
       s.chi[0] += chi_l * phi;
       s.eta[0] += eta_l * phi;
       if (polarizable && has_grad) {                    // kurucz.c:701-708
@@ -191,45 +202,48 @@ __device__ __forceinline__ void line_sums(LineSums &s, const double lambda, cons
   }
 }
 
-// FUSED: total opacity + source vector + reduced propagation matrix per ray-point,
-// written in the DELO kernel's layout [depth][RP_NFIELD][nray].
-// block = (32 rays) x (4 depths); grid = (ceil(nray/32), ceil(ndep/4))
-__global__ void __launch_bounds__(128)
+// Thread mapping of both opacity kernels: one thread per ray-point, flattened with DEPTH
+// fastest (t = ray*ndep + k).  A warp therefore holds 32 consecutive depths of one wavelength
+// (occasionally the tail of one ray and the head of the next): the Doppler coordinate
+// v = (lambda/lambda0 - 1) c / vbroad(k) varies slowly along the warp, so all lanes take the same
+// Humlicek region except near region boundaries (ncu: 21 -> ~30 active threads / instruction
+// against the wavelength-along-warp mapping), and every global access is unit stride:
+// chi_ai/eta_ai[ray][k] (the reference's own layout), lineprep[col][line][field][k], atmos[col][f][k].
+
+// FUSED: total opacity + source vector + reduced propagation matrix per ray-point, written as
+// one 64-byte record {chi_I, K'_Q, K'_U, K'_V, S_I, S_Q, S_U, S_V} at raypts[ray][k].
+template <int MINB, class ZT>
+__global__ void __launch_bounds__(128, MINB)
 opacity_fused_kernel(int ncol, int nlambda, int ndep, int to_obs, int nline,
                      const double *__restrict__ lambda, const int *__restrict__ wfirst,
                      const int *__restrict__ wcount, const int *__restrict__ widx,
-                     const double *__restrict__ lines, const int *__restrict__ zq,
-                     const double *__restrict__ zshift, const double *__restrict__ zstrength,
+                     const double *__restrict__ lines, const __grid_constant__ ZT zee,
                      const double *__restrict__ atmos, const double *__restrict__ lineprep,
                      const double *__restrict__ chi_ai, const double *__restrict__ eta_ai,
                      double *__restrict__ raypts)
 {
-  const size_t nray = (size_t) ncol * nlambda;
-  const size_t r = (size_t) blockIdx.x * 32 + threadIdx.x;
-  const int k = blockIdx.y * blockDim.y + threadIdx.y;
-  if (r >= nray || k >= ndep) return;
+  const size_t npts = (size_t) ncol * nlambda * ndep;
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= npts) return;
+  const size_t r = t / ndep;
+  const int k = (int) (t - r * ndep);
   const int col = (int) (r / nlambda), l = (int) (r - (size_t) col * nlambda);
   const double *at = atmos + (size_t) col * RHB200_AT_NFIELD * ndep;
 
   LineSums s;
   line_sums(s, __ldg(lambda + l), to_obs, __ldg(wfirst + l), __ldg(wcount + l), widx, lines,
-            zq, zshift, zstrength,
-            lineprep + ((size_t) col*nline*ndep + k) * LP_NFIELD, (size_t) ndep * LP_NFIELD,
+            zee, lineprep + (size_t) col*nline*LP_NFIELD*ndep + k, ndep,
             __ldg(at + RHB200_AT_COS_GAMMA*ndep + k), __ldg(at + RHB200_AT_COS_2CHI*ndep + k),
             __ldg(at + RHB200_AT_SIN_2CHI*ndep + k));
 
   // background.c:476-537: chi_c = chi_ai + chi_lines (I), 0 + lines (Q,U,V);
   // formal.c:178-208: chi = 0 + chi_c, S = (0 + eta_c)/chi; stokesopac.c:72-77: K' = chi_QUV/chi_I
-  const double chi = __ldg(chi_ai + r*ndep + k) + s.chi[0];
-  double *o = raypts + (size_t) k * RP_NFIELD * nray + r;
-  o[(size_t) RP_CHI*nray] = chi;
-  o[(size_t) RP_KQ*nray]  = s.chi[1] / chi;
-  o[(size_t) RP_KU*nray]  = s.chi[2] / chi;
-  o[(size_t) RP_KV*nray]  = s.chi[3] / chi;
-  o[(size_t) RP_SI*nray]  = (__ldg(eta_ai + r*ndep + k) + s.eta[0]) / chi;
-  o[(size_t) RP_SQ*nray]  = s.eta[1] / chi;
-  o[(size_t) RP_SU*nray]  = s.eta[2] / chi;
-  o[(size_t) RP_SV*nray]  = s.eta[3] / chi;
+  const double chi = __ldg(chi_ai + t) + s.chi[0];
+  double2 *o = reinterpret_cast<double2 *>(raypts + t * RP_NFIELD);
+  o[0] = make_double2(chi, s.chi[1] / chi);
+  o[1] = make_double2(s.chi[2] / chi, s.chi[3] / chi);
+  o[2] = make_double2((__ldg(eta_ai + t) + s.eta[0]) / chi, s.eta[1] / chi);
+  o[3] = make_double2(s.eta[2] / chi, s.eta[3] / chi);
 }
 
 // RAW: exactly the output of rlk_opacity(), chi/eta [ncol][nlambda][4][ndep]
@@ -242,16 +256,17 @@ opacity_raw_kernel(int ncol, int nlambda, int ndep, int to_obs, int nline,
                    const double *__restrict__ atmos, const double *__restrict__ lineprep,
                    double *__restrict__ chi, double *__restrict__ eta)
 {
-  const size_t nray = (size_t) ncol * nlambda;
-  const size_t r = (size_t) blockIdx.x * 32 + threadIdx.x;
-  const int k = blockIdx.y * blockDim.y + threadIdx.y;
-  if (r >= nray || k >= ndep) return;
+  const size_t npts = (size_t) ncol * nlambda * ndep;
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= npts) return;
+  const size_t r = t / ndep;
+  const int k = (int) (t - r * ndep);
   const int col = (int) (r / nlambda), l = (int) (r - (size_t) col * nlambda);
   const double *at = atmos + (size_t) col * RHB200_AT_NFIELD * ndep;
   LineSums s;
+  const ZeemanGlobal zee{zq, zshift, zstrength};
   line_sums(s, __ldg(lambda + l), to_obs, __ldg(wfirst + l), __ldg(wcount + l), widx, lines,
-            zq, zshift, zstrength,
-            lineprep + ((size_t) col*nline*ndep + k) * LP_NFIELD, (size_t) ndep * LP_NFIELD,
+            zee, lineprep + (size_t) col*nline*LP_NFIELD*ndep + k, ndep,
             __ldg(at + RHB200_AT_COS_GAMMA*ndep + k), __ldg(at + RHB200_AT_COS_2CHI*ndep + k),
             __ldg(at + RHB200_AT_SIN_2CHI*ndep + k));
 #pragma unroll
@@ -312,13 +327,31 @@ int rh_launch_opacity_fused(rhb200_ctx *ctx, int ncol, int ndep, int to_obs,
 {
   const size_t nray = (size_t) ncol * ctx->wav.nlambda;
   if (nray == 0) return RHB200_OK;
-  dim3 block(32, 4), grid((unsigned) ((nray + 31) / 32), (unsigned) ((ndep + 3) / 4));
+  const size_t npts = nray * (size_t) ndep;
+  const unsigned block = 128, grid = (unsigned) ((npts + block - 1) / block);
   {
     ScopedKernelTimer t(ctx, RHB200_K_OPACITY);
-    opacity_fused_kernel<<<grid, block, 0, ctx->stream>>>(ncol, ctx->wav.nlambda, ndep, to_obs,
-        ctx->tab.nline, ctx->wav.lambda, ctx->wav.first, ctx->wav.count, ctx->wav.idx,
-        ctx->tab.lines, ctx->tab.zq, ctx->tab.zshift, ctx->tab.zstrength, d_atmos, d_lineprep,
-        d_chi_ai, d_eta_ai, d_raypts);
+    static int variant = -1;
+    if (variant < 0) { const char *e = getenv("RHB200_OPACITY_MINB"); variant = e ? atoi(e) : 8; }
+#define RH_LAUNCH_OPF(M, ZT, Z) opacity_fused_kernel<M, ZT><<<grid, block, 0, ctx->stream>>>(ncol, ctx->wav.nlambda, ndep, \
+        to_obs, ctx->tab.nline, ctx->wav.lambda, ctx->wav.first, ctx->wav.count, ctx->wav.idx, \
+        ctx->tab.lines, Z, d_atmos, d_lineprep, d_chi_ai, d_eta_ai, d_raypts)
+#define RH_LAUNCH_OPF_V(ZT, Z) switch (variant) {             \
+    case 4: RH_LAUNCH_OPF(4, ZT, Z); break;                   \
+    case 5: RH_LAUNCH_OPF(5, ZT, Z); break;                   \
+    case 6: RH_LAUNCH_OPF(6, ZT, Z); break;                   \
+    default: RH_LAUNCH_OPF(8, ZT, Z); break; }
+    if (ctx->tab.ncomp <= RH_ZPARAM_MAX && !getenv("RHB200_ZEEMAN_GLOBAL")) {
+      ZeemanParam zp;
+      memset(&zp, 0, sizeof(zp));
+      for (int i = 0; i < ctx->tab.ncomp; i++) {
+        zp.shift[i] = ctx->h_zshift[i]; zp.strength[i] = ctx->h_zstrength[i]; zp.q[i] = (signed char) ctx->h_zq[i];
+      }
+      RH_LAUNCH_OPF_V(ZeemanParam, zp)
+    } else {
+      const ZeemanGlobal zg{ctx->tab.zq, ctx->tab.zshift, ctx->tab.zstrength};
+      RH_LAUNCH_OPF_V(ZeemanGlobal, zg)
+    }
   }
   RH_CUDA(cudaGetLastError());
   return RHB200_OK;
@@ -330,7 +363,8 @@ int rh_launch_opacity_raw(rhb200_ctx *ctx, int ncol, int ndep, int to_obs,
 {
   const size_t nray = (size_t) ncol * ctx->wav.nlambda;
   if (nray == 0) return RHB200_OK;
-  dim3 block(32, 4), grid((unsigned) ((nray + 31) / 32), (unsigned) ((ndep + 3) / 4));
+  const size_t npts = nray * (size_t) ndep;
+  const unsigned block = 128, grid = (unsigned) ((npts + block - 1) / block);
   {
     ScopedKernelTimer t(ctx, RHB200_K_OPACITY);
     opacity_raw_kernel<<<grid, block, 0, ctx->stream>>>(ncol, ctx->wav.nlambda, ndep, to_obs,

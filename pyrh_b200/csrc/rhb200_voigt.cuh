@@ -27,13 +27,24 @@ __device__ __forceinline__ int humlicek_region(double a, double v) {
   return 4;
 }
 
-__device__ __noinline__ double humlicek(double a, double v, double *F) {
-  cplx z = {a, -v}, z1, z2, W;
+// NEED_F = false drops everything that only feeds Im W (the Faraday-Voigt function is used by
+// RLKProfile only when MAGNETO_OPTICAL is on, kurucz.c:815-822): the imaginary quotient of the
+// final complex division and, in region IV, the whole sin() evaluation.  Re W is unchanged bit
+// for bit.
+template <bool NEED_F>
+__device__ __forceinline__ double humlicek_t(double a, double v, double *F) {
+  cplx z = {a, -v}, z1, z2;
+  double Wr, Wi = 0.0;
   const int reg = humlicek_region(a, v);
+  // complex quotient z1/z2 (complex.c:84-99); the imaginary part only when needed
+#define RH_CDIV_OUT(NUM, DEN)                                                   \
+  { const double d__ = (DEN).r*(DEN).r + (DEN).i*(DEN).i;                       \
+    Wr = ((NUM).r*(DEN).r + (NUM).i*(DEN).i) / d__;                             \
+    if (NEED_F) Wi = ((NUM).i*(DEN).r - (NUM).r*(DEN).i) / d__; }
   if (reg == 1) {                               // humlicek.c:28-38
     z1.r = 0.5641896*z.r; z1.i = 0.5641896*z.i;
     z2 = cmul(z, z); z2.r = z2.r + 0.5;
-    W = cdiv(z1, z2);
+    RH_CDIV_OUT(z1, z2)
   } else if (reg == 2) {                        // humlicek.c:43-55
     cplx u = cmul(z, z), t;
     z1.r = 0.5641896*u.r; z1.i = 0.5641896*u.i;
@@ -42,7 +53,7 @@ __device__ __noinline__ double humlicek(double a, double v, double *F) {
     t.r = u.r + 3.0; t.i = u.i;
     z2 = cmul(u, t);
     z2.r = z2.r + 0.75;
-    W = cdiv(z1, z2);
+    RH_CDIV_OUT(z1, z2)
   } else if (reg == 3) {                        // humlicek.c:62-83
     const double A[5] = {0.5642236, 3.778987, 11.96482, 20.20933, 16.4955};
     const double B[5] = {6.699398, 21.69274, 39.27121, 38.82363, 16.4955};
@@ -53,7 +64,7 @@ __device__ __noinline__ double humlicek(double a, double v, double *F) {
       z1 = cmul(z1, z); z1.r = z1.r + A[n];
       z2 = cmul(z2, z); z2.r = z2.r + B[n];
     }
-    W = cdiv(z1, z2);
+    RH_CDIV_OUT(z1, z2)
   } else {                                      // humlicek.c:90-117
     const double A[7] = {0.56419, 1.320522, 35.7668, 219.031, 1540.787, 3321.99, 36183.31};
     const double B[7] = {1.841439, 61.57037, 364.2191, 2186.181, 9022.228, 24322.84, 32066.6};
@@ -67,13 +78,18 @@ __device__ __noinline__ double humlicek(double a, double v, double *F) {
       z2 = cmul(u, z2); z2.r = z2.r + B[n];
     }
     cplx mu = {-1.0*u.r, -1.0*u.i};
-    double ex = rhm::rh_exp(mu.r);               // complex.c:104-109
-    cplx e = {ex*rhm::rh_cos(mu.i), ex*rhm::rh_sin(mu.i)};
-    cplx q = cdiv(cmul(z, z1), z2);
-    W.r = e.r - q.r; W.i = e.i - q.i;
+    const double ex = rhm::rh_exp(mu.r);         // complex.c:104-109
+    const cplx zz = cmul(z, z1);
+    RH_CDIV_OUT(zz, z2)
+    Wr = ex*rhm::rh_cos(mu.i) - Wr;
+    if (NEED_F) Wi = ex*rhm::rh_sin(mu.i) - Wi;
   }
-  *F = W.i;
-  return W.r;
+#undef RH_CDIV_OUT
+  if (NEED_F) *F = Wi;
+  return Wr;
 }
+
+__device__ __noinline__ double humlicek(double a, double v, double *F) { return humlicek_t<true>(a, v, F); }
+__device__ __forceinline__ double humlicek_H(double a, double v) { return humlicek_t<false>(a, v, nullptr); }
 
 }  // namespace rhv
