@@ -34,7 +34,8 @@ METRIC = "formal-solution ray-points/s"
 NCOL_DEFAULT, NDEP, NLAMBDA = 16384, 70, 301
 
 # algorithmic FP64 work per ray-point (SURVEY.md 8(d) counting rule)
-FLOP_DELO = 1170.0
+FLOP_DELO = 400.0                              # structure-exploiting DELO-Bezier3 step (reference formulation: 1170)
+FLOP_DELO_REFERENCE_FORMULATION = 1170.0
 FLOP_OPACITY = 16 * 32.8 + 2 * 45.0 + 30.0     # 16 Humlicek evals (measured region mix) + 2 line preambles + combine
 BYTES_DELO = 64.0                              # chi, K'(3), S(4) read per ray-point
 
@@ -321,6 +322,10 @@ def main():
                 "peak_source": "rhb200_fp64_peak(): DFMA micro-benchmark run in this process (2 flop/FMA); "
                                f"non-FMA FP64 issue rate {nofma_tf:.1f} Tinst/s",
                 "algorithmic_flop_per_raypoint": flop_pt, "ms_per_launch": dom_ms,
+                "delo": {"ms_per_launch": kt.get("delo", (0, 0))[0],
+                         "achieved_tflops": (pts_per_launch * FLOP_DELO / (kt["delo"][0] * 1e-3) / 1e12) if "delo" in kt else None,
+                         "algorithmic_flop_per_raypoint": FLOP_DELO,
+                         "reference_formulation_flop_per_raypoint": FLOP_DELO_REFERENCE_FORMULATION},
                 "hbm": {"achieved": pts_per_launch * (BYTES_DELO if dom == "delo" else 80.0) / (dom_ms * 1e-3) / 1e9,
                         "peak": hbm_peak, "unit": "GB/s",
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"},

@@ -48,7 +48,8 @@ struct GenericIO {
   __device__ __forceinline__ void storePsi(int k, double p) { if (Psi_) Psi_[k] = p; }
 };
 
-__global__ void __launch_bounds__(128)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
 delo_raypts_kernel(int ncol, int nlambda, int ndep, double muz, int bc_top, int bc_bottom,
                    const double *__restrict__ atmos, const double *__restrict__ lambda,
                    const double *__restrict__ raypts, double *__restrict__ stokes)
@@ -106,9 +107,16 @@ int rh_launch_delo_raypts(rhb200_ctx *ctx, int ncol, int ndep, double muz, int b
   const unsigned blocks = (unsigned) ((nray + threads - 1) / threads);
   {
     ScopedKernelTimer t(ctx, RHB200_K_DELO);
-    delo_raypts_kernel<<<blocks, threads, 0, ctx->stream>>>(ncol, ctx->wav.nlambda, ndep, muz, bc_top,
-                                                             bc_bottom, d_atmos, ctx->wav.lambda,
-                                                             d_raypts, d_stokes);
+    static int variant = -1;
+    if (variant < 0) { const char *e = getenv("RHB200_DELO_MINB"); variant = e ? atoi(e) : 4; }
+#define RH_LAUNCH_DELO(M) delo_raypts_kernel<M><<<blocks, threads, 0, ctx->stream>>>(ncol, ctx->wav.nlambda, ndep, muz, \
+        bc_top, bc_bottom, d_atmos, ctx->wav.lambda, d_raypts, d_stokes)
+    switch (variant) {
+    case 4: RH_LAUNCH_DELO(4); break;
+    case 5: RH_LAUNCH_DELO(5); break;
+    case 6: RH_LAUNCH_DELO(6); break;
+    default: RH_LAUNCH_DELO(3); break;
+    }
   }
   RH_CUDA(cudaGetLastError());
   return RHB200_OK;
