@@ -143,41 +143,53 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------- reference arm
-def _ref_worker(args):
-    first, n, ndep = args
+_REF = {}
+
+
+def _ref_init(ndep):
     from oracle import refdriver as rd
+    _REF["rd"] = rd
+    _REF["base"] = np.load(ROOT / "tests" / "golden" / "falc_base.npy")
+    _REF["wave"] = rd.hinode_wave(NLAMBDA)
+    _REF["cwd"] = rd.make_workdir("benchmark")
+    _REF["ndep"] = ndep
+
+
+def _ref_step(args):
+    first, n = args
     from pyrh_b200 import synthetic
-    base = np.load(ROOT / "tests" / "golden" / "falc_base.npy")
-    wave = rd.hinode_wave(NLAMBDA)
-    cwd = rd.make_workdir("benchmark")
-    atms = synthetic.perturbed_batch(base, n, ndep=ndep, first=first)
-    rd.rhf1d(atms[0], wave, cwd)           # warm-up: page in the library and the atomic data
+    rd = _REF["rd"]
+    atms = synthetic.perturbed_batch(_REF["base"], n, ndep=_REF["ndep"], first=first)
     t0 = time.perf_counter()
     for a in atms:
-        rd.rhf1d(a, wave, cwd)
+        rd.rhf1d(a, _REF["wave"], _REF["cwd"])
     return time.perf_counter() - t0
 
 
-def reference_throughput(cols_per_proc=4, procs=None, variant="scalar"):
-    """rhf1d() of the unmodified reference (oracle/_ref) on `procs` host cores, one process per
-    core; returns (ray-points/s, spectra/s, procs, ncolumns, wall)."""
+def reference_throughput(steps=5, warmup=3, cols_per_proc=2, procs=None, variant="scalar"):
+    """rhf1d() of the unmodified reference (oracle/_ref), one process per host core (the only
+    parallel mode the reference supports).  One step = every process synthesises `cols_per_proc`
+    columns of the benchmark workload; `warmup` untimed + `steps` timed steps (a step lasts as
+    long as its slowest process; synthetic-atmosphere generation is outside the timed section).  Returns dict(rps, sps, procs, ncols, wall)."""
     import multiprocessing as mp
     from oracle import refdriver as rd
     if not rd.available(variant):
         raise RuntimeError("oracle/_ref is not built (make -C oracle ref where /root/reference exists)")
     procs = procs or os.cpu_count() or 1
     ctx = mp.get_context("fork")
-    t0 = time.perf_counter()
-    with ctx.Pool(procs) as pool:
-        pool.map(_ref_worker, [(1000 + p * cols_per_proc, cols_per_proc, NDEP) for p in range(procs)])
-    wall_all = time.perf_counter() - t0
-    # second pass, timed: pools are warm only per process, so time inside the workers and
-    # use the slowest worker (all run concurrently)
-    with ctx.Pool(procs) as pool:
-        t = pool.map(_ref_worker, [(2000 + p * cols_per_proc, cols_per_proc, NDEP) for p in range(procs)])
-    wall = max(t)
-    ncols = procs * cols_per_proc
-    return ncols * NLAMBDA * NDEP / wall, ncols / wall, procs, ncols, wall, wall_all
+    with ctx.Pool(procs, initializer=_ref_init, initargs=(NDEP,)) as pool:
+        col = 1000
+        for _ in range(warmup):
+            pool.map(_ref_step, [(col + p * cols_per_proc, cols_per_proc) for p in range(procs)], chunksize=1)
+            col += procs * cols_per_proc
+        wall = 0.0
+        for _ in range(steps):
+            t = pool.map(_ref_step, [(col + p * cols_per_proc, cols_per_proc) for p in range(procs)], chunksize=1)
+            wall += max(t)       # all processes run concurrently: a step lasts as long as its slowest process
+            col += procs * cols_per_proc
+    ncols = steps * procs * cols_per_proc
+    return dict(rps=ncols * NLAMBDA * NDEP / wall, sps=ncols / wall, procs=procs, ncols=ncols, wall=wall,
+                cols_per_step=procs * cols_per_proc)
 
 
 # ------------------------------------------------------------------------- main
@@ -189,7 +201,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ncol", type=int, default=NCOL_DEFAULT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ref-cols-per-proc", type=int, default=4)
+    ap.add_argument("--ref-cols-per-proc", type=int, default=3)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -204,14 +216,16 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        rps, sps, procs, ncols, wall, _ = reference_throughput(args.ref_cols_per_proc)
+        r = reference_throughput(args.steps, args.warmup, args.ref_cols_per_proc)
+        rps, sps, procs, ncols, wall = r["rps"], r["sps"], r["procs"], r["ncols"], r["wall"]
         line = {"impl": "reference", "metric": METRIC, "value": rps, "unit": "ray-points/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": config, "spectra_per_s": sps,
                 "cpu_baseline": {"value": rps, "unit": "ray-points/s", "cores": procs, "kind": "reference",
-                                 "sample": f"{ncols} perturbed FAL-C columns ({args.ref_cols_per_proc}/process), full rhf1d() "
-                                           "per column incl. input parsing + continuum (the reference has no way to "
+                                 "sample": f"{ncols} perturbed FAL-C columns in {args.steps} steps of {r['cols_per_step']} "
+                                           f"({args.ref_cols_per_proc}/process x {procs} processes), {wall:.1f} s wall; full "
+                                           "rhf1d() per column incl. input parsing + continuum (the reference cannot "
                                            "run the hot path alone)"},
                 "e2e": {"value": rps, "unit": "ray-points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -251,19 +265,18 @@ def main():
     # ---- device-resident arm
     d_at, d_chi, d_eta, d_st = (ctx.dev_alloc(x.nbytes) for x in (at, chi, eta, stokes))
     ctx.h2d(d_at, at); ctx.h2d(d_chi, chi); ctx.h2d(d_eta, eta)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         ctx.lte_stokes_batch_dev(ncol, NDEP, d_at, d_chi, d_eta, d_st)
     ctx.timing(False)
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
     ctx.timer_begin()
     for _ in range(args.steps):
         ctx.lte_stokes_batch_dev(ncol, NDEP, d_at, d_chi, d_eta, d_st)
     ms_dev = ctx.timer_end()
     launches = sum(v[1] for v in ctx.timing_get().values())
     barrier()
-    clocks = sampler.stop()
     ms_dev = maxreduce(ms_dev)
     dev_out = np.empty((ncol, 4, NLAMBDA))
     ctx.d2h(dev_out, d_st)
@@ -290,6 +303,7 @@ def main():
     ms_e2e = max(ms_e2e_dev, 1e3 * (time.perf_counter() - t0))
     barrier()
     ms_e2e = maxreduce(ms_e2e)
+    clocks = sampler.stop()          # sampled from the first warm-up step to the end of the e2e region
     same = bool(np.array_equal(dev_out, stokes))
 
     fma_tf, nofma_tf = ctx.fp64_peak()
@@ -343,7 +357,8 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
     if world == 1 and not args.no_cpu_baseline:
         try:
-            rps, sps, procs, ncols, wall, _ = reference_throughput(args.ref_cols_per_proc)
+            r = reference_throughput(5, 2, args.ref_cols_per_proc)
+            rps, sps, procs, ncols, wall = r["rps"], r["sps"], r["procs"], r["ncols"], r["wall"]
             line["cpu_baseline"] = {"value": rps, "unit": "ray-points/s", "cores": procs, "kind": "reference",
                                     "spectra_per_s": sps,
                                     "sample": f"{ncols} perturbed FAL-C columns (70 depths, 301 wavelengths), one rhf1d() "
