@@ -170,6 +170,13 @@ int rhb200_bezier3_batch(rhb200_ctx *ctx, int nray, int ncol, int ndep, double m
                          const double *height, const double *T,
                          const double *chi, const double *S, double *I, double *Psi);
 
+/* Feautrier (feautrier.c:56-202, F_order = STANDARD): chi, S [nray][ndep]; out P [nray][ndep]
+   (Feautrier mean intensity along the ray), Psi [nray][ndep] or NULL, Iem [nray] emergent intensity */
+int rhb200_feautrier_batch(rhb200_ctx *ctx, int nray, int ncol, int ndep, double muz,
+                           int bc_top, int bc_bottom, const int *ray_col, const double *ray_lambda,
+                           const double *height, const double *T, const double *chi, const double *S,
+                           double *P, double *Psi, double *Iem);
+
 /* Voigt(a, v, &F, HUMLICEK) (voigt.c:381-419, humlicek.c): H, F for n (a, v) pairs;
    region[n] (1..4) may be NULL */
 int rhb200_voigt_humlicek(rhb200_ctx *ctx, int n, const double *a, const double *v,

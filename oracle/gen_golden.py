@@ -206,6 +206,46 @@ def validate_port(name, g, extra):
           f"QUV/Ic {np.abs(st[1:]-ref[1:]).max()/Ic:.2e} exact={np.array_equal(st, ref)}")
 
 
+def make_scalar_case(name, atm, wave):
+    """NO_STOKES LTE run on a grid wider than the line windows: the reference then solves
+    line-window wavelengths with Piecewise_Bezier3_1D (formal.c:234-235) and line-free ones with
+    Feautrier (formal.c:289-309).  Records every such call (inputs + outputs)."""
+    cwd = rd.make_workdir("benchmark", keywords={"STOKES_MODE": "NO_STOKES"})
+    full = rd.rhf1d(atm, wave, cwd, variant="scalar", probe=rd.PROBE_ALL)
+    R = recs_by_tag(full["records"])
+    lam, flags = one(R, "lambda"), one(R, "flags")
+    nd = atm.shape[1]
+    bez = [(m, d.reshape(4, nd)) for m, d in R.get("bez", [])]
+    feau = [(m, d) for m, d in R.get("feau", [])]
+    out = dict(atmosphere=atm, wave=wave, lam_spect=lam, flags=flags, muz=one(R, "muz"),
+               backgrflags=one(R, "backgrflags").reshape(len(lam), 2).astype(np.int32),
+               bez_meta=np.array([m[:4] for m, _ in bez], np.int32), bez=np.array([d for _, d in bez]),
+               feau_meta=np.array([m[:4] for m, _ in feau], np.int32),
+               feau=np.array([d[:4 * nd].reshape(4, nd) for _, d in feau]),
+               feau_Iem=np.array([d[4 * nd] for _, d in feau]),
+               I_scalar=full["I"], lam_out=full["lam"])
+    for f in ("T", "height"):
+        out["col_" + f] = one(R, f)
+    np.savez_compressed(GOLD / f"{name}.npz", **out)
+    print(f"[golden] {name}: {len(bez)} Bezier3 rays, {len(feau)} Feautrier rays "
+          f"-> {(GOLD / (name + '.npz')).stat().st_size/1e6:.2f} MB")
+    return out
+
+
+def validate_scalar_port(name, g):
+    from oracle import portdriver as pd
+    nb = nf = 0
+    for m, d in zip(g["bez_meta"], g["bez"]):
+        I, Psi = pd.bezier3_scalar(g["col_height"], float(g["muz"][m[1]]), int(m[2]), d[0], d[1], g["col_T"],
+                                   g["lam_spect"][m[0]], want_psi=True)
+        nb += np.array_equal(I, d[2]) and (not m[3] or np.array_equal(Psi, d[3]))
+    for m, d, Iem in zip(g["feau_meta"], g["feau"], g["feau_Iem"]):
+        P, Psi, I0 = pd.feautrier(g["col_height"], float(g["muz"][m[1]]), d[0], d[1], g["col_T"],
+                                  g["lam_spect"][m[0]])
+        nf += np.array_equal(P, d[2]) and I0 == Iem and (not m[3] or np.array_equal(Psi, d[3]))
+    print(f"[port-vs-ref] {name}: Bezier3 exact {nb}/{len(g['bez'])}, Feautrier exact {nf}/{len(g['feau'])}")
+
+
 def falc_case_atm():
     atm = rd.falc("benchmark")
     atm[5] = 1000.0                                   # B [G]; gamma, chi from falc.dat (pi/4, pi/3)
@@ -218,6 +258,14 @@ def main():
     wave = rd.hinode_wave()
     g, ex = make_case("falc_B1kG", falc_case_atm(), wave)
     validate_port("falc_B1kG", g, ex)
+    gs = make_scalar_case("falc_scalar", falc_case_atm(), rd.air_to_vacuum(np.linspace(629.7, 630.7, 101)))
+    validate_scalar_port("falc_scalar", gs)
+    # FULL_STOKES on the same wide grid: DELO inside the line windows, Feautrier outside
+    g, ex = make_case("falc_B1kG_wide", falc_case_atm(), rd.air_to_vacuum(np.linspace(629.7, 630.7, 101)),
+                      subset_step=25)
+    validate_port("falc_B1kG_wide", g, ex)
+    if "--scalar-only" in sys.argv:
+        return
     # BASELINE config 2 columns: perturbed FAL-C resampled to 70 depths
     base = rd.falc("tests")
     np.save(GOLD / "falc_base.npy", base)

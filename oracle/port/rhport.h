@@ -95,6 +95,10 @@ void rp_bezier3_scalar(int Ndep, const double *height, double muz, int to_obs,
                        const double *chi, const double *S, const double *T, double lambda,
                        int bc_top, int bc_bottom, double *I, double *Psi);
 
+/* feautrier.c:56-202 (STANDARD order); returns emergent I */
+double rp_feautrier(int Ndep, const double *height, double muz, const double *chi, const double *S,
+                    const double *T, double lambda, int bc_top, int bc_bottom, double *P, double *Psi);
+
 /* formal.c:157-275 restricted to LTE (solve_NLTE = FALSE, Nrays = 1, emergent up-ray only):
    cont: chi_ai, eta_ai [Nlambda][Ndep] (angle-independent background, background.c:343-465)
    out:  stokes [4][Nlambda] */

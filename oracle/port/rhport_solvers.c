@@ -426,6 +426,68 @@ void rp_bezier3_scalar(int Ndep, const double *z, double muz, int to_obs,
   }
 }
 
+/* Feautrier, rh/rhf1d/feautrier.c:56-202, F_order = STANDARD (the only order Formal() requests,
+   formal.c:299).  Returns the emergent intensity; fills P and (if non-NULL) Psi. */
+double rp_feautrier(int Ndep, const double *z, double muz, const double *chi, const double *S,
+                    const double *T, double lambda, int bc_top, int bc_bottom, double *P, double *Psi)
+{
+  int k;
+  double r0 = 0.0, h0 = 0.0, rN = 0.0, hN = 0.0, f0, fN, zmu = 0.5 / muz, dtau_mid, Iplus;
+  double *dtau = malloc(Ndep*sizeof(double)), *abc = malloc(Ndep*sizeof(double)),
+         *A1 = malloc(Ndep*sizeof(double)), *C1 = malloc(Ndep*sizeof(double)),
+         *F = malloc(Ndep*sizeof(double)), *G = malloc(Ndep*sizeof(double)),
+         *ztmp = malloc(Ndep*sizeof(double)), *Stmp = malloc(Ndep*sizeof(double));
+
+  for (k = 0; k < Ndep-1; k++) dtau[k] = zmu * (chi[k] + chi[k+1]) * (z[k] - z[k+1]);
+
+  if (bc_top == RP_THERMALIZED) {
+    double B0 = rp_planck(T[0], lambda), B1 = rp_planck(T[1], lambda);
+    h0 = B0 - (B1 - B0) / dtau[0];
+  }
+  f0      = (1.0 - r0) / (1.0 + r0);
+  abc[0]  = 1.0 + 2.0*f0 / dtau[0];
+  C1[0]   = 2.0 / (dtau[0]*dtau[0]);
+  Stmp[0] = S[0] + 2.0*h0 / ((1.0 + r0)*dtau[0]);
+
+  if (bc_bottom == RP_THERMALIZED) {
+    double B0 = rp_planck(T[Ndep-2], lambda), B1 = rp_planck(T[Ndep-1], lambda);
+    hN = B1 - (B0 - B1) / dtau[Ndep-2];
+  }
+  fN           = (1.0 - rN) / (1.0 + rN);
+  abc[Ndep-1]  = 1.0 + 2.0*fN / dtau[Ndep-2];
+  A1[Ndep-1]   = 2.0 / (dtau[Ndep-2]*dtau[Ndep-2]);
+  Stmp[Ndep-1] = S[Ndep-1] + 2.0*hN / ((1.0 + rN)*dtau[Ndep-2]);
+
+  for (k = 1; k < Ndep-1; k++) {
+    dtau_mid = 0.5*(dtau[k] + dtau[k-1]);
+    A1[k]   = 1.0 / (dtau_mid * dtau[k-1]);
+    C1[k]   = 1.0 / (dtau_mid * dtau[k]);
+    abc[k]  = 1.0;
+    Stmp[k] = S[k];
+  }
+  F[0]    = abc[0] / C1[0];
+  ztmp[0] = Stmp[0] / (abc[0] + C1[0]);
+  for (k = 1; k < Ndep-1; k++) {
+    F[k]    = (abc[k] + A1[k]*F[k-1]/(1.0 + F[k-1])) / C1[k];
+    ztmp[k] = (Stmp[k] + A1[k]*ztmp[k-1]) / (C1[k] * (1.0 + F[k]));
+  }
+  P[Ndep-1] = (Stmp[Ndep-1]+ A1[Ndep-1]*ztmp[Ndep-2]) /
+    (abc[Ndep-1] + A1[Ndep-1]*(F[Ndep-2] / (1.0 + F[Ndep-2])));
+  for (k = Ndep-2; k >= 0; k--) P[k] = P[k+1] / (1.0 + F[k]) + ztmp[k];
+
+  if (Psi) {
+    G[Ndep-1] = abc[Ndep-1] / A1[Ndep-1];
+    for (k = Ndep-2; k >= 1; k--) G[k] = (abc[k] + C1[k]*G[k+1]/(1.0 + G[k+1])) / A1[k];
+    Psi[0] = 1.0 / (abc[0] + C1[0]*G[1]/(1.0 + G[1]));
+    for (k = 1; k < Ndep-1; k++)
+      Psi[k] = 1.0 / (abc[k] + A1[k]*F[k-1]/(1.0 + F[k-1]) + C1[k]*G[k+1]/(1.0 + G[k+1]));
+    Psi[Ndep-1] = 1.0 / (abc[Ndep-1] + A1[Ndep-1]*F[Ndep-2]/(1.0 + F[Ndep-2]));
+  }
+  Iplus = (1.0 + f0)*P[0] - h0/(1.0 + r0);
+  free(dtau); free(abc); free(A1); free(C1); free(F); free(G); free(ztmp); free(Stmp);
+  return Iplus;
+}
+
 /* Formal() for the LTE FULL_STOKES case, formal.c:157-275 with solve_NLTE =
    FALSE (no sca_c*J term), Nrays = 1, and only the emergent (to_obs) ray:
    chi_c = chi_ai + chi_lines (background.c:476-537), S = eta/chi (formal.c:178-208) */
@@ -454,9 +516,17 @@ void rp_lte_stokes_column(const rp_linetable *lt, const rp_column *col,
     for (k = N; k < 4*N; k++) { chiQUV[k-N] = 0.0 + chl[k]; S[k] = 0.0 + (0.0 + etl[k]); }
     for (n = 0; n < 4; n++)
       for (k = 0; k < N; k++) S[n*N+k] /= chi[k];
-    rp_stokes_bezier3(N, col->height, col->muz, 1, chi, S, chiQUV, col->T, lambda[nl],
-                      bc_top, bc_bottom, lt->matinv_simd, I, NULL);
-    for (n = 0; n < 4; n++) stokes[(long) n*Nlambda + nl] = I[n*N];
+    if (fl & 1) {
+      rp_stokes_bezier3(N, col->height, col->muz, 1, chi, S, chiQUV, col->T, lambda[nl],
+                        bc_top, bc_bottom, lt->matinv_simd, I, NULL);
+      for (n = 0; n < 4; n++) stokes[(long) n*Nlambda + nl] = I[n*N];
+    } else {
+      /* no line in the window: not angle dependent -> Feautrier (formal.c:100-103, 289-309);
+         J = 0 on the single LTE pass so the sca_c*Jdag term vanishes */
+      stokes[nl] = rp_feautrier(N, col->height, col->muz, chi, S, col->T, lambda[nl],
+                                bc_top, bc_bottom, I, NULL);
+      for (n = 1; n < 4; n++) stokes[(long) n*Nlambda + nl] = 0.0;
+    }
   }
   free(elem_n); free(chl); free(etl); free(chi); free(S); free(I); free(chiQUV);
 }

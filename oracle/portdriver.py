@@ -140,6 +140,17 @@ def bezier3_scalar(height, muz, to_obs, chi, S, T, lam, bc_top=1, bc_bottom=2, w
     return (I, Psi) if want_psi else I
 
 
+def feautrier(height, muz, chi, S, T, lam, bc_top=1, bc_bottom=2):
+    n = len(chi)
+    arr = [np.ascontiguousarray(x, np.float64) for x in (height, chi, S, T)]
+    P, Psi = np.zeros(n), np.zeros(n)
+    f = lib().rp_feautrier
+    f.restype = C.c_double
+    I0 = f(n, _d(arr[0]), C.c_double(muz), _d(arr[1]), _d(arr[2]), _d(arr[3]), C.c_double(lam),
+           int(bc_top), int(bc_bottom), _d(P), _d(Psi))
+    return P, Psi, I0
+
+
 def lte_stokes_column(tab: PortTables, col: PortColumn, lam, chi_ai, eta_ai, bc_top=1, bc_bottom=2):
     lam = np.ascontiguousarray(lam, np.float64)
     chi_ai = np.ascontiguousarray(chi_ai, np.float64)

@@ -37,6 +37,8 @@ SYMBOLS = [
                                               C.c_int, ip, dp, dp, dp, dp, dp, dp, dp, dp]),
     ("rhb200_bezier3_batch", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
                                        ip, dp, dp, dp, dp, dp, dp, dp]),
+    ("rhb200_feautrier_batch", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, ip, dp,
+                                         dp, dp, dp, dp, dp, dp, dp]),
     ("rhb200_voigt_humlicek", C.c_int, [vp, C.c_int, dp, dp, dp, dp, ip]),
     ("rhb200_math_probe", C.c_int, [vp, C.c_int, C.c_int, dp, dp, dp]),
     ("rhb200_dev_alloc", C.c_int, [vp, C.c_size_t, C.POINTER(vp)]),

@@ -205,6 +205,24 @@ class Context:
             _dp(Psi) if want_psi else None))
         return (I, Psi) if want_psi else I
 
+    def feautrier(self, ray_col, ray_lambda, height, T, chi, S, mu=1.0, bc_top=_lib.BC_ZERO,
+                  bc_bottom=_lib.BC_THERMALIZED, want_psi=False):
+        rc = np.ascontiguousarray(ray_col, np.int32)
+        rl = np.ascontiguousarray(ray_lambda, np.float64)
+        h = np.ascontiguousarray(np.atleast_2d(height), np.float64)
+        t = np.ascontiguousarray(np.atleast_2d(T), np.float64)
+        chi = np.ascontiguousarray(chi, np.float64)
+        S = np.ascontiguousarray(S, np.float64)
+        nray, ndep = chi.shape
+        P = np.zeros((nray, ndep))
+        Iem = np.zeros(nray)
+        Psi = np.zeros((nray, ndep)) if want_psi else None
+        _lib.check(self.lib.rhb200_feautrier_batch(
+            self.h, nray, h.shape[0], ndep, float(mu), int(bc_top), int(bc_bottom),
+            rc.ctypes.data_as(_lib.ip), _dp(rl), _dp(h), _dp(t), _dp(chi), _dp(S), _dp(P),
+            _dp(Psi) if want_psi else None, _dp(Iem)))
+        return (P, Psi, Iem) if want_psi else (P, Iem)
+
     def voigt(self, a, v):
         a = np.ascontiguousarray(a, np.float64)
         v = np.ascontiguousarray(v, np.float64)

@@ -72,7 +72,7 @@ static void free_tables(rhb200_ctx *c)
 static void free_wave(rhb200_ctx *c)
 {
   DevWave &w = c->wav;
-  cudaFree(w.lambda); cudaFree(w.first); cudaFree(w.count); cudaFree(w.idx); cudaFree(w.flags);
+  cudaFree(w.lambda); cudaFree(w.first); cudaFree(w.count); cudaFree(w.idx); cudaFree(w.flags); cudaFree(w.noline);
   w = DevWave();
 }
 
@@ -215,6 +215,10 @@ extern "C" int rhb200_set_wavelengths(rhb200_ctx *c, int nlambda, const double *
   RH_CHECK(upload(&w.flags, c->h_flags.data(), (size_t) nlambda));
   if (w.nidx) RH_CHECK(upload(&w.idx, c->h_idx.data(), (size_t) w.nidx));
   else RH_CUDA(cudaMalloc((void **) &w.idx, sizeof(int)));
+  c->h_noline.clear();
+  for (int l = 0; l < nlambda; l++) if ((c->h_flags[l] & 1) == 0) c->h_noline.push_back(l);
+  w.nnoline = (int) c->h_noline.size();
+  if (w.nnoline) RH_CHECK(upload(&w.noline, c->h_noline.data(), (size_t) w.nnoline));
   return RHB200_OK;
 }
 
@@ -272,6 +276,7 @@ static int run_chunk_dev(rhb200_ctx *c, int cc, int ndep, double muz, int moving
   RH_CHECK(rh_launch_prep(c, cc, ndep, muz, moving, d_atmos, d_elem_n, d_lineprep));
   RH_CHECK(rh_launch_opacity_fused(c, cc, ndep, 1, d_atmos, d_lineprep, d_chi_ai, d_eta_ai, d_raypts));
   RH_CHECK(rh_launch_delo_raypts(c, cc, ndep, muz, bc_top, bc_bottom, d_atmos, d_raypts, d_stokes));
+  RH_CHECK(rh_launch_feautrier_raypts(c, cc, ndep, muz, bc_top, bc_bottom, d_atmos, d_raypts, d_stokes));
   return RHB200_OK;
 }
 
@@ -279,7 +284,7 @@ static int check_batch_args(rhb200_ctx *c, int ncol, int ndep, double muz, int b
 {
   RH_CHECK(need_state(c, true));
   if (ncol < 0 || ndep < 3 || !(muz > 0.0 && muz <= 1.0)) { rhb200_set_error("bad ncol/ndep/muz (%d, %d, %g)", ncol, ndep, muz); return RHB200_EINVAL; }
-  if (bc_top != RHB200_BC_ZERO) { rhb200_set_error("top boundary: only ZERO is implemented"); return RHB200_EUNSUPPORTED; }
+  if (bc_top != RHB200_BC_ZERO && bc_top != RHB200_BC_THERMALIZED) { rhb200_set_error("top boundary: only ZERO / THERMALIZED are implemented"); return RHB200_EUNSUPPORTED; }
   if (bc_bottom != RHB200_BC_THERMALIZED && bc_bottom != RHB200_BC_ZERO) { rhb200_set_error("bottom boundary: only THERMALIZED / ZERO are implemented"); return RHB200_EUNSUPPORTED; }
   return RHB200_OK;
 }
@@ -477,6 +482,35 @@ extern "C" int rhb200_bezier3_batch(rhb200_ctx *c, int nray, int ncol, int ndep,
   RH_CUDA(cudaStreamSynchronize(c->stream));
   RH_CHECK(to_host(I, dI.p, rb));
   if (Psi) RH_CHECK(to_host(Psi, dP.p, rb));
+  return RHB200_OK;
+}
+
+extern "C" int rhb200_feautrier_batch(rhb200_ctx *c, int nray, int ncol, int ndep, double muz,
+                                      int bc_top, int bc_bottom, const int *ray_col, const double *ray_lambda,
+                                      const double *height, const double *T, const double *chi, const double *S,
+                                      double *P, double *Psi, double *Iem)
+{
+  RH_NEED_CTX(c);
+  if (nray <= 0 || ncol <= 0 || ndep < 3 || !ray_col || !ray_lambda || !height || !T || !chi || !S || !P || !Iem) {
+    rhb200_set_error("bad arguments"); return RHB200_EINVAL;
+  }
+  for (int r = 0; r < nray; r++) if (ray_col[r] < 0 || ray_col[r] >= ncol) { rhb200_set_error("ray_col[%d] out of range", r); return RHB200_EINVAL; }
+  DevBuf rc, rl, h, t, dchi, dS, dP, dPsi, dI, scr;
+  const size_t rb = (size_t) nray * ndep * sizeof(double);
+  RH_CHECK(rc.from_host(ray_col, (size_t) nray * sizeof(int)));
+  RH_CHECK(rl.from_host(ray_lambda, (size_t) nray * sizeof(double)));
+  RH_CHECK(h.from_host(height, (size_t) ncol * ndep * sizeof(double)));
+  RH_CHECK(t.from_host(T, (size_t) ncol * ndep * sizeof(double)));
+  RH_CHECK(dchi.from_host(chi, rb)); RH_CHECK(dS.from_host(S, rb));
+  RH_CHECK(dP.alloc(rb)); RH_CHECK(dI.alloc((size_t) nray * sizeof(double))); RH_CHECK(scr.alloc(2*rb));
+  if (Psi) RH_CHECK(dPsi.alloc(rb));
+  RH_CHECK(rh_launch_feautrier(c, nray, ndep, muz, bc_top, bc_bottom, rc.as<int>(), rl.as<double>(),
+                               h.as<double>(), t.as<double>(), dchi.as<double>(), dS.as<double>(),
+                               dP.as<double>(), Psi ? dPsi.as<double>() : nullptr, dI.as<double>(), scr.as<double>()));
+  RH_CUDA(cudaStreamSynchronize(c->stream));
+  RH_CHECK(to_host(P, dP.p, rb));
+  RH_CHECK(to_host(Iem, dI.p, (size_t) nray * sizeof(double)));
+  if (Psi) RH_CHECK(to_host(Psi, dPsi.p, rb));
   return RHB200_OK;
 }
 

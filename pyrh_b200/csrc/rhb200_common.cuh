@@ -56,6 +56,7 @@ struct DevWave {
   int nlambda = 0, nidx = 0;
   double *lambda = nullptr;   // [nlambda]
   int *first = nullptr, *count = nullptr, *idx = nullptr, *flags = nullptr;
+  int *noline = nullptr, nnoline = 0;   // wavelengths without any line in the window (Feautrier rays)
 };
 
 struct KTimer {
@@ -70,7 +71,7 @@ struct rhb200_ctx {
   DevWave wav;
   std::vector<double> h_lines, h_elems, h_lambda, h_zshift, h_zstrength;
   std::vector<int> h_zq;
-  std::vector<int> h_first, h_count, h_idx, h_flags;
+  std::vector<int> h_first, h_count, h_idx, h_flags, h_noline;
   // workspace (grown on demand)
   void *ws = nullptr; size_t ws_bytes = 0;
   void *flush = nullptr; size_t flush_bytes = 0;
@@ -123,6 +124,12 @@ int rh_launch_bezier3(rhb200_ctx *ctx, int nray, int ndep, double muz, int to_ob
                       int bc_top, int bc_bottom, const int *d_ray_col,
                       const double *d_ray_lambda, const double *d_height, const double *d_T,
                       const double *d_chi, const double *d_S, double *d_I, double *d_Psi);
+int rh_launch_feautrier_raypts(rhb200_ctx *ctx, int ncol, int ndep, double muz, int bc_top, int bc_bottom,
+                               const double *d_atmos, double *d_raypts, double *d_stokes);
+int rh_launch_feautrier(rhb200_ctx *ctx, int nray, int ndep, double muz, int bc_top, int bc_bottom,
+                        const int *d_ray_col, const double *d_ray_lambda, const double *d_height,
+                        const double *d_T, const double *d_chi, const double *d_S,
+                        double *d_P, double *d_Psi, double *d_Iem, double *d_scratch);
 int rh_launch_voigt(rhb200_ctx *ctx, int n, const double *d_a, const double *d_v,
                     double *d_H, double *d_F, int *d_region);
 int rh_launch_math_probe(rhb200_ctx *ctx, int n, int func, const double *d_x, const double *d_y,

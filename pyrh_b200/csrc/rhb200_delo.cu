@@ -2,6 +2,7 @@
 // scalar cubic-Bezier short-characteristics solver (one thread per ray, depth sequential).
 #include "rhb200_delo.cuh"
 #include "rhb200_bezier.cuh"
+#include "rhb200_feautrier.cuh"
 
 namespace {
 
@@ -52,12 +53,14 @@ template <int MINB>
 __global__ void __launch_bounds__(128, MINB)
 delo_raypts_kernel(int ncol, int nlambda, int ndep, double muz, int bc_top, int bc_bottom,
                    const double *__restrict__ atmos, const double *__restrict__ lambda,
+                   const int *__restrict__ wflags,
                    const double *__restrict__ raypts, double *__restrict__ stokes)
 {
   const size_t nray = (size_t) ncol * nlambda;
   const size_t r = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= nray) return;
   const int col = (int) (r / nlambda), l = (int) (r - (size_t) col * nlambda);
+  if ((__ldg(wflags + l) & 1) == 0) return;      // no line at this wavelength: Feautrier kernel (formal.c:100-103)
   const double *at = atmos + (size_t) col * RHB200_AT_NFIELD * ndep;
   RayPtsIO io{reinterpret_cast<const double2 *>(raypts + r * (size_t) ndep * RP_NFIELD),
               stokes + (size_t) col * 4 * nlambda + l, nlambda, 0};
@@ -96,6 +99,73 @@ bezier3_kernel(int nray, int ndep, double muz, int to_obs, int bc_top, int bc_bo
                    I + (size_t) r*ndep, Psi ? Psi + (size_t) r*ndep : nullptr);
 }
 
+// ---- Feautrier IO policies
+struct FeauRayPtsIO {           // fused LTE path: line-free rays; F and z live in the unused K' slots
+  double *rp;                   // this ray's records [k][RP_NFIELD]
+  const double *__restrict__ h;
+  __device__ __forceinline__ double chi(int k) const { return rp[(size_t) k*RP_NFIELD + RP_CHI]; }
+  __device__ __forceinline__ double S(int k) const { return rp[(size_t) k*RP_NFIELD + RP_SI]; }
+  __device__ __forceinline__ double z(int k) const { return __ldg(h + k); }
+  __device__ __forceinline__ void putF(int k, double v) { rp[(size_t) k*RP_NFIELD + RP_KQ] = v; }
+  __device__ __forceinline__ void putZ(int k, double v) { rp[(size_t) k*RP_NFIELD + RP_KU] = v; }
+  __device__ __forceinline__ double getF(int k) const { return rp[(size_t) k*RP_NFIELD + RP_KQ]; }
+  __device__ __forceinline__ double getZ(int k) const { return rp[(size_t) k*RP_NFIELD + RP_KU]; }
+  __device__ __forceinline__ void storeP(int, double) {}
+  __device__ __forceinline__ void storePsi(int, double) {}
+  __device__ __forceinline__ bool wantPsi() const { return false; }
+};
+struct FeauGenericIO {          // reference layouts; P and Psi double as the F / z scratch
+  const double *__restrict__ chi_, *__restrict__ S_, *__restrict__ h;
+  double *P_, *Psi_, *scr;      // scr: [2][ndep] scratch when Psi is not requested
+  int ndep;
+  __device__ __forceinline__ double chi(int k) const { return chi_[k]; }
+  __device__ __forceinline__ double S(int k) const { return S_[k]; }
+  __device__ __forceinline__ double z(int k) const { return h[k]; }
+  __device__ __forceinline__ void putF(int k, double v) { scr[k] = v; }
+  __device__ __forceinline__ void putZ(int k, double v) { scr[ndep + k] = v; }
+  __device__ __forceinline__ double getF(int k) const { return scr[k]; }
+  __device__ __forceinline__ double getZ(int k) const { return scr[ndep + k]; }
+  __device__ __forceinline__ void storeP(int k, double v) { P_[k] = v; }
+  __device__ __forceinline__ void storePsi(int k, double v) { Psi_[k] = v; }
+  __device__ __forceinline__ bool wantPsi() const { return Psi_ != nullptr; }
+};
+
+// line-free rays of the fused LTE path (formal.c:289-309): flags bit0 == 0
+__global__ void __launch_bounds__(128)
+feautrier_raypts_kernel(int ncol, int nlambda, int ndep, double muz, int bc_top, int bc_bottom,
+                        const int *__restrict__ nolines, int nnoline,
+                        const double *__restrict__ atmos, const double *__restrict__ lambda,
+                        double *__restrict__ raypts, double *__restrict__ stokes)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t) ncol * nnoline) return;
+  const int col = (int) (t / nnoline), l = __ldg(nolines + (int) (t - (size_t) col * nnoline));
+  const size_t r = (size_t) col * nlambda + l;
+  const double *at = atmos + (size_t) col * RHB200_AT_NFIELD * ndep;
+  FeauRayPtsIO io{raypts + r * (size_t) ndep * RP_NFIELD, at + RHB200_AT_HEIGHT * ndep};
+  const double I0 = rhf::feautrier_ray(io, ndep, muz, bc_top, bc_bottom, at + RHB200_AT_T * ndep,
+                                       __ldg(lambda + l));
+  double *out = stokes + (size_t) col * 4 * nlambda + l;
+  out[0] = I0; out[nlambda] = 0.0; out[2*(size_t) nlambda] = 0.0; out[3*(size_t) nlambda] = 0.0;
+}
+
+__global__ void __launch_bounds__(128)
+feautrier_generic_kernel(int nray, int ndep, double muz, int bc_top, int bc_bottom,
+                         const int *__restrict__ ray_col, const double *__restrict__ ray_lambda,
+                         const double *__restrict__ height, const double *__restrict__ T,
+                         const double *__restrict__ chi, const double *__restrict__ S,
+                         double *__restrict__ P, double *__restrict__ Psi, double *__restrict__ Iem,
+                         double *__restrict__ scratch)
+{
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nray) return;
+  const int col = ray_col[r];
+  FeauGenericIO io{chi + (size_t) r*ndep, S + (size_t) r*ndep, height + (size_t) col*ndep,
+                   P + (size_t) r*ndep, Psi ? Psi + (size_t) r*ndep : nullptr,
+                   scratch + (size_t) r*2*ndep, ndep};
+  Iem[r] = rhf::feautrier_ray(io, ndep, muz, bc_top, bc_bottom, T + (size_t) col*ndep, ray_lambda[r]);
+}
+
 }  // namespace
 
 int rh_launch_delo_raypts(rhb200_ctx *ctx, int ncol, int ndep, double muz, int bc_top, int bc_bottom,
@@ -110,7 +180,7 @@ int rh_launch_delo_raypts(rhb200_ctx *ctx, int ncol, int ndep, double muz, int b
     static int variant = -1;
     if (variant < 0) { const char *e = getenv("RHB200_DELO_MINB"); variant = e ? atoi(e) : 4; }
 #define RH_LAUNCH_DELO(M) delo_raypts_kernel<M><<<blocks, threads, 0, ctx->stream>>>(ncol, ctx->wav.nlambda, ndep, muz, \
-        bc_top, bc_bottom, d_atmos, ctx->wav.lambda, d_raypts, d_stokes)
+        bc_top, bc_bottom, d_atmos, ctx->wav.lambda, ctx->wav.flags, d_raypts, d_stokes)
     switch (variant) {
     case 4: RH_LAUNCH_DELO(4); break;
     case 5: RH_LAUNCH_DELO(5); break;
@@ -152,6 +222,38 @@ int rh_launch_bezier3(rhb200_ctx *ctx, int nray, int ndep, double muz, int to_ob
     bezier3_kernel<<<blocks, threads, 0, ctx->stream>>>(nray, ndep, muz, to_obs, bc_top, bc_bottom,
                                                          d_ray_col, d_ray_lambda, d_height, d_T,
                                                          d_chi, d_S, d_I, d_Psi);
+  }
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}
+
+int rh_launch_feautrier_raypts(rhb200_ctx *ctx, int ncol, int ndep, double muz, int bc_top, int bc_bottom,
+                               const double *d_atmos, double *d_raypts, double *d_stokes)
+{
+  const int nn = ctx->wav.nnoline;
+  if (nn == 0 || ncol == 0) return RHB200_OK;
+  const size_t n = (size_t) ncol * nn;
+  {
+    ScopedKernelTimer t(ctx, RHB200_K_BEZIER);
+    feautrier_raypts_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, ctx->stream>>>(
+        ncol, ctx->wav.nlambda, ndep, muz, bc_top, bc_bottom, ctx->wav.noline, nn, d_atmos,
+        ctx->wav.lambda, d_raypts, d_stokes);
+  }
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}
+
+int rh_launch_feautrier(rhb200_ctx *ctx, int nray, int ndep, double muz, int bc_top, int bc_bottom,
+                        const int *d_ray_col, const double *d_ray_lambda, const double *d_height,
+                        const double *d_T, const double *d_chi, const double *d_S,
+                        double *d_P, double *d_Psi, double *d_Iem, double *d_scratch)
+{
+  if (nray == 0) return RHB200_OK;
+  {
+    ScopedKernelTimer t(ctx, RHB200_K_BEZIER);
+    feautrier_generic_kernel<<<(nray + 127) / 128, 128, 0, ctx->stream>>>(
+        nray, ndep, muz, bc_top, bc_bottom, d_ray_col, d_ray_lambda, d_height, d_T, d_chi, d_S,
+        d_P, d_Psi, d_Iem, d_scratch);
   }
   RH_CUDA(cudaGetLastError());
   return RHB200_OK;

@@ -9,7 +9,7 @@ if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 
 GOLD = ROOT / "tests" / "golden"
-CASES = ["falc_B1kG", "synth70_c0", "synth70_c1", "synth70_c2"]
+CASES = ["falc_B1kG", "falc_B1kG_wide", "synth70_c0", "synth70_c1", "synth70_c2"]
 
 
 def pytest_configure(config):

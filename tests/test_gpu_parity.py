@@ -277,3 +277,27 @@ def test_bit_exact_against_reference(ctx, case):
                                 g["col_height"], g["col_T"], d[:, 0], d[:, 1:5], d[:, 10:13],
                                 want_psi=True)
     assert np.array_equal(I, d[:, 5:9]) and np.array_equal(Psi, d[:, 9])
+
+
+def test_scalar_bezier3_and_feautrier_vs_reference(ctx):
+    """Piecewise_Bezier3_1D (both directions) and Feautrier against the reference's recorded calls."""
+    g = dict(np.load(GOLD / "falc_scalar.npz"))
+    m, d = g["bez_meta"], g["bez"]
+    for to_obs in (0, 1):
+        sel = m[:, 2] == to_obs
+        assert sel.sum() > 10
+        I, Psi = ctx.bezier3(np.zeros(sel.sum(), np.int32), g["lam_spect"][m[sel, 0]], g["col_height"],
+                             g["col_T"], d[sel, 0], d[sel, 1], to_obs=bool(to_obs), want_psi=True)
+        REPORT[f"bezier3_to_obs{to_obs}_exact"] = bool(np.array_equal(I, d[sel, 2]))
+        assert np.array_equal(I, d[sel, 2])
+        assert np.array_equal(Psi, d[sel, 3])
+    m, d = g["feau_meta"], g["feau"]
+    P, Psi, Iem = ctx.feautrier(np.zeros(len(d), np.int32), g["lam_spect"][m[:, 0]], g["col_height"],
+                                g["col_T"], d[:, 0], d[:, 1], want_psi=True)
+    REPORT["feautrier_exact"] = bool(np.array_equal(P, d[:, 2]) and np.array_equal(Iem, g["feau_Iem"]))
+    assert np.array_equal(P, d[:, 2])
+    assert np.array_equal(Iem, g["feau_Iem"])
+    assert np.array_equal(Psi, d[:, 3])
+    P2, Iem2 = ctx.feautrier(np.zeros(len(d), np.int32), g["lam_spect"][m[:, 0]], g["col_height"],
+                             g["col_T"], d[:, 0], d[:, 1])
+    assert np.array_equal(P2, P) and np.array_equal(Iem2, Iem)

@@ -84,3 +84,23 @@ def test_matinv_scalar_inverts():
         inv = m.copy()
         pd.lib().rp_matinv_scalar(inv.ctypes.data_as(C.POINTER(C.c_float)))
         assert np.abs(inv.astype(np.float64) @ m.astype(np.float64) - np.eye(4)).max() < 1e-4
+
+
+def test_scalar_bezier3_and_feautrier_bit_exact():
+    """NO_STOKES reference run on a grid wider than the line windows: Piecewise_Bezier3_1D inside,
+    Feautrier outside (golden falc_scalar)."""
+    from conftest import GOLD
+    g = dict(np.load(GOLD / "falc_scalar.npz"))
+    assert len(g["bez"]) > 50 and len(g["feau"]) > 20
+    for m, d in zip(g["bez_meta"], g["bez"]):
+        I, Psi = pd.bezier3_scalar(g["col_height"], float(g["muz"][m[1]]), int(m[2]), d[0], d[1],
+                                   g["col_T"], g["lam_spect"][m[0]], want_psi=True)
+        assert np.array_equal(I, d[2])
+        if m[3]:
+            assert np.array_equal(Psi, d[3])
+    for m, d, Iem in zip(g["feau_meta"], g["feau"], g["feau_Iem"]):
+        P, Psi, I0 = pd.feautrier(g["col_height"], float(g["muz"][m[1]]), d[0], d[1], g["col_T"],
+                                  g["lam_spect"][m[0]])
+        assert np.array_equal(P, d[2]) and I0 == Iem
+        if m[3]:
+            assert np.array_equal(Psi, d[3])
