@@ -172,3 +172,69 @@ def region_hist(tab: PortTables, col: PortColumn, lam, to_obs: int = 1):
     h = (C.c_long * 5)()
     lib().rp_region_hist(C.byref(tab.c), C.byref(col.c), len(lam), _d(lam), int(to_obs), h)
     return np.array(list(h))
+
+
+# ------------------------------------------------------------------ NLTE port
+class RpNlte(C.Structure):
+    _fields_ = ([(n, C.c_int) for n in ("Nspect", "Nrays", "Ndep", "Natom", "Ntrans", "moving", "Ngorder",
+                                         "Ngdelay", "Ngperiod", "isum", "bc_top", "bc_bottom")] +
+                [(n, dp) for n in ("lam", "muz", "wmu", "T", "height")] + [("atom_nlevel", ip)] +
+                [(n, dp) for n in ("trans", "tr_lambda", "tr_wlambda", "tr_alpha")] +
+                [(n, ip) for n in ("as_first", "as_trans", "bg_hasline")] +
+                [(n, dp) for n in ("nstar", "ntotal", "C", "phi", "wphi", "chi_c", "eta_c", "sca_c",
+                                   "n", "J", "Gamma", "Rij", "Rji")])
+
+
+class PortNlte:
+    """Builds an rp_nlte from the flat golden layout (oracle/gen_golden_nlte.py) and keeps the arrays alive."""
+
+    def __init__(self, g):
+        hdr = g["hdr"]
+        f64 = lambda x: np.ascontiguousarray(x, np.float64)   # noqa: E731
+        i32 = lambda x: np.ascontiguousarray(x, np.int32)     # noqa: E731
+        N = int(hdr[3])
+        a = dict(lam=f64(g["lam"]), muz=f64(g["muz"]), wmu=f64(g["wmu"]), T=f64(g["T"]), height=f64(g["height"]),
+                 atom_nlevel=i32(g["atom_nlevel"]), trans=f64(g["trans"]), tr_lambda=f64(g["tr_lambda"]),
+                 tr_wlambda=f64(g["tr_wlambda"]), tr_alpha=f64(g["tr_alpha"]), as_first=i32(g["as_first"]),
+                 as_trans=i32(g["as_trans"]), bg_hasline=i32(g["bgflags"][:, 0]), nstar=f64(g["nstar"]),
+                 ntotal=f64(g["ntotal"]), C=f64(g["C"]), phi=f64(g["phi"]), wphi=f64(g["wphi"]),
+                 chi_c=f64(g["bg"][0]), eta_c=f64(g["bg"][1]), sca_c=f64(g["bg"][2]),
+                 n=f64(g["n0"]).copy(), J=f64(g["J0"]).copy())
+        ntr = a["trans"].shape[0]
+        a["Gamma"] = np.zeros_like(a["C"])
+        a["Rij"], a["Rji"] = np.zeros((ntr, N)), np.zeros((ntr, N))
+        self.a = a
+        ptr = lambda k: a[k].ctypes.data_as(ip if a[k].dtype == np.int32 else dp)   # noqa: E731
+        self.c = RpNlte(int(hdr[0]), int(hdr[1]), N, int(hdr[2]), ntr, int(hdr[4]), int(hdr[5]), int(hdr[6]),
+                        int(hdr[7]), int(hdr[8]), int(hdr[13]), int(hdr[14]),
+                        *[ptr(k) for k in ("lam", "muz", "wmu", "T", "height", "atom_nlevel", "trans", "tr_lambda",
+                                           "tr_wlambda", "tr_alpha", "as_first", "as_trans", "bg_hasline", "nstar",
+                                           "ntotal", "C", "phi", "wphi", "chi_c", "eta_c", "sca_c", "n", "J",
+                                           "Gamma", "Rij", "Rji")])
+        self.N, self.ntr = N, ntr
+
+    def iterate(self, nmax, limit):
+        a = self.a
+        nh = np.zeros((nmax,) + a["n"].shape)
+        gh = np.zeros((nmax,) + a["C"].shape)
+        rh = np.zeros((nmax, 2 * self.ntr, self.N))
+        dh = np.zeros(nmax)
+        f = lib().rp_nlte_iterate
+        f.restype = C.c_int
+        it = f(C.byref(self.c), int(nmax), C.c_double(limit), _d(nh), _d(gh), _d(rh), _d(dh))
+        return it, nh[:it], gh[:it], rh[:it], dh[:it]
+
+
+def solve_linear_eq(A, b, improve=True):
+    A = np.ascontiguousarray(A, np.float64).copy()
+    b = np.ascontiguousarray(b, np.float64).copy()
+    lib().rp_solve_linear_eq(A.shape[0], _d(A), _d(b), int(improve))
+    return b
+
+
+def stat_equil(Gamma, ntotal, n, isum=-1):
+    n = np.ascontiguousarray(n, np.float64).copy()
+    Gamma = np.ascontiguousarray(Gamma, np.float64)
+    ntotal = np.ascontiguousarray(ntotal, np.float64)
+    lib().rp_stat_equil(n.shape[0], n.shape[1], _d(Gamma), _d(ntotal), int(isum), _d(n))
+    return n

@@ -357,3 +357,157 @@ bool_t __wrap_Accelerate(struct Ng *Ngs, double *solution)
   }
   return acc;
 }
+
+/* ===================================================================== NLTE
+   Full dump of the NLTE problem the reference is about to iterate (state after
+   initSolution + initScatter), taken at the entry of Iterate() (rh/iterate.c:48),
+   per-iteration Gamma / rates / populations from updatePopulations()
+   (rh/statequil.c:177), and every SolveLinearEq() call (rh/ludcmp.c:36).       */
+
+static void dump_nlte_problem(int NmaxIter, double iterLimit)
+{
+  int N = atmos.Nspace, a, kr, n, la, k, Ns = spectrum.Nspect;
+  {
+    double *d = rec_new("nl_hdr", 16, 0,0,0,0,0,0);
+    d[0] = Ns; d[1] = atmos.Nrays; d[2] = atmos.Nactiveatom; d[3] = N; d[4] = atmos.moving;
+    d[5] = input.Ngorder; d[6] = input.Ngdelay; d[7] = input.Ngperiod; d[8] = input.isum;
+    d[9] = NmaxIter; d[10] = iterLimit; d[11] = input.NmaxScatter; d[12] = input.StokesMode;
+    d[13] = geometry.vboundary[TOP]; d[14] = geometry.vboundary[BOTTOM]; d[15] = input.S_interpolation;
+  }
+  rec_copy("nl_lambda", spectrum.lambda, Ns, 0,0,0,0);
+  rec_copy("nl_muz", geometry.muz, geometry.Nrays, 0,0,0,0);
+  rec_copy("nl_wmu", geometry.wmu, geometry.Nrays, 0,0,0,0);
+  rec_copy("nl_T", atmos.T, N, 0,0,0,0);
+  rec_copy("nl_height", geometry.height, N, 0,0,0,0);
+  {
+    double *J = rec_new("nl_J", (long) Ns*N, 0,0,0,0,0,0);
+    double *b = rec_new("nl_bg", (long) 3*Ns*N, 0,0,0,0,0,0);
+    double *f = rec_new("nl_bgflags", 2*Ns, 0,0,0,0,0,0);
+    for (n = 0; n < Ns; n++) {
+      memcpy(J + (long) n*N, spectrum.J[n], N*sizeof(double));
+      memcpy(b + (long) n*N, spectrum.chi_c_lam[n], N*sizeof(double));
+      memcpy(b + (long) (Ns + n)*N, spectrum.eta_c_lam[n], N*sizeof(double));
+      memcpy(b + (long) (2*Ns + n)*N, spectrum.sca_c_lam[n], N*sizeof(double));
+      f[2*n] = atmos.backgrflags[n].hasline; f[2*n+1] = atmos.backgrflags[n].ispolarized;
+    }
+  }
+  for (a = 0; a < atmos.Nactiveatom; a++) {
+    Atom *atom = atmos.activeatoms[a];
+    int Nl = atom->Nlevel;
+    double *d = rec_new("nl_atom", 2*Nl, a, Nl, atom->Nline, atom->Ncont, 0, 0);
+    for (n = 0; n < Nl; n++) { d[n] = atom->g[n]; d[Nl+n] = atom->E[n]; }
+    rec_copy("nl_n", atom->n[0], (long) Nl*N, a,0,0,0);
+    rec_copy("nl_nstar", atom->nstar[0], (long) Nl*N, a,0,0,0);
+    rec_copy("nl_ntotal", atom->ntotal, N, a,0,0,0);
+    rec_copy("nl_C", atom->C[0], (long) Nl*Nl*N, a,0,0,0);
+    for (kr = 0; kr < atom->Nline; kr++) {
+      AtomicLine *L = &atom->line[kr];
+      int Nla = L->Nlambda;
+      double *h = rec_new("nl_line", 8 + 2*Nla + N, a, kr, L->i, L->j, Nla, L->Nblue);
+      h[0] = L->lambda0; h[1] = L->Aji; h[2] = L->Bji; h[3] = L->Bij; h[4] = L->isotope_frac;
+      h[5] = L->symmetric; h[6] = L->PRD; h[7] = L->polarizable;
+      for (la = 0; la < Nla; la++) { h[8+la] = L->lambda[la]; h[8+Nla+la] = getwlambda_line(L, la); }
+      memcpy(h + 8 + 2*Nla, L->wphi, N*sizeof(double));
+      {
+        int nrow = (atmos.moving) ? 2*atmos.Nrays*Nla : Nla;
+        double *p = rec_new("nl_phi", (long) nrow*N, a, kr, nrow, 0,0,0);
+        for (n = 0; n < nrow; n++) memcpy(p + (long) n*N, L->phi[n], N*sizeof(double));
+      }
+    }
+    for (kr = 0; kr < atom->Ncont; kr++) {
+      AtomicContinuum *Cn = &atom->continuum[kr];
+      int Nla = Cn->Nlambda;
+      double *h = rec_new("nl_cont", 4 + 3*Nla, a, kr, Cn->i, Cn->j, Nla, Cn->Nblue);
+      h[0] = Cn->lambda0; h[1] = Cn->alpha0; h[2] = Cn->hydrogenic; h[3] = Cn->isotope_frac;
+      for (la = 0; la < Nla; la++) {
+        h[4+la] = Cn->lambda[la]; h[4+Nla+la] = Cn->alpha[la]; h[4+2*Nla+la] = getwlambda_cont(Cn, la);
+      }
+    }
+  }
+  for (n = 0; n < Ns; n++) {
+    ActiveSet *as = &spectrum.as[n];
+    int cnt = 0, m;
+    for (a = 0; a < atmos.Nactiveatom; a++) cnt += as->Nactiveatomrt[a];
+    double *d = rec_new("nl_as", 3*cnt + 1, n, cnt, 0,0,0,0);
+    cnt = 0;
+    for (a = 0; a < atmos.Nactiveatom; a++) {
+      Atom *atom = atmos.activeatoms[a];
+      for (m = 0; m < as->Nactiveatomrt[a]; m++) {
+        d[3*cnt] = a;
+        if (as->art[a][m].type == ATOMIC_LINE) {
+          d[3*cnt+1] = 0; d[3*cnt+2] = (double) (as->art[a][m].ptype.line - atom->line);
+        } else {
+          d[3*cnt+1] = 1; d[3*cnt+2] = (double) (as->art[a][m].ptype.continuum - atom->continuum);
+        }
+        cnt++;
+      }
+    }
+    d[3*cnt] = 0;
+  }
+  (void) k;
+}
+
+void __real_Iterate(int NmaxIter, double iterLimit);
+void __wrap_Iterate(int NmaxIter, double iterLimit)
+{
+  int a, N = atmos.Nspace, n;
+  if ((probe_mask & PROBE_NLTE) && atmos.Nactiveatom > 0) dump_nlte_problem(NmaxIter, iterLimit);
+  /* Iterate() frees atom->Gamma at exit but keeps n and J */
+  __real_Iterate(NmaxIter, iterLimit);
+  if ((probe_mask & PROBE_NLTE) && atmos.Nactiveatom > 0) {
+    for (a = 0; a < atmos.Nactiveatom; a++) {
+      Atom *atom = atmos.activeatoms[a];
+      rec_copy("nl_n_final", atom->n[0], (long) atom->Nlevel*N, a,0,0,0);
+    }
+    double *J = rec_new("nl_J_final", (long) spectrum.Nspect*N, 0,0,0,0,0,0);
+    for (n = 0; n < spectrum.Nspect; n++) memcpy(J + (long) n*N, spectrum.J[n], N*sizeof(double));
+  }
+}
+
+static int up_count = 0;
+double __real_updatePopulations(int niter);
+double __wrap_updatePopulations(int niter)
+{
+  int a, N = atmos.Nspace, kr;
+  if (probe_mask & PROBE_NLTE) {
+    for (a = 0; a < atmos.Nactiveatom; a++) {
+      Atom *atom = atmos.activeatoms[a];
+      int Nl = atom->Nlevel;
+      rec_copy("up_gamma", atom->Gamma[0], (long) Nl*Nl*N, a, niter, 0,0);
+      double *r = rec_new("up_rates", (long) 2*(atom->Nline + atom->Ncont)*N, a, niter, atom->Nline, atom->Ncont, 0,0);
+      for (kr = 0; kr < atom->Nline; kr++) {
+        memcpy(r + (long) (2*kr)*N, atom->line[kr].Rij, N*sizeof(double));
+        memcpy(r + (long) (2*kr+1)*N, atom->line[kr].Rji, N*sizeof(double));
+      }
+      for (kr = 0; kr < atom->Ncont; kr++) {
+        memcpy(r + (long) (2*(atom->Nline+kr))*N, atom->continuum[kr].Rij, N*sizeof(double));
+        memcpy(r + (long) (2*(atom->Nline+kr)+1)*N, atom->continuum[kr].Rji, N*sizeof(double));
+      }
+    }
+  }
+  double dp = __real_updatePopulations(niter);
+  if (probe_mask & PROBE_NLTE) {
+    for (a = 0; a < atmos.Nactiveatom; a++) {
+      Atom *atom = atmos.activeatoms[a];
+      double *d = rec_new("up_n", (long) atom->Nlevel*N + 1, a, niter, 0,0,0,0);
+      memcpy(d, atom->n[0], (long) atom->Nlevel*N*sizeof(double));
+      d[(long) atom->Nlevel*N] = dp;
+    }
+  }
+  up_count++;
+  return dp;
+}
+
+void __real_SolveLinearEq(int N, double **A, double *b, bool_t improve);
+void __wrap_SolveLinearEq(int N, double **A, double *b, bool_t improve)
+{
+  double *d = NULL;
+  int i;
+  if ((probe_mask & PROBE_NLTE) && N <= 32) {
+    d = rec_new("lu", (long) N*N + 2*N, N, improve, 0,0,0,0);
+    for (i = 0; i < N; i++) memcpy(d + (long) i*N, A[i], N*sizeof(double));
+    memcpy(d + (long) N*N, b, N*sizeof(double));
+  }
+  __real_SolveLinearEq(N, A, b, improve);
+  if (d) memcpy(d + (long) N*N + N, b, N*sizeof(double));
+}

@@ -89,7 +89,7 @@ def load(variant: str = "scalar") -> C.CDLL:
 
 def make_workdir(kind: str = "benchmark", keywords: dict | None = None,
                  atoms_active: tuple = (), kurucz_lines: str | None = None,
-                 no_kurucz: bool = False, root: str | None = None) -> str:
+                 no_kurucz: bool = False, atoms_extra: tuple = (), root: str | None = None) -> str:
     """Stage a cwd for rhf1d(): the reference's own input set (`benchmark/` or
     `tests/`) with optional keyword overrides (``KEY = value`` lines replaced or
     appended) and optional ACTIVE atoms."""
@@ -120,6 +120,19 @@ def make_workdir(kind: str = "benchmark", keywords: dict | None = None,
             w = ln.split()
             if w and w[0] in atoms_active:
                 lines[i] = ln.replace("PASSIVE", "ACTIVE ")
+        p.write_text("\n".join(lines) + "\n")
+    if atoms_extra:
+        # append model atoms that the shipped atoms.input lacks (e.g. CaII.atom) and bump Nmetal
+        p = Path(d) / "atoms.input"
+        lines = p.read_text().splitlines()
+        for i, ln in enumerate(lines):
+            w = ln.split()
+            if w and not ln.strip().startswith("#") and w[0].isdigit():
+                lines[i] = f"   {int(w[0]) + len(atoms_extra)}"
+                break
+        last = max(i for i, ln in enumerate(lines) if ".atom" in ln)
+        for name, mode in atoms_extra:
+            lines.insert(last + 1, f"  {name}        {mode}     LTE_POPULATIONS   pops.{name.split('.')[0]}.out")
         p.write_text("\n".join(lines) + "\n")
     if kurucz_lines is not None:
         (Path(d) / "kurucz_lines.dat").write_text(kurucz_lines)
