@@ -187,6 +187,58 @@ int rhb200_voigt_humlicek(rhb200_ctx *ctx, int n, const double *a, const double 
 int rhb200_math_probe(rhb200_ctx *ctx, int n, int func /*0 exp 1 sin 2 cos 3 pow*/,
                       const double *x, const double *y, double *out);
 
+/* ---- NLTE: MALI iteration for active atoms (CRD, unpolarised radiation) ------------------
+   Replaces Iterate() (iterate.c:48-143): per iteration initGammaAtom, solveSpectrum(eval_operator)
+   = per wavelength Formal() with Opacity, Piecewise_Bezier3_1D / Feautrier, addtoCoupling,
+   addtoGamma, addtoRates (formal.c:44-346, opacity.c:64-390, fillgamma.c), then updatePopulations =
+   statEquil + Accelerate + MaxChange (statequil.c:177-216).  `ncol` independent columns share one
+   atomic model / wavelength structure (the "plan"); each column stops at its own ITER_LIMIT.
+
+   Transition rows (doubles), one per radiative transition, lines first then continua per atom: */
+enum {
+  RHB200_TR_ATOM = 0, RHB200_TR_TYPE /* 0 line, 1 continuum */, RHB200_TR_I, RHB200_TR_J,
+  RHB200_TR_NBLUE, RHB200_TR_NLAMBDA,            /* AtomicLine/AtomicContinuum Nblue, Nlambda (atom.h:50-75) */
+  RHB200_TR_AJI, RHB200_TR_BJI, RHB200_TR_BIJ, RHB200_TR_ISOFRAC,
+  RHB200_TR_WOFF,                                /* offset of this transition in tr_lambda/tr_wlambda/tr_alpha */
+  RHB200_TR_PHIROW,                              /* first row of line->phi[2*Nrays*Nlambda] in the phi table */
+  RHB200_TR_KR, RHB200_TR_LINEIDX,               /* index in atom->line / row of wphi */
+  RHB200_TR_NFIELD = 16
+};
+typedef struct {
+  int Nspect, Nrays, Ndep, Natom, Ntrans, moving;
+  int Ngorder, Ngdelay, Ngperiod, isum;          /* keywords NG_ORDER, NG_DELAY, NG_PERIOD, I_SUM */
+  int bc_top, bc_bottom;
+  int ntrl, nphirow, nline;                      /* lengths of the concatenated tables below */
+  const double *lambda;                          /* [Nspect] spectrum.lambda */
+  const double *muz, *wmu;                       /* [Nrays] */
+  const int    *atom_nlevel;                     /* [Natom] */
+  const double *trans;                           /* [Ntrans][RHB200_TR_NFIELD] */
+  const double *tr_lambda, *tr_wlambda, *tr_alpha;   /* [ntrl]: transition wavelengths, getwlambda_line/_cont weights, alpha */
+  const int    *as_first;                        /* [Nspect+1] CSR of the active sets (spectrum.as[].art) */
+  const int    *as_trans;                        /* [as_first[Nspect]] transition rows in the reference's order */
+  const int    *bg_hasline;                      /* [Nspect] atmos.backgrflags[].hasline */
+} rhb200_nlte_plan;
+typedef struct {                                 /* per-column arrays, column-major blocks [ncol][...] */
+  const double *T, *height;                      /* [ncol][Ndep] */
+  const double *nstar;                           /* [ncol][sum Nlevel][Ndep] */
+  const double *ntotal;                          /* [ncol][Natom][Ndep] */
+  const double *C;                               /* [ncol][sum Nlevel^2][Ndep] collisional rates (atom->C) */
+  const double *phi;                             /* [ncol][nphirow][Ndep]  line->phi (Profile(), profile.c:67) */
+  const double *wphi;                            /* [ncol][nline][Ndep] */
+  const double *chi_c, *eta_c, *sca_c;           /* [ncol][Nspect][Ndep] background (spectrum.*_c_lam) */
+  double *n;                                     /* [ncol][sum Nlevel][Ndep]  in: initial, out: converged */
+  double *J;                                     /* [ncol][Nspect][Ndep]      in: after initScatter, out: final */
+} rhb200_nlte_columns;
+/* niter [ncol] iterations done; dpops_hist [ncol][NmaxIter] or NULL; when dump_iter >= 1 the Gamma
+   matrices [ncol][sum Nl^2][Ndep] and rates {Rij [ncol][Ntrans][Ndep], Rji ...} of that iteration are
+   copied out before statEquil (test hooks, may be NULL). */
+int rhb200_nlte_iterate(rhb200_ctx *ctx, const rhb200_nlte_plan *plan, int ncol,
+                        const rhb200_nlte_columns *cols, int NmaxIter, double iterLimit,
+                        int *niter, double *dpops_hist, int dump_iter, double *gamma_dump,
+                        double *rates_dump);
+/* SolveLinearEq (ludcmp.c:36-86) for nsys systems: A [nsys][N][N] (untouched), b [nsys][N] in/out; N <= 32 */
+int rhb200_solve_linear_eq_batch(rhb200_ctx *ctx, int nsys, int N, double *A, double *b, int improve);
+
 /* ---- device memory helpers (for callers that keep inputs resident) -------- */
 int rhb200_dev_alloc(rhb200_ctx *ctx, size_t bytes, void **dptr);
 int rhb200_dev_free(rhb200_ctx *ctx, void *dptr);

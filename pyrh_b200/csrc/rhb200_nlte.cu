@@ -1,0 +1,672 @@
+// rhb200_nlte.cu -- NLTE (MALI) machinery on the device: atoms, CRD, unpolarised radiation.
+//
+// Reference (all file:line relative to the reference root):
+//   Iterate / solveSpectrum / updatePopulations   rh/iterate.c:48-253, rh/statequil.c:177-216
+//   Formal (scalar branches)                      rh/rhf1d/formal.c:44-346
+//   Opacity                                       rh/opacity.c:64-390
+//   addtoCoupling / addtoGamma / addtoRates       rh/fillgamma.c:251-332, :82-246, :375-461
+//   statEquil, SolveLinearEq/LUdecomp/LUbacksubst rh/statequil.c:40-103, rh/ludcmp.c:36-177
+//   NgInit / Accelerate / MaxChange               rh/accelerate.c:34-147, rh/maxchange.c:32-50
+//
+// B200 design.  The reference walks wavelengths one at a time and adds
+// every ray's contribution into Gamma and the rates as it goes.  Here one MALI iteration is
+//   (1) opacity   : one thread per (column, ray, depth)      -> chi, S
+//   (2) rays      : one thread per (column, ray), sequential in depth (Bezier3 / Feautrier) -> I, Psi
+//   (3) J         : one thread per (column, lambda, depth), rays summed in the reference's order
+//   (4) Gamma     : one thread per (column, transition, depth): walks the transition's own
+//                   wavelengths and rays IN THE REFERENCE'S ORDER and keeps the two Gamma entries
+//                   and the two rates of that transition in registers.  A Gamma pair {ij, ji} is
+//                   only ever touched while its own transition is processed (fillgamma.c:139-187),
+//                   so the sequence of floating-point additions into every element is exactly the
+//                   reference's: results are bit-identical and run-to-run deterministic, with no
+//                   atomics and no cross-thread reduction.
+//   (5) statEquil : one thread per (column, atom, depth): Crout LU with implicit-scaling partial
+//                   pivoting + one refinement step, same pivot choices as ludcmp.c
+//   (6) Ng        : one block per (column, atom); every normal-equation entry is summed by one
+//                   thread in the reference's k-order
+// Columns that reached ITER_LIMIT are frozen (per-column `active` flag), like separate rhf1d calls.
+#include <algorithm>
+#include <vector>
+#include "rhb200_common.cuh"
+#include "rhb200_bezier.cuh"
+#include "rhb200_feautrier.cuh"
+
+namespace {
+
+enum { TR_ATOM = RHB200_TR_ATOM, TR_TYPE = RHB200_TR_TYPE, TR_I = RHB200_TR_I, TR_J = RHB200_TR_J,
+       TR_NBLUE = RHB200_TR_NBLUE, TR_NLAMBDA = RHB200_TR_NLAMBDA, TR_AJI = RHB200_TR_AJI,
+       TR_BJI = RHB200_TR_BJI, TR_BIJ = RHB200_TR_BIJ, TR_ISOFRAC = RHB200_TR_ISOFRAC,
+       TR_WOFF = RHB200_TR_WOFF, TR_PHIROW = RHB200_TR_PHIROW, TR_LINEIDX = RHB200_TR_LINEIDX,
+       TR_NFIELD = RHB200_TR_NFIELD };
+
+struct Plan {            // device copy of the shared problem structure
+  int Nspect, Nrays, Ndep, Natom, Ntrans, nas, nray, nlev, ngam, nphirow, nline, bc_top, bc_bottom;
+  const double *lambda, *muz, *wmu, *trans, *tr_lambda, *tr_wlambda, *tr_alpha;
+  const int *atom_nlevel, *lev_off, *gam_off, *as_first, *as_trans, *angle_dep, *ray_off,
+            *ray_ns, *ray_mu, *ray_dir;
+};
+
+struct Cols {            // device per-column arrays
+  const double *T, *height, *nstar, *ntotal, *C, *phi, *wphi, *chi_c, *eta_c, *sca_c;
+  double *n, *J, *Gamma, *Rij, *Rji, *gw, *chi, *S, *I, *Psi, *scr, *dJ;
+  const int *active;
+};
+
+// ---- (0) wavelength-integration weights and g_ij per active-set entry (opacity.c:214-217, 233-243):
+//      they depend only on nstar, T, wphi, so they are evaluated once per column
+__global__ void __launch_bounds__(128)
+nlte_setup_kernel(Plan P, Cols C, int ncol)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = P.Ndep;
+  if (t >= (size_t) ncol * P.nas * N) return;
+  const int k = (int) (t % N);
+  const size_t ce = t / N;
+  const int e = (int) (ce % P.nas), col = (int) (ce / P.nas);
+  // wavelength of this entry: find ns by scanning is avoided: entry -> ns table is not needed,
+  // la follows from the transition's position; we store ns in as_ns (packed after as_trans)
+  const int tr_id = P.as_trans[e], ns = P.as_trans[P.nas + e];
+  const double *tr = P.trans + (size_t) tr_id * TR_NFIELD;
+  const int la = ns - (int) tr[TR_NBLUE], a = (int) tr[TR_ATOM];
+  const double hc = RH_HPLANCK * RH_CLIGHT, fourPI = 4.0 * RH_PI, hc_4PI = hc / fourPI;
+  const double hc_k = hc / (RH_KBOLTZMANN * RH_NM_TO_M);
+  double g, w;
+  if (tr[TR_TYPE] == 0.0) {
+    g = tr[TR_BJI] / tr[TR_BIJ];
+    const double wlambda = P.tr_wlambda[(int) tr[TR_WOFF] + la];
+    w = wlambda * C.wphi[((size_t) col * P.nline + (int) tr[TR_LINEIDX]) * N + k] / hc_4PI;
+  } else {
+    const double lc = P.tr_lambda[(int) tr[TR_WOFF] + la], wlambda = P.tr_wlambda[(int) tr[TR_WOFF] + la];
+    const double *ns_i = C.nstar + ((size_t) col * P.nlev + P.lev_off[a] + (int) tr[TR_I]) * N;
+    const double *ns_j = C.nstar + ((size_t) col * P.nlev + P.lev_off[a] + (int) tr[TR_J]) * N;
+    g = ns_i[k] / ns_j[k] * rhm::rh_exp(-hc_k / (lc * C.T[(size_t) col * N + k]));
+    w = fourPI/RH_HPLANCK * (wlambda/lc);
+  }
+  double *o = C.gw + (((size_t) col * P.nas + e) * 2) * N + k;
+  o[0] = g; o[N] = w;
+}
+
+// V_ij of active-set entry e at (ray, depth): Bij hc/4pi phi for lines (opacity.c:188-193),
+// alpha(lambda) for continua (:236)
+__device__ __forceinline__ double vij_of(const Plan &P, const Cols &C, int col, const double *tr, int ns,
+                                         int mu, int dir, int k)
+{
+  const int la = ns - (int) tr[TR_NBLUE];
+  if (tr[TR_TYPE] == 0.0) {
+    const double hc_4PI = (RH_HPLANCK * RH_CLIGHT) / (4.0 * RH_PI);
+    const double Bijxhc_4PI = hc_4PI * tr[TR_BIJ] * tr[TR_ISOFRAC];
+    const int lamu = 2*(P.Nrays*la + mu) + dir;
+    return Bijxhc_4PI * __ldg(C.phi + ((size_t) col * P.nphirow + (int) tr[TR_PHIROW] + lamu) * P.Ndep + k);
+  }
+  return P.tr_alpha[(int) tr[TR_WOFF] + la];
+}
+__device__ __forceinline__ double twohnu3_of(const Plan &P, const double *tr, int ns)
+{
+  if (tr[TR_TYPE] == 0.0) return tr[TR_AJI] / tr[TR_BJI];
+  const double nm3 = RH_NM_TO_M*RH_NM_TO_M*RH_NM_TO_M;
+  const double twohc = 2.0*(RH_HPLANCK * RH_CLIGHT) / nm3;
+  const double lc = P.tr_lambda[(int) tr[TR_WOFF] + ns - (int) tr[TR_NBLUE]];
+  return twohc / (lc*lc*lc);
+}
+
+// ---- (1) Opacity() + the chi/S assembly of Formal(): one thread per (column, ray, depth)
+__global__ void __launch_bounds__(128)
+nlte_opacity_kernel(Plan P, Cols C, int ncol)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = P.Ndep;
+  if (t >= (size_t) ncol * P.nray * N) return;
+  const int k = (int) (t % N);
+  const size_t cr = t / N;
+  const int r = (int) (cr % P.nray), col = (int) (cr / P.nray);
+  if (!C.active[col]) return;
+  const int ns = P.ray_ns[r], mu = P.ray_mu[r], dir = P.ray_dir[r];
+  const int first = P.as_first[ns], nact = P.as_first[ns+1] - first;
+  const double *ncol_ = C.n + (size_t) col * P.nlev * N;
+  double as_chi = 0.0, as_eta = 0.0, eta_atom = 0.0;
+  int cur_atom = -1;
+  for (int n = 0; n < nact; n++) {
+    const double *tr = P.trans + (size_t) P.as_trans[first+n] * TR_NFIELD;
+    const int a = (int) tr[TR_ATOM];
+    if (a != cur_atom) {                      // as->eta += atom->rhth.eta, opacity.c:375-380
+      if (cur_atom >= 0) as_eta += eta_atom;
+      eta_atom = 0.0; cur_atom = a;
+    }
+    const double V = vij_of(P, C, col, tr, ns, mu, dir, k);
+    const double g = C.gw[(((size_t) col * P.nas + first + n) * 2) * N + k];
+    const double n_i = ncol_[(size_t)(P.lev_off[a] + (int) tr[TR_I]) * N + k];
+    const double n_j = ncol_[(size_t)(P.lev_off[a] + (int) tr[TR_J]) * N + k];
+    const double thn = twohnu3_of(P, tr, ns);
+    if (thn != 0.0) {                         // opacity.c:252-260
+      as_chi += V * (n_i - g*n_j);
+      eta_atom += thn * g * V * n_j;
+    }
+  }
+  if (cur_atom >= 0) as_eta += eta_atom;
+  const size_t lk = ((size_t) col * P.Nspect + ns) * N + k;
+  const double chi = as_chi + C.chi_c[lk];                                   // formal.c:178-182, 293-296
+  const double S = (as_eta + C.eta_c[lk] + C.sca_c[lk] * C.J[lk]) / chi;     // J still holds Jdag here
+  C.chi[cr * N + k] = chi;
+  C.S[cr * N + k] = S;
+}
+
+// ---- (2) formal solution of every ray: Piecewise_Bezier3_1D for angle-dependent wavelengths,
+//      Feautrier otherwise (formal.c:157-309)
+struct NlteFeauIO {
+  const double *__restrict__ chi_, *__restrict__ S_, *__restrict__ h;
+  double *P_, *Psi_, *scr; int ndep;
+  __device__ __forceinline__ double chi(int k) const { return chi_[k]; }
+  __device__ __forceinline__ double S(int k) const { return S_[k]; }
+  __device__ __forceinline__ double z(int k) const { return h[k]; }
+  __device__ __forceinline__ void putF(int k, double v) { scr[k] = v; }
+  __device__ __forceinline__ void putZ(int k, double v) { scr[ndep + k] = v; }
+  __device__ __forceinline__ double getF(int k) const { return scr[k]; }
+  __device__ __forceinline__ double getZ(int k) const { return scr[ndep + k]; }
+  __device__ __forceinline__ void storeP(int k, double v) { P_[k] = v; }
+  __device__ __forceinline__ void storePsi(int k, double v) { Psi_[k] = v; }
+  __device__ __forceinline__ bool wantPsi() const { return Psi_ != nullptr; }
+};
+
+__global__ void __launch_bounds__(128)
+nlte_ray_kernel(Plan P, Cols C, int ncol, int eval_operator)
+{
+  const size_t cr = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (cr >= (size_t) ncol * P.nray) return;
+  const int r = (int) (cr % P.nray), col = (int) (cr / P.nray), N = P.Ndep;
+  if (!C.active[col]) return;
+  const int ns = P.ray_ns[r], mu = P.ray_mu[r], dir = P.ray_dir[r];
+  const double *h = C.height + (size_t) col * N, *T = C.T + (size_t) col * N;
+  double *Psi = eval_operator ? C.Psi + cr * N : nullptr;
+  if (P.angle_dep[ns]) {
+    rhz::bezier3_ray(N, h, P.muz[mu], dir, P.bc_top, P.bc_bottom, T, P.lambda[ns], C.chi + cr * N,
+                     C.S + cr * N, C.I + cr * N, Psi);
+  } else {
+    NlteFeauIO io{C.chi + cr * N, C.S + cr * N, h, C.I + cr * N, Psi, C.scr + cr * 2 * N, N};
+    rhf::feautrier_ray(io, N, P.muz[mu], P.bc_top, P.bc_bottom, T, P.lambda[ns]);
+  }
+}
+
+// ---- (3) J = sum_rays wmu I in the reference's ray order; dJ = |1 - Jdag/J| (formal.c:252-256, 313-318)
+__global__ void __launch_bounds__(128)
+nlte_J_kernel(Plan P, Cols C, int ncol)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = P.Ndep;
+  if (t >= (size_t) ncol * P.Nspect * N) return;
+  const int k = (int) (t % N);
+  const size_t cl = t / N;
+  const int ns = (int) (cl % P.Nspect), col = (int) (cl / P.Nspect);
+  if (!C.active[col]) return;
+  const int ad = P.angle_dep[ns];
+  double J = 0.0;
+  for (int r = P.ray_off[ns]; r < P.ray_off[ns+1]; r++) {
+    const double wmu = ad ? 0.5 * P.wmu[P.ray_mu[r]] : P.wmu[P.ray_mu[r]];
+    J += wmu * C.I[((size_t) col * P.nray + r) * N + k];
+  }
+  const double Jdag = C.J[t];
+  C.J[t] = J;
+  C.dJ[t] = fabs(1.0 - Jdag / J);
+}
+
+// ---- (4) addtoCoupling + addtoGamma + addtoRates for one transition at one depth
+__global__ void __launch_bounds__(64)
+nlte_gamma_kernel(Plan P, Cols C, int ncol)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = P.Ndep;
+  if (t >= (size_t) ncol * P.Ntrans * N) return;
+  const int k = (int) (t % N);
+  const size_t ct = t / N;
+  const int tid = (int) (ct % P.Ntrans), col = (int) (ct / P.Ntrans);
+  if (!C.active[col]) return;
+  const double *trs = P.trans + (size_t) tid * TR_NFIELD;
+  const int a = (int) trs[TR_ATOM], i = (int) trs[TR_I], j = (int) trs[TR_J], Nl = P.atom_nlevel[a];
+  const int Nblue = (int) trs[TR_NBLUE], Nla = (int) trs[TR_NLAMBDA];
+  const double *ncol_ = C.n + (size_t) col * P.nlev * N;
+  const size_t gbase = ((size_t) col * P.ngam + P.gam_off[a]) * N;
+  double Gij = C.C[gbase + (size_t)(i*Nl + j) * N + k], Gji = C.C[gbase + (size_t)(j*Nl + i) * N + k];   // initGammaAtom
+  double Rij = 0.0, Rji = 0.0;                                                                          // zeroRates
+
+  for (int ns = Nblue; ns < Nblue + Nla; ns++) {
+    const int first = P.as_first[ns], nact = P.as_first[ns+1] - first;
+    const int ad = P.angle_dep[ns];
+    for (int r = P.ray_off[ns]; r < P.ray_off[ns+1]; r++) {
+      const int mu = P.ray_mu[r], dir = P.ray_dir[r];
+      const double wmu = ad ? 0.5 * P.wmu[mu] : P.wmu[mu];
+      // per-ray quantities of this atom's active transitions (opacity.c / addtoCoupling)
+      double eta_atom = 0.0, chi_up_i = 0.0, Uji_down_j = 0.0, chi_down_j = 0.0, Uji_down_i = 0.0;
+      double Vs = 0.0, gs = 0.0, ws = 0.0, thns = 0.0;
+      int n_jp_eq_i = 0;
+      for (int n = 0; n < nact; n++) {
+        const int tm = P.as_trans[first+n];
+        const double *tr = P.trans + (size_t) tm * TR_NFIELD;
+        if ((int) tr[TR_ATOM] != a) continue;
+        const int im = (int) tr[TR_I], jm = (int) tr[TR_J];
+        const double V = vij_of(P, C, col, tr, ns, mu, dir, k);
+        const double *gw = C.gw + (((size_t) col * P.nas + first + n) * 2) * N + k;
+        const double g = gw[0], w = gw[N];
+        const double thn = twohnu3_of(P, tr, ns);
+        const double n_i = ncol_[(size_t)(P.lev_off[a] + im) * N + k], n_j = ncol_[(size_t)(P.lev_off[a] + jm) * N + k];
+        if (thn != 0.0) {
+          eta_atom += thn * g * V * n_j;                          // opacity.c:257-258
+          const double chicc = V * w * (n_i - g*n_j);             // fillgamma.c:321-327
+          if (im == i) chi_up_i += chicc;
+          if (jm == j) { chi_down_j += chicc; Uji_down_j += thn * g * V; }
+          if (jm == i) Uji_down_i += thn * g * V;
+        }
+        if (jm == i) n_jp_eq_i++;
+        if (tm == tid) { Vs = V; gs = g; ws = w; thns = thn; }
+      }
+      const size_t rk = ((size_t) col * P.nray + r) * N + k;
+      const double I = C.I[rk], Psi = C.Psi[rk] / C.chi[rk];       // formal.c:248 / :301
+      const double Ieff = I - Psi * eta_atom;                      // fillgamma.c:130-133
+      const double wlamu = Vs * ws * wmu;
+      Gji += Ieff * wlamu;                                         // fillgamma.c:163-168
+      Gij += (thns + Ieff) * gs * wlamu;
+      Gij -= chi_up_i * Psi * Uji_down_j * wmu;                    // fillgamma.c:172-175
+      for (int m = 0; m < n_jp_eq_i; m++)                          // fillgamma.c:180-196
+        Gji += chi_down_j * Psi * Uji_down_i * wmu;
+      Rij += I * wlamu;                                            // fillgamma.c:448-452
+      Rji += gs * (thns + I) * wlamu;
+    }
+  }
+  C.Gamma[gbase + (size_t)(i*Nl + j) * N + k] = Gij;
+  C.Gamma[gbase + (size_t)(j*Nl + i) * N + k] = Gji;
+  C.Rij[((size_t) col * P.Ntrans + tid) * N + k] = Rij;
+  C.Rji[((size_t) col * P.Ntrans + tid) * N + k] = Rji;
+}
+
+// Gamma entries that belong to no radiative transition keep the collisional value (initGammaAtom)
+__global__ void nlte_gamma_init_kernel(Plan P, Cols C, int ncol)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t per = (size_t) P.ngam * P.Ndep;
+  if (t >= (size_t) ncol * per) return;
+  if (!C.active[t / per]) return;
+  C.Gamma[t] = C.C[t];
+}
+
+// ---- (5) SolveLinearEq (ludcmp.c:36-177) on thread-local storage
+template <int MAXN>
+__device__ void solve_linear_eq(const int N, double *A, double *b, const bool improve)
+{
+  int index[MAXN];
+  double vv[MAXN], A_copy[MAXN*MAXN], b_copy[MAXN], residual[MAXN];
+  if (improve) {
+    for (int i = 0; i < N; i++) { b_copy[i] = b[i]; for (int j = 0; j < N; j++) A_copy[i*N+j] = A[i*N+j]; }
+  }
+  // LUdecomp, ludcmp.c:92-150
+  int imax = 0;
+  for (int i = 0; i < N; i++) {
+    double big = 0.0;
+    for (int j = 0; j < N; j++) { const double temp = fabs(A[i*N+j]); if (temp > big) big = temp; }
+    vv[i] = 1.0 / big;
+  }
+  for (int j = 0; j < N; j++) {
+    for (int i = 0; i < j; i++) {
+      double sum = A[i*N+j];
+      for (int k = 0; k < i; k++) sum -= A[i*N+k] * A[k*N+j];
+      A[i*N+j] = sum;
+    }
+    double big = 0.0;
+    for (int i = j; i < N; i++) {
+      double sum = A[i*N+j];
+      for (int k = 0; k < j; k++) sum -= A[i*N+k] * A[k*N+j];
+      A[i*N+j] = sum;
+      const double dum = vv[i]*fabs(sum);
+      if (dum >= big) { big = dum; imax = i; }
+    }
+    if (j != imax) {
+      for (int k = 0; k < N; k++) { const double dum = A[imax*N+k]; A[imax*N+k] = A[j*N+k]; A[j*N+k] = dum; }
+      vv[imax] = vv[j];
+    }
+    index[j] = imax;
+    if (A[j*N+j] == 0.0) A[j*N+j] = 1.0e-20;
+    const double dum = 1.0 / A[j*N+j];
+    for (int i = j+1; i < N; i++) A[i*N+j] *= dum;
+  }
+  // LUbacksubst, ludcmp.c:156-177
+  auto backsubst = [&](double *x) {
+    int ii = -1;
+    for (int i = 0; i < N; i++) {
+      const int ip = index[i];
+      double sum = x[ip];
+      x[ip] = x[i];
+      if (ii >= 0) { for (int j = ii; j < i; j++) sum -= A[i*N+j] * x[j]; }
+      else if (sum != 0.0) ii = i;
+      x[i] = sum;
+    }
+    for (int i = N-1; i >= 0; i--) {
+      double sum = x[i];
+      for (int j = i+1; j < N; j++) sum -= A[i*N+j]*x[j];
+      x[i] = sum / A[i*N+i];
+    }
+  };
+  backsubst(b);
+  if (improve) {
+    for (int i = 0; i < N; i++) {
+      residual[i] = b_copy[i];
+      for (int j = 0; j < N; j++) residual[i] -= A_copy[i*N+j] * b[j];
+    }
+    backsubst(residual);
+    for (int i = 0; i < N; i++) b[i] += residual[i];
+  }
+}
+
+// statEquil, statequil.c:40-103: one thread per (column, atom, depth)
+template <int MAXN>
+__global__ void __launch_bounds__(64)
+nlte_statequil_kernel(Plan P, Cols C, int ncol, int isum)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = P.Ndep;
+  if (t >= (size_t) ncol * P.Natom * N) return;
+  const int k = (int) (t % N);
+  const size_t ca = t / N;
+  const int a = (int) (ca % P.Natom), col = (int) (ca / P.Natom);
+  if (!C.active[col]) return;
+  const int Nl = P.atom_nlevel[a];
+  double G[MAXN*MAXN], nk[MAXN];
+  double *n = C.n + ((size_t) col * P.nlev + P.lev_off[a]) * N;
+  const double *Gam = C.Gamma + ((size_t) col * P.ngam + P.gam_off[a]) * N;
+  for (int i = 0; i < Nl; i++) {
+    nk[i] = n[(size_t) i*N + k];
+    for (int j = 0; j < Nl; j++) G[i*Nl+j] = Gam[(size_t)(i*Nl+j)*N + k];
+  }
+  int ie = isum;
+  if (isum == -1) {
+    ie = 0; double nmax = 0.0;
+    for (int i = 0; i < Nl; i++) if (nk[i] > nmax) { nmax = nk[i]; ie = i; }
+  }
+  for (int i = 0; i < Nl; i++) {
+    double GamDiag = 0.0;
+    G[i*Nl+i] = 0.0; nk[i] = 0.0;
+    for (int j = 0; j < Nl; j++) GamDiag += G[j*Nl+i];
+    G[i*Nl+i] = -GamDiag;
+  }
+  nk[ie] = C.ntotal[((size_t) col * P.Natom + a) * N + k];
+  for (int j = 0; j < Nl; j++) G[ie*Nl+j] = 1.0;
+  solve_linear_eq<MAXN>(Nl, G, nk, true);
+  for (int i = 0; i < Nl; i++) n[(size_t) i*N + k] = nk[i];
+}
+
+// batched SolveLinearEq entry (test hook): systems [nsys][N*N] + [nsys][N]
+template <int MAXN>
+__global__ void solve_batch_kernel(int nsys, int N, double *A, double *b, int improve)
+{
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nsys) return;
+  double G[MAXN*MAXN], x[MAXN];
+  for (int i = 0; i < N*N; i++) G[i] = A[(size_t) s*N*N + i];
+  for (int i = 0; i < N; i++) x[i] = b[(size_t) s*N + i];
+  solve_linear_eq<MAXN>(N, G, x, improve != 0);
+  for (int i = 0; i < N; i++) b[(size_t) s*N + i] = x[i];
+}
+
+// ---- (6) Accelerate + MaxChange (accelerate.c:68-147, maxchange.c:32-50): one block per (column, atom)
+__global__ void __launch_bounds__(128)
+nlte_ng_kernel(Plan P, Cols C, int ncol, double *previous /*[col][atom-offset][(Norder+2)][Nl*N]*/,
+               const size_t *prev_off, int Norder, int Ndelay, int Nperiod, int count, double *dpops)
+{
+  const int ca = blockIdx.x, a = ca % P.Natom, col = ca / P.Natom;
+  if (col >= ncol || !C.active[col]) return;
+  const int Nn = P.atom_nlevel[a] * P.Ndep, tid = threadIdx.x, nt = blockDim.x;
+  double *sol = C.n + ((size_t) col * P.nlev + P.lev_off[a]) * P.Ndep;
+  double *prev = previous + ((size_t) col * prev_off[P.Natom] + prev_off[a]);
+  __shared__ double sA[16], sb[4], smax[128];
+  // store the current solution (count is the value BEFORE the increment)
+  const int slot = count % (Norder + 2);
+  for (int k = tid; k < Nn; k += nt) prev[(size_t) slot*Nn + k] = sol[k];
+  __syncthreads();
+  const int cnt = count + 1;
+  if ((Norder > 0) && (cnt >= Ndelay) && !((cnt - Ndelay) % Nperiod)) {
+    auto delta = [&](int i, int k) {
+      const int ip = (cnt - 1 - i) % (Norder + 2), ipp = (cnt - 2 - i) % (Norder + 2);
+      return prev[(size_t) ip*Nn + k] - prev[(size_t) ipp*Nn + k];
+    };
+    // entries: b[j] (j < Norder) then A[i][j]; each summed sequentially over k by one thread
+    if (tid < Norder + Norder*Norder) {
+      double s = 0.0;
+      if (tid < Norder) {
+        const int j = tid;
+        for (int k = 0; k < Nn; k++) {
+          const double w = 1.0 / fabs(sol[k]), d0 = delta(0, k);
+          s += w * d0*(d0 - delta(j+1, k));
+        }
+        sb[j] = s;
+      } else {
+        const int e = tid - Norder, i = e / Norder, j = e % Norder;
+        for (int k = 0; k < Nn; k++) {
+          const double w = 1.0 / fabs(sol[k]), d0 = delta(0, k);
+          s += w * (delta(j+1, k) - d0) * (delta(i+1, k) - d0);
+        }
+        sA[i*Norder + j] = s;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double A[16], b[4];
+      for (int i = 0; i < Norder*Norder; i++) A[i] = sA[i];
+      for (int i = 0; i < Norder; i++) b[i] = sb[i];
+      solve_linear_eq<4>(Norder, A, b, true);
+      for (int i = 0; i < Norder; i++) sb[i] = b[i];
+    }
+    __syncthreads();
+    const int i0 = (cnt - 1) % (Norder + 2);
+    for (int k = tid; k < Nn; k += nt) {
+      double s = sol[k];
+      for (int i = 0; i < Norder; i++) {
+        const int ip = (cnt - 2 - i) % (Norder + 2);
+        s += sb[i] * (prev[(size_t) ip*Nn + k] - prev[(size_t) i0*Nn + k]);
+      }
+      sol[k] = s;
+    }
+    __syncthreads();
+    for (int k = tid; k < Nn; k += nt) prev[(size_t) i0*Nn + k] = sol[k];
+    __syncthreads();
+  }
+  // MaxChange
+  double dmax = 0.0;
+  if (cnt >= 2) {
+    const double *old = prev + (size_t)((cnt - 2) % (Norder + 2))*Nn, *nw = prev + (size_t)((cnt - 1) % (Norder + 2))*Nn;
+    for (int k = tid; k < Nn; k += nt)
+      if (nw[k] != 0.0) dmax = fmax(dmax, fabs((nw[k] - old[k]) / nw[k]));
+  }
+  smax[tid] = dmax;
+  __syncthreads();
+  for (int s = nt/2; s > 0; s >>= 1) { if (tid < s) smax[tid] = fmax(smax[tid], smax[tid+s]); __syncthreads(); }
+  if (tid == 0) dpops[(size_t) col * P.Natom + a] = smax[0];
+}
+
+template <class T> int up(T **d, const T *h, size_t n)
+{
+  *d = nullptr;
+  RH_CUDA(cudaMalloc((void **) d, std::max<size_t>(n, 1) * sizeof(T)));
+  if (n) RH_CUDA(cudaMemcpy(*d, h, n * sizeof(T), cudaMemcpyHostToDevice));
+  return RHB200_OK;
+}
+
+struct DevArena {           // everything allocated for one call, freed on scope exit
+  std::vector<void *> ptrs;
+  ~DevArena() { for (void *p : ptrs) cudaFree(p); }
+  template <class T> int alloc(T **d, size_t n, bool zero = false) {
+    *d = nullptr;
+    cudaError_t e = cudaMalloc((void **) d, std::max<size_t>(n, 1) * sizeof(T));
+    if (e != cudaSuccess) { cudaGetLastError(); rhb200_set_error("cudaMalloc(%zu): %s", n * sizeof(T), cudaGetErrorString(e)); return RHB200_ENOMEM; }
+    ptrs.push_back(*d);
+    if (zero) RH_CUDA(cudaMemset(*d, 0, std::max<size_t>(n, 1) * sizeof(T)));
+    return RHB200_OK;
+  }
+  template <class T> int upload(T **d, const T *h, size_t n) {
+    int rc = alloc(d, n);
+    if (rc != RHB200_OK) return rc;
+    if (n) RH_CUDA(cudaMemcpy(*d, h, n * sizeof(T), cudaMemcpyHostToDevice));
+    return RHB200_OK;
+  }
+};
+
+#define RH_CHECK(expr) do { int rc__ = (expr); if (rc__ != RHB200_OK) return rc__; } while (0)
+#define RH_GRID(n, b) (unsigned) (((size_t) (n) + (b) - 1) / (b)), (b)
+
+}  // namespace
+
+extern "C" int rhb200_solve_linear_eq_batch(rhb200_ctx *c, int nsys, int N, double *A, double *b, int improve)
+{
+  if (!c) { rhb200_set_error("null context"); return RHB200_EINVAL; }
+  RH_CUDA(cudaSetDevice(c->device));
+  if (nsys <= 0 || N <= 0 || N > 32 || !A || !b) { rhb200_set_error("bad arguments (N <= 32)"); return RHB200_EINVAL; }
+  DevArena ar;
+  double *dA, *db;
+  RH_CHECK(ar.upload(&dA, A, (size_t) nsys*N*N));
+  RH_CHECK(ar.upload(&db, b, (size_t) nsys*N));
+  if (N <= 8) solve_batch_kernel<8><<<RH_GRID(nsys, 64), 0, c->stream>>>(nsys, N, dA, db, improve);
+  else if (N <= 16) solve_batch_kernel<16><<<RH_GRID(nsys, 64), 0, c->stream>>>(nsys, N, dA, db, improve);
+  else solve_batch_kernel<32><<<RH_GRID(nsys, 32), 0, c->stream>>>(nsys, N, dA, db, improve);
+  RH_CUDA(cudaGetLastError());
+  RH_CUDA(cudaStreamSynchronize(c->stream));
+  RH_CUDA(cudaMemcpy(b, db, (size_t) nsys*N*sizeof(double), cudaMemcpyDeviceToHost));
+  return RHB200_OK;
+}
+
+extern "C" int rhb200_nlte_iterate(rhb200_ctx *c, const rhb200_nlte_plan *pl, int ncol,
+                                   const rhb200_nlte_columns *cols, int NmaxIter, double iterLimit,
+                                   int *niter_out, double *dpops_hist, int dump_iter,
+                                   double *gamma_dump, double *rates_dump)
+{
+  if (!c || !pl || !cols) { rhb200_set_error("null argument"); return RHB200_EINVAL; }
+  RH_CUDA(cudaSetDevice(c->device));
+  const int Ns = pl->Nspect, N = pl->Ndep, Na = pl->Natom, Nt = pl->Ntrans, Nr = pl->Nrays;
+  if (ncol <= 0 || Ns <= 0 || N < 3 || Na <= 0 || Na > 15 || Nt <= 0 || Nr <= 0 || NmaxIter < 0) {
+    rhb200_set_error("rhb200_nlte_iterate: bad sizes"); return RHB200_EINVAL;
+  }
+  if (!pl->moving) { rhb200_set_error("static atmospheres (angle-independent line profiles) are not implemented"); return RHB200_EUNSUPPORTED; }
+  if (pl->Ngorder > 4 || pl->Ngorder < 0) { rhb200_set_error("NG_ORDER > 4 is not implemented"); return RHB200_EUNSUPPORTED; }
+  int maxnl = 0;
+  std::vector<int> lev_off(Na+1, 0), gam_off(Na+1, 0);
+  for (int a = 0; a < Na; a++) {
+    maxnl = std::max(maxnl, pl->atom_nlevel[a]);
+    lev_off[a+1] = lev_off[a] + pl->atom_nlevel[a];
+    gam_off[a+1] = gam_off[a] + pl->atom_nlevel[a]*pl->atom_nlevel[a];
+  }
+  if (maxnl > 32) { rhb200_set_error("atoms with more than 32 levels are not implemented"); return RHB200_EUNSUPPORTED; }
+  const int nlev = lev_off[Na], ngam = gam_off[Na], nas = pl->as_first[Ns];
+
+  // derived host tables: angle dependence (formal.c:100-103), ray list in the reference's order
+  std::vector<int> angle_dep(Ns), ray_off(Ns+1, 0), ray_ns, ray_mu, ray_dir, as_pack(2*(size_t) nas);
+  for (int ns = 0; ns < Ns; ns++) {
+    bool bb = false;
+    for (int e = pl->as_first[ns]; e < pl->as_first[ns+1]; e++) {
+      as_pack[e] = pl->as_trans[e]; as_pack[nas + e] = ns;
+      if (pl->trans[(size_t) pl->as_trans[e]*RHB200_TR_NFIELD + RHB200_TR_TYPE] == 0.0) bb = true;
+      if (pl->trans[(size_t) pl->as_trans[e]*RHB200_TR_NFIELD + RHB200_TR_TYPE] != 0.0 &&
+          pl->trans[(size_t) pl->as_trans[e]*RHB200_TR_NFIELD + RHB200_TR_TYPE] != 1.0) {
+        rhb200_set_error("transition type must be 0 (line) or 1 (continuum)"); return RHB200_EINVAL;
+      }
+    }
+    angle_dep[ns] = pl->moving && (bb || pl->bg_hasline[ns]);
+    for (int mu = 0; mu < Nr; mu++)
+      for (int dir = 0; dir <= (angle_dep[ns] ? 1 : 0); dir++) { ray_ns.push_back(ns); ray_mu.push_back(mu); ray_dir.push_back(dir); }
+    ray_off[ns+1] = (int) ray_ns.size();
+  }
+  const int nray = (int) ray_ns.size();
+
+  DevArena ar;
+  Plan P{};
+  P.Nspect = Ns; P.Nrays = Nr; P.Ndep = N; P.Natom = Na; P.Ntrans = Nt; P.nas = nas; P.nray = nray;
+  P.nlev = nlev; P.ngam = ngam; P.nphirow = pl->nphirow; P.nline = pl->nline; P.bc_top = pl->bc_top; P.bc_bottom = pl->bc_bottom;
+  double *dd; int *di;
+#define UPD(field, src, n) RH_CHECK(ar.upload(&dd, src, (size_t) (n))); P.field = dd
+#define UPI(field, src, n) RH_CHECK(ar.upload(&di, src, (size_t) (n))); P.field = di
+  UPD(lambda, pl->lambda, Ns); UPD(muz, pl->muz, Nr); UPD(wmu, pl->wmu, Nr);
+  UPD(trans, pl->trans, (size_t) Nt*RHB200_TR_NFIELD);
+  UPD(tr_lambda, pl->tr_lambda, pl->ntrl); UPD(tr_wlambda, pl->tr_wlambda, pl->ntrl); UPD(tr_alpha, pl->tr_alpha, pl->ntrl);
+  UPI(atom_nlevel, pl->atom_nlevel, Na); UPI(lev_off, lev_off.data(), Na+1); UPI(gam_off, gam_off.data(), Na+1);
+  UPI(as_first, pl->as_first, Ns+1); UPI(as_trans, as_pack.data(), 2*(size_t) nas);
+  UPI(angle_dep, angle_dep.data(), Ns); UPI(ray_off, ray_off.data(), Ns+1);
+  UPI(ray_ns, ray_ns.data(), nray); UPI(ray_mu, ray_mu.data(), nray); UPI(ray_dir, ray_dir.data(), nray);
+
+  Cols C{};
+  const size_t cN = (size_t) ncol * N;
+#define UPC(field, src, n) RH_CHECK(ar.upload(&dd, src, (size_t) (n))); C.field = dd
+  UPC(T, cols->T, cN); UPC(height, cols->height, cN);
+  UPC(nstar, cols->nstar, cN*nlev); UPC(ntotal, cols->ntotal, cN*Na); UPC(C, cols->C, cN*ngam);
+  UPC(phi, cols->phi, cN*pl->nphirow); UPC(wphi, cols->wphi, cN*pl->nline);
+  UPC(chi_c, cols->chi_c, cN*Ns); UPC(eta_c, cols->eta_c, cN*Ns); UPC(sca_c, cols->sca_c, cN*Ns);
+  RH_CHECK(ar.upload(&C.n, cols->n, cN*nlev));
+  RH_CHECK(ar.upload(&C.J, cols->J, cN*Ns));
+  RH_CHECK(ar.alloc(&C.Gamma, cN*ngam)); RH_CHECK(ar.alloc(&C.Rij, cN*Nt, true)); RH_CHECK(ar.alloc(&C.Rji, cN*Nt, true));
+  RH_CHECK(ar.alloc(&C.gw, cN*nas*2));
+  RH_CHECK(ar.alloc(&C.chi, cN*nray)); RH_CHECK(ar.alloc(&C.S, cN*nray)); RH_CHECK(ar.alloc(&C.I, cN*nray));
+  RH_CHECK(ar.alloc(&C.Psi, cN*nray)); RH_CHECK(ar.alloc(&C.scr, cN*nray*2)); RH_CHECK(ar.alloc(&C.dJ, cN*Ns));
+  int *d_active;
+  std::vector<int> active(ncol, 1);
+  RH_CHECK(ar.upload(&d_active, active.data(), ncol));
+  C.active = d_active;
+
+  // Ng storage: previous[col][atom][(Norder+2)][Nl*N]; NgInit copies the initial solution (accelerate.c:57-59)
+  const int Norder = pl->Ngorder, Ndelay = std::max(pl->Ngdelay, Norder + 2), Nperiod = std::max(1, pl->Ngperiod);
+  std::vector<size_t> prev_off(Na+1, 0);
+  for (int a = 0; a < Na; a++) prev_off[a+1] = prev_off[a] + (size_t)(Norder+2) * pl->atom_nlevel[a] * N;
+  double *d_prev; size_t *d_prev_off; double *d_dpops;
+  RH_CHECK(ar.alloc(&d_prev, (size_t) ncol * prev_off[Na], true));
+  RH_CHECK(ar.upload(&d_prev_off, prev_off.data(), Na+1));
+  RH_CHECK(ar.alloc(&d_dpops, (size_t) ncol * Na, true));
+  for (int col = 0; col < ncol; col++)
+    for (int a = 0; a < Na; a++)
+      RH_CUDA(cudaMemcpyAsync(d_prev + (size_t) col*prev_off[Na] + prev_off[a],
+                              C.n + ((size_t) col*nlev + lev_off[a])*N, (size_t) pl->atom_nlevel[a]*N*sizeof(double),
+                              cudaMemcpyDeviceToDevice, c->stream));
+
+  cudaStream_t st = c->stream;
+  { ScopedKernelTimer t(c, RHB200_K_OTHER);
+    nlte_setup_kernel<<<RH_GRID(cN*nas, 128), 0, st>>>(P, C, ncol); }
+  RH_CUDA(cudaGetLastError());
+
+  std::vector<double> h_dpops((size_t) ncol * Na);
+  std::vector<int> niter(ncol, 0);
+  int nactive = ncol;
+  for (int it = 1; it <= NmaxIter && nactive > 0; it++) {
+    { ScopedKernelTimer t(c, RHB200_K_OTHER);
+      nlte_gamma_init_kernel<<<RH_GRID(cN*ngam, 256), 0, st>>>(P, C, ncol); }
+    { ScopedKernelTimer t(c, RHB200_K_OPACITY);
+      nlte_opacity_kernel<<<RH_GRID(cN*nray, 128), 0, st>>>(P, C, ncol); }
+    { ScopedKernelTimer t(c, RHB200_K_BEZIER);
+      nlte_ray_kernel<<<RH_GRID((size_t) ncol*nray, 128), 0, st>>>(P, C, ncol, 1); }
+    { ScopedKernelTimer t(c, RHB200_K_OTHER);
+      nlte_gamma_kernel<<<RH_GRID(cN*Nt, 64), 0, st>>>(P, C, ncol); }
+    { ScopedKernelTimer t(c, RHB200_K_OTHER);
+      nlte_J_kernel<<<RH_GRID(cN*Ns, 128), 0, st>>>(P, C, ncol); }
+    if (it == dump_iter) {
+      RH_CUDA(cudaStreamSynchronize(st));
+      if (gamma_dump) RH_CUDA(cudaMemcpy(gamma_dump, C.Gamma, cN*ngam*sizeof(double), cudaMemcpyDeviceToHost));
+      if (rates_dump) {
+        RH_CUDA(cudaMemcpy(rates_dump, C.Rij, cN*Nt*sizeof(double), cudaMemcpyDeviceToHost));
+        RH_CUDA(cudaMemcpy(rates_dump + cN*Nt, C.Rji, cN*Nt*sizeof(double), cudaMemcpyDeviceToHost));
+      }
+    }
+    { ScopedKernelTimer t(c, RHB200_K_OTHER);
+      if (maxnl <= 8) nlte_statequil_kernel<8><<<RH_GRID(cN*Na, 64), 0, st>>>(P, C, ncol, pl->isum);
+      else if (maxnl <= 16) nlte_statequil_kernel<16><<<RH_GRID(cN*Na, 64), 0, st>>>(P, C, ncol, pl->isum);
+      else nlte_statequil_kernel<32><<<RH_GRID(cN*Na, 64), 0, st>>>(P, C, ncol, pl->isum); }
+    { ScopedKernelTimer t(c, RHB200_K_OTHER);
+      nlte_ng_kernel<<<ncol*Na, 128, 0, st>>>(P, C, ncol, d_prev, d_prev_off, Norder, Ndelay, Nperiod, it, d_dpops); }
+    RH_CUDA(cudaGetLastError());
+    RH_CUDA(cudaMemcpyAsync(h_dpops.data(), d_dpops, h_dpops.size()*sizeof(double), cudaMemcpyDeviceToHost, st));
+    RH_CUDA(cudaStreamSynchronize(st));
+    bool changed = false;
+    for (int col = 0; col < ncol; col++) {
+      if (!active[col]) continue;
+      double d = 0.0;
+      for (int a = 0; a < Na; a++) d = std::max(d, h_dpops[(size_t) col*Na + a]);
+      niter[col] = it;
+      if (dpops_hist) dpops_hist[(size_t) col*NmaxIter + it-1] = d;
+      if (d < iterLimit) { active[col] = 0; nactive--; changed = true; }     // iterate.c:114
+    }
+    if (changed) RH_CUDA(cudaMemcpyAsync(d_active, active.data(), ncol*sizeof(int), cudaMemcpyHostToDevice, st));
+  }
+  RH_CUDA(cudaStreamSynchronize(st));
+  RH_CUDA(cudaMemcpy(cols->n, C.n, cN*nlev*sizeof(double), cudaMemcpyDeviceToHost));
+  RH_CUDA(cudaMemcpy(cols->J, C.J, cN*Ns*sizeof(double), cudaMemcpyDeviceToHost));
+  if (niter_out) memcpy(niter_out, niter.data(), ncol*sizeof(int));
+  return RHB200_OK;
+}

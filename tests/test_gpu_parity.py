@@ -301,3 +301,62 @@ def test_scalar_bezier3_and_feautrier_vs_reference(ctx):
     P2, Iem2 = ctx.feautrier(np.zeros(len(d), np.int32), g["lam_spect"][m[:, 0]], g["col_height"],
                              g["col_T"], d[:, 0], d[:, 1])
     assert np.array_equal(P2, P) and np.array_equal(Iem2, Iem)
+
+
+def test_solve_linear_eq_batch_vs_reference(ctx):
+    """SolveLinearEq (Crout LU, implicit-scaled partial pivoting, one refinement step): same pivots,
+    same bits as the reference's recorded calls (statEquil 6x6 systems and Ng 2x2 systems)."""
+    from pyrh_b200 import nlte
+    g = dict(np.load(GOLD / "nlte_caii.npz"))
+    off, by_n = 0, {}
+    for N in g["lu_n"]:
+        d = g["lu_data"][off:off + N * N + 2 * N]
+        off += N * N + 2 * N
+        by_n.setdefault(int(N), []).append(d)
+    for N, lst in by_n.items():
+        A = np.array([d[:N * N] for d in lst])
+        b = np.array([d[N * N:N * N + N] for d in lst])
+        x = nlte.solve_linear_eq(ctx, A, b)
+        assert np.array_equal(x, np.array([d[N * N + N:] for d in lst])), N
+
+
+def test_nlte_mali_iteration_vs_reference(ctx):
+    """config 4 class problem (CaII 6-level + continuum, FAL-C, NRAYS=3, Ng order 2, ITER_LIMIT 1e-4):
+    Gamma and rates of the first iterations, populations of every iteration, iteration count and the
+    converged populations/J must match the reference (north_star: 1e-6 relative; achieved: bitwise)."""
+    from pyrh_b200 import nlte
+    g = dict(np.load(GOLD / "nlte_caii.npz"))
+    prob = nlte.NlteProblem.from_golden(g, ncol=1)
+    for idx, it in enumerate(g["iter_keep"][:2]):
+        out = nlte.iterate(ctx, prob, nmax=int(it) + 1, limit=0.0, dump_iter=int(it) + 1)
+        ref = g["gamma_iter"][idx]
+        REPORT[f"nlte_gamma_iter{int(it)+1}_exact"] = bool(np.array_equal(out["gamma"][0], ref))
+        assert np.allclose(out["gamma"][0], ref, rtol=1e-10, atol=0)
+        assert np.array_equal(out["gamma"][0], ref)
+        assert np.array_equal(out["rij"][0], g["rates_iter"][idx][0::2])
+        assert np.array_equal(out["rji"][0], g["rates_iter"][idx][1::2])
+        assert np.array_equal(out["n"][0], g["n_iter"][int(it)])
+    out = nlte.iterate(ctx, prob)
+    assert out["niter"][0] == int(g["niter"])
+    rel = np.max(np.abs(out["n"][0] / g["n_final"] - 1))
+    REPORT["nlte_final_pops_maxrel"] = float(rel)
+    REPORT["nlte_final_pops_exact"] = bool(np.array_equal(out["n"][0], g["n_final"]))
+    assert rel < 1e-6
+    assert np.array_equal(out["n"][0], g["n_final"])
+    assert np.array_equal(out["J"][0], g["J_final"])
+    assert np.array_equal(out["dpops"][0, :out["niter"][0]], g["dpops_iter"])
+
+
+def test_nlte_batch_columns_converge_independently(ctx):
+    """Three columns: the fixture, a copy with a looser start (already converged populations: stops
+    after 1-2 iterations) and another copy of the fixture.  Frozen columns must not change."""
+    from pyrh_b200 import nlte
+    g = dict(np.load(GOLD / "nlte_caii.npz"))
+    prob = nlte.NlteProblem.from_golden(g, ncol=3)
+    prob.n0[1] = g["n_final"]
+    prob.J0[1] = g["J_final"]
+    out = nlte.iterate(ctx, prob)
+    assert out["niter"][0] == int(g["niter"]) and out["niter"][2] == int(g["niter"])
+    assert out["niter"][1] < 5
+    assert np.array_equal(out["n"][0], g["n_final"]) and np.array_equal(out["n"][2], g["n_final"])
+    assert np.max(np.abs(out["n"][1] / g["n_final"] - 1)) < 1e-3

@@ -104,3 +104,33 @@ def test_scalar_bezier3_and_feautrier_bit_exact():
         assert np.array_equal(P, d[2]) and I0 == Iem
         if m[3]:
             assert np.array_equal(Psi, d[3])
+
+
+def test_nlte_port_bit_exact_all_iterations():
+    """MALI iteration (Opacity, addtoGamma/Coupling/Rates, statEquil, Ng) of the C restatement vs the
+    reference's recorded Gamma, rates and populations: CaII 6-level atom on FAL-C, 31 iterations."""
+    from conftest import GOLD
+    g = dict(np.load(GOLD / "nlte_caii.npz"))
+    P = pd.PortNlte(g)
+    it, nh, gh, rh, dh = P.iterate(int(g["hdr"][9]), float(g["hdr"][10]))
+    assert it == int(g["niter"])
+    assert np.array_equal(dh, g["dpops_iter"])
+    assert np.array_equal(nh, g["n_iter"])
+    ntr = P.ntr
+    for idx, i in enumerate(g["iter_keep"]):
+        assert np.array_equal(gh[i], g["gamma_iter"][idx])
+        assert np.array_equal(rh[i][:ntr], g["rates_iter"][idx][0::2])
+        assert np.array_equal(rh[i][ntr:], g["rates_iter"][idx][1::2])
+    assert np.array_equal(nh[-1], g["n_final"]) and np.array_equal(nh[-1], g["pops_final"])
+    assert np.array_equal(P.a["J"], g["J_final"])
+
+
+def test_solve_linear_eq_bit_exact():
+    from conftest import GOLD
+    g = dict(np.load(GOLD / "nlte_caii.npz"))
+    off = 0
+    for N in g["lu_n"]:
+        d = g["lu_data"][off:off + N * N + 2 * N]
+        off += N * N + 2 * N
+        x = pd.solve_linear_eq(d[:N * N].reshape(N, N), d[N * N:N * N + N])
+        assert np.array_equal(x, d[N * N + N:])
