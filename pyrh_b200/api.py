@@ -233,7 +233,7 @@ class Context:
         return H, F, reg
 
     def math_probe(self, func: str, x, y=None):
-        code = dict(exp=0, sin=1, cos=2, pow=3)[func]
+        code = dict(exp=0, sin=1, cos=2, pow=3, div_recip=4, div=5)[func]
         x = np.ascontiguousarray(x, np.float64)
         out = np.zeros_like(x)
         yy = np.ascontiguousarray(y, np.float64) if y is not None else None

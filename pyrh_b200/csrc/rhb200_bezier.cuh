@@ -14,6 +14,7 @@ __device__ __forceinline__ void bezier3_ray(const int ndep, const double *__rest
 {
   using namespace rhd;
   const double zmu = 1.0 / muz;
+  const rhdiv::Recip third(3.0);
   const int dk = to_obs ? -1 : 1;
   const int ks = to_obs ? ndep-1 : 0, ke = to_obs ? 0 : ndep-1;
 
@@ -38,8 +39,9 @@ __device__ __forceinline__ void bezier3_ray(const int ndep, const double *__rest
   double fchi = (chi[k+dk] - chi[k]) / dsdn;
   double dchi_c = fb_deriv(dchi_up, fchi, fb_alpha(dsup, dsdn));
   {
-    const double c1 = RH_MAX0(chi[k]    - (dsup/3.0) * dchi_c);
-    const double c2 = RH_MAX0(chi[k-dk] + (dsup/3.0) * dchi_up);
+    const double dsup3 = third.div(dsup);
+    const double c1 = RH_MAX0(chi[k]    - dsup3 * dchi_c);
+    const double c2 = RH_MAX0(chi[k-dk] + dsup3 * dchi_up);
     dtau_uw = dsup * (chi[k] + chi[k-dk] + c1 + c2) * 0.25;
   }
   double dS_up = (S[k] - S[k-dk]) / dtau_uw;
@@ -55,10 +57,11 @@ __device__ __forceinline__ void bezier3_ray(const int ndep, const double *__rest
         dchi_dn = fb_deriv(fchi, fnext, fb_alpha(dsdn, dsdn2));
       } else
         dchi_dn = fchi;
-      double c1 = RH_MAX0(chi[k]    + (dsdn/3.0) * dchi_c);
-      double c2 = RH_MAX0(chi[k+dk] - (dsdn/3.0) * dchi_dn);
+      const double dsdn3 = third.div(dsdn);
+      double c1 = RH_MAX0(chi[k]    + dsdn3 * dchi_c);
+      double c2 = RH_MAX0(chi[k+dk] - dsdn3 * dchi_dn);
       dtau_dw = dsdn * (chi[k] + chi[k+dk] + c1 + c2) * 0.25;
-      const double dt03 = dtau_uw / 3.0;
+      const double dt03 = third.div(dtau_uw);
       double alpha, beta, gamma, theta, eps;
       bezier3_coeffs(dtau_uw, alpha, beta, gamma, theta, eps);
       const double fi = (S[k+dk] - S[k]) / dtau_dw;

@@ -28,6 +28,9 @@ struct RayPtsIO {
     }
   }
   __device__ __forceinline__ void storePsi(int, double) {}
+  __device__ __forceinline__ void prefetch(int k, int ndep) const {
+    if (k >= 0 && k < ndep) asm volatile("prefetch.global.L1 [%0];" :: "l"(rp + 4*(size_t)k));
+  }
 };
 
 // ---- IO policy: reference layouts chi[nray][ndep], S[nray][4][ndep], chiQUV[nray][3][ndep]
@@ -47,6 +50,7 @@ struct GenericIO {
     I_[k] = I[0]; I_[ndep+k] = I[1]; I_[2*ndep+k] = I[2]; I_[3*ndep+k] = I[3];
   }
   __device__ __forceinline__ void storePsi(int k, double p) { if (Psi_) Psi_[k] = p; }
+  __device__ __forceinline__ void prefetch(int, int) const {}
 };
 
 template <int MINB>

@@ -22,6 +22,7 @@
 #pragma once
 #include "rhb200_common.cuh"
 #include "rhb200_math.cuh"
+#include "rhb200_div.cuh"
 
 namespace rhd {
 
@@ -54,8 +55,9 @@ __device__ __forceinline__ void bezier3_coeffs(double dt, double &alpha, double 
   double dt3 = dt2*dt;
   if (dt >= 5.e-2) {
     eps = rhm::rh_exp(-dt);
-    alpha = (-6.0 + 6.0*dt - 3.0*dt2 + dt3 + 6.0*eps) / dt3;
-    dt3 = 1.0/dt3;
+    const rhdiv::Recip rdt3(dt3);                // x/dt3 and 1.0/dt3 share one reciprocal refinement
+    alpha = rdt3.div(-6.0 + 6.0*dt - 3.0*dt2 + dt3 + 6.0*eps);
+    dt3 = rdt3.div(1.0);
     beta  = (6.0 + (-6.0 - dt*(6.0 + dt*(3.0 + dt)))*eps) * dt3;
     gamma = 3.0 * (6.0 + (-4.0 + dt)*dt - 2.0*(3.0 + dt)*eps) * dt3;
     theta = 3.0 * (eps*(6.0 + dt2 + 4.0*dt) + 2.0*dt - 6.0) * dt3;
@@ -136,6 +138,7 @@ __device__ __forceinline__ void delo_bezier3_ray(IO &io, const int ndep, const d
   const double imu = 1.0 / muz;
   const int dk = to_obs ? -1 : 1;
   const int ks = to_obs ? ndep-1 : 0, ke = to_obs ? 0 : ndep-1;
+  const rhdiv::Recip third(3.0);                 // x / 3.0 (IEEE quotient, not x * (1/3))
 
   double c_m = io.chi(ks), c_0 = io.chi(ks+dk);
   double z_m = z[ks], z_0 = z[ks+dk];
@@ -160,8 +163,9 @@ __device__ __forceinline__ void delo_bezier3_ray(IO &io, const int ndep, const d
   double dchi_c = fb_deriv(dchi_up, fchi, fb_alpha(dsup, dsdn));
 
   {
-    const double c2 = RH_MAX0(c_0 - (dsup/3.0) * dchi_c);
-    const double c1 = RH_MAX0(c_m + (dsup/3.0) * dchi_up);
+    const double dsup3 = third.div(dsup);
+    const double c2 = RH_MAX0(c_0 - dsup3 * dchi_c);
+    const double c1 = RH_MAX0(c_m + dsup3 * dchi_up);
     dtau_uw = 0.25 * dsup * (c_0 + c_m + c1 + c2);
   }
 
@@ -169,12 +173,16 @@ __device__ __forceinline__ void delo_bezier3_ray(IO &io, const int ndep, const d
   double Su[4], S0[4], Sd[4], dSu[4], dS0[4], fS[4];
   io.K(ks, Ku);  io.K(k, K0);
   io.S(ks, Su);  io.S(k, S0);
+  {
+    const rhdiv::Recip ruw(dtau_uw);
 #pragma unroll
-  for (int n = 0; n < 4; n++) { dSu[n] = (S0[n] - Su[n]) / dtau_uw; fS[n] = dSu[n]; }
+    for (int n = 0; n < 4; n++) { dSu[n] = ruw.div(S0[n] - Su[n]); fS[n] = dSu[n]; }
 #pragma unroll
-  for (int n = 0; n < 3; n++) { dKu[n] = (K0[n] - Ku[n]) / dtau_uw; fK[n] = dKu[n]; }
+    for (int n = 0; n < 3; n++) { dKu[n] = ruw.div(K0[n] - Ku[n]); fK[n] = dKu[n]; }
+  }
 
   for (; k != ke; k += dk) {
+    io.prefetch(k + 4*dk, ndep);                   // pull the records of a later depth into L1
     dsdn = fabs(z_p - z_0) * imu;
     double dchi_dn, c_pp = 0.0, z_pp = 0.0, fnext = fchi;
     if (abs(k - ke) > 1) {
@@ -185,10 +193,11 @@ __device__ __forceinline__ void delo_bezier3_ray(IO &io, const int ndep, const d
     } else
       dchi_dn = fchi;
 
-    const double c2 = RH_MAX0(c_0 + (dsdn/3.0) * dchi_c);
-    const double c1 = RH_MAX0(c_p - (dsdn/3.0) * dchi_dn);
+    const double dsdn3 = third.div(dsdn);
+    const double c2 = RH_MAX0(c_0 + dsdn3 * dchi_c);
+    const double c1 = RH_MAX0(c_p - dsdn3 * dchi_dn);
     const double dtau_dw = 0.25 * dsdn * (c_0 + c_p + c1 + c2);
-    const double dt = dtau_uw, dt03 = dt / 3.0;
+    const double dt = dtau_uw, dt03 = third.div(dt);
 
     double alpha, beta, gamma, theta, eps;
     bezier3_coeffs(dt, alpha, beta, gamma, theta, eps);
@@ -198,15 +207,16 @@ __device__ __forceinline__ void delo_bezier3_ray(IO &io, const int ndep, const d
     io.S(k+dk, Sd);
 
     const double ca = fb_alpha(dtau_uw, dtau_dw);
+    const rhdiv::Recip rdw(dtau_dw);             // seven slopes share the divisor dtau_dw
 #pragma unroll
     for (int n = 0; n < 3; n++) {
-      const double fi = (Kd[n] - K0[n]) / dtau_dw;
+      const double fi = rdw.div(Kd[n] - K0[n]);
       dK0[n] = fb_deriv(fK[n], fi, ca);
       fK[n] = fi;
     }
 #pragma unroll
     for (int n = 0; n < 4; n++) {
-      const double fi = (Sd[n] - S0[n]) / dtau_dw;
+      const double fi = rdw.div(Sd[n] - S0[n]);
       dS0[n] = fb_deriv(fS[n], fi, ca);
       fS[n] = fi;
     }

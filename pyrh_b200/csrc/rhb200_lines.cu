@@ -17,6 +17,7 @@
 // wavelength-dependent part: the Zeeman-component loop of Humlicek W(z) evaluations.
 #include "rhb200_common.cuh"
 #include "rhb200_voigt.cuh"
+#include "rhb200_div.cuh"
 
 namespace {
 
@@ -239,11 +240,12 @@ opacity_fused_kernel(int ncol, int nlambda, int ndep, int to_obs, int nline,
   // background.c:476-537: chi_c = chi_ai + chi_lines (I), 0 + lines (Q,U,V);
   // formal.c:178-208: chi = 0 + chi_c, S = (0 + eta_c)/chi; stokesopac.c:72-77: K' = chi_QUV/chi_I
   const double chi = __ldg(chi_ai + t) + s.chi[0];
+  const rhdiv::Recip rchi(chi);                  // seven IEEE quotients, one reciprocal refinement
   double2 *o = reinterpret_cast<double2 *>(raypts + t * RP_NFIELD);
-  o[0] = make_double2(chi, s.chi[1] / chi);
-  o[1] = make_double2(s.chi[2] / chi, s.chi[3] / chi);
-  o[2] = make_double2((__ldg(eta_ai + t) + s.eta[0]) / chi, s.eta[1] / chi);
-  o[3] = make_double2(s.eta[2] / chi, s.eta[3] / chi);
+  o[0] = make_double2(chi, rchi.div(s.chi[1]));
+  o[1] = make_double2(rchi.div(s.chi[2]), rchi.div(s.chi[3]));
+  o[2] = make_double2(rchi.div(__ldg(eta_ai + t) + s.eta[0]), rchi.div(s.eta[1]));
+  o[3] = make_double2(rchi.div(s.eta[2]), rchi.div(s.eta[3]));
 }
 
 // RAW: exactly the output of rlk_opacity(), chi/eta [ncol][nlambda][4][ndep]
@@ -297,6 +299,8 @@ __global__ void math_probe_kernel(int n, int func, const double *__restrict__ x,
   case 0: r = rhm::rh_exp(x[i]); break;
   case 1: r = rhm::rh_sin(x[i]); break;
   case 2: r = rhm::rh_cos(x[i]); break;
+  case 4: { rhdiv::Recip rc(y[i]); r = rc.div(x[i]); break; }     // shared-reciprocal division
+  case 5: r = x[i] / y[i]; break;                                  // compiler's IEEE division
   default: r = rhm::rh_pow(x[i], y[i]); break;
   }
   out[i] = r;

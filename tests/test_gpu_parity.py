@@ -360,3 +360,25 @@ def test_nlte_batch_columns_converge_independently(ctx):
     assert out["niter"][1] < 5
     assert np.array_equal(out["n"][0], g["n_final"]) and np.array_equal(out["n"][2], g["n_final"])
     assert np.max(np.abs(out["n"][1] / g["n_final"] - 1)) < 1e-3
+
+
+def test_shared_reciprocal_division_is_ieee(ctx):
+    """rhdiv::Recip (one reciprocal refinement shared by several numerators) must return exactly
+    the compiler's round-to-nearest quotient, including tiny/huge/zero/denormal operands."""
+    rng = np.random.default_rng(11)
+    n = 2_000_000
+    a = rng.standard_normal(n) * 10.0 ** rng.uniform(-300, 300, n)
+    b = rng.standard_normal(n) * 10.0 ** rng.uniform(-300, 300, n)
+    a[:1000] = 0.0
+    a[1000:2000] = 5e-324 * rng.integers(1, 1000, 1000)
+    b[2000:3000] = 5e-324 * rng.integers(1, 1000, 1000)
+    b[3000:3100] = 1.7e308
+    a2 = rng.uniform(-1, 1, n); b2 = rng.uniform(1e-12, 1e3, n)      # the path's typical magnitudes
+    for x, y in ((a, b), (a2, b2), (b2, np.full(n, 3.0))):
+        got = ctx.math_probe("div_recip", x, y)
+        ref = ctx.math_probe("div", x, y)
+        host = x / y
+        same = (got == ref) | (np.isnan(got) & np.isnan(ref))
+        assert same.all(), np.flatnonzero(~same)[:5]
+        ok = (ref == host) | (np.isnan(ref) & np.isnan(host))
+        assert ok.all()
