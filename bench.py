@@ -329,10 +329,20 @@ def main():
     pts_per_launch = cols_per_launch * NLAMBDA * NDEP
     flop_pt = {"delo": FLOP_DELO, "opacity": FLOP_OPACITY}.get(dom, 0.0)
     achieved_tf = pts_per_launch * flop_pt / (dom_ms * 1e-3) / 1e12
+    traffic = None            # dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu capture
+    try:
+        import csv
+        for row in csv.DictReader(open(ROOT / "profiles" / "r1_lte_kernels.csv")):
+            if {"delo": "delo_raypts", "opacity": "opacity_fused"}.get(dom, "@") in row["kernel"]:
+                gb = float(row["dram__bytes_read.sum"]) + float(row["dram__bytes_write.sum"])
+                traffic = gb * 1e9 * (cols_per_launch / 4096.0)      # capture was taken at 4096 columns/launch
+    except (OSError, KeyError, ValueError):
+        pass
     roofline = {"kernel": {"delo": "delo_raypts_kernel", "opacity": "opacity_fused_kernel",
                            "prep": "prep_kernel"}.get(dom, dom),
                 "bound": "fp64", "achieved": achieved_tf, "peak": fma_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / fma_tf if fma_tf else None, "traffic": None,
+                "frac": achieved_tf / fma_tf if fma_tf else None, "traffic": traffic,
+                "algorithmic_bytes": pts_per_launch * (BYTES_DELO if dom == "delo" else 80.0),
                 "peak_source": "rhb200_fp64_peak(): DFMA micro-benchmark run in this process (2 flop/FMA); "
                                f"non-FMA FP64 issue rate {nofma_tf:.1f} Tinst/s",
                 "algorithmic_flop_per_raypoint": flop_pt, "ms_per_launch": dom_ms,
