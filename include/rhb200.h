@@ -182,6 +182,10 @@ int rhb200_feautrier_batch(rhb200_ctx *ctx, int nray, int ncol, int ndep, double
 int rhb200_voigt_humlicek(rhb200_ctx *ctx, int n, const double *a, const double *v,
                           double *H, double *F, int *region);
 
+/* Voigt(a, v, NULL, ARMSTRONG) (voigt.c:126-243): H for n (a, v) pairs; region[n] = 1,2,3 for
+   VoigtK1/K2/K3 (may be NULL) */
+int rhb200_voigt_armstrong(rhb200_ctx *ctx, int n, const double *a, const double *v, double *H, int *region);
+
 /* exp / pow / sin / cos exactly as the device code evaluates them (test hook for
    the glibc-equivalence of the device math) */
 int rhb200_math_probe(rhb200_ctx *ctx, int n, int func /*0 exp 1 sin 2 cos 3 pow 4 x/y via shared reciprocal 5 x/y*/,
@@ -202,6 +206,7 @@ enum {
   RHB200_TR_WOFF,                                /* offset of this transition in tr_lambda/tr_wlambda/tr_alpha */
   RHB200_TR_PHIROW,                              /* first row of line->phi[2*Nrays*Nlambda] in the phi table */
   RHB200_TR_KR, RHB200_TR_LINEIDX,               /* index in atom->line / row of wphi */
+  RHB200_TR_LAMBDA0,                             /* line->lambda0 [nm] (used when profiles are computed on the device) */
   RHB200_TR_NFIELD = 16
 };
 typedef struct {
@@ -225,17 +230,23 @@ typedef struct {                                 /* per-column arrays, column-ma
   const double *C;                               /* [ncol][sum Nlevel^2][Ndep] collisional rates (atom->C) */
   const double *phi;                             /* [ncol][nphirow][Ndep]  line->phi (Profile(), profile.c:67) */
   const double *wphi;                            /* [ncol][nline][Ndep] */
+  /* When phi == NULL the profiles are evaluated on the device (Profile(), field-free branch
+     profile.c:311-323, single-component lines, VoigtArmstrong) from: */
+  const double *adamp;                           /* [ncol][nline][Ndep]  Damping() (broad.c:273), host */
+  const double *vbroad;                          /* [ncol][Natom][Ndep]  atom->vbroad */
+  const double *vel;                             /* [ncol][Ndep]         geometry.vel [m/s] */
   const double *chi_c, *eta_c, *sca_c;           /* [ncol][Nspect][Ndep] background (spectrum.*_c_lam) */
   double *n;                                     /* [ncol][sum Nlevel][Ndep]  in: initial, out: converged */
   double *J;                                     /* [ncol][Nspect][Ndep]      in: after initScatter, out: final */
 } rhb200_nlte_columns;
 /* niter [ncol] iterations done; dpops_hist [ncol][NmaxIter] or NULL; when dump_iter >= 1 the Gamma
    matrices [ncol][sum Nl^2][Ndep] and rates {Rij [ncol][Ntrans][Ndep], Rji ...} of that iteration are
-   copied out before statEquil (test hooks, may be NULL). */
+   copied out before statEquil (test hooks, may be NULL); phi_out/wphi_out receive the device-evaluated
+   profiles [ncol][nphirow][Ndep] / [ncol][nline][Ndep] when cols->phi == NULL (may be NULL). */
 int rhb200_nlte_iterate(rhb200_ctx *ctx, const rhb200_nlte_plan *plan, int ncol,
                         const rhb200_nlte_columns *cols, int NmaxIter, double iterLimit,
                         int *niter, double *dpops_hist, int dump_iter, double *gamma_dump,
-                        double *rates_dump);
+                        double *rates_dump, double *phi_out, double *wphi_out);
 /* SolveLinearEq (ludcmp.c:36-86) for nsys systems: A [nsys][N][N] (untouched), b [nsys][N] in/out; N <= 32 */
 int rhb200_solve_linear_eq_batch(rhb200_ctx *ctx, int nsys, int N, double *A, double *b, int improve);
 

@@ -246,6 +246,30 @@ def validate_scalar_port(name, g):
     print(f"[port-vs-ref] {name}: Bezier3 exact {nb}/{len(g['bez'])}, Feautrier exact {nf}/{len(g['feau'])}")
 
 
+def make_voigt_armstrong():
+    """Voigt(a, v, NULL, ARMSTRONG) of the reference itself (rh/voigt.c:83,126-243) on random (a, v)
+    covering the K1 / K2 / K3 branches."""
+    import ctypes as C
+    from oracle import portdriver as pd
+    ref = rd.load("scalar")
+    ref.Voigt.restype = C.c_double
+    ref.Voigt.argtypes = [C.c_double, C.c_double, C.POINTER(C.c_double), C.c_int]
+    port = pd.lib()
+    port.rp_voigt_armstrong.restype = C.c_double
+    port.rp_voigt_armstrong.argtypes = [C.c_double, C.c_double]
+    port.rp_armstrong_region.argtypes = [C.c_double, C.c_double]
+    rng = np.random.default_rng(5)
+    n = 20000
+    a = 10 ** rng.uniform(-5, 1.2, n)
+    v = rng.uniform(-12, 12, n)
+    v[:3000] = rng.uniform(-300, 300, 3000)
+    H = np.array([ref.Voigt(a[i], v[i], None, 0) for i in range(n)])          # enum ARMSTRONG = 0 (rh.h)
+    P = np.array([port.rp_voigt_armstrong(a[i], v[i]) for i in range(n)])
+    reg = np.array([port.rp_armstrong_region(a[i], v[i]) for i in range(n)], np.int8)
+    np.savez_compressed(GOLD / "voigt_armstrong.npz", a=a, v=v, H=H, region=reg)
+    print(f"[golden] voigt_armstrong: {n} points, regions {np.bincount(reg)[1:]}; port exact = {np.array_equal(H, P)}")
+
+
 def falc_case_atm():
     atm = rd.falc("benchmark")
     atm[5] = 1000.0                                   # B [G]; gamma, chi from falc.dat (pi/4, pi/3)
@@ -258,6 +282,7 @@ def main():
     wave = rd.hinode_wave()
     g, ex = make_case("falc_B1kG", falc_case_atm(), wave)
     validate_port("falc_B1kG", g, ex)
+    make_voigt_armstrong()
     gs = make_scalar_case("falc_scalar", falc_case_atm(), rd.air_to_vacuum(np.linspace(629.7, 630.7, 101)))
     validate_scalar_port("falc_scalar", gs)
     # FULL_STOKES on the same wide grid: DELO inside the line windows, Feautrier outside

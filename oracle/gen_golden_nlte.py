@@ -76,6 +76,20 @@ def flatten(R):
     out["trans"] = np.array(rows)
     out["tr_lambda"], out["tr_wlambda"], out["tr_alpha"] = np.array(wl), np.array(wlam), np.array(alpha)
     out["phi"], out["wphi"] = np.concatenate(phis), np.array(wphi)
+    # inputs of Profile(): damping parameter per line, Doppler width per atom, line-of-sight velocity
+    ad, l0, comp_ok = [], [], True
+    for a in range(Natom):
+        for m, d in sorted([x for x in R["nl_adamp"] if x[0][0] == a], key=lambda x: x[0][1]):
+            ad.append(d)
+            comp_ok &= (m[3] == 1)
+        for m, d in sorted([x for x in R["nl_line"] if x[0][0] == a], key=lambda x: x[0][1]):
+            l0.append(d[0])
+        for m, d in R["nl_comp"]:
+            comp_ok &= (m[2] == 1 and d[0] == 0.0 and d[1] == 1.0)
+    assert comp_ok, "multi-component lines are not covered by the fixture"
+    out["adamp"], out["line_lambda0"] = np.array(ad), np.array(l0)
+    out["vbroad"] = np.array([d for m, d in sorted(R["nl_vbroad"], key=lambda x: x[0][0])])
+    out["vel"] = one(R, "nl_vel")
     first, lst = [0], []
     for m, d in sorted(R["nl_as"], key=lambda x: x[0][0]):
         cnt = m[1]

@@ -107,6 +107,10 @@ void rp_lte_stokes_column(const rp_linetable *lt, const rp_column *col,
                           const double *chi_ai, const double *eta_ai,
                           int bc_top, int bc_bottom, double *stokes);
 
+/* voigt.c:126-243 */
+double rp_voigt_armstrong(double a, double v);
+int    rp_armstrong_region(double a, double v);
+
 /* ---- NLTE (rhport_nlte.c): see the struct there; driven from oracle/portdriver.py ---- */
 void rp_solve_linear_eq(int N, double *A /*row-major, destroyed*/, double *b, int improve);
 void rp_stat_equil(int Nl, int N, const double *Gamma, const double *ntotal, int isum, double *n);

@@ -311,3 +311,86 @@ void rp_region_hist(const rp_linetable *lt, const rp_column *c, int Nlambda,
     }
   }
 }
+
+/* ---- VoigtArmstrong (K1/K2/K3), rh/voigt.c:126-243: unpolarised Voigt function used by
+        Profile() for NO_STOKES active lines, by passive_bb and by non-polarizable Kurucz lines */
+static const double arm_t[10] = {0.2453407083, 0.7374737285, 1.2340762153, 1.7385377121,
+                                 2.2549740020, 2.7888060584, 3.3478545673, 3.9447640401,
+                                 4.6036824495, 5.3874808900};
+static const double arm_w[10] = {4.6224366960e-01, 2.8667550536e-01, 1.0901720602e-01,
+                                 2.4810520887e-02, 3.2437733422e-03, 2.2833863601e-04,
+                                 7.8025564785e-06, 1.0860693707e-07, 4.3993409922e-10,
+                                 2.2293936455e-13};
+static const double arm_c[34] = { 0.1999999999972224, -0.1840000000029998, 0.1558399999965025, -0.1216640000043988,
+  0.0877081599940391, -0.0585141248086907, 0.0362157301623914, -0.0208497654398036, 0.0111960116346270,
+  -0.56231896167109e-02, 0.26487634172265e-02, -0.11732670757704e-02, 0.4899519978088e-03, -0.1933630801528e-03,
+  0.722877446788e-04, -0.256555124979e-04, 0.86620736841e-05, -0.27876379719e-05, 0.8566873627e-06,
+  -0.2518433784e-06, 0.709360221e-07, -0.191732257e-07, 0.49801256e-08, -0.12447734e-08, 0.2997777e-09,
+  -0.696450e-10, 0.156262e-10, -0.33897e-11, 0.7116e-12, -0.1447e-12, 0.285e-13, -0.55e-14, 0.10e-14, -0.2e-15 };
+
+static double voigt_k1(double a, double v)              /* voigt.c:146-211 */
+{
+  int n;
+  double a2 = a*a, v2 = v*v, u1, dn01, dn02, dn, v2i, funct, an, q, g, coef, bn01, bn02, bn = 0.0, v1;
+  if ((v2 - a2) > 70.0) u1 = 0.0;
+  else u1 = exp(a2 - v2) * cos(2.0*v*a);
+  if (v > 5.0) {
+    v2i = 1.0 / v2;
+    dn01 = -v2i * (0.5 + v2i*(0.75 + v2i*(1.875 + v2i*(6.5625 +
+           v2i*(29.53125 + v2i*(1162.4218 + v2i*1055.7421))))));
+    dn02 = (1.0 - dn01) / (2.0 * v);
+  } else {
+    bn01 = bn02 = 0.0;
+    v1   = v / 5.0;
+    coef = 4.0 * v1*v1 - 2.0;
+    for (n = 33; n >= 0; n--) { bn = coef*bn01 - bn02 + arm_c[n]; bn02 = bn01; bn01 = bn; }
+    dn02 = (double) (v1*(bn - bn02));
+    dn01 = 1.0 - 2.0*v*dn02;
+  }
+  funct = a*dn01;
+  if (a > 1.0E-08) {
+    q = 1.0; an = a;
+    for (n = 2; n <= 50; n++) {
+      dn = (v*dn01 + dn02) * (-2.0/n);
+      dn02 = dn01; dn01 = dn;
+      if (n % 2) {
+        q = -q; an *= a2; g = dn * an; funct += q*g;
+        if (fabs(g/funct) <= 1.0E-08) return (u1 - 1.12837917*funct);
+      }
+    }
+  }
+  return (u1 - 1.12837917*funct);
+}
+static double voigt_k2(double a, double v)              /* voigt.c:215-229 */
+{
+  double g = 0.0, r, s, a2 = a*a;
+  for (int n = 0; n < 10; n++) {
+    r = arm_t[n] - v; s = arm_t[n] + v;
+    g += (4.0*arm_t[n]*arm_t[n] - 2.0) * (r*atan(r/a) + s*atan(s/a) -
+          0.5*a*(log(a2 + r*r) + log(a2 + s*s))) * arm_w[n];
+  }
+  return g/RP_PI;
+}
+static double voigt_k3(double a, double v)              /* voigt.c:233-243 */
+{
+  double g = 0.0, a2 = a*a;
+  for (int n = 0; n < 10; n++)
+    g += (1.0/((v - arm_t[n])*(v - arm_t[n]) + a2) + 1.0/((v + arm_t[n])*(v + arm_t[n]) + a2)) * arm_w[n];
+  return (a*g)/RP_PI;
+}
+int rp_armstrong_region(double a, double v)             /* voigt.c:126-137 */
+{
+  if (v < 0.0) v = -v;
+  if ((a < 1.0 && v < 4.0) || (a < 1.8/(v + 1.0))) return 1;
+  if (a < 2.5 && v < 4.0) return 2;
+  return 3;
+}
+double rp_voigt_armstrong(double a, double v)
+{
+  if (v < 0.0) v = -v;
+  switch (rp_armstrong_region(a, v)) {
+  case 1: return voigt_k1(a, v);
+  case 2: return voigt_k2(a, v);
+  default: return voigt_k3(a, v);
+  }
+}

@@ -417,3 +417,31 @@ int rp_nlte_iterate(rp_nlte *P, int NmaxIter, double iterLimit, double *n_hist, 
   free(ng);
   return done;
 }
+
+/* Profile() for one un-polarised, single-component line in a moving atmosphere, profile.c:67-372
+   (field-free branch :311-322, normalisation :323,358): phi [2*Nrays*Nlambda][N], wphi [N] */
+double rp_voigt_armstrong(double a, double v);
+void rp_profile_line(int N, int Nrays, int Nlambda, double lambda0, const double *lambda, const double *wlambda,
+                     const double *adamp, const double *vbroad, const double *vel, const double *muz,
+                     const double *wmu, double *phi, double *wphi)
+{
+  int la, mu, to_obs, k;
+  for (k = 0; k < N; k++) wphi[k] = 0.0;
+  for (la = 0; la < Nlambda; la++) {
+    for (mu = 0; mu < Nrays; mu++) {
+      const double wlamu = wlambda[la] * 0.5*wmu[mu];
+      for (to_obs = 0; to_obs <= 1; to_obs++) {
+        const double sign = to_obs ? 1.0 : -1.0;
+        double *p = phi + (size_t)(2*(Nrays*la + mu) + to_obs)*N;
+        for (k = 0; k < N; k++) {
+          const double v = (lambda[la] - lambda0 - 0.0) * RP_CLIGHT / (vbroad[k] * lambda0);
+          const double v_los = (muz[mu] * vel[k]) / vbroad[k];
+          const double vk = v + sign * v_los;
+          p[k] = 0.0 + rp_voigt_armstrong(adamp[k], vk) * 1.0 / (RP_SQRTPI * vbroad[k]);
+          wphi[k] += p[k] * wlamu;
+        }
+      }
+    }
+  }
+  for (k = 0; k < N; k++) wphi[k] = 1.0 / wphi[k];
+}

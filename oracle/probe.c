@@ -379,6 +379,7 @@ static void dump_nlte_problem(int NmaxIter, double iterLimit)
   rec_copy("nl_wmu", geometry.wmu, geometry.Nrays, 0,0,0,0);
   rec_copy("nl_T", atmos.T, N, 0,0,0,0);
   rec_copy("nl_height", geometry.height, N, 0,0,0,0);
+  rec_copy("nl_vel", geometry.vel, N, 0,0,0,0);
   {
     double *J = rec_new("nl_J", (long) Ns*N, 0,0,0,0,0,0);
     double *b = rec_new("nl_bg", (long) 3*Ns*N, 0,0,0,0,0,0);
@@ -400,12 +401,20 @@ static void dump_nlte_problem(int NmaxIter, double iterLimit)
     rec_copy("nl_nstar", atom->nstar[0], (long) Nl*N, a,0,0,0);
     rec_copy("nl_ntotal", atom->ntotal, N, a,0,0,0);
     rec_copy("nl_C", atom->C[0], (long) Nl*Nl*N, a,0,0,0);
+    rec_copy("nl_vbroad", atom->vbroad, N, a,0,0,0);
     for (kr = 0; kr < atom->Nline; kr++) {
       AtomicLine *L = &atom->line[kr];
       int Nla = L->Nlambda;
       double *h = rec_new("nl_line", 8 + 2*Nla + N, a, kr, L->i, L->j, Nla, L->Nblue);
       h[0] = L->lambda0; h[1] = L->Aji; h[2] = L->Bji; h[3] = L->Bij; h[4] = L->isotope_frac;
       h[5] = L->symmetric; h[6] = L->PRD; h[7] = L->polarizable;
+      {   /* inputs of Profile() (profile.c:67): damping parameter, components */
+        double *ad = rec_new("nl_adamp", N, a, kr, L->Voigt, L->Ncomponent, 0, 0);
+        memset(ad, 0, N*sizeof(double));
+        if (L->Voigt) Damping(L, ad);
+        double *cc = rec_new("nl_comp", 2*L->Ncomponent, a, kr, L->Ncomponent, 0,0,0);
+        for (n = 0; n < L->Ncomponent; n++) { cc[n] = L->c_shift[n]; cc[L->Ncomponent+n] = L->c_fraction[n]; }
+      }
       for (la = 0; la < Nla; la++) { h[8+la] = L->lambda[la]; h[8+Nla+la] = getwlambda_line(L, la); }
       memcpy(h + 8 + 2*Nla, L->wphi, N*sizeof(double));
       {

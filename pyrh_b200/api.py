@@ -232,6 +232,15 @@ class Context:
                                                   reg.ctypes.data_as(_lib.ip)))
         return H, F, reg
 
+    def voigt_armstrong(self, a, v):
+        a = np.ascontiguousarray(a, np.float64)
+        v = np.ascontiguousarray(v, np.float64)
+        H = np.zeros_like(a)
+        reg = np.zeros(a.shape, np.int32)
+        _lib.check(self.lib.rhb200_voigt_armstrong(self.h, a.size, _dp(a), _dp(v), _dp(H),
+                                                   reg.ctypes.data_as(_lib.ip)))
+        return H, reg
+
     def math_probe(self, func: str, x, y=None):
         code = dict(exp=0, sin=1, cos=2, pow=3, div_recip=4, div=5)[func]
         x = np.ascontiguousarray(x, np.float64)

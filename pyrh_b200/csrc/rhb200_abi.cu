@@ -532,6 +532,23 @@ extern "C" int rhb200_voigt_humlicek(rhb200_ctx *c, int n, const double *a, cons
   return RHB200_OK;
 }
 
+extern "C" int rhb200_voigt_armstrong(rhb200_ctx *c, int n, const double *a, const double *v,
+                                      double *H, int *region)
+{
+  RH_NEED_CTX(c);
+  if (n <= 0 || !a || !v || !H) { rhb200_set_error("bad arguments"); return RHB200_EINVAL; }
+  DevBuf da, dv, dH, dR;
+  const size_t b = (size_t) n * sizeof(double);
+  RH_CHECK(da.from_host(a, b)); RH_CHECK(dv.from_host(v, b)); RH_CHECK(dH.alloc(b));
+  if (region) RH_CHECK(dR.alloc((size_t) n * sizeof(int)));
+  RH_CHECK(rh_launch_voigt_armstrong(c, n, da.as<double>(), dv.as<double>(), dH.as<double>(),
+                                     region ? dR.as<int>() : nullptr));
+  RH_CUDA(cudaStreamSynchronize(c->stream));
+  RH_CHECK(to_host(H, dH.p, b));
+  if (region) RH_CHECK(to_host(region, dR.p, (size_t) n * sizeof(int)));
+  return RHB200_OK;
+}
+
 extern "C" int rhb200_math_probe(rhb200_ctx *c, int n, int func, const double *x, const double *y, double *out)
 {
   RH_NEED_CTX(c);

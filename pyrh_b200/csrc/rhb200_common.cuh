@@ -132,6 +132,8 @@ int rh_launch_feautrier(rhb200_ctx *ctx, int nray, int ndep, double muz, int bc_
                         double *d_P, double *d_Psi, double *d_Iem, double *d_scratch);
 int rh_launch_voigt(rhb200_ctx *ctx, int n, const double *d_a, const double *d_v,
                     double *d_H, double *d_F, int *d_region);
+int rh_launch_voigt_armstrong(rhb200_ctx *ctx, int n, const double *d_a, const double *d_v,
+                              double *d_H, int *d_region);
 int rh_launch_math_probe(rhb200_ctx *ctx, int n, int func, const double *d_x, const double *d_y,
                          double *d_out);
 int rh_fp64_peak(rhb200_ctx *ctx, double *tf_fma, double *tf_nofma);

@@ -289,6 +289,15 @@ __global__ void voigt_kernel(int n, const double *__restrict__ a, const double *
   if (region) region[i] = rhv::humlicek_region(a[i], v[i]);
 }
 
+__global__ void voigt_armstrong_kernel(int n, const double *__restrict__ a, const double *__restrict__ v,
+                                       double *__restrict__ H, int *__restrict__ region)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  H[i] = rhv::voigt_armstrong(a[i], v[i]);
+  if (region) region[i] = rhv::armstrong_region(a[i], v[i]);
+}
+
 __global__ void math_probe_kernel(int n, int func, const double *__restrict__ x,
                                   const double *__restrict__ y, double *__restrict__ out)
 {
@@ -387,6 +396,18 @@ int rh_launch_voigt(rhb200_ctx *ctx, int n, const double *d_a, const double *d_v
   {
     ScopedKernelTimer t(ctx, RHB200_K_OTHER);
     voigt_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(n, d_a, d_v, d_H, d_F, d_region);
+  }
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}
+
+int rh_launch_voigt_armstrong(rhb200_ctx *ctx, int n, const double *d_a, const double *d_v,
+                              double *d_H, int *d_region)
+{
+  if (n == 0) return RHB200_OK;
+  {
+    ScopedKernelTimer t(ctx, RHB200_K_OTHER);
+    voigt_armstrong_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(n, d_a, d_v, d_H, d_region);
   }
   RH_CUDA(cudaGetLastError());
   return RHB200_OK;

@@ -30,6 +30,7 @@
 #include "rhb200_common.cuh"
 #include "rhb200_bezier.cuh"
 #include "rhb200_feautrier.cuh"
+#include "rhb200_voigt.cuh"
 
 namespace {
 
@@ -37,17 +38,19 @@ enum { TR_ATOM = RHB200_TR_ATOM, TR_TYPE = RHB200_TR_TYPE, TR_I = RHB200_TR_I, T
        TR_NBLUE = RHB200_TR_NBLUE, TR_NLAMBDA = RHB200_TR_NLAMBDA, TR_AJI = RHB200_TR_AJI,
        TR_BJI = RHB200_TR_BJI, TR_BIJ = RHB200_TR_BIJ, TR_ISOFRAC = RHB200_TR_ISOFRAC,
        TR_WOFF = RHB200_TR_WOFF, TR_PHIROW = RHB200_TR_PHIROW, TR_LINEIDX = RHB200_TR_LINEIDX,
+       TR_LAMBDA0 = RHB200_TR_LAMBDA0,
        TR_NFIELD = RHB200_TR_NFIELD };
 
 struct Plan {            // device copy of the shared problem structure
   int Nspect, Nrays, Ndep, Natom, Ntrans, nas, nray, nlev, ngam, nphirow, nline, bc_top, bc_bottom;
   const double *lambda, *muz, *wmu, *trans, *tr_lambda, *tr_wlambda, *tr_alpha;
   const int *atom_nlevel, *lev_off, *gam_off, *as_first, *as_trans, *angle_dep, *ray_off,
-            *ray_ns, *ray_mu, *ray_dir;
+            *ray_ns, *ray_mu, *ray_dir, *prow_tr, *line_tr;
 };
 
 struct Cols {            // device per-column arrays
-  const double *T, *height, *nstar, *ntotal, *C, *phi, *wphi, *chi_c, *eta_c, *sca_c;
+  const double *T, *height, *nstar, *ntotal, *C, *chi_c, *eta_c, *sca_c, *adamp, *vbroad, *vel;
+  double *phi, *wphi;
   double *n, *J, *Gamma, *Rij, *Rji, *gw, *chi, *S, *I, *Psi, *scr, *dJ;
   const int *active;
 };
@@ -84,6 +87,53 @@ nlte_setup_kernel(Plan P, Cols C, int ncol)
   }
   double *o = C.gw + (((size_t) col * P.nas + e) * 2) * N + k;
   o[0] = g; o[N] = w;
+}
+
+// ---- Profile() of un-polarised single-component lines in a moving atmosphere (profile.c:311-323):
+//      one thread per (column, profile row, depth); row = (line, la, mu, to_obs)
+__global__ void __launch_bounds__(128)
+nlte_profile_kernel(Plan P, Cols C, int ncol)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = P.Ndep;
+  if (t >= (size_t) ncol * P.nphirow * N) return;
+  const int k = (int) (t % N);
+  const size_t cr = t / N;
+  const int row = (int) (cr % P.nphirow), col = (int) (cr / P.nphirow);
+  const double *tr = P.trans + (size_t) P.prow_tr[row] * TR_NFIELD;
+  const int lamu = row - (int) tr[TR_PHIROW];
+  const int to_obs = lamu & 1, mu = (lamu >> 1) % P.Nrays, la = (lamu >> 1) / P.Nrays;
+  const int a = (int) tr[TR_ATOM], li = (int) tr[TR_LINEIDX];
+  const double lambda0 = tr[TR_LAMBDA0], lam = P.tr_lambda[(int) tr[TR_WOFF] + la];
+  const double vbroad = C.vbroad[((size_t) col * P.Natom + a) * N + k];
+  const double v = (lam - lambda0 - 0.0) * RH_CLIGHT / (vbroad * lambda0);            // profile.c:196-197
+  const double v_los = (P.muz[mu] * C.vel[(size_t) col * N + k]) / vbroad;               // :188-190
+  const double sign = to_obs ? 1.0 : -1.0;
+  const double vk = v + sign * v_los;
+  const double H = rhv::voigt_armstrong(C.adamp[((size_t) col * P.nline + li) * N + k], vk);
+  C.phi[t] = 0.0 + H * 1.0 / (RH_SQRTPI * vbroad);                                      // :317-318
+}
+
+// wphi[k] = 1 / sum_{la,mu,dir} phi wlambda 0.5 wmu, summed in the reference's order (profile.c:320,358)
+__global__ void __launch_bounds__(64)
+nlte_wphi_kernel(Plan P, Cols C, int ncol)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = P.Ndep;
+  if (t >= (size_t) ncol * P.nline * N) return;
+  const int k = (int) (t % N);
+  const size_t cl = t / N;
+  const int li = (int) (cl % P.nline), col = (int) (cl / P.nline);
+  const double *tr = P.trans + (size_t) P.line_tr[li] * TR_NFIELD;
+  const int Nla = (int) tr[TR_NLAMBDA], row0 = (int) tr[TR_PHIROW];
+  double w = 0.0;
+  for (int la = 0; la < Nla; la++)
+    for (int mu = 0; mu < P.Nrays; mu++) {
+      const double wlamu = P.tr_wlambda[(int) tr[TR_WOFF] + la] * 0.5*P.wmu[mu];
+      for (int to_obs = 0; to_obs <= 1; to_obs++)
+        w += C.phi[((size_t) col * P.nphirow + row0 + 2*(P.Nrays*la + mu) + to_obs) * N + k] * wlamu;
+    }
+  C.wphi[t] = 1.0 / w;
 }
 
 // V_ij of active-set entry e at (ray, depth): Bij hc/4pi phi for lines (opacity.c:188-193),
@@ -531,7 +581,7 @@ extern "C" int rhb200_solve_linear_eq_batch(rhb200_ctx *c, int nsys, int N, doub
 extern "C" int rhb200_nlte_iterate(rhb200_ctx *c, const rhb200_nlte_plan *pl, int ncol,
                                    const rhb200_nlte_columns *cols, int NmaxIter, double iterLimit,
                                    int *niter_out, double *dpops_hist, int dump_iter,
-                                   double *gamma_dump, double *rates_dump)
+                                   double *gamma_dump, double *rates_dump, double *phi_out, double *wphi_out)
 {
   if (!c || !pl || !cols) { rhb200_set_error("null argument"); return RHB200_EINVAL; }
   RH_CUDA(cudaSetDevice(c->device));
@@ -590,7 +640,30 @@ extern "C" int rhb200_nlte_iterate(rhb200_ctx *c, const rhb200_nlte_plan *pl, in
 #define UPC(field, src, n) RH_CHECK(ar.upload(&dd, src, (size_t) (n))); C.field = dd
   UPC(T, cols->T, cN); UPC(height, cols->height, cN);
   UPC(nstar, cols->nstar, cN*nlev); UPC(ntotal, cols->ntotal, cN*Na); UPC(C, cols->C, cN*ngam);
-  UPC(phi, cols->phi, cN*pl->nphirow); UPC(wphi, cols->wphi, cN*pl->nline);
+  const bool device_profiles = (cols->phi == nullptr);
+  if (device_profiles) {
+    if (!cols->adamp || !cols->vbroad || !cols->vel) { rhb200_set_error("phi == NULL needs adamp, vbroad and vel"); return RHB200_EINVAL; }
+    std::vector<int> prow_tr(pl->nphirow, -1), line_tr(pl->nline, -1);
+    for (int t = 0; t < Nt; t++) {
+      const double *tr = pl->trans + (size_t) t*RHB200_TR_NFIELD;
+      if (tr[RHB200_TR_TYPE] != 0.0) continue;
+      const int row0 = (int) tr[RHB200_TR_PHIROW], nrow = 2*Nr*(int) tr[RHB200_TR_NLAMBDA], li = (int) tr[RHB200_TR_LINEIDX];
+      if (row0 < 0 || row0 + nrow > pl->nphirow || li < 0 || li >= pl->nline || !(tr[RHB200_TR_LAMBDA0] > 0.0)) {
+        rhb200_set_error("transition %d: bad profile rows / line index / lambda0", t); return RHB200_EINVAL;
+      }
+      for (int r = 0; r < nrow; r++) prow_tr[row0 + r] = t;
+      line_tr[li] = t;
+    }
+    for (int v : prow_tr) if (v < 0) { rhb200_set_error("profile rows are not covered by the line transitions"); return RHB200_EINVAL; }
+    for (int v : line_tr) if (v < 0) { rhb200_set_error("line index table has holes"); return RHB200_EINVAL; }
+    UPI(prow_tr, prow_tr.data(), pl->nphirow); UPI(line_tr, line_tr.data(), pl->nline);
+    UPC(adamp, cols->adamp, cN*pl->nline); UPC(vbroad, cols->vbroad, cN*Na); UPC(vel, cols->vel, cN);
+    RH_CHECK(ar.alloc(&C.phi, cN*pl->nphirow)); RH_CHECK(ar.alloc(&C.wphi, cN*pl->nline));
+  } else {
+    if (!cols->wphi) { rhb200_set_error("wphi missing"); return RHB200_EINVAL; }
+    RH_CHECK(ar.upload(&C.phi, cols->phi, cN*pl->nphirow));
+    RH_CHECK(ar.upload(&C.wphi, cols->wphi, cN*pl->nline));
+  }
   UPC(chi_c, cols->chi_c, cN*Ns); UPC(eta_c, cols->eta_c, cN*Ns); UPC(sca_c, cols->sca_c, cN*Ns);
   RH_CHECK(ar.upload(&C.n, cols->n, cN*nlev));
   RH_CHECK(ar.upload(&C.J, cols->J, cN*Ns));
@@ -618,6 +691,21 @@ extern "C" int rhb200_nlte_iterate(rhb200_ctx *c, const rhb200_nlte_plan *pl, in
                               cudaMemcpyDeviceToDevice, c->stream));
 
   cudaStream_t st = c->stream;
+  if (device_profiles) {
+    { ScopedKernelTimer t(c, RHB200_K_PREP);
+      nlte_profile_kernel<<<RH_GRID(cN*pl->nphirow, 128), 0, st>>>(P, C, ncol); }
+    { ScopedKernelTimer t(c, RHB200_K_PREP);
+      nlte_wphi_kernel<<<RH_GRID(cN*pl->nline, 64), 0, st>>>(P, C, ncol); }
+    RH_CUDA(cudaGetLastError());
+    if (phi_out) {
+      RH_CUDA(cudaStreamSynchronize(st));
+      RH_CUDA(cudaMemcpy(phi_out, C.phi, cN*pl->nphirow*sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    if (wphi_out) {
+      RH_CUDA(cudaStreamSynchronize(st));
+      RH_CUDA(cudaMemcpy(wphi_out, C.wphi, cN*pl->nline*sizeof(double), cudaMemcpyDeviceToHost));
+    }
+  }
   { ScopedKernelTimer t(c, RHB200_K_OTHER);
     nlte_setup_kernel<<<RH_GRID(cN*nas, 128), 0, st>>>(P, C, ncol); }
   RH_CUDA(cudaGetLastError());

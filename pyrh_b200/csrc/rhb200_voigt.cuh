@@ -6,6 +6,9 @@
 // that must be bit-exact.
 #pragma once
 #include "rhb200_math.cuh"
+#ifndef RH_PI
+#define RH_PI 3.14159265358979
+#endif
 
 namespace rhv {
 
@@ -89,7 +92,87 @@ __device__ __forceinline__ double humlicek_t(double a, double v, double *F) {
   return Wr;
 }
 
-__device__ __noinline__ double humlicek(double a, double v, double *F) { return humlicek_t<true>(a, v, F); }
+static __device__ __noinline__ double humlicek(double a, double v, double *F) { return humlicek_t<true>(a, v, F); }
 __device__ __forceinline__ double humlicek_H(double a, double v) { return humlicek_t<false>(a, v, nullptr); }
+
+// ---- VoigtArmstrong (voigt.c:126-243): unpolarised Voigt function H(a, v) of Profile() for
+//      NO_STOKES active lines.  K1 (Chebyshev series + recurrence with data-dependent exit) and K3
+//      (10-point quadrature) are pure + - * / plus exp/cos, hence bit-identical to the reference;
+//      K2 (1 <= a < 2.5, v < 4) calls atan() and log(), for which the toolchain's libm is used
+//      (<= 2 ulp from glibc's): the only branch of this header that is tolerance- not bit-exact.
+__device__ __forceinline__ int armstrong_region(double a, double v) {
+  v = fabs(v);
+  if ((a < 1.0 && v < 4.0) || (a < 1.8/(v + 1.0))) return 1;
+  if (a < 2.5 && v < 4.0) return 2;
+  return 3;
+}
+
+static __device__ __noinline__ double voigt_armstrong(double a, double v) {
+  const double T[10] = {0.2453407083, 0.7374737285, 1.2340762153, 1.7385377121, 2.2549740020,
+                        2.7888060584, 3.3478545673, 3.9447640401, 4.6036824495, 5.3874808900};
+  const double W[10] = {4.6224366960e-01, 2.8667550536e-01, 1.0901720602e-01, 2.4810520887e-02,
+                        3.2437733422e-03, 2.2833863601e-04, 7.8025564785e-06, 1.0860693707e-07,
+                        4.3993409922e-10, 2.2293936455e-13};
+  if (v < 0.0) v = -v;
+  const int reg = armstrong_region(a, v);
+  if (reg == 1) {                                           // VoigtK1, voigt.c:146-211
+    const double Cc[34] = { 0.1999999999972224, -0.1840000000029998, 0.1558399999965025, -0.1216640000043988,
+      0.0877081599940391, -0.0585141248086907, 0.0362157301623914, -0.0208497654398036, 0.0111960116346270,
+      -0.56231896167109e-02, 0.26487634172265e-02, -0.11732670757704e-02, 0.4899519978088e-03, -0.1933630801528e-03,
+      0.722877446788e-04, -0.256555124979e-04, 0.86620736841e-05, -0.27876379719e-05, 0.8566873627e-06,
+      -0.2518433784e-06, 0.709360221e-07, -0.191732257e-07, 0.49801256e-08, -0.12447734e-08, 0.2997777e-09,
+      -0.696450e-10, 0.156262e-10, -0.33897e-11, 0.7116e-12, -0.1447e-12, 0.285e-13, -0.55e-14, 0.10e-14, -0.2e-15 };
+    const double a2 = a*a, v2 = v*v;
+    double u1, dn01, dn02;
+    if ((v2 - a2) > 70.0) u1 = 0.0;
+    else u1 = rhm::rh_exp(a2 - v2) * rhm::rh_cos(2.0*v*a);
+    if (v > 5.0) {
+      const double v2i = 1.0 / v2;
+      dn01 = -v2i * (0.5 + v2i*(0.75 + v2i*(1.875 + v2i*(6.5625 +
+             v2i*(29.53125 + v2i*(1162.4218 + v2i*1055.7421))))));
+      dn02 = (1.0 - dn01) / (2.0 * v);
+    } else {
+      double bn01 = 0.0, bn02 = 0.0, bn = 0.0;
+      const double v1 = v / 5.0, coef = 4.0 * v1*v1 - 2.0;
+#pragma unroll 1
+      for (int n = 33; n >= 0; n--) { bn = coef*bn01 - bn02 + Cc[n]; bn02 = bn01; bn01 = bn; }
+      dn02 = v1*(bn - bn02);
+      dn01 = 1.0 - 2.0*v*dn02;
+    }
+    double funct = a*dn01;
+    if (a > 1.0E-08) {
+      double q = 1.0, an = a;
+#pragma unroll 1
+      for (int n = 2; n <= 50; n++) {
+        const double dn = (v*dn01 + dn02) * (-2.0/n);
+        dn02 = dn01; dn01 = dn;
+        if (n % 2) {
+          q = -q; an *= a2;
+          const double g = dn * an;
+          funct += q*g;
+          if (fabs(g/funct) <= 1.0E-08) return (u1 - 1.12837917*funct);
+        }
+      }
+    }
+    return (u1 - 1.12837917*funct);
+  }
+  if (reg == 2) {                                           // VoigtK2, voigt.c:215-229
+    double g = 0.0;
+    const double a2 = a*a;
+#pragma unroll 1
+    for (int n = 0; n < 10; n++) {
+      const double r = T[n] - v, s = T[n] + v;
+      g += (4.0*T[n]*T[n] - 2.0) * (r*atan(r/a) + s*atan(s/a) -
+            0.5*a*(log(a2 + r*r) + log(a2 + s*s))) * W[n];
+    }
+    return g/RH_PI;
+  }
+  double g = 0.0;                                           // VoigtK3, voigt.c:233-243
+  const double a2 = a*a;
+#pragma unroll 1
+  for (int n = 0; n < 10; n++)
+    g += (1.0/((v - T[n])*(v - T[n]) + a2) + 1.0/((v + T[n])*(v + T[n]) + a2)) * W[n];
+  return (a*g)/RH_PI;
+}
 
 }  // namespace rhv

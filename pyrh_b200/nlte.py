@@ -16,7 +16,7 @@ from . import _lib
 
 TR_NFIELD = 16
 (TR_ATOM, TR_TYPE, TR_I, TR_J, TR_NBLUE, TR_NLAMBDA, TR_AJI, TR_BJI, TR_BIJ, TR_ISOFRAC, TR_WOFF,
- TR_PHIROW, TR_KR, TR_LINEIDX) = range(14)
+ TR_PHIROW, TR_KR, TR_LINEIDX, TR_LAMBDA0) = range(15)
 
 dp, ip = _lib.dp, _lib.ip
 
@@ -31,8 +31,8 @@ class PlanStruct(C.Structure):
 
 
 class ColumnsStruct(C.Structure):
-    _fields_ = [(n, dp) for n in ("T", "height", "nstar", "ntotal", "C", "phi", "wphi", "chi_c", "eta_c",
-                                  "sca_c", "n", "J")]
+    _fields_ = [(n, dp) for n in ("T", "height", "nstar", "ntotal", "C", "phi", "wphi", "adamp", "vbroad",
+                                  "vel", "chi_c", "eta_c", "sca_c", "n", "J")]
 
 
 @dataclass
@@ -63,6 +63,9 @@ class NlteProblem:
     sca_c: np.ndarray
     n0: np.ndarray
     J0: np.ndarray
+    adamp: np.ndarray | None = None      # [ncol, nline, Ndep]  Damping() output (host)
+    vbroad: np.ndarray | None = None     # [ncol, Natom, Ndep]
+    vel: np.ndarray | None = None        # [ncol, Ndep]
 
     @classmethod
     def from_golden(cls, g, ncol: int = 1) -> "NlteProblem":
@@ -72,8 +75,15 @@ class NlteProblem:
                    Ngorder=int(h[5]), Ngdelay=int(h[6]), Ngperiod=int(h[7]), isum=int(h[8]),
                    NmaxIter=int(h[9]), iterLimit=float(h[10]), bc_top=int(h[13]), bc_bottom=int(h[14]))
         rep = lambda x: np.ascontiguousarray(np.broadcast_to(x, (ncol,) + x.shape), np.float64)   # noqa: E731
-        return cls(hdr=hdr, lam=g["lam"], muz=g["muz"], wmu=g["wmu"], atom_nlevel=g["atom_nlevel"],
-                   trans=g["trans"], tr_lambda=g["tr_lambda"], tr_wlambda=g["tr_wlambda"],
+        trans = np.array(g["trans"], np.float64)
+        if "line_lambda0" in g:
+            lines = trans[:, TR_TYPE] == 0
+            trans[lines, TR_LAMBDA0] = g["line_lambda0"][trans[lines, TR_LINEIDX].astype(int)]
+        extra = {}
+        if "adamp" in g:
+            extra = dict(adamp=rep(g["adamp"]), vbroad=rep(g["vbroad"]), vel=rep(g["vel"]))
+        return cls(**extra, hdr=hdr, lam=g["lam"], muz=g["muz"], wmu=g["wmu"], atom_nlevel=g["atom_nlevel"],
+                   trans=trans, tr_lambda=g["tr_lambda"], tr_wlambda=g["tr_wlambda"],
                    tr_alpha=g["tr_alpha"], as_first=g["as_first"], as_trans=g["as_trans"],
                    bg_hasline=g["bgflags"][:, 0], T=rep(g["T"]), height=rep(g["height"]),
                    nstar=rep(g["nstar"]), ntotal=rep(g["ntotal"]), C=rep(g["C"]), phi=rep(g["phi"]),
@@ -82,8 +92,10 @@ class NlteProblem:
 
 
 def iterate(ctx, prob: NlteProblem, nmax: int | None = None, limit: float | None = None,
-            dump_iter: int = 0):
-    """Run the MALI iteration on the GPU.  Returns dict(n, J, niter, dpops[, gamma, rij, rji])."""
+            dump_iter: int = 0, device_profiles: bool = False):
+    """Run the MALI iteration on the GPU.  Returns dict(n, J, niter, dpops[, gamma, rij, rji]).
+    With ``device_profiles`` the line profiles are evaluated on the device from adamp/vbroad/vel
+    (``Profile()``) instead of being passed in; they are returned as ``phi``/``wphi``."""
     f64 = lambda x: np.ascontiguousarray(x, np.float64)   # noqa: E731
     i32 = lambda x: np.ascontiguousarray(x, np.int32)     # noqa: E731
     h = prob.hdr
@@ -101,9 +113,13 @@ def iterate(ctx, prob: NlteProblem, nmax: int | None = None, limit: float | None
                                                "tr_wlambda", "tr_alpha", "as_first", "as_trans", "bg_hasline")])
     ncol = prob.T.shape[0]
     n, J = f64(prob.n0).copy(), f64(prob.J0).copy()
-    cols_keep = [f64(getattr(prob, k)) for k in ("T", "height", "nstar", "ntotal", "C", "phi", "wphi",
-                                                 "chi_c", "eta_c", "sca_c")]
-    cols = ColumnsStruct(*[ptr(a) for a in cols_keep], ptr(n), ptr(J))
+    names = ("T", "height", "nstar", "ntotal", "C", "phi", "wphi", "adamp", "vbroad", "vel",
+             "chi_c", "eta_c", "sca_c")
+    skip = {"phi", "wphi"} if device_profiles else {"adamp", "vbroad", "vel"}
+    cols_keep = {k: f64(getattr(prob, k)) for k in names if k not in skip and getattr(prob, k) is not None}
+    cols = ColumnsStruct(*[ptr(cols_keep[k]) if k in cols_keep else None for k in names], ptr(n), ptr(J))
+    phi_out = np.zeros(prob.phi.shape) if device_profiles else None
+    wphi_out = np.zeros(prob.wphi.shape) if device_profiles else None
     niter = np.zeros(ncol, np.int32)
     dpops = np.zeros((ncol, max(nmax, 1)))
     ngam = int(np.sum(np.asarray(prob.atom_nlevel) ** 2))
@@ -113,8 +129,12 @@ def iterate(ctx, prob: NlteProblem, nmax: int | None = None, limit: float | None
     lib = ctx.lib
     _lib.check(lib.rhb200_nlte_iterate(ctx.h, C.byref(plan), ncol, C.byref(cols), int(nmax), float(limit),
                                        niter.ctypes.data_as(ip), ptr(dpops), int(dump_iter),
-                                       ptr(gam) if dump_iter else None, ptr(rates) if dump_iter else None))
+                                       ptr(gam) if dump_iter else None, ptr(rates) if dump_iter else None,
+                                       ptr(phi_out) if device_profiles else None,
+                                       ptr(wphi_out) if device_profiles else None))
     out = dict(n=n, J=J, niter=niter, dpops=dpops)
+    if device_profiles:
+        out.update(phi=phi_out, wphi=wphi_out)
     if dump_iter:
         out.update(gamma=gam, rij=rates[0], rji=rates[1])
     return out

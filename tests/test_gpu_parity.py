@@ -382,3 +382,31 @@ def test_shared_reciprocal_division_is_ieee(ctx):
         assert same.all(), np.flatnonzero(~same)[:5]
         ok = (ref == host) | (np.isnan(ref) & np.isnan(host))
         assert ok.all()
+
+
+def test_voigt_armstrong_vs_reference(ctx):
+    """Voigt(a, v, NULL, ARMSTRONG) recorded from the reference library itself: branch choice is
+    integer work (bit-exact); K1 and K3 are bit-exact, K2 (atan/log from the CUDA libm) within 1e-13."""
+    g = dict(np.load(GOLD / "voigt_armstrong.npz"))
+    H, reg = ctx.voigt_armstrong(g["a"], g["v"])
+    assert np.array_equal(reg, g["region"])
+    m = g["region"] != 2
+    REPORT["armstrong_K1K3_exact"] = bool(np.array_equal(H[m], g["H"][m]))
+    REPORT["armstrong_K2_maxrel"] = float(np.max(np.abs(H[~m] / g["H"][~m] - 1)))
+    assert np.array_equal(H[m], g["H"][m])
+    assert np.max(np.abs(H[~m] / g["H"][~m] - 1)) < 1e-13
+
+
+def test_nlte_profiles_on_device_vs_reference(ctx):
+    """Profile() (profile.c:67-372, field-free branch) evaluated on the device from Damping() output,
+    Doppler widths and v_los: phi and wphi equal the reference's tables bit for bit, and the MALI
+    iteration started from them reproduces the reference populations."""
+    from pyrh_b200 import nlte
+    g = dict(np.load(GOLD / "nlte_caii.npz"))
+    prob = nlte.NlteProblem.from_golden(g, ncol=2)
+    out = nlte.iterate(ctx, prob, device_profiles=True)
+    REPORT["nlte_device_phi_exact"] = bool(np.array_equal(out["phi"][0], g["phi"]))
+    assert np.array_equal(out["phi"][1], g["phi"])
+    assert np.array_equal(out["wphi"][0], g["wphi"])
+    assert out["niter"][0] == int(g["niter"])
+    assert np.array_equal(out["n"][0], g["n_final"]) and np.array_equal(out["n"][1], g["n_final"])

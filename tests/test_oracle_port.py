@@ -134,3 +134,15 @@ def test_solve_linear_eq_bit_exact():
         off += N * N + 2 * N
         x = pd.solve_linear_eq(d[:N * N].reshape(N, N), d[N * N:N * N + N])
         assert np.array_equal(x, d[N * N + N:])
+
+
+def test_voigt_armstrong_port_bit_exact():
+    import ctypes as C
+    from conftest import GOLD
+    g = dict(np.load(GOLD / "voigt_armstrong.npz"))
+    f = pd.lib().rp_voigt_armstrong
+    f.restype = C.c_double
+    f.argtypes = [C.c_double, C.c_double]
+    H = np.array([f(a, v) for a, v in zip(g["a"], g["v"])])
+    assert np.array_equal(H, g["H"])
+    assert set(np.unique(g["region"])) == {1, 2, 3}
