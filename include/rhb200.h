@@ -244,9 +244,18 @@ typedef struct {                                 /* per-column arrays, column-ma
    copied out before statEquil (test hooks, may be NULL); phi_out/wphi_out receive the device-evaluated
    profiles [ncol][nphirow][Ndep] / [ncol][nline][Ndep] when cols->phi == NULL (may be NULL). */
 int rhb200_nlte_iterate(rhb200_ctx *ctx, const rhb200_nlte_plan *plan, int ncol,
-                        const rhb200_nlte_columns *cols, int NmaxIter, double iterLimit,
+                        const rhb200_nlte_columns *cols, int NmaxScatter /* initScatter passes first, initscatter.c:62 */,
+                        int NmaxIter, double iterLimit,
                         int *niter, double *dpops_hist, int dump_iter, double *gamma_dump,
                         double *rates_dump, double *phi_out, double *wphi_out);
+/* solveSpectrum(FALSE, FALSE) (iterate.c:148-253) repeated up to npass times: the Lambda iteration of
+   initScatter() (update_J = 1; a column stops when dJmax < dJlimit, initscatter.c:62-68) or the final
+   formal solution of _solveray() (npass = 1, update_J = 0: J is used but not modified,
+   pyrh_solveray.c:84-106).  Iem [ncol][Nspect][Nrays] = spectrum.I[nspect][mu] (may be NULL);
+   cols->n is not modified, cols->J only when update_J. */
+int rhb200_nlte_formal(rhb200_ctx *ctx, const rhb200_nlte_plan *plan, int ncol,
+                       const rhb200_nlte_columns *cols, int npass, int update_J, double dJlimit,
+                       double *Iem, int *npass_done);
 /* SolveLinearEq (ludcmp.c:36-86) for nsys systems: A [nsys][N][N] (untouched), b [nsys][N] in/out; N <= 32 */
 int rhb200_solve_linear_eq_batch(rhb200_ctx *ctx, int nsys, int N, double *A, double *b, int improve);
 

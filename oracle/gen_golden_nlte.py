@@ -126,6 +126,14 @@ def main():
     lus = [(m, d) for m, d in R["lu"] if m[0] == nl][:N] + [(m, d) for m, d in R["lu"] if m[0] == 2][-6:]
     g["lu_n"] = np.array([m[0] for m, _ in lus], np.int32)
     g["lu_data"] = np.concatenate([d for _, d in lus])
+    # final single-mu pass of _solveray(): recomputed background + profiles, emergent intensities
+    Ns = len(g["lam"])
+    g["fs_bg"] = one(R, "fs_bg").reshape(3, Ns, N)
+    g["fs_bgflags"] = one(R, "fs_bgflags").reshape(Ns, 2).astype(np.int32)
+    g["fs_muz"], g["fs_wmu"] = one(R, "fs_muz"), one(R, "fs_wmu")
+    g["fs_phi"] = np.concatenate([d.reshape(-1, N) for m, d in sorted(R["fs_phi"], key=lambda x: (x[0][0], x[0][1]))])
+    g["fs_wphi"] = np.array([d for m, d in sorted(R["fs_wphi"], key=lambda x: (x[0][0], x[0][1]))])
+    g["fs_I"] = one(R, "fs_I")
     g["spec_lam"], g["spec_I"] = o["lam"], o["I"]
     g["pops_final"] = o["pops"]["CA"]["n"]
     np.savez_compressed(GOLD / "nlte_caii.npz", **g)

@@ -520,3 +520,40 @@ void __wrap_SolveLinearEq(int N, double **A, double *b, bool_t improve)
   __real_SolveLinearEq(N, A, b, improve);
   if (d) memcpy(d + (long) N*N + N, b, N*sizeof(double));
 }
+
+/* The final single-mu formal solution of _solveray() (rh/rhf1d/pyrh_solveray.c:75-106):
+   background and line profiles were recomputed for the new angle set; record them + the result */
+double __real_solveSpectrum(bool_t eval_operator, bool_t redistribute);
+double __wrap_solveSpectrum(bool_t eval_operator, bool_t redistribute)
+{
+  int rec = (probe_mask & PROBE_NLTE) && atmos.Nactiveatom > 0 && atmos.Nrays == 1 && !spectrum.updateJ;
+  int N = atmos.Nspace, Ns = spectrum.Nspect, n, a, kr;
+  if (rec) {
+    double *b = rec_new("fs_bg", (long) 3*Ns*N, 0,0,0,0,0,0);
+    double *f = rec_new("fs_bgflags", 2*Ns, 0,0,0,0,0,0);
+    for (n = 0; n < Ns; n++) {
+      memcpy(b + (long) n*N, spectrum.chi_c_lam[n], N*sizeof(double));
+      memcpy(b + (long) (Ns + n)*N, spectrum.eta_c_lam[n], N*sizeof(double));
+      memcpy(b + (long) (2*Ns + n)*N, spectrum.sca_c_lam[n], N*sizeof(double));
+      f[2*n] = atmos.backgrflags[n].hasline; f[2*n+1] = atmos.backgrflags[n].ispolarized;
+    }
+    rec_copy("fs_muz", geometry.muz, 1, 0,0,0,0);
+    rec_copy("fs_wmu", geometry.wmu, 1, 0,0,0,0);
+    for (a = 0; a < atmos.Nactiveatom; a++) {
+      Atom *atom = atmos.activeatoms[a];
+      for (kr = 0; kr < atom->Nline; kr++) {
+        AtomicLine *L = &atom->line[kr];
+        int nrow = 2*L->Nlambda;
+        double *p = rec_new("fs_phi", (long) nrow*N, a, kr, nrow, 0,0,0);
+        for (n = 0; n < nrow; n++) memcpy(p + (long) n*N, L->phi[n], N*sizeof(double));
+        rec_copy("fs_wphi", L->wphi, N, a, kr, 0,0);
+      }
+    }
+  }
+  double dJ = __real_solveSpectrum(eval_operator, redistribute);
+  if (rec) {
+    double *I = rec_new("fs_I", Ns, 0,0,0,0,0,0);
+    for (n = 0; n < Ns; n++) I[n] = spectrum.I[n][0];
+  }
+  return dJ;
+}

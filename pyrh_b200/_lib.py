@@ -42,7 +42,8 @@ SYMBOLS = [
     ("rhb200_voigt_humlicek", C.c_int, [vp, C.c_int, dp, dp, dp, dp, ip]),
     ("rhb200_voigt_armstrong", C.c_int, [vp, C.c_int, dp, dp, dp, ip]),
     ("rhb200_math_probe", C.c_int, [vp, C.c_int, C.c_int, dp, dp, dp]),
-    ("rhb200_nlte_iterate", C.c_int, [vp, vp, C.c_int, vp, C.c_int, C.c_double, ip, dp, C.c_int, dp, dp, dp, dp]),
+    ("rhb200_nlte_iterate", C.c_int, [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_double, ip, dp, C.c_int, dp, dp, dp, dp]),
+    ("rhb200_nlte_formal", C.c_int, [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_double, dp, ip]),
     ("rhb200_solve_linear_eq_batch", C.c_int, [vp, C.c_int, C.c_int, dp, dp, C.c_int]),
     ("rhb200_dev_alloc", C.c_int, [vp, C.c_size_t, C.POINTER(vp)]),
     ("rhb200_dev_free", C.c_int, [vp, vp]),

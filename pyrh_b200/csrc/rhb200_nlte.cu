@@ -51,7 +51,7 @@ struct Plan {            // device copy of the shared problem structure
 struct Cols {            // device per-column arrays
   const double *T, *height, *nstar, *ntotal, *C, *chi_c, *eta_c, *sca_c, *adamp, *vbroad, *vel;
   double *phi, *wphi;
-  double *n, *J, *Gamma, *Rij, *Rji, *gw, *chi, *S, *I, *Psi, *scr, *dJ;
+  double *n, *J, *Gamma, *Rij, *Rji, *gw, *chi, *S, *I, *Psi, *scr, *dJ, *Iem;
   const int *active;
 };
 
@@ -230,9 +230,10 @@ nlte_ray_kernel(Plan P, Cols C, int ncol, int eval_operator)
   if (P.angle_dep[ns]) {
     rhz::bezier3_ray(N, h, P.muz[mu], dir, P.bc_top, P.bc_bottom, T, P.lambda[ns], C.chi + cr * N,
                      C.S + cr * N, C.I + cr * N, Psi);
+    C.Iem[cr] = C.I[cr * N];                         // spectrum.I[nspect][mu] = I[0] (formal.c:270)
   } else {
     NlteFeauIO io{C.chi + cr * N, C.S + cr * N, h, C.I + cr * N, Psi, C.scr + cr * 2 * N, N};
-    rhf::feautrier_ray(io, N, P.muz[mu], P.bc_top, P.bc_bottom, T, P.lambda[ns]);
+    C.Iem[cr] = rhf::feautrier_ray(io, N, P.muz[mu], P.bc_top, P.bc_bottom, T, P.lambda[ns]);   // formal.c:299
   }
 }
 
@@ -256,6 +257,25 @@ nlte_J_kernel(Plan P, Cols C, int ncol)
   const double Jdag = C.J[t];
   C.J[t] = J;
   C.dJ[t] = fabs(1.0 - Jdag / J);
+}
+
+// dJmax per column (solveSpectrum's return value, iterate.c:236-244): max is order independent
+__global__ void __launch_bounds__(256)
+nlte_dJmax_kernel(Plan P, Cols C, int ncol, double *dJmax)
+{
+  const int col = blockIdx.x;
+  if (col >= ncol || !C.active[col]) return;
+  __shared__ double sm[256];
+  const size_t per = (size_t) P.Nspect * P.Ndep;
+  double m = 0.0;
+  for (size_t i = threadIdx.x; i < per; i += blockDim.x) {
+    const double d = C.dJ[(size_t) col * per + i];
+    if (d > m) m = d;                                 // NaN (J = 0 and Jdag = 0) never wins, like the reference's MAX
+  }
+  sm[threadIdx.x] = m;
+  __syncthreads();
+  for (int s2 = 128; s2 > 0; s2 >>= 1) { if (threadIdx.x < s2) sm[threadIdx.x] = fmax(sm[threadIdx.x], sm[threadIdx.x + s2]); __syncthreads(); }
+  if (threadIdx.x == 0) dJmax[col] = sm[0];
 }
 
 // ---- (4) addtoCoupling + addtoGamma + addtoRates for one transition at one depth
@@ -578,10 +598,11 @@ extern "C" int rhb200_solve_linear_eq_batch(rhb200_ctx *c, int nsys, int N, doub
   return RHB200_OK;
 }
 
-extern "C" int rhb200_nlte_iterate(rhb200_ctx *c, const rhb200_nlte_plan *pl, int ncol,
-                                   const rhb200_nlte_columns *cols, int NmaxIter, double iterLimit,
-                                   int *niter_out, double *dpops_hist, int dump_iter,
-                                   double *gamma_dump, double *rates_dump, double *phi_out, double *wphi_out)
+static int nlte_run(rhb200_ctx *c, const rhb200_nlte_plan *pl, int ncol,
+                    const rhb200_nlte_columns *cols, int NmaxScatter, int update_J, int NmaxIter, double iterLimit,
+                    int *niter_out, double *dpops_hist, int dump_iter,
+                    double *gamma_dump, double *rates_dump, double *phi_out, double *wphi_out,
+                    double *Iem_out, int *nscatter_out)
 {
   if (!c || !pl || !cols) { rhb200_set_error("null argument"); return RHB200_EINVAL; }
   RH_CUDA(cudaSetDevice(c->device));
@@ -670,7 +691,8 @@ extern "C" int rhb200_nlte_iterate(rhb200_ctx *c, const rhb200_nlte_plan *pl, in
   RH_CHECK(ar.alloc(&C.Gamma, cN*ngam)); RH_CHECK(ar.alloc(&C.Rij, cN*Nt, true)); RH_CHECK(ar.alloc(&C.Rji, cN*Nt, true));
   RH_CHECK(ar.alloc(&C.gw, cN*nas*2));
   RH_CHECK(ar.alloc(&C.chi, cN*nray)); RH_CHECK(ar.alloc(&C.S, cN*nray)); RH_CHECK(ar.alloc(&C.I, cN*nray));
-  RH_CHECK(ar.alloc(&C.Psi, cN*nray)); RH_CHECK(ar.alloc(&C.scr, cN*nray*2)); RH_CHECK(ar.alloc(&C.dJ, cN*Ns));
+  RH_CHECK(ar.alloc(&C.Psi, cN*nray)); RH_CHECK(ar.alloc(&C.scr, cN*nray*2)); RH_CHECK(ar.alloc(&C.dJ, cN*Ns, true));
+  RH_CHECK(ar.alloc(&C.Iem, (size_t) ncol*nray, true));
   int *d_active;
   std::vector<int> active(ncol, 1);
   RH_CHECK(ar.upload(&d_active, active.data(), ncol));
@@ -709,6 +731,50 @@ extern "C" int rhb200_nlte_iterate(rhb200_ctx *c, const rhb200_nlte_plan *pl, in
   { ScopedKernelTimer t(c, RHB200_K_OTHER);
     nlte_setup_kernel<<<RH_GRID(cN*nas, 128), 0, st>>>(P, C, ncol); }
   RH_CUDA(cudaGetLastError());
+
+  // ---- initScatter (initscatter.c:62-68) / final formal pass: solveSpectrum(FALSE, FALSE) repeated
+  std::vector<int> nscat(ncol, 0);
+  if (NmaxScatter > 0) {
+    double *d_dJmax;
+    RH_CHECK(ar.alloc(&d_dJmax, ncol, true));
+    std::vector<double> h_dJ(ncol, 0.0);
+    std::vector<int> act(ncol, 1);
+    int nact_s = ncol;
+    for (int it = 0; it < NmaxScatter && nact_s > 0; it++) {
+      { ScopedKernelTimer t(c, RHB200_K_OPACITY);
+        nlte_opacity_kernel<<<RH_GRID(cN*nray, 128), 0, st>>>(P, C, ncol); }
+      { ScopedKernelTimer t(c, RHB200_K_BEZIER);
+        nlte_ray_kernel<<<RH_GRID((size_t) ncol*nray, 128), 0, st>>>(P, C, ncol, 0); }
+      if (update_J) {
+        { ScopedKernelTimer t(c, RHB200_K_OTHER);
+          nlte_J_kernel<<<RH_GRID(cN*Ns, 128), 0, st>>>(P, C, ncol); }
+        nlte_dJmax_kernel<<<ncol, 256, 0, st>>>(P, C, ncol, d_dJmax);
+        RH_CUDA(cudaGetLastError());
+        RH_CUDA(cudaMemcpyAsync(h_dJ.data(), d_dJmax, ncol*sizeof(double), cudaMemcpyDeviceToHost, st));
+        RH_CUDA(cudaStreamSynchronize(st));
+      }
+      bool changed = false;
+      for (int col = 0; col < ncol; col++) {
+        if (!act[col]) continue;
+        nscat[col] = it + 1;
+        if (!update_J || h_dJ[col] < iterLimit) { act[col] = 0; nact_s--; changed = true; }    // initscatter.c:65
+      }
+      if (changed && nact_s > 0) RH_CUDA(cudaMemcpyAsync(d_active, act.data(), ncol*sizeof(int), cudaMemcpyHostToDevice, st));
+    }
+    RH_CUDA(cudaStreamSynchronize(st));
+    RH_CUDA(cudaMemcpyAsync(d_active, active.data(), ncol*sizeof(int), cudaMemcpyHostToDevice, st));   // all columns active again
+    if (Iem_out) {
+      // emergent intensity per (column, wavelength, mu): the up-ray of angle-dependent wavelengths
+      std::vector<double> h_Iem((size_t) ncol*nray);
+      RH_CUDA(cudaStreamSynchronize(st));
+      RH_CUDA(cudaMemcpy(h_Iem.data(), C.Iem, h_Iem.size()*sizeof(double), cudaMemcpyDeviceToHost));
+      for (int col = 0; col < ncol; col++)
+        for (int r = 0; r < nray; r++)
+          if (!angle_dep[ray_ns[r]] || ray_dir[r] == 1)
+            Iem_out[((size_t) col*Ns + ray_ns[r])*Nr + ray_mu[r]] = h_Iem[(size_t) col*nray + r];
+    }
+  }
+  if (nscatter_out) memcpy(nscatter_out, nscat.data(), ncol*sizeof(int));
 
   std::vector<double> h_dpops((size_t) ncol * Na);
   std::vector<int> niter(ncol, 0);
@@ -757,4 +823,22 @@ extern "C" int rhb200_nlte_iterate(rhb200_ctx *c, const rhb200_nlte_plan *pl, in
   RH_CUDA(cudaMemcpy(cols->J, C.J, cN*Ns*sizeof(double), cudaMemcpyDeviceToHost));
   if (niter_out) memcpy(niter_out, niter.data(), ncol*sizeof(int));
   return RHB200_OK;
+}
+
+extern "C" int rhb200_nlte_iterate(rhb200_ctx *c, const rhb200_nlte_plan *pl, int ncol,
+                                   const rhb200_nlte_columns *cols, int NmaxScatter, int NmaxIter, double iterLimit,
+                                   int *niter_out, double *dpops_hist, int dump_iter,
+                                   double *gamma_dump, double *rates_dump, double *phi_out, double *wphi_out)
+{
+  return nlte_run(c, pl, ncol, cols, NmaxScatter, 1, NmaxIter, iterLimit, niter_out, dpops_hist, dump_iter,
+                  gamma_dump, rates_dump, phi_out, wphi_out, nullptr, nullptr);
+}
+
+extern "C" int rhb200_nlte_formal(rhb200_ctx *c, const rhb200_nlte_plan *pl, int ncol,
+                                  const rhb200_nlte_columns *cols, int npass, int update_J, double dJlimit,
+                                  double *Iem, int *npass_done)
+{
+  if (npass < 1) { rhb200_set_error("npass must be >= 1"); return RHB200_EINVAL; }
+  return nlte_run(c, pl, ncol, cols, npass, update_J, 0, dJlimit, nullptr, nullptr, 0, nullptr, nullptr,
+                  nullptr, nullptr, Iem, npass_done);
 }

@@ -91,8 +91,66 @@ class NlteProblem:
                    n0=rep(g["n0"]), J0=rep(g["J0"]))
 
 
+def _structs(prob: NlteProblem, device_profiles: bool):
+    f64 = lambda x: np.ascontiguousarray(x, np.float64)   # noqa: E731
+    i32 = lambda x: np.ascontiguousarray(x, np.int32)     # noqa: E731
+    h = prob.hdr
+    keep = dict(lam=f64(prob.lam), muz=f64(prob.muz), wmu=f64(prob.wmu), atom_nlevel=i32(prob.atom_nlevel),
+                trans=f64(prob.trans), tr_lambda=f64(prob.tr_lambda), tr_wlambda=f64(prob.tr_wlambda),
+                tr_alpha=f64(prob.tr_alpha), as_first=i32(prob.as_first), as_trans=i32(prob.as_trans),
+                bg_hasline=i32(prob.bg_hasline))
+    ptr = lambda a: a.ctypes.data_as(ip if a.dtype == np.int32 else dp)   # noqa: E731
+    plan = PlanStruct(h["Nspect"], len(keep["muz"]), h["Ndep"], h["Natom"], keep["trans"].shape[0], h["moving"],
+                      h["Ngorder"], h["Ngdelay"], h["Ngperiod"], h["isum"], h["bc_top"], h["bc_bottom"],
+                      len(keep["tr_lambda"]), prob.phi.shape[1], prob.wphi.shape[1],
+                      *[ptr(keep[k]) for k in ("lam", "muz", "wmu", "atom_nlevel", "trans", "tr_lambda",
+                                               "tr_wlambda", "tr_alpha", "as_first", "as_trans", "bg_hasline")])
+    n, J = f64(prob.n0).copy(), f64(prob.J0).copy()
+    names = ("T", "height", "nstar", "ntotal", "C", "phi", "wphi", "adamp", "vbroad", "vel",
+             "chi_c", "eta_c", "sca_c")
+    skip = {"phi", "wphi"} if device_profiles else {"adamp", "vbroad", "vel"}
+    cols_keep = {k: f64(getattr(prob, k)) for k in names if k not in skip and getattr(prob, k) is not None}
+    cols = ColumnsStruct(*[ptr(cols_keep[k]) if k in cols_keep else None for k in names], ptr(n), ptr(J))
+    return plan, cols, n, J, (keep, cols_keep), ptr
+
+
+def formal(ctx, prob: NlteProblem, npass: int = 1, update_J: bool = False, limit: float = 0.0,
+           device_profiles: bool = False):
+    """``solveSpectrum(FALSE, FALSE)`` repeated: initScatter (update_J) or the final pass of _solveray.
+    Returns dict(J, Iem [ncol, Nspect, Nrays], npass)."""
+    plan, cols, n, J, keep, ptr = _structs(prob, device_profiles)
+    ncol = prob.T.shape[0]
+    Iem = np.zeros((ncol, prob.hdr["Nspect"], len(prob.muz)))
+    done = np.zeros(ncol, np.int32)
+    _lib.check(ctx.lib.rhb200_nlte_formal(ctx.h, C.byref(plan), ncol, C.byref(cols), int(npass), int(update_J),
+                                          float(limit), ptr(Iem), done.ctypes.data_as(ip)))
+    return dict(J=J, Iem=Iem, npass=done)
+
+
+def single_mu_problem(g, mu: float | None = None, ncol: int = 1) -> NlteProblem:
+    """The problem _solveray() solves after convergence (pyrh_solveray.c:75-106): one angle,
+    profiles and background recomputed for it (fixture keys fs_*), converged n and J."""
+    prob = NlteProblem.from_golden(g, ncol=ncol)
+    rep = lambda x: np.ascontiguousarray(np.broadcast_to(x, (ncol,) + x.shape), np.float64)   # noqa: E731
+    prob.muz = np.array(g["fs_muz"] if mu is None else [mu], np.float64)
+    prob.wmu = np.array(g["fs_wmu"], np.float64)
+    prob.hdr = dict(prob.hdr, Nrays=1)
+    tr = prob.trans.copy()
+    row = 0
+    for t in tr:
+        if t[TR_TYPE] == 0:
+            t[TR_PHIROW] = row
+            row += 2 * int(t[TR_NLAMBDA])
+    prob.trans = tr
+    prob.phi, prob.wphi = rep(g["fs_phi"]), rep(g["fs_wphi"])
+    prob.chi_c, prob.eta_c, prob.sca_c = rep(g["fs_bg"][0]), rep(g["fs_bg"][1]), rep(g["fs_bg"][2])
+    prob.bg_hasline = g["fs_bgflags"][:, 0]
+    prob.n0, prob.J0 = rep(g["n_final"]), rep(g["J_final"])
+    return prob
+
+
 def iterate(ctx, prob: NlteProblem, nmax: int | None = None, limit: float | None = None,
-            dump_iter: int = 0, device_profiles: bool = False):
+            dump_iter: int = 0, device_profiles: bool = False, nscatter: int = 0):
     """Run the MALI iteration on the GPU.  Returns dict(n, J, niter, dpops[, gamma, rij, rji]).
     With ``device_profiles`` the line profiles are evaluated on the device from adamp/vbroad/vel
     (``Profile()``) instead of being passed in; they are returned as ``phi``/``wphi``."""
@@ -127,7 +185,7 @@ def iterate(ctx, prob: NlteProblem, nmax: int | None = None, limit: float | None
     gam = np.zeros((ncol, ngam, h["Ndep"])) if dump_iter else None
     rates = np.zeros((2, ncol, ntr, h["Ndep"])) if dump_iter else None
     lib = ctx.lib
-    _lib.check(lib.rhb200_nlte_iterate(ctx.h, C.byref(plan), ncol, C.byref(cols), int(nmax), float(limit),
+    _lib.check(lib.rhb200_nlte_iterate(ctx.h, C.byref(plan), ncol, C.byref(cols), int(nscatter), int(nmax), float(limit),
                                        niter.ctypes.data_as(ip), ptr(dpops), int(dump_iter),
                                        ptr(gam) if dump_iter else None, ptr(rates) if dump_iter else None,
                                        ptr(phi_out) if device_profiles else None,

@@ -410,3 +410,31 @@ def test_nlte_profiles_on_device_vs_reference(ctx):
     assert np.array_equal(out["wphi"][0], g["wphi"])
     assert out["niter"][0] == int(g["niter"])
     assert np.array_equal(out["n"][0], g["n_final"]) and np.array_equal(out["n"][1], g["n_final"])
+
+
+def test_nlte_initscatter_and_final_pass_vs_reference(ctx):
+    """(1) initScatter: from J = 0 (calloc'd by initSolution) two Lambda iterations of
+    solveSpectrum(FALSE,FALSE) must give the J the reference enters Iterate() with.
+    (2) the final single-mu pass of _solveray() with converged n, J and the recomputed
+    profiles/background gives the emergent spectrum rhf1d() returns."""
+    from pyrh_b200 import nlte
+    g = dict(np.load(GOLD / "nlte_caii.npz"))
+    prob = nlte.NlteProblem.from_golden(g, ncol=1)
+    prob.J0 = np.zeros_like(prob.J0)
+    out = nlte.formal(ctx, prob, npass=int(g["hdr"][11]), update_J=True, limit=float(g["hdr"][10]))
+    REPORT["nlte_initscatter_J_exact"] = bool(np.array_equal(out["J"][0], g["J0"]))
+    assert np.array_equal(out["J"][0], g["J0"])
+    # initScatter + Iterate in one call
+    full = nlte.iterate(ctx, prob, nscatter=int(g["hdr"][11]))
+    assert np.array_equal(full["n"][0], g["n_final"])
+    fin = nlte.single_mu_problem(g)
+    res = nlte.formal(ctx, fin, npass=1, update_J=False)
+    REPORT["nlte_final_spectrum_exact"] = bool(np.array_equal(res["Iem"][0, :, 0], g["fs_I"]))
+    assert np.max(np.abs(res["Iem"][0, :, 0] / g["fs_I"] - 1)) < 1e-9
+    assert np.array_equal(res["Iem"][0, :, 0], g["fs_I"])
+    keep = g["lam"] != 500.0
+    assert np.array_equal(res["Iem"][0, keep, 0], g["spec_I"])           # what rhf1d() hands back
+    assert np.array_equal(res["J"][0], g["J_final"])                      # update_J = FALSE leaves J alone
+    # same pass with the profiles evaluated on the device for the new angle
+    res2 = nlte.formal(ctx, fin, npass=1, update_J=False, device_profiles=True)
+    assert np.array_equal(res2["Iem"], res["Iem"])
