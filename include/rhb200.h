@@ -249,7 +249,9 @@ int rhb200_nlte_iterate(rhb200_ctx *ctx, const rhb200_nlte_plan *plan, int ncol,
                         int *niter, double *dpops_hist, int dump_iter, double *gamma_dump,
                         double *rates_dump, double *phi_out, double *wphi_out);
 /* solveSpectrum(FALSE, FALSE) (iterate.c:148-253) repeated up to npass times: the Lambda iteration of
-   initScatter() (update_J = 1; a column stops when dJmax < dJlimit, initscatter.c:62-68) or the final
+   initScatter() (update_J = 1; a column stops when dJmax < dJlimit, initscatter.c:62-68), the extra
+   scattering passes rhf1d() runs after Iterate() (update_J = 2: stops on dJmax <= dJlimit,
+   pyrh_compute1dray.c:333-337) or the final
    formal solution of _solveray() (npass = 1, update_J = 0: J is used but not modified,
    pyrh_solveray.c:84-106).  Iem [ncol][Nspect][Nrays] = spectrum.I[nspect][mu] (may be NULL);
    cols->n is not modified, cols->J only when update_J. */

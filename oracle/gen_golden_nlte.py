@@ -134,6 +134,9 @@ def main():
     g["fs_phi"] = np.concatenate([d.reshape(-1, N) for m, d in sorted(R["fs_phi"], key=lambda x: (x[0][0], x[0][1]))])
     g["fs_wphi"] = np.array([d for m, d in sorted(R["fs_wphi"], key=lambda x: (x[0][0], x[0][1]))])
     g["fs_I"] = one(R, "fs_I")
+    g["fs_adamp"] = np.array([d for m, d in sorted(R["fs_adamp"], key=lambda x: (x[0][0], x[0][1]))])
+    g["fs_vbroad"] = np.array([d for m, d in sorted(R["fs_vbroad"], key=lambda x: x[0][0])])
+    g["fs_vel"] = one(R, "fs_vel")
     g["spec_lam"], g["spec_I"] = o["lam"], o["I"]
     g["pops_final"] = o["pops"]["CA"]["n"]
     np.savez_compressed(GOLD / "nlte_caii.npz", **g)

@@ -192,6 +192,8 @@ typedef struct {
   const double *nstar, *ntotal, *C, *phi, *wphi, *chi_c, *eta_c, *sca_c;
   double *n, *J;            /* state, in/out */
   double *Gamma, *Rij, *Rji;  /* [sum Nl^2][Ndep], [Ntrans][Ndep] work/output */
+  int updateJ;                /* spectrum.updateJ */
+  double *Iem;                /* [Nspect][Nrays] spectrum.I[nspect][mu] */
 } rp_nlte;
 
 #define MAXACT 64
@@ -222,7 +224,7 @@ static double formal_lambda(const rp_nlte *P, int ns, int eval_operator,
     if (P->trans[(size_t) P->as_trans[first+n]*TR_NFIELD + TR_TYPE] == 0) boundbound = 1;
   const int angle_dep = P->moving && (boundbound || P->bg_hasline[ns]);
   memcpy(Jdag, J, N*sizeof(double));
-  for (k = 0; k < N; k++) J[k] = 0.0;
+  if (P->updateJ) for (k = 0; k < N; k++) J[k] = 0.0;
 
   for (mu = 0; mu < Nrays; mu++) {
     for (to_obs = 0; to_obs <= (angle_dep ? 1 : 0); to_obs++) {
@@ -305,12 +307,15 @@ static double formal_lambda(const rp_nlte *P, int ns, int eval_operator,
         chi[k] = as_chi[k] + chi_c[k];
         S[k] = (as_eta[k] + eta_c[k] + sca_c[k]*Jdag[k]) / chi[k];
       }
-      if (angle_dep)
+      if (angle_dep) {
         rp_bezier3_scalar(N, P->height, P->muz[mu], to_obs, chi, S, P->T, P->lambda[ns], P->bc_top, P->bc_bottom,
                           I, eval_operator ? Psi : NULL);
-      else
-        rp_feautrier(N, P->height, P->muz[mu], chi, S, P->T, P->lambda[ns], P->bc_top, P->bc_bottom,
-                     I, eval_operator ? Psi : NULL);
+        if (P->Iem) P->Iem[(size_t) ns*Nrays + mu] = I[0];            /* formal.c:270 (last ray = up-ray) */
+      } else {
+        double Iplus = rp_feautrier(N, P->height, P->muz[mu], chi, S, P->T, P->lambda[ns], P->bc_top, P->bc_bottom,
+                                    I, eval_operator ? Psi : NULL);
+        if (P->Iem) P->Iem[(size_t) ns*Nrays + mu] = Iplus;           /* formal.c:299 */
+      }
       if (eval_operator) {                                            /* addtoGamma, fillgamma.c:82-246 */
         for (k = 0; k < N; k++) Psi[k] /= chi[k];
         for (n = 0; n < nact; n++) {
@@ -336,6 +341,7 @@ static double formal_lambda(const rp_nlte *P, int ns, int eval_operator,
           }
         }
       }
+      if (!P->updateJ) continue;
       for (k = 0; k < N; k++) J[k] += wmu * I[k];                     /* formal.c:254-256 / :306 */
       for (n = 0; n < nact; n++) {                                    /* addtoRates, fillgamma.c:375-461 */
         const int t = P->as_trans[first+n];
@@ -349,7 +355,8 @@ static double formal_lambda(const rp_nlte *P, int ns, int eval_operator,
       }
     }
   }
-  for (k = 0; k < N; k++) { double dJ = fabs(1.0 - Jdag[k]/J[k]); if (dJ > dJmax) dJmax = dJ; }
+  if (P->updateJ)
+    for (k = 0; k < N; k++) { double dJ = fabs(1.0 - Jdag[k]/J[k]); if (dJ > dJmax) dJmax = dJ; }
   free(Vij); free(gij); free(wla); free(as_chi); free(as_eta); free(eta_atom); free(chi_up); free(chi_down);
   free(Uji_down); free(chi); free(S); free(I); free(Psi); free(Jdag); free(Ieff);
   return dJmax;

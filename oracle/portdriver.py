@@ -182,7 +182,7 @@ class RpNlte(C.Structure):
                 [(n, dp) for n in ("trans", "tr_lambda", "tr_wlambda", "tr_alpha")] +
                 [(n, ip) for n in ("as_first", "as_trans", "bg_hasline")] +
                 [(n, dp) for n in ("nstar", "ntotal", "C", "phi", "wphi", "chi_c", "eta_c", "sca_c",
-                                   "n", "J", "Gamma", "Rij", "Rji")])
+                                   "n", "J", "Gamma", "Rij", "Rji")] + [("updateJ", C.c_int), ("Iem", dp)])
 
 
 class PortNlte:
@@ -203,15 +203,24 @@ class PortNlte:
         ntr = a["trans"].shape[0]
         a["Gamma"] = np.zeros_like(a["C"])
         a["Rij"], a["Rji"] = np.zeros((ntr, N)), np.zeros((ntr, N))
+        a["Iem"] = np.zeros((int(hdr[0]), len(a["muz"])))
         self.a = a
         ptr = lambda k: a[k].ctypes.data_as(ip if a[k].dtype == np.int32 else dp)   # noqa: E731
-        self.c = RpNlte(int(hdr[0]), int(hdr[1]), N, int(hdr[2]), ntr, int(hdr[4]), int(hdr[5]), int(hdr[6]),
+        self.c = RpNlte(int(hdr[0]), len(a["muz"]), N, int(hdr[2]), ntr, int(hdr[4]), int(hdr[5]), int(hdr[6]),
                         int(hdr[7]), int(hdr[8]), int(hdr[13]), int(hdr[14]),
                         *[ptr(k) for k in ("lam", "muz", "wmu", "T", "height", "atom_nlevel", "trans", "tr_lambda",
                                            "tr_wlambda", "tr_alpha", "as_first", "as_trans", "bg_hasline", "nstar",
                                            "ntotal", "C", "phi", "wphi", "chi_c", "eta_c", "sca_c", "n", "J",
-                                           "Gamma", "Rij", "Rji")])
+                                           "Gamma", "Rij", "Rji")], 1, ptr("Iem"))
         self.N, self.ntr = N, ntr
+
+    def solve_spectrum(self, eval_operator=False, updateJ=True):
+        f = lib().rp_nlte_solve_spectrum
+        f.restype = C.c_double
+        self.c.updateJ = int(updateJ)
+        d = f(C.byref(self.c), int(eval_operator))
+        self.c.updateJ = 1
+        return d
 
     def iterate(self, nmax, limit):
         a = self.a
@@ -238,3 +247,17 @@ def stat_equil(Gamma, ntotal, n, isum=-1):
     ntotal = np.ascontiguousarray(ntotal, np.float64)
     lib().rp_stat_equil(n.shape[0], n.shape[1], _d(Gamma), _d(ntotal), int(isum), _d(n))
     return n
+
+
+def profile_line(lambda0, lam, wlam, adamp, vbroad, vel, muz, wmu):
+    """Profile() (profile.c:67-372) of one un-polarised single-component line: phi [2*Nrays*Nla][N], wphi [N]."""
+    L = lib()
+    dp = C.POINTER(C.c_double)
+    L.rp_profile_line.restype = None
+    L.rp_profile_line.argtypes = [C.c_int] * 3 + [C.c_double] + [dp] * 9
+    arrs = [np.ascontiguousarray(x, np.float64) for x in (lam, wlam, adamp, vbroad, vel, muz, wmu)]
+    N, Nrays, Nla = len(arrs[2]), len(arrs[5]), len(arrs[0])
+    phi, wphi = np.zeros((2 * Nrays * Nla, N)), np.zeros(N)
+    L.rp_profile_line(N, Nrays, Nla, float(lambda0), *[_d(a) for a in arrs], _d(phi), _d(wphi))
+    return phi, wphi
+

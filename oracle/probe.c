@@ -547,8 +547,15 @@ double __wrap_solveSpectrum(bool_t eval_operator, bool_t redistribute)
         double *p = rec_new("fs_phi", (long) nrow*N, a, kr, nrow, 0,0,0);
         for (n = 0; n < nrow; n++) memcpy(p + (long) n*N, L->phi[n], N*sizeof(double));
         rec_copy("fs_wphi", L->wphi, N, a, kr, 0,0);
+        {   /* Profile() inputs as they stand at this (second) getProfiles call */
+          double *ad = rec_new("fs_adamp", N, a, kr, L->Voigt, 0,0,0);
+          memset(ad, 0, N*sizeof(double));
+          if (L->Voigt) Damping(L, ad);
+        }
       }
+      rec_copy("fs_vbroad", atom->vbroad, N, a,0,0,0);
     }
+    rec_copy("fs_vel", geometry.vel, N, 0,0,0,0);
   }
   double dJ = __real_solveSpectrum(eval_operator, redistribute);
   if (rec) {

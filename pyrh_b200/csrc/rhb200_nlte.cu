@@ -757,7 +757,8 @@ static int nlte_run(rhb200_ctx *c, const rhb200_nlte_plan *pl, int ncol,
       for (int col = 0; col < ncol; col++) {
         if (!act[col]) continue;
         nscat[col] = it + 1;
-        if (!update_J || h_dJ[col] < iterLimit) { act[col] = 0; nact_s--; changed = true; }    // initscatter.c:65
+        // initscatter.c:65 stops on dJmax < limit; the post-Iterate loop of rhf1d() on <= (pyrh_compute1dray.c:335)
+        if (!update_J || (update_J == 2 ? h_dJ[col] <= iterLimit : h_dJ[col] < iterLimit)) { act[col] = 0; nact_s--; changed = true; }
       }
       if (changed && nact_s > 0) RH_CUDA(cudaMemcpyAsync(d_active, act.data(), ncol*sizeof(int), cudaMemcpyHostToDevice, st));
     }

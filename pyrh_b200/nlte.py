@@ -114,7 +114,7 @@ def _structs(prob: NlteProblem, device_profiles: bool):
     return plan, cols, n, J, (keep, cols_keep), ptr
 
 
-def formal(ctx, prob: NlteProblem, npass: int = 1, update_J: bool = False, limit: float = 0.0,
+def formal(ctx, prob: NlteProblem, npass: int = 1, update_J: int = 0, limit: float = 0.0,
            device_profiles: bool = False):
     """``solveSpectrum(FALSE, FALSE)`` repeated: initScatter (update_J) or the final pass of _solveray.
     Returns dict(J, Iem [ncol, Nspect, Nrays], npass)."""
@@ -143,6 +143,8 @@ def single_mu_problem(g, mu: float | None = None, ncol: int = 1) -> NlteProblem:
             row += 2 * int(t[TR_NLAMBDA])
     prob.trans = tr
     prob.phi, prob.wphi = rep(g["fs_phi"]), rep(g["fs_wphi"])
+    if "fs_adamp" in g:       # Damping() re-evaluated after the second Background(): differs by 1 ulp
+        prob.adamp = rep(g["fs_adamp"])
     prob.chi_c, prob.eta_c, prob.sca_c = rep(g["fs_bg"][0]), rep(g["fs_bg"][1]), rep(g["fs_bg"][2])
     prob.bg_hasline = g["fs_bgflags"][:, 0]
     prob.n0, prob.J0 = rep(g["n_final"]), rep(g["J_final"])

@@ -146,3 +146,25 @@ def test_voigt_armstrong_port_bit_exact():
     H = np.array([f(a, v) for a, v in zip(g["a"], g["v"])])
     assert np.array_equal(H, g["H"])
     assert set(np.unique(g["region"])) == {1, 2, 3}
+
+
+def test_profile_port_bit_exact_both_angle_sets():
+    """Profile() (profile.c:67) for the 3-ray MALI angle set and for the single-mu set _solveray()
+    re-evaluates it on (pyrh_solveray.c:75-106; Damping() there is 1 ulp off the first call's)."""
+    from conftest import GOLD
+    g = dict(np.load(GOLD / "nlte_caii.npz"))
+    for adamp, muz, wmu, phis, wphis in ((g["adamp"], g["muz"], g["wmu"], g["phi"], g["wphi"]),
+                                         (g["fs_adamp"], g["fs_muz"], g["fs_wmu"], g["fs_phi"], g["fs_wphi"])):
+        row, li = 0, 0
+        for t in g["trans"]:
+            if t[1] != 0:
+                continue
+            Nla, woff = int(t[5]), int(t[10])
+            phi, wphi = pd.profile_line(g["line_lambda0"][li], g["tr_lambda"][woff:woff + Nla],
+                                        g["tr_wlambda"][woff:woff + Nla], adamp[li], g["vbroad"][0], g["vel"],
+                                        muz, wmu)
+            assert np.array_equal(phi, phis[row:row + phi.shape[0]]) and np.array_equal(wphi, wphis[li])
+            row += phi.shape[0]
+            li += 1
+        assert li == 5
+
