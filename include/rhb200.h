@@ -170,6 +170,30 @@ int rhb200_bezier3_batch(rhb200_ctx *ctx, int nray, int ncol, int ndep, double m
                          const double *height, const double *T,
                          const double *chi, const double *S, double *I, double *Psi);
 
+/* Formal-solver selection = keyword.input S_INTERPOLATION / S_INTERPOLATION_STOKES (readvalue.c:366-404;
+   enum values of inputs.h:26-27).  Applies to rhb200_lte_stokes_batch(_dev) (Stokes solver) and to
+   rhb200_nlte_iterate / rhb200_nlte_formal (scalar solver).  Defaults: S_BEZIER3, DELO_BEZIER3. */
+enum { RHB200_S_LINEAR = 0, RHB200_S_PARABOLIC = 1, RHB200_S_BEZIER3 = 2 };
+enum { RHB200_DELO_PARABOLIC = 0, RHB200_DELO_BEZIER3 = 1 };
+int rhb200_set_solvers(rhb200_ctx *ctx, int s_interpolation, int s_interpolation_stokes);
+
+/* One scalar ray per entry with the chosen solver: Piecewise_Linear_1D (piecewise_1D.c:44-127),
+   Piecewise_1D (piecewise_1D.c:134-253) or Piecewise_Bezier3_1D.  Layout as rhb200_bezier3_batch. */
+int rhb200_scalar_ray_batch(rhb200_ctx *ctx, int solver, int nray, int ncol, int ndep, double muz, int to_obs,
+                            int bc_top, int bc_bottom,
+                            const int *ray_col, const double *ray_lambda,
+                            const double *height, const double *T,
+                            const double *chi, const double *S, double *I, double *Psi);
+
+/* One polarised ray per entry: Piece_Stokes_1D (piecestokes_1D.c:49-174, DELO_PARABOLIC) or
+   Piece_Stokes_Bezier3_1D.  Layout as rhb200_stokes_bezier3_batch. */
+int rhb200_stokes_ray_batch(rhb200_ctx *ctx, int solver, int nray, int ncol, int ndep, double muz, int to_obs,
+                            int bc_top, int bc_bottom,
+                            const int *ray_col, const double *ray_lambda,
+                            const double *height, const double *T,
+                            const double *chi, const double *S, const double *chiQUV,
+                            double *I, double *Psi);
+
 /* Feautrier (feautrier.c:56-202, F_order = STANDARD): chi, S [nray][ndep]; out P [nray][ndep]
    (Feautrier mean intensity along the ray), Psi [nray][ndep] or NULL, Iem [nray] emergent intensity */
 int rhb200_feautrier_batch(rhb200_ctx *ctx, int nray, int ncol, int ndep, double muz,

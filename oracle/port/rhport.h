@@ -95,6 +95,19 @@ void rp_bezier3_scalar(int Ndep, const double *height, double muz, int to_obs,
                        const double *chi, const double *S, const double *T, double lambda,
                        int bc_top, int bc_bottom, double *I, double *Psi);
 
+/* piecewise_1D.c:44-253, piecestokes_1D.c:49-174, w3.c:25 (rhport_piecewise.c) */
+void rp_w2(double dtau, double *w);
+void rp_piecewise_linear(int Ndep, const double *height, double muz, int to_obs,
+                         const double *chi, const double *S, const double *T, double lambda,
+                         int bc_top, int bc_bottom, double *I, double *Psi);
+void rp_piecewise_parabolic(int Ndep, const double *height, double muz, int to_obs,
+                            const double *chi, const double *S, const double *T, double lambda,
+                            int bc_top, int bc_bottom, double *I, double *Psi);
+void rp_stokes_parabolic(int Ndep, const double *height, double muz, int to_obs,
+                         const double *chi_I, const double *S, const double *chiQUV,
+                         const double *T, double lambda, int bc_top, int bc_bottom,
+                         double *I, double *Psi);
+
 /* feautrier.c:56-202 (STANDARD order); returns emergent I */
 double rp_feautrier(int Ndep, const double *height, double muz, const double *chi, const double *S,
                     const double *T, double lambda, int bc_top, int bc_bottom, double *P, double *Psi);

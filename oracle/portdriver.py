@@ -140,6 +140,30 @@ def bezier3_scalar(height, muz, to_obs, chi, S, T, lam, bc_top=1, bc_bottom=2, w
     return (I, Psi) if want_psi else I
 
 
+def piecewise_scalar(kind, height, muz, to_obs, chi, S, T, lam, bc_top=1, bc_bottom=2, want_psi=False):
+    """kind: 'linear' (Piecewise_Linear_1D) | 'parabolic' (Piecewise_1D), piecewise_1D.c:44,134."""
+    n = len(chi)
+    arr = [np.ascontiguousarray(x, np.float64) for x in (height, chi, S, T)]
+    I = np.zeros(n)
+    Psi = np.zeros(n)
+    f = {"linear": lib().rp_piecewise_linear, "parabolic": lib().rp_piecewise_parabolic}[kind]
+    f(n, _d(arr[0]), C.c_double(muz), int(to_obs), _d(arr[1]), _d(arr[2]), _d(arr[3]), C.c_double(lam),
+      int(bc_top), int(bc_bottom), _d(I), _d(Psi) if want_psi else None)
+    return (I, Psi) if want_psi else I
+
+
+def stokes_parabolic(height, muz, to_obs, chi, S, chiQUV, T, lam, bc_top=1, bc_bottom=2, want_psi=False):
+    """Piece_Stokes_1D, piecestokes_1D.c:49-174."""
+    n = len(chi)
+    arr = [np.ascontiguousarray(x, np.float64) for x in (height, chi, S, chiQUV, T)]
+    I = np.zeros((4, n))
+    Psi = np.zeros(n)
+    lib().rp_stokes_parabolic(n, _d(arr[0]), C.c_double(muz), int(to_obs), _d(arr[1]), _d(arr[2]),
+                              _d(arr[3]), _d(arr[4]), C.c_double(lam), int(bc_top), int(bc_bottom),
+                              _d(I), _d(Psi) if want_psi else None)
+    return (I, Psi) if want_psi else I
+
+
 def feautrier(height, muz, chi, S, T, lam, bc_top=1, bc_bottom=2):
     n = len(chi)
     arr = [np.ascontiguousarray(x, np.float64) for x in (height, chi, S, T)]

@@ -254,6 +254,55 @@ void __wrap_Piecewise_Bezier3_1D(int nspect, int mu, bool_t to_obs, double *chi,
   }
 }
 
+/* Piecewise_Linear_1D / Piecewise_1D (rh/rhf1d/piecewise_1D.c:44,134): S_INTERPOLATION = S_LINEAR | S_PARABOLIC */
+static void rec_scalar_ray(const char *tag, int nspect, int mu, int to_obs, double *chi, double *S,
+                           double *I, double *Psi)
+{
+  int N = atmos.Nspace;
+  double *d = rec_new(tag, 4*N, nspect, mu, to_obs, Psi != NULL, 0, 0);
+  memcpy(d, chi, N*sizeof(double));
+  memcpy(d + N, S, N*sizeof(double));
+  memcpy(d + 2*N, I, N*sizeof(double));
+  if (Psi) memcpy(d + 3*N, Psi, N*sizeof(double));
+  else memset(d + 3*N, 0, N*sizeof(double));
+}
+void __real_Piecewise_1D(int nspect, int mu, bool_t to_obs, double *chi, double *S, double *I, double *Psi);
+void __wrap_Piecewise_1D(int nspect, int mu, bool_t to_obs, double *chi, double *S, double *I, double *Psi)
+{
+  __real_Piecewise_1D(nspect, mu, to_obs, chi, S, I, Psi);
+  if (probe_mask & PROBE_BEZ) rec_scalar_ray("par", nspect, mu, to_obs, chi, S, I, Psi);
+}
+void __real_Piecewise_Linear_1D(int nspect, int mu, bool_t to_obs, double *chi, double *S, double *I, double *Psi);
+void __wrap_Piecewise_Linear_1D(int nspect, int mu, bool_t to_obs, double *chi, double *S, double *I, double *Psi)
+{
+  __real_Piecewise_Linear_1D(nspect, mu, to_obs, chi, S, I, Psi);
+  if (probe_mask & PROBE_BEZ) rec_scalar_ray("lin", nspect, mu, to_obs, chi, S, I, Psi);
+}
+
+/* Piece_Stokes_1D (rh/rhf1d/piecestokes_1D.c:49): S_INTERPOLATION_STOKES = DELO_PARABOLIC; same record
+   layout as "delo" */
+void __real_Piece_Stokes_1D(int nspect, int mu, bool_t to_obs, double *chi, double **S, double **I, double *Psi);
+void __wrap_Piece_Stokes_1D(int nspect, int mu, bool_t to_obs, double *chi, double **S, double **I, double *Psi)
+{
+  __real_Piece_Stokes_1D(nspect, mu, to_obs, chi, S, I, Psi);
+  if (probe_mask & PROBE_DELO) {
+    int N = atmos.Nspace, n;
+    ActiveSet *as = &spectrum.as[nspect];
+    double *d = rec_new("pst", 13*N, nspect, mu, to_obs, Psi != NULL, 0, 0);
+    memcpy(d, chi, N*sizeof(double));
+    for (n = 0; n < 4; n++) memcpy(d + (1+n)*N, S[n], N*sizeof(double));
+    for (n = 0; n < 4; n++) memcpy(d + (5+n)*N, I[n], N*sizeof(double));
+    if (Psi) memcpy(d + 9*N, Psi, N*sizeof(double));
+    else memset(d + 9*N, 0, N*sizeof(double));
+    for (n = 0; n < 3*N; n++) {
+      double v = 0.0;
+      if (containsPolarized(as)) v += as->chi[N + n];
+      if (atmos.backgrflags[nspect].ispolarized) v += as->chi_c[N + n];
+      d[10*N + n] = v;
+    }
+  }
+}
+
 double __real_Feautrier(int nspect, int mu, double *chi, double *S,
                         enum FeautrierOrder order, double *P, double *Psi);
 double __wrap_Feautrier(int nspect, int mu, double *chi, double *S,

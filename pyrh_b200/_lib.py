@@ -37,6 +37,11 @@ SYMBOLS = [
                                               C.c_int, ip, dp, dp, dp, dp, dp, dp, dp, dp]),
     ("rhb200_bezier3_batch", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
                                        ip, dp, dp, dp, dp, dp, dp, dp]),
+    ("rhb200_set_solvers", C.c_int, [vp, C.c_int, C.c_int]),
+    ("rhb200_scalar_ray_batch", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
+                                          C.c_int, ip, dp, dp, dp, dp, dp, dp, dp]),
+    ("rhb200_stokes_ray_batch", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
+                                          C.c_int, ip, dp, dp, dp, dp, dp, dp, dp, dp]),
     ("rhb200_feautrier_batch", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, ip, dp,
                                          dp, dp, dp, dp, dp, dp, dp]),
     ("rhb200_voigt_humlicek", C.c_int, [vp, C.c_int, dp, dp, dp, dp, ip]),

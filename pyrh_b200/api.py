@@ -67,6 +67,11 @@ def is_moving(atmosphere: np.ndarray, vmacro_tresh: float = 0.0) -> bool:
     return bool(np.any(np.abs(np.asarray(atmosphere)[..., 3, :] * KM_TO_M) >= vmacro_tresh))
 
 
+# enum S_interpol / S_interpol_stokes of the reference (inputs.h:26-27), keyed by the keyword.input spelling
+S_INTERPOLATION = {"S_LINEAR": 0, "S_PARABOLIC": 1, "S_BEZIER3": 2}
+S_INTERPOLATION_STOKES = {"DELO_PARABOLIC": 0, "DELO_BEZIER3": 1}
+
+
 class Context:
     """One GPU context (``rhb200_open``): shared line tables + wavelength grid."""
 
@@ -170,8 +175,14 @@ class Context:
                                                      flags.ctypes.data_as(_lib.ip)))
         return chi, eta, flags
 
+    def set_solvers(self, s_interpolation="S_BEZIER3", s_interpolation_stokes="DELO_BEZIER3"):
+        """keyword.input S_INTERPOLATION / S_INTERPOLATION_STOKES (readvalue.c:366-404)."""
+        _lib.check(self.lib.rhb200_set_solvers(self.h, S_INTERPOLATION[s_interpolation],
+                                               S_INTERPOLATION_STOKES[s_interpolation_stokes]))
+
     def stokes_bezier3(self, ray_col, ray_lambda, height, T, chi, S, chiQUV, mu=1.0, to_obs=True,
-                       bc_top=_lib.BC_ZERO, bc_bottom=_lib.BC_THERMALIZED, want_psi=False):
+                       bc_top=_lib.BC_ZERO, bc_bottom=_lib.BC_THERMALIZED, want_psi=False,
+                       solver="DELO_BEZIER3"):
         rc = np.ascontiguousarray(ray_col, np.int32)
         rl = np.ascontiguousarray(ray_lambda, np.float64)
         h = np.ascontiguousarray(np.atleast_2d(height), np.float64)
@@ -182,14 +193,14 @@ class Context:
         nray, ndep = chi.shape
         I = np.zeros((nray, 4, ndep))
         Psi = np.zeros((nray, ndep)) if want_psi else None
-        _lib.check(self.lib.rhb200_stokes_bezier3_batch(
-            self.h, nray, h.shape[0], ndep, float(mu), int(to_obs), int(bc_top), int(bc_bottom),
+        _lib.check(self.lib.rhb200_stokes_ray_batch(
+            self.h, S_INTERPOLATION_STOKES[solver], nray, h.shape[0], ndep, float(mu), int(to_obs), int(bc_top), int(bc_bottom),
             rc.ctypes.data_as(_lib.ip), _dp(rl), _dp(h), _dp(t), _dp(chi), _dp(S), _dp(q), _dp(I),
             _dp(Psi) if want_psi else None))
         return (I, Psi) if want_psi else I
 
     def bezier3(self, ray_col, ray_lambda, height, T, chi, S, mu=1.0, to_obs=True,
-                bc_top=_lib.BC_ZERO, bc_bottom=_lib.BC_THERMALIZED, want_psi=False):
+                bc_top=_lib.BC_ZERO, bc_bottom=_lib.BC_THERMALIZED, want_psi=False, solver="S_BEZIER3"):
         rc = np.ascontiguousarray(ray_col, np.int32)
         rl = np.ascontiguousarray(ray_lambda, np.float64)
         h = np.ascontiguousarray(np.atleast_2d(height), np.float64)
@@ -199,8 +210,8 @@ class Context:
         nray, ndep = chi.shape
         I = np.zeros((nray, ndep))
         Psi = np.zeros((nray, ndep)) if want_psi else None
-        _lib.check(self.lib.rhb200_bezier3_batch(
-            self.h, nray, h.shape[0], ndep, float(mu), int(to_obs), int(bc_top), int(bc_bottom),
+        _lib.check(self.lib.rhb200_scalar_ray_batch(
+            self.h, S_INTERPOLATION[solver], nray, h.shape[0], ndep, float(mu), int(to_obs), int(bc_top), int(bc_bottom),
             rc.ctypes.data_as(_lib.ip), _dp(rl), _dp(h), _dp(t), _dp(chi), _dp(S), _dp(I),
             _dp(Psi) if want_psi else None))
         return (I, Psi) if want_psi else I

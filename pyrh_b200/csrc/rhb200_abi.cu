@@ -428,13 +428,40 @@ extern "C" int rhb200_rlk_opacity_batch(rhb200_ctx *c, int ncol, int ndep, doubl
   return RHB200_OK;
 }
 
+extern "C" int rhb200_set_solvers(rhb200_ctx *c, int s_interpolation, int s_interpolation_stokes)
+{
+  RH_NEED_CTX(c);
+  if (s_interpolation < RHB200_S_LINEAR || s_interpolation > RHB200_S_BEZIER3) {
+    rhb200_set_error("Unknown radiation solver: %d", s_interpolation); return RHB200_EINVAL;     /* formal.c:240 */
+  }
+  if (s_interpolation_stokes != RHB200_DELO_PARABOLIC && s_interpolation_stokes != RHB200_DELO_BEZIER3) {
+    rhb200_set_error("Unknown polarization solver: %d", s_interpolation_stokes); return RHB200_EINVAL;   /* formal.c:218 */
+  }
+  c->s_interpolation = s_interpolation;
+  c->s_interpolation_stokes = s_interpolation_stokes;
+  return RHB200_OK;
+}
+
 extern "C" int rhb200_stokes_bezier3_batch(rhb200_ctx *c, int nray, int ncol, int ndep, double muz, int to_obs,
                                            int bc_top, int bc_bottom, const int *ray_col,
                                            const double *ray_lambda, const double *height, const double *T,
                                            const double *chi, const double *S, const double *chiQUV,
                                            double *I, double *Psi)
 {
+  return rhb200_stokes_ray_batch(c, RHB200_DELO_BEZIER3, nray, ncol, ndep, muz, to_obs, bc_top, bc_bottom, ray_col,
+                                 ray_lambda, height, T, chi, S, chiQUV, I, Psi);
+}
+
+extern "C" int rhb200_stokes_ray_batch(rhb200_ctx *c, int solver, int nray, int ncol, int ndep, double muz, int to_obs,
+                                       int bc_top, int bc_bottom, const int *ray_col,
+                                       const double *ray_lambda, const double *height, const double *T,
+                                       const double *chi, const double *S, const double *chiQUV,
+                                       double *I, double *Psi)
+{
   RH_NEED_CTX(c);
+  if (solver != RHB200_DELO_PARABOLIC && solver != RHB200_DELO_BEZIER3) {
+    rhb200_set_error("Unknown polarization solver: %d", solver); return RHB200_EINVAL;
+  }
   if (nray <= 0 || ncol <= 0 || ndep < 3 || !ray_col || !ray_lambda || !height || !T || !chi || !S || !chiQUV || !I) {
     rhb200_set_error("bad arguments"); return RHB200_EINVAL;
   }
@@ -448,7 +475,7 @@ extern "C" int rhb200_stokes_bezier3_batch(rhb200_ctx *c, int nray, int ncol, in
   RH_CHECK(dchi.from_host(chi, rb)); RH_CHECK(dS.from_host(S, 4*rb)); RH_CHECK(dq.from_host(chiQUV, 3*rb));
   RH_CHECK(dI.alloc(4*rb));
   if (Psi) RH_CHECK(dP.alloc(rb));
-  RH_CHECK(rh_launch_delo_generic(c, nray, ndep, muz, to_obs, bc_top, bc_bottom, rc.as<int>(), rl.as<double>(),
+  RH_CHECK(rh_launch_delo_generic(c, solver, nray, ndep, muz, to_obs, bc_top, bc_bottom, rc.as<int>(), rl.as<double>(),
                                   h.as<double>(), t.as<double>(), dchi.as<double>(), dS.as<double>(),
                                   dq.as<double>(), dI.as<double>(), Psi ? dP.as<double>() : nullptr));
   RH_CUDA(cudaStreamSynchronize(c->stream));
@@ -462,7 +489,19 @@ extern "C" int rhb200_bezier3_batch(rhb200_ctx *c, int nray, int ncol, int ndep,
                                     const double *height, const double *T, const double *chi, const double *S,
                                     double *I, double *Psi)
 {
+  return rhb200_scalar_ray_batch(c, RHB200_S_BEZIER3, nray, ncol, ndep, muz, to_obs, bc_top, bc_bottom, ray_col,
+                                 ray_lambda, height, T, chi, S, I, Psi);
+}
+
+extern "C" int rhb200_scalar_ray_batch(rhb200_ctx *c, int solver, int nray, int ncol, int ndep, double muz, int to_obs,
+                                       int bc_top, int bc_bottom, const int *ray_col, const double *ray_lambda,
+                                       const double *height, const double *T, const double *chi, const double *S,
+                                       double *I, double *Psi)
+{
   RH_NEED_CTX(c);
+  if (solver < RHB200_S_LINEAR || solver > RHB200_S_BEZIER3) {
+    rhb200_set_error("Unknown radiation solver: %d", solver); return RHB200_EINVAL;
+  }
   if (nray <= 0 || ncol <= 0 || ndep < 3 || !ray_col || !ray_lambda || !height || !T || !chi || !S || !I) {
     rhb200_set_error("bad arguments"); return RHB200_EINVAL;
   }
@@ -476,7 +515,7 @@ extern "C" int rhb200_bezier3_batch(rhb200_ctx *c, int nray, int ncol, int ndep,
   RH_CHECK(dchi.from_host(chi, rb)); RH_CHECK(dS.from_host(S, rb));
   RH_CHECK(dI.alloc(rb));
   if (Psi) RH_CHECK(dP.alloc(rb));
-  RH_CHECK(rh_launch_bezier3(c, nray, ndep, muz, to_obs, bc_top, bc_bottom, rc.as<int>(), rl.as<double>(),
+  RH_CHECK(rh_launch_bezier3(c, solver, nray, ndep, muz, to_obs, bc_top, bc_bottom, rc.as<int>(), rl.as<double>(),
                              h.as<double>(), t.as<double>(), dchi.as<double>(), dS.as<double>(),
                              dI.as<double>(), Psi ? dP.as<double>() : nullptr));
   RH_CUDA(cudaStreamSynchronize(c->stream));

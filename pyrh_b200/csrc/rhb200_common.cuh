@@ -72,6 +72,8 @@ struct rhb200_ctx {
   std::vector<double> h_lines, h_elems, h_lambda, h_zshift, h_zstrength;
   std::vector<int> h_zq;
   std::vector<int> h_first, h_count, h_idx, h_flags, h_noline;
+  // formal solver selection (keyword.input S_INTERPOLATION / S_INTERPOLATION_STOKES, inputs.h:26-27)
+  int s_interpolation = RHB200_S_BEZIER3, s_interpolation_stokes = RHB200_DELO_BEZIER3;
   // workspace (grown on demand)
   void *ws = nullptr; size_t ws_bytes = 0;
   void *flush = nullptr; size_t flush_bytes = 0;
@@ -115,12 +117,12 @@ int rh_launch_opacity_raw(rhb200_ctx *ctx, int ncol, int ndep, int to_obs,
 int rh_launch_delo_raypts(rhb200_ctx *ctx, int ncol, int ndep, double muz, int bc_top, int bc_bottom,
                           const double *d_atmos, const double *d_raypts,
                           double *d_stokes /* [ncol][4][nlambda] */);
-int rh_launch_delo_generic(rhb200_ctx *ctx, int nray, int ndep, double muz, int to_obs,
+int rh_launch_delo_generic(rhb200_ctx *ctx, int solver /* RHB200_DELO_* */, int nray, int ndep, double muz, int to_obs,
                            int bc_top, int bc_bottom, const int *d_ray_col,
                            const double *d_ray_lambda, const double *d_height, const double *d_T,
                            const double *d_chi, const double *d_S, const double *d_chiQUV,
                            double *d_I, double *d_Psi);
-int rh_launch_bezier3(rhb200_ctx *ctx, int nray, int ndep, double muz, int to_obs,
+int rh_launch_bezier3(rhb200_ctx *ctx, int solver /* RHB200_S_* */, int nray, int ndep, double muz, int to_obs,
                       int bc_top, int bc_bottom, const int *d_ray_col,
                       const double *d_ray_lambda, const double *d_height, const double *d_T,
                       const double *d_chi, const double *d_S, double *d_I, double *d_Psi);

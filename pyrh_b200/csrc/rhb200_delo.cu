@@ -3,6 +3,7 @@
 #include "rhb200_delo.cuh"
 #include "rhb200_bezier.cuh"
 #include "rhb200_feautrier.cuh"
+#include "rhb200_piecewise.cuh"
 
 namespace {
 
@@ -72,8 +73,27 @@ delo_raypts_kernel(int ncol, int nlambda, int ndep, double muz, int bc_top, int 
                         at + RHB200_AT_T * ndep, __ldg(lambda + l));
 }
 
+// fused LTE path with S_INTERPOLATION_STOKES = DELO_PARABOLIC (formal.c:215-216)
 __global__ void __launch_bounds__(128)
-delo_generic_kernel(int nray, int ndep, double muz, int to_obs, int bc_top, int bc_bottom,
+stokes_parabolic_raypts_kernel(int ncol, int nlambda, int ndep, double muz, int bc_top, int bc_bottom,
+                               const double *__restrict__ atmos, const double *__restrict__ lambda,
+                               const int *__restrict__ wflags,
+                               const double *__restrict__ raypts, double *__restrict__ stokes)
+{
+  const size_t nray = (size_t) ncol * nlambda;
+  const size_t r = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nray) return;
+  const int col = (int) (r / nlambda), l = (int) (r - (size_t) col * nlambda);
+  if ((__ldg(wflags + l) & 1) == 0) return;
+  const double *at = atmos + (size_t) col * RHB200_AT_NFIELD * ndep;
+  RayPtsIO io{reinterpret_cast<const double2 *>(raypts + r * (size_t) ndep * RP_NFIELD),
+              stokes + (size_t) col * 4 * nlambda + l, nlambda, 0};
+  rhp::stokes_parabolic_ray(io, ndep, at + RHB200_AT_HEIGHT * ndep, muz, 1, bc_top, bc_bottom,
+                            at + RHB200_AT_T * ndep, __ldg(lambda + l));
+}
+
+__global__ void __launch_bounds__(128)
+delo_generic_kernel(int solver, int nray, int ndep, double muz, int to_obs, int bc_top, int bc_bottom,
                     const int *__restrict__ ray_col, const double *__restrict__ ray_lambda,
                     const double *__restrict__ height, const double *__restrict__ T,
                     const double *__restrict__ chi, const double *__restrict__ S,
@@ -84,12 +104,16 @@ delo_generic_kernel(int nray, int ndep, double muz, int to_obs, int bc_top, int 
   const int col = ray_col[r];
   GenericIO io{chi + (size_t) r*ndep, S + (size_t) r*4*ndep, chiQUV + (size_t) r*3*ndep,
                I + (size_t) r*4*ndep, Psi ? Psi + (size_t) r*ndep : nullptr, ndep};
-  rhd::delo_bezier3_ray(io, ndep, height + (size_t) col*ndep, muz, to_obs, bc_top, bc_bottom,
-                        T + (size_t) col*ndep, ray_lambda[r]);
+  if (solver == RHB200_DELO_PARABOLIC)
+    rhp::stokes_parabolic_ray(io, ndep, height + (size_t) col*ndep, muz, to_obs, bc_top, bc_bottom,
+                              T + (size_t) col*ndep, ray_lambda[r]);
+  else
+    rhd::delo_bezier3_ray(io, ndep, height + (size_t) col*ndep, muz, to_obs, bc_top, bc_bottom,
+                          T + (size_t) col*ndep, ray_lambda[r]);
 }
 
 __global__ void __launch_bounds__(128)
-bezier3_kernel(int nray, int ndep, double muz, int to_obs, int bc_top, int bc_bottom,
+bezier3_kernel(int solver, int nray, int ndep, double muz, int to_obs, int bc_top, int bc_bottom,
                const int *__restrict__ ray_col, const double *__restrict__ ray_lambda,
                const double *__restrict__ height, const double *__restrict__ T,
                const double *__restrict__ chi, const double *__restrict__ S,
@@ -98,9 +122,14 @@ bezier3_kernel(int nray, int ndep, double muz, int to_obs, int bc_top, int bc_bo
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= nray) return;
   const int col = ray_col[r];
-  rhz::bezier3_ray(ndep, height + (size_t) col*ndep, muz, to_obs, bc_top, bc_bottom,
-                   T + (size_t) col*ndep, ray_lambda[r], chi + (size_t) r*ndep, S + (size_t) r*ndep,
-                   I + (size_t) r*ndep, Psi ? Psi + (size_t) r*ndep : nullptr);
+  const double *z = height + (size_t) col*ndep, *Tc = T + (size_t) col*ndep;
+  const double *c = chi + (size_t) r*ndep, *s = S + (size_t) r*ndep;
+  double *Ir = I + (size_t) r*ndep, *Pr = Psi ? Psi + (size_t) r*ndep : nullptr;
+  switch (solver) {                                           // formal.c:229-235
+  case RHB200_S_LINEAR:    rhp::linear_ray(ndep, z, muz, to_obs, bc_top, bc_bottom, Tc, ray_lambda[r], c, s, Ir, Pr); break;
+  case RHB200_S_PARABOLIC: rhp::parabolic_ray(ndep, z, muz, to_obs, bc_top, bc_bottom, Tc, ray_lambda[r], c, s, Ir, Pr); break;
+  default:                 rhz::bezier3_ray(ndep, z, muz, to_obs, bc_top, bc_bottom, Tc, ray_lambda[r], c, s, Ir, Pr);
+  }
 }
 
 // ---- Feautrier IO policies
@@ -185,7 +214,10 @@ int rh_launch_delo_raypts(rhb200_ctx *ctx, int ncol, int ndep, double muz, int b
     if (variant < 0) { const char *e = getenv("RHB200_DELO_MINB"); variant = e ? atoi(e) : 4; }
 #define RH_LAUNCH_DELO(M) delo_raypts_kernel<M><<<blocks, threads, 0, ctx->stream>>>(ncol, ctx->wav.nlambda, ndep, muz, \
         bc_top, bc_bottom, d_atmos, ctx->wav.lambda, ctx->wav.flags, d_raypts, d_stokes)
-    switch (variant) {
+    if (ctx->s_interpolation_stokes == RHB200_DELO_PARABOLIC)
+      stokes_parabolic_raypts_kernel<<<blocks, threads, 0, ctx->stream>>>(ncol, ctx->wav.nlambda, ndep, muz,
+          bc_top, bc_bottom, d_atmos, ctx->wav.lambda, ctx->wav.flags, d_raypts, d_stokes);
+    else switch (variant) {
     case 4: RH_LAUNCH_DELO(4); break;
     case 5: RH_LAUNCH_DELO(5); break;
     case 6: RH_LAUNCH_DELO(6); break;
@@ -196,7 +228,7 @@ int rh_launch_delo_raypts(rhb200_ctx *ctx, int ncol, int ndep, double muz, int b
   return RHB200_OK;
 }
 
-int rh_launch_delo_generic(rhb200_ctx *ctx, int nray, int ndep, double muz, int to_obs,
+int rh_launch_delo_generic(rhb200_ctx *ctx, int solver, int nray, int ndep, double muz, int to_obs,
                            int bc_top, int bc_bottom, const int *d_ray_col,
                            const double *d_ray_lambda, const double *d_height, const double *d_T,
                            const double *d_chi, const double *d_S, const double *d_chiQUV,
@@ -206,7 +238,7 @@ int rh_launch_delo_generic(rhb200_ctx *ctx, int nray, int ndep, double muz, int 
   const int threads = 128, blocks = (nray + threads - 1) / threads;
   {
     ScopedKernelTimer t(ctx, RHB200_K_DELO);
-    delo_generic_kernel<<<blocks, threads, 0, ctx->stream>>>(nray, ndep, muz, to_obs, bc_top, bc_bottom,
+    delo_generic_kernel<<<blocks, threads, 0, ctx->stream>>>(solver, nray, ndep, muz, to_obs, bc_top, bc_bottom,
                                                               d_ray_col, d_ray_lambda, d_height, d_T,
                                                               d_chi, d_S, d_chiQUV, d_I, d_Psi);
   }
@@ -214,7 +246,7 @@ int rh_launch_delo_generic(rhb200_ctx *ctx, int nray, int ndep, double muz, int 
   return RHB200_OK;
 }
 
-int rh_launch_bezier3(rhb200_ctx *ctx, int nray, int ndep, double muz, int to_obs,
+int rh_launch_bezier3(rhb200_ctx *ctx, int solver, int nray, int ndep, double muz, int to_obs,
                       int bc_top, int bc_bottom, const int *d_ray_col,
                       const double *d_ray_lambda, const double *d_height, const double *d_T,
                       const double *d_chi, const double *d_S, double *d_I, double *d_Psi)
@@ -223,7 +255,7 @@ int rh_launch_bezier3(rhb200_ctx *ctx, int nray, int ndep, double muz, int to_ob
   const int threads = 128, blocks = (nray + threads - 1) / threads;
   {
     ScopedKernelTimer t(ctx, RHB200_K_BEZIER);
-    bezier3_kernel<<<blocks, threads, 0, ctx->stream>>>(nray, ndep, muz, to_obs, bc_top, bc_bottom,
+    bezier3_kernel<<<blocks, threads, 0, ctx->stream>>>(solver, nray, ndep, muz, to_obs, bc_top, bc_bottom,
                                                          d_ray_col, d_ray_lambda, d_height, d_T,
                                                          d_chi, d_S, d_I, d_Psi);
   }

@@ -30,6 +30,8 @@
 #include "rhb200_common.cuh"
 #include "rhb200_bezier.cuh"
 #include "rhb200_feautrier.cuh"
+#include "rhb200_lu.cuh"
+#include "rhb200_piecewise.cuh"
 #include "rhb200_voigt.cuh"
 
 namespace {
@@ -42,7 +44,7 @@ enum { TR_ATOM = RHB200_TR_ATOM, TR_TYPE = RHB200_TR_TYPE, TR_I = RHB200_TR_I, T
        TR_NFIELD = RHB200_TR_NFIELD };
 
 struct Plan {            // device copy of the shared problem structure
-  int Nspect, Nrays, Ndep, Natom, Ntrans, nas, nray, nlev, ngam, nphirow, nline, bc_top, bc_bottom;
+  int Nspect, Nrays, Ndep, Natom, Ntrans, nas, nray, nlev, ngam, nphirow, nline, bc_top, bc_bottom, solver;
   const double *lambda, *muz, *wmu, *trans, *tr_lambda, *tr_wlambda, *tr_alpha;
   const int *atom_nlevel, *lev_off, *gam_off, *as_first, *as_trans, *angle_dep, *ray_off,
             *ray_ns, *ray_mu, *ray_dir, *prow_tr, *line_tr;
@@ -228,8 +230,19 @@ nlte_ray_kernel(Plan P, Cols C, int ncol, int eval_operator)
   const double *h = C.height + (size_t) col * N, *T = C.T + (size_t) col * N;
   double *Psi = eval_operator ? C.Psi + cr * N : nullptr;
   if (P.angle_dep[ns]) {
-    rhz::bezier3_ray(N, h, P.muz[mu], dir, P.bc_top, P.bc_bottom, T, P.lambda[ns], C.chi + cr * N,
-                     C.S + cr * N, C.I + cr * N, Psi);
+    switch (P.solver) {                              // S_INTERPOLATION, formal.c:229-235
+    case RHB200_S_LINEAR:
+      rhp::linear_ray(N, h, P.muz[mu], dir, P.bc_top, P.bc_bottom, T, P.lambda[ns], C.chi + cr * N,
+                      C.S + cr * N, C.I + cr * N, Psi);
+      break;
+    case RHB200_S_PARABOLIC:
+      rhp::parabolic_ray(N, h, P.muz[mu], dir, P.bc_top, P.bc_bottom, T, P.lambda[ns], C.chi + cr * N,
+                         C.S + cr * N, C.I + cr * N, Psi);
+      break;
+    default:
+      rhz::bezier3_ray(N, h, P.muz[mu], dir, P.bc_top, P.bc_bottom, T, P.lambda[ns], C.chi + cr * N,
+                       C.S + cr * N, C.I + cr * N, Psi);
+    }
     C.Iem[cr] = C.I[cr * N];                         // spectrum.I[nspect][mu] = I[0] (formal.c:270)
   } else {
     NlteFeauIO io{C.chi + cr * N, C.S + cr * N, h, C.I + cr * N, Psi, C.scr + cr * 2 * N, N};
@@ -356,72 +369,8 @@ __global__ void nlte_gamma_init_kernel(Plan P, Cols C, int ncol)
   C.Gamma[t] = C.C[t];
 }
 
-// ---- (5) SolveLinearEq (ludcmp.c:36-177) on thread-local storage
-template <int MAXN>
-__device__ void solve_linear_eq(const int N, double *A, double *b, const bool improve)
-{
-  int index[MAXN];
-  double vv[MAXN], A_copy[MAXN*MAXN], b_copy[MAXN], residual[MAXN];
-  if (improve) {
-    for (int i = 0; i < N; i++) { b_copy[i] = b[i]; for (int j = 0; j < N; j++) A_copy[i*N+j] = A[i*N+j]; }
-  }
-  // LUdecomp, ludcmp.c:92-150
-  int imax = 0;
-  for (int i = 0; i < N; i++) {
-    double big = 0.0;
-    for (int j = 0; j < N; j++) { const double temp = fabs(A[i*N+j]); if (temp > big) big = temp; }
-    vv[i] = 1.0 / big;
-  }
-  for (int j = 0; j < N; j++) {
-    for (int i = 0; i < j; i++) {
-      double sum = A[i*N+j];
-      for (int k = 0; k < i; k++) sum -= A[i*N+k] * A[k*N+j];
-      A[i*N+j] = sum;
-    }
-    double big = 0.0;
-    for (int i = j; i < N; i++) {
-      double sum = A[i*N+j];
-      for (int k = 0; k < j; k++) sum -= A[i*N+k] * A[k*N+j];
-      A[i*N+j] = sum;
-      const double dum = vv[i]*fabs(sum);
-      if (dum >= big) { big = dum; imax = i; }
-    }
-    if (j != imax) {
-      for (int k = 0; k < N; k++) { const double dum = A[imax*N+k]; A[imax*N+k] = A[j*N+k]; A[j*N+k] = dum; }
-      vv[imax] = vv[j];
-    }
-    index[j] = imax;
-    if (A[j*N+j] == 0.0) A[j*N+j] = 1.0e-20;
-    const double dum = 1.0 / A[j*N+j];
-    for (int i = j+1; i < N; i++) A[i*N+j] *= dum;
-  }
-  // LUbacksubst, ludcmp.c:156-177
-  auto backsubst = [&](double *x) {
-    int ii = -1;
-    for (int i = 0; i < N; i++) {
-      const int ip = index[i];
-      double sum = x[ip];
-      x[ip] = x[i];
-      if (ii >= 0) { for (int j = ii; j < i; j++) sum -= A[i*N+j] * x[j]; }
-      else if (sum != 0.0) ii = i;
-      x[i] = sum;
-    }
-    for (int i = N-1; i >= 0; i--) {
-      double sum = x[i];
-      for (int j = i+1; j < N; j++) sum -= A[i*N+j]*x[j];
-      x[i] = sum / A[i*N+i];
-    }
-  };
-  backsubst(b);
-  if (improve) {
-    for (int i = 0; i < N; i++) {
-      residual[i] = b_copy[i];
-      for (int j = 0; j < N; j++) residual[i] -= A_copy[i*N+j] * b[j];
-    }
-    backsubst(residual);
-    for (int i = 0; i < N; i++) b[i] += residual[i];
-  }
-}
+// ---- (5) SolveLinearEq: rhb200_lu.cuh
+using rhlu::solve_linear_eq;
 
 // statEquil, statequil.c:40-103: one thread per (column, atom, depth)
 template <int MAXN>
@@ -645,6 +594,7 @@ static int nlte_run(rhb200_ctx *c, const rhb200_nlte_plan *pl, int ncol,
   Plan P{};
   P.Nspect = Ns; P.Nrays = Nr; P.Ndep = N; P.Natom = Na; P.Ntrans = Nt; P.nas = nas; P.nray = nray;
   P.nlev = nlev; P.ngam = ngam; P.nphirow = pl->nphirow; P.nline = pl->nline; P.bc_top = pl->bc_top; P.bc_bottom = pl->bc_bottom;
+  P.solver = c->s_interpolation;
   double *dd; int *di;
 #define UPD(field, src, n) RH_CHECK(ar.upload(&dd, src, (size_t) (n))); P.field = dd
 #define UPI(field, src, n) RH_CHECK(ar.upload(&di, src, (size_t) (n))); P.field = di

@@ -443,3 +443,76 @@ def test_nlte_initscatter_and_final_pass_vs_reference(ctx):
     # same pass with the profiles evaluated on the device for the new angle
     res2 = nlte.formal(ctx, fin, npass=1, update_J=False, device_profiles=True)
     assert np.array_equal(res2["Iem"], res["Iem"])
+
+
+@pytest.mark.parametrize("tag,solver", [("lin", "S_LINEAR"), ("par", "S_PARABOLIC")])
+def test_piecewise_scalar_solvers_vs_reference(ctx, tag, solver):
+    """Piecewise_Linear_1D / Piecewise_1D (piecewise_1D.c:44,134): up and down rays recorded from the
+    reference in LTE (no Psi) and in two MALI iterations of the CaII problem (with Psi)."""
+    g = dict(np.load(GOLD / "falc_solvers.npz"))
+    for meta, d, h, T, lam, muz, psi in ((g[tag + "_meta"], g[tag], g["col_height"], g["col_T"], g["lam_spect"],
+                                          g["muz"], False),
+                                         (g[tag + "psi_meta"], g[tag + "psi"], g["n_height"], g["n_T"],
+                                          g["n_lam_spect"], g["n_muz"], True)):
+        for mu in np.unique(meta[:, 1]):
+            for to_obs in (0, 1):
+                sel = (meta[:, 1] == mu) & (meta[:, 2] == to_obs)
+                if not sel.any():
+                    continue
+                res = ctx.bezier3(np.zeros(sel.sum(), np.int32), lam[meta[sel, 0]], h, T, d[sel, 0], d[sel, 1],
+                                  mu=float(muz[mu]), to_obs=bool(to_obs), want_psi=psi, solver=solver)
+                I = res[0] if psi else res
+                assert np.array_equal(I, d[sel, 2])
+                if psi:
+                    assert np.array_equal(res[1], d[sel, 3])
+    REPORT[f"piecewise_{tag}_exact"] = True
+
+
+def test_delo_parabolic_vs_reference(ctx, golden_falc):
+    """Piece_Stokes_1D (piecestokes_1D.c:49-174, SolveLinearEq 4x4 with improvement): recorded rays, then
+    the fused LTE path with S_INTERPOLATION_STOKES = DELO_PARABOLIC against the reference's rhf1d()."""
+    g = dict(np.load(GOLD / "falc_solvers.npz"))
+    meta, d = g["pst_meta"], g["pst"]
+    for to_obs in (0, 1):
+        sel = meta[:, 2] == to_obs
+        I = ctx.stokes_bezier3(np.zeros(sel.sum(), np.int32), g["pst_lam_spect"][meta[sel, 0]], g["col_height"],
+                               g["col_T"], d[sel, 0], d[sel, 1:5], d[sel, 10:13], mu=float(g["muz"][0]),
+                               to_obs=bool(to_obs), solver="DELO_PARABOLIC")
+        assert np.array_equal(I, d[sel, 5:9])
+    f = golden_falc
+    assert np.array_equal(f["atmosphere"], g["atmosphere"])
+    setup_ctx(ctx, f)
+    k = f["lam_keep"]
+    ctx.set_solvers(s_interpolation_stokes="DELO_PARABOLIC")
+    try:
+        st = ctx.lte_stokes_batch(rows_of(f)[None], f["chi_ai"][k][None], f["eta_ai"][k][None],
+                                  mu=float(f["muz"][0]), moving=bool(f["flags"][0]))[0]
+    finally:
+        ctx.set_solvers()
+    REPORT["spectrum_delo_parabolic_exact"] = bool(np.array_equal(st, g["pst_spec"]))
+    assert np.array_equal(st, g["pst_spec"])
+    assert not np.array_equal(st, f["stokes_scalar"])            # it really is a different solver
+    from pyrh_b200 import _lib
+    with pytest.raises(_lib.RHB200Error):                        # "Unknown radiation solver" (formal.c:240)
+        _lib.check(ctx.lib.rhb200_set_solvers(ctx.h, 7, 1))
+
+
+@pytest.mark.parametrize("tag,solver", [("lin", "S_LINEAR"), ("par", "S_PARABOLIC")])
+def test_nlte_with_other_scalar_solvers(ctx, tag, solver):
+    """initScatter + two MALI iterations of the CaII problem with S_INTERPOLATION = S_LINEAR / S_PARABOLIC:
+    populations must equal the reference's run with that keyword."""
+    from pyrh_b200 import nlte
+    g = dict(np.load(GOLD / "nlte_caii.npz"))
+    s = dict(np.load(GOLD / "falc_solvers.npz"))
+    prob = nlte.NlteProblem.from_golden(g, ncol=1)
+    prob.J0 = np.zeros_like(prob.J0)
+    ctx.set_solvers(s_interpolation=solver)
+    try:
+        out = nlte.iterate(ctx, prob, nmax=2, nscatter=int(g["hdr"][11]))
+    finally:
+        ctx.set_solvers()
+    assert int(out["niter"][0]) == 2
+    REPORT[f"nlte_{tag}_2iter_exact"] = bool(np.array_equal(out["n"][0], s[tag + "_nlte_n"]))
+    assert np.max(np.abs(out["n"][0] / s[tag + "_nlte_n"] - 1)) < 1e-6
+    assert np.array_equal(out["n"][0], s[tag + "_nlte_n"])
+    assert not np.array_equal(out["n"][0], g["n_iter"][1])

@@ -168,3 +168,24 @@ def test_profile_port_bit_exact_both_angle_sets():
             li += 1
         assert li == 5
 
+
+
+def test_piecewise_and_delo_parabolic_port_bit_exact():
+    """Piecewise_Linear_1D, Piecewise_1D (piecewise_1D.c:44,134) and Piece_Stokes_1D (piecestokes_1D.c:49)
+    restatements vs calls recorded from the reference (LTE up/down rays; NLTE rays with Psi)."""
+    from conftest import GOLD
+    g = dict(np.load(GOLD / "falc_solvers.npz"))
+    h, T, muz = g["col_height"], g["col_T"], g["muz"]
+    for tag, kind in (("lin", "linear"), ("par", "parabolic")):
+        assert {0, 1} <= set(g[tag + "_meta"][:, 2])
+        for m, d in zip(g[tag + "_meta"], g[tag]):
+            I = pd.piecewise_scalar(kind, h, float(muz[m[1]]), int(m[2]), d[0], d[1], T, g["lam_spect"][m[0]])
+            assert np.array_equal(I, d[2])
+        for m, d in zip(g[tag + "psi_meta"], g[tag + "psi"]):
+            I, Psi = pd.piecewise_scalar(kind, g["n_height"], float(g["n_muz"][m[1]]), int(m[2]), d[0], d[1],
+                                         g["n_T"], g["n_lam_spect"][m[0]], want_psi=True)
+            assert np.array_equal(I, d[2]) and np.array_equal(Psi, d[3])
+    for m, d in zip(g["pst_meta"], g["pst"]):
+        I = pd.stokes_parabolic(h, float(muz[m[1]]), int(m[2]), d[0], d[1:5], d[10:13], T,
+                                g["pst_lam_spect"][m[0]])
+        assert np.array_equal(I, d[5:9])
