@@ -170,6 +170,25 @@ int rhb200_bezier3_batch(rhb200_ctx *ctx, int nray, int ncol, int ndep, double m
                          const double *height, const double *T,
                          const double *chi, const double *S, double *I, double *Psi);
 
+/* ---- Host-side Zeeman machinery (once per line list; pure host code, no device needed) ----
+   These return a count / flag >= 0 on success and a negative RHB200_E* code on error.
+   RLKdeterminate (kurucz.c:925-969): S, L of both levels from the 10-character Kurucz term labels;
+   returns 1 if determined (the line is then polarizable in Stokes mode, kurucz.c:295), else 0. */
+int rhb200_rlk_determinate(const char *labeli, const char *labelj, double *Si, int *Li, double *Sj, int *Lj);
+/* Lande (zeeman.c:139-146): LS-coupling g factor */
+double rhb200_lande(double S, int L, double J);
+/* RLKZeeman (kurucz.c:832-921): Zeeman components of a Kurucz line, in the reference's (Ml outer,
+   Mu inner) order, strengths normalised per q.  gL_i/gL_j: Lande factors from the line list
+   (-99e-3 = not given), used unless LS_Lande (keyword LS_LANDE).  Returns Ncomponent; nothing is
+   written when Ncomponent > cap. */
+int rhb200_rlk_zeeman(double gi, double gj, double Si, int Li, double Sj, int Lj, double gL_i, double gL_j,
+                      int LS_Lande, int cap, int *q, double *shift, double *strength);
+/* determinate (zeeman.c:37-85): n, S, L, J of a model-atom level from its 20-character label; 1 = determined */
+int rhb200_determinate(const char *label, double g, int *n, double *S, int *L, double *J);
+/* Zeeman (zeeman.c:186-281): pattern of a model-atom line; g_Lande_eff != 0 selects the normal triplet */
+int rhb200_zeeman(const char *label_i, double g_i, const char *label_j, double g_j, double g_Lande_eff,
+                  int cap, int *q, double *shift, double *strength);
+
 /* Formal-solver selection = keyword.input S_INTERPOLATION / S_INTERPOLATION_STOKES (readvalue.c:366-404;
    enum values of inputs.h:26-27).  Applies to rhb200_lte_stokes_batch(_dev) (Stokes solver) and to
    rhb200_nlte_iterate / rhb200_nlte_formal (scalar solver).  Defaults: S_BEZIER3, DELO_BEZIER3. */

@@ -613,3 +613,71 @@ double __wrap_solveSpectrum(bool_t eval_operator, bool_t redistribute)
   }
   return dJ;
 }
+
+/* ------------------------------------------------------------------ Zeeman helpers
+   Direct calls into the reference's host-side Zeeman machinery (kurucz.c:832-969, zeeman.c:37-299)
+   on caller-built structs: used by oracle/gen_golden_zeeman.py only. */
+ZeemanMultiplet *RLKZeeman(RLK_Line *rlk);
+bool_t RLKdeterminate(char *labeli, char *labelj, RLK_Line *rlk);
+
+int probe_rlk_determinate(const char *labeli, const char *labelj, double gi, double gj, double *out /*Si,Li,Sj,Lj*/)
+{
+  RLK_Line r;
+  char li[64], lj[64];
+  memset(&r, 0, sizeof(r));
+  r.gi = gi; r.gj = gj;
+  strncpy(li, labeli, 63); li[63] = 0;
+  strncpy(lj, labelj, 63); lj[63] = 0;
+  int ok = RLKdeterminate(li, lj, &r);
+  out[0] = r.Si; out[1] = r.Li; out[2] = r.Sj; out[3] = r.Lj;
+  return ok;
+}
+
+int probe_rlk_zeeman(double gi, double gj, double Si, int Li, double Sj, int Lj, double gL_i, double gL_j,
+                     int LS_Lande, int cap, int *q, double *shift, double *strength)
+{
+  RLK_Line r;
+  int n, save = input.LS_Lande;
+  memset(&r, 0, sizeof(r));
+  r.gi = gi; r.gj = gj; r.Si = Si; r.Li = Li; r.Sj = Sj; r.Lj = Lj; r.gL_i = gL_i; r.gL_j = gL_j;
+  input.LS_Lande = LS_Lande;
+  ZeemanMultiplet *zm = RLKZeeman(&r);
+  input.LS_Lande = save;
+  int nc = zm->Ncomponent;
+  for (n = 0; n < nc && n < cap; n++) { q[n] = zm->q[n]; shift[n] = zm->shift[n]; strength[n] = zm->strength[n]; }
+  free(zm->q); free(zm->shift); free(zm->strength); free(zm);
+  return nc;
+}
+
+/* Zeeman() of a model-atom line (zeeman.c:186-281): labels/statistical weights of the two levels */
+int probe_zeeman_atom(const char *label_i, double g_i, const char *label_j, double g_j, double g_Lande_eff,
+                      int cap, int *q, double *shift, double *strength)
+{
+  Atom atom;
+  AtomicLine line;
+  char *labels[2], li[ATOM_LABEL_WIDTH+1], lj[ATOM_LABEL_WIDTH+1];
+  double g[2];
+  int n;
+  memset(&atom, 0, sizeof(atom)); memset(&line, 0, sizeof(line));
+  strncpy(li, label_i, ATOM_LABEL_WIDTH); li[ATOM_LABEL_WIDTH] = 0;
+  strncpy(lj, label_j, ATOM_LABEL_WIDTH); lj[ATOM_LABEL_WIDTH] = 0;
+  labels[0] = li; labels[1] = lj; g[0] = g_i; g[1] = g_j;
+  atom.label = labels; atom.g = g;
+  line.atom = &atom; line.i = 0; line.j = 1; line.g_Lande_eff = g_Lande_eff;
+  ZeemanMultiplet *zm = Zeeman(&line);
+  int nc = zm->Ncomponent;
+  for (n = 0; n < nc && n < cap; n++) { q[n] = zm->q[n]; shift[n] = zm->shift[n]; strength[n] = zm->strength[n]; }
+  free(zm->q); free(zm->shift); free(zm->strength); free(zm);
+  return nc;
+}
+
+int probe_determinate(const char *label, double g, double *out /* n, S, L, J */)
+{
+  char l[ATOM_LABEL_WIDTH+1];
+  int n = 0, L = 0;
+  double S = 0, J = 0;
+  strncpy(l, label, ATOM_LABEL_WIDTH); l[ATOM_LABEL_WIDTH] = 0;
+  int ok = determinate(l, g, &n, &S, &L, &J);
+  out[0] = n; out[1] = S; out[2] = L; out[3] = J;
+  return ok;
+}

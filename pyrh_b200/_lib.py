@@ -37,6 +37,12 @@ SYMBOLS = [
                                               C.c_int, ip, dp, dp, dp, dp, dp, dp, dp, dp]),
     ("rhb200_bezier3_batch", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
                                        ip, dp, dp, dp, dp, dp, dp, dp]),
+    ("rhb200_rlk_determinate", C.c_int, [C.c_char_p, C.c_char_p, dp, ip, dp, ip]),
+    ("rhb200_lande", C.c_double, [C.c_double, C.c_int, C.c_double]),
+    ("rhb200_rlk_zeeman", C.c_int, [C.c_double, C.c_double, C.c_double, C.c_int, C.c_double, C.c_int, C.c_double,
+                                    C.c_double, C.c_int, C.c_int, ip, dp, dp]),
+    ("rhb200_determinate", C.c_int, [C.c_char_p, C.c_double, ip, dp, ip, dp]),
+    ("rhb200_zeeman", C.c_int, [C.c_char_p, C.c_double, C.c_char_p, C.c_double, C.c_double, C.c_int, ip, dp, dp]),
     ("rhb200_set_solvers", C.c_int, [vp, C.c_int, C.c_int]),
     ("rhb200_scalar_ray_batch", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
                                           C.c_int, ip, dp, dp, dp, dp, dp, dp, dp]),
