@@ -301,6 +301,21 @@ int rhb200_nlte_iterate(rhb200_ctx *ctx, const rhb200_nlte_plan *plan, int ncol,
 int rhb200_nlte_formal(rhb200_ctx *ctx, const rhb200_nlte_plan *plan, int ncol,
                        const rhb200_nlte_columns *cols, int npass, int update_J, double dJlimit,
                        double *Iem, int *npass_done);
+
+/* ---- Wavelength sharding of ONE atmosphere across ranks ("config 4") ----
+   Each rank formally solves a contiguous chunk of the sorted wavelengths (balanced by ray count,
+   rhb200_nlte_shard_range) and the per-depth radiative rates are summed over ranks once per MALI
+   iteration: Gamma [ncol][ngam][Ndep] (collisional part added on rank 0 only), Rij, Rji
+   [ncol][Ntrans][Ndep]; dJmax [ncol] is max-reduced in the scattering passes; J and the emergent
+   intensities are sum-reduced once at the end.  The library does not link a communication library:
+   the host supplies the reduction, e.g. ncclAllReduce(buf, buf, count, ncclDouble, op, comm, stream)
+   + cudaStreamSynchronize.  `fn` is called with a DEVICE pointer to `count` doubles after the
+   library has drained its stream, must reduce in place over all ranks, and must have completed
+   when it returns 0.  nrank = 1 switches sharding off. */
+enum { RHB200_REDUCE_SUM = 0, RHB200_REDUCE_MAX = 1 };
+typedef int (*rhb200_allreduce_fn)(void *user, double *device_buf, size_t count, int op);
+int rhb200_nlte_set_shard(rhb200_ctx *ctx, int rank, int nrank, rhb200_allreduce_fn fn, void *user);
+int rhb200_nlte_shard_range(const rhb200_nlte_plan *plan, int rank, int nrank, int *ns_lo, int *ns_hi);
 /* SolveLinearEq (ludcmp.c:36-86) for nsys systems: A [nsys][N][N] (untouched), b [nsys][N] in/out; N <= 32 */
 int rhb200_solve_linear_eq_batch(rhb200_ctx *ctx, int nsys, int N, double *A, double *b, int improve);
 

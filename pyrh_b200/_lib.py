@@ -16,6 +16,10 @@ BC_IRRADIATED, BC_ZERO, BC_THERMALIZED = 0, 1, 2
 K_PREP, K_OPACITY, K_DELO, K_BEZIER, K_OTHER = range(5)
 
 # every symbol include/rhb200.h declares: (name, restype, argtypes)
+# int (*rhb200_allreduce_fn)(void *user, double *device_buf, size_t count, int op)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int)
+REDUCE_SUM, REDUCE_MAX = 0, 1
+
 SYMBOLS = [
     ("rhb200_version", C.c_int, []),
     ("rhb200_last_error", C.c_char_p, []),
@@ -43,6 +47,8 @@ SYMBOLS = [
                                     C.c_double, C.c_int, C.c_int, ip, dp, dp]),
     ("rhb200_determinate", C.c_int, [C.c_char_p, C.c_double, ip, dp, ip, dp]),
     ("rhb200_zeeman", C.c_int, [C.c_char_p, C.c_double, C.c_char_p, C.c_double, C.c_double, C.c_int, ip, dp, dp]),
+    ("rhb200_nlte_set_shard", C.c_int, [vp, C.c_int, C.c_int, ALLREDUCE_FN, vp]),
+    ("rhb200_nlte_shard_range", C.c_int, [vp, C.c_int, C.c_int, ip, ip]),
     ("rhb200_set_solvers", C.c_int, [vp, C.c_int, C.c_int]),
     ("rhb200_scalar_ray_batch", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
                                           C.c_int, ip, dp, dp, dp, dp, dp, dp, dp]),

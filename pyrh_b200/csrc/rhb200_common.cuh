@@ -74,6 +74,9 @@ struct rhb200_ctx {
   std::vector<int> h_first, h_count, h_idx, h_flags, h_noline;
   // formal solver selection (keyword.input S_INTERPOLATION / S_INTERPOLATION_STOKES, inputs.h:26-27)
   int s_interpolation = RHB200_S_BEZIER3, s_interpolation_stokes = RHB200_DELO_BEZIER3;
+  // wavelength shard of the NLTE solve (rhb200_nlte_set_shard)
+  int shard_rank = 0, shard_nrank = 1;
+  rhb200_allreduce_fn shard_fn = nullptr; void *shard_user = nullptr;
   // workspace (grown on demand)
   void *ws = nullptr; size_t ws_bytes = 0;
   void *flush = nullptr; size_t flush_bytes = 0;

@@ -45,6 +45,7 @@ enum { TR_ATOM = RHB200_TR_ATOM, TR_TYPE = RHB200_TR_TYPE, TR_I = RHB200_TR_I, T
 
 struct Plan {            // device copy of the shared problem structure
   int Nspect, Nrays, Ndep, Natom, Ntrans, nas, nray, nlev, ngam, nphirow, nline, bc_top, bc_bottom, solver;
+  int ns_lo, ns_hi, add_C;   // wavelength shard [ns_lo, ns_hi) of this rank; add_C: this rank adds the collisional part
   const double *lambda, *muz, *wmu, *trans, *tr_lambda, *tr_wlambda, *tr_alpha;
   const int *atom_nlevel, *lev_off, *gam_off, *as_first, *as_trans, *angle_dep, *ray_off,
             *ray_ns, *ray_mu, *ray_dir, *prow_tr, *line_tr;
@@ -173,6 +174,7 @@ nlte_opacity_kernel(Plan P, Cols C, int ncol)
   const int r = (int) (cr % P.nray), col = (int) (cr / P.nray);
   if (!C.active[col]) return;
   const int ns = P.ray_ns[r], mu = P.ray_mu[r], dir = P.ray_dir[r];
+  if (ns < P.ns_lo || ns >= P.ns_hi) return;           // another rank's wavelength
   const int first = P.as_first[ns], nact = P.as_first[ns+1] - first;
   const double *ncol_ = C.n + (size_t) col * P.nlev * N;
   double as_chi = 0.0, as_eta = 0.0, eta_atom = 0.0;
@@ -227,6 +229,7 @@ nlte_ray_kernel(Plan P, Cols C, int ncol, int eval_operator)
   const int r = (int) (cr % P.nray), col = (int) (cr / P.nray), N = P.Ndep;
   if (!C.active[col]) return;
   const int ns = P.ray_ns[r], mu = P.ray_mu[r], dir = P.ray_dir[r];
+  if (ns < P.ns_lo || ns >= P.ns_hi) return;
   const double *h = C.height + (size_t) col * N, *T = C.T + (size_t) col * N;
   double *Psi = eval_operator ? C.Psi + cr * N : nullptr;
   if (P.angle_dep[ns]) {
@@ -261,6 +264,7 @@ nlte_J_kernel(Plan P, Cols C, int ncol)
   const size_t cl = t / N;
   const int ns = (int) (cl % P.Nspect), col = (int) (cl / P.Nspect);
   if (!C.active[col]) return;
+  if (ns < P.ns_lo || ns >= P.ns_hi) return;
   const int ad = P.angle_dep[ns];
   double J = 0.0;
   for (int r = P.ray_off[ns]; r < P.ray_off[ns+1]; r++) {
@@ -307,10 +311,12 @@ nlte_gamma_kernel(Plan P, Cols C, int ncol)
   const int Nblue = (int) trs[TR_NBLUE], Nla = (int) trs[TR_NLAMBDA];
   const double *ncol_ = C.n + (size_t) col * P.nlev * N;
   const size_t gbase = ((size_t) col * P.ngam + P.gam_off[a]) * N;
-  double Gij = C.C[gbase + (size_t)(i*Nl + j) * N + k], Gji = C.C[gbase + (size_t)(j*Nl + i) * N + k];   // initGammaAtom
+  double Gij = 0.0, Gji = 0.0;
+  if (P.add_C) { Gij = C.C[gbase + (size_t)(i*Nl + j) * N + k]; Gji = C.C[gbase + (size_t)(j*Nl + i) * N + k]; }   // initGammaAtom
   double Rij = 0.0, Rji = 0.0;                                                                          // zeroRates
 
-  for (int ns = Nblue; ns < Nblue + Nla; ns++) {
+  const int ns_first = Nblue > P.ns_lo ? Nblue : P.ns_lo, ns_last = Nblue + Nla < P.ns_hi ? Nblue + Nla : P.ns_hi;
+  for (int ns = ns_first; ns < ns_last; ns++) {
     const int first = P.as_first[ns], nact = P.as_first[ns+1] - first;
     const int ad = P.angle_dep[ns];
     for (int r = P.ray_off[ns]; r < P.ray_off[ns+1]; r++) {
@@ -366,7 +372,17 @@ __global__ void nlte_gamma_init_kernel(Plan P, Cols C, int ncol)
   const size_t per = (size_t) P.ngam * P.Ndep;
   if (t >= (size_t) ncol * per) return;
   if (!C.active[t / per]) return;
-  C.Gamma[t] = C.C[t];
+  C.Gamma[t] = P.add_C ? C.C[t] : 0.0;
+}
+
+// wavelength shard: entries of J owned by other ranks are zeroed before the closing sum-allreduce
+__global__ void nlte_zero_foreign_J_kernel(Plan P, Cols C, int ncol)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = P.Ndep;
+  if (t >= (size_t) ncol * P.Nspect * N) return;
+  const int ns = (int) ((t / N) % P.Nspect);
+  if (ns < P.ns_lo || ns >= P.ns_hi) C.J[t] = 0.0;
 }
 
 // ---- (5) SolveLinearEq: rhb200_lu.cuh
@@ -547,6 +563,8 @@ extern "C" int rhb200_solve_linear_eq_batch(rhb200_ctx *c, int nsys, int N, doub
   return RHB200_OK;
 }
 
+void rh_nlte_shard_range(int Nspect, const int *ray_off, int rank, int nrank, int *lo, int *hi);
+
 static int nlte_run(rhb200_ctx *c, const rhb200_nlte_plan *pl, int ncol,
                     const rhb200_nlte_columns *cols, int NmaxScatter, int update_J, int NmaxIter, double iterLimit,
                     int *niter_out, double *dpops_hist, int dump_iter,
@@ -595,6 +613,16 @@ static int nlte_run(rhb200_ctx *c, const rhb200_nlte_plan *pl, int ncol,
   P.Nspect = Ns; P.Nrays = Nr; P.Ndep = N; P.Natom = Na; P.Ntrans = Nt; P.nas = nas; P.nray = nray;
   P.nlev = nlev; P.ngam = ngam; P.nphirow = pl->nphirow; P.nline = pl->nline; P.bc_top = pl->bc_top; P.bc_bottom = pl->bc_bottom;
   P.solver = c->s_interpolation;
+  // wavelength shard of one atmosphere (rhb200_nlte_set_shard): contiguous chunk balanced by ray count
+  const int nrank = c->shard_nrank > 1 ? c->shard_nrank : 1, rank = nrank > 1 ? c->shard_rank : 0;
+  rh_nlte_shard_range(Ns, ray_off.data(), rank, nrank, &P.ns_lo, &P.ns_hi);
+  P.add_C = (rank == 0);
+  auto allreduce = [&](double *buf, size_t count, int op) -> int {
+    if (nrank == 1) return RHB200_OK;
+    RH_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->shard_fn(c->shard_user, buf, count, op) != 0) { rhb200_set_error("allreduce callback failed"); return RHB200_ECUDA; }
+    return RHB200_OK;
+  };
   double *dd; int *di;
 #define UPD(field, src, n) RH_CHECK(ar.upload(&dd, src, (size_t) (n))); P.field = dd
 #define UPI(field, src, n) RH_CHECK(ar.upload(&di, src, (size_t) (n))); P.field = di
@@ -700,6 +728,7 @@ static int nlte_run(rhb200_ctx *c, const rhb200_nlte_plan *pl, int ncol,
           nlte_J_kernel<<<RH_GRID(cN*Ns, 128), 0, st>>>(P, C, ncol); }
         nlte_dJmax_kernel<<<ncol, 256, 0, st>>>(P, C, ncol, d_dJmax);
         RH_CUDA(cudaGetLastError());
+        RH_CHECK(allreduce(d_dJmax, ncol, RHB200_REDUCE_MAX));
         RH_CUDA(cudaMemcpyAsync(h_dJ.data(), d_dJmax, ncol*sizeof(double), cudaMemcpyDeviceToHost, st));
         RH_CUDA(cudaStreamSynchronize(st));
       }
@@ -717,6 +746,7 @@ static int nlte_run(rhb200_ctx *c, const rhb200_nlte_plan *pl, int ncol,
     if (Iem_out) {
       // emergent intensity per (column, wavelength, mu): the up-ray of angle-dependent wavelengths
       std::vector<double> h_Iem((size_t) ncol*nray);
+      RH_CHECK(allreduce(C.Iem, (size_t) ncol*nray, RHB200_REDUCE_SUM));     // foreign rays hold 0
       RH_CUDA(cudaStreamSynchronize(st));
       RH_CUDA(cudaMemcpy(h_Iem.data(), C.Iem, h_Iem.size()*sizeof(double), cudaMemcpyDeviceToHost));
       for (int col = 0; col < ncol; col++)
@@ -741,6 +771,10 @@ static int nlte_run(rhb200_ctx *c, const rhb200_nlte_plan *pl, int ncol,
       nlte_gamma_kernel<<<RH_GRID(cN*Nt, 64), 0, st>>>(P, C, ncol); }
     { ScopedKernelTimer t(c, RHB200_K_OTHER);
       nlte_J_kernel<<<RH_GRID(cN*Ns, 128), 0, st>>>(P, C, ncol); }
+    // the exchange step of a wavelength-sharded atmosphere: radiative rates add up over ranks
+    RH_CHECK(allreduce(C.Gamma, cN*ngam, RHB200_REDUCE_SUM));
+    RH_CHECK(allreduce(C.Rij, cN*Nt, RHB200_REDUCE_SUM));
+    RH_CHECK(allreduce(C.Rji, cN*Nt, RHB200_REDUCE_SUM));
     if (it == dump_iter) {
       RH_CUDA(cudaStreamSynchronize(st));
       if (gamma_dump) RH_CUDA(cudaMemcpy(gamma_dump, C.Gamma, cN*ngam*sizeof(double), cudaMemcpyDeviceToHost));
@@ -769,10 +803,53 @@ static int nlte_run(rhb200_ctx *c, const rhb200_nlte_plan *pl, int ncol,
     }
     if (changed) RH_CUDA(cudaMemcpyAsync(d_active, active.data(), ncol*sizeof(int), cudaMemcpyHostToDevice, st));
   }
+  if (nrank > 1) {                                   // every rank returns the full J
+    nlte_zero_foreign_J_kernel<<<RH_GRID(cN*Ns, 256), 0, st>>>(P, C, ncol);
+    RH_CUDA(cudaGetLastError());
+    RH_CHECK(allreduce(C.J, cN*Ns, RHB200_REDUCE_SUM));
+  }
   RH_CUDA(cudaStreamSynchronize(st));
   RH_CUDA(cudaMemcpy(cols->n, C.n, cN*nlev*sizeof(double), cudaMemcpyDeviceToHost));
   RH_CUDA(cudaMemcpy(cols->J, C.J, cN*Ns*sizeof(double), cudaMemcpyDeviceToHost));
   if (niter_out) memcpy(niter_out, niter.data(), ncol*sizeof(int));
+  return RHB200_OK;
+}
+
+// contiguous wavelength chunk of rank `rank`: boundaries where the cumulative ray count crosses rank*nray/nrank
+void rh_nlte_shard_range(int Nspect, const int *ray_off, int rank, int nrank, int *lo, int *hi)
+{
+  const long nray = ray_off[Nspect];
+  auto bound = [&](int r) {
+    if (r <= 0) return 0;
+    if (r >= nrank) return Nspect;
+    const long target = nray * r / nrank;
+    int ns = 0;
+    while (ns < Nspect && ray_off[ns] < target) ns++;
+    return ns;
+  };
+  *lo = bound(rank); *hi = bound(rank + 1);
+}
+
+extern "C" int rhb200_nlte_set_shard(rhb200_ctx *c, int rank, int nrank, rhb200_allreduce_fn fn, void *user)
+{
+  if (!c) { rhb200_set_error("null context"); return RHB200_EINVAL; }
+  if (nrank < 1 || rank < 0 || rank >= nrank || (nrank > 1 && !fn)) { rhb200_set_error("bad shard arguments"); return RHB200_EINVAL; }
+  c->shard_rank = rank; c->shard_nrank = nrank; c->shard_fn = fn; c->shard_user = user;
+  return RHB200_OK;
+}
+
+extern "C" int rhb200_nlte_shard_range(const rhb200_nlte_plan *pl, int rank, int nrank, int *ns_lo, int *ns_hi)
+{
+  if (!pl || !ns_lo || !ns_hi || nrank < 1 || rank < 0 || rank >= nrank) { rhb200_set_error("bad arguments"); return RHB200_EINVAL; }
+  std::vector<int> ray_off(pl->Nspect + 1, 0);
+  for (int ns = 0; ns < pl->Nspect; ns++) {
+    bool bb = false;
+    for (int e = pl->as_first[ns]; e < pl->as_first[ns+1]; e++)
+      if (pl->trans[(size_t) pl->as_trans[e]*RHB200_TR_NFIELD + RHB200_TR_TYPE] == 0.0) bb = true;
+    const bool ad = pl->moving && (bb || pl->bg_hasline[ns]);
+    ray_off[ns+1] = ray_off[ns] + pl->Nrays * (ad ? 2 : 1);
+  }
+  rh_nlte_shard_range(pl->Nspect, ray_off.data(), rank, nrank, ns_lo, ns_hi);
   return RHB200_OK;
 }
 

@@ -207,3 +207,12 @@ def solve_linear_eq(ctx, A, b, improve=True):
     _lib.check(ctx.lib.rhb200_solve_linear_eq_batch(ctx.h, nsys, N, A.ctypes.data_as(dp), b.ctypes.data_as(dp),
                                                     int(improve)))
     return b
+
+
+def shard_range(prob: NlteProblem, rank: int, nrank: int) -> tuple[int, int]:
+    """Wavelength chunk [ns_lo, ns_hi) of ``rank`` when one atmosphere is split over ``nrank`` GPUs
+    (rhb200_nlte_shard_range; host-only, balanced by ray count)."""
+    plan, _cols, _n, _J, _keep, _ptr = _structs(prob, False)
+    lo, hi = C.c_int(0), C.c_int(0)
+    _lib.check(_lib.load().rhb200_nlte_shard_range(C.byref(plan), int(rank), int(nrank), C.byref(lo), C.byref(hi)))
+    return lo.value, hi.value

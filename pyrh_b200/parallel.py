@@ -54,3 +54,58 @@ def max_over_ranks(x: float) -> float:
     t = torch.tensor([x], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+# ---- wavelength sharding of ONE atmosphere (second mode): the exchange step -------
+
+class _RawBuffer:
+    """A raw pointer dressed as an array for torch: CUDA array interface for device memory, the numpy
+    array interface for host memory (gloo tests)."""
+
+    def __init__(self, ptr: int, count: int, cuda: bool):
+        iface = dict(shape=(count,), typestr="<f8", data=(ptr, False), version=3, strides=None)
+        if cuda:
+            self.__cuda_array_interface__ = iface
+        else:
+            self.__array_interface__ = iface
+
+
+def make_allreduce(group=None):
+    """A ``rhb200_allreduce_fn`` (include/rhb200.h) that reduces the library's buffer in place with
+    ``torch.distributed.all_reduce``: NCCL over NVLink on the GPUs (the pointer is device memory and is
+    wrapped without a copy), gloo on host memory in the CPU tests.  Returns (callback, stats); keep the
+    callback alive while it is registered with ``rhb200_nlte_set_shard``."""
+    import torch
+    import torch.distributed as dist
+    from . import _lib
+    cuda = dist.get_backend(group) == "nccl"
+    stats = {"calls": 0, "bytes": 0}
+
+    def reduce(_user, ptr, count, op):
+        try:
+            if cuda:
+                t = torch.as_tensor(_RawBuffer(int(ptr), int(count), True), device=torch.device("cuda", torch.cuda.current_device()))
+            else:
+                t = torch.from_numpy(np.asarray(_RawBuffer(int(ptr), int(count), False)))
+            dist.all_reduce(t, op=dist.ReduceOp.MAX if op == _lib.REDUCE_MAX else dist.ReduceOp.SUM, group=group)
+            if cuda:
+                torch.cuda.current_stream().synchronize()
+            stats["calls"] += 1
+            stats["bytes"] += 8 * int(count)
+            return 0
+        except Exception as e:          # never unwind through the C frame
+            print(f"[pyrh_b200] allreduce callback failed: {e!r}", flush=True)
+            return 1
+
+    return _lib.ALLREDUCE_FN(reduce), stats
+
+
+def shard_nlte(ctx, group=None):
+    """Register this rank's wavelength shard with the context: later ``nlte.iterate`` / ``nlte.formal``
+    calls formally solve only this rank's wavelengths and all-reduce rates once per iteration."""
+    import torch.distributed as dist
+    from . import _lib
+    fn, stats = make_allreduce(group)
+    ctx._shard_fn = fn                                      # keep the ctypes thunk alive
+    _lib.check(ctx.lib.rhb200_nlte_set_shard(ctx.h, dist.get_rank(group), dist.get_world_size(group), fn, None))
+    return stats

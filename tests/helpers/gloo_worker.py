@@ -22,10 +22,20 @@ def main():
     local = cols[:, None, None] * 10.0 + np.arange(4)[None, :, None] + 0.001 * np.arange(5)[None, None, :]
     full = gather_spectra(local, ncol, dst=0)
     t = max_over_ranks(float(rank + 1))
+    # the allreduce callback the wavelength-sharded NLTE solve hands to librhb200 (host buffer under gloo)
+    import ctypes
+    from pyrh_b200 import _lib
+    from pyrh_b200.parallel import make_allreduce
+    fn, stats = make_allreduce()
+    buf = np.arange(6, dtype=np.float64) * (rank + 1)
+    mx = np.array([1.0 + rank, 5.0 - rank])
+    rc = fn(None, buf.ctypes.data_as(ctypes.c_void_p), buf.size, _lib.REDUCE_SUM)
+    rc |= fn(None, mx.ctypes.data_as(ctypes.c_void_p), mx.size, _lib.REDUCE_MAX)
     dist.barrier()
     if full is not None:
         np.save(out + f".rank{rank}.npy", full)
-    Path(out + f".rank{rank}.json").write_text(json.dumps({"t": t, "has_full": full is not None}))
+    Path(out + f".rank{rank}.json").write_text(json.dumps({"t": t, "has_full": full is not None, "rc": rc, "sum": buf.tolist(),
+                                                            "max": mx.tolist(), "calls": stats["calls"]}))
     dist.destroy_process_group()
 
 

@@ -516,3 +516,23 @@ def test_nlte_with_other_scalar_solvers(ctx, tag, solver):
     assert np.max(np.abs(out["n"][0] / s[tag + "_nlte_n"] - 1)) < 1e-6
     assert np.array_equal(out["n"][0], s[tag + "_nlte_n"])
     assert not np.array_equal(out["n"][0], g["n_iter"][1])
+
+
+def test_nlte_wavelength_sharded_two_gpus(tmp_path):
+    """One atmosphere split by wavelength over 2 GPUs, Gamma/rates all-reduced over NCCL each MALI
+    iteration: same iteration count as the reference, populations within north_star's 1e-6."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    root = Path(__file__).resolve().parent.parent
+    out = tmp_path / "shard.json"
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29631",
+                        str(root / "tests" / "helpers" / "nlte_shard_worker.py"), str(out)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    rep = json.loads(out.read_text())
+    REPORT["nlte_lambda_shard_2gpu"] = rep
+    assert rep["niter"] == rep["niter_ref"] and rep["pops_max_rel_vs_reference"] < 1e-6
