@@ -213,6 +213,19 @@ int rhb200_stokes_ray_batch(rhb200_ctx *ctx, int solver, int nray, int ncol, int
                             const double *chi, const double *S, const double *chiQUV,
                             double *I, double *Psi);
 
+/* Analytic log gf response function (get_atomic_rfs; bezier_1D.c:416-428, 477-490, 509-516): the two
+   Piecewise_Bezier3_1D passes Formal() makes at one (wavelength, mu) in NO_STOKES mode (formal.c:167-283).
+   chi_dn/S_dn: opacity and source function of the down-ray (to_obs = 0), chi_up/S_up of the up-ray
+   [nray][ndep]; dchi, deta [nray][ndep][npar] = spectrum.dchi_c_lam / deta_c_lam (kurucz.c:696-699);
+   out I [nray][ndep] (up-ray), dI [nray][ndep][npar]; atmos.atomic_rfs[nspect][mu][p] = dI[ray][0][p]
+   (formal.c:278-282).  npar <= 16. */
+int rhb200_bezier3_rf_batch(rhb200_ctx *ctx, int nray, int ncol, int ndep, double muz,
+                            int bc_top, int bc_bottom,
+                            const int *ray_col, const double *ray_lambda,
+                            const double *height, const double *T,
+                            const double *chi_dn, const double *S_dn, const double *chi_up, const double *S_up,
+                            int npar, const double *dchi, const double *deta, double *I, double *dI);
+
 /* Feautrier (feautrier.c:56-202, F_order = STANDARD): chi, S [nray][ndep]; out P [nray][ndep]
    (Feautrier mean intensity along the ray), Psi [nray][ndep] or NULL, Iem [nray] emergent intensity */
 int rhb200_feautrier_batch(rhb200_ctx *ctx, int nray, int ncol, int ndep, double muz,

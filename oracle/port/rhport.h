@@ -108,6 +108,13 @@ void rp_stokes_parabolic(int Ndep, const double *height, double muz, int to_obs,
                          const double *T, double lambda, int bc_top, int bc_bottom,
                          double *I, double *Psi);
 
+/* the same with the log gf response function of the up-ray (bezier_1D.c:416-428, 477-490, 509-516) */
+#define RP_MAXPAR 16
+void rp_bezier3_scalar_rf(int Ndep, const double *height, double muz, int to_obs,
+                          const double *chi, const double *S, const double *T, double lambda,
+                          int bc_top, int bc_bottom, double *I, double *Psi,
+                          int npar, const double *dchi, const double *deta, double *dI);
+
 /* feautrier.c:56-202 (STANDARD order); returns emergent I */
 double rp_feautrier(int Ndep, const double *height, double muz, const double *chi, const double *S,
                     const double *T, double lambda, int bc_top, int bc_bottom, double *P, double *Psi);

@@ -362,8 +362,20 @@ void rp_stokes_bezier3(int Ndep, const double *z, double muz, int to_obs,
 void rp_bezier3_scalar(int Ndep, const double *z, double muz, int to_obs,
                        const double *chi, const double *S, const double *T, double lambda,
                        int bc_top, int bc_bottom, double *I, double *Psi)
+{
+  rp_bezier3_scalar_rf(Ndep, z, muz, to_obs, chi, S, T, lambda, bc_top, bc_bottom, I, Psi, 0, NULL, NULL, NULL);
+}
+
+/* With npar > 0 (get_atomic_rfs, up-ray only): dchi, deta [Ndep][npar] = spectrum.dchi_c_lam / deta_c_lam
+   [nspect]; dI [Ndep][npar] out.  I must enter holding the preceding down-ray solution: the reference
+   reads the not yet overwritten I[k], I[k+dk] (bezier_1D.c:424, 483). */
+void rp_bezier3_scalar_rf(int Ndep, const double *z, double muz, int to_obs,
+                          const double *chi, const double *S, const double *T, double lambda,
+                          int bc_top, int bc_bottom, double *I, double *Psi,
+                          int npar, const double *dchi, const double *deta, double *dI)
 {                                                     /* bezier_1D.c:306-541 */
-  int k, k_start, k_end, dk;
+  int k, k_start, k_end, dk, idp;
+  double Zk, Zkm1, Zkp1, dZk[RP_MAXPAR], dZup[RP_MAXPAR], dI_upw[RP_MAXPAR];
   double dtau_uw, dtau_dw = 0.0, dS_uw, I_upw = 0.0, c1, c2, w[3], zmu = 1.0 / muz;
   double dsup, dsdn, dt03, eps = 0, alpha = 0, beta = 0, gamma = 0, theta = 0;
   double dS_up, dS_c = 0.0, dchi_up, dchi_c, dchi_dn = 0.0, dsdn2;
@@ -396,6 +408,15 @@ void rp_bezier3_scalar(int Ndep, const double *z, double muz, int to_obs,
   dtau_uw = dsup * (chi[k] + chi[k-dk] + c1 + c2) * 0.25;
   dS_up = (S[k] - S[k-dk]) / dtau_uw;
 
+  if (!to_obs || npar > RP_MAXPAR) npar = 0;
+  for (idp = 0; idp < npar; idp++) {                  /* bezier_1D.c:416-428 */
+    dI[k_start*npar + idp] = 0.0;
+    dI_upw[idp] = 0.0;
+    Zk = -dchi[k*npar + idp]/chi[k] * I[k] + deta[k*npar + idp]/chi[k];
+    Zkm1 = -dchi[(k-dk)*npar + idp]/chi[k-dk] * I[k-dk] + deta[(k-dk)*npar + idp]/chi[k-dk];
+    dZup[idp] = (Zk - Zkm1) / dtau_uw;
+  }
+
   for (k = k_start+dk; k != k_end+dk; k += dk) {
     if (k != k_end) {
       dsdn = fabs(z[k+dk] - z[k]) * zmu;
@@ -413,16 +434,35 @@ void rp_bezier3_scalar(int Ndep, const double *z, double muz, int to_obs,
       c1 = RP_MAX(S[k]    - dt03 * dS_c , 0.0);
       c2 = RP_MAX(S[k-dk] + dt03 * dS_up, 0.0);
       I[k] = I_upw*eps + alpha*S[k] + beta*S[k-dk] + gamma * c1 + theta * c2;
+      for (idp = 0; idp < npar; idp++) {              /* bezier_1D.c:477-490 */
+        Zk = -dchi[k*npar + idp] * I[k] + deta[k*npar + idp];
+        Zk /= chi[k];
+        Zkm1 = -dchi[(k-dk)*npar + idp] * I[k-dk] + deta[(k-dk)*npar + idp];
+        Zkm1 /= chi[k-dk];
+        Zkp1 = -dchi[(k+dk)*npar + idp] * I[k+dk] + deta[(k+dk)*npar + idp];
+        Zkp1 /= chi[k+dk];
+        dZk[idp] = rp_cent_deriv(dtau_uw, dtau_dw, Zkm1, Zk, Zkp1);
+        c1 = RP_MAX(Zk - dt03 * dZk[idp], 0.0);
+        c2 = RP_MAX(Zkm1 + dt03 * dZup[idp], 0.0);
+        dI[k*npar + idp] = dI_upw[idp]*eps + alpha*Zk + beta*Zkm1 + gamma*c1 + theta*c2;
+      }
       if (Psi) Psi[k] = alpha + gamma;
     } else {
       dtau_uw = 0.5 * zmu * (chi[k] + chi[k-dk]) * fabs(z[k] - z[k-dk]);
       dS_uw = -(S[k] - S[k-dk]) / dtau_uw;
       rp_w3(dtau_uw, w);
       I[k] = (1.0 - w[0])*I_upw + w[0]*S[k] + w[1]*dS_uw;
+      for (idp = 0; idp < npar; idp++) {              /* bezier_1D.c:509-516 */
+        Zk = dchi[k*npar + idp]/chi[k] * I[k] - deta[k*npar + idp]/chi[k];
+        Zkm1 = dchi[(k-dk)*npar + idp]/chi[k-dk] * I[k-dk] - deta[(k-dk)*npar + idp]/chi[k-dk];
+        dZk[idp] = -(Zk - Zkm1) / dtau_uw;
+        dI[k*npar + idp] = (1.0 - w[0])*dI_upw[idp] + w[0]*Zk + w[1]*dZk[idp];
+      }
       if (Psi) Psi[k] = w[0] - w[1] / dtau_uw;
     }
     I_upw = I[k];
     dsup = dsdn; dchi_up = dchi_c; dchi_c = dchi_dn; dtau_uw = dtau_dw; dS_up = dS_c;
+    for (idp = 0; idp < npar; idp++) { dI_upw[idp] = dI[k*npar + idp]; dZup[idp] = dZk[idp]; }
   }
 }
 

@@ -140,6 +140,21 @@ def bezier3_scalar(height, muz, to_obs, chi, S, T, lam, bc_top=1, bc_bottom=2, w
     return (I, Psi) if want_psi else I
 
 
+def bezier3_scalar_rf(height, muz, chi, S, T, lam, I_in, dchi, deta, bc_top=1, bc_bottom=2):
+    """Up-ray of Piecewise_Bezier3_1D with the log gf response function; I_in = the down-ray solution
+    left in the buffer.  dchi, deta: [Ndep, npar].  Returns (I, dI[Ndep, npar])."""
+    n = len(chi)
+    arr = [np.ascontiguousarray(x, np.float64) for x in (height, chi, S, T, dchi, deta)]
+    npar = arr[4].shape[1]
+    I = np.ascontiguousarray(I_in, np.float64).copy()
+    dI = np.zeros((n, npar))
+    f = lib().rp_bezier3_scalar_rf
+    f.restype = None
+    f(n, _d(arr[0]), C.c_double(muz), 1, _d(arr[1]), _d(arr[2]), _d(arr[3]), C.c_double(lam),
+      int(bc_top), int(bc_bottom), _d(I), None, int(npar), _d(arr[4]), _d(arr[5]), _d(dI))
+    return I, dI
+
+
 def piecewise_scalar(kind, height, muz, to_obs, chi, S, T, lam, bc_top=1, bc_bottom=2, want_psi=False):
     """kind: 'linear' (Piecewise_Linear_1D) | 'parabolic' (Piecewise_1D), piecewise_1D.c:44,134."""
     n = len(chi)

@@ -242,7 +242,27 @@ void __real_Piecewise_Bezier3_1D(int nspect, int mu, bool_t to_obs, double *chi,
 void __wrap_Piecewise_Bezier3_1D(int nspect, int mu, bool_t to_obs, double *chi,
                                  double *S, double *I, double *Psi, double **dI)
 {
+  /* log gf response function (bezier_1D.c:416-428, 477-490, 509-516): the up-ray reads the not yet
+     overwritten I[] of the preceding down-ray, so that array is part of the input */
+  int rf = (probe_mask & PROBE_BEZ) && input.get_atomic_rfs && to_obs && dI != NULL;
+  double *rfrec = NULL;
+  int np_ = input.n_atomic_pars;
+  if (rf) {
+    int N = atmos.Nspace, k, p;
+    rfrec = rec_new("bezrf", (long) N + 3L*N*np_, nspect, mu, np_, 0, 0, 0);
+    memcpy(rfrec, I, N*sizeof(double));                                   /* I before the call */
+    for (k = 0; k < N; k++)
+      for (p = 0; p < np_; p++) {
+        rfrec[N + (long) k*np_ + p] = spectrum.dchi_c_lam[nspect][k][p];
+        rfrec[N + (long) N*np_ + (long) k*np_ + p] = spectrum.deta_c_lam[nspect][k][p];
+      }
+  }
   __real_Piecewise_Bezier3_1D(nspect, mu, to_obs, chi, S, I, Psi, dI);
+  if (rf) {
+    int N = atmos.Nspace, k, p;
+    for (k = 0; k < N; k++)
+      for (p = 0; p < np_; p++) rfrec[N + 2L*N*np_ + (long) k*np_ + p] = dI[k][p];
+  }
   if (probe_mask & PROBE_BEZ) {
     int N = atmos.Nspace;
     double *d = rec_new("bez", 4*N, nspect, mu, to_obs, Psi != NULL, 0, 0);

@@ -54,6 +54,8 @@ SYMBOLS = [
                                           C.c_int, ip, dp, dp, dp, dp, dp, dp, dp]),
     ("rhb200_stokes_ray_batch", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
                                           C.c_int, ip, dp, dp, dp, dp, dp, dp, dp, dp]),
+    ("rhb200_bezier3_rf_batch", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, ip, dp,
+                                          dp, dp, dp, dp, dp, dp, C.c_int, dp, dp, dp, dp]),
     ("rhb200_feautrier_batch", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, ip, dp,
                                          dp, dp, dp, dp, dp, dp, dp]),
     ("rhb200_voigt_humlicek", C.c_int, [vp, C.c_int, dp, dp, dp, dp, ip]),

@@ -216,6 +216,25 @@ class Context:
             _dp(Psi) if want_psi else None))
         return (I, Psi) if want_psi else I
 
+    def bezier3_rf(self, ray_col, ray_lambda, height, T, chi_dn, S_dn, chi_up, S_up, dchi, deta, mu=1.0,
+                   bc_top=_lib.BC_ZERO, bc_bottom=_lib.BC_THERMALIZED):
+        """Down-ray + up-ray with the analytic log gf response function (get_atomic_rfs):
+        dchi, deta [nray, ndep, npar].  Returns (I [nray, ndep], dI [nray, ndep, npar])."""
+        rc = np.ascontiguousarray(ray_col, np.int32)
+        rl = np.ascontiguousarray(ray_lambda, np.float64)
+        h = np.ascontiguousarray(np.atleast_2d(height), np.float64)
+        t = np.ascontiguousarray(np.atleast_2d(T), np.float64)
+        a = [np.ascontiguousarray(x, np.float64) for x in (chi_dn, S_dn, chi_up, S_up, dchi, deta)]
+        nray, ndep = a[0].shape
+        npar = a[4].shape[2]
+        I = np.zeros((nray, ndep))
+        dI = np.zeros((nray, ndep, npar))
+        _lib.check(self.lib.rhb200_bezier3_rf_batch(
+            self.h, nray, h.shape[0], ndep, float(mu), int(bc_top), int(bc_bottom),
+            rc.ctypes.data_as(_lib.ip), _dp(rl), _dp(h), _dp(t), *[_dp(x) for x in a[:4]], int(npar),
+            _dp(a[4]), _dp(a[5]), _dp(I), _dp(dI)))
+        return I, dI
+
     def feautrier(self, ray_col, ray_lambda, height, T, chi, S, mu=1.0, bc_top=_lib.BC_ZERO,
                   bc_bottom=_lib.BC_THERMALIZED, want_psi=False):
         rc = np.ascontiguousarray(ray_col, np.int32)

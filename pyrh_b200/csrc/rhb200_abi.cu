@@ -524,6 +524,36 @@ extern "C" int rhb200_scalar_ray_batch(rhb200_ctx *c, int solver, int nray, int 
   return RHB200_OK;
 }
 
+extern "C" int rhb200_bezier3_rf_batch(rhb200_ctx *c, int nray, int ncol, int ndep, double muz,
+                                       int bc_top, int bc_bottom, const int *ray_col, const double *ray_lambda,
+                                       const double *height, const double *T,
+                                       const double *chi_dn, const double *S_dn, const double *chi_up, const double *S_up,
+                                       int npar, const double *dchi, const double *deta, double *I, double *dI)
+{
+  RH_NEED_CTX(c);
+  if (nray <= 0 || ncol <= 0 || ndep < 3 || !ray_col || !ray_lambda || !height || !T || !chi_dn || !S_dn ||
+      !chi_up || !S_up || !dchi || !deta || !I || !dI) { rhb200_set_error("bad arguments"); return RHB200_EINVAL; }
+  if (npar < 1 || npar > 16) { rhb200_set_error("npar must be in 1..16"); return RHB200_EINVAL; }
+  for (int r = 0; r < nray; r++) if (ray_col[r] < 0 || ray_col[r] >= ncol) { rhb200_set_error("ray_col[%d] out of range", r); return RHB200_EINVAL; }
+  DevBuf rc, rl, h, t, cd, sd, cu, su, dc, de, dIb, ddI;
+  const size_t rb = (size_t) nray * ndep * sizeof(double);
+  RH_CHECK(rc.from_host(ray_col, (size_t) nray * sizeof(int)));
+  RH_CHECK(rl.from_host(ray_lambda, (size_t) nray * sizeof(double)));
+  RH_CHECK(h.from_host(height, (size_t) ncol * ndep * sizeof(double)));
+  RH_CHECK(t.from_host(T, (size_t) ncol * ndep * sizeof(double)));
+  RH_CHECK(cd.from_host(chi_dn, rb)); RH_CHECK(sd.from_host(S_dn, rb));
+  RH_CHECK(cu.from_host(chi_up, rb)); RH_CHECK(su.from_host(S_up, rb));
+  RH_CHECK(dc.from_host(dchi, rb * npar)); RH_CHECK(de.from_host(deta, rb * npar));
+  RH_CHECK(dIb.alloc(rb)); RH_CHECK(ddI.alloc(rb * npar));
+  RH_CHECK(rh_launch_bezier3_rf(c, nray, ndep, muz, bc_top, bc_bottom, rc.as<int>(), rl.as<double>(), h.as<double>(),
+                                t.as<double>(), cd.as<double>(), sd.as<double>(), cu.as<double>(), su.as<double>(),
+                                npar, dc.as<double>(), de.as<double>(), dIb.as<double>(), ddI.as<double>()));
+  RH_CUDA(cudaStreamSynchronize(c->stream));
+  RH_CHECK(to_host(I, dIb.p, rb));
+  RH_CHECK(to_host(dI, ddI.p, rb * npar));
+  return RHB200_OK;
+}
+
 extern "C" int rhb200_feautrier_batch(rhb200_ctx *c, int nray, int ncol, int ndep, double muz,
                                       int bc_top, int bc_bottom, const int *ray_col, const double *ray_lambda,
                                       const double *height, const double *T, const double *chi, const double *S,

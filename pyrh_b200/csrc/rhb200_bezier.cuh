@@ -1,16 +1,23 @@
 // rhb200_bezier.cuh -- scalar cubic-Bezier short-characteristics ray (unpolarised).
-// Reference: Piecewise_Bezier3_1D rh/rhf1d/bezier_1D.c:306-541 (the log gf response-function
-// branch, :416-428/:477-490/:509-516, is not part of this kernel).
+// Reference: Piecewise_Bezier3_1D rh/rhf1d/bezier_1D.c:306-541.  RF = true adds the log gf
+// response-function branch (:416-428, :477-490, :509-516): dchi/deta [ndep][npar] are
+// spectrum.dchi_c_lam/deta_c_lam of the wavelength, dI [ndep][npar] the output; I must then enter
+// holding the preceding down-ray solution, which the reference reads at not yet updated depths.
 #pragma once
 #include "rhb200_delo.cuh"
 
 namespace rhz {
 
-__device__ __forceinline__ void bezier3_ray(const int ndep, const double *__restrict__ z, const double muz,
-                                            const int to_obs, const int bc_top, const int bc_bottom,
-                                            const double *__restrict__ T, const double lambda,
-                                            const double *__restrict__ chi, const double *__restrict__ S,
-                                            double *__restrict__ I, double *__restrict__ Psi)
+#define RHB200_MAXPAR 16
+
+template <bool RF>
+__device__ __forceinline__ void bezier3_ray_t(const int ndep, const double *__restrict__ z, const double muz,
+                                              const int to_obs, const int bc_top, const int bc_bottom,
+                                              const double *__restrict__ T, const double lambda,
+                                              const double *__restrict__ chi, const double *__restrict__ S,
+                                              double *I, double *__restrict__ Psi,
+                                              const int npar, const double *__restrict__ dchi,
+                                              const double *__restrict__ deta, double *__restrict__ dI)
 {
   using namespace rhd;
   const double zmu = 1.0 / muz;
@@ -46,6 +53,16 @@ __device__ __forceinline__ void bezier3_ray(const int ndep, const double *__rest
   }
   double dS_up = (S[k] - S[k-dk]) / dtau_uw;
   double fS = dS_up, dtau_dw = 0.0, dchi_dn = 0.0, dS_c = 0.0;
+  double dZk[RF ? RHB200_MAXPAR : 1], dZup[RF ? RHB200_MAXPAR : 1], dI_upw[RF ? RHB200_MAXPAR : 1];
+  if (RF) {
+    for (int p = 0; p < npar; p++) {                     // bezier_1D.c:416-428
+      dI[ks*npar + p] = 0.0;
+      dI_upw[p] = 0.0;
+      const double Zk = -dchi[k*npar + p]/chi[k] * I[k] + deta[k*npar + p]/chi[k];
+      const double Zkm1 = -dchi[(k-dk)*npar + p]/chi[k-dk] * I[k-dk] + deta[(k-dk)*npar + p]/chi[k-dk];
+      dZup[p] = (Zk - Zkm1) / dtau_uw;
+    }
+  }
 
   for (; k != ke + dk; k += dk) {
     if (k != ke) {
@@ -70,6 +87,21 @@ __device__ __forceinline__ void bezier3_ray(const int ndep, const double *__rest
       c1 = RH_MAX0(S[k]    - dt03 * dS_c);
       c2 = RH_MAX0(S[k-dk] + dt03 * dS_up);
       I[k] = I_upw*eps + alpha*S[k] + beta*S[k-dk] + gamma * c1 + theta * c2;
+      if (RF) {
+        const double ca = fb_alpha(dtau_uw, dtau_dw);
+        for (int p = 0; p < npar; p++) {                 // bezier_1D.c:477-490
+          double Zk = -dchi[k*npar + p] * I[k] + deta[k*npar + p];
+          Zk /= chi[k];
+          double Zkm1 = -dchi[(k-dk)*npar + p] * I[k-dk] + deta[(k-dk)*npar + p];
+          Zkm1 /= chi[k-dk];
+          double Zkp1 = -dchi[(k+dk)*npar + p] * I[k+dk] + deta[(k+dk)*npar + p];   // I[k+dk]: down-ray value
+          Zkp1 /= chi[k+dk];
+          dZk[p] = fb_deriv((Zk - Zkm1) / dtau_uw, (Zkp1 - Zk) / dtau_dw, ca);
+          const double z1 = RH_MAX0(Zk - dt03 * dZk[p]);
+          const double z2 = RH_MAX0(Zkm1 + dt03 * dZup[p]);
+          dI[k*npar + p] = dI_upw[p]*eps + alpha*Zk + beta*Zkm1 + gamma*z1 + theta*z2;
+        }
+      }
       if (Psi) Psi[k] = alpha + gamma;
       fchi = fnext;
     } else {
@@ -78,11 +110,29 @@ __device__ __forceinline__ void bezier3_ray(const int ndep, const double *__rest
       double w0, w1;
       w3(dtau_uw, w0, w1);
       I[k] = (1.0 - w0)*I_upw + w0*S[k] + w1*dS_uw;
+      if (RF) {
+        for (int p = 0; p < npar; p++) {                 // bezier_1D.c:509-516
+          const double Zk = dchi[k*npar + p]/chi[k] * I[k] - deta[k*npar + p]/chi[k];
+          const double Zkm1 = dchi[(k-dk)*npar + p]/chi[k-dk] * I[k-dk] - deta[(k-dk)*npar + p]/chi[k-dk];
+          dZk[p] = -(Zk - Zkm1) / dtau_uw;
+          dI[k*npar + p] = (1.0 - w0)*dI_upw[p] + w0*Zk + w1*dZk[p];
+        }
+      }
       if (Psi) Psi[k] = w0 - w1 / dtau_uw;
     }
     I_upw = I[k];
     dsup = dsdn; dchi_up = dchi_c; dchi_c = dchi_dn; dtau_uw = dtau_dw; dS_up = dS_c;
+    if (RF) for (int p = 0; p < npar; p++) { dI_upw[p] = dI[k*npar + p]; dZup[p] = dZk[p]; }
   }
+}
+
+__device__ __forceinline__ void bezier3_ray(const int ndep, const double *__restrict__ z, const double muz,
+                                            const int to_obs, const int bc_top, const int bc_bottom,
+                                            const double *__restrict__ T, const double lambda,
+                                            const double *__restrict__ chi, const double *__restrict__ S,
+                                            double *__restrict__ I, double *__restrict__ Psi)
+{
+  bezier3_ray_t<false>(ndep, z, muz, to_obs, bc_top, bc_bottom, T, lambda, chi, S, I, Psi, 0, nullptr, nullptr, nullptr);
 }
 
 }  // namespace rhz

@@ -125,6 +125,10 @@ int rh_launch_delo_generic(rhb200_ctx *ctx, int solver /* RHB200_DELO_* */, int 
                            const double *d_ray_lambda, const double *d_height, const double *d_T,
                            const double *d_chi, const double *d_S, const double *d_chiQUV,
                            double *d_I, double *d_Psi);
+int rh_launch_bezier3_rf(rhb200_ctx *ctx, int nray, int ndep, double muz, int bc_top, int bc_bottom,
+                         const int *d_ray_col, const double *d_ray_lambda, const double *d_height, const double *d_T,
+                         const double *d_chi_dn, const double *d_S_dn, const double *d_chi_up, const double *d_S_up,
+                         int npar, const double *d_dchi, const double *d_deta, double *d_I, double *d_dI);
 int rh_launch_bezier3(rhb200_ctx *ctx, int solver /* RHB200_S_* */, int nray, int ndep, double muz, int to_obs,
                       int bc_top, int bc_bottom, const int *d_ray_col,
                       const double *d_ray_lambda, const double *d_height, const double *d_T,

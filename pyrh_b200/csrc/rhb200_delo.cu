@@ -132,6 +132,30 @@ bezier3_kernel(int solver, int nray, int ndep, double muz, int to_obs, int bc_to
   }
 }
 
+// Formal()'s two passes at one (wavelength, mu) in NO_STOKES mode with get_atomic_rfs (formal.c:167-283):
+// the down-ray fills I, the up-ray overwrites it while its response-function branch still reads the
+// down-ray values at the depths it has not reached yet.
+__global__ void __launch_bounds__(128)
+bezier3_rf_kernel(int nray, int ndep, double muz, int bc_top, int bc_bottom,
+                  const int *__restrict__ ray_col, const double *__restrict__ ray_lambda,
+                  const double *__restrict__ height, const double *__restrict__ T,
+                  const double *__restrict__ chi_dn, const double *__restrict__ S_dn,
+                  const double *__restrict__ chi_up, const double *__restrict__ S_up,
+                  int npar, const double *__restrict__ dchi, const double *__restrict__ deta,
+                  double *I, double *__restrict__ dI)
+{
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nray) return;
+  const int col = ray_col[r];
+  const double *z = height + (size_t) col*ndep, *Tc = T + (size_t) col*ndep;
+  double *Ir = I + (size_t) r*ndep;
+  rhz::bezier3_ray_t<false>(ndep, z, muz, 0, bc_top, bc_bottom, Tc, ray_lambda[r], chi_dn + (size_t) r*ndep,
+                            S_dn + (size_t) r*ndep, Ir, nullptr, 0, nullptr, nullptr, nullptr);
+  rhz::bezier3_ray_t<true>(ndep, z, muz, 1, bc_top, bc_bottom, Tc, ray_lambda[r], chi_up + (size_t) r*ndep,
+                           S_up + (size_t) r*ndep, Ir, nullptr, npar, dchi + (size_t) r*ndep*npar,
+                           deta + (size_t) r*ndep*npar, dI + (size_t) r*ndep*npar);
+}
+
 // ---- Feautrier IO policies
 struct FeauRayPtsIO {           // fused LTE path: line-free rays; F and z live in the unused K' slots
   double *rp;                   // this ray's records [k][RP_NFIELD]
@@ -258,6 +282,21 @@ int rh_launch_bezier3(rhb200_ctx *ctx, int solver, int nray, int ndep, double mu
     bezier3_kernel<<<blocks, threads, 0, ctx->stream>>>(solver, nray, ndep, muz, to_obs, bc_top, bc_bottom,
                                                          d_ray_col, d_ray_lambda, d_height, d_T,
                                                          d_chi, d_S, d_I, d_Psi);
+  }
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}
+
+int rh_launch_bezier3_rf(rhb200_ctx *ctx, int nray, int ndep, double muz, int bc_top, int bc_bottom,
+                         const int *d_ray_col, const double *d_ray_lambda, const double *d_height, const double *d_T,
+                         const double *d_chi_dn, const double *d_S_dn, const double *d_chi_up, const double *d_S_up,
+                         int npar, const double *d_dchi, const double *d_deta, double *d_I, double *d_dI)
+{
+  if (nray == 0) return RHB200_OK;
+  {
+    ScopedKernelTimer t(ctx, RHB200_K_BEZIER);
+    bezier3_rf_kernel<<<(nray + 127) / 128, 128, 0, ctx->stream>>>(nray, ndep, muz, bc_top, bc_bottom, d_ray_col,
+        d_ray_lambda, d_height, d_T, d_chi_dn, d_S_dn, d_chi_up, d_S_up, npar, d_dchi, d_deta, d_I, d_dI);
   }
   RH_CUDA(cudaGetLastError());
   return RHB200_OK;

@@ -536,3 +536,19 @@ def test_nlte_wavelength_sharded_two_gpus(tmp_path):
     rep = json.loads(out.read_text())
     REPORT["nlte_lambda_shard_2gpu"] = rep
     assert rep["niter"] == rep["niter_ref"] and rep["pops_max_rel_vs_reference"] < 1e-6
+
+
+def test_loggf_response_function_vs_reference(ctx):
+    """Analytic log gf RF (get_atomic_rfs): both Formal() passes on the device, dI and the returned
+    mySpectrum.rfs bit-identical to the reference's."""
+    g = dict(np.load(GOLD / "falc_rf.npz"))
+    nray = len(g["ns"])
+    I, dI = ctx.bezier3_rf(np.zeros(nray, np.int32), g["lam_spect"][g["ns"]], g["col_height"], g["col_T"],
+                           g["down"][:, 0], g["down"][:, 1], g["up"][:, 0], g["up"][:, 1], g["dchi"], g["deta"],
+                           mu=float(g["muz"][0]))
+    REPORT["loggf_rf_exact"] = bool(np.array_equal(dI, g["dI"]))
+    assert np.array_equal(I, g["up"][:, 2])
+    assert np.array_equal(dI, g["dI"])
+    keep = (g["lam_spect"] != 500.0)[g["ns"]]
+    assert np.array_equal(dI[keep][:, 0], g["rfs"])
+    assert np.array_equal(I[keep][:, 0], g["I_spec"])

@@ -189,3 +189,17 @@ def test_piecewise_and_delo_parabolic_port_bit_exact():
         I = pd.stokes_parabolic(h, float(muz[m[1]]), int(m[2]), d[0], d[1:5], d[10:13], T,
                                 g["pst_lam_spect"][m[0]])
         assert np.array_equal(I, d[5:9])
+
+
+def test_loggf_response_function_port_bit_exact():
+    """Up-ray of Piecewise_Bezier3_1D with get_atomic_rfs (bezier_1D.c:416-516) vs the reference's recorded
+    dI; the reference's returned rfs are dI at the top of the atmosphere (formal.c:278-282)."""
+    from conftest import GOLD
+    g = dict(np.load(GOLD / "falc_rf.npz"))
+    assert np.array_equal(g["I_in"], g["down"][:, 2])          # the RF branch sees the down-ray solution
+    for i, ns in enumerate(g["ns"]):
+        I, dI = pd.bezier3_scalar_rf(g["col_height"], float(g["muz"][0]), g["up"][i, 0], g["up"][i, 1], g["col_T"],
+                                     g["lam_spect"][ns], g["I_in"][i], g["dchi"][i], g["deta"][i])
+        assert np.array_equal(I, g["up"][i, 2]) and np.array_equal(dI, g["dI"][i])
+    keep = (g["lam_spect"] != 500.0)[g["ns"]]
+    assert np.array_equal(g["dI"][keep][:, 0], g["rfs"])
