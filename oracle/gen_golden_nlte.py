@@ -100,25 +100,33 @@ def flatten(R):
     return out
 
 
-def main():
+def build(name, keywords=KW, atoms_active=(), atoms_extra=(("CaII.atom", "ACTIVE"),), pops_keys=("CA",)):
+    """Run the reference and write tests/golden/<name>.npz.  Several ACTIVE atoms are concatenated in the
+    order of atmos.activeatoms (levels, Gamma blocks, transitions), which is the device layout."""
     atm = rd.falc("tests")
     atm[5] = 500.0
     wave = np.linspace(630.25, 630.5, 21)
-    cwd = rd.make_workdir("tests", keywords=KW, atoms_extra=(("CaII.atom", "ACTIVE"),))
+    cwd = rd.make_workdir("tests", keywords=keywords, atoms_active=atoms_active, atoms_extra=atoms_extra)
     o = rd.rhf1d(atm, wave, cwd, probe=rd.PROBE_NLTE, get_populations=True)
     R = recs_by_tag(o["records"])
     g = flatten(R)
-    N = int(g["hdr"][3])
-    ups = sorted(R["up_gamma"], key=lambda x: x[0][1])
-    g["niter"] = np.int32(len(ups))
-    keep = [0, 1, len(ups) - 1]
+    N, Natom = int(g["hdr"][3]), int(g["hdr"][2])
+
+    def per_iter(tag):
+        """[iteration][atom-concatenated rows]: records carry (atom, niter) in their meta"""
+        its = sorted({m[1] for m, _ in R[tag]})
+        return its, [[d for m, d in sorted(R[tag], key=lambda x: x[0][0]) if m[1] == it] for it in its]
+
+    its, gam = per_iter("up_gamma")
+    g["niter"] = np.int32(len(its))
+    keep = [0, 1, len(its) - 1]
     g["iter_keep"] = np.array(keep, np.int32)
-    g["gamma_iter"] = np.array([ups[i][1].reshape(-1, N) for i in keep])
-    rates = sorted(R["up_rates"], key=lambda x: x[0][1])
-    g["rates_iter"] = np.array([rates[i][1].reshape(-1, N) for i in keep])
-    upn = sorted(R["up_n"], key=lambda x: x[0][1])
-    g["n_iter"] = np.array([u[1][:-1].reshape(-1, N) for u in upn])          # all iterations (small)
-    g["dpops_iter"] = np.array([u[1][-1] for u in upn])
+    g["gamma_iter"] = np.array([np.concatenate([d.reshape(-1, N) for d in gam[i]]) for i in keep])
+    _, rates = per_iter("up_rates")
+    g["rates_iter"] = np.array([np.concatenate([d.reshape(-1, N) for d in rates[i]]) for i in keep])
+    _, upn = per_iter("up_n")
+    g["n_iter"] = np.array([np.concatenate([d[:-1].reshape(-1, N) for d in row]) for row in upn])   # all iterations
+    g["dpops_iter"] = np.array([row[0][-1] for row in upn])
     g["n_final"] = np.concatenate([d.reshape(-1, N) for m, d in sorted(R["nl_n_final"], key=lambda x: x[0][0])])
     g["J_final"] = one(R, "nl_J_final").reshape(-1, N)
     # SolveLinearEq samples: the statEquil systems (N == Nlevel) of iteration 1 and the Ng systems
@@ -138,11 +146,18 @@ def main():
     g["fs_vbroad"] = np.array([d for m, d in sorted(R["fs_vbroad"], key=lambda x: x[0][0])])
     g["fs_vel"] = one(R, "fs_vel")
     g["spec_lam"], g["spec_I"] = o["lam"], o["I"]
-    g["pops_final"] = o["pops"]["CA"]["n"]
-    np.savez_compressed(GOLD / "nlte_caii.npz", **g)
-    print(f"[golden] nlte_caii: Nspect={len(g['lam'])} Ntrans={len(g['trans'])} iterations={int(g['niter'])} "
-          f"dpops_last={g['dpops_iter'][-1]:.3e} -> {(GOLD / 'nlte_caii.npz').stat().st_size/1e6:.2f} MB")
+    g["pops_final"] = np.concatenate([o["pops"][k]["n"] for k in pops_keys])
+    np.savez_compressed(GOLD / f"{name}.npz", **g)
+    print(f"[golden] {name}: Natom={Natom} Nspect={len(g['lam'])} Ntrans={len(g['trans'])} iterations={int(g['niter'])} "
+          f"dpops_last={g['dpops_iter'][-1]:.3e} -> {(GOLD / (name + '.npz')).stat().st_size/1e6:.2f} MB")
     return g
+
+
+def main():
+    if "--two-atom-only" not in sys.argv:
+        build("nlte_caii")
+    # BASELINE config 4: H (6 levels, 10 lines, 5 continua) + Ca II, both ACTIVE, CRD
+    build("nlte_h_caii", keywords=dict(KW, HYDROGEN_LTE="FALSE"), atoms_active=("H_6.atom",), pops_keys=("H ", "CA"))
 
 
 if __name__ == "__main__":

@@ -320,17 +320,19 @@ def test_solve_linear_eq_batch_vs_reference(ctx):
         assert np.array_equal(x, np.array([d[N * N + N:] for d in lst])), N
 
 
-def test_nlte_mali_iteration_vs_reference(ctx):
-    """config 4 class problem (CaII 6-level + continuum, FAL-C, NRAYS=3, Ng order 2, ITER_LIMIT 1e-4):
-    Gamma and rates of the first iterations, populations of every iteration, iteration count and the
-    converged populations/J must match the reference (north_star: 1e-6 relative; achieved: bitwise)."""
+@pytest.mark.parametrize("fixture", ["nlte_caii", "nlte_h_caii"])
+def test_nlte_mali_iteration_vs_reference(ctx, fixture):
+    """config 4 (FAL-C, NRAYS=3, Ng order 2, ITER_LIMIT 1e-4): CaII 6-level alone, and H 6-level + CaII both
+    ACTIVE (895 wavelengths, 25 transitions).  Gamma and rates of the first iterations, populations of every
+    iteration, iteration count and the converged populations/J must match the reference (north_star: 1e-6
+    relative; achieved: bitwise)."""
     from pyrh_b200 import nlte
-    g = dict(np.load(GOLD / "nlte_caii.npz"))
+    g = dict(np.load(GOLD / f"{fixture}.npz"))
     prob = nlte.NlteProblem.from_golden(g, ncol=1)
     for idx, it in enumerate(g["iter_keep"][:2]):
         out = nlte.iterate(ctx, prob, nmax=int(it) + 1, limit=0.0, dump_iter=int(it) + 1)
         ref = g["gamma_iter"][idx]
-        REPORT[f"nlte_gamma_iter{int(it)+1}_exact"] = bool(np.array_equal(out["gamma"][0], ref))
+        REPORT[f"{fixture}_gamma_iter{int(it)+1}_exact"] = bool(np.array_equal(out["gamma"][0], ref))
         assert np.allclose(out["gamma"][0], ref, rtol=1e-10, atol=0)
         assert np.array_equal(out["gamma"][0], ref)
         assert np.array_equal(out["rij"][0], g["rates_iter"][idx][0::2])
@@ -339,8 +341,9 @@ def test_nlte_mali_iteration_vs_reference(ctx):
     out = nlte.iterate(ctx, prob)
     assert out["niter"][0] == int(g["niter"])
     rel = np.max(np.abs(out["n"][0] / g["n_final"] - 1))
-    REPORT["nlte_final_pops_maxrel"] = float(rel)
-    REPORT["nlte_final_pops_exact"] = bool(np.array_equal(out["n"][0], g["n_final"]))
+    REPORT[f"{fixture}_final_pops_maxrel"] = float(rel)
+    REPORT[f"{fixture}_final_pops_exact"] = bool(np.array_equal(out["n"][0], g["n_final"]))
+    REPORT[f"{fixture}_iterations"] = int(out["niter"][0])
     assert rel < 1e-6
     assert np.array_equal(out["n"][0], g["n_final"])
     assert np.array_equal(out["J"][0], g["J_final"])

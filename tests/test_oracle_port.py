@@ -106,11 +106,14 @@ def test_scalar_bezier3_and_feautrier_bit_exact():
             assert np.array_equal(Psi, d[3])
 
 
-def test_nlte_port_bit_exact_all_iterations():
+@pytest.mark.parametrize("fixture,niter", [("nlte_caii", 31), ("nlte_h_caii", 34)])
+def test_nlte_port_bit_exact_all_iterations(fixture, niter):
     """MALI iteration (Opacity, addtoGamma/Coupling/Rates, statEquil, Ng) of the C restatement vs the
-    reference's recorded Gamma, rates and populations: CaII 6-level atom on FAL-C, 31 iterations."""
+    reference's recorded Gamma, rates and populations: CaII 6-level atom on FAL-C (31 iterations) and
+    BASELINE config 4, H 6-level + CaII both ACTIVE (895 wavelengths, 25 transitions, 34 iterations)."""
     from conftest import GOLD
-    g = dict(np.load(GOLD / "nlte_caii.npz"))
+    g = dict(np.load(GOLD / f"{fixture}.npz"))
+    assert int(g["niter"]) == niter
     P = pd.PortNlte(g)
     it, nh, gh, rh, dh = P.iterate(int(g["hdr"][9]), float(g["hdr"][10]))
     assert it == int(g["niter"])
