@@ -295,22 +295,28 @@ nlte_dJmax_kernel(Plan P, Cols C, int ncol, double *dJmax)
   if (threadIdx.x == 0) dJmax[col] = sm[0];
 }
 
-// ---- (4) addtoCoupling + addtoGamma + addtoRates for one transition at one depth
-__global__ void __launch_bounds__(64)
+// ---- (4) addtoCoupling + addtoGamma + addtoRates for one transition at one depth.
+// blockIdx.y = transition, threads over (column, depth): the walk over this transition's wavelengths,
+// rays and active-set entries is uniform across the block (no divergent trip counts, broadcast loads of
+// the plan tables).  Everything that does not depend on the ray is gathered once per wavelength into a
+// small per-thread cache: the products are formed in the reference's association order
+// (V*w)*(n_i - g n_j), (thn*g)*V, ((thn*g)*V)*n_j, so hoisting the right-hand factors changes no rounding.
+#define NLTE_MAXACT 12
+#define NLTE_RB 6
+__global__ void __launch_bounds__(64, 8)
 nlte_gamma_kernel(Plan P, Cols C, int ncol)
 {
   const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
   const int N = P.Ndep;
-  if (t >= (size_t) ncol * P.Ntrans * N) return;
-  const int k = (int) (t % N);
-  const size_t ct = t / N;
-  const int tid = (int) (ct % P.Ntrans), col = (int) (ct / P.Ntrans);
+  if (t >= (size_t) ncol * N) return;
+  const int k = (int) (t % N), col = (int) (t / N), tid = blockIdx.y;
   if (!C.active[col]) return;
   const double *trs = P.trans + (size_t) tid * TR_NFIELD;
   const int a = (int) trs[TR_ATOM], i = (int) trs[TR_I], j = (int) trs[TR_J], Nl = P.atom_nlevel[a];
   const int Nblue = (int) trs[TR_NBLUE], Nla = (int) trs[TR_NLAMBDA];
   const double *ncol_ = C.n + (size_t) col * P.nlev * N;
   const size_t gbase = ((size_t) col * P.ngam + P.gam_off[a]) * N;
+  const double hc_4PI = (RH_HPLANCK * RH_CLIGHT) / (4.0 * RH_PI);
   double Gij = 0.0, Gji = 0.0;
   if (P.add_C) { Gij = C.C[gbase + (size_t)(i*Nl + j) * N + k]; Gji = C.C[gbase + (size_t)(j*Nl + i) * N + k]; }   // initGammaAtom
   double Rij = 0.0, Rji = 0.0;                                                                          // zeroRates
@@ -319,44 +325,97 @@ nlte_gamma_kernel(Plan P, Cols C, int ncol)
   for (int ns = ns_first; ns < ns_last; ns++) {
     const int first = P.as_first[ns], nact = P.as_first[ns+1] - first;
     const int ad = P.angle_dep[ns];
-    for (int r = P.ray_off[ns]; r < P.ray_off[ns+1]; r++) {
-      const int mu = P.ray_mu[r], dir = P.ray_dir[r];
-      const double wmu = ad ? 0.5 * P.wmu[mu] : P.wmu[mu];
-      // per-ray quantities of this atom's active transitions (opacity.c / addtoCoupling)
-      double eta_atom = 0.0, chi_up_i = 0.0, Uji_down_j = 0.0, chi_down_j = 0.0, Uji_down_i = 0.0;
-      double Vs = 0.0, gs = 0.0, ws = 0.0, thns = 0.0;
-      int n_jp_eq_i = 0;
-      for (int n = 0; n < nact; n++) {
-        const int tm = P.as_trans[first+n];
-        const double *tr = P.trans + (size_t) tm * TR_NFIELD;
-        if ((int) tr[TR_ATOM] != a) continue;
-        const int im = (int) tr[TR_I], jm = (int) tr[TR_J];
-        const double V = vij_of(P, C, col, tr, ns, mu, dir, k);
-        const double *gw = C.gw + (((size_t) col * P.nas + first + n) * 2) * N + k;
-        const double g = gw[0], w = gw[N];
-        const double thn = twohnu3_of(P, tr, ns);
-        const double n_i = ncol_[(size_t)(P.lev_off[a] + im) * N + k], n_j = ncol_[(size_t)(P.lev_off[a] + jm) * N + k];
-        if (thn != 0.0) {
-          eta_atom += thn * g * V * n_j;                          // opacity.c:257-258
-          const double chicc = V * w * (n_i - g*n_j);             // fillgamma.c:321-327
-          if (im == i) chi_up_i += chicc;
-          if (jm == j) { chi_down_j += chicc; Uji_down_j += thn * g * V; }
-          if (jm == i) Uji_down_i += thn * g * V;
-        }
-        if (jm == i) n_jp_eq_i++;
-        if (tm == tid) { Vs = V; gs = g; ws = w; thns = thn; }
+    // ---- entries of this atom at this wavelength (ray independent part)
+    int    e_flag[NLTE_MAXACT];                 // bit0 im==i, bit1 jm==j, bit2 jm==i, bit3 self, bit4 thn != 0, bit5 line
+    double e_w[NLTE_MAXACT], e_diff[NLTE_MAXACT], e_tg[NLTE_MAXACT], e_nj[NLTE_MAXACT], e_c[NLTE_MAXACT];
+    const double *e_phi[NLTE_MAXACT];
+    double gs = 0.0, thns = 0.0;
+    int m = 0, n_jp_eq_i = 0;
+    for (int n = 0; n < nact; n++) {
+      const int tm = P.as_trans[first+n];
+      const double *tr = P.trans + (size_t) tm * TR_NFIELD;
+      if ((int) tr[TR_ATOM] != a) continue;
+      if (m == NLTE_MAXACT) { m++; break; }
+      const int im = (int) tr[TR_I], jm = (int) tr[TR_J], la = ns - (int) tr[TR_NBLUE];
+      const double *gw = C.gw + (((size_t) col * P.nas + first + n) * 2) * N + k;
+      const double g = gw[0], w = gw[N];
+      const double thn = twohnu3_of(P, tr, ns);
+      const double n_i = ncol_[(size_t)(P.lev_off[a] + im) * N + k], n_j = ncol_[(size_t)(P.lev_off[a] + jm) * N + k];
+      const bool line = tr[TR_TYPE] == 0.0;
+      e_flag[m] = (im == i ? 1 : 0) | (jm == j ? 2 : 0) | (jm == i ? 4 : 0) | (tm == tid ? 8 : 0) |
+                  (thn != 0.0 ? 16 : 0) | (line ? 32 : 0);
+      e_w[m] = w; e_diff[m] = n_i - g*n_j; e_tg[m] = thn * g; e_nj[m] = n_j;
+      if (line) {                                // V = Bij hc/4pi phi(ray), opacity.c:188-193
+        e_c[m] = hc_4PI * tr[TR_BIJ] * tr[TR_ISOFRAC];
+        e_phi[m] = C.phi + ((size_t) col * P.nphirow + (int) tr[TR_PHIROW] + 2*P.Nrays*la) * N + k;
+      } else {                                   // V = alpha(lambda), opacity.c:236
+        e_c[m] = P.tr_alpha[(int) tr[TR_WOFF] + la];
+        e_phi[m] = nullptr;
       }
-      const size_t rk = ((size_t) col * P.nray + r) * N + k;
-      const double I = C.I[rk], Psi = C.Psi[rk] / C.chi[rk];       // formal.c:248 / :301
-      const double Ieff = I - Psi * eta_atom;                      // fillgamma.c:130-133
-      const double wlamu = Vs * ws * wmu;
-      Gji += Ieff * wlamu;                                         // fillgamma.c:163-168
-      Gij += (thns + Ieff) * gs * wlamu;
-      Gij -= chi_up_i * Psi * Uji_down_j * wmu;                    // fillgamma.c:172-175
-      for (int m = 0; m < n_jp_eq_i; m++)                          // fillgamma.c:180-196
-        Gji += chi_down_j * Psi * Uji_down_i * wmu;
-      Rij += I * wlamu;                                            // fillgamma.c:448-452
-      Rji += gs * (thns + I) * wlamu;
+      if (jm == i) n_jp_eq_i++;
+      if (tm == tid) { gs = g; thns = thn; }
+      m++;
+    }
+    if (m > NLTE_MAXACT) { Gij = Gji = Rij = Rji = __longlong_as_double(0x7ff8000000000000LL); break; }   // refused on the host
+    // ---- rays of this wavelength in batches of NLTE_RB: all loads of a batch are issued before the
+    //      (ordered) accumulation, which is what hides the memory latency of this otherwise serial walk
+    const int r_end = P.ray_off[ns+1];
+    for (int r0 = P.ray_off[ns]; r0 < r_end; r0 += NLTE_RB) {
+      const int nb = r_end - r0 < NLTE_RB ? r_end - r0 : NLTE_RB;
+      double Iv[NLTE_RB], Pv[NLTE_RB], wmuv[NLTE_RB];
+      int lamu[NLTE_RB];
+      double eta_atom[NLTE_RB], chi_up_i[NLTE_RB], Uji_down_j[NLTE_RB], chi_down_j[NLTE_RB], Uji_down_i[NLTE_RB], Vs[NLTE_RB];
+      double ws = 0.0;
+#pragma unroll
+      for (int q = 0; q < NLTE_RB; q++) {
+        eta_atom[q] = chi_up_i[q] = Uji_down_j[q] = chi_down_j[q] = Uji_down_i[q] = Vs[q] = 0.0;
+        Iv[q] = Pv[q] = wmuv[q] = 0.0; lamu[q] = 0;
+        if (q < nb) {
+          const int r = r0 + q, mu = P.ray_mu[r];
+          const size_t rk = ((size_t) col * P.nray + r) * N + k;
+          Iv[q] = __ldg(C.I + rk);
+          Pv[q] = __ldg(C.Psi + rk) / __ldg(C.chi + rk);           // formal.c:248 / :301
+          wmuv[q] = ad ? 0.5 * P.wmu[mu] : P.wmu[mu];
+          lamu[q] = 2*mu + P.ray_dir[r];
+        }
+      }
+      for (int e = 0; e < m; e++) {               // entries in active-set order: per-ray sums keep their order
+        const int f = e_flag[e];
+        const double c = e_c[e], tg = e_tg[e], w = e_w[e], diff = e_diff[e], nj = e_nj[e];
+        const double *ph = e_phi[e];
+        double V[NLTE_RB];
+#pragma unroll
+        for (int q = 0; q < NLTE_RB; q++)
+          V[q] = (q < nb) ? ((f & 32) ? c * __ldg(ph + (size_t) lamu[q] * N) : c) : 0.0;
+        if (f & 8) ws = w;
+#pragma unroll
+        for (int q = 0; q < NLTE_RB; q++) {
+          if (f & 16) {
+            const double tgV = tg * V[q];
+            eta_atom[q] += tgV * nj;                              // opacity.c:257-258
+            const double chicc = V[q] * w * diff;                 // fillgamma.c:321-327
+            if (f & 1) chi_up_i[q] += chicc;
+            if (f & 2) { chi_down_j[q] += chicc; Uji_down_j[q] += tgV; }
+            if (f & 4) Uji_down_i[q] += tgV;
+          }
+          if (f & 8) Vs[q] = V[q];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < NLTE_RB; q++) {
+        if (q < nb) {
+          const double I = Iv[q], Psi = Pv[q], wmu = wmuv[q];
+          const double Ieff = I - Psi * eta_atom[q];               // fillgamma.c:130-133
+          const double wlamu = Vs[q] * ws * wmu;
+          Gji += Ieff * wlamu;                                     // fillgamma.c:163-168
+          Gij += (thns + Ieff) * gs * wlamu;
+          Gij -= chi_up_i[q] * Psi * Uji_down_j[q] * wmu;          // fillgamma.c:172-175
+          for (int z = 0; z < n_jp_eq_i; z++)                      // fillgamma.c:180-196
+            Gji += chi_down_j[q] * Psi * Uji_down_i[q] * wmu;
+          Rij += I * wlamu;                                        // fillgamma.c:448-452
+          Rji += gs * (thns + I) * wlamu;
+        }
+      }
     }
   }
   C.Gamma[gbase + (size_t)(i*Nl + j) * N + k] = Gij;
@@ -601,6 +660,17 @@ static int nlte_run(rhb200_ctx *c, const rhb200_nlte_plan *pl, int ncol,
         rhb200_set_error("transition type must be 0 (line) or 1 (continuum)"); return RHB200_EINVAL;
       }
     }
+    {                                          // the rate kernel caches one atom's entries of a wavelength
+      std::vector<int> per_atom(Na, 0);
+      for (int e = pl->as_first[ns]; e < pl->as_first[ns+1]; e++) {
+        const int a = (int) pl->trans[(size_t) pl->as_trans[e]*RHB200_TR_NFIELD + RHB200_TR_ATOM];
+        if (a < 0 || a >= Na) { rhb200_set_error("transition atom index out of range"); return RHB200_EINVAL; }
+        if (++per_atom[a] > NLTE_MAXACT) {
+          rhb200_set_error("more than %d active transitions of one atom at one wavelength", NLTE_MAXACT);
+          return RHB200_EUNSUPPORTED;
+        }
+      }
+    }
     angle_dep[ns] = pl->moving && (bb || pl->bg_hasline[ns]);
     for (int mu = 0; mu < Nr; mu++)
       for (int dir = 0; dir <= (angle_dep[ns] ? 1 : 0); dir++) { ray_ns.push_back(ns); ray_mu.push_back(mu); ray_dir.push_back(dir); }
@@ -768,7 +838,7 @@ static int nlte_run(rhb200_ctx *c, const rhb200_nlte_plan *pl, int ncol,
     { ScopedKernelTimer t(c, RHB200_K_BEZIER);
       nlte_ray_kernel<<<RH_GRID((size_t) ncol*nray, 128), 0, st>>>(P, C, ncol, 1); }
     { ScopedKernelTimer t(c, RHB200_K_OTHER);
-      nlte_gamma_kernel<<<RH_GRID(cN*Nt, 64), 0, st>>>(P, C, ncol); }
+      nlte_gamma_kernel<<<dim3((unsigned) ((cN + 63) / 64), (unsigned) Nt), 64, 0, st>>>(P, C, ncol); }
     { ScopedKernelTimer t(c, RHB200_K_OTHER);
       nlte_J_kernel<<<RH_GRID(cN*Ns, 128), 0, st>>>(P, C, ncol); }
     // the exchange step of a wavelength-sharded atmosphere: radiative rates add up over ranks
