@@ -162,46 +162,84 @@ __device__ __forceinline__ double twohnu3_of(const Plan &P, const double *tr, in
   return twohc / (lc*lc*lc);
 }
 
-// ---- (1) Opacity() + the chi/S assembly of Formal(): one thread per (column, ray, depth)
+// ---- (1) Opacity() + the chi/S assembly of Formal(): one wavelength per block, threads over (column,
+// depth); one thread evaluates all rays of its wavelength (batches of NLTE_RB) so that the
+// ray-independent factors (n_i - g n_j, thn g, n_j, background, Jdag) are loaded once, and the walk over
+// the active set is uniform across the block.  Products keep the reference's association:
+// V*(n_i - g n_j), ((thn*g)*V)*n_j (opacity.c:252-260).
+#define NLTE_RB 6
 __global__ void __launch_bounds__(128)
 nlte_opacity_kernel(Plan P, Cols C, int ncol)
 {
-  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-  const int N = P.Ndep;
-  if (t >= (size_t) ncol * P.nray * N) return;
-  const int k = (int) (t % N);
-  const size_t cr = t / N;
-  const int r = (int) (cr % P.nray), col = (int) (cr / P.nray);
+  // consecutive blocks take consecutive wavelengths of the same (column, depth) chunk: their rays are
+  // adjacent in memory, which keeps the DRAM pages of chi/S/phi open
+  const int N = P.Ndep, ns = (int) (blockIdx.x % P.Nspect);
+  const size_t t = (size_t) (blockIdx.x / P.Nspect) * blockDim.x + threadIdx.x;
+  if (t >= (size_t) ncol * N) return;
+  const int k = (int) (t % N), col = (int) (t / N);
   if (!C.active[col]) return;
-  const int ns = P.ray_ns[r], mu = P.ray_mu[r], dir = P.ray_dir[r];
   if (ns < P.ns_lo || ns >= P.ns_hi) return;           // another rank's wavelength
   const int first = P.as_first[ns], nact = P.as_first[ns+1] - first;
   const double *ncol_ = C.n + (size_t) col * P.nlev * N;
-  double as_chi = 0.0, as_eta = 0.0, eta_atom = 0.0;
-  int cur_atom = -1;
-  for (int n = 0; n < nact; n++) {
-    const double *tr = P.trans + (size_t) P.as_trans[first+n] * TR_NFIELD;
-    const int a = (int) tr[TR_ATOM];
-    if (a != cur_atom) {                      // as->eta += atom->rhth.eta, opacity.c:375-380
-      if (cur_atom >= 0) as_eta += eta_atom;
-      eta_atom = 0.0; cur_atom = a;
+  const double hc_4PI = (RH_HPLANCK * RH_CLIGHT) / (4.0 * RH_PI);
+  const size_t lk = ((size_t) col * P.Nspect + ns) * N + k;
+  const double chi_c = __ldg(C.chi_c + lk), eta_c = __ldg(C.eta_c + lk);
+  const double scaJ = __ldg(C.sca_c + lk) * C.J[lk];                         // J still holds Jdag here
+  const int r_end = P.ray_off[ns+1];
+  for (int r0 = P.ray_off[ns]; r0 < r_end; r0 += NLTE_RB) {
+    const int nb = r_end - r0 < NLTE_RB ? r_end - r0 : NLTE_RB;
+    double as_chi[NLTE_RB], as_eta[NLTE_RB], eta_atom[NLTE_RB];
+    int lamu[NLTE_RB];
+#pragma unroll
+    for (int q = 0; q < NLTE_RB; q++) {
+      as_chi[q] = as_eta[q] = eta_atom[q] = 0.0;
+      lamu[q] = (q < nb) ? 2*P.ray_mu[r0 + q] + P.ray_dir[r0 + q] : 0;
     }
-    const double V = vij_of(P, C, col, tr, ns, mu, dir, k);
-    const double g = C.gw[(((size_t) col * P.nas + first + n) * 2) * N + k];
-    const double n_i = ncol_[(size_t)(P.lev_off[a] + (int) tr[TR_I]) * N + k];
-    const double n_j = ncol_[(size_t)(P.lev_off[a] + (int) tr[TR_J]) * N + k];
-    const double thn = twohnu3_of(P, tr, ns);
-    if (thn != 0.0) {                         // opacity.c:252-260
-      as_chi += V * (n_i - g*n_j);
-      eta_atom += thn * g * V * n_j;
+    int cur_atom = -1;
+    for (int n = 0; n < nact; n++) {
+      const double *tr = P.trans + (size_t) P.as_trans[first+n] * TR_NFIELD;
+      const int a = (int) tr[TR_ATOM], la = ns - (int) tr[TR_NBLUE];
+      if (a != cur_atom) {                      // as->eta += atom->rhth.eta, opacity.c:375-380
+        if (cur_atom >= 0) {
+#pragma unroll
+          for (int q = 0; q < NLTE_RB; q++) as_eta[q] += eta_atom[q];
+        }
+#pragma unroll
+        for (int q = 0; q < NLTE_RB; q++) eta_atom[q] = 0.0;
+        cur_atom = a;
+      }
+      const double thn = twohnu3_of(P, tr, ns);
+      if (thn == 0.0) continue;                 // opacity.c:252
+      const double g = C.gw[(((size_t) col * P.nas + first + n) * 2) * N + k];
+      const double n_i = ncol_[(size_t)(P.lev_off[a] + (int) tr[TR_I]) * N + k];
+      const double n_j = ncol_[(size_t)(P.lev_off[a] + (int) tr[TR_J]) * N + k];
+      const double diff = n_i - g*n_j, tg = thn * g;
+      if (tr[TR_TYPE] == 0.0) {                 // line: V = Bij hc/4pi phi(ray), opacity.c:188-193
+        const double c = hc_4PI * tr[TR_BIJ] * tr[TR_ISOFRAC];
+        const double *ph = C.phi + ((size_t) col * P.nphirow + (int) tr[TR_PHIROW] + 2*P.Nrays*la) * N + k;
+        double V[NLTE_RB];
+#pragma unroll
+        for (int q = 0; q < NLTE_RB; q++) V[q] = (q < nb) ? c * __ldg(ph + (size_t) lamu[q] * N) : 0.0;
+#pragma unroll
+        for (int q = 0; q < NLTE_RB; q++) { as_chi[q] += V[q] * diff; eta_atom[q] += tg * V[q] * n_j; }
+      } else {                                  // continuum: V = alpha(lambda), opacity.c:236
+        const double V = P.tr_alpha[(int) tr[TR_WOFF] + la];
+#pragma unroll
+        for (int q = 0; q < NLTE_RB; q++) { as_chi[q] += V * diff; eta_atom[q] += tg * V * n_j; }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NLTE_RB; q++) {
+      if (q < nb) {
+        if (cur_atom >= 0) as_eta[q] += eta_atom[q];
+        const double chi = as_chi[q] + chi_c;                                // formal.c:178-182, 293-296
+        const double S = (as_eta[q] + eta_c + scaJ) / chi;
+        const size_t rk = ((size_t) col * P.nray + r0 + q) * N + k;
+        C.chi[rk] = chi;
+        C.S[rk] = S;
+      }
     }
   }
-  if (cur_atom >= 0) as_eta += eta_atom;
-  const size_t lk = ((size_t) col * P.Nspect + ns) * N + k;
-  const double chi = as_chi + C.chi_c[lk];                                   // formal.c:178-182, 293-296
-  const double S = (as_eta + C.eta_c[lk] + C.sca_c[lk] * C.J[lk]) / chi;     // J still holds Jdag here
-  C.chi[cr * N + k] = chi;
-  C.S[cr * N + k] = S;
 }
 
 // ---- (2) formal solution of every ray: Piecewise_Bezier3_1D for angle-dependent wavelengths,
@@ -221,7 +259,9 @@ struct NlteFeauIO {
   __device__ __forceinline__ bool wantPsi() const { return Psi_ != nullptr; }
 };
 
-__global__ void __launch_bounds__(128)
+// SOLVER is a template parameter so that each instantiation carries one solver's registers only
+template <int SOLVER, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 nlte_ray_kernel(Plan P, Cols C, int ncol, int eval_operator)
 {
   const size_t cr = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -233,19 +273,15 @@ nlte_ray_kernel(Plan P, Cols C, int ncol, int eval_operator)
   const double *h = C.height + (size_t) col * N, *T = C.T + (size_t) col * N;
   double *Psi = eval_operator ? C.Psi + cr * N : nullptr;
   if (P.angle_dep[ns]) {
-    switch (P.solver) {                              // S_INTERPOLATION, formal.c:229-235
-    case RHB200_S_LINEAR:
+    if (SOLVER == RHB200_S_LINEAR)                   // S_INTERPOLATION, formal.c:229-235
       rhp::linear_ray(N, h, P.muz[mu], dir, P.bc_top, P.bc_bottom, T, P.lambda[ns], C.chi + cr * N,
                       C.S + cr * N, C.I + cr * N, Psi);
-      break;
-    case RHB200_S_PARABOLIC:
+    else if (SOLVER == RHB200_S_PARABOLIC)
       rhp::parabolic_ray(N, h, P.muz[mu], dir, P.bc_top, P.bc_bottom, T, P.lambda[ns], C.chi + cr * N,
                          C.S + cr * N, C.I + cr * N, Psi);
-      break;
-    default:
+    else
       rhz::bezier3_ray(N, h, P.muz[mu], dir, P.bc_top, P.bc_bottom, T, P.lambda[ns], C.chi + cr * N,
                        C.S + cr * N, C.I + cr * N, Psi);
-    }
     C.Iem[cr] = C.I[cr * N];                         // spectrum.I[nspect][mu] = I[0] (formal.c:270)
   } else {
     NlteFeauIO io{C.chi + cr * N, C.S + cr * N, h, C.I + cr * N, Psi, C.scr + cr * 2 * N, N};
@@ -257,7 +293,7 @@ nlte_ray_kernel(Plan P, Cols C, int ncol, int eval_operator)
 __global__ void __launch_bounds__(128)
 nlte_J_kernel(Plan P, Cols C, int ncol)
 {
-  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;     // linear in memory: (column, wavelength, depth)
   const int N = P.Ndep;
   if (t >= (size_t) ncol * P.Nspect * N) return;
   const int k = (int) (t % N);
@@ -267,9 +303,18 @@ nlte_J_kernel(Plan P, Cols C, int ncol)
   if (ns < P.ns_lo || ns >= P.ns_hi) return;
   const int ad = P.angle_dep[ns];
   double J = 0.0;
-  for (int r = P.ray_off[ns]; r < P.ray_off[ns+1]; r++) {
-    const double wmu = ad ? 0.5 * P.wmu[P.ray_mu[r]] : P.wmu[P.ray_mu[r]];
-    J += wmu * C.I[((size_t) col * P.nray + r) * N + k];
+  const int r_end = P.ray_off[ns+1];
+  for (int r0 = P.ray_off[ns]; r0 < r_end; r0 += NLTE_RB) {            // loads of a batch first, ordered sum after
+    double Iv[NLTE_RB], wv[NLTE_RB];
+#pragma unroll
+    for (int q = 0; q < NLTE_RB; q++) {
+      const bool on = r0 + q < r_end;
+      Iv[q] = on ? __ldg(C.I + ((size_t) col * P.nray + r0 + q) * N + k) : 0.0;
+      wv[q] = on ? P.wmu[P.ray_mu[r0 + q]] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < NLTE_RB; q++)
+      if (r0 + q < r_end) J += (ad ? 0.5 * wv[q] : wv[q]) * Iv[q];
   }
   const double Jdag = C.J[t];
   C.J[t] = J;
@@ -296,20 +341,19 @@ nlte_dJmax_kernel(Plan P, Cols C, int ncol, double *dJmax)
 }
 
 // ---- (4) addtoCoupling + addtoGamma + addtoRates for one transition at one depth.
-// blockIdx.y = transition, threads over (column, depth): the walk over this transition's wavelengths,
+// One transition per block, threads over (column, depth): the walk over this transition's wavelengths,
 // rays and active-set entries is uniform across the block (no divergent trip counts, broadcast loads of
 // the plan tables).  Everything that does not depend on the ray is gathered once per wavelength into a
 // small per-thread cache: the products are formed in the reference's association order
 // (V*w)*(n_i - g n_j), (thn*g)*V, ((thn*g)*V)*n_j, so hoisting the right-hand factors changes no rounding.
 #define NLTE_MAXACT 12
-#define NLTE_RB 6
 __global__ void __launch_bounds__(64, 8)
 nlte_gamma_kernel(Plan P, Cols C, int ncol)
 {
   const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
   const int N = P.Ndep;
   if (t >= (size_t) ncol * N) return;
-  const int k = (int) (t % N), col = (int) (t / N), tid = blockIdx.y;
+  const int k = (int) (t % N), col = (int) (t / N), tid = blockIdx.y;   // heavy transitions (lines) start first
   if (!C.active[col]) return;
   const double *trs = P.trans + (size_t) tid * TR_NFIELD;
   const int a = (int) trs[TR_ATOM], i = (int) trs[TR_I], j = (int) trs[TR_J], Nl = P.atom_nlevel[a];
@@ -760,6 +804,16 @@ static int nlte_run(rhb200_ctx *c, const rhb200_nlte_plan *pl, int ncol,
                               C.n + ((size_t) col*nlev + lev_off[a])*N, (size_t) pl->atom_nlevel[a]*N*sizeof(double),
                               cudaMemcpyDeviceToDevice, c->stream));
 
+  static int ray_minb = -1;
+  if (ray_minb < 0) { const char *e = getenv("RHB200_NLTE_RAY_MINB"); ray_minb = e ? atoi(e) : 8; }
+  auto launch_rays = [&](int eval_operator) {
+    const unsigned blocks = (unsigned) (((size_t) ncol*nray + 127) / 128);
+#define RH_RAYS(S, M) nlte_ray_kernel<S, M><<<blocks, 128, 0, c->stream>>>(P, C, ncol, eval_operator)
+#define RH_RAYS_M(S) do { if (ray_minb >= 8) RH_RAYS(S, 8); else if (ray_minb >= 6) RH_RAYS(S, 6); else RH_RAYS(S, 4); } while (0)
+    if (P.solver == RHB200_S_LINEAR) RH_RAYS_M(RHB200_S_LINEAR);
+    else if (P.solver == RHB200_S_PARABOLIC) RH_RAYS_M(RHB200_S_PARABOLIC);
+    else RH_RAYS_M(RHB200_S_BEZIER3);
+  };
   cudaStream_t st = c->stream;
   if (device_profiles) {
     { ScopedKernelTimer t(c, RHB200_K_PREP);
@@ -790,9 +844,9 @@ static int nlte_run(rhb200_ctx *c, const rhb200_nlte_plan *pl, int ncol,
     int nact_s = ncol;
     for (int it = 0; it < NmaxScatter && nact_s > 0; it++) {
       { ScopedKernelTimer t(c, RHB200_K_OPACITY);
-        nlte_opacity_kernel<<<RH_GRID(cN*nray, 128), 0, st>>>(P, C, ncol); }
+        nlte_opacity_kernel<<<(unsigned) (((cN + 127) / 128) * Ns), 128, 0, st>>>(P, C, ncol); }
       { ScopedKernelTimer t(c, RHB200_K_BEZIER);
-        nlte_ray_kernel<<<RH_GRID((size_t) ncol*nray, 128), 0, st>>>(P, C, ncol, 0); }
+        launch_rays(0); }
       if (update_J) {
         { ScopedKernelTimer t(c, RHB200_K_OTHER);
           nlte_J_kernel<<<RH_GRID(cN*Ns, 128), 0, st>>>(P, C, ncol); }
@@ -834,9 +888,9 @@ static int nlte_run(rhb200_ctx *c, const rhb200_nlte_plan *pl, int ncol,
     { ScopedKernelTimer t(c, RHB200_K_OTHER);
       nlte_gamma_init_kernel<<<RH_GRID(cN*ngam, 256), 0, st>>>(P, C, ncol); }
     { ScopedKernelTimer t(c, RHB200_K_OPACITY);
-      nlte_opacity_kernel<<<RH_GRID(cN*nray, 128), 0, st>>>(P, C, ncol); }
+      nlte_opacity_kernel<<<(unsigned) (((cN + 127) / 128) * Ns), 128, 0, st>>>(P, C, ncol); }
     { ScopedKernelTimer t(c, RHB200_K_BEZIER);
-      nlte_ray_kernel<<<RH_GRID((size_t) ncol*nray, 128), 0, st>>>(P, C, ncol, 1); }
+      launch_rays(1); }
     { ScopedKernelTimer t(c, RHB200_K_OTHER);
       nlte_gamma_kernel<<<dim3((unsigned) ((cN + 63) / 64), (unsigned) Nt), 64, 0, st>>>(P, C, ncol); }
     { ScopedKernelTimer t(c, RHB200_K_OTHER);
