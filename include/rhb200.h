@@ -151,6 +151,26 @@ int rhb200_ltepops_elem_batch(rhb200_ctx *ctx, int ncol, int ndep, const double 
 int rhb200_rlk_opacity_batch(rhb200_ctx *ctx, int ncol, int ndep, double muz, int moving,
                              int to_obs, const double *atmos, double *chi, double *eta, int *flags);
 
+/* MolecularOpacity + MolProfile + the window tests that mrt_locate serves (opacity.c:656-916): LTE lines of
+   PASSIVE molecules at every given wavelength, direction to_obs.
+   mlines [nmline][RHB200_ML_NFIELD], grouped by molecule in the reference's order (molecule index
+   ascending, lines as read = ascending lambda0); Zeeman slices as for Kurucz lines (MolZeeman output;
+   non-polarizable lines use VoigtArmstrong, opacity.c:911).
+   mol [ncol][nmol][3][ndep] = molecule->n [m^-3], molecule->pf, molecule->vbroad [m/s] (host: chemical
+   equilibrium).  Out: chi, eta [ncol][nlambda][4][ndep] accumulated from 0 in line order,
+   flags [nlambda] bit0 hasline, bit1 ispolarized (may be NULL). */
+enum {
+  RHB200_ML_LAMBDA0 = 0, RHB200_ML_EI, RHB200_ML_GI, RHB200_ML_BIJ, RHB200_ML_AJI, RHB200_ML_BJI,
+  RHB200_ML_ISO_FRAC, RHB200_ML_QWING, RHB200_ML_POLARIZABLE, RHB200_ML_MOL, RHB200_ML_ZOFF, RHB200_ML_NCOMP,
+  RHB200_ML_NFIELD = 16
+};
+int rhb200_molecular_opacity_batch(rhb200_ctx *ctx, int ncol, int ndep, double muz, int moving, int to_obs,
+                                   int nmol, int nmline, const double *mlines,
+                                   int ncomp, const int *zq, const double *zshift, const double *zstrength,
+                                   double vmicro_char, int nlambda, const double *lambda,
+                                   const double *atmos, const double *mol,
+                                   double *chi, double *eta, int *flags);
+
 /* Piece_Stokes_Bezier3_1D (bezier_1D.c:52-300) + StokesK (stokesopac.c:28-87) for nray rays.
    ray_col[nray] selects the column (height, T) of each ray, ray_lambda[nray] its wavelength [nm].
    chi [nray][ndep], S [nray][4][ndep], chiQUV [nray][3][ndep] (numerators of K', un-divided),

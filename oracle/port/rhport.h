@@ -131,6 +131,14 @@ void rp_lte_stokes_column(const rp_linetable *lt, const rp_column *col,
 double rp_voigt_armstrong(double a, double v);
 int    rp_armstrong_region(double a, double v);
 
+/* opacity.c:711-916 (rhport_molecules.c) */
+int rp_molecular_opacity(int N, int nmol, int nmline, const double *mlines,
+                         const int *zq, const double *zshift, const double *zstrength,
+                         double vmicro_char, double lambda, double muz, int moving, int to_obs,
+                         const double *T, const double *vel, const double *B,
+                         const double *cos_gamma, const double *cos_2chi, const double *sin_2chi,
+                         const double *mol, double *chi, double *eta);
+
 /* ---- NLTE (rhport_nlte.c): see the struct there; driven from oracle/portdriver.py ---- */
 void rp_solve_linear_eq(int N, double *A /*row-major, destroyed*/, double *b, int improve);
 void rp_stat_equil(int Nl, int N, const double *Gamma, const double *ntotal, int isum, double *n);

@@ -300,3 +300,21 @@ def profile_line(lambda0, lam, wlam, adamp, vbroad, vel, muz, wmu):
     L.rp_profile_line(N, Nrays, Nla, float(lambda0), *[_d(a) for a in arrs], _d(phi), _d(wphi))
     return phi, wphi
 
+
+def molecular_opacity(mlines, zq, zshift, zstrength, vmicro_char, lam, muz, moving, to_obs,
+                      T, vel, B, cos_gamma, cos_2chi, sin_2chi, mol):
+    """MolecularOpacity() (opacity.c:711-839) of one column at one wavelength: (chi[4,N], eta[4,N], flags)."""
+    f64 = lambda x: np.ascontiguousarray(x, np.float64)   # noqa: E731
+    ml, mol = f64(mlines), f64(mol)
+    N = len(T)
+    zq_ = np.ascontiguousarray(zq if len(zq) else [0], np.int32)
+    zs, zt = f64(zshift if len(zshift) else [0.0]), f64(zstrength if len(zstrength) else [0.0])
+    arrs = [f64(x) for x in (T, vel, B, cos_gamma, cos_2chi, sin_2chi)]
+    chi, eta = np.zeros((4, N)), np.zeros((4, N))
+    fn = lib().rp_molecular_opacity
+    fn.restype = C.c_int
+    fl = fn(N, mol.shape[0], ml.shape[0], _d(ml), zq_.ctypes.data_as(C.POINTER(C.c_int)), _d(zs), _d(zt),
+            C.c_double(vmicro_char), C.c_double(lam), C.c_double(muz), int(moving), int(to_obs),
+            *[_d(a) for a in arrs], _d(mol), _d(chi), _d(eta))
+    return chi, eta, fl
+

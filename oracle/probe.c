@@ -50,6 +50,7 @@ static ProbeRec *recs = NULL;
 static long nrec = 0, cap = 0;
 static unsigned probe_mask = 0;   /* bit field, see PROBE_* below */
 static int snapshot_done = 0;
+static int mol_snapshot_done = 0;
 
 enum { PROBE_RLK = 1, PROBE_BG = 2, PROBE_DELO = 4, PROBE_SNAP = 8,
        PROBE_BEZ = 16, PROBE_FEAU = 32, PROBE_NLTE = 64, PROBE_FORMAL = 128 };
@@ -61,6 +62,7 @@ void probe_reset(void)
   for (long i = 0; i < nrec; i++) free(recs[i].data);
   nrec = 0;
   snapshot_done = 0;
+  mol_snapshot_done = 0;
 }
 long      probe_count(void)       { return nrec; }
 ProbeRec *probe_get(long i)       { return (i >= 0 && i < nrec) ? &recs[i] : NULL; }
@@ -700,4 +702,48 @@ int probe_determinate(const char *label, double g, double *out /* n, S, L, J */)
   int ok = determinate(l, g, &n, &S, &L, &J);
   out[0] = n; out[1] = S; out[2] = L; out[3] = J;
   return ok;
+}
+
+/* ------------------------------------------------------------------ molecular background lines
+   MolecularOpacity (rh/opacity.c:711-839): outputs per (wavelength, mu, direction) and, once, the
+   molecules that own a line list: n, pf, vbroad [Nspace] and the line table with Zeeman patterns. */
+ZeemanMultiplet *MolZeeman(MolecularLine *mrt);
+flags __real_MolecularOpacity(double lambda, int nspect, int mu, bool_t to_obs,
+                              double *chi, double *eta, double *chip);
+flags __wrap_MolecularOpacity(double lambda, int nspect, int mu, bool_t to_obs,
+                              double *chi, double *eta, double *chip)
+{
+  flags f = __real_MolecularOpacity(lambda, nspect, mu, to_obs, chi, eta, chip);
+  if (probe_mask & PROBE_RLK) {
+    int N = atmos.Nspace, ns = atmos.Stokes ? 4 : 1, n, kr, c;
+    if (f.hasline) {
+      double *d = rec_new("mol", 2*ns*N, nspect, mu, to_obs, f.hasline, f.ispolarized, ns);
+      memcpy(d, chi, ns*N*sizeof(double));
+      memcpy(d + ns*N, eta, ns*N*sizeof(double));
+    }
+    if (!mol_snapshot_done && mu == atmos.Nrays-1 && to_obs) {
+      for (n = 0; n < atmos.Nmolecule; n++) {
+        Molecule *m = &atmos.molecules[n];
+        if (m->Nrt <= 0 || m->active) continue;
+        double *d = rec_new("mol_col", 3*N, n, m->Nrt, 0,0,0,0);
+        memcpy(d, m->n, N*sizeof(double));
+        memcpy(d + N, m->pf, N*sizeof(double));
+        memcpy(d + 2*N, m->vbroad, N*sizeof(double));
+        for (kr = 0; kr < m->Nrt; kr++) {
+          MolecularLine *l = &m->mrt[kr];
+          ZeemanMultiplet *zm = l->zm;
+          int own = 0;
+          if (l->polarizable && zm == NULL) { zm = MolZeeman(l); own = 1; }   /* lazily built in the reference too */
+          int nc = zm ? zm->Ncomponent : 0;
+          double *r = rec_new("mol_line", 10 + 3*nc, n, kr, nc, l->polarizable, 0, 0);
+          r[0] = l->lambda0; r[1] = l->Ei; r[2] = l->gi; r[3] = l->Bij; r[4] = l->Aji; r[5] = l->Bji;
+          r[6] = l->isotope_frac; r[7] = l->qwing; r[8] = l->polarizable; r[9] = l->gj;
+          for (c = 0; c < nc; c++) { r[10+c] = zm->q[c]; r[10+nc+c] = zm->shift[c]; r[10+2*nc+c] = zm->strength[c]; }
+          if (own) { free(zm->q); free(zm->shift); free(zm->strength); free(zm); }
+        }
+      }
+      mol_snapshot_done = 1;
+    }
+  }
+  return f;
 }

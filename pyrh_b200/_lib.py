@@ -49,6 +49,8 @@ SYMBOLS = [
     ("rhb200_zeeman", C.c_int, [C.c_char_p, C.c_double, C.c_char_p, C.c_double, C.c_double, C.c_int, ip, dp, dp]),
     ("rhb200_nlte_set_shard", C.c_int, [vp, C.c_int, C.c_int, ALLREDUCE_FN, vp]),
     ("rhb200_nlte_shard_range", C.c_int, [vp, C.c_int, C.c_int, ip, ip]),
+    ("rhb200_molecular_opacity_batch", C.c_int, [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                 dp, C.c_int, ip, dp, dp, C.c_double, C.c_int, dp, dp, dp, dp, dp, ip]),
     ("rhb200_set_solvers", C.c_int, [vp, C.c_int, C.c_int]),
     ("rhb200_scalar_ray_batch", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
                                           C.c_int, ip, dp, dp, dp, dp, dp, dp, dp]),

@@ -180,6 +180,26 @@ class Context:
         _lib.check(self.lib.rhb200_set_solvers(self.h, S_INTERPOLATION[s_interpolation],
                                                S_INTERPOLATION_STOKES[s_interpolation_stokes]))
 
+    def molecular_opacity(self, atmos_rows, mol, mlines, zq, zshift, zstrength, lam, vmicro_char, mu=1.0,
+                          moving=True, to_obs=True):
+        """MolecularOpacity() for every column and wavelength: mol [ncol, nmol, 3, ndep] (n, pf, vbroad),
+        mlines [nmline, ML_NFIELD].  Returns (chi, eta [ncol, nlambda, 4, ndep], flags [nlambda])."""
+        at = np.ascontiguousarray(atmos_rows, np.float64)
+        mol = np.ascontiguousarray(mol, np.float64)
+        ml = np.ascontiguousarray(mlines, np.float64)
+        zq = np.ascontiguousarray(zq, np.int32)
+        zs, zt = np.ascontiguousarray(zshift, np.float64), np.ascontiguousarray(zstrength, np.float64)
+        lam = np.ascontiguousarray(lam, np.float64)
+        ncol, _, ndep = at.shape
+        chi = np.zeros((ncol, len(lam), 4, ndep))
+        eta = np.zeros_like(chi)
+        flags = np.zeros(len(lam), np.int32)
+        _lib.check(self.lib.rhb200_molecular_opacity_batch(
+            self.h, ncol, ndep, float(mu), int(moving), int(to_obs), mol.shape[1], ml.shape[0], _dp(ml), len(zq),
+            zq.ctypes.data_as(_lib.ip), _dp(zs), _dp(zt), float(vmicro_char), len(lam), _dp(lam), _dp(at), _dp(mol),
+            _dp(chi), _dp(eta), flags.ctypes.data_as(_lib.ip)))
+        return chi, eta, flags
+
     def stokes_bezier3(self, ray_col, ray_lambda, height, T, chi, S, chiQUV, mu=1.0, to_obs=True,
                        bc_top=_lib.BC_ZERO, bc_bottom=_lib.BC_THERMALIZED, want_psi=False,
                        solver="DELO_BEZIER3"):

@@ -428,6 +428,76 @@ extern "C" int rhb200_rlk_opacity_batch(rhb200_ctx *c, int ncol, int ndep, doubl
   return RHB200_OK;
 }
 
+extern "C" int rhb200_molecular_opacity_batch(rhb200_ctx *c, int ncol, int ndep, double muz, int moving, int to_obs,
+                                              int nmol, int nmline, const double *mlines,
+                                              int ncomp, const int *zq, const double *zshift, const double *zstrength,
+                                              double vmicro_char, int nlambda, const double *lambda,
+                                              const double *atmos, const double *mol,
+                                              double *chi, double *eta, int *flags)
+{
+  RH_NEED_CTX(c);
+  if (ncol <= 0 || ndep <= 0 || nmol <= 0 || nmline <= 0 || nlambda <= 0 || !mlines || !lambda || !atmos || !mol ||
+      !chi || !eta || ncomp < 0 || (ncomp > 0 && (!zq || !zshift || !zstrength))) {
+    rhb200_set_error("bad arguments"); return RHB200_EINVAL;
+  }
+  // first / last line of each molecule (the reference's outer window test uses mrt[0] and mrt[Nrt-1])
+  std::vector<int> mfirst(nmol, -1), mlast(nmol, -1);
+  for (int n = 0; n < nmline; n++) {
+    const double *L = mlines + (size_t) n * RHB200_ML_NFIELD;
+    const int m = (int) L[RHB200_ML_MOL];
+    if (m < 0 || m >= nmol) { rhb200_set_error("molecular line %d: molecule index out of range", n); return RHB200_EINVAL; }
+    if (n > 0 && m < (int) L[RHB200_ML_MOL - RHB200_ML_NFIELD]) { rhb200_set_error("molecular lines must be grouped by molecule"); return RHB200_EINVAL; }
+    const int zo = (int) L[RHB200_ML_ZOFF], nc = (int) L[RHB200_ML_NCOMP];
+    if (zo < 0 || nc < 0 || zo + nc > ncomp) { rhb200_set_error("molecular line %d: Zeeman slice out of range", n); return RHB200_EINVAL; }
+    if (mfirst[m] < 0) mfirst[m] = n;
+    mlast[m] = n;
+  }
+  std::vector<int> first(nlambda, 0), count(nlambda, 0), idx, fl(nlambda, 0);
+  const double vc = vmicro_char / RH_CLIGHT;
+  for (int l = 0; l < nlambda; l++) {
+    const double lam = lambda[l];
+    first[l] = (int) idx.size();
+    for (int m = 0; m < nmol; m++) {
+      if (mfirst[m] < 0) continue;
+      const double *L0 = mlines + (size_t) mfirst[m] * RHB200_ML_NFIELD, *LN = mlines + (size_t) mlast[m] * RHB200_ML_NFIELD;
+      const double dl0 = lam * L0[RHB200_ML_QWING] * vc, dlN = lam * LN[RHB200_ML_QWING] * vc;        // opacity.c:774-777
+      if (!(lam >= L0[RHB200_ML_LAMBDA0] - dl0 && lam <= LN[RHB200_ML_LAMBDA0] + dlN)) continue;     // :779-780
+      for (int n = mfirst[m]; n <= mlast[m]; n++) {
+        const double *L = mlines + (size_t) n * RHB200_ML_NFIELD;
+        const double dl = lam * L[RHB200_ML_QWING] * vc;
+        if (std::fabs(L[RHB200_ML_LAMBDA0] - lam) <= dl) {                                           // :784-786
+          idx.push_back(n);
+          fl[l] |= 1;
+          if (L[RHB200_ML_POLARIZABLE] != 0.0) fl[l] |= 2;
+        }
+      }
+    }
+    count[l] = (int) idx.size() - first[l];
+  }
+  DevBuf dl_, df, dc, di, dm, dq, dsh, dst, dat, dmol, dchi, deta;
+  const size_t ob = (size_t) ncol * nlambda * 4 * ndep * sizeof(double);
+  RH_CHECK(dl_.from_host(lambda, (size_t) nlambda * sizeof(double)));
+  RH_CHECK(df.from_host(first.data(), (size_t) nlambda * sizeof(int)));
+  RH_CHECK(dc.from_host(count.data(), (size_t) nlambda * sizeof(int)));
+  RH_CHECK(di.from_host(idx.data(), idx.size() * sizeof(int)));
+  RH_CHECK(dm.from_host(mlines, (size_t) nmline * RHB200_ML_NFIELD * sizeof(double)));
+  RH_CHECK(dq.from_host(zq, (size_t) ncomp * sizeof(int)));
+  RH_CHECK(dsh.from_host(zshift, (size_t) ncomp * sizeof(double)));
+  RH_CHECK(dst.from_host(zstrength, (size_t) ncomp * sizeof(double)));
+  RH_CHECK(dat.from_host(atmos, (size_t) ncol * RHB200_AT_NFIELD * ndep * sizeof(double)));
+  RH_CHECK(dmol.from_host(mol, (size_t) ncol * nmol * 3 * ndep * sizeof(double)));
+  RH_CHECK(dchi.alloc(ob)); RH_CHECK(deta.alloc(ob));
+  RH_CHECK(rh_launch_mol_opacity_raw(c, ncol, nlambda, ndep, nmol, muz, moving, to_obs, dl_.as<double>(), df.as<int>(),
+                                     dc.as<int>(), di.as<int>(), dm.as<double>(), dq.as<int>(), dsh.as<double>(),
+                                     dst.as<double>(), dat.as<double>(), dmol.as<double>(), dchi.as<double>(),
+                                     deta.as<double>()));
+  RH_CUDA(cudaStreamSynchronize(c->stream));
+  RH_CHECK(to_host(chi, dchi.p, ob));
+  RH_CHECK(to_host(eta, deta.p, ob));
+  if (flags) memcpy(flags, fl.data(), (size_t) nlambda * sizeof(int));
+  return RHB200_OK;
+}
+
 extern "C" int rhb200_set_solvers(rhb200_ctx *c, int s_interpolation, int s_interpolation_stokes)
 {
   RH_NEED_CTX(c);

@@ -278,6 +278,91 @@ opacity_raw_kernel(int ncol, int nlambda, int ndep, int to_obs, int nline,
   }
 }
 
+// MolecularOpacity + MolProfile (opacity.c:711-916): LTE lines of PASSIVE molecules in the background.
+// One thread per (column, wavelength, depth); widx lists, per wavelength, the lines that pass the
+// reference's window tests (opacity.c:774-787, evaluated on the host) in molecule / line order, so the
+// accumulation order is the reference's.  mol: [ncol][nmol][3][ndep] = molecule->n, pf, vbroad.
+__global__ void __launch_bounds__(128)
+mol_opacity_raw_kernel(int ncol, int nlambda, int ndep, int nmol, double muz, int moving, int to_obs,
+                       const double *__restrict__ lambda, const int *__restrict__ wfirst,
+                       const int *__restrict__ wcount, const int *__restrict__ widx,
+                       const double *__restrict__ mlines, const int *__restrict__ zq,
+                       const double *__restrict__ zshift, const double *__restrict__ zstrength,
+                       const double *__restrict__ atmos, const double *__restrict__ mol,
+                       double *__restrict__ chi, double *__restrict__ eta)
+{
+  const size_t npts = (size_t) ncol * nlambda * ndep;
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= npts) return;
+  const size_t r = t / ndep;
+  const int k = (int) (t - r * ndep);
+  const int col = (int) (r / nlambda), l = (int) (r - (size_t) col * nlambda);
+  const double *at = atmos + (size_t) col * RHB200_AT_NFIELD * ndep;
+  const double T = at[RHB200_AT_T*ndep + k], vel = at[RHB200_AT_VEL*ndep + k], B = at[RHB200_AT_B*ndep + k];
+  const double cos_gamma = at[RHB200_AT_COS_GAMMA*ndep + k], cos_2chi = at[RHB200_AT_COS_2CHI*ndep + k],
+               sin_2chi = at[RHB200_AT_SIN_2CHI*ndep + k];
+  const double lam = __ldg(lambda + l);
+  const double hc_4PI = (RH_HPLANCK * RH_CLIGHT) / (4.0 * RH_PI);
+  double c4[4] = {0.0, 0.0, 0.0, 0.0}, e4[4] = {0.0, 0.0, 0.0, 0.0};
+  const int first = __ldg(wfirst + l), count = __ldg(wcount + l);
+  for (int j = 0; j < count; j++) {
+    const double *L = mlines + (size_t) __ldg(widx + first + j) * RHB200_ML_NFIELD;
+    const double *M = mol + (((size_t) col * nmol + (int) L[RHB200_ML_MOL]) * 3) * ndep + k;
+    const double n = M[0], pf = M[ndep], vbroad = M[2*(size_t) ndep];
+    if (!(n > 0.0)) continue;                                            // opacity.c:797
+    const double lambda0 = L[RHB200_ML_LAMBDA0];
+    // MolProfile, opacity.c:844-916
+    const double adamp = L[RHB200_ML_AJI] * (lambda0 * RH_NM_TO_M) / (4.0*RH_PI * vbroad);
+    double v = (lam/lambda0 - 1.0) * RH_CLIGHT/vbroad;
+    if (moving) { if (to_obs) v += (muz * vel) / vbroad; else v -= (muz * vel) / vbroad; }
+    const double sv = 1.0 / (RH_SQRTPI * vbroad);
+    double phi, phi_Q = 0.0, phi_U = 0.0, phi_V = 0.0;
+    const bool polarizable = L[RHB200_ML_POLARIZABLE] != 0.0;
+    if (polarizable) {
+      const double sin2_gamma = 1.0 - cos_gamma*cos_gamma;
+      const double vB = (RH_LARMOR * lambda0) * B / vbroad;
+      const double sign = to_obs ? 1.0 : -1.0;
+      double phi_sm = 0.0, phi_pi = 0.0, phi_sp = 0.0;
+      const int zoff = (int) L[RHB200_ML_ZOFF], nc = (int) L[RHB200_ML_NCOMP];
+      for (int nz = 0; nz < nc; nz++) {
+        const double H = rhv::humlicek_H(adamp, v - __ldg(zshift + zoff + nz)*vB);
+        const int q = __ldg(zq + zoff + nz);
+        const double st = __ldg(zstrength + zoff + nz);
+        if (q == -1)     phi_sm += st * H;
+        else if (q == 0) phi_pi += st * H;
+        else if (q == 1) phi_sp += st * H;
+      }
+      const double phi_sigma = phi_sp + phi_sm;
+      const double phi_delta = 0.5*phi_pi - 0.25*phi_sigma;
+      phi   = (phi_delta*sin2_gamma + 0.5*phi_sigma) * sv;
+      phi_Q = sign * phi_delta * sin2_gamma * cos_2chi * sv;
+      phi_U = phi_delta * sin2_gamma * sin_2chi * sv;
+      phi_V = sign * 0.5*(phi_sp - phi_sm) * cos_gamma * sv;
+    } else
+      phi = rhv::voigt_armstrong(adamp, v) * sv;
+    // MolecularOpacity, opacity.c:786-788, 802-822
+    const double hc_la     = (RH_HPLANCK * RH_CLIGHT) / (lambda0 * RH_NM_TO_M);
+    const double Bijhc_4PI = hc_4PI * L[RHB200_ML_BIJ] * L[RHB200_ML_ISO_FRAC] * L[RHB200_ML_GI];
+    const double twohnu3_c2 = L[RHB200_ML_AJI] / L[RHB200_ML_BJI];
+    const double kT    = 1.0 / (RH_KBOLTZMANN * T);
+    const double ni_gi = n * rhm::rh_exp(-L[RHB200_ML_EI] * kT) / pf;
+    const double nj_gj = ni_gi * rhm::rh_exp(-hc_la * kT);
+    const double chi_l = Bijhc_4PI * (ni_gi - nj_gj);
+    const double eta_l = Bijhc_4PI * twohnu3_c2 * nj_gj;
+    c4[0] += chi_l * phi;
+    e4[0] += eta_l * phi;
+    if (polarizable) {
+      c4[1] += chi_l * phi_Q;  c4[2] += chi_l * phi_U;  c4[3] += chi_l * phi_V;
+      e4[1] += eta_l * phi_Q;  e4[2] += eta_l * phi_U;  e4[3] += eta_l * phi_V;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    chi[(r*4 + i)*ndep + k] = c4[i];
+    eta[(r*4 + i)*ndep + k] = e4[i];
+  }
+}
+
 __global__ void voigt_kernel(int n, const double *__restrict__ a, const double *__restrict__ v,
                              double *__restrict__ H, double *__restrict__ F, int *__restrict__ region)
 {
@@ -316,6 +401,24 @@ __global__ void math_probe_kernel(int n, int func, const double *__restrict__ x,
 }
 
 }  // namespace
+
+int rh_launch_mol_opacity_raw(rhb200_ctx *ctx, int ncol, int nlambda, int ndep, int nmol, double muz, int moving,
+                              int to_obs, const double *d_lambda, const int *d_first, const int *d_count,
+                              const int *d_idx, const double *d_mlines, const int *d_zq, const double *d_zshift,
+                              const double *d_zstrength, const double *d_atmos, const double *d_mol,
+                              double *d_chi, double *d_eta)
+{
+  const size_t n = (size_t) ncol * nlambda * ndep;
+  if (n == 0) return RHB200_OK;
+  {
+    ScopedKernelTimer t(ctx, RHB200_K_OPACITY);
+    mol_opacity_raw_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, ctx->stream>>>(ncol, nlambda, ndep, nmol, muz,
+        moving, to_obs, d_lambda, d_first, d_count, d_idx, d_mlines, d_zq, d_zshift, d_zstrength, d_atmos, d_mol,
+        d_chi, d_eta);
+  }
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}
 
 int rh_launch_prep(rhb200_ctx *ctx, int ncol, int ndep, double muz, int moving,
                    const double *d_atmos, double *d_elem_n, double *d_lineprep)

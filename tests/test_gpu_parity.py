@@ -555,3 +555,68 @@ def test_loggf_response_function_vs_reference(ctx):
     keep = (g["lam_spect"] != 500.0)[g["ns"]]
     assert np.array_equal(dI[keep][:, 0], g["rfs"])
     assert np.array_equal(I[keep][:, 0], g["I_spec"])
+
+
+def _mol_rows(g):
+    from pyrh_b200 import api
+    at = np.zeros((len(api.AT), len(g["col_T"])))
+    for f, i in api.AT.items():
+        if "col_" + f in g:
+            at[i] = g["col_" + f]
+    return at
+
+
+def test_molecular_opacity_vs_reference(ctx):
+    """MolecularOpacity / MolProfile (opacity.c:711-916): CN B-X lines of the reference's own list at 847 nm.
+    Window membership (integer) must be exact; chi/eta are compared with every recorded call."""
+    g = dict(np.load(GOLD / "falc_molecules.npz"))
+    fl = g["flags"]
+    lam = g["lam_spect"]
+    at = _mol_rows(g)[None]
+    hit = {}
+    for to_obs in (0, 1):
+        chi, eta, wf = ctx.molecular_opacity(at, g["mol"][None], g["mlines"], g["zq"], g["zshift"], g["zstrength"],
+                                             lam, fl[6], mu=float(g["muz"][0]), moving=bool(fl[0]), to_obs=bool(to_obs))
+        sel = g["mol_meta"][:, 2] == to_obs
+        ns = g["mol_meta"][sel, 0]
+        assert np.array_equal(np.flatnonzero(wf & 1), ns)              # same wavelengths see a line
+        assert not np.any(wf & 2)
+        ref = g["mol_chi_eta"][sel]
+        got_chi, got_eta = chi[0, ns], eta[0, ns]
+        scale = np.abs(ref[:, 0, 0]).max(axis=1)[:, None, None]
+        err = max((np.abs(got_chi - ref[:, 0]) / scale).max(), (np.abs(got_eta - ref[:, 1]) / np.abs(ref[:, 1, 0]).max(axis=1)[:, None, None]).max())
+        hit[to_obs] = bool(np.array_equal(got_chi, ref[:, 0]) and np.array_equal(got_eta, ref[:, 1]))
+        REPORT[f"molecular_opacity_dir{to_obs}_maxerr"] = float(err)
+        assert err < 1e-12
+        rest = np.setdiff1d(np.arange(len(lam)), ns)
+        assert not chi[0, rest].any() and not eta[0, rest].any()
+    REPORT["molecular_opacity_exact"] = hit
+
+
+def test_molecular_opacity_polarizable_branch_matches_port(ctx):
+    """The shipped CN list is not polarizable; give its lines a Zeeman triplet to drive the Humlicek branch of
+    MolProfile (opacity.c:871-908) and check the device against the oracle port (same code path as the pinned
+    Kurucz profile)."""
+    from oracle import portdriver as pd
+    g = dict(np.load(GOLD / "falc_molecules.npz"))
+    fl = g["flags"]
+    ml = g["mlines"].copy()
+    nl = len(ml)
+    ml[:, 8] = 1.0
+    ml[:, 10] = 3 * np.arange(nl)
+    ml[:, 11] = 3
+    zq = np.tile(np.array([-1, 0, 1], np.int32), nl)
+    zs = np.tile(np.array([-1.2, 0.0, 1.2]), nl) * np.repeat(1.0 + 0.01 * np.arange(nl), 3)
+    zt = np.ones(3 * nl)
+    lam = g["lam_spect"][g["mol_meta"][::2, 0]]
+    chi, eta, wf = ctx.molecular_opacity(_mol_rows(g)[None], g["mol"][None], ml, zq, zs, zt, lam, fl[6],
+                                         mu=float(g["muz"][0]), moving=bool(fl[0]), to_obs=True)
+    assert np.all(wf == 3)
+    for i, la in enumerate(lam):
+        c, e, f = pd.molecular_opacity(ml, zq, zs, zt, fl[6], la, float(g["muz"][0]), bool(fl[0]), 1, g["col_T"],
+                                       g["col_vel"], g["col_B"], g["col_cos_gamma"], g["col_cos_2chi"],
+                                       g["col_sin_2chi"], g["mol"])
+        assert f == 3
+        assert np.abs(chi[0, i] - c).max() <= 1e-13 * np.abs(c[0]).max()
+        assert np.abs(eta[0, i] - e).max() <= 1e-13 * np.abs(e[0]).max()
+        assert np.abs(c[3]).max() > 0

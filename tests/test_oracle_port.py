@@ -206,3 +206,19 @@ def test_loggf_response_function_port_bit_exact():
         assert np.array_equal(I, g["up"][i, 2]) and np.array_equal(dI, g["dI"][i])
     keep = (g["lam_spect"] != 500.0)[g["ns"]]
     assert np.array_equal(g["dI"][keep][:, 0], g["rfs"])
+
+
+def test_molecular_opacity_port_bit_exact():
+    """MolecularOpacity + MolProfile (opacity.c:711-916) vs the reference's recorded calls: CN B-X lines
+    around 847.3 nm, FAL-C with B = 1 kG (the shipped list is not polarizable -> VoigtArmstrong)."""
+    from conftest import GOLD
+    g = dict(np.load(GOLD / "falc_molecules.npz"))
+    fl = g["flags"]
+    assert len(g["mol_meta"]) == 12 and set(g["mol_meta"][:, 2]) == {0, 1}
+    for m, d in zip(g["mol_meta"], g["mol_chi_eta"]):
+        chi, eta, flg = pd.molecular_opacity(g["mlines"], g["zq"], g["zshift"], g["zstrength"], fl[6],
+                                             g["lam_spect"][m[0]], float(g["muz"][m[1]]), bool(fl[0]), int(m[2]),
+                                             g["col_T"], g["col_vel"], g["col_B"], g["col_cos_gamma"],
+                                             g["col_cos_2chi"], g["col_sin_2chi"], g["mol"])
+        assert np.array_equal(chi, d[0]) and np.array_equal(eta, d[1])
+        assert flg == (m[3] | (m[4] << 1))
