@@ -171,6 +171,20 @@ int rhb200_molecular_opacity_batch(rhb200_ctx *ctx, int ncol, int ndep, double m
                                    const double *atmos, const double *mol,
                                    double *chi, double *eta, int *flags);
 
+/* passive_bb (metal.c:174-344): bound-bound lines of PASSIVE model atoms (hydrogen included) in the
+   background, unpolarised: VoigtArmstrong with the host's Damping() output, Gaussian when line->Voigt is off,
+   line components (c_shift, c_fraction).  plines [nline][RHB200_PB_NFIELD] in the reference's order (atoms, then
+   lines of each atom); pcol [ncol][nline][4][ndep] = n_i, n_j (LTE or NLTE populations the host holds), atom
+   vbroad, adamp.  Out: chi, eta [ncol][nlambda][ndep]; flags [nlambda] bit0 hasline (may be NULL). */
+enum {
+  RHB200_PB_LAMBDA0 = 0, RHB200_PB_QWING, RHB200_PB_BIJ, RHB200_PB_BJI, RHB200_PB_AJI, RHB200_PB_VOIGT,
+  RHB200_PB_NCOMP, RHB200_PB_COMPOFF, RHB200_PB_NFIELD = 8
+};
+int rhb200_passive_bb_batch(rhb200_ctx *ctx, int ncol, int ndep, double muz, int moving, int to_obs,
+                            int nline, const double *plines, int ncomp, const double *c_shift,
+                            const double *c_fraction, double vmicro_char, int nlambda, const double *lambda,
+                            const double *atmos, const double *pcol, double *chi, double *eta, int *flags);
+
 /* Piece_Stokes_Bezier3_1D (bezier_1D.c:52-300) + StokesK (stokesopac.c:28-87) for nray rays.
    ray_col[nray] selects the column (height, T) of each ray, ray_lambda[nray] its wavelength [nm].
    chi [nray][ndep], S [nray][4][ndep], chiQUV [nray][3][ndep] (numerators of K', un-divided),

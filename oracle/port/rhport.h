@@ -139,6 +139,11 @@ int rp_molecular_opacity(int N, int nmol, int nmline, const double *mlines,
                          const double *cos_gamma, const double *cos_2chi, const double *sin_2chi,
                          const double *mol, double *chi, double *eta);
 
+/* metal.c:174-344 (rhport_molecules.c) */
+int rp_passive_bb(int N, int nline, const double *plines, const double *c_shift, const double *c_fraction,
+                  double vmicro_char, double lambda, double muz, int moving, int to_obs,
+                  const double *vel, const double *pcol, double *chi, double *eta);
+
 /* ---- NLTE (rhport_nlte.c): see the struct there; driven from oracle/portdriver.py ---- */
 void rp_solve_linear_eq(int N, double *A /*row-major, destroyed*/, double *b, int improve);
 void rp_stat_equil(int Nl, int N, const double *Gamma, const double *ntotal, int isum, double *n);

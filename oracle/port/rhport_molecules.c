@@ -82,3 +82,38 @@ int rp_molecular_opacity(int N, int nmol, int nmline, const double *mlines,
   }
   return flags;
 }
+
+/* passive_bb, rh/metal.c:174-344: bound-bound lines of PASSIVE model atoms in the background (unpolarised,
+   VoigtArmstrong with the Damping() output supplied per line, Gaussian when line->Voigt is off).
+   plines [nline][8]: lambda0, qwing, Bij, Bji, Aji, Voigt, Ncomponent, comp_off;  comp: c_shift / c_fraction;
+   pcol [nline][4][N]: n_i, n_j, vbroad, adamp.  chi, eta [N].  Returns hasline. */
+int rp_passive_bb(int N, int nline, const double *plines, const double *c_shift, const double *c_fraction,
+                  double vmicro_char, double lambda, double muz, int moving, int to_obs,
+                  const double *vel, const double *pcol, double *chi, double *eta)
+{
+  const double hc_4PI = (RP_HPLANCK * RP_CLIGHT) / (4.0 * RP_PI);
+  int hasline = 0, n, nc, k;
+  for (k = 0; k < N; k++) { chi[k] = 0.0; eta[k] = 0.0; }
+  for (n = 0; n < nline; n++) {
+    const double *L = plines + n*8;
+    const double *ni = pcol + (size_t) n*4*N, *nj = ni + N, *vbroad = ni + 2*N, *adamp = ni + 3*N;
+    double lambda0 = L[0], dlambda = lambda0 * L[1] * (vmicro_char / RP_CLIGHT);
+    if (!(fabs(lambda - lambda0) <= dlambda)) continue;
+    hasline = 1;
+    double gij = L[3] / L[2], twohnu3_c2 = L[4] / L[3];
+    int ncomp = (int) L[6], off = (int) L[7];
+    for (nc = 0; nc < ncomp; nc++) {
+      for (k = 0; k < N; k++) {
+        double phi, Vij;
+        double v = (lambda - lambda0 - c_shift[off+nc]) * RP_CLIGHT / (lambda0 * vbroad[k]);
+        if (moving) { if (to_obs) v += (muz * vel[k]) / vbroad[k]; else v -= (muz * vel[k]) / vbroad[k]; }
+        if (L[5] != 0.0) phi = rp_voigt_armstrong(adamp[k], v) * c_fraction[off+nc];
+        else             phi = exp(-(v*v));
+        Vij = hc_4PI * L[2] * phi / (RP_SQRTPI*vbroad[k]);
+        chi[k] += Vij * (ni[k] - gij * nj[k]);
+        eta[k] += twohnu3_c2 * gij * Vij * nj[k];
+      }
+    }
+  }
+  return hasline;
+}

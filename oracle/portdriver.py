@@ -318,3 +318,16 @@ def molecular_opacity(mlines, zq, zshift, zstrength, vmicro_char, lam, muz, movi
             *[_d(a) for a in arrs], _d(mol), _d(chi), _d(eta))
     return chi, eta, fl
 
+
+def passive_bb(plines, c_shift, c_fraction, vmicro_char, lam, muz, moving, to_obs, vel, pcol):
+    """passive_bb() (metal.c:174-344) of one column at one wavelength: (chi[N], eta[N], hasline)."""
+    f64 = lambda x: np.ascontiguousarray(x, np.float64)   # noqa: E731
+    pl, pc, cs, cf, vel = f64(plines), f64(pcol), f64(c_shift), f64(c_fraction), f64(vel)
+    N = len(vel)
+    chi, eta = np.zeros(N), np.zeros(N)
+    fn = lib().rp_passive_bb
+    fn.restype = C.c_int
+    has = fn(N, pl.shape[0], _d(pl), _d(cs), _d(cf), C.c_double(vmicro_char), C.c_double(lam), C.c_double(muz),
+             int(moving), int(to_obs), _d(vel), _d(pc), _d(chi), _d(eta))
+    return chi, eta, has
+

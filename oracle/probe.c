@@ -30,6 +30,7 @@
 #include "spectrum.h"
 #include "background.h"
 #include "inputs.h"
+#include "constant.h"
 #include "accelerate.h"
 
 extern Atmosphere atmos;
@@ -51,6 +52,9 @@ static long nrec = 0, cap = 0;
 static unsigned probe_mask = 0;   /* bit field, see PROBE_* below */
 static int snapshot_done = 0;
 static int mol_snapshot_done = 0;
+#define PBB_MAXSEEN 256
+static AtomicLine *pbb_seen[PBB_MAXSEEN];
+static int pbb_nseen = 0;
 
 enum { PROBE_RLK = 1, PROBE_BG = 2, PROBE_DELO = 4, PROBE_SNAP = 8,
        PROBE_BEZ = 16, PROBE_FEAU = 32, PROBE_NLTE = 64, PROBE_FORMAL = 128 };
@@ -63,6 +67,7 @@ void probe_reset(void)
   nrec = 0;
   snapshot_done = 0;
   mol_snapshot_done = 0;
+  pbb_nseen = 0;
 }
 long      probe_count(void)       { return nrec; }
 ProbeRec *probe_get(long i)       { return (i >= 0 && i < nrec) ? &recs[i] : NULL; }
@@ -743,6 +748,46 @@ flags __wrap_MolecularOpacity(double lambda, int nspect, int mu, bool_t to_obs,
         }
       }
       mol_snapshot_done = 1;
+    }
+  }
+  return f;
+}
+
+/* ------------------------------------------------------------------ passive bound-bound lines
+   passive_bb (rh/metal.c:174-344): outputs per (wavelength, mu, direction) that found a line, and once per
+   contributing line its parameters + the per-depth inputs (n_i, n_j, vbroad, Damping()). */
+flags __real_passive_bb(double lambda, int nspect, int mu, bool_t to_obs, double *chi, double *eta, double *chip);
+flags __wrap_passive_bb(double lambda, int nspect, int mu, bool_t to_obs, double *chi, double *eta, double *chip)
+{
+  flags f = __real_passive_bb(lambda, nspect, mu, to_obs, chi, eta, chip);
+  if ((probe_mask & PROBE_RLK) && f.hasline) {
+    int N = atmos.Nspace, m, kr, l, c;
+    double *d = rec_new("pbb", 2*N, nspect, mu, to_obs, 0, 0, 0);
+    memcpy(d, chi, N*sizeof(double));
+    memcpy(d + N, eta, N*sizeof(double));
+    for (m = 0; m < atmos.Natom; m++) {
+      Atom *atom = atmos.atoms + m;
+      if (atom->active) continue;
+      double **n = (atom->n != atom->nstar) ? atom->n : atom->nstar;
+      for (kr = 0; kr < atom->Nline; kr++) {
+        AtomicLine *line = atom->line + kr;
+        double dlambda = line->lambda0 * line->qwing * (atmos.vmicro_char / CLIGHT);
+        if (!(fabs(lambda - line->lambda0) <= dlambda)) continue;
+        int seen = 0;
+        for (l = 0; l < pbb_nseen; l++) if (pbb_seen[l] == line) seen = 1;
+        if (seen || pbb_nseen == PBB_MAXSEEN) continue;
+        pbb_seen[pbb_nseen++] = line;
+        int nc = line->Ncomponent;
+        double *r = rec_new("pbb_line", 8 + 2*nc + 4L*N, m, kr, nc, line->Voigt, line->i, line->j);
+        r[0] = line->lambda0; r[1] = line->qwing; r[2] = line->Bij; r[3] = line->Bji; r[4] = line->Aji;
+        r[5] = line->Voigt; r[6] = nc; r[7] = 0.0;
+        for (c = 0; c < nc; c++) { r[8+c] = line->c_shift[c]; r[8+nc+c] = line->c_fraction[c]; }
+        double *a = r + 8 + 2*nc;
+        memcpy(a, n[line->i], N*sizeof(double));
+        memcpy(a + N, n[line->j], N*sizeof(double));
+        memcpy(a + 2*N, atom->vbroad, N*sizeof(double));
+        if (line->Voigt) Damping(line, a + 3*N); else memset(a + 3*N, 0, N*sizeof(double));
+      }
     }
   }
   return f;

@@ -200,6 +200,25 @@ class Context:
             _dp(chi), _dp(eta), flags.ctypes.data_as(_lib.ip)))
         return chi, eta, flags
 
+    def passive_bb(self, atmos_rows, pcol, plines, c_shift, c_fraction, lam, vmicro_char, mu=1.0, moving=True,
+                   to_obs=True):
+        """passive_bb() for every column and wavelength: pcol [ncol, nline, 4, ndep] (n_i, n_j, vbroad, adamp),
+        plines [nline, PB_NFIELD].  Returns (chi, eta [ncol, nlambda, ndep], flags [nlambda])."""
+        at = np.ascontiguousarray(atmos_rows, np.float64)
+        pc = np.ascontiguousarray(pcol, np.float64)
+        pl = np.ascontiguousarray(plines, np.float64)
+        cs, cf = np.ascontiguousarray(c_shift, np.float64), np.ascontiguousarray(c_fraction, np.float64)
+        lam = np.ascontiguousarray(lam, np.float64)
+        ncol, _, ndep = at.shape
+        chi = np.zeros((ncol, len(lam), ndep))
+        eta = np.zeros_like(chi)
+        flags = np.zeros(len(lam), np.int32)
+        _lib.check(self.lib.rhb200_passive_bb_batch(
+            self.h, ncol, ndep, float(mu), int(moving), int(to_obs), pl.shape[0], _dp(pl), len(cs), _dp(cs), _dp(cf),
+            float(vmicro_char), len(lam), _dp(lam), _dp(at), _dp(pc), _dp(chi), _dp(eta),
+            flags.ctypes.data_as(_lib.ip)))
+        return chi, eta, flags
+
     def stokes_bezier3(self, ray_col, ray_lambda, height, T, chi, S, chiQUV, mu=1.0, to_obs=True,
                        bc_top=_lib.BC_ZERO, bc_bottom=_lib.BC_THERMALIZED, want_psi=False,
                        solver="DELO_BEZIER3"):

@@ -498,6 +498,51 @@ extern "C" int rhb200_molecular_opacity_batch(rhb200_ctx *c, int ncol, int ndep,
   return RHB200_OK;
 }
 
+extern "C" int rhb200_passive_bb_batch(rhb200_ctx *c, int ncol, int ndep, double muz, int moving, int to_obs,
+                                       int nline, const double *plines, int ncomp, const double *c_shift,
+                                       const double *c_fraction, double vmicro_char, int nlambda, const double *lambda,
+                                       const double *atmos, const double *pcol, double *chi, double *eta, int *flags)
+{
+  RH_NEED_CTX(c);
+  if (ncol <= 0 || ndep <= 0 || nline <= 0 || nlambda <= 0 || ncomp <= 0 || !plines || !c_shift || !c_fraction ||
+      !lambda || !atmos || !pcol || !chi || !eta) { rhb200_set_error("bad arguments"); return RHB200_EINVAL; }
+  for (int n = 0; n < nline; n++) {
+    const double *L = plines + (size_t) n * RHB200_PB_NFIELD;
+    const int nc = (int) L[RHB200_PB_NCOMP], off = (int) L[RHB200_PB_COMPOFF];
+    if (nc < 1 || off < 0 || off + nc > ncomp) { rhb200_set_error("passive line %d: component slice out of range", n); return RHB200_EINVAL; }
+  }
+  std::vector<int> first(nlambda, 0), count(nlambda, 0), idx, fl(nlambda, 0);
+  for (int l = 0; l < nlambda; l++) {
+    first[l] = (int) idx.size();
+    for (int n = 0; n < nline; n++) {
+      const double *L = plines + (size_t) n * RHB200_PB_NFIELD;
+      const double dlambda = L[RHB200_PB_LAMBDA0] * L[RHB200_PB_QWING] * (vmicro_char / RH_CLIGHT);   // metal.c:245-246
+      if (std::fabs(lambda[l] - L[RHB200_PB_LAMBDA0]) <= dlambda) { idx.push_back(n); fl[l] |= 1; }     // :248
+    }
+    count[l] = (int) idx.size() - first[l];
+  }
+  DevBuf dl_, df, dc, di, dp_, dcs, dcf, dat, dcol, dchi, deta;
+  const size_t ob = (size_t) ncol * nlambda * ndep * sizeof(double);
+  RH_CHECK(dl_.from_host(lambda, (size_t) nlambda * sizeof(double)));
+  RH_CHECK(df.from_host(first.data(), (size_t) nlambda * sizeof(int)));
+  RH_CHECK(dc.from_host(count.data(), (size_t) nlambda * sizeof(int)));
+  RH_CHECK(di.from_host(idx.data(), idx.size() * sizeof(int)));
+  RH_CHECK(dp_.from_host(plines, (size_t) nline * RHB200_PB_NFIELD * sizeof(double)));
+  RH_CHECK(dcs.from_host(c_shift, (size_t) ncomp * sizeof(double)));
+  RH_CHECK(dcf.from_host(c_fraction, (size_t) ncomp * sizeof(double)));
+  RH_CHECK(dat.from_host(atmos, (size_t) ncol * RHB200_AT_NFIELD * ndep * sizeof(double)));
+  RH_CHECK(dcol.from_host(pcol, (size_t) ncol * nline * 4 * ndep * sizeof(double)));
+  RH_CHECK(dchi.alloc(ob)); RH_CHECK(deta.alloc(ob));
+  RH_CHECK(rh_launch_passive_bb(c, ncol, nlambda, ndep, nline, muz, moving, to_obs, dl_.as<double>(), df.as<int>(),
+                                dc.as<int>(), di.as<int>(), dp_.as<double>(), dcs.as<double>(), dcf.as<double>(),
+                                dat.as<double>(), dcol.as<double>(), dchi.as<double>(), deta.as<double>()));
+  RH_CUDA(cudaStreamSynchronize(c->stream));
+  RH_CHECK(to_host(chi, dchi.p, ob));
+  RH_CHECK(to_host(eta, deta.p, ob));
+  if (flags) memcpy(flags, fl.data(), (size_t) nlambda * sizeof(int));
+  return RHB200_OK;
+}
+
 extern "C" int rhb200_set_solvers(rhb200_ctx *c, int s_interpolation, int s_interpolation_stokes)
 {
   RH_NEED_CTX(c);

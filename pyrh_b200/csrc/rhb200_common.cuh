@@ -113,6 +113,10 @@ int rh_launch_mol_opacity_raw(rhb200_ctx *ctx, int ncol, int nlambda, int ndep, 
                               const int *d_idx, const double *d_mlines, const int *d_zq, const double *d_zshift,
                               const double *d_zstrength, const double *d_atmos, const double *d_mol,
                               double *d_chi, double *d_eta);
+int rh_launch_passive_bb(rhb200_ctx *ctx, int ncol, int nlambda, int ndep, int nline, double muz, int moving,
+                         int to_obs, const double *d_lambda, const int *d_first, const int *d_count,
+                         const int *d_idx, const double *d_plines, const double *d_cshift, const double *d_cfrac,
+                         const double *d_atmos, const double *d_pcol, double *d_chi, double *d_eta);
 int rh_launch_prep(rhb200_ctx *ctx, int ncol, int ndep, double muz, int moving,
                    const double *d_atmos, double *d_elem_n, double *d_lineprep);
 int rh_launch_opacity_fused(rhb200_ctx *ctx, int ncol, int ndep, int to_obs,

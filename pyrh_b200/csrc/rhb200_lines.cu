@@ -363,6 +363,51 @@ mol_opacity_raw_kernel(int ncol, int nlambda, int ndep, int nmol, double muz, in
   }
 }
 
+// passive_bb (metal.c:174-344): bound-bound lines of PASSIVE model atoms, unpolarised.  One thread per
+// (column, wavelength, depth); lines in the reference's order (atoms, then lines), components inside.
+// pcol: [ncol][nline][4][ndep] = n_i, n_j, vbroad, Damping() output.
+__global__ void __launch_bounds__(128)
+passive_bb_kernel(int ncol, int nlambda, int ndep, int nline, double muz, int moving, int to_obs,
+                  const double *__restrict__ lambda, const int *__restrict__ wfirst,
+                  const int *__restrict__ wcount, const int *__restrict__ widx,
+                  const double *__restrict__ plines, const double *__restrict__ c_shift,
+                  const double *__restrict__ c_fraction, const double *__restrict__ atmos,
+                  const double *__restrict__ pcol, double *__restrict__ chi, double *__restrict__ eta)
+{
+  const size_t npts = (size_t) ncol * nlambda * ndep;
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= npts) return;
+  const size_t r = t / ndep;
+  const int k = (int) (t - r * ndep);
+  const int col = (int) (r / nlambda), l = (int) (r - (size_t) col * nlambda);
+  const double vel = atmos[((size_t) col * RHB200_AT_NFIELD + RHB200_AT_VEL) * ndep + k];
+  const double lam = __ldg(lambda + l);
+  const double hc_4PI = (RH_HPLANCK * RH_CLIGHT) / (4.0 * RH_PI);
+  double c = 0.0, e = 0.0;
+  const int first = __ldg(wfirst + l), count = __ldg(wcount + l);
+  for (int jn = 0; jn < count; jn++) {
+    const int n = __ldg(widx + first + jn);
+    const double *L = plines + (size_t) n * RHB200_PB_NFIELD;
+    const double *P = pcol + (((size_t) col * nline + n) * 4) * ndep + k;
+    const double n_i = P[0], n_j = P[ndep], vbroad = P[2*(size_t) ndep], adamp = P[3*(size_t) ndep];
+    const double lambda0 = L[RHB200_PB_LAMBDA0], Bij = L[RHB200_PB_BIJ];
+    const double gij = L[RHB200_PB_BJI] / Bij, twohnu3_c2 = L[RHB200_PB_AJI] / L[RHB200_PB_BJI];
+    const bool voigt = L[RHB200_PB_VOIGT] != 0.0;
+    const int ncomp = (int) L[RHB200_PB_NCOMP], off = (int) L[RHB200_PB_COMPOFF];
+    for (int nc = 0; nc < ncomp; nc++) {
+      double v = (lam - lambda0 - __ldg(c_shift + off + nc)) * RH_CLIGHT / (lambda0 * vbroad);
+      if (moving) { if (to_obs) v += (muz * vel) / vbroad; else v -= (muz * vel) / vbroad; }
+      const double phi = voigt ? rhv::voigt_armstrong(adamp, v) * __ldg(c_fraction + off + nc)
+                               : rhm::rh_exp(-(v*v));
+      const double Vij = hc_4PI * Bij * phi / (RH_SQRTPI*vbroad);
+      c += Vij * (n_i - gij * n_j);
+      e += twohnu3_c2 * gij * Vij * n_j;
+    }
+  }
+  chi[t] = c;
+  eta[t] = e;
+}
+
 __global__ void voigt_kernel(int n, const double *__restrict__ a, const double *__restrict__ v,
                              double *__restrict__ H, double *__restrict__ F, int *__restrict__ region)
 {
@@ -415,6 +460,22 @@ int rh_launch_mol_opacity_raw(rhb200_ctx *ctx, int ncol, int nlambda, int ndep, 
     mol_opacity_raw_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, ctx->stream>>>(ncol, nlambda, ndep, nmol, muz,
         moving, to_obs, d_lambda, d_first, d_count, d_idx, d_mlines, d_zq, d_zshift, d_zstrength, d_atmos, d_mol,
         d_chi, d_eta);
+  }
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}
+
+int rh_launch_passive_bb(rhb200_ctx *ctx, int ncol, int nlambda, int ndep, int nline, double muz, int moving,
+                         int to_obs, const double *d_lambda, const int *d_first, const int *d_count,
+                         const int *d_idx, const double *d_plines, const double *d_cshift, const double *d_cfrac,
+                         const double *d_atmos, const double *d_pcol, double *d_chi, double *d_eta)
+{
+  const size_t n = (size_t) ncol * nlambda * ndep;
+  if (n == 0) return RHB200_OK;
+  {
+    ScopedKernelTimer t(ctx, RHB200_K_OPACITY);
+    passive_bb_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, ctx->stream>>>(ncol, nlambda, ndep, nline, muz, moving,
+        to_obs, d_lambda, d_first, d_count, d_idx, d_plines, d_cshift, d_cfrac, d_atmos, d_pcol, d_chi, d_eta);
   }
   RH_CUDA(cudaGetLastError());
   return RHB200_OK;

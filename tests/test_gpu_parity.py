@@ -620,3 +620,31 @@ def test_molecular_opacity_polarizable_branch_matches_port(ctx):
         assert np.abs(chi[0, i] - c).max() <= 1e-13 * np.abs(c[0]).max()
         assert np.abs(eta[0, i] - e).max() <= 1e-13 * np.abs(e[0]).max()
         assert np.abs(c[3]).max() > 0
+
+
+def test_passive_bb_vs_reference(ctx):
+    """passive_bb (metal.c:174-344): Na I D and H-alpha of PASSIVE model atoms; window membership exact, chi/eta
+    against every recorded call (VoigtArmstrong: K1/K3 exact, K2 within 1e-13, see test_voigt_armstrong_*)."""
+    from pyrh_b200 import api
+    g = dict(np.load(GOLD / "falc_passive_bb.npz"))
+    fl = g["flags"]
+    lam = g["lam_spect"]
+    N = len(g["col_vel"])
+    at = np.zeros((1, len(api.AT), N))
+    at[0, api.AT["vel"]] = g["col_vel"]
+    exact = {}
+    for to_obs in (0, 1):
+        chi, eta, wf = ctx.passive_bb(at, g["pcol"][None], g["plines"], g["c_shift"], g["c_fraction"], lam, fl[6],
+                                      mu=float(g["muz"][0]), moving=bool(fl[0]), to_obs=bool(to_obs))
+        sel = g["pbb_meta"][:, 2] == to_obs
+        ns = g["pbb_meta"][sel, 0]
+        assert np.array_equal(np.flatnonzero(wf & 1), ns)
+        ref = g["pbb"][sel]
+        err = max((np.abs(chi[0, ns] - ref[:, 0]) / np.abs(ref[:, 0]).max(axis=1)[:, None]).max(),
+                  (np.abs(eta[0, ns] - ref[:, 1]) / np.abs(ref[:, 1]).max(axis=1)[:, None]).max())
+        exact[to_obs] = bool(np.array_equal(chi[0, ns], ref[:, 0]) and np.array_equal(eta[0, ns], ref[:, 1]))
+        REPORT[f"passive_bb_dir{to_obs}_maxerr"] = float(err)
+        assert err < 1e-12
+        rest = np.setdiff1d(np.arange(len(lam)), ns)
+        assert not chi[0, rest].any() and not eta[0, rest].any()
+    REPORT["passive_bb_exact"] = exact

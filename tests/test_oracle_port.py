@@ -222,3 +222,16 @@ def test_molecular_opacity_port_bit_exact():
                                              g["col_cos_2chi"], g["col_sin_2chi"], g["mol"])
         assert np.array_equal(chi, d[0]) and np.array_equal(eta, d[1])
         assert flg == (m[3] | (m[4] << 1))
+
+
+def test_passive_bb_port_bit_exact():
+    """passive_bb (metal.c:174-344) vs the reference's recorded calls: Na I D and H-alpha of the PASSIVE
+    Na.atom / H_6.atom on FAL-C, both directions."""
+    from conftest import GOLD
+    g = dict(np.load(GOLD / "falc_passive_bb.npz"))
+    fl = g["flags"]
+    assert len(g["pbb"]) == 36 and len(g["plines"]) == 2
+    for m, d in zip(g["pbb_meta"], g["pbb"]):
+        chi, eta, has = pd.passive_bb(g["plines"], g["c_shift"], g["c_fraction"], fl[6], g["lam_spect"][m[0]],
+                                      float(g["muz"][m[1]]), bool(fl[0]), int(m[2]), g["col_vel"], g["pcol"])
+        assert has == 1 and np.array_equal(chi, d[0]) and np.array_equal(eta, d[1])
