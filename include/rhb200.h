@@ -223,6 +223,46 @@ int rhb200_determinate(const char *label, double g, int *n, double *S, int *L, d
 int rhb200_zeeman(const char *label_i, double g_i, const char *label_j, double g_j, double g_Lande_eff,
                   int cap, int *q, double *shift, double *strength);
 
+/* ---- Background continuum on the device ----
+   The angle-independent part of Background() (background.c:343-465): Thomson, H- bf/ff, OH/CH bf, H bf/ff,
+   Rayleigh (H, He, H2), H2+ ff, H2- ff and the bound-free continua of all PASSIVE model atoms, summed in the
+   reference's order with its expressions.  The RH host keeps what does not depend on the column (the model
+   below, filled once) and what it computes per column anyway (LTE populations + chemical equilibrium); the
+   library evaluates everything that scales with columns x wavelengths x depths.
+   Opacity fudge factors (do_fudge) and lambda >= 9113 nm (Hminus_ff_long) return RHB200_EUNSUPPORTED. */
+typedef struct rhb200_continuum_model {
+  int natom, nlev, ncont, ntab, nray;
+  const double *lev;         /* [nlev][5]  atom index, E [J], stage, g, atom->active; atmos.atoms order, H first */
+  const double *bf;          /* [ncont][10] atom, level i, level j (rows of lev), lambda0, lambda[0], hydrogenic,
+                                alpha0, Nlambda, offset into tab_*, atom->active */
+  const double *tab_lambda, *tab_alpha;      /* [ntab] continuum->lambda / ->alpha of the tabulated edges */
+  const double *ray;         /* [nray][8] lines from the ground state for Rayleigh(): 0 = H / 1 = He, lambda0,
+                                qwing, Aji, g_j, g_0, (unused), (unused) */
+  int nlev_H;                /* atmos.H->Nlevel (levels 0 .. nlev_H-1 of lev; the last is the proton) */
+  int atom_He;               /* atom index of the helium model, -1 if absent (background.c:285) */
+  int H_active, has_OH, has_CH, has_H2, solve_NLTE, do_fudge;
+  double vmicro_char;        /* [m/s] */
+  /* published tables the reference holds as function-static arrays (hydrogen.c, ohchbf.c) */
+  const double *hmbf_lambda, *hmbf_alpha;                     int n_hmbf;
+  const double *hmff_lambda, *hmff_theta, *hmff_kappa;        int n_hmff_lambda, n_hmff_theta;
+  const double *h2mff_lambda, *h2mff_theta, *h2mff_kappa;     int n_h2mff_lambda, n_h2mff_theta;
+  const double *h2pff_lambda, *h2pff_temp, *h2pff_kappa;      int n_h2pff_lambda, n_h2pff_temp;
+  const double *rh2_a, *rh2_lambda, *rh2_sigma;               int n_rh2;
+  const double *oh_T, *oh_E, *oh_cross;                       int n_oh_T, n_oh_E;
+  const double *ch_T, *ch_E, *ch_cross;                       int n_ch_T, n_ch_E;
+} rhb200_continuum_model;
+/* T, ne, nHmin, nH2, nOH, nCH [ncol][ndep] (SI; the molecular ones may be NULL when has_* is 0);
+   pops_n, pops_nstar [ncol][nlev][ndep] = atom->n / atom->nstar of every level (may be the same pointer);
+   out chi_ai, eta_ai, sca_ai [ncol][nlambda][ndep] (sca_ai may be NULL). */
+int rhb200_continuum_batch(rhb200_ctx *ctx, const rhb200_continuum_model *model, int nlambda, const double *lambda,
+                           int ncol, int ndep, const double *T, const double *ne, const double *nHmin,
+                           const double *nH2, const double *nOH, const double *nCH,
+                           const double *pops_n, const double *pops_nstar,
+                           double *chi_ai, double *eta_ai, double *sca_ai,
+                           double *contrib /* NULL, or [ncol][nlambda][13][2][ndep]: every contribution on its own
+                              (diagnostics; order Thomson, H- bf, H- ff, OH bf, CH bf, H bf, H ff, Rayleigh H,
+                              Rayleigh He, H2+ ff, Rayleigh H2, H2- ff, metal bf; [..][0] = chi or scatt, [..][1] = eta) */);
+
 /* Formal-solver selection = keyword.input S_INTERPOLATION / S_INTERPOLATION_STOKES (readvalue.c:366-404;
    enum values of inputs.h:26-27).  Applies to rhb200_lte_stokes_batch(_dev) (Stokes solver) and to
    rhb200_nlte_iterate / rhb200_nlte_formal (scalar solver).  Defaults: S_BEZIER3, DELO_BEZIER3. */

@@ -52,6 +52,7 @@ static long nrec = 0, cap = 0;
 static unsigned probe_mask = 0;   /* bit field, see PROBE_* below */
 static int snapshot_done = 0;
 static int mol_snapshot_done = 0;
+static int cont_snapshot_done = 0;
 #define PBB_MAXSEEN 256
 static AtomicLine *pbb_seen[PBB_MAXSEEN];
 static int pbb_nseen = 0;
@@ -68,6 +69,7 @@ void probe_reset(void)
   snapshot_done = 0;
   mol_snapshot_done = 0;
   pbb_nseen = 0;
+  cont_snapshot_done = 0;
 }
 long      probe_count(void)       { return nrec; }
 ProbeRec *probe_get(long i)       { return (i >= 0 && i < nrec) ? &recs[i] : NULL; }
@@ -791,4 +793,113 @@ flags __wrap_passive_bb(double lambda, int nspect, int mu, bool_t to_obs, double
     }
   }
   return f;
+}
+
+/* ------------------------------------------------------------------ background continuum
+   The angle-independent contributions Background() sums per wavelength (rh/background.c:343-465).
+   PROBE_CONT records each contribution's output (tag "cont", meta[0] = function id below, data[0] = lambda)
+   and, once, every input they read: level populations of all model atoms, bound-free continua with their
+   cross-section tables, the ground-state lines Rayleigh() sums, molecular densities, nHmin. */
+#define PROBE_CONT 256
+enum { CF_THOMSON = 0, CF_HMINUS_BF, CF_HMINUS_FF, CF_OH_BF, CF_CH_BF, CF_H_BF, CF_H_FF, CF_RAYLEIGH_H,
+       CF_RAYLEIGH_HE, CF_H2PLUS_FF, CF_RAYLEIGH_H2, CF_H2MINUS_FF, CF_METAL_BF };
+static void cont_snapshot(void)
+{
+  int N = atmos.Nspace, m, i, kr, nlev = 0, ncont = 0, ntab = 0, nray = 0;
+  if (cont_snapshot_done) return;
+  cont_snapshot_done = 1;
+  for (m = 0; m < atmos.Natom; m++) {
+    Atom *a = &atmos.atoms[m];
+    nlev += a->Nlevel; ncont += a->Ncont;
+    for (kr = 0; kr < a->Ncont; kr++) ntab += a->continuum[kr].Nlambda;
+    if (m < 2) for (kr = 0; kr < a->Nline; kr++) if (a->line[kr].i == 0) nray++;
+  }
+  double *h = rec_new("ct_hdr", 16, atmos.Natom, nlev, ncont, ntab, nray, 0);
+  h[0] = atmos.Natom; h[1] = nlev; h[2] = ncont; h[3] = ntab; h[4] = nray; h[5] = atmos.H->active;
+  h[6] = (atmos.elements[1].model != NULL); h[7] = (atmos.OH != NULL); h[8] = (atmos.CH != NULL);
+  h[9] = (atmos.H2 != NULL); h[10] = input.solve_NLTE; h[11] = atmos.vmicro_char; h[12] = input.do_fudge;
+  h[13] = atmos.H->Nlevel; h[14] = atmos.moving; h[15] = atmos.Stokes;
+  double *lev = rec_new("ct_lev", 5L*nlev, 0,0,0,0,0,0);          /* atom, E, stage, g, active */
+  double *pn = rec_new("ct_n", (long) nlev*N, 0,0,0,0,0,0);
+  double *ps = rec_new("ct_nstar", (long) nlev*N, 0,0,0,0,0,0);
+  double *bf = rec_new("ct_bf", 10L*ncont, 0,0,0,0,0,0);
+  double *tl = rec_new("ct_tab_lambda", ntab > 0 ? ntab : 1, 0,0,0,0,0,0);
+  double *ta = rec_new("ct_tab_alpha", ntab > 0 ? ntab : 1, 0,0,0,0,0,0);
+  double *ry = rec_new("ct_ray", 8L*(nray > 0 ? nray : 1), 0,0,0,0,0,0);
+  int l0 = 0, c0 = 0, t0 = 0, r0 = 0;
+  for (m = 0; m < atmos.Natom; m++) {
+    Atom *a = &atmos.atoms[m];
+    for (i = 0; i < a->Nlevel; i++) {
+      lev[5*(l0+i)] = m; lev[5*(l0+i)+1] = a->E[i]; lev[5*(l0+i)+2] = a->stage[i]; lev[5*(l0+i)+3] = a->g[i];
+      lev[5*(l0+i)+4] = a->active;
+      memcpy(pn + (long) (l0+i)*N, a->n[i], N*sizeof(double));
+      memcpy(ps + (long) (l0+i)*N, a->nstar[i], N*sizeof(double));
+    }
+    for (kr = 0; kr < a->Ncont; kr++) {
+      AtomicContinuum *c = &a->continuum[kr];
+      double *b = bf + 10L*(c0+kr);
+      b[0] = m; b[1] = l0 + c->i; b[2] = l0 + c->j; b[3] = c->lambda0; b[4] = c->lambda[0]; b[5] = c->hydrogenic;
+      b[6] = c->alpha0; b[7] = c->Nlambda; b[8] = t0; b[9] = a->active;
+      memcpy(tl + t0, c->lambda, c->Nlambda*sizeof(double));
+      memcpy(ta + t0, c->alpha, c->Nlambda*sizeof(double));
+      t0 += c->Nlambda;
+    }
+    if (m < 2) for (kr = 0; kr < a->Nline; kr++) if (a->line[kr].i == 0) {
+      AtomicLine *L = &a->line[kr];
+      double *r = ry + 8L*r0++;
+      r[0] = m; r[1] = L->lambda0; r[2] = L->qwing; r[3] = L->Aji; r[4] = a->g[L->j]; r[5] = a->g[0]; r[6] = l0; r[7] = a->stage[0];
+    }
+    l0 += a->Nlevel; c0 += a->Ncont;
+  }
+  rec_copy("ct_T", atmos.T, N, 0,0,0,0);
+  rec_copy("ct_ne", atmos.ne, N, 0,0,0,0);
+  rec_copy("ct_nHmin", atmos.nHmin, N, 0,0,0,0);
+  if (atmos.H2) rec_copy("ct_nH2", atmos.H2->n, N, 0,0,0,0);
+  if (atmos.OH) rec_copy("ct_nOH", atmos.OH->n, N, 0,0,0,0);
+  if (atmos.CH) rec_copy("ct_nCH", atmos.CH->n, N, 0,0,0,0);
+}
+
+static void cont_rec(int id, double lambda, int ok, const double *a, const double *b)
+{
+  int N = atmos.Nspace;
+  double *d = rec_new("cont", 1 + 2L*N, id, ok, 0,0,0,0);
+  d[0] = lambda;
+  if (a && ok) memcpy(d + 1, a, N*sizeof(double)); else memset(d + 1, 0, N*sizeof(double));
+  if (b && ok) memcpy(d + 1 + N, b, N*sizeof(double)); else memset(d + 1 + N, 0, N*sizeof(double));
+}
+#define CONT_ON ((probe_mask & PROBE_CONT) && atmos.active_layer == -1)
+
+void __real_Thomson(double *chi);
+void __wrap_Thomson(double *chi) { __real_Thomson(chi); if (CONT_ON) { cont_snapshot(); cont_rec(CF_THOMSON, 0.0, 1, chi, NULL); } }
+#define WRAP2(NAME, ID) \
+  bool_t __real_##NAME(double lambda, double *chi, double *eta); \
+  bool_t __wrap_##NAME(double lambda, double *chi, double *eta) { \
+    bool_t ok = __real_##NAME(lambda, chi, eta); if (CONT_ON) cont_rec(ID, lambda, ok, chi, eta); return ok; }
+#define WRAP1(NAME, ID) \
+  bool_t __real_##NAME(double lambda, double *chi); \
+  bool_t __wrap_##NAME(double lambda, double *chi) { \
+    bool_t ok = __real_##NAME(lambda, chi); if (CONT_ON && lambda != 0.0) cont_rec(ID, lambda, ok, chi, NULL); return ok; }
+WRAP2(Hminus_bf, CF_HMINUS_BF)
+WRAP1(Hminus_ff, CF_HMINUS_FF)
+WRAP2(OH_bf_opac, CF_OH_BF)
+WRAP2(CH_bf_opac, CF_CH_BF)
+WRAP2(Hydrogen_bf, CF_H_BF)
+WRAP1(H2plus_ff, CF_H2PLUS_FF)
+WRAP1(Rayleigh_H2, CF_RAYLEIGH_H2)
+WRAP1(H2minus_ff, CF_H2MINUS_FF)
+void __real_Hydrogen_ff(double lambda, double *chi);
+void __wrap_Hydrogen_ff(double lambda, double *chi) { __real_Hydrogen_ff(lambda, chi); if (CONT_ON) cont_rec(CF_H_FF, lambda, 1, chi, NULL); }
+bool_t __real_Rayleigh(double lambda, Atom *atom, double *scatt);
+bool_t __wrap_Rayleigh(double lambda, Atom *atom, double *scatt)
+{
+  bool_t ok = __real_Rayleigh(lambda, atom, scatt);
+  if (CONT_ON) cont_rec(atom == atmos.H ? CF_RAYLEIGH_H : CF_RAYLEIGH_HE, lambda, ok, scatt, NULL);
+  return ok;
+}
+bool_t __real_Metal_bf(double lambda, int Nmetal, struct Atom *metals, double *chi, double *eta);
+bool_t __wrap_Metal_bf(double lambda, int Nmetal, struct Atom *metals, double *chi, double *eta)
+{
+  bool_t ok = __real_Metal_bf(lambda, Nmetal, metals, chi, eta);
+  if (CONT_ON) cont_rec(CF_METAL_BF, lambda, ok, chi, eta);
+  return ok;
 }

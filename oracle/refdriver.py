@@ -26,6 +26,7 @@ REFDIR = HERE / "_ref"
 PROBE_RLK, PROBE_BG, PROBE_DELO, PROBE_SNAP = 1, 2, 4, 8
 PROBE_BEZ, PROBE_FEAU, PROBE_NLTE, PROBE_FORMAL = 16, 32, 64, 128
 PROBE_ALL = 255
+PROBE_CONT = 256
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int)

@@ -1,0 +1,577 @@
+// rhb200_continuum.cu -- the angle-independent background continuum of Background() on the device.
+//
+// Reference: Background            rh/background.c:329-466   (order of the sums, Planck, fudge = off)
+//            Thomson               rh/thomson.c:31-44
+//            Hminus_bf, Hminus_ff  rh/hydrogen.c:310-365, 367-549   (tables: Geltman 1962; Stilley & Callaway 1970)
+//            Hydrogen_bf/_ff, Gaunt_bf/_ff   rh/hydrogen.c:151-305
+//            H2plus_ff, H2minus_ff, Rayleigh_H2   rh/hydrogen.c:621-995 (Bates 1952; Bell 1980; Victor & Dalgarno 1969)
+//            Rayleigh              rh/rayleigh.c:33-100
+//            OH_bf_opac, CH_bf_opac   rh/ohchbf.c:53-691      (Kurucz, van Dishoeck & Tarafdar 1987)
+//            Metal_bf              rh/metal.c:71-170
+//            splineCoef/splineEval rh/spline.c:33-97; Linear rh/linear.c:22-58; Locate/Hunt rh/hunt.c; bilinear hydrogen.c:998
+//
+// Split: everything that depends on the wavelength only (spline and table look-ups in lambda, Gaunt
+// factors, Rayleigh cross-sections, which bound-free edges are open) is evaluated ONCE per wavelength grid
+// on the host with the reference's expressions and the same libm; the device evaluates the per-depth part
+// (Boltzmann/stimulated-emission factors with the glibc-exact exp, populations, the T-interpolations) for
+// every (column, wavelength, depth) and sums the contributions in Background()'s order.
+// The published cross-section tables are inputs (the RH host owns them), see INTEGRATION.md.
+#include <cmath>
+#include <vector>
+#include "rhb200_common.cuh"
+#include "rhb200_math.cuh"
+#include "rhb200_delo.cuh"
+
+#ifndef RH_CHECK
+#define RH_CHECK(expr) do { int rc__ = (expr); if (rc__ != RHB200_OK) return rc__; } while (0)
+#endif
+
+namespace {
+
+#define RH_E_RYDBERG  2.1798741E-18
+#define RH_EV         1.60217733E-19
+#define RH_THETA0     5.03974756E+03
+#define RH_MEGABARN_TO_M2 1.0E-22
+#define RH_LG10       2.30258509299404568402
+#define RH_CM_TO_M    1.0E-02
+#define RH_Q_ELECTRON 1.60217733E-19
+#define RH_EPSILON_0  8.854187817E-12
+#define SQ(x)   ((x)*(x))
+#define CUBE(x) ((x)*(x)*(x))
+
+// ---- host: hunt.c Locate (= Hunt's result for in-range values of a strictly monotonic table)
+int locate(int n, const double *a, double v)
+{
+  const bool ascend = a[n-1] > a[0];
+  int lo = 0, hi = n;
+  while (hi - lo > 1) {
+    const int mid = (hi + lo) >> 1;
+    if (ascend ? (v >= a[mid]) : (v <= a[mid])) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// spline.c:33-97
+struct Spline {
+  std::vector<double> M;
+  const double *x, *y; int N; bool ascend; double xmin, xmax;
+  void coef(int n, const double *xt, const double *yt) {
+    N = n; x = xt; y = yt;
+    ascend = x[1] > x[0];
+    xmin = ascend ? x[0] : x[N-1];
+    xmax = ascend ? x[N-1] : x[0];
+    std::vector<double> q(N), u(N);
+    M.assign(N, 0.0);
+    double hj = x[1] - x[0], D = (y[1] - y[0]) / hj;
+    q[0] = u[0] = 0.0;
+    for (int j = 1; j < N-1; j++) {
+      const double hj1 = x[j+1] - x[j];
+      const double mu = hj / (hj + hj1);
+      const double D1 = (y[j+1] - y[j]) / hj1;
+      const double p = mu*q[j-1] + 2;
+      q[j] = (mu - 1) / p;
+      u[j] = ((D1 - D) * 6/(hj + hj1) - mu*u[j-1]) / p;
+      hj = hj1; D = D1;
+    }
+    M[N-1] = 0.0;
+    for (int j = N-2; j >= 0; j--) M[j] = q[j]*M[j+1] + u[j];
+  }
+  double eval(double xv) const {
+    if (xv <= xmin) return ascend ? y[0] : y[N-1];
+    if (xv >= xmax) return ascend ? y[N-1] : y[0];
+    const int j = locate(N, x, xv);
+    const double hj = x[j+1] - x[j], fx = (xv - x[j]) / hj, fx1 = 1 - fx;
+    return fx1*y[j] + fx*y[j+1] + (fx1*(SQ(fx1) - 1) * M[j] + fx*(SQ(fx) - 1) * M[j+1]) * SQ(hj)/6.0;
+  }
+};
+
+double linear_host(int n, const double *xt, const double *yt, double x)      // linear.c:22-58
+{
+  const bool ascend = xt[1] > xt[0];
+  const double xmin = ascend ? xt[0] : xt[n-1], xmax = ascend ? xt[n-1] : xt[0];
+  if (x <= xmin) return ascend ? yt[0] : yt[n-1];
+  if (x >= xmax) return ascend ? yt[n-1] : yt[0];
+  const int j = locate(n, xt, x);
+  const double fx = (xt[j+1] - x) / (xt[j+1] - xt[j]);
+  return fx*yt[j] + (1 - fx)*yt[j+1];
+}
+
+double gaunt_bf(double lambda, double n_eff, int charge)                     // hydrogen.c:269-282
+{
+  const double x = ((RH_HPLANCK*RH_CLIGHT)/(lambda * RH_NM_TO_M)) / (RH_E_RYDBERG * SQ(charge));
+  const double x3 = pow(x, 0.33333333);
+  const double nsqx = 1.0 / (SQ(n_eff) * x);
+  return 1.0 + 0.1728*x3 * (1.0 - 2.0*nsqx) - 0.0496*SQ(x3) * (1.0 - (1.0 - nsqx)*0.66666667*nsqx);
+}
+
+// per-wavelength coefficient record (doubles), then the lists of open bound-free edges
+enum { WC_FLAGS = 0, WC_LAMBDA, WC_HCKLA_B, WC_TWOHNU3_B, WC_HCKLA_A, WC_TWOHNU3_A, WC_ALPHA_HMBF, WC_LI_HMFF,
+       WC_E_OH, WC_E_CH, WC_NU3, WC_CY, WC_GA1, WC_GA2, WC_SIG_RAY_H, WC_SIG_RAY_HE, WC_LI_H2P, WC_SIG_RH2,
+       WC_LI_H2M, WC_HBF_FIRST, WC_HBF_COUNT, WC_MBF_FIRST, WC_MBF_COUNT, WC_NFIELD = 24 };
+enum { F_HMBF = 1, F_HMFF = 2, F_OH = 4, F_CH = 8, F_RAY_H = 16, F_RAY_HE = 32, F_H2P = 64, F_RH2 = 128, F_H2M = 256 };
+
+struct DevModel {       // device copies
+  double *wc = nullptr, *bfl = nullptr;        // [nlambda][WC_NFIELD]; bound-free list entries {i, j, alpha}
+  double *hmff_kappa = nullptr, *h2m_kappa = nullptr, *h2p_kappa = nullptr, *oh_cross = nullptr, *ch_cross = nullptr;
+  double *hmff_theta = nullptr, *h2m_theta = nullptr, *h2p_temp = nullptr, *oh_T = nullptr, *ch_T = nullptr;
+  int n_hmff_lambda, n_hmff_theta, n_h2m_lambda, n_h2m_theta, n_h2p_lambda, n_h2p_temp, n_oh_T, n_oh_E, n_ch_T, n_ch_E;
+  int nlev, nlev_H, lev0_He, H_active, solve_NLTE;
+  double sigma_T, sigma_ff;
+};
+
+// ---- device
+__device__ __forceinline__ double bilinear_d(int Ncol, int Nrow, const double *__restrict__ f, double x, double y)
+{                                                                          // hydrogen.c:998-1020
+  const int i = (int) x; const double fx = x - i;
+  const int i1 = (i == Ncol-1) ? i : i + 1;
+  const int j = (int) y; const double fy = y - j;
+  const int j1 = (j == Nrow-1) ? j : j + 1;
+  return (1.0 - fx)*(1.0 - fy) * f[j*Ncol+i] + fx*(1.0 - fy) * f[j*Ncol+i1] +
+         (1.0 - fx)*fy * f[j1*Ncol+i] + fx*fy * f[j1*Ncol+i1];
+}
+
+__device__ __forceinline__ int locate_d(int n, const double *__restrict__ a, double v)   // ascending tables
+{
+  int lo = 0, hi = n;
+  while (hi - lo > 1) { const int mid = (hi + lo) >> 1; if (v >= a[mid]) lo = mid; else hi = mid; }
+  return lo;
+}
+
+// fractional index used by Hminus_ff / H2minus_ff (theta) and H2plus_ff (T): hydrogen.c:480-494
+__device__ __forceinline__ double frac_index(int n, const double *__restrict__ tab, double v)
+{
+  if (v <= tab[0]) return 0;
+  if (v >= tab[n-1]) return n - 1;
+  const int idx = locate_d(n, tab, v);
+  return (double) idx + (v - tab[idx]) / (tab[idx+1] - tab[idx]);
+}
+
+// T-only quantities per (column, depth): tprep[col][TP_NFIELD][ndep]
+enum { TP_TH_HMFF = 0, TP_TH_H2M, TP_T_H2P, TP_T_OH, TP_T_CH, TP_NFIELD };
+__global__ void __launch_bounds__(128)
+cont_prep_kernel(int ncol, int ndep, DevModel M, const double *__restrict__ T, double *__restrict__ tprep)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t) ncol * ndep) return;
+  const int col = (int) (t / ndep), k = (int) (t % ndep);
+  const double Tk = T[t], theta = RH_THETA0 / Tk;
+  double *o = tprep + (size_t) col * TP_NFIELD * ndep + k;
+  o[(size_t) TP_TH_HMFF*ndep] = frac_index(M.n_hmff_theta, M.hmff_theta, theta);
+  o[(size_t) TP_TH_H2M*ndep]  = M.h2m_theta ? frac_index(M.n_h2m_theta, M.h2m_theta, theta) : 0.0;
+  o[(size_t) TP_T_H2P*ndep]   = frac_index(M.n_h2p_temp, M.h2p_temp, Tk);
+  // OH / CH (ohchbf.c:360-366): outside the tabulated temperatures the contribution is zero -> index -1
+  double ti = -1.0;
+  if (M.oh_T && !(Tk < M.oh_T[0] || Tk > M.oh_T[M.n_oh_T-1])) {
+    const int i2 = locate_d(M.n_oh_T, M.oh_T, Tk);
+    ti = (double) i2 + (Tk - M.oh_T[i2]) / (M.oh_T[i2+1] - M.oh_T[i2]);
+  }
+  o[(size_t) TP_T_OH*ndep] = ti;
+  ti = -1.0;
+  if (M.ch_T && !(Tk < M.ch_T[0] || Tk > M.ch_T[M.n_ch_T-1])) {
+    const int i2 = locate_d(M.n_ch_T, M.ch_T, Tk);
+    ti = (double) i2 + (Tk - M.ch_T[i2]) / (M.ch_T[i2+1] - M.ch_T[i2]);
+  }
+  o[(size_t) TP_T_CH*ndep] = ti;
+}
+
+// one thread per (column, wavelength, depth); sums in Background()'s order (background.c:343-465)
+__global__ void __launch_bounds__(128)
+continuum_kernel(int ncol, int nlambda, int ndep, DevModel M,
+                 const double *__restrict__ T, const double *__restrict__ ne, const double *__restrict__ nHmin,
+                 const double *__restrict__ nH2, const double *__restrict__ nOH, const double *__restrict__ nCH,
+                 const double *__restrict__ pn, const double *__restrict__ ps, const double *__restrict__ tprep,
+                 double *__restrict__ chi_ai, double *__restrict__ eta_ai, double *__restrict__ sca_ai,
+                 double *__restrict__ contrib /* optional [ray][13][2][ndep]: each contribution on its own */)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t) ncol * nlambda * ndep) return;
+  const size_t r = t / ndep;
+  const int k = (int) (t - r * ndep);
+  const int col = (int) (r / nlambda), l = (int) (r - (size_t) col * nlambda);
+  const size_t ck = (size_t) col * ndep + k;
+#define RH_DBG(id, a, b) do { if (contrib) { contrib[((r*13 + (id))*2 + 0)*ndep + k] = (a); contrib[((r*13 + (id))*2 + 1)*ndep + k] = (b); } } while (0)
+  const double *W = M.wc + (size_t) l * WC_NFIELD;
+  const int flags = (int) W[WC_FLAGS];
+  const double lambda = W[WC_LAMBDA];
+  const double Tk = T[ck], nek = ne[ck];
+  const double *n_ = pn + (size_t) col * M.nlev * ndep + k, *s_ = ps + (size_t) col * M.nlev * ndep + k;
+  const double *tp = tprep + (size_t) col * TP_NFIELD * ndep + k;
+  const double Bnu = rhd::planck(Tk, lambda);                               // background.c:334
+  const double nH0 = n_[0], np = n_[(size_t) (M.nlev_H-1) * ndep];
+
+  double chi_a = 0.0, eta_a = 0.0, sca_a = nek * M.sigma_T;                 // Thomson, thomson.c:42
+  RH_DBG(0, sca_a, 0.0);
+  const double hc_kla_B = W[WC_HCKLA_B], twohnu3_B = W[WC_TWOHNU3_B];
+  const double stimB = rhm::rh_exp(-hc_kla_B/Tk);
+  if (flags & F_HMBF) {                                                     // hydrogen.c:357-361
+    const double alpha_bf = W[WC_ALPHA_HMBF];
+    chi_a += nHmin[ck] * (1.0 - stimB) * alpha_bf;
+    eta_a += nHmin[ck] * twohnu3_B * stimB * alpha_bf;
+    RH_DBG(1, nHmin[ck] * (1.0 - stimB) * alpha_bf, nHmin[ck] * twohnu3_B * stimB * alpha_bf);
+  }
+  const double pe = nek * RH_KBOLTZMANN * Tk;
+  if (flags & F_HMFF) {                                                     // hydrogen.c:541-546
+    const double kappa = bilinear_d(M.n_hmff_theta, M.n_hmff_lambda, M.hmff_kappa, tp[(size_t) TP_TH_HMFF*ndep], W[WC_LI_HMFF]);
+    const double chi = (nH0 * 1.0E-29) * pe * kappa;
+    chi_a += chi; eta_a += chi * Bnu;
+    RH_DBG(2, chi, 0.0);
+  }
+  if (flags & F_OH) {                                                       // ohchbf.c:372-388
+    const double ti = tp[(size_t) TP_T_OH*ndep];
+    double chi = 0.0, eta = 0.0;
+    if (ti >= 0.0) {
+      const double kappa = rhm::rh_exp(RH_LG10 * bilinear_d(M.n_oh_T, M.n_oh_E, M.oh_cross, ti, W[WC_E_OH])) * SQ(RH_CM_TO_M);
+      chi = nOH[ck] * (1.0 - stimB) * kappa;
+      eta = nOH[ck] * twohnu3_B * stimB * kappa;
+    }
+    chi_a += chi; eta_a += eta;
+    RH_DBG(3, chi, eta);
+  }
+  if (flags & F_CH) {
+    const double ti = tp[(size_t) TP_T_CH*ndep];
+    double chi = 0.0, eta = 0.0;
+    if (ti >= 0.0) {
+      const double kappa = rhm::rh_exp(RH_LG10 * bilinear_d(M.n_ch_T, M.n_ch_E, M.ch_cross, ti, W[WC_E_CH])) * SQ(RH_CM_TO_M);
+      chi = nCH[ck] * (1.0 - stimB) * kappa;
+      eta = nCH[ck] * twohnu3_B * stimB * kappa;
+    }
+    chi_a += chi; eta_a += eta;
+    RH_DBG(4, chi, eta);
+  }
+  const double hc_kla_A = W[WC_HCKLA_A], twohnu3_A = W[WC_TWOHNU3_A];
+  const double explaA = rhm::rh_exp(-hc_kla_A/Tk);
+  {                                                                         // Hydrogen_bf, hydrogen.c:189-224
+    const int first = (int) W[WC_HBF_FIRST], cnt = (int) W[WC_HBF_COUNT];
+    if (cnt > 0) {
+      const double npstar = s_[(size_t) (M.nlev_H-1) * ndep];
+      double chi = 0.0, eta = 0.0;
+      for (int c = 0; c < cnt; c++) {
+        const double *e = M.bfl + (size_t) (first + c) * 3;
+        const int i = (int) e[0];
+        const double sigma = e[2];
+        const double gijk = s_[(size_t) i * ndep]/npstar * explaA;
+        chi += sigma * (1.0 - explaA) * n_[(size_t) i * ndep];
+        eta += twohnu3_A * gijk * sigma * np;
+      }
+      chi_a += chi; eta_a += eta;
+      RH_DBG(5, chi, eta);
+    }
+  }
+  {                                                                         // Hydrogen_ff, hydrogen.c:255-260
+    const double stim = 1.0 - stimB;
+    const double y = (W[WC_CY] * Tk) / (RH_HPLANCK*RH_CLIGHT);                // Gaunt_ff, hydrogen.c:296-303
+    const double gIII = 1.0 + W[WC_GA1] * (1.0 + y) - W[WC_GA2] * (1.0 + (1.0 + y)*0.33333333*y);
+    const double g_ff = (gIII > 1.0) ? gIII : 1.0;
+    const double chi = M.sigma_ff / sqrt(Tk) * W[WC_NU3] * nek * np * stim * g_ff;
+    chi_a += chi; eta_a += chi * Bnu;
+    RH_DBG(6, chi, 0.0);
+  }
+  if (flags & F_RAY_H)  { sca_a += W[WC_SIG_RAY_H] * nH0; RH_DBG(7, W[WC_SIG_RAY_H] * nH0, 0.0); }   // rayleigh.c:92-93
+  if (flags & F_RAY_HE) { sca_a += W[WC_SIG_RAY_HE] * n_[(size_t) M.lev0_He * ndep]; RH_DBG(8, W[WC_SIG_RAY_HE] * n_[(size_t) M.lev0_He * ndep], 0.0); }
+  if (flags & F_H2P) {                                                      // hydrogen.c:929-933
+    const double kappa = bilinear_d(M.n_h2p_temp, M.n_h2p_lambda, M.h2p_kappa, tp[(size_t) TP_T_H2P*ndep], W[WC_LI_H2P]);
+    const double chi = (nH0 * 1.0E-29) * (np * 1.0E-20) * kappa;
+    chi_a += chi; eta_a += chi * Bnu;
+    RH_DBG(9, chi, 0.0);
+  }
+  if (flags & F_RH2) { sca_a += W[WC_SIG_RH2] * nH2[ck]; RH_DBG(10, W[WC_SIG_RH2] * nH2[ck], 0.0); }   // hydrogen.c:985-986
+  if (flags & F_H2M) {                                                      // hydrogen.c:782-790
+    double chi = 0.0;
+    if (nH2[ck] > 0.0) {
+      const double kappa = bilinear_d(M.n_h2m_theta, M.n_h2m_lambda, M.h2m_kappa, tp[(size_t) TP_TH_H2M*ndep], W[WC_LI_H2M]);
+      chi = (nH2[ck] * 1.0E-29) * pe * kappa;
+    }
+    chi_a += chi; eta_a += chi * Bnu;
+    RH_DBG(11, chi, 0.0);
+  }
+  {                                                                         // Metal_bf, metal.c:104-158 (fudge = 1)
+    const int first = (int) W[WC_MBF_FIRST], cnt = (int) W[WC_MBF_COUNT];
+    double chi = 0.0, eta = 0.0;
+    for (int c = 0; c < cnt; c++) {
+      const double *e = M.bfl + (size_t) (first + c) * 3;
+      const int i = (int) e[0], j = (int) e[1];
+      const double alpha_la = e[2];
+      const double gijk = s_[(size_t) i * ndep]/s_[(size_t) j * ndep] * explaA;
+      chi += alpha_la * (1.0 - explaA) * n_[(size_t) i * ndep];
+      eta += twohnu3_A * gijk * alpha_la * n_[(size_t) j * ndep];
+    }
+    chi_a += chi * 1.0; eta_a += eta * 1.0;
+    if (cnt > 0) RH_DBG(12, chi, eta);
+  }
+  sca_a *= 1.0;
+  if (M.solve_NLTE) chi_a += sca_a;                                         // background.c:462
+  chi_ai[t] = chi_a; eta_ai[t] = eta_a;
+  if (sca_ai) sca_ai[t] = sca_a;
+}
+
+template <class T> int up(T **d, const T *h, size_t n)
+{
+  *d = nullptr;
+  if (n == 0 || !h) return RHB200_OK;
+  RH_CUDA(cudaMalloc((void **) d, n * sizeof(T)));
+  RH_CUDA(cudaMemcpy(*d, h, n * sizeof(T), cudaMemcpyHostToDevice));
+  return RHB200_OK;
+}
+
+struct Holder {          // frees the device copies
+  std::vector<void *> p;
+  ~Holder() { for (void *q : p) if (q) cudaFree(q); }
+  template <class T> int put(T **d, const T *h, size_t n) { int rc = up(d, h, n); if (*d) p.push_back(*d); return rc; }
+};
+
+}  // namespace
+
+// builds the per-wavelength coefficients on the host (reference expressions, same libm) and uploads everything
+static int build_model(const rhb200_continuum_model *m, int nlambda, const double *lambda, DevModel &D, Holder &H)
+{
+  const double *lev = m->lev;
+  auto lvE = [&](int g) { return lev[5*(size_t) g + 1]; };
+  auto lvStage = [&](int g) { return (int) lev[5*(size_t) g + 2]; };
+  if (m->do_fudge) { rhb200_set_error("opacity fudge factors are not implemented"); return RHB200_EUNSUPPORTED; }
+  // splines of the tabulated bound-free cross-sections (metal.c:137-140) and of H- bf (hydrogen.c:343)
+  std::vector<Spline> sp(m->ncont);
+  for (int c = 0; c < m->ncont; c++) {
+    const double *b = m->bf + 10*(size_t) c;
+    if (b[5] == 0.0 && (int) b[0] != 0)
+      sp[c].coef((int) b[7], m->tab_lambda + (int) b[8], m->tab_alpha + (int) b[8]);
+  }
+  Spline hm;
+  hm.coef(m->n_hmbf, m->hmbf_lambda, m->hmbf_alpha);
+
+  const double twohc  = (2.0 * RH_HPLANCK * RH_CLIGHT) / CUBE(RH_NM_TO_M);
+  const double hc_k   = (RH_HPLANCK * RH_CLIGHT) / (RH_KBOLTZMANN * RH_NM_TO_M);
+  const double sigma0 = 32.0/(3.0*sqrt(3.0)) * SQ(RH_Q_ELECTRON)/(4.0*RH_PI*RH_EPSILON_0) /
+                        (RH_M_ELECTRON * RH_CLIGHT) * RH_HPLANCK/(2.0*RH_E_RYDBERG);
+  const double C_ray = 2*RH_PI * (RH_Q_ELECTRON/RH_EPSILON_0) * (RH_Q_ELECTRON/RH_M_ELECTRON) / RH_CLIGHT;
+  const double sigma_e = 8.0*RH_PI/3.0 * pow(RH_Q_ELECTRON/(sqrt(4.0*RH_PI*RH_EPSILON_0) * (sqrt(RH_M_ELECTRON)*RH_CLIGHT)), 4);
+  {
+    const double C0 = SQ(RH_Q_ELECTRON)/(4.0*RH_PI*RH_EPSILON_0) / sqrt(RH_M_ELECTRON);
+    D.sigma_ff = 4.0/3.0 * sqrt(2.0*RH_PI/(3.0 * RH_KBOLTZMANN)) * CUBE(C0) / (RH_HPLANCK * RH_CLIGHT);
+    D.sigma_T = sigma_e;
+  }
+  std::vector<double> wc((size_t) nlambda * WC_NFIELD, 0.0), bfl;
+  for (int l = 0; l < nlambda; l++) {
+    const double lam = lambda[l];
+    double *W = wc.data() + (size_t) l * WC_NFIELD;
+    int flags = 0;
+    if (!(lam > 0.0)) { rhb200_set_error("wavelength %d is not positive", l); return RHB200_EINVAL; }
+    W[WC_LAMBDA] = lam;
+    W[WC_HCKLA_B]   = (RH_HPLANCK * RH_CLIGHT) / (RH_KBOLTZMANN * RH_NM_TO_M * lam);
+    W[WC_TWOHNU3_B] = (2.0 * RH_HPLANCK * RH_CLIGHT) / CUBE(RH_NM_TO_M * lam);
+    W[WC_HCKLA_A]   = hc_k / lam;
+    W[WC_TWOHNU3_A] = twohc / CUBE(lam);
+    // Hminus_bf, hydrogen.c:340-349
+    if (!((lam <= m->hmbf_lambda[0]) || (lam >= m->hmbf_lambda[m->n_hmbf-1]))) {
+      double a = hm.eval(lam);
+      a *= 1.0E-21;
+      W[WC_ALPHA_HMBF] = a; flags |= F_HMBF;
+    }
+    // Hminus_ff, hydrogen.c:474-476, 523-525
+    if (lam >= m->hmff_lambda[m->n_hmff_lambda-1]) { rhb200_set_error("Hminus_ff_long (lambda >= %g nm) is not implemented", m->hmff_lambda[m->n_hmff_lambda-1]); return RHB200_EUNSUPPORTED; }
+    {
+      const int idx = locate(m->n_hmff_lambda, m->hmff_lambda, lam);
+      W[WC_LI_HMFF] = (double) idx + (lam - m->hmff_lambda[idx]) / (m->hmff_lambda[idx+1] - m->hmff_lambda[idx]);
+      flags |= F_HMFF;
+    }
+    // OH / CH, ohchbf.c:345-351
+    const double Eev = (RH_HPLANCK * RH_CLIGHT) / (lam * RH_NM_TO_M) / RH_EV;
+    if (m->has_OH && m->oh_E && !(Eev < m->oh_E[0] || Eev > m->oh_E[m->n_oh_E-1])) {
+      const int idx = locate(m->n_oh_E, m->oh_E, Eev);
+      W[WC_E_OH] = (double) idx + (Eev - m->oh_E[idx]) / (m->oh_E[idx+1] - m->oh_E[idx]); flags |= F_OH;
+    }
+    if (m->has_CH && m->ch_E && !(Eev < m->ch_E[0] || Eev > m->ch_E[m->n_ch_E-1])) {
+      const int idx = locate(m->n_ch_E, m->ch_E, Eev);
+      W[WC_E_CH] = (double) idx + (Eev - m->ch_E[idx]) / (m->ch_E[idx+1] - m->ch_E[idx]); flags |= F_CH;
+    }
+    // Hydrogen_bf, hydrogen.c:189-206 (H continua are the entries with atom == 0)
+    W[WC_HBF_FIRST] = (double) (bfl.size() / 3);
+    if (!m->H_active) {
+      for (int c = 0; c < m->ncont; c++) {
+        const double *b = m->bf + 10*(size_t) c;
+        if ((int) b[0] != 0) continue;
+        const double lambdaEdge = b[3];
+        if (lam <= lambdaEdge && lam >= b[4]) {
+          const int i = (int) b[1], j = (int) b[2];
+          const double n_eff = sqrt(RH_E_RYDBERG / (lvE(j) - lvE(i)));
+          const double g_bf = gaunt_bf(lam, n_eff, lvStage(i) + 1);
+          const double sigma = sigma0 * n_eff * g_bf * CUBE(lam/lambdaEdge);
+          bfl.push_back(i); bfl.push_back(j); bfl.push_back(sigma);
+        }
+      }
+    }
+    W[WC_HBF_COUNT] = (double) (bfl.size() / 3) - W[WC_HBF_FIRST];
+    // Hydrogen_ff + Gaunt_ff, hydrogen.c:243-246, 296-300
+    W[WC_NU3] = CUBE((lam * RH_NM_TO_M) / RH_CLIGHT);
+    {
+      const double x = ((RH_HPLANCK * RH_CLIGHT)/(lam * RH_NM_TO_M)) / (RH_E_RYDBERG * SQ(1));
+      const double x3 = pow(x, 0.33333333);
+      W[WC_CY] = 2.0 * lam * RH_NM_TO_M * RH_KBOLTZMANN;
+      W[WC_GA1] = 0.1728*x3;
+      W[WC_GA2] = 0.0496*SQ(x3);
+    }
+    // Rayleigh (H: atom 0, He: atom 1), rayleigh.c:55-93
+    for (int atom = 0; atom < 2; atom++) {             // ray[][0]: 0 = hydrogen, 1 = helium
+      if (atom == 1 && m->atom_He < 0) continue;
+      double lambda_limit = 1.0E6; int nl = 0;
+      for (int r = 0; r < m->nray; r++) {
+        const double *R = m->ray + 8*(size_t) r;
+        if ((int) R[0] != atom) continue;
+        nl++;
+        const double lambda_red = R[1] * (1.0 + R[2] * m->vmicro_char / RH_CLIGHT);
+        lambda_limit = lambda_limit < lambda_red ? lambda_limit : lambda_red;
+      }
+      if (nl == 0) continue;                       // no line from the ground state: lambda_limit stays LONG_WAVELENGTH
+      if (lam > lambda_limit) {
+        double fomega = 0.0;
+        for (int r = 0; r < m->nray; r++) {
+          const double *R = m->ray + 8*(size_t) r;
+          if ((int) R[0] != atom) continue;
+          const double lambda_red = R[1] * (1.0 + R[2] * m->vmicro_char / RH_CLIGHT);
+          if (lam > lambda_red) {
+            const double lambda2 = 1.0 / (SQ(lam / R[1]) - 1.0);
+            const double f = R[3] * (R[4] / R[5]) * SQ(R[1]*RH_NM_TO_M) / C_ray;
+            fomega += f * SQ(lambda2);
+          }
+        }
+        W[atom == 0 ? WC_SIG_RAY_H : WC_SIG_RAY_HE] = sigma_e * fomega;
+        flags |= (atom == 0 ? F_RAY_H : F_RAY_HE);
+      }
+    }
+    // H2plus_ff, hydrogen.c:883-884, 917-919
+    if (lam < m->h2pff_lambda[m->n_h2pff_lambda-1]) {
+      const int idx = locate(m->n_h2pff_lambda, m->h2pff_lambda, lam);
+      W[WC_LI_H2P] = idx + (lam - m->h2pff_lambda[idx]) / (m->h2pff_lambda[idx+1] - m->h2pff_lambda[idx]); flags |= F_H2P;
+    }
+    // Rayleigh_H2, hydrogen.c:970-981
+    if (m->has_H2 && lam >= 121.57) {
+      double s;
+      if (lam <= m->rh2_lambda[m->n_rh2-1]) s = linear_host(m->n_rh2, m->rh2_lambda, m->rh2_sigma, lam);
+      else { const double lambda2 = 1.0 / SQ(lam); s = (m->rh2_a[0] + (m->rh2_a[1] + m->rh2_a[2]*lambda2) * lambda2) * SQ(lambda2); }
+      s *= RH_MEGABARN_TO_M2;
+      W[WC_SIG_RH2] = s; flags |= F_RH2;
+    }
+    // H2minus_ff, hydrogen.c:724-725, 762-764
+    if (m->has_H2 && lam < m->h2mff_lambda[m->n_h2mff_lambda-1]) {
+      const int idx = locate(m->n_h2mff_lambda, m->h2mff_lambda, lam);
+      W[WC_LI_H2M] = idx + (lam - m->h2mff_lambda[idx]) / (m->h2mff_lambda[idx+1] - m->h2mff_lambda[idx]); flags |= F_H2M;
+    }
+    // Metal_bf, metal.c:104-141: PASSIVE atoms other than hydrogen
+    W[WC_MBF_FIRST] = (double) (bfl.size() / 3);
+    for (int c = 0; c < m->ncont; c++) {
+      const double *b = m->bf + 10*(size_t) c;
+      if ((int) b[0] == 0 || b[9] != 0.0) continue;
+      if (lam <= b[3] && lam >= b[4]) {
+        const int i = (int) b[1], j = (int) b[2];
+        double alpha_la;
+        if (b[5] != 0.0) {
+          const int Z = lvStage(j);
+          const double n_eff = Z*sqrt(RH_E_RYDBERG / (lvE(j) - lvE(i)));
+          const double gbf_0 = gaunt_bf(b[3], n_eff, Z);
+          alpha_la = b[6] * CUBE(lam/b[3]) * gaunt_bf(lam, n_eff, Z) / gbf_0;
+        } else
+          alpha_la = sp[c].eval(lam);
+        bfl.push_back(i); bfl.push_back(j); bfl.push_back(alpha_la);
+      }
+    }
+    W[WC_MBF_COUNT] = (double) (bfl.size() / 3) - W[WC_MBF_FIRST];
+    W[WC_FLAGS] = (double) flags;
+  }
+  if (bfl.empty()) bfl.assign(3, 0.0);
+  RH_CHECK(H.put(&D.wc, wc.data(), wc.size()));
+  RH_CHECK(H.put(&D.bfl, bfl.data(), bfl.size()));
+  RH_CHECK(H.put(&D.hmff_kappa, m->hmff_kappa, (size_t) m->n_hmff_lambda * m->n_hmff_theta));
+  RH_CHECK(H.put(&D.hmff_theta, m->hmff_theta, (size_t) m->n_hmff_theta));
+  RH_CHECK(H.put(&D.h2m_kappa, m->h2mff_kappa, (size_t) m->n_h2mff_lambda * m->n_h2mff_theta));
+  RH_CHECK(H.put(&D.h2m_theta, m->h2mff_theta, (size_t) m->n_h2mff_theta));
+  RH_CHECK(H.put(&D.h2p_kappa, m->h2pff_kappa, (size_t) m->n_h2pff_lambda * m->n_h2pff_temp));
+  RH_CHECK(H.put(&D.h2p_temp, m->h2pff_temp, (size_t) m->n_h2pff_temp));
+  if (m->has_OH) { RH_CHECK(H.put(&D.oh_cross, m->oh_cross, (size_t) m->n_oh_T * m->n_oh_E)); RH_CHECK(H.put(&D.oh_T, m->oh_T, (size_t) m->n_oh_T)); }
+  if (m->has_CH) { RH_CHECK(H.put(&D.ch_cross, m->ch_cross, (size_t) m->n_ch_T * m->n_ch_E)); RH_CHECK(H.put(&D.ch_T, m->ch_T, (size_t) m->n_ch_T)); }
+  D.n_hmff_lambda = m->n_hmff_lambda; D.n_hmff_theta = m->n_hmff_theta;
+  D.n_h2m_lambda = m->n_h2mff_lambda; D.n_h2m_theta = m->n_h2mff_theta;
+  D.n_h2p_lambda = m->n_h2pff_lambda; D.n_h2p_temp = m->n_h2pff_temp;
+  D.n_oh_T = m->n_oh_T; D.n_oh_E = m->n_oh_E; D.n_ch_T = m->n_ch_T; D.n_ch_E = m->n_ch_E;
+  D.nlev = m->nlev; D.nlev_H = m->nlev_H; D.H_active = m->H_active; D.solve_NLTE = m->solve_NLTE;
+  D.lev0_He = 0;
+  for (int g = 0; g < m->nlev; g++) if ((int) lev[5*(size_t) g] == m->atom_He) { D.lev0_He = g; break; }
+  return RHB200_OK;
+}
+
+static int check_model(const rhb200_continuum_model *m)
+{
+  if (!m || m->natom < 1 || m->nlev < 2 || m->nlev_H < 2 || m->ncont < 0 || !m->lev || (m->ncont && !m->bf) ||
+      !m->hmbf_lambda || !m->hmbf_alpha || m->n_hmbf < 3 || !m->hmff_lambda || !m->hmff_theta || !m->hmff_kappa ||
+      !m->h2pff_lambda || !m->h2pff_temp || !m->h2pff_kappa ||
+      (m->has_H2 && (!m->h2mff_lambda || !m->h2mff_theta || !m->h2mff_kappa || !m->rh2_lambda || !m->rh2_sigma || !m->rh2_a)) ||
+      (m->has_OH && (!m->oh_T || !m->oh_E || !m->oh_cross)) || (m->has_CH && (!m->ch_T || !m->ch_E || !m->ch_cross))) {
+    rhb200_set_error("incomplete continuum model"); return RHB200_EINVAL;
+  }
+  for (int c = 0; c < m->ncont; c++) {
+    const double *b = m->bf + 10*(size_t) c;
+    if ((int) b[1] < 0 || (int) b[1] >= m->nlev || (int) b[2] < 0 || (int) b[2] >= m->nlev ||
+        (b[5] == 0.0 && ((int) b[7] < 3 || (int) b[8] < 0 || (int) b[8] + (int) b[7] > m->ntab))) {
+      rhb200_set_error("continuum %d: level index or table slice out of range", c); return RHB200_EINVAL;
+    }
+  }
+  return RHB200_OK;
+}
+
+// device-pointer core shared by the host entry point and the fused LTE path
+int rh_continuum_dev(rhb200_ctx *c, const rhb200_continuum_model *m, int nlambda, const double *h_lambda,
+                     int ncol, int ndep, const double *d_T, const double *d_ne, const double *d_nHmin,
+                     const double *d_nH2, const double *d_nOH, const double *d_nCH, const double *d_n,
+                     const double *d_nstar, double *d_chi, double *d_eta, double *d_sca, double *d_contrib)
+{
+  RH_CHECK(check_model(m));
+  DevModel D; Holder H;
+  RH_CHECK(build_model(m, nlambda, h_lambda, D, H));
+  double *d_tprep = nullptr;
+  RH_CUDA(cudaMalloc((void **) &d_tprep, (size_t) ncol * TP_NFIELD * ndep * sizeof(double)));
+  H.p.push_back(d_tprep);
+  {
+    ScopedKernelTimer t(c, RHB200_K_PREP);
+    cont_prep_kernel<<<(unsigned) (((size_t) ncol * ndep + 127) / 128), 128, 0, c->stream>>>(ncol, ndep, D, d_T, d_tprep);
+  }
+  {
+    ScopedKernelTimer t(c, RHB200_K_OTHER);
+    const size_t n = (size_t) ncol * nlambda * ndep;
+    continuum_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(ncol, nlambda, ndep, D, d_T, d_ne, d_nHmin,
+        d_nH2, d_nOH, d_nCH, d_n, d_nstar, d_tprep, d_chi, d_eta, d_sca, d_contrib);
+  }
+  RH_CUDA(cudaGetLastError());
+  RH_CUDA(cudaStreamSynchronize(c->stream));      // the Holder frees the tables on return
+  return RHB200_OK;
+}
+
+extern "C" int rhb200_continuum_batch(rhb200_ctx *c, const rhb200_continuum_model *m, int nlambda, const double *lambda,
+                                      int ncol, int ndep, const double *T, const double *ne, const double *nHmin,
+                                      const double *nH2, const double *nOH, const double *nCH,
+                                      const double *pops_n, const double *pops_nstar,
+                                      double *chi_ai, double *eta_ai, double *sca_ai, double *contrib)
+{
+  if (!c) { rhb200_set_error("null context"); return RHB200_EINVAL; }
+  RH_CUDA(cudaSetDevice(c->device));
+  RH_CHECK(check_model(m));
+  if (nlambda <= 0 || ncol <= 0 || ndep <= 0 || !lambda || !T || !ne || !nHmin || !pops_n || !pops_nstar || !chi_ai || !eta_ai ||
+      (m->has_H2 && !nH2) || (m->has_OH && !nOH) || (m->has_CH && !nCH)) { rhb200_set_error("bad arguments"); return RHB200_EINVAL; }
+  Holder H;
+  const size_t cn = (size_t) ncol * ndep, pn = (size_t) ncol * m->nlev * ndep, on = (size_t) ncol * nlambda * ndep;
+  double *dT, *dne, *dHm, *dH2 = nullptr, *dOH = nullptr, *dCH = nullptr, *dn, *ds, *dchi, *deta, *dsca;
+  RH_CHECK(H.put(&dT, T, cn)); RH_CHECK(H.put(&dne, ne, cn)); RH_CHECK(H.put(&dHm, nHmin, cn));
+  if (m->has_H2) RH_CHECK(H.put(&dH2, nH2, cn));
+  if (m->has_OH) RH_CHECK(H.put(&dOH, nOH, cn));
+  if (m->has_CH) RH_CHECK(H.put(&dCH, nCH, cn));
+  RH_CHECK(H.put(&dn, pops_n, pn));
+  if (pops_nstar == pops_n) ds = dn; else RH_CHECK(H.put(&ds, pops_nstar, pn));
+  RH_CUDA(cudaMalloc((void **) &dchi, on * sizeof(double))); H.p.push_back(dchi);
+  RH_CUDA(cudaMalloc((void **) &deta, on * sizeof(double))); H.p.push_back(deta);
+  RH_CUDA(cudaMalloc((void **) &dsca, on * sizeof(double))); H.p.push_back(dsca);
+  double *dcon = nullptr;
+  if (contrib) { RH_CUDA(cudaMalloc((void **) &dcon, on * 26 * sizeof(double))); H.p.push_back(dcon); RH_CUDA(cudaMemset(dcon, 0, on * 26 * sizeof(double))); }
+  RH_CHECK(rh_continuum_dev(c, m, nlambda, lambda, ncol, ndep, dT, dne, dHm, dH2, dOH, dCH, dn, ds, dchi, deta, dsca, dcon));
+  if (contrib) RH_CUDA(cudaMemcpy(contrib, dcon, on * 26 * sizeof(double), cudaMemcpyDeviceToHost));
+  RH_CUDA(cudaMemcpy(chi_ai, dchi, on * sizeof(double), cudaMemcpyDeviceToHost));
+  RH_CUDA(cudaMemcpy(eta_ai, deta, on * sizeof(double), cudaMemcpyDeviceToHost));
+  if (sca_ai) RH_CUDA(cudaMemcpy(sca_ai, dsca, on * sizeof(double), cudaMemcpyDeviceToHost));
+  return RHB200_OK;
+}

@@ -648,3 +648,46 @@ def test_passive_bb_vs_reference(ctx):
         rest = np.setdiff1d(np.arange(len(lam)), ns)
         assert not chi[0, rest].any() and not eta[0, rest].any()
     REPORT["passive_bb_exact"] = exact
+
+
+def test_background_continuum_vs_reference(ctx):
+    """Angle-independent background of Background() (background.c:343-465) on the device: Thomson, H- bf/ff,
+    OH/CH bf, H bf/ff, Rayleigh H/He/H2, H2+ ff, H2- ff, bound-free of 10 PASSIVE metals (157 continua), on 21
+    wavelengths from 180 nm to 2.3 micron, against the chi_c / eta_c / sca_c the reference stores for a
+    line-free run."""
+    from pyrh_b200 import continuum
+    g = dict(np.load(GOLD / "falc_continuum.npz"))
+    model = continuum.ContinuumModel(g)
+    one = lambda x: np.ascontiguousarray(x)[None]   # noqa: E731
+    chi, eta, sca, con = continuum.continuum_batch(ctx, model, g["lam_spect"], one(g["ct_T"]), one(g["ct_ne"]),
+                                                   one(g["ct_nHmin"]), one(g["ct_nH2"]), one(g["ct_nOH"]),
+                                                   one(g["ct_nCH"]), one(g["ct_n"]), one(g["ct_nstar"]), contrib=True)
+    # every contribution on its own first (this is what localises a mismatch)
+    per = {}
+    for i, name in enumerate(g["names"]):
+        want = g["contrib"][i]                                    # [nlambda, 2, ndep]
+        got = con[0, :, i]
+        on = g["contrib_ok"][i].astype(bool)
+        scale = np.abs(want[on]).max(axis=2, keepdims=True) if on.any() else 1.0
+        per[str(name)] = float(np.max(np.abs(got[on] - want[on]) / np.where(scale == 0, 1, scale))) if on.any() else 0.0
+        assert not got[~on].any(), name                          # absent where the reference returned FALSE
+    REPORT["continuum_per_contribution_maxerr"] = per
+    assert max(per.values()) < 1e-13, per
+    pure = g["hasline"] == 0                 # 1700 nm carries a molecular line in chi_c: not part of this path
+    assert pure.sum() == len(pure) - 1
+    ref = g["total"][pure]
+    chi, eta, sca = chi[:, pure], eta[:, pure], sca[:, pure]
+    rel = {}
+    for name, got, want in (("chi", chi[0], ref[:, 0]), ("eta", eta[0], ref[:, 1]), ("sca", sca[0], ref[:, 2])):
+        rel[name] = float(np.max(np.abs(got / want - 1)))
+        REPORT[f"continuum_{name}_maxrel"] = rel[name]
+        REPORT[f"continuum_{name}_exact"] = bool(np.array_equal(got, want))
+    assert max(rel.values()) < 1e-12, rel
+    assert np.array_equal(chi[0], ref[:, 0]) and np.array_equal(eta[0], ref[:, 1]) and np.array_equal(sca[0], ref[:, 2])
+    # two columns with different temperatures give independent results
+    T2 = np.stack([g["ct_T"], g["ct_T"] * 1.01])
+    rep = lambda x: np.stack([x, x])   # noqa: E731
+    c2, e2, s2 = continuum.continuum_batch(ctx, model, g["lam_spect"], T2, rep(g["ct_ne"]), rep(g["ct_nHmin"]),
+                                           rep(g["ct_nH2"]), rep(g["ct_nOH"]), rep(g["ct_nCH"]), rep(g["ct_n"]),
+                                           rep(g["ct_nstar"]))
+    assert np.array_equal(c2[0][pure], chi[0]) and not np.array_equal(c2[1][pure], chi[0])
