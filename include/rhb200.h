@@ -263,6 +263,18 @@ int rhb200_continuum_batch(rhb200_ctx *ctx, const rhb200_continuum_model *model,
                               (diagnostics; order Thomson, H- bf, H- ff, OH bf, CH bf, H bf, H ff, Rayleigh H,
                               Rayleigh He, H2+ ff, Rayleigh H2, H2- ff, metal bf; [..][0] = chi or scatt, [..][1] = eta) */);
 
+/* Fused LTE path with the continuum on the device.  rhb200_set_continuum (after rhb200_set_wavelengths)
+   builds the per-wavelength coefficients once; abundance [natom] = atom->abundance (readatom.c:190).
+   rhb200_lte_stokes_batch_pops is rhb200_lte_stokes_batch without chi_ai / eta_ai: per column it takes
+   chem [ncol][natom+4][ndep] = the factor ChemicalEquilibrium() applies to each model atom's populations
+   (ntotal_after / ntotal_before, chemequil.c:336; 1 for atoms in no molecule), then nHmin, nH2, nOH, nCH;
+   the library evaluates LTEpops (ltepops.c:33-113), the continuum, the line opacity and the formal solution.
+   All model atoms must be PASSIVE with LTE populations. */
+int rhb200_set_continuum(rhb200_ctx *ctx, const rhb200_continuum_model *model, const double *abundance);
+int rhb200_lte_stokes_batch_pops(rhb200_ctx *ctx, int ncol, int ndep, double muz, int moving,
+                                 int bc_top, int bc_bottom, const double *atmos, const double *chem,
+                                 double *stokes);
+
 /* Formal-solver selection = keyword.input S_INTERPOLATION / S_INTERPOLATION_STOKES (readvalue.c:366-404;
    enum values of inputs.h:26-27).  Applies to rhb200_lte_stokes_batch(_dev) (Stokes solver) and to
    rhb200_nlte_iterate / rhb200_nlte_formal (scalar solver).  Defaults: S_BEZIER3, DELO_BEZIER3. */

@@ -43,7 +43,7 @@ wrap=""
 for s in rlk_opacity writeBackground Piece_Stokes_Bezier3_1D Piecewise_Bezier3_1D Feautrier \
          Formal Opacity addtoGamma addtoRates statEquil Accelerate Iterate updatePopulations SolveLinearEq solveSpectrum \
          Piecewise_1D Piecewise_Linear_1D Piece_Stokes_1D MolecularOpacity passive_bb \
-         Thomson Hminus_bf Hminus_ff OH_bf_opac CH_bf_opac Hydrogen_bf Hydrogen_ff Rayleigh H2plus_ff Rayleigh_H2 H2minus_ff Metal_bf; do
+         Thomson Hminus_bf Hminus_ff OH_bf_opac CH_bf_opac Hydrogen_bf Hydrogen_ff Rayleigh H2plus_ff Rayleigh_H2 H2minus_ff Metal_bf ChemicalEquilibrium; do
   wrap="$wrap -Wl,--wrap=$s"
 done
 gcc -shared -o "$out/liboracle_$variant.so" "$obj"/*.o $wrap -lm -lpthread

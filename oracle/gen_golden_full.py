@@ -1,0 +1,46 @@
+"""TEST INFRASTRUCTURE ONLY (oracle).  Inputs of the fused LTE path WITH the continuum on the device.
+
+Same run as fixture falc_B1kG (FAL-C, B = 1 kG, Hinode grid, the two Fe I lines): records, next to what that
+fixture already holds, the continuum model (all model atoms, bound-free edges, Rayleigh lines), what
+ChemicalEquilibrium() did to the atomic populations (ntotal before / after, rh/chemequil.c:336-342), nHmin and
+the molecular densities.  Expected outputs are falc_B1kG's (chi_ai, eta_ai, stokes_scalar).
+Output: tests/golden/falc_full.npz.   Usage: python -m oracle.gen_golden_full
+"""
+import numpy as np
+
+from oracle import refdriver as rd
+from oracle.gen_golden import GOLD, recs_by_tag, one, falc_case_atm
+from oracle.scrape_tables import continuum_tables
+
+
+def main():
+    atm = falc_case_atm()
+    wave = rd.hinode_wave()
+    cwd = rd.make_workdir("benchmark")
+    o = rd.rhf1d(atm, wave, cwd, probe=rd.PROBE_CONT | rd.PROBE_SNAP)
+    R = recs_by_tag(o["records"])
+    N = atm.shape[1]
+    out = dict(atmosphere=atm, wave=wave, lam_spect=one(R, "lambda"))
+    for k in ("hdr", "lev", "bf", "tab_lambda", "tab_alpha", "ray", "T", "ne", "nHmin", "nH2", "nOH", "nCH"):
+        out["ct_" + k] = one(R, "ct_" + k)
+    nlev, natom = int(out["ct_hdr"][1]), int(out["ct_hdr"][0])
+    out["ct_lev"] = out["ct_lev"].reshape(nlev, 5)
+    out["ct_bf"] = out["ct_bf"].reshape(-1, 10)
+    out["ct_ray"] = out["ct_ray"].reshape(-1, 8)
+    out["ct_nstar"] = one(R, "ct_nstar").reshape(nlev, N)
+    for k, v in continuum_tables().items():
+        out["tab_" + k] = v
+    pre, post = one(R, "ce_ntotal_pre").reshape(natom, N), one(R, "ce_ntotal_post").reshape(natom, N)
+    out["abundance"] = one(R, "ce_abundance")
+    out["fraction"] = post / pre                       # the reference's own division (chemequil.c:336)
+    out["chem"] = np.concatenate([out["fraction"], [out["ct_nHmin"], out["ct_nH2"], out["ct_nOH"], out["ct_nCH"]]])
+    out["stokes"] = np.array([o["I"], o["Q"], o["U"], o["V"]])
+    np.savez_compressed(GOLD / "falc_full.npz", **out)
+    g = np.load(GOLD / "falc_B1kG.npz")
+    print(f"[golden] falc_full: {natom} atoms, {nlev} levels; atoms rescaled by chemistry: "
+          f"{int(np.sum(np.any(out['fraction'] != 1.0, axis=1)))}; spectrum equals falc_B1kG: "
+          f"{np.array_equal(out['stokes'], g['stokes_scalar'])} -> {(GOLD / 'falc_full.npz').stat().st_size/1e3:.0f} kB")
+
+
+if __name__ == "__main__":
+    main()

@@ -903,3 +903,23 @@ bool_t __wrap_Metal_bf(double lambda, int Nmetal, struct Atom *metals, double *c
   if (CONT_ON) cont_rec(CF_METAL_BF, lambda, ok, chi, eta);
   return ok;
 }
+
+/* ChemicalEquilibrium (rh/chemequil.c:107-392) rescales the populations of every model atom that is bound in
+   molecules by n_after / ntotal_before (:336-342): record both ntotal arrays and the abundances. */
+void __real_ChemicalEquilibrium(int NmaxIter, double iterLimit);
+void __wrap_ChemicalEquilibrium(int NmaxIter, double iterLimit)
+{
+  int rec = (probe_mask & PROBE_CONT) && atmos.active_layer == -1, N = atmos.Nspace, m;
+  double *pre = NULL;
+  if (rec) {
+    pre = rec_new("ce_ntotal_pre", (long) atmos.Natom*N, atmos.Natom, 0,0,0,0,0);
+    for (m = 0; m < atmos.Natom; m++) memcpy(pre + (long) m*N, atmos.atoms[m].ntotal, N*sizeof(double));
+    double *ab = rec_new("ce_abundance", atmos.Natom, 0,0,0,0,0,0);
+    for (m = 0; m < atmos.Natom; m++) ab[m] = atmos.atoms[m].abundance;
+  }
+  __real_ChemicalEquilibrium(NmaxIter, iterLimit);
+  if (rec) {
+    double *post = rec_new("ce_ntotal_post", (long) atmos.Natom*N, atmos.Natom, 0,0,0,0,0);
+    for (m = 0; m < atmos.Natom; m++) memcpy(post + (long) m*N, atmos.atoms[m].ntotal, N*sizeof(double));
+  }
+}

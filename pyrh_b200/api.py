@@ -150,6 +150,27 @@ class Context:
                                                     _vp(ea), _vp(out)))
         return out
 
+    def set_continuum(self, model, abundance):
+        """Background continuum on the device for the wavelengths set before (rhb200_set_continuum).
+        ``model``: pyrh_b200.continuum.ContinuumModel; ``abundance`` [natom] = atom->abundance."""
+        self._cont_model = model                       # the struct points into its arrays
+        ab = np.ascontiguousarray(abundance, np.float64)
+        _lib.check(self.lib.rhb200_set_continuum(self.h, C.byref(model.struct), _dp(ab)))
+
+    def lte_stokes_batch_pops(self, atmos_rows, chem, mu=1.0, moving=True, bc_top=_lib.BC_ZERO,
+                              bc_bottom=_lib.BC_THERMALIZED, out=None):
+        """``lte_stokes_batch`` with LTE populations, continuum, line opacity and formal solution all on the
+        device: chem [ncol, natom+4, ndep] = ChemicalEquilibrium's population factor per model atom, nHmin, nH2,
+        nOH, nCH."""
+        at = np.ascontiguousarray(atmos_rows, np.float64)
+        ch = np.ascontiguousarray(chem, np.float64)
+        ncol, _, ndep = at.shape
+        nl = self.nlambda
+        st = np.empty((ncol, 4, nl)) if out is None else out
+        _lib.check(self.lib.rhb200_lte_stokes_batch_pops(self.h, ncol, ndep, float(mu), int(moving), int(bc_top),
+                                                         int(bc_bottom), _vp(at), _vp(ch), _vp(st)))
+        return st
+
     def lte_stokes_batch_dev(self, ncol, ndep, d_atmos, d_chi_ai, d_eta_ai, d_stokes, mu=1.0,
                              moving=True, bc_top=_lib.BC_ZERO, bc_bottom=_lib.BC_THERMALIZED):
         _lib.check(self.lib.rhb200_lte_stokes_batch_dev(self.h, int(ncol), int(ndep), float(mu),

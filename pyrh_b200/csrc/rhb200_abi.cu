@@ -81,7 +81,7 @@ extern "C" void rhb200_close(rhb200_ctx *c)
   if (!c) return;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
-  free_tables(c); free_wave(c);
+  free_tables(c); free_wave(c); rh_continuum_free(c);
   cudaFree(c->ws); cudaFree(c->flush);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -260,6 +260,7 @@ static int chunk_columns(const rhb200_ctx *c, int ncol, int ndep, int nslots)
   if (const char *e = getenv("RHB200_WS_GB")) { double g = atof(e); if (g > 0.01) budget = (size_t) (g * (double) ((size_t) 1 << 30)); }
   ChunkLayout one(c, 1, ndep);
   size_t per = one.total + (size_t) (RHB200_AT_NFIELD * ndep + 2 * c->wav.nlambda * ndep + 4 * c->wav.nlambda) * sizeof(double);
+  if (c->cont) per += (size_t) (rh_continuum_natom(c) + 4 + rh_continuum_nlev(c) + 8) * ndep * sizeof(double);
   size_t cc = budget / ((size_t) nslots * per);
   if (cc < 1) cc = 1;
   if (const char *e = getenv("RHB200_CHUNK_COLS")) { int v = atoi(e); if (v > 0) cc = (size_t) v; }
@@ -314,14 +315,17 @@ extern "C" int rhb200_lte_stokes_batch_dev(rhb200_ctx *c, int ncol, int ndep, do
 // HOST pointers.  Two slots (device input/output buffers + workspace), each driven by its own
 // stream: the H2D copy of chunk i+1 overlaps the kernels of chunk i when the host buffers are
 // pinned (rhb200_host_alloc_pinned); pageable memory still works, just without overlap.
-extern "C" int rhb200_lte_stokes_batch(rhb200_ctx *c, int ncol, int ndep, double muz, int moving,
-                                       int bc_top, int bc_bottom, const double *atmos,
-                                       const double *chi_ai, const double *eta_ai, double *stokes)
+// chem != NULL: the background continuum is evaluated on the device from LTE populations
+// (rhb200_set_continuum) instead of being copied in as chi_ai / eta_ai
+static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int moving,
+                          int bc_top, int bc_bottom, const double *atmos,
+                          const double *chi_ai, const double *eta_ai, const double *chem, double *stokes)
 {
   RH_NEED_CTX(c);
   RH_CHECK(check_batch_args(c, ncol, ndep, muz, bc_top, bc_bottom));
   if (ncol == 0) return RHB200_OK;
-  if (!atmos || !chi_ai || !eta_ai || !stokes) { rhb200_set_error("null buffer"); return RHB200_EINVAL; }
+  if (!atmos || !stokes || (!chem && (!chi_ai || !eta_ai))) { rhb200_set_error("null buffer"); return RHB200_EINVAL; }
+  if (chem && !c->cont) { rhb200_set_error("rhb200_set_continuum() has not been called"); return RHB200_ESTATE; }
   const int nl = c->wav.nlambda;
   const int nslots = 2;
   const int cc = chunk_columns(c, ncol, ndep, nslots);
@@ -329,7 +333,11 @@ extern "C" int rhb200_lte_stokes_batch(rhb200_ctx *c, int ncol, int ndep, double
   const size_t b_at = align_up((size_t) cc * RHB200_AT_NFIELD * ndep * sizeof(double));
   const size_t b_op = align_up((size_t) cc * nl * ndep * sizeof(double));
   const size_t b_st = align_up((size_t) cc * 4 * nl * sizeof(double));
-  const size_t slot = L.total + b_at + 2*b_op + b_st;
+  const int nchem = chem ? rh_continuum_natom(c) + 4 : 0;
+  const size_t b_ch = chem ? align_up((size_t) cc * nchem * ndep * sizeof(double)) : 0;
+  const size_t b_pp = chem ? align_up((size_t) cc * rh_continuum_nlev(c) * ndep * sizeof(double)) : 0;
+  const size_t b_tp = chem ? align_up((size_t) cc * 8 * ndep * sizeof(double)) : 0;
+  const size_t slot = L.total + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp;
   RH_CHECK(rh_ws_reserve(c, nslots * slot));
   cudaStream_t streams[2] = {c->stream, c->copy_stream};
   cudaStream_t saved = c->stream;
@@ -339,13 +347,24 @@ extern "C" int rhb200_lte_stokes_batch(rhb200_ctx *c, int ncol, int ndep, double
     char *base = (char *) c->ws + (size_t) (i % nslots) * slot;
     double *d_at = (double *) base, *d_chi = (double *) (base + b_at), *d_eta = (double *) (base + b_at + b_op),
            *d_st = (double *) (base + b_at + 2*b_op);
-    char *ws = base + b_at + 2*b_op + b_st;
+    double *d_ch = (double *) (base + b_at + 2*b_op + b_st), *d_pp = (double *) (base + b_at + 2*b_op + b_st + b_ch),
+           *d_tp = (double *) (base + b_at + 2*b_op + b_st + b_ch + b_pp);
+    char *ws = base + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp;
     cudaStream_t st = streams[i % nslots];
     c->stream = st;
     cudaError_t e;
     if ((e = cudaMemcpyAsync(d_at, atmos + (size_t) c0 * RHB200_AT_NFIELD * ndep,
-                             (size_t) n * RHB200_AT_NFIELD * ndep * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess ||
-        (e = cudaMemcpyAsync(d_chi, chi_ai + (size_t) c0 * nl * ndep, (size_t) n * nl * ndep * sizeof(double),
+                             (size_t) n * RHB200_AT_NFIELD * ndep * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess) {
+      rhb200_set_error("H2D copy failed: %s", cudaGetErrorString(e)); rc = RHB200_ECUDA; break;
+    }
+    if (chem) {
+      if ((e = cudaMemcpyAsync(d_ch, chem + (size_t) c0 * nchem * ndep, (size_t) n * nchem * ndep * sizeof(double),
+                               cudaMemcpyHostToDevice, st)) != cudaSuccess) {
+        rhb200_set_error("H2D copy failed: %s", cudaGetErrorString(e)); rc = RHB200_ECUDA; break;
+      }
+      rc = rh_continuum_chunk(c, n, ndep, d_at, d_ch, d_pp, d_tp, d_chi, d_eta);
+      if (rc != RHB200_OK) break;
+    } else if ((e = cudaMemcpyAsync(d_chi, chi_ai + (size_t) c0 * nl * ndep, (size_t) n * nl * ndep * sizeof(double),
                              cudaMemcpyHostToDevice, st)) != cudaSuccess ||
         (e = cudaMemcpyAsync(d_eta, eta_ai + (size_t) c0 * nl * ndep, (size_t) n * nl * ndep * sizeof(double),
                              cudaMemcpyHostToDevice, st)) != cudaSuccess) {
@@ -365,6 +384,22 @@ extern "C" int rhb200_lte_stokes_batch(rhb200_ctx *c, int ncol, int ndep, double
     rc = RHB200_ECUDA;
   }
   return rc;
+}
+
+extern "C" int rhb200_lte_stokes_batch(rhb200_ctx *c, int ncol, int ndep, double muz, int moving,
+                                       int bc_top, int bc_bottom, const double *atmos,
+                                       const double *chi_ai, const double *eta_ai, double *stokes)
+{
+  if (!chi_ai || !eta_ai) { rhb200_set_error("null buffer"); return RHB200_EINVAL; }
+  return lte_batch_host(c, ncol, ndep, muz, moving, bc_top, bc_bottom, atmos, chi_ai, eta_ai, nullptr, stokes);
+}
+
+extern "C" int rhb200_lte_stokes_batch_pops(rhb200_ctx *c, int ncol, int ndep, double muz, int moving,
+                                            int bc_top, int bc_bottom, const double *atmos,
+                                            const double *chem, double *stokes)
+{
+  if (!chem) { rhb200_set_error("null buffer"); return RHB200_EINVAL; }
+  return lte_batch_host(c, ncol, ndep, muz, moving, bc_top, bc_bottom, atmos, nullptr, nullptr, chem, stokes);
 }
 
 // ------------------------------------------------ function-level entry points

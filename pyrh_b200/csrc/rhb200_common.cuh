@@ -77,6 +77,7 @@ struct rhb200_ctx {
   // wavelength shard of the NLTE solve (rhb200_nlte_set_shard)
   int shard_rank = 0, shard_nrank = 1;
   rhb200_allreduce_fn shard_fn = nullptr; void *shard_user = nullptr;
+  void *cont = nullptr;      // background-continuum state (rhb200_set_continuum), owned by rhb200_continuum.cu
   // workspace (grown on demand)
   void *ws = nullptr; size_t ws_bytes = 0;
   void *flush = nullptr; size_t flush_bytes = 0;
@@ -106,6 +107,11 @@ struct ScopedKernelTimer {
 };
 
 int rh_ws_reserve(rhb200_ctx *ctx, size_t bytes);
+void rh_continuum_free(rhb200_ctx *ctx);
+int rh_continuum_nlev(const rhb200_ctx *ctx);
+int rh_continuum_natom(const rhb200_ctx *ctx);
+int rh_continuum_chunk(rhb200_ctx *ctx, int cc, int ndep, const double *d_atmos, const double *d_chem,
+                       double *d_pops, double *d_tprep, double *d_chi, double *d_eta);
 
 // launchers implemented in the .cu files (device pointers)
 int rh_launch_mol_opacity_raw(rhb200_ctx *ctx, int ncol, int nlambda, int ndep, int nmol, double muz, int moving,

@@ -149,12 +149,12 @@ __device__ __forceinline__ double frac_index(int n, const double *__restrict__ t
 // T-only quantities per (column, depth): tprep[col][TP_NFIELD][ndep]
 enum { TP_TH_HMFF = 0, TP_TH_H2M, TP_T_H2P, TP_T_OH, TP_T_CH, TP_NFIELD };
 __global__ void __launch_bounds__(128)
-cont_prep_kernel(int ncol, int ndep, DevModel M, const double *__restrict__ T, double *__restrict__ tprep)
+cont_prep_kernel(int ncol, int ndep, DevModel M, const double *__restrict__ T, size_t Tstride, double *__restrict__ tprep)
 {
   const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t) ncol * ndep) return;
   const int col = (int) (t / ndep), k = (int) (t % ndep);
-  const double Tk = T[t], theta = RH_THETA0 / Tk;
+  const double Tk = T[(size_t) col * Tstride + k], theta = RH_THETA0 / Tk;
   double *o = tprep + (size_t) col * TP_NFIELD * ndep + k;
   o[(size_t) TP_TH_HMFF*ndep] = frac_index(M.n_hmff_theta, M.hmff_theta, theta);
   o[(size_t) TP_TH_H2M*ndep]  = M.h2m_theta ? frac_index(M.n_h2m_theta, M.h2m_theta, theta) : 0.0;
@@ -177,8 +177,9 @@ cont_prep_kernel(int ncol, int ndep, DevModel M, const double *__restrict__ T, d
 // one thread per (column, wavelength, depth); sums in Background()'s order (background.c:343-465)
 __global__ void __launch_bounds__(128)
 continuum_kernel(int ncol, int nlambda, int ndep, DevModel M,
-                 const double *__restrict__ T, const double *__restrict__ ne, const double *__restrict__ nHmin,
-                 const double *__restrict__ nH2, const double *__restrict__ nOH, const double *__restrict__ nCH,
+                 const double *__restrict__ T, const double *__restrict__ ne, size_t astride,
+                 const double *__restrict__ nHmin, const double *__restrict__ nH2, const double *__restrict__ nOH,
+                 const double *__restrict__ nCH, size_t cstride,
                  const double *__restrict__ pn, const double *__restrict__ ps, const double *__restrict__ tprep,
                  double *__restrict__ chi_ai, double *__restrict__ eta_ai, double *__restrict__ sca_ai,
                  double *__restrict__ contrib /* optional [ray][13][2][ndep]: each contribution on its own */)
@@ -188,12 +189,13 @@ continuum_kernel(int ncol, int nlambda, int ndep, DevModel M,
   const size_t r = t / ndep;
   const int k = (int) (t - r * ndep);
   const int col = (int) (r / nlambda), l = (int) (r - (size_t) col * nlambda);
-  const size_t ck = (size_t) col * ndep + k;
+  const size_t ak = (size_t) col * astride + k;      // T, ne: [col][astride]
+  const size_t ck = (size_t) col * cstride + k;      // nHmin, nH2, nOH, nCH: [col][cstride]
 #define RH_DBG(id, a, b) do { if (contrib) { contrib[((r*13 + (id))*2 + 0)*ndep + k] = (a); contrib[((r*13 + (id))*2 + 1)*ndep + k] = (b); } } while (0)
   const double *W = M.wc + (size_t) l * WC_NFIELD;
   const int flags = (int) W[WC_FLAGS];
   const double lambda = W[WC_LAMBDA];
-  const double Tk = T[ck], nek = ne[ck];
+  const double Tk = T[ak], nek = ne[ak];
   const double *n_ = pn + (size_t) col * M.nlev * ndep + k, *s_ = ps + (size_t) col * M.nlev * ndep + k;
   const double *tp = tprep + (size_t) col * TP_NFIELD * ndep + k;
   const double Bnu = rhd::planck(Tk, lambda);                               // background.c:334
@@ -530,16 +532,135 @@ int rh_continuum_dev(rhb200_ctx *c, const rhb200_continuum_model *m, int nlambda
   H.p.push_back(d_tprep);
   {
     ScopedKernelTimer t(c, RHB200_K_PREP);
-    cont_prep_kernel<<<(unsigned) (((size_t) ncol * ndep + 127) / 128), 128, 0, c->stream>>>(ncol, ndep, D, d_T, d_tprep);
+    cont_prep_kernel<<<(unsigned) (((size_t) ncol * ndep + 127) / 128), 128, 0, c->stream>>>(ncol, ndep, D, d_T, (size_t) ndep, d_tprep);
   }
   {
     ScopedKernelTimer t(c, RHB200_K_OTHER);
     const size_t n = (size_t) ncol * nlambda * ndep;
-    continuum_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(ncol, nlambda, ndep, D, d_T, d_ne, d_nHmin,
-        d_nH2, d_nOH, d_nCH, d_n, d_nstar, d_tprep, d_chi, d_eta, d_sca, d_contrib);
+    continuum_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(ncol, nlambda, ndep, D, d_T, d_ne, (size_t) ndep,
+        d_nHmin, d_nH2, d_nOH, d_nCH, (size_t) ndep, d_n, d_nstar, d_tprep, d_chi, d_eta, d_sca, d_contrib);
   }
   RH_CUDA(cudaGetLastError());
   RH_CUDA(cudaStreamSynchronize(c->stream));      // the Holder frees the tables on return
+  return RHB200_OK;
+}
+
+// ---- LTEpops (ltepops.c:33-113, Debeye forced off as in the reference) + the per-atom rescaling of
+//      ChemicalEquilibrium (chemequil.c:334-343).  One thread per (column, depth); chem [col][natom+4][ndep] =
+//      fraction per atom (1 for atoms that are in no molecule), nHmin, nH2, nOH, nCH.
+__global__ void __launch_bounds__(128)
+ltepops_kernel(int ncol, int ndep, int natom, int nlev, const double *__restrict__ lev /*[nlev][5]*/,
+               const int *__restrict__ atom_first /*[natom+1]*/, const double *__restrict__ abundance,
+               const double *__restrict__ atmos, const double *__restrict__ chem, double *__restrict__ pops)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t) ncol * ndep) return;
+  const int col = (int) (t / ndep), k = (int) (t % ndep);
+  const double *at = atmos + (size_t) col * RHB200_AT_NFIELD * ndep;
+  const double T = at[RHB200_AT_T*ndep + k], ne = at[RHB200_AT_NE*ndep + k], nHtot = at[RHB200_AT_NHTOT*ndep + k];
+  const double c1 = (RH_HPLANCK/(2.0*RH_PI*RH_M_ELECTRON)) * (RH_HPLANCK/RH_KBOLTZMANN);
+  const double cNe_T = 0.5*ne * rhm::rh_pow(c1/T, 1.5);
+  double *P = pops + (size_t) col * nlev * ndep + k;
+  for (int a = 0; a < natom; a++) {
+    const int l0 = atom_first[a], l1 = atom_first[a+1];
+    const double E0 = lev[5*(size_t) l0 + 1], g0 = lev[5*(size_t) l0 + 3];
+    const int st0 = (int) lev[5*(size_t) l0 + 2];
+    double sum = 1.0;
+    for (int i = l0 + 1; i < l1; i++) {
+      const double dE = lev[5*(size_t) i + 1] - E0;
+      const double gi0 = lev[5*(size_t) i + 3] / g0;
+      const int dZ = (int) lev[5*(size_t) i + 2] - st0;
+      const double dE_kT = dE / (RH_KBOLTZMANN * T);
+      double ns = gi0 * rhm::rh_exp(-dE_kT);
+      for (int m = 1; m <= dZ; m++) ns /= cNe_T;
+      P[(size_t) i * ndep] = ns;
+      sum += ns;
+    }
+    const double ntotal = abundance[a] * nHtot;                     // readatom.c:190
+    const double n0 = ntotal / sum;
+    const double fraction = chem[((size_t) col * (natom + 4) + a) * ndep + k];
+    P[(size_t) l0 * ndep] = n0 * fraction;                          // chemequil.c:339
+    for (int i = l0 + 1; i < l1; i++) P[(size_t) i * ndep] = (P[(size_t) i * ndep] * n0) * fraction;
+  }
+}
+
+struct ContinuumState {
+  DevModel D; Holder H;
+  int natom = 0, nlev = 0, nlambda = 0, has_H2 = 0, has_OH = 0, has_CH = 0;
+  double *d_lev = nullptr, *d_abund = nullptr; int *d_first = nullptr;
+};
+
+void rh_continuum_free(rhb200_ctx *c)
+{
+  if (c->cont) { delete (ContinuumState *) c->cont; c->cont = nullptr; }
+}
+
+int rh_continuum_nlev(const rhb200_ctx *c) { return c->cont ? ((ContinuumState *) c->cont)->nlev : 0; }
+int rh_continuum_natom(const rhb200_ctx *c) { return c->cont ? ((ContinuumState *) c->cont)->natom : 0; }
+
+// LTE populations + continuum of one chunk of columns, all on ctx->stream.
+// d_pops [cc][nlev][ndep] and d_tprep [cc][5][ndep] are workspace; out d_chi, d_eta [cc][nlambda][ndep].
+int rh_continuum_chunk(rhb200_ctx *c, int cc, int ndep, const double *d_atmos, const double *d_chem,
+                       double *d_pops, double *d_tprep, double *d_chi, double *d_eta)
+{
+  ContinuumState *S = (ContinuumState *) c->cont;
+  if (!S) { rhb200_set_error("rhb200_set_continuum() has not been called"); return RHB200_ESTATE; }
+  if (S->nlambda != c->wav.nlambda) { rhb200_set_error("wavelengths changed after rhb200_set_continuum()"); return RHB200_ESTATE; }
+  const size_t cn = (size_t) cc * ndep;
+  const int na = S->natom;
+  {
+    ScopedKernelTimer t(c, RHB200_K_PREP);
+    ltepops_kernel<<<(unsigned) ((cn + 127) / 128), 128, 0, c->stream>>>(cc, ndep, na, S->nlev, S->d_lev, S->d_first,
+                                                                         S->d_abund, d_atmos, d_chem, d_pops);
+  }
+  // T and ne are rows of the atmosphere block; the chem block carries nHmin, nH2, nOH, nCH after the fractions.
+  // The kernels index [col][ndep] arrays, so they get strided views through small gather kernels' absence:
+  // both blocks are [col][field][ndep], hence a per-column stride -- handled by passing field pointers and strides.
+  {
+    ScopedKernelTimer t(c, RHB200_K_PREP);
+    cont_prep_kernel<<<(unsigned) ((cn + 127) / 128), 128, 0, c->stream>>>(cc, ndep, S->D, d_atmos + (size_t) RHB200_AT_T * ndep,
+                                                                           (size_t) RHB200_AT_NFIELD * ndep, d_tprep);
+  }
+  {
+    ScopedKernelTimer t(c, RHB200_K_OTHER);
+    const size_t n = (size_t) cc * S->nlambda * ndep;
+    const size_t as = (size_t) RHB200_AT_NFIELD * ndep, cs = (size_t) (na + 4) * ndep;
+    continuum_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, c->stream>>>(cc, S->nlambda, ndep, S->D,
+        d_atmos + (size_t) RHB200_AT_T * ndep, d_atmos + (size_t) RHB200_AT_NE * ndep, as,
+        d_chem + (size_t) na * ndep, d_chem + (size_t) (na + 1) * ndep, d_chem + (size_t) (na + 2) * ndep,
+        d_chem + (size_t) (na + 3) * ndep, cs, d_pops, d_pops, d_tprep, d_chi, d_eta, nullptr, nullptr);
+  }
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}
+
+extern "C" int rhb200_set_continuum(rhb200_ctx *c, const rhb200_continuum_model *m, const double *abundance)
+{
+  if (!c) { rhb200_set_error("null context"); return RHB200_EINVAL; }
+  RH_CUDA(cudaSetDevice(c->device));
+  RH_CHECK(check_model(m));
+  if (!abundance) { rhb200_set_error("abundance missing"); return RHB200_EINVAL; }
+  if (c->wav.nlambda == 0) { rhb200_set_error("rhb200_set_wavelengths() has not been called"); return RHB200_ESTATE; }
+  for (int g = 0; g < m->nlev; g++)
+    if (m->lev[5*(size_t) g + 4] != 0.0) { rhb200_set_error("ACTIVE atoms are not part of the LTE background path"); return RHB200_EUNSUPPORTED; }
+  rh_continuum_free(c);
+  ContinuumState *S = new ContinuumState();
+  c->cont = S;
+  int rc = build_model(m, c->wav.nlambda, c->h_lambda.data(), S->D, S->H);
+  if (rc != RHB200_OK) { rh_continuum_free(c); return rc; }
+  S->natom = m->natom; S->nlev = m->nlev; S->nlambda = c->wav.nlambda;
+  S->has_H2 = m->has_H2; S->has_OH = m->has_OH; S->has_CH = m->has_CH;
+  std::vector<int> first(m->natom + 1, -1);
+  for (int g = 0; g < m->nlev; g++) {
+    const int a = (int) m->lev[5*(size_t) g];
+    if (a < 0 || a >= m->natom || (g > 0 && a < (int) m->lev[5*(size_t) (g-1)])) { rh_continuum_free(c); rhb200_set_error("level table must be grouped by atom"); return RHB200_EINVAL; }
+    if (first[a] < 0) first[a] = g;
+  }
+  first[m->natom] = m->nlev;
+  for (int a = m->natom - 1; a >= 0; a--) if (first[a] < 0) first[a] = first[a+1];
+  if ((rc = S->H.put(&S->d_lev, m->lev, (size_t) m->nlev * 5)) != RHB200_OK ||
+      (rc = S->H.put(&S->d_abund, abundance, (size_t) m->natom)) != RHB200_OK ||
+      (rc = S->H.put(&S->d_first, first.data(), first.size())) != RHB200_OK) { rh_continuum_free(c); return rc; }
   return RHB200_OK;
 }
 

@@ -691,3 +691,45 @@ def test_background_continuum_vs_reference(ctx):
                                            rep(g["ct_nH2"]), rep(g["ct_nOH"]), rep(g["ct_nCH"]), rep(g["ct_n"]),
                                            rep(g["ct_nstar"]))
     assert np.array_equal(c2[0][pure], chi[0]) and not np.array_equal(c2[1][pure], chi[0])
+
+
+def test_lte_path_with_continuum_on_device(ctx, golden_falc):
+    """The whole LTE column on the device: LTEpops of the 11 model atoms (ltepops.c:33) with the chemical
+    equilibrium factors, Background()'s continuum, Kurucz line opacity, DELO-Bezier3.  Inputs per column: the
+    atmosphere rows and 15 small per-depth vectors; expected: the spectrum rhf1d() returns (fixture falc_B1kG),
+    bit for bit, and the reference's own chi_ai / eta_ai on the way."""
+    from pyrh_b200 import continuum
+    f = golden_falc
+    g = dict(np.load(GOLD / "falc_full.npz"))
+    assert np.array_equal(g["atmosphere"], f["atmosphere"])
+    model = continuum.ContinuumModel(g)
+    k = f["lam_keep"]
+    lam = f["lam_spect"][k]
+    # (1) continuum alone at the run's wavelengths, from the reference's populations
+    one = lambda x: np.ascontiguousarray(x)[None]   # noqa: E731
+    chi, eta, _ = continuum.continuum_batch(ctx, model, lam, one(g["ct_T"]), one(g["ct_ne"]), one(g["ct_nHmin"]),
+                                            one(g["ct_nH2"]), one(g["ct_nOH"]), one(g["ct_nCH"]), one(g["ct_nstar"]))
+    REPORT["continuum_hinode_chi_ai_exact"] = bool(np.array_equal(chi[0], f["chi_ai"][k]))
+    assert np.array_equal(chi[0], f["chi_ai"][k]) and np.array_equal(eta[0], f["eta_ai"][k])
+    # (2) fused path
+    setup_ctx(ctx, f)
+    ctx.set_continuum(model, g["abundance"])
+    st = ctx.lte_stokes_batch_pops(rows_of(f)[None], g["chem"][None], mu=float(f["muz"][0]), moving=bool(f["flags"][0]))[0]
+    ref = f["stokes_scalar"]
+    REPORT["spectrum_continuum_on_device_exact"] = bool(np.array_equal(st, ref))
+    REPORT["spectrum_continuum_on_device_I_maxrel"] = float(np.max(np.abs(st[0] / ref[0] - 1)))
+    assert np.max(np.abs(st[0] / ref[0] - 1)) < TOL_I_REL
+    assert np.max(np.abs(st[1:] - ref[1:])) / ref[0].max() < TOL_QUV_IC
+    assert np.array_equal(st, ref)
+    # same result as the chi_ai-input entry point, and independent of chunking
+    st2 = ctx.lte_stokes_batch(rows_of(f)[None], f["chi_ai"][k][None], f["eta_ai"][k][None], mu=float(f["muz"][0]),
+                               moving=bool(f["flags"][0]))[0]
+    assert np.array_equal(st2, st)
+    at3 = np.repeat(rows_of(f)[None], 3, axis=0)
+    ch3 = np.repeat(g["chem"][None], 3, axis=0)
+    os.environ["RHB200_CHUNK_COLS"] = "2"
+    try:
+        st3 = ctx.lte_stokes_batch_pops(at3, ch3, mu=float(f["muz"][0]), moving=bool(f["flags"][0]))
+    finally:
+        del os.environ["RHB200_CHUNK_COLS"]
+    assert all(np.array_equal(st3[i], st) for i in range(3))
