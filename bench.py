@@ -98,6 +98,28 @@ def synth_inputs(ncol, rank=0, pinned=True):
     return gs[0], lam, at, chi, eta
 
 
+def synth_chem(ncol, rank=0, pinned=True):
+    """Per-column inputs of the path with the continuum on the device: the population factors of the chemical
+    equilibrium and nHmin / nH2 / nOH / nCH of the three base columns (produced by the reference's host code),
+    tiled like synth_inputs() and perturbed by smooth +-2 %."""
+    from pyrh_b200 import api
+    rng = np.random.default_rng(77 + 1000 * rank)
+    sc = dict(np.load(ROOT / "tests" / "golden" / "synth70_chem.npz"))
+    base = sc["chem"]                                   # [3, natom+4, NDEP]
+    natom = base.shape[1] - 4
+    alloc = api.pinned_empty if pinned else (lambda s: np.empty(s))
+    chem = alloc((ncol,) + base.shape[1:])
+    sel = np.arange(ncol) % 3
+    blk = 4096
+    for c0 in range(0, ncol, blk):
+        s = slice(c0, min(ncol, c0 + blk))
+        n = s.stop - s.start
+        b = base[sel[s]].copy()
+        b[:, natom:] *= (1.0 + 0.02 * smooth_noise(rng, n, NDEP))[:, None, :]
+        chem[s] = b
+    return chem, sc["abundance"]
+
+
 # ------------------------------------------------------------------------- clocks
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -291,7 +313,7 @@ def main():
     for p in (d_at, d_chi, d_eta, d_st):
         ctx.dev_free(p)
 
-    # ---- end-to-end arm: host (pinned) buffers through the C ABI
+    # ---- end-to-end arm A: host (pinned) buffers through the C ABI, background opacities supplied by the host
     for _ in range(max(1, args.warmup - 1)):
         ctx.lte_stokes_batch(at, chi, eta, out=stokes)
     barrier()
@@ -300,11 +322,38 @@ def main():
     for _ in range(args.steps):
         ctx.lte_stokes_batch(at, chi, eta, out=stokes)
     ms_e2e_dev = ctx.timer_end()
+    ms_e2e_bg = max(ms_e2e_dev, 1e3 * (time.perf_counter() - t0))
+    barrier()
+    ms_e2e_bg = maxreduce(ms_e2e_bg)
+    same = bool(np.array_equal(dev_out, stokes))
+
+    # ---- end-to-end arm B (the headline): LTE populations + continuum evaluated on the device; the host sends
+    #      the atmosphere rows and 15 per-depth vectors per column
+    from pyrh_b200 import continuum
+    chem, abundance = synth_chem(ncol, rank)
+    model = continuum.ContinuumModel(dict(np.load(ROOT / "tests" / "golden" / "falc_full.npz")))
+    ctx.set_continuum(model, abundance)
+    stokes_b = api.pinned_empty((ncol, 4, NLAMBDA))
+    ctx.timing(False)
+    for _ in range(max(1, args.warmup - 1)):
+        ctx.lte_stokes_batch_pops(at, chem, out=stokes_b)
+    launches_b0 = sum(v[1] for v in ctx.timing_get().values())
+    barrier()
+    t0 = time.perf_counter()
+    ctx.timer_begin()
+    for _ in range(args.steps):
+        ctx.lte_stokes_batch_pops(at, chem, out=stokes_b)
+    ms_e2e_dev = ctx.timer_end()
     ms_e2e = max(ms_e2e_dev, 1e3 * (time.perf_counter() - t0))
     barrier()
     ms_e2e = maxreduce(ms_e2e)
-    clocks = sampler.stop()          # sampled from the first warm-up step to the end of the e2e region
-    same = bool(np.array_equal(dev_out, stokes))
+    launches_b = sum(v[1] for v in ctx.timing_get().values()) - launches_b0
+    ctx.timing(True)
+    ctx.lte_stokes_batch_pops(at, chem, out=stokes_b)
+    kt_b = {n: (ms / max(cnt, 1), cnt) for n, (ms, cnt) in ctx.timing_get().items() if cnt}
+    ctx.timing(False)
+    clocks = sampler.stop()          # sampled from the first warm-up step to the end of the e2e regions
+    finite_b = bool(np.isfinite(stokes_b).all())
 
     fma_tf, nofma_tf = ctx.fp64_peak()
 
@@ -360,9 +409,17 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "spectra_per_s": world * ncol * args.steps / (ms_dev * 1e-3),
             "e2e": {"value": e2e_val, "unit": "ray-points/s",
-                    "h2d_bytes_per_step": int(at.nbytes + chi.nbytes + eta.nbytes),
-                    "d2h_bytes_per_step": int(stokes.nbytes), "ms_per_step": ms_e2e / args.steps,
+                    "call": "rhb200_lte_stokes_batch_pops: LTE populations + background continuum + line opacity + "
+                            "DELO-Bezier3 on the device",
+                    "h2d_bytes_per_step": int(at.nbytes + chem.nbytes),
+                    "d2h_bytes_per_step": int(stokes_b.nbytes), "ms_per_step": ms_e2e / args.steps,
                     "spectra_per_s": world * ncol * args.steps / (ms_e2e * 1e-3),
+                    "gpu_launches": int(launches_b), "all_finite": finite_b,
+                    "kernels_ms_per_launch": {n: v[0] for n, v in kt_b.items()}},
+            "e2e_background_from_host": {"value": world * units * args.steps / (ms_e2e_bg * 1e-3), "unit": "ray-points/s",
+                    "call": "rhb200_lte_stokes_batch: chi_ai / eta_ai computed by the RH host and copied in",
+                    "h2d_bytes_per_step": int(at.nbytes + chi.nbytes + eta.nbytes),
+                    "d2h_bytes_per_step": int(stokes.nbytes), "ms_per_step": ms_e2e_bg / args.steps,
                     "bitwise_equal_to_device_resident_run": same},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
     if world == 1 and not args.no_cpu_baseline:

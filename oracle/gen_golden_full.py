@@ -42,5 +42,29 @@ def main():
           f"{np.array_equal(out['stokes'], g['stokes_scalar'])} -> {(GOLD / 'falc_full.npz').stat().st_size/1e3:.0f} kB")
 
 
+def synth70():
+    """chem inputs of the three 70-depth benchmark base columns (fixtures synth70_c0..2)."""
+    from pyrh_b200 import synthetic
+    base = np.load(GOLD / "falc_base.npy")
+    wave = rd.hinode_wave()
+    chems, ab = [], None
+    for c in range(3):
+        atm = synthetic.perturbed_batch(base, 1, first=c)[0]
+        g = np.load(GOLD / f"synth70_c{c}.npz")
+        assert np.array_equal(g["atmosphere"], atm)
+        cwd = rd.make_workdir("benchmark")
+        o = rd.rhf1d(atm, wave, cwd, probe=rd.PROBE_CONT | rd.PROBE_SNAP)
+        R = recs_by_tag(o["records"])
+        N = atm.shape[1]
+        natom = int(one(R, "ct_hdr")[0])
+        pre, post = one(R, "ce_ntotal_pre").reshape(natom, N), one(R, "ce_ntotal_post").reshape(natom, N)
+        chems.append(np.concatenate([post / pre, [one(R, "ct_nHmin"), one(R, "ct_nH2"), one(R, "ct_nOH"), one(R, "ct_nCH")]]))
+        ab = one(R, "ce_abundance")
+        assert np.array_equal(np.array([o["I"], o["Q"], o["U"], o["V"]]), g["stokes_scalar"])
+    np.savez_compressed(GOLD / "synth70_chem.npz", chem=np.array(chems), abundance=ab)
+    print(f"[golden] synth70_chem: {np.array(chems).shape} -> {(GOLD / 'synth70_chem.npz').stat().st_size/1e3:.0f} kB")
+
+
 if __name__ == "__main__":
     main()
+    synth70()

@@ -733,3 +733,20 @@ def test_lte_path_with_continuum_on_device(ctx, golden_falc):
     finally:
         del os.environ["RHB200_CHUNK_COLS"]
     assert all(np.array_equal(st3[i], st) for i in range(3))
+
+
+def test_benchmark_columns_with_continuum_on_device(ctx):
+    """The three 70-depth base columns of the benchmark workload (fixtures synth70_c0..2) through the fused path
+    with LTE populations and continuum on the device: spectra equal the reference's rhf1d() bit for bit."""
+    from pyrh_b200 import continuum
+    full = dict(np.load(GOLD / "falc_full.npz"))
+    sc = dict(np.load(GOLD / "synth70_chem.npz"))
+    gs = [dict(np.load(GOLD / f"synth70_c{c}.npz")) for c in range(3)]
+    setup_ctx(ctx, gs[0])
+    ctx.set_continuum(continuum.ContinuumModel(full), sc["abundance"])
+    at = np.stack([rows_of(g) for g in gs])
+    st = ctx.lte_stokes_batch_pops(at, sc["chem"])
+    for c, g in enumerate(gs):
+        REPORT[f"spectrum_synth70_c{c}_continuum_on_device_exact"] = bool(np.array_equal(st[c], g["stokes_scalar"]))
+        assert np.array_equal(st[c], g["stokes_scalar"])
+
