@@ -22,6 +22,7 @@
 #include <cmath>
 #include <cstring>
 #include "rhb200_math_tables.inc"
+#include "rhb200_log_tables.inc"
 
 #if defined(__CUDACC__)
 #define RH_FN __device__ __forceinline__
@@ -268,6 +269,88 @@ RH_FN double rh_cos(double x)
   }
   if (k < 0x419921fbu) { double a, da; const int n = reduce_sincos(x, a, da); return do_sincos(a, da, n + 1); }
   return cos(x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// log: glibc 2.39 sysdeps/ieee754/dbl-64/e_log.c (S. Nagy), the __log_fma ifunc variant.  Fused operations are
+// placed exactly as in that variant's instruction sequence (libm.so.6 of this image, function at the
+// IRELATIVE target of log@GLIBC_2.29); tables: rhb200_log_tables.inc.
+RH_TABLE double rh_log_A[5] = {RH_LOG_POLY_A};
+RH_TABLE double rh_log_B[11] = {RH_LOG_POLY_B};
+RH_TABLE double rh_log_T[256] = {RH_LOG_TAB};      // {invc, logc} x 128
+
+RH_FN double rh_log(double x)
+{
+  uint64_t ix = RH_ASUINT(x);
+  const uint64_t LO = 0x3FEE000000000000ULL, HI = 0x3FF1090000000000ULL;     // 1 - 2^-4, 1 + 0x1.09p-4
+  if (ix - LO < HI - LO) {
+    if (ix == 0x3FF0000000000000ULL) return 0.0;
+    const double *B = rh_log_B;
+    const double r = x - 1.0, r2 = r * r, r3 = r * r2;
+    double p2 = RH_FMA(r, B[2], B[1]);   p2 = RH_FMA(r2, B[3], p2);           // B1 + r B2 + r2 B3
+    double p5 = RH_FMA(r, B[5], B[4]);   p5 = RH_FMA(r2, B[6], p5);           // B4 + r B5 + r2 B6
+    double p8 = RH_FMA(r, B[8], B[7]);   p8 = RH_FMA(r2, B[9], p8);  p8 = RH_FMA(r3, B[10], p8);
+    double P = RH_FMA(p8, r3, p5);
+    P = RH_FMA(P, r3, p2);
+    const double w = RH_FMA(r, 0x1p27, r);                                   // r + r*2^27
+    const double rhi = RH_FMA(-0x1p27, r, w);
+    const double rlo = r - rhi;
+    const double rhi2 = rhi * rhi;
+    const double hi = RH_FMA(rhi2, B[0], r);
+    double lo = RH_FMA(rhi2, B[0], r - hi);
+    lo = RH_FMA(B[0] * rlo, rhi + r, lo);
+    const double y = RH_FMA(P, r3, lo);
+    return hi + y;
+  }
+  const uint32_t top = (uint32_t) (ix >> 48);
+  if (top - 0x0010 >= 0x7ff0 - 0x0010) {
+    if (ix * 2 == 0) return -1.0 / 0.0;                                      // log(+-0) = -inf
+    if (ix == 0x7FF0000000000000ULL) return x;                               // log(inf) = inf
+    if ((top & 0x8000) || (top & 0x7ff0) == 0x7ff0) return (x - x) / (x - x);
+    ix = RH_ASUINT(x * 0x1p52);                                              // subnormal: normalise
+    ix -= 52ULL << 52;
+  }
+  const uint64_t tmp = ix - 0x3FE6000000000000ULL;
+  const int i = (int) ((tmp >> 45) & 127);
+  const int64_t k = (int64_t) tmp >> 52;
+  const uint64_t iz = ix - (tmp & (0xFFFULL << 52));
+  const double invc = rh_log_T[2*i], logc = rh_log_T[2*i + 1];
+  const double z = RH_ASDOUBLE(iz);
+  const double r = RH_FMA(z, invc, -1.0);
+  const double kd = (double) k;
+  const double w = RH_FMA(kd, RH_LOG_LN2HI, logc);
+  const double hi = w + r;
+  const double lo = RH_FMA(kd, RH_LOG_LN2LO, (w - hi) + r);
+  const double r2 = r * r;
+  const double *A = rh_log_A;
+  const double q = RH_FMA(RH_FMA(r, A[4], A[3]), r2, RH_FMA(r, A[2], A[1]));
+  const double y = RH_FMA(r * r2, q, RH_FMA(r2, A[0], lo));
+  return y + hi;
+}
+
+// log10: glibc 2.39 sysdeps/ieee754/dbl-64/e_log10.c (fdlibm scaling around the log above; no fused operations)
+RH_FN double rh_log10(double x)
+{
+  const double two54 = 1.80143985094819840000e+16, ivln10 = 4.34294481903251816668e-01,
+               log10_2hi = 3.01029995663611771306e-01, log10_2lo = 3.69423907715893078616e-13;
+  uint64_t u = RH_ASUINT(x);
+  int32_t hx = (int32_t) (u >> 32);
+  const uint32_t lx = (uint32_t) u;
+  int32_t k = 0;
+  if (hx < 0x00100000) {
+    if (((hx & 0x7fffffff) | lx) == 0) return -two54 / fabs(x);
+    if (hx < 0) return (x - x) / (x - x);
+    k -= 54; x *= two54;
+    u = RH_ASUINT(x); hx = (int32_t) (u >> 32);
+  }
+  if (hx >= 0x7ff00000) return x + x;
+  k += (hx >> 20) - 1023;
+  const int32_t i = (int32_t) (((uint32_t) k & 0x80000000u) >> 31);
+  hx = (hx & 0x000fffff) | ((0x3ff - i) << 20);
+  const double y = (double) (k + i);
+  x = RH_ASDOUBLE(((uint64_t) (uint32_t) hx << 32) | (RH_ASUINT(x) & 0xffffffffULL));
+  const double z = y * log10_2lo + ivln10 * rh_log(x);
+  return z + y * log10_2hi;
 }
 
 }  // namespace rhm

@@ -1,5 +1,5 @@
 // tests/helpers/mathcheck.cpp -- host build of pyrh_b200/csrc/rhb200_math.cuh compared bit
-// for bit with this machine's libm (glibc 2.39: exp/pow/sin/cos).  Prints one line per
+// for bit with this machine's libm (glibc 2.39: exp/pow/sin/cos/log/log10).  Prints one line per
 // (function, range): "<name> <n> <mismatches> <max_ulp>".
 #include <cstdio>
 #include <cstdlib>
@@ -61,6 +61,15 @@ int main(int argc, char **argv)
   bad += run1("cos[-12,12]", n, Cc, Cg, uni(-12, 12));
   bad += run1("cos[-1e4,1e4]", n, Cc, Cg, uni(-1e4, 1e4));
   bad += run1("cos[log 1e-300..1e8]", n, Cc, Cg, logu(1e-300, 1.0e8));
+  auto L = [](double x) { return rhm::rh_log(x); };    auto Lg = [](double x) { return std::log(x); };
+  auto L10 = [](double x) { return rhm::rh_log10(x); }; auto L10g = [](double x) { return std::log10(x); };
+  auto pos = [&](double lo, double hi) { return [&gen, lo, hi]() { double e = std::uniform_real_distribution<double>(std::log(lo), std::log(hi))(gen); return std::exp(e); }; };
+  bad += run1("log[0.9,1.1]", n, L, Lg, uni(0.9, 1.1));
+  bad += run1("log[0.93,1.07]", n, L, Lg, uni(0.93, 1.07));
+  bad += run1("log[1e3,2e4]", n, L, Lg, uni(1e3, 2e4));
+  bad += run1("log[log 1e-320..1e300]", n, L, Lg, pos(1e-320, 1e300));
+  bad += run1("log10[0.2,3]", n, L10, L10g, uni(0.2, 3.0));
+  bad += run1("log10[log 1e-320..1e300]", n, L10, L10g, pos(1e-320, 1e300));
   {
     const double ys[] = {0.3, 0.38, 0.375, -1.5, 1.5, 0.5, 2.0, -0.25};
     for (double y : ys) {
