@@ -275,6 +275,19 @@ int rhb200_lte_stokes_batch_pops(rhb200_ctx *ctx, int ncol, int ndep, double muz
                                  int bc_top, int bc_bottom, const double *atmos, const double *chem,
                                  double *stokes);
 
+/* ChemicalEquilibrium (chemequil.c:107-392) on the device.  After rhb200_set_continuum: the nuclei that are bound
+   in molecules (atmos.elements order, hydrogen first) with the index of their model atom, and per molecule a
+   32-double record {fit (enum fit_type, atom.h:32), charge, Nnuclei, Nelement, Neqc, Tmin, Tmax, Ediss [J],
+   eqc_coef[8], nucleus index of each element [4], pt_count[4], is H2, is OH, is CH, 0...}.
+   rhb200_lte_stokes_batch_atmos then needs nothing per column but the atmosphere rows: LTEpops, chemical
+   equilibrium, continuum, line opacity and formal solution all run on the device.
+   rhb200_chemistry_batch exposes the first two steps: chem [ncol][natom+4][ndep] (layout of
+   rhb200_lte_stokes_batch_pops), pops [ncol][nlev][ndep] (may be NULL). */
+int rhb200_set_chemistry(rhb200_ctx *ctx, int nnuclei, const int *nucleus_atom, int nmol, const double *mol);
+int rhb200_chemistry_batch(rhb200_ctx *ctx, int ncol, int ndep, const double *atmos, double *chem, double *pops);
+int rhb200_lte_stokes_batch_atmos(rhb200_ctx *ctx, int ncol, int ndep, double muz, int moving,
+                                  int bc_top, int bc_bottom, const double *atmos, double *stokes);
+
 /* Formal-solver selection = keyword.input S_INTERPOLATION / S_INTERPOLATION_STOKES (readvalue.c:366-404;
    enum values of inputs.h:26-27).  Applies to rhb200_lte_stokes_batch(_dev) (Stokes solver) and to
    rhb200_nlte_iterate / rhb200_nlte_formal (scalar solver).  Defaults: S_BEZIER3, DELO_BEZIER3. */

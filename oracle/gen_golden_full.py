@@ -35,6 +35,10 @@ def main():
     out["fraction"] = post / pre                       # the reference's own division (chemequil.c:336)
     out["chem"] = np.concatenate([out["fraction"], [out["ct_nHmin"], out["ct_nH2"], out["ct_nOH"], out["ct_nCH"]]])
     out["stokes"] = np.array([o["I"], o["Q"], o["U"], o["V"]])
+    # chemical network (for ChemicalEquilibrium on the device)
+    out["ce_nuclei"] = one(R, "ce_nuclei").reshape(-1, 2)
+    out["ce_mol"] = np.array([d for m, d in sorted(R["ce_mol"], key=lambda x: x[0][0])])
+    out["col_nHtot"] = one(R, "nHtot")
     np.savez_compressed(GOLD / "falc_full.npz", **out)
     g = np.load(GOLD / "falc_B1kG.npz")
     print(f"[golden] falc_full: {natom} atoms, {nlev} levels; atoms rescaled by chemistry: "

@@ -916,6 +916,31 @@ void __wrap_ChemicalEquilibrium(int NmaxIter, double iterLimit)
     for (m = 0; m < atmos.Natom; m++) memcpy(pre + (long) m*N, atmos.atoms[m].ntotal, N*sizeof(double));
     double *ab = rec_new("ce_abundance", atmos.Natom, 0,0,0,0,0,0);
     for (m = 0; m < atmos.Natom; m++) ab[m] = atmos.atoms[m].abundance;
+    /* the chemical network: nuclei (elements bound in some molecule, atmos.elements order) with the index of
+       their model atom, and per molecule the fit data equilconstant() reads (chemequil.c:456-530) */
+    {
+      int i, j, nn = 0, nu, idx[128];
+      for (i = 0; i < atmos.Nelem; i++) if (atmos.elements[i].Nmolecule > 0) idx[nn++] = i;
+      double *nuc = rec_new("ce_nuclei", 2L*nn, nn, 0,0,0,0,0);
+      for (i = 0; i < nn; i++) {
+        Element *e = &atmos.elements[idx[i]];
+        nuc[2*i] = idx[i];
+        nuc[2*i+1] = e->model ? (double) (e->model - atmos.atoms) : -1.0;
+      }
+      for (i = 0; i < atmos.Nmolecule; i++) {
+        Molecule *mo = &atmos.molecules[i];
+        double *r = rec_new("ce_mol", 32, i, mo->fit, mo->charge, mo->Nnuclei, mo->Nelement, mo->Neqc);
+        memset(r, 0, 32*sizeof(double));
+        r[0] = mo->fit; r[1] = mo->charge; r[2] = mo->Nnuclei; r[3] = mo->Nelement; r[4] = mo->Neqc;
+        r[5] = mo->Tmin; r[6] = mo->Tmax; r[7] = mo->Ediss;
+        for (j = 0; j < mo->Neqc && j < 8; j++) r[8+j] = mo->eqc_coef[j];
+        for (j = 0; j < mo->Nelement && j < 4; j++) {
+          for (nu = 0; nu < nn; nu++) if (idx[nu] == mo->pt_index[j]) r[16+j] = nu;
+          r[20+j] = mo->pt_count[j];
+        }
+        r[24] = (mo == atmos.H2); r[25] = (mo == atmos.OH); r[26] = (mo == atmos.CH);
+      }
+    }
   }
   __real_ChemicalEquilibrium(NmaxIter, iterLimit);
   if (rec) {

@@ -171,6 +171,34 @@ class Context:
                                                          int(bc_bottom), _vp(at), _vp(ch), _vp(st)))
         return st
 
+    def set_chemistry(self, nucleus_atom, mol):
+        """ChemicalEquilibrium on the device: nucleus_atom [nnuclei] = model-atom index of each nucleus, mol
+        [nmol, 32] = per-molecule fit records (include/rhb200.h)."""
+        na = np.ascontiguousarray(nucleus_atom, np.int32)
+        mo = np.ascontiguousarray(mol, np.float64)
+        _lib.check(self.lib.rhb200_set_chemistry(self.h, len(na), na.ctypes.data_as(_lib.ip), mo.shape[0], _dp(mo)))
+        self._natom_lev = None
+
+    def chemistry(self, atmos_rows, natom, nlev):
+        """(chem [ncol, natom+4, ndep], pops [ncol, nlev, ndep]) from LTEpops + ChemicalEquilibrium on the device."""
+        at = np.ascontiguousarray(atmos_rows, np.float64)
+        ncol, _, ndep = at.shape
+        chem = np.zeros((ncol, natom + 4, ndep))
+        pops = np.zeros((ncol, nlev, ndep))
+        _lib.check(self.lib.rhb200_chemistry_batch(self.h, ncol, ndep, _dp(at), _dp(chem), _dp(pops)))
+        return chem, pops
+
+    def lte_stokes_batch_atmos(self, atmos_rows, mu=1.0, moving=True, bc_top=_lib.BC_ZERO,
+                               bc_bottom=_lib.BC_THERMALIZED, out=None):
+        """The whole LTE column from the atmosphere rows alone (set_lines, set_wavelengths, set_continuum and
+        set_chemistry done before)."""
+        at = np.ascontiguousarray(atmos_rows, np.float64)
+        ncol, _, ndep = at.shape
+        st = np.empty((ncol, 4, self.nlambda)) if out is None else out
+        _lib.check(self.lib.rhb200_lte_stokes_batch_atmos(self.h, ncol, ndep, float(mu), int(moving), int(bc_top),
+                                                          int(bc_bottom), _vp(at), _vp(st)))
+        return st
+
     def lte_stokes_batch_dev(self, ncol, ndep, d_atmos, d_chi_ai, d_eta_ai, d_stokes, mu=1.0,
                              moving=True, bc_top=_lib.BC_ZERO, bc_bottom=_lib.BC_THERMALIZED):
         _lib.check(self.lib.rhb200_lte_stokes_batch_dev(self.h, int(ncol), int(ndep), float(mu),

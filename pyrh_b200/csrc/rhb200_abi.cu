@@ -319,13 +319,15 @@ extern "C" int rhb200_lte_stokes_batch_dev(rhb200_ctx *c, int ncol, int ndep, do
 // (rhb200_set_continuum) instead of being copied in as chi_ai / eta_ai
 static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int moving,
                           int bc_top, int bc_bottom, const double *atmos,
-                          const double *chi_ai, const double *eta_ai, const double *chem, double *stokes)
+                          const double *chi_ai, const double *eta_ai, const double *chem, double *stokes,
+                          int chem_on_device = 0)
 {
   RH_NEED_CTX(c);
   RH_CHECK(check_batch_args(c, ncol, ndep, muz, bc_top, bc_bottom));
   if (ncol == 0) return RHB200_OK;
-  if (!atmos || !stokes || (!chem && (!chi_ai || !eta_ai))) { rhb200_set_error("null buffer"); return RHB200_EINVAL; }
-  if (chem && !c->cont) { rhb200_set_error("rhb200_set_continuum() has not been called"); return RHB200_ESTATE; }
+  if (!atmos || !stokes || (!chem && !chem_on_device && (!chi_ai || !eta_ai))) { rhb200_set_error("null buffer"); return RHB200_EINVAL; }
+  const bool cont_dev = chem || chem_on_device;
+  if (cont_dev && !c->cont) { rhb200_set_error("rhb200_set_continuum() has not been called"); return RHB200_ESTATE; }
   const int nl = c->wav.nlambda;
   const int nslots = 2;
   const int cc = chunk_columns(c, ncol, ndep, nslots);
@@ -333,10 +335,10 @@ static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int mov
   const size_t b_at = align_up((size_t) cc * RHB200_AT_NFIELD * ndep * sizeof(double));
   const size_t b_op = align_up((size_t) cc * nl * ndep * sizeof(double));
   const size_t b_st = align_up((size_t) cc * 4 * nl * sizeof(double));
-  const int nchem = chem ? rh_continuum_natom(c) + 4 : 0;
-  const size_t b_ch = chem ? align_up((size_t) cc * nchem * ndep * sizeof(double)) : 0;
-  const size_t b_pp = chem ? align_up((size_t) cc * rh_continuum_nlev(c) * ndep * sizeof(double)) : 0;
-  const size_t b_tp = chem ? align_up((size_t) cc * 8 * ndep * sizeof(double)) : 0;
+  const int nchem = cont_dev ? rh_continuum_natom(c) + 4 : 0;
+  const size_t b_ch = cont_dev ? align_up((size_t) cc * nchem * ndep * sizeof(double)) : 0;
+  const size_t b_pp = cont_dev ? align_up((size_t) cc * rh_continuum_nlev(c) * ndep * sizeof(double)) : 0;
+  const size_t b_tp = cont_dev ? align_up((size_t) cc * 8 * ndep * sizeof(double)) : 0;
   const size_t slot = L.total + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp;
   RH_CHECK(rh_ws_reserve(c, nslots * slot));
   cudaStream_t streams[2] = {c->stream, c->copy_stream};
@@ -357,12 +359,12 @@ static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int mov
                              (size_t) n * RHB200_AT_NFIELD * ndep * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess) {
       rhb200_set_error("H2D copy failed: %s", cudaGetErrorString(e)); rc = RHB200_ECUDA; break;
     }
-    if (chem) {
-      if ((e = cudaMemcpyAsync(d_ch, chem + (size_t) c0 * nchem * ndep, (size_t) n * nchem * ndep * sizeof(double),
+    if (cont_dev) {
+      if (chem && (e = cudaMemcpyAsync(d_ch, chem + (size_t) c0 * nchem * ndep, (size_t) n * nchem * ndep * sizeof(double),
                                cudaMemcpyHostToDevice, st)) != cudaSuccess) {
         rhb200_set_error("H2D copy failed: %s", cudaGetErrorString(e)); rc = RHB200_ECUDA; break;
       }
-      rc = rh_continuum_chunk(c, n, ndep, d_at, d_ch, d_pp, d_tp, d_chi, d_eta);
+      rc = rh_continuum_chunk(c, n, ndep, d_at, d_ch, d_pp, d_tp, d_chi, d_eta, chem ? 0 : 1);
       if (rc != RHB200_OK) break;
     } else if ((e = cudaMemcpyAsync(d_chi, chi_ai + (size_t) c0 * nl * ndep, (size_t) n * nl * ndep * sizeof(double),
                              cudaMemcpyHostToDevice, st)) != cudaSuccess ||
@@ -400,6 +402,12 @@ extern "C" int rhb200_lte_stokes_batch_pops(rhb200_ctx *c, int ncol, int ndep, d
 {
   if (!chem) { rhb200_set_error("null buffer"); return RHB200_EINVAL; }
   return lte_batch_host(c, ncol, ndep, muz, moving, bc_top, bc_bottom, atmos, nullptr, nullptr, chem, stokes);
+}
+
+extern "C" int rhb200_lte_stokes_batch_atmos(rhb200_ctx *c, int ncol, int ndep, double muz, int moving,
+                                             int bc_top, int bc_bottom, const double *atmos, double *stokes)
+{
+  return lte_batch_host(c, ncol, ndep, muz, moving, bc_top, bc_bottom, atmos, nullptr, nullptr, nullptr, stokes, 1);
 }
 
 // ------------------------------------------------ function-level entry points

@@ -111,7 +111,7 @@ void rh_continuum_free(rhb200_ctx *ctx);
 int rh_continuum_nlev(const rhb200_ctx *ctx);
 int rh_continuum_natom(const rhb200_ctx *ctx);
 int rh_continuum_chunk(rhb200_ctx *ctx, int cc, int ndep, const double *d_atmos, const double *d_chem,
-                       double *d_pops, double *d_tprep, double *d_chi, double *d_eta);
+                       double *d_pops, double *d_tprep, double *d_chi, double *d_eta, int chem_on_device);
 
 // launchers implemented in the .cu files (device pointers)
 int rh_launch_mol_opacity_raw(rhb200_ctx *ctx, int ncol, int nlambda, int ndep, int nmol, double muz, int moving,

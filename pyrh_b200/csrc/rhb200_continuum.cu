@@ -21,6 +21,7 @@
 #include "rhb200_common.cuh"
 #include "rhb200_math.cuh"
 #include "rhb200_delo.cuh"
+#include "rhb200_lu.cuh"
 
 #ifndef RH_CHECK
 #define RH_CHECK(expr) do { int rc__ = (expr); if (rc__ != RHB200_OK) return rc__; } while (0)
@@ -776,16 +777,151 @@ ltepops_kernel(int ncol, int ndep, int natom, int nlev, const double *__restrict
     }
     const double ntotal = abundance[a] * nHtot;                     // readatom.c:190
     const double n0 = ntotal / sum;
-    const double fraction = chem[((size_t) col * (natom + 4) + a) * ndep + k];
+    const double fraction = chem ? chem[((size_t) col * (natom + 4) + a) * ndep + k] : 1.0;   // else chemeq_kernel rescales
     P[(size_t) l0 * ndep] = n0 * fraction;                          // chemequil.c:339
     for (int i = l0 + 1; i < l1; i++) P[(size_t) i * ndep] = (P[(size_t) i * ndep] * n0) * fraction;
   }
+}
+
+// ---- ChemicalEquilibrium (chemequil.c:107-392) with equilconstant (:456-530): Newton-Raphson on the number
+//      conservation + Saha equations of the nuclei bound in molecules, per (column, depth).  NG_CHEM_ORDER = 0,
+//      so Accelerate() only stores iterates and MaxChange() decides convergence (N_MAX_CHEM_ITER 10,
+//      CHEM_ITER_LIMIT 1e-3, background.h:18-19).  Writes the chem block the continuum consumes and rescales
+//      the LTE populations of the nuclei's model atoms (:334-343).
+#define CHEM_MAXEQ 24
+#define CHEM_MAXNUC 8
+enum { MC_FIT = 0, MC_CHARGE, MC_NNUCLEI, MC_NELEMENT, MC_NEQC, MC_TMIN, MC_TMAX, MC_EDISS, MC_EQC0 = 8, MC_NUC0 = 16,
+       MC_CNT0 = 20, MC_NFIELD = 32 };
+
+__device__ __forceinline__ double equilconstant_d(const double *__restrict__ m, double T)
+{
+  if (T < m[MC_TMIN] || T > m[MC_TMAX]) return 0.0;
+  const int fit = (int) m[MC_FIT], neqc = (int) m[MC_NEQC], nnuc = (int) m[MC_NNUCLEI], charge = (int) m[MC_CHARGE];
+  const double *c = m + MC_EQC0;
+  double eqc = c[0], cgs_to_SI = 1.0;
+  if (fit == 0 || fit == 1) {                               // KURUCZ_70 / KURUCZ_85
+    const double t = (fit == 0) ? T : T * 1.0E-4;
+    const double kT = RH_KBOLTZMANN * T;
+    const int mk = nnuc - 1 - charge;
+    for (int i = 1; i < neqc; i++) eqc = eqc*t + c[i];
+    eqc = rhm::rh_exp(m[MC_EDISS]/kT + eqc - 1.5*mk*rhm::rh_log(T));
+    cgs_to_SI = rhm::rh_pow(CUBE(RH_CM_TO_M), (double) mk);
+  } else if (fit == 2 || fit == 3) {                        // SAUVAL_TATUM_84 (IRWIN_81 falls through to it)
+    const double theta = RH_THETA0 / T;
+    const double t = rhm::rh_log10(theta);
+    const double kT = RH_KBOLTZMANN * T;
+    for (int i = 1; i < neqc; i++) eqc = eqc*t + c[i];
+    eqc = rhm::rh_exp(RH_LG10 * ((m[MC_EDISS]/RH_EV) * theta - eqc)) * kT;
+  } else {                                                  // TSUJI_73
+    const double theta = RH_THETA0 / T;
+    const double kT = RH_KBOLTZMANN * T;
+    for (int i = 1; i < neqc; i++) eqc = eqc*theta + c[i];
+    eqc = SQ(kT) * rhm::rh_exp(RH_LG10 * (-eqc));
+    cgs_to_SI = rhm::rh_pow(CUBE(RH_CM_TO_M) / 1.0E-07, (double) (nnuc - 1));
+  }
+  return eqc * cgs_to_SI;
+}
+
+__global__ void __launch_bounds__(64)
+chemeq_kernel(int ncol, int ndep, int natom, int nlev, const double *__restrict__ lev, const int *__restrict__ atom_first,
+              const double *__restrict__ abundance, const double *__restrict__ atmos,
+              int nnuc, const int *__restrict__ nuc_atom, int nmol, const double *__restrict__ mol,
+              int iH2, int iOH, int iCH, int NmaxIter, double iterLimit,
+              double *__restrict__ pops, double *__restrict__ chem)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t) ncol * ndep) return;
+  const int col = (int) (t / ndep), k = (int) (t % ndep);
+  const double *at = atmos + (size_t) col * RHB200_AT_NFIELD * ndep;
+  const double T = at[RHB200_AT_T*ndep + k], ne = at[RHB200_AT_NE*ndep + k], nHtot = at[RHB200_AT_NHTOT*ndep + k];
+  double *P = pops + (size_t) col * nlev * ndep + k;
+  const int Neq = nnuc + nmol;
+  double n[CHEM_MAXEQ], f[CHEM_MAXEQ], a[CHEM_MAXEQ], df[CHEM_MAXEQ*CHEM_MAXEQ], prev[2][CHEM_MAXEQ];
+  double fn0[CHEM_MAXNUC], Phi[CHEM_MAXEQ];
+  for (int i = 0; i < Neq; i++) a[i] = 0.0;
+  for (int i = 0; i < nnuc; i++) {                           // chemequil.c:233-245 (every nucleus has a model atom)
+    const int am = nuc_atom[i], l0 = atom_first[am], l1 = atom_first[am+1];
+    double s = 0.0;
+    for (int j = l0; j < l1; j++) {
+      if ((int) lev[5*(size_t) j + 2] > 0) break;
+      s += P[(size_t) j * ndep];
+    }
+    a[i] = abundance[am] * nHtot;
+    fn0[i] = s / a[i];                                        // atom->ntotal[k] == abundance * nHtot here (readatom.c:190)
+  }
+  const double CI = (RH_HPLANCK/(2.0*RH_PI*RH_M_ELECTRON)) * (RH_HPLANCK/RH_KBOLTZMANN);
+  const double PhiHmin = 0.25*rhm::rh_pow(CI/T, 1.5) * rhm::rh_exp(0.754 * RH_EV / (RH_KBOLTZMANN * T));
+  const double fHmin = ne * fn0[0]*PhiHmin;
+  for (int i = 0; i < nmol; i++) Phi[i] = equilconstant_d(mol + (size_t) i * MC_NFIELD, T);
+  for (int i = 0; i < nnuc; i++) n[i] = a[i];
+  for (int i = 0; i < nmol; i++) n[nnuc+i] = 0.0;
+  int count = 1;
+  for (int i = 0; i < Neq; i++) prev[0][i] = n[i];
+  int niter = 1;
+  while (niter <= NmaxIter) {
+    for (int i = 0; i < Neq; i++) {
+      f[i] = n[i] - a[i];
+      for (int j = 0; j < Neq; j++) df[i*Neq + j] = 0.0;
+      df[i*Neq + i] = 1.0;
+    }
+    f[0] += fHmin * n[0];
+    df[0] += fHmin;
+    for (int i = 0; i < nmol; i++) {
+      const double *m = mol + (size_t) i * MC_NFIELD;
+      const int nel = (int) m[MC_NELEMENT];
+      double saha = Phi[i];
+      for (int j = 0; j < nel; j++) {
+        const int nu = (int) m[MC_NUC0 + j];
+        const int cnt = (int) m[MC_CNT0 + j];
+        saha *= rhm::rh_pow(fn0[nu] * n[nu], (double) cnt);
+        f[nu] += cnt * n[nnuc + i];
+      }
+      saha /= rhm::rh_pow(ne, (double) (int) m[MC_CHARGE]);
+      f[nnuc + i] -= saha;
+      for (int j = 0; j < nel; j++) {
+        const int nu = (int) m[MC_NUC0 + j];
+        const int cnt = (int) m[MC_CNT0 + j];
+        df[nu*Neq + nnuc + i] += cnt;
+        df[(nnuc + i)*Neq + nu] = -saha * (cnt/n[nu]);
+      }
+    }
+    rhlu::solve_linear_eq<CHEM_MAXEQ>(Neq, df, f, true);
+    for (int i = 0; i < Neq; i++) n[i] -= f[i];
+    {                                                        // Accelerate (store) + MaxChange, accelerate.c:75-79, maxchange.c:38-46
+      const int slot = count % 2;
+      for (int i = 0; i < Neq; i++) prev[slot][i] = n[i];
+      count++;
+    }
+    double dmax = 0.0;
+    {
+      const double *old = prev[(count - 2) % 2], *nw = prev[(count - 1) % 2];
+      for (int i = 0; i < Neq; i++)
+        if (nw[i] != 0.0) { const double d = fabs((nw[i] - old[i]) / nw[i]); dmax = (dmax > d) ? dmax : d; }
+    }
+    if (dmax <= iterLimit) break;
+    niter++;
+  }
+  double *ch = chem + (size_t) col * (natom + 4) * ndep + k;
+  for (int am = 0; am < natom; am++) ch[(size_t) am * ndep] = 1.0;
+  for (int i = 0; i < nnuc; i++) {                           // chemequil.c:334-343
+    const int am = nuc_atom[i];
+    const double fraction = n[i] / a[i];
+    ch[(size_t) am * ndep] = fraction;
+    for (int j = atom_first[am]; j < atom_first[am+1]; j++) P[(size_t) j * ndep] *= fraction;
+  }
+  ch[(size_t) natom * ndep] = ne * (n[0] * PhiHmin);         // nHmin, chemequil.c:347
+  ch[(size_t) (natom + 1) * ndep] = iH2 >= 0 ? n[nnuc + iH2] : 0.0;
+  ch[(size_t) (natom + 2) * ndep] = iOH >= 0 ? n[nnuc + iOH] : 0.0;
+  ch[(size_t) (natom + 3) * ndep] = iCH >= 0 ? n[nnuc + iCH] : 0.0;
 }
 
 struct ContinuumState {
   DevModel D; Holder H;
   int natom = 0, nlev = 0, nlambda = 0, has_H2 = 0, has_OH = 0, has_CH = 0;
   double *d_lev = nullptr, *d_abund = nullptr; int *d_first = nullptr;
+  // chemistry on the device (rhb200_set_chemistry)
+  int nnuc = 0, nmol = 0, iH2 = -1, iOH = -1, iCH = -1;
+  int *d_nuc_atom = nullptr; double *d_mol = nullptr;
 };
 
 void rh_continuum_free(rhb200_ctx *c)
@@ -799,7 +935,7 @@ int rh_continuum_natom(const rhb200_ctx *c) { return c->cont ? ((ContinuumState 
 // LTE populations + continuum of one chunk of columns, all on ctx->stream.
 // d_pops [cc][nlev][ndep] and d_tprep [cc][5][ndep] are workspace; out d_chi, d_eta [cc][nlambda][ndep].
 int rh_continuum_chunk(rhb200_ctx *c, int cc, int ndep, const double *d_atmos, const double *d_chem,
-                       double *d_pops, double *d_tprep, double *d_chi, double *d_eta)
+                       double *d_pops, double *d_tprep, double *d_chi, double *d_eta, int chem_on_device)
 {
   ContinuumState *S = (ContinuumState *) c->cont;
   if (!S) { rhb200_set_error("rhb200_set_continuum() has not been called"); return RHB200_ESTATE; }
@@ -809,7 +945,13 @@ int rh_continuum_chunk(rhb200_ctx *c, int cc, int ndep, const double *d_atmos, c
   {
     ScopedKernelTimer t(c, RHB200_K_PREP);
     ltepops_kernel<<<(unsigned) ((cn + 127) / 128), 128, 0, c->stream>>>(cc, ndep, na, S->nlev, S->d_lev, S->d_first,
-                                                                         S->d_abund, d_atmos, d_chem, d_pops);
+                                                                         S->d_abund, d_atmos, chem_on_device ? nullptr : d_chem, d_pops);
+  }
+  if (chem_on_device) {
+    if (S->nmol == 0) { rhb200_set_error("rhb200_set_chemistry() has not been called"); return RHB200_ESTATE; }
+    ScopedKernelTimer t(c, RHB200_K_PREP);
+    chemeq_kernel<<<(unsigned) ((cn + 63) / 64), 64, 0, c->stream>>>(cc, ndep, na, S->nlev, S->d_lev, S->d_first, S->d_abund,
+        d_atmos, S->nnuc, S->d_nuc_atom, S->nmol, S->d_mol, S->iH2, S->iOH, S->iCH, 10, 1.0E-3, d_pops, (double *) d_chem);
   }
   // T and ne are rows of the atmosphere block; the chem block carries nHmin, nH2, nOH, nCH after the fractions.
   // The kernels index [col][ndep] arrays, so they get strided views through small gather kernels' absence:
@@ -861,6 +1003,61 @@ extern "C" int rhb200_set_continuum(rhb200_ctx *c, const rhb200_continuum_model 
   if ((rc = S->H.put(&S->d_lev, m->lev, (size_t) m->nlev * 5)) != RHB200_OK ||
       (rc = S->H.put(&S->d_abund, abundance, (size_t) m->natom)) != RHB200_OK ||
       (rc = S->H.put(&S->d_first, first.data(), first.size())) != RHB200_OK) { rh_continuum_free(c); return rc; }
+  return RHB200_OK;
+}
+
+extern "C" int rhb200_set_chemistry(rhb200_ctx *c, int nnuclei, const int *nucleus_atom, int nmol, const double *mol)
+{
+  if (!c) { rhb200_set_error("null context"); return RHB200_EINVAL; }
+  RH_CUDA(cudaSetDevice(c->device));
+  ContinuumState *S = (ContinuumState *) c->cont;
+  if (!S) { rhb200_set_error("rhb200_set_continuum() has not been called"); return RHB200_ESTATE; }
+  if (nnuclei < 1 || nnuclei > CHEM_MAXNUC || nmol < 1 || nnuclei + nmol > CHEM_MAXEQ || !nucleus_atom || !mol) {
+    rhb200_set_error("chemical network: 1..%d nuclei and at most %d equations", CHEM_MAXNUC, CHEM_MAXEQ); return RHB200_EINVAL;
+  }
+  for (int i = 0; i < nnuclei; i++)
+    if (nucleus_atom[i] < 0 || nucleus_atom[i] >= S->natom) {
+      rhb200_set_error("nucleus %d has no model atom (getfjk path, solvene.c:143, is not implemented)", i); return RHB200_EUNSUPPORTED;
+    }
+  if (nucleus_atom[0] != 0) { rhb200_set_error("first nucleus must be hydrogen (chemequil.c:146)"); return RHB200_EINVAL; }
+  S->iH2 = S->iOH = S->iCH = -1;
+  for (int i = 0; i < nmol; i++) {
+    const double *m = mol + (size_t) i * MC_NFIELD;
+    const int nel = (int) m[MC_NELEMENT], fit = (int) m[MC_FIT];
+    if (nel < 1 || nel > 4 || (int) m[MC_NEQC] < 1 || (int) m[MC_NEQC] > 8 || fit < 0 || fit > 4) { rhb200_set_error("molecule %d: bad element / coefficient count or fit", i); return RHB200_EINVAL; }
+    for (int j = 0; j < nel; j++) if ((int) m[MC_NUC0 + j] < 0 || (int) m[MC_NUC0 + j] >= nnuclei) { rhb200_set_error("molecule %d: nucleus index out of range", i); return RHB200_EINVAL; }
+    if (m[24] != 0.0) S->iH2 = i;
+    if (m[25] != 0.0) S->iOH = i;
+    if (m[26] != 0.0) S->iCH = i;
+  }
+  S->nnuc = nnuclei; S->nmol = nmol;
+  RH_CHECK(S->H.put(&S->d_nuc_atom, nucleus_atom, (size_t) nnuclei));
+  RH_CHECK(S->H.put(&S->d_mol, mol, (size_t) nmol * MC_NFIELD));
+  return RHB200_OK;
+}
+
+// unit-level: LTE populations + chemical equilibrium of ncol columns; chem [ncol][natom+4][ndep], pops [ncol][nlev][ndep]
+extern "C" int rhb200_chemistry_batch(rhb200_ctx *c, int ncol, int ndep, const double *atmos, double *chem, double *pops)
+{
+  if (!c) { rhb200_set_error("null context"); return RHB200_EINVAL; }
+  RH_CUDA(cudaSetDevice(c->device));
+  ContinuumState *S = (ContinuumState *) c->cont;
+  if (!S || S->nmol == 0) { rhb200_set_error("rhb200_set_continuum() / rhb200_set_chemistry() have not been called"); return RHB200_ESTATE; }
+  if (ncol <= 0 || ndep <= 0 || !atmos || !chem) { rhb200_set_error("bad arguments"); return RHB200_EINVAL; }
+  Holder H;
+  const size_t cn = (size_t) ncol * ndep;
+  double *d_at, *d_ch, *d_pp;
+  RH_CHECK(H.put(&d_at, atmos, cn * RHB200_AT_NFIELD));
+  RH_CUDA(cudaMalloc((void **) &d_ch, cn * (S->natom + 4) * sizeof(double))); H.p.push_back(d_ch);
+  RH_CUDA(cudaMalloc((void **) &d_pp, cn * S->nlev * sizeof(double))); H.p.push_back(d_pp);
+  ltepops_kernel<<<(unsigned) ((cn + 127) / 128), 128, 0, c->stream>>>(ncol, ndep, S->natom, S->nlev, S->d_lev, S->d_first,
+                                                                       S->d_abund, d_at, nullptr, d_pp);
+  chemeq_kernel<<<(unsigned) ((cn + 63) / 64), 64, 0, c->stream>>>(ncol, ndep, S->natom, S->nlev, S->d_lev, S->d_first, S->d_abund,
+      d_at, S->nnuc, S->d_nuc_atom, S->nmol, S->d_mol, S->iH2, S->iOH, S->iCH, 10, 1.0E-3, d_pp, d_ch);
+  RH_CUDA(cudaGetLastError());
+  RH_CUDA(cudaStreamSynchronize(c->stream));
+  RH_CUDA(cudaMemcpy(chem, d_ch, cn * (S->natom + 4) * sizeof(double), cudaMemcpyDeviceToHost));
+  if (pops) RH_CUDA(cudaMemcpy(pops, d_pp, cn * S->nlev * sizeof(double), cudaMemcpyDeviceToHost));
   return RHB200_OK;
 }
 

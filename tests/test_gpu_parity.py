@@ -750,3 +750,41 @@ def test_benchmark_columns_with_continuum_on_device(ctx):
         REPORT[f"spectrum_synth70_c{c}_continuum_on_device_exact"] = bool(np.array_equal(st[c], g["stokes_scalar"]))
         assert np.array_equal(st[c], g["stokes_scalar"])
 
+
+
+def test_chemical_equilibrium_and_atmosphere_only_path(ctx, golden_falc):
+    """LTEpops + ChemicalEquilibrium (chemequil.c:107-392: Newton-Raphson over 4 nuclei + 12 molecules per depth,
+    equilibrium constants with the glibc-exact log / log10) on the device: population factors, nHmin, nH2, nOH,
+    nCH and the level populations equal the reference's; then the LTE spectrum from the atmosphere rows ALONE."""
+    from pyrh_b200 import continuum
+    f = golden_falc
+    g = dict(np.load(GOLD / "falc_full.npz"))
+    setup_ctx(ctx, f)
+    ctx.set_continuum(continuum.ContinuumModel(g), g["abundance"])
+    ctx.set_chemistry(g["ce_nuclei"][:, 1].astype(np.int32), g["ce_mol"])
+    natom, nlev = int(g["ct_hdr"][0]), int(g["ct_hdr"][1])
+    chem, pops = ctx.chemistry(rows_of(f)[None], natom, nlev)
+    names = ["fraction"] * natom + ["nHmin", "nH2", "nOH", "nCH"]
+    for r in range(natom + 4):
+        ref = g["chem"][r]
+        ok = np.array_equal(chem[0, r], ref)
+        REPORT.setdefault("chemistry_rows_exact", {})[f"{names[r]}[{r}]"] = bool(ok)
+        nz = ref != 0
+        assert np.max(np.abs(chem[0, r][nz] / ref[nz] - 1)) < 1e-12 and not chem[0, r][~nz].any(), (names[r], r)
+        assert ok, (names[r], r)
+    assert np.array_equal(pops[0], g["ct_nstar"])
+    st = ctx.lte_stokes_batch_atmos(rows_of(f)[None], mu=float(f["muz"][0]), moving=bool(f["flags"][0]))[0]
+    REPORT["spectrum_from_atmosphere_only_exact"] = bool(np.array_equal(st, f["stokes_scalar"]))
+    assert np.array_equal(st, f["stokes_scalar"])
+    # the three 70-depth benchmark base columns
+    sc = dict(np.load(GOLD / "synth70_chem.npz"))
+    gs = [dict(np.load(GOLD / f"synth70_c{c}.npz")) for c in range(3)]
+    setup_ctx(ctx, gs[0])
+    ctx.set_continuum(continuum.ContinuumModel(g), sc["abundance"])
+    ctx.set_chemistry(g["ce_nuclei"][:, 1].astype(np.int32), g["ce_mol"])
+    at = np.stack([rows_of(x) for x in gs])
+    chem3, _ = ctx.chemistry(at, natom, nlev)
+    assert np.array_equal(chem3, sc["chem"])
+    st3 = ctx.lte_stokes_batch_atmos(at)
+    for c, x in enumerate(gs):
+        assert np.array_equal(st3[c], x["stokes_scalar"])
