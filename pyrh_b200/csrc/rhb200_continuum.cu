@@ -822,6 +822,7 @@ __device__ __forceinline__ double equilconstant_d(const double *__restrict__ m, 
   return eqc * cgs_to_SI;
 }
 
+template <int MAXEQ>
 __global__ void __launch_bounds__(64)
 chemeq_kernel(int ncol, int ndep, int natom, int nlev, const double *__restrict__ lev, const int *__restrict__ atom_first,
               const double *__restrict__ abundance, const double *__restrict__ atmos,
@@ -836,8 +837,8 @@ chemeq_kernel(int ncol, int ndep, int natom, int nlev, const double *__restrict_
   const double T = at[RHB200_AT_T*ndep + k], ne = at[RHB200_AT_NE*ndep + k], nHtot = at[RHB200_AT_NHTOT*ndep + k];
   double *P = pops + (size_t) col * nlev * ndep + k;
   const int Neq = nnuc + nmol;
-  double n[CHEM_MAXEQ], f[CHEM_MAXEQ], a[CHEM_MAXEQ], df[CHEM_MAXEQ*CHEM_MAXEQ], prev[2][CHEM_MAXEQ];
-  double fn0[CHEM_MAXNUC], Phi[CHEM_MAXEQ];
+  double n[MAXEQ], f[MAXEQ], a[MAXEQ], df[MAXEQ*MAXEQ], prev[2][MAXEQ];
+  double fn0[CHEM_MAXNUC], Phi[MAXEQ];
   for (int i = 0; i < Neq; i++) a[i] = 0.0;
   for (int i = 0; i < nnuc; i++) {                           // chemequil.c:233-245 (every nucleus has a model atom)
     const int am = nuc_atom[i], l0 = atom_first[am], l1 = atom_first[am+1];
@@ -885,7 +886,7 @@ chemeq_kernel(int ncol, int ndep, int natom, int nlev, const double *__restrict_
         df[(nnuc + i)*Neq + nu] = -saha * (cnt/n[nu]);
       }
     }
-    rhlu::solve_linear_eq<CHEM_MAXEQ>(Neq, df, f, true);
+    rhlu::solve_linear_eq<MAXEQ>(Neq, df, f, true);
     for (int i = 0; i < Neq; i++) n[i] -= f[i];
     {                                                        // Accelerate (store) + MaxChange, accelerate.c:75-79, maxchange.c:38-46
       const int slot = count % 2;
@@ -950,7 +951,9 @@ int rh_continuum_chunk(rhb200_ctx *c, int cc, int ndep, const double *d_atmos, c
   if (chem_on_device) {
     if (S->nmol == 0) { rhb200_set_error("rhb200_set_chemistry() has not been called"); return RHB200_ESTATE; }
     ScopedKernelTimer t(c, RHB200_K_PREP);
-    chemeq_kernel<<<(unsigned) ((cn + 63) / 64), 64, 0, c->stream>>>(cc, ndep, na, S->nlev, S->d_lev, S->d_first, S->d_abund,
+    if (S->nnuc + S->nmol <= 16) chemeq_kernel<16><<<(unsigned) ((cn + 63) / 64), 64, 0, c->stream>>>(cc, ndep, na, S->nlev, S->d_lev, S->d_first, S->d_abund,
+        d_atmos, S->nnuc, S->d_nuc_atom, S->nmol, S->d_mol, S->iH2, S->iOH, S->iCH, 10, 1.0E-3, d_pops, (double *) d_chem);
+    else chemeq_kernel<CHEM_MAXEQ><<<(unsigned) ((cn + 63) / 64), 64, 0, c->stream>>>(cc, ndep, na, S->nlev, S->d_lev, S->d_first, S->d_abund,
         d_atmos, S->nnuc, S->d_nuc_atom, S->nmol, S->d_mol, S->iH2, S->iOH, S->iCH, 10, 1.0E-3, d_pops, (double *) d_chem);
   }
   // T and ne are rows of the atmosphere block; the chem block carries nHmin, nH2, nOH, nCH after the fractions.
@@ -1052,7 +1055,9 @@ extern "C" int rhb200_chemistry_batch(rhb200_ctx *c, int ncol, int ndep, const d
   RH_CUDA(cudaMalloc((void **) &d_pp, cn * S->nlev * sizeof(double))); H.p.push_back(d_pp);
   ltepops_kernel<<<(unsigned) ((cn + 127) / 128), 128, 0, c->stream>>>(ncol, ndep, S->natom, S->nlev, S->d_lev, S->d_first,
                                                                        S->d_abund, d_at, nullptr, d_pp);
-  chemeq_kernel<<<(unsigned) ((cn + 63) / 64), 64, 0, c->stream>>>(ncol, ndep, S->natom, S->nlev, S->d_lev, S->d_first, S->d_abund,
+  if (S->nnuc + S->nmol <= 16) chemeq_kernel<16><<<(unsigned) ((cn + 63) / 64), 64, 0, c->stream>>>(ncol, ndep, S->natom, S->nlev, S->d_lev, S->d_first, S->d_abund,
+      d_at, S->nnuc, S->d_nuc_atom, S->nmol, S->d_mol, S->iH2, S->iOH, S->iCH, 10, 1.0E-3, d_pp, d_ch);
+    else chemeq_kernel<CHEM_MAXEQ><<<(unsigned) ((cn + 63) / 64), 64, 0, c->stream>>>(ncol, ndep, S->natom, S->nlev, S->d_lev, S->d_first, S->d_abund,
       d_at, S->nnuc, S->d_nuc_atom, S->nmol, S->d_mol, S->iH2, S->iOH, S->iCH, 10, 1.0E-3, d_pp, d_ch);
   RH_CUDA(cudaGetLastError());
   RH_CUDA(cudaStreamSynchronize(c->stream));
