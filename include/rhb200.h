@@ -288,6 +288,25 @@ int rhb200_chemistry_batch(rhb200_ctx *ctx, int ncol, int ndep, const double *at
 int rhb200_lte_stokes_batch_atmos(rhb200_ctx *ctx, int ncol, int ndep, double muz, int moving,
                                   int bc_top, int bc_bottom, const double *atmos, double *stokes);
 
+/* pyrh.compute1d() / rhf1d() for a batch of columns, LTE (pyrh.pyx:537-668; pyrh_compute1dray.h:26-36,
+   pyrh_compute1dray.c:112-357).  `atmosphere` [ncol][nrow >= 9][ndep] holds the rows pyrh.compute1d takes, in its
+   units (pyrh.pyx:621-625): 0 scale (log10 tau500 | log10 column mass [g cm^-2] | height [km] for atm_scale
+   0 | 1 | 2, pyrh_compute1dray.c:230-246), 1 T [K], 2 ne [cm^-3], 3 v_z [km/s], 4 v_mic [km/s], 5 B [G],
+   6 gamma [rad], 7 chi [rad], 8 nH_tot [cm^-3].  Everything the reference derives per column runs on the device:
+   the unit conversion (:263-270), Bproject() for mu == 1 and inclined rays (rhf1d/project.c:38-80), atmos.moving
+   against VMACRO_TRESH (`vmacro_tresh`, m/s; :272-278), LTEpops, ChemicalEquilibrium, the proton density
+   (kurucz.c:772), the background continuum, the line opacity, convertScales() (rhf1d/multiatmos.c:100-177) and the
+   formal solution.  Needs rhb200_set_lines, rhb200_set_wavelengths, rhb200_set_continuum, rhb200_set_chemistry.
+   The wavelength grid is spectrum.lambda, i.e. it CONTAINS the reference wavelength (500 nm, atmos.lambda_ref) at
+   index `iref` (sortlambda.c adds it; convertScales looks it up with Locate()); `stokes` [ncol][4][nlambda]
+   therefore has one more column than the spectrum _solveray() packs (pyrh_solveray.c:130-150 drops it).
+   `wght_per_H` = sum over elements of abundance x atomic weight (abundance.c:186-220).
+   `scales` (may be NULL) [ncol][2][ndep]: height [m] and tau_ref the reference would hold in geometry.height /
+   geometry.tau_ref (not written for atm_scale 2, where the heights are the input). */
+int rhb200_compute1d_batch(rhb200_ctx *ctx, int ncol, int ndep, int nrow, double mu, int atm_scale,
+                           const double *atmosphere, int iref, double wght_per_H, double vmacro_tresh,
+                           int bc_top, int bc_bottom, double *stokes, double *scales);
+
 /* Formal-solver selection = keyword.input S_INTERPOLATION / S_INTERPOLATION_STOKES (readvalue.c:366-404;
    enum values of inputs.h:26-27).  Applies to rhb200_lte_stokes_batch(_dev) (Stokes solver) and to
    rhb200_nlte_iterate / rhb200_nlte_formal (scalar solver).  Defaults: S_BEZIER3, DELO_BEZIER3. */

@@ -114,6 +114,10 @@ static void snapshot(void)
   rec_copy("height", geometry.height, N, 0,0,0,0);
   rec_copy("tau_ref", geometry.tau_ref, N, 0,0,0,0);
   rec_copy("cmass", geometry.cmass, N, 0,0,0,0);
+  {
+    double *d = rec_new("abund_sums", 4, 0,0,0,0,0,0);     /* abundance.c:219-221 */
+    d[0] = atmos.wght_per_H; d[1] = atmos.totalAbund; d[2] = atmos.avgMolWght; d[3] = atmos.gravity;
+  }
   if (atmos.Stokes && atmos.B) {
     rec_copy("B", atmos.B, N, 0,0,0,0);
     rec_copy("gamma_B", atmos.gamma_B, N, 0,0,0,0);

@@ -59,6 +59,8 @@ SYMBOLS = [
     ("rhb200_set_chemistry", C.c_int, [vp, C.c_int, ip, C.c_int, dp]),
     ("rhb200_chemistry_batch", C.c_int, [vp, C.c_int, C.c_int, dp, dp, dp]),
     ("rhb200_lte_stokes_batch_atmos", C.c_int, [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, vp, vp]),
+    ("rhb200_compute1d_batch", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, vp, C.c_int, C.c_double,
+                                         C.c_double, C.c_int, C.c_int, vp, vp]),
     ("rhb200_set_solvers", C.c_int, [vp, C.c_int, C.c_int]),
     ("rhb200_scalar_ray_batch", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
                                           C.c_int, ip, dp, dp, dp, dp, dp, dp, dp]),

@@ -199,6 +199,31 @@ class Context:
                                                           int(bc_bottom), _vp(at), _vp(st)))
         return st
 
+    def compute1d_batch(self, atmosphere, mu=1.0, atm_scale=0, lambda_ref=500.0, wght_per_H=0.0, vmacro_tresh=0.0,
+                        bc_top=_lib.BC_ZERO, bc_bottom=_lib.BC_THERMALIZED, out=None, get_scales=False,
+                        keep_lambda_ref=False):
+        """``pyrh.compute1d`` (pyrh.pyx:537-668) for a batch of columns in LTE: ``atmosphere[ncol, 9+, ndep]`` in
+        pyrh's own units and scales (``atm_scale`` 0 log tau500, 1 log column mass, 2 height km) -> Stokes spectra
+        ``[ncol, 4, nlambda]``; nothing is derived on the host.  The context's wavelength grid must be
+        ``spectrum.lambda``, i.e. contain ``lambda_ref``; its column is dropped from the result like ``_solveray``
+        does (pyrh_solveray.c:130-150) unless ``keep_lambda_ref``.  ``vmacro_tresh`` in km/s like the keyword."""
+        a = np.ascontiguousarray(atmosphere, np.float64)
+        if a.ndim != 3 or a.shape[1] < 9:
+            raise ValueError("atmosphere must be [ncol, >=9, ndep] (pyrh.pyx:621-625)")
+        ncol, nrow, ndep = a.shape
+        lam = np.asarray(self.lam)
+        hit = np.nonzero(lam == lambda_ref)[0]
+        if len(hit) != 1:
+            raise ValueError("the wavelength grid must contain lambda_ref once (sortlambda.c adds it to spectrum.lambda)")
+        iref = int(hit[0])
+        st = np.empty((ncol, 4, self.nlambda)) if out is None else out
+        sc = np.empty((ncol, 2, ndep)) if get_scales else None
+        _lib.check(self.lib.rhb200_compute1d_batch(self.h, ncol, ndep, nrow, float(mu), int(atm_scale), _vp(a), iref,
+                                                   float(wght_per_H), float(vmacro_tresh) * KM_TO_M, int(bc_top),
+                                                   int(bc_bottom), _vp(st), _vp(sc) if sc is not None else None))
+        res = st if keep_lambda_ref else np.delete(st, iref, axis=2)
+        return (res, sc) if get_scales else res
+
     def lte_stokes_batch_dev(self, ncol, ndep, d_atmos, d_chi_ai, d_eta_ai, d_stokes, mu=1.0,
                              moving=True, bc_top=_lib.BC_ZERO, bc_bottom=_lib.BC_THERMALIZED):
         _lib.check(self.lib.rhb200_lte_stokes_batch_dev(self.h, int(ncol), int(ndep), float(mu),

@@ -267,15 +267,25 @@ static int chunk_columns(const rhb200_ctx *c, int ncol, int ndep, int nslots)
   return (int) std::min((size_t) ncol, cc);
 }
 
+// pyrh boundary (rhb200_compute1d_batch): the columns arrive as pyrh.compute1d's nine rows
+struct PyrhIn {
+  const double *atmosphere; int nrow, atm_scale, iref; double wght_per_H, vmacro_tresh; double *scales;
+};
+struct ScalesStep { int iref, atm_scale; double wght_per_H; double *d_scratch, *d_scales_out; };
+
 static int run_chunk_dev(rhb200_ctx *c, int cc, int ndep, double muz, int moving, int bc_top, int bc_bottom,
                          const double *d_atmos, const double *d_chi_ai, const double *d_eta_ai,
-                         double *d_stokes, char *ws)
+                         double *d_stokes, char *ws, const ScalesStep *sc = nullptr)
 {
   ChunkLayout L(c, cc, ndep);
   double *d_elem_n = (double *) ws, *d_lineprep = (double *) (ws + L.elem_n),
          *d_raypts = (double *) (ws + L.elem_n + L.lineprep);
   RH_CHECK(rh_launch_prep(c, cc, ndep, muz, moving, d_atmos, d_elem_n, d_lineprep));
   RH_CHECK(rh_launch_opacity_fused(c, cc, ndep, 1, d_atmos, d_lineprep, d_chi_ai, d_eta_ai, d_raypts));
+  // convertScales() sits between Background() and Iterate() (pyrh_compute1dray.c:310-311): the height row is
+  // only read by the formal solvers below
+  if (sc) RH_CHECK(rh_launch_scales(c, cc, ndep, sc->iref, sc->atm_scale, sc->wght_per_H, d_raypts,
+                                    (double *) d_atmos, sc->d_scratch, sc->d_scales_out));
   RH_CHECK(rh_launch_delo_raypts(c, cc, ndep, muz, bc_top, bc_bottom, d_atmos, d_raypts, d_stokes));
   RH_CHECK(rh_launch_feautrier_raypts(c, cc, ndep, muz, bc_top, bc_bottom, d_atmos, d_raypts, d_stokes));
   return RHB200_OK;
@@ -320,12 +330,12 @@ extern "C" int rhb200_lte_stokes_batch_dev(rhb200_ctx *c, int ncol, int ndep, do
 static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int moving,
                           int bc_top, int bc_bottom, const double *atmos,
                           const double *chi_ai, const double *eta_ai, const double *chem, double *stokes,
-                          int chem_on_device = 0)
+                          int chem_on_device = 0, const PyrhIn *py = nullptr)
 {
   RH_NEED_CTX(c);
   RH_CHECK(check_batch_args(c, ncol, ndep, muz, bc_top, bc_bottom));
   if (ncol == 0) return RHB200_OK;
-  if (!atmos || !stokes || (!chem && !chem_on_device && (!chi_ai || !eta_ai))) { rhb200_set_error("null buffer"); return RHB200_EINVAL; }
+  if ((!atmos && !py) || !stokes || (!chem && !chem_on_device && (!chi_ai || !eta_ai))) { rhb200_set_error("null buffer"); return RHB200_EINVAL; }
   const bool cont_dev = chem || chem_on_device;
   if (cont_dev && !c->cont) { rhb200_set_error("rhb200_set_continuum() has not been called"); return RHB200_ESTATE; }
   const int nl = c->wav.nlambda;
@@ -339,7 +349,9 @@ static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int mov
   const size_t b_ch = cont_dev ? align_up((size_t) cc * nchem * ndep * sizeof(double)) : 0;
   const size_t b_pp = cont_dev ? align_up((size_t) cc * rh_continuum_nlev(c) * ndep * sizeof(double)) : 0;
   const size_t b_tp = cont_dev ? align_up((size_t) cc * 8 * ndep * sizeof(double)) : 0;
-  const size_t slot = L.total + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp;
+  const size_t b_in = py ? align_up((size_t) cc * py->nrow * ndep * sizeof(double)) : 0;     // pyrh rows as they arrive
+  const size_t b_sc = py ? align_up((size_t) cc * 3 * ndep * sizeof(double)) : 0;            // tau scratch + {height, tau_ref} out
+  const size_t slot = L.total + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp + b_in + b_sc;
   RH_CHECK(rh_ws_reserve(c, nslots * slot));
   cudaStream_t streams[2] = {c->stream, c->copy_stream};
   cudaStream_t saved = c->stream;
@@ -351,10 +363,20 @@ static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int mov
            *d_st = (double *) (base + b_at + 2*b_op);
     double *d_ch = (double *) (base + b_at + 2*b_op + b_st), *d_pp = (double *) (base + b_at + 2*b_op + b_st + b_ch),
            *d_tp = (double *) (base + b_at + 2*b_op + b_st + b_ch + b_pp);
-    char *ws = base + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp;
+    double *d_in = (double *) (base + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp);
+    double *d_sc = (double *) (base + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp + b_in);
+    char *ws = base + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp + b_in + b_sc;
     cudaStream_t st = streams[i % nslots];
     c->stream = st;
     cudaError_t e;
+    if (py) {
+      if ((e = cudaMemcpyAsync(d_in, py->atmosphere + (size_t) c0 * py->nrow * ndep,
+                               (size_t) n * py->nrow * ndep * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess) {
+        rhb200_set_error("H2D copy failed: %s", cudaGetErrorString(e)); rc = RHB200_ECUDA; break;
+      }
+      rc = rh_launch_pyrh_rows(c, n, ndep, py->nrow, py->atm_scale, muz, py->vmacro_tresh, d_in, d_at);
+      if (rc != RHB200_OK) break;
+    } else
     if ((e = cudaMemcpyAsync(d_at, atmos + (size_t) c0 * RHB200_AT_NFIELD * ndep,
                              (size_t) n * RHB200_AT_NFIELD * ndep * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess) {
       rhb200_set_error("H2D copy failed: %s", cudaGetErrorString(e)); rc = RHB200_ECUDA; break;
@@ -366,14 +388,24 @@ static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int mov
       }
       rc = rh_continuum_chunk(c, n, ndep, d_at, d_ch, d_pp, d_tp, d_chi, d_eta, chem ? 0 : 1);
       if (rc != RHB200_OK) break;
+      if (py) {                                  // np = atmos.H->n[Nlevel-1] (kurucz.c:772); H is the first model atom
+        rc = rh_launch_proton(c, n, ndep, rh_continuum_nlev(c), rh_continuum_proton_level(c), d_pp, d_at);
+        if (rc != RHB200_OK) break;
+      }
     } else if ((e = cudaMemcpyAsync(d_chi, chi_ai + (size_t) c0 * nl * ndep, (size_t) n * nl * ndep * sizeof(double),
                              cudaMemcpyHostToDevice, st)) != cudaSuccess ||
         (e = cudaMemcpyAsync(d_eta, eta_ai + (size_t) c0 * nl * ndep, (size_t) n * nl * ndep * sizeof(double),
                              cudaMemcpyHostToDevice, st)) != cudaSuccess) {
       rhb200_set_error("H2D copy failed: %s", cudaGetErrorString(e)); rc = RHB200_ECUDA; break;
     }
-    rc = run_chunk_dev(c, n, ndep, muz, moving, bc_top, bc_bottom, d_at, d_chi, d_eta, d_st, ws);
+    ScalesStep sc{py ? py->iref : 0, py ? py->atm_scale : 0, py ? py->wght_per_H : 0.0, d_sc,
+                  (py && py->scales && py->atm_scale != 2) ? d_sc + (size_t) cc * ndep : nullptr};
+    rc = run_chunk_dev(c, n, ndep, muz, moving, bc_top, bc_bottom, d_at, d_chi, d_eta, d_st, ws, py ? &sc : nullptr);
     if (rc != RHB200_OK) break;
+    if (sc.d_scales_out && (e = cudaMemcpyAsync(py->scales + (size_t) c0 * 2 * ndep, sc.d_scales_out, (size_t) n * 2 * ndep * sizeof(double),
+                                                cudaMemcpyDeviceToHost, st)) != cudaSuccess) {
+      rhb200_set_error("D2H copy failed: %s", cudaGetErrorString(e)); rc = RHB200_ECUDA; break;
+    }
     if ((e = cudaMemcpyAsync(stokes + (size_t) c0 * 4 * nl, d_st, (size_t) n * 4 * nl * sizeof(double),
                              cudaMemcpyDeviceToHost, st)) != cudaSuccess) {
       rhb200_set_error("D2H copy failed: %s", cudaGetErrorString(e)); rc = RHB200_ECUDA; break;
@@ -408,6 +440,23 @@ extern "C" int rhb200_lte_stokes_batch_atmos(rhb200_ctx *c, int ncol, int ndep, 
                                              int bc_top, int bc_bottom, const double *atmos, double *stokes)
 {
   return lte_batch_host(c, ncol, ndep, muz, moving, bc_top, bc_bottom, atmos, nullptr, nullptr, nullptr, stokes, 1);
+}
+
+// pyrh.compute1d() / rhf1d() in LTE for a batch of columns (pyrh.pyx:537-668, pyrh_compute1dray.c:112-357):
+// the nine pyrh rows in, Stokes spectra on the context's wavelength grid (lambda_ref included, as in
+// spectrum.lambda; _solveray drops it when packing, pyrh_solveray.c:130-150) out
+extern "C" int rhb200_compute1d_batch(rhb200_ctx *c, int ncol, int ndep, int nrow, double mu, int atm_scale,
+                                      const double *atmosphere, int iref, double wght_per_H, double vmacro_tresh,
+                                      int bc_top, int bc_bottom, double *stokes, double *scales)
+{
+  RH_NEED_CTX(c);
+  if (!atmosphere) { rhb200_set_error("null buffer"); return RHB200_EINVAL; }
+  if (nrow < 9) { rhb200_set_error("atmosphere needs the 9 rows of pyrh.compute1d (pyrh.pyx:621-625), got %d", nrow); return RHB200_EINVAL; }
+  if (atm_scale < 0 || atm_scale > 2) { rhb200_set_error("atm_scale must be 0 (tau500), 1 (column mass) or 2 (height)"); return RHB200_EINVAL; }
+  if (iref < 0 || iref >= c->wav.nlambda) { rhb200_set_error("iref outside the wavelength grid"); return RHB200_EINVAL; }
+  if (!(wght_per_H > 0.0) && atm_scale == 1) { rhb200_set_error("wght_per_H (abundance.c:220) is needed for the column-mass scale"); return RHB200_EINVAL; }
+  PyrhIn py{atmosphere, nrow, atm_scale, iref, wght_per_H, vmacro_tresh, scales};
+  return lte_batch_host(c, ncol, ndep, mu, 1, bc_top, bc_bottom, nullptr, nullptr, nullptr, nullptr, stokes, 1, &py);
 }
 
 // ------------------------------------------------ function-level entry points

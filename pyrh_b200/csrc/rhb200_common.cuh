@@ -110,6 +110,12 @@ int rh_ws_reserve(rhb200_ctx *ctx, size_t bytes);
 void rh_continuum_free(rhb200_ctx *ctx);
 int rh_continuum_nlev(const rhb200_ctx *ctx);
 int rh_continuum_natom(const rhb200_ctx *ctx);
+int rh_continuum_proton_level(const rhb200_ctx *ctx);
+int rh_launch_pyrh_rows(rhb200_ctx *ctx, int ncol, int ndep, int nrow_in, int atm_scale, double muz, double vmacro_tresh,
+                        const double *d_in, double *d_atmos);
+int rh_launch_proton(rhb200_ctx *ctx, int ncol, int ndep, int nlev, int proton_level, const double *d_pops, double *d_atmos);
+int rh_launch_scales(rhb200_ctx *ctx, int ncol, int ndep, int iref, int atm_scale, double wght_per_H,
+                     const double *d_raypts, double *d_atmos, double *d_scratch, double *d_scales_out);
 int rh_continuum_chunk(rhb200_ctx *ctx, int cc, int ndep, const double *d_atmos, const double *d_chem,
                        double *d_pops, double *d_tprep, double *d_chi, double *d_eta, int chem_on_device);
 

@@ -918,7 +918,7 @@ chemeq_kernel(int ncol, int ndep, int natom, int nlev, const double *__restrict_
 
 struct ContinuumState {
   DevModel D; Holder H;
-  int natom = 0, nlev = 0, nlambda = 0, has_H2 = 0, has_OH = 0, has_CH = 0;
+  int natom = 0, nlev = 0, nlambda = 0, has_H2 = 0, has_OH = 0, has_CH = 0, proton_level = 0;
   double *d_lev = nullptr, *d_abund = nullptr; int *d_first = nullptr;
   // chemistry on the device (rhb200_set_chemistry)
   int nnuc = 0, nmol = 0, iH2 = -1, iOH = -1, iCH = -1;
@@ -932,6 +932,8 @@ void rh_continuum_free(rhb200_ctx *c)
 
 int rh_continuum_nlev(const rhb200_ctx *c) { return c->cont ? ((ContinuumState *) c->cont)->nlev : 0; }
 int rh_continuum_natom(const rhb200_ctx *c) { return c->cont ? ((ContinuumState *) c->cont)->natom : 0; }
+// last level of the first model atom: hydrogen comes first in atoms.input (atmos.H = &atmos.atoms[0], readatom.c)
+int rh_continuum_proton_level(const rhb200_ctx *c) { return c->cont ? ((ContinuumState *) c->cont)->proton_level : 0; }
 
 // LTE populations + continuum of one chunk of columns, all on ctx->stream.
 // d_pops [cc][nlev][ndep] and d_tprep [cc][5][ndep] are workspace; out d_chi, d_eta [cc][nlambda][ndep].
@@ -1003,6 +1005,7 @@ extern "C" int rhb200_set_continuum(rhb200_ctx *c, const rhb200_continuum_model 
   }
   first[m->natom] = m->nlev;
   for (int a = m->natom - 1; a >= 0; a--) if (first[a] < 0) first[a] = first[a+1];
+  S->proton_level = first[1] - 1;
   if ((rc = S->H.put(&S->d_lev, m->lev, (size_t) m->nlev * 5)) != RHB200_OK ||
       (rc = S->H.put(&S->d_abund, abundance, (size_t) m->natom)) != RHB200_OK ||
       (rc = S->H.put(&S->d_first, first.data(), first.size())) != RHB200_OK) { rh_continuum_free(c); return rc; }

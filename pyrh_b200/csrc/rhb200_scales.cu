@@ -1,0 +1,190 @@
+// rhb200_scales.cu -- the pyrh boundary of one column on the device: what rhf1d() does to the nine
+// atmosphere rows pyrh.compute1d hands it before Background() and between Background() and Iterate().
+//
+//   pyrh_rows_kernel   unit conversion in place of pyrh_compute1dray.c:230-270 (the reference's own
+//                      expressions: *= KM_TO_M, /= CUBE(CM_TO_M), /= 1e4; POW10 = exp(LG10*x), rh.h:50)
+//                      and Bproject(), rhf1d/project.c:38-80, both branches (mu == 1 and inclined rays)
+//   static_cols_kernel atmos.moving per column (pyrh_compute1dray.c:272-278)
+//   proton_kernel      np = atmos.H->n[Nlevel-1] after ChemicalEquilibrium (kurucz.c:772)
+//   scales_kernel      convertScales(), rhf1d/multiatmos.c:100-177: tau_500 / column mass -> height with the
+//                      reference-wavelength opacity, then the shift that puts tau_ref = 1 at height 0
+//                      (Linear(), linear.c:22-51 with Locate(), hunt.c:92-117)
+#include "rhb200_common.cuh"
+#include "rhb200_math.cuh"
+
+#define RH_KM_TO_M  1.0E+03
+#define RH_CM_TO_M  1.0E-02
+#define RH_G_TO_KG  1.0E-03
+#define RH_LG10     2.30258509299404568402
+#define SQ(x)   ((x)*(x))
+#define CUBE(x) ((x)*(x)*(x))
+
+// one thread per (column, depth).  in: [ncol][9][ndep] pyrh rows (pyrh.pyx:621-625); out: [ncol][RHB200_AT_NFIELD][ndep].
+// The height row receives the scale the column came with, already in SI: tau_ref (TAU500), cmass (COLUMN_MASS)
+// or height (GEOMETRIC); scales_kernel turns the first two into heights.
+__global__ void __launch_bounds__(128)
+pyrh_rows_kernel(int ncol, int ndep, int nrow_in, int atm_scale, double muz,
+                 const double *__restrict__ in, double *__restrict__ atmos)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t) ncol * ndep) return;
+  const int col = (int) (t / ndep), k = (int) (t % ndep);
+  const double *a = in + (size_t) col * nrow_in * ndep + k;
+  double *at = atmos + (size_t) col * RHB200_AT_NFIELD * ndep + k;
+  const double scale = a[0];
+  double s;
+  if (atm_scale == 0)      s = rhm::rh_exp(RH_LG10 * (scale));                                      // :232-233
+  else if (atm_scale == 1) s = rhm::rh_exp(RH_LG10 * (scale)) * (RH_G_TO_KG / SQ(RH_CM_TO_M));      // :237-238
+  else                     s = scale * RH_KM_TO_M;                                                  // :243-244
+  at[(size_t) RHB200_AT_HEIGHT * ndep] = s;
+  at[(size_t) RHB200_AT_T * ndep]     = a[(size_t) 1 * ndep];
+  at[(size_t) RHB200_AT_NE * ndep]    = a[(size_t) 2 * ndep] / CUBE(RH_CM_TO_M);
+  at[(size_t) RHB200_AT_VEL * ndep]   = a[(size_t) 3 * ndep] * RH_KM_TO_M;
+  at[(size_t) RHB200_AT_VTURB * ndep] = a[(size_t) 4 * ndep] * RH_KM_TO_M;
+  at[(size_t) RHB200_AT_B * ndep]     = a[(size_t) 5 * ndep] / 1e4;
+  at[(size_t) RHB200_AT_NHTOT * ndep] = a[(size_t) 8 * ndep] / CUBE(RH_CM_TO_M);
+  at[(size_t) RHB200_AT_NP * ndep]    = 0.0;
+  const double gamma_B = a[(size_t) 6 * ndep], chi_B = a[(size_t) 7 * ndep];
+  double cg, c2, s2;
+  if (muz == 1.0) {                                                                                 // project.c:52-58
+    cg = rhm::rh_cos(gamma_B);
+    c2 = rhm::rh_cos(2.0 * chi_B);
+    s2 = rhm::rh_sin(2.0 * chi_B);
+  } else {                                                                                          // project.c:60-77
+    const double mux = sqrt(1.0 - SQ(muz)), muy = 0.0;                                              // pyrh_compute1dray.c:294-296
+    const double csc_theta = 1.0 / sqrt(1.0 - SQ(muz));
+    const double sin_gamma = rhm::rh_sin(gamma_B);
+    const double bx = sin_gamma * rhm::rh_cos(chi_B);
+    const double by = sin_gamma * rhm::rh_sin(chi_B);
+    const double bz = rhm::rh_cos(gamma_B);
+    const double b3 = mux*bx + muy*by + muz*bz;
+    const double b1 = csc_theta * (bz - muz*b3);
+    const double b2 = csc_theta * (muy*bx - mux*by);
+    cg = b3;
+    c2 = (SQ(b1) - SQ(b2)) / (1.0 - SQ(b3));
+    s2 = 2.0 * b1*b2 / (1.0 - SQ(b3));
+  }
+  at[(size_t) RHB200_AT_COS_GAMMA * ndep] = cg;
+  at[(size_t) RHB200_AT_COS_2CHI * ndep]  = c2;
+  at[(size_t) RHB200_AT_SIN_2CHI * ndep]  = s2;
+}
+
+// one thread per column: a column none of whose |v| reaches VMACRO_TRESH is static (atmos.moving = FALSE), and
+// the only thing the LTE path does with atmos.moving is to drop the Doppler shift (kurucz.c:749-754); zeroing
+// the device copy of the velocity row gives the same +0.0 shift
+__global__ void static_cols_kernel(int ncol, int ndep, double vmacro_tresh, double *__restrict__ atmos)
+{
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncol) return;
+  double *v = atmos + ((size_t) col * RHB200_AT_NFIELD + RHB200_AT_VEL) * ndep;
+  bool moving = false;
+  for (int k = 0; k < ndep; k++) if (fabs(v[k]) >= vmacro_tresh) { moving = true; break; }
+  if (!moving) for (int k = 0; k < ndep; k++) v[k] = 0.0;
+}
+
+__global__ void __launch_bounds__(128)
+proton_kernel(int ncol, int ndep, int nlev, int proton_level, const double *__restrict__ pops, double *__restrict__ atmos)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t) ncol * ndep) return;
+  const int col = (int) (t / ndep), k = (int) (t % ndep);
+  atmos[((size_t) col * RHB200_AT_NFIELD + RHB200_AT_NP) * ndep + k] = pops[((size_t) col * nlev + proton_level) * ndep + k];
+}
+
+// one thread per column, sequential in depth like the reference.  chi_ref = total opacity at the reference
+// wavelength (spectrum.chi_c_lam[ref_index], readj.c:319: the last record written for that wavelength, i.e.
+// continuum + lines of the up-ray), read from the ray-point records of wavelength iref.
+// scratch [ncol][ndep] keeps tau_ref (COLUMN_MASS) for the Linear() look-up.
+__global__ void scales_kernel(int ncol, int ndep, int nlambda, int iref, int atm_scale, double wght_per_H,
+                              const double *__restrict__ raypts, double *__restrict__ atmos,
+                              double *__restrict__ scratch, double *__restrict__ scales_out)
+{
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncol) return;
+  double *height = atmos + ((size_t) col * RHB200_AT_NFIELD + RHB200_AT_HEIGHT) * ndep;
+  const double *nHtot = atmos + ((size_t) col * RHB200_AT_NFIELD + RHB200_AT_NHTOT) * ndep;
+  const double *rp = raypts + ((size_t) col * nlambda + iref) * ndep * RP_NFIELD + RP_CHI;
+  double *tau = scratch + (size_t) col * ndep;
+#define CHI(k) rp[(size_t) (k) * RP_NFIELD]
+#define RHO(k) ((RH_AMU * wght_per_H) * nHtot[k])
+  if (atm_scale == 0) {                                  // TAU500, multiatmos.c:140-151; height row holds tau_ref
+    double tprev = height[0], hprev = 0.0;
+    tau[0] = tprev;
+    height[0] = 0.0;
+    for (int k = 1; k < ndep; k++) {
+      const double tk = height[k];
+      tau[k] = tk;
+      const double hk = hprev - 2.0 * (tk - tprev) / (CHI(k-1) + CHI(k));
+      height[k] = hk;
+      hprev = hk; tprev = tk;
+    }
+  } else {                                               // COLUMN_MASS, :128-138; height row holds cmass
+    double cprev = height[0], hprev = 0.0;
+    double tprev = CHI(0) / RHO(0) * cprev;
+    tau[0] = tprev;
+    height[0] = 0.0;
+    for (int k = 1; k < ndep; k++) {
+      const double ck = height[k];
+      const double hk = hprev - 2.0*(ck - cprev) / (RHO(k-1) + RHO(k));
+      const double tk = tprev + 0.5*(CHI(k-1) + CHI(k)) * (hprev - hk);
+      height[k] = hk; tau[k] = tk;
+      hprev = hk; cprev = ck; tprev = tk;
+    }
+  }
+  // Linear(Ndep, tau_ref, height, 1, &unity, &h_zero, FALSE), multiatmos.c:166-173
+  const double unity = 1.0;
+  double h_zero;
+  const bool ascend = tau[1] > tau[0];
+  const double xmin = ascend ? tau[0] : tau[ndep-1], xmax = ascend ? tau[ndep-1] : tau[0];
+  if (unity <= xmin)      h_zero = ascend ? height[0] : height[ndep-1];
+  else if (unity >= xmax) h_zero = ascend ? height[ndep-1] : height[0];
+  else {
+    const bool asc2 = tau[ndep-1] > tau[0];              // Locate(), hunt.c:97
+    int lo = 0, hi = ndep;
+    while (hi - lo > 1) {
+      const int mid = (hi + lo) >> 1;
+      if (asc2 ? (unity >= tau[mid]) : (unity <= tau[mid])) lo = mid; else hi = mid;
+    }
+    const double fx = (tau[lo+1] - unity) / (tau[lo+1] - tau[lo]);
+    h_zero = fx*height[lo] + (1 - fx)*height[lo+1];
+  }
+  for (int k = 0; k < ndep; k++) height[k] = height[k] - h_zero;
+  if (scales_out) {
+    double *o = scales_out + (size_t) col * 2 * ndep;
+    for (int k = 0; k < ndep; k++) { o[k] = height[k]; o[ndep + k] = tau[k]; }
+  }
+#undef CHI
+#undef RHO
+}
+
+int rh_launch_pyrh_rows(rhb200_ctx *c, int ncol, int ndep, int nrow_in, int atm_scale, double muz, double vmacro_tresh,
+                        const double *d_in, double *d_atmos)
+{
+  const size_t cn = (size_t) ncol * ndep;
+  ScopedKernelTimer t(c, RHB200_K_PREP);
+  pyrh_rows_kernel<<<(unsigned) ((cn + 127) / 128), 128, 0, c->stream>>>(ncol, ndep, nrow_in, atm_scale, muz, d_in, d_atmos);
+  if (vmacro_tresh > 0.0)
+    static_cols_kernel<<<(unsigned) ((ncol + 63) / 64), 64, 0, c->stream>>>(ncol, ndep, vmacro_tresh, d_atmos);
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}
+
+int rh_launch_proton(rhb200_ctx *c, int ncol, int ndep, int nlev, int proton_level, const double *d_pops, double *d_atmos)
+{
+  const size_t cn = (size_t) ncol * ndep;
+  ScopedKernelTimer t(c, RHB200_K_PREP);
+  proton_kernel<<<(unsigned) ((cn + 127) / 128), 128, 0, c->stream>>>(ncol, ndep, nlev, proton_level, d_pops, d_atmos);
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}
+
+int rh_launch_scales(rhb200_ctx *c, int ncol, int ndep, int iref, int atm_scale, double wght_per_H,
+                     const double *d_raypts, double *d_atmos, double *d_scratch, double *d_scales_out)
+{
+  if (atm_scale == 2) return RHB200_OK;                  // GEOMETRIC: the heights are the input
+  ScopedKernelTimer t(c, RHB200_K_PREP);
+  scales_kernel<<<(unsigned) ((ncol + 31) / 32), 32, 0, c->stream>>>(ncol, ndep, c->wav.nlambda, iref, atm_scale, wght_per_H,
+                                                                    d_raypts, d_atmos, d_scratch, d_scales_out);
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}

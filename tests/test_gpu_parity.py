@@ -788,3 +788,53 @@ def test_chemical_equilibrium_and_atmosphere_only_path(ctx, golden_falc):
     st3 = ctx.lte_stokes_batch_atmos(at)
     for c, x in enumerate(gs):
         assert np.array_equal(st3[c], x["stokes_scalar"])
+
+
+def _pyrh_ctx(ctx, lam):
+    """Context for the pyrh-unit entry point: the Fe I line pair, spectrum.lambda (lambda_ref included), the
+    continuum model and the chemical network of the benchmark inputs."""
+    from pyrh_b200 import continuum
+    full = dict(np.load(GOLD / "falc_full.npz"))
+    sc = dict(np.load(GOLD / "synth70_chem.npz"))
+    g0 = dict(np.load(GOLD / "synth70_c0.npz"))
+    setup_ctx(ctx, g0, lam=lam)
+    ctx.set_continuum(continuum.ContinuumModel(full), sc["abundance"])
+    ctx.set_chemistry(full["ce_nuclei"][:, 1].astype(np.int32), full["ce_mol"])
+
+
+@pytest.mark.parametrize("case", ["tau", "tau_mu06", "cmass", "height"])
+def test_compute1d_batch_from_pyrh_rows(ctx, case):
+    """rhb200_compute1d_batch = pyrh.compute1d for a batch: the nine pyrh rows in pyrh units, all three depth scales
+    (pyrh_compute1dray.c:230-246) and an inclined ray (Bproject, project.c:60-77).  Height scale, tau_ref and the
+    spectrum equal the reference's rhf1d() bit for bit (fixture pyrh_scales, oracle/gen_golden_scales.py)."""
+    p = dict(np.load(GOLD / "pyrh_scales.npz"))
+    lam = p[f"{case}_lambda"]
+    _pyrh_ctx(ctx, lam)
+    sc, mu = int(p[f"{case}_scale_mu"][0]), float(p[f"{case}_scale_mu"][1])
+    atm = p[f"{case}_atmosphere"]
+    ncol = 5                                             # same column several times: chunk-internal indexing
+    st, scales = ctx.compute1d_batch(np.repeat(atm[None], ncol, axis=0), mu=mu, atm_scale=sc,
+                                     wght_per_H=float(p[f"{case}_abund_sums"][0]), get_scales=True)
+    ref = p[f"{case}_stokes"]
+    for c in range(ncol):
+        if sc != 2:
+            assert np.array_equal(scales[c, 0], p[f"{case}_height"]), "height"
+            assert np.array_equal(scales[c, 1], p[f"{case}_tau_ref"]), "tau_ref"
+        REPORT[f"compute1d_batch_{case}_exact"] = bool(np.array_equal(st[c], ref))
+        assert np.max(np.abs(st[c][0] / ref[0] - 1)) < 1e-9
+        assert np.array_equal(st[c], ref)
+
+
+def test_compute1d_batch_static_columns_and_vmacro_tresh(ctx):
+    """VMACRO_TRESH (pyrh_compute1dray.c:272-278): a column whose velocities stay below the threshold is static,
+    i.e. gives the spectrum of the same column with v = 0."""
+    p = dict(np.load(GOLD / "pyrh_scales.npz"))
+    _pyrh_ctx(ctx, p["tau_lambda"])
+    atm = p["tau_atmosphere"].copy()
+    atm[3] = 0.05 * np.sin(np.arange(atm.shape[1]))      # |v| <= 0.05 km/s
+    still = atm.copy(); still[3] = 0.0
+    w = float(p["tau_abund_sums"][0])
+    a = ctx.compute1d_batch(np.stack([atm, still]), wght_per_H=w, vmacro_tresh=0.1)
+    b = ctx.compute1d_batch(np.stack([atm, still]), wght_per_H=w, vmacro_tresh=0.0)
+    assert np.array_equal(a[0], a[1]) and np.array_equal(a[1], b[1])
+    assert not np.array_equal(b[0], b[1])
