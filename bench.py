@@ -9,8 +9,9 @@ columns ("weak" scaling, no data-path collective).
 One step = one pass of the hot path (prep + line opacity + DELO-Bezier3) over the rank's batch.
   value : ray-points/s (ncol x nlambda x ndep useful up-ray depth steps per step, summed over
           ranks) with inputs resident in HBM, timed with CUDA events on the launching stream.
-  e2e   : the same through rhb200_lte_stokes_batch() with pinned HOST buffers (H2D of the
-          atmosphere + background opacities and D2H of the spectra inside the timed region).
+  e2e   : the same workload through rhb200_compute1d_batch() (= pyrh.compute1d per column) with pinned
+          HOST buffers: the nine pyrh rows per column go in, the spectra come back, copies inside the
+          timed region; everything rhf1d() derives per column runs on the device.
   --impl reference : the unmodified reference rhf1d() (oracle/_ref) on the host cores
           (fork farm over all cores: the only parallel mode the reference supports).
 """
@@ -188,7 +189,14 @@ def _ref_step(args):
     return time.perf_counter() - t0
 
 
-def reference_throughput(steps=5, warmup=3, cols_per_proc=2, procs=None, variant="scalar"):
+def _ref_spectrum(column):
+    from pyrh_b200 import synthetic
+    a = synthetic.perturbed_batch(_REF["base"], 1, ndep=_REF["ndep"], first=column)[0]
+    o = _REF["rd"].rhf1d(a, _REF["wave"], _REF["cwd"])
+    return np.array([o[k] for k in "IQUV"])
+
+
+def reference_throughput(steps=5, warmup=3, cols_per_proc=2, procs=None, variant="scalar", probe_cols=()):
     """rhf1d() of the unmodified reference (oracle/_ref), one process per host core (the only
     parallel mode the reference supports).  One step = every process synthesises `cols_per_proc`
     columns of the benchmark workload; `warmup` untimed + `steps` timed steps (a step lasts as
@@ -209,8 +217,9 @@ def reference_throughput(steps=5, warmup=3, cols_per_proc=2, procs=None, variant
             t = pool.map(_ref_step, [(col + p * cols_per_proc, cols_per_proc) for p in range(procs)], chunksize=1)
             wall += max(t)       # all processes run concurrently: a step lasts as long as its slowest process
             col += procs * cols_per_proc
+        spectra = pool.map(_ref_spectrum, list(probe_cols), chunksize=1) if len(probe_cols) else []
     ncols = steps * procs * cols_per_proc
-    return dict(rps=ncols * NLAMBDA * NDEP / wall, sps=ncols / wall, procs=procs, ncols=ncols, wall=wall,
+    return dict(spectra=spectra, rps=ncols * NLAMBDA * NDEP / wall, sps=ncols / wall, procs=procs, ncols=ncols, wall=wall,
                 cols_per_step=procs * cols_per_proc)
 
 
@@ -333,25 +342,36 @@ def main():
     full = dict(np.load(ROOT / "tests" / "golden" / "falc_full.npz"))
     abundance = np.load(ROOT / "tests" / "golden" / "synth70_chem.npz")["abundance"]
     model = continuum.ContinuumModel(full)
+    #      These are the columns of pyrh_b200.synthetic (SURVEY 8(d) recipe) in pyrh's own units -- exactly what
+    #      pyrh.compute1d takes and what the reference arm feeds rhf1d() -- through rhb200_compute1d_batch.
+    from pyrh_b200 import synthetic
+    scales = dict(np.load(ROOT / "tests" / "golden" / "pyrh_scales.npz"))
+    wght_per_H = float(scales["tau_abund_sums"][0])
+    lam_spect = g0["lam_spect"]                       # spectrum.lambda: the 301 user wavelengths + lambda_ref
+    ctx.set_wavelengths(lam_spect)
     ctx.set_continuum(model, abundance)
     ctx.set_chemistry(full["ce_nuclei"][:, 1].astype(np.int32), full["ce_mol"])
-    stokes_b = api.pinned_empty((ncol, 4, NLAMBDA))
+    base = np.load(ROOT / "tests" / "golden" / "falc_base.npy")
+    pyrh_atm = api.pinned_empty((ncol, 9, NDEP))
+    pyrh_atm[:] = synthetic.perturbed_batch(base, ncol, ndep=NDEP, first=rank * ncol)
+    stokes_b = api.pinned_empty((ncol, 4, NLAMBDA + 1))
     ctx.timing(False)
+    run_b = lambda: ctx.compute1d_batch(pyrh_atm, wght_per_H=wght_per_H, out=stokes_b, keep_lambda_ref=True)
     for _ in range(max(1, args.warmup - 1)):
-        ctx.lte_stokes_batch_atmos(at, out=stokes_b)
+        run_b()
     launches_b0 = sum(v[1] for v in ctx.timing_get().values())
     barrier()
     t0 = time.perf_counter()
     ctx.timer_begin()
     for _ in range(args.steps):
-        ctx.lte_stokes_batch_atmos(at, out=stokes_b)
+        run_b()
     ms_e2e_dev = ctx.timer_end()
     ms_e2e = max(ms_e2e_dev, 1e3 * (time.perf_counter() - t0))
     barrier()
     ms_e2e = maxreduce(ms_e2e)
     launches_b = sum(v[1] for v in ctx.timing_get().values()) - launches_b0
     ctx.timing(True)
-    ctx.lte_stokes_batch_atmos(at, out=stokes_b)
+    run_b()
     kt_b = {n: (ms / max(cnt, 1), cnt) for n, (ms, cnt) in ctx.timing_get().items() if cnt}
     ctx.timing(False)
     clocks = sampler.stop()          # sampled from the first warm-up step to the end of the e2e regions
@@ -411,10 +431,12 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "spectra_per_s": world * ncol * args.steps / (ms_dev * 1e-3),
             "e2e": {"value": e2e_val, "unit": "ray-points/s",
-                    "call": "rhb200_lte_stokes_batch_atmos: LTE populations + chemical equilibrium + background "
-                            "continuum + line opacity + DELO-Bezier3 on the device; the host supplies the atmosphere "
-                            "rows (incl. the proton density and the height scale RH derives per column)",
-                    "h2d_bytes_per_step": int(at.nbytes),
+                    "call": "rhb200_compute1d_batch (= pyrh.compute1d per column): the nine pyrh rows in pyrh units in, "
+                            "Stokes spectra out; unit conversion, Bproject, LTE populations, chemical equilibrium, "
+                            "proton density, background continuum, line opacity, tau500->height (convertScales) and "
+                            "DELO-Bezier3 all on the device; ray-points counted on the 301 user wavelengths only "
+                            "(the lambda_ref ray is computed too, like the reference, and not counted)",
+                    "h2d_bytes_per_step": int(pyrh_atm.nbytes),
                     "d2h_bytes_per_step": int(stokes_b.nbytes), "ms_per_step": ms_e2e / args.steps,
                     "spectra_per_s": world * ncol * args.steps / (ms_e2e * 1e-3),
                     "gpu_launches": int(launches_b), "all_finite": finite_b,
@@ -427,8 +449,15 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
     if world == 1 and not args.no_cpu_baseline:
         try:
-            r = reference_throughput(5, 2, args.ref_cols_per_proc)
+            probe_cols = [c for c in (0, 1000, 4097, ncol - 1) if c < ncol]
+            r = reference_throughput(5, 2, args.ref_cols_per_proc, probe_cols=probe_cols)
             rps, sps, procs, ncols, wall = r["rps"], r["sps"], r["procs"], r["ncols"], r["wall"]
+            # the checker, not the product: the same columns went through rhb200_compute1d_batch above
+            keep = lam_spect != 500.0
+            line["e2e"]["parity_vs_reference"] = {
+                "columns": probe_cols,
+                "bitwise_equal": [bool(np.array_equal(stokes_b[c][:, keep], sp)) for c, sp in zip(probe_cols, r["spectra"])],
+                "max_rel_err_I": float(max(np.max(np.abs(stokes_b[c][0, keep] / sp[0] - 1)) for c, sp in zip(probe_cols, r["spectra"])))}
             line["cpu_baseline"] = {"value": rps, "unit": "ray-points/s", "cores": procs, "kind": "reference",
                                     "spectra_per_s": sps,
                                     "sample": f"{ncols} perturbed FAL-C columns (70 depths, 301 wavelengths), one rhf1d() "

@@ -11,16 +11,21 @@ from __future__ import annotations
 import numpy as np
 
 SEED0 = 20261017
+_KERNELS: dict = {}
 
 
 def _smooth_noise(rng, logtau, sigma_dex=0.5):
     """Unit-variance Gaussian noise smoothed with a sigma = 0.5 dex Gaussian kernel."""
     x = rng.standard_normal(logtau.size)
-    d = (logtau[:, None] - logtau[None, :]) / sigma_dex
-    w = np.exp(-0.5 * d * d)
-    w /= w.sum(axis=1, keepdims=True)
+    key = (logtau.tobytes(), sigma_dex)
+    if key not in _KERNELS:
+        d = (logtau[:, None] - logtau[None, :]) / sigma_dex
+        w = np.exp(-0.5 * d * d)
+        w /= w.sum(axis=1, keepdims=True)
+        _KERNELS[key] = (w, np.sqrt((w * w).sum(axis=1)))
+    w, norm = _KERNELS[key]
     y = w @ x
-    return y / np.sqrt((w * w).sum(axis=1))
+    return y / norm
 
 
 def resample_falc(base: np.ndarray, ndep: int = 70, lo: float = -6.0, hi: float = 1.4) -> np.ndarray:
