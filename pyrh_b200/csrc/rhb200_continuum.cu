@@ -822,7 +822,9 @@ __device__ __forceinline__ double equilconstant_d(const double *__restrict__ m, 
   return eqc * cgs_to_SI;
 }
 
-template <int MAXEQ>
+// SH: the Jacobian lives in shared memory, one element per thread interleaved (rhlu::Interleaved) -- the O(N^3)
+// accesses of the LU then never leave the SM; with the matrix in thread-local memory the kernel is L2-bound.
+template <int MAXEQ, bool SH>
 __global__ void __launch_bounds__(64)
 chemeq_kernel(int ncol, int ndep, int natom, int nlev, const double *__restrict__ lev, const int *__restrict__ atom_first,
               const double *__restrict__ abundance, const double *__restrict__ atmos,
@@ -837,8 +839,13 @@ chemeq_kernel(int ncol, int ndep, int natom, int nlev, const double *__restrict_
   const double T = at[RHB200_AT_T*ndep + k], ne = at[RHB200_AT_NE*ndep + k], nHtot = at[RHB200_AT_NHTOT*ndep + k];
   double *P = pops + (size_t) col * nlev * ndep + k;
   const int Neq = nnuc + nmol;
-  double n[MAXEQ], f[MAXEQ], a[MAXEQ], df[MAXEQ*MAXEQ], prev[2][MAXEQ];
+  double n[MAXEQ], f[MAXEQ], a[MAXEQ], df_local[SH ? 1 : MAXEQ*MAXEQ], prev[2][MAXEQ];
   double fn0[CHEM_MAXNUC], Phi[MAXEQ];
+  extern __shared__ double chem_smem[];
+  auto DF = [&](int i, int j) -> double & {
+    if constexpr (SH) return chem_smem[(size_t) (i*Neq + j) * blockDim.x + threadIdx.x];
+    else return df_local[i*Neq + j];
+  };
   for (int i = 0; i < Neq; i++) a[i] = 0.0;
   for (int i = 0; i < nnuc; i++) {                           // chemequil.c:233-245 (every nucleus has a model atom)
     const int am = nuc_atom[i], l0 = atom_first[am], l1 = atom_first[am+1];
@@ -862,11 +869,11 @@ chemeq_kernel(int ncol, int ndep, int natom, int nlev, const double *__restrict_
   while (niter <= NmaxIter) {
     for (int i = 0; i < Neq; i++) {
       f[i] = n[i] - a[i];
-      for (int j = 0; j < Neq; j++) df[i*Neq + j] = 0.0;
-      df[i*Neq + i] = 1.0;
+      for (int j = 0; j < Neq; j++) DF(i, j) = 0.0;
+      DF(i, i) = 1.0;
     }
     f[0] += fHmin * n[0];
-    df[0] += fHmin;
+    DF(0, 0) += fHmin;
     for (int i = 0; i < nmol; i++) {
       const double *m = mol + (size_t) i * MC_NFIELD;
       const int nel = (int) m[MC_NELEMENT];
@@ -882,11 +889,12 @@ chemeq_kernel(int ncol, int ndep, int natom, int nlev, const double *__restrict_
       for (int j = 0; j < nel; j++) {
         const int nu = (int) m[MC_NUC0 + j];
         const int cnt = (int) m[MC_CNT0 + j];
-        df[nu*Neq + nnuc + i] += cnt;
-        df[(nnuc + i)*Neq + nu] = -saha * (cnt/n[nu]);
+        DF(nu, nnuc + i) += cnt;
+        DF(nnuc + i, nu) = -saha * (cnt/n[nu]);
       }
     }
-    rhlu::solve_linear_eq<MAXEQ>(Neq, df, f, true);
+    if constexpr (SH) rhlu::solve_linear_eq_mat<MAXEQ>(Neq, rhlu::Interleaved{chem_smem + threadIdx.x, Neq, (int) blockDim.x}, f, true);
+    else rhlu::solve_linear_eq<MAXEQ>(Neq, df_local, f, true);
     for (int i = 0; i < Neq; i++) n[i] -= f[i];
     {                                                        // Accelerate (store) + MaxChange, accelerate.c:75-79, maxchange.c:38-46
       const int slot = count % 2;
@@ -916,6 +924,194 @@ chemeq_kernel(int ncol, int ndep, int natom, int nlev, const double *__restrict_
   ch[(size_t) (natom + 3) * ndep] = iCH >= 0 ? n[nnuc + iCH] : 0.0;
 }
 
+// ---- the same Newton-Raphson, LPS lanes per system (LPS = 16: two systems per warp; 32: one).  Thread-per-system
+//      keeps 5.4 KB of matrices in local memory and is L2-bound; here lane l owns row l of the Jacobian, which
+//      lives in shared memory (row stride LPS+1: conflict-free column walks).  Every floating-point result keeps
+//      the reference's operation order:
+//        * Crout's sums A[i][j] -= A[i][k]*A[k][j] run k = 0, 1, ... for every element (ludcmp.c:108-124); the
+//          lanes do them right-looking -- as soon as A[k][j] is final it is broadcast and every lane i > k
+//          subtracts its product -- which only changes WHEN each subtraction happens, not their order;
+//        * the pivot is the LAST row attaining the maximum of vv[i]*|A[i][j]| (`>=`, :121): ballot + highest lane;
+//        * forward substitution likewise right-looking with the reference's skip of leading zeros (`ii`, :163-168),
+//          the row interchanges applied up front (equivalent: index[i] >= i);
+//        * back substitution sums j = i+1 .. N-1 ascending while x[j] become known descending (:170-175): that
+//          order is inherently serial, one lane does it;
+//        * residual rows, the molecule rows (pow, the expensive part) and equilconstant run one per lane.
+template <int LPS>
+__global__ void __launch_bounds__(128)
+chemeq_coop_kernel(int ncol, int ndep, int natom, int nlev, const double *__restrict__ lev, const int *__restrict__ atom_first,
+                   const double *__restrict__ abundance, const double *__restrict__ atmos,
+                   int nnuc, const int *__restrict__ nuc_atom, int nmol, const double *__restrict__ mol,
+                   int iH2, int iOH, int iCH, int NmaxIter, double iterLimit,
+                   double *__restrict__ pops, double *__restrict__ chem)
+{
+  constexpr int LD = LPS + 1, SPB = 128 / LPS, PER = 2*LPS*LD + 9*LPS;
+  constexpr unsigned FULL = 0xffffffffu;
+  extern __shared__ double chem_smem[];
+  const int l = threadIdx.x % LPS, sl = threadIdx.x / LPS;
+  const size_t t = (size_t) blockIdx.x * SPB + sl;
+  const bool live = t < (size_t) ncol * ndep;
+  const size_t tt = live ? t : 0;
+  const int col = (int) (tt / ndep), k = (int) (tt % ndep);
+  double *A = chem_smem + (size_t) sl * PER, *Ac = A + LPS*LD, *x = Ac + LPS*LD, *bc = x + LPS, *r = bc + LPS,
+         *nv = r + LPS, *av = nv + LPS, *vv = av + LPS, *fn0 = vv + LPS, *Phi = fn0 + LPS;
+  int *idx = (int *) (Phi + LPS);
+  const unsigned half_shift = (LPS == 32) ? 0u : (unsigned) (16 * ((threadIdx.x & 31) / 16));
+  const unsigned half_mask = (LPS == 32) ? FULL : 0xffffu;
+
+  const double *at = atmos + (size_t) col * RHB200_AT_NFIELD * ndep;
+  const double T = at[RHB200_AT_T*ndep + k], ne = at[RHB200_AT_NE*ndep + k], nHtot = at[RHB200_AT_NHTOT*ndep + k];
+  double *P = pops + (size_t) col * nlev * ndep + k;
+  const int Neq = nnuc + nmol;
+  const bool row = l < Neq;
+  if (l < nnuc) {                                            // chemequil.c:233-245
+    const int am = nuc_atom[l], l0 = atom_first[am], l1 = atom_first[am+1];
+    double s = 0.0;
+    for (int j = l0; j < l1; j++) {
+      if ((int) lev[5*(size_t) j + 2] > 0) break;
+      s += P[(size_t) j * ndep];
+    }
+    av[l] = abundance[am] * nHtot;
+    fn0[l] = s / av[l];
+    nv[l] = av[l];
+  } else if (row) { av[l] = 0.0; nv[l] = 0.0; }
+  if (l < nmol) Phi[l] = equilconstant_d(mol + (size_t) l * MC_NFIELD, T);
+  __syncwarp();
+  const double CI = (RH_HPLANCK/(2.0*RH_PI*RH_M_ELECTRON)) * (RH_HPLANCK/RH_KBOLTZMANN);
+  const double PhiHmin = 0.25*rhm::rh_pow(CI/T, 1.5) * rhm::rh_exp(0.754 * RH_EV / (RH_KBOLTZMANN * T));
+  const double fHmin = ne * fn0[0]*PhiHmin;
+  double n_l = row ? nv[l] : 0.0, n_old = n_l;              // Accelerate()'s two stored iterates, element l
+  bool done = !live;
+  int imax = 0;
+
+  auto backsubst = [&](double *v) {                          // LUbacksubst, ludcmp.c:156-177
+    if (l == 0)
+      for (int i = 0; i < Neq; i++) { const int ip = idx[i]; const double tmp = v[ip]; v[ip] = v[i]; v[i] = tmp; }
+    __syncwarp();
+    double s = row ? v[l] : 0.0;
+    int ii = -1;
+    for (int j = 0; j < Neq; j++) {
+      const double xj = __shfl_sync(FULL, s, j, LPS);
+      if (ii < 0 && xj != 0.0) ii = j;
+      if (row && l > j && ii >= 0) s -= A[l*LD + j] * xj;
+    }
+    if (row) v[l] = s;
+    __syncwarp();
+    if (l == 0)
+      for (int i = Neq - 1; i >= 0; i--) {
+        double sum = v[i];
+        for (int j = i + 1; j < Neq; j++) sum -= A[i*LD + j] * v[j];
+        v[i] = sum / A[i*LD + i];
+      }
+    __syncwarp();
+  };
+
+  for (int niter = 1; niter <= NmaxIter; niter++) {
+    // ---- f and the Jacobian, row l (chemequil.c:262-298)
+    if (row) {
+      double fl = nv[l] - av[l];
+      for (int j = 0; j < Neq; j++) A[l*LD + j] = 0.0;
+      A[l*LD + l] = 1.0;
+      if (l == 0) { fl += fHmin * nv[0]; A[0] += fHmin; }
+      if (l < nnuc) {
+        for (int i = 0; i < nmol; i++) {
+          const double *m = mol + (size_t) i * MC_NFIELD;
+          const int nel = (int) m[MC_NELEMENT];
+          for (int j = 0; j < nel; j++)
+            if ((int) m[MC_NUC0 + j] == l) fl += (int) m[MC_CNT0 + j] * nv[nnuc + i];
+          for (int j = 0; j < nel; j++)
+            if ((int) m[MC_NUC0 + j] == l) A[l*LD + nnuc + i] += (int) m[MC_CNT0 + j];
+        }
+      } else {
+        const int i = l - nnuc;
+        const double *m = mol + (size_t) i * MC_NFIELD;
+        const int nel = (int) m[MC_NELEMENT];
+        double saha = Phi[i];
+        for (int j = 0; j < nel; j++) {
+          const int nu = (int) m[MC_NUC0 + j];
+          saha *= rhm::rh_pow(fn0[nu] * nv[nu], (double) (int) m[MC_CNT0 + j]);
+        }
+        saha /= rhm::rh_pow(ne, (double) (int) m[MC_CHARGE]);
+        fl -= saha;
+        for (int j = 0; j < nel; j++) {
+          const int nu = (int) m[MC_NUC0 + j];
+          const int cnt = (int) m[MC_CNT0 + j];
+          A[l*LD + nu] = -saha * (cnt/nv[nu]);
+        }
+      }
+      x[l] = fl; bc[l] = fl;
+      for (int j = 0; j < Neq; j++) Ac[l*LD + j] = A[l*LD + j];
+      double big = 0.0;                                      // LUdecomp, ludcmp.c:92-101
+      for (int j = 0; j < Neq; j++) { const double temp = fabs(A[l*LD + j]); if (temp > big) big = temp; }
+      vv[l] = 1.0 / big;
+    }
+    __syncwarp();
+    imax = 0;
+    for (int j = 0; j < Neq; j++) {                          // ludcmp.c:103-150
+      double s = row ? A[l*LD + j] : 0.0;
+      for (int kk = 0; kk < j; kk++) {
+        const double v = __shfl_sync(FULL, s, kk, LPS);
+        if (row && l > kk) s -= A[l*LD + kk] * v;
+      }
+      if (row) A[l*LD + j] = s;
+      const bool cand = row && l >= j;
+      const double dum = cand ? vv[l]*fabs(s) : -1.0;
+      double mx = dum;
+      for (int off = LPS/2; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, off, LPS));
+      const unsigned bal = (__ballot_sync(FULL, cand && dum == mx) >> half_shift) & half_mask;
+      if (bal) imax = 31 - __clz(bal);
+      __syncwarp();
+      if (j != imax) {
+        if (row) { const double d2 = A[imax*LD + l]; A[imax*LD + l] = A[j*LD + l]; A[j*LD + l] = d2; }
+        if (l == 0) vv[imax] = vv[j];
+      }
+      if (l == 0) idx[j] = imax;
+      __syncwarp();
+      double piv = A[j*LD + j];
+      __syncwarp();
+      if (piv == 0.0) { piv = 1.0e-20; if (l == 0) A[j*LD + j] = piv; }
+      const double inv = 1.0 / piv;
+      if (row && l > j) A[l*LD + j] *= inv;
+      __syncwarp();
+    }
+    backsubst(x);
+    if (row) {                                               // one step of iterative improvement, ludcmp.c:60-73
+      double rr = bc[l];
+      for (int j = 0; j < Neq; j++) rr -= Ac[l*LD + j] * x[j];
+      r[l] = rr;
+    }
+    __syncwarp();
+    backsubst(r);
+    double d = 0.0;
+    if (row && !done) {
+      const double nw = n_l - (x[l] + r[l]);
+      n_old = n_l; n_l = nw;
+      nv[l] = nw;
+      if (nw != 0.0) d = fabs((nw - n_old) / nw);           // MaxChange, maxchange.c:38-46
+    }
+    for (int off = LPS/2; off > 0; off >>= 1) d = fmax(d, __shfl_xor_sync(FULL, d, off, LPS));
+    if (d <= iterLimit) done = true;
+    __syncwarp();
+    if (__all_sync(FULL, done)) break;
+  }
+  if (!live) return;
+  double *ch = chem + (size_t) col * (natom + 4) * ndep + k;
+  for (int am = l; am < natom; am += LPS) ch[(size_t) am * ndep] = 1.0;
+  __syncwarp(__activemask());
+  if (l < nnuc) {                                            // chemequil.c:334-343
+    const int am = nuc_atom[l];
+    const double fraction = nv[l] / av[l];
+    ch[(size_t) am * ndep] = fraction;
+    for (int j = atom_first[am]; j < atom_first[am+1]; j++) P[(size_t) j * ndep] *= fraction;
+  }
+  if (l == 0) {
+    ch[(size_t) natom * ndep] = ne * (nv[0] * PhiHmin);      // nHmin, chemequil.c:347
+    ch[(size_t) (natom + 1) * ndep] = iH2 >= 0 ? nv[nnuc + iH2] : 0.0;
+    ch[(size_t) (natom + 2) * ndep] = iOH >= 0 ? nv[nnuc + iOH] : 0.0;
+    ch[(size_t) (natom + 3) * ndep] = iCH >= 0 ? nv[nnuc + iCH] : 0.0;
+  }
+}
+
 struct ContinuumState {
   DevModel D; Holder H;
   int natom = 0, nlev = 0, nlambda = 0, has_H2 = 0, has_OH = 0, has_CH = 0, proton_level = 0;
@@ -935,6 +1131,45 @@ int rh_continuum_natom(const rhb200_ctx *c) { return c->cont ? ((ContinuumState 
 // last level of the first model atom: hydrogen comes first in atoms.input (atmos.H = &atmos.atoms[0], readatom.c)
 int rh_continuum_proton_level(const rhb200_ctx *c) { return c->cont ? ((ContinuumState *) c->cont)->proton_level : 0; }
 
+static int launch_chemeq(rhb200_ctx *c, ContinuumState *S, int cc, int ndep, const double *d_atmos, double *d_pops, double *d_chem)
+{
+  const size_t cn = (size_t) cc * ndep;
+  const int na = S->natom;
+  const int Neq = S->nnuc + S->nmol;
+  // RHB200_CHEM_KERNEL = coop (default) | local | shared: A/B switch between the three bit-identical variants.
+  // Measured per 2048 columns x 70 depths (B200): coop 3.0 ms (issue-bound: 48 % issue slots, the serial back
+  // substitution is 27 % of the instructions), local 3.3 ms (L2-bound), shared 4.5 ms (3 warps/SM, latency-bound)
+  static const char *variant = getenv("RHB200_CHEM_KERNEL");
+  const bool serial = variant && !strcmp(variant, "local"), coop = !variant || !strcmp(variant, "coop");
+  const int TPB = 32;
+#define CHEM_ARGS cc, ndep, na, S->nlev, S->d_lev, S->d_first, S->d_abund, d_atmos, S->nnuc, S->d_nuc_atom, S->nmol, S->d_mol, \
+                S->iH2, S->iOH, S->iCH, 10, 1.0E-3, d_pops, d_chem
+  if (serial) {
+    if (Neq <= 16) chemeq_kernel<16, false><<<(unsigned) ((cn + 63) / 64), 64, 0, c->stream>>>(CHEM_ARGS);
+    else chemeq_kernel<CHEM_MAXEQ, false><<<(unsigned) ((cn + 63) / 64), 64, 0, c->stream>>>(CHEM_ARGS);
+  } else if (!coop) {
+    const size_t sh = (size_t) Neq * Neq * TPB * sizeof(double);
+    if (Neq <= 16) {
+      RH_CUDA(cudaFuncSetAttribute(chemeq_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sh));
+      chemeq_kernel<16, true><<<(unsigned) ((cn + TPB - 1) / TPB), TPB, sh, c->stream>>>(CHEM_ARGS);
+    } else {
+      RH_CUDA(cudaFuncSetAttribute(chemeq_kernel<CHEM_MAXEQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sh));
+      chemeq_kernel<CHEM_MAXEQ, true><<<(unsigned) ((cn + TPB - 1) / TPB), TPB, sh, c->stream>>>(CHEM_ARGS);
+    }
+  } else if (Neq <= 16) {
+    const size_t sh = (size_t) 8 * (2*16*17 + 9*16) * sizeof(double);
+    RH_CUDA(cudaFuncSetAttribute(chemeq_coop_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sh));
+    chemeq_coop_kernel<16><<<(unsigned) ((cn + 7) / 8), 128, sh, c->stream>>>(CHEM_ARGS);
+  } else {
+    const size_t sh = (size_t) 4 * (2*32*33 + 9*32) * sizeof(double);
+    RH_CUDA(cudaFuncSetAttribute(chemeq_coop_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sh));
+    chemeq_coop_kernel<32><<<(unsigned) ((cn + 3) / 4), 128, sh, c->stream>>>(CHEM_ARGS);
+  }
+#undef CHEM_ARGS
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}
+
 // LTE populations + continuum of one chunk of columns, all on ctx->stream.
 // d_pops [cc][nlev][ndep] and d_tprep [cc][5][ndep] are workspace; out d_chi, d_eta [cc][nlambda][ndep].
 int rh_continuum_chunk(rhb200_ctx *c, int cc, int ndep, const double *d_atmos, const double *d_chem,
@@ -953,10 +1188,7 @@ int rh_continuum_chunk(rhb200_ctx *c, int cc, int ndep, const double *d_atmos, c
   if (chem_on_device) {
     if (S->nmol == 0) { rhb200_set_error("rhb200_set_chemistry() has not been called"); return RHB200_ESTATE; }
     ScopedKernelTimer t(c, RHB200_K_PREP);
-    if (S->nnuc + S->nmol <= 16) chemeq_kernel<16><<<(unsigned) ((cn + 63) / 64), 64, 0, c->stream>>>(cc, ndep, na, S->nlev, S->d_lev, S->d_first, S->d_abund,
-        d_atmos, S->nnuc, S->d_nuc_atom, S->nmol, S->d_mol, S->iH2, S->iOH, S->iCH, 10, 1.0E-3, d_pops, (double *) d_chem);
-    else chemeq_kernel<CHEM_MAXEQ><<<(unsigned) ((cn + 63) / 64), 64, 0, c->stream>>>(cc, ndep, na, S->nlev, S->d_lev, S->d_first, S->d_abund,
-        d_atmos, S->nnuc, S->d_nuc_atom, S->nmol, S->d_mol, S->iH2, S->iOH, S->iCH, 10, 1.0E-3, d_pops, (double *) d_chem);
+    RH_CHECK(launch_chemeq(c, S, cc, ndep, d_atmos, d_pops, (double *) d_chem));
   }
   // T and ne are rows of the atmosphere block; the chem block carries nHmin, nH2, nOH, nCH after the fractions.
   // The kernels index [col][ndep] arrays, so they get strided views through small gather kernels' absence:
@@ -1058,10 +1290,7 @@ extern "C" int rhb200_chemistry_batch(rhb200_ctx *c, int ncol, int ndep, const d
   RH_CUDA(cudaMalloc((void **) &d_pp, cn * S->nlev * sizeof(double))); H.p.push_back(d_pp);
   ltepops_kernel<<<(unsigned) ((cn + 127) / 128), 128, 0, c->stream>>>(ncol, ndep, S->natom, S->nlev, S->d_lev, S->d_first,
                                                                        S->d_abund, d_at, nullptr, d_pp);
-  if (S->nnuc + S->nmol <= 16) chemeq_kernel<16><<<(unsigned) ((cn + 63) / 64), 64, 0, c->stream>>>(ncol, ndep, S->natom, S->nlev, S->d_lev, S->d_first, S->d_abund,
-      d_at, S->nnuc, S->d_nuc_atom, S->nmol, S->d_mol, S->iH2, S->iOH, S->iCH, 10, 1.0E-3, d_pp, d_ch);
-    else chemeq_kernel<CHEM_MAXEQ><<<(unsigned) ((cn + 63) / 64), 64, 0, c->stream>>>(ncol, ndep, S->natom, S->nlev, S->d_lev, S->d_first, S->d_abund,
-      d_at, S->nnuc, S->d_nuc_atom, S->nmol, S->d_mol, S->iH2, S->iOH, S->iCH, 10, 1.0E-3, d_pp, d_ch);
+  RH_CHECK(launch_chemeq(c, S, ncol, ndep, d_at, d_pp, d_ch));
   RH_CUDA(cudaGetLastError());
   RH_CUDA(cudaStreamSynchronize(c->stream));
   RH_CUDA(cudaMemcpy(chem, d_ch, cn * (S->natom + 4) * sizeof(double), cudaMemcpyDeviceToHost));
