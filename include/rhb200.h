@@ -307,6 +307,20 @@ int rhb200_compute1d_batch(rhb200_ctx *ctx, int ncol, int ndep, int nrow, double
                            const double *atmosphere, int iref, double wght_per_H, double vmacro_tresh,
                            int bc_top, int bc_bottom, double *stokes, double *scales);
 
+/* Finite-difference response functions of the LTE Stokes spectrum to the atmosphere rows (BASELINE config 3: T,
+   v_LOS, B, inclination, azimuth per depth).  pyrh has no entry point for these: its callers perturb one row at
+   one depth by +-delta and call pyrh.compute1d twice (2 x npar x ndep calls per column); this does the same for a
+   batch, expanding the perturbed columns on the device and returning only
+       rf [ncol][npar][ndep][4][nlambda] = (S(x_k + delta) - S(x_k - delta)) / (2 delta)
+   with S exactly what rhb200_compute1d_batch returns for the perturbed column (so the result equals the one
+   formed from the reference's own rhf1d() spectra bit for bit).  par_rows[p] = row of `atmosphere` (1 T, 3 v_z,
+   4 v_mic, 5 B, 6 gamma, 7 chi, also 2 ne, 8 nH), par_delta[p] > 0 in the row's unit.  Other arguments as in
+   rhb200_compute1d_batch; nlambda includes the reference wavelength. */
+int rhb200_rf_fd_batch(rhb200_ctx *ctx, int ncol, int ndep, int nrow, double mu, int atm_scale,
+                       const double *atmosphere, int iref, double wght_per_H, double vmacro_tresh,
+                       int bc_top, int bc_bottom, int npar, const int *par_rows, const double *par_delta,
+                       double *rf);
+
 /* Formal-solver selection = keyword.input S_INTERPOLATION / S_INTERPOLATION_STOKES (readvalue.c:366-404;
    enum values of inputs.h:26-27).  Applies to rhb200_lte_stokes_batch(_dev) (Stokes solver) and to
    rhb200_nlte_iterate / rhb200_nlte_formal (scalar solver).  Defaults: S_BEZIER3, DELO_BEZIER3. */

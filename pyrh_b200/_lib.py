@@ -61,6 +61,8 @@ SYMBOLS = [
     ("rhb200_lte_stokes_batch_atmos", C.c_int, [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, vp, vp]),
     ("rhb200_compute1d_batch", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, vp, C.c_int, C.c_double,
                                          C.c_double, C.c_int, C.c_int, vp, vp]),
+    ("rhb200_rf_fd_batch", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, vp, C.c_int, C.c_double,
+                                     C.c_double, C.c_int, C.c_int, C.c_int, ip, dp, vp]),
     ("rhb200_set_solvers", C.c_int, [vp, C.c_int, C.c_int]),
     ("rhb200_scalar_ray_batch", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
                                           C.c_int, ip, dp, dp, dp, dp, dp, dp, dp]),

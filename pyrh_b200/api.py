@@ -224,6 +224,30 @@ class Context:
         res = st if keep_lambda_ref else np.delete(st, iref, axis=2)
         return (res, sc) if get_scales else res
 
+    def _iref(self, lambda_ref):
+        hit = np.nonzero(np.asarray(self.lam) == lambda_ref)[0]
+        if len(hit) != 1:
+            raise ValueError("the wavelength grid must contain lambda_ref once (sortlambda.c adds it to spectrum.lambda)")
+        return int(hit[0])
+
+    def rf_fd_batch(self, atmosphere, par_rows, par_delta, mu=1.0, atm_scale=0, lambda_ref=500.0, wght_per_H=0.0,
+                    vmacro_tresh=0.0, bc_top=_lib.BC_ZERO, bc_bottom=_lib.BC_THERMALIZED, out=None,
+                    keep_lambda_ref=False):
+        """Centred finite-difference response functions ``[ncol, npar, ndep, 4, nlambda]`` of the spectrum
+        ``compute1d_batch`` returns, to ``atmosphere`` row ``par_rows[p]`` at every depth (step ``par_delta[p]``).
+        The perturbed columns are generated and differenced on the device."""
+        a = np.ascontiguousarray(atmosphere, np.float64)
+        ncol, nrow, ndep = a.shape
+        rows = np.ascontiguousarray(par_rows, np.int32)
+        delta = np.ascontiguousarray(par_delta, np.float64)
+        iref = self._iref(lambda_ref)
+        rf = np.empty((ncol, len(rows), ndep, 4, self.nlambda)) if out is None else out
+        _lib.check(self.lib.rhb200_rf_fd_batch(self.h, ncol, ndep, nrow, float(mu), int(atm_scale), _vp(a), iref,
+                                               float(wght_per_H), float(vmacro_tresh) * KM_TO_M, int(bc_top),
+                                               int(bc_bottom), len(rows), rows.ctypes.data_as(C.POINTER(C.c_int)),
+                                               _dp(delta), _vp(rf)))
+        return rf if keep_lambda_ref else np.delete(rf, iref, axis=4)
+
     def lte_stokes_batch_dev(self, ncol, ndep, d_atmos, d_chi_ai, d_eta_ai, d_stokes, mu=1.0,
                              moving=True, bc_top=_lib.BC_ZERO, bc_bottom=_lib.BC_THERMALIZED):
         _lib.check(self.lib.rhb200_lte_stokes_batch_dev(self.h, int(ncol), int(ndep), float(mu),

@@ -270,6 +270,11 @@ static int chunk_columns(const rhb200_ctx *c, int ncol, int ndep, int nslots)
 // pyrh boundary (rhb200_compute1d_batch): the columns arrive as pyrh.compute1d's nine rows
 struct PyrhIn {
   const double *atmosphere; int nrow, atm_scale, iref; double wght_per_H, vmacro_tresh; double *scales;
+  // finite-difference response functions (rhb200_rf_fd_batch): the columns of the call are VIRTUAL -- column
+  // v = ((base*npar + p)*ndep + k)*2 + s is base column `base` with row rf_rows[p] changed by +delta (s = 0) or
+  // -delta (s = 1) at depth k; they are expanded on the device from d_base and only the differences travel back
+  int rf_npar = 0; const int *d_rf_rows = nullptr; const double *d_rf_delta = nullptr; const double *d_base = nullptr;
+  double *rf_out = nullptr;
 };
 struct ScalesStep { int iref, atm_scale; double wght_per_H; double *d_scratch, *d_scales_out; };
 
@@ -335,12 +340,13 @@ static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int mov
   RH_NEED_CTX(c);
   RH_CHECK(check_batch_args(c, ncol, ndep, muz, bc_top, bc_bottom));
   if (ncol == 0) return RHB200_OK;
-  if ((!atmos && !py) || !stokes || (!chem && !chem_on_device && (!chi_ai || !eta_ai))) { rhb200_set_error("null buffer"); return RHB200_EINVAL; }
+  if ((!atmos && !py) || (!stokes && !(py && py->rf_out)) || (!chem && !chem_on_device && (!chi_ai || !eta_ai))) { rhb200_set_error("null buffer"); return RHB200_EINVAL; }
   const bool cont_dev = chem || chem_on_device;
   if (cont_dev && !c->cont) { rhb200_set_error("rhb200_set_continuum() has not been called"); return RHB200_ESTATE; }
   const int nl = c->wav.nlambda;
   const int nslots = 2;
-  const int cc = chunk_columns(c, ncol, ndep, nslots);
+  int cc = chunk_columns(c, ncol, ndep, nslots);
+  if (py && py->rf_npar && (cc & 1)) cc = std::max(2, cc - 1);      // +delta / -delta pairs stay in one chunk
   ChunkLayout L(c, cc, ndep);
   const size_t b_at = align_up((size_t) cc * RHB200_AT_NFIELD * ndep * sizeof(double));
   const size_t b_op = align_up((size_t) cc * nl * ndep * sizeof(double));
@@ -370,6 +376,10 @@ static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int mov
     c->stream = st;
     cudaError_t e;
     if (py) {
+      if (py->rf_npar) {
+        rc = rh_launch_rf_expand(c, c0, n, ndep, py->nrow, py->rf_npar, py->d_rf_rows, py->d_rf_delta, py->d_base, d_in);
+        if (rc != RHB200_OK) break;
+      } else
       if ((e = cudaMemcpyAsync(d_in, py->atmosphere + (size_t) c0 * py->nrow * ndep,
                                (size_t) n * py->nrow * ndep * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess) {
         rhb200_set_error("H2D copy failed: %s", cudaGetErrorString(e)); rc = RHB200_ECUDA; break;
@@ -406,6 +416,14 @@ static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int mov
                                                 cudaMemcpyDeviceToHost, st)) != cudaSuccess) {
       rhb200_set_error("D2H copy failed: %s", cudaGetErrorString(e)); rc = RHB200_ECUDA; break;
     }
+    if (py && py->rf_npar) {                     // (S+ - S-) / (2 delta); d_chi is free once the opacity kernel has run
+      rc = rh_launch_rf_diff(c, c0, n, ndep, nl, py->rf_npar, py->d_rf_delta, d_st, d_chi);
+      if (rc != RHB200_OK) break;
+      if ((e = cudaMemcpyAsync(py->rf_out + (size_t) (c0 / 2) * 4 * nl, d_chi, (size_t) (n / 2) * 4 * nl * sizeof(double),
+                               cudaMemcpyDeviceToHost, st)) != cudaSuccess) {
+        rhb200_set_error("D2H copy failed: %s", cudaGetErrorString(e)); rc = RHB200_ECUDA; break;
+      }
+    } else
     if ((e = cudaMemcpyAsync(stokes + (size_t) c0 * 4 * nl, d_st, (size_t) n * 4 * nl * sizeof(double),
                              cudaMemcpyDeviceToHost, st)) != cudaSuccess) {
       rhb200_set_error("D2H copy failed: %s", cudaGetErrorString(e)); rc = RHB200_ECUDA; break;
@@ -475,6 +493,37 @@ struct DevBuf {
   }
   template <class T> T *as() { return (T *) p; }
 };
+
+// Finite-difference response functions of the LTE Stokes spectrum to the atmosphere rows, per depth point:
+// what a pyrh caller (an inversion code) obtains from 2 x npar x ndep calls of pyrh.compute1d per column.
+extern "C" int rhb200_rf_fd_batch(rhb200_ctx *c, int ncol, int ndep, int nrow, double mu, int atm_scale,
+                                  const double *atmosphere, int iref, double wght_per_H, double vmacro_tresh,
+                                  int bc_top, int bc_bottom, int npar, const int *par_rows, const double *par_delta,
+                                  double *rf)
+{
+  RH_NEED_CTX(c);
+  if (!atmosphere || !rf || !par_rows || !par_delta) { rhb200_set_error("null buffer"); return RHB200_EINVAL; }
+  if (nrow < 9 || atm_scale < 0 || atm_scale > 2 || iref < 0 || iref >= c->wav.nlambda || npar < 1 || ncol < 0) {
+    rhb200_set_error("bad arguments"); return RHB200_EINVAL;
+  }
+  for (int p = 0; p < npar; p++)
+    if (par_rows[p] < 0 || par_rows[p] >= nrow || !(par_delta[p] > 0.0)) { rhb200_set_error("parameter %d: row %d / delta %g", p, par_rows[p], par_delta[p]); return RHB200_EINVAL; }
+  const long long nvirt = (long long) ncol * npar * ndep * 2;
+  if (nvirt > 0x7fffffffLL) { rhb200_set_error("too many perturbed columns in one call (%lld)", nvirt); return RHB200_EINVAL; }
+  if (ncol == 0) return RHB200_OK;
+  RH_CUDA(cudaSetDevice(c->device));
+  DevBuf base, rows, delta;
+  RH_CHECK(base.alloc((size_t) ncol * nrow * ndep * sizeof(double)));
+  RH_CHECK(rows.alloc((size_t) npar * sizeof(int)));
+  RH_CHECK(delta.alloc((size_t) npar * sizeof(double)));
+  RH_CUDA(cudaMemcpy(base.p, atmosphere, (size_t) ncol * nrow * ndep * sizeof(double), cudaMemcpyHostToDevice));
+  RH_CUDA(cudaMemcpy(rows.p, par_rows, (size_t) npar * sizeof(int), cudaMemcpyHostToDevice));
+  RH_CUDA(cudaMemcpy(delta.p, par_delta, (size_t) npar * sizeof(double), cudaMemcpyHostToDevice));
+  PyrhIn py{nullptr, nrow, atm_scale, iref, wght_per_H, vmacro_tresh, nullptr};
+  py.rf_npar = npar; py.d_rf_rows = (const int *) rows.p; py.d_rf_delta = (const double *) delta.p;
+  py.d_base = (const double *) base.p; py.rf_out = rf;
+  return lte_batch_host(c, (int) nvirt, ndep, mu, 1, bc_top, bc_bottom, nullptr, nullptr, nullptr, nullptr, nullptr, 1, &py);
+}
 static int to_host(void *h, const void *d, size_t bytes)
 {
   if (bytes) RH_CUDA(cudaMemcpy(h, d, bytes, cudaMemcpyDeviceToHost));

@@ -113,6 +113,10 @@ int rh_continuum_natom(const rhb200_ctx *ctx);
 int rh_continuum_proton_level(const rhb200_ctx *ctx);
 int rh_launch_pyrh_rows(rhb200_ctx *ctx, int ncol, int ndep, int nrow_in, int atm_scale, double muz, double vmacro_tresh,
                         const double *d_in, double *d_atmos);
+int rh_launch_rf_expand(rhb200_ctx *ctx, int v0, int n, int ndep, int nrow, int npar, const int *d_rows,
+                        const double *d_delta, const double *d_base, double *d_in);
+int rh_launch_rf_diff(rhb200_ctx *ctx, int v0, int n, int ndep, int nlambda, int npar, const double *d_delta,
+                      const double *d_stokes, double *d_rf);
 int rh_launch_proton(rhb200_ctx *ctx, int ncol, int ndep, int nlev, int proton_level, const double *d_pops, double *d_atmos);
 int rh_launch_scales(rhb200_ctx *ctx, int ncol, int ndep, int iref, int atm_scale, double wght_per_H,
                      const double *d_raypts, double *d_atmos, double *d_scratch, double *d_scales_out);

@@ -157,6 +157,56 @@ __global__ void scales_kernel(int ncol, int ndep, int nlambda, int iref, int atm
 #undef RHO
 }
 
+// ---- finite-difference response functions: perturbed copies of the base columns, made where they are consumed.
+// virtual column v = ((base*npar + p)*ndep + kp)*2 + s: row rows[p] of column `base` changed at depth kp by
+// +delta[p] (s = 0) or -delta[p] (s = 1); everything else is copied.  One thread per (virtual column, row, depth).
+__global__ void __launch_bounds__(128)
+rf_expand_kernel(int v0, int n, int ndep, int nrow, int npar, const int *__restrict__ rows, const double *__restrict__ delta,
+                 const double *__restrict__ base, double *__restrict__ out)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t) n * nrow * ndep) return;
+  const int k = (int) (t % ndep), r = (int) ((t / ndep) % nrow);
+  const int v = v0 + (int) (t / ((size_t) ndep * nrow));
+  const int s = v & 1, kp = (v >> 1) % ndep, p = ((v >> 1) / ndep) % npar, b = ((v >> 1) / ndep) / npar;
+  double x = base[((size_t) b * nrow + r) * ndep + k];
+  if (r == rows[p] && k == kp) x = s ? x - delta[p] : x + delta[p];
+  out[t] = x;
+}
+
+// rf[pair][4][nlambda] = (S(+delta) - S(-delta)) / (2 delta); one thread per element
+__global__ void __launch_bounds__(128)
+rf_diff_kernel(int v0, int npair, int ndep, int n4l, int npar, const double *__restrict__ delta,
+               const double *__restrict__ stokes, double *__restrict__ rf)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t) npair * n4l) return;
+  const int pair = (int) (t / n4l), e = (int) (t % n4l);
+  const int p = (((v0 >> 1) + pair) / ndep) % npar;
+  const double a = stokes[(size_t) (2*pair) * n4l + e], b = stokes[(size_t) (2*pair + 1) * n4l + e];
+  rf[t] = (a - b) / (2.0 * delta[p]);
+}
+
+int rh_launch_rf_expand(rhb200_ctx *c, int v0, int n, int ndep, int nrow, int npar, const int *d_rows,
+                        const double *d_delta, const double *d_base, double *d_in)
+{
+  const size_t tot = (size_t) n * nrow * ndep;
+  ScopedKernelTimer t(c, RHB200_K_PREP);
+  rf_expand_kernel<<<(unsigned) ((tot + 127) / 128), 128, 0, c->stream>>>(v0, n, ndep, nrow, npar, d_rows, d_delta, d_base, d_in);
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}
+
+int rh_launch_rf_diff(rhb200_ctx *c, int v0, int n, int ndep, int nlambda, int npar, const double *d_delta,
+                      const double *d_stokes, double *d_rf)
+{
+  const size_t tot = (size_t) (n / 2) * 4 * nlambda;
+  ScopedKernelTimer t(c, RHB200_K_PREP);
+  rf_diff_kernel<<<(unsigned) ((tot + 127) / 128), 128, 0, c->stream>>>(v0, n / 2, ndep, 4 * nlambda, npar, d_delta, d_stokes, d_rf);
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}
+
 int rh_launch_pyrh_rows(rhb200_ctx *c, int ncol, int ndep, int nrow_in, int atm_scale, double muz, double vmacro_tresh,
                         const double *d_in, double *d_atmos)
 {

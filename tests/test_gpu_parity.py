@@ -838,3 +838,22 @@ def test_compute1d_batch_static_columns_and_vmacro_tresh(ctx):
     b = ctx.compute1d_batch(np.stack([atm, still]), wght_per_H=w, vmacro_tresh=0.0)
     assert np.array_equal(a[0], a[1]) and np.array_equal(a[1], b[1])
     assert not np.array_equal(b[0], b[1])
+
+
+def test_rf_fd_batch_equals_reference_differences(ctx):
+    """BASELINE config 3: centred finite-difference response functions (T, v_z, B, gamma, chi per depth) from the
+    device-expanded perturbed columns equal, bit for bit, the differences formed from the reference's own rhf1d()
+    spectra of the same perturbed columns (fixture rf_fd, oracle/gen_golden_rf_fd.py)."""
+    g = dict(np.load(GOLD / "rf_fd.npz"))
+    p = dict(np.load(GOLD / "pyrh_scales.npz"))
+    _pyrh_ctx(ctx, p["tau_lambda"])
+    other = p["tau_atmosphere"]                        # a second base column: indexing of the virtual columns
+    rf = ctx.rf_fd_batch(np.stack([other, g["atmosphere"]]), g["rows"], g["delta"],
+                         wght_per_H=float(p["tau_abund_sums"][0]))
+    assert rf.shape == (2, 5, 70, 4, 301)
+    got = rf[1][:, g["depths"]]
+    scale = np.abs(g["rf"]).max(axis=(2, 3), keepdims=True)
+    REPORT["rf_fd_exact"] = bool(np.array_equal(got, g["rf"]))
+    REPORT["rf_fd_max_err_over_peak"] = float(np.max(np.abs(got - g["rf"]) / scale))
+    assert np.array_equal(got, g["rf"])
+    assert np.isfinite(rf).all() and np.abs(rf[0]).max() > 0

@@ -1,0 +1,28 @@
+"""BASELINE config 3: finite-difference response functions (T, v_z, B, gamma, chi per depth) of NCOL atmospheres."""
+import sys, time, json
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import numpy as np
+from pyrh_b200 import api, continuum, synthetic
+from pyrh_b200.linelist import LineTable
+ncol = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+G = ROOT / "tests" / "golden"
+g0 = dict(np.load(G / "synth70_c0.npz")); full = dict(np.load(G / "falc_full.npz"))
+ctx = api.Context(0)
+ctx.set_lines(LineTable.from_npz(g0)); ctx.set_wavelengths(g0["lam_spect"])
+ctx.set_continuum(continuum.ContinuumModel(full), np.load(G / "synth70_chem.npz")["abundance"])
+ctx.set_chemistry(full["ce_nuclei"][:, 1].astype(np.int32), full["ce_mol"])
+w = float(np.load(G / "pyrh_scales.npz")["tau_abund_sums"][0])
+atm = synthetic.perturbed_batch(np.load(G / "falc_base.npy"), ncol)
+rows = np.array([1, 3, 5, 6, 7], np.int32); delta = np.array([1.0, 0.01, 1.0, 1e-3, 1e-3])
+out = api.pinned_empty((ncol, 5, 70, 4, 302))
+ctx.rf_fd_batch(atm[:4], rows, delta, wght_per_H=w, out=out[:4], keep_lambda_ref=True)
+ctx.synchronize(); t0 = time.perf_counter()
+ctx.rf_fd_batch(atm, rows, delta, wght_per_H=w, out=out, keep_lambda_ref=True)
+ctx.synchronize(); dt = time.perf_counter() - t0
+nsyn = ncol * 5 * 70 * 2
+print(json.dumps({"workload": f"config 3: centred FD response functions, {ncol} atmospheres x 5 parameters x 70 depths",
+                  "atmospheres": ncol, "syntheses": nsyn, "seconds": dt, "atmospheres_per_s": ncol / dt,
+                  "syntheses_per_s": nsyn / dt, "ray_points_per_s": nsyn * 301 * 70 / dt,
+                  "h2d_bytes": int(atm.nbytes), "d2h_bytes": int(out.nbytes), "finite": bool(np.isfinite(out).all())}))
