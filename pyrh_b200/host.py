@@ -1,0 +1,473 @@
+"""Host side of the pyrh boundary: ``compute1d(cwd, mu, atm_scale, atmosphere, wave, ...)`` with the argument list
+of ``pyrh.compute1d`` (pyrh.pyx:537-551), reading the working directory's text inputs itself and running every
+per-column step on the B200 through ``rhb200_compute1d_batch``.
+
+What is parsed here (once per working directory, cached), with the reference's own expressions:
+
+* ``keyword.input``                      readInput, rh/readinput.c:43-420 (the keywords the LTE path looks at)
+* ``abundance.input`` + ``pf_Kurucz.input`` (XDR)   readAbundance, rh/abundance.c:72-222
+* the Kurucz line lists of ``KURUCZ_DATA``          readKuruczLines, rh/kurucz.c:121-431; getUnsoldcross :985-1024;
+  getABOcross, rh/barklem.c:199-212; Zeeman patterns by the library's RLKdeterminate / RLKZeeman
+* the merged wavelength grid                         SortLambda, rh/sortlambda.c:180-210 (user grid + lambda_ref)
+
+What is NOT parsed yet: ``*.atom`` / ``*.molecule`` files.  The background model of the reference's standard
+``atoms.input`` (11 PASSIVE atoms) and ``molecules.input`` ships as ``data/background_falc11.npz``; a working
+directory that lists other atoms, ACTIVE atoms, opacity fudge factors or anything else this path does not
+implement is refused loudly (``NotImplementedError``), never approximated.
+"""
+from __future__ import annotations
+
+import math
+import os
+import re
+import struct
+from dataclasses import dataclass
+from pathlib import Path
+
+import numpy as np
+
+from . import linelist as ll
+from . import zeeman
+
+DATA = Path(__file__).resolve().parent / "data"
+
+# rh/constant.h:27-60, rh/rh.h:36 (same literals)
+CLIGHT, HPLANCK, KBOLTZMANN, AMU = 2.99792458E+08, 6.6260755E-34, 1.380658E-23, 1.6605402E-27
+M_ELECTRON, Q_ELECTRON, EPSILON_0 = 9.1093897E-31, 1.60217733E-19, 8.854187817E-12
+RBOHR, E_RYDBERG, ABARH = 5.29177349E-11, 2.1798741E-18, 7.42E-41
+NM_TO_M, CM_TO_M, PI, LG10, MILLI = 1.0E-09, 1.0E-02, 3.14159265358979, 2.30258509299404568402, 1.0E-03
+AIR_TO_VACUUM_LIMIT = 199.9352           # spectrum.h:20
+RLK_RECORD_LENGTH, RLK_LABEL_LENGTH = 171, 10   # kurucz.c:88, atom.h:25
+
+
+def POW10(x):                            # rh.h:50
+    return math.exp(LG10 * x)
+
+
+_FLOAT = re.compile(r"\s*([+-]?(?:\d+\.?\d*(?:[eEdD][+-]?\d+)?|\.\d+(?:[eEdD][+-]?\d+)?))")
+_INT = re.compile(r"\s*([+-]?\d+)")
+
+
+def _scan_float(s: str):
+    """sscanf(s, "%lf"): leading float or None."""
+    m = _FLOAT.match(s)
+    return (float(m.group(1).replace("d", "e").replace("D", "e")), m.end()) if m else (None, 0)
+
+
+def _scan_int_w(s: str, width: int):
+    """sscanf(s, "%<width>d"): skips white space, then reads at most `width` characters."""
+    t = s.lstrip()
+    m = _INT.match(t[:width])
+    return (int(m.group(1)), len(s) - len(t) + m.end()) if m else (None, 0)
+
+
+# ------------------------------------------------------------------------------------------- keyword.input
+KEYWORD_DEFAULTS = {"LS_LANDE": "TRUE", "KURUCZ_DATA": "none", "METALLICITY": "0.0", "LAMBDA_REF": "500.0",
+                    "VMACRO_TRESH": "0.1", "STOKES_MODE": "NO_STOKES", "MAGNETO_OPTICAL": "TRUE",
+                    "RLK_SCATTER": "FALSE", "N_MAX_SCATTER": "5", "S_INTERPOLATION": "S_BEZIER3",
+                    "S_INTERPOLATION_STOKES": "DELO_BEZIER3", "ATOMS_FILE": "atoms.input",
+                    "MOLECULES_FILE": "molecules.input", "HYDROGEN_LTE": "FALSE", "SOLVE_NE": "NONE",
+                    "OPACITY_FUDGE": "none", "ALLOW_PASSIVE_BB": "TRUE"}
+
+
+def read_keywords(cwd) -> dict:
+    """``KEY = VALUE`` pairs of ``<cwd>/keyword.input`` ('#' starts a comment), defaults of readinput.c:43-215 for
+    the keywords this path reads."""
+    kw = dict(KEYWORD_DEFAULTS)
+    for ln in (Path(cwd) / "keyword.input").read_text().splitlines():
+        ln = ln.split("#", 1)[0].strip()
+        if "=" in ln:
+            k, v = ln.split("=", 1)
+            kw[k.strip().upper()] = v.strip()
+    if "VMICRO_CHAR" not in kw:
+        raise ValueError("keyword.input: VMICRO_CHAR is required (readinput.c:169)")
+    return kw
+
+
+def _true(v: str) -> bool:
+    return v.strip().upper() == "TRUE"
+
+
+# ------------------------------------------------------------------------------------------- elements
+@dataclass
+class Elements:
+    ID: list                 # 99 two-character IDs
+    weight: np.ndarray
+    abund: np.ndarray        # linear, relative to H (0 where not set)
+    abundance_set: np.ndarray
+    nstage: np.ndarray
+    ionpot: list             # per element [nstage] J
+    pf: list                 # per element [nstage][Npf] ln U
+    Tpf: np.ndarray
+    totalAbund: float
+    wght_per_H: float
+    avgMolWght: float
+
+
+def pyrh_path(explicit=None) -> Path:
+    p = explicit or os.environ.get("PYRH_PATH")
+    if not p:
+        raise RuntimeError("PYRH_PATH is not set (readinput.c:227: the reference finds rh/Atoms/* through it)")
+    return Path(p)
+
+
+def read_elements(path=None, kw=None, atomic_number=None, atomic_abundance=None) -> Elements:
+    """readAbundance (rh/abundance.c:72-222): abundance.input, metallicity, the XDR partition-function file."""
+    kw = kw or KEYWORD_DEFAULTS
+    atoms_dir = pyrh_path(path) / "rh" / "Atoms"
+    tab = np.load(DATA / "elements.npz")
+    ID, weight = [str(x) for x in tab["ID"]], np.array(tab["weight"], np.float64)
+    ne = len(ID)
+    abund, aset = np.zeros(ne), np.zeros(ne, bool)
+    DEX = False
+    reading = 1
+    for ln in Path(kw.get("ABUND_FILE") or atoms_dir / "abundance.input").read_text().splitlines():
+        if not ln.strip() or ln[0] == "#":                      # getLine(), rh/getline.c
+            continue
+        f = ln.split()
+        if len(f) < 2:
+            raise ValueError(f"abundance.input: cannot read '{ln}'")
+        eid, a = f[0].upper(), float(f[1])
+        if len(eid) == 1:
+            eid += " "
+        if atomic_number is not None:                            # abundance.c:118-126: position in the file, 1-based
+            for n, v in zip(atomic_number, atomic_abundance):
+                if int(n) == reading:
+                    a = float(v)
+                    break
+        reading += 1
+        for n in range(ne):
+            if eid in ID[n]:
+                abund[n] = a
+                if eid == "H " and a == 12.0:
+                    DEX = True
+                aset[n] = True
+                break
+    metallicity = POW10(float(kw.get("METALLICITY", "0.0")))
+    raw = Path(kw.get("KURUCZ_PF_DATA") or atoms_dir / "pf_Kurucz.input").read_bytes()
+    off = 0
+
+    def xint():
+        nonlocal off
+        v = struct.unpack_from(">i", raw, off)[0]
+        off += 4
+        return v
+
+    def xdoubles(n):
+        nonlocal off
+        v = np.frombuffer(raw, ">f8", n, off).astype(np.float64)
+        off += 8 * n
+        return v
+
+    npf = xint()
+    Tpf = xdoubles(npf)
+    total = avg = 0.0
+    nstage, ionpot, pf = np.zeros(ne, np.int32), [None] * ne, [None] * ne
+    for n in range(ne):
+        if aset[n]:
+            if DEX:
+                abund[n] = POW10(abund[n] - 12.0)
+            if metallicity != 1.0 and ID[n] != "H ":
+                abund[n] *= metallicity
+            total += abund[n]
+            avg += abund[n] * weight[n]
+        xint()                                                   # pti
+        nstage[n] = xint()
+        p = xdoubles(nstage[n] * npf).reshape(nstage[n], npf)
+        ip = xdoubles(nstage[n])
+        if aset[n]:
+            ip = np.array([x * ((HPLANCK * CLIGHT) / CM_TO_M) for x in ip])     # `*=`: abundance.c:212
+            p = np.array([[math.log(x) for x in row] for row in p])
+        ionpot[n], pf[n] = ip, p
+    return Elements(ID, weight, abund, aset, nstage, ionpot, pf, Tpf, total, avg, avg / total)
+
+
+# ------------------------------------------------------------------------------------------- Kurucz lines
+def air_to_vacuum(lambda_air: float) -> float:               # rh/vacuumtoair.c (air_to_vacuum)
+    if lambda_air >= AIR_TO_VACUUM_LIMIT:
+        sqwave = (1.0E+07 / lambda_air) * (1.0E+07 / lambda_air)
+        increase = 1.0000834213E+00 + 2.406030E+06 / (1.30E+10 - sqwave) + 1.5997E+04 / (3.89E+09 - sqwave)
+        return lambda_air * increase
+    return lambda_air
+
+
+def _gammln(xx: float) -> float:                              # rh/gammafunc.c
+    cof = (76.18009172947146, -86.50532032941677, 24.01409824083091, -1.231739572450155, 0.1208650973866179e-2,
+           -0.5395239384953e-5)
+    x = y = xx
+    tmp = x + 5.5
+    tmp -= (x + 0.5) * math.log(tmp)
+    ser = 1.000000000190015
+    for c in cof:
+        y += 1
+        ser += c / y
+    return -tmp + math.log(2.5066282746310005 * ser / x)
+
+
+def read_kurucz_records(cwd, kurucz_data: str):
+    """The fixed-length records of every list named in KURUCZ_DATA (kurucz.c:157-184): list entries are opened
+    relative to the process cwd in the reference (kurucz.c:160-165); here relative to `cwd`."""
+    recs = []
+    for ln in (Path(cwd) / kurucz_data).read_text().splitlines():
+        if not ln.strip() or ln[0] == "#":
+            continue
+        text = (Path(cwd) / ln.split()[0]).read_text()
+        for phys in text.split("\n"):
+            phys_nl = phys + "\n"
+            while phys_nl:                                       # fgets(inputLine, RLK_RECORD_LENGTH+1, ...)
+                rec, phys_nl = phys_nl[:RLK_RECORD_LENGTH], phys_nl[RLK_RECORD_LENGTH:]
+                if rec.strip("\n") == "" and not phys:
+                    continue
+                if rec[0] != "#":
+                    recs.append(rec.rstrip("\n"))
+    return recs
+
+
+def read_kurucz_lines(cwd, kw: dict, el: Elements, loggf_ids=None, loggf_values=None, lam_ids=None,
+                      lam_values=None) -> ll.LineTable:
+    """readKuruczLines (kurucz.c:121-431) + the lazily built Zeeman patterns (kurucz.c:832-921) -> LineTable,
+    sorted by lambda0 (background.c:292-294)."""
+    C = 2.0 * PI * (Q_ELECTRON / EPSILON_0) * (Q_ELECTRON / M_ELECTRON) / CLIGHT
+    LS_Lande = _true(kw["LS_LANDE"])
+    rows, patterns, used = [], [], {}
+    if kw["KURUCZ_DATA"].lower() == "none":
+        raise NotImplementedError("KURUCZ_DATA = none: the LTE path needs a Kurucz line list")
+    for line_index, rec in enumerate(read_kurucz_records(cwd, kw["KURUCZ_DATA"])):
+        f = rec.split()
+        lambda_air, gf, elem_code, Ei = float(f[0]), float(f[1]), f[2], float(f[3])
+        pt_index, stage = (int(x) for x in elem_code.split("."))
+        Ej = _scan_float(rec[53:])[0]
+        Ei = abs(Ei) * (HPLANCK * CLIGHT) / CM_TO_M
+        Ej = abs(Ej) * (HPLANCK * CLIGHT) / CM_TO_M
+        swap = Ej < Ei
+        if swap:
+            rEi, rEj = Ej, Ei
+            labeli, labelj = rec[69:69 + RLK_LABEL_LENGTH], rec[41:41 + RLK_LABEL_LENGTH]
+        else:
+            rEi, rEj = Ei, Ej
+            labeli, labelj = rec[41:41 + RLK_LABEL_LENGTH], rec[69:69 + RLK_LABEL_LENGTH]
+        Ji, Jj = _scan_float(rec[35:])[0], _scan_float(rec[63:])[0]
+        if swap:
+            Ji, Jj = Jj, Ji
+        gi, gj = 2 * Ji + 1, 2 * Jj + 1
+        if lam_ids is not None:
+            for i, v in zip(lam_ids, lam_values):
+                if int(i) == line_index:
+                    lambda_air += float(v)
+        lambda0 = air_to_vacuum(lambda_air)                      # USE_TABULATED_WAVELENGTH, kurucz.c:236-243
+        lambda0 *= NM_TO_M
+        rEj = rEi + (HPLANCK * CLIGHT) / lambda0
+        Aji = C / (lambda0 * lambda0) * POW10(gf) / gj
+        if loggf_ids is not None:
+            for i, v in zip(loggf_ids, loggf_values):
+                if int(i) == line_index:
+                    Aji = C / (lambda0 * lambda0) * POW10(float(v)) / gj
+        Bji = (lambda0 * lambda0 * lambda0) / (2.0 * HPLANCK * CLIGHT) * Aji
+        Bij = (gj / gi) * Bji
+        e = pt_index - 1
+        if not el.abundance_set[e]:
+            raise ValueError(f"line {line_index}: no abundance for element {el.ID[e]}")
+        # ABO columns (kurucz.c:271-294).  The shipped lists end before column 160: the reference then scans
+        # whatever its buffer holds there; no information is the only defined reading
+        cross = alpha = 0.0
+        li = lj = -1
+        got_ABO = False
+        if len(rec) > 160:
+            a, n1 = _scan_float(rec[160:])
+            s = _scan_float(rec[160 + n1:])[0] if a is not None else None
+            if a is not None and s is not None:
+                if a in (0.0, 1.0, 2.0, 3.0) or s in (0.0, 1.0, 2.0, 3.0):
+                    li, lj = (int(s), int(a)) if swap else (int(a), int(s))
+                else:
+                    got_ABO, alpha, cross = True, a, s
+        determined, Si, Li, Sj, Lj = zeeman.rlk_determinate(labeli, labelj)
+        polarizable = determined                                 # atmos.Stokes is TRUE on the pyrh path (:259)
+        G = rec[79:79 + 18]
+        Grad, n1 = _scan_float(G)
+        GStark, n2 = _scan_float(G[n1:])
+        GvdW = _scan_float(G[n1 + n2:])[0]
+        GStark = POW10(GStark) * (CM_TO_M * CM_TO_M * CM_TO_M) if GStark != 0.0 else 0.0
+        GvdW = POW10(GvdW) * (CM_TO_M * CM_TO_M * CM_TO_M) if GvdW != 0.0 else 0.0
+        vdw = None
+        if got_ABO:                                              # getABOcross, barklem.c:199-212
+            reducedmass = AMU / (1.0 / el.weight[0] + 1.0 / el.weight[e])
+            meanvelocity = math.sqrt(8.0 * KBOLTZMANN / (PI * reducedmass))
+            crossmean = (RBOHR * RBOHR) * math.pow(meanvelocity / 1.0E4, -alpha)
+            cross *= 2.0 * math.pow(4.0 / PI, alpha / 2.0) * math.exp(_gammln((4.0 - alpha) / 2.0)) * meanvelocity * crossmean
+            vdw = ll.VDW_BARKLEM
+        elif {li, lj} in ({0, 1}, {1, 2}, {2, 3}) and stage == 0:
+            raise NotImplementedError(f"line {line_index}: Barklem table interpolation (barklem.c:139-196, cubeconvol.c) "
+                                      "is not ported; give the ABO alpha / sigma in columns 161+ instead of the "
+                                      "orbital numbers")
+        if vdw is None:                                          # getUnsoldcross, kurucz.c:985-1024
+            if stage > el.nstage[e] - 1:
+                vdw = ll.VDW_KURUCZ
+            else:
+                Z = stage + 1
+                d1, d2 = E_RYDBERG / (el.ionpot[e][stage] - rEj), E_RYDBERG / (el.ionpot[e][stage] - rEi)
+                deltaR = d1 * d1 - d2 * d2
+                if deltaR <= 0.0:
+                    vdw = ll.VDW_KURUCZ
+                else:
+                    FOURPIEPS0 = 4.0 * PI * EPSILON_0
+                    w = el.weight[e]
+                    vrel35_H = math.pow(8.0 * KBOLTZMANN / (PI * AMU * w) * (1.0 + w / el.weight[0]), 0.3)
+                    vrel35_He = math.pow(8.0 * KBOLTZMANN / (PI * AMU * w) * (1.0 + w / el.weight[1]), 0.3)
+                    ZR = Z * RBOHR
+                    C625 = math.pow(2.5 * ((Q_ELECTRON * Q_ELECTRON) / FOURPIEPS0) * (ABARH / FOURPIEPS0) *
+                                    2 * PI * (ZR * ZR) / HPLANCK * deltaR, 0.4)
+                    cross = 8.08 * (vrel35_H + el.abund[1] * vrel35_He) * C625
+                    vdw = ll.VDW_UNSOLD
+        Grad = POW10(Grad) if Grad != 0.0 else Aji
+        iso_frac = POW10(_scan_float(rec[108:])[0])
+        hfs_frac = POW10(_scan_float(rec[117:])[0])
+        g1, n1 = _scan_int_w(rec[143:], 5)
+        g2 = _scan_int_w(rec[143 + n1:], 5)[0]
+        gL_i, gL_j = g1 * MILLI, g2 * MILLI
+        if swap:
+            gL_i, gL_j = gL_j, gL_i
+        if not LS_Lande and gL_i != -99 * MILLI and gL_j != -99 * MILLI:    # kurucz.c:381-385
+            polarizable = True
+        r = np.zeros(ll.RL_NFIELD)
+        r[ll.RL_LAMBDA0] = lambda0 / NM_TO_M
+        r[ll.RL_GI], r[ll.RL_GJ], r[ll.RL_EI], r[ll.RL_EJ] = gi, gj, rEi, rEj
+        r[ll.RL_BJI], r[ll.RL_AJI], r[ll.RL_BIJ] = Bji, Aji, Bij
+        r[ll.RL_GRAD], r[ll.RL_GSTARK], r[ll.RL_GVDW] = Grad, GStark, GvdW
+        r[ll.RL_HFS_FRAC], r[ll.RL_ISO_FRAC] = hfs_frac, iso_frac
+        r[ll.RL_CROSS], r[ll.RL_ALPHA] = cross, alpha
+        r[ll.RL_POLARIZABLE], r[ll.RL_VDWAALS], r[ll.RL_STAGE] = float(polarizable), vdw, stage
+        if e not in used:
+            used[e] = len(used)
+        r[ll.RL_ELEM] = used[e]
+        pat = zeeman.rlk_zeeman(gi, gj, Si, Li, Sj, Lj, gL_i, gL_j, LS_Lande) if polarizable else None
+        rows.append(r)
+        patterns.append(pat)
+    order = sorted(range(len(rows)), key=lambda i: rows[i][ll.RL_LAMBDA0])       # stable; qsort in the reference
+    zq, zs, zst, out = [], [], [], []
+    for i in order:
+        r, pat = rows[i], patterns[i]
+        r[ll.RL_ZOFF] = len(zq)
+        if pat is not None:
+            r[ll.RL_NCOMP] = len(pat[0])
+            zq += list(pat[0]); zs += list(pat[1]); zst += list(pat[2])
+        out.append(r)
+    elems, pfrows = [], []
+    for e, _ in sorted(used.items(), key=lambda kv: kv[1]):
+        nst = int(el.nstage[e])
+        if nst > ll.RE_MAXSTAGE:
+            raise ValueError(f"element {el.ID[e]}: {nst} ionisation stages exceed RE_MAXSTAGE")
+        row = np.zeros(ll.RE_NFIELD)
+        row[ll.RE_WEIGHT], row[ll.RE_ABUND], row[ll.RE_NSTAGE], row[ll.RE_PFROW] = el.weight[e], el.abund[e], nst, len(pfrows)
+        row[ll.RE_IONPOT0:ll.RE_IONPOT0 + nst] = el.ionpot[e]
+        pfrows += list(el.pf[e])
+        elems.append(row)
+    lt = ll.LineTable(lines=np.array(out), zq=np.array(zq, np.int32), zshift=np.array(zs, np.float64),
+                      zstrength=np.array(zst, np.float64), elems=np.array(elems), pf=np.array(pfrows), Tpf=el.Tpf,
+                      vmicro_char=float(kw["VMICRO_CHAR"]) * 1.0E+03)
+    lt.validate()
+    return lt
+
+
+# ------------------------------------------------------------------------------------------- session
+def _atoms_listed(cwd, kw):
+    out = []
+    for ln in (Path(cwd) / kw["ATOMS_FILE"]).read_text().splitlines():
+        f = ln.split("#", 1)[0].split()
+        if len(f) >= 2 and f[0].endswith(".atom"):
+            out.append((f[0], f[1].upper()))
+    return out
+
+
+def sort_lambda(wave, lambda_ref):
+    """spectrum.lambda of an all-PASSIVE run (sortlambda.c:180-210): user grid + lambda_ref, ascending, unique."""
+    return np.unique(np.concatenate([np.asarray(wave, np.float64), [float(lambda_ref)]]))
+
+
+class Session:
+    """Everything of one working directory + wavelength grid that does not depend on the column, resident on one
+    GPU: SURVEY 8(b)'s ``rhb200_open(cwd, ...)``."""
+
+    def __init__(self, cwd, wave, device=0, path=None, loggf_ids=None, loggf_values=None, lam_ids=None,
+                 lam_values=None, fudge_wave=None, fudge_value=None, atomic_number=None, atomic_abundance=None):
+        from . import api, continuum
+        self.cwd = Path(cwd)
+        kw = self.kw = read_keywords(cwd)
+        if fudge_wave is not None or fudge_value is not None or kw["OPACITY_FUDGE"].lower() != "none":
+            raise NotImplementedError("opacity fudge factors (background.c:372-400) are not implemented on the device path")
+        if _true(kw["MAGNETO_OPTICAL"]):
+            raise NotImplementedError("MAGNETO_OPTICAL = TRUE is refused (the reference overflows chip_c there, readj.c:328)")
+        if _true(kw["RLK_SCATTER"]):
+            raise NotImplementedError("RLK_SCATTER = TRUE is not implemented")
+        if int(kw["N_MAX_SCATTER"]) != 0:
+            raise NotImplementedError("N_MAX_SCATTER > 0 in LTE (pyrh_compute1dray.c:332-337) is not implemented")
+        bg = dict(np.load(DATA / "background_falc11.npz"))
+        listed = _atoms_listed(cwd, kw)
+        if [a for a, _ in listed] != [str(x) for x in bg["atom_files"]]:
+            raise NotImplementedError(f"atoms.input lists {[a for a, _ in listed]}; only the standard background set "
+                                      f"{[str(x) for x in bg['atom_files']]} ships with pyrh_b200.host (no *.atom parser yet)")
+        if any(s != "PASSIVE" for _, s in listed):
+            raise NotImplementedError("ACTIVE atoms: use pyrh_b200.nlte (the NLTE entry points take the parsed problem)")
+        self.el = read_elements(path, kw, atomic_number, atomic_abundance)
+        self.lt = read_kurucz_lines(cwd, kw, self.el, loggf_ids, loggf_values, lam_ids, lam_values)
+        self.lambda_ref = float(kw["LAMBDA_REF"])
+        self.lam = sort_lambda(wave, self.lambda_ref)
+        self.ctx = api.Context(device)
+        self.ctx.set_lines(self.lt, magneto_optical=False, rlkscatter=False)
+        self.ctx.set_wavelengths(self.lam)
+        self.ctx.set_solvers(kw["S_INTERPOLATION"], kw["S_INTERPOLATION_STOKES"])
+        abundance = np.array([self.el.abund[int(p) - 1] for p in bg["atom_pt_index"]])
+        self.model = continuum.ContinuumModel(bg)
+        self.ctx.set_continuum(self.model, abundance)
+        self.ctx.set_chemistry(bg["ce_nuclei"][:, 1].astype(np.int32), bg["ce_mol"])
+        self.vmacro_tresh = float(kw["VMACRO_TRESH"])
+
+    def compute(self, atmosphere, mu=1.0, atm_scale=0, get_scales=False):
+        """``atmosphere`` [9+, ndep] or [ncol, 9+, ndep] (pyrh units) -> Stokes [.., 4, nlambda] on ``self.wavelengths``."""
+        a = np.asarray(atmosphere, np.float64)
+        single = a.ndim == 2
+        r = self.ctx.compute1d_batch(a[None] if single else a, mu=mu, atm_scale=atm_scale, lambda_ref=self.lambda_ref,
+                                     wght_per_H=self.el.wght_per_H, vmacro_tresh=self.vmacro_tresh, get_scales=get_scales)
+        if get_scales:
+            return (r[0][0], r[1][0]) if single else r
+        return r[0] if single else r
+
+    @property
+    def wavelengths(self):
+        return self.lam[self.lam != self.lambda_ref]
+
+    def close(self):
+        self.ctx.close()
+
+
+_SESSIONS: dict = {}
+
+
+def _session_key(cwd, wave, extra):
+    st = []
+    for f in ("keyword.input", "atoms.input", "kurucz.input"):
+        p = Path(cwd) / f
+        st.append((f, p.stat().st_mtime_ns if p.exists() else 0))
+    return (str(Path(cwd).resolve()), tuple(st), np.asarray(wave, np.float64).tobytes(), extra)
+
+
+def compute1d(cwd, mu, atm_scale, atmosphere, wave, loggf_ids=None, loggf_values=None, lam_ids=None, lam_values=None,
+              fudge_wave=None, fudge_value=None, atomic_number=None, atomic_abundance=None, get_atomic_rfs=False,
+              get_populations=False, device=0):
+    """Drop-in for ``pyrh.compute1d`` (pyrh.pyx:537-668) in LTE: returns ``(sI, sQ, sU, sV, lam)``.  The parsed
+    working directory stays resident on the GPU between calls (per-process cache keyed on the directory, the input
+    files' mtimes, the wavelength grid and the per-call line / abundance overrides)."""
+    if get_atomic_rfs:
+        raise NotImplementedError("get_atomic_rfs: the analytic log gf response function is available at ray level "
+                                  "(Context.bezier3_rf); the fused Stokes path has none in the reference either "
+                                  "(Piece_Stokes_Bezier3_1D carries no dI)")
+    if get_populations:
+        raise NotImplementedError("get_populations returns ACTIVE-atom populations (pyrh_solveray.c); see pyrh_b200.nlte")
+    tob = lambda x: None if x is None else np.asarray(x).tobytes()   # noqa: E731
+    key = _session_key(cwd, wave, (tob(loggf_ids), tob(loggf_values), tob(lam_ids), tob(lam_values),
+                                   tob(atomic_number), tob(atomic_abundance), device))
+    s = _SESSIONS.get(key)
+    if s is None:
+        s = _SESSIONS[key] = Session(cwd, wave, device, None, loggf_ids, loggf_values, lam_ids, lam_values, fudge_wave,
+                                     fudge_value, atomic_number, atomic_abundance)
+    st = s.compute(atmosphere, mu=mu, atm_scale=atm_scale)
+    return st[0], st[1], st[2], st[3], s.wavelengths

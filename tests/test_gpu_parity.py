@@ -857,3 +857,27 @@ def test_rf_fd_batch_equals_reference_differences(ctx):
     REPORT["rf_fd_max_err_over_peak"] = float(np.max(np.abs(got - g["rf"]) / scale))
     assert np.array_equal(got, g["rf"])
     assert np.isfinite(rf).all() and np.abs(rf[0]).max() > 0
+
+
+def test_host_compute1d_drop_in():
+    """pyrh_b200.host.compute1d = pyrh.compute1d's argument list: parses the working directory (keyword.input,
+    abundance, partition functions, Kurucz list) in Python and runs the column on the device.  BASELINE config 1
+    (FAL-C 57 depths, B = 1 kG, Hinode window) and a 70-depth benchmark column: bit-identical to rhf1d()."""
+    from pyrh_b200 import host
+    root = Path(__file__).resolve().parent.parent
+    cwd, pp = root / "oracle" / "_ref" / "inputs" / "benchmark", root / "oracle" / "_ref" / "pyrh_path"
+    if not (cwd / "keyword.input").exists():
+        pytest.skip("reference input files not staged (oracle/_ref)")
+    os.environ["PYRH_PATH"] = str(pp)
+    full = dict(np.load(GOLD / "falc_full.npz"))
+    sI, sQ, sU, sV, lam = host.compute1d(str(cwd), 1.0, 0, full["atmosphere"], full["wave"])
+    assert np.array_equal(lam, full["lam_spect"][full["lam_spect"] != 500.0])
+    got = np.array([sI, sQ, sU, sV])
+    REPORT["host_compute1d_config1_exact"] = bool(np.array_equal(got, full["stokes"]))
+    assert np.array_equal(got, full["stokes"])
+    g = dict(np.load(GOLD / "synth70_c2.npz"))
+    out = host.compute1d(str(cwd), 1.0, 0, g["atmosphere"], g["wave"])           # second call: cached session
+    assert len(host._SESSIONS) == 1
+    assert np.array_equal(np.array(out[:4]), g["stokes_scalar"])
+    with pytest.raises(NotImplementedError):
+        host.compute1d(str(cwd), 1.0, 0, g["atmosphere"], g["wave"], get_populations=True)

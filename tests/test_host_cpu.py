@@ -1,0 +1,78 @@
+"""pyrh_b200.host: the text inputs of a pyrh working directory parsed in Python (readInput / readAbundance /
+readKuruczLines of the reference) must give, bit for bit, the tables recorded from the reference's own parsed
+state (fixtures synth70_c0, pyrh_scales, synth70_chem).  Needs the reference's data files staged under
+oracle/_ref (make -C oracle ref); they travel to the GPU box with the snapshot."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import GOLD
+
+ROOT = Path(__file__).resolve().parent.parent
+CWD = ROOT / "oracle" / "_ref" / "inputs" / "benchmark"
+PYRH_PATH = ROOT / "oracle" / "_ref" / "pyrh_path"
+
+pytestmark = pytest.mark.skipif(not (CWD / "keyword.input").exists() or not (PYRH_PATH / "rh" / "Atoms").exists(),
+                                reason="reference input files not staged (oracle/_ref)")
+
+
+def test_keywords_and_elements():
+    from pyrh_b200 import host
+    kw = host.read_keywords(CWD)
+    assert kw["KURUCZ_DATA"] == "kurucz.input" and kw["STOKES_MODE"] == "FULL_STOKES" and float(kw["VMICRO_CHAR"]) == 5.0
+    el = host.read_elements(PYRH_PATH, kw)
+    sums = np.load(GOLD / "pyrh_scales.npz")["tau_abund_sums"]          # abundance.c:219-221 of the reference run
+    assert el.wght_per_H == sums[0] and el.totalAbund == sums[1] and el.avgMolWght == sums[2]
+    bg = np.load(ROOT / "pyrh_b200" / "data" / "background_falc11.npz")
+    ab = np.array([el.abund[int(p) - 1] for p in bg["atom_pt_index"]])
+    assert np.array_equal(ab, np.load(GOLD / "synth70_chem.npz")["abundance"])
+    assert len(el.ID) == 99 and el.ID[25] == "FE" and el.nstage[25] == 6
+
+
+def test_kurucz_lines_equal_reference_tables():
+    from pyrh_b200 import host, linelist as ll
+    kw = host.read_keywords(CWD)
+    el = host.read_elements(PYRH_PATH, kw)
+    lt = host.read_kurucz_lines(CWD, kw, el)
+    ref = ll.LineTable.from_npz(np.load(GOLD / "synth70_c0.npz"))
+    cols = [i for i in range(ll.RL_NFIELD) if i != ll.RL_ALPHA]      # alpha is uninitialised memory for Unsold lines
+    assert np.array_equal(lt.lines[:, cols], ref.lines[:, cols])
+    assert np.array_equal(lt.zq, ref.zq) and np.array_equal(lt.zshift, ref.zshift)
+    assert np.array_equal(lt.zstrength, ref.zstrength)
+    assert np.array_equal(lt.pf, ref.pf) and np.array_equal(lt.Tpf, ref.Tpf) and lt.vmicro_char == ref.vmicro_char
+    n = int(ref.elems[0, ll.RE_NSTAGE])
+    assert np.array_equal(lt.elems[:, :ll.RE_IONPOT0 + n - 1], ref.elems[:, :ll.RE_IONPOT0 + n - 1])
+
+
+def test_loggf_and_wavelength_overrides():
+    """loggf_ids / lam_ids of pyrh.compute1d (kurucz.c:224-234, 247-257) address lines by their position in the list."""
+    from pyrh_b200 import host, linelist as ll
+    kw = host.read_keywords(CWD)
+    el = host.read_elements(PYRH_PATH, kw)
+    a = host.read_kurucz_lines(CWD, kw, el)
+    b = host.read_kurucz_lines(CWD, kw, el, loggf_ids=[1], loggf_values=[-0.5], lam_ids=[0], lam_values=[0.001])
+    assert b.lines[0, ll.RL_LAMBDA0] > a.lines[0, ll.RL_LAMBDA0] and b.lines[1, ll.RL_LAMBDA0] == a.lines[1, ll.RL_LAMBDA0]
+    assert b.lines[1, ll.RL_AJI] / a.lines[1, ll.RL_AJI] == pytest.approx(10 ** (-0.5 + 0.968), rel=1e-12)
+
+
+def test_abundance_override_and_sort_lambda():
+    from pyrh_b200 import host
+    kw = host.read_keywords(CWD)
+    a = host.read_elements(PYRH_PATH, kw)
+    b = host.read_elements(PYRH_PATH, kw, atomic_number=[26], atomic_abundance=[7.60])
+    assert b.abund[25] == host.POW10(7.60 - 12.0) and b.abund[25] != a.abund[25] and b.abund[24] == a.abund[24]
+    lam = host.sort_lambda([630.2, 630.1, 630.2], 500.0)
+    assert list(lam) == [500.0, 630.1, 630.2]
+
+
+def test_unsupported_inputs_are_refused(tmp_path):
+    import shutil
+    from pyrh_b200 import host
+    for f in CWD.iterdir():
+        if f.is_file() and f.stat().st_size < 1_000_000:
+            shutil.copy(f, tmp_path / f.name)
+    kwf = tmp_path / "keyword.input"
+    kwf.write_text(kwf.read_text().replace("MAGNETO_OPTICAL = FALSE", "MAGNETO_OPTICAL = TRUE"))
+    with pytest.raises(NotImplementedError, match="MAGNETO_OPTICAL"):
+        host.Session(tmp_path, [630.1, 630.2], path=PYRH_PATH)
