@@ -107,6 +107,13 @@ int rhb200_set_lines(rhb200_ctx *ctx,
    windows of rlk_opacity (kurucz.c:538-566,608) on the host: integer work,
    bit-exact. */
 int rhb200_set_wavelengths(rhb200_ctx *ctx, int nlambda, const double *lambda);
+
+/* Lines of the explicit (PASSIVE) model atoms: inside the wing window of such a line a Kurucz line of the same
+   element and ionisation stage does not contribute (rlk_opacity, kurucz.c:617-633: passive_bb accounts for it).
+   rows [n][4] = {element row of the table given to rhb200_set_lines, stage of the model line's lower level,
+   lambda0 [nm, vacuum], qwing}.  Call after rhb200_set_lines (which clears the table) and before
+   rhb200_set_wavelengths. */
+int rhb200_set_model_lines(rhb200_ctx *ctx, int n, const double *rows);
 /* read back the window table: for wavelength i the lines first[i] .. first[i]+count[i]-1
    of the *contributing* list idx[] (test hook for the integer part) */
 int rhb200_get_line_windows(rhb200_ctx *ctx, int *first /*[nlambda]*/, int *count /*[nlambda]*/,

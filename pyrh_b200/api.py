@@ -115,6 +115,12 @@ class Context:
         self.lt = lt
         self.nlambda = 0
 
+    def set_model_lines(self, rows):
+        """Lines of the PASSIVE model atoms that switch off Kurucz lines of the same element and stage inside their
+        wing windows (kurucz.c:617-633): rows [n, 4] = element row, lower-level stage, lambda0 [nm], qwing."""
+        rows = np.ascontiguousarray(rows, np.float64).reshape(-1, 4)
+        _lib.check(self.lib.rhb200_set_model_lines(self.h, len(rows), _dp(rows)))
+
     def set_wavelengths(self, lam):
         lam = np.ascontiguousarray(lam, np.float64)
         _lib.check(self.lib.rhb200_set_wavelengths(self.h, len(lam), _dp(lam)))

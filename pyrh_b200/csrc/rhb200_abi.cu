@@ -72,7 +72,7 @@ static void free_tables(rhb200_ctx *c)
 static void free_wave(rhb200_ctx *c)
 {
   DevWave &w = c->wav;
-  cudaFree(w.lambda); cudaFree(w.first); cudaFree(w.count); cudaFree(w.idx); cudaFree(w.flags); cudaFree(w.noline);
+  cudaFree(w.lambda); cudaFree(w.first); cudaFree(w.count); cudaFree(w.idx); cudaFree(w.flags); cudaFree(w.noline); cudaFree(w.unpol_rank);
   w = DevWave();
 }
 
@@ -139,10 +139,6 @@ extern "C" int rhb200_set_lines(rhb200_ctx *c, int nline, const double *lines, i
     if (ie < 0 || ie >= nelem) { rhb200_set_error("line %d: element row %d out of range", n, ie); return RHB200_EINVAL; }
     const int zo = (int) L[RHB200_RL_ZOFF], nc = (int) L[RHB200_RL_NCOMP];
     if (zo < 0 || nc < 0 || zo + nc > ncomp) { rhb200_set_error("line %d: Zeeman slice out of range", n); return RHB200_EINVAL; }
-    if (L[RHB200_RL_GRAD] != 0.0 && L[RHB200_RL_POLARIZABLE] == 0.0) {
-      rhb200_set_error("line %d is not polarizable: the VoigtArmstrong branch (kurucz.c:824) is not implemented", n);
-      return RHB200_EUNSUPPORTED;
-    }
   }
   for (int e = 0; e < nelem; e++) {
     const double *E = elems + (size_t) e * RHB200_RE_NFIELD;
@@ -167,6 +163,21 @@ extern "C" int rhb200_set_lines(rhb200_ctx *c, int nline, const double *lines, i
   c->h_elems.assign(elems, elems + (size_t) nelem * RHB200_RE_NFIELD);
   c->h_zq.assign(zq, zq + ncomp); c->h_zshift.assign(zshift, zshift + ncomp); c->h_zstrength.assign(zstrength, zstrength + ncomp);
   free_wave(c);     // windows depend on the line table
+  c->h_model_lines.clear();
+  return RHB200_OK;
+}
+
+// Lines of the explicit model atoms (PASSIVE atoms of atoms.input): a Kurucz line of the same element and
+// ionisation stage does not contribute at wavelengths inside such a line's wing window, where passive_bb already
+// accounts for it (kurucz.c:617-633).  rows [n][4] = {row of the element in the table of rhb200_set_lines,
+// stage of the model line's lower level, lambda0 [nm], qwing}.  Call between rhb200_set_lines and
+// rhb200_set_wavelengths; rhb200_set_lines clears the table.
+extern "C" int rhb200_set_model_lines(rhb200_ctx *c, int n, const double *rows)
+{
+  RH_NEED_CTX(c);
+  if (n < 0 || (n > 0 && !rows)) { rhb200_set_error("rhb200_set_model_lines: bad arguments"); return RHB200_EINVAL; }
+  c->h_model_lines.assign(rows, rows + (size_t) n * 4);
+  free_wave(c);
   return RHB200_OK;
 }
 
@@ -197,7 +208,14 @@ extern "C" int rhb200_set_wavelengths(rhb200_ctx *c, int nlambda, const double *
       if (std::fabs(lam0(n) - lam) <= dlamb_char) {
         const double *L = LT + (size_t) n * RHB200_RL_NFIELD;
         const double *E = c->h_elems.data() + (size_t) ((int) L[RHB200_RL_ELEM]) * RHB200_RE_NFIELD;
-        if ((int) L[RHB200_RL_STAGE] < (int) E[RHB200_RE_NSTAGE] - 1) {   // kurucz.c:614
+        bool contributes = (int) L[RHB200_RL_STAGE] < (int) E[RHB200_RE_NSTAGE] - 1;   // kurucz.c:614
+        for (size_t kr = 0; contributes && kr < c->h_model_lines.size() / 4; kr++) {           // kurucz.c:617-633
+          const double *M = c->h_model_lines.data() + 4 * kr;
+          if ((int) M[0] != (int) L[RHB200_RL_ELEM]) continue;
+          const double dlamb_wing = M[2] * M[3] * (c->tab.vmicro_char / RH_CLIGHT);
+          if (std::fabs(lam - M[2]) <= dlamb_wing && (int) M[1] == (int) L[RHB200_RL_STAGE]) contributes = false;
+        }
+        if (contributes) {
           c->h_idx.push_back(n);
           c->h_flags[l] |= 1;
           if (L[RHB200_RL_POLARIZABLE] != 0.0) c->h_flags[l] |= 2;
@@ -216,9 +234,15 @@ extern "C" int rhb200_set_wavelengths(rhb200_ctx *c, int nlambda, const double *
   if (w.nidx) RH_CHECK(upload(&w.idx, c->h_idx.data(), (size_t) w.nidx));
   else RH_CUDA(cudaMalloc((void **) &w.idx, sizeof(int)));
   c->h_noline.clear();
-  for (int l = 0; l < nlambda; l++) if ((c->h_flags[l] & 1) == 0) c->h_noline.push_back(l);
+  std::vector<int> rank(nlambda, -1);
+  w.nunpol = 0;
+  for (int l = 0; l < nlambda; l++) {
+    if ((c->h_flags[l] & 2) == 0) c->h_noline.push_back(l);     // no polarised line: solved for I alone
+    if (c->h_flags[l] == 1) rank[l] = w.nunpol++;               // ... with the scalar ray in moving columns
+  }
   w.nnoline = (int) c->h_noline.size();
   if (w.nnoline) RH_CHECK(upload(&w.noline, c->h_noline.data(), (size_t) w.nnoline));
+  RH_CHECK(upload(&w.unpol_rank, rank.data(), (size_t) nlambda));
   return RHB200_OK;
 }
 
@@ -245,12 +269,14 @@ static int need_state(rhb200_ctx *c, bool wave)
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t) 255; }
 
 struct ChunkLayout {
-  size_t elem_n, lineprep, raypts, total;
+  size_t elem_n, lineprep, raypts, scal, colmov, total;
   ChunkLayout(const rhb200_ctx *c, int cc, int ndep) {
     elem_n   = align_up((size_t) cc * std::max(1, c->tab.nelem) * RHB200_RE_MAXSTAGE * ndep * sizeof(double));
     lineprep = align_up((size_t) cc * std::max(1, c->tab.nline) * ndep * LP_NFIELD * sizeof(double));
     raypts   = align_up((size_t) cc * c->wav.nlambda * ndep * RP_NFIELD * sizeof(double));
-    total = elem_n + lineprep + raypts;
+    scal     = align_up((size_t) cc * std::max(1, c->wav.nunpol) * 3 * ndep * sizeof(double));
+    colmov   = align_up((size_t) cc * sizeof(int));
+    total = elem_n + lineprep + raypts + scal + colmov;
   }
 };
 
@@ -263,8 +289,17 @@ static int chunk_columns(const rhb200_ctx *c, int ncol, int ndep, int nslots)
   if (c->cont) per += (size_t) (rh_continuum_natom(c) + 4 + rh_continuum_nlev(c) + 8) * ndep * sizeof(double);
   size_t cc = budget / ((size_t) nslots * per);
   if (cc < 1) cc = 1;
-  if (const char *e = getenv("RHB200_CHUNK_COLS")) { int v = atoi(e); if (v > 0) cc = (size_t) v; }
-  return (int) std::min((size_t) ncol, cc);
+  if (const char *e = getenv("RHB200_CHUNK_COLS")) { int v = atoi(e); if (v > 0) return std::min(ncol, v); }
+  if (cc >= (size_t) ncol) return ncol;
+  const size_t nchunk = ((size_t) ncol + cc - 1) / cc;      // equal chunks instead of full ones plus a small tail
+  return (int) (((size_t) ncol + nchunk - 1) / nchunk);
+}
+
+// per-column atmos.moving flags of a chunk (written by the pyrh-rows step when VMACRO_TRESH > 0)
+static int *chunk_col_moving(const rhb200_ctx *c, int cc, int ndep, char *ws)
+{
+  ChunkLayout L(c, cc, ndep);
+  return (int *) (ws + L.elem_n + L.lineprep + L.raypts + L.scal);
 }
 
 // pyrh boundary (rhb200_compute1d_batch): the columns arrive as pyrh.compute1d's nine rows
@@ -280,11 +315,12 @@ struct ScalesStep { int iref, atm_scale; double wght_per_H; double *d_scratch, *
 
 static int run_chunk_dev(rhb200_ctx *c, int cc, int ndep, double muz, int moving, int bc_top, int bc_bottom,
                          const double *d_atmos, const double *d_chi_ai, const double *d_eta_ai,
-                         double *d_stokes, char *ws, const ScalesStep *sc = nullptr)
+                         double *d_stokes, char *ws, const ScalesStep *sc = nullptr, bool per_column_moving = false)
 {
   ChunkLayout L(c, cc, ndep);
   double *d_elem_n = (double *) ws, *d_lineprep = (double *) (ws + L.elem_n),
-         *d_raypts = (double *) (ws + L.elem_n + L.lineprep);
+         *d_raypts = (double *) (ws + L.elem_n + L.lineprep), *d_scal = (double *) (ws + L.elem_n + L.lineprep + L.raypts);
+  const int *d_colmov = per_column_moving ? chunk_col_moving(c, cc, ndep, ws) : nullptr;
   RH_CHECK(rh_launch_prep(c, cc, ndep, muz, moving, d_atmos, d_elem_n, d_lineprep));
   RH_CHECK(rh_launch_opacity_fused(c, cc, ndep, 1, d_atmos, d_lineprep, d_chi_ai, d_eta_ai, d_raypts));
   // convertScales() sits between Background() and Iterate() (pyrh_compute1dray.c:310-311): the height row is
@@ -292,7 +328,8 @@ static int run_chunk_dev(rhb200_ctx *c, int cc, int ndep, double muz, int moving
   if (sc) RH_CHECK(rh_launch_scales(c, cc, ndep, sc->iref, sc->atm_scale, sc->wght_per_H, d_raypts,
                                     (double *) d_atmos, sc->d_scratch, sc->d_scales_out));
   RH_CHECK(rh_launch_delo_raypts(c, cc, ndep, muz, bc_top, bc_bottom, d_atmos, d_raypts, d_stokes));
-  RH_CHECK(rh_launch_feautrier_raypts(c, cc, ndep, muz, bc_top, bc_bottom, d_atmos, d_raypts, d_stokes));
+  RH_CHECK(rh_launch_feautrier_raypts(c, cc, ndep, muz, bc_top, bc_bottom, d_atmos, d_raypts, d_stokes,
+                                      moving, d_colmov, d_scal));
   return RHB200_OK;
 }
 
@@ -384,7 +421,8 @@ static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int mov
                                (size_t) n * py->nrow * ndep * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess) {
         rhb200_set_error("H2D copy failed: %s", cudaGetErrorString(e)); rc = RHB200_ECUDA; break;
       }
-      rc = rh_launch_pyrh_rows(c, n, ndep, py->nrow, py->atm_scale, muz, py->vmacro_tresh, d_in, d_at);
+      rc = rh_launch_pyrh_rows(c, n, ndep, py->nrow, py->atm_scale, muz, py->vmacro_tresh, d_in, d_at,
+                               chunk_col_moving(c, n, ndep, ws));
       if (rc != RHB200_OK) break;
     } else
     if ((e = cudaMemcpyAsync(d_at, atmos + (size_t) c0 * RHB200_AT_NFIELD * ndep,
@@ -410,7 +448,8 @@ static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int mov
     }
     ScalesStep sc{py ? py->iref : 0, py ? py->atm_scale : 0, py ? py->wght_per_H : 0.0, d_sc,
                   (py && py->scales && py->atm_scale != 2) ? d_sc + (size_t) cc * ndep : nullptr};
-    rc = run_chunk_dev(c, n, ndep, muz, moving, bc_top, bc_bottom, d_at, d_chi, d_eta, d_st, ws, py ? &sc : nullptr);
+    rc = run_chunk_dev(c, n, ndep, muz, moving, bc_top, bc_bottom, d_at, d_chi, d_eta, d_st, ws, py ? &sc : nullptr,
+                       py && py->vmacro_tresh > 0.0);
     if (rc != RHB200_OK) break;
     if (sc.d_scales_out && (e = cudaMemcpyAsync(py->scales + (size_t) c0 * 2 * ndep, sc.d_scales_out, (size_t) n * 2 * ndep * sizeof(double),
                                                 cudaMemcpyDeviceToHost, st)) != cudaSuccess) {

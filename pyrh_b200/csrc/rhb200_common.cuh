@@ -56,7 +56,10 @@ struct DevWave {
   int nlambda = 0, nidx = 0;
   double *lambda = nullptr;   // [nlambda]
   int *first = nullptr, *count = nullptr, *idx = nullptr, *flags = nullptr;
-  int *noline = nullptr, nnoline = 0;   // wavelengths without any line in the window (Feautrier rays)
+  // wavelengths without a POLARISED line (flags bit 1 clear): solved for I alone (formal.c:84-103, 223-236, 289-309)
+  // -- Feautrier when there is no line at all or the column is static, else the scalar S_INTERPOLATION ray
+  int *noline = nullptr, nnoline = 0;
+  int *unpol_rank = nullptr, nunpol = 0;   // [nlambda] rank among the wavelengths with flags == 1 (line, unpolarised), else -1
 };
 
 struct KTimer {
@@ -72,6 +75,7 @@ struct rhb200_ctx {
   std::vector<double> h_lines, h_elems, h_lambda, h_zshift, h_zstrength;
   std::vector<int> h_zq;
   std::vector<int> h_first, h_count, h_idx, h_flags, h_noline;
+  std::vector<double> h_model_lines;     // rhb200_set_model_lines: [n][4] element row, stage, lambda0 [nm], qwing
   // formal solver selection (keyword.input S_INTERPOLATION / S_INTERPOLATION_STOKES, inputs.h:26-27)
   int s_interpolation = RHB200_S_BEZIER3, s_interpolation_stokes = RHB200_DELO_BEZIER3;
   // wavelength shard of the NLTE solve (rhb200_nlte_set_shard)
@@ -112,7 +116,7 @@ int rh_continuum_nlev(const rhb200_ctx *ctx);
 int rh_continuum_natom(const rhb200_ctx *ctx);
 int rh_continuum_proton_level(const rhb200_ctx *ctx);
 int rh_launch_pyrh_rows(rhb200_ctx *ctx, int ncol, int ndep, int nrow_in, int atm_scale, double muz, double vmacro_tresh,
-                        const double *d_in, double *d_atmos);
+                        const double *d_in, double *d_atmos, int *d_col_moving);
 int rh_launch_rf_expand(rhb200_ctx *ctx, int v0, int n, int ndep, int nrow, int npar, const int *d_rows,
                         const double *d_delta, const double *d_base, double *d_in);
 int rh_launch_rf_diff(rhb200_ctx *ctx, int v0, int n, int ndep, int nlambda, int npar, const double *d_delta,
@@ -159,7 +163,8 @@ int rh_launch_bezier3(rhb200_ctx *ctx, int solver /* RHB200_S_* */, int nray, in
                       const double *d_ray_lambda, const double *d_height, const double *d_T,
                       const double *d_chi, const double *d_S, double *d_I, double *d_Psi);
 int rh_launch_feautrier_raypts(rhb200_ctx *ctx, int ncol, int ndep, double muz, int bc_top, int bc_bottom,
-                               const double *d_atmos, double *d_raypts, double *d_stokes);
+                               const double *d_atmos, double *d_raypts, double *d_stokes,
+                               int moving, const int *d_col_moving, double *d_scratch /* [ncol][nunpol][3][ndep] */);
 int rh_launch_feautrier(rhb200_ctx *ctx, int nray, int ndep, double muz, int bc_top, int bc_bottom,
                         const int *d_ray_col, const double *d_ray_lambda, const double *d_height,
                         const double *d_T, const double *d_chi, const double *d_S,

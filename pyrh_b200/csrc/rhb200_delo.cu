@@ -65,7 +65,7 @@ delo_raypts_kernel(int ncol, int nlambda, int ndep, double muz, int bc_top, int 
   const size_t r = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= nray) return;
   const int col = (int) (r / nlambda), l = (int) (r - (size_t) col * nlambda);
-  if ((__ldg(wflags + l) & 1) == 0) return;      // no line at this wavelength: Feautrier kernel (formal.c:100-103)
+  if ((__ldg(wflags + l) & 2) == 0) return;      // no polarised line at this wavelength: scalar kernel (formal.c:84-103)
   const double *at = atmos + (size_t) col * RHB200_AT_NFIELD * ndep;
   RayPtsIO io{reinterpret_cast<const double2 *>(raypts + r * (size_t) ndep * RP_NFIELD),
               stokes + (size_t) col * 4 * nlambda + l, nlambda, 0};
@@ -84,7 +84,7 @@ stokes_parabolic_raypts_kernel(int ncol, int nlambda, int ndep, double muz, int 
   const size_t r = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= nray) return;
   const int col = (int) (r / nlambda), l = (int) (r - (size_t) col * nlambda);
-  if ((__ldg(wflags + l) & 1) == 0) return;
+  if ((__ldg(wflags + l) & 2) == 0) return;
   const double *at = atmos + (size_t) col * RHB200_AT_NFIELD * ndep;
   RayPtsIO io{reinterpret_cast<const double2 *>(raypts + r * (size_t) ndep * RP_NFIELD),
               stokes + (size_t) col * 4 * nlambda + l, nlambda, 0};
@@ -187,21 +187,40 @@ struct FeauGenericIO {          // reference layouts; P and Psi double as the F 
   __device__ __forceinline__ bool wantPsi() const { return Psi_ != nullptr; }
 };
 
-// line-free rays of the fused LTE path (formal.c:289-309): flags bit0 == 0
+// rays of the fused LTE path without a polarised line, solved for I alone.  formal.c:84-103: angle_dep is false when
+// the wavelength has no line, or has one but the column is static -> Feautrier (:289-309); a moving column with an
+// unpolarised line takes the scalar S_INTERPOLATION ray (:223-236).  scratch [ncol][nunpol][3][ndep]: chi, S, I.
 __global__ void __launch_bounds__(128)
 feautrier_raypts_kernel(int ncol, int nlambda, int ndep, double muz, int bc_top, int bc_bottom,
                         const int *__restrict__ nolines, int nnoline,
                         const double *__restrict__ atmos, const double *__restrict__ lambda,
-                        double *__restrict__ raypts, double *__restrict__ stokes)
+                        double *__restrict__ raypts, double *__restrict__ stokes,
+                        const int *__restrict__ wflags, const int *__restrict__ unpol_rank, int nunpol,
+                        int solver, int moving, const int *__restrict__ col_moving, double *__restrict__ scratch)
 {
   const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t) ncol * nnoline) return;
   const int col = (int) (t / nnoline), l = __ldg(nolines + (int) (t - (size_t) col * nnoline));
   const size_t r = (size_t) col * nlambda + l;
   const double *at = atmos + (size_t) col * RHB200_AT_NFIELD * ndep;
-  FeauRayPtsIO io{raypts + r * (size_t) ndep * RP_NFIELD, at + RHB200_AT_HEIGHT * ndep};
-  const double I0 = rhf::feautrier_ray(io, ndep, muz, bc_top, bc_bottom, at + RHB200_AT_T * ndep,
-                                       __ldg(lambda + l));
+  double *rp = raypts + r * (size_t) ndep * RP_NFIELD;
+  double I0;
+  const bool scalar_ray = (__ldg(wflags + l) & 1) && (col_moving ? col_moving[col] != 0 : moving != 0);
+  if (scalar_ray) {
+    double *c = scratch + ((size_t) col * nunpol + __ldg(unpol_rank + l)) * 3 * ndep, *s = c + ndep, *Ir = s + ndep;
+    for (int k = 0; k < ndep; k++) { c[k] = rp[(size_t) k * RP_NFIELD + RP_CHI]; s[k] = rp[(size_t) k * RP_NFIELD + RP_SI]; }
+    const double *z = at + RHB200_AT_HEIGHT * ndep, *Tc = at + RHB200_AT_T * ndep;
+    const double lam = __ldg(lambda + l);
+    switch (solver) {                                         // formal.c:229-235
+    case RHB200_S_LINEAR:    rhp::linear_ray(ndep, z, muz, 1, bc_top, bc_bottom, Tc, lam, c, s, Ir, nullptr); break;
+    case RHB200_S_PARABOLIC: rhp::parabolic_ray(ndep, z, muz, 1, bc_top, bc_bottom, Tc, lam, c, s, Ir, nullptr); break;
+    default:                 rhz::bezier3_ray(ndep, z, muz, 1, bc_top, bc_bottom, Tc, lam, c, s, Ir, nullptr);
+    }
+    I0 = Ir[0];
+  } else {
+    FeauRayPtsIO io{rp, at + RHB200_AT_HEIGHT * ndep};
+    I0 = rhf::feautrier_ray(io, ndep, muz, bc_top, bc_bottom, at + RHB200_AT_T * ndep, __ldg(lambda + l));
+  }
   double *out = stokes + (size_t) col * 4 * nlambda + l;
   out[0] = I0; out[nlambda] = 0.0; out[2*(size_t) nlambda] = 0.0; out[3*(size_t) nlambda] = 0.0;
 }
@@ -303,7 +322,8 @@ int rh_launch_bezier3_rf(rhb200_ctx *ctx, int nray, int ndep, double muz, int bc
 }
 
 int rh_launch_feautrier_raypts(rhb200_ctx *ctx, int ncol, int ndep, double muz, int bc_top, int bc_bottom,
-                               const double *d_atmos, double *d_raypts, double *d_stokes)
+                               const double *d_atmos, double *d_raypts, double *d_stokes,
+                               int moving, const int *d_col_moving, double *d_scratch)
 {
   const int nn = ctx->wav.nnoline;
   if (nn == 0 || ncol == 0) return RHB200_OK;
@@ -312,7 +332,8 @@ int rh_launch_feautrier_raypts(rhb200_ctx *ctx, int ncol, int ndep, double muz, 
     ScopedKernelTimer t(ctx, RHB200_K_BEZIER);
     feautrier_raypts_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, ctx->stream>>>(
         ncol, ctx->wav.nlambda, ndep, muz, bc_top, bc_bottom, ctx->wav.noline, nn, d_atmos,
-        ctx->wav.lambda, d_raypts, d_stokes);
+        ctx->wav.lambda, d_raypts, d_stokes, ctx->wav.flags, ctx->wav.unpol_rank, ctx->wav.nunpol,
+        ctx->s_interpolation, moving, d_col_moving, d_scratch);
   }
   RH_CUDA(cudaGetLastError());
   return RHB200_OK;

@@ -146,7 +146,9 @@ __device__ __forceinline__ double zstrength_of(const ZeemanGlobal &z, int i) { r
 // Sum of all contributing lines at one (column, depth, wavelength): the body of the
 // n-loop of rlk_opacity (kurucz.c:605-720) with RLKProfile (kurucz.c:729-828) inlined.
 // lp_colk points at lineprep[col][0][0][k]; line nl / field f is at lp_colk[(nl*LP_NFIELD + f)*ndep].
-template <class ZT>
+// ARM: the table holds lines that are not polarizable (VoigtArmstrong branch); compiled out otherwise, the branch
+// costs the hot kernel 2 % in registers and code even when never taken
+template <bool ARM, class ZT>
 __device__ __forceinline__ void line_sums(LineSums &s, const double lambda, const int to_obs,
                                           const int first, const int count,
                                           const int *__restrict__ widx,
@@ -171,6 +173,8 @@ __device__ __forceinline__ void line_sums(LineSums &s, const double lambda, cons
     const bool polarizable = (__ldg(L + RHB200_RL_POLARIZABLE) != 0.0);
     if (!has_grad) {
       phi = ((fabs(v) <= RH_MAX_GAUSS_DOPPLER) ? rhm::rh_exp(-v*v) : 0.0) * sv;   // kurucz.c:777-778
+    } else if (ARM && !polarizable) {                   // kurucz.c:823-824: Voigt(adamp, v, NULL, ARMSTRONG) * sv
+      phi = rhv::voigt_armstrong(__ldg(P + (size_t) LP_ADAMP*ndep), v) * sv;
     } else {
       const double adamp = __ldg(P + (size_t) LP_ADAMP*ndep), vB = __ldg(P + (size_t) LP_VB*ndep);
       const double sin2_gamma = 1.0 - cos_gamma*cos_gamma;
@@ -213,7 +217,7 @@ __device__ __forceinline__ void line_sums(LineSums &s, const double lambda, cons
 
 // FUSED: total opacity + source vector + reduced propagation matrix per ray-point, written as
 // one 64-byte record {chi_I, K'_Q, K'_U, K'_V, S_I, S_Q, S_U, S_V} at raypts[ray][k].
-template <int MINB, class ZT>
+template <int MINB, class ZT, bool ARM>
 __global__ void __launch_bounds__(128, MINB)
 opacity_fused_kernel(int ncol, int nlambda, int ndep, int to_obs, int nline,
                      const double *__restrict__ lambda, const int *__restrict__ wfirst,
@@ -232,7 +236,7 @@ opacity_fused_kernel(int ncol, int nlambda, int ndep, int to_obs, int nline,
   const double *at = atmos + (size_t) col * RHB200_AT_NFIELD * ndep;
 
   LineSums s;
-  line_sums(s, __ldg(lambda + l), to_obs, __ldg(wfirst + l), __ldg(wcount + l), widx, lines,
+  line_sums<ARM>(s, __ldg(lambda + l), to_obs, __ldg(wfirst + l), __ldg(wcount + l), widx, lines,
             zee, lineprep + (size_t) col*nline*LP_NFIELD*ndep + k, ndep,
             __ldg(at + RHB200_AT_COS_GAMMA*ndep + k), __ldg(at + RHB200_AT_COS_2CHI*ndep + k),
             __ldg(at + RHB200_AT_SIN_2CHI*ndep + k));
@@ -267,7 +271,7 @@ opacity_raw_kernel(int ncol, int nlambda, int ndep, int to_obs, int nline,
   const double *at = atmos + (size_t) col * RHB200_AT_NFIELD * ndep;
   LineSums s;
   const ZeemanGlobal zee{zq, zshift, zstrength};
-  line_sums(s, __ldg(lambda + l), to_obs, __ldg(wfirst + l), __ldg(wcount + l), widx, lines,
+  line_sums<true>(s, __ldg(lambda + l), to_obs, __ldg(wfirst + l), __ldg(wcount + l), widx, lines,
             zee, lineprep + (size_t) col*nline*LP_NFIELD*ndep + k, ndep,
             __ldg(at + RHB200_AT_COS_GAMMA*ndep + k), __ldg(at + RHB200_AT_COS_2CHI*ndep + k),
             __ldg(at + RHB200_AT_SIN_2CHI*ndep + k));
@@ -510,9 +514,15 @@ int rh_launch_opacity_fused(rhb200_ctx *ctx, int ncol, int ndep, int to_obs,
     ScopedKernelTimer t(ctx, RHB200_K_OPACITY);
     static int variant = -1;
     if (variant < 0) { const char *e = getenv("RHB200_OPACITY_MINB"); variant = e ? atoi(e) : 8; }
-#define RH_LAUNCH_OPF(M, ZT, Z) opacity_fused_kernel<M, ZT><<<grid, block, 0, ctx->stream>>>(ncol, ctx->wav.nlambda, ndep, \
-        to_obs, ctx->tab.nline, ctx->wav.lambda, ctx->wav.first, ctx->wav.count, ctx->wav.idx, \
-        ctx->tab.lines, Z, d_atmos, d_lineprep, d_chi_ai, d_eta_ai, d_raypts)
+    bool arm = false;                                     // any line with damping wings that is not polarizable
+    for (int n = 0; n < ctx->tab.nline; n++) {
+      const double *L = ctx->h_lines.data() + (size_t) n * RHB200_RL_NFIELD;
+      arm = arm || (L[RHB200_RL_GRAD] != 0.0 && L[RHB200_RL_POLARIZABLE] == 0.0);
+    }
+#define RH_OPF_ARGS(Z) (ncol, ctx->wav.nlambda, ndep, to_obs, ctx->tab.nline, ctx->wav.lambda, ctx->wav.first, \
+        ctx->wav.count, ctx->wav.idx, ctx->tab.lines, Z, d_atmos, d_lineprep, d_chi_ai, d_eta_ai, d_raypts)
+#define RH_LAUNCH_OPF(M, ZT, Z) do { if (arm) opacity_fused_kernel<M, ZT, true><<<grid, block, 0, ctx->stream>>>RH_OPF_ARGS(Z); \
+        else opacity_fused_kernel<M, ZT, false><<<grid, block, 0, ctx->stream>>>RH_OPF_ARGS(Z); } while (0)
 #define RH_LAUNCH_OPF_V(ZT, Z) switch (variant) {             \
     case 4: RH_LAUNCH_OPF(4, ZT, Z); break;                   \
     case 5: RH_LAUNCH_OPF(5, ZT, Z); break;                   \

@@ -72,7 +72,8 @@ pyrh_rows_kernel(int ncol, int ndep, int nrow_in, int atm_scale, double muz,
 // one thread per column: a column none of whose |v| reaches VMACRO_TRESH is static (atmos.moving = FALSE), and
 // the only thing the LTE path does with atmos.moving is to drop the Doppler shift (kurucz.c:749-754); zeroing
 // the device copy of the velocity row gives the same +0.0 shift
-__global__ void static_cols_kernel(int ncol, int ndep, double vmacro_tresh, double *__restrict__ atmos)
+__global__ void static_cols_kernel(int ncol, int ndep, double vmacro_tresh, double *__restrict__ atmos,
+                                   int *__restrict__ col_moving)
 {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= ncol) return;
@@ -80,6 +81,7 @@ __global__ void static_cols_kernel(int ncol, int ndep, double vmacro_tresh, doub
   bool moving = false;
   for (int k = 0; k < ndep; k++) if (fabs(v[k]) >= vmacro_tresh) { moving = true; break; }
   if (!moving) for (int k = 0; k < ndep; k++) v[k] = 0.0;
+  col_moving[col] = moving ? 1 : 0;      // also selects the solver of unpolarised-line wavelengths (formal.c:100-103)
 }
 
 __global__ void __launch_bounds__(128)
@@ -208,13 +210,13 @@ int rh_launch_rf_diff(rhb200_ctx *c, int v0, int n, int ndep, int nlambda, int n
 }
 
 int rh_launch_pyrh_rows(rhb200_ctx *c, int ncol, int ndep, int nrow_in, int atm_scale, double muz, double vmacro_tresh,
-                        const double *d_in, double *d_atmos)
+                        const double *d_in, double *d_atmos, int *d_col_moving)
 {
   const size_t cn = (size_t) ncol * ndep;
   ScopedKernelTimer t(c, RHB200_K_PREP);
   pyrh_rows_kernel<<<(unsigned) ((cn + 127) / 128), 128, 0, c->stream>>>(ncol, ndep, nrow_in, atm_scale, muz, d_in, d_atmos);
   if (vmacro_tresh > 0.0)
-    static_cols_kernel<<<(unsigned) ((ncol + 63) / 64), 64, 0, c->stream>>>(ncol, ndep, vmacro_tresh, d_atmos);
+    static_cols_kernel<<<(unsigned) ((ncol + 63) / 64), 64, 0, c->stream>>>(ncol, ndep, vmacro_tresh, d_atmos, d_col_moving);
   RH_CUDA(cudaGetLastError());
   return RHB200_OK;
 }

@@ -365,7 +365,41 @@ def read_kurucz_lines(cwd, kw: dict, el: Elements, loggf_ids=None, loggf_values=
                       zstrength=np.array(zst, np.float64), elems=np.array(elems), pf=np.array(pfrows), Tpf=el.Tpf,
                       vmicro_char=float(kw["VMICRO_CHAR"]) * 1.0E+03)
     lt.validate()
+    lt.elem_rows = dict(used)                                    # periodic-table index - 1 -> row of lt.elems
     return lt
+
+
+def read_atom_lines(atom_file):
+    """(ID, [(stage of the lower level, lambda0 [nm], qwing), ...]) of one model atom: the part of readAtom
+    (rh/readatom.c:100-243) rlk_opacity's duplicate check needs (kurucz.c:617-633)."""
+    data = [ln for ln in Path(atom_file).read_text().splitlines() if ln.strip() and ln[0] != "#"]
+    ID = data[0].split()[0][:2].upper().ljust(2)
+    nlevel, nline = (int(x) for x in data[1].split()[:2])
+    E, stage = [], []
+    for ln in data[2:2 + nlevel]:
+        head, tail = ln.split("'")[0].split(), ln.split("'")[2].split()
+        E.append(float(head[0]) * ((HPLANCK * CLIGHT) / CM_TO_M))           # `*=`, readatom.c:175
+        stage.append(int(tail[0]))
+    lines = []
+    for ln in data[2 + nlevel:2 + nlevel + nline]:
+        f = ln.split()
+        j, i = int(f[0]), int(f[1])
+        i, j = min(i, j), max(i, j)
+        lambda0 = (HPLANCK * CLIGHT) / (E[j] - E[i])
+        lines.append((stage[i], lambda0 / NM_TO_M, float(f[7])))
+    return ID, lines
+
+
+def model_line_rows(cwd, kw, el: Elements, lt_elem_order, path=None):
+    """rows for Context.set_model_lines: the lines of every listed model atom whose element also has Kurucz lines."""
+    rows = []
+    atoms_dir = pyrh_path(path) / "rh" / "Atoms"
+    for fname, _ in _atoms_listed(cwd, kw):
+        ID, lines = read_atom_lines(atoms_dir / fname)
+        e = el.ID.index(ID)
+        if e in lt_elem_order:
+            rows += [(lt_elem_order[e], st, lam0, qw) for st, lam0, qw in lines]
+    return np.array(rows, np.float64).reshape(-1, 4)
 
 
 # ------------------------------------------------------------------------------------------- session
@@ -413,6 +447,8 @@ class Session:
         self.lam = sort_lambda(wave, self.lambda_ref)
         self.ctx = api.Context(device)
         self.ctx.set_lines(self.lt, magneto_optical=False, rlkscatter=False)
+        self.model_lines = model_line_rows(cwd, kw, self.el, self.lt.elem_rows, path)
+        self.ctx.set_model_lines(self.model_lines)
         self.ctx.set_wavelengths(self.lam)
         self.ctx.set_solvers(kw["S_INTERPOLATION"], kw["S_INTERPOLATION_STOKES"])
         abundance = np.array([self.el.abund[int(p) - 1] for p in bg["atom_pt_index"]])

@@ -881,3 +881,96 @@ def test_host_compute1d_drop_in():
     assert np.array_equal(np.array(out[:4]), g["stokes_scalar"])
     with pytest.raises(NotImplementedError):
         host.compute1d(str(cwd), 1.0, 0, g["atmosphere"], g["wave"], get_populations=True)
+
+
+def _stage_cwd(tmp_path, kurucz="lines_4016", keywords=None):
+    import shutil
+    root = Path(__file__).resolve().parent.parent
+    src, pp = root / "oracle" / "_ref" / "inputs" / "benchmark", root / "oracle" / "_ref" / "pyrh_path"
+    if not (src / "keyword.input").exists():
+        pytest.skip("reference input files not staged (oracle/_ref)")
+    os.environ["PYRH_PATH"] = str(pp)
+    for f in src.iterdir():
+        if f.is_file() and f.suffix not in (".fits", ".spec", ".py"):
+            shutil.copy(f, tmp_path / f.name)
+    (tmp_path / "kurucz.input").write_text(kurucz + "\n")
+    if keywords:
+        txt = (tmp_path / "keyword.input").read_text()
+        for k, (old, new) in keywords.items():
+            assert f"{k} = {old}" in txt
+            txt = txt.replace(f"{k} = {old}", f"{k} = {new}")
+        (tmp_path / "keyword.input").write_text(txt)
+    return str(tmp_path)
+
+
+def test_many_line_list_with_unpolarizable_lines(tmp_path):
+    """benchmark/lines_4016: 18 Kurucz lines of eight elements in two ionisation stages around 401.7 nm, five of
+    them not polarizable (VoigtArmstrong, kurucz.c:823-824).  Wavelengths with a polarised line go through the Stokes
+    DELO ray, those with unpolarised lines only through the scalar Bezier ray (formal.c:223-236), line-free ones
+    through Feautrier -- all three classes equal the reference's rhf1d() bit for bit, at mu = 1 and mu = 0.7."""
+    from pyrh_b200 import host
+    g = dict(np.load(GOLD / "lines4016.npz"))
+    cwd = _stage_cwd(tmp_path)
+    for name, mu in (("mu1", 1.0), ("mu07", 0.7)):
+        out = host.compute1d(cwd, mu, 0, g["atmosphere"], g["wave"])
+        got, ref, f = np.array(out[:4]), g[name + "_stokes"], g[name + "_backgrflags"]
+        assert np.array_equal(out[4], g["lam"])
+        keep = np.ones(len(f), bool); keep[0] = False           # flags are per spectrum.lambda (lambda_ref first)
+        f = f[keep]
+        for cls, sel in (("polarised", f[:, 1] == 1), ("unpolarised_line", (f[:, 0] == 1) & (f[:, 1] == 0)),
+                         ("no_line", f[:, 0] == 0)):
+            assert sel.sum() > 0
+            exact = bool(np.array_equal(got[:, sel], ref[:, sel]))
+            REPORT[f"lines4016_{name}_{cls}_exact"] = exact
+            eI = float(np.max(np.abs(got[0, sel] / ref[0, sel] - 1)))
+            eP = float(np.max(np.abs(got[1:, sel] - ref[1:, sel])) / ref[0].max())
+            REPORT[f"lines4016_{name}_{cls}_err"] = [eI, eP]
+            # north_star tolerances: I 1e-9 relative, Q/U/V 1e-12 of the continuum.  Bit-exact except where a
+            # damping parameter 1 <= a < 2.5 sends VoigtArmstrong to K2 (atan from the CUDA libm, <= 2 ulp)
+            assert eI < 1e-9 and eP < 1e-12, (cls, eI, eP)
+            if name == "mu1":
+                assert exact, cls
+
+
+def test_static_column_takes_feautrier_on_unpolarised_lines(tmp_path):
+    """VMACRO_TRESH = 0.1 and v = 0: atmos.moving is FALSE, so wavelengths whose lines are all unpolarised are
+    angle independent and solved by Feautrier (formal.c:100-103, 289-309) instead of the scalar Bezier ray."""
+    from pyrh_b200 import host
+    g = dict(np.load(GOLD / "lines4016.npz"))
+    cwd = _stage_cwd(tmp_path, keywords={"VMACRO_TRESH": ("0", "0.1")})
+    out = host.compute1d(cwd, 1.0, 0, g["static_atmosphere"], g["wave"])
+    got, ref = np.array(out[:4]), g["static_stokes"]
+    f = g["mu1_backgrflags"][1:]
+    sel = f[:, 1] == 0                                       # every wavelength solved for I alone: bit-exact
+    assert np.array_equal(got[:, sel], ref[:, sel])
+    moving = host.compute1d(_stage_cwd(tmp_path), 1.0, 0, g["static_atmosphere"], g["wave"])   # VMACRO_TRESH = 0
+    unpol = (f[:, 0] == 1) & (f[:, 1] == 0)
+    assert not np.array_equal(np.array(moving[:4])[0, unpol], got[0, unpol])    # the two solvers do differ
+    # polarised wavelengths: bit-exact except at the cores of the unpolarizable lines in the deepest layers, where
+    # 1 <= a < 2.5 sends VoigtArmstrong to K2 (atan of the CUDA libm): two wavelengths, 1 ulp
+    REPORT["lines4016_static_n_inexact"] = int(np.sum(np.any(got != ref, axis=0)))
+    assert np.max(np.abs(got[0] / ref[0] - 1)) < 1e-9 and np.max(np.abs(got[1:] - ref[1:])) / ref[0].max() < 1e-12
+    assert np.sum(np.any(got != ref, axis=0)) <= 4
+
+
+def test_model_atom_lines_switch_off_kurucz_duplicates(ctx):
+    """rlk_opacity's duplicate check (kurucz.c:617-633): inside the wing window of a line of an explicit model atom,
+    Kurucz lines of the same element and ionisation stage do not contribute (passive_bb accounts for them)."""
+    g = dict(np.load(GOLD / "synth70_c0.npz"))
+    lam = g["lam_spect"][g["lam_keep"]]
+    setup_ctx(ctx, g)
+    first0, count0, _ = ctx.line_windows()
+    assert count0.max() == 2
+    lam0 = g["lt_lines"][0, 0]
+    # a model line of the same element (row 0), stage 0, 0.05 nm to the red, qwing 2: window = lam0 * 2 * 5 km/s / c
+    ctx.set_model_lines([[0, 0, lam0 + 0.05, 2.0]])
+    ctx.set_wavelengths(lam)
+    _, count1, _ = ctx.line_windows()
+    half = (lam0 + 0.05) * 2.0 * (5.0e3 / 2.99792458E+08)
+    inside = np.abs(lam - (lam0 + 0.05)) <= half
+    assert inside.any() and not inside.all()
+    assert np.array_equal(count1[inside], np.zeros(inside.sum(), count1.dtype))
+    assert np.array_equal(count1[~inside], count0[~inside])
+    ctx.set_model_lines([[0, 1, lam0 + 0.05, 2.0]])             # other ionisation stage: no effect
+    ctx.set_wavelengths(lam)
+    assert np.array_equal(ctx.line_windows()[1], count0)
