@@ -308,11 +308,22 @@ int rhb200_lte_stokes_batch_atmos(rhb200_ctx *ctx, int ncol, int ndep, double mu
    index `iref` (sortlambda.c adds it; convertScales looks it up with Locate()); `stokes` [ncol][4][nlambda]
    therefore has one more column than the spectrum _solveray() packs (pyrh_solveray.c:130-150 drops it).
    `wght_per_H` = sum over elements of abundance x atomic weight (abundance.c:186-220).
-   `scales` (may be NULL) [ncol][2][ndep]: height [m] and tau_ref the reference would hold in geometry.height /
-   geometry.tau_ref (not written for atm_scale 2, where the heights are the input). */
+   `scales` (may be NULL) [ncol][3][ndep]: height [m], tau_ref and column mass [kg m^-2] the reference would hold in
+   geometry.height / tau_ref / cmass after convertScales() (for atm_scale 2 the column-mass row needs total_abund
+   and gravity: use rhb200_get_scales_batch). */
 int rhb200_compute1d_batch(rhb200_ctx *ctx, int ncol, int ndep, int nrow, double mu, int atm_scale,
                            const double *atmosphere, int iref, double wght_per_H, double vmacro_tresh,
                            int bc_top, int bc_bottom, double *stokes, double *scales);
+
+/* pyrh.get_scales() for a batch (pyrh.pyx:491-534, rhf1d/pyrh_hse.c:402-553): Background() at the reference
+   wavelength and convertScales(), nothing else.  The reference sets atmos.Nrlk = 0 there, so the context normally
+   holds an empty line table (rhb200_set_lines with nline = 0) and the one-wavelength grid {lam_ref}, iref = 0.
+   total_abund = sum of abundances, gravity = 10^4.4 cm s^-2 in m s^-2 (multiatmos.c:69,82; abundance.c:219) enter
+   the column mass of a height scale (multiatmos.c:153-155).  scales [ncol][3][ndep] = height [m], tau_ref,
+   column mass [kg m^-2]. */
+int rhb200_get_scales_batch(rhb200_ctx *ctx, int ncol, int ndep, int nrow, int atm_scale, const double *atmosphere,
+                            int iref, double wght_per_H, double total_abund, double gravity, double vmacro_tresh,
+                            double *scales);
 
 /* Finite-difference response functions of the LTE Stokes spectrum to the atmosphere rows (BASELINE config 3: T,
    v_LOS, B, inclination, azimuth per depth).  pyrh has no entry point for these: its callers perturb one row at

@@ -223,12 +223,24 @@ class Context:
             raise ValueError("the wavelength grid must contain lambda_ref once (sortlambda.c adds it to spectrum.lambda)")
         iref = int(hit[0])
         st = np.empty((ncol, 4, self.nlambda)) if out is None else out
-        sc = np.empty((ncol, 2, ndep)) if get_scales else None
+        sc = np.empty((ncol, 3, ndep)) if get_scales else None
         _lib.check(self.lib.rhb200_compute1d_batch(self.h, ncol, ndep, nrow, float(mu), int(atm_scale), _vp(a), iref,
                                                    float(wght_per_H), float(vmacro_tresh) * KM_TO_M, int(bc_top),
                                                    int(bc_bottom), _vp(st), _vp(sc) if sc is not None else None))
         res = st if keep_lambda_ref else np.delete(st, iref, axis=2)
         return (res, sc) if get_scales else res
+
+    def get_scales_batch(self, atmosphere, atm_scale=0, lambda_ref=500.0, wght_per_H=0.0, total_abund=0.0,
+                         gravity=None, vmacro_tresh=0.0):
+        """``pyrh.get_scales`` for a batch: ``[ncol, 3, ndep]`` = height [m], tau_ref, column mass [kg m^-2]."""
+        a = np.ascontiguousarray(atmosphere, np.float64)
+        ncol, nrow, ndep = a.shape
+        g = math.exp(2.30258509299404568402 * 4.4) * 1.0E-02 if gravity is None else gravity    # multiatmos.c:69,82
+        sc = np.empty((ncol, 3, ndep))
+        _lib.check(self.lib.rhb200_get_scales_batch(self.h, ncol, ndep, nrow, int(atm_scale), _vp(a), self._iref(lambda_ref),
+                                                    float(wght_per_H), float(total_abund), float(g),
+                                                    float(vmacro_tresh) * KM_TO_M, _vp(sc)))
+        return sc
 
     def _iref(self, lambda_ref):
         hit = np.nonzero(np.asarray(self.lam) == lambda_ref)[0]

@@ -305,13 +305,15 @@ static int *chunk_col_moving(const rhb200_ctx *c, int cc, int ndep, char *ws)
 // pyrh boundary (rhb200_compute1d_batch): the columns arrive as pyrh.compute1d's nine rows
 struct PyrhIn {
   const double *atmosphere; int nrow, atm_scale, iref; double wght_per_H, vmacro_tresh; double *scales;
+  double total_abund = 0.0, gravity = 1.0; int scales_only = 0;      // rhb200_get_scales_batch
   // finite-difference response functions (rhb200_rf_fd_batch): the columns of the call are VIRTUAL -- column
   // v = ((base*npar + p)*ndep + k)*2 + s is base column `base` with row rf_rows[p] changed by +delta (s = 0) or
   // -delta (s = 1) at depth k; they are expanded on the device from d_base and only the differences travel back
   int rf_npar = 0; const int *d_rf_rows = nullptr; const double *d_rf_delta = nullptr; const double *d_base = nullptr;
   double *rf_out = nullptr;
 };
-struct ScalesStep { int iref, atm_scale; double wght_per_H; double *d_scratch, *d_scales_out; };
+struct ScalesStep { int iref, atm_scale; double wght_per_H; double *d_scratch, *d_scales_out;
+                    double total_abund = 0.0, gravity = 1.0; int scales_only = 0; };
 
 static int run_chunk_dev(rhb200_ctx *c, int cc, int ndep, double muz, int moving, int bc_top, int bc_bottom,
                          const double *d_atmos, const double *d_chi_ai, const double *d_eta_ai,
@@ -325,8 +327,9 @@ static int run_chunk_dev(rhb200_ctx *c, int cc, int ndep, double muz, int moving
   RH_CHECK(rh_launch_opacity_fused(c, cc, ndep, 1, d_atmos, d_lineprep, d_chi_ai, d_eta_ai, d_raypts));
   // convertScales() sits between Background() and Iterate() (pyrh_compute1dray.c:310-311): the height row is
   // only read by the formal solvers below
-  if (sc) RH_CHECK(rh_launch_scales(c, cc, ndep, sc->iref, sc->atm_scale, sc->wght_per_H, d_raypts,
-                                    (double *) d_atmos, sc->d_scratch, sc->d_scales_out));
+  if (sc) RH_CHECK(rh_launch_scales(c, cc, ndep, sc->iref, sc->atm_scale, sc->wght_per_H, sc->total_abund, sc->gravity,
+                                    d_raypts, (double *) d_atmos, sc->d_scratch, sc->d_scales_out));
+  if (sc && sc->scales_only) return RHB200_OK;
   RH_CHECK(rh_launch_delo_raypts(c, cc, ndep, muz, bc_top, bc_bottom, d_atmos, d_raypts, d_stokes));
   RH_CHECK(rh_launch_feautrier_raypts(c, cc, ndep, muz, bc_top, bc_bottom, d_atmos, d_raypts, d_stokes,
                                       moving, d_colmov, d_scal));
@@ -377,7 +380,7 @@ static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int mov
   RH_NEED_CTX(c);
   RH_CHECK(check_batch_args(c, ncol, ndep, muz, bc_top, bc_bottom));
   if (ncol == 0) return RHB200_OK;
-  if ((!atmos && !py) || (!stokes && !(py && py->rf_out)) || (!chem && !chem_on_device && (!chi_ai || !eta_ai))) { rhb200_set_error("null buffer"); return RHB200_EINVAL; }
+  if ((!atmos && !py) || (!stokes && !(py && (py->rf_out || py->scales_only))) || (!chem && !chem_on_device && (!chi_ai || !eta_ai))) { rhb200_set_error("null buffer"); return RHB200_EINVAL; }
   const bool cont_dev = chem || chem_on_device;
   if (cont_dev && !c->cont) { rhb200_set_error("rhb200_set_continuum() has not been called"); return RHB200_ESTATE; }
   const int nl = c->wav.nlambda;
@@ -393,7 +396,7 @@ static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int mov
   const size_t b_pp = cont_dev ? align_up((size_t) cc * rh_continuum_nlev(c) * ndep * sizeof(double)) : 0;
   const size_t b_tp = cont_dev ? align_up((size_t) cc * 8 * ndep * sizeof(double)) : 0;
   const size_t b_in = py ? align_up((size_t) cc * py->nrow * ndep * sizeof(double)) : 0;     // pyrh rows as they arrive
-  const size_t b_sc = py ? align_up((size_t) cc * 3 * ndep * sizeof(double)) : 0;            // tau scratch + {height, tau_ref} out
+  const size_t b_sc = py ? align_up((size_t) cc * 5 * ndep * sizeof(double)) : 0;            // {tau, cmass} scratch + {height, tau_ref, cmass} out
   const size_t slot = L.total + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp + b_in + b_sc;
   RH_CHECK(rh_ws_reserve(c, nslots * slot));
   cudaStream_t streams[2] = {c->stream, c->copy_stream};
@@ -447,14 +450,16 @@ static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int mov
       rhb200_set_error("H2D copy failed: %s", cudaGetErrorString(e)); rc = RHB200_ECUDA; break;
     }
     ScalesStep sc{py ? py->iref : 0, py ? py->atm_scale : 0, py ? py->wght_per_H : 0.0, d_sc,
-                  (py && py->scales && py->atm_scale != 2) ? d_sc + (size_t) cc * ndep : nullptr};
+                  (py && py->scales) ? d_sc + (size_t) cc * 2 * ndep : nullptr};
+    if (py) { sc.total_abund = py->total_abund; sc.gravity = py->gravity; sc.scales_only = py->scales_only; }
     rc = run_chunk_dev(c, n, ndep, muz, moving, bc_top, bc_bottom, d_at, d_chi, d_eta, d_st, ws, py ? &sc : nullptr,
                        py && py->vmacro_tresh > 0.0);
     if (rc != RHB200_OK) break;
-    if (sc.d_scales_out && (e = cudaMemcpyAsync(py->scales + (size_t) c0 * 2 * ndep, sc.d_scales_out, (size_t) n * 2 * ndep * sizeof(double),
+    if (sc.d_scales_out && (e = cudaMemcpyAsync(py->scales + (size_t) c0 * 3 * ndep, sc.d_scales_out, (size_t) n * 3 * ndep * sizeof(double),
                                                 cudaMemcpyDeviceToHost, st)) != cudaSuccess) {
       rhb200_set_error("D2H copy failed: %s", cudaGetErrorString(e)); rc = RHB200_ECUDA; break;
     }
+    if (py && py->scales_only) continue;
     if (py && py->rf_npar) {                     // (S+ - S-) / (2 delta); d_chi is free once the opacity kernel has run
       rc = rh_launch_rf_diff(c, c0, n, ndep, nl, py->rf_npar, py->d_rf_delta, d_st, d_chi);
       if (rc != RHB200_OK) break;
@@ -514,6 +519,22 @@ extern "C" int rhb200_compute1d_batch(rhb200_ctx *c, int ncol, int ndep, int nro
   if (!(wght_per_H > 0.0) && atm_scale == 1) { rhb200_set_error("wght_per_H (abundance.c:220) is needed for the column-mass scale"); return RHB200_EINVAL; }
   PyrhIn py{atmosphere, nrow, atm_scale, iref, wght_per_H, vmacro_tresh, scales};
   return lte_batch_host(c, ncol, ndep, mu, 1, bc_top, bc_bottom, nullptr, nullptr, nullptr, nullptr, stokes, 1, &py);
+}
+
+// pyrh.get_scales() (pyrh.pyx:491-534, rhf1d/pyrh_hse.c:402-553) for a batch: Background() at the reference
+// wavelength + convertScales(); the context's line table is normally empty (the reference sets Nrlk = 0 there)
+extern "C" int rhb200_get_scales_batch(rhb200_ctx *c, int ncol, int ndep, int nrow, int atm_scale,
+                                       const double *atmosphere, int iref, double wght_per_H, double total_abund,
+                                       double gravity, double vmacro_tresh, double *scales)
+{
+  RH_NEED_CTX(c);
+  if (!atmosphere || !scales) { rhb200_set_error("null buffer"); return RHB200_EINVAL; }
+  if (nrow < 9 || atm_scale < 0 || atm_scale > 2 || iref < 0 || iref >= c->wav.nlambda) { rhb200_set_error("bad arguments"); return RHB200_EINVAL; }
+  if (!(wght_per_H > 0.0) || !(total_abund > 0.0) || !(gravity > 0.0)) { rhb200_set_error("wght_per_H, total_abund (abundance.c:219-220) and gravity [m/s^2] must be positive"); return RHB200_EINVAL; }
+  PyrhIn py{atmosphere, nrow, atm_scale, iref, wght_per_H, vmacro_tresh, scales};
+  py.total_abund = total_abund; py.gravity = gravity; py.scales_only = 1;
+  return lte_batch_host(c, ncol, ndep, 1.0, 1, RHB200_BC_ZERO, RHB200_BC_THERMALIZED, nullptr, nullptr, nullptr, nullptr,
+                        nullptr, 1, &py);
 }
 
 // ------------------------------------------------ function-level entry points

@@ -123,7 +123,7 @@ int rh_launch_rf_diff(rhb200_ctx *ctx, int v0, int n, int ndep, int nlambda, int
                       const double *d_stokes, double *d_rf);
 int rh_launch_proton(rhb200_ctx *ctx, int ncol, int ndep, int nlev, int proton_level, const double *d_pops, double *d_atmos);
 int rh_launch_scales(rhb200_ctx *ctx, int ncol, int ndep, int iref, int atm_scale, double wght_per_H,
-                     const double *d_raypts, double *d_atmos, double *d_scratch, double *d_scales_out);
+                     double total_abund, double gravity, const double *d_raypts, double *d_atmos, double *d_scratch, double *d_scales_out);
 int rh_continuum_chunk(rhb200_ctx *ctx, int cc, int ndep, const double *d_atmos, const double *d_chem,
                        double *d_pops, double *d_tprep, double *d_chi, double *d_eta, int chem_on_device);
 

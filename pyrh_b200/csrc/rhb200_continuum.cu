@@ -317,7 +317,8 @@ continuum_kernel(int ncol, int nlambda, int ndep, DevModel M,
 // wavelength; every wavelength keeps its own accumulators and receives its terms in the same order, so the
 // sums are bit-identical to continuum_kernel's.  Tiles whose wavelengths do not share the same open edges fall
 // back to the per-wavelength walk.
-__global__ void __launch_bounds__(128, 8)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
 continuum_tile_kernel(int ncol, int nlambda, int ndep, DevModel M,
                       const double *__restrict__ T, const double *__restrict__ ne, size_t astride,
                       const double *__restrict__ nHmin, const double *__restrict__ nH2, const double *__restrict__ nOH,
@@ -426,7 +427,9 @@ continuum_tile_kernel(int ncol, int nlambda, int ndep, DevModel M,
         }
       }
     } else {
-      for (int q = 0; q < nl; q++) {
+#pragma unroll
+      for (int q = 0; q < CONT_TL; q++) {                  // static indices: the per-wavelength arrays stay in registers
+        if (q >= nl) continue;
         const double *W = shW[q];
         const int first = (int) W[FI], cnt = (int) W[CI];
         double chi = 0.0, eta = 0.0;
@@ -1204,10 +1207,18 @@ int rh_continuum_chunk(rhb200_ctx *c, int cc, int ndep, const double *d_atmos, c
     const size_t as = (size_t) RHB200_AT_NFIELD * ndep, cs = (size_t) (na + 4) * ndep;
     const size_t nck = (cn + 127) / 128;
     if (nck > 65535) { rhb200_set_error("chunk too large for the continuum kernel grid"); return RHB200_EINVAL; }
-    continuum_tile_kernel<<<dim3((unsigned) ntile, (unsigned) nck), 128, 0, c->stream>>>(cc, S->nlambda, ndep, S->D,
-        d_atmos + (size_t) RHB200_AT_T * ndep, d_atmos + (size_t) RHB200_AT_NE * ndep, as,
-        d_chem + (size_t) na * ndep, d_chem + (size_t) (na + 1) * ndep, d_chem + (size_t) (na + 2) * ndep,
-        d_chem + (size_t) (na + 3) * ndep, cs, d_pops, d_pops, d_tprep, d_chi, d_eta);
+    static int minb = -1;                                   // RHB200_CONT_MINB: occupancy / spill trade-off
+    if (minb < 0) { const char *e = getenv("RHB200_CONT_MINB"); minb = e ? atoi(e) : 8; }
+#define RH_CONT_ARGS (cc, S->nlambda, ndep, S->D, d_atmos + (size_t) RHB200_AT_T * ndep, d_atmos + (size_t) RHB200_AT_NE * ndep, as, d_chem + (size_t) na * ndep, d_chem + (size_t) (na + 1) * ndep, d_chem + (size_t) (na + 2) * ndep, d_chem + (size_t) (na + 3) * ndep, cs, d_pops, d_pops, d_tprep, d_chi, d_eta)
+    const dim3 grid((unsigned) ntile, (unsigned) nck);
+    switch (minb) {
+    case 4: continuum_tile_kernel<4><<<grid, 128, 0, c->stream>>>RH_CONT_ARGS; break;
+    case 5: continuum_tile_kernel<5><<<grid, 128, 0, c->stream>>>RH_CONT_ARGS; break;
+    case 6: continuum_tile_kernel<6><<<grid, 128, 0, c->stream>>>RH_CONT_ARGS; break;
+    default: continuum_tile_kernel<8><<<grid, 128, 0, c->stream>>>RH_CONT_ARGS; break;
+    }
+#undef RH_CONT_ARGS
+
   }
   RH_CUDA(cudaGetLastError());
   return RHB200_OK;

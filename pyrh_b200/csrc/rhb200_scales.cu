@@ -96,64 +96,83 @@ proton_kernel(int ncol, int ndep, int nlev, int proton_level, const double *__re
 // one thread per column, sequential in depth like the reference.  chi_ref = total opacity at the reference
 // wavelength (spectrum.chi_c_lam[ref_index], readj.c:319: the last record written for that wavelength, i.e.
 // continuum + lines of the up-ray), read from the ray-point records of wavelength iref.
-// scratch [ncol][ndep] keeps tau_ref (COLUMN_MASS) for the Linear() look-up.
+// scratch [ncol][2][ndep] keeps tau_ref and cmass; scales_out [ncol][3][ndep] = height, tau_ref, cmass.
 __global__ void scales_kernel(int ncol, int ndep, int nlambda, int iref, int atm_scale, double wght_per_H,
+                              double total_abund, double gravity,
                               const double *__restrict__ raypts, double *__restrict__ atmos,
                               double *__restrict__ scratch, double *__restrict__ scales_out)
 {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= ncol) return;
+  const double *at = atmos + (size_t) col * RHB200_AT_NFIELD * ndep;
   double *height = atmos + ((size_t) col * RHB200_AT_NFIELD + RHB200_AT_HEIGHT) * ndep;
-  const double *nHtot = atmos + ((size_t) col * RHB200_AT_NFIELD + RHB200_AT_NHTOT) * ndep;
+  const double *nHtot = at + (size_t) RHB200_AT_NHTOT * ndep;
   const double *rp = raypts + ((size_t) col * nlambda + iref) * ndep * RP_NFIELD + RP_CHI;
-  double *tau = scratch + (size_t) col * ndep;
+  double *tau = scratch + (size_t) col * 2 * ndep, *cmass = tau + ndep;
 #define CHI(k) rp[(size_t) (k) * RP_NFIELD]
 #define RHO(k) ((RH_AMU * wght_per_H) * nHtot[k])
   if (atm_scale == 0) {                                  // TAU500, multiatmos.c:140-151; height row holds tau_ref
     double tprev = height[0], hprev = 0.0;
     tau[0] = tprev;
     height[0] = 0.0;
+    double cprev = (tprev / CHI(0)) * RHO(0);
+    cmass[0] = cprev;
     for (int k = 1; k < ndep; k++) {
       const double tk = height[k];
       tau[k] = tk;
       const double hk = hprev - 2.0 * (tk - tprev) / (CHI(k-1) + CHI(k));
-      height[k] = hk;
-      hprev = hk; tprev = tk;
+      const double ck = cprev + 0.5*(RHO(k-1) + RHO(k)) * (hprev - hk);
+      height[k] = hk; cmass[k] = ck;
+      hprev = hk; tprev = tk; cprev = ck;
     }
-  } else {                                               // COLUMN_MASS, :128-138; height row holds cmass
+  } else if (atm_scale == 1) {                           // COLUMN_MASS, :128-138; height row holds cmass
     double cprev = height[0], hprev = 0.0;
     double tprev = CHI(0) / RHO(0) * cprev;
-    tau[0] = tprev;
+    tau[0] = tprev; cmass[0] = cprev;
     height[0] = 0.0;
     for (int k = 1; k < ndep; k++) {
       const double ck = height[k];
       const double hk = hprev - 2.0*(ck - cprev) / (RHO(k-1) + RHO(k));
       const double tk = tprev + 0.5*(CHI(k-1) + CHI(k)) * (hprev - hk);
-      height[k] = hk; tau[k] = tk;
+      height[k] = hk; tau[k] = tk; cmass[k] = ck;
       hprev = hk; cprev = ck; tprev = tk;
     }
-  }
-  // Linear(Ndep, tau_ref, height, 1, &unity, &h_zero, FALSE), multiatmos.c:166-173
-  const double unity = 1.0;
-  double h_zero;
-  const bool ascend = tau[1] > tau[0];
-  const double xmin = ascend ? tau[0] : tau[ndep-1], xmax = ascend ? tau[ndep-1] : tau[0];
-  if (unity <= xmin)      h_zero = ascend ? height[0] : height[ndep-1];
-  else if (unity >= xmax) h_zero = ascend ? height[ndep-1] : height[0];
-  else {
-    const bool asc2 = tau[ndep-1] > tau[0];              // Locate(), hunt.c:97
-    int lo = 0, hi = ndep;
-    while (hi - lo > 1) {
-      const int mid = (hi + lo) >> 1;
-      if (asc2 ? (unity >= tau[mid]) : (unity <= tau[mid])) lo = mid; else hi = mid;
+  } else {                                               // GEOMETRIC, :153-163: heights stay as they came
+    const double *T = at + (size_t) RHB200_AT_T * ndep, *ne = at + (size_t) RHB200_AT_NE * ndep;
+    double cprev = (nHtot[0] * total_abund + ne[0]) * (RH_KBOLTZMANN * T[0] / gravity);
+    double tprev = 0.5 * CHI(0) * (height[0] - height[1]);
+    if (tprev > 1.0) tprev = 0.0;
+    cmass[0] = cprev; tau[0] = tprev;
+    for (int k = 1; k < ndep; k++) {
+      const double ck = cprev + 0.5*(RHO(k-1) + RHO(k)) * (height[k-1] - height[k]);
+      const double tk = tprev + 0.5*(CHI(k-1) + CHI(k)) * (height[k-1] - height[k]);
+      cmass[k] = ck; tau[k] = tk;
+      cprev = ck; tprev = tk;
     }
-    const double fx = (tau[lo+1] - unity) / (tau[lo+1] - tau[lo]);
-    h_zero = fx*height[lo] + (1 - fx)*height[lo+1];
   }
-  for (int k = 0; k < ndep; k++) height[k] = height[k] - h_zero;
+  if (atm_scale != 2) {
+    // Linear(Ndep, tau_ref, height, 1, &unity, &h_zero, FALSE), multiatmos.c:166-173
+    const double unity = 1.0;
+    double h_zero;
+    const bool ascend = tau[1] > tau[0];
+    const double xmin = ascend ? tau[0] : tau[ndep-1], xmax = ascend ? tau[ndep-1] : tau[0];
+    if (unity <= xmin)      h_zero = ascend ? height[0] : height[ndep-1];
+    else if (unity >= xmax) h_zero = ascend ? height[ndep-1] : height[0];
+    else {
+      const bool asc2 = tau[ndep-1] > tau[0];              // Locate(), hunt.c:97
+      int lo = 0, hi = ndep;
+      while (hi - lo > 1) {
+        const int mid = (hi + lo) >> 1;
+        if (asc2 ? (unity >= tau[mid]) : (unity <= tau[mid])) lo = mid; else hi = mid;
+      }
+      const double fx = (tau[lo+1] - unity) / (tau[lo+1] - tau[lo]);
+      h_zero = fx*height[lo] + (1 - fx)*height[lo+1];
+    }
+    for (int k = 0; k < ndep; k++) height[k] = height[k] - h_zero;
+  }
   if (scales_out) {
-    double *o = scales_out + (size_t) col * 2 * ndep;
-    for (int k = 0; k < ndep; k++) { o[k] = height[k]; o[ndep + k] = tau[k]; }
+    double *o = scales_out + (size_t) col * 3 * ndep;
+    for (int k = 0; k < ndep; k++) { o[k] = height[k]; o[ndep + k] = tau[k]; o[2*ndep + k] = cmass[k]; }
   }
 #undef CHI
 #undef RHO
@@ -231,12 +250,13 @@ int rh_launch_proton(rhb200_ctx *c, int ncol, int ndep, int nlev, int proton_lev
 }
 
 int rh_launch_scales(rhb200_ctx *c, int ncol, int ndep, int iref, int atm_scale, double wght_per_H,
+                     double total_abund, double gravity,
                      const double *d_raypts, double *d_atmos, double *d_scratch, double *d_scales_out)
 {
-  if (atm_scale == 2) return RHB200_OK;                  // GEOMETRIC: the heights are the input
+  if (atm_scale == 2 && !d_scales_out) return RHB200_OK; // GEOMETRIC: the heights are the input
   ScopedKernelTimer t(c, RHB200_K_PREP);
   scales_kernel<<<(unsigned) ((ncol + 31) / 32), 32, 0, c->stream>>>(ncol, ndep, c->wav.nlambda, iref, atm_scale, wght_per_H,
-                                                                    d_raypts, d_atmos, d_scratch, d_scales_out);
+                                                                    total_abund, gravity, d_raypts, d_atmos, d_scratch, d_scales_out);
   RH_CUDA(cudaGetLastError());
   return RHB200_OK;
 }

@@ -475,6 +475,34 @@ class Session:
         self.ctx.close()
 
 
+def get_scales(cwd, atm_scale, scale, atmosphere, lam_ref, atomic_number=None, atomic_abundance=None, device=0):
+    """Drop-in for ``pyrh.get_scales`` (pyrh.pyx:491-534): ``(tau, height [m], cmass [kg m^-2])`` of one column from
+    Background() at ``lam_ref`` and convertScales().  Like the reference it looks at no Kurucz line
+    (pyrh_hse.c:441) and takes the depth scale from ``scale`` (``atmosphere`` row 0 is ignored)."""
+    from . import api, continuum
+    kw = read_keywords(cwd)
+    el = read_elements(None, kw, atomic_number, atomic_abundance)
+    bg = dict(np.load(DATA / "background_falc11.npz"))
+    if [a for a, _ in _atoms_listed(cwd, kw)] != [str(x) for x in bg["atom_files"]]:
+        raise NotImplementedError("only the standard background atom set ships with pyrh_b200.host")
+    ctx = api.Context(device)
+    try:
+        empty = ll.LineTable(lines=np.zeros((0, ll.RL_NFIELD)), zq=np.zeros(0, np.int32), zshift=np.zeros(0),
+                             zstrength=np.zeros(0), elems=np.zeros((0, ll.RE_NFIELD)), pf=np.zeros((0, len(el.Tpf))),
+                             Tpf=el.Tpf, vmicro_char=float(kw["VMICRO_CHAR"]) * 1.0E+03)
+        ctx.set_lines(empty)
+        ctx.set_wavelengths(np.array([float(lam_ref)]))
+        ctx.set_continuum(continuum.ContinuumModel(bg), np.array([el.abund[int(p) - 1] for p in bg["atom_pt_index"]]))
+        ctx.set_chemistry(bg["ce_nuclei"][:, 1].astype(np.int32), bg["ce_mol"])
+        a = np.array(atmosphere, np.float64)[None, :9].copy()
+        a[0, 0] = scale
+        sc = ctx.get_scales_batch(a, atm_scale, float(lam_ref), el.wght_per_H, el.totalAbund,
+                                  vmacro_tresh=float(kw["VMACRO_TRESH"]))[0]
+    finally:
+        ctx.close()
+    return sc[1], sc[0], sc[2]
+
+
 _SESSIONS: dict = {}
 
 

@@ -974,3 +974,46 @@ def test_model_atom_lines_switch_off_kurucz_duplicates(ctx):
     ctx.set_model_lines([[0, 1, lam0 + 0.05, 2.0]])             # other ionisation stage: no effect
     ctx.set_wavelengths(lam)
     assert np.array_equal(ctx.line_windows()[1], count0)
+
+
+def test_chunking_does_not_change_results(ctx, monkeypatch):
+    """Edge cases of the batched entry points: empty batch, one column, and chunk sizes that do not divide the
+    batch (RHB200_CHUNK_COLS = 3: ragged last chunk; the response-function path keeps +-delta pairs together)."""
+    p = dict(np.load(GOLD / "pyrh_scales.npz"))
+    _pyrh_ctx(ctx, p["tau_lambda"])
+    w = float(p["tau_abund_sums"][0])
+    gs = [np.load(GOLD / f"synth70_c{c}.npz")["atmosphere"] for c in range(3)]
+    atm = np.stack([gs[c % 3] for c in range(8)])
+    assert ctx.compute1d_batch(atm[:0], wght_per_H=w).shape == (0, 4, 301)
+    whole = ctx.compute1d_batch(atm, wght_per_H=w)
+    assert np.array_equal(ctx.compute1d_batch(atm[5:6], wght_per_H=w)[0], whole[5])
+    rows, delta = np.array([1, 5], np.int32), np.array([2.0, 5.0])
+    rf_whole = ctx.rf_fd_batch(atm[:2], rows, delta, wght_per_H=w)
+    monkeypatch.setenv("RHB200_CHUNK_COLS", "3")
+    assert np.array_equal(ctx.compute1d_batch(atm, wght_per_H=w), whole)
+    assert np.array_equal(ctx.rf_fd_batch(atm[:2], rows, delta, wght_per_H=w), rf_whole)
+    for c in range(3):
+        assert np.array_equal(whole[c], np.load(GOLD / f"synth70_c{c}.npz")["stokes_scalar"])
+
+
+def test_get_scales_drop_in():
+    """pyrh_b200.host.get_scales = pyrh.get_scales (pyrh.pyx:491-534): Background() at lam_ref + convertScales() for
+    log tau500, log column mass and height input; every returned array equals the reference's bit for bit
+    (fixture get_scales, oracle/gen_golden_get_scales.py)."""
+    from pyrh_b200 import host
+    root = Path(__file__).resolve().parent.parent
+    cwd, pp = root / "oracle" / "_ref" / "inputs" / "benchmark", root / "oracle" / "_ref" / "pyrh_path"
+    if not (cwd / "keyword.input").exists():
+        pytest.skip("reference input files not staged (oracle/_ref)")
+    os.environ["PYRH_PATH"] = str(pp)
+    g = dict(np.load(GOLD / "get_scales.npz"))
+    a = g["tau_atmosphere"]
+    tau, height, cmass = host.get_scales(str(cwd), 0, a[0], a, 500.0)
+    assert np.array_equal(height, g["tau_height"]) and np.array_equal(cmass, g["tau_cmass"])
+    a = g["cmass_atmosphere"]
+    tau, height, cmass = host.get_scales(str(cwd), 1, a[0], a, 500.0)
+    assert np.array_equal(height, g["cmass_height"]) and np.array_equal(tau, g["cmass_tau"])
+    a = g["height_atmosphere"]
+    tau, height, cmass = host.get_scales(str(cwd), 2, a[0], a, 500.0)
+    assert np.array_equal(tau, g["height_tau"]) and np.array_equal(cmass, g["height_cmass"])
+    assert np.array_equal(height, a[0] * 1.0e3)
