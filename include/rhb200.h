@@ -325,6 +325,17 @@ int rhb200_get_scales_batch(rhb200_ctx *ctx, int ncol, int ndep, int nrow, int a
                             int iref, double wght_per_H, double total_abund, double gravity, double vmacro_tresh,
                             double *scales);
 
+/* Electron density from the LTE ionisation equilibrium of all elements: Solve_ne (rh/solvene.c:55-140), the
+   computation behind pyrh.get_ne_from_nH (pyrh.pyx:396-425, rhf1d/pyrh_hse.c:555-677: Background(FALSE, TRUE) with
+   SOLVE_NE = ONCE, hydrogen in LTE).  rhb200_set_elements hands over atmos.elements[] -- all elements of the
+   periodic table, hydrogen first, rows RHB200_RE_* as in rhb200_set_lines, pf = ln U [npf_rows][npf] -- once;
+   rhb200_solve_ne_batch solves n independent depth points: T [K], nHtot [m^-3] in, ne [m^-3] out (and starting
+   guess when fromscratch == 0). */
+int rhb200_set_elements(rhb200_ctx *ctx, int nelem, const double *elems, int npf_rows, int npf,
+                        const double *pf, const double *Tpf);
+int rhb200_solve_ne_batch(rhb200_ctx *ctx, size_t n, const double *T, const double *nHtot, double *ne,
+                          int fromscratch);
+
 /* Finite-difference response functions of the LTE Stokes spectrum to the atmosphere rows (BASELINE config 3: T,
    v_LOS, B, inclination, azimuth per depth).  pyrh has no entry point for these: its callers perturb one row at
    one depth by +-delta and call pyrh.compute1d twice (2 x npar x ndep calls per column); this does the same for a

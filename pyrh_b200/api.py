@@ -230,6 +230,22 @@ class Context:
         res = st if keep_lambda_ref else np.delete(st, iref, axis=2)
         return (res, sc) if get_scales else res
 
+    def set_elements(self, elems, pf, Tpf):
+        """atmos.elements[] for Solve_ne: ``elems[nelem, RE_NFIELD]`` (hydrogen first), ``pf[rows, npf]`` = ln U."""
+        elems = np.ascontiguousarray(elems, np.float64)
+        pf = np.ascontiguousarray(pf, np.float64)
+        Tpf = np.ascontiguousarray(Tpf, np.float64)
+        _lib.check(self.lib.rhb200_set_elements(self.h, len(elems), _dp(elems), len(pf), pf.shape[1], _dp(pf), _dp(Tpf)))
+
+    def solve_ne(self, T, nHtot, ne0=None):
+        """Solve_ne (solvene.c:55-140) at every point of ``T`` / ``nHtot`` [K, m^-3] -> ne [m^-3]; ``ne0`` = starting
+        guess (else from scratch: ionisation of hydrogen alone)."""
+        T = np.ascontiguousarray(T, np.float64)
+        nH = np.ascontiguousarray(nHtot, np.float64)
+        ne = np.zeros(T.shape) if ne0 is None else np.array(ne0, np.float64, copy=True)
+        _lib.check(self.lib.rhb200_solve_ne_batch(self.h, T.size, _dp(T), _dp(nH), _dp(ne), int(ne0 is None)))
+        return ne
+
     def get_scales_batch(self, atmosphere, atm_scale=0, lambda_ref=500.0, wght_per_H=0.0, total_abund=0.0,
                          gravity=None, vmacro_tresh=0.0):
         """``pyrh.get_scales`` for a batch: ``[ncol, 3, ndep]`` = height [m], tau_ref, column mass [kg m^-2]."""

@@ -14,7 +14,7 @@ from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB = CSRC / "librhb200.so"
-SOURCES = ["rhb200_abi.cu", "rhb200_lines.cu", "rhb200_delo.cu", "rhb200_peak.cu", "rhb200_nlte.cu", "rhb200_zeeman.cu", "rhb200_continuum.cu", "rhb200_scales.cu"]
+SOURCES = ["rhb200_abi.cu", "rhb200_lines.cu", "rhb200_delo.cu", "rhb200_peak.cu", "rhb200_nlte.cu", "rhb200_zeeman.cu", "rhb200_continuum.cu", "rhb200_scales.cu", "rhb200_hse.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",

@@ -81,6 +81,7 @@ struct rhb200_ctx {
   // wavelength shard of the NLTE solve (rhb200_nlte_set_shard)
   int shard_rank = 0, shard_nrank = 1;
   rhb200_allreduce_fn shard_fn = nullptr; void *shard_user = nullptr;
+  void *elements = nullptr;  // all elements + partition functions (rhb200_set_elements), owned by rhb200_hse.cu
   void *cont = nullptr;      // background-continuum state (rhb200_set_continuum), owned by rhb200_continuum.cu
   // workspace (grown on demand)
   void *ws = nullptr; size_t ws_bytes = 0;
@@ -112,6 +113,7 @@ struct ScopedKernelTimer {
 
 int rh_ws_reserve(rhb200_ctx *ctx, size_t bytes);
 void rh_continuum_free(rhb200_ctx *ctx);
+void rh_elements_free(rhb200_ctx *ctx);
 int rh_continuum_nlev(const rhb200_ctx *ctx);
 int rh_continuum_natom(const rhb200_ctx *ctx);
 int rh_continuum_proton_level(const rhb200_ctx *ctx);

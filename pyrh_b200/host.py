@@ -503,6 +503,42 @@ def get_scales(cwd, atm_scale, scale, atmosphere, lam_ref, atomic_number=None, a
     return sc[1], sc[0], sc[2]
 
 
+def element_table(el: Elements):
+    """All elements as RHB200_RE_* rows + their ln U rows (for Context.set_elements)."""
+    rows, pfrows = [], []
+    for e in range(len(el.ID)):
+        nst = int(el.nstage[e])
+        if nst > ll.RE_MAXSTAGE:
+            raise ValueError(f"element {el.ID[e]}: {nst} ionisation stages exceed RE_MAXSTAGE")
+        r = np.zeros(ll.RE_NFIELD)
+        r[ll.RE_WEIGHT], r[ll.RE_ABUND], r[ll.RE_NSTAGE], r[ll.RE_PFROW] = el.weight[e], el.abund[e], nst, len(pfrows)
+        r[ll.RE_IONPOT0:ll.RE_IONPOT0 + nst] = el.ionpot[e]
+        pfrows += list(el.pf[e])
+        rows.append(r)
+    return np.array(rows), np.array(pfrows)
+
+
+def get_ne_from_nH(cwd, atm_scale, scale, temperature, nH, device=0):
+    """Drop-in for ``pyrh.get_ne_from_nH`` (pyrh.pyx:396-425): electron density [cm^-3] from temperature [K] and total
+    hydrogen density [cm^-3] by the LTE ionisation equilibrium of all elements (Solve_ne from scratch, hydrogen in
+    LTE).  ``atm_scale`` / ``scale`` are accepted like the reference's and, like there, do not enter the result."""
+    from . import api
+    kw = read_keywords(cwd)
+    el = read_elements(None, kw)
+    if not el.abundance_set.all():
+        raise NotImplementedError("elements without an abundance: the reference feeds their raw partition functions "
+                                  "into Solve_ne (abundance.c:207-215); not reproduced")
+    ctx = api.Context(device)
+    try:
+        ctx.set_elements(*element_table(el), el.Tpf)
+        CUBE_CM = 1.0E-02 * 1.0E-02 * 1.0E-02
+        nHtot = np.array([x / CUBE_CM for x in np.asarray(nH, np.float64)])          # pyrh_hse.c:626
+        ne = ctx.solve_ne(np.asarray(temperature, np.float64), nHtot)
+    finally:
+        ctx.close()
+    return np.array([x * CUBE_CM for x in ne])                                       # pyrh_hse.c:647
+
+
 _SESSIONS: dict = {}
 
 

@@ -1017,3 +1017,20 @@ def test_get_scales_drop_in():
     tau, height, cmass = host.get_scales(str(cwd), 2, a[0], a, 500.0)
     assert np.array_equal(tau, g["height_tau"]) and np.array_equal(cmass, g["height_cmass"])
     assert np.array_equal(height, a[0] * 1.0e3)
+
+
+def test_get_ne_from_nH_drop_in():
+    """pyrh_b200.host.get_ne_from_nH = pyrh.get_ne_from_nH (Solve_ne over all 99 elements, solvene.c:55-140): the
+    electron densities equal the reference's bit for bit (fixture ne_hse, oracle/gen_golden_ne.py)."""
+    from pyrh_b200 import host
+    root = Path(__file__).resolve().parent.parent
+    cwd, pp = root / "oracle" / "_ref" / "inputs" / "benchmark", root / "oracle" / "_ref" / "pyrh_path"
+    if not (cwd / "keyword.input").exists():
+        pytest.skip("reference input files not staged (oracle/_ref)")
+    os.environ["PYRH_PATH"] = str(pp)
+    g = dict(np.load(GOLD / "ne_hse.npz"))
+    for c in (0, 1):
+        ne = host.get_ne_from_nH(str(cwd), 0, np.zeros(70), g[f"c{c}_T"], g[f"c{c}_nH"])
+        REPORT[f"get_ne_from_nH_c{c}_exact"] = bool(np.array_equal(ne, g[f"c{c}_ne"]))
+        assert np.max(np.abs(ne / g[f"c{c}_ne"] - 1)) < 1e-12
+        assert np.array_equal(ne, g[f"c{c}_ne"])
