@@ -336,6 +336,19 @@ int rhb200_set_elements(rhb200_ctx *ctx, int nelem, const double *elems, int npf
 int rhb200_solve_ne_batch(rhb200_ctx *ctx, size_t n, const double *T, const double *nHtot, double *ne,
                           int fromscratch);
 
+/* pyrh.hse (pyrh.pyx:427-489; hse(), rhf1d/pyrh_hse.c:67-400) for a batch of columns: the gas pressure, electron
+   density, total hydrogen density and mass density of an atmosphere in hydrostatic equilibrium, from its
+   temperature run on a tau500 (atm_scale 0, scale = log10 tau500) or height (atm_scale 2, scale in km) grid and the
+   gas pressure at the top.  Per layer, top down, the reference iterates {rho, get_ne() from scratch, LTE populations,
+   ChemicalEquilibrium, pyrh_Background() = the 500 nm continuum without Metal_bf but with Thomson and Rayleigh
+   scattering, pressure integration, new nHtot} until nHtot changes by <= 1 %; every step of that walk is a kernel
+   over all columns here.  Needs rhb200_set_elements, the one-wavelength grid {500 nm} (rhb200_set_lines with
+   nline = 0, rhb200_set_wavelengths), rhb200_set_continuum and rhb200_set_chemistry.
+   scale, T [ncol][ndep]; pg_top [ncol] in Pa; outputs [ncol][ndep] in SI (m^-3, kg m^-3, Pa) like the reference's. */
+int rhb200_hse_batch(rhb200_ctx *ctx, int ncol, int ndep, int atm_scale, const double *scale, const double *T,
+                     const double *pg_top, double wght_per_H, double total_abund, double gravity,
+                     double *ne, double *nHtot, double *rho, double *pg);
+
 /* Finite-difference response functions of the LTE Stokes spectrum to the atmosphere rows (BASELINE config 3: T,
    v_LOS, B, inclination, azimuth per depth).  pyrh has no entry point for these: its callers perturb one row at
    one depth by +-delta and call pyrh.compute1d twice (2 x npar x ndep calls per column); this does the same for a

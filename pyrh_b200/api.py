@@ -246,6 +246,18 @@ class Context:
         _lib.check(self.lib.rhb200_solve_ne_batch(self.h, T.size, _dp(T), _dp(nH), _dp(ne), int(ne0 is None)))
         return ne
 
+    def hse_batch(self, scale, T, pg_top, atm_scale=0, wght_per_H=0.0, total_abund=0.0, gravity=None):
+        """``pyrh.hse`` for a batch: ``scale``, ``T`` [ncol, ndep], ``pg_top`` [ncol] (Pa) -> ne, nHtot, rho, pg (SI)."""
+        scale = np.ascontiguousarray(scale, np.float64)
+        T = np.ascontiguousarray(T, np.float64)
+        ncol, ndep = T.shape
+        pg_top = np.ascontiguousarray(np.broadcast_to(np.asarray(pg_top, np.float64), (ncol,)))
+        g = math.exp(2.30258509299404568402 * 4.4) * 1.0E-02 if gravity is None else gravity    # multiatmos.c:69,82
+        out = [np.empty((ncol, ndep)) for _ in range(4)]
+        _lib.check(self.lib.rhb200_hse_batch(self.h, ncol, ndep, int(atm_scale), _dp(scale), _dp(T), _dp(pg_top),
+                                             float(wght_per_H), float(total_abund), float(g), *[_dp(o) for o in out]))
+        return tuple(out)
+
     def get_scales_batch(self, atmosphere, atm_scale=0, lambda_ref=500.0, wght_per_H=0.0, total_abund=0.0,
                          gravity=None, vmacro_tresh=0.0):
         """``pyrh.get_scales`` for a batch: ``[ncol, 3, ndep]`` = height [m], tau_ref, column mass [kg m^-2]."""

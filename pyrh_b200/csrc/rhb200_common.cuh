@@ -117,6 +117,9 @@ void rh_elements_free(rhb200_ctx *ctx);
 int rh_continuum_nlev(const rhb200_ctx *ctx);
 int rh_continuum_natom(const rhb200_ctx *ctx);
 int rh_continuum_proton_level(const rhb200_ctx *ctx);
+void rh_continuum_set_hse_mode(rhb200_ctx *ctx, int on);
+int rh_continuum_nlambda(const rhb200_ctx *ctx);
+int rh_continuum_has_chemistry(const rhb200_ctx *ctx);
 int rh_launch_pyrh_rows(rhb200_ctx *ctx, int ncol, int ndep, int nrow_in, int atm_scale, double muz, double vmacro_tresh,
                         const double *d_in, double *d_atmos, int *d_col_moving);
 int rh_launch_rf_expand(rhb200_ctx *ctx, int v0, int n, int ndep, int nrow, int npar, const int *d_rows,

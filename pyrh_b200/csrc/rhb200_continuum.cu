@@ -120,6 +120,7 @@ struct DevModel {       // device copies
   double *hmff_theta = nullptr, *h2m_theta = nullptr, *h2p_temp = nullptr, *oh_T = nullptr, *ch_T = nullptr;
   int n_hmff_lambda, n_hmff_theta, n_h2m_lambda, n_h2m_theta, n_h2p_lambda, n_h2p_temp, n_oh_T, n_oh_E, n_ch_T, n_ch_E;
   int nlev, nlev_H, lev0_He, H_active, solve_NLTE;
+  int hse_mode = 0;      // pyrh_Background() of the HSE solver: no Metal_bf, scattering added (rhf1d/pyrh_background.c:144-430)
   double sigma_T, sigma_ff;
 };
 
@@ -472,9 +473,9 @@ continuum_tile_kernel(int ncol, int nlambda, int ndep, DevModel M,
             chi_a[q] += chi; eta_a[q] += chi * Bnu[q];
           }
         } else {
-          chi_a[q] += chi_f[q] * 1.0; eta_a[q] += eta_f[q] * 1.0;             // metal_fudge = 1
+          if (!M.hse_mode) { chi_a[q] += chi_f[q] * 1.0; eta_a[q] += eta_f[q] * 1.0; }   // metal_fudge = 1
           double chi_out = chi_a[q];
-          if (M.solve_NLTE) {                                                 // background.c:462 needs sca_ai
+          if (M.solve_NLTE || M.hse_mode) {                                                 // background.c:462 needs sca_ai
             double sca = nek * M.sigma_T;
             if (flags & F_RAY_H)  sca += W[WC_SIG_RAY_H] * nH0;
             if (flags & F_RAY_HE) sca += W[WC_SIG_RAY_HE] * n_[(size_t) M.lev0_He * ndep];
@@ -1132,6 +1133,9 @@ void rh_continuum_free(rhb200_ctx *c)
 int rh_continuum_nlev(const rhb200_ctx *c) { return c->cont ? ((ContinuumState *) c->cont)->nlev : 0; }
 int rh_continuum_natom(const rhb200_ctx *c) { return c->cont ? ((ContinuumState *) c->cont)->natom : 0; }
 // last level of the first model atom: hydrogen comes first in atoms.input (atmos.H = &atmos.atoms[0], readatom.c)
+void rh_continuum_set_hse_mode(rhb200_ctx *c, int on) { if (c->cont) ((ContinuumState *) c->cont)->D.hse_mode = on; }
+int rh_continuum_nlambda(const rhb200_ctx *c) { return c->cont ? ((ContinuumState *) c->cont)->nlambda : 0; }
+int rh_continuum_has_chemistry(const rhb200_ctx *c) { return c->cont && ((ContinuumState *) c->cont)->nmol > 0; }
 int rh_continuum_proton_level(const rhb200_ctx *c) { return c->cont ? ((ContinuumState *) c->cont)->proton_level : 0; }
 
 static int launch_chemeq(rhb200_ctx *c, ContinuumState *S, int cc, int ndep, const double *d_atmos, double *d_pops, double *d_chem)

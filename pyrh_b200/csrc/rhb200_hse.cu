@@ -3,6 +3,8 @@
 // layer-by-layer variant get_ne() of the hydrostatic-equilibrium solver (rhf1d/pyrh_background.c).
 #include "rhb200_common.cuh"
 #include "rhb200_math.cuh"
+#include <algorithm>
+#include <cmath>
 
 #define RH_EV 1.60217733E-19
 #define N_MAX_ELECTRON_ITERATIONS 10      // solvene.c:38
@@ -93,7 +95,142 @@ solve_ne_kernel(size_t n, int nelem, int npf, const double *__restrict__ elems, 
   ne[t] = solve_ne_point(nelem, npf, elems, pf, Tpf, T[t], nHtot[t], ne[t], fromscratch, uk_zero);
 }
 
+// ---- hydrostatic equilibrium, hse() of rhf1d/pyrh_hse.c:67-400, for a batch of columns.  The reference walks the
+//      layers top-down and iterates each to convergence; here every step of that walk is a kernel over the columns.
+struct HseCols {
+  int ncol, ndep, atm_scale;
+  double wght_per_H, total_abund, gravity, LOG10;
+  double *scale /* tau_ref or height [m] */, *T, *ne, *nHtot, *rho, *pg, *opac;   // [ncol][ndep]
+  int *done, *iter, *nactive;
+};
+
+// start of layer k (pyrh_hse.c:212-216, 281-296)
+__global__ void hse_layer_init_kernel(HseCols H, int k)
+{
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= H.ncol) return;
+  const size_t o = (size_t) col * H.ndep + k;
+  if (k == 0) {
+    H.ne[o] = 0;
+    H.nHtot[o] = (H.pg[o]/RH_KBOLTZMANN/H.T[o] - H.ne[o])/H.total_abund;
+  } else {
+    double deltaP;
+    if (H.atm_scale == 2) deltaP = H.gravity * H.rho[o-1] * (H.scale[o-1] - H.scale[o]);
+    else                  deltaP = H.gravity * H.rho[o-1]/H.opac[o-1] * (H.scale[o] - H.scale[o-1]);
+    H.pg[o] = H.pg[o-1] + deltaP;
+    H.nHtot[o] = (H.pg[o]/RH_KBOLTZMANN/H.T[o] - H.ne[o-1])/H.total_abund;
+  }
+  H.done[col] = 0; H.iter[col] = 0;
+}
+
+// first half of one iteration of layer k: density, electron density (get_ne from scratch), the one-depth atmosphere
+// rows the LTE-population / chemistry / continuum kernels read (pyrh_hse.c:227-234, 299-306)
+__global__ void hse_pre_kernel(HseCols H, int k, int nelem, int npf, const double *__restrict__ elems,
+                               const double *__restrict__ pf, const double *__restrict__ Tpf, double *__restrict__ atL)
+{
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= H.ncol || H.done[col]) return;
+  const size_t o = (size_t) col * H.ndep + k;
+  H.rho[o] = (RH_AMU * H.wght_per_H) * H.nHtot[o];
+  const double ne = solve_ne_point(nelem, npf, elems, pf, Tpf, H.T[o], H.nHtot[o], 0.0, 1, 1);
+  H.ne[o] = ne;
+  double *a = atL + (size_t) col * RHB200_AT_NFIELD;
+  for (int f = 0; f < RHB200_AT_NFIELD; f++) a[f] = 0.0;
+  a[RHB200_AT_T] = H.T[o]; a[RHB200_AT_NE] = ne; a[RHB200_AT_NHTOT] = H.nHtot[o];
+}
+
+// second half: pressure integration and the new total hydrogen density (pyrh_hse.c:236-254, 308-372)
+__global__ void hse_post_kernel(HseCols H, int k, const double *__restrict__ chi_layer)
+{
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= H.ncol || H.done[col]) return;
+  const size_t o = (size_t) col * H.ndep + k;
+  H.opac[o] = chi_layer[col];
+  if (k > 0) {
+    if (H.atm_scale == 0) {
+      const double dlogtau = rhm::rh_log10(H.scale[o]) - rhm::rh_log10(H.scale[o-1]);
+      const double beta1 = H.rho[o-1]/H.opac[o-1] * H.scale[o-1];
+      const double beta2 = H.rho[o]/H.opac[o] * H.scale[o];
+      H.pg[o] = H.pg[o-1] + H.LOG10 * H.gravity * (beta2 + beta1)/2 * dlogtau;
+    } else {
+      const double deltaP = H.gravity * (H.scale[o-1] - H.scale[o]) * sqrt(H.rho[o]*H.rho[o-1]);
+      H.pg[o] = H.pg[o-1] + deltaP;
+    }
+  }
+  const double nHtot_old = H.nHtot[o];
+  H.nHtot[o] = (H.pg[o]/RH_KBOLTZMANN/H.T[o] - H.ne[o]) / H.total_abund;
+  H.iter[col] += 1;
+  const double eta = fabs((H.nHtot[o] - nHtot_old)/H.nHtot[o]);
+  if (eta <= 1e-2 || H.iter[col] >= 50) { H.done[col] = 1; atomicSub(H.nactive, 1); }       // NMAX_HSE_ITER, pyrh_hse.c:63
+}
+
 }  // namespace
+
+// pyrh.hse (pyrh.pyx:427-489) for a batch of columns: gas pressure, electron and hydrogen densities of an atmosphere
+// in hydrostatic equilibrium from its temperature run and the pressure at the top.
+extern "C" int rhb200_hse_batch(rhb200_ctx *c, int ncol, int ndep, int atm_scale, const double *scale, const double *T,
+                                const double *pg_top, double wght_per_H, double total_abund, double gravity,
+                                double *ne, double *nHtot, double *rho, double *pg)
+{
+  if (!c) { rhb200_set_error("null context"); return RHB200_EINVAL; }
+  RH_CUDA(cudaSetDevice(c->device));
+  ElementTable *t = (ElementTable *) c->elements;
+  if (!t) { rhb200_set_error("rhb200_set_elements() has not been called"); return RHB200_ESTATE; }
+  if (!c->cont || !rh_continuum_has_chemistry(c)) { rhb200_set_error("rhb200_set_continuum() / rhb200_set_chemistry() have not been called"); return RHB200_ESTATE; }
+  if (rh_continuum_nlambda(c) != 1 || c->wav.nlambda != 1) { rhb200_set_error("the HSE solver works at the reference wavelength alone: set the one-wavelength grid {500 nm} (pyrh_hse.c:197-200)"); return RHB200_ESTATE; }
+  if (atm_scale != 0 && atm_scale != 2) { rhb200_set_error("hse(): only the tau500 (0) and height (2) scales are integrated by the reference (pyrh_hse.c:284-289)"); return RHB200_EUNSUPPORTED; }
+  if (ncol < 0 || ndep < 2 || !scale || !T || !pg_top || !ne || !nHtot || !rho || !pg) { rhb200_set_error("bad arguments"); return RHB200_EINVAL; }
+  if (ncol == 0) return RHB200_OK;
+  const size_t n = (size_t) ncol * ndep;
+  const int natom = rh_continuum_natom(c), nlev = rh_continuum_nlev(c);
+  double *d = nullptr; int *di = nullptr;
+  const size_t layer_doubles = (size_t) ncol * (RHB200_AT_NFIELD + (natom + 4) + nlev + 8 + 2);
+  RH_CUDA(cudaMalloc((void **) &d, (7 * n + layer_doubles) * sizeof(double)));
+  if (cudaMalloc((void **) &di, (2 * (size_t) ncol + 1) * sizeof(int)) != cudaSuccess) { cudaFree(d); rhb200_set_error("cudaMalloc failed"); return RHB200_ENOMEM; }
+  HseCols H{ncol, ndep, atm_scale, wght_per_H, total_abund, gravity, log(10.0),
+            d, d + n, d + 2*n, d + 3*n, d + 4*n, d + 5*n, d + 6*n, di, di + ncol, di + 2*(size_t) ncol};
+  double *atL = d + 7*n, *chemL = atL + (size_t) ncol * RHB200_AT_NFIELD, *popsL = chemL + (size_t) ncol * (natom + 4),
+         *tprepL = popsL + (size_t) ncol * nlev, *chiL = tprepL + (size_t) ncol * 8, *etaL = chiL + ncol;
+  int rc = RHB200_OK;
+  cudaError_t e = cudaSuccess;
+  auto fail = [&](const char *what) { rhb200_set_error("rhb200_hse_batch: %s: %s", what, cudaGetErrorString(e)); rc = RHB200_ECUDA; };
+  std::vector<double> h(n);
+  for (int col = 0; col < ncol && rc == RHB200_OK; col++)                 // pyrh_hse.c:150-165: tau = POW10(scale), height = km -> m
+    for (int k = 0; k < ndep; k++) {
+      const double s = scale[(size_t) col * ndep + k];
+      h[(size_t) col * ndep + k] = atm_scale == 0 ? exp(2.30258509299404568402 * (s)) : s * 1.0E+03;
+    }
+  if ((e = cudaMemcpy(H.scale, h.data(), n * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(H.T, T, n * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemset(H.ne, 0, 5 * n * sizeof(double))) != cudaSuccess) fail("upload");
+  if (rc == RHB200_OK) {
+    std::fill(h.begin(), h.end(), 0.0);
+    for (int col = 0; col < ncol; col++) h[(size_t) col * ndep] = pg_top[col];
+    if ((e = cudaMemcpy(H.pg, h.data(), n * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) fail("upload");
+  }
+  rh_continuum_set_hse_mode(c, 1);
+  const unsigned gb = (unsigned) ((ncol + 63) / 64);
+  for (int k = 0; k < ndep && rc == RHB200_OK; k++) {
+    hse_layer_init_kernel<<<gb, 64, 0, c->stream>>>(H, k);
+    int nactive = ncol;
+    if ((e = cudaMemcpyAsync(H.nactive, &nactive, sizeof(int), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) { fail("flag"); break; }
+    for (int it = 0; it < 50 && nactive > 0 && rc == RHB200_OK; it++) {
+      hse_pre_kernel<<<gb, 64, 0, c->stream>>>(H, k, t->nelem, t->npf, t->elems, t->pf, t->Tpf, atL);
+      rc = rh_continuum_chunk(c, ncol, 1, atL, chemL, popsL, tprepL, chiL, etaL, 1);
+      if (rc != RHB200_OK) break;
+      hse_post_kernel<<<gb, 64, 0, c->stream>>>(H, k, chiL);
+      if ((e = cudaMemcpyAsync(&nactive, H.nactive, sizeof(int), cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
+          (e = cudaStreamSynchronize(c->stream)) != cudaSuccess) fail("iteration");
+    }
+  }
+  rh_continuum_set_hse_mode(c, 0);
+  if (rc == RHB200_OK && ((e = cudaMemcpy(ne, H.ne, n * sizeof(double), cudaMemcpyDeviceToHost)) != cudaSuccess ||
+      (e = cudaMemcpy(nHtot, H.nHtot, n * sizeof(double), cudaMemcpyDeviceToHost)) != cudaSuccess ||
+      (e = cudaMemcpy(rho, H.rho, n * sizeof(double), cudaMemcpyDeviceToHost)) != cudaSuccess ||
+      (e = cudaMemcpy(pg, H.pg, n * sizeof(double), cudaMemcpyDeviceToHost)) != cudaSuccess)) fail("download");
+  cudaFree(d); cudaFree(di);
+  return rc;
+}
 
 void rh_elements_free(rhb200_ctx *c)
 {

@@ -518,6 +518,53 @@ def element_table(el: Elements):
     return np.array(rows), np.array(pfrows)
 
 
+class HseSession:
+    """The parsed working directory of ``hse`` resident on one GPU (elements, the 500 nm continuum model, chemistry)."""
+
+    def __init__(self, cwd, device=0, atomic_number=None, atomic_abundance=None):
+        from . import api, continuum
+        kw = read_keywords(cwd)
+        self.el = el = read_elements(None, kw, atomic_number, atomic_abundance)
+        bg = dict(np.load(DATA / "background_falc11.npz"))
+        if [a for a, _ in _atoms_listed(cwd, kw)] != [str(x) for x in bg["atom_files"]]:
+            raise NotImplementedError("only the standard background atom set ships with pyrh_b200.host")
+        if not el.abundance_set.all():
+            raise NotImplementedError("elements without an abundance are not supported by the electron-density solver")
+        self.ctx = ctx = api.Context(device)
+        empty = ll.LineTable(lines=np.zeros((0, ll.RL_NFIELD)), zq=np.zeros(0, np.int32), zshift=np.zeros(0),
+                             zstrength=np.zeros(0), elems=np.zeros((0, ll.RE_NFIELD)), pf=np.zeros((0, len(el.Tpf))),
+                             Tpf=el.Tpf, vmicro_char=float(kw["VMICRO_CHAR"]) * 1.0E+03)
+        ctx.set_lines(empty)
+        ctx.set_wavelengths(np.array([500.0]))                              # pyrh_hse.c:197-200
+        ctx.set_elements(*element_table(el), el.Tpf)
+        ctx.set_continuum(continuum.ContinuumModel(bg), np.array([el.abund[int(p) - 1] for p in bg["atom_pt_index"]]))
+        ctx.set_chemistry(bg["ce_nuclei"][:, 1].astype(np.int32), bg["ce_mol"])
+
+    def hse(self, atm_scale, scale, temp, pg_top=0.1):
+        """``scale``, ``temp`` [ndep] or [ncol, ndep] -> ne, nHtot, rho, pg (SI, like the reference's arrays)."""
+        scale, temp = np.asarray(scale, np.float64), np.asarray(temp, np.float64)
+        single = temp.ndim == 1
+        out = self.ctx.hse_batch(np.atleast_2d(scale), np.atleast_2d(temp), pg_top, atm_scale, self.el.wght_per_H,
+                                 self.el.totalAbund)
+        return tuple(o[0] for o in out) if single else out
+
+    def close(self):
+        self.ctx.close()
+
+
+def hse(cwd, atm_scale, scale, temp, pg_top=0.1, fudge_wave=None, fudge_value=None, atomic_number=None,
+        atomic_abundance=None, full_output=False, device=0):
+    """Drop-in for ``pyrh.hse`` (pyrh.pyx:427-489): ``(ne, nHtot)`` or, with ``full_output``, ``(ne, nHtot, rho, pg)``."""
+    if fudge_wave is not None or fudge_value is not None:
+        raise NotImplementedError("opacity fudge factors are not implemented on the device path")
+    s = HseSession(cwd, device, atomic_number, atomic_abundance)
+    try:
+        ne, nH, rho, pg = s.hse(atm_scale, scale, temp, pg_top)
+    finally:
+        s.close()
+    return (ne, nH, rho, pg) if full_output else (ne, nH)
+
+
 def get_ne_from_nH(cwd, atm_scale, scale, temperature, nH, device=0):
     """Drop-in for ``pyrh.get_ne_from_nH`` (pyrh.pyx:396-425): electron density [cm^-3] from temperature [K] and total
     hydrogen density [cm^-3] by the LTE ionisation equilibrium of all elements (Solve_ne from scratch, hydrogen in

@@ -1034,3 +1034,29 @@ def test_get_ne_from_nH_drop_in():
         REPORT[f"get_ne_from_nH_c{c}_exact"] = bool(np.array_equal(ne, g[f"c{c}_ne"]))
         assert np.max(np.abs(ne / g[f"c{c}_ne"] - 1)) < 1e-12
         assert np.array_equal(ne, g[f"c{c}_ne"])
+
+
+def test_hse_drop_in():
+    """pyrh_b200.host.hse = pyrh.hse (rhf1d/pyrh_hse.c:67-400): hydrostatic equilibrium on a log tau500 grid, layer
+    by layer with the electron density, LTE populations, chemical equilibrium and the 500 nm opacity of every
+    iteration on the device.  Gas pressure, densities and electron density equal the reference's bit for bit for
+    two top pressures, and a batch gives the same as single columns (fixture ne_hse)."""
+    from pyrh_b200 import host
+    root = Path(__file__).resolve().parent.parent
+    cwd, pp = root / "oracle" / "_ref" / "inputs" / "benchmark", root / "oracle" / "_ref" / "pyrh_path"
+    if not (cwd / "keyword.input").exists():
+        pytest.skip("reference input files not staged (oracle/_ref)")
+    os.environ["PYRH_PATH"] = str(pp)
+    g = dict(np.load(GOLD / "ne_hse.npz"))
+    for name in ("hse01", "hse1"):
+        out = host.hse(str(cwd), 0, g[name + "_scale"], g[name + "_T"], float(g[name + "_pgtop"]), full_output=True)
+        for arr, key in zip(out, ("ne", "nH", "rho", "pg")):
+            ref = g[f"{name}_{key}"]
+            REPORT[f"hse_{name}_{key}_exact"] = bool(np.array_equal(arr, ref))
+            assert np.max(np.abs(arr / ref - 1)) < 1e-10, (name, key, float(np.max(np.abs(arr / ref - 1))))
+            assert np.array_equal(arr, ref), (name, key)
+    s = host.HseSession(str(cwd))
+    both = s.hse(0, np.stack([g["hse01_scale"], g["hse1_scale"]]), np.stack([g["hse01_T"], g["hse1_T"]]),
+                 np.array([0.1, 1.0]))
+    s.close()
+    assert np.array_equal(both[3][0], g["hse01_pg"]) and np.array_equal(both[3][1], g["hse1_pg"])
