@@ -390,6 +390,33 @@ def read_atom_lines(atom_file):
     return ID, lines
 
 
+def passive_line_windows(cwd, kw, path=None):
+    """Wavelength windows [lo, hi] (nm) in which the reference's Background() adds lines this package's fused LTE path
+    does not sum yet: passive_bb (lines of the PASSIVE model atoms, metal.c:245-246) and MolecularOpacity (line lists
+    of PASSIVE molecules, opacity.c:774-787).  Session refuses grids that touch them instead of silently missing
+    opacity."""
+    root = pyrh_path(path) / "rh"
+    vchar = float(kw["VMICRO_CHAR"]) * 1.0E+03 / CLIGHT
+    out = []
+    if _true(kw.get("ALLOW_PASSIVE_BB", "TRUE")):
+        for fname, _ in _atoms_listed(cwd, kw):
+            ID, lines = read_atom_lines(root / "Atoms" / fname)
+            out += [(lam0 - lam0 * qw * vchar, lam0 + lam0 * qw * vchar, f"{ID.strip()} line at {lam0:.3f} nm") for _, lam0, qw in lines]
+    for ln in (Path(cwd) / kw["MOLECULES_FILE"]).read_text().splitlines():
+        f = ln.split("#", 1)[0].split()
+        if len(f) >= 2 and f[0].endswith(".molecule"):
+            body = [x.strip() for x in (root / "Molecules" / f[0]).read_text().splitlines() if x.strip() and x[0] != "#"]
+            for item in body:
+                lst = root / "Molecules" / item
+                if "/" in item and lst.is_file():
+                    rows = lst.read_text().splitlines()
+                    qwing = float(rows[1].split()[1])
+                    lam = [float(r[:10]) for r in rows[2:] if r.strip()]
+                    lo, hi = min(lam), max(lam)
+                    out.append((lo - lo * qwing * vchar, hi + hi * qwing * vchar, f"{f[0]} line list {item}"))
+    return out
+
+
 def model_line_rows(cwd, kw, el: Elements, lt_elem_order, path=None):
     """rows for Context.set_model_lines: the lines of every listed model atom whose element also has Kurucz lines."""
     rows = []
@@ -445,6 +472,12 @@ class Session:
         self.lt = read_kurucz_lines(cwd, kw, self.el, loggf_ids, loggf_values, lam_ids, lam_values)
         self.lambda_ref = float(kw["LAMBDA_REF"])
         self.lam = sort_lambda(wave, self.lambda_ref)
+        for lo, hi, what in passive_line_windows(cwd, kw, path):
+            hit = self.lam[(self.lam >= lo) & (self.lam <= hi)]
+            if len(hit):
+                raise NotImplementedError(f"wavelength {hit[0]:.4f} nm lies inside the window of the {what}: passive_bb / "
+                                          "MolecularOpacity exist at unit level (Context.passive_bb, .molecular_opacity) "
+                                          "but are not summed into the fused LTE path yet")
         self.ctx = api.Context(device)
         self.ctx.set_lines(self.lt, magneto_optical=False, rlkscatter=False)
         self.model_lines = model_line_rows(cwd, kw, self.el, self.lt.elem_rows, path)

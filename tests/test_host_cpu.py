@@ -76,3 +76,15 @@ def test_unsupported_inputs_are_refused(tmp_path):
     kwf.write_text(kwf.read_text().replace("MAGNETO_OPTICAL = FALSE", "MAGNETO_OPTICAL = TRUE"))
     with pytest.raises(NotImplementedError, match="MAGNETO_OPTICAL"):
         host.Session(tmp_path, [630.1, 630.2], path=PYRH_PATH)
+
+
+def test_grids_touching_passive_lines_are_refused():
+    """Background() would add passive_bb / MolecularOpacity lines there (H-alpha, the CN list at 847 nm); the fused
+    path does not sum them yet, so the session refuses instead of returning a spectrum without those lines."""
+    from pyrh_b200 import host
+    kw = host.read_keywords(CWD)
+    w = host.passive_line_windows(CWD, kw, PYRH_PATH)
+    assert any("H line at 656.4" in x[2] for x in w) and any("CN.molecule" in x[2] for x in w)
+    for grid, what in (([656.0, 656.3], "H line"), ([847.0], "CN.molecule")):
+        with pytest.raises(NotImplementedError, match=what):
+            host.Session(CWD, grid, path=PYRH_PATH)
