@@ -108,6 +108,31 @@ int rhb200_set_lines(rhb200_ctx *ctx,
    bit-exact. */
 int rhb200_set_wavelengths(rhb200_ctx *ctx, int nlambda, const double *lambda);
 
+/* passive_bb in the fused LTE path (metal.c:174-344): bound-bound lines of the PASSIVE model atoms, hydrogen
+   included, unpolarised, added to the background before the Kurucz lines exactly like Background() does
+   (background.c:494-515); they also set hasline, i.e. select the scalar ray for their wavelengths.  plines
+   [nline][RHB200_PL_NFIELD] in the reference's order (atoms, then lines) with the depth-independent factors of
+   Damping() (broad.c:60-314) evaluated by the host; populations, Doppler widths and damping parameters are formed
+   on the device from the LTE populations of the continuum model (entry points with the continuum on the device
+   only).  Call after rhb200_set_lines and before rhb200_set_wavelengths; rhb200_set_lines clears the table. */
+enum {
+  RHB200_PL_ATOM = 0,        /* model-atom index (order of atoms.input) */
+  RHB200_PL_LEVEL_I, RHB200_PL_LEVEL_J,          /* rows of the level table of rhb200_continuum_model */
+  RHB200_PL_LAMBDA0, RHB200_PL_QWING, RHB200_PL_BIJ, RHB200_PL_BJI, RHB200_PL_AJI,
+  RHB200_PL_VOIGT,           /* 0: Gaussian */
+  RHB200_PL_NCOMP, RHB200_PL_COMPOFF,            /* slice of c_shift / c_fraction */
+  RHB200_PL_GRAD,
+  RHB200_PL_VDW_TYPE,        /* -1 none, 0 UNSOLD: A * T^0.3, 1 RIDDER_RENSBERGEN: A T^B + C T^D * He abundance */
+  RHB200_PL_VDW_A, RHB200_PL_VDW_B, RHB200_PL_VDW_C, RHB200_PL_VDW_D, RHB200_PL_HE_ABUND,
+  RHB200_PL_STARK_TYPE,      /* 0 none, 1: A * ne (cStark < 0), 2: A * (C T)^(1/6) * Cm * ne */
+  RHB200_PL_STARK_A, RHB200_PL_STARK_C, RHB200_PL_STARK_CM,
+  RHB200_PL_LINSTARK_C,      /* hydrogen: C * ne^(2/3) (StarkLinear) */
+  RHB200_PL_IS_H, RHB200_PL_WEIGHT,
+  RHB200_PL_NFIELD = 28
+};
+int rhb200_set_passive_lines(rhb200_ctx *ctx, int nline, const double *plines, int ncomp,
+                             const double *c_shift, const double *c_fraction);
+
 /* Lines of the explicit (PASSIVE) model atoms: inside the wing window of such a line a Kurucz line of the same
    element and ionisation stage does not contribute (rlk_opacity, kurucz.c:617-633: passive_bb accounts for it).
    rows [n][4] = {element row of the table given to rhb200_set_lines, stage of the model line's lower level,

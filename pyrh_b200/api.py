@@ -121,6 +121,12 @@ class Context:
         rows = np.ascontiguousarray(rows, np.float64).reshape(-1, 4)
         _lib.check(self.lib.rhb200_set_model_lines(self.h, len(rows), _dp(rows)))
 
+    def set_passive_lines(self, rows, c_shift, c_fraction):
+        """Bound-bound lines of the PASSIVE model atoms for the fused path (passive_bb): rows [n, RHB200_PL_NFIELD]."""
+        rows = np.ascontiguousarray(rows, np.float64).reshape(-1, 28)
+        cs, cf = np.ascontiguousarray(c_shift, np.float64), np.ascontiguousarray(c_fraction, np.float64)
+        _lib.check(self.lib.rhb200_set_passive_lines(self.h, len(rows), _dp(rows), len(cs), _dp(cs), _dp(cf)))
+
     def set_wavelengths(self, lam):
         lam = np.ascontiguousarray(lam, np.float64)
         _lib.check(self.lib.rhb200_set_wavelengths(self.h, len(lam), _dp(lam)))

@@ -73,6 +73,7 @@ static void free_wave(rhb200_ctx *c)
 {
   DevWave &w = c->wav;
   cudaFree(w.lambda); cudaFree(w.first); cudaFree(w.count); cudaFree(w.idx); cudaFree(w.flags); cudaFree(w.noline); cudaFree(w.unpol_rank);
+  cudaFree(w.pw_first); cudaFree(w.pw_count); cudaFree(w.pw_idx); cudaFree(w.pl_rows); cudaFree(w.pl_pb); cudaFree(w.pl_cshift); cudaFree(w.pl_cfrac);
   w = DevWave();
 }
 
@@ -164,6 +165,24 @@ extern "C" int rhb200_set_lines(rhb200_ctx *c, int nline, const double *lines, i
   c->h_zq.assign(zq, zq + ncomp); c->h_zshift.assign(zshift, zshift + ncomp); c->h_zstrength.assign(zstrength, zstrength + ncomp);
   free_wave(c);     // windows depend on the line table
   c->h_model_lines.clear();
+  c->h_plines.clear(); c->h_pcshift.clear(); c->h_pcfrac.clear();
+  return RHB200_OK;
+}
+
+extern "C" int rhb200_set_passive_lines(rhb200_ctx *c, int nline, const double *plines, int ncomp,
+                                        const double *c_shift, const double *c_fraction)
+{
+  RH_NEED_CTX(c);
+  if (nline < 0 || ncomp < 0 || (nline > 0 && (!plines || !c_shift || !c_fraction))) { rhb200_set_error("rhb200_set_passive_lines: bad arguments"); return RHB200_EINVAL; }
+  for (int n = 0; n < nline; n++) {
+    const double *L = plines + (size_t) n * RHB200_PL_NFIELD;
+    const int off = (int) L[RHB200_PL_COMPOFF], nc = (int) L[RHB200_PL_NCOMP];
+    if (off < 0 || nc < 1 || off + nc > ncomp) { rhb200_set_error("passive line %d: component slice out of range", n); return RHB200_EINVAL; }
+  }
+  c->h_plines.assign(plines, plines + (size_t) nline * RHB200_PL_NFIELD);
+  c->h_pcshift.assign(c_shift, c_shift + ncomp);
+  c->h_pcfrac.assign(c_fraction, c_fraction + ncomp);
+  free_wave(c);
   return RHB200_OK;
 }
 
@@ -224,8 +243,47 @@ extern "C" int rhb200_set_wavelengths(rhb200_ctx *c, int nlambda, const double *
     }
     c->h_count[l] = (int) c->h_idx.size() - c->h_first[l];
   }
+  // passive_bb windows (metal.c:245-249) over the lines of rhb200_set_passive_lines, in table order; the lines that
+  // are hit anywhere form the compact ACTIVE table the kernels index
+  const int NPL = (int) (c->h_plines.size() / RHB200_PL_NFIELD);
+  std::vector<int> prank(NPL, -1), pact, pw_first(nlambda, 0), pw_count(nlambda, 0), pw_idx;
+  std::vector<std::vector<int>> hits(nlambda);
+  for (int l = 0; l < nlambda; l++)
+    for (int n = 0; n < NPL; n++) {
+      const double *L = c->h_plines.data() + (size_t) n * RHB200_PL_NFIELD;
+      const double dlambda = L[RHB200_PL_LAMBDA0] * L[RHB200_PL_QWING] * (c->tab.vmicro_char / RH_CLIGHT);
+      if (std::fabs(lambda[l] - L[RHB200_PL_LAMBDA0]) <= dlambda) {
+        if (prank[n] < 0) { prank[n] = 0; }
+        hits[l].push_back(n);
+        c->h_flags[l] |= 1;                                  // backgrflags.hasline
+      }
+    }
+  for (int n = 0; n < NPL; n++) if (prank[n] == 0) { prank[n] = (int) pact.size(); pact.push_back(n); }
+  for (int l = 0; l < nlambda; l++) {
+    pw_first[l] = (int) pw_idx.size(); pw_count[l] = (int) hits[l].size();
+    for (int n : hits[l]) pw_idx.push_back(prank[n]);
+  }
   free_wave(c);
   DevWave &w = c->wav;
+  w.npl = (int) pact.size(); w.npw = (int) pw_idx.size();
+  if (w.npl) {
+    std::vector<double> rows((size_t) w.npl * RHB200_PL_NFIELD), pb((size_t) w.npl * RHB200_PB_NFIELD, 0.0);
+    for (int a = 0; a < w.npl; a++) {
+      const double *L = c->h_plines.data() + (size_t) pact[a] * RHB200_PL_NFIELD;
+      std::copy(L, L + RHB200_PL_NFIELD, rows.begin() + (size_t) a * RHB200_PL_NFIELD);
+      double *B = pb.data() + (size_t) a * RHB200_PB_NFIELD;
+      B[RHB200_PB_LAMBDA0] = L[RHB200_PL_LAMBDA0]; B[RHB200_PB_QWING] = L[RHB200_PL_QWING]; B[RHB200_PB_BIJ] = L[RHB200_PL_BIJ];
+      B[RHB200_PB_BJI] = L[RHB200_PL_BJI]; B[RHB200_PB_AJI] = L[RHB200_PL_AJI]; B[RHB200_PB_VOIGT] = L[RHB200_PL_VOIGT];
+      B[RHB200_PB_NCOMP] = L[RHB200_PL_NCOMP]; B[RHB200_PB_COMPOFF] = L[RHB200_PL_COMPOFF];
+    }
+    RH_CHECK(upload(&w.pl_rows, rows.data(), rows.size()));
+    RH_CHECK(upload(&w.pl_pb, pb.data(), pb.size()));
+    RH_CHECK(upload(&w.pl_cshift, c->h_pcshift.data(), c->h_pcshift.size()));
+    RH_CHECK(upload(&w.pl_cfrac, c->h_pcfrac.data(), c->h_pcfrac.size()));
+    RH_CHECK(upload(&w.pw_first, pw_first.data(), (size_t) nlambda));
+    RH_CHECK(upload(&w.pw_count, pw_count.data(), (size_t) nlambda));
+    RH_CHECK(upload(&w.pw_idx, pw_idx.data(), pw_idx.size()));
+  }
   w.nlambda = nlambda; w.nidx = (int) c->h_idx.size();
   RH_CHECK(upload(&w.lambda, lambda, (size_t) nlambda));
   RH_CHECK(upload(&w.first, c->h_first.data(), (size_t) nlambda));
@@ -397,7 +455,9 @@ static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int mov
   const size_t b_tp = cont_dev ? align_up((size_t) cc * 8 * ndep * sizeof(double)) : 0;
   const size_t b_in = py ? align_up((size_t) cc * py->nrow * ndep * sizeof(double)) : 0;     // pyrh rows as they arrive
   const size_t b_sc = py ? align_up((size_t) cc * 5 * ndep * sizeof(double)) : 0;            // {tau, cmass} scratch + {height, tau_ref, cmass} out
-  const size_t slot = L.total + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp + b_in + b_sc;
+  if (c->wav.npl > 0 && !cont_dev) { rhb200_set_error("passive_bb lines need the populations of the device continuum: use the *_pops, *_atmos or compute1d entry points"); return RHB200_ESTATE; }
+  const size_t b_pc = align_up((size_t) cc * std::max(1, c->wav.npl) * 4 * ndep * sizeof(double));   // passive_bb: n_i, n_j, vbroad, adamp
+  const size_t slot = L.total + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp + b_in + b_sc + b_pc;
   RH_CHECK(rh_ws_reserve(c, nslots * slot));
   cudaStream_t streams[2] = {c->stream, c->copy_stream};
   cudaStream_t saved = c->stream;
@@ -411,7 +471,8 @@ static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int mov
            *d_tp = (double *) (base + b_at + 2*b_op + b_st + b_ch + b_pp);
     double *d_in = (double *) (base + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp);
     double *d_sc = (double *) (base + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp + b_in);
-    char *ws = base + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp + b_in + b_sc;
+    double *d_pc = (double *) (base + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp + b_in + b_sc);
+    char *ws = base + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp + b_in + b_sc + b_pc;
     cudaStream_t st = streams[i % nslots];
     c->stream = st;
     cudaError_t e;
@@ -438,6 +499,8 @@ static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int mov
         rhb200_set_error("H2D copy failed: %s", cudaGetErrorString(e)); rc = RHB200_ECUDA; break;
       }
       rc = rh_continuum_chunk(c, n, ndep, d_at, d_ch, d_pp, d_tp, d_chi, d_eta, chem ? 0 : 1);
+      if (rc != RHB200_OK) break;
+      rc = rh_passive_chunk(c, n, ndep, muz, d_at, d_pp, rh_continuum_nlev(c), d_pc, d_chi, d_eta);   // background.c:494-515
       if (rc != RHB200_OK) break;
       if (py) {                                  // np = atmos.H->n[Nlevel-1] (kurucz.c:772); H is the first model atom
         rc = rh_launch_proton(c, n, ndep, rh_continuum_nlev(c), rh_continuum_proton_level(c), d_pp, d_at);

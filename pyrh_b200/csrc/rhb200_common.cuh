@@ -59,7 +59,11 @@ struct DevWave {
   // wavelengths without a POLARISED line (flags bit 1 clear): solved for I alone (formal.c:84-103, 223-236, 289-309)
   // -- Feautrier when there is no line at all or the column is static, else the scalar S_INTERPOLATION ray
   int *noline = nullptr, nnoline = 0;
-  int *unpol_rank = nullptr, nunpol = 0;   // [nlambda] rank among the wavelengths with flags == 1 (line, unpolarised), else -1
+  int *unpol_rank = nullptr, nunpol = 0;
+  // passive_bb lines whose windows touch the grid (rhb200_set_passive_lines): compact tables of the ACTIVE subset
+  int npl = 0, npw = 0;
+  int *pw_first = nullptr, *pw_count = nullptr, *pw_idx = nullptr;
+  double *pl_rows = nullptr /* [npl][RHB200_PL_NFIELD] */, *pl_pb = nullptr /* [npl][RHB200_PB_NFIELD] */, *pl_cshift = nullptr, *pl_cfrac = nullptr;   // [nlambda] rank among the wavelengths with flags == 1 (line, unpolarised), else -1
 };
 
 struct KTimer {
@@ -75,7 +79,8 @@ struct rhb200_ctx {
   std::vector<double> h_lines, h_elems, h_lambda, h_zshift, h_zstrength;
   std::vector<int> h_zq;
   std::vector<int> h_first, h_count, h_idx, h_flags, h_noline;
-  std::vector<double> h_model_lines;     // rhb200_set_model_lines: [n][4] element row, stage, lambda0 [nm], qwing
+  std::vector<double> h_model_lines;
+  std::vector<double> h_plines, h_pcshift, h_pcfrac;   // rhb200_set_passive_lines     // rhb200_set_model_lines: [n][4] element row, stage, lambda0 [nm], qwing
   // formal solver selection (keyword.input S_INTERPOLATION / S_INTERPOLATION_STOKES, inputs.h:26-27)
   int s_interpolation = RHB200_S_BEZIER3, s_interpolation_stokes = RHB200_DELO_BEZIER3;
   // wavelength shard of the NLTE solve (rhb200_nlte_set_shard)
@@ -142,6 +147,8 @@ int rh_launch_passive_bb(rhb200_ctx *ctx, int ncol, int nlambda, int ndep, int n
                          int to_obs, const double *d_lambda, const int *d_first, const int *d_count,
                          const int *d_idx, const double *d_plines, const double *d_cshift, const double *d_cfrac,
                          const double *d_atmos, const double *d_pcol, double *d_chi, double *d_eta);
+int rh_passive_chunk(rhb200_ctx *ctx, int ncol, int ndep, double muz, const double *d_atmos, const double *d_pops, int nlev,
+                      double *d_pcol /* [ncol][npl][4][ndep] */, double *d_chi_ai, double *d_eta_ai);
 int rh_launch_prep(rhb200_ctx *ctx, int ncol, int ndep, double muz, int moving,
                    const double *d_atmos, double *d_elem_n, double *d_lineprep);
 int rh_launch_opacity_fused(rhb200_ctx *ctx, int ncol, int ndep, int to_obs,

@@ -371,7 +371,7 @@ mol_opacity_raw_kernel(int ncol, int nlambda, int ndep, int nmol, double muz, in
 // (column, wavelength, depth); lines in the reference's order (atoms, then lines), components inside.
 // pcol: [ncol][nline][4][ndep] = n_i, n_j, vbroad, Damping() output.
 __global__ void __launch_bounds__(128)
-passive_bb_kernel(int ncol, int nlambda, int ndep, int nline, double muz, int moving, int to_obs,
+passive_bb_kernel(int accumulate, int ncol, int nlambda, int ndep, int nline, double muz, int moving, int to_obs,
                   const double *__restrict__ lambda, const int *__restrict__ wfirst,
                   const int *__restrict__ wcount, const int *__restrict__ widx,
                   const double *__restrict__ plines, const double *__restrict__ c_shift,
@@ -408,8 +408,56 @@ passive_bb_kernel(int ncol, int nlambda, int ndep, int nline, double muz, int mo
       e += twohnu3_c2 * gij * Vij * n_j;
     }
   }
-  chi[t] = c;
-  eta[t] = e;
+  if (accumulate) {                 // fused path: chi_c = chi_ai + passive lines, only where there is one (background.c:500-515)
+    if (count > 0) { chi[t] += c; eta[t] += e; }
+  } else {
+    chi[t] = c;
+    eta[t] = e;
+  }
+}
+
+// Per (column, passive line, depth): populations of the two levels, the atom's Doppler width (readatom.c:199-201) and
+// Damping() (broad.c:273-314: van der Waals + quadratic Stark + hydrogen's linear Stark, in that order) -> pcol.
+__global__ void __launch_bounds__(128)
+passive_prep_kernel(int ncol, int ndep, int npl, int nlev, const double *__restrict__ plrows,
+                    const double *__restrict__ atmos, const double *__restrict__ pops, double *__restrict__ pcol)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t) ncol * npl * ndep) return;
+  const int k = (int) (t % ndep), n = (int) ((t / ndep) % npl), col = (int) (t / ((size_t) ndep * npl));
+  const double *L = plrows + (size_t) n * RHB200_PL_NFIELD;
+  const double *at = atmos + (size_t) col * RHB200_AT_NFIELD * ndep;
+  const double *P = pops + (size_t) col * nlev * ndep + k;
+  const double T = at[RHB200_AT_T*ndep + k], ne = at[RHB200_AT_NE*ndep + k], vturb = at[RHB200_AT_VTURB*ndep + k];
+  const double vtherm = 2.0*RH_KBOLTZMANN/(RH_AMU * L[RHB200_PL_WEIGHT]);
+  const double vbroad = sqrt(vtherm*T + vturb*vturb);
+  double adamp = 0.0;
+  if (L[RHB200_PL_VOIGT] != 0.0) {
+    double Qelast = 0.0;
+    const int vdw = (int) L[RHB200_PL_VDW_TYPE];
+    if (vdw >= 0) {                                                            // VanderWaals, broad.c:60-140
+      double GvdW;
+      if (vdw == 0) GvdW = L[RHB200_PL_VDW_A] * rhm::rh_pow(T, 0.3);
+      else GvdW = L[RHB200_PL_VDW_A] * rhm::rh_pow(T, L[RHB200_PL_VDW_B]) +
+                  L[RHB200_PL_VDW_C] * rhm::rh_pow(T, L[RHB200_PL_VDW_D]) * L[RHB200_PL_HE_ABUND];
+      GvdW *= P[0];                                                            // atmos.H->n[0][k]
+      Qelast += GvdW;
+    }
+    const int stark = (int) L[RHB200_PL_STARK_TYPE];
+    if (stark == 1) Qelast += L[RHB200_PL_STARK_A] * ne;                       // Stark, broad.c:147-215
+    else if (stark == 2) {
+      const double vrel = rhm::rh_pow(L[RHB200_PL_STARK_C] * T, 0.16666667) * L[RHB200_PL_STARK_CM];
+      Qelast += L[RHB200_PL_STARK_A] * vrel * ne;
+    }
+    if (L[RHB200_PL_IS_H] != 0.0) Qelast += L[RHB200_PL_LINSTARK_C] * rhm::rh_pow(ne, 0.66666667);   // StarkLinear
+    const double cDop = (RH_NM_TO_M * L[RHB200_PL_LAMBDA0]) / (4.0 * RH_PI);
+    adamp = (L[RHB200_PL_GRAD] + Qelast) * cDop / vbroad;
+  }
+  double *o = pcol + (((size_t) col * npl + n) * 4) * ndep + k;
+  o[0] = P[(size_t) ((int) L[RHB200_PL_LEVEL_I]) * ndep];
+  o[ndep] = P[(size_t) ((int) L[RHB200_PL_LEVEL_J]) * ndep];
+  o[2*(size_t) ndep] = vbroad;
+  o[3*(size_t) ndep] = adamp;
 }
 
 __global__ void voigt_kernel(int n, const double *__restrict__ a, const double *__restrict__ v,
@@ -478,8 +526,30 @@ int rh_launch_passive_bb(rhb200_ctx *ctx, int ncol, int nlambda, int ndep, int n
   if (n == 0) return RHB200_OK;
   {
     ScopedKernelTimer t(ctx, RHB200_K_OPACITY);
-    passive_bb_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, ctx->stream>>>(ncol, nlambda, ndep, nline, muz, moving,
+    passive_bb_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, ctx->stream>>>(0, ncol, nlambda, ndep, nline, muz, moving,
         to_obs, d_lambda, d_first, d_count, d_idx, d_plines, d_cshift, d_cfrac, d_atmos, d_pcol, d_chi, d_eta);
+  }
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}
+
+// passive_bb of one chunk in the fused path: damping parameters and populations, then the lines are added to the
+// background the Kurucz-line kernel starts from
+int rh_passive_chunk(rhb200_ctx *ctx, int ncol, int ndep, double muz, const double *d_atmos, const double *d_pops, int nlev,
+                     double *d_pcol, double *d_chi_ai, double *d_eta_ai)
+{
+  const DevWave &w = ctx->wav;
+  if (w.npl == 0 || ncol == 0) return RHB200_OK;
+  {
+    ScopedKernelTimer t(ctx, RHB200_K_PREP);
+    const size_t n = (size_t) ncol * w.npl * ndep;
+    passive_prep_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, ctx->stream>>>(ncol, ndep, w.npl, nlev, w.pl_rows, d_atmos, d_pops, d_pcol);
+  }
+  {
+    ScopedKernelTimer t(ctx, RHB200_K_OPACITY);
+    const size_t n = (size_t) ncol * w.nlambda * ndep;
+    passive_bb_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, ctx->stream>>>(1, ncol, w.nlambda, ndep, w.npl, muz, 1, 1,
+        w.lambda, w.pw_first, w.pw_count, w.pw_idx, w.pl_pb, w.pl_cshift, w.pl_cfrac, d_atmos, d_pcol, d_chi_ai, d_eta_ai);
   }
   RH_CUDA(cudaGetLastError());
   return RHB200_OK;

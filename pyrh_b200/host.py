@@ -369,28 +369,138 @@ def read_kurucz_lines(cwd, kw: dict, el: Elements, loggf_ids=None, loggf_values=
     return lt
 
 
-def read_atom_lines(atom_file):
-    """(ID, [(stage of the lower level, lambda0 [nm], qwing), ...]) of one model atom: the part of readAtom
-    (rh/readatom.c:100-243) rlk_opacity's duplicate check needs (kurucz.c:617-633)."""
+VDW_NONE, VDW_UNSOLD_A, VDW_RIDDER_A = -1, 0, 1
+# passive-line rows of the device table -- include/rhb200.h RHB200_PL_*
+(PL_ATOM, PL_LEVEL_I, PL_LEVEL_J, PL_LAMBDA0, PL_QWING, PL_BIJ, PL_BJI, PL_AJI, PL_VOIGT, PL_NCOMP, PL_COMPOFF, PL_GRAD,
+ PL_VDW_TYPE, PL_VDW_A, PL_VDW_B, PL_VDW_C, PL_VDW_D, PL_HE_ABUND, PL_STARK_TYPE, PL_STARK_A, PL_STARK_C, PL_STARK_CM,
+ PL_LINSTARK_C, PL_IS_H, PL_WEIGHT) = range(25)
+PL_NFIELD = 28
+
+
+def read_atom(atom_file):
+    """Levels and bound-bound lines of one model atom: the part of readAtom (rh/readatom.c:100-330) that passive_bb
+    (metal.c:174-344), Damping (broad.c:273-314) and rlk_opacity's duplicate check (kurucz.c:617-633) use."""
     data = [ln for ln in Path(atom_file).read_text().splitlines() if ln.strip() and ln[0] != "#"]
     ID = data[0].split()[0][:2].upper().ljust(2)
     nlevel, nline = (int(x) for x in data[1].split()[:2])
-    E, stage = [], []
+    E, g, label, stage = [], [], [], []
     for ln in data[2:2 + nlevel]:
         head, tail = ln.split("'")[0].split(), ln.split("'")[2].split()
         E.append(float(head[0]) * ((HPLANCK * CLIGHT) / CM_TO_M))           # `*=`, readatom.c:175
+        g.append(float(head[1]))
+        label.append(ln.split("'")[1])
         stage.append(int(tail[0]))
-    lines = []
-    for ln in data[2 + nlevel:2 + nlevel + nline]:
-        f = ln.split()
+    C = 2 * PI * (Q_ELECTRON / EPSILON_0) * (Q_ELECTRON / M_ELECTRON) / CLIGHT      # readatom.c:213
+    lines, pos = [], 2 + nlevel
+    for _ in range(nline):
+        f = data[pos].split()
+        pos += 1
         j, i = int(f[0]), int(f[1])
         i, j = min(i, j), max(i, j)
         lambda0 = (HPLANCK * CLIGHT) / (E[j] - E[i])
-        lines.append((stage[i], lambda0 / NM_TO_M, float(f[7])))
-    return ID, lines
+        Aji = C / (lambda0 * lambda0) * (g[i] / g[j]) * float(f[2])
+        Bji = (lambda0 * lambda0 * lambda0) / (2.0 * HPLANCK * CLIGHT) * Aji
+        Bij = (g[j] / g[i]) * Bji
+        shape, vdw = f[3], f[8]
+        cvdW = [float(x) for x in f[9:13]]
+        c_shift, c_fraction = [0.0], [1.0]
+        if "COMPOSIT" in shape:
+            nc = int(data[pos].split()[0])
+            comp = [data[pos + 1 + n].split() for n in range(nc)]
+            pos += 1 + nc
+            c_shift, c_fraction = [float(x[0]) for x in comp], [float(x[1]) for x in comp]
+        if "UNSOLD" in vdw:
+            cvdW[1] = cvdW[3] = 0.0
+        lines.append(dict(i=i, j=j, lambda0=lambda0 / NM_TO_M, Aji=Aji, Bji=Bji, Bij=Bij, voigt="GAUSS" not in shape,
+                          qwing=float(f[7]), vdw=vdw, cvdW=cvdW, Grad=float(f[13]), cStark=float(f[14]),
+                          c_shift=c_shift, c_fraction=c_fraction))
+    return dict(ID=ID, E=E, g=g, label=label, stage=stage, lines=lines)
 
 
-def passive_line_windows(cwd, kw, path=None):
+def read_atom_lines(atom_file):
+    """(ID, [(stage of the lower level, lambda0 [nm], qwing), ...]) for rlk_opacity's duplicate check."""
+    a = read_atom(atom_file)
+    return a["ID"], [(a["stage"][ln["i"]], ln["lambda0"], ln["qwing"]) for ln in a["lines"]]
+
+
+def passive_line_table(cwd, kw, el: Elements, level_first, path=None):
+    """Device table of the bound-bound lines of the PASSIVE model atoms (passive_bb, metal.c:174-344) with the
+    depth-independent factors of Damping() (broad.c:60-314) evaluated here: rows [nline, PL_NFIELD] in the reference's
+    order (atoms, then lines), component shifts and fractions.  ``level_first[a]`` = row of atom a's first level in
+    the population table."""
+    atoms_dir = pyrh_path(path) / "rh" / "Atoms"
+    rows, cs, cf = [], [], []
+    FOURPIEPS0 = 4.0 * PI * EPSILON_0
+    H_weight, He_weight, He_abund = el.weight[0], el.weight[1], el.abund[1]
+    for a, (fname, _) in enumerate(_atoms_listed(cwd, kw)):
+        at = read_atom(atoms_dir / fname)
+        e = el.ID.index(at["ID"])
+        weight, E, stage = el.weight[e], at["E"], at["stage"]
+        for ln in at["lines"]:
+            i, j, cv = ln["i"], ln["j"], ln["cvdW"]
+            r = np.zeros(PL_NFIELD)
+            r[PL_ATOM], r[PL_LEVEL_I], r[PL_LEVEL_J] = a, level_first[a] + i, level_first[a] + j
+            r[PL_LAMBDA0], r[PL_QWING] = ln["lambda0"], ln["qwing"]
+            r[PL_BIJ], r[PL_BJI], r[PL_AJI], r[PL_VOIGT] = ln["Bij"], ln["Bji"], ln["Aji"], float(ln["voigt"])
+            r[PL_NCOMP], r[PL_COMPOFF], r[PL_GRAD] = len(ln["c_shift"]), len(cs), ln["Grad"]
+            r[PL_WEIGHT], r[PL_IS_H], r[PL_HE_ABUND] = weight, float(at["ID"] == "H "), He_abund
+            cs += ln["c_shift"]; cf += ln["c_fraction"]
+            r[PL_VDW_TYPE] = VDW_NONE
+            if cv[0] > 0.0 or cv[2] > 0.0:                                   # VanderWaals, broad.c:60-140
+                if "UNSOLD" in ln["vdw"]:
+                    vrel35_He = math.pow(8.0 * KBOLTZMANN / (PI * AMU * weight) * (1.0 + weight / He_weight), 0.3)
+                    Z = stage[j] + 1
+                    ic = j + 1
+                    while stage[ic] < stage[j] + 1:
+                        ic += 1
+                    d1, d2 = E_RYDBERG / (E[ic] - E[j]), E_RYDBERG / (E[ic] - E[i])
+                    deltaR = d1 * d1 - d2 * d2
+                    ZR = Z * RBOHR
+                    C625 = math.pow(2.5 * ((Q_ELECTRON * Q_ELECTRON) / FOURPIEPS0) * (ABARH / FOURPIEPS0) *
+                                    2 * PI * (ZR * ZR) / HPLANCK * deltaR, 0.4)
+                    vrel35_H = math.pow(8.0 * KBOLTZMANN / (PI * AMU * weight) * (1.0 + weight / H_weight), 0.3)
+                    r[PL_VDW_TYPE] = VDW_UNSOLD_A
+                    r[PL_VDW_A] = 8.08 * (cv[0] * vrel35_H + cv[2] * He_abund * vrel35_He) * C625
+                elif "PARAMTR" in ln["vdw"]:
+                    CUBE_CM = CM_TO_M * CM_TO_M * CM_TO_M
+                    gH = 1.0E-8 * CUBE_CM * math.pow(1.0 + H_weight / weight, cv[1])
+                    gHe = 1.0E-9 * CUBE_CM * math.pow(1.0 + He_weight / weight, cv[3])
+                    r[PL_VDW_TYPE] = VDW_RIDDER_A
+                    r[PL_VDW_A], r[PL_VDW_B], r[PL_VDW_C], r[PL_VDW_D] = gH * cv[0], cv[1], gHe * cv[2], cv[3]
+                else:
+                    raise NotImplementedError(f"{fname} line {j}->{i}: BARKLEM broadening of model-atom lines needs the "
+                                              "Barklem table interpolation (barklem.c:214-330), not ported")
+            cS = ln["cStark"]
+            if cS < 0.0:                                                     # Stark, broad.c:147-215
+                r[PL_STARK_TYPE], r[PL_STARK_A] = 1, abs(cS)
+            elif cS != 0.0:
+                m_electron = M_ELECTRON / AMU
+                Cc = 8.0 * KBOLTZMANN / (PI * AMU * weight)
+                Cm = math.pow(1.0 + weight / m_electron, 0.16666667) + math.pow(1.0 + weight / 28.0, 0.16666667)
+                Z = stage[i] + 1
+                ic = i + 1
+                while stage[ic] < stage[i] + 1 and ic < len(stage):
+                    ic += 1
+                E_Ryd = E_RYDBERG / (1.0 + M_ELECTRON / (weight * AMU))
+                neff_l = Z * math.sqrt(E_Ryd / (E[ic] - E[i]))
+                neff_u = Z * math.sqrt(E_Ryd / (E[ic] - E[j]))
+                Z2 = Z * Z
+                tu, tl = neff_u * (5.0 * (neff_u * neff_u) + 1.0), neff_l * (5.0 * (neff_l * neff_l) + 1.0)
+                C4 = ((Q_ELECTRON * Q_ELECTRON) / (4.0 * PI * EPSILON_0)) * RBOHR * \
+                    (2.0 * PI * (RBOHR * RBOHR) / HPLANCK) / (18.0 * Z2 * Z2) * (tu * tu - tl * tl)
+                r[PL_STARK_TYPE], r[PL_STARK_A], r[PL_STARK_C], r[PL_STARK_CM] = 2, 11.37 * math.pow(cS * C4, 0.66666667), Cc, Cm
+            if at["ID"] == "H ":                                             # StarkLinear, broad.c:222-264
+                def nq(lab):
+                    m = re.match(r"H I (\d+)", lab)
+                    return int(m.group(1))
+                n_lower, n_upper = nq(at["label"][i]), nq(at["label"][j])
+                a1 = 0.642 if n_upper - n_lower == 1 else 1.0
+                r[PL_LINSTARK_C] = a1 * 0.6 * (n_upper * n_upper - n_lower * n_lower) * (CM_TO_M * CM_TO_M)
+            rows.append(r)
+    return np.array(rows).reshape(-1, PL_NFIELD), np.array(cs), np.array(cf)
+
+
+def passive_line_windows(cwd, kw, path=None, atoms=True):
     """Wavelength windows [lo, hi] (nm) in which the reference's Background() adds lines this package's fused LTE path
     does not sum yet: passive_bb (lines of the PASSIVE model atoms, metal.c:245-246) and MolecularOpacity (line lists
     of PASSIVE molecules, opacity.c:774-787).  Session refuses grids that touch them instead of silently missing
@@ -398,7 +508,7 @@ def passive_line_windows(cwd, kw, path=None):
     root = pyrh_path(path) / "rh"
     vchar = float(kw["VMICRO_CHAR"]) * 1.0E+03 / CLIGHT
     out = []
-    if _true(kw.get("ALLOW_PASSIVE_BB", "TRUE")):
+    if atoms and _true(kw.get("ALLOW_PASSIVE_BB", "TRUE")):
         for fname, _ in _atoms_listed(cwd, kw):
             ID, lines = read_atom_lines(root / "Atoms" / fname)
             out += [(lam0 - lam0 * qw * vchar, lam0 + lam0 * qw * vchar, f"{ID.strip()} line at {lam0:.3f} nm") for _, lam0, qw in lines]
@@ -472,14 +582,18 @@ class Session:
         self.lt = read_kurucz_lines(cwd, kw, self.el, loggf_ids, loggf_values, lam_ids, lam_values)
         self.lambda_ref = float(kw["LAMBDA_REF"])
         self.lam = sort_lambda(wave, self.lambda_ref)
-        for lo, hi, what in passive_line_windows(cwd, kw, path):
+        for lo, hi, what in passive_line_windows(cwd, kw, path, atoms=False):
             hit = self.lam[(self.lam >= lo) & (self.lam <= hi)]
             if len(hit):
-                raise NotImplementedError(f"wavelength {hit[0]:.4f} nm lies inside the window of the {what}: passive_bb / "
-                                          "MolecularOpacity exist at unit level (Context.passive_bb, .molecular_opacity) "
-                                          "but are not summed into the fused LTE path yet")
+                raise NotImplementedError(f"wavelength {hit[0]:.4f} nm lies inside the window of the {what}: "
+                                          "MolecularOpacity exists at unit level (Context.molecular_opacity) but is not "
+                                          "summed into the fused LTE path yet")
         self.ctx = api.Context(device)
         self.ctx.set_lines(self.lt, magneto_optical=False, rlkscatter=False)
+        if _true(kw.get("ALLOW_PASSIVE_BB", "TRUE")):                       # passive_bb, metal.c:174-344
+            lev = bg["ct_lev"]
+            first = [int(np.flatnonzero(lev[:, 0] == a)[0]) for a in range(len(listed))]
+            self.ctx.set_passive_lines(*passive_line_table(cwd, kw, self.el, first, path))
         self.model_lines = model_line_rows(cwd, kw, self.el, self.lt.elem_rows, path)
         self.ctx.set_model_lines(self.model_lines)
         self.ctx.set_wavelengths(self.lam)

@@ -1060,3 +1060,27 @@ def test_hse_drop_in():
                  np.array([0.1, 1.0]))
     s.close()
     assert np.array_equal(both[3][0], g["hse01_pg"]) and np.array_equal(both[3][1], g["hse1_pg"])
+
+
+@pytest.mark.parametrize("window", ["NaD", "Halpha", "Mgb"])
+def test_passive_bb_in_the_fused_path(window):
+    """Lines of the PASSIVE model atoms (passive_bb, metal.c:174-344, with Damping(), broad.c:60-314, and the
+    populations / Doppler widths formed on the device) summed into the fused LTE path: Na I D, H-alpha (linear
+    Stark) and the Mg I b region equal the reference's rhf1d() bit for bit at mu = 1 and 0.8 (fixture passive_fused)."""
+    from pyrh_b200 import host
+    root = Path(__file__).resolve().parent.parent
+    cwd, pp = root / "oracle" / "_ref" / "inputs" / "benchmark", root / "oracle" / "_ref" / "pyrh_path"
+    if not (cwd / "keyword.input").exists():
+        pytest.skip("reference input files not staged (oracle/_ref)")
+    os.environ["PYRH_PATH"] = str(pp)
+    g = dict(np.load(GOLD / "passive_fused.npz"))
+    for tag, mu in (("mu1", 1.0), ("mu08", 0.8)):
+        out = host.compute1d(str(cwd), mu, 0, g["atmosphere"], g[f"{window}_wave"])
+        got, ref = np.array(out[:4]), g[f"{window}_{tag}_stokes"]
+        assert np.array_equal(out[4], g[f"{window}_lam"])
+        eI = float(np.max(np.abs(got[0] / ref[0] - 1)))
+        nbad = int(np.sum(np.any(got != ref, axis=0)))
+        REPORT[f"passive_fused_{window}_{tag}"] = {"max_rel_I": eI, "n_inexact": nbad, "n": int(ref.shape[1])}
+        assert eI < 1e-9, (window, tag, eI)
+        assert np.array_equal(got, ref), (window, tag, nbad)
+        assert not got[1:].any() and not ref[1:].any()          # no polarised line in these windows
