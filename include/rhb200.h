@@ -443,7 +443,7 @@ int rhb200_voigt_armstrong(rhb200_ctx *ctx, int n, const double *a, const double
 
 /* exp / pow / sin / cos exactly as the device code evaluates them (test hook for
    the glibc-equivalence of the device math) */
-int rhb200_math_probe(rhb200_ctx *ctx, int n, int func /*0 exp 1 sin 2 cos 3 pow 4 x/y via shared reciprocal 5 x/y*/,
+int rhb200_math_probe(rhb200_ctx *ctx, int n, int func /*0 exp 1 sin 2 cos 3 pow 4 x/y via shared reciprocal 5 x/y 6 atan 7 log 8 log10*/,
                       const double *x, const double *y, double *out);
 
 /* ---- NLTE: MALI iteration for active atoms (CRD, unpolarised radiation) ------------------

@@ -461,7 +461,7 @@ class Context:
         return H, reg
 
     def math_probe(self, func: str, x, y=None):
-        code = dict(exp=0, sin=1, cos=2, pow=3, div_recip=4, div=5)[func]
+        code = dict(exp=0, sin=1, cos=2, pow=3, div_recip=4, div=5, atan=6, log=7, log10=8)[func]
         x = np.ascontiguousarray(x, np.float64)
         out = np.zeros_like(x)
         yy = np.ascontiguousarray(y, np.float64) if y is not None else None

@@ -492,6 +492,9 @@ __global__ void math_probe_kernel(int n, int func, const double *__restrict__ x,
   case 2: r = rhm::rh_cos(x[i]); break;
   case 4: { rhdiv::Recip rc(y[i]); r = rc.div(x[i]); break; }     // shared-reciprocal division
   case 5: r = x[i] / y[i]; break;                                  // compiler's IEEE division
+  case 6: r = rhm::rh_atan(x[i]); break;
+  case 7: r = rhm::rh_log(x[i]); break;
+  case 8: r = rhm::rh_log10(x[i]); break;
   default: r = rhm::rh_pow(x[i], y[i]); break;
   }
   out[i] = r;

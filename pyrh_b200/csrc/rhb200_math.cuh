@@ -23,6 +23,7 @@
 #include <cstring>
 #include "rhb200_math_tables.inc"
 #include "rhb200_log_tables.inc"
+#include "rhb200_atan_table.inc"
 
 #if defined(__CUDACC__)
 #define RH_FN __device__ __forceinline__
@@ -351,6 +352,78 @@ RH_FN double rh_log10(double x)
   x = RH_ASDOUBLE(((uint64_t) (uint32_t) hx << 32) | (RH_ASUINT(x) & 0xffffffffULL));
   const double z = y * log10_2lo + ivln10 * rh_log(x);
   return z + y * log10_2hi;
+}
+
+
+// ------------------------------------------------------------------------ atan
+// glibc 2.39 sysdeps/ieee754/dbl-64/s_atan.c (IBM Accurate Mathematical Library, slow paths removed in 2.28), as
+// compiled for FMA hosts (__atan_fma): five ranges of u = |x| with the fused operations where that variant has them.
+//   u < A = 0x1.bb67ap-27: x;  A <= u < 1/16: odd polynomial d3..d13;  1/16 <= u < 1: table cij (241 rows: x_i,
+//   atan x_i, c1..c5) + degree-5 polynomial in u - x_i;  1 <= u < 16: pi/2 - atan(1/u) through the same table with the
+//   rounding error of 1/u carried along;  16 <= u < 0x1.49ff2p+52: pi/2 - (1/u) polynomial;  beyond: +-pi/2.
+RH_TABLE double atan_cij[241 * 7] = { RH_ATAN_TABLE };
+
+RH_FN double rh_atan(double x)
+{
+  const double A = 0x1.bb67a00000000p-27, B = 0x1.0p-4, C = 1.0, D = 16.0, E = 0x1.49ff200000000p+52;
+  const double d3 = -0x1.5555555555555p-2, d5 = 0x1.99999999997fdp-3, d7 = -0x1.24924923f7603p-3,
+               d9 = 0x1.c71c6e5129a3bp-4, d11 = -0x1.7458022b13c25p-4, d13 = 0x1.375f08b31cbcep-4;
+  const double HPI = 0x1.921fb54442d18p+0, HPI1 = 0x1.1a62633145c07p-54, TWO52 = 0x1.0p+52, TWO8 = 256.0;
+  if (x != x) return x + x;
+  const double u = (x < 0) ? -x : x;
+  const uint64_t sign = RH_ASUINT(x) & 0x8000000000000000ULL;
+  double y;
+  if (u < C) {
+    if (u < B) {
+      if (u < A) return x;
+      const double v = x * x;
+      double yy = RH_FMA(d13, v, d11);
+      yy = RH_FMA(yy, v, d9);
+      yy = RH_FMA(yy, v, d7);
+      yy = RH_FMA(yy, v, d5);
+      yy = RH_FMA(yy, v, d3);
+      return RH_FMA(x * v, yy, x);
+    }
+    const int i = (int) (RH_FMA(u, TWO8, TWO52) - TWO52) - 16;
+    const double *c = atan_cij + 7 * i;
+    const double z = u - c[0];
+    double yy = RH_FMA(c[6], z, c[5]);
+    yy = RH_FMA(yy, z, c[4]);
+    yy = RH_FMA(yy, z, c[3]);
+    yy = RH_FMA(yy, z, c[2]);
+    y = RH_FMA(z, yy, c[1]);
+  } else if (u < D) {
+    const double w = 1.0 / u;
+    const double t1 = w * u;
+    const double t2 = RH_FMA(u, w, -t1);
+    const double a = (1.0 - t1) - t2;                       // ww = w * a, fused below
+    const int i = (int) (RH_FMA(w, TWO8, TWO52) - TWO52) - 16;
+    const double *c = atan_cij + 7 * i;
+    const double z = RH_FMA(a, w, w - c[0]);
+    double yy = RH_FMA(c[6], z, c[5]);
+    yy = RH_FMA(yy, z, c[4]);
+    yy = RH_FMA(yy, z, c[3]);
+    yy = RH_FMA(yy, z, c[2]);
+    yy = RH_FMA(-z, yy, HPI1);
+    y = (HPI - c[1]) + yy;
+  } else if (u < E) {
+    const double w = 1.0 / u;
+    const double t1 = w * u;
+    const double t3 = HPI - w;
+    const double v = w * w;
+    double yy = RH_FMA(d13, v, d11);
+    yy = RH_FMA(yy, v, d9);
+    yy = RH_FMA(yy, v, d7);
+    yy = RH_FMA(yy, v, d5);
+    yy = RH_FMA(yy, v, d3);
+    const double t2 = RH_FMA(u, w, -t1);
+    const double a = (1.0 - t1) - t2;
+    const double cor = ((HPI - t3) - w) + HPI1;
+    const double r = RH_FMA(-a, w, cor);
+    const double r2 = RH_FMA(-(w * v), yy, r);
+    y = t3 + r2;
+  } else y = HPI;
+  return RH_ASDOUBLE((RH_ASUINT(y) & 0x7fffffffffffffffULL) | sign);
 }
 
 }  // namespace rhm

@@ -97,9 +97,9 @@ __device__ __forceinline__ double humlicek_H(double a, double v) { return humlic
 
 // ---- VoigtArmstrong (voigt.c:126-243): unpolarised Voigt function H(a, v) of Profile() for
 //      NO_STOKES active lines.  K1 (Chebyshev series + recurrence with data-dependent exit) and K3
-//      (10-point quadrature) are pure + - * / plus exp/cos, hence bit-identical to the reference;
-//      K2 (1 <= a < 2.5, v < 4) calls atan() and log(), for which the toolchain's libm is used
-//      (<= 2 ulp from glibc's): the only branch of this header that is tolerance- not bit-exact.
+//      (10-point quadrature) are pure + - * / plus exp/cos; K2 (1 <= a < 2.5, v < 4) calls atan() and log(),
+//      evaluated with the glibc-exact rh_atan / rh_log of rhb200_math.cuh: all three branches are
+//      bit-identical to the reference.
 __device__ __forceinline__ int armstrong_region(double a, double v) {
   v = fabs(v);
   if ((a < 1.0 && v < 4.0) || (a < 1.8/(v + 1.0))) return 1;
@@ -162,8 +162,8 @@ static __device__ __noinline__ double voigt_armstrong(double a, double v) {
 #pragma unroll 1
     for (int n = 0; n < 10; n++) {
       const double r = T[n] - v, s = T[n] + v;
-      g += (4.0*T[n]*T[n] - 2.0) * (r*atan(r/a) + s*atan(s/a) -
-            0.5*a*(log(a2 + r*r) + log(a2 + s*s))) * W[n];
+      g += (4.0*T[n]*T[n] - 2.0) * (r*rhm::rh_atan(r/a) + s*rhm::rh_atan(s/a) -
+            0.5*a*(rhm::rh_log(a2 + r*r) + rhm::rh_log(a2 + s*s))) * W[n];
     }
     return g/RH_PI;
   }

@@ -68,6 +68,10 @@ int main(int argc, char **argv)
   bad += run1("log[0.93,1.07]", n, L, Lg, uni(0.93, 1.07));
   bad += run1("log[1e3,2e4]", n, L, Lg, uni(1e3, 2e4));
   bad += run1("log[log 1e-320..1e300]", n, L, Lg, pos(1e-320, 1e300));
+  auto AT = [](double x) { return rhm::rh_atan(x); }; auto ATg = [](double x) { return std::atan(x); };
+  bad += run1("atan[-1,1]", n, AT, ATg, uni(-1.0, 1.0));
+  bad += run1("atan[-20,20]", n, AT, ATg, uni(-20.0, 20.0));
+  bad += run1("atan[log 1e-12..1e20]", n, AT, ATg, logu(1e-12, 1e20));
   bad += run1("log10[0.2,3]", n, L10, L10g, uni(0.2, 3.0));
   bad += run1("log10[log 1e-320..1e300]", n, L10, L10g, pos(1e-320, 1e300));
   {
