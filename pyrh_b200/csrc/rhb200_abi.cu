@@ -1000,7 +1000,7 @@ extern "C" int rhb200_voigt_armstrong(rhb200_ctx *c, int n, const double *a, con
 extern "C" int rhb200_math_probe(rhb200_ctx *c, int n, int func, const double *x, const double *y, double *out)
 {
   RH_NEED_CTX(c);
-  if (n <= 0 || !x || !out || func < 0 || func > 5 || (func >= 3 && !y)) { rhb200_set_error("bad arguments"); return RHB200_EINVAL; }
+  if (n <= 0 || !x || !out || func < 0 || func > 8 || (func >= 3 && func <= 5 && !y)) { rhb200_set_error("bad arguments"); return RHB200_EINVAL; }
   DevBuf dx, dy, dout;
   const size_t b = (size_t) n * sizeof(double);
   RH_CHECK(dx.from_host(x, b));
