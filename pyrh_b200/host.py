@@ -10,10 +10,14 @@ What is parsed here (once per working directory, cached), with the reference's o
   getABOcross, rh/barklem.c:199-212; Zeeman patterns by the library's RLKdeterminate / RLKZeeman
 * the merged wavelength grid                         SortLambda, rh/sortlambda.c:180-210 (user grid + lambda_ref)
 
-What is NOT parsed yet: ``*.atom`` / ``*.molecule`` files.  The background model of the reference's standard
-``atoms.input`` (11 PASSIVE atoms) and ``molecules.input`` ships as ``data/background_falc11.npz``; a working
-directory that lists other atoms, ACTIVE atoms, opacity fudge factors or anything else this path does not
-implement is refused loudly (``NotImplementedError``), never approximated.
+* the ``*.atom`` files of ``atoms.input``   readAtom, rh/readatom.c:100-425 (levels, lines with their damping
+  constants, bound-free continua) and the ``*.molecule`` files of ``molecules.input`` (readMolecule,
+  rh/readmolecule.c:60-215: constituents, dissociation energy, equilibrium-constant fit)
+
+Only the published opacity tables RH keeps inside its C sources (H-, H2-, H2+, OH, CH) come from a data file
+(``data/background_falc11.npz``).  A working directory that asks for ACTIVE atoms, opacity fudge factors, molecular
+line lists inside the wavelength grid or anything else this path does not implement is refused loudly
+(``NotImplementedError``), never approximated.
 """
 from __future__ import annotations
 
@@ -409,6 +413,8 @@ def read_atom(atom_file):
             comp = [data[pos + 1 + n].split() for n in range(nc)]
             pos += 1 + nc
             c_shift, c_fraction = [float(x[0]) for x in comp], [float(x[1]) for x in comp]
+        if "BARKLEM" in vdw and stage[i] > 0:                    # getBarklemactivecross: ABO tables are for neutrals only
+            vdw = "UNSOLD"                                       # (barklem.c:232-233) -> readatom.c:313-319 falls back
         if "UNSOLD" in vdw:
             cvdW[1] = cvdW[3] = 0.0
         lines.append(dict(i=i, j=j, lambda0=lambda0 / NM_TO_M, Aji=Aji, Bji=Bji, Bij=Bij, voigt="GAUSS" not in shape,
@@ -539,6 +545,132 @@ def model_line_rows(cwd, kw, el: Elements, lt_elem_order, path=None):
     return np.array(rows, np.float64).reshape(-1, 4)
 
 
+# ------------------------------------------------------------------------------------------- background model
+EV = 1.60217733E-19
+FIT_TYPES = ("KURUCZ_70", "KURUCZ_85", "SAUVAL_TATUM_84", "IRWIN_81", "TSUJI_73")        # enum fit_type, atom.h:32
+
+
+def read_atom_continua(atom_file, atom):
+    """Bound-free continua of one model atom (readatom.c:372-425): [(j, i, alpha0, hydrogenic, lambda0, lambda[], alpha[])]."""
+    data = [ln for ln in Path(atom_file).read_text().splitlines() if ln.strip() and ln[0] != "#"]
+    nlevel, nline, ncont = (int(x) for x in data[1].split()[:3])
+    pos = 2 + nlevel
+    for _ in range(nline):                                       # skip the lines (and their component records)
+        shape = data[pos].split()[3]
+        pos += 1
+        if "COMPOSIT" in shape:
+            pos += 1 + int(data[pos].split()[0])
+    E, out = atom["E"], []
+    for _ in range(ncont):
+        f = data[pos].split()
+        pos += 1
+        j, i = int(f[0]), int(f[1])
+        i, j = min(i, j), max(i, j)
+        alpha0, nlam, dep, lambdamin = float(f[2]), int(f[3]), f[4], float(f[5])
+        lambda0 = ((HPLANCK * CLIGHT) / (E[j] - E[i])) / NM_TO_M
+        lam, alp = [0.0] * nlam, [0.0] * nlam
+        if "EXPLICIT" in dep:
+            for la in range(nlam - 1, -1, -1):                   # the file lists the table from red to blue
+                w = data[pos].split()
+                pos += 1
+                lam[la], alp[la] = float(w[0]), float(w[1])
+            hydrogenic = 0.0
+        elif "HYDROGENIC" in dep:
+            dlamb = (lambda0 - lambdamin) / (nlam - 1)           # getLambdaCont, readatom.c
+            lam[0] = lambdamin
+            for la in range(1, nlam):
+                lam[la] = lam[la - 1] + dlamb
+            hydrogenic = 1.0
+        else:
+            raise ValueError(f"{atom_file}: wavelength dependence {dep}")
+        out.append((j, i, alpha0, hydrogenic, lambda0, lam, alp))
+    return out
+
+
+def read_molecule(mol_file, el: Elements):
+    """One *.molecule file up to the equilibrium-constant fit (readmolecule.c:60-215)."""
+    data = [ln.split("#")[0] for ln in Path(mol_file).read_text().splitlines() if ln.strip() and ln.lstrip()[0] != "#"]
+    ID, charge = data[0].split()[0], int(data[1].split()[0])
+    pt_index, pt_count = [], []
+    for tok in re.split(r"[ ,]+", data[2].strip()):
+        m = re.match(r"(\d*)(\S+)", tok)
+        cnt, sym = (int(m.group(1)) if m.group(1) else 1), m.group(2).upper()
+        if len(sym) == 1:
+            sym += " "
+        e = next(k for k in range(len(el.ID)) if el.ID[k] in sym)          # strstr(elementID, elements[m].ID)
+        if not el.abundance_set[e]:
+            raise ValueError(f"{mol_file}: no abundance for {sym}")
+        pt_index.append(e); pt_count.append(cnt)
+    Ediss = float(data[3].split()[0]) * EV
+    fit = next(k for k, nme in enumerate(FIT_TYPES) if nme in data[4].split()[0])
+    Tmin, Tmax = (float(x) for x in data[5].split()[:2])
+    eq = data[7].split()
+    neqc = int(eq[0])
+    coef = [0.0] * neqc
+    for n in range(neqc - 1, -1, -1):                            # stored last-to-first (readmolecule.c:196-198)
+        coef[n] = float(eq[1 + (neqc - 1 - n)])
+    return dict(ID=ID, charge=charge, pt_index=pt_index, pt_count=pt_count, Ediss=Ediss, fit=fit, Tmin=Tmin, Tmax=Tmax,
+                eqc=coef, has_lines=len(data) > 8)
+
+
+def read_background_model(cwd, kw, el: Elements, path=None):
+    """The flat background model the device continuum / chemistry kernels take (rhb200_continuum_model,
+    rhb200_set_chemistry) from the *.atom and *.molecule files of the working directory's lists: level table,
+    bound-free edges with their cross-section tables, the Rayleigh lines of H and He, the chemical network.  The
+    published opacity tables RH keeps in its source (H-, H2-, H2+, OH, CH) come from data/background_falc11.npz."""
+    root = pyrh_path(path) / "rh"
+    listed = _atoms_listed(cwd, kw)
+    if any(s != "PASSIVE" for _, s in listed):
+        raise NotImplementedError("ACTIVE atoms: use pyrh_b200.nlte (the NLTE entry points take the parsed problem)")
+    tabs = {k: v for k, v in np.load(DATA / "background_falc11.npz").items() if k.startswith("tab_")}
+    lev, bf, tl, ta, ray, pt, atoms = [], [], [], [], [], [], []
+    l0 = 0
+    for m, (fname, _) in enumerate(listed):
+        at = read_atom(root / "Atoms" / fname)
+        if m == 0 and at["ID"] != "H ":
+            raise ValueError("First atomic model is not hydrogen (readatom.c:845-849)")
+        atoms.append(at)
+        pt.append(el.ID.index(at["ID"]) + 1)
+        for i in range(len(at["E"])):
+            lev.append([m, at["E"][i], at["stage"][i], at["g"][i], 0.0])
+        for j, i, alpha0, hyd, lambda0, lam, alp in read_atom_continua(root / "Atoms" / fname, at):
+            bf.append([m, l0 + i, l0 + j, lambda0, lam[0], hyd, alpha0, len(lam), len(tl), 0.0])
+            tl += lam; ta += alp
+        if m < 2:                                                # Rayleigh(): lines from the ground level of H and He
+            for ln in at["lines"]:
+                if ln["i"] == 0:
+                    ray.append([m, ln["lambda0"], ln["qwing"], ln["Aji"], at["g"][ln["j"]], at["g"][0], l0, at["stage"][0]])
+        l0 += len(at["E"])
+    mols = []
+    for ln in (Path(cwd) / kw["MOLECULES_FILE"]).read_text().splitlines():
+        f = ln.split("#", 1)[0].split()
+        if len(f) >= 2 and f[0].endswith(".molecule"):
+            if f[1].upper() != "PASSIVE":
+                raise NotImplementedError("ACTIVE molecules are not implemented")
+            mols.append(read_molecule(root / "Molecules" / f[0], el))
+    nuc_elems = sorted({e for mo in mols for e in mo["pt_index"]})
+    atom_of = {p - 1: a for a, p in enumerate(pt)}
+    nuclei = [[e, atom_of.get(e, -1)] for e in nuc_elems]
+    if any(a < 0 for _, a in nuclei):
+        raise NotImplementedError("a nucleus bound in molecules has no model atom (chemequil.c:222-228 then uses getfjk)")
+    ce_mol = np.zeros((len(mols), 32))
+    for r, mo in zip(ce_mol, mols):
+        r[0:8] = mo["fit"], mo["charge"], sum(mo["pt_count"]), len(mo["pt_index"]), len(mo["eqc"]), mo["Tmin"], mo["Tmax"], mo["Ediss"]
+        r[8:8 + len(mo["eqc"])] = mo["eqc"]
+        for j, (e, cnt) in enumerate(zip(mo["pt_index"], mo["pt_count"])):
+            r[16 + j], r[20 + j] = nuc_elems.index(e), cnt
+        r[24], r[25], r[26] = mo["ID"] == "H2", mo["ID"] == "OH", mo["ID"] == "CH"
+    ids = [mo["ID"] for mo in mols]
+    hdr = np.array([len(listed), len(lev), len(bf), len(tl), len(ray), 0.0, float(len(pt) > 1 and pt[1] == 2),
+                    float("OH" in ids), float("CH" in ids), float("H2" in ids), 0.0, float(kw["VMICRO_CHAR"]) * 1.0E+03, 0.0,
+                    len(atoms[0]["E"]), 1.0, 1.0])
+    out = dict(ct_hdr=hdr, ct_lev=np.array(lev), ct_bf=np.array(bf).reshape(-1, 10), ct_tab_lambda=np.array(tl),
+               ct_tab_alpha=np.array(ta), ct_ray=np.array(ray).reshape(-1, 8), ce_nuclei=np.array(nuclei, np.float64),
+               ce_mol=ce_mol, atom_files=np.array([a for a, _ in listed]), atom_pt_index=np.array(pt, np.int32))
+    out.update(tabs)
+    return out
+
+
 # ------------------------------------------------------------------------------------------- session
 def _atoms_listed(cwd, kw):
     out = []
@@ -571,14 +703,9 @@ class Session:
             raise NotImplementedError("RLK_SCATTER = TRUE is not implemented")
         if int(kw["N_MAX_SCATTER"]) != 0:
             raise NotImplementedError("N_MAX_SCATTER > 0 in LTE (pyrh_compute1dray.c:332-337) is not implemented")
-        bg = dict(np.load(DATA / "background_falc11.npz"))
         listed = _atoms_listed(cwd, kw)
-        if [a for a, _ in listed] != [str(x) for x in bg["atom_files"]]:
-            raise NotImplementedError(f"atoms.input lists {[a for a, _ in listed]}; only the standard background set "
-                                      f"{[str(x) for x in bg['atom_files']]} ships with pyrh_b200.host (no *.atom parser yet)")
-        if any(s != "PASSIVE" for _, s in listed):
-            raise NotImplementedError("ACTIVE atoms: use pyrh_b200.nlte (the NLTE entry points take the parsed problem)")
         self.el = read_elements(path, kw, atomic_number, atomic_abundance)
+        bg = self.background = read_background_model(cwd, kw, self.el, path)
         self.lt = read_kurucz_lines(cwd, kw, self.el, loggf_ids, loggf_values, lam_ids, lam_values)
         self.lambda_ref = float(kw["LAMBDA_REF"])
         self.lam = sort_lambda(wave, self.lambda_ref)
@@ -629,9 +756,7 @@ def get_scales(cwd, atm_scale, scale, atmosphere, lam_ref, atomic_number=None, a
     from . import api, continuum
     kw = read_keywords(cwd)
     el = read_elements(None, kw, atomic_number, atomic_abundance)
-    bg = dict(np.load(DATA / "background_falc11.npz"))
-    if [a for a, _ in _atoms_listed(cwd, kw)] != [str(x) for x in bg["atom_files"]]:
-        raise NotImplementedError("only the standard background atom set ships with pyrh_b200.host")
+    bg = read_background_model(cwd, kw, el)
     ctx = api.Context(device)
     try:
         empty = ll.LineTable(lines=np.zeros((0, ll.RL_NFIELD)), zq=np.zeros(0, np.int32), zshift=np.zeros(0),
@@ -672,9 +797,7 @@ class HseSession:
         from . import api, continuum
         kw = read_keywords(cwd)
         self.el = el = read_elements(None, kw, atomic_number, atomic_abundance)
-        bg = dict(np.load(DATA / "background_falc11.npz"))
-        if [a for a, _ in _atoms_listed(cwd, kw)] != [str(x) for x in bg["atom_files"]]:
-            raise NotImplementedError("only the standard background atom set ships with pyrh_b200.host")
+        bg = read_background_model(cwd, kw, el)
         if not el.abundance_set.all():
             raise NotImplementedError("elements without an abundance are not supported by the electron-density solver")
         self.ctx = ctx = api.Context(device)

@@ -1082,3 +1082,28 @@ def test_passive_bb_in_the_fused_path(window):
         assert eI < 1e-9, (window, tag, eI)
         assert np.array_equal(got, ref), (window, tag, nbad)
         assert not got[1:].any() and not ref[1:].any()          # no polarised line in these windows
+
+
+def test_other_atom_set_parsed_from_files(tmp_path):
+    """A working directory whose atoms.input is not the shipped one (CaII.atom added as twelfth PASSIVE atom): the
+    background model, the passive-line table and the duplicate check all come from the *.atom / *.molecule files
+    (pyrh_b200.host.read_background_model); Ca II K (passive_bb with van der Waals + quadratic Stark damping) and the
+    Hinode window equal the reference's rhf1d() bit for bit (fixture atoms12)."""
+    from pyrh_b200 import host
+    g = dict(np.load(GOLD / "atoms12.npz"))
+    cwd = Path(_stage_cwd(tmp_path, kurucz="fe6300"))
+    lines = (cwd / "atoms.input").read_text().splitlines()
+    for i, ln in enumerate(lines):
+        w = ln.split()
+        if w and not ln.strip().startswith("#") and w[0].isdigit():
+            lines[i] = f"   {int(w[0]) + 1}"
+            break
+    last = max(i for i, ln in enumerate(lines) if ".atom" in ln)
+    lines.insert(last + 1, "  CaII.atom        PASSIVE     LTE_POPULATIONS   pops.CaII.out")
+    (cwd / "atoms.input").write_text("\n".join(lines) + "\n")
+    for name in ("CaK", "hinode"):
+        out = host.compute1d(str(cwd), 1.0, 0, g["atmosphere"], g[name + "_wave"])
+        got, ref = np.array(out[:4]), g[name + "_stokes"]
+        REPORT[f"atoms12_{name}_exact"] = bool(np.array_equal(got, ref))
+        assert np.max(np.abs(got[0] / ref[0] - 1)) < 1e-9, name
+        assert np.array_equal(got, ref), name

@@ -88,3 +88,34 @@ def test_grids_touching_passive_lines_are_refused():
     assert any("H line at 656.4" in x[2] for x in w) and any("CN.molecule" in x[2] for x in w)
     with pytest.raises(NotImplementedError, match="CN.molecule"):
         host.Session(CWD, [847.0], path=PYRH_PATH)
+
+
+def test_background_model_from_atom_and_molecule_files():
+    """read_background_model (readAtom / readMolecule in Python) reproduces, bit for bit, the model recorded from the
+    reference's parsed state: 221 levels, 157 bound-free edges with 6368 table points, the Rayleigh lines, the chemical
+    network of 4 nuclei and 12 molecules.  (The reference leaves the alpha table of HYDROGENIC edges uninitialised.)"""
+    from pyrh_b200 import host
+    kw = host.read_keywords(CWD)
+    el = host.read_elements(PYRH_PATH, kw)
+    m = host.read_background_model(CWD, kw, el, PYRH_PATH)
+    ref = dict(np.load(ROOT / "pyrh_b200" / "data" / "background_falc11.npz"))
+    for k in ("ct_hdr", "ct_lev", "ct_bf", "ct_tab_lambda", "ct_ray", "ce_nuclei", "ce_mol", "atom_pt_index"):
+        assert np.array_equal(np.asarray(m[k]), ref[k]), k
+    explicit = np.zeros(len(ref["ct_tab_alpha"]), bool)
+    for b in ref["ct_bf"]:
+        if b[5] == 0.0:
+            explicit[int(b[8]):int(b[8]) + int(b[7])] = True
+    assert explicit.sum() > 4000
+    assert np.array_equal(m["ct_tab_alpha"][explicit], ref["ct_tab_alpha"][explicit])
+
+
+def test_passive_line_table_shapes():
+    from pyrh_b200 import host
+    kw = host.read_keywords(CWD)
+    el = host.read_elements(PYRH_PATH, kw)
+    bg = host.read_background_model(CWD, kw, el, PYRH_PATH)
+    first = [int(np.flatnonzero(bg["ct_lev"][:, 0] == a)[0]) for a in range(11)]
+    rows, cs, cf = host.passive_line_table(CWD, kw, el, first, PYRH_PATH)
+    assert rows.shape == (202, host.PL_NFIELD) and len(cs) == len(cf) == 202
+    ha = rows[np.argmin(np.abs(rows[:, host.PL_LAMBDA0] - 656.47))]
+    assert ha[host.PL_IS_H] == 1 and ha[host.PL_LINSTARK_C] > 0 and ha[host.PL_VDW_TYPE] == host.VDW_UNSOLD_A
