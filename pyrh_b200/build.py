@@ -18,7 +18,7 @@ SOURCES = ["rhb200_abi.cu", "rhb200_lines.cu", "rhb200_delo.cu", "rhb200_peak.cu
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
-         "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-Xptxas", "-v"]
+         "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-Xptxas", "-v"] + os.environ.get("RHB200_NVCC_EXTRA", "").split()
 
 
 def needs_build() -> bool:

@@ -105,7 +105,9 @@ double gaunt_bf(double lambda, double n_eff, int charge)                     // 
   return 1.0 + 0.1728*x3 * (1.0 - 2.0*nsqx) - 0.0496*SQ(x3) * (1.0 - (1.0 - nsqx)*0.66666667*nsqx);
 }
 
+#ifndef CONT_TL        // -DCONT_TL=n through RHB200_NVCC_EXTRA; measured per 2048-column call: 2 -> 16.7 ms, 3 -> 15.9, 4 -> 15.5
 #define CONT_TL 4      // wavelengths per thread of the tiled kernel
+#endif
 #define CONT_MAXBF 96  // open bound-free edges per family staged in shared memory
 // per-wavelength coefficient record (doubles), then the lists of open bound-free edges
 enum { WC_FLAGS = 0, WC_LAMBDA, WC_HCKLA_B, WC_TWOHNU3_B, WC_HCKLA_A, WC_TWOHNU3_A, WC_ALPHA_HMBF, WC_LI_HMFF,
