@@ -108,6 +108,11 @@ int rhb200_set_lines(rhb200_ctx *ctx,
    bit-exact. */
 int rhb200_set_wavelengths(rhb200_ctx *ctx, int nlambda, const double *lambda);
 
+/* keyword STOKES_MODE: 1 = FULL_STOKES (default), 0 = NO_STOKES -- I alone at every wavelength with the scalar
+   S_INTERPOLATION ray (formal.c:93-103, 223-236), Q = U = V = 0; the reference's own test configuration
+   (tests/keyword.input).  Call before rhb200_set_wavelengths. */
+int rhb200_set_stokes_mode(rhb200_ctx *ctx, int full_stokes);
+
 /* passive_bb in the fused LTE path (metal.c:174-344): bound-bound lines of the PASSIVE model atoms, hydrogen
    included, unpolarised, added to the background before the Kurucz lines exactly like Background() does
    (background.c:494-515); they also set hasline, i.e. select the scalar ray for their wavelengths.  plines

@@ -121,6 +121,12 @@ class Context:
         rows = np.ascontiguousarray(rows, np.float64).reshape(-1, 4)
         _lib.check(self.lib.rhb200_set_model_lines(self.h, len(rows), _dp(rows)))
 
+    def set_stokes_mode(self, mode="FULL_STOKES"):
+        """keyword STOKES_MODE: FULL_STOKES or NO_STOKES (call before set_wavelengths)."""
+        if mode not in ("FULL_STOKES", "NO_STOKES"):
+            raise NotImplementedError(f"STOKES_MODE = {mode}: only FULL_STOKES and NO_STOKES are implemented")
+        _lib.check(self.lib.rhb200_set_stokes_mode(self.h, int(mode == "FULL_STOKES")))
+
     def set_passive_lines(self, rows, c_shift, c_fraction):
         """Bound-bound lines of the PASSIVE model atoms for the fused path (passive_bb): rows [n, RHB200_PL_NFIELD]."""
         rows = np.ascontiguousarray(rows, np.float64).reshape(-1, 28)

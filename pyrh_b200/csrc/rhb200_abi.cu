@@ -169,6 +169,17 @@ extern "C" int rhb200_set_lines(rhb200_ctx *c, int nline, const double *lines, i
   return RHB200_OK;
 }
 
+// keyword STOKES_MODE (inputs.h enum StokesMode): FULL_STOKES solves I, Q, U, V where a polarised line is present;
+// NO_STOKES solves I alone everywhere (Q = U = V = 0) -- the line profiles are the same Zeeman-split ones either way,
+// because pyrh always sets atmos.Stokes (pyrh_compute1dray.c:259).  Call before rhb200_set_wavelengths.
+extern "C" int rhb200_set_stokes_mode(rhb200_ctx *c, int full_stokes)
+{
+  RH_NEED_CTX(c);
+  c->no_stokes = full_stokes ? 0 : 1;
+  free_wave(c);
+  return RHB200_OK;
+}
+
 extern "C" int rhb200_set_passive_lines(rhb200_ctx *c, int nline, const double *plines, int ncomp,
                                         const double *c_shift, const double *c_fraction)
 {
@@ -295,8 +306,11 @@ extern "C" int rhb200_set_wavelengths(rhb200_ctx *c, int nlambda, const double *
   std::vector<int> rank(nlambda, -1);
   w.nunpol = 0;
   for (int l = 0; l < nlambda; l++) {
-    if ((c->h_flags[l] & 2) == 0) c->h_noline.push_back(l);     // no polarised line: solved for I alone
-    if (c->h_flags[l] == 1) rank[l] = w.nunpol++;               // ... with the scalar ray in moving columns
+    // FULL_STOKES: wavelengths without a polarised line are solved for I alone -- with the scalar ray where a line is
+    // present and the column moves; NO_STOKES (solveStokes false, formal.c:93-95): every wavelength is, and a polarised
+    // background line still makes the wavelength angle dependent, i.e. takes the scalar ray (formal.c:100-103)
+    if (c->no_stokes || (c->h_flags[l] & 2) == 0) c->h_noline.push_back(l);
+    if (c->no_stokes ? (c->h_flags[l] & 1) : (c->h_flags[l] == 1)) rank[l] = w.nunpol++;
   }
   w.nnoline = (int) c->h_noline.size();
   if (w.nnoline) RH_CHECK(upload(&w.noline, c->h_noline.data(), (size_t) w.nnoline));
@@ -388,7 +402,7 @@ static int run_chunk_dev(rhb200_ctx *c, int cc, int ndep, double muz, int moving
   if (sc) RH_CHECK(rh_launch_scales(c, cc, ndep, sc->iref, sc->atm_scale, sc->wght_per_H, sc->total_abund, sc->gravity,
                                     d_raypts, (double *) d_atmos, sc->d_scratch, sc->d_scales_out));
   if (sc && sc->scales_only) return RHB200_OK;
-  RH_CHECK(rh_launch_delo_raypts(c, cc, ndep, muz, bc_top, bc_bottom, d_atmos, d_raypts, d_stokes));
+  if (!c->no_stokes) RH_CHECK(rh_launch_delo_raypts(c, cc, ndep, muz, bc_top, bc_bottom, d_atmos, d_raypts, d_stokes));
   RH_CHECK(rh_launch_feautrier_raypts(c, cc, ndep, muz, bc_top, bc_bottom, d_atmos, d_raypts, d_stokes,
                                       moving, d_colmov, d_scal));
   return RHB200_OK;

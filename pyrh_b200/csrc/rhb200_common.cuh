@@ -83,6 +83,7 @@ struct rhb200_ctx {
   std::vector<double> h_plines, h_pcshift, h_pcfrac;   // rhb200_set_passive_lines     // rhb200_set_model_lines: [n][4] element row, stage, lambda0 [nm], qwing
   // formal solver selection (keyword.input S_INTERPOLATION / S_INTERPOLATION_STOKES, inputs.h:26-27)
   int s_interpolation = RHB200_S_BEZIER3, s_interpolation_stokes = RHB200_DELO_BEZIER3;
+  int no_stokes = 0;         // STOKES_MODE = NO_STOKES (rhb200_set_stokes_mode)
   // wavelength shard of the NLTE solve (rhb200_nlte_set_shard)
   int shard_rank = 0, shard_nrank = 1;
   rhb200_allreduce_fn shard_fn = nullptr; void *shard_user = nullptr;

@@ -205,7 +205,8 @@ feautrier_raypts_kernel(int ncol, int nlambda, int ndep, double muz, int bc_top,
   const double *at = atmos + (size_t) col * RHB200_AT_NFIELD * ndep;
   double *rp = raypts + r * (size_t) ndep * RP_NFIELD;
   double I0;
-  const bool scalar_ray = (__ldg(wflags + l) & 1) && (col_moving ? col_moving[col] != 0 : moving != 0);
+  const int fl = __ldg(wflags + l);                  // polarised line (NO_STOKES only): always angle dependent
+  const bool scalar_ray = (fl & 2) || ((fl & 1) && (col_moving ? col_moving[col] != 0 : moving != 0));
   if (scalar_ray) {
     double *c = scratch + ((size_t) col * nunpol + __ldg(unpol_rank + l)) * 3 * ndep, *s = c + ndep, *Ir = s + ndep;
     for (int k = 0; k < ndep; k++) { c[k] = rp[(size_t) k * RP_NFIELD + RP_CHI]; s[k] = rp[(size_t) k * RP_NFIELD + RP_SI]; }

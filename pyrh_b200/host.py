@@ -7,7 +7,8 @@ What is parsed here (once per working directory, cached), with the reference's o
 * ``keyword.input``                      readInput, rh/readinput.c:43-420 (the keywords the LTE path looks at)
 * ``abundance.input`` + ``pf_Kurucz.input`` (XDR)   readAbundance, rh/abundance.c:72-222
 * the Kurucz line lists of ``KURUCZ_DATA``          readKuruczLines, rh/kurucz.c:121-431; getUnsoldcross :985-1024;
-  getABOcross, rh/barklem.c:199-212; Zeeman patterns by the library's RLKdeterminate / RLKZeeman
+  getABOcross / getBarklemcross with the Barklem tables and cubeconvol, rh/barklem.c:61-212, rh/cubeconvol.c;
+  Zeeman patterns by the library's RLKdeterminate / RLKZeeman
 * the merged wavelength grid                         SortLambda, rh/sortlambda.c:180-210 (user grid + lambda_ref)
 
 * the ``*.atom`` files of ``atoms.input``   readAtom, rh/readatom.c:100-425 (levels, lines with their damping
@@ -208,6 +209,148 @@ def _gammln(xx: float) -> float:                              # rh/gammafunc.c
     return -tmp + math.log(2.5066282746310005 * ser / x)
 
 
+# Barklem / Anstee / O'Mara tables (barklem.c:31-49)
+BARKLEM = {"SP": ("Barklem_spdata.dat", 21, 18, 1.0, 1.3), "PD": ("Barklem_pddata.dat", 18, 18, 1.3, 2.3),
+           "DF": ("Barklem_dfdata.dat", 18, 18, 2.3, 3.3)}
+BARKLEM_DELTA_NEFF = 0.1
+
+
+def read_barklem_table(kind, path=None):
+    """readBarklemTable (barklem.c:61-132): 3 header lines, N1 x N2 cross-sections, 2 more lines, N1 x N2 alphas."""
+    fname, n1, n2, neff1_0, neff2_0 = BARKLEM[kind]
+    lines = (pyrh_path(path) / "rh" / "Atoms" / fname).read_text().splitlines()
+    nums = []
+    pos = 3
+    while len(nums) < n1 * n2:
+        nums += [float(x) for x in lines[pos].split()]
+        pos += 1
+    cross = nums[:n1 * n2]
+    pos += 2                                                     # fgets x2 after fscanf left the newline unread: the
+    nums = []                                                    # rest of the last data line + one comment line
+    tail = lines[pos - 1:]
+    for ln in tail:
+        try:
+            nums += [float(x) for x in ln.split()]
+        except ValueError:
+            nums = []
+        if len(nums) >= n1 * n2:
+            break
+    alpha = nums[:n1 * n2]
+    neff1 = [neff1_0 + n * BARKLEM_DELTA_NEFF for n in range(n1)]
+    neff2 = [neff2_0 + n * BARKLEM_DELTA_NEFF for n in range(n2)]
+    return dict(N1=n1, N2=n2, neff1=neff1, neff2=neff2, cross=cross, alpha=alpha)
+
+
+def _cc_kernel(s):                                               # cubeconvol.c:143-151
+    return [-s * (1.0 - s * (2.0 - s)) / 2.0, 1.0 + s * s * (3.0 * s - 5.0) / 2.0,
+            s * (1.0 + s * (4.0 - 3.0 * s)) / 2.0, s * s * (s - 1.0) / 2.0]
+
+
+def cubeconvol(Nx, Ny, f, x, y):
+    """Cubic-convolution interpolation in a row-major table f[Ny][Nx] at fractional indices (x, y): cubeconvol.c:30-139."""
+    if x <= 0.0:
+        i, ux = 0, _cc_kernel(0.0)
+    elif x >= float(Nx - 1):
+        i, ux = Nx - 2, _cc_kernel(1.0)
+    else:
+        fr, ip = math.modf(x)
+        ux, i = _cc_kernel(fr), int(ip)
+    if y <= 0.0:
+        j, uy = 0, _cc_kernel(0.0)
+    elif y >= float(Ny - 1):
+        j, uy = Ny - 2, _cc_kernel(1.0)
+    else:
+        fr, jp = math.modf(y)
+        uy, j = _cc_kernel(fr), int(jp)
+    base = Nx * (j - 1) + i - 1
+    c = [[0.0] * 4 for _ in range(4)]
+
+    def fill(m, row_base):
+        if i == 0:
+            for n in range(1, 4):
+                c[m][n] = f[row_base + n]
+            c[m][0] = 3.0 * (c[m][1] - c[m][2]) + c[m][3]
+        elif i == Nx - 2:
+            for n in range(0, 3):
+                c[m][n] = f[row_base + n]
+            c[m][3] = 3.0 * (c[m][2] - c[m][1]) + c[m][0]
+        else:
+            for n in range(4):
+                c[m][n] = f[row_base + n]
+
+    if j == 0:
+        fc = base + Nx
+        for m in range(1, 4):
+            fill(m, fc)
+            fc += Nx
+        for n in range(4):
+            c[0][n] = 3.0 * (c[1][n] - c[2][n]) + c[3][n]
+    elif j == Ny - 2:
+        fc = base
+        for m in range(0, 3):
+            fill(m, fc)
+            fc += Nx
+        for n in range(4):
+            c[3][n] = 3.0 * (c[2][n] - c[1][n]) + c[0][n]
+    else:
+        fc = base
+        if i != 0 and i != Nx - 2:                               # interior: convolve without copying
+            g = 0.0
+            for m in range(4):
+                for n in range(4):
+                    g += f[fc + n] * ux[n] * uy[m]
+                fc += Nx
+            return g
+        for m in range(4):
+            fill(m, fc)
+            fc += Nx
+    g = 0.0
+    for m in range(4):
+        for n in range(4):
+            g += c[m][n] * ux[n] * uy[m]
+    return g
+
+
+def barklem_cross(bs, stage, Ei, Ej, li, lj, ionpot, weight, H_weight):
+    """getBarklemcross (barklem.c:139-196): (cross, alpha) or None where the reference falls back to Unsold."""
+    if stage > 0:
+        return None
+    deltaEi, deltaEj = ionpot - Ei, ionpot - Ej
+    if deltaEi <= 0.0 or deltaEj <= 0.0:
+        return None
+    Z = float(stage + 1)
+    E_Ryd = E_RYDBERG / (1.0 + M_ELECTRON / (weight * AMU))
+    neff1, neff2 = Z * math.sqrt(E_Ryd / deltaEi), Z * math.sqrt(E_Ryd / deltaEj)
+    if li > lj:
+        neff1, neff2 = neff2, neff1
+    t1, t2 = bs["neff1"], bs["neff2"]
+    if neff1 < t1[0] or neff1 > t1[-1]:
+        return None
+
+    def locate(arr, v):                                          # hunt.c:92-117, ascending
+        lo, hi = 0, len(arr)
+        while hi - lo > 1:
+            mid = (hi + lo) >> 1
+            if v >= arr[mid]:
+                lo = mid
+            else:
+                hi = mid
+        return lo
+    k = locate(t1, neff1)
+    findex1 = float(k) + (neff1 - t1[k]) / BARKLEM_DELTA_NEFF
+    if neff2 < t2[0] or neff2 > t2[-1]:
+        return None
+    k = locate(t2, neff2)
+    findex2 = float(k) + (neff2 - t2[k]) / BARKLEM_DELTA_NEFF
+    cross = cubeconvol(bs["N2"], bs["N1"], bs["cross"], findex2, findex1)
+    alpha = cubeconvol(bs["N2"], bs["N1"], bs["alpha"], findex2, findex1)
+    reducedmass = AMU / (1.0 / H_weight + 1.0 / weight)
+    meanvelocity = math.sqrt(8.0 * KBOLTZMANN / (PI * reducedmass))
+    crossmean = (RBOHR * RBOHR) * math.pow(meanvelocity / 1.0E4, -alpha)
+    cross *= 2.0 * math.pow(4.0 / PI, alpha / 2.0) * math.exp(_gammln((4.0 - alpha) / 2.0)) * meanvelocity * crossmean
+    return cross, alpha
+
+
 def read_kurucz_records(cwd, kurucz_data: str):
     """The fixed-length records of every list named in KURUCZ_DATA (kurucz.c:157-184): list entries are opened
     relative to the process cwd in the reference (kurucz.c:160-165); here relative to `cwd`."""
@@ -228,12 +371,12 @@ def read_kurucz_records(cwd, kurucz_data: str):
 
 
 def read_kurucz_lines(cwd, kw: dict, el: Elements, loggf_ids=None, loggf_values=None, lam_ids=None,
-                      lam_values=None) -> ll.LineTable:
+                      lam_values=None, path=None) -> ll.LineTable:
     """readKuruczLines (kurucz.c:121-431) + the lazily built Zeeman patterns (kurucz.c:832-921) -> LineTable,
     sorted by lambda0 (background.c:292-294)."""
     C = 2.0 * PI * (Q_ELECTRON / EPSILON_0) * (Q_ELECTRON / M_ELECTRON) / CLIGHT
     LS_Lande = _true(kw["LS_LANDE"])
-    rows, patterns, used = [], [], {}
+    rows, patterns, used, barklem = [], [], {}, {}
     if kw["KURUCZ_DATA"].lower() == "none":
         raise NotImplementedError("KURUCZ_DATA = none: the LTE path needs a Kurucz line list")
     for line_index, rec in enumerate(read_kurucz_records(cwd, kw["KURUCZ_DATA"])):
@@ -299,10 +442,15 @@ def read_kurucz_lines(cwd, kw: dict, el: Elements, loggf_ids=None, loggf_values=
             crossmean = (RBOHR * RBOHR) * math.pow(meanvelocity / 1.0E4, -alpha)
             cross *= 2.0 * math.pow(4.0 / PI, alpha / 2.0) * math.exp(_gammln((4.0 - alpha) / 2.0)) * meanvelocity * crossmean
             vdw = ll.VDW_BARKLEM
-        elif {li, lj} in ({0, 1}, {1, 2}, {2, 3}) and stage == 0:
-            raise NotImplementedError(f"line {line_index}: Barklem table interpolation (barklem.c:139-196, cubeconvol.c) "
-                                      "is not ported; give the ABO alpha / sigma in columns 161+ instead of the "
-                                      "orbital numbers")
+        else:                                                    # kurucz.c:322-332: tables by orbital quantum numbers
+            kind = {frozenset((0, 1)): "SP", frozenset((1, 2)): "PD", frozenset((2, 3)): "DF"}.get(frozenset((li, lj)))
+            if kind and li != lj:
+                if kind not in barklem:
+                    barklem[kind] = read_barklem_table(kind, path)
+                hit = barklem_cross(barklem[kind], stage, rEi, rEj, li, lj, el.ionpot[e][stage], el.weight[e], el.weight[0])
+                if hit:
+                    cross, alpha = hit
+                    vdw = ll.VDW_BARKLEM
         if vdw is None:                                          # getUnsoldcross, kurucz.c:985-1024
             if stage > el.nstage[e] - 1:
                 vdw = ll.VDW_KURUCZ
@@ -706,7 +854,7 @@ class Session:
         listed = _atoms_listed(cwd, kw)
         self.el = read_elements(path, kw, atomic_number, atomic_abundance)
         bg = self.background = read_background_model(cwd, kw, self.el, path)
-        self.lt = read_kurucz_lines(cwd, kw, self.el, loggf_ids, loggf_values, lam_ids, lam_values)
+        self.lt = read_kurucz_lines(cwd, kw, self.el, loggf_ids, loggf_values, lam_ids, lam_values, path)
         self.lambda_ref = float(kw["LAMBDA_REF"])
         self.lam = sort_lambda(wave, self.lambda_ref)
         for lo, hi, what in passive_line_windows(cwd, kw, path, atoms=False):
@@ -723,6 +871,8 @@ class Session:
             self.ctx.set_passive_lines(*passive_line_table(cwd, kw, self.el, first, path))
         self.model_lines = model_line_rows(cwd, kw, self.el, self.lt.elem_rows, path)
         self.ctx.set_model_lines(self.model_lines)
+        self.stokes_mode = kw["STOKES_MODE"].upper()
+        self.ctx.set_stokes_mode(self.stokes_mode)
         self.ctx.set_wavelengths(self.lam)
         self.ctx.set_solvers(kw["S_INTERPOLATION"], kw["S_INTERPOLATION_STOKES"])
         abundance = np.array([self.el.abund[int(p) - 1] for p in bg["atom_pt_index"]])
@@ -887,4 +1037,6 @@ def compute1d(cwd, mu, atm_scale, atmosphere, wave, loggf_ids=None, loggf_values
         s = _SESSIONS[key] = Session(cwd, wave, device, None, loggf_ids, loggf_values, lam_ids, lam_values, fudge_wave,
                                      fudge_value, atomic_number, atomic_abundance)
     st = s.compute(atmosphere, mu=mu, atm_scale=atm_scale)
+    if s.stokes_mode == "NO_STOKES":                             # spec.stokes is false: pyrh.pyx:647-652
+        return st[0], None, None, None, s.wavelengths
     return st[0], st[1], st[2], st[3], s.wavelengths

@@ -1107,3 +1107,30 @@ def test_other_atom_set_parsed_from_files(tmp_path):
         REPORT[f"atoms12_{name}_exact"] = bool(np.array_equal(got, ref))
         assert np.max(np.abs(got[0] / ref[0] - 1)) < 1e-9, name
         assert np.array_equal(got, ref), name
+
+
+def test_reference_own_test_compute1d(tmp_path):
+    """The reference's own test (tests/test_compute1d.py): FAL-C with B = 500 G in its tests/ directory
+    (STOKES_MODE = NO_STOKES), wave = linspace(630.25, 630.5, 100), through pyrh_b200.host.compute1d with the same
+    call.  NO_STOKES solves I alone with the scalar Bezier ray at every line wavelength (formal.c:93-103, 223-236);
+    I equals the reference's bit for bit and Q, U, V come back as None like from pyrh (pyrh.pyx:647-652)."""
+    import shutil
+    from pyrh_b200 import host
+    root = Path(__file__).resolve().parent.parent
+    src, pp = root / "oracle" / "_ref" / "inputs" / "tests", root / "oracle" / "_ref" / "pyrh_path"
+    if not (src / "keyword.input").exists():
+        pytest.skip("reference input files not staged (oracle/_ref)")
+    os.environ["PYRH_PATH"] = str(pp)
+    for f in src.iterdir():
+        if f.is_file() and f.suffix not in (".py", ".dat"):
+            shutil.copy(f, tmp_path / f.name)
+    g = dict(np.load(GOLD / "ref_test_compute1d.npz"))
+    cwd, atm_scale = str(tmp_path), 0
+    spec = host.compute1d(cwd, 1.0, atm_scale, g["atmosphere"], g["wave"])
+    assert spec[1] is None and spec[2] is None and spec[3] is None
+    assert np.array_equal(spec[-1], g["lam"])
+    REPORT["ref_test_compute1d_exact"] = bool(np.array_equal(spec[0], g["I"]))
+    assert np.max(np.abs(spec[0] / g["I"] - 1)) < 1e-9
+    assert np.array_equal(spec[0], g["I"])
+    spec = host.compute1d(cwd, 0.5, atm_scale, g["moving_atmosphere"], g["wave"])
+    assert np.array_equal(spec[0], g["moving_I"])

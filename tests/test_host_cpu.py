@@ -119,3 +119,20 @@ def test_passive_line_table_shapes():
     assert rows.shape == (202, host.PL_NFIELD) and len(cs) == len(cf) == 202
     ha = rows[np.argmin(np.abs(rows[:, host.PL_LAMBDA0] - 656.47))]
     assert ha[host.PL_IS_H] == 1 and ha[host.PL_LINSTARK_C] > 0 and ha[host.PL_VDW_TYPE] == host.VDW_UNSOLD_A
+
+
+def test_barklem_tables_and_cubic_convolution():
+    """tests/fe6300 of the reference gives the orbital quantum numbers of the Fe I pair, so readKuruczLines takes the
+    Anstee-Barklem-O'Mara s-p table (getBarklemcross, barklem.c:139-196, with cubeconvol.c): cross-section and
+    velocity exponent equal the reference's parsed values bit for bit."""
+    from pyrh_b200 import host, linelist as ll
+    cwd = ROOT / "oracle" / "_ref" / "inputs" / "tests"
+    if not (cwd / "keyword.input").exists():
+        pytest.skip("reference tests/ inputs not staged")
+    g = np.load(GOLD / "ref_test_compute1d.npz")
+    kw = host.read_keywords(cwd)
+    el = host.read_elements(PYRH_PATH, kw)
+    lt = host.read_kurucz_lines(cwd, kw, el, path=PYRH_PATH)
+    assert np.array_equal(lt.lines[:, ll.RL_VDWAALS], g["rlk_vdwaals"]) and lt.lines[0, ll.RL_VDWAALS] == ll.VDW_BARKLEM
+    assert np.array_equal(lt.lines[:, ll.RL_CROSS], g["rlk_cross"])
+    assert np.array_equal(lt.lines[:, ll.RL_ALPHA], g["rlk_alpha"])
