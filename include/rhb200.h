@@ -108,6 +108,16 @@ int rhb200_set_lines(rhb200_ctx *ctx,
    bit-exact. */
 int rhb200_set_wavelengths(rhb200_ctx *ctx, int nlambda, const double *lambda);
 
+/* MolecularOpacity in the fused LTE path (opacity.c:711-839, MolProfile :844-916): LTE lines of PASSIVE molecules,
+   added to the background after the Kurucz lines like Background() does (background.c:548-566); unpolarizable lines
+   only (lines with Hund's-case data need MolZeeman patterns: rhb200_molecular_opacity_batch takes them from the
+   host).  mlines [nline][RHB200_ML_NFIELD] grouped by molecule, ascending lambda0 inside each, RHB200_ML_MOL = row
+   of `molecules`; molecules [nmol][16] = {index in the chemical network of rhb200_set_chemistry, molecular weight,
+   enum fit_type, Tmin, Tmax, Npf, pf_coef[0..7]}.  Densities come from the chemistry kernel, partition functions
+   (partfunction, chemequil.c:395-443) and Doppler widths are formed on the device.  Call after rhb200_set_continuum /
+   rhb200_set_chemistry and before rhb200_set_wavelengths; rhb200_set_lines clears the table. */
+int rhb200_set_molecular_lines(rhb200_ctx *ctx, int nline, const double *mlines, int nmol, const double *molecules);
+
 /* keyword STOKES_MODE: 1 = FULL_STOKES (default), 0 = NO_STOKES -- I alone at every wavelength with the scalar
    S_INTERPOLATION ray (formal.c:93-103, 223-236), Q = U = V = 0; the reference's own test configuration
    (tests/keyword.input).  Call before rhb200_set_wavelengths. */

@@ -121,6 +121,13 @@ class Context:
         rows = np.ascontiguousarray(rows, np.float64).reshape(-1, 4)
         _lib.check(self.lib.rhb200_set_model_lines(self.h, len(rows), _dp(rows)))
 
+    def set_molecular_lines(self, mlines, molecules):
+        """Unpolarizable lines of PASSIVE molecules for the fused path: ``mlines [n, 16]``, ``molecules [nmol, 16]``
+        (after set_continuum / set_chemistry, before set_wavelengths)."""
+        ml = np.ascontiguousarray(mlines, np.float64).reshape(-1, 16)
+        ms = np.ascontiguousarray(molecules, np.float64).reshape(-1, 16)
+        _lib.check(self.lib.rhb200_set_molecular_lines(self.h, len(ml), _dp(ml), len(ms), _dp(ms)))
+
     def set_stokes_mode(self, mode="FULL_STOKES"):
         """keyword STOKES_MODE: FULL_STOKES or NO_STOKES (call before set_wavelengths)."""
         if mode not in ("FULL_STOKES", "NO_STOKES"):

@@ -73,6 +73,7 @@ static void free_wave(rhb200_ctx *c)
 {
   DevWave &w = c->wav;
   cudaFree(w.lambda); cudaFree(w.first); cudaFree(w.count); cudaFree(w.idx); cudaFree(w.flags); cudaFree(w.noline); cudaFree(w.unpol_rank);
+  cudaFree(w.mw_first); cudaFree(w.mw_count); cudaFree(w.mw_idx); cudaFree(w.ml_rows); cudaFree(w.ml_sel);
   cudaFree(w.pw_first); cudaFree(w.pw_count); cudaFree(w.pw_idx); cudaFree(w.pl_rows); cudaFree(w.pl_pb); cudaFree(w.pl_cshift); cudaFree(w.pl_cfrac);
   w = DevWave();
 }
@@ -166,6 +167,35 @@ extern "C" int rhb200_set_lines(rhb200_ctx *c, int nline, const double *lines, i
   free_wave(c);     // windows depend on the line table
   c->h_model_lines.clear();
   c->h_plines.clear(); c->h_pcshift.clear(); c->h_pcfrac.clear();
+  c->h_mlines.clear(); c->h_msel.clear();
+  return RHB200_OK;
+}
+
+// MolecularOpacity in the fused LTE path (opacity.c:711-839): LTE lines of PASSIVE molecules, unpolarizable ones only
+// (lines with Hund's-case data need MolZeeman patterns: use rhb200_molecular_opacity_batch with host patterns).
+// mlines [nline][RHB200_ML_NFIELD] grouped by molecule, ascending in lambda0 inside each (RHB200_ML_MOL = row of
+// `molecules`); molecules [nmol][16] = {index in the chemical network of rhb200_set_chemistry, molecular weight,
+// enum fit_type, Tmin, Tmax, Npf, pf_coef[0..7]} (readmolecule.c:199-237).  Needs rhb200_set_continuum and
+// rhb200_set_chemistry before the first batch call; call before rhb200_set_wavelengths; rhb200_set_lines clears the table.
+extern "C" int rhb200_set_molecular_lines(rhb200_ctx *c, int nline, const double *mlines, int nmol, const double *molecules)
+{
+  RH_NEED_CTX(c);
+  if (nline < 0 || nmol < 0 || (nline > 0 && (!mlines || !molecules || nmol == 0))) { rhb200_set_error("rhb200_set_molecular_lines: bad arguments"); return RHB200_EINVAL; }
+  std::vector<int> chem(nmol);
+  for (int m = 0; m < nmol; m++) {
+    chem[m] = (int) molecules[(size_t) m * 16];
+    if ((int) molecules[(size_t) m * 16 + 5] > 8) { rhb200_set_error("molecule %d: more than 8 partition-function coefficients", m); return RHB200_EINVAL; }
+  }
+  for (int n = 0; n < nline; n++) {
+    const double *L = mlines + (size_t) n * RHB200_ML_NFIELD;
+    const int m = (int) L[RHB200_ML_MOL];
+    if (m < 0 || m >= nmol) { rhb200_set_error("molecular line %d: molecule index out of range", n); return RHB200_EINVAL; }
+    if (n > 0 && m < (int) L[RHB200_ML_MOL - RHB200_ML_NFIELD]) { rhb200_set_error("molecular lines must be grouped by molecule"); return RHB200_EINVAL; }
+    if (L[RHB200_ML_POLARIZABLE] != 0.0) { rhb200_set_error("molecular line %d is polarizable: MolZeeman patterns are not part of the fused path", n); return RHB200_EUNSUPPORTED; }
+  }
+  c->h_mlines.assign(mlines, mlines + (size_t) nline * RHB200_ML_NFIELD);
+  c->h_msel.assign(molecules, molecules + (size_t) nmol * 16);
+  free_wave(c);
   return RHB200_OK;
 }
 
@@ -274,8 +304,40 @@ extern "C" int rhb200_set_wavelengths(rhb200_ctx *c, int nlambda, const double *
     pw_first[l] = (int) pw_idx.size(); pw_count[l] = (int) hits[l].size();
     for (int n : hits[l]) pw_idx.push_back(prank[n]);
   }
+  // MolecularOpacity windows (opacity.c:774-787), molecule by molecule, lines in table order
+  const int NML = (int) (c->h_mlines.size() / RHB200_ML_NFIELD), NMS = (int) (c->h_msel.size() / 16);
+  std::vector<int> mw_first(nlambda, 0), mw_count(nlambda, 0), mw_idx, mfirst(NMS, -1), mlast(NMS, -1);
+  for (int n = 0; n < NML; n++) {
+    const int m = (int) c->h_mlines[(size_t) n * RHB200_ML_NFIELD + RHB200_ML_MOL];
+    if (mfirst[m] < 0) mfirst[m] = n;
+    mlast[m] = n;
+  }
+  for (int l = 0; l < nlambda; l++) {
+    const double lam = lambda[l], vc = c->tab.vmicro_char / RH_CLIGHT;
+    mw_first[l] = (int) mw_idx.size();
+    for (int m = 0; m < NMS; m++) {
+      if (mfirst[m] < 0) continue;
+      const double *L0 = c->h_mlines.data() + (size_t) mfirst[m] * RHB200_ML_NFIELD, *LN = c->h_mlines.data() + (size_t) mlast[m] * RHB200_ML_NFIELD;
+      const double dl0 = lam * L0[RHB200_ML_QWING] * vc, dlN = lam * LN[RHB200_ML_QWING] * vc;
+      if (!(lam >= L0[RHB200_ML_LAMBDA0] - dl0 && lam <= LN[RHB200_ML_LAMBDA0] + dlN)) continue;
+      for (int n = mfirst[m]; n <= mlast[m]; n++) {
+        const double *L = c->h_mlines.data() + (size_t) n * RHB200_ML_NFIELD;
+        const double dl = lam * L[RHB200_ML_QWING] * vc;
+        if (std::fabs(L[RHB200_ML_LAMBDA0] - lam) <= dl) { mw_idx.push_back(n); c->h_flags[l] |= 1; }
+      }
+    }
+    mw_count[l] = (int) mw_idx.size() - mw_first[l];
+  }
   free_wave(c);
   DevWave &w = c->wav;
+  w.nml = NML; w.nmsel = NMS; w.nmw = (int) mw_idx.size();
+  if (w.nmw) {
+    RH_CHECK(upload(&w.ml_rows, c->h_mlines.data(), c->h_mlines.size()));
+    RH_CHECK(upload(&w.ml_sel, c->h_msel.data(), c->h_msel.size()));
+    RH_CHECK(upload(&w.mw_first, mw_first.data(), (size_t) nlambda));
+    RH_CHECK(upload(&w.mw_count, mw_count.data(), (size_t) nlambda));
+    RH_CHECK(upload(&w.mw_idx, mw_idx.data(), mw_idx.size()));
+  }
   w.npl = (int) pact.size(); w.npw = (int) pw_idx.size();
   if (w.npl) {
     std::vector<double> rows((size_t) w.npl * RHB200_PL_NFIELD), pb((size_t) w.npl * RHB200_PB_NFIELD, 0.0);
@@ -389,14 +451,15 @@ struct ScalesStep { int iref, atm_scale; double wght_per_H; double *d_scratch, *
 
 static int run_chunk_dev(rhb200_ctx *c, int cc, int ndep, double muz, int moving, int bc_top, int bc_bottom,
                          const double *d_atmos, const double *d_chi_ai, const double *d_eta_ai,
-                         double *d_stokes, char *ws, const ScalesStep *sc = nullptr, bool per_column_moving = false)
+                         double *d_stokes, char *ws, const ScalesStep *sc = nullptr, bool per_column_moving = false,
+                         const double *d_molchi = nullptr, const double *d_moleta = nullptr)
 {
   ChunkLayout L(c, cc, ndep);
   double *d_elem_n = (double *) ws, *d_lineprep = (double *) (ws + L.elem_n),
          *d_raypts = (double *) (ws + L.elem_n + L.lineprep), *d_scal = (double *) (ws + L.elem_n + L.lineprep + L.raypts);
   const int *d_colmov = per_column_moving ? chunk_col_moving(c, cc, ndep, ws) : nullptr;
   RH_CHECK(rh_launch_prep(c, cc, ndep, muz, moving, d_atmos, d_elem_n, d_lineprep));
-  RH_CHECK(rh_launch_opacity_fused(c, cc, ndep, 1, d_atmos, d_lineprep, d_chi_ai, d_eta_ai, d_raypts));
+  RH_CHECK(rh_launch_opacity_fused(c, cc, ndep, 1, d_atmos, d_lineprep, d_chi_ai, d_eta_ai, d_raypts, d_molchi, d_moleta));
   // convertScales() sits between Background() and Iterate() (pyrh_compute1dray.c:310-311): the height row is
   // only read by the formal solvers below
   if (sc) RH_CHECK(rh_launch_scales(c, cc, ndep, sc->iref, sc->atm_scale, sc->wght_per_H, sc->total_abund, sc->gravity,
@@ -471,7 +534,16 @@ static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int mov
   const size_t b_sc = py ? align_up((size_t) cc * 5 * ndep * sizeof(double)) : 0;            // {tau, cmass} scratch + {height, tau_ref, cmass} out
   if (c->wav.npl > 0 && !cont_dev) { rhb200_set_error("passive_bb lines need the populations of the device continuum: use the *_pops, *_atmos or compute1d entry points"); return RHB200_ESTATE; }
   const size_t b_pc = align_up((size_t) cc * std::max(1, c->wav.npl) * 4 * ndep * sizeof(double));   // passive_bb: n_i, n_j, vbroad, adamp
-  const size_t slot = L.total + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp + b_in + b_sc + b_pc;
+  if (c->wav.nmw > 0 && !cont_dev) { rhb200_set_error("molecular lines need the chemistry of the device continuum: use the *_atmos or compute1d entry points"); return RHB200_ESTATE; }
+  const bool mol_on = c->wav.nmw > 0;
+  if (mol_on) {                                  // tell the chemistry kernel which densities to keep
+    std::vector<int> chem(c->wav.nmsel);
+    for (int m = 0; m < c->wav.nmsel; m++) chem[m] = (int) c->h_msel[(size_t) m * 16];
+    RH_CHECK(rh_continuum_set_molsel(c, c->wav.nmsel, chem.data()));
+  }
+  const size_t b_md = mol_on ? align_up((size_t) cc * c->wav.nmsel * 4 * ndep * sizeof(double)) : 0;   // densities + {n, pf, vbroad}
+  const size_t b_mo = mol_on ? b_op : 0;                                                                // chi, eta of the molecular lines
+  const size_t slot = L.total + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp + b_in + b_sc + b_pc + b_md + 2*b_mo;
   RH_CHECK(rh_ws_reserve(c, nslots * slot));
   cudaStream_t streams[2] = {c->stream, c->copy_stream};
   cudaStream_t saved = c->stream;
@@ -486,7 +558,10 @@ static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int mov
     double *d_in = (double *) (base + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp);
     double *d_sc = (double *) (base + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp + b_in);
     double *d_pc = (double *) (base + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp + b_in + b_sc);
-    char *ws = base + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp + b_in + b_sc + b_pc;
+    double *d_md = (double *) (base + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp + b_in + b_sc + b_pc);
+    double *d_mchi = mol_on ? (double *) (base + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp + b_in + b_sc + b_pc + b_md) : nullptr;
+    double *d_meta = mol_on ? (double *) (base + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp + b_in + b_sc + b_pc + b_md + b_mo) : nullptr;
+    char *ws = base + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp + b_in + b_sc + b_pc + b_md + 2*b_mo;
     cudaStream_t st = streams[i % nslots];
     c->stream = st;
     cudaError_t e;
@@ -512,8 +587,13 @@ static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int mov
                                cudaMemcpyHostToDevice, st)) != cudaSuccess) {
         rhb200_set_error("H2D copy failed: %s", cudaGetErrorString(e)); rc = RHB200_ECUDA; break;
       }
-      rc = rh_continuum_chunk(c, n, ndep, d_at, d_ch, d_pp, d_tp, d_chi, d_eta, chem ? 0 : 1);
+      if (mol_on && chem) { rhb200_set_error("molecular lines need the chemistry on the device (not the *_pops entry point)"); rc = RHB200_ESTATE; break; }
+      rc = rh_continuum_chunk(c, n, ndep, d_at, d_ch, d_pp, d_tp, d_chi, d_eta, chem ? 0 : 1, mol_on ? d_md : nullptr);
       if (rc != RHB200_OK) break;
+      if (mol_on) {                              // MolecularOpacity, background.c:548-566
+        rc = rh_molecular_chunk(c, n, ndep, muz, d_at, d_md, d_md + (size_t) n * c->wav.nmsel * ndep, d_mchi, d_meta);
+        if (rc != RHB200_OK) break;
+      }
       rc = rh_passive_chunk(c, n, ndep, muz, d_at, d_pp, rh_continuum_nlev(c), d_pc, d_chi, d_eta);   // background.c:494-515
       if (rc != RHB200_OK) break;
       if (py) {                                  // np = atmos.H->n[Nlevel-1] (kurucz.c:772); H is the first model atom
@@ -530,7 +610,7 @@ static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int mov
                   (py && py->scales) ? d_sc + (size_t) cc * 2 * ndep : nullptr};
     if (py) { sc.total_abund = py->total_abund; sc.gravity = py->gravity; sc.scales_only = py->scales_only; }
     rc = run_chunk_dev(c, n, ndep, muz, moving, bc_top, bc_bottom, d_at, d_chi, d_eta, d_st, ws, py ? &sc : nullptr,
-                       py && py->vmacro_tresh > 0.0);
+                       py && py->vmacro_tresh > 0.0, d_mchi, d_meta);
     if (rc != RHB200_OK) break;
     if (sc.d_scales_out && (e = cudaMemcpyAsync(py->scales + (size_t) c0 * 3 * ndep, sc.d_scales_out, (size_t) n * 3 * ndep * sizeof(double),
                                                 cudaMemcpyDeviceToHost, st)) != cudaSuccess) {

@@ -63,6 +63,10 @@ struct DevWave {
   // passive_bb lines whose windows touch the grid (rhb200_set_passive_lines): compact tables of the ACTIVE subset
   int npl = 0, npw = 0;
   int *pw_first = nullptr, *pw_count = nullptr, *pw_idx = nullptr;
+  // molecular lines of PASSIVE molecules (rhb200_set_molecular_lines): all lines on the device, windows per wavelength
+  int nml = 0, nmsel = 0, nmw = 0;
+  int *mw_first = nullptr, *mw_count = nullptr, *mw_idx = nullptr;
+  double *ml_rows = nullptr /* [nml][RHB200_ML_NFIELD] */, *ml_sel = nullptr /* [nmsel][16] */;
   double *pl_rows = nullptr /* [npl][RHB200_PL_NFIELD] */, *pl_pb = nullptr /* [npl][RHB200_PB_NFIELD] */, *pl_cshift = nullptr, *pl_cfrac = nullptr;   // [nlambda] rank among the wavelengths with flags == 1 (line, unpolarised), else -1
 };
 
@@ -80,7 +84,8 @@ struct rhb200_ctx {
   std::vector<int> h_zq;
   std::vector<int> h_first, h_count, h_idx, h_flags, h_noline;
   std::vector<double> h_model_lines;
-  std::vector<double> h_plines, h_pcshift, h_pcfrac;   // rhb200_set_passive_lines     // rhb200_set_model_lines: [n][4] element row, stage, lambda0 [nm], qwing
+  std::vector<double> h_plines, h_pcshift, h_pcfrac;   // rhb200_set_passive_lines
+  std::vector<double> h_mlines, h_msel;                // rhb200_set_molecular_lines     // rhb200_set_model_lines: [n][4] element row, stage, lambda0 [nm], qwing
   // formal solver selection (keyword.input S_INTERPOLATION / S_INTERPOLATION_STOKES, inputs.h:26-27)
   int s_interpolation = RHB200_S_BEZIER3, s_interpolation_stokes = RHB200_DELO_BEZIER3;
   int no_stokes = 0;         // STOKES_MODE = NO_STOKES (rhb200_set_stokes_mode)
@@ -136,7 +141,9 @@ int rh_launch_proton(rhb200_ctx *ctx, int ncol, int ndep, int nlev, int proton_l
 int rh_launch_scales(rhb200_ctx *ctx, int ncol, int ndep, int iref, int atm_scale, double wght_per_H,
                      double total_abund, double gravity, const double *d_raypts, double *d_atmos, double *d_scratch, double *d_scales_out);
 int rh_continuum_chunk(rhb200_ctx *ctx, int cc, int ndep, const double *d_atmos, const double *d_chem,
-                       double *d_pops, double *d_tprep, double *d_chi, double *d_eta, int chem_on_device);
+                       double *d_pops, double *d_tprep, double *d_chi, double *d_eta, int chem_on_device,
+                       double *d_molout = nullptr);
+int rh_continuum_set_molsel(rhb200_ctx *ctx, int nsel, const int *chem_index);
 
 // launchers implemented in the .cu files (device pointers)
 int rh_launch_mol_opacity_raw(rhb200_ctx *ctx, int ncol, int nlambda, int ndep, int nmol, double muz, int moving,
@@ -150,12 +157,15 @@ int rh_launch_passive_bb(rhb200_ctx *ctx, int ncol, int nlambda, int ndep, int n
                          const double *d_atmos, const double *d_pcol, double *d_chi, double *d_eta);
 int rh_passive_chunk(rhb200_ctx *ctx, int ncol, int ndep, double muz, const double *d_atmos, const double *d_pops, int nlev,
                       double *d_pcol /* [ncol][npl][4][ndep] */, double *d_chi_ai, double *d_eta_ai);
+int rh_molecular_chunk(rhb200_ctx *ctx, int ncol, int ndep, double muz, const double *d_atmos, const double *d_molden,
+                        double *d_mol /* [ncol][nmsel][3][ndep] */, double *d_molchi, double *d_moleta /* [ncol][nlambda][ndep] */);
 int rh_launch_prep(rhb200_ctx *ctx, int ncol, int ndep, double muz, int moving,
                    const double *d_atmos, double *d_elem_n, double *d_lineprep);
 int rh_launch_opacity_fused(rhb200_ctx *ctx, int ncol, int ndep, int to_obs,
                             const double *d_atmos, const double *d_lineprep,
                             const double *d_chi_ai, const double *d_eta_ai,
-                            double *d_raypts /* [nray][ndep][RP_NFIELD] */);
+                            double *d_raypts /* [nray][ndep][RP_NFIELD] */,
+                            const double *d_molchi = nullptr, const double *d_moleta = nullptr);
 int rh_launch_opacity_raw(rhb200_ctx *ctx, int ncol, int ndep, int to_obs,
                           const double *d_atmos, const double *d_lineprep,
                           double *d_chi, double *d_eta /* [ncol][nlambda][4][ndep] */);

@@ -836,7 +836,8 @@ chemeq_kernel(int ncol, int ndep, int natom, int nlev, const double *__restrict_
               const double *__restrict__ abundance, const double *__restrict__ atmos,
               int nnuc, const int *__restrict__ nuc_atom, int nmol, const double *__restrict__ mol,
               int iH2, int iOH, int iCH, int NmaxIter, double iterLimit,
-              double *__restrict__ pops, double *__restrict__ chem)
+              double *__restrict__ pops, double *__restrict__ chem,
+              int nsel, const int *__restrict__ molsel, double *__restrict__ molout /* [ncol][nsel][ndep] or NULL */)
 {
   const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t) ncol * ndep) return;
@@ -928,6 +929,7 @@ chemeq_kernel(int ncol, int ndep, int natom, int nlev, const double *__restrict_
   ch[(size_t) (natom + 1) * ndep] = iH2 >= 0 ? n[nnuc + iH2] : 0.0;
   ch[(size_t) (natom + 2) * ndep] = iOH >= 0 ? n[nnuc + iOH] : 0.0;
   ch[(size_t) (natom + 3) * ndep] = iCH >= 0 ? n[nnuc + iCH] : 0.0;
+  if (molout) for (int q = 0; q < nsel; q++) molout[((size_t) col * nsel + q) * ndep + k] = n[nnuc + molsel[q]];   // molecule->n of those with line lists
 }
 
 // ---- the same Newton-Raphson, LPS lanes per system (LPS = 16: two systems per warp; 32: one).  Thread-per-system
@@ -949,7 +951,8 @@ chemeq_coop_kernel(int ncol, int ndep, int natom, int nlev, const double *__rest
                    const double *__restrict__ abundance, const double *__restrict__ atmos,
                    int nnuc, const int *__restrict__ nuc_atom, int nmol, const double *__restrict__ mol,
                    int iH2, int iOH, int iCH, int NmaxIter, double iterLimit,
-                   double *__restrict__ pops, double *__restrict__ chem)
+                   double *__restrict__ pops, double *__restrict__ chem,
+              int nsel, const int *__restrict__ molsel, double *__restrict__ molout /* [ncol][nsel][ndep] or NULL */)
 {
   constexpr int LD = LPS + 1, SPB = 128 / LPS, PER = 2*LPS*LD + 9*LPS;
   constexpr unsigned FULL = 0xffffffffu;
@@ -1115,6 +1118,7 @@ chemeq_coop_kernel(int ncol, int ndep, int natom, int nlev, const double *__rest
     ch[(size_t) (natom + 1) * ndep] = iH2 >= 0 ? nv[nnuc + iH2] : 0.0;
     ch[(size_t) (natom + 2) * ndep] = iOH >= 0 ? nv[nnuc + iOH] : 0.0;
     ch[(size_t) (natom + 3) * ndep] = iCH >= 0 ? nv[nnuc + iCH] : 0.0;
+    if (molout) for (int q = 0; q < nsel; q++) molout[((size_t) col * nsel + q) * ndep + k] = nv[nnuc + molsel[q]];
   }
 }
 
@@ -1125,6 +1129,8 @@ struct ContinuumState {
   // chemistry on the device (rhb200_set_chemistry)
   int nnuc = 0, nmol = 0, iH2 = -1, iOH = -1, iCH = -1;
   int *d_nuc_atom = nullptr; double *d_mol = nullptr;
+  int nsel = 0; int *d_molsel = nullptr;      // molecules whose densities the molecular-line kernels need
+  std::vector<int> h_molsel;
 };
 
 void rh_continuum_free(rhb200_ctx *c)
@@ -1135,12 +1141,24 @@ void rh_continuum_free(rhb200_ctx *c)
 int rh_continuum_nlev(const rhb200_ctx *c) { return c->cont ? ((ContinuumState *) c->cont)->nlev : 0; }
 int rh_continuum_natom(const rhb200_ctx *c) { return c->cont ? ((ContinuumState *) c->cont)->natom : 0; }
 // last level of the first model atom: hydrogen comes first in atoms.input (atmos.H = &atmos.atoms[0], readatom.c)
+int rh_continuum_set_molsel(rhb200_ctx *c, int nsel, const int *chem_index)
+{
+  ContinuumState *S = (ContinuumState *) c->cont;
+  if (!S) { rhb200_set_error("rhb200_set_continuum() has not been called"); return RHB200_ESTATE; }
+  for (int q = 0; q < nsel; q++)
+    if (chem_index[q] < 0 || chem_index[q] >= S->nmol) { rhb200_set_error("molecule index %d outside the chemical network (rhb200_set_chemistry first)", chem_index[q]); return RHB200_EINVAL; }
+  if ((int) S->h_molsel.size() == nsel && std::equal(chem_index, chem_index + nsel, S->h_molsel.begin()) && S->nsel == nsel) return RHB200_OK;
+  S->h_molsel.assign(chem_index, chem_index + nsel);
+  S->nsel = nsel;
+  return nsel ? S->H.put(&S->d_molsel, chem_index, (size_t) nsel) : RHB200_OK;
+}
 void rh_continuum_set_hse_mode(rhb200_ctx *c, int on) { if (c->cont) ((ContinuumState *) c->cont)->D.hse_mode = on; }
 int rh_continuum_nlambda(const rhb200_ctx *c) { return c->cont ? ((ContinuumState *) c->cont)->nlambda : 0; }
 int rh_continuum_has_chemistry(const rhb200_ctx *c) { return c->cont && ((ContinuumState *) c->cont)->nmol > 0; }
 int rh_continuum_proton_level(const rhb200_ctx *c) { return c->cont ? ((ContinuumState *) c->cont)->proton_level : 0; }
 
-static int launch_chemeq(rhb200_ctx *c, ContinuumState *S, int cc, int ndep, const double *d_atmos, double *d_pops, double *d_chem)
+static int launch_chemeq(rhb200_ctx *c, ContinuumState *S, int cc, int ndep, const double *d_atmos, double *d_pops, double *d_chem,
+                         double *d_molout = nullptr)
 {
   const size_t cn = (size_t) cc * ndep;
   const int na = S->natom;
@@ -1152,7 +1170,7 @@ static int launch_chemeq(rhb200_ctx *c, ContinuumState *S, int cc, int ndep, con
   const bool serial = variant && !strcmp(variant, "local"), coop = !variant || !strcmp(variant, "coop");
   const int TPB = 32;
 #define CHEM_ARGS cc, ndep, na, S->nlev, S->d_lev, S->d_first, S->d_abund, d_atmos, S->nnuc, S->d_nuc_atom, S->nmol, S->d_mol, \
-                S->iH2, S->iOH, S->iCH, 10, 1.0E-3, d_pops, d_chem
+                S->iH2, S->iOH, S->iCH, 10, 1.0E-3, d_pops, d_chem, S->nsel, S->d_molsel, d_molout
   if (serial) {
     if (Neq <= 16) chemeq_kernel<16, false><<<(unsigned) ((cn + 63) / 64), 64, 0, c->stream>>>(CHEM_ARGS);
     else chemeq_kernel<CHEM_MAXEQ, false><<<(unsigned) ((cn + 63) / 64), 64, 0, c->stream>>>(CHEM_ARGS);
@@ -1182,7 +1200,7 @@ static int launch_chemeq(rhb200_ctx *c, ContinuumState *S, int cc, int ndep, con
 // LTE populations + continuum of one chunk of columns, all on ctx->stream.
 // d_pops [cc][nlev][ndep] and d_tprep [cc][5][ndep] are workspace; out d_chi, d_eta [cc][nlambda][ndep].
 int rh_continuum_chunk(rhb200_ctx *c, int cc, int ndep, const double *d_atmos, const double *d_chem,
-                       double *d_pops, double *d_tprep, double *d_chi, double *d_eta, int chem_on_device)
+                       double *d_pops, double *d_tprep, double *d_chi, double *d_eta, int chem_on_device, double *d_molout)
 {
   ContinuumState *S = (ContinuumState *) c->cont;
   if (!S) { rhb200_set_error("rhb200_set_continuum() has not been called"); return RHB200_ESTATE; }
@@ -1197,7 +1215,7 @@ int rh_continuum_chunk(rhb200_ctx *c, int cc, int ndep, const double *d_atmos, c
   if (chem_on_device) {
     if (S->nmol == 0) { rhb200_set_error("rhb200_set_chemistry() has not been called"); return RHB200_ESTATE; }
     ScopedKernelTimer t(c, RHB200_K_PREP);
-    RH_CHECK(launch_chemeq(c, S, cc, ndep, d_atmos, d_pops, (double *) d_chem));
+    RH_CHECK(launch_chemeq(c, S, cc, ndep, d_atmos, d_pops, (double *) d_chem, d_molout));
   }
   // T and ne are rows of the atmosphere block; the chem block carries nHmin, nH2, nOH, nCH after the fractions.
   // The kernels index [col][ndep] arrays, so they get strided views through small gather kernels' absence:

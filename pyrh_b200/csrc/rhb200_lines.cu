@@ -225,7 +225,8 @@ opacity_fused_kernel(int ncol, int nlambda, int ndep, int to_obs, int nline,
                      const double *__restrict__ lines, const __grid_constant__ ZT zee,
                      const double *__restrict__ atmos, const double *__restrict__ lineprep,
                      const double *__restrict__ chi_ai, const double *__restrict__ eta_ai,
-                     double *__restrict__ raypts)
+                     double *__restrict__ raypts,
+                     const double *__restrict__ mol_chi, const double *__restrict__ mol_eta)
 {
   const size_t npts = (size_t) ncol * nlambda * ndep;
   const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -243,12 +244,14 @@ opacity_fused_kernel(int ncol, int nlambda, int ndep, int to_obs, int nline,
 
   // background.c:476-537: chi_c = chi_ai + chi_lines (I), 0 + lines (Q,U,V);
   // formal.c:178-208: chi = 0 + chi_c, S = (0 + eta_c)/chi; stokesopac.c:72-77: K' = chi_QUV/chi_I
-  const double chi = __ldg(chi_ai + t) + s.chi[0];
+  // molecular lines come last in Background() (background.c:548-566): chi_c = (chi_ai + Kurucz) + molecules
+  double chi = __ldg(chi_ai + t) + s.chi[0], eta = __ldg(eta_ai + t) + s.eta[0];
+  if (mol_chi) { chi += __ldg(mol_chi + t); eta += __ldg(mol_eta + t); }
   const rhdiv::Recip rchi(chi);                  // seven IEEE quotients, one reciprocal refinement
   double2 *o = reinterpret_cast<double2 *>(raypts + t * RP_NFIELD);
   o[0] = make_double2(chi, rchi.div(s.chi[1]));
   o[1] = make_double2(rchi.div(s.chi[2]), rchi.div(s.chi[3]));
-  o[2] = make_double2(rchi.div(__ldg(eta_ai + t) + s.eta[0]), rchi.div(s.eta[1]));
+  o[2] = make_double2(rchi.div(eta), rchi.div(s.eta[1]));
   o[3] = make_double2(rchi.div(s.eta[2]), rchi.div(s.eta[3]));
 }
 
@@ -287,7 +290,7 @@ opacity_raw_kernel(int ncol, int nlambda, int ndep, int to_obs, int nline,
 // reference's window tests (opacity.c:774-787, evaluated on the host) in molecule / line order, so the
 // accumulation order is the reference's.  mol: [ncol][nmol][3][ndep] = molecule->n, pf, vbroad.
 __global__ void __launch_bounds__(128)
-mol_opacity_raw_kernel(int ncol, int nlambda, int ndep, int nmol, double muz, int moving, int to_obs,
+mol_opacity_raw_kernel(int intensity_only, int ncol, int nlambda, int ndep, int nmol, double muz, int moving, int to_obs,
                        const double *__restrict__ lambda, const int *__restrict__ wfirst,
                        const int *__restrict__ wcount, const int *__restrict__ widx,
                        const double *__restrict__ mlines, const int *__restrict__ zq,
@@ -360,11 +363,57 @@ mol_opacity_raw_kernel(int ncol, int nlambda, int ndep, int nmol, double muz, in
       e4[1] += eta_l * phi_Q;  e4[2] += eta_l * phi_U;  e4[3] += eta_l * phi_V;
     }
   }
+  if (intensity_only) {          // fused path (unpolarizable lines): [ncol][nlambda][ndep], zero where there is no line
+    chi[t] = c4[0];
+    eta[t] = e4[0];
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     chi[(r*4 + i)*ndep + k] = c4[i];
     eta[(r*4 + i)*ndep + k] = e4[i];
   }
+}
+
+// molecule->n (from the chemistry kernel), molecule->pf = partfunction(T) (chemequil.c:395-443) and the Doppler width
+// (readmolecule.c:233-237) of the molecules that have line lists: mol [ncol][nsel][3][ndep].
+// msel [nsel][16] = chem index, weight, fit, Tmin, Tmax, Npf, pf_coef[8]
+__global__ void __launch_bounds__(128)
+mol_prep_kernel(int ncol, int ndep, int nsel, const double *__restrict__ msel, const double *__restrict__ atmos,
+                const double *__restrict__ molden, double *__restrict__ mol)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t) ncol * nsel * ndep) return;
+  const int k = (int) (t % ndep), q = (int) ((t / ndep) % nsel), col = (int) (t / ((size_t) ndep * nsel));
+  const double *M = msel + (size_t) q * 16;
+  const double *at = atmos + (size_t) col * RHB200_AT_NFIELD * ndep;
+  const double T = at[RHB200_AT_T*ndep + k], vturb = at[RHB200_AT_VTURB*ndep + k];
+  double pf = 0.0;
+  if (!(T < M[3] || T > M[4])) {
+    const int fit = (int) M[2], npf = (int) M[5];
+    const double *c = M + 6;
+    if (fit == 0) {            // KURUCZ_70
+      pf = c[0]; for (int i = 1; i < npf; i++) pf = pf*T + c[i];
+      pf = rhm::rh_exp(pf);
+    } else if (fit == 1) {     // KURUCZ_85
+      const double x = T * 1.0E-4;
+      pf = c[0]; for (int i = 1; i < npf; i++) pf = pf*x + c[i];
+      pf = rhm::rh_exp(pf);
+    } else if (fit == 2) {     // SAUVAL_TATUM_84
+      const double x = rhm::rh_log10(5.03974756E+03 / T);
+      pf = c[0]; for (int i = 1; i < npf; i++) pf = pf*x + c[i];
+      pf = rhm::rh_exp(2.30258509299404568402 * (pf));
+    } else if (fit == 3) {     // IRWIN_81
+      const double x = rhm::rh_log(T);
+      pf = c[0]; for (int i = 1; i < npf; i++) pf = pf*x + c[i];
+      pf = rhm::rh_exp(pf);
+    }
+  }
+  const double vtherm = 2.0*RH_KBOLTZMANN / (RH_AMU * M[1]);
+  double *o = mol + (((size_t) col * nsel + q) * 3) * ndep + k;
+  o[0] = molden[((size_t) col * nsel + q) * ndep + k];
+  o[ndep] = pf;
+  o[2*(size_t) ndep] = sqrt(vtherm*T + vturb*vturb);
 }
 
 // passive_bb (metal.c:174-344): bound-bound lines of PASSIVE model atoms, unpolarised.  One thread per
@@ -512,9 +561,32 @@ int rh_launch_mol_opacity_raw(rhb200_ctx *ctx, int ncol, int nlambda, int ndep, 
   if (n == 0) return RHB200_OK;
   {
     ScopedKernelTimer t(ctx, RHB200_K_OPACITY);
-    mol_opacity_raw_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, ctx->stream>>>(ncol, nlambda, ndep, nmol, muz,
+    mol_opacity_raw_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, ctx->stream>>>(0, ncol, nlambda, ndep, nmol, muz,
         moving, to_obs, d_lambda, d_first, d_count, d_idx, d_mlines, d_zq, d_zshift, d_zstrength, d_atmos, d_mol,
         d_chi, d_eta);
+  }
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}
+
+// MolecularOpacity of one chunk in the fused path (unpolarizable lines): densities / partition functions / Doppler
+// widths of the molecules with line lists, then chi and eta of their lines per ray-point, which the Kurucz-line
+// kernel adds last (background.c:548-566)
+int rh_molecular_chunk(rhb200_ctx *ctx, int ncol, int ndep, double muz, const double *d_atmos, const double *d_molden,
+                       double *d_mol, double *d_molchi, double *d_moleta)
+{
+  const DevWave &w = ctx->wav;
+  if (w.nmw == 0 || ncol == 0) return RHB200_OK;
+  {
+    ScopedKernelTimer t(ctx, RHB200_K_PREP);
+    const size_t n = (size_t) ncol * w.nmsel * ndep;
+    mol_prep_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, ctx->stream>>>(ncol, ndep, w.nmsel, w.ml_sel, d_atmos, d_molden, d_mol);
+  }
+  {
+    ScopedKernelTimer t(ctx, RHB200_K_OPACITY);
+    const size_t n = (size_t) ncol * w.nlambda * ndep;
+    mol_opacity_raw_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, ctx->stream>>>(1, ncol, w.nlambda, ndep, w.nmsel, muz, 1, 1,
+        w.lambda, w.mw_first, w.mw_count, w.mw_idx, w.ml_rows, nullptr, nullptr, nullptr, d_atmos, d_mol, d_molchi, d_moleta);
   }
   RH_CUDA(cudaGetLastError());
   return RHB200_OK;
@@ -577,7 +649,8 @@ int rh_launch_prep(rhb200_ctx *ctx, int ncol, int ndep, double muz, int moving,
 
 int rh_launch_opacity_fused(rhb200_ctx *ctx, int ncol, int ndep, int to_obs,
                             const double *d_atmos, const double *d_lineprep,
-                            const double *d_chi_ai, const double *d_eta_ai, double *d_raypts)
+                            const double *d_chi_ai, const double *d_eta_ai, double *d_raypts,
+                            const double *d_molchi, const double *d_moleta)
 {
   const size_t nray = (size_t) ncol * ctx->wav.nlambda;
   if (nray == 0) return RHB200_OK;
@@ -593,7 +666,7 @@ int rh_launch_opacity_fused(rhb200_ctx *ctx, int ncol, int ndep, int to_obs,
       arm = arm || (L[RHB200_RL_GRAD] != 0.0 && L[RHB200_RL_POLARIZABLE] == 0.0);
     }
 #define RH_OPF_ARGS(Z) (ncol, ctx->wav.nlambda, ndep, to_obs, ctx->tab.nline, ctx->wav.lambda, ctx->wav.first, \
-        ctx->wav.count, ctx->wav.idx, ctx->tab.lines, Z, d_atmos, d_lineprep, d_chi_ai, d_eta_ai, d_raypts)
+        ctx->wav.count, ctx->wav.idx, ctx->tab.lines, Z, d_atmos, d_lineprep, d_chi_ai, d_eta_ai, d_raypts, d_molchi, d_moleta)
 #define RH_LAUNCH_OPF(M, ZT, Z) do { if (arm) opacity_fused_kernel<M, ZT, true><<<grid, block, 0, ctx->stream>>>RH_OPF_ARGS(Z); \
         else opacity_fused_kernel<M, ZT, false><<<grid, block, 0, ctx->stream>>>RH_OPF_ARGS(Z); } while (0)
 #define RH_LAUNCH_OPF_V(ZT, Z) switch (variant) {             \

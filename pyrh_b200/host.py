@@ -752,13 +752,83 @@ def read_molecule(mol_file, el: Elements):
     Ediss = float(data[3].split()[0]) * EV
     fit = next(k for k, nme in enumerate(FIT_TYPES) if nme in data[4].split()[0])
     Tmin, Tmax = (float(x) for x in data[5].split()[:2])
+    pfl = data[6].split()
+    npf = int(pfl[0])
+    pf_coef = [0.0] * npf
+    for n in range(npf - 1, -1, -1):                             # readmolecule.c:209-213
+        pf_coef[n] = float(pfl[1 + (npf - 1 - n)])
     eq = data[7].split()
     neqc = int(eq[0])
     coef = [0.0] * neqc
     for n in range(neqc - 1, -1, -1):                            # stored last-to-first (readmolecule.c:196-198)
         coef[n] = float(eq[1 + (neqc - 1 - n)])
+    weight = 0.0
+    for e, cnt in zip(pt_index, pt_count):                       # readmolecule.c:226-229
+        weight += cnt * el.weight[e]
     return dict(ID=ID, charge=charge, pt_index=pt_index, pt_count=pt_count, Ediss=Ediss, fit=fit, Tmin=Tmin, Tmax=Tmax,
-                eqc=coef, has_lines=len(data) > 8)
+                eqc=coef, pf_coef=pf_coef, weight=weight, line_lists=[x.split()[0] for x in data[8:]])
+
+
+(ML_LAMBDA0, ML_EI, ML_GI, ML_BIJ, ML_AJI, ML_BJI, ML_ISO_FRAC, ML_QWING, ML_POLARIZABLE, ML_MOL, ML_ZOFF, ML_NCOMP) = range(12)
+ML_NFIELD = 16
+MS_NFIELD = 16         # molecule rows of Context.set_molecular_lines: chem index, weight, fit, Tmin, Tmax, Npf, pf_coef[8]
+
+
+def read_molecular_lines(list_file, mol_sel):
+    """One line list of a molecule (readMolecularLines, readmolecule.c:437-770, KURUCZ_NEW / KURUCZ_CD18 formats) ->
+    rows [n, ML_NFIELD].  Lines that carry Hund's-case data are polarizable (MolZeeman) and refused."""
+    data = [ln for ln in Path(list_file).read_text().splitlines() if ln.strip() and ln[0] != "#"]
+    h = data[0].split()
+    nrt, fmt = int(h[0]), h[2]
+    if not any(f in fmt for f in ("KURUCZ_NEW", "KURUCZ_CD18")):
+        raise NotImplementedError(f"{list_file}: molecular line format {fmt} is not ported")
+    qwing = float(data[1].split()[1])
+    C = 2 * PI * (Q_ELECTRON / EPSILON_0) * (Q_ELECTRON / M_ELECTRON) / CLIGHT
+    rows = []
+    for ln in data[2:2 + nrt]:
+        if len(ln) > 71:
+            raise NotImplementedError(f"{list_file}: lines with Hund's-case data are polarizable (MolZeeman, "
+                                      "molzeeman.c) -- not ported")
+        log_gf, gi, Ei, gj, Ej = float(ln[10:17]), float(ln[17:22]), float(ln[22:32]), float(ln[32:37]), float(ln[37:48])
+        Ei = (HPLANCK * CLIGHT) / CM_TO_M * abs(Ei)
+        Ej = (HPLANCK * CLIGHT) / CM_TO_M * abs(Ej)
+        gi, gj = 2 * gi + 1, 2 * gj + 1
+        lambda0 = (HPLANCK * CLIGHT) / (Ej - Ei)
+        Aji = C / (lambda0 * lambda0) * POW10(log_gf) / gj
+        Bji = (lambda0 * lambda0 * lambda0) / (2.0 * HPLANCK * CLIGHT) * Aji
+        Bij = (gj / gi) * Bji
+        r = np.zeros(ML_NFIELD)
+        r[ML_LAMBDA0], r[ML_EI], r[ML_GI], r[ML_BIJ], r[ML_AJI], r[ML_BJI] = lambda0 / NM_TO_M, Ei, gi, Bij, Aji, Bji
+        r[ML_ISO_FRAC], r[ML_QWING], r[ML_MOL] = 1.0, qwing, mol_sel
+        rows.append(r)
+    return rows
+
+
+def molecular_line_table(cwd, kw, el: Elements, path=None):
+    """(mlines [n, ML_NFIELD], molecules [nsel, MS_NFIELD]) of the PASSIVE molecules that come with line lists, in the
+    order of molecules.input; each molecule's lines ascending in lambda0 (qsort(mrt_ascend), readmolecule.c:247)."""
+    root = pyrh_path(path) / "rh" / "Molecules"
+    rows, sel = [], []
+    k = -1
+    for ln in (Path(cwd) / kw["MOLECULES_FILE"]).read_text().splitlines():
+        f = ln.split("#", 1)[0].split()
+        if len(f) >= 2 and f[0].endswith(".molecule"):
+            k += 1
+            mo = read_molecule(root / f[0], el)
+            if not mo["line_lists"]:
+                continue
+            mine = []
+            for lst in mo["line_lists"]:
+                mine += read_molecular_lines(root / lst, len(sel))
+            mine.sort(key=lambda r: r[ML_LAMBDA0])
+            rows += mine
+            if len(mo["pf_coef"]) > 8:
+                raise ValueError(f"{f[0]}: more than 8 partition-function coefficients")
+            m = np.zeros(MS_NFIELD)
+            m[0:6] = k, mo["weight"], mo["fit"], mo["Tmin"], mo["Tmax"], len(mo["pf_coef"])
+            m[6:6 + len(mo["pf_coef"])] = mo["pf_coef"]
+            sel.append(m)
+    return np.array(rows).reshape(-1, ML_NFIELD), np.array(sel).reshape(-1, MS_NFIELD)
 
 
 def read_background_model(cwd, kw, el: Elements, path=None):
@@ -857,14 +927,11 @@ class Session:
         self.lt = read_kurucz_lines(cwd, kw, self.el, loggf_ids, loggf_values, lam_ids, lam_values, path)
         self.lambda_ref = float(kw["LAMBDA_REF"])
         self.lam = sort_lambda(wave, self.lambda_ref)
-        for lo, hi, what in passive_line_windows(cwd, kw, path, atoms=False):
-            hit = self.lam[(self.lam >= lo) & (self.lam <= hi)]
-            if len(hit):
-                raise NotImplementedError(f"wavelength {hit[0]:.4f} nm lies inside the window of the {what}: "
-                                          "MolecularOpacity exists at unit level (Context.molecular_opacity) but is not "
-                                          "summed into the fused LTE path yet")
+        mlines, msel = molecular_line_table(cwd, kw, self.el, path)      # refuses polarizable lists (MolZeeman)
         self.ctx = api.Context(device)
         self.ctx.set_lines(self.lt, magneto_optical=False, rlkscatter=False)
+        if len(mlines):                                                  # MolecularOpacity, opacity.c:711-839
+            self.ctx.set_molecular_lines(mlines, msel)
         if _true(kw.get("ALLOW_PASSIVE_BB", "TRUE")):                       # passive_bb, metal.c:174-344
             lev = bg["ct_lev"]
             first = [int(np.flatnonzero(lev[:, 0] == a)[0]) for a in range(len(listed))]

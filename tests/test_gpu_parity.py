@@ -1134,3 +1134,24 @@ def test_reference_own_test_compute1d(tmp_path):
     assert np.array_equal(spec[0], g["I"])
     spec = host.compute1d(cwd, 0.5, atm_scale, g["moving_atmosphere"], g["wave"])
     assert np.array_equal(spec[0], g["moving_I"])
+
+
+def test_molecular_lines_in_the_fused_path():
+    """MolecularOpacity summed into the fused LTE path: the CN B-X list the reference ships (99 unpolarizable lines
+    around 847 nm) with the CN density from the chemistry kernel, partfunction() and the Doppler width formed on
+    the device.  FAL-C, B = 1 kG, 846.9 - 847.8 nm: identical to the reference's rhf1d() (fixture falc_molecules)."""
+    from pyrh_b200 import host
+    root = Path(__file__).resolve().parent.parent
+    cwd, pp = root / "oracle" / "_ref" / "inputs" / "benchmark", root / "oracle" / "_ref" / "pyrh_path"
+    if not (cwd / "keyword.input").exists():
+        pytest.skip("reference input files not staged (oracle/_ref)")
+    os.environ["PYRH_PATH"] = str(pp)
+    g = dict(np.load(GOLD / "falc_molecules.npz"))
+    out = host.compute1d(str(cwd), 1.0, 0, g["atmosphere"], g["wave"])
+    got, ref = np.array(out[:4]), g["stokes"]
+    assert np.array_equal(out[4], g["lam_out"])
+    REPORT["molecular_fused_exact"] = bool(np.array_equal(got, ref))
+    REPORT["molecular_fused_max_rel_I"] = float(np.max(np.abs(got[0] / ref[0] - 1)))
+    assert np.max(np.abs(got[0] / ref[0] - 1)) < 1e-9
+    assert np.array_equal(got, ref)
+    assert 1 - ref[0].min() / ref[0].max() > 1e-4          # the lines are there

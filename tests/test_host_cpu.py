@@ -78,16 +78,16 @@ def test_unsupported_inputs_are_refused(tmp_path):
         host.Session(tmp_path, [630.1, 630.2], path=PYRH_PATH)
 
 
-def test_grids_touching_passive_lines_are_refused():
-    """Background() would add MolecularOpacity lines there (the CN list at 847 nm); the fused path does not sum them
-    yet, so the session refuses instead of returning a spectrum without those lines.  (Lines of the model atoms --
-    passive_bb -- are part of the fused path.)"""
+def test_molecular_line_list_equals_reference_tables():
+    """readMolecularLines in Python (KURUCZ_NEW format): the 99 CN B-X lines the reference ships equal, bit for bit,
+    the line table recorded from the reference's parsed state (fixture falc_molecules)."""
     from pyrh_b200 import host
     kw = host.read_keywords(CWD)
-    w = host.passive_line_windows(CWD, kw, PYRH_PATH)
-    assert any("H line at 656.4" in x[2] for x in w) and any("CN.molecule" in x[2] for x in w)
-    with pytest.raises(NotImplementedError, match="CN.molecule"):
-        host.Session(CWD, [847.0], path=PYRH_PATH)
+    el = host.read_elements(PYRH_PATH, kw)
+    rows, sel = host.molecular_line_table(CWD, kw, el, PYRH_PATH)
+    g = np.load(GOLD / "falc_molecules.npz")
+    assert rows.shape == (99, host.ML_NFIELD) and np.array_equal(rows[:, :9], g["mlines"][:, :9])
+    assert sel.shape == (1, host.MS_NFIELD) and sel[0, 0] == 7 and sel[0, 1] == 12.01 + 14.01       # CN: 8th molecule
 
 
 def test_background_model_from_atom_and_molecule_files():
