@@ -276,7 +276,7 @@ int rhb200_zeeman(const char *label_i, double g_i, const char *label_j, double g
    reference's order with its expressions.  The RH host keeps what does not depend on the column (the model
    below, filled once) and what it computes per column anyway (LTE populations + chemical equilibrium); the
    library evaluates everything that scales with columns x wavelengths x depths.
-   Opacity fudge factors (do_fudge) and lambda >= 9113 nm (Hminus_ff_long) return RHB200_EUNSUPPORTED. */
+   lambda >= 9113 nm (Hminus_ff_long) returns RHB200_EUNSUPPORTED. */
 typedef struct rhb200_continuum_model {
   int natom, nlev, ncont, ntab, nray;
   const double *lev;         /* [nlev][5]  atom index, E [J], stage, g, atom->active; atmos.atoms order, H first */
@@ -297,6 +297,10 @@ typedef struct rhb200_continuum_model {
   const double *rh2_a, *rh2_lambda, *rh2_sigma;               int n_rh2;
   const double *oh_T, *oh_E, *oh_cross;                       int n_oh_T, n_oh_E;
   const double *ch_T, *ch_E, *ch_cross;                       int n_ch_T, n_ch_E;
+  /* opacity fudge factors (do_fudge != 0; pyrh.compute1d's fudge_wave / fudge_value, pyrh_compute1dray.c:183-196,
+     background.c:364-371, 438-451, 456-464): n_fudge wavelengths [nm] and three rows of factors -- H-, scattering,
+     metal bound-free -- interpolated linearly in wavelength */
+  int n_fudge;  const double *fudge_lambda, *fudge /* [3][n_fudge] */;
 } rhb200_continuum_model;
 /* T, ne, nHmin, nH2, nOH, nCH [ncol][ndep] (SI; the molecular ones may be NULL when has_* is 0);
    pops_n, pops_nstar [ncol][nlev][ndep] = atom->n / atom->nstar of every level (may be the same pointer);

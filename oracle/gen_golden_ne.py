@@ -33,7 +33,7 @@ def get_ne_from_nH(cwd, atm_scale, scale, T, nH):
     return ne
 
 
-def hse(cwd, atm_scale, scale, T, pg_top):
+def hse(cwd, atm_scale, scale, T, pg_top, fudge_wave=None, fudge_value=None):
     lib = rd.load("scalar")
     lib.hse.restype = None
     lib.hse.argtypes = [C.c_char_p, C.c_int, dp, dp, dp, dp, dp, dp, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
@@ -42,9 +42,13 @@ def hse(cwd, atm_scale, scale, T, pg_top):
     n = len(T)
     ne, nH, rho, pg = (np.full(n, np.nan) for _ in range(4))
     pg[0] = pg_top
+    nf = 0 if fudge_wave is None else len(fudge_wave)
+    fw = np.ascontiguousarray(fudge_wave if nf else [0.0], np.float64)
+    fv = np.ascontiguousarray(fudge_value if nf else [0.0], np.float64)
     _call(cwd, lambda: lib.hse(str(cwd).encode(), n, scale.ctypes.data_as(dp), T.ctypes.data_as(dp),
                                ne.ctypes.data_as(dp), nH.ctypes.data_as(dp), rho.ctypes.data_as(dp),
-                               pg.ctypes.data_as(dp), int(atm_scale), 0, None, None, 0, None, None))
+                               pg.ctypes.data_as(dp), int(atm_scale), nf, fw.ctypes.data_as(dp) if nf else None,
+                               fv.ctypes.data_as(dp) if nf else None, 0, None, None))
     return ne, nH, rho, pg
 
 
@@ -62,6 +66,11 @@ def main():
         out[name + "_scale"], out[name + "_T"], out[name + "_pgtop"] = a[0], a[1], np.float64(pg_top)
         out[name + "_ne"], out[name + "_nH"], out[name + "_rho"], out[name + "_pg"] = ne, nH, rho, pg
         print(f"[golden] hse pg_top={pg_top}: pg[-1] = {pg[-1]:.5e} nH[-1] = {nH[-1]:.5e} ne[-1] = {ne[-1]:.5e}")
+    fw = np.array([400.0, 500.0, 700.0])
+    fv = np.array([[1.3, 1.2, 1.0], [1.0, 1.5, 1.0], [0.7, 1.4, 1.0]])
+    ne, nH, rho, pg = hse(cwd, 0, a[0], a[1], 0.1, fw, fv)
+    out.update(hsef_wave=fw, hsef_value=fv, hsef_ne=ne, hsef_nH=nH, hsef_rho=rho, hsef_pg=pg)
+    print(f"[golden] hse with fudge: pg[-1] = {pg[-1]:.5e} (without: {out['hse01_pg'][-1]:.5e})")
     np.savez_compressed(GOLD / "ne_hse.npz", **out)
 
 

@@ -151,7 +151,7 @@ def _dp(a):
 def rhf1d(atmosphere: np.ndarray, wave: np.ndarray, cwd: str, mu: float = 1.0,
           atm_scale: int = 0, variant: str = "scalar", probe: int = 0,
           loggf_ids=None, loggf_values=None, get_atomic_rfs: bool = False,
-          get_populations: bool = False):
+          get_populations: bool = False, fudge_wave=None, fudge_value=None):
     """Call the reference rhf1d().  `atmosphere` is the pyrh layout [9+, Ndep]
     (pyrh.pyx:621-625): scale, T[K], ne[cm^-3], vz[km/s], vmic[km/s], B[G],
     gamma[rad], chi[rad], nH[cm^-3].  Returns dict(lam, I, Q, U, V[, rfs][, records])."""
@@ -163,6 +163,9 @@ def rhf1d(atmosphere: np.ndarray, wave: np.ndarray, cwd: str, mu: float = 1.0,
     nl = 0 if loggf_ids is None else len(loggf_ids)
     lg_ids = np.ascontiguousarray(loggf_ids if nl else [0], dtype=np.int32)
     lg_val = np.ascontiguousarray(loggf_values if nl else [0.0], dtype=np.float64)
+    nf = 0 if fudge_wave is None else len(fudge_wave)
+    f_lam = np.ascontiguousarray(fudge_wave if nf else [0.0], dtype=np.float64)
+    f_val = np.ascontiguousarray(fudge_value if nf else [0.0], dtype=np.float64)     # [3][nf] row-major
     lib.probe_reset()
     lib.probe_enable(probe)
     old = os.getcwd()
@@ -171,7 +174,7 @@ def rhf1d(atmosphere: np.ndarray, wave: np.ndarray, cwd: str, mu: float = 1.0,
         spec = lib.rhf1d(str(cwd).encode(), float(mu), ndep,
                          *[_dp(r) for r in rows], int(atm_scale),
                          len(wave), _dp(wave),
-                         0, None, None,
+                         nf, _dp(f_lam) if nf else None, _dp(f_val) if nf else None,
                          nl, lg_ids.ctypes.data_as(c_int_p), _dp(lg_val),
                          0, None, None,
                          0, None, None,

@@ -32,14 +32,15 @@ class ModelStruct(C.Structure):
                  ("h2pff_lambda", dp), ("h2pff_temp", dp), ("h2pff_kappa", dp), ("n_h2pff_lambda", C.c_int), ("n_h2pff_temp", C.c_int),
                  ("rh2_a", dp), ("rh2_lambda", dp), ("rh2_sigma", dp), ("n_rh2", C.c_int),
                  ("oh_T", dp), ("oh_E", dp), ("oh_cross", dp), ("n_oh_T", C.c_int), ("n_oh_E", C.c_int),
-                 ("ch_T", dp), ("ch_E", dp), ("ch_cross", dp), ("n_ch_T", C.c_int), ("n_ch_E", C.c_int)])
+                 ("ch_T", dp), ("ch_E", dp), ("ch_cross", dp), ("n_ch_T", C.c_int), ("n_ch_E", C.c_int),
+                 ("n_fudge", C.c_int), ("fudge_lambda", dp), ("fudge", dp)])
 
 
 class ContinuumModel:
     """Keeps the numpy arrays alive and exposes the C struct.  ``g`` is a mapping with the keys of the fixture
     tests/golden/falc_continuum.npz (the flat form of atmos.atoms[] + the reference's static tables)."""
 
-    def __init__(self, g):
+    def __init__(self, g, fudge_wave=None, fudge_value=None):
         f64 = lambda x: np.ascontiguousarray(x, np.float64)   # noqa: E731
         h = g["ct_hdr"]
         self.a = {k: f64(g["ct_" + k]) for k in _PTRS}
@@ -64,6 +65,14 @@ class ContinuumModel:
         s.n_rh2 = len(a["rh2_lambda"])
         s.n_oh_T, s.n_oh_E = len(a["oh_T"]), len(a["oh_E"])
         s.n_ch_T, s.n_ch_E = len(a["ch_T"]), len(a["ch_E"])
+        s.n_fudge = 0
+        if fudge_wave is not None:                      # pyrh.compute1d's fudge_wave [n] / fudge_value [3, n]
+            self.a["fudge_lambda"] = f64(fudge_wave)
+            self.a["fudge"] = f64(fudge_value)
+            if self.a["fudge"].shape != (3, len(self.a["fudge_lambda"])):
+                raise ValueError("fudge_value must be [3, len(fudge_wave)] (H-, scattering, metals)")
+            s.do_fudge, s.n_fudge = 1, len(self.a["fudge_lambda"])
+            s.fudge_lambda, s.fudge = self.a["fudge_lambda"].ctypes.data_as(dp), self.a["fudge"].ctypes.data_as(dp)
         self.struct = s
         self.nlev = s.nlev
 

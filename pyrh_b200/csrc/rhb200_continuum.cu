@@ -112,7 +112,8 @@ double gaunt_bf(double lambda, double n_eff, int charge)                     // 
 // per-wavelength coefficient record (doubles), then the lists of open bound-free edges
 enum { WC_FLAGS = 0, WC_LAMBDA, WC_HCKLA_B, WC_TWOHNU3_B, WC_HCKLA_A, WC_TWOHNU3_A, WC_ALPHA_HMBF, WC_LI_HMFF,
        WC_E_OH, WC_E_CH, WC_NU3, WC_CY, WC_GA1, WC_GA2, WC_SIG_RAY_H, WC_SIG_RAY_HE, WC_LI_H2P, WC_SIG_RH2,
-       WC_LI_H2M, WC_HBF_FIRST, WC_HBF_COUNT, WC_MBF_FIRST, WC_MBF_COUNT, WC_NFIELD = 24 };
+       WC_LI_H2M, WC_HBF_FIRST, WC_HBF_COUNT, WC_MBF_FIRST, WC_MBF_COUNT,
+       WC_FUDGE_HMIN, WC_FUDGE_SCAT, WC_FUDGE_METAL /* 1.0 without fudge: exact */, WC_NFIELD = 28 };
 enum { F_HMBF = 1, F_HMFF = 2, F_OH = 4, F_CH = 8, F_RAY_H = 16, F_RAY_HE = 32, F_H2P = 64, F_RH2 = 128, F_H2M = 256 };
 
 struct DevModel {       // device copies
@@ -225,6 +226,7 @@ continuum_kernel(int ncol, int nlambda, int ndep, DevModel M,
     chi_a += chi; eta_a += chi * Bnu;
     RH_DBG(2, chi, 0.0);
   }
+  chi_a *= W[WC_FUDGE_HMIN]; eta_a *= W[WC_FUDGE_HMIN];                      // background.c:364-371 (1.0 without fudge)
   if (flags & F_OH) {                                                       // ohchbf.c:372-388
     const double ti = tp[(size_t) TP_T_OH*ndep];
     double chi = 0.0, eta = 0.0;
@@ -304,10 +306,10 @@ continuum_kernel(int ncol, int nlambda, int ndep, DevModel M,
       chi += alpha_la * (1.0 - explaA) * n_[(size_t) i * ndep];
       eta += twohnu3_A * gijk * alpha_la * n_[(size_t) j * ndep];
     }
-    chi_a += chi * 1.0; eta_a += eta * 1.0;
+    chi_a += chi * W[WC_FUDGE_METAL]; eta_a += eta * W[WC_FUDGE_METAL];       // background.c:447-451
     if (cnt > 0) RH_DBG(12, chi, eta);
   }
-  sca_a *= 1.0;
+  sca_a *= W[WC_FUDGE_SCAT];                                                // background.c:456-464
   if (M.solve_NLTE) chi_a += sca_a;                                         // background.c:462
   chi_ai[t] = chi_a; eta_ai[t] = eta_a;
   if (sca_ai) sca_ai[t] = sca_a;
@@ -385,6 +387,7 @@ continuum_tile_kernel(int ncol, int nlambda, int ndep, DevModel M,
         const double chi = (nH0 * 1.0E-29) * pe * kappa;
         chi_a[q] += chi; eta_a[q] += chi * Bnu[q];
       }
+      chi_a[q] *= W[WC_FUDGE_HMIN]; eta_a[q] *= W[WC_FUDGE_HMIN];            // background.c:364-371 (1.0 without fudge)
       if (flags & F_OH) {
         double chi = 0.0, eta = 0.0;
         if (ti_oh >= 0.0) {
@@ -475,14 +478,14 @@ continuum_tile_kernel(int ncol, int nlambda, int ndep, DevModel M,
             chi_a[q] += chi; eta_a[q] += chi * Bnu[q];
           }
         } else {
-          if (!M.hse_mode) { chi_a[q] += chi_f[q] * 1.0; eta_a[q] += eta_f[q] * 1.0; }   // metal_fudge = 1
+          if (!M.hse_mode) { chi_a[q] += chi_f[q] * W[WC_FUDGE_METAL]; eta_a[q] += eta_f[q] * W[WC_FUDGE_METAL]; }
           double chi_out = chi_a[q];
           if (M.solve_NLTE || M.hse_mode) {                                                 // background.c:462 needs sca_ai
             double sca = nek * M.sigma_T;
             if (flags & F_RAY_H)  sca += W[WC_SIG_RAY_H] * nH0;
             if (flags & F_RAY_HE) sca += W[WC_SIG_RAY_HE] * n_[(size_t) M.lev0_He * ndep];
             if (flags & F_RH2)    sca += W[WC_SIG_RH2] * nH2k;
-            sca *= 1.0;
+            sca *= W[WC_FUDGE_SCAT];
             chi_out += sca;
           }
           const size_t o = ((size_t) col * nlambda + l0 + q) * ndep + k;
@@ -516,7 +519,20 @@ static int build_model(const rhb200_continuum_model *m, int nlambda, const doubl
   const double *lev = m->lev;
   auto lvE = [&](int g) { return lev[5*(size_t) g + 1]; };
   auto lvStage = [&](int g) { return (int) lev[5*(size_t) g + 2]; };
-  if (m->do_fudge) { rhb200_set_error("opacity fudge factors are not implemented"); return RHB200_EUNSUPPORTED; }
+  if (m->do_fudge && (m->n_fudge < 2 || !m->fudge_lambda || !m->fudge)) { rhb200_set_error("do_fudge without a fudge table"); return RHB200_EINVAL; }
+  auto fudge_at = [&](int row, double lam) {                 // Linear(), linear.c:22-51 with Locate()
+    if (!m->do_fudge) return 1.0;
+    const int N = m->n_fudge; const double *x = m->fudge_lambda, *y = m->fudge + (size_t) row * N;
+    const bool ascend = x[1] > x[0];
+    const double xmin = ascend ? x[0] : x[N-1], xmax = ascend ? x[N-1] : x[0];
+    if (lam <= xmin) return ascend ? y[0] : y[N-1];
+    if (lam >= xmax) return ascend ? y[N-1] : y[0];
+    int lo = 0, hi = N;
+    const bool asc2 = x[N-1] > x[0];
+    while (hi - lo > 1) { const int mid = (hi + lo) >> 1; if (asc2 ? (lam >= x[mid]) : (lam <= x[mid])) lo = mid; else hi = mid; }
+    const double fx = (x[lo+1] - lam) / (x[lo+1] - x[lo]);
+    return fx*y[lo] + (1 - fx)*y[lo+1];
+  };
   // splines of the tabulated bound-free cross-sections (metal.c:137-140) and of H- bf (hydrogen.c:343)
   std::vector<Spline> sp(m->ncont);
   for (int c = 0; c < m->ncont; c++) {
@@ -545,6 +561,7 @@ static int build_model(const rhb200_continuum_model *m, int nlambda, const doubl
     int flags = 0;
     if (!(lam > 0.0)) { rhb200_set_error("wavelength %d is not positive", l); return RHB200_EINVAL; }
     W[WC_LAMBDA] = lam;
+    W[WC_FUDGE_HMIN] = fudge_at(0, lam); W[WC_FUDGE_SCAT] = fudge_at(1, lam); W[WC_FUDGE_METAL] = fudge_at(2, lam);
     W[WC_HCKLA_B]   = (RH_HPLANCK * RH_CLIGHT) / (RH_KBOLTZMANN * RH_NM_TO_M * lam);
     W[WC_TWOHNU3_B] = (2.0 * RH_HPLANCK * RH_CLIGHT) / CUBE(RH_NM_TO_M * lam);
     W[WC_HCKLA_A]   = hc_k / lam;

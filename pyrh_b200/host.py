@@ -913,8 +913,8 @@ class Session:
         from . import api, continuum
         self.cwd = Path(cwd)
         kw = self.kw = read_keywords(cwd)
-        if fudge_wave is not None or fudge_value is not None or kw["OPACITY_FUDGE"].lower() != "none":
-            raise NotImplementedError("opacity fudge factors (background.c:372-400) are not implemented on the device path")
+        if kw["OPACITY_FUDGE"].lower() != "none":
+            raise NotImplementedError("OPACITY_FUDGE file: pyrh takes the factors as compute1d arguments (fudge_wave, fudge_value)")
         if _true(kw["MAGNETO_OPTICAL"]):
             raise NotImplementedError("MAGNETO_OPTICAL = TRUE is refused (the reference overflows chip_c there, readj.c:328)")
         if _true(kw["RLK_SCATTER"]):
@@ -943,7 +943,7 @@ class Session:
         self.ctx.set_wavelengths(self.lam)
         self.ctx.set_solvers(kw["S_INTERPOLATION"], kw["S_INTERPOLATION_STOKES"])
         abundance = np.array([self.el.abund[int(p) - 1] for p in bg["atom_pt_index"]])
-        self.model = continuum.ContinuumModel(bg)
+        self.model = continuum.ContinuumModel(bg, fudge_wave, fudge_value)
         self.ctx.set_continuum(self.model, abundance)
         self.ctx.set_chemistry(bg["ce_nuclei"][:, 1].astype(np.int32), bg["ce_mol"])
         self.vmacro_tresh = float(kw["VMACRO_TRESH"])
@@ -1010,7 +1010,7 @@ def element_table(el: Elements):
 class HseSession:
     """The parsed working directory of ``hse`` resident on one GPU (elements, the 500 nm continuum model, chemistry)."""
 
-    def __init__(self, cwd, device=0, atomic_number=None, atomic_abundance=None):
+    def __init__(self, cwd, device=0, atomic_number=None, atomic_abundance=None, fudge_wave=None, fudge_value=None):
         from . import api, continuum
         kw = read_keywords(cwd)
         self.el = el = read_elements(None, kw, atomic_number, atomic_abundance)
@@ -1024,7 +1024,8 @@ class HseSession:
         ctx.set_lines(empty)
         ctx.set_wavelengths(np.array([500.0]))                              # pyrh_hse.c:197-200
         ctx.set_elements(*element_table(el), el.Tpf)
-        ctx.set_continuum(continuum.ContinuumModel(bg), np.array([el.abund[int(p) - 1] for p in bg["atom_pt_index"]]))
+        self.model = continuum.ContinuumModel(bg, fudge_wave, fudge_value)
+        ctx.set_continuum(self.model, np.array([el.abund[int(p) - 1] for p in bg["atom_pt_index"]]))
         ctx.set_chemistry(bg["ce_nuclei"][:, 1].astype(np.int32), bg["ce_mol"])
 
     def hse(self, atm_scale, scale, temp, pg_top=0.1):
@@ -1042,9 +1043,7 @@ class HseSession:
 def hse(cwd, atm_scale, scale, temp, pg_top=0.1, fudge_wave=None, fudge_value=None, atomic_number=None,
         atomic_abundance=None, full_output=False, device=0):
     """Drop-in for ``pyrh.hse`` (pyrh.pyx:427-489): ``(ne, nHtot)`` or, with ``full_output``, ``(ne, nHtot, rho, pg)``."""
-    if fudge_wave is not None or fudge_value is not None:
-        raise NotImplementedError("opacity fudge factors are not implemented on the device path")
-    s = HseSession(cwd, device, atomic_number, atomic_abundance)
+    s = HseSession(cwd, device, atomic_number, atomic_abundance, fudge_wave, fudge_value)
     try:
         ne, nH, rho, pg = s.hse(atm_scale, scale, temp, pg_top)
     finally:
@@ -1098,7 +1097,7 @@ def compute1d(cwd, mu, atm_scale, atmosphere, wave, loggf_ids=None, loggf_values
         raise NotImplementedError("get_populations returns ACTIVE-atom populations (pyrh_solveray.c); see pyrh_b200.nlte")
     tob = lambda x: None if x is None else np.asarray(x).tobytes()   # noqa: E731
     key = _session_key(cwd, wave, (tob(loggf_ids), tob(loggf_values), tob(lam_ids), tob(lam_values),
-                                   tob(atomic_number), tob(atomic_abundance), device))
+                                   tob(atomic_number), tob(atomic_abundance), tob(fudge_wave), tob(fudge_value), device))
     s = _SESSIONS.get(key)
     if s is None:
         s = _SESSIONS[key] = Session(cwd, wave, device, None, loggf_ids, loggf_values, lam_ids, lam_values, fudge_wave,

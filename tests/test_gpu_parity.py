@@ -1053,6 +1053,11 @@ def test_hse_drop_in():
             REPORT[f"hse_{name}_{key}_exact"] = bool(np.array_equal(arr, ref))
             assert np.max(np.abs(arr / ref - 1)) < 1e-10, (name, key, float(np.max(np.abs(arr / ref - 1))))
             assert np.array_equal(arr, ref), (name, key)
+    out = host.hse(str(cwd), 0, g["hse01_scale"], g["hse01_T"], 0.1, fudge_wave=g["hsef_wave"], fudge_value=g["hsef_value"],
+                   full_output=True)
+    for arr, key in zip(out, ("ne", "nH", "rho", "pg")):
+        assert np.array_equal(arr, g[f"hsef_{key}"]), ("fudge", key)
+    assert not np.array_equal(out[3], g["hse01_pg"])
     s = host.HseSession(str(cwd))
     both = s.hse(0, np.stack([g["hse01_scale"], g["hse1_scale"]]), np.stack([g["hse01_T"], g["hse1_T"]]),
                  np.array([0.1, 1.0]))
@@ -1155,3 +1160,23 @@ def test_molecular_lines_in_the_fused_path():
     assert np.max(np.abs(got[0] / ref[0] - 1)) < 1e-9
     assert np.array_equal(got, ref)
     assert 1 - ref[0].min() / ref[0].max() > 1e-4          # the lines are there
+
+
+def test_opacity_fudge_factors():
+    """pyrh.compute1d's fudge_wave / fudge_value (H-, scattering and metal bound-free factors interpolated in
+    wavelength, background.c:364-371, 438-464) on the device: identical to rhf1d() with the same factors, which also
+    move the height scale through the 500 nm opacity (fixture fudge)."""
+    from pyrh_b200 import host
+    root = Path(__file__).resolve().parent.parent
+    cwd, pp = root / "oracle" / "_ref" / "inputs" / "benchmark", root / "oracle" / "_ref" / "pyrh_path"
+    if not (cwd / "keyword.input").exists():
+        pytest.skip("reference input files not staged (oracle/_ref)")
+    os.environ["PYRH_PATH"] = str(pp)
+    g = dict(np.load(GOLD / "fudge.npz"))
+    out = host.compute1d(str(cwd), 1.0, 0, g["atmosphere"], g["wave"], fudge_wave=g["fudge_wave"], fudge_value=g["fudge_value"])
+    got = np.array(out[:4])
+    REPORT["fudge_exact"] = bool(np.array_equal(got, g["stokes"]))
+    assert np.max(np.abs(got[0] / g["stokes"][0] - 1)) < 1e-9
+    assert np.array_equal(got, g["stokes"])
+    plain = np.array(host.compute1d(str(cwd), 1.0, 0, g["atmosphere"], g["wave"])[:4])
+    assert not np.array_equal(plain, got)
