@@ -1093,8 +1093,6 @@ def compute1d(cwd, mu, atm_scale, atmosphere, wave, loggf_ids=None, loggf_values
         raise NotImplementedError("get_atomic_rfs: the analytic log gf response function is available at ray level "
                                   "(Context.bezier3_rf); the fused Stokes path has none in the reference either "
                                   "(Piece_Stokes_Bezier3_1D carries no dI)")
-    if get_populations:
-        raise NotImplementedError("get_populations returns ACTIVE-atom populations (pyrh_solveray.c); see pyrh_b200.nlte")
     tob = lambda x: None if x is None else np.asarray(x).tobytes()   # noqa: E731
     key = _session_key(cwd, wave, (tob(loggf_ids), tob(loggf_values), tob(lam_ids), tob(lam_values),
                                    tob(atomic_number), tob(atomic_abundance), tob(fudge_wave), tob(fudge_value), device))
@@ -1103,6 +1101,8 @@ def compute1d(cwd, mu, atm_scale, atmosphere, wave, loggf_ids=None, loggf_values
         s = _SESSIONS[key] = Session(cwd, wave, device, None, loggf_ids, loggf_values, lam_ids, lam_values, fudge_wave,
                                      fudge_value, atomic_number, atomic_abundance)
     st = s.compute(atmosphere, mu=mu, atm_scale=atm_scale)
-    if s.stokes_mode == "NO_STOKES":                             # spec.stokes is false: pyrh.pyx:647-652
-        return st[0], None, None, None, s.wavelengths
-    return st[0], st[1], st[2], st[3], s.wavelengths
+    output = (st[0], None, None, None, s.wavelengths) if s.stokes_mode == "NO_STOKES" else \
+        (st[0], st[1], st[2], st[3], s.wavelengths)                # spec.stokes false: pyrh.pyx:647-652
+    if get_populations:                                          # populations of the ACTIVE atoms: none in LTE
+        return output, ()                                        # (pyrh.pyx:654-673)
+    return output
