@@ -118,6 +118,12 @@ int rhb200_set_wavelengths(rhb200_ctx *ctx, int nlambda, const double *lambda);
    rhb200_set_chemistry and before rhb200_set_wavelengths; rhb200_set_lines clears the table. */
 int rhb200_set_molecular_lines(rhb200_ctx *ctx, int nline, const double *mlines, int nmol, const double *molecules);
 
+/* keywords N_MAX_SCATTER and ITER_LIMIT in LTE (pyrh_compute1dray.c:332-337): n_max_scatter > 0 makes the batched LTE
+   entry points Lambda-iterate the continuum-scattering term of the angle-independent (Feautrier) wavelengths,
+   S = (eta + sca J)/chi (formal.c:289-309), per column until max |1 - Jdag/J| <= iter_limit or n_max_scatter passes.
+   Default 0: the single pass of Iterate().  Only with the continuum on the device. */
+int rhb200_set_scatter(rhb200_ctx *ctx, int n_max_scatter, double iter_limit);
+
 /* keyword STOKES_MODE: 1 = FULL_STOKES (default), 0 = NO_STOKES -- I alone at every wavelength with the scalar
    S_INTERPOLATION ray (formal.c:93-103, 223-236), Q = U = V = 0; the reference's own test configuration
    (tests/keyword.input).  Call before rhb200_set_wavelengths. */

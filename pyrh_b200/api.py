@@ -128,6 +128,10 @@ class Context:
         ms = np.ascontiguousarray(molecules, np.float64).reshape(-1, 16)
         _lib.check(self.lib.rhb200_set_molecular_lines(self.h, len(ml), _dp(ml), len(ms), _dp(ms)))
 
+    def set_scatter(self, n_max_scatter=0, iter_limit=1.0e-2):
+        """keywords N_MAX_SCATTER / ITER_LIMIT in LTE: scattering passes of the line-free wavelengths."""
+        _lib.check(self.lib.rhb200_set_scatter(self.h, int(n_max_scatter), float(iter_limit)))
+
     def set_stokes_mode(self, mode="FULL_STOKES"):
         """keyword STOKES_MODE: FULL_STOKES or NO_STOKES (call before set_wavelengths)."""
         if mode not in ("FULL_STOKES", "NO_STOKES"):

@@ -199,6 +199,18 @@ extern "C" int rhb200_set_molecular_lines(rhb200_ctx *c, int nline, const double
   return RHB200_OK;
 }
 
+// keywords N_MAX_SCATTER / ITER_LIMIT in LTE (pyrh_compute1dray.c:332-337): after the formal solution the reference
+// Lambda-iterates the continuum-scattering term of the angle-independent wavelengths, S = (eta + sca J)/chi, until
+// max |1 - Jdag/J| <= iter_limit or n_max_scatter passes.  0 (default) = the single pass of Iterate().  Needs the
+// continuum on the device (the scattering opacity comes from there).
+extern "C" int rhb200_set_scatter(rhb200_ctx *c, int n_max_scatter, double iter_limit)
+{
+  RH_NEED_CTX(c);
+  if (n_max_scatter < 0 || !(iter_limit >= 0.0)) { rhb200_set_error("rhb200_set_scatter: bad arguments"); return RHB200_EINVAL; }
+  c->n_max_scatter = n_max_scatter; c->scatter_limit = iter_limit;
+  return RHB200_OK;
+}
+
 // keyword STOKES_MODE (inputs.h enum StokesMode): FULL_STOKES solves I, Q, U, V where a polarised line is present;
 // NO_STOKES solves I alone everywhere (Q = U = V = 0) -- the line profiles are the same Zeeman-split ones either way,
 // because pyrh always sets atmos.Stokes (pyrh_compute1dray.c:259).  Call before rhb200_set_wavelengths.
@@ -409,7 +421,7 @@ struct ChunkLayout {
     lineprep = align_up((size_t) cc * std::max(1, c->tab.nline) * ndep * LP_NFIELD * sizeof(double));
     raypts   = align_up((size_t) cc * c->wav.nlambda * ndep * RP_NFIELD * sizeof(double));
     scal     = align_up((size_t) cc * std::max(1, c->wav.nunpol) * 3 * ndep * sizeof(double));
-    colmov   = align_up((size_t) cc * sizeof(int));
+    colmov   = align_up((size_t) cc * (2 * sizeof(int) + sizeof(unsigned long long)));     // moving flags, scatter done flags, dJmax
     total = elem_n + lineprep + raypts + scal + colmov;
   }
 };
@@ -433,7 +445,7 @@ static int chunk_columns(const rhb200_ctx *c, int ncol, int ndep, int nslots)
 static int *chunk_col_moving(const rhb200_ctx *c, int cc, int ndep, char *ws)
 {
   ChunkLayout L(c, cc, ndep);
-  return (int *) (ws + L.elem_n + L.lineprep + L.raypts + L.scal);
+  return (int *) (ws + L.elem_n + L.lineprep + L.raypts + L.scal + (size_t) cc * sizeof(unsigned long long));   // after dJmax[cc]
 }
 
 // pyrh boundary (rhb200_compute1d_batch): the columns arrive as pyrh.compute1d's nine rows
@@ -452,14 +464,14 @@ struct ScalesStep { int iref, atm_scale; double wght_per_H; double *d_scratch, *
 static int run_chunk_dev(rhb200_ctx *c, int cc, int ndep, double muz, int moving, int bc_top, int bc_bottom,
                          const double *d_atmos, const double *d_chi_ai, const double *d_eta_ai,
                          double *d_stokes, char *ws, const ScalesStep *sc = nullptr, bool per_column_moving = false,
-                         const double *d_molchi = nullptr, const double *d_moleta = nullptr)
+                         const double *d_molchi = nullptr, const double *d_moleta = nullptr, const double *d_sca = nullptr)
 {
   ChunkLayout L(c, cc, ndep);
   double *d_elem_n = (double *) ws, *d_lineprep = (double *) (ws + L.elem_n),
          *d_raypts = (double *) (ws + L.elem_n + L.lineprep), *d_scal = (double *) (ws + L.elem_n + L.lineprep + L.raypts);
   const int *d_colmov = per_column_moving ? chunk_col_moving(c, cc, ndep, ws) : nullptr;
   RH_CHECK(rh_launch_prep(c, cc, ndep, muz, moving, d_atmos, d_elem_n, d_lineprep));
-  RH_CHECK(rh_launch_opacity_fused(c, cc, ndep, 1, d_atmos, d_lineprep, d_chi_ai, d_eta_ai, d_raypts, d_molchi, d_moleta));
+  RH_CHECK(rh_launch_opacity_fused(c, cc, ndep, 1, d_atmos, d_lineprep, d_chi_ai, d_eta_ai, d_raypts, d_molchi, d_moleta, d_sca));
   // convertScales() sits between Background() and Iterate() (pyrh_compute1dray.c:310-311): the height row is
   // only read by the formal solvers below
   if (sc) RH_CHECK(rh_launch_scales(c, cc, ndep, sc->iref, sc->atm_scale, sc->wght_per_H, sc->total_abund, sc->gravity,
@@ -468,6 +480,14 @@ static int run_chunk_dev(rhb200_ctx *c, int cc, int ndep, double muz, int moving
   if (!c->no_stokes) RH_CHECK(rh_launch_delo_raypts(c, cc, ndep, muz, bc_top, bc_bottom, d_atmos, d_raypts, d_stokes));
   RH_CHECK(rh_launch_feautrier_raypts(c, cc, ndep, muz, bc_top, bc_bottom, d_atmos, d_raypts, d_stokes,
                                       moving, d_colmov, d_scal));
+  if (c->n_max_scatter > 0) {
+    if (!d_sca) { rhb200_set_error("N_MAX_SCATTER > 0 needs the continuum on the device (the *_pops, *_atmos or compute1d entry points)"); return RHB200_ESTATE; }
+    char *flagbase = ws + L.elem_n + L.lineprep + L.raypts + L.scal;
+    unsigned long long *d_colmax = (unsigned long long *) flagbase;
+    int *d_done = (int *) (flagbase + (size_t) cc * sizeof(unsigned long long)) + cc;       // after the moving flags
+    RH_CHECK(rh_launch_scatter_passes(c, cc, ndep, muz, bc_top, bc_bottom, d_atmos, d_raypts, d_stokes, moving, d_colmov,
+                                      d_colmax, d_done));
+  }
   return RHB200_OK;
 }
 
@@ -543,7 +563,8 @@ static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int mov
   }
   const size_t b_md = mol_on ? align_up((size_t) cc * c->wav.nmsel * 4 * ndep * sizeof(double)) : 0;   // densities + {n, pf, vbroad}
   const size_t b_mo = mol_on ? b_op : 0;                                                                // chi, eta of the molecular lines
-  const size_t slot = L.total + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp + b_in + b_sc + b_pc + b_md + 2*b_mo;
+  const size_t b_sa = (c->n_max_scatter > 0 && cont_dev) ? b_op : 0;                                  // scattering opacity
+  const size_t slot = L.total + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp + b_in + b_sc + b_pc + b_md + 2*b_mo + b_sa;
   RH_CHECK(rh_ws_reserve(c, nslots * slot));
   cudaStream_t streams[2] = {c->stream, c->copy_stream};
   cudaStream_t saved = c->stream;
@@ -561,7 +582,8 @@ static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int mov
     double *d_md = (double *) (base + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp + b_in + b_sc + b_pc);
     double *d_mchi = mol_on ? (double *) (base + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp + b_in + b_sc + b_pc + b_md) : nullptr;
     double *d_meta = mol_on ? (double *) (base + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp + b_in + b_sc + b_pc + b_md + b_mo) : nullptr;
-    char *ws = base + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp + b_in + b_sc + b_pc + b_md + 2*b_mo;
+    double *d_sa = b_sa ? (double *) (base + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp + b_in + b_sc + b_pc + b_md + 2*b_mo) : nullptr;
+    char *ws = base + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp + b_in + b_sc + b_pc + b_md + 2*b_mo + b_sa;
     cudaStream_t st = streams[i % nslots];
     c->stream = st;
     cudaError_t e;
@@ -588,7 +610,7 @@ static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int mov
         rhb200_set_error("H2D copy failed: %s", cudaGetErrorString(e)); rc = RHB200_ECUDA; break;
       }
       if (mol_on && chem) { rhb200_set_error("molecular lines need the chemistry on the device (not the *_pops entry point)"); rc = RHB200_ESTATE; break; }
-      rc = rh_continuum_chunk(c, n, ndep, d_at, d_ch, d_pp, d_tp, d_chi, d_eta, chem ? 0 : 1, mol_on ? d_md : nullptr);
+      rc = rh_continuum_chunk(c, n, ndep, d_at, d_ch, d_pp, d_tp, d_chi, d_eta, chem ? 0 : 1, mol_on ? d_md : nullptr, d_sa);
       if (rc != RHB200_OK) break;
       if (mol_on) {                              // MolecularOpacity, background.c:548-566
         rc = rh_molecular_chunk(c, n, ndep, muz, d_at, d_md, d_md + (size_t) n * c->wav.nmsel * ndep, d_mchi, d_meta);
@@ -610,7 +632,7 @@ static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int mov
                   (py && py->scales) ? d_sc + (size_t) cc * 2 * ndep : nullptr};
     if (py) { sc.total_abund = py->total_abund; sc.gravity = py->gravity; sc.scales_only = py->scales_only; }
     rc = run_chunk_dev(c, n, ndep, muz, moving, bc_top, bc_bottom, d_at, d_chi, d_eta, d_st, ws, py ? &sc : nullptr,
-                       py && py->vmacro_tresh > 0.0, d_mchi, d_meta);
+                       py && py->vmacro_tresh > 0.0, d_mchi, d_meta, d_sa);
     if (rc != RHB200_OK) break;
     if (sc.d_scales_out && (e = cudaMemcpyAsync(py->scales + (size_t) c0 * 3 * ndep, sc.d_scales_out, (size_t) n * 3 * ndep * sizeof(double),
                                                 cudaMemcpyDeviceToHost, st)) != cudaSuccess) {

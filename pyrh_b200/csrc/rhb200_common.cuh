@@ -89,6 +89,7 @@ struct rhb200_ctx {
   // formal solver selection (keyword.input S_INTERPOLATION / S_INTERPOLATION_STOKES, inputs.h:26-27)
   int s_interpolation = RHB200_S_BEZIER3, s_interpolation_stokes = RHB200_DELO_BEZIER3;
   int no_stokes = 0;         // STOKES_MODE = NO_STOKES (rhb200_set_stokes_mode)
+  int n_max_scatter = 0; double scatter_limit = 1.0e-2;   // N_MAX_SCATTER / ITER_LIMIT in LTE (rhb200_set_scatter)
   // wavelength shard of the NLTE solve (rhb200_nlte_set_shard)
   int shard_rank = 0, shard_nrank = 1;
   rhb200_allreduce_fn shard_fn = nullptr; void *shard_user = nullptr;
@@ -142,7 +143,7 @@ int rh_launch_scales(rhb200_ctx *ctx, int ncol, int ndep, int iref, int atm_scal
                      double total_abund, double gravity, const double *d_raypts, double *d_atmos, double *d_scratch, double *d_scales_out);
 int rh_continuum_chunk(rhb200_ctx *ctx, int cc, int ndep, const double *d_atmos, const double *d_chem,
                        double *d_pops, double *d_tprep, double *d_chi, double *d_eta, int chem_on_device,
-                       double *d_molout = nullptr);
+                       double *d_molout = nullptr, double *d_sca = nullptr);
 int rh_continuum_set_molsel(rhb200_ctx *ctx, int nsel, const int *chem_index);
 
 // launchers implemented in the .cu files (device pointers)
@@ -165,7 +166,7 @@ int rh_launch_opacity_fused(rhb200_ctx *ctx, int ncol, int ndep, int to_obs,
                             const double *d_atmos, const double *d_lineprep,
                             const double *d_chi_ai, const double *d_eta_ai,
                             double *d_raypts /* [nray][ndep][RP_NFIELD] */,
-                            const double *d_molchi = nullptr, const double *d_moleta = nullptr);
+                            const double *d_molchi = nullptr, const double *d_moleta = nullptr, const double *d_sca = nullptr);
 int rh_launch_opacity_raw(rhb200_ctx *ctx, int ncol, int ndep, int to_obs,
                           const double *d_atmos, const double *d_lineprep,
                           double *d_chi, double *d_eta /* [ncol][nlambda][4][ndep] */);
@@ -188,6 +189,9 @@ int rh_launch_bezier3(rhb200_ctx *ctx, int solver /* RHB200_S_* */, int nray, in
 int rh_launch_feautrier_raypts(rhb200_ctx *ctx, int ncol, int ndep, double muz, int bc_top, int bc_bottom,
                                const double *d_atmos, double *d_raypts, double *d_stokes,
                                int moving, const int *d_col_moving, double *d_scratch /* [ncol][nunpol][3][ndep] */);
+int rh_launch_scatter_passes(rhb200_ctx *ctx, int ncol, int ndep, double muz, int bc_top, int bc_bottom, const double *d_atmos,
+                             double *d_raypts, double *d_stokes, int moving, const int *d_col_moving,
+                             unsigned long long *d_colmax /* [ncol] */, int *d_done /* [ncol] */);
 int rh_launch_feautrier(rhb200_ctx *ctx, int nray, int ndep, double muz, int bc_top, int bc_bottom,
                         const int *d_ray_col, const double *d_ray_lambda, const double *d_height,
                         const double *d_T, const double *d_chi, const double *d_S,

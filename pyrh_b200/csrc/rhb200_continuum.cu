@@ -329,7 +329,7 @@ continuum_tile_kernel(int ncol, int nlambda, int ndep, DevModel M,
                       const double *__restrict__ nHmin, const double *__restrict__ nH2, const double *__restrict__ nOH,
                       const double *__restrict__ nCH, size_t cstride,
                       const double *__restrict__ pn, const double *__restrict__ ps, const double *__restrict__ tprep,
-                      double *__restrict__ chi_ai, double *__restrict__ eta_ai)
+                      double *__restrict__ chi_ai, double *__restrict__ eta_ai, double *__restrict__ sca_ai /* or NULL */)
 {
   // blockIdx.x = wavelength tile, blockIdx.y = chunk of 128 (column, depth) pairs: the tile's coefficient
   // records and cross-sections are staged in shared memory once per block
@@ -480,15 +480,16 @@ continuum_tile_kernel(int ncol, int nlambda, int ndep, DevModel M,
         } else {
           if (!M.hse_mode) { chi_a[q] += chi_f[q] * W[WC_FUDGE_METAL]; eta_a[q] += eta_f[q] * W[WC_FUDGE_METAL]; }
           double chi_out = chi_a[q];
-          if (M.solve_NLTE || M.hse_mode) {                                                 // background.c:462 needs sca_ai
+          const size_t o = ((size_t) col * nlambda + l0 + q) * ndep + k;
+          if (M.solve_NLTE || M.hse_mode || sca_ai) {                                       // background.c:456-464
             double sca = nek * M.sigma_T;
             if (flags & F_RAY_H)  sca += W[WC_SIG_RAY_H] * nH0;
             if (flags & F_RAY_HE) sca += W[WC_SIG_RAY_HE] * n_[(size_t) M.lev0_He * ndep];
             if (flags & F_RH2)    sca += W[WC_SIG_RH2] * nH2k;
             sca *= W[WC_FUDGE_SCAT];
-            chi_out += sca;
+            if (M.solve_NLTE || M.hse_mode) chi_out += sca;                                 // LTE: sca_c stays separate
+            if (sca_ai) sca_ai[o] = sca;
           }
-          const size_t o = ((size_t) col * nlambda + l0 + q) * ndep + k;
           chi_ai[o] = chi_out; eta_ai[o] = eta_a[q];
         }
       }
@@ -1217,7 +1218,8 @@ static int launch_chemeq(rhb200_ctx *c, ContinuumState *S, int cc, int ndep, con
 // LTE populations + continuum of one chunk of columns, all on ctx->stream.
 // d_pops [cc][nlev][ndep] and d_tprep [cc][5][ndep] are workspace; out d_chi, d_eta [cc][nlambda][ndep].
 int rh_continuum_chunk(rhb200_ctx *c, int cc, int ndep, const double *d_atmos, const double *d_chem,
-                       double *d_pops, double *d_tprep, double *d_chi, double *d_eta, int chem_on_device, double *d_molout)
+                       double *d_pops, double *d_tprep, double *d_chi, double *d_eta, int chem_on_device, double *d_molout,
+                       double *d_sca)
 {
   ContinuumState *S = (ContinuumState *) c->cont;
   if (!S) { rhb200_set_error("rhb200_set_continuum() has not been called"); return RHB200_ESTATE; }
@@ -1250,7 +1252,7 @@ int rh_continuum_chunk(rhb200_ctx *c, int cc, int ndep, const double *d_atmos, c
     if (nck > 65535) { rhb200_set_error("chunk too large for the continuum kernel grid"); return RHB200_EINVAL; }
     static int minb = -1;                                   // RHB200_CONT_MINB: occupancy / spill trade-off
     if (minb < 0) { const char *e = getenv("RHB200_CONT_MINB"); minb = e ? atoi(e) : 8; }
-#define RH_CONT_ARGS (cc, S->nlambda, ndep, S->D, d_atmos + (size_t) RHB200_AT_T * ndep, d_atmos + (size_t) RHB200_AT_NE * ndep, as, d_chem + (size_t) na * ndep, d_chem + (size_t) (na + 1) * ndep, d_chem + (size_t) (na + 2) * ndep, d_chem + (size_t) (na + 3) * ndep, cs, d_pops, d_pops, d_tprep, d_chi, d_eta)
+#define RH_CONT_ARGS (cc, S->nlambda, ndep, S->D, d_atmos + (size_t) RHB200_AT_T * ndep, d_atmos + (size_t) RHB200_AT_NE * ndep, as, d_chem + (size_t) na * ndep, d_chem + (size_t) (na + 1) * ndep, d_chem + (size_t) (na + 2) * ndep, d_chem + (size_t) (na + 3) * ndep, cs, d_pops, d_pops, d_tprep, d_chi, d_eta, d_sca)
     const dim3 grid((unsigned) ntile, (unsigned) nck);
     switch (minb) {
     case 4: continuum_tile_kernel<4><<<grid, 128, 0, c->stream>>>RH_CONT_ARGS; break;

@@ -167,7 +167,16 @@ struct FeauRayPtsIO {           // fused LTE path: line-free rays; F and z live 
   __device__ __forceinline__ void putZ(int k, double v) { rp[(size_t) k*RP_NFIELD + RP_KU] = v; }
   __device__ __forceinline__ double getF(int k) const { return rp[(size_t) k*RP_NFIELD + RP_KQ]; }
   __device__ __forceinline__ double getZ(int k) const { return rp[(size_t) k*RP_NFIELD + RP_KU]; }
-  __device__ __forceinline__ void storeP(int, double) {}
+  bool keepP = false;           // N_MAX_SCATTER > 0: J = P (one ray, wmu = 1) goes into the S_Q slot
+  double dJ = 0.0;              // max |1 - Jdag/J| over the depths (formal.c:312-316), Jdag = what the slot held
+  __device__ __forceinline__ void storeP(int k, double v) {
+    if (keepP) {
+      double *j = rp + (size_t) k*RP_NFIELD + RP_SQ;
+      const double d = fabs(1.0 - *j / v);
+      dJ = (dJ > d) ? dJ : d;
+      *j = v;
+    }
+  }
   __device__ __forceinline__ void storePsi(int, double) {}
   __device__ __forceinline__ bool wantPsi() const { return false; }
 };
@@ -196,7 +205,7 @@ feautrier_raypts_kernel(int ncol, int nlambda, int ndep, double muz, int bc_top,
                         const double *__restrict__ atmos, const double *__restrict__ lambda,
                         double *__restrict__ raypts, double *__restrict__ stokes,
                         const int *__restrict__ wflags, const int *__restrict__ unpol_rank, int nunpol,
-                        int solver, int moving, const int *__restrict__ col_moving, double *__restrict__ scratch)
+                        int solver, int moving, const int *__restrict__ col_moving, double *__restrict__ scratch, int keepP)
 {
   const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t) ncol * nnoline) return;
@@ -220,10 +229,48 @@ feautrier_raypts_kernel(int ncol, int nlambda, int ndep, double muz, int bc_top,
     I0 = Ir[0];
   } else {
     FeauRayPtsIO io{rp, at + RHB200_AT_HEIGHT * ndep};
+    io.keepP = keepP != 0;                                   // S_Q slot holds 0 = the J Iterate() starts from
     I0 = rhf::feautrier_ray(io, ndep, muz, bc_top, bc_bottom, at + RHB200_AT_T * ndep, __ldg(lambda + l));
   }
   double *out = stokes + (size_t) col * 4 * nlambda + l;
   out[0] = I0; out[nlambda] = 0.0; out[2*(size_t) nlambda] = 0.0; out[3*(size_t) nlambda] = 0.0;
+}
+
+// One pass of the LTE scattering iteration (pyrh_compute1dray.c:332-337 -> solveSpectrum -> Formal, angle-independent
+// branch formal.c:289-309) over the Feautrier wavelengths of the columns that have not converged yet:
+// S = (eta + sca Jdag)/chi, new J = P, the column's dJmax through an atomic max on the bit pattern (dJ >= 0).
+__global__ void __launch_bounds__(128)
+scatter_pass_kernel(int ncol, int nlambda, int ndep, double muz, int bc_top, int bc_bottom,
+                    const int *__restrict__ nolines, int nnoline, const double *__restrict__ atmos,
+                    const double *__restrict__ lambda, double *__restrict__ raypts, double *__restrict__ stokes,
+                    const int *__restrict__ wflags, int moving, const int *__restrict__ col_moving,
+                    const int *__restrict__ done, unsigned long long *__restrict__ colmax)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t) ncol * nnoline) return;
+  const int col = (int) (t / nnoline), l = __ldg(nolines + (int) (t - (size_t) col * nnoline));
+  if (done[col]) return;
+  const int fl = __ldg(wflags + l);
+  if ((fl & 2) || ((fl & 1) && (col_moving ? col_moving[col] != 0 : moving != 0))) return;   // angle dependent: no J feedback in LTE
+  const double *at = atmos + (size_t) col * RHB200_AT_NFIELD * ndep;
+  double *rp = raypts + ((size_t) col * nlambda + l) * (size_t) ndep * RP_NFIELD;
+  for (int k = 0; k < ndep; k++) {
+    double *r = rp + (size_t) k * RP_NFIELD;
+    r[RP_SI] = (r[RP_SU] + r[RP_SV] * r[RP_SQ]) / r[RP_CHI];
+  }
+  FeauRayPtsIO io{rp, at + RHB200_AT_HEIGHT * ndep};
+  io.keepP = true;
+  const double I0 = rhf::feautrier_ray(io, ndep, muz, bc_top, bc_bottom, at + RHB200_AT_T * ndep, __ldg(lambda + l));
+  stokes[(size_t) col * 4 * nlambda + l] = I0;
+  atomicMax(colmax + col, (unsigned long long) __double_as_longlong(io.dJ));
+}
+
+__global__ void scatter_update_kernel(int ncol, double limit, int *__restrict__ done, unsigned long long *__restrict__ colmax)
+{
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncol) return;
+  if (!done[col] && __longlong_as_double((long long) colmax[col]) <= limit) done[col] = 1;   // solveSpectrum() <= iterLimit: break
+  colmax[col] = 0ull;
 }
 
 __global__ void __launch_bounds__(128)
@@ -334,7 +381,7 @@ int rh_launch_feautrier_raypts(rhb200_ctx *ctx, int ncol, int ndep, double muz, 
     feautrier_raypts_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, ctx->stream>>>(
         ncol, ctx->wav.nlambda, ndep, muz, bc_top, bc_bottom, ctx->wav.noline, nn, d_atmos,
         ctx->wav.lambda, d_raypts, d_stokes, ctx->wav.flags, ctx->wav.unpol_rank, ctx->wav.nunpol,
-        ctx->s_interpolation, moving, d_col_moving, d_scratch);
+        ctx->s_interpolation, moving, d_col_moving, d_scratch, ctx->n_max_scatter > 0);
   }
   RH_CUDA(cudaGetLastError());
   return RHB200_OK;
@@ -351,6 +398,25 @@ int rh_launch_feautrier(rhb200_ctx *ctx, int nray, int ndep, double muz, int bc_
     feautrier_generic_kernel<<<(nray + 127) / 128, 128, 0, ctx->stream>>>(
         nray, ndep, muz, bc_top, bc_bottom, d_ray_col, d_ray_lambda, d_height, d_T, d_chi, d_S,
         d_P, d_Psi, d_Iem, d_scratch);
+  }
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}
+
+int rh_launch_scatter_passes(rhb200_ctx *ctx, int ncol, int ndep, double muz, int bc_top, int bc_bottom, const double *d_atmos,
+                             double *d_raypts, double *d_stokes, int moving, const int *d_col_moving,
+                             unsigned long long *d_colmax, int *d_done)
+{
+  const int nn = ctx->wav.nnoline;
+  if (ctx->n_max_scatter <= 0 || nn == 0 || ncol == 0) return RHB200_OK;
+  RH_CUDA(cudaMemsetAsync(d_colmax, 0, (size_t) ncol * sizeof(unsigned long long), ctx->stream));
+  RH_CUDA(cudaMemsetAsync(d_done, 0, (size_t) ncol * sizeof(int), ctx->stream));
+  const size_t n = (size_t) ncol * nn;
+  for (int it = 0; it < ctx->n_max_scatter; it++) {
+    ScopedKernelTimer t(ctx, RHB200_K_BEZIER);
+    scatter_pass_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, ctx->stream>>>(ncol, ctx->wav.nlambda, ndep, muz, bc_top, bc_bottom,
+        ctx->wav.noline, nn, d_atmos, ctx->wav.lambda, d_raypts, d_stokes, ctx->wav.flags, moving, d_col_moving, d_done, d_colmax);
+    scatter_update_kernel<<<(unsigned) ((ncol + 127) / 128), 128, 0, ctx->stream>>>(ncol, ctx->scatter_limit, d_done, d_colmax);
   }
   RH_CUDA(cudaGetLastError());
   return RHB200_OK;

@@ -226,7 +226,8 @@ opacity_fused_kernel(int ncol, int nlambda, int ndep, int to_obs, int nline,
                      const double *__restrict__ atmos, const double *__restrict__ lineprep,
                      const double *__restrict__ chi_ai, const double *__restrict__ eta_ai,
                      double *__restrict__ raypts,
-                     const double *__restrict__ mol_chi, const double *__restrict__ mol_eta)
+                     const double *__restrict__ mol_chi, const double *__restrict__ mol_eta,
+                     const double *__restrict__ sca_ai, const int *__restrict__ wflags, int all_scalar)
 {
   const size_t npts = (size_t) ncol * nlambda * ndep;
   const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -253,6 +254,9 @@ opacity_fused_kernel(int ncol, int nlambda, int ndep, int to_obs, int nline,
   o[1] = make_double2(rchi.div(s.chi[2]), rchi.div(s.chi[3]));
   o[2] = make_double2(rchi.div(eta), rchi.div(s.eta[1]));
   o[3] = make_double2(rchi.div(s.eta[2]), rchi.div(s.eta[3]));
+  // N_MAX_SCATTER > 0: wavelengths solved for I alone keep the emissivity and the scattering opacity for the Lambda
+  // iteration of S = (eta + sca J)/chi (formal.c:289-309) in the slots their (zero) S_U, S_V would take
+  if (sca_ai && (all_scalar || (__ldg(wflags + l) & 2) == 0)) o[3] = make_double2(eta, __ldg(sca_ai + t));
 }
 
 // RAW: exactly the output of rlk_opacity(), chi/eta [ncol][nlambda][4][ndep]
@@ -650,7 +654,7 @@ int rh_launch_prep(rhb200_ctx *ctx, int ncol, int ndep, double muz, int moving,
 int rh_launch_opacity_fused(rhb200_ctx *ctx, int ncol, int ndep, int to_obs,
                             const double *d_atmos, const double *d_lineprep,
                             const double *d_chi_ai, const double *d_eta_ai, double *d_raypts,
-                            const double *d_molchi, const double *d_moleta)
+                            const double *d_molchi, const double *d_moleta, const double *d_sca)
 {
   const size_t nray = (size_t) ncol * ctx->wav.nlambda;
   if (nray == 0) return RHB200_OK;
@@ -666,7 +670,7 @@ int rh_launch_opacity_fused(rhb200_ctx *ctx, int ncol, int ndep, int to_obs,
       arm = arm || (L[RHB200_RL_GRAD] != 0.0 && L[RHB200_RL_POLARIZABLE] == 0.0);
     }
 #define RH_OPF_ARGS(Z) (ncol, ctx->wav.nlambda, ndep, to_obs, ctx->tab.nline, ctx->wav.lambda, ctx->wav.first, \
-        ctx->wav.count, ctx->wav.idx, ctx->tab.lines, Z, d_atmos, d_lineprep, d_chi_ai, d_eta_ai, d_raypts, d_molchi, d_moleta)
+        ctx->wav.count, ctx->wav.idx, ctx->tab.lines, Z, d_atmos, d_lineprep, d_chi_ai, d_eta_ai, d_raypts, d_molchi, d_moleta, d_sca, ctx->wav.flags, ctx->no_stokes)
 #define RH_LAUNCH_OPF(M, ZT, Z) do { if (arm) opacity_fused_kernel<M, ZT, true><<<grid, block, 0, ctx->stream>>>RH_OPF_ARGS(Z); \
         else opacity_fused_kernel<M, ZT, false><<<grid, block, 0, ctx->stream>>>RH_OPF_ARGS(Z); } while (0)
 #define RH_LAUNCH_OPF_V(ZT, Z) switch (variant) {             \

@@ -919,8 +919,6 @@ class Session:
             raise NotImplementedError("MAGNETO_OPTICAL = TRUE is refused (the reference overflows chip_c there, readj.c:328)")
         if _true(kw["RLK_SCATTER"]):
             raise NotImplementedError("RLK_SCATTER = TRUE is not implemented")
-        if int(kw["N_MAX_SCATTER"]) != 0:
-            raise NotImplementedError("N_MAX_SCATTER > 0 in LTE (pyrh_compute1dray.c:332-337) is not implemented")
         listed = _atoms_listed(cwd, kw)
         self.el = read_elements(path, kw, atomic_number, atomic_abundance)
         bg = self.background = read_background_model(cwd, kw, self.el, path)
@@ -938,6 +936,7 @@ class Session:
             self.ctx.set_passive_lines(*passive_line_table(cwd, kw, self.el, first, path))
         self.model_lines = model_line_rows(cwd, kw, self.el, self.lt.elem_rows, path)
         self.ctx.set_model_lines(self.model_lines)
+        self.ctx.set_scatter(int(kw["N_MAX_SCATTER"]), float(kw.get("ITER_LIMIT", "1.0E-2")))   # pyrh_compute1dray.c:332-337
         self.stokes_mode = kw["STOKES_MODE"].upper()
         self.ctx.set_stokes_mode(self.stokes_mode)
         self.ctx.set_wavelengths(self.lam)

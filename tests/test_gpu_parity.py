@@ -1182,3 +1182,23 @@ def test_opacity_fudge_factors():
     assert np.array_equal(got, g["stokes"])
     plain = np.array(host.compute1d(str(cwd), 1.0, 0, g["atmosphere"], g["wave"])[:4])
     assert not np.array_equal(plain, got)
+
+
+@pytest.mark.parametrize("case,kw", [("n5", {"N_MAX_SCATTER": ("0", "5")}),
+                                     ("n5_tight", {"N_MAX_SCATTER": ("0", "5"), "ITER_LIMIT": ("1.0E-2", "1.0E-4")}),
+                                     ("n1", {"N_MAX_SCATTER": ("0", "1"), "ITER_LIMIT": ("1.0E-2", "1.0E-6")})])
+def test_lte_scattering_passes(tmp_path, case, kw):
+    """N_MAX_SCATTER > 0 in LTE (the keyword's default is 5): after the formal solution the reference Lambda-iterates
+    the continuum-scattering term of the line-free wavelengths (pyrh_compute1dray.c:332-337, formal.c:289-309).  The
+    device does the same passes per column; a grid reaching outside the line windows equals rhf1d() bit for bit for
+    three combinations of N_MAX_SCATTER / ITER_LIMIT, and differs from the single pass (fixture scatter)."""
+    from pyrh_b200 import host
+    g = dict(np.load(GOLD / "scatter.npz"))
+    cwd = _stage_cwd(tmp_path, kurucz="fe6300", keywords=kw)
+    out = host.compute1d(cwd, 1.0, 0, g["atmosphere"], g["wave"])
+    got, ref = np.array(out[:4]), g[case + "_stokes"]
+    REPORT[f"scatter_{case}_exact"] = bool(np.array_equal(got, ref))
+    REPORT[f"scatter_{case}_max_rel_I"] = float(np.max(np.abs(got[0] / ref[0] - 1)))
+    assert np.max(np.abs(got[0] / ref[0] - 1)) < 1e-9
+    assert np.array_equal(got, ref)
+    assert not np.array_equal(ref, g["n0_stokes"])
