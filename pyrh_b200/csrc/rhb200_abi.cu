@@ -128,7 +128,7 @@ extern "C" int rhb200_set_lines(rhb200_ctx *c, int nline, const double *lines, i
 {
   RH_NEED_CTX(c);
   if (magneto_optical) { rhb200_set_error("MAGNETO_OPTICAL = TRUE is not implemented (the reference overflows chip_c there, readj.c:328)"); return RHB200_EUNSUPPORTED; }
-  if (rlkscatter) { rhb200_set_error("RLK_SCATTER = TRUE is not implemented"); return RHB200_EUNSUPPORTED; }
+
   if (nline < 0 || nelem < 0 || npf < 2 || (nline > 0 && (!lines || !elems || !pf || !Tpf))) {
     rhb200_set_error("rhb200_set_lines: bad arguments"); return RHB200_EINVAL;
   }
@@ -154,6 +154,7 @@ extern "C" int rhb200_set_lines(rhb200_ctx *c, int nline, const double *lines, i
   DevTables &t = c->tab;
   t.nline = nline; t.ncomp = ncomp; t.nelem = nelem; t.npf_rows = npf_rows; t.npf = npf;
   t.vmicro_char = vmicro_char;
+  t.rlkscatter = rlkscatter ? 1 : 0;
   RH_CHECK(upload(&t.lines, lines, (size_t) nline * RHB200_RL_NFIELD));
   RH_CHECK(upload(&t.zq, zq, (size_t) ncomp));
   RH_CHECK(upload(&t.zshift, zshift, (size_t) ncomp));
@@ -789,6 +790,7 @@ extern "C" int rhb200_rlk_opacity_batch(rhb200_ctx *c, int ncol, int ndep, doubl
                                         int to_obs, const double *atmos, double *chi, double *eta, int *flags)
 {
   RH_NEED_CTX(c);
+  if (c->tab.rlkscatter) { rhb200_set_error("rhb200_rlk_opacity_batch returns chi / eta only: RLK_SCATTER = TRUE is part of the fused path"); return RHB200_EUNSUPPORTED; }
   RH_CHECK(need_state(c, true));
   if (ncol <= 0 || ndep <= 0 || !atmos || !chi || !eta) { rhb200_set_error("bad arguments"); return RHB200_EINVAL; }
   const int nl = c->wav.nlambda;

@@ -40,7 +40,7 @@ void rhb200_set_error(const char *fmt, ...);
 
 // per-(column, line, depth) quantities that do not depend on wavelength
 // (hoisted out of RLKProfile / rlk_opacity, kurucz.c:669-691,744-783)
-enum { LP_VBROAD = 0, LP_ADAMP, LP_VB, LP_W, LP_SV, LP_CHIL, LP_ETAL, LP_NFIELD = 8 };
+enum { LP_VBROAD = 0, LP_ADAMP, LP_VB, LP_W, LP_SV, LP_CHIL, LP_ETAL, LP_EPS /* RLK_SCATTER: destruction probability */, LP_NFIELD = 8 };
 // ray-point record handed from the opacity kernel to the DELO kernel
 enum { RP_CHI = 0, RP_KQ, RP_KU, RP_KV, RP_SI, RP_SQ, RP_SU, RP_SV, RP_NFIELD };
 
@@ -50,6 +50,7 @@ struct DevTables {
          *pf = nullptr, *Tpf = nullptr;
   int *zq = nullptr;
   double vmicro_char = 0.0;
+  int rlkscatter = 0;        // keyword RLK_SCATTER (kurucz.c:641-652, 682-694)
 };
 
 struct DevWave {

@@ -39,7 +39,7 @@ __device__ __forceinline__ double linear_interp(int nt, const double *__restrict
 
 // one thread per (column, depth)
 __global__ void __launch_bounds__(128)
-prep_kernel(int ncol, int ndep, double muz, int moving,
+prep_kernel(int ncol, int ndep, double muz, int moving, int rlkscatter,
             int nline, int nelem, int npf,
             const double *__restrict__ lines, const double *__restrict__ elems,
             const double *__restrict__ pf, const double *__restrict__ Tpf,
@@ -122,10 +122,20 @@ prep_kernel(int ncol, int ndep, double muz, int moving,
     out[(size_t) LP_SV*ndep]     = sv;
     out[(size_t) LP_CHIL*ndep]   = Bijhc_4PI * (ni_gi - nj_gj);
     out[(size_t) LP_ETAL*ndep]   = Bijhc_4PI * twohnu3_c2 * nj_gj;
+    double epsilon = 1.0;
+    if (rlkscatter) {                                                            // kurucz.c:641-652, 682-685
+      const double Cc = 2 * RH_PI * (RH_Q_ELECTRON/8.854187817E-12) * (RH_Q_ELECTRON/RH_M_ELECTRON) / RH_CLIGHT;
+      const double l0m = lambda0 * RH_NM_TO_M;
+      const double x = (st == 0) ? 0.68 : 0.0;
+      const double C3 = Cc / (((st == 0) ? 2.15E-6 : 3.96E-6) * (l0m * l0m));
+      const double dE = L[RHB200_RL_EJ] - L[RHB200_RL_EI];
+      epsilon = 1.0 / (1.0 + C3 * rhm::rh_pow(T, 1.5) / (ne * rhm::rh_pow(RH_KBOLTZMANN * T / dE, 1 + x)));
+    }
+    out[(size_t) LP_EPS*ndep]    = epsilon;
   }
 }
 
-struct LineSums { double chi[4], eta[4]; };
+struct LineSums { double chi[4], eta[4], scatt; };
 
 // Zeeman components are read with a warp-uniform index.  Small line lists pass them BY VALUE in
 // the kernel parameter block (constant bank: one broadcast LDC per read, no L1 traffic);
@@ -148,7 +158,9 @@ __device__ __forceinline__ double zstrength_of(const ZeemanGlobal &z, int i) { r
 // lp_colk points at lineprep[col][0][0][k]; line nl / field f is at lp_colk[(nl*LP_NFIELD + f)*ndep].
 // ARM: the table holds lines that are not polarizable (VoigtArmstrong branch); compiled out otherwise, the branch
 // costs the hot kernel 2 % in registers and code even when never taken
-template <bool ARM, class ZT>
+// RLKS: keyword RLK_SCATTER -- each line's opacity is split into a thermal part (epsilon) and a scattering part that
+// only enters the total opacity (kurucz.c:682-694, background.c:538-543)
+template <bool ARM, bool RLKS, class ZT>
 __device__ __forceinline__ void line_sums(LineSums &s, const double lambda, const int to_obs,
                                           const int first, const int count,
                                           const int *__restrict__ widx,
@@ -159,6 +171,7 @@ __device__ __forceinline__ void line_sums(LineSums &s, const double lambda, cons
 {
 #pragma unroll
   for (int i = 0; i < 4; i++) { s.chi[i] = 0.0; s.eta[i] = 0.0; }
+  s.scatt = 0.0;
   const double sign = to_obs ? 1.0 : -1.0;
   for (int j = 0; j < count; j++) {
     const int nl = __ldg(widx + first + j);
@@ -196,7 +209,13 @@ __device__ __forceinline__ void line_sums(LineSums &s, const double lambda, cons
       phi_V = sign * 0.5*(phi_sp - phi_sm) * cos_gamma * sv;
     }
     if (phi != 0.0) {                                   // kurucz.c:674
-      const double chi_l = __ldg(P + (size_t) LP_CHIL*ndep), eta_l = __ldg(P + (size_t) LP_ETAL*ndep);
+      double chi_l = __ldg(P + (size_t) LP_CHIL*ndep), eta_l = __ldg(P + (size_t) LP_ETAL*ndep);
+      if (RLKS) {
+        const double epsilon = __ldg(P + (size_t) LP_EPS*ndep);
+        s.scatt += (1.0 - epsilon) * chi_l * phi;
+        chi_l *= epsilon;
+        eta_l *= epsilon;
+      }
       s.chi[0] += chi_l * phi;
       s.eta[0] += eta_l * phi;
       if (polarizable && has_grad) {                    // kurucz.c:701-708
@@ -217,7 +236,7 @@ __device__ __forceinline__ void line_sums(LineSums &s, const double lambda, cons
 
 // FUSED: total opacity + source vector + reduced propagation matrix per ray-point, written as
 // one 64-byte record {chi_I, K'_Q, K'_U, K'_V, S_I, S_Q, S_U, S_V} at raypts[ray][k].
-template <int MINB, class ZT, bool ARM>
+template <int MINB, class ZT, bool ARM, bool RLKS>
 __global__ void __launch_bounds__(128, MINB)
 opacity_fused_kernel(int ncol, int nlambda, int ndep, int to_obs, int nline,
                      const double *__restrict__ lambda, const int *__restrict__ wfirst,
@@ -238,7 +257,7 @@ opacity_fused_kernel(int ncol, int nlambda, int ndep, int to_obs, int nline,
   const double *at = atmos + (size_t) col * RHB200_AT_NFIELD * ndep;
 
   LineSums s;
-  line_sums<ARM>(s, __ldg(lambda + l), to_obs, __ldg(wfirst + l), __ldg(wcount + l), widx, lines,
+  line_sums<ARM, RLKS>(s, __ldg(lambda + l), to_obs, __ldg(wfirst + l), __ldg(wcount + l), widx, lines,
             zee, lineprep + (size_t) col*nline*LP_NFIELD*ndep + k, ndep,
             __ldg(at + RHB200_AT_COS_GAMMA*ndep + k), __ldg(at + RHB200_AT_COS_2CHI*ndep + k),
             __ldg(at + RHB200_AT_SIN_2CHI*ndep + k));
@@ -247,6 +266,7 @@ opacity_fused_kernel(int ncol, int nlambda, int ndep, int to_obs, int nline,
   // formal.c:178-208: chi = 0 + chi_c, S = (0 + eta_c)/chi; stokesopac.c:72-77: K' = chi_QUV/chi_I
   // molecular lines come last in Background() (background.c:548-566): chi_c = (chi_ai + Kurucz) + molecules
   double chi = __ldg(chi_ai + t) + s.chi[0], eta = __ldg(eta_ai + t) + s.eta[0];
+  if (RLKS) chi += s.scatt;                        // background.c:538-543: sca_c += scatt; chi_c += scatt
   if (mol_chi) { chi += __ldg(mol_chi + t); eta += __ldg(mol_eta + t); }
   const rhdiv::Recip rchi(chi);                  // seven IEEE quotients, one reciprocal refinement
   double2 *o = reinterpret_cast<double2 *>(raypts + t * RP_NFIELD);
@@ -256,7 +276,7 @@ opacity_fused_kernel(int ncol, int nlambda, int ndep, int to_obs, int nline,
   o[3] = make_double2(rchi.div(s.eta[2]), rchi.div(s.eta[3]));
   // N_MAX_SCATTER > 0: wavelengths solved for I alone keep the emissivity and the scattering opacity for the Lambda
   // iteration of S = (eta + sca J)/chi (formal.c:289-309) in the slots their (zero) S_U, S_V would take
-  if (sca_ai && (all_scalar || (__ldg(wflags + l) & 2) == 0)) o[3] = make_double2(eta, __ldg(sca_ai + t));
+  if (sca_ai && (all_scalar || (__ldg(wflags + l) & 2) == 0)) o[3] = make_double2(eta, RLKS ? __ldg(sca_ai + t) + s.scatt : __ldg(sca_ai + t));
 }
 
 // RAW: exactly the output of rlk_opacity(), chi/eta [ncol][nlambda][4][ndep]
@@ -278,7 +298,7 @@ opacity_raw_kernel(int ncol, int nlambda, int ndep, int to_obs, int nline,
   const double *at = atmos + (size_t) col * RHB200_AT_NFIELD * ndep;
   LineSums s;
   const ZeemanGlobal zee{zq, zshift, zstrength};
-  line_sums<true>(s, __ldg(lambda + l), to_obs, __ldg(wfirst + l), __ldg(wcount + l), widx, lines,
+  line_sums<true, false>(s, __ldg(lambda + l), to_obs, __ldg(wfirst + l), __ldg(wcount + l), widx, lines,
             zee, lineprep + (size_t) col*nline*LP_NFIELD*ndep + k, ndep,
             __ldg(at + RHB200_AT_COS_GAMMA*ndep + k), __ldg(at + RHB200_AT_COS_2CHI*ndep + k),
             __ldg(at + RHB200_AT_SIN_2CHI*ndep + k));
@@ -643,7 +663,7 @@ int rh_launch_prep(rhb200_ctx *ctx, int ncol, int ndep, double muz, int moving,
   const unsigned blocks = (unsigned) ((n + threads - 1) / threads);
   {
     ScopedKernelTimer t(ctx, RHB200_K_PREP);
-    prep_kernel<<<blocks, threads, 0, ctx->stream>>>(ncol, ndep, muz, moving, ctx->tab.nline,
+    prep_kernel<<<blocks, threads, 0, ctx->stream>>>(ncol, ndep, muz, moving, ctx->tab.rlkscatter, ctx->tab.nline,
         ctx->tab.nelem, ctx->tab.npf, ctx->tab.lines, ctx->tab.elems, ctx->tab.pf, ctx->tab.Tpf,
         d_atmos, d_elem_n, d_lineprep);
   }
@@ -671,8 +691,9 @@ int rh_launch_opacity_fused(rhb200_ctx *ctx, int ncol, int ndep, int to_obs,
     }
 #define RH_OPF_ARGS(Z) (ncol, ctx->wav.nlambda, ndep, to_obs, ctx->tab.nline, ctx->wav.lambda, ctx->wav.first, \
         ctx->wav.count, ctx->wav.idx, ctx->tab.lines, Z, d_atmos, d_lineprep, d_chi_ai, d_eta_ai, d_raypts, d_molchi, d_moleta, d_sca, ctx->wav.flags, ctx->no_stokes)
-#define RH_LAUNCH_OPF(M, ZT, Z) do { if (arm) opacity_fused_kernel<M, ZT, true><<<grid, block, 0, ctx->stream>>>RH_OPF_ARGS(Z); \
-        else opacity_fused_kernel<M, ZT, false><<<grid, block, 0, ctx->stream>>>RH_OPF_ARGS(Z); } while (0)
+#define RH_LAUNCH_OPF(M, ZT, Z) do { if (ctx->tab.rlkscatter) opacity_fused_kernel<M, ZT, true, true><<<grid, block, 0, ctx->stream>>>RH_OPF_ARGS(Z); \
+        else if (arm) opacity_fused_kernel<M, ZT, true, false><<<grid, block, 0, ctx->stream>>>RH_OPF_ARGS(Z); \
+        else opacity_fused_kernel<M, ZT, false, false><<<grid, block, 0, ctx->stream>>>RH_OPF_ARGS(Z); } while (0)
 #define RH_LAUNCH_OPF_V(ZT, Z) switch (variant) {             \
     case 4: RH_LAUNCH_OPF(4, ZT, Z); break;                   \
     case 5: RH_LAUNCH_OPF(5, ZT, Z); break;                   \

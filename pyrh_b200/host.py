@@ -917,8 +917,6 @@ class Session:
             raise NotImplementedError("OPACITY_FUDGE file: pyrh takes the factors as compute1d arguments (fudge_wave, fudge_value)")
         if _true(kw["MAGNETO_OPTICAL"]):
             raise NotImplementedError("MAGNETO_OPTICAL = TRUE is refused (the reference overflows chip_c there, readj.c:328)")
-        if _true(kw["RLK_SCATTER"]):
-            raise NotImplementedError("RLK_SCATTER = TRUE is not implemented")
         listed = _atoms_listed(cwd, kw)
         self.el = read_elements(path, kw, atomic_number, atomic_abundance)
         bg = self.background = read_background_model(cwd, kw, self.el, path)
@@ -927,7 +925,7 @@ class Session:
         self.lam = sort_lambda(wave, self.lambda_ref)
         mlines, msel = molecular_line_table(cwd, kw, self.el, path)      # refuses polarizable lists (MolZeeman)
         self.ctx = api.Context(device)
-        self.ctx.set_lines(self.lt, magneto_optical=False, rlkscatter=False)
+        self.ctx.set_lines(self.lt, magneto_optical=False, rlkscatter=_true(kw["RLK_SCATTER"]))
         if len(mlines):                                                  # MolecularOpacity, opacity.c:711-839
             self.ctx.set_molecular_lines(mlines, msel)
         if _true(kw.get("ALLOW_PASSIVE_BB", "TRUE")):                       # passive_bb, metal.c:174-344

@@ -1202,3 +1202,22 @@ def test_lte_scattering_passes(tmp_path, case, kw):
     assert np.max(np.abs(got[0] / ref[0] - 1)) < 1e-9
     assert np.array_equal(got, ref)
     assert not np.array_equal(ref, g["n0_stokes"])
+
+
+def test_rlk_scatter_keyword(tmp_path):
+    """RLK_SCATTER = TRUE: each Kurucz line's opacity is split by the destruction probability epsilon(T, ne) into a
+    thermal part and a scattering part that only enters the total opacity (kurucz.c:641-652, 682-694,
+    background.c:538-543).  Hinode window, and the 18-line list at mu = 0.8 together with N_MAX_SCATTER = 3:
+    identical to rhf1d() (fixture rlkscatter)."""
+    from pyrh_b200 import host
+    g = dict(np.load(GOLD / "rlkscatter.npz"))
+    (tmp_path / "a").mkdir(); (tmp_path / "b").mkdir()
+    cwd = _stage_cwd(tmp_path / "a", kurucz="fe6300", keywords={"RLK_SCATTER": ("FALSE", "TRUE")})
+    got = np.array(host.compute1d(cwd, 1.0, 0, g["atmosphere"], g["hinode_wave"])[:4])
+    REPORT["rlkscatter_hinode_exact"] = bool(np.array_equal(got, g["hinode_stokes"]))
+    assert np.max(np.abs(got[0] / g["hinode_stokes"][0] - 1)) < 1e-9
+    assert np.array_equal(got, g["hinode_stokes"])
+    cwd = _stage_cwd(tmp_path / "b", keywords={"RLK_SCATTER": ("FALSE", "TRUE"), "N_MAX_SCATTER": ("0", "3")})
+    got = np.array(host.compute1d(cwd, 0.8, 0, g["atmosphere"], g["l4016_wave"])[:4])
+    REPORT["rlkscatter_lines4016_exact"] = bool(np.array_equal(got, g["l4016_stokes"]))
+    assert np.array_equal(got, g["l4016_stokes"])
