@@ -118,6 +118,11 @@ int rhb200_set_wavelengths(rhb200_ctx *ctx, int nlambda, const double *lambda);
    rhb200_set_chemistry and before rhb200_set_wavelengths; rhb200_set_lines clears the table. */
 int rhb200_set_molecular_lines(rhb200_ctx *ctx, int nline, const double *mlines, int nmol, const double *molecules);
 
+/* get_atomic_rfs (rh/inputs.h:92, pyrh.pyx:604-606): the Kurucz lines whose log gf the analytic response function is
+   taken for.  line_rows[p] = row of the table passed to rhb200_set_lines that carries parameter p (the reference's
+   RLK_Line.loggf_rf_ind, kurucz.c:254-257), or -1 for a parameter no line carries (its column is 0); npar <= 16.  rhb200_set_lines() clears the registration. */
+int rhb200_set_loggf_rf(rhb200_ctx *ctx, int npar, const int *line_rows);
+
 /* keywords N_MAX_SCATTER and ITER_LIMIT in LTE (pyrh_compute1dray.c:332-337): n_max_scatter > 0 makes the batched LTE
    entry points Lambda-iterate the continuum-scattering term of the angle-independent (Feautrier) wavelengths,
    S = (eta + sca J)/chi (formal.c:289-309), per column until max |1 - Jdag/J| <= iter_limit or n_max_scatter passes.
@@ -364,6 +369,18 @@ int rhb200_lte_stokes_batch_atmos(rhb200_ctx *ctx, int ncol, int ndep, double mu
 int rhb200_compute1d_batch(rhb200_ctx *ctx, int ncol, int ndep, int nrow, double mu, int atm_scale,
                            const double *atmosphere, int iref, double wght_per_H, double vmacro_tresh,
                            int bc_top, int bc_bottom, double *stokes, double *scales);
+
+/* rhb200_compute1d_batch with get_atomic_rfs = 1: additionally rfs [ncol][nlambda][npar] = atmos.atomic_rfs[nspect][0][p]
+   (formal.c:278-282, pyrh_solveray.c:144-147; pyrh.compute1d returns its transpose without the lambda_ref entry), the
+   response of the emergent intensity to log gf of the lines registered with rhb200_set_loggf_rf.  As in the reference
+   it is non-zero only at wavelengths Formal() solves with Piecewise_Bezier3_1D (bezier_1D.c:416-516): an unpolarised
+   line in a moving column, or any line in NO_STOKES mode; wavelengths solved by the polarised solver or by Feautrier
+   return 0.  Where the reference reads uninitialised memory (a registered line outside the wavelength's window:
+   sortlambda.c:608-611 mallocs dchi_c_lam, kurucz.c:696 only writes inside the window) the entry is 0 here.
+   stokes, scales may be NULL. */
+int rhb200_compute1d_rf_batch(rhb200_ctx *ctx, int ncol, int ndep, int nrow, double mu, int atm_scale,
+                              const double *atmosphere, int iref, double wght_per_H, double vmacro_tresh,
+                              int bc_top, int bc_bottom, double *stokes, double *scales, double *rfs);
 
 /* pyrh.get_scales() for a batch (pyrh.pyx:491-534, rhf1d/pyrh_hse.c:402-553): Background() at the reference
    wavelength and convertScales(), nothing else.  The reference sets atmos.Nrlk = 0 there, so the context normally

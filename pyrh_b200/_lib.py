@@ -61,6 +61,9 @@ SYMBOLS = [
     ("rhb200_lte_stokes_batch_atmos", C.c_int, [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, vp, vp]),
     ("rhb200_compute1d_batch", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, vp, C.c_int, C.c_double,
                                          C.c_double, C.c_int, C.c_int, vp, vp]),
+    ("rhb200_compute1d_rf_batch", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, vp, C.c_int, C.c_double,
+                                            C.c_double, C.c_int, C.c_int, vp, vp, vp]),
+    ("rhb200_set_loggf_rf", C.c_int, [vp, C.c_int, ip]),
     ("rhb200_rf_fd_batch", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, vp, C.c_int, C.c_double,
                                      C.c_double, C.c_int, C.c_int, C.c_int, ip, dp, vp]),
     ("rhb200_set_model_lines", C.c_int, [vp, C.c_int, dp]),

@@ -107,6 +107,7 @@ class Context:
         el = np.ascontiguousarray(lt.elems, np.float64)
         pf = np.ascontiguousarray(lt.pf, np.float64)
         tp = np.ascontiguousarray(lt.Tpf, np.float64)
+        self.lrf_npar = 0
         _lib.check(self.lib.rhb200_set_lines(self.h, lines.shape[0], _dp(lines), len(zq),
                                              zq.ctypes.data_as(_lib.ip), _dp(zs), _dp(zt),
                                              el.shape[0], _dp(el), pf.shape[0], pf.shape[1], _dp(pf),
@@ -252,6 +253,36 @@ class Context:
                                                    int(bc_bottom), _vp(st), _vp(sc) if sc is not None else None))
         res = st if keep_lambda_ref else np.delete(st, iref, axis=2)
         return (res, sc) if get_scales else res
+
+    def set_loggf_rf(self, line_rows):
+        """``get_atomic_rfs``: rows of the line table (sorted by wavelength) whose log gf the analytic response
+        function is taken for; parameter p <-> ``line_rows[p]``.  ``set_lines`` clears it."""
+        rows = np.ascontiguousarray(line_rows, np.int32)
+        _lib.check(self.lib.rhb200_set_loggf_rf(self.h, len(rows), rows.ctypes.data_as(_lib.ip)))
+        self.lrf_npar = len(rows)
+
+    def compute1d_rf_batch(self, atmosphere, mu=1.0, atm_scale=0, lambda_ref=500.0, wght_per_H=0.0, vmacro_tresh=0.0,
+                           bc_top=_lib.BC_ZERO, bc_bottom=_lib.BC_THERMALIZED, keep_lambda_ref=False):
+        """``compute1d_batch`` with ``get_atomic_rfs``: ``(stokes [ncol, 4, nlambda], rfs [ncol, nlambda, npar])`` --
+        ``mySpectrum.rfs`` (pyrh_solveray.c:144-147) for the lines registered with ``set_loggf_rf``."""
+        a = np.ascontiguousarray(atmosphere, np.float64)
+        if a.ndim != 3 or a.shape[1] < 9:
+            raise ValueError("atmosphere must be [ncol, >=9, ndep] (pyrh.pyx:621-625)")
+        ncol, nrow, ndep = a.shape
+        hit = np.nonzero(np.asarray(self.lam) == lambda_ref)[0]
+        if len(hit) != 1:
+            raise ValueError("the wavelength grid must contain lambda_ref once (sortlambda.c adds it to spectrum.lambda)")
+        iref = int(hit[0])
+        npar = getattr(self, "lrf_npar", 0)
+        st = np.empty((ncol, 4, self.nlambda))
+        rf = np.empty((ncol, self.nlambda, max(npar, 1)))
+        _lib.check(self.lib.rhb200_compute1d_rf_batch(self.h, ncol, ndep, nrow, float(mu), int(atm_scale), _vp(a), iref,
+                                                      float(wght_per_H), float(vmacro_tresh) * KM_TO_M, int(bc_top),
+                                                      int(bc_bottom), _vp(st), None, _vp(rf)))
+        rf = rf[:, :, :npar]
+        if keep_lambda_ref:
+            return st, rf
+        return np.delete(st, iref, axis=2), np.delete(rf, iref, axis=1)
 
     def set_elements(self, elems, pf, Tpf):
         """atmos.elements[] for Solve_ne: ``elems[nelem, RE_NFIELD]`` (hydrogen first), ``pf[rows, npf]`` = ln U."""

@@ -68,6 +68,7 @@ static void free_tables(rhb200_ctx *c)
   cudaFree(t.lines); cudaFree(t.zshift); cudaFree(t.zstrength); cudaFree(t.elems);
   cudaFree(t.pf); cudaFree(t.Tpf); cudaFree(t.zq);
   t = DevTables();
+  cudaFree(c->d_lrf_lines); c->d_lrf_lines = nullptr; c->lrf_npar = 0;      // rows of the table that is going away
 }
 static void free_wave(rhb200_ctx *c)
 {
@@ -220,6 +221,23 @@ extern "C" int rhb200_set_stokes_mode(rhb200_ctx *c, int full_stokes)
   RH_NEED_CTX(c);
   c->no_stokes = full_stokes ? 0 : 1;
   free_wave(c);
+  return RHB200_OK;
+}
+
+// get_atomic_rfs (inputs.h:92): the lines whose log gf the response function is taken for -- rows of the table passed
+// to rhb200_set_lines (which is sorted by wavelength; RLK_Line.loggf_rf_ind = p for row line_rows[p], kurucz.c:254-257)
+extern "C" int rhb200_set_loggf_rf(rhb200_ctx *c, int npar, const int *line_rows)
+{
+  RH_NEED_CTX(c);
+  if (npar < 0 || npar > 16 || (npar > 0 && !line_rows)) { rhb200_set_error("rhb200_set_loggf_rf: 0 <= npar <= 16"); return RHB200_EINVAL; }
+  for (int p = 0; p < npar; p++)
+    if (line_rows[p] < -1 || line_rows[p] >= c->tab.nline) { rhb200_set_error("rhb200_set_loggf_rf: row %d outside the line table", line_rows[p]); return RHB200_EINVAL; }   // -1: a parameter no line carries (all zero)
+  if (c->d_lrf_lines) { cudaFree(c->d_lrf_lines); c->d_lrf_lines = nullptr; }
+  c->lrf_npar = npar;
+  if (npar > 0) {
+    RH_CUDA(cudaMalloc((void **) &c->d_lrf_lines, (size_t) npar * sizeof(int)));
+    RH_CUDA(cudaMemcpy(c->d_lrf_lines, line_rows, (size_t) npar * sizeof(int), cudaMemcpyHostToDevice));
+  }
   return RHB200_OK;
 }
 
@@ -421,7 +439,7 @@ struct ChunkLayout {
     elem_n   = align_up((size_t) cc * std::max(1, c->tab.nelem) * RHB200_RE_MAXSTAGE * ndep * sizeof(double));
     lineprep = align_up((size_t) cc * std::max(1, c->tab.nline) * ndep * LP_NFIELD * sizeof(double));
     raypts   = align_up((size_t) cc * c->wav.nlambda * ndep * RP_NFIELD * sizeof(double));
-    scal     = align_up((size_t) cc * std::max(1, c->wav.nunpol) * 3 * ndep * sizeof(double));
+    scal     = align_up((size_t) cc * std::max(1, c->wav.nunpol) * c->scal_fields() * ndep * sizeof(double));
     colmov   = align_up((size_t) cc * (2 * sizeof(int) + sizeof(unsigned long long)));     // moving flags, scatter done flags, dJmax
     total = elem_n + lineprep + raypts + scal + colmov;
   }
@@ -458,6 +476,7 @@ struct PyrhIn {
   // -delta (s = 1) at depth k; they are expanded on the device from d_base and only the differences travel back
   int rf_npar = 0; const int *d_rf_rows = nullptr; const double *d_rf_delta = nullptr; const double *d_base = nullptr;
   double *rf_out = nullptr;
+  double *lrf_out = nullptr;                     // analytic log gf response functions [ncol][nlambda][lrf_npar] (rhb200_compute1d_rf_batch)
 };
 struct ScalesStep { int iref, atm_scale; double wght_per_H; double *d_scratch, *d_scales_out;
                     double total_abund = 0.0, gravity = 1.0; int scales_only = 0; };
@@ -465,7 +484,8 @@ struct ScalesStep { int iref, atm_scale; double wght_per_H; double *d_scratch, *
 static int run_chunk_dev(rhb200_ctx *c, int cc, int ndep, double muz, int moving, int bc_top, int bc_bottom,
                          const double *d_atmos, const double *d_chi_ai, const double *d_eta_ai,
                          double *d_stokes, char *ws, const ScalesStep *sc = nullptr, bool per_column_moving = false,
-                         const double *d_molchi = nullptr, const double *d_moleta = nullptr, const double *d_sca = nullptr)
+                         const double *d_molchi = nullptr, const double *d_moleta = nullptr, const double *d_sca = nullptr,
+                         double *d_lrf = nullptr)
 {
   ChunkLayout L(c, cc, ndep);
   double *d_elem_n = (double *) ws, *d_lineprep = (double *) (ws + L.elem_n),
@@ -488,6 +508,10 @@ static int run_chunk_dev(rhb200_ctx *c, int cc, int ndep, double muz, int moving
     int *d_done = (int *) (flagbase + (size_t) cc * sizeof(unsigned long long)) + cc;       // after the moving flags
     RH_CHECK(rh_launch_scatter_passes(c, cc, ndep, muz, bc_top, bc_bottom, d_atmos, d_raypts, d_stokes, moving, d_colmov,
                                       d_colmax, d_done));
+  }
+  if (d_lrf) {                                   // get_atomic_rfs
+    RH_CHECK(rh_launch_loggf_dopac(c, cc, ndep, d_atmos, d_lineprep, d_scal));
+    RH_CHECK(rh_launch_loggf_rf(c, cc, ndep, muz, bc_top, bc_bottom, d_atmos, moving, d_colmov, d_scal, d_lrf));
   }
   return RHB200_OK;
 }
@@ -538,6 +562,10 @@ static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int mov
   if (ncol == 0) return RHB200_OK;
   if ((!atmos && !py) || (!stokes && !(py && (py->rf_out || py->scales_only))) || (!chem && !chem_on_device && (!chi_ai || !eta_ai))) { rhb200_set_error("null buffer"); return RHB200_EINVAL; }
   const bool cont_dev = chem || chem_on_device;
+  if (py && py->lrf_out) {
+    if (c->lrf_npar <= 0) { rhb200_set_error("rhb200_set_loggf_rf() has not been called"); return RHB200_ESTATE; }
+    if (c->lrf_npar > ndep) { rhb200_set_error("log gf response functions: npar (%d) must not exceed ndep (%d)", c->lrf_npar, ndep); return RHB200_EINVAL; }
+  }
   if (cont_dev && !c->cont) { rhb200_set_error("rhb200_set_continuum() has not been called"); return RHB200_ESTATE; }
   const int nl = c->wav.nlambda;
   const int nslots = 2;
@@ -633,8 +661,13 @@ static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int mov
                   (py && py->scales) ? d_sc + (size_t) cc * 2 * ndep : nullptr};
     if (py) { sc.total_abund = py->total_abund; sc.gravity = py->gravity; sc.scales_only = py->scales_only; }
     rc = run_chunk_dev(c, n, ndep, muz, moving, bc_top, bc_bottom, d_at, d_chi, d_eta, d_st, ws, py ? &sc : nullptr,
-                       py && py->vmacro_tresh > 0.0, d_mchi, d_meta, d_sa);
+                       py && py->vmacro_tresh > 0.0, d_mchi, d_meta, d_sa, (py && py->lrf_out) ? d_eta : nullptr);
     if (rc != RHB200_OK) break;
+    // d_eta (eta_ai, [n][nl][ndep]) is free once the opacity kernel has run: the response functions live there
+    if (py && py->lrf_out && (e = cudaMemcpyAsync(py->lrf_out + (size_t) c0 * nl * c->lrf_npar, d_eta, (size_t) n * nl * c->lrf_npar * sizeof(double),
+                                                  cudaMemcpyDeviceToHost, st)) != cudaSuccess) {
+      rhb200_set_error("D2H copy failed: %s", cudaGetErrorString(e)); rc = RHB200_ECUDA; break;
+    }
     if (sc.d_scales_out && (e = cudaMemcpyAsync(py->scales + (size_t) c0 * 3 * ndep, sc.d_scales_out, (size_t) n * 3 * ndep * sizeof(double),
                                                 cudaMemcpyDeviceToHost, st)) != cudaSuccess) {
       rhb200_set_error("D2H copy failed: %s", cudaGetErrorString(e)); rc = RHB200_ECUDA; break;
@@ -698,6 +731,23 @@ extern "C" int rhb200_compute1d_batch(rhb200_ctx *c, int ncol, int ndep, int nro
   if (iref < 0 || iref >= c->wav.nlambda) { rhb200_set_error("iref outside the wavelength grid"); return RHB200_EINVAL; }
   if (!(wght_per_H > 0.0) && atm_scale == 1) { rhb200_set_error("wght_per_H (abundance.c:220) is needed for the column-mass scale"); return RHB200_EINVAL; }
   PyrhIn py{atmosphere, nrow, atm_scale, iref, wght_per_H, vmacro_tresh, scales};
+  return lte_batch_host(c, ncol, ndep, mu, 1, bc_top, bc_bottom, nullptr, nullptr, nullptr, nullptr, stokes, 1, &py);
+}
+
+// get_atomic_rfs = 1 (pyrh.pyx:604-606, 658-660): rhb200_compute1d_batch plus mySpectrum.rfs for the log gf parameters
+// registered with rhb200_set_loggf_rf
+extern "C" int rhb200_compute1d_rf_batch(rhb200_ctx *c, int ncol, int ndep, int nrow, double mu, int atm_scale,
+                                         const double *atmosphere, int iref, double wght_per_H, double vmacro_tresh,
+                                         int bc_top, int bc_bottom, double *stokes, double *scales, double *rfs)
+{
+  RH_NEED_CTX(c);
+  if (!atmosphere || !rfs) { rhb200_set_error("null buffer"); return RHB200_EINVAL; }
+  if (nrow < 9) { rhb200_set_error("atmosphere needs the 9 rows of pyrh.compute1d (pyrh.pyx:621-625), got %d", nrow); return RHB200_EINVAL; }
+  if (atm_scale < 0 || atm_scale > 2) { rhb200_set_error("atm_scale must be 0 (tau500), 1 (column mass) or 2 (height)"); return RHB200_EINVAL; }
+  if (iref < 0 || iref >= c->wav.nlambda) { rhb200_set_error("iref outside the wavelength grid"); return RHB200_EINVAL; }
+  if (!(wght_per_H > 0.0) && atm_scale == 1) { rhb200_set_error("wght_per_H (abundance.c:220) is needed for the column-mass scale"); return RHB200_EINVAL; }
+  PyrhIn py{atmosphere, nrow, atm_scale, iref, wght_per_H, vmacro_tresh, scales};
+  py.lrf_out = rfs;
   return lte_batch_host(c, ncol, ndep, mu, 1, bc_top, bc_bottom, nullptr, nullptr, nullptr, nullptr, stokes, 1, &py);
 }
 

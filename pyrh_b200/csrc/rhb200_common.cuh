@@ -91,6 +91,10 @@ struct rhb200_ctx {
   int s_interpolation = RHB200_S_BEZIER3, s_interpolation_stokes = RHB200_DELO_BEZIER3;
   int no_stokes = 0;         // STOKES_MODE = NO_STOKES (rhb200_set_stokes_mode)
   int n_max_scatter = 0; double scatter_limit = 1.0e-2;   // N_MAX_SCATTER / ITER_LIMIT in LTE (rhb200_set_scatter)
+  // analytic log gf response functions (rhb200_set_loggf_rf): parameter p belongs to row lrf_lines[p] of the line table
+  int lrf_npar = 0; int *d_lrf_lines = nullptr;
+  // doubles per depth point of the scalar-ray scratch: chi, S, I (+ dchi, deta, dI[npar] in RF mode)
+  int scal_fields() const { return 3 + 3*lrf_npar; }
   // wavelength shard of the NLTE solve (rhb200_nlte_set_shard)
   int shard_rank = 0, shard_nrank = 1;
   rhb200_allreduce_fn shard_fn = nullptr; void *shard_user = nullptr;
@@ -168,6 +172,11 @@ int rh_launch_opacity_fused(rhb200_ctx *ctx, int ncol, int ndep, int to_obs,
                             const double *d_chi_ai, const double *d_eta_ai,
                             double *d_raypts /* [nray][ndep][RP_NFIELD] */,
                             const double *d_molchi = nullptr, const double *d_moleta = nullptr, const double *d_sca = nullptr);
+int rh_launch_loggf_dopac(rhb200_ctx *ctx, int ncol, int ndep, const double *d_atmos, const double *d_lineprep,
+                          double *d_scratch /* [ncol][nunpol][scal_fields()][ndep] */);
+int rh_launch_loggf_rf(rhb200_ctx *ctx, int ncol, int ndep, double muz, int bc_top, int bc_bottom, const double *d_atmos,
+                       int moving, const int *d_col_moving,
+                       double *d_scratch, double *d_rf /* [ncol][nlambda][npar] */);
 int rh_launch_opacity_raw(rhb200_ctx *ctx, int ncol, int ndep, int to_obs,
                           const double *d_atmos, const double *d_lineprep,
                           double *d_chi, double *d_eta /* [ncol][nlambda][4][ndep] */);

@@ -198,14 +198,14 @@ struct FeauGenericIO {          // reference layouts; P and Psi double as the F 
 
 // rays of the fused LTE path without a polarised line, solved for I alone.  formal.c:84-103: angle_dep is false when
 // the wavelength has no line, or has one but the column is static -> Feautrier (:289-309); a moving column with an
-// unpolarised line takes the scalar S_INTERPOLATION ray (:223-236).  scratch [ncol][nunpol][3][ndep]: chi, S, I.
+// unpolarised line takes the scalar S_INTERPOLATION ray (:223-236).  scratch [ncol][nunpol][fields][ndep]: chi, S, I, ...
 __global__ void __launch_bounds__(128)
 feautrier_raypts_kernel(int ncol, int nlambda, int ndep, double muz, int bc_top, int bc_bottom,
                         const int *__restrict__ nolines, int nnoline,
                         const double *__restrict__ atmos, const double *__restrict__ lambda,
                         double *__restrict__ raypts, double *__restrict__ stokes,
                         const int *__restrict__ wflags, const int *__restrict__ unpol_rank, int nunpol,
-                        int solver, int moving, const int *__restrict__ col_moving, double *__restrict__ scratch, int keepP)
+                        int solver, int moving, const int *__restrict__ col_moving, double *__restrict__ scratch, int fields, int keepP)
 {
   const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t) ncol * nnoline) return;
@@ -217,7 +217,7 @@ feautrier_raypts_kernel(int ncol, int nlambda, int ndep, double muz, int bc_top,
   const int fl = __ldg(wflags + l);                  // polarised line (NO_STOKES only): always angle dependent
   const bool scalar_ray = (fl & 2) || ((fl & 1) && (col_moving ? col_moving[col] != 0 : moving != 0));
   if (scalar_ray) {
-    double *c = scratch + ((size_t) col * nunpol + __ldg(unpol_rank + l)) * 3 * ndep, *s = c + ndep, *Ir = s + ndep;
+    double *c = scratch + ((size_t) col * nunpol + __ldg(unpol_rank + l)) * fields * ndep, *s = c + ndep, *Ir = s + ndep;
     for (int k = 0; k < ndep; k++) { c[k] = rp[(size_t) k * RP_NFIELD + RP_CHI]; s[k] = rp[(size_t) k * RP_NFIELD + RP_SI]; }
     const double *z = at + RHB200_AT_HEIGHT * ndep, *Tc = at + RHB200_AT_T * ndep;
     const double lam = __ldg(lambda + l);
@@ -263,6 +263,41 @@ scatter_pass_kernel(int ncol, int nlambda, int ndep, double muz, int bc_top, int
   const double I0 = rhf::feautrier_ray(io, ndep, muz, bc_top, bc_bottom, at + RHB200_AT_T * ndep, __ldg(lambda + l));
   stokes[(size_t) col * 4 * nlambda + l] = I0;
   atomicMax(colmax + col, (unsigned long long) __double_as_longlong(io.dJ));
+}
+
+// get_atomic_rfs (formal.c:59-65, 124-127, 278-282): the log gf response function of the emergent intensity at the
+// wavelengths Formal() solves with Piecewise_Bezier3_1D, i.e. the scalar rays of feautrier_raypts_kernel when
+// S_INTERPOLATION = S_BEZIER3; every other wavelength keeps the zeros Formal() starts from.  The down-ray that
+// precedes the up-ray in Formal() -- its intensities are what the response-function branch reads at the depths the
+// up-ray has not reached (bezier_1D.c:483) -- sees the SAME opacity as the up-ray: pyrh keeps one background record
+// per wavelength in memory (spectrum.chi_c_lam[nspect], no direction index), and the last Background() pass, the one
+// that stays, is to_obs = 1.  The scratch row of the ray still holds chi, S of feautrier_raypts_kernel; dchi/deta
+// were written by loggf_dopac_kernel.  One thread per (column, wavelength).
+__global__ void __launch_bounds__(128)
+loggf_rf_kernel(int ncol, int nlambda, int ndep, double muz, int bc_top, int bc_bottom, const double *__restrict__ atmos,
+                const double *__restrict__ lambda, const int *__restrict__ wflags,
+                const int *__restrict__ unpol_rank, int nunpol, int solver, int no_stokes, int moving,
+                const int *__restrict__ col_moving, double *__restrict__ scratch, int fields, int npar, double *__restrict__ rf)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t) ncol * nlambda) return;
+  const int col = (int) (t / nlambda), l = (int) (t - (size_t) col * nlambda);
+  double *out = rf + t * npar;
+  const int fl = __ldg(wflags + l), rank = __ldg(unpol_rank + l);
+  const bool mov = col_moving ? col_moving[col] != 0 : moving != 0;
+  const bool scalar_ray = rank >= 0 && (no_stokes ? ((fl & 2) || ((fl & 1) && mov)) : (fl == 1 && mov));
+  if (!scalar_ray || solver != RHB200_S_BEZIER3) {
+    for (int p = 0; p < npar; p++) out[p] = 0.0;
+    return;
+  }
+  const double *at = atmos + (size_t) col * RHB200_AT_NFIELD * ndep;
+  const double *z = at + RHB200_AT_HEIGHT * ndep, *Tc = at + RHB200_AT_T * ndep;
+  double *c = scratch + ((size_t) col * nunpol + rank) * fields * ndep, *s = c + ndep, *Ir = s + ndep,
+         *dchi = Ir + ndep, *deta = dchi + (size_t) npar * ndep, *dI = deta + (size_t) npar * ndep;
+  const double lam = __ldg(lambda + l);
+  rhz::bezier3_ray_t<false>(ndep, z, muz, 0, bc_top, bc_bottom, Tc, lam, c, s, Ir, nullptr, 0, nullptr, nullptr, nullptr);
+  rhz::bezier3_ray_t<true>(ndep, z, muz, 1, bc_top, bc_bottom, Tc, lam, c, s, Ir, nullptr, npar, dchi, deta, dI);
+  for (int p = 0; p < npar; p++) out[p] = dI[p];       // dI[0][p], formal.c:278-282
 }
 
 __global__ void scatter_update_kernel(int ncol, double limit, int *__restrict__ done, unsigned long long *__restrict__ colmax)
@@ -381,7 +416,23 @@ int rh_launch_feautrier_raypts(rhb200_ctx *ctx, int ncol, int ndep, double muz, 
     feautrier_raypts_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, ctx->stream>>>(
         ncol, ctx->wav.nlambda, ndep, muz, bc_top, bc_bottom, ctx->wav.noline, nn, d_atmos,
         ctx->wav.lambda, d_raypts, d_stokes, ctx->wav.flags, ctx->wav.unpol_rank, ctx->wav.nunpol,
-        ctx->s_interpolation, moving, d_col_moving, d_scratch, ctx->n_max_scatter > 0);
+        ctx->s_interpolation, moving, d_col_moving, d_scratch, ctx->scal_fields(), ctx->n_max_scatter > 0);
+  }
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}
+
+int rh_launch_loggf_rf(rhb200_ctx *ctx, int ncol, int ndep, double muz, int bc_top, int bc_bottom, const double *d_atmos,
+                       int moving, const int *d_col_moving, double *d_scratch, double *d_rf)
+{
+  const size_t n = (size_t) ncol * ctx->wav.nlambda;
+  if (n == 0 || ctx->lrf_npar == 0) return RHB200_OK;
+  {
+    ScopedKernelTimer t(ctx, RHB200_K_BEZIER);
+    loggf_rf_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, ctx->stream>>>(
+        ncol, ctx->wav.nlambda, ndep, muz, bc_top, bc_bottom, d_atmos, ctx->wav.lambda, ctx->wav.flags,
+        ctx->wav.unpol_rank, ctx->wav.nunpol, ctx->s_interpolation, ctx->no_stokes, moving, d_col_moving, d_scratch,
+        ctx->scal_fields(), ctx->lrf_npar, d_rf);
   }
   RH_CUDA(cudaGetLastError());
   return RHB200_OK;

@@ -309,6 +309,50 @@ opacity_raw_kernel(int ncol, int nlambda, int ndep, int to_obs, int nline,
   }
 }
 
+// d chi_c / d log gf and d eta_c / d log gf of the wavelengths solved with the scalar ray (kurucz.c:696-699:
+// spectrum.dchi_c_lam[nspect][k][p] = chi_l * phi * LN10 of the line parameter p belongs to, in the up direction -- the
+// last rlk_opacity() call before the up-ray of Formal() reads it).  One thread per (column, I-only wavelength, depth).
+// The reference leaves the entry uninitialised (matrix3d_double mallocs) where the line is outside the wavelength's
+// window; it is 0 here.  scratch [ncol][nunpol][fields][ndep]: dchi [ndep][npar] at field 3, deta at field 3 + npar.
+template <bool ARM, bool RLKS>
+__global__ void __launch_bounds__(128)
+loggf_dopac_kernel(int ncol, int nlambda, int ndep, int nline, const int *__restrict__ nolines, int nnoline,
+                   const int *__restrict__ unpol_rank, int nunpol, int fields, int npar, const int *__restrict__ par_line,
+                   const double *__restrict__ lambda, const int *__restrict__ wfirst, const int *__restrict__ wcount,
+                   const int *__restrict__ widx, const double *__restrict__ lines, const int *__restrict__ zq,
+                   const double *__restrict__ zshift, const double *__restrict__ zstrength,
+                   const double *__restrict__ atmos, const double *__restrict__ lineprep, double *__restrict__ scratch)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t) ncol * nnoline * ndep) return;
+  const size_t r = t / ndep;
+  const int k = (int) (t - r * ndep);
+  const int col = (int) (r / nnoline), l = __ldg(nolines + (int) (r - (size_t) col * nnoline));
+  const int rank = __ldg(unpol_rank + l);
+  if (rank < 0) return;
+  const double *at = atmos + (size_t) col * RHB200_AT_NFIELD * ndep;
+  const ZeemanGlobal zee{zq, zshift, zstrength};
+  double *dchi = scratch + ((size_t) col * nunpol + rank) * fields * ndep + (size_t) 3 * ndep, *deta = dchi + (size_t) npar * ndep;
+  const int first = __ldg(wfirst + l), count = __ldg(wcount + l);
+  for (int p = 0; p < npar; p++) {
+    const int nl = __ldg(par_line + p);
+    double dc = 0.0, de = 0.0;
+    for (int j = 0; j < count; j++) {
+      if (__ldg(widx + first + j) != nl) continue;
+      LineSums s;
+      line_sums<ARM, RLKS>(s, __ldg(lambda + l), 1, first + j, 1, widx, lines, zee,
+                           lineprep + (size_t) col*nline*LP_NFIELD*ndep + k, ndep,
+                           __ldg(at + RHB200_AT_COS_GAMMA*ndep + k), __ldg(at + RHB200_AT_COS_2CHI*ndep + k),
+                           __ldg(at + RHB200_AT_SIN_2CHI*ndep + k));
+      dc = s.chi[0] * 2.30258509299404568402;          // LN10 = log(10), kurucz.c:94
+      de = s.eta[0] * 2.30258509299404568402;
+      break;
+    }
+    dchi[(size_t) k * npar + p] = dc;
+    deta[(size_t) k * npar + p] = de;
+  }
+}
+
 // MolecularOpacity + MolProfile (opacity.c:711-916): LTE lines of PASSIVE molecules in the background.
 // One thread per (column, wavelength, depth); widx lists, per wavelength, the lines that pass the
 // reference's window tests (opacity.c:774-787, evaluated on the host) in molecule / line order, so the
@@ -712,6 +756,30 @@ int rh_launch_opacity_fused(rhb200_ctx *ctx, int ncol, int ndep, int to_obs,
       const ZeemanGlobal zg{ctx->tab.zq, ctx->tab.zshift, ctx->tab.zstrength};
       RH_LAUNCH_OPF_V(ZeemanGlobal, zg)
     }
+  }
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}
+
+int rh_launch_loggf_dopac(rhb200_ctx *ctx, int ncol, int ndep, const double *d_atmos, const double *d_lineprep, double *d_scratch)
+{
+  const int nn = ctx->wav.nnoline;
+  if (nn == 0 || ncol == 0 || ctx->lrf_npar == 0) return RHB200_OK;
+  const size_t n = (size_t) ncol * nn * ndep;
+  const unsigned grid = (unsigned) ((n + 127) / 128);
+  bool arm = false;
+  for (int i = 0; i < ctx->tab.nline; i++) {
+    const double *L = ctx->h_lines.data() + (size_t) i * RHB200_RL_NFIELD;
+    arm = arm || (L[RHB200_RL_GRAD] != 0.0 && L[RHB200_RL_POLARIZABLE] == 0.0);
+  }
+#define RH_DOPAC_ARGS (ncol, ctx->wav.nlambda, ndep, ctx->tab.nline, ctx->wav.noline, nn, ctx->wav.unpol_rank, ctx->wav.nunpol, \
+      ctx->scal_fields(), ctx->lrf_npar, ctx->d_lrf_lines, ctx->wav.lambda, ctx->wav.first, ctx->wav.count, ctx->wav.idx, ctx->tab.lines, \
+      ctx->tab.zq, ctx->tab.zshift, ctx->tab.zstrength, d_atmos, d_lineprep, d_scratch)
+  {
+    ScopedKernelTimer t(ctx, RHB200_K_OPACITY);
+    if (ctx->tab.rlkscatter) loggf_dopac_kernel<true, true><<<grid, 128, 0, ctx->stream>>>RH_DOPAC_ARGS;
+    else if (arm) loggf_dopac_kernel<true, false><<<grid, 128, 0, ctx->stream>>>RH_DOPAC_ARGS;
+    else loggf_dopac_kernel<false, false><<<grid, 128, 0, ctx->stream>>>RH_DOPAC_ARGS;
   }
   RH_CUDA(cudaGetLastError());
   return RHB200_OK;

@@ -518,6 +518,7 @@ def read_kurucz_lines(cwd, kw: dict, el: Elements, loggf_ids=None, loggf_values=
                       vmicro_char=float(kw["VMICRO_CHAR"]) * 1.0E+03)
     lt.validate()
     lt.elem_rows = dict(used)                                    # periodic-table index - 1 -> row of lt.elems
+    lt.file_index = np.array(order, np.int64)                    # table row -> line number in the Kurucz files
     return lt
 
 
@@ -944,6 +945,26 @@ class Session:
         self.ctx.set_continuum(self.model, abundance)
         self.ctx.set_chemistry(bg["ce_nuclei"][:, 1].astype(np.int32), bg["ce_mol"])
         self.vmacro_tresh = float(kw["VMACRO_TRESH"])
+        # get_atomic_rfs: parameter p <-> the line loggf_ids[p] names (RLK_Line.loggf_rf_ind = the LAST p that names
+        # it, kurucz.c:250-259); input.n_atomic_pars = Nloggf + Nlam, and no line carries a parameter beyond Nloggf
+        ids = [] if loggf_ids is None else [int(i) for i in loggf_ids]
+        row_of = {int(f): r for r, f in enumerate(self.lt.file_index)}
+        self.loggf_rows = [row_of.get(i, -1) if i not in ids[p + 1:] else -1 for p, i in enumerate(ids)]
+        self.n_atomic_pars = len(ids) + (0 if lam_ids is None else len(lam_ids))
+
+    def compute_rf(self, atmosphere, mu=1.0, atm_scale=0):
+        """``compute`` with ``get_atomic_rfs``: ``(stokes [.., 4, nlambda], rfs [.., n_atomic_pars, nlambda])``."""
+        if not self.loggf_rows:
+            raise ValueError("get_atomic_rfs needs loggf_ids")
+        if self.ctx.lrf_npar != len(self.loggf_rows):
+            self.ctx.set_loggf_rf(self.loggf_rows)
+        a = np.asarray(atmosphere, np.float64)
+        single = a.ndim == 2
+        st, rf = self.ctx.compute1d_rf_batch(a[None] if single else a, mu=mu, atm_scale=atm_scale, lambda_ref=self.lambda_ref,
+                                             wght_per_H=self.el.wght_per_H, vmacro_tresh=self.vmacro_tresh)
+        full = np.zeros((rf.shape[0], self.n_atomic_pars, rf.shape[1]))
+        full[:, :rf.shape[2]] = rf.transpose(0, 2, 1)
+        return (st[0], full[0]) if single else (st, full)
 
     def compute(self, atmosphere, mu=1.0, atm_scale=0, get_scales=False):
         """``atmosphere`` [9+, ndep] or [ncol, 9+, ndep] (pyrh units) -> Stokes [.., 4, nlambda] on ``self.wavelengths``."""
@@ -1086,10 +1107,6 @@ def compute1d(cwd, mu, atm_scale, atmosphere, wave, loggf_ids=None, loggf_values
     """Drop-in for ``pyrh.compute1d`` (pyrh.pyx:537-668) in LTE: returns ``(sI, sQ, sU, sV, lam)``.  The parsed
     working directory stays resident on the GPU between calls (per-process cache keyed on the directory, the input
     files' mtimes, the wavelength grid and the per-call line / abundance overrides)."""
-    if get_atomic_rfs:
-        raise NotImplementedError("get_atomic_rfs: the analytic log gf response function is available at ray level "
-                                  "(Context.bezier3_rf); the fused Stokes path has none in the reference either "
-                                  "(Piece_Stokes_Bezier3_1D carries no dI)")
     tob = lambda x: None if x is None else np.asarray(x).tobytes()   # noqa: E731
     key = _session_key(cwd, wave, (tob(loggf_ids), tob(loggf_values), tob(lam_ids), tob(lam_values),
                                    tob(atomic_number), tob(atomic_abundance), tob(fudge_wave), tob(fudge_value), device))
@@ -1097,9 +1114,14 @@ def compute1d(cwd, mu, atm_scale, atmosphere, wave, loggf_ids=None, loggf_values
     if s is None:
         s = _SESSIONS[key] = Session(cwd, wave, device, None, loggf_ids, loggf_values, lam_ids, lam_values, fudge_wave,
                                      fudge_value, atomic_number, atomic_abundance)
-    st = s.compute(atmosphere, mu=mu, atm_scale=atm_scale)
+    if get_atomic_rfs:                                           # pyrh.pyx:658-660: (output, rf.T); lam_ids columns stay 0
+        st, rf = s.compute_rf(atmosphere, mu=mu, atm_scale=atm_scale)
+    else:
+        st = s.compute(atmosphere, mu=mu, atm_scale=atm_scale)
     output = (st[0], None, None, None, s.wavelengths) if s.stokes_mode == "NO_STOKES" else \
         (st[0], st[1], st[2], st[3], s.wavelengths)                # spec.stokes false: pyrh.pyx:647-652
+    if get_atomic_rfs:
+        output = (output, rf)
     if get_populations:                                          # populations of the ACTIVE atoms: none in LTE
         return output, ()                                        # (pyrh.pyx:654-673)
     return output

@@ -1221,3 +1221,48 @@ def test_rlk_scatter_keyword(tmp_path):
     got = np.array(host.compute1d(cwd, 0.8, 0, g["atmosphere"], g["l4016_wave"])[:4])
     REPORT["rlkscatter_lines4016_exact"] = bool(np.array_equal(got, g["l4016_stokes"]))
     assert np.array_equal(got, g["l4016_stokes"])
+
+
+def test_get_atomic_rfs_whole_call(tmp_path):
+    """pyrh.compute1d(..., get_atomic_rfs=True): the analytic log gf response function (kurucz.c:696-699,
+    bezier_1D.c:416-516, formal.c:278-282) from the nine atmosphere rows -- down-ray and up-ray opacities, d chi / d log gf
+    and the Bezier recursion all on the device.  NO_STOKES at mu = 1, NO_STOKES + RLK_SCATTER at mu = 0.7, three lines
+    of the 18-line list, and FULL_STOKES (zeros: the polarised solver carries no dI).  Entries the reference computes
+    from uninitialised memory (a registered line outside the wavelength's window) are excluded through the fixture's
+    repeatability mask and must be 0 here."""
+    from pyrh_b200 import host
+    g = dict(np.load(GOLD / "loggf_rf.npz"))
+    for d in "abcd":
+        (tmp_path / d).mkdir()
+    ids, vals = g["ids"], g["vals"]
+    cwd = _stage_cwd(tmp_path / "a", kurucz="fe6300", keywords={"STOKES_MODE": ("FULL_STOKES", "NO_STOKES")})
+    (sI, sQ, sU, sV, lam), rf = host.compute1d(cwd, 1.0, 0, g["atmosphere"], g["wave"], loggf_ids=ids, loggf_values=vals,
+                                               get_atomic_rfs=True)
+    assert sQ is None and rf.shape == (2, len(g["wave"]))
+    REPORT["loggf_rf_ns_exact"] = bool(np.array_equal(rf.T, g["ns_rfs"]))
+    assert np.array_equal(sI, g["ns_stokes"][0])
+    assert np.max(np.abs(rf.T / g["ns_rfs"] - 1)) < 1e-9
+    assert np.array_equal(rf.T, g["ns_rfs"])
+    cwd = _stage_cwd(tmp_path / "b", kurucz="fe6300", keywords={"STOKES_MODE": ("FULL_STOKES", "NO_STOKES"),
+                                                                 "RLK_SCATTER": ("FALSE", "TRUE")})
+    (sI, *_), rf = host.compute1d(cwd, 0.7, 0, g["atmosphere"], g["wave"], loggf_ids=ids, loggf_values=vals,
+                                  get_atomic_rfs=True)
+    REPORT["loggf_rf_ns_mu_rlkscatter_exact"] = bool(np.array_equal(rf.T, g["ns_mu_rfs"]))
+    assert np.array_equal(sI, g["ns_mu_stokes"][0])
+    assert np.array_equal(rf.T, g["ns_mu_rfs"])
+    cwd = _stage_cwd(tmp_path / "c", keywords={"STOKES_MODE": ("FULL_STOKES", "NO_STOKES")})
+    (sI, *_), rf = host.compute1d(cwd, 1.0, 0, g["atmosphere"], g["l4016_wave"], loggf_ids=g["l4016_ids"],
+                                  loggf_values=g["l4016_vals"], get_atomic_rfs=True)
+    assert np.array_equal(sI, g["l4016_stokes"][0])
+    s = host._SESSIONS[next(k for k in host._SESSIONS if k[0] == str(Path(cwd).resolve()))]
+    first, count, idx = s.ctx.line_windows()
+    inwin = np.array([[r in idx[first[l]:first[l] + count[l]] for r in s.loggf_rows]
+                      for l in range(len(s.lam)) if s.lam[l] != s.lambda_ref])
+    ok = inwin & g["l4016_defined"]
+    REPORT["loggf_rf_l4016"] = {"compared": int(ok.sum()), "of": int(ok.size), "exact": bool(np.array_equal(rf.T[ok], g["l4016_rfs"][ok]))}
+    assert ok.sum() > ok.size // 3
+    assert np.array_equal(rf.T[ok], g["l4016_rfs"][ok])
+    assert not rf.T[~inwin].any()
+    cwd = _stage_cwd(tmp_path / "d", kurucz="fe6300")
+    out, rf = host.compute1d(cwd, 1.0, 0, g["atmosphere"], g["wave"], loggf_ids=ids, loggf_values=vals, get_atomic_rfs=True)
+    assert np.array_equal(np.array(out[:4]), g["fs_stokes"]) and not rf.any() and not g["fs_rfs"].any()

@@ -56,6 +56,23 @@ def test_loggf_and_wavelength_overrides():
     assert b.lines[1, ll.RL_AJI] / a.lines[1, ll.RL_AJI] == pytest.approx(10 ** (-0.5 + 0.968), rel=1e-12)
 
 
+def test_kurucz_table_remembers_file_positions(tmp_path):
+    """get_atomic_rfs addresses lines by their position in the Kurucz files while the device table is sorted by
+    wavelength: LineTable.file_index maps one onto the other (RLK_Line.loggf_rf_ind, kurucz.c:250-259)."""
+    import shutil
+    from pyrh_b200 import host, linelist as ll
+    for f in Path(CWD).iterdir():
+        if f.is_file() and f.suffix not in (".fits", ".spec", ".py"):
+            shutil.copy(f, tmp_path / f.name)
+    (tmp_path / "kurucz.input").write_text("lines_4016\n")
+    kw = host.read_keywords(tmp_path)
+    el = host.read_elements(PYRH_PATH, kw)
+    lt = host.read_kurucz_lines(tmp_path, kw, el)
+    assert sorted(lt.file_index) == list(range(len(lt.lines)))
+    lam_file = [float(r.split()[0]) for r in host.read_kurucz_records(tmp_path, kw["KURUCZ_DATA"])]
+    assert np.allclose(lt.lines[:, ll.RL_LAMBDA0], [host.air_to_vacuum(lam_file[i]) for i in lt.file_index], rtol=1e-12)
+
+
 def test_abundance_override_and_sort_lambda():
     from pyrh_b200 import host
     kw = host.read_keywords(CWD)
