@@ -148,7 +148,8 @@ enum {
   RHB200_PL_VOIGT,           /* 0: Gaussian */
   RHB200_PL_NCOMP, RHB200_PL_COMPOFF,            /* slice of c_shift / c_fraction */
   RHB200_PL_GRAD,
-  RHB200_PL_VDW_TYPE,        /* -1 none, 0 UNSOLD: A * T^0.3, 1 RIDDER_RENSBERGEN: A T^B + C T^D * He abundance */
+  RHB200_PL_VDW_TYPE,        /* -1 none, 0 UNSOLD: A * T^0.3, 1 RIDDER_RENSBERGEN: A T^B + C T^D * He abundance,
+                                2 BARKLEM (barklem.c:216-312, broad.c:125-136): A T^B + C T^0.3, B = (1 - alpha)/2, C = the Unsold helium term */
   RHB200_PL_VDW_A, RHB200_PL_VDW_B, RHB200_PL_VDW_C, RHB200_PL_VDW_D, RHB200_PL_HE_ABUND,
   RHB200_PL_STARK_TYPE,      /* 0 none, 1: A * ne (cStark < 0), 2: A * (C T)^(1/6) * Cm * ne */
   RHB200_PL_STARK_A, RHB200_PL_STARK_C, RHB200_PL_STARK_CM,

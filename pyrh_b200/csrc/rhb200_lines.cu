@@ -555,6 +555,8 @@ passive_prep_kernel(int ncol, int ndep, int npl, int nlev, const double *__restr
     if (vdw >= 0) {                                                            // VanderWaals, broad.c:60-140
       double GvdW;
       if (vdw == 0) GvdW = L[RHB200_PL_VDW_A] * rhm::rh_pow(T, 0.3);
+      else if (vdw == 2) GvdW = L[RHB200_PL_VDW_A] * rhm::rh_pow(T, L[RHB200_PL_VDW_B]) +      // BARKLEM, broad.c:125-136
+                                L[RHB200_PL_VDW_C] * rhm::rh_pow(T, 0.3);
       else GvdW = L[RHB200_PL_VDW_A] * rhm::rh_pow(T, L[RHB200_PL_VDW_B]) +
                   L[RHB200_PL_VDW_C] * rhm::rh_pow(T, L[RHB200_PL_VDW_D]) * L[RHB200_PL_HE_ABUND];
       GvdW *= P[0];                                                            // atmos.H->n[0][k]

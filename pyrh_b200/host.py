@@ -16,8 +16,8 @@ What is parsed here (once per working directory, cached), with the reference's o
   rh/readmolecule.c:60-215: constituents, dissociation energy, equilibrium-constant fit)
 
 Only the published opacity tables RH keeps inside its C sources (H-, H2-, H2+, OH, CH) come from a data file
-(``data/background_falc11.npz``).  A working directory that asks for ACTIVE atoms, opacity fudge factors, molecular
-line lists inside the wavelength grid or anything else this path does not implement is refused loudly
+(``data/background_falc11.npz``).  A working directory that asks for ACTIVE atoms, an OPACITY_FUDGE file,
+MAGNETO_OPTICAL, polarizable molecular line lists or anything else this path does not implement is refused loudly
 (``NotImplementedError``), never approximated.
 """
 from __future__ import annotations
@@ -321,6 +321,38 @@ def barklem_cross(bs, stage, Ei, Ej, li, lj, ionpot, weight, H_weight):
     Z = float(stage + 1)
     E_Ryd = E_RYDBERG / (1.0 + M_ELECTRON / (weight * AMU))
     neff1, neff2 = Z * math.sqrt(E_Ryd / deltaEi), Z * math.sqrt(E_Ryd / deltaEj)
+    return _barklem_interpolate(bs, neff1, neff2, li, lj, weight, H_weight)
+
+
+def barklem_active_cross(at, ln, weight, H_weight, path=None):
+    """getBarklemactivecross (barklem.c:216-312) for a model-atom line: (cvdWaals[0], cvdWaals[1]) or None where
+    readatom.c:313-319 falls back to UNSOLD."""
+    from . import zeeman
+    i, j, stage, E = ln["i"], ln["j"], at["stage"], at["E"]
+    if stage[i] > 0:
+        return None
+    if at["abo_level"][i] != -1 and at["abo_level"][j] != -1:
+        Ll, Lu = at["abo_level"][i], at["abo_level"][j]
+    else:
+        di, dj = zeeman.determinate(at["label"][i], at["g"][i]), zeeman.determinate(at["label"][j], at["g"][j])
+        if not (di[0] and dj[0]):
+            return None
+        Ll, Lu = di[3], dj[3]
+    kind = {frozenset((0, 1)): "SP", frozenset((1, 2)): "PD", frozenset((2, 3)): "DF"}.get(frozenset((Ll, Lu)))
+    if kind is None or Ll == Lu:
+        return None
+    bs = read_barklem_table(kind, path)
+    Z = float(stage[j] + 1)
+    ic = j + 1
+    while stage[ic] < stage[j] + 1:
+        ic += 1
+    deltaEi, deltaEj = E[ic] - E[i], E[ic] - E[j]
+    E_Ryd = E_RYDBERG / (1.0 + M_ELECTRON / (weight * AMU))
+    neff1, neff2 = Z * math.sqrt(E_Ryd / deltaEi), Z * math.sqrt(E_Ryd / deltaEj)
+    return _barklem_interpolate(bs, neff1, neff2, Ll, Lu, weight, H_weight)
+
+
+def _barklem_interpolate(bs, neff1, neff2, li, lj, weight, H_weight):
     if li > lj:
         neff1, neff2 = neff2, neff1
     t1, t2 = bs["neff1"], bs["neff2"]
@@ -536,13 +568,14 @@ def read_atom(atom_file):
     data = [ln for ln in Path(atom_file).read_text().splitlines() if ln.strip() and ln[0] != "#"]
     ID = data[0].split()[0][:2].upper().ljust(2)
     nlevel, nline = (int(x) for x in data[1].split()[:2])
-    E, g, label, stage = [], [], [], []
+    E, g, label, stage, abo_level = [], [], [], [], []
     for ln in data[2:2 + nlevel]:
         head, tail = ln.split("'")[0].split(), ln.split("'")[2].split()
         E.append(float(head[0]) * ((HPLANCK * CLIGHT) / CM_TO_M))           # `*=`, readatom.c:175
         g.append(float(head[1]))
         label.append(ln.split("'")[1])
         stage.append(int(tail[0]))
+        abo_level.append(int(tail[2]) if len(tail) > 2 and re.fullmatch(r"[+-]?\d+", tail[2]) else -1)   # readatom.c:166-168
     C = 2 * PI * (Q_ELECTRON / EPSILON_0) * (Q_ELECTRON / M_ELECTRON) / CLIGHT      # readatom.c:213
     lines, pos = [], 2 + nlevel
     for _ in range(nline):
@@ -569,7 +602,7 @@ def read_atom(atom_file):
         lines.append(dict(i=i, j=j, lambda0=lambda0 / NM_TO_M, Aji=Aji, Bji=Bji, Bij=Bij, voigt="GAUSS" not in shape,
                           qwing=float(f[7]), vdw=vdw, cvdW=cvdW, Grad=float(f[13]), cStark=float(f[14]),
                           c_shift=c_shift, c_fraction=c_fraction))
-    return dict(ID=ID, E=E, g=g, label=label, stage=stage, lines=lines)
+    return dict(ID=ID, E=E, g=g, label=label, stage=stage, abo_level=abo_level, lines=lines)
 
 
 def read_atom_lines(atom_file):
@@ -601,8 +634,15 @@ def passive_line_table(cwd, kw, el: Elements, level_first, path=None):
             r[PL_WEIGHT], r[PL_IS_H], r[PL_HE_ABUND] = weight, float(at["ID"] == "H "), He_abund
             cs += ln["c_shift"]; cf += ln["c_fraction"]
             r[PL_VDW_TYPE] = VDW_NONE
+            vdw_kind = ln["vdw"]
+            if "BARKLEM" in vdw_kind:                                        # readatom.c:311-320
+                hit = barklem_active_cross(at, ln, weight, H_weight, path)
+                if hit:
+                    cv = [hit[0], hit[1], 1.0, 0.0]                          # barklem.c:295-310
+                else:
+                    vdw_kind, cv = "UNSOLD", [cv[0], 0.0, cv[2], 0.0]
             if cv[0] > 0.0 or cv[2] > 0.0:                                   # VanderWaals, broad.c:60-140
-                if "UNSOLD" in ln["vdw"]:
+                if "UNSOLD" in vdw_kind or "BARKLEM" in vdw_kind:
                     vrel35_He = math.pow(8.0 * KBOLTZMANN / (PI * AMU * weight) * (1.0 + weight / He_weight), 0.3)
                     Z = stage[j] + 1
                     ic = j + 1
@@ -613,18 +653,22 @@ def passive_line_table(cwd, kw, el: Elements, level_first, path=None):
                     ZR = Z * RBOHR
                     C625 = math.pow(2.5 * ((Q_ELECTRON * Q_ELECTRON) / FOURPIEPS0) * (ABARH / FOURPIEPS0) *
                                     2 * PI * (ZR * ZR) / HPLANCK * deltaR, 0.4)
-                    vrel35_H = math.pow(8.0 * KBOLTZMANN / (PI * AMU * weight) * (1.0 + weight / H_weight), 0.3)
-                    r[PL_VDW_TYPE] = VDW_UNSOLD_A
-                    r[PL_VDW_A] = 8.08 * (cv[0] * vrel35_H + cv[2] * He_abund * vrel35_He) * C625
-                elif "PARAMTR" in ln["vdw"]:
+                    if "BARKLEM" in vdw_kind:                                # broad.c:125-136
+                        r[PL_VDW_TYPE] = 2
+                        r[PL_VDW_A], r[PL_VDW_B] = cv[0], (1.0 - cv[1]) / 2.0
+                        r[PL_VDW_C] = 8.08 * cv[2] * He_abund * vrel35_He * C625
+                    else:
+                        vrel35_H = math.pow(8.0 * KBOLTZMANN / (PI * AMU * weight) * (1.0 + weight / H_weight), 0.3)
+                        r[PL_VDW_TYPE] = VDW_UNSOLD_A
+                        r[PL_VDW_A] = 8.08 * (cv[0] * vrel35_H + cv[2] * He_abund * vrel35_He) * C625
+                elif "PARAMTR" in vdw_kind:
                     CUBE_CM = CM_TO_M * CM_TO_M * CM_TO_M
                     gH = 1.0E-8 * CUBE_CM * math.pow(1.0 + H_weight / weight, cv[1])
                     gHe = 1.0E-9 * CUBE_CM * math.pow(1.0 + He_weight / weight, cv[3])
                     r[PL_VDW_TYPE] = VDW_RIDDER_A
                     r[PL_VDW_A], r[PL_VDW_B], r[PL_VDW_C], r[PL_VDW_D] = gH * cv[0], cv[1], gHe * cv[2], cv[3]
                 else:
-                    raise NotImplementedError(f"{fname} line {j}->{i}: BARKLEM broadening of model-atom lines needs the "
-                                              "Barklem table interpolation (barklem.c:214-330), not ported")
+                    raise ValueError(f"{fname} line {j}->{i}: invalid van der Waals keyword {vdw_kind} (readatom.c:322)")
             cS = ln["cStark"]
             if cS < 0.0:                                                     # Stark, broad.c:147-215
                 r[PL_STARK_TYPE], r[PL_STARK_A] = 1, abs(cS)

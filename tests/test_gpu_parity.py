@@ -1266,3 +1266,34 @@ def test_get_atomic_rfs_whole_call(tmp_path):
     cwd = _stage_cwd(tmp_path / "d", kurucz="fe6300")
     out, rf = host.compute1d(cwd, 1.0, 0, g["atmosphere"], g["wave"], loggf_ids=ids, loggf_values=vals, get_atomic_rfs=True)
     assert np.array_equal(np.array(out[:4]), g["fs_stokes"]) and not rf.any() and not g["fs_rfs"].any()
+
+
+def _stage_barklem_atoms(tmp_path):
+    cwd = Path(_stage_cwd(tmp_path, kurucz="fe6300"))
+    lines = (cwd / "atoms.input").read_text().replace("Mg.atom ", "MgI_6level.atom ").splitlines()
+    for i, ln in enumerate(lines):
+        w = ln.split()
+        if w and not ln.strip().startswith("#") and w[0].isdigit():
+            lines[i] = f"   {int(w[0]) + 1}"
+            break
+    last = max(i for i, ln in enumerate(lines) if ".atom" in ln)
+    lines.insert(last + 1, "  CaI.atom        PASSIVE     LTE_POPULATIONS   pops.CaI.out")
+    (cwd / "atoms.input").write_text("\n".join(lines) + "\n")
+    return cwd
+
+
+def test_barklem_broadening_of_model_atom_lines(tmp_path):
+    """BARKLEM van der Waals broadening of neutral model-atom lines (readatom.c:311-320, getBarklemactivecross
+    barklem.c:216-312, VanderWaals broad.c:125-136): Mg b triplet of MgI_6level.atom and Ca I 422.7 nm of CaI.atom
+    as passive_bb lines; orbital quantum numbers from the level labels, cross-section and velocity exponent from the
+    s-p table by cubic convolution on the host, A T^((1-alpha)/2) + Unsold helium term on the device.  Identical to
+    rhf1d() (fixture barklem_atom)."""
+    from pyrh_b200 import host
+    g = dict(np.load(GOLD / "barklem_atom.npz"))
+    cwd = _stage_barklem_atoms(tmp_path)
+    for name in ("Mgb", "CaI"):
+        out = host.compute1d(str(cwd), 1.0, 0, g["atmosphere"], g[name + "_wave"])
+        got, ref = np.array(out[:4]), g[name + "_stokes"]
+        REPORT[f"barklem_atom_{name}_exact"] = bool(np.array_equal(got, ref))
+        assert np.max(np.abs(got[0] / ref[0] - 1)) < 1e-9, name
+        assert np.array_equal(got, ref), name

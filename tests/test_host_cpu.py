@@ -153,3 +153,21 @@ def test_barklem_tables_and_cubic_convolution():
     assert np.array_equal(lt.lines[:, ll.RL_VDWAALS], g["rlk_vdwaals"]) and lt.lines[0, ll.RL_VDWAALS] == ll.VDW_BARKLEM
     assert np.array_equal(lt.lines[:, ll.RL_CROSS], g["rlk_cross"])
     assert np.array_equal(lt.lines[:, ll.RL_ALPHA], g["rlk_alpha"])
+
+
+def test_barklem_cross_section_of_model_atom_lines():
+    """getBarklemactivecross (barklem.c:216-312) on the host: the Mg b lines of MgI_6level.atom (3s3p 3P - 3s4s 3S)
+    and Ca I 422.7 nm take the s-p table; the intercombination line keeps UNSOLD; lines of ions fall back to UNSOLD."""
+    from pyrh_b200 import host
+    kw = host.read_keywords(CWD)
+    el = host.read_elements(PYRH_PATH, kw)
+    atoms = PYRH_PATH / "rh" / "Atoms"
+    mg = host.read_atom(atoms / "MgI_6level.atom")
+    assert mg["abo_level"] == [-1] * 6
+    w = el.weight[el.ID.index("MG")]
+    hits = [host.barklem_active_cross(mg, ln, w, el.weight[0], PYRH_PATH) for ln in mg["lines"] if "BARKLEM" in ln["vdw"]]
+    assert len(hits) == 3 and all(h is not None for h in hits)
+    for cross, alpha in hits:
+        assert 0.2 < alpha < 0.35 and 1e-15 < cross < 1e-13          # ABO: sigma ~ 300-700 a0^2, alpha ~ 0.25-0.3
+    ca2 = host.read_atom(atoms / "CaII.atom")
+    assert all("BARKLEM" not in ln["vdw"] for ln in ca2["lines"])      # ions: readatom.c:313-319 -> UNSOLD
