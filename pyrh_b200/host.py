@@ -998,8 +998,9 @@ class Session:
 
     def compute_rf(self, atmosphere, mu=1.0, atm_scale=0):
         """``compute`` with ``get_atomic_rfs``: ``(stokes [.., 4, nlambda], rfs [.., n_atomic_pars, nlambda])``."""
-        if not self.loggf_rows:
-            raise ValueError("get_atomic_rfs needs loggf_ids")
+        if not self.loggf_rows:                                      # no log gf parameter: rfs is [n_atomic_pars][nlw] of
+            st = self.compute(atmosphere, mu=mu, atm_scale=atm_scale)      # columns no line carries
+            return st, np.zeros(st.shape[:-2] + (self.n_atomic_pars, st.shape[-1]))
         if self.ctx.lrf_npar != len(self.loggf_rows):
             self.ctx.set_loggf_rf(self.loggf_rows)
         a = np.asarray(atmosphere, np.float64)

@@ -884,8 +884,8 @@ def test_host_compute1d_drop_in():
     assert np.array_equal(np.array(out[:4]), g["stokes_scalar"])
     out, pops = host.compute1d(str(cwd), 1.0, 0, g["atmosphere"], g["wave"], get_populations=True)
     assert pops == () and np.array_equal(np.array(out[:4]), g["stokes_scalar"])      # no ACTIVE atom: empty tuple
-    with pytest.raises(NotImplementedError):
-        host.compute1d(str(cwd), 1.0, 0, g["atmosphere"], g["wave"], get_atomic_rfs=True)
+    out, rf = host.compute1d(str(cwd), 1.0, 0, g["atmosphere"], g["wave"], get_atomic_rfs=True)   # no parameter named
+    assert rf.shape == (0, len(g["wave"])) and np.array_equal(np.array(out[:4]), g["stokes_scalar"])
 
 
 def _stage_cwd(tmp_path, kurucz="lines_4016", keywords=None):
