@@ -16,7 +16,7 @@ What is parsed here (once per working directory, cached), with the reference's o
   rh/readmolecule.c:60-215: constituents, dissociation energy, equilibrium-constant fit)
 
 Only the published opacity tables RH keeps inside its C sources (H-, H2-, H2+, OH, CH) come from a data file
-(``data/background_falc11.npz``).  A working directory that asks for ACTIVE atoms, an OPACITY_FUDGE file,
+(``data/background_falc11.npz``).  A working directory that asks for ACTIVE atoms,
 MAGNETO_OPTICAL, polarizable molecular line lists or anything else this path does not implement is refused loudly
 (``NotImplementedError``), never approximated.
 """
@@ -958,8 +958,11 @@ class Session:
         from . import api, continuum
         self.cwd = Path(cwd)
         kw = self.kw = read_keywords(cwd)
-        if kw["OPACITY_FUDGE"].lower() != "none":
-            raise NotImplementedError("OPACITY_FUDGE file: pyrh takes the factors as compute1d arguments (fudge_wave, fudge_value)")
+        # OPACITY_FUDGE names a file the pyrh build never opens (the reader is commented out, background.c:181-208): the
+        # factors come from compute1d's fudge_wave / fudge_value alone.  DO_FUDGE = TRUE without them leaves the
+        # reference interpolating in an empty table (undefined) -- refused
+        if _true(kw.get("DO_FUDGE", "FALSE")) and fudge_wave is None:
+            raise NotImplementedError("DO_FUDGE = TRUE without fudge_wave / fudge_value is undefined in the reference")
         if _true(kw["MAGNETO_OPTICAL"]):
             raise NotImplementedError("MAGNETO_OPTICAL = TRUE is refused (the reference overflows chip_c there, readj.c:328)")
         listed = _atoms_listed(cwd, kw)
