@@ -86,6 +86,16 @@ class Context:
         self.nlambda = 0
         self.lt: LineTable | None = None
 
+    def _staging(self, name, shape):
+        """Page-locked result buffer kept with the context (grown on demand): D2H copies into pageable numpy memory
+        run at a fraction of the PCIe rate and do not overlap the kernels of the next chunk."""
+        cache = self.__dict__.setdefault("_stage", {})
+        n = int(np.prod(shape))
+        buf = cache.get(name)
+        if buf is None or buf.size < n:
+            buf = cache[name] = pinned_empty((max(n, 1),))
+        return buf[:n].reshape(shape)
+
     def close(self):
         if getattr(self, "h", None):
             self.lib.rhb200_close(self.h)
@@ -246,12 +256,15 @@ class Context:
         if len(hit) != 1:
             raise ValueError("the wavelength grid must contain lambda_ref once (sortlambda.c adds it to spectrum.lambda)")
         iref = int(hit[0])
-        st = np.empty((ncol, 4, self.nlambda)) if out is None else out
+        st = self._staging("stokes", (ncol, 4, self.nlambda)) if out is None else out
         sc = np.empty((ncol, 3, ndep)) if get_scales else None
         _lib.check(self.lib.rhb200_compute1d_batch(self.h, ncol, ndep, nrow, float(mu), int(atm_scale), _vp(a), iref,
                                                    float(wght_per_H), float(vmacro_tresh) * KM_TO_M, int(bc_top),
                                                    int(bc_bottom), _vp(st), _vp(sc) if sc is not None else None))
-        res = st if keep_lambda_ref else np.delete(st, iref, axis=2)
+        if keep_lambda_ref:
+            res = st if out is not None else st.copy()           # never hand out the context's staging buffer
+        else:
+            res = np.delete(st, iref, axis=2)
         return (res, sc) if get_scales else res
 
     def set_loggf_rf(self, line_rows):
@@ -274,14 +287,14 @@ class Context:
             raise ValueError("the wavelength grid must contain lambda_ref once (sortlambda.c adds it to spectrum.lambda)")
         iref = int(hit[0])
         npar = getattr(self, "lrf_npar", 0)
-        st = np.empty((ncol, 4, self.nlambda))
-        rf = np.empty((ncol, self.nlambda, max(npar, 1)))
+        st = self._staging("stokes", (ncol, 4, self.nlambda))
+        rf = self._staging("rfs", (ncol, self.nlambda, max(npar, 1)))
         _lib.check(self.lib.rhb200_compute1d_rf_batch(self.h, ncol, ndep, nrow, float(mu), int(atm_scale), _vp(a), iref,
                                                       float(wght_per_H), float(vmacro_tresh) * KM_TO_M, int(bc_top),
                                                       int(bc_bottom), _vp(st), None, _vp(rf)))
         rf = rf[:, :, :npar]
         if keep_lambda_ref:
-            return st, rf
+            return st.copy(), rf.copy()
         return np.delete(st, iref, axis=2), np.delete(rf, iref, axis=1)
 
     def set_elements(self, elems, pf, Tpf):

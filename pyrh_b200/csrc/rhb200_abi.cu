@@ -560,7 +560,7 @@ static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int mov
   RH_NEED_CTX(c);
   RH_CHECK(check_batch_args(c, ncol, ndep, muz, bc_top, bc_bottom));
   if (ncol == 0) return RHB200_OK;
-  if ((!atmos && !py) || (!stokes && !(py && (py->rf_out || py->scales_only))) || (!chem && !chem_on_device && (!chi_ai || !eta_ai))) { rhb200_set_error("null buffer"); return RHB200_EINVAL; }
+  if ((!atmos && !py) || (!stokes && !(py && (py->rf_out || py->scales_only || py->lrf_out))) || (!chem && !chem_on_device && (!chi_ai || !eta_ai))) { rhb200_set_error("null buffer"); return RHB200_EINVAL; }
   const bool cont_dev = chem || chem_on_device;
   if (py && py->lrf_out) {
     if (c->lrf_npar <= 0) { rhb200_set_error("rhb200_set_loggf_rf() has not been called"); return RHB200_ESTATE; }
@@ -681,7 +681,7 @@ static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int mov
         rhb200_set_error("D2H copy failed: %s", cudaGetErrorString(e)); rc = RHB200_ECUDA; break;
       }
     } else
-    if ((e = cudaMemcpyAsync(stokes + (size_t) c0 * 4 * nl, d_st, (size_t) n * 4 * nl * sizeof(double),
+    if (stokes && (e = cudaMemcpyAsync(stokes + (size_t) c0 * 4 * nl, d_st, (size_t) n * 4 * nl * sizeof(double),
                              cudaMemcpyDeviceToHost, st)) != cudaSuccess) {
       rhb200_set_error("D2H copy failed: %s", cudaGetErrorString(e)); rc = RHB200_ECUDA; break;
     }
