@@ -6,7 +6,7 @@ import sys
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
-WANT = ("opacity_fused_kernelILi8ENS_11ZeemanParamELb0", "delo_raypts_kernelILi4", "continuum_tile_kernelILi8",
+WANT = ("opacity_fused_kernelILi10ENS_11ZeemanParamELb0ELb0", "delo_raypts_kernelILi4", "continuum_tile_kernelILi8",
         "chemeq_coop_kernelILi16")
 
 
