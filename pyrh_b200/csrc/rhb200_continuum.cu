@@ -817,6 +817,17 @@ ltepops_kernel(int ncol, int ndep, int natom, int nlev, const double *__restrict
 enum { MC_FIT = 0, MC_CHARGE, MC_NNUCLEI, MC_NELEMENT, MC_NEQC, MC_TMIN, MC_TMAX, MC_EDISS, MC_EQC0 = 8, MC_NUC0 = 16,
        MC_CNT0 = 20, MC_NFIELD = 32 };
 
+// pow(x, n) for the small integer exponents of the chemical network (constituent counts, molecular charge): pow() of
+// this libm returns x itself for y = 1 and 1 for y = 0 (the exact result is representable and the routine's error is
+// far below half an ulp; checked on 3 M arguments over the whole exponent range), so those two cases -- the molecular
+// charge always, most constituent counts -- skip the log/exp evaluation; every other exponent takes rh_pow
+__device__ __forceinline__ double pow_count(double x, int n)
+{
+  if (n == 1 && x > 1.0e-300 && x < 1.0e300) return x;
+  if (n == 0) return 1.0;
+  return rhm::rh_pow(x, (double) n);
+}
+
 __device__ __forceinline__ double equilconstant_d(const double *__restrict__ m, double T)
 {
   if (T < m[MC_TMIN] || T > m[MC_TMAX]) return 0.0;
@@ -906,10 +917,10 @@ chemeq_kernel(int ncol, int ndep, int natom, int nlev, const double *__restrict_
       for (int j = 0; j < nel; j++) {
         const int nu = (int) m[MC_NUC0 + j];
         const int cnt = (int) m[MC_CNT0 + j];
-        saha *= rhm::rh_pow(fn0[nu] * n[nu], (double) cnt);
+        saha *= pow_count(fn0[nu] * n[nu], cnt);
         f[nu] += cnt * n[nnuc + i];
       }
-      saha /= rhm::rh_pow(ne, (double) (int) m[MC_CHARGE]);
+      saha /= pow_count(ne, (int) m[MC_CHARGE]);
       f[nnuc + i] -= saha;
       for (int j = 0; j < nel; j++) {
         const int nu = (int) m[MC_NUC0 + j];
@@ -1056,9 +1067,9 @@ chemeq_coop_kernel(int ncol, int ndep, int natom, int nlev, const double *__rest
         double saha = Phi[i];
         for (int j = 0; j < nel; j++) {
           const int nu = (int) m[MC_NUC0 + j];
-          saha *= rhm::rh_pow(fn0[nu] * nv[nu], (double) (int) m[MC_CNT0 + j]);
+          saha *= pow_count(fn0[nu] * nv[nu], (int) m[MC_CNT0 + j]);
         }
-        saha /= rhm::rh_pow(ne, (double) (int) m[MC_CHARGE]);
+        saha /= pow_count(ne, (int) m[MC_CHARGE]);
         fl -= saha;
         for (int j = 0; j < nel; j++) {
           const int nu = (int) m[MC_NUC0 + j];
