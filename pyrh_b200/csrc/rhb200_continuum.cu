@@ -975,7 +975,7 @@ chemeq_kernel(int ncol, int ndep, int natom, int nlev, const double *__restrict_
 //          order is inherently serial, one lane does it;
 //        * residual rows, the molecule rows (pow, the expensive part) and equilconstant run one per lane.
 template <int LPS>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 7)      // 72 registers, 7 x 27 KB of shared memory per SM; measured e2e per 2048 columns: unbounded (80 regs) 15.38 ms, 7 -> 15.16, 8 -> 15.24
 chemeq_coop_kernel(int ncol, int ndep, int natom, int nlev, const double *__restrict__ lev, const int *__restrict__ atom_first,
                    const double *__restrict__ abundance, const double *__restrict__ atmos,
                    int nnuc, const int *__restrict__ nuc_atom, int nmol, const double *__restrict__ mol,
@@ -983,7 +983,7 @@ chemeq_coop_kernel(int ncol, int ndep, int natom, int nlev, const double *__rest
                    double *__restrict__ pops, double *__restrict__ chem,
               int nsel, const int *__restrict__ molsel, double *__restrict__ molout /* [ncol][nsel][ndep] or NULL */)
 {
-  constexpr int LD = LPS + 1, SPB = 128 / LPS, PER = 2*LPS*LD + 9*LPS;
+  constexpr int LD = LPS + 1, SPB = 128 / LPS, PER = LPS*LD + 9*LPS;
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ double chem_smem[];
   const int l = threadIdx.x % LPS, sl = threadIdx.x / LPS;
@@ -991,7 +991,7 @@ chemeq_coop_kernel(int ncol, int ndep, int natom, int nlev, const double *__rest
   const bool live = t < (size_t) ncol * ndep;
   const size_t tt = live ? t : 0;
   const int col = (int) (tt / ndep), k = (int) (tt % ndep);
-  double *A = chem_smem + (size_t) sl * PER, *Ac = A + LPS*LD, *x = Ac + LPS*LD, *bc = x + LPS, *r = bc + LPS,
+  double *A = chem_smem + (size_t) sl * PER, *x = A + LPS*LD, *bc = x + LPS, *r = bc + LPS,
          *nv = r + LPS, *av = nv + LPS, *vv = av + LPS, *fn0 = vv + LPS, *Phi = fn0 + LPS;
   int *idx = (int *) (Phi + LPS);
   const unsigned half_shift = (LPS == 32) ? 0u : (unsigned) (16 * ((threadIdx.x & 31) / 16));
@@ -1018,6 +1018,24 @@ chemeq_coop_kernel(int ncol, int ndep, int natom, int nlev, const double *__rest
   const double CI = (RH_HPLANCK/(2.0*RH_PI*RH_M_ELECTRON)) * (RH_HPLANCK/RH_KBOLTZMANN);
   const double PhiHmin = 0.25*rhm::rh_pow(CI/T, 1.5) * rhm::rh_exp(0.754 * RH_EV / (RH_KBOLTZMANN * T));
   const double fHmin = ne * fn0[0]*PhiHmin;
+  // The Jacobian is kept only as LU factors; SolveLinearEq's iterative improvement (ludcmp.c:60-73) needs the original
+  // matrix again, and row l regenerates its entries instead of reading a copy (44 -> 27 KB of shared memory per block):
+  // a nucleus row is 1 (+ fHmin) on the diagonal and the constituent counts -- 4 bits per molecule -- in the molecule
+  // columns; a molecule row is 1 on the diagonal and the <= 4 derivatives it has just computed
+  unsigned long long cpack[LPS / 16];
+#pragma unroll
+  for (int w = 0; w < LPS / 16; w++) cpack[w] = 0ull;
+  if (l < nnuc)
+    for (int i = 0; i < nmol; i++) {
+      const double *m = mol + (size_t) i * MC_NFIELD;
+      const int nel = (int) m[MC_NELEMENT];
+      int cl = 0;
+      for (int j = 0; j < nel; j++) if ((int) m[MC_NUC0 + j] == l) cl += (int) m[MC_CNT0 + j];
+#pragma unroll
+      for (int w = 0; w < LPS / 16; w++) if (i / 16 == w) cpack[w] |= (unsigned long long) (cl & 15) << (4 * (i % 16));
+    }
+  int jn[4] = {-1, -1, -1, -1};
+  double jv[4] = {0.0, 0.0, 0.0, 0.0};
   double n_l = row ? nv[l] : 0.0, n_old = n_l;              // Accelerate()'s two stored iterates, element l
   bool done = !live;
   int imax = 0;
@@ -1071,14 +1089,17 @@ chemeq_coop_kernel(int ncol, int ndep, int natom, int nlev, const double *__rest
         }
         saha /= pow_count(ne, (int) m[MC_CHARGE]);
         fl -= saha;
-        for (int j = 0; j < nel; j++) {
-          const int nu = (int) m[MC_NUC0 + j];
-          const int cnt = (int) m[MC_CNT0 + j];
-          A[l*LD + nu] = -saha * (cnt/nv[nu]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          if (j < nel) {
+            const int nu = (int) m[MC_NUC0 + j];
+            const int cnt = (int) m[MC_CNT0 + j];
+            jn[j] = nu; jv[j] = -saha * (cnt/nv[nu]);
+            A[l*LD + nu] = jv[j];
+          } else jn[j] = -1;
         }
       }
       x[l] = fl; bc[l] = fl;
-      for (int j = 0; j < Neq; j++) Ac[l*LD + j] = A[l*LD + j];
       double big = 0.0;                                      // LUdecomp, ludcmp.c:92-101
       for (int j = 0; j < Neq; j++) { const double temp = fabs(A[l*LD + j]); if (temp > big) big = temp; }
       vv[l] = 1.0 / big;
@@ -1115,7 +1136,23 @@ chemeq_coop_kernel(int ncol, int ndep, int natom, int nlev, const double *__rest
     backsubst(x);
     if (row) {                                               // one step of iterative improvement, ludcmp.c:60-73
       double rr = bc[l];
-      for (int j = 0; j < Neq; j++) rr -= Ac[l*LD + j] * x[j];
+      if (l < nnuc) {
+        const double diag = (l == 0) ? 1.0 + fHmin : 1.0;
+        for (int j = 0; j < nnuc; j++) rr -= ((j == l) ? diag : 0.0) * x[j];
+        for (int i = 0; i < nmol; i++) {
+          unsigned long long wsel = cpack[0];
+#pragma unroll
+          for (int w = 1; w < LPS / 16; w++) if (i / 16 == w) wsel = cpack[w];
+          rr -= (double) (int) ((wsel >> (4 * (i % 16))) & 15ull) * x[nnuc + i];
+        }
+      } else {
+        for (int j = 0; j < Neq; j++) {
+          double a = (j == l) ? 1.0 : 0.0;
+#pragma unroll
+          for (int e = 0; e < 4; e++) if (jn[e] == j) a = jv[e];
+          rr -= a * x[j];
+        }
+      }
       r[l] = rr;
     }
     __syncwarp();
@@ -1213,11 +1250,11 @@ static int launch_chemeq(rhb200_ctx *c, ContinuumState *S, int cc, int ndep, con
       chemeq_kernel<CHEM_MAXEQ, true><<<(unsigned) ((cn + TPB - 1) / TPB), TPB, sh, c->stream>>>(CHEM_ARGS);
     }
   } else if (Neq <= 16) {
-    const size_t sh = (size_t) 8 * (2*16*17 + 9*16) * sizeof(double);
+    const size_t sh = (size_t) 8 * (16*17 + 9*16) * sizeof(double);
     RH_CUDA(cudaFuncSetAttribute(chemeq_coop_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sh));
     chemeq_coop_kernel<16><<<(unsigned) ((cn + 7) / 8), 128, sh, c->stream>>>(CHEM_ARGS);
   } else {
-    const size_t sh = (size_t) 4 * (2*32*33 + 9*32) * sizeof(double);
+    const size_t sh = (size_t) 4 * (32*33 + 9*32) * sizeof(double);
     RH_CUDA(cudaFuncSetAttribute(chemeq_coop_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sh));
     chemeq_coop_kernel<32><<<(unsigned) ((cn + 3) / 4), 128, sh, c->stream>>>(CHEM_ARGS);
   }
@@ -1331,6 +1368,10 @@ extern "C" int rhb200_set_chemistry(rhb200_ctx *c, int nnuclei, const int *nucle
     const int nel = (int) m[MC_NELEMENT], fit = (int) m[MC_FIT];
     if (nel < 1 || nel > 4 || (int) m[MC_NEQC] < 1 || (int) m[MC_NEQC] > 8 || fit < 0 || fit > 4) { rhb200_set_error("molecule %d: bad element / coefficient count or fit", i); return RHB200_EINVAL; }
     for (int j = 0; j < nel; j++) if ((int) m[MC_NUC0 + j] < 0 || (int) m[MC_NUC0 + j] >= nnuclei) { rhb200_set_error("molecule %d: nucleus index out of range", i); return RHB200_EINVAL; }
+    for (int j = 0, tot = 0; j < nel; j++) {                 // the cooperative kernel packs a nucleus' count per molecule in 4 bits
+      tot += (int) m[MC_CNT0 + j];
+      if ((int) m[MC_CNT0 + j] < 1 || tot > 15) { rhb200_set_error("molecule %d: constituent counts must be 1..15 in total", i); return RHB200_EINVAL; }
+    }
     if (m[24] != 0.0) S->iH2 = i;
     if (m[25] != 0.0) S->iOH = i;
     if (m[26] != 0.0) S->iCH = i;
