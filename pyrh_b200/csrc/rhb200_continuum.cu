@@ -1034,6 +1034,19 @@ chemeq_coop_kernel(int ncol, int ndep, int natom, int nlev, const double *__rest
 #pragma unroll
       for (int w = 0; w < LPS / 16; w++) if (i / 16 == w) cpack[w] |= (unsigned long long) (cl & 15) << (4 * (i % 16));
     }
+  // a molecule row keeps its own record in registers (12 bits per constituent: nucleus, count; then the number of
+  // constituents) so that the Newton loop reads nothing from global memory; the host routes networks that name a
+  // nucleus twice in one molecule to the per-thread kernel
+  unsigned long long mpack = 0ull;
+  int mcharge = 0;
+  if (row && l >= nnuc) {
+    const double *m = mol + (size_t) (l - nnuc) * MC_NFIELD;
+    const int nel = (int) m[MC_NELEMENT];
+    for (int j = 0; j < nel; j++)
+      mpack |= ((unsigned long long) ((int) m[MC_NUC0 + j] & 255) | ((unsigned long long) ((int) m[MC_CNT0 + j] & 15) << 8)) << (12 * j);
+    mpack |= (unsigned long long) nel << 48;
+    mcharge = (int) m[MC_CHARGE];
+  }
   int jn[4] = {-1, -1, -1, -1};
   double jv[4] = {0.0, 0.0, 0.0, 0.0};
   double n_l = row ? nv[l] : 0.0, n_old = n_l;              // Accelerate()'s two stored iterates, element l
@@ -1070,30 +1083,27 @@ chemeq_coop_kernel(int ncol, int ndep, int natom, int nlev, const double *__rest
       A[l*LD + l] = 1.0;
       if (l == 0) { fl += fHmin * nv[0]; A[0] += fHmin; }
       if (l < nnuc) {
-        for (int i = 0; i < nmol; i++) {
-          const double *m = mol + (size_t) i * MC_NFIELD;
-          const int nel = (int) m[MC_NELEMENT];
-          for (int j = 0; j < nel; j++)
-            if ((int) m[MC_NUC0 + j] == l) fl += (int) m[MC_CNT0 + j] * nv[nnuc + i];
-          for (int j = 0; j < nel; j++)
-            if ((int) m[MC_NUC0 + j] == l) A[l*LD + nnuc + i] += (int) m[MC_CNT0 + j];
+        for (int i = 0; i < nmol; i++) {                     // chemequil.c:268-281 through the packed counts
+          unsigned long long wsel = cpack[0];
+#pragma unroll
+          for (int w = 1; w < LPS / 16; w++) if (i / 16 == w) wsel = cpack[w];
+          const int cnt = (int) ((wsel >> (4 * (i % 16))) & 15ull);
+          if (cnt) { fl += cnt * nv[nnuc + i]; A[l*LD + nnuc + i] += cnt; }
         }
       } else {
-        const int i = l - nnuc;
-        const double *m = mol + (size_t) i * MC_NFIELD;
-        const int nel = (int) m[MC_NELEMENT];
-        double saha = Phi[i];
+        const int nel = (int) (mpack >> 48);
+        double saha = Phi[l - nnuc];
         for (int j = 0; j < nel; j++) {
-          const int nu = (int) m[MC_NUC0 + j];
-          saha *= pow_count(fn0[nu] * nv[nu], (int) m[MC_CNT0 + j]);
+          const int nu = (int) ((mpack >> (12 * j)) & 255ull);
+          saha *= pow_count(fn0[nu] * nv[nu], (int) ((mpack >> (12 * j + 8)) & 15ull));
         }
-        saha /= pow_count(ne, (int) m[MC_CHARGE]);
+        saha /= pow_count(ne, mcharge);
         fl -= saha;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           if (j < nel) {
-            const int nu = (int) m[MC_NUC0 + j];
-            const int cnt = (int) m[MC_CNT0 + j];
+            const int nu = (int) ((mpack >> (12 * j)) & 255ull);
+            const int cnt = (int) ((mpack >> (12 * j + 8)) & 15ull);
             jn[j] = nu; jv[j] = -saha * (cnt/nv[nu]);
             A[l*LD + nu] = jv[j];
           } else jn[j] = -1;
@@ -1194,6 +1204,7 @@ struct ContinuumState {
   double *d_lev = nullptr, *d_abund = nullptr; int *d_first = nullptr;
   // chemistry on the device (rhb200_set_chemistry)
   int nnuc = 0, nmol = 0, iH2 = -1, iOH = -1, iCH = -1;
+  bool mol_repeats = false;      // some molecule names a nucleus twice, or a count above 15: per-thread kernel
   int *d_nuc_atom = nullptr; double *d_mol = nullptr;
   int nsel = 0; int *d_molsel = nullptr;      // molecules whose densities the molecular-line kernels need
   std::vector<int> h_molsel;
@@ -1233,7 +1244,7 @@ static int launch_chemeq(rhb200_ctx *c, ContinuumState *S, int cc, int ndep, con
   // Measured per 2048 columns x 70 depths (B200): coop 3.0 ms (issue-bound: 48 % issue slots, the serial back
   // substitution is 27 % of the instructions), local 3.3 ms (L2-bound), shared 4.5 ms (3 warps/SM, latency-bound)
   static const char *variant = getenv("RHB200_CHEM_KERNEL");
-  const bool serial = variant && !strcmp(variant, "local"), coop = !variant || !strcmp(variant, "coop");
+  const bool serial = (variant && !strcmp(variant, "local")) || S->mol_repeats, coop = !variant || !strcmp(variant, "coop");
   const int TPB = 32;
 #define CHEM_ARGS cc, ndep, na, S->nlev, S->d_lev, S->d_first, S->d_abund, d_atmos, S->nnuc, S->d_nuc_atom, S->nmol, S->d_mol, \
                 S->iH2, S->iOH, S->iCH, 10, 1.0E-3, d_pops, d_chem, S->nsel, S->d_molsel, d_molout
@@ -1363,14 +1374,18 @@ extern "C" int rhb200_set_chemistry(rhb200_ctx *c, int nnuclei, const int *nucle
     }
   if (nucleus_atom[0] != 0) { rhb200_set_error("first nucleus must be hydrogen (chemequil.c:146)"); return RHB200_EINVAL; }
   S->iH2 = S->iOH = S->iCH = -1;
+  S->mol_repeats = false;
   for (int i = 0; i < nmol; i++) {
     const double *m = mol + (size_t) i * MC_NFIELD;
     const int nel = (int) m[MC_NELEMENT], fit = (int) m[MC_FIT];
     if (nel < 1 || nel > 4 || (int) m[MC_NEQC] < 1 || (int) m[MC_NEQC] > 8 || fit < 0 || fit > 4) { rhb200_set_error("molecule %d: bad element / coefficient count or fit", i); return RHB200_EINVAL; }
     for (int j = 0; j < nel; j++) if ((int) m[MC_NUC0 + j] < 0 || (int) m[MC_NUC0 + j] >= nnuclei) { rhb200_set_error("molecule %d: nucleus index out of range", i); return RHB200_EINVAL; }
     for (int j = 0, tot = 0; j < nel; j++) {                 // the cooperative kernel packs a nucleus' count per molecule in 4 bits
-      tot += (int) m[MC_CNT0 + j];
-      if ((int) m[MC_CNT0 + j] < 1 || tot > 15) { rhb200_set_error("molecule %d: constituent counts must be 1..15 in total", i); return RHB200_EINVAL; }
+      const int cnt = (int) m[MC_CNT0 + j];
+      if (cnt < 1) { rhb200_set_error("molecule %d: constituent count %d", i, cnt); return RHB200_EINVAL; }
+      tot += cnt;
+      if (tot > 15) S->mol_repeats = true;
+      for (int q = 0; q < j; q++) if ((int) m[MC_NUC0 + q] == (int) m[MC_NUC0 + j]) S->mol_repeats = true;
     }
     if (m[24] != 0.0) S->iH2 = i;
     if (m[25] != 0.0) S->iOH = i;
