@@ -1064,14 +1064,18 @@ chemeq_coop_kernel(int ncol, int ndep, int natom, int nlev, const double *__rest
       if (ii < 0 && xj != 0.0) ii = j;
       if (row && l > j && ii >= 0) s -= A[l*LD + j] * xj;
     }
-    if (row) v[l] = s;
-    __syncwarp();
-    if (l == 0)
-      for (int i = Neq - 1; i >= 0; i--) {
-        double sum = v[i];
-        for (int j = i + 1; j < Neq; j++) sum -= A[i*LD + j] * v[j];
-        v[i] = sum / A[i*LD + i];
-      }
+    // back substitution, ludcmp.c:170-175: x_i = (v_i - sum_{j>i} A_ij x_j) / A_ii with the subtractions in ascending j.
+    // Lane j forms its product A_ij x_j as soon as x_j exists; the ordered sum then runs over register values fetched
+    // with shuffles that do not depend on the running sum, instead of one lane walking shared memory serially
+    double xv = row ? s : 0.0;
+    for (int i = Neq - 1; i >= 0; i--) {
+      const double p = (row && l > i) ? A[i*LD + l] * xv : 0.0;
+      double sum = __shfl_sync(FULL, xv, i, LPS);
+      for (int j = i + 1; j < Neq; j++) sum -= __shfl_sync(FULL, p, j, LPS);
+      const double xi = sum / A[i*LD + i];
+      if (l == i) xv = xi;
+    }
+    if (row) v[l] = xv;
     __syncwarp();
   };
 
