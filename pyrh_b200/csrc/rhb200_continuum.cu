@@ -1054,10 +1054,11 @@ chemeq_coop_kernel(int ncol, int ndep, int natom, int nlev, const double *__rest
   int imax = 0;
 
   auto backsubst = [&](double *v) {                          // LUbacksubst, ludcmp.c:156-177
-    if (l == 0)
-      for (int i = 0; i < Neq; i++) { const int ip = idx[i]; const double tmp = v[ip]; v[ip] = v[i]; v[i] = tmp; }
-    __syncwarp();
-    double s = row ? v[l] : 0.0;
+    double s = row ? v[l] : 0.0;                              // the row exchanges of the decomposition, element l in lane l
+    for (int i = 0; i < Neq; i++) {
+      const int ip = idx[i];
+      s = __shfl_sync(FULL, s, (l == i) ? ip : (l == ip) ? i : l, LPS);
+    }
     int ii = -1;
     for (int j = 0; j < Neq; j++) {
       const double xj = __shfl_sync(FULL, s, j, LPS);
