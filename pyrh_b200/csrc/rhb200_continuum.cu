@@ -417,6 +417,7 @@ continuum_tile_kernel(int ncol, int nlambda, int ndep, DevModel M,
     for (int q = 0; q < CONT_TL; q++) chi_f[q] = eta_f[q] = 0.0;
     if (uniform) {
       const int cnt = (int) shW[0][CI];
+#pragma unroll 2       // measured e2e per 2048 columns: 1 -> 14.53 ms (680 B stack), 2 -> 14.49 (416 B), 4 -> 14.57 (336 B)
       for (int c = 0; c < cnt; c++) {
         const int i = sh_ij[fam][c][0], j = sh_ij[fam][c][1];
         const double n_i = n_[(size_t) i * ndep];
