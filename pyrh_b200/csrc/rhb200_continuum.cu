@@ -1323,6 +1323,7 @@ int rh_continuum_chunk(rhb200_ctx *c, int cc, int ndep, const double *d_atmos, c
     case 4: continuum_tile_kernel<4><<<grid, 128, 0, c->stream>>>RH_CONT_ARGS; break;
     case 5: continuum_tile_kernel<5><<<grid, 128, 0, c->stream>>>RH_CONT_ARGS; break;
     case 6: continuum_tile_kernel<6><<<grid, 128, 0, c->stream>>>RH_CONT_ARGS; break;
+    case 7: continuum_tile_kernel<7><<<grid, 128, 0, c->stream>>>RH_CONT_ARGS; break;
     case 10: continuum_tile_kernel<10><<<grid, 128, 0, c->stream>>>RH_CONT_ARGS; break;
     case 12: continuum_tile_kernel<12><<<grid, 128, 0, c->stream>>>RH_CONT_ARGS; break;
     default: continuum_tile_kernel<8><<<grid, 128, 0, c->stream>>>RH_CONT_ARGS; break;
