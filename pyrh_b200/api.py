@@ -98,8 +98,10 @@ class Context:
 
     def close(self):
         if getattr(self, "h", None):
-            self.lib.rhb200_close(self.h)
+            self.lib.rhb200_close(self.h)                      # synchronises the device first
             self.h = None
+            for buf in self.__dict__.pop("_stage", {}).values():   # results were always handed out as copies
+                self.lib.rhb200_host_free_pinned(C.c_void_p(buf.ctypes.data))
 
     def __del__(self):
         try:
