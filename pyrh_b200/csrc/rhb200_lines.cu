@@ -729,7 +729,7 @@ int rh_launch_opacity_fused(rhb200_ctx *ctx, int ncol, int ndep, int to_obs,
   {
     ScopedKernelTimer t(ctx, RHB200_K_OPACITY);
     static int variant = -1;
-    if (variant < 0) { const char *e = getenv("RHB200_OPACITY_MINB"); variant = e ? atoi(e) : 10; }      // measured (ms per 4096 columns): 4 -> 11.7, 5 -> 10.1, 6 -> 9.2, 8 -> 8.84, 10 -> 8.70, 12 -> 8.91
+    if (variant < 0) { const char *e = getenv("RHB200_OPACITY_MINB"); variant = e ? atoi(e) : 10; }      // measured (ms per 4096 columns): 4 -> 11.7, 5 -> 10.1, 6 -> 9.2, 8 -> 8.84, 10 -> 8.70, 12 -> 8.91; 9 is 0.06 ms per 2048-column e2e call behind 10
     bool arm = false;                                     // any line with damping wings that is not polarizable
     for (int n = 0; n < ctx->tab.nline; n++) {
       const double *L = ctx->h_lines.data() + (size_t) n * RHB200_RL_NFIELD;
@@ -744,6 +744,7 @@ int rh_launch_opacity_fused(rhb200_ctx *ctx, int ncol, int ndep, int to_obs,
     case 4: RH_LAUNCH_OPF(4, ZT, Z); break;                   \
     case 5: RH_LAUNCH_OPF(5, ZT, Z); break;                   \
     case 6: RH_LAUNCH_OPF(6, ZT, Z); break;                   \
+    case 9: RH_LAUNCH_OPF(9, ZT, Z); break;                   \
     case 10: RH_LAUNCH_OPF(10, ZT, Z); break;                 \
     case 12: RH_LAUNCH_OPF(12, ZT, Z); break;                 \
     default: RH_LAUNCH_OPF(8, ZT, Z); break; }
