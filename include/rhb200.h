@@ -170,6 +170,9 @@ int rhb200_set_model_lines(rhb200_ctx *ctx, int n, const double *rows);
    of the *contributing* list idx[] (test hook for the integer part) */
 int rhb200_get_line_windows(rhb200_ctx *ctx, int *first /*[nlambda]*/, int *count /*[nlambda]*/,
                             int *idx /*[cap]*/, int cap, int *nidx);
+/* atmos.backgrflags of the current grid (background.c:335-338, 500-566): flags[nlambda], bit 0 = hasline (a Kurucz,
+   passive_bb or molecular line has the wavelength in its window), bit 1 = ispolarized */
+int rhb200_get_wavelength_flags(rhb200_ctx *ctx, int *flags);
 
 /* ---- the hot path ------------------------------------------------------
    LTE FULL_STOKES synthesis of `ncol` independent columns.  Replaces, per column,
@@ -571,6 +574,55 @@ enum { RHB200_REDUCE_SUM = 0, RHB200_REDUCE_MAX = 1 };
 typedef int (*rhb200_allreduce_fn)(void *user, double *device_buf, size_t count, int op);
 int rhb200_nlte_set_shard(rhb200_ctx *ctx, int rank, int nrank, rhb200_allreduce_fn fn, void *user);
 int rhb200_nlte_shard_range(const rhb200_nlte_plan *plan, int rank, int nrank, int *ns_lo, int *ns_hi);
+/* ---- NLTE through the drop-in call: everything rhf1d() does per column for a working directory with ACTIVE atoms
+   (pyrh_compute1dray.c:112-388 with input.solve_NLTE, STOKES_MODE = NO_STOKES, CRD), on the device, for a batch:
+       unit conversion, Bproject                                   pyrh_compute1dray.c:248-299
+       Background(): SetLTEQuantities = LTEpops + CollisionRate (ltepops.c:224-249, collision.c:450-946),
+                     ChemicalEquilibrium, continuum, passive_bb, rlk_opacity, MolecularOpacity -- for the LAST ray
+                     (mu = Nrays-1, up): pyrh keeps one background record per wavelength (readj.c:319-345)
+       convertScales                                               multiatmos.c:100-177
+       getProfiles (Damping + Profile), initSolution (LTE_POPULATIONS, J = 0), initScatter
+       Iterate, the N_MAX_SCATTER passes after it                  pyrh_compute1dray.c:330-337
+       _solveray(): Bproject, Background, getProfiles for the one ray mu, solveSpectrum(FALSE, FALSE), packing
+   Needs on the context: rhb200_set_lines, rhb200_set_passive_lines (lines of the PASSIVE atoms only),
+   rhb200_set_model_lines (all atoms), rhb200_set_wavelengths(plan->lambda), rhb200_set_continuum with solve_NLTE = 1
+   (levels of ACTIVE atoms flagged in lev[][4], their continua in bf[][9], H_active), rhb200_set_chemistry.
+   Collisional records, one per line of the atom files' collisional sections, in file order: */
+enum {
+  RHB200_CO_ATOM = 0,        /* ACTIVE-atom index */
+  RHB200_CO_TYPE,            /* RHB200_CO_OMEGA ... */
+  RHB200_CO_I, RHB200_CO_J,  /* i < j, levels of that atom */
+  RHB200_CO_NT, RHB200_CO_TOFF,   /* slice of coll_T / coll_coef / coll_M */
+  RHB200_CO_DE,              /* E[j] - E[i] [J] */
+  RHB200_CO_NFIELD = 8
+};
+enum { RHB200_CO_OMEGA = 0, RHB200_CO_CE, RHB200_CO_CI, RHB200_CO_CP, RHB200_CO_CH, RHB200_CO_CH0, RHB200_CO_CHPLUS };
+typedef struct {
+  const int    *atom_model;       /* [plan->Natom] index of each ACTIVE atom among the model atoms of rhb200_set_continuum */
+  int ncoll, ncolltab;
+  const double *coll;             /* [ncoll][RHB200_CO_NFIELD] */
+  const double *coll_T, *coll_coef, *coll_M;   /* [ncolltab]: temperature grids, coefficients, spline second derivatives
+                                     (splineCoef, spline.c:31-66; unused for grids of <= 2 points: Linear) */
+  const double *line_rows;        /* [plan->nline][RHB200_PL_NFIELD]: Damping() constants of the ACTIVE lines, line-index order;
+                                     RHB200_PL_LEVEL_I/J are rows of the model-atom level table */
+  int NmaxScatter, NmaxIter;      /* keywords N_MAX_SCATTER, N_MAX_ITER */
+  double iterLimit;               /* ITER_LIMIT */
+  const rhb200_nlte_plan *plan1;  /* the same plan with Nrays = 1 and the profile rows of one ray (muz/wmu are set by the call) */
+} rhb200_nlte_front;
+/* atmosphere [ncol][nrow][ndep] as in rhb200_compute1d_batch.  Out (any may be NULL): spectrum [ncol][Nspect] = spectrum.I[][0]
+   of the final pass on plan->lambda (lambda_ref included; _solveray drops it), pops_n / pops_nstar [ncol][sum Nlevel][ndep]
+   = AtomPops.n / .nstar, niter [ncol] iterations Iterate() took, scales [ncol][3][ndep] = height, tau_ref, column mass. */
+int rhb200_nlte_compute1d_batch(rhb200_ctx *ctx, const rhb200_nlte_plan *plan, const rhb200_nlte_front *front,
+                                int ncol, int ndep, int nrow, double mu, int atm_scale, const double *atmosphere,
+                                int iref, double wght_per_H, double vmacro_tresh,
+                                double *spectrum, double *pops_n, double *pops_nstar, int *niter, double *scales);
+/* test hook: the per-column inputs the front end hands to Iterate() for the columns of the LAST
+   rhb200_nlte_compute1d_batch call that fit in one chunk: which = 0 C, 1 nstar, 2 ntotal, 3 adamp, 4 vbroad,
+   5 chi_c, 6 eta_c, 7 sca_c, 8 height, 9 J after the last pass, 10..12 chi_c/eta_c/sca_c of the final pass,
+   13..15 phi / wphi / adamp of the final pass; out
+   must hold the array ([ncol][...][ndep] in the layouts of rhb200_nlte_columns). */
+int rhb200_nlte_front_debug(rhb200_ctx *ctx, int which, double *out, size_t count);
+
 /* SolveLinearEq (ludcmp.c:36-86) for nsys systems: A [nsys][N][N] (untouched), b [nsys][N] in/out; N <= 32 */
 int rhb200_solve_linear_eq_batch(rhb200_ctx *ctx, int nsys, int N, double *A, double *b, int improve);
 

@@ -100,14 +100,17 @@ def flatten(R):
     return out
 
 
-def build(name, keywords=KW, atoms_active=(), atoms_extra=(("CaII.atom", "ACTIVE"),), pops_keys=("CA",)):
+def build(name, keywords=KW, atoms_active=(), atoms_extra=(("CaII.atom", "ACTIVE"),), pops_keys=("CA",), atm=None,
+          wave=None, mu=1.0, drop=()):
     """Run the reference and write tests/golden/<name>.npz.  Several ACTIVE atoms are concatenated in the
     order of atmos.activeatoms (levels, Gamma blocks, transitions), which is the device layout."""
-    atm = rd.falc("tests")
-    atm[5] = 500.0
-    wave = np.linspace(630.25, 630.5, 21)
+    if atm is None:
+        atm = rd.falc("tests")
+        atm[5] = 500.0
+    if wave is None:
+        wave = np.linspace(630.25, 630.5, 21)
     cwd = rd.make_workdir("tests", keywords=keywords, atoms_active=atoms_active, atoms_extra=atoms_extra)
-    o = rd.rhf1d(atm, wave, cwd, probe=rd.PROBE_NLTE, get_populations=True)
+    o = rd.rhf1d(atm, wave, cwd, mu=mu, probe=rd.PROBE_NLTE, get_populations=True)
     R = recs_by_tag(o["records"])
     g = flatten(R)
     N, Natom = int(g["hdr"][3]), int(g["hdr"][2])
@@ -147,6 +150,9 @@ def build(name, keywords=KW, atoms_active=(), atoms_extra=(("CaII.atom", "ACTIVE
     g["fs_vel"] = one(R, "fs_vel")
     g["spec_lam"], g["spec_I"] = o["lam"], o["I"]
     g["pops_final"] = np.concatenate([o["pops"][k]["n"] for k in pops_keys])
+    g["atmosphere"], g["wave"], g["mu"] = np.array(atm), np.array(wave), np.float64(mu)
+    for k in drop:
+        g.pop(k, None)
     np.savez_compressed(GOLD / f"{name}.npz", **g)
     print(f"[golden] {name}: Natom={Natom} Nspect={len(g['lam'])} Ntrans={len(g['trans'])} iterations={int(g['niter'])} "
           f"dpops_last={g['dpops_iter'][-1]:.3e} -> {(GOLD / (name + '.npz')).stat().st_size/1e6:.2f} MB")
@@ -154,6 +160,14 @@ def build(name, keywords=KW, atoms_active=(), atoms_extra=(("CaII.atom", "ACTIVE
 
 
 def main():
+    if "--perturbed" in sys.argv:
+        # one PERTURBED, moving 70-depth column (pyrh_b200.synthetic) with the user grid inside the ACTIVE
+        # Ca II 8542 line and the final pass at mu = 0.8: every input of Iterate() and of _solveray()'s pass
+        from pyrh_b200 import synthetic
+        atm = synthetic.perturbed_batch(np.load(GOLD / "falc_base.npy"), 1, ndep=70)[0]
+        build("nlte_caii_pert", atm=atm, wave=np.linspace(854.2, 854.7, 41), mu=0.8,
+              drop=("phi", "gamma_iter", "rates_iter", "n_iter", "lu_n", "lu_data", "J0"))
+        return
     if "--two-atom-only" not in sys.argv:
         build("nlte_caii")
     # BASELINE config 4: H (6 levels, 10 lines, 5 continua) + Ca II, both ACTIVE, CRD

@@ -1,0 +1,74 @@
+"""oracle/gen_golden_nlte_front.py -- TEST INFRASTRUCTURE ONLY.
+
+Golden vectors for NLTE through the drop-in call on PERTURBED columns: the UNMODIFIED reference's rhf1d() with
+get_populations on 8 synthetic perturbed FAL-C columns (70 depths, SURVEY 8(d) recipe, pyrh_b200.synthetic) for
+    caii_r3 / caii_r5       Ca II (5 levels + continuum) ACTIVE, hydrogen PASSIVE in LTE, NRAYS = 3 / 5, Ca II 8542 window
+    h_caii_r3 / h_caii_r5   H (6 levels) + Ca II ACTIVE (BASELINE config 4), NRAYS = 3 / 5, Hinode window
+CRD (PRD_N_MAX_ITER = 0), Ng order 2, ITER_LIMIT 1e-4, NO_STOKES.  Recorded: spectrum, populations n / nstar of the
+ACTIVE atoms, and the number of MALI iterations (counted from the probe's updatePopulations records).
+
+    python -m oracle.gen_golden_nlte_front
+"""
+from __future__ import annotations
+
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from oracle import refdriver as rd  # noqa: E402
+from oracle.gen_golden import recs_by_tag  # noqa: E402
+from pyrh_b200 import synthetic  # noqa: E402
+
+GOLD = ROOT / "tests" / "golden"
+KW = {"N_MAX_SCATTER": 2, "N_MAX_ITER": 100, "NG_ORDER": 2, "NG_DELAY": 10, "NG_PERIOD": 3,
+      "ITER_LIMIT": "1.0E-4", "PRD_N_MAX_ITER": 0, "STOKES_MODE": "NO_STOKES"}
+CASES = {
+    "caii_r3": dict(kw=dict(KW, NRAYS=3, HYDROGEN_LTE="TRUE"), active=(), wave=(854.2, 854.7, 41), keys=("CA",), mu=1.0),
+    "caii_r5": dict(kw=dict(KW, NRAYS=5, HYDROGEN_LTE="TRUE"), active=(), wave=(854.2, 854.7, 41), keys=("CA",), mu=0.8),
+    "h_caii_r3": dict(kw=dict(KW, NRAYS=3, HYDROGEN_LTE="FALSE"), active=("H_6.atom",), wave=(630.25, 630.5, 21),
+                      keys=("H ", "CA"), mu=1.0),
+    "h_caii_r5": dict(kw=dict(KW, NRAYS=5, HYDROGEN_LTE="FALSE"), active=("H_6.atom",), wave=(630.25, 630.5, 21),
+                      keys=("H ", "CA"), mu=0.8),
+}
+# columns of the synthetic batch; column 4 is left out: its MALI iteration does not converge in the reference (100
+# iterations at NRAYS = 3) and ends in "Singular matrix" -> exit() at NRAYS = 5, so there is nothing to be identical to
+COLUMNS = (0, 1, 2, 3, 5, 6, 7, 8)
+NCOL = len(COLUMNS)
+
+
+def workdir(case):
+    c = CASES[case]
+    return rd.make_workdir("tests", keywords=c["kw"], atoms_active=c["active"], atoms_extra=(("CaII.atom", "ACTIVE"),))
+
+
+def main():
+    base = np.load(GOLD / "falc_base.npy")
+    atm = synthetic.perturbed_batch(base, max(COLUMNS) + 1, ndep=70)[list(COLUMNS)]
+    out = dict(atmosphere=atm)
+    for case, c in CASES.items():
+        cwd = workdir(case)
+        wave = np.linspace(*c["wave"])
+        I, n, ns, nit = [], [], [], []
+        for col in range(NCOL):
+            o = rd.rhf1d(atm[col], wave, cwd, mu=c["mu"], probe=rd.PROBE_NLTE, get_populations=True)
+            R = recs_by_tag(o["records"])
+            nit.append(len({m[1] for m, _ in R["up_n"]}))
+            I.append(o["I"])
+            n.append(np.concatenate([o["pops"][k]["n"] for k in c["keys"]]))
+            ns.append(np.concatenate([o["pops"][k]["nstar"] for k in c["keys"]]))
+            lam = o["lam"]
+            print(f"[golden] {case} column {col}: {nit[-1]} iterations, {len(lam)} wavelengths", flush=True)
+        out.update({f"{case}_wave": wave, f"{case}_lam": lam, f"{case}_I": np.array(I), f"{case}_n": np.array(n),
+                    f"{case}_nstar": np.array(ns), f"{case}_niter": np.array(nit, np.int32),
+                    f"{case}_mu": np.float64(c["mu"])})
+    out["cases"] = np.array(json.dumps({k: dict(kw=v["kw"], active=list(v["active"]), keys=list(v["keys"])) for k, v in CASES.items()}))
+    np.savez_compressed(GOLD / "nlte_front.npz", **out)
+    print(f"[golden] nlte_front.npz: {(GOLD / 'nlte_front.npz').stat().st_size/1e6:.2f} MB")
+
+
+if __name__ == "__main__":
+    main()

@@ -31,6 +31,10 @@ SYMBOLS = [
                                    dp, dp, C.c_double, C.c_int, C.c_int]),
     ("rhb200_set_wavelengths", C.c_int, [vp, C.c_int, dp]),
     ("rhb200_get_line_windows", C.c_int, [vp, ip, ip, ip, C.c_int, ip]),
+    ("rhb200_get_wavelength_flags", C.c_int, [vp, ip]),
+    ("rhb200_nlte_compute1d_batch", C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, vp, C.c_int,
+                                              C.c_double, C.c_double, vp, vp, vp, vp, vp]),
+    ("rhb200_nlte_front_debug", C.c_int, [vp, C.c_int, dp, C.c_size_t]),
     ("rhb200_lte_stokes_batch", C.c_int, [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
                                           vp, vp, vp, vp]),
     ("rhb200_lte_stokes_batch_dev", C.c_int, [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,

@@ -93,6 +93,8 @@ class Context:
         n = int(np.prod(shape))
         buf = cache.get(name)
         if buf is None or buf.size < n:
+            if buf is not None:                                # grown: the old page-locked block goes back first
+                self.lib.rhb200_host_free_pinned(C.c_void_p(buf.ctypes.data))
             buf = cache[name] = pinned_empty((max(n, 1),))
         return buf[:n].reshape(shape)
 

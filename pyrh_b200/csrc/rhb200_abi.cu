@@ -421,6 +421,15 @@ extern "C" int rhb200_get_line_windows(rhb200_ctx *c, int *first, int *count, in
   return RHB200_OK;
 }
 
+// atmos.backgrflags of the grid (background.c:335-338): bit 0 hasline (Kurucz, passive_bb or molecular line in the
+// window), bit 1 ispolarized -- the integer part of Background(), fixed once the tables and the grid are set
+extern "C" int rhb200_get_wavelength_flags(rhb200_ctx *c, int *flags)
+{
+  if (!c || c->wav.nlambda == 0 || !flags) { rhb200_set_error("wavelengths not set"); return RHB200_ESTATE; }
+  memcpy(flags, c->h_flags.data(), c->h_flags.size()*sizeof(int));
+  return RHB200_OK;
+}
+
 static int need_state(rhb200_ctx *c, bool wave)
 {
   if (c->tab.nelem == 0 && c->tab.nline == 0 && c->tab.Tpf == nullptr) {
@@ -491,6 +500,8 @@ static int run_chunk_dev(rhb200_ctx *c, int cc, int ndep, double muz, int moving
   double *d_elem_n = (double *) ws, *d_lineprep = (double *) (ws + L.elem_n),
          *d_raypts = (double *) (ws + L.elem_n + L.lineprep), *d_scal = (double *) (ws + L.elem_n + L.lineprep + L.raypts);
   const int *d_colmov = per_column_moving ? chunk_col_moving(c, cc, ndep, ws) : nullptr;
+  // NO_STOKES: only I is solved; Q, U, V are the zeros initSolution() callocs (spectrum.Stokes_Q/U/V, initial_xdr.c:96-100)
+  if (c->no_stokes && d_stokes) RH_CUDA(cudaMemsetAsync(d_stokes, 0, (size_t) cc * 4 * c->wav.nlambda * sizeof(double), c->stream));
   RH_CHECK(rh_launch_prep(c, cc, ndep, muz, moving, d_atmos, d_elem_n, d_lineprep));
   RH_CHECK(rh_launch_opacity_fused(c, cc, ndep, 1, d_atmos, d_lineprep, d_chi_ai, d_eta_ai, d_raypts, d_molchi, d_moleta, d_sca));
   // convertScales() sits between Background() and Iterate() (pyrh_compute1dray.c:310-311): the height row is

@@ -150,6 +150,17 @@ int rh_continuum_chunk(rhb200_ctx *ctx, int cc, int ndep, const double *d_atmos,
                        double *d_pops, double *d_tprep, double *d_chi, double *d_eta, int chem_on_device,
                        double *d_molout = nullptr, double *d_sca = nullptr);
 int rh_continuum_set_molsel(rhb200_ctx *ctx, int nsel, const int *chem_index);
+int rh_continuum_ltepops(rhb200_ctx *ctx, int cc, int ndep, const double *d_atmos, const double *d_chem_host, double *d_pops,
+                         const double *d_ntot_in);
+int rh_continuum_chemeq(rhb200_ctx *ctx, int cc, int ndep, const double *d_atmos, double *d_pops, double *d_chem,
+                        double *d_molout, double *d_ntot, int ntot_is_input);
+int rh_continuum_opac(rhb200_ctx *ctx, int cc, int ndep, const double *d_atmos, const double *d_chem, const double *d_pops_n,
+                      const double *d_pops_star, double *d_tprep, double *d_chi, double *d_eta, double *d_sca);
+int rh_continuum_atom_first(const rhb200_ctx *ctx, int atom);
+double rh_continuum_abundance(const rhb200_ctx *ctx, int atom);
+int rh_launch_scales_chi(rhb200_ctx *ctx, int ncol, int ndep, int nlambda, int iref, int atm_scale, double wght_per_H,
+                         double total_abund, double gravity,
+                         const double *d_chi_c, double *d_atmos, double *d_scratch, double *d_scales_out);
 
 // launchers implemented in the .cu files (device pointers)
 int rh_launch_mol_opacity_raw(rhb200_ctx *ctx, int ncol, int nlambda, int ndep, int nmol, double muz, int moving,
@@ -177,6 +188,12 @@ int rh_launch_loggf_dopac(rhb200_ctx *ctx, int ncol, int ndep, const double *d_a
 int rh_launch_loggf_rf(rhb200_ctx *ctx, int ncol, int ndep, double muz, int bc_top, int bc_bottom, const double *d_atmos,
                        int moving, const int *d_col_moving,
                        double *d_scratch, double *d_rf /* [ncol][nlambda][npar] */);
+int rh_launch_opacity_addI(rhb200_ctx *ctx, int ncol, int ndep, int to_obs, const double *d_atmos, const double *d_lineprep,
+                           double *d_chi_c, double *d_eta_c);
+int rh_launch_add_molecular(rhb200_ctx *ctx, int ncol, int ndep, const double *d_molchi, const double *d_moleta,
+                            double *d_chi_c, double *d_eta_c);
+int rh_launch_line_damping(rhb200_ctx *ctx, int ncol, int ndep, int nline, const double *d_plrows, const double *d_atmos,
+                           const double *d_pops, int nlev, double *d_pcol);
 int rh_launch_opacity_raw(rhb200_ctx *ctx, int ncol, int ndep, int to_obs,
                           const double *d_atmos, const double *d_lineprep,
                           double *d_chi, double *d_eta /* [ncol][nlambda][4][ndep] */);

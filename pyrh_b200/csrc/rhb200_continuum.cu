@@ -775,7 +775,9 @@ int rh_continuum_dev(rhb200_ctx *c, const rhb200_continuum_model *m, int nlambda
 __global__ void __launch_bounds__(128)
 ltepops_kernel(int ncol, int ndep, int natom, int nlev, const double *__restrict__ lev /*[nlev][5]*/,
                const int *__restrict__ atom_first /*[natom+1]*/, const double *__restrict__ abundance,
-               const double *__restrict__ atmos, const double *__restrict__ chem, double *__restrict__ pops)
+               const double *__restrict__ atmos, const double *__restrict__ chem, double *__restrict__ pops,
+               const double *__restrict__ ntot_in /* [ncol][natom][ndep] or NULL: atom->ntotal as a previous
+                                                     ChemicalEquilibrium() left it (second Background() of an NLTE run) */)
 {
   const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t) ncol * ndep) return;
@@ -800,7 +802,7 @@ ltepops_kernel(int ncol, int ndep, int natom, int nlev, const double *__restrict
       P[(size_t) i * ndep] = ns;
       sum += ns;
     }
-    const double ntotal = abundance[a] * nHtot;                     // readatom.c:190
+    const double ntotal = ntot_in ? ntot_in[((size_t) col * natom + a) * ndep + k] : abundance[a] * nHtot;   // readatom.c:190
     const double n0 = ntotal / sum;
     const double fraction = chem ? chem[((size_t) col * (natom + 4) + a) * ndep + k] : 1.0;   // else chemeq_kernel rescales
     P[(size_t) l0 * ndep] = n0 * fraction;                          // chemequil.c:339
@@ -867,7 +869,9 @@ chemeq_kernel(int ncol, int ndep, int natom, int nlev, const double *__restrict_
               int nnuc, const int *__restrict__ nuc_atom, int nmol, const double *__restrict__ mol,
               int iH2, int iOH, int iCH, int NmaxIter, double iterLimit,
               double *__restrict__ pops, double *__restrict__ chem,
-              int nsel, const int *__restrict__ molsel, double *__restrict__ molout /* [ncol][nsel][ndep] or NULL */)
+              int nsel, const int *__restrict__ molsel, double *__restrict__ molout /* [ncol][nsel][ndep] or NULL */,
+              double *__restrict__ ntot_out /* [ncol][natom][ndep] or NULL: atom->ntotal after chemequil.c:342 */,
+              int ntot_is_input /* the array holds atom->ntotal of a previous call: the fraction is relative to it (:336) */)
 {
   const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t) ncol * ndep) return;
@@ -892,7 +896,8 @@ chemeq_kernel(int ncol, int ndep, int natom, int nlev, const double *__restrict_
       s += P[(size_t) j * ndep];
     }
     a[i] = abundance[am] * nHtot;
-    fn0[i] = s / a[i];                                        // atom->ntotal[k] == abundance * nHtot here (readatom.c:190)
+    // atom->ntotal[k] == abundance * nHtot (readatom.c:190) unless a previous call reduced it (chemequil.c:342)
+    fn0[i] = s / (ntot_is_input ? ntot_out[((size_t) col * natom + am) * ndep + k] : a[i]);
   }
   const double CI = (RH_HPLANCK/(2.0*RH_PI*RH_M_ELECTRON)) * (RH_HPLANCK/RH_KBOLTZMANN);
   const double PhiHmin = 0.25*rhm::rh_pow(CI/T, 1.5) * rhm::rh_exp(0.754 * RH_EV / (RH_KBOLTZMANN * T));
@@ -951,9 +956,10 @@ chemeq_kernel(int ncol, int ndep, int natom, int nlev, const double *__restrict_
   for (int am = 0; am < natom; am++) ch[(size_t) am * ndep] = 1.0;
   for (int i = 0; i < nnuc; i++) {                           // chemequil.c:334-343
     const int am = nuc_atom[i];
-    const double fraction = n[i] / a[i];
+    const double fraction = n[i] / (ntot_is_input ? ntot_out[((size_t) col * natom + am) * ndep + k] : a[i]);
     ch[(size_t) am * ndep] = fraction;
     for (int j = atom_first[am]; j < atom_first[am+1]; j++) P[(size_t) j * ndep] *= fraction;
+    if (ntot_out) ntot_out[((size_t) col * natom + am) * ndep + k] = n[i];
   }
   ch[(size_t) natom * ndep] = ne * (n[0] * PhiHmin);         // nHmin, chemequil.c:347
   ch[(size_t) (natom + 1) * ndep] = iH2 >= 0 ? n[nnuc + iH2] : 0.0;
@@ -982,7 +988,9 @@ chemeq_coop_kernel(int ncol, int ndep, int natom, int nlev, const double *__rest
                    int nnuc, const int *__restrict__ nuc_atom, int nmol, const double *__restrict__ mol,
                    int iH2, int iOH, int iCH, int NmaxIter, double iterLimit,
                    double *__restrict__ pops, double *__restrict__ chem,
-              int nsel, const int *__restrict__ molsel, double *__restrict__ molout /* [ncol][nsel][ndep] or NULL */)
+              int nsel, const int *__restrict__ molsel, double *__restrict__ molout /* [ncol][nsel][ndep] or NULL */,
+              double *__restrict__ ntot_out /* [ncol][natom][ndep] or NULL: atom->ntotal after chemequil.c:342 */,
+              int ntot_is_input /* the array holds atom->ntotal of a previous call: the fraction is relative to it (:336) */)
 {
   constexpr int LD = LPS + 1, SPB = 128 / LPS, PER = LPS*LD + 9*LPS;
   constexpr unsigned FULL = 0xffffffffu;
@@ -1011,7 +1019,7 @@ chemeq_coop_kernel(int ncol, int ndep, int natom, int nlev, const double *__rest
       s += P[(size_t) j * ndep];
     }
     av[l] = abundance[am] * nHtot;
-    fn0[l] = s / av[l];
+    fn0[l] = s / (ntot_is_input ? ntot_out[((size_t) col * natom + am) * ndep + k] : av[l]);
     nv[l] = av[l];
   } else if (row) { av[l] = 0.0; nv[l] = 0.0; }
   if (l < nmol) Phi[l] = equilconstant_d(mol + (size_t) l * MC_NFIELD, T);
@@ -1191,9 +1199,10 @@ chemeq_coop_kernel(int ncol, int ndep, int natom, int nlev, const double *__rest
   __syncwarp(__activemask());
   if (l < nnuc) {                                            // chemequil.c:334-343
     const int am = nuc_atom[l];
-    const double fraction = nv[l] / av[l];
+    const double fraction = nv[l] / (ntot_is_input ? ntot_out[((size_t) col * natom + am) * ndep + k] : av[l]);
     ch[(size_t) am * ndep] = fraction;
     for (int j = atom_first[am]; j < atom_first[am+1]; j++) P[(size_t) j * ndep] *= fraction;
+    if (ntot_out) ntot_out[((size_t) col * natom + am) * ndep + k] = nv[l];
   }
   if (l == 0) {
     ch[(size_t) natom * ndep] = ne * (nv[0] * PhiHmin);      // nHmin, chemequil.c:347
@@ -1213,7 +1222,8 @@ struct ContinuumState {
   bool mol_repeats = false;      // some molecule names a nucleus twice, or a count above 15: per-thread kernel
   int *d_nuc_atom = nullptr; double *d_mol = nullptr;
   int nsel = 0; int *d_molsel = nullptr;      // molecules whose densities the molecular-line kernels need
-  std::vector<int> h_molsel;
+  std::vector<int> h_molsel, h_first;
+  std::vector<double> h_abund;
 };
 
 void rh_continuum_free(rhb200_ctx *c)
@@ -1241,7 +1251,7 @@ int rh_continuum_has_chemistry(const rhb200_ctx *c) { return c->cont && ((Contin
 int rh_continuum_proton_level(const rhb200_ctx *c) { return c->cont ? ((ContinuumState *) c->cont)->proton_level : 0; }
 
 static int launch_chemeq(rhb200_ctx *c, ContinuumState *S, int cc, int ndep, const double *d_atmos, double *d_pops, double *d_chem,
-                         double *d_molout = nullptr)
+                         double *d_molout = nullptr, double *d_ntot = nullptr, int ntot_is_input = 0)
 {
   const size_t cn = (size_t) cc * ndep;
   const int na = S->natom;
@@ -1253,7 +1263,7 @@ static int launch_chemeq(rhb200_ctx *c, ContinuumState *S, int cc, int ndep, con
   const bool serial = (variant && !strcmp(variant, "local")) || S->mol_repeats, coop = !variant || !strcmp(variant, "coop");
   const int TPB = 32;
 #define CHEM_ARGS cc, ndep, na, S->nlev, S->d_lev, S->d_first, S->d_abund, d_atmos, S->nnuc, S->d_nuc_atom, S->nmol, S->d_mol, \
-                S->iH2, S->iOH, S->iCH, 10, 1.0E-3, d_pops, d_chem, S->nsel, S->d_molsel, d_molout
+                S->iH2, S->iOH, S->iCH, 10, 1.0E-3, d_pops, d_chem, S->nsel, S->d_molsel, d_molout, d_ntot, ntot_is_input
   if (serial) {
     if (Neq <= 16) chemeq_kernel<16, false><<<(unsigned) ((cn + 63) / 64), 64, 0, c->stream>>>(CHEM_ARGS);
     else chemeq_kernel<CHEM_MAXEQ, false><<<(unsigned) ((cn + 63) / 64), 64, 0, c->stream>>>(CHEM_ARGS);
@@ -1280,30 +1290,44 @@ static int launch_chemeq(rhb200_ctx *c, ContinuumState *S, int cc, int ndep, con
   return RHB200_OK;
 }
 
-// LTE populations + continuum of one chunk of columns, all on ctx->stream.
+// LTE populations + continuum of one chunk of columns, all on ctx->stream, in three stages (the NLTE front end runs
+// CollisionRate between the first two, like SetLTEQuantities does: ltepops.c:224-249).
 // d_pops [cc][nlev][ndep] and d_tprep [cc][5][ndep] are workspace; out d_chi, d_eta [cc][nlambda][ndep].
-int rh_continuum_chunk(rhb200_ctx *c, int cc, int ndep, const double *d_atmos, const double *d_chem,
-                       double *d_pops, double *d_tprep, double *d_chi, double *d_eta, int chem_on_device, double *d_molout,
-                       double *d_sca)
+int rh_continuum_ltepops(rhb200_ctx *c, int cc, int ndep, const double *d_atmos, const double *d_chem_host, double *d_pops,
+                         const double *d_ntot_in)
 {
   ContinuumState *S = (ContinuumState *) c->cont;
   if (!S) { rhb200_set_error("rhb200_set_continuum() has not been called"); return RHB200_ESTATE; }
   if (S->nlambda != c->wav.nlambda) { rhb200_set_error("wavelengths changed after rhb200_set_continuum()"); return RHB200_ESTATE; }
   const size_t cn = (size_t) cc * ndep;
+  ScopedKernelTimer t(c, RHB200_K_PREP);
+  ltepops_kernel<<<(unsigned) ((cn + 127) / 128), 128, 0, c->stream>>>(cc, ndep, S->natom, S->nlev, S->d_lev, S->d_first,
+                                                                       S->d_abund, d_atmos, d_chem_host, d_pops, d_ntot_in);
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}
+
+int rh_continuum_chemeq(rhb200_ctx *c, int cc, int ndep, const double *d_atmos, double *d_pops, double *d_chem,
+                        double *d_molout, double *d_ntot, int ntot_is_input)
+{
+  ContinuumState *S = (ContinuumState *) c->cont;
+  if (!S) { rhb200_set_error("rhb200_set_continuum() has not been called"); return RHB200_ESTATE; }
+  if (S->nmol == 0) { rhb200_set_error("rhb200_set_chemistry() has not been called"); return RHB200_ESTATE; }
+  ScopedKernelTimer t(c, RHB200_K_PREP);
+  return launch_chemeq(c, S, cc, ndep, d_atmos, d_pops, d_chem, d_molout, d_ntot, ntot_is_input);
+}
+
+// d_pops_n: the populations Background() reads through atom->n (differs from the LTE populations d_pops_star only for
+// an ACTIVE hydrogen atom, whose n is the NLTE solution -- zero before initSolution(): hydrogen.c:100-141)
+int rh_continuum_opac(rhb200_ctx *c, int cc, int ndep, const double *d_atmos, const double *d_chem, const double *d_pops_n,
+                      const double *d_pops_star, double *d_tprep, double *d_chi, double *d_eta, double *d_sca)
+{
+  ContinuumState *S = (ContinuumState *) c->cont;
+  if (!S) { rhb200_set_error("rhb200_set_continuum() has not been called"); return RHB200_ESTATE; }
+  const size_t cn = (size_t) cc * ndep;
   const int na = S->natom;
-  {
-    ScopedKernelTimer t(c, RHB200_K_PREP);
-    ltepops_kernel<<<(unsigned) ((cn + 127) / 128), 128, 0, c->stream>>>(cc, ndep, na, S->nlev, S->d_lev, S->d_first,
-                                                                         S->d_abund, d_atmos, chem_on_device ? nullptr : d_chem, d_pops);
-  }
-  if (chem_on_device) {
-    if (S->nmol == 0) { rhb200_set_error("rhb200_set_chemistry() has not been called"); return RHB200_ESTATE; }
-    ScopedKernelTimer t(c, RHB200_K_PREP);
-    RH_CHECK(launch_chemeq(c, S, cc, ndep, d_atmos, d_pops, (double *) d_chem, d_molout));
-  }
-  // T and ne are rows of the atmosphere block; the chem block carries nHmin, nH2, nOH, nCH after the fractions.
-  // The kernels index [col][ndep] arrays, so they get strided views through small gather kernels' absence:
-  // both blocks are [col][field][ndep], hence a per-column stride -- handled by passing field pointers and strides.
+  // T and ne are rows of the atmosphere block; the chem block carries nHmin, nH2, nOH, nCH after the fractions:
+  // both blocks are [col][field][ndep], hence field pointers and per-column strides.
   {
     ScopedKernelTimer t(c, RHB200_K_PREP);
     cont_prep_kernel<<<(unsigned) ((cn + 127) / 128), 128, 0, c->stream>>>(cc, ndep, S->D, d_atmos + (size_t) RHB200_AT_T * ndep,
@@ -1317,7 +1341,7 @@ int rh_continuum_chunk(rhb200_ctx *c, int cc, int ndep, const double *d_atmos, c
     if (nck > 65535) { rhb200_set_error("chunk too large for the continuum kernel grid"); return RHB200_EINVAL; }
     static int minb = -1;                                   // RHB200_CONT_MINB: occupancy / spill trade-off
     if (minb < 0) { const char *e = getenv("RHB200_CONT_MINB"); minb = e ? atoi(e) : 8; }
-#define RH_CONT_ARGS (cc, S->nlambda, ndep, S->D, d_atmos + (size_t) RHB200_AT_T * ndep, d_atmos + (size_t) RHB200_AT_NE * ndep, as, d_chem + (size_t) na * ndep, d_chem + (size_t) (na + 1) * ndep, d_chem + (size_t) (na + 2) * ndep, d_chem + (size_t) (na + 3) * ndep, cs, d_pops, d_pops, d_tprep, d_chi, d_eta, d_sca)
+#define RH_CONT_ARGS (cc, S->nlambda, ndep, S->D, d_atmos + (size_t) RHB200_AT_T * ndep, d_atmos + (size_t) RHB200_AT_NE * ndep, as, d_chem + (size_t) na * ndep, d_chem + (size_t) (na + 1) * ndep, d_chem + (size_t) (na + 2) * ndep, d_chem + (size_t) (na + 3) * ndep, cs, d_pops_n, d_pops_star, d_tprep, d_chi, d_eta, d_sca)
     const dim3 grid((unsigned) ntile, (unsigned) nck);
     switch (minb) {
     case 4: continuum_tile_kernel<4><<<grid, 128, 0, c->stream>>>RH_CONT_ARGS; break;
@@ -1329,10 +1353,30 @@ int rh_continuum_chunk(rhb200_ctx *c, int cc, int ndep, const double *d_atmos, c
     default: continuum_tile_kernel<8><<<grid, 128, 0, c->stream>>>RH_CONT_ARGS; break;
     }
 #undef RH_CONT_ARGS
-
   }
   RH_CUDA(cudaGetLastError());
   return RHB200_OK;
+}
+
+int rh_continuum_chunk(rhb200_ctx *c, int cc, int ndep, const double *d_atmos, const double *d_chem,
+                       double *d_pops, double *d_tprep, double *d_chi, double *d_eta, int chem_on_device, double *d_molout,
+                       double *d_sca)
+{
+  RH_CHECK(rh_continuum_ltepops(c, cc, ndep, d_atmos, chem_on_device ? nullptr : d_chem, d_pops, nullptr));
+  if (chem_on_device) RH_CHECK(rh_continuum_chemeq(c, cc, ndep, d_atmos, d_pops, (double *) d_chem, d_molout, nullptr, 0));
+  return rh_continuum_opac(c, cc, ndep, d_atmos, d_chem, d_pops, d_pops, d_tprep, d_chi, d_eta, d_sca);
+}
+
+// model-atom bookkeeping the NLTE front end needs: first level row of each atom, abundance * nHtot is formed there
+int rh_continuum_atom_first(const rhb200_ctx *c, int atom)
+{
+  const ContinuumState *S = (const ContinuumState *) c->cont;
+  return (S && atom >= 0 && atom <= S->natom) ? S->h_first[atom] : -1;
+}
+double rh_continuum_abundance(const rhb200_ctx *c, int atom)
+{
+  const ContinuumState *S = (const ContinuumState *) c->cont;
+  return (S && atom >= 0 && atom < S->natom) ? S->h_abund[atom] : 0.0;
 }
 
 extern "C" int rhb200_set_continuum(rhb200_ctx *c, const rhb200_continuum_model *m, const double *abundance)
@@ -1342,8 +1386,14 @@ extern "C" int rhb200_set_continuum(rhb200_ctx *c, const rhb200_continuum_model 
   RH_CHECK(check_model(m));
   if (!abundance) { rhb200_set_error("abundance missing"); return RHB200_EINVAL; }
   if (c->wav.nlambda == 0) { rhb200_set_error("rhb200_set_wavelengths() has not been called"); return RHB200_ESTATE; }
-  for (int g = 0; g < m->nlev; g++)
-    if (m->lev[5*(size_t) g + 4] != 0.0) { rhb200_set_error("ACTIVE atoms are not part of the LTE background path"); return RHB200_EUNSUPPORTED; }
+  // lev[g][4] != 0 marks the levels of an ACTIVE atom: its bound-free continua must then carry bf[c][9] != 0 so that
+  // Metal_bf skips them (metal.c:105), and hydrogen's go with H_active (hydrogen.c:179)
+  for (int cb = 0; cb < m->ncont; cb++) {
+    const double *b = m->bf + 10*(size_t) cb;
+    const bool act = m->lev[5*(size_t) ((int) b[1]) + 4] != 0.0;
+    if (act && (int) b[0] != 0 && b[9] == 0.0) { rhb200_set_error("continuum %d belongs to an ACTIVE atom but is not flagged (bf[9])", cb); return RHB200_EINVAL; }
+    if (act && (int) b[0] == 0 && !m->H_active) { rhb200_set_error("hydrogen levels are flagged ACTIVE but H_active is 0"); return RHB200_EINVAL; }
+  }
   rh_continuum_free(c);
   ContinuumState *S = new ContinuumState();
   c->cont = S;
@@ -1360,6 +1410,7 @@ extern "C" int rhb200_set_continuum(rhb200_ctx *c, const rhb200_continuum_model 
   first[m->natom] = m->nlev;
   for (int a = m->natom - 1; a >= 0; a--) if (first[a] < 0) first[a] = first[a+1];
   S->proton_level = first[1] - 1;
+  S->h_first = first; S->h_abund.assign(abundance, abundance + m->natom);
   if ((rc = S->H.put(&S->d_lev, m->lev, (size_t) m->nlev * 5)) != RHB200_OK ||
       (rc = S->H.put(&S->d_abund, abundance, (size_t) m->natom)) != RHB200_OK ||
       (rc = S->H.put(&S->d_first, first.data(), first.size())) != RHB200_OK) { rh_continuum_free(c); return rc; }
@@ -1419,7 +1470,7 @@ extern "C" int rhb200_chemistry_batch(rhb200_ctx *c, int ncol, int ndep, const d
   RH_CUDA(cudaMalloc((void **) &d_ch, cn * (S->natom + 4) * sizeof(double))); H.p.push_back(d_ch);
   RH_CUDA(cudaMalloc((void **) &d_pp, cn * S->nlev * sizeof(double))); H.p.push_back(d_pp);
   ltepops_kernel<<<(unsigned) ((cn + 127) / 128), 128, 0, c->stream>>>(ncol, ndep, S->natom, S->nlev, S->d_lev, S->d_first,
-                                                                       S->d_abund, d_at, nullptr, d_pp);
+                                                                       S->d_abund, d_at, nullptr, d_pp, nullptr);
   RH_CHECK(launch_chemeq(c, S, ncol, ndep, d_at, d_pp, d_ch));
   RH_CUDA(cudaGetLastError());
   RH_CUDA(cudaStreamSynchronize(c->stream));

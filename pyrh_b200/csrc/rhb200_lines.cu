@@ -309,6 +309,50 @@ opacity_raw_kernel(int ncol, int nlambda, int ndep, int to_obs, int nline,
   }
 }
 
+// NLTE background (background.c:519-546 with atmos.Stokes set but only the intensity record used, NO_STOKES): the I
+// component of rlk_opacity() is added to chi_c / eta_c [ncol][nlambda][ndep] in place, where a line is in the window
+// (hasline: the reference adds nothing otherwise).  Same line_sums as the raw kernel, hence the same roundings.
+__global__ void __launch_bounds__(128)
+opacity_addI_kernel(int ncol, int nlambda, int ndep, int to_obs, int nline,
+                    const double *__restrict__ lambda, const int *__restrict__ wfirst,
+                    const int *__restrict__ wcount, const int *__restrict__ widx,
+                    const double *__restrict__ lines, const int *__restrict__ zq,
+                    const double *__restrict__ zshift, const double *__restrict__ zstrength,
+                    const double *__restrict__ atmos, const double *__restrict__ lineprep,
+                    double *__restrict__ chi_c, double *__restrict__ eta_c)
+{
+  const size_t npts = (size_t) ncol * nlambda * ndep;
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= npts) return;
+  const size_t r = t / ndep;
+  const int k = (int) (t - r * ndep);
+  const int col = (int) (r / nlambda), l = (int) (r - (size_t) col * nlambda);
+  const int count = __ldg(wcount + l);
+  if (count == 0) return;
+  const double *at = atmos + (size_t) col * RHB200_AT_NFIELD * ndep;
+  LineSums s;
+  const ZeemanGlobal zee{zq, zshift, zstrength};
+  line_sums<true, false>(s, __ldg(lambda + l), to_obs, __ldg(wfirst + l), count, widx, lines,
+            zee, lineprep + (size_t) col*nline*LP_NFIELD*ndep + k, ndep,
+            __ldg(at + RHB200_AT_COS_GAMMA*ndep + k), __ldg(at + RHB200_AT_COS_2CHI*ndep + k),
+            __ldg(at + RHB200_AT_SIN_2CHI*ndep + k));
+  chi_c[t] += s.chi[0];
+  eta_c[t] += s.eta[0];
+}
+
+// chi_c += a, eta_c += b where the wavelength has entries in the window list (molecular lines of the NLTE background)
+__global__ void __launch_bounds__(128)
+add_where_kernel(size_t n, int nlambda, int ndep, const int *__restrict__ wcount, const double *__restrict__ a,
+                 const double *__restrict__ b, double *__restrict__ chi_c, double *__restrict__ eta_c)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int l = (int) ((t / ndep) % nlambda);
+  if (__ldg(wcount + l) == 0) return;
+  chi_c[t] += a[t];
+  eta_c[t] += b[t];
+}
+
 // d chi_c / d log gf and d eta_c / d log gf of the wavelengths solved with the scalar ray (kurucz.c:696-699:
 // spectrum.dchi_c_lam[nspect][k][p] = chi_l * phi * LN10 of the line parameter p belongs to, in the up direction -- the
 // last rlk_opacity() call before the up-ray of Formal() reads it).  One thread per (column, I-only wavelength, depth).
@@ -784,6 +828,46 @@ int rh_launch_loggf_dopac(rhb200_ctx *ctx, int ncol, int ndep, const double *d_a
     else if (arm) loggf_dopac_kernel<true, false><<<grid, 128, 0, ctx->stream>>>RH_DOPAC_ARGS;
     else loggf_dopac_kernel<false, false><<<grid, 128, 0, ctx->stream>>>RH_DOPAC_ARGS;
   }
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}
+
+int rh_launch_opacity_addI(rhb200_ctx *ctx, int ncol, int ndep, int to_obs, const double *d_atmos, const double *d_lineprep,
+                           double *d_chi_c, double *d_eta_c)
+{
+  const size_t npts = (size_t) ncol * ctx->wav.nlambda * ndep;
+  if (npts == 0 || ctx->tab.nline == 0) return RHB200_OK;
+  if (ctx->tab.rlkscatter) { rhb200_set_error("RLK_SCATTER in the NLTE background is not implemented"); return RHB200_EUNSUPPORTED; }
+  {
+    ScopedKernelTimer t(ctx, RHB200_K_OPACITY);
+    opacity_addI_kernel<<<(unsigned) ((npts + 127) / 128), 128, 0, ctx->stream>>>(ncol, ctx->wav.nlambda, ndep, to_obs,
+        ctx->tab.nline, ctx->wav.lambda, ctx->wav.first, ctx->wav.count, ctx->wav.idx,
+        ctx->tab.lines, ctx->tab.zq, ctx->tab.zshift, ctx->tab.zstrength, d_atmos, d_lineprep, d_chi_c, d_eta_c);
+  }
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}
+
+int rh_launch_add_molecular(rhb200_ctx *ctx, int ncol, int ndep, const double *d_molchi, const double *d_moleta,
+                            double *d_chi_c, double *d_eta_c)
+{
+  const size_t n = (size_t) ncol * ctx->wav.nlambda * ndep;
+  if (n == 0 || ctx->wav.nmw == 0) return RHB200_OK;
+  add_where_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, ctx->stream>>>(n, ctx->wav.nlambda, ndep, ctx->wav.mw_count,
+                                                                          d_molchi, d_moleta, d_chi_c, d_eta_c);
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}
+
+// Damping() + Doppler width of an arbitrary line table (rows RHB200_PL_*): the ACTIVE lines of the NLTE front end.
+// d_pcol [ncol][nline][4][ndep] = n_i, n_j, vbroad, adamp
+int rh_launch_line_damping(rhb200_ctx *ctx, int ncol, int ndep, int nline, const double *d_plrows, const double *d_atmos,
+                           const double *d_pops, int nlev, double *d_pcol)
+{
+  const size_t n = (size_t) ncol * nline * ndep;
+  if (n == 0) return RHB200_OK;
+  ScopedKernelTimer t(ctx, RHB200_K_PREP);
+  passive_prep_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, ctx->stream>>>(ncol, ndep, nline, nlev, d_plrows, d_atmos, d_pops, d_pcol);
   RH_CUDA(cudaGetLastError());
   return RHB200_OK;
 }

@@ -616,6 +616,18 @@ nlte_ng_kernel(Plan P, Cols C, int ncol, double *previous /*[col][atom-offset][(
   if (tid == 0) dpops[(size_t) col * P.Natom + a] = smax[0];
 }
 
+// spectrum.I[nspect][0] of every wavelength -> spec[col][Nspect]: the up-ray of ray mu = 0 (formal.c:270), Feautrier's
+// emergent intensity where the wavelength is angle independent (formal.c:299-305)
+__global__ void __launch_bounds__(128)
+nlte_pack_spectrum_kernel(Plan P, Cols C, int ncol, double *__restrict__ spec)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t) ncol * P.Nspect) return;
+  const int ns = (int) (t % P.Nspect), col = (int) (t / P.Nspect);
+  const int r = P.ray_off[ns] + (P.angle_dep[ns] ? 1 : 0);      // rays of a wavelength: (mu 0, down), (mu 0, up), ...
+  spec[t] = C.Iem[(size_t) col * P.nray + r];
+}
+
 template <class T> int up(T **d, const T *h, size_t n)
 {
   *d = nullptr;
@@ -668,177 +680,228 @@ extern "C" int rhb200_solve_linear_eq_batch(rhb200_ctx *c, int nsys, int N, doub
 
 void rh_nlte_shard_range(int Nspect, const int *ray_off, int rank, int nrank, int *lo, int *hi);
 
-static int nlte_run(rhb200_ctx *c, const rhb200_nlte_plan *pl, int ncol,
-                    const rhb200_nlte_columns *cols, int NmaxScatter, int update_J, int NmaxIter, double iterLimit,
-                    int *niter_out, double *dpops_hist, int dump_iter,
-                    double *gamma_dump, double *rates_dump, double *phi_out, double *wphi_out,
-                    double *Iem_out, int *nscatter_out)
-{
-  if (!c || !pl || !cols) { rhb200_set_error("null argument"); return RHB200_EINVAL; }
-  RH_CUDA(cudaSetDevice(c->device));
-  const int Ns = pl->Nspect, N = pl->Ndep, Na = pl->Natom, Nt = pl->Ntrans, Nr = pl->Nrays;
-  if (ncol <= 0 || Ns <= 0 || N < 3 || Na <= 0 || Na > 15 || Nt <= 0 || Nr <= 0 || NmaxIter < 0) {
-    rhb200_set_error("rhb200_nlte_iterate: bad sizes"); return RHB200_EINVAL;
-  }
-  if (!pl->moving) { rhb200_set_error("static atmospheres (angle-independent line profiles) are not implemented"); return RHB200_EUNSUPPORTED; }
-  if (pl->Ngorder > 4 || pl->Ngorder < 0) { rhb200_set_error("NG_ORDER > 4 is not implemented"); return RHB200_EUNSUPPORTED; }
-  int maxnl = 0;
-  std::vector<int> lev_off(Na+1, 0), gam_off(Na+1, 0);
-  for (int a = 0; a < Na; a++) {
-    maxnl = std::max(maxnl, pl->atom_nlevel[a]);
-    lev_off[a+1] = lev_off[a] + pl->atom_nlevel[a];
-    gam_off[a+1] = gam_off[a] + pl->atom_nlevel[a]*pl->atom_nlevel[a];
-  }
-  if (maxnl > 32) { rhb200_set_error("atoms with more than 32 levels are not implemented"); return RHB200_EUNSUPPORTED; }
-  const int nlev = lev_off[Na], ngam = gam_off[Na], nas = pl->as_first[Ns];
-
-  // derived host tables: angle dependence (formal.c:100-103), ray list in the reference's order
-  std::vector<int> angle_dep(Ns), ray_off(Ns+1, 0), ray_ns, ray_mu, ray_dir, as_pack(2*(size_t) nas);
-  for (int ns = 0; ns < Ns; ns++) {
-    bool bb = false;
-    for (int e = pl->as_first[ns]; e < pl->as_first[ns+1]; e++) {
-      as_pack[e] = pl->as_trans[e]; as_pack[nas + e] = ns;
-      if (pl->trans[(size_t) pl->as_trans[e]*RHB200_TR_NFIELD + RHB200_TR_TYPE] == 0.0) bb = true;
-      if (pl->trans[(size_t) pl->as_trans[e]*RHB200_TR_NFIELD + RHB200_TR_TYPE] != 0.0 &&
-          pl->trans[(size_t) pl->as_trans[e]*RHB200_TR_NFIELD + RHB200_TR_TYPE] != 1.0) {
-        rhb200_set_error("transition type must be 0 (line) or 1 (continuum)"); return RHB200_EINVAL;
-      }
-    }
-    {                                          // the rate kernel caches one atom's entries of a wavelength
-      std::vector<int> per_atom(Na, 0);
-      for (int e = pl->as_first[ns]; e < pl->as_first[ns+1]; e++) {
-        const int a = (int) pl->trans[(size_t) pl->as_trans[e]*RHB200_TR_NFIELD + RHB200_TR_ATOM];
-        if (a < 0 || a >= Na) { rhb200_set_error("transition atom index out of range"); return RHB200_EINVAL; }
-        if (++per_atom[a] > NLTE_MAXACT) {
-          rhb200_set_error("more than %d active transitions of one atom at one wavelength", NLTE_MAXACT);
-          return RHB200_EUNSUPPORTED;
-        }
-      }
-    }
-    angle_dep[ns] = pl->moving && (bb || pl->bg_hasline[ns]);
-    for (int mu = 0; mu < Nr; mu++)
-      for (int dir = 0; dir <= (angle_dep[ns] ? 1 : 0); dir++) { ray_ns.push_back(ns); ray_mu.push_back(mu); ray_dir.push_back(dir); }
-    ray_off[ns+1] = (int) ray_ns.size();
-  }
-  const int nray = (int) ray_ns.size();
-
-  DevArena ar;
+// ---- the solver as an engine: plan-level tables built once (build), per-batch work arrays (alloc), inputs either
+//      uploaded from the host (the function-level entry points) or bound as device arrays the front end filled
+//      (rhb200_nlte_compute1d_batch); then prepare -> scatter / iterate in any order, all on ctx->stream.
+struct NlteEngine {
+  rhb200_ctx *c = nullptr;
+  DevArena plan_ar, work_ar;
   Plan P{};
-  P.Nspect = Ns; P.Nrays = Nr; P.Ndep = N; P.Natom = Na; P.Ntrans = Nt; P.nas = nas; P.nray = nray;
-  P.nlev = nlev; P.ngam = ngam; P.nphirow = pl->nphirow; P.nline = pl->nline; P.bc_top = pl->bc_top; P.bc_bottom = pl->bc_bottom;
-  P.solver = c->s_interpolation;
-  // wavelength shard of one atmosphere (rhb200_nlte_set_shard): contiguous chunk balanced by ray count
-  const int nrank = c->shard_nrank > 1 ? c->shard_nrank : 1, rank = nrank > 1 ? c->shard_rank : 0;
-  rh_nlte_shard_range(Ns, ray_off.data(), rank, nrank, &P.ns_lo, &P.ns_hi);
-  P.add_C = (rank == 0);
-  auto allreduce = [&](double *buf, size_t count, int op) -> int {
+  Cols C{};
+  int Ns = 0, N = 0, Na = 0, Nt = 0, Nr = 0, nlev = 0, ngam = 0, nas = 0, nray = 0, maxnl = 0, nphirow = 0, nline = 0;
+  int isum = -1, Norder = 0, Ndelay = 0, Nperiod = 1, ncol = 0, nrank = 1, rank = 0;
+  bool device_profiles = false;
+  std::vector<int> lev_off, gam_off, angle_dep, ray_off, ray_ns, ray_mu, ray_dir, nlevel;
+  std::vector<size_t> prev_off;
+  int *d_active = nullptr; double *d_prev = nullptr; size_t *d_prev_off = nullptr; double *d_dpops = nullptr, *d_dJmax = nullptr;
+  std::vector<int> active;
+
+  int allreduce(double *buf, size_t count, int op) {
     if (nrank == 1) return RHB200_OK;
     RH_CUDA(cudaStreamSynchronize(c->stream));
     if (c->shard_fn(c->shard_user, buf, count, op) != 0) { rhb200_set_error("allreduce callback failed"); return RHB200_ECUDA; }
     return RHB200_OK;
-  };
-  double *dd; int *di;
+  }
+
+  int build(rhb200_ctx *ctx, const rhb200_nlte_plan *pl) {
+    c = ctx;
+    Ns = pl->Nspect; N = pl->Ndep; Na = pl->Natom; Nt = pl->Ntrans; Nr = pl->Nrays;
+    if (Ns <= 0 || N < 3 || Na <= 0 || Na > 15 || Nt <= 0 || Nr <= 0) { rhb200_set_error("rhb200_nlte: bad plan sizes"); return RHB200_EINVAL; }
+    if (!pl->moving) { rhb200_set_error("static atmospheres (angle-independent line profiles) are not implemented"); return RHB200_EUNSUPPORTED; }
+    if (pl->Ngorder > 4 || pl->Ngorder < 0) { rhb200_set_error("NG_ORDER > 4 is not implemented"); return RHB200_EUNSUPPORTED; }
+    lev_off.assign(Na+1, 0); gam_off.assign(Na+1, 0); nlevel.assign(pl->atom_nlevel, pl->atom_nlevel + Na);
+    for (int a = 0; a < Na; a++) {
+      maxnl = std::max(maxnl, pl->atom_nlevel[a]);
+      lev_off[a+1] = lev_off[a] + pl->atom_nlevel[a];
+      gam_off[a+1] = gam_off[a] + pl->atom_nlevel[a]*pl->atom_nlevel[a];
+    }
+    if (maxnl > 32) { rhb200_set_error("atoms with more than 32 levels are not implemented"); return RHB200_EUNSUPPORTED; }
+    nlev = lev_off[Na]; ngam = gam_off[Na]; nas = pl->as_first[Ns]; nphirow = pl->nphirow; nline = pl->nline;
+    isum = pl->isum;
+    // derived host tables: angle dependence (formal.c:100-103), ray list in the reference's order
+    angle_dep.assign(Ns, 0); ray_off.assign(Ns+1, 0);
+    std::vector<int> as_pack(2*(size_t) nas);
+    for (int ns = 0; ns < Ns; ns++) {
+      bool bb = false;
+      for (int e = pl->as_first[ns]; e < pl->as_first[ns+1]; e++) {
+        as_pack[e] = pl->as_trans[e]; as_pack[nas + e] = ns;
+        const double ty = pl->trans[(size_t) pl->as_trans[e]*RHB200_TR_NFIELD + RHB200_TR_TYPE];
+        if (ty == 0.0) bb = true;
+        if (ty != 0.0 && ty != 1.0) { rhb200_set_error("transition type must be 0 (line) or 1 (continuum)"); return RHB200_EINVAL; }
+      }
+      {                                          // the rate kernel caches one atom's entries of a wavelength
+        std::vector<int> per_atom(Na, 0);
+        for (int e = pl->as_first[ns]; e < pl->as_first[ns+1]; e++) {
+          const int a = (int) pl->trans[(size_t) pl->as_trans[e]*RHB200_TR_NFIELD + RHB200_TR_ATOM];
+          if (a < 0 || a >= Na) { rhb200_set_error("transition atom index out of range"); return RHB200_EINVAL; }
+          if (++per_atom[a] > NLTE_MAXACT) {
+            rhb200_set_error("more than %d active transitions of one atom at one wavelength", NLTE_MAXACT);
+            return RHB200_EUNSUPPORTED;
+          }
+        }
+      }
+      angle_dep[ns] = pl->moving && (bb || pl->bg_hasline[ns]);
+      for (int mu = 0; mu < Nr; mu++)
+        for (int dir = 0; dir <= (angle_dep[ns] ? 1 : 0); dir++) { ray_ns.push_back(ns); ray_mu.push_back(mu); ray_dir.push_back(dir); }
+      ray_off[ns+1] = (int) ray_ns.size();
+    }
+    nray = (int) ray_ns.size();
+    P.Nspect = Ns; P.Nrays = Nr; P.Ndep = N; P.Natom = Na; P.Ntrans = Nt; P.nas = nas; P.nray = nray;
+    P.nlev = nlev; P.ngam = ngam; P.nphirow = nphirow; P.nline = nline; P.bc_top = pl->bc_top; P.bc_bottom = pl->bc_bottom;
+    P.solver = c->s_interpolation;
+    // wavelength shard of one atmosphere (rhb200_nlte_set_shard): contiguous chunk balanced by ray count
+    nrank = c->shard_nrank > 1 ? c->shard_nrank : 1; rank = nrank > 1 ? c->shard_rank : 0;
+    rh_nlte_shard_range(Ns, ray_off.data(), rank, nrank, &P.ns_lo, &P.ns_hi);
+    P.add_C = (rank == 0);
+    DevArena &ar = plan_ar;
+    double *dd; int *di;
 #define UPD(field, src, n) RH_CHECK(ar.upload(&dd, src, (size_t) (n))); P.field = dd
 #define UPI(field, src, n) RH_CHECK(ar.upload(&di, src, (size_t) (n))); P.field = di
-  UPD(lambda, pl->lambda, Ns); UPD(muz, pl->muz, Nr); UPD(wmu, pl->wmu, Nr);
-  UPD(trans, pl->trans, (size_t) Nt*RHB200_TR_NFIELD);
-  UPD(tr_lambda, pl->tr_lambda, pl->ntrl); UPD(tr_wlambda, pl->tr_wlambda, pl->ntrl); UPD(tr_alpha, pl->tr_alpha, pl->ntrl);
-  UPI(atom_nlevel, pl->atom_nlevel, Na); UPI(lev_off, lev_off.data(), Na+1); UPI(gam_off, gam_off.data(), Na+1);
-  UPI(as_first, pl->as_first, Ns+1); UPI(as_trans, as_pack.data(), 2*(size_t) nas);
-  UPI(angle_dep, angle_dep.data(), Ns); UPI(ray_off, ray_off.data(), Ns+1);
-  UPI(ray_ns, ray_ns.data(), nray); UPI(ray_mu, ray_mu.data(), nray); UPI(ray_dir, ray_dir.data(), nray);
-
-  Cols C{};
-  const size_t cN = (size_t) ncol * N;
-#define UPC(field, src, n) RH_CHECK(ar.upload(&dd, src, (size_t) (n))); C.field = dd
-  UPC(T, cols->T, cN); UPC(height, cols->height, cN);
-  UPC(nstar, cols->nstar, cN*nlev); UPC(ntotal, cols->ntotal, cN*Na); UPC(C, cols->C, cN*ngam);
-  const bool device_profiles = (cols->phi == nullptr);
-  if (device_profiles) {
-    if (!cols->adamp || !cols->vbroad || !cols->vel) { rhb200_set_error("phi == NULL needs adamp, vbroad and vel"); return RHB200_EINVAL; }
-    std::vector<int> prow_tr(pl->nphirow, -1), line_tr(pl->nline, -1);
-    for (int t = 0; t < Nt; t++) {
-      const double *tr = pl->trans + (size_t) t*RHB200_TR_NFIELD;
-      if (tr[RHB200_TR_TYPE] != 0.0) continue;
-      const int row0 = (int) tr[RHB200_TR_PHIROW], nrow = 2*Nr*(int) tr[RHB200_TR_NLAMBDA], li = (int) tr[RHB200_TR_LINEIDX];
-      if (row0 < 0 || row0 + nrow > pl->nphirow || li < 0 || li >= pl->nline || !(tr[RHB200_TR_LAMBDA0] > 0.0)) {
-        rhb200_set_error("transition %d: bad profile rows / line index / lambda0", t); return RHB200_EINVAL;
+    UPD(lambda, pl->lambda, Ns); UPD(muz, pl->muz, Nr); UPD(wmu, pl->wmu, Nr);
+    UPD(trans, pl->trans, (size_t) Nt*RHB200_TR_NFIELD);
+    UPD(tr_lambda, pl->tr_lambda, pl->ntrl); UPD(tr_wlambda, pl->tr_wlambda, pl->ntrl); UPD(tr_alpha, pl->tr_alpha, pl->ntrl);
+    UPI(atom_nlevel, pl->atom_nlevel, Na); UPI(lev_off, lev_off.data(), Na+1); UPI(gam_off, gam_off.data(), Na+1);
+    UPI(as_first, pl->as_first, Ns+1); UPI(as_trans, as_pack.data(), 2*(size_t) nas);
+    UPI(angle_dep, angle_dep.data(), Ns); UPI(ray_off, ray_off.data(), Ns+1);
+    UPI(ray_ns, ray_ns.data(), nray); UPI(ray_mu, ray_mu.data(), nray); UPI(ray_dir, ray_dir.data(), nray);
+    {                                            // profile-row and line-index maps (device-side Profile())
+      std::vector<int> prow_tr(std::max(1, nphirow), -1), line_tr(std::max(1, nline), -1);
+      bool ok = true;
+      for (int t = 0; t < Nt; t++) {
+        const double *tr = pl->trans + (size_t) t*RHB200_TR_NFIELD;
+        if (tr[RHB200_TR_TYPE] != 0.0) continue;
+        const int row0 = (int) tr[RHB200_TR_PHIROW], nrow = 2*Nr*(int) tr[RHB200_TR_NLAMBDA], li = (int) tr[RHB200_TR_LINEIDX];
+        if (row0 < 0 || row0 + nrow > nphirow || li < 0 || li >= nline) { rhb200_set_error("transition %d: bad profile rows / line index", t); return RHB200_EINVAL; }
+        if (!(tr[RHB200_TR_LAMBDA0] > 0.0)) ok = false;
+        for (int r = 0; r < nrow; r++) prow_tr[row0 + r] = t;
+        line_tr[li] = t;
       }
-      for (int r = 0; r < nrow; r++) prow_tr[row0 + r] = t;
-      line_tr[li] = t;
+      for (int r = 0; r < nphirow; r++) if (prow_tr[r] < 0) ok = false;
+      for (int l = 0; l < nline; l++) if (line_tr[l] < 0) ok = false;
+      profile_maps_ok = ok;
+      UPI(prow_tr, prow_tr.data(), prow_tr.size()); UPI(line_tr, line_tr.data(), line_tr.size());
     }
-    for (int v : prow_tr) if (v < 0) { rhb200_set_error("profile rows are not covered by the line transitions"); return RHB200_EINVAL; }
-    for (int v : line_tr) if (v < 0) { rhb200_set_error("line index table has holes"); return RHB200_EINVAL; }
-    UPI(prow_tr, prow_tr.data(), pl->nphirow); UPI(line_tr, line_tr.data(), pl->nline);
-    UPC(adamp, cols->adamp, cN*pl->nline); UPC(vbroad, cols->vbroad, cN*Na); UPC(vel, cols->vel, cN);
-    RH_CHECK(ar.alloc(&C.phi, cN*pl->nphirow)); RH_CHECK(ar.alloc(&C.wphi, cN*pl->nline));
-  } else {
-    if (!cols->wphi) { rhb200_set_error("wphi missing"); return RHB200_EINVAL; }
-    RH_CHECK(ar.upload(&C.phi, cols->phi, cN*pl->nphirow));
-    RH_CHECK(ar.upload(&C.wphi, cols->wphi, cN*pl->nline));
+#undef UPD
+#undef UPI
+    Norder = pl->Ngorder; Ndelay = std::max(pl->Ngdelay, Norder + 2); Nperiod = std::max(1, pl->Ngperiod);
+    prev_off.assign(Na+1, 0);
+    for (int a = 0; a < Na; a++) prev_off[a+1] = prev_off[a] + (size_t)(Norder+2) * pl->atom_nlevel[a] * N;
+    RH_CHECK(ar.upload(&d_prev_off, prev_off.data(), Na+1));
+    return RHB200_OK;
   }
-  UPC(chi_c, cols->chi_c, cN*Ns); UPC(eta_c, cols->eta_c, cN*Ns); UPC(sca_c, cols->sca_c, cN*Ns);
-  RH_CHECK(ar.upload(&C.n, cols->n, cN*nlev));
-  RH_CHECK(ar.upload(&C.J, cols->J, cN*Ns));
-  RH_CHECK(ar.alloc(&C.Gamma, cN*ngam)); RH_CHECK(ar.alloc(&C.Rij, cN*Nt, true)); RH_CHECK(ar.alloc(&C.Rji, cN*Nt, true));
-  RH_CHECK(ar.alloc(&C.gw, cN*nas*2));
-  RH_CHECK(ar.alloc(&C.chi, cN*nray)); RH_CHECK(ar.alloc(&C.S, cN*nray)); RH_CHECK(ar.alloc(&C.I, cN*nray));
-  RH_CHECK(ar.alloc(&C.Psi, cN*nray)); RH_CHECK(ar.alloc(&C.scr, cN*nray*2)); RH_CHECK(ar.alloc(&C.dJ, cN*Ns, true));
-  RH_CHECK(ar.alloc(&C.Iem, (size_t) ncol*nray, true));
-  int *d_active;
-  std::vector<int> active(ncol, 1);
-  RH_CHECK(ar.upload(&d_active, active.data(), ncol));
-  C.active = d_active;
+  bool profile_maps_ok = false;
 
-  // Ng storage: previous[col][atom][(Norder+2)][Nl*N]; NgInit copies the initial solution (accelerate.c:57-59)
-  const int Norder = pl->Ngorder, Ndelay = std::max(pl->Ngdelay, Norder + 2), Nperiod = std::max(1, pl->Ngperiod);
-  std::vector<size_t> prev_off(Na+1, 0);
-  for (int a = 0; a < Na; a++) prev_off[a+1] = prev_off[a] + (size_t)(Norder+2) * pl->atom_nlevel[a] * N;
-  double *d_prev; size_t *d_prev_off; double *d_dpops;
-  RH_CHECK(ar.alloc(&d_prev, (size_t) ncol * prev_off[Na], true));
-  RH_CHECK(ar.upload(&d_prev_off, prev_off.data(), Na+1));
-  RH_CHECK(ar.alloc(&d_dpops, (size_t) ncol * Na, true));
-  for (int col = 0; col < ncol; col++)
-    for (int a = 0; a < Na; a++)
-      RH_CUDA(cudaMemcpyAsync(d_prev + (size_t) col*prev_off[Na] + prev_off[a],
-                              C.n + ((size_t) col*nlev + lev_off[a])*N, (size_t) pl->atom_nlevel[a]*N*sizeof(double),
-                              cudaMemcpyDeviceToDevice, c->stream));
+  // doubles of device memory per column that alloc() takes (chunk sizing of the front end)
+  size_t doubles_per_column(bool own_inputs) const {
+    size_t d = (size_t) N * ((size_t) ngam + 2*(size_t) Nt + 2*(size_t) nas + 6*(size_t) nray + (size_t) Ns + nphirow + nline) + nray
+             + prev_off[Na] + Na;
+    if (own_inputs) d += (size_t) N * (2 + 2*(size_t) nlev + Na + ngam + nline + Na + 1 + 4*(size_t) Ns);
+    return d;
+  }
 
-  static int ray_minb = -1;
-  if (ray_minb < 0) { const char *e = getenv("RHB200_NLTE_RAY_MINB"); ray_minb = e ? atoi(e) : 8; }
-  auto launch_rays = [&](int eval_operator) {
+  // work arrays of one batch.  own_inputs: also the input arrays (the front end's kernels fill them on the device)
+  int alloc(int ncol_, bool device_profiles_, bool own_inputs) {
+    ncol = ncol_; device_profiles = device_profiles_;
+    if (ncol <= 0) { rhb200_set_error("rhb200_nlte: ncol must be positive"); return RHB200_EINVAL; }
+    if (device_profiles && !profile_maps_ok) { rhb200_set_error("profile rows / lambda0 of the line transitions are incomplete"); return RHB200_EINVAL; }
+    DevArena &ar = work_ar;
+    const size_t cN = (size_t) ncol * N;
+    RH_CHECK(ar.alloc(&C.phi, cN*nphirow)); RH_CHECK(ar.alloc(&C.wphi, cN*nline));
+    RH_CHECK(ar.alloc(&C.Gamma, cN*ngam)); RH_CHECK(ar.alloc(&C.Rij, cN*Nt, true)); RH_CHECK(ar.alloc(&C.Rji, cN*Nt, true));
+    RH_CHECK(ar.alloc(&C.gw, cN*nas*2));
+    RH_CHECK(ar.alloc(&C.chi, cN*nray)); RH_CHECK(ar.alloc(&C.S, cN*nray)); RH_CHECK(ar.alloc(&C.I, cN*nray));
+    RH_CHECK(ar.alloc(&C.Psi, cN*nray)); RH_CHECK(ar.alloc(&C.scr, cN*nray*2)); RH_CHECK(ar.alloc(&C.dJ, cN*Ns, true));
+    RH_CHECK(ar.alloc(&C.Iem, (size_t) ncol*nray, true));
+    active.assign(ncol, 1);
+    RH_CHECK(ar.upload(&d_active, active.data(), ncol));
+    C.active = d_active;
+    RH_CHECK(ar.alloc(&d_prev, (size_t) ncol * prev_off[Na], true));
+    RH_CHECK(ar.alloc(&d_dpops, (size_t) ncol * Na, true));
+    RH_CHECK(ar.alloc(&d_dJmax, ncol, true));
+    if (own_inputs) {
+      double *dd;
+#define OWN(field, n) RH_CHECK(ar.alloc(&dd, (size_t) (n))); C.field = dd
+      OWN(T, cN); OWN(height, cN); OWN(nstar, cN*nlev); OWN(ntotal, cN*Na); OWN(C, cN*ngam);
+      OWN(adamp, cN*nline); OWN(vbroad, cN*Na); OWN(vel, cN);
+      OWN(chi_c, cN*Ns); OWN(eta_c, cN*Ns); OWN(sca_c, cN*Ns);
+#undef OWN
+      RH_CHECK(ar.alloc(&C.n, cN*nlev)); RH_CHECK(ar.alloc(&C.J, cN*Ns, true));
+    }
+    return RHB200_OK;
+  }
+
+  int bind_host(const rhb200_nlte_columns *cols) {
+    DevArena &ar = work_ar;
+    const size_t cN = (size_t) ncol * N;
+    double *dd;
+#define UPC(field, src, n) RH_CHECK(ar.upload(&dd, src, (size_t) (n))); C.field = dd
+    UPC(T, cols->T, cN); UPC(height, cols->height, cN);
+    UPC(nstar, cols->nstar, cN*nlev); UPC(ntotal, cols->ntotal, cN*Na); UPC(C, cols->C, cN*ngam);
+    if (device_profiles) {
+      if (!cols->adamp || !cols->vbroad || !cols->vel) { rhb200_set_error("phi == NULL needs adamp, vbroad and vel"); return RHB200_EINVAL; }
+      UPC(adamp, cols->adamp, cN*nline); UPC(vbroad, cols->vbroad, cN*Na); UPC(vel, cols->vel, cN);
+    } else {
+      if (!cols->wphi) { rhb200_set_error("wphi missing"); return RHB200_EINVAL; }
+      RH_CUDA(cudaMemcpy(C.phi, cols->phi, cN*nphirow*sizeof(double), cudaMemcpyHostToDevice));
+      RH_CUDA(cudaMemcpy(C.wphi, cols->wphi, cN*nline*sizeof(double), cudaMemcpyHostToDevice));
+    }
+    UPC(chi_c, cols->chi_c, cN*Ns); UPC(eta_c, cols->eta_c, cN*Ns); UPC(sca_c, cols->sca_c, cN*Ns);
+#undef UPC
+    RH_CHECK(ar.upload(&C.n, cols->n, cN*nlev));
+    RH_CHECK(ar.upload(&C.J, cols->J, cN*Ns));
+    return RHB200_OK;
+  }
+
+  void launch_rays(int eval_operator) {
+    static int ray_minb = -1;
+    if (ray_minb < 0) { const char *e = getenv("RHB200_NLTE_RAY_MINB"); ray_minb = e ? atoi(e) : 8; }
     const unsigned blocks = (unsigned) (((size_t) ncol*nray + 127) / 128);
 #define RH_RAYS(S, M) nlte_ray_kernel<S, M><<<blocks, 128, 0, c->stream>>>(P, C, ncol, eval_operator)
 #define RH_RAYS_M(S) do { if (ray_minb >= 8) RH_RAYS(S, 8); else if (ray_minb >= 6) RH_RAYS(S, 6); else RH_RAYS(S, 4); } while (0)
     if (P.solver == RHB200_S_LINEAR) RH_RAYS_M(RHB200_S_LINEAR);
     else if (P.solver == RHB200_S_PARABOLIC) RH_RAYS_M(RHB200_S_PARABOLIC);
     else RH_RAYS_M(RHB200_S_BEZIER3);
-  };
-  cudaStream_t st = c->stream;
-  if (device_profiles) {
-    { ScopedKernelTimer t(c, RHB200_K_PREP);
-      nlte_profile_kernel<<<RH_GRID(cN*pl->nphirow, 128), 0, st>>>(P, C, ncol); }
-    { ScopedKernelTimer t(c, RHB200_K_PREP);
-      nlte_wphi_kernel<<<RH_GRID(cN*pl->nline, 64), 0, st>>>(P, C, ncol); }
-    RH_CUDA(cudaGetLastError());
-    if (phi_out) {
-      RH_CUDA(cudaStreamSynchronize(st));
-      RH_CUDA(cudaMemcpy(phi_out, C.phi, cN*pl->nphirow*sizeof(double), cudaMemcpyDeviceToHost));
-    }
-    if (wphi_out) {
-      RH_CUDA(cudaStreamSynchronize(st));
-      RH_CUDA(cudaMemcpy(wphi_out, C.wphi, cN*pl->nline*sizeof(double), cudaMemcpyDeviceToHost));
-    }
+#undef RH_RAYS_M
+#undef RH_RAYS
   }
-  { ScopedKernelTimer t(c, RHB200_K_OTHER);
-    nlte_setup_kernel<<<RH_GRID(cN*nas, 128), 0, st>>>(P, C, ncol); }
-  RH_CUDA(cudaGetLastError());
 
-  // ---- initScatter (initscatter.c:62-68) / final formal pass: solveSpectrum(FALSE, FALSE) repeated
-  std::vector<int> nscat(ncol, 0);
-  if (NmaxScatter > 0) {
-    double *d_dJmax;
-    RH_CHECK(ar.alloc(&d_dJmax, ncol, true));
+  // Profile() + wphi (when evaluated here), the per-entry weights, NgInit (accelerate.c:57-59)
+  int prepare(double *phi_out, double *wphi_out, bool ng_init) {
+    cudaStream_t st = c->stream;
+    const size_t cN = (size_t) ncol * N;
+    if (device_profiles) {
+      { ScopedKernelTimer t(c, RHB200_K_PREP);
+        nlte_profile_kernel<<<RH_GRID(cN*nphirow, 128), 0, st>>>(P, C, ncol); }
+      { ScopedKernelTimer t(c, RHB200_K_PREP);
+        nlte_wphi_kernel<<<RH_GRID(cN*nline, 64), 0, st>>>(P, C, ncol); }
+      RH_CUDA(cudaGetLastError());
+      if (phi_out) {
+        RH_CUDA(cudaStreamSynchronize(st));
+        RH_CUDA(cudaMemcpy(phi_out, C.phi, cN*nphirow*sizeof(double), cudaMemcpyDeviceToHost));
+      }
+      if (wphi_out) {
+        RH_CUDA(cudaStreamSynchronize(st));
+        RH_CUDA(cudaMemcpy(wphi_out, C.wphi, cN*nline*sizeof(double), cudaMemcpyDeviceToHost));
+      }
+    }
+    { ScopedKernelTimer t(c, RHB200_K_OTHER);
+      nlte_setup_kernel<<<RH_GRID(cN*nas, 128), 0, st>>>(P, C, ncol); }
+    RH_CUDA(cudaGetLastError());
+    if (ng_init)
+      for (int col = 0; col < ncol; col++)
+        for (int a = 0; a < Na; a++)
+          RH_CUDA(cudaMemcpyAsync(d_prev + (size_t) col*prev_off[Na] + prev_off[a],
+                                  C.n + ((size_t) col*nlev + lev_off[a])*N, (size_t) nlevel[a]*N*sizeof(double),
+                                  cudaMemcpyDeviceToDevice, st));
+    return RHB200_OK;
+  }
+
+  // solveSpectrum(FALSE, FALSE) repeated: initScatter (update_J 1), the passes after Iterate() (2), the final formal
+  // solution (0).  Iem_host [ncol][Ns][Nr] or NULL; d_Iem_spec: device [ncol][Ns] emergent intensity of ray mu = 0 or NULL
+  int scatter(int NmaxScatter, int update_J, double limit, int *nscat_out, double *Iem_host, double *d_Iem_spec) {
+    cudaStream_t st = c->stream;
+    const size_t cN = (size_t) ncol * N;
+    std::vector<int> nscat(ncol, 0);
     std::vector<double> h_dJ(ncol, 0.0);
     std::vector<int> act(ncol, 1);
     int nact_s = ncol;
@@ -861,81 +924,121 @@ static int nlte_run(rhb200_ctx *c, const rhb200_nlte_plan *pl, int ncol,
         if (!act[col]) continue;
         nscat[col] = it + 1;
         // initscatter.c:65 stops on dJmax < limit; the post-Iterate loop of rhf1d() on <= (pyrh_compute1dray.c:335)
-        if (!update_J || (update_J == 2 ? h_dJ[col] <= iterLimit : h_dJ[col] < iterLimit)) { act[col] = 0; nact_s--; changed = true; }
+        if (!update_J || (update_J == 2 ? h_dJ[col] <= limit : h_dJ[col] < limit)) { act[col] = 0; nact_s--; changed = true; }
       }
       if (changed && nact_s > 0) RH_CUDA(cudaMemcpyAsync(d_active, act.data(), ncol*sizeof(int), cudaMemcpyHostToDevice, st));
     }
-    RH_CUDA(cudaStreamSynchronize(st));
-    RH_CUDA(cudaMemcpyAsync(d_active, active.data(), ncol*sizeof(int), cudaMemcpyHostToDevice, st));   // all columns active again
-    if (Iem_out) {
-      // emergent intensity per (column, wavelength, mu): the up-ray of angle-dependent wavelengths
-      std::vector<double> h_Iem((size_t) ncol*nray);
-      RH_CHECK(allreduce(C.Iem, (size_t) ncol*nray, RHB200_REDUCE_SUM));     // foreign rays hold 0
+    if (NmaxScatter > 0) {
       RH_CUDA(cudaStreamSynchronize(st));
-      RH_CUDA(cudaMemcpy(h_Iem.data(), C.Iem, h_Iem.size()*sizeof(double), cudaMemcpyDeviceToHost));
-      for (int col = 0; col < ncol; col++)
-        for (int r = 0; r < nray; r++)
-          if (!angle_dep[ray_ns[r]] || ray_dir[r] == 1)
-            Iem_out[((size_t) col*Ns + ray_ns[r])*Nr + ray_mu[r]] = h_Iem[(size_t) col*nray + r];
-    }
-  }
-  if (nscatter_out) memcpy(nscatter_out, nscat.data(), ncol*sizeof(int));
-
-  std::vector<double> h_dpops((size_t) ncol * Na);
-  std::vector<int> niter(ncol, 0);
-  int nactive = ncol;
-  for (int it = 1; it <= NmaxIter && nactive > 0; it++) {
-    { ScopedKernelTimer t(c, RHB200_K_OTHER);
-      nlte_gamma_init_kernel<<<RH_GRID(cN*ngam, 256), 0, st>>>(P, C, ncol); }
-    { ScopedKernelTimer t(c, RHB200_K_OPACITY);
-      nlte_opacity_kernel<<<(unsigned) (((cN + 127) / 128) * Ns), 128, 0, st>>>(P, C, ncol); }
-    { ScopedKernelTimer t(c, RHB200_K_BEZIER);
-      launch_rays(1); }
-    { ScopedKernelTimer t(c, RHB200_K_OTHER);
-      nlte_gamma_kernel<<<dim3((unsigned) ((cN + 63) / 64), (unsigned) Nt), 64, 0, st>>>(P, C, ncol); }
-    { ScopedKernelTimer t(c, RHB200_K_OTHER);
-      nlte_J_kernel<<<RH_GRID(cN*Ns, 128), 0, st>>>(P, C, ncol); }
-    // the exchange step of a wavelength-sharded atmosphere: radiative rates add up over ranks
-    RH_CHECK(allreduce(C.Gamma, cN*ngam, RHB200_REDUCE_SUM));
-    RH_CHECK(allreduce(C.Rij, cN*Nt, RHB200_REDUCE_SUM));
-    RH_CHECK(allreduce(C.Rji, cN*Nt, RHB200_REDUCE_SUM));
-    if (it == dump_iter) {
-      RH_CUDA(cudaStreamSynchronize(st));
-      if (gamma_dump) RH_CUDA(cudaMemcpy(gamma_dump, C.Gamma, cN*ngam*sizeof(double), cudaMemcpyDeviceToHost));
-      if (rates_dump) {
-        RH_CUDA(cudaMemcpy(rates_dump, C.Rij, cN*Nt*sizeof(double), cudaMemcpyDeviceToHost));
-        RH_CUDA(cudaMemcpy(rates_dump + cN*Nt, C.Rji, cN*Nt*sizeof(double), cudaMemcpyDeviceToHost));
+      std::vector<int> all(ncol, 1);
+      RH_CUDA(cudaMemcpy(d_active, all.data(), ncol*sizeof(int), cudaMemcpyHostToDevice));   // all columns active again
+      if (Iem_host) {
+        // emergent intensity per (column, wavelength, mu): the up-ray of angle-dependent wavelengths
+        std::vector<double> h_Iem((size_t) ncol*nray);
+        RH_CHECK(allreduce(C.Iem, (size_t) ncol*nray, RHB200_REDUCE_SUM));     // foreign rays hold 0
+        RH_CUDA(cudaStreamSynchronize(st));
+        RH_CUDA(cudaMemcpy(h_Iem.data(), C.Iem, h_Iem.size()*sizeof(double), cudaMemcpyDeviceToHost));
+        for (int col = 0; col < ncol; col++)
+          for (int r = 0; r < nray; r++)
+            if (!angle_dep[ray_ns[r]] || ray_dir[r] == 1)
+              Iem_host[((size_t) col*Ns + ray_ns[r])*Nr + ray_mu[r]] = h_Iem[(size_t) col*nray + r];
+      }
+      if (d_Iem_spec) {
+        nlte_pack_spectrum_kernel<<<RH_GRID((size_t) ncol*Ns, 128), 0, st>>>(P, C, ncol, d_Iem_spec);
+        RH_CUDA(cudaGetLastError());
       }
     }
-    { ScopedKernelTimer t(c, RHB200_K_OTHER);
-      if (maxnl <= 8) nlte_statequil_kernel<8><<<RH_GRID(cN*Na, 64), 0, st>>>(P, C, ncol, pl->isum);
-      else if (maxnl <= 16) nlte_statequil_kernel<16><<<RH_GRID(cN*Na, 64), 0, st>>>(P, C, ncol, pl->isum);
-      else nlte_statequil_kernel<32><<<RH_GRID(cN*Na, 64), 0, st>>>(P, C, ncol, pl->isum); }
-    { ScopedKernelTimer t(c, RHB200_K_OTHER);
-      nlte_ng_kernel<<<ncol*Na, 128, 0, st>>>(P, C, ncol, d_prev, d_prev_off, Norder, Ndelay, Nperiod, it, d_dpops); }
-    RH_CUDA(cudaGetLastError());
-    RH_CUDA(cudaMemcpyAsync(h_dpops.data(), d_dpops, h_dpops.size()*sizeof(double), cudaMemcpyDeviceToHost, st));
-    RH_CUDA(cudaStreamSynchronize(st));
-    bool changed = false;
-    for (int col = 0; col < ncol; col++) {
-      if (!active[col]) continue;
-      double d = 0.0;
-      for (int a = 0; a < Na; a++) d = std::max(d, h_dpops[(size_t) col*Na + a]);
-      niter[col] = it;
-      if (dpops_hist) dpops_hist[(size_t) col*NmaxIter + it-1] = d;
-      if (d < iterLimit) { active[col] = 0; nactive--; changed = true; }     // iterate.c:114
+    if (nscat_out) memcpy(nscat_out, nscat.data(), ncol*sizeof(int));
+    return RHB200_OK;
+  }
+
+  // Iterate(): the MALI loop (iterate.c:48-143)
+  int iterate(int NmaxIter, double iterLimit, int *niter_out, double *dpops_hist, int dump_iter,
+              double *gamma_dump, double *rates_dump) {
+    cudaStream_t st = c->stream;
+    const size_t cN = (size_t) ncol * N;
+    std::vector<double> h_dpops((size_t) ncol * Na);
+    std::vector<int> niter(ncol, 0);
+    active.assign(ncol, 1);
+    int nactive = ncol;
+    for (int it = 1; it <= NmaxIter && nactive > 0; it++) {
+      { ScopedKernelTimer t(c, RHB200_K_OTHER);
+        nlte_gamma_init_kernel<<<RH_GRID(cN*ngam, 256), 0, st>>>(P, C, ncol); }
+      { ScopedKernelTimer t(c, RHB200_K_OPACITY);
+        nlte_opacity_kernel<<<(unsigned) (((cN + 127) / 128) * Ns), 128, 0, st>>>(P, C, ncol); }
+      { ScopedKernelTimer t(c, RHB200_K_BEZIER);
+        launch_rays(1); }
+      { ScopedKernelTimer t(c, RHB200_K_OTHER);
+        nlte_gamma_kernel<<<dim3((unsigned) ((cN + 63) / 64), (unsigned) Nt), 64, 0, st>>>(P, C, ncol); }
+      { ScopedKernelTimer t(c, RHB200_K_OTHER);
+        nlte_J_kernel<<<RH_GRID(cN*Ns, 128), 0, st>>>(P, C, ncol); }
+      // the exchange step of a wavelength-sharded atmosphere: radiative rates add up over ranks
+      RH_CHECK(allreduce(C.Gamma, cN*ngam, RHB200_REDUCE_SUM));
+      RH_CHECK(allreduce(C.Rij, cN*Nt, RHB200_REDUCE_SUM));
+      RH_CHECK(allreduce(C.Rji, cN*Nt, RHB200_REDUCE_SUM));
+      if (it == dump_iter) {
+        RH_CUDA(cudaStreamSynchronize(st));
+        if (gamma_dump) RH_CUDA(cudaMemcpy(gamma_dump, C.Gamma, cN*ngam*sizeof(double), cudaMemcpyDeviceToHost));
+        if (rates_dump) {
+          RH_CUDA(cudaMemcpy(rates_dump, C.Rij, cN*Nt*sizeof(double), cudaMemcpyDeviceToHost));
+          RH_CUDA(cudaMemcpy(rates_dump + cN*Nt, C.Rji, cN*Nt*sizeof(double), cudaMemcpyDeviceToHost));
+        }
+      }
+      { ScopedKernelTimer t(c, RHB200_K_OTHER);
+        if (maxnl <= 8) nlte_statequil_kernel<8><<<RH_GRID(cN*Na, 64), 0, st>>>(P, C, ncol, isum);
+        else if (maxnl <= 16) nlte_statequil_kernel<16><<<RH_GRID(cN*Na, 64), 0, st>>>(P, C, ncol, isum);
+        else nlte_statequil_kernel<32><<<RH_GRID(cN*Na, 64), 0, st>>>(P, C, ncol, isum); }
+      { ScopedKernelTimer t(c, RHB200_K_OTHER);
+        nlte_ng_kernel<<<ncol*Na, 128, 0, st>>>(P, C, ncol, d_prev, d_prev_off, Norder, Ndelay, Nperiod, it, d_dpops); }
+      RH_CUDA(cudaGetLastError());
+      RH_CUDA(cudaMemcpyAsync(h_dpops.data(), d_dpops, h_dpops.size()*sizeof(double), cudaMemcpyDeviceToHost, st));
+      RH_CUDA(cudaStreamSynchronize(st));
+      bool changed = false;
+      for (int col = 0; col < ncol; col++) {
+        if (!active[col]) continue;
+        double d = 0.0;
+        for (int a = 0; a < Na; a++) d = std::max(d, h_dpops[(size_t) col*Na + a]);
+        niter[col] = it;
+        if (dpops_hist) dpops_hist[(size_t) col*NmaxIter + it-1] = d;
+        if (d < iterLimit) { active[col] = 0; nactive--; changed = true; }     // iterate.c:114
+      }
+      if (changed) RH_CUDA(cudaMemcpyAsync(d_active, active.data(), ncol*sizeof(int), cudaMemcpyHostToDevice, st));
     }
-    if (changed) RH_CUDA(cudaMemcpyAsync(d_active, active.data(), ncol*sizeof(int), cudaMemcpyHostToDevice, st));
+    if (nrank > 1) {                                   // every rank returns the full J
+      nlte_zero_foreign_J_kernel<<<RH_GRID(cN*Ns, 256), 0, st>>>(P, C, ncol);
+      RH_CUDA(cudaGetLastError());
+      RH_CHECK(allreduce(C.J, cN*Ns, RHB200_REDUCE_SUM));
+    }
+    RH_CUDA(cudaStreamSynchronize(st));
+    {                                                  // frozen columns thaw: later passes treat every column
+      std::vector<int> all(ncol, 1);
+      RH_CUDA(cudaMemcpy(d_active, all.data(), ncol*sizeof(int), cudaMemcpyHostToDevice));
+    }
+    if (niter_out) memcpy(niter_out, niter.data(), ncol*sizeof(int));
+    return RHB200_OK;
   }
-  if (nrank > 1) {                                   // every rank returns the full J
-    nlte_zero_foreign_J_kernel<<<RH_GRID(cN*Ns, 256), 0, st>>>(P, C, ncol);
-    RH_CUDA(cudaGetLastError());
-    RH_CHECK(allreduce(C.J, cN*Ns, RHB200_REDUCE_SUM));
-  }
-  RH_CUDA(cudaStreamSynchronize(st));
-  RH_CUDA(cudaMemcpy(cols->n, C.n, cN*nlev*sizeof(double), cudaMemcpyDeviceToHost));
-  RH_CUDA(cudaMemcpy(cols->J, C.J, cN*Ns*sizeof(double), cudaMemcpyDeviceToHost));
-  if (niter_out) memcpy(niter_out, niter.data(), ncol*sizeof(int));
+};
+
+static int nlte_run(rhb200_ctx *c, const rhb200_nlte_plan *pl, int ncol,
+                    const rhb200_nlte_columns *cols, int NmaxScatter, int update_J, int NmaxIter, double iterLimit,
+                    int *niter_out, double *dpops_hist, int dump_iter,
+                    double *gamma_dump, double *rates_dump, double *phi_out, double *wphi_out,
+                    double *Iem_out, int *nscatter_out)
+{
+  if (!c || !pl || !cols) { rhb200_set_error("null argument"); return RHB200_EINVAL; }
+  RH_CUDA(cudaSetDevice(c->device));
+  if (NmaxIter < 0) { rhb200_set_error("rhb200_nlte_iterate: bad sizes"); return RHB200_EINVAL; }
+  NlteEngine E;
+  RH_CHECK(E.build(c, pl));
+  RH_CHECK(E.alloc(ncol, cols->phi == nullptr, false));
+  RH_CHECK(E.bind_host(cols));
+  RH_CHECK(E.prepare(phi_out, wphi_out, true));
+  RH_CHECK(E.scatter(NmaxScatter, update_J, iterLimit, nscatter_out, Iem_out, nullptr));
+  RH_CHECK(E.iterate(NmaxIter, iterLimit, niter_out, dpops_hist, dump_iter, gamma_dump, rates_dump));
+  const size_t cN = (size_t) ncol * E.N;
+  RH_CUDA(cudaStreamSynchronize(c->stream));
+  RH_CUDA(cudaMemcpy(cols->n, E.C.n, cN*E.nlev*sizeof(double), cudaMemcpyDeviceToHost));
+  RH_CUDA(cudaMemcpy(cols->J, E.C.J, cN*E.Ns*sizeof(double), cudaMemcpyDeviceToHost));
   return RHB200_OK;
 }
 
@@ -994,3 +1097,5 @@ extern "C" int rhb200_nlte_formal(rhb200_ctx *c, const rhb200_nlte_plan *pl, int
   return nlte_run(c, pl, ncol, cols, npass, update_J, 0, dJlimit, nullptr, nullptr, 0, nullptr, nullptr,
                   nullptr, nullptr, Iem, npass_done);
 }
+
+#include "rhb200_nlte_front.cuh"

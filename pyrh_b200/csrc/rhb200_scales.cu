@@ -97,9 +97,10 @@ proton_kernel(int ncol, int ndep, int nlev, int proton_level, const double *__re
 // wavelength (spectrum.chi_c_lam[ref_index], readj.c:319: the last record written for that wavelength, i.e.
 // continuum + lines of the up-ray), read from the ray-point records of wavelength iref.
 // scratch [ncol][2][ndep] keeps tau_ref and cmass; scales_out [ncol][3][ndep] = height, tau_ref, cmass.
-__global__ void scales_kernel(int ncol, int ndep, int nlambda, int iref, int atm_scale, double wght_per_H,
+__global__ void scales_kernel(int ncol, int ndep, int atm_scale, double wght_per_H,
                               double total_abund, double gravity,
-                              const double *__restrict__ raypts, double *__restrict__ atmos,
+                              const double *__restrict__ chi_ref, size_t chi_col_stride, size_t chi_k_stride,
+                              double *__restrict__ atmos,
                               double *__restrict__ scratch, double *__restrict__ scales_out)
 {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
@@ -107,9 +108,9 @@ __global__ void scales_kernel(int ncol, int ndep, int nlambda, int iref, int atm
   const double *at = atmos + (size_t) col * RHB200_AT_NFIELD * ndep;
   double *height = atmos + ((size_t) col * RHB200_AT_NFIELD + RHB200_AT_HEIGHT) * ndep;
   const double *nHtot = at + (size_t) RHB200_AT_NHTOT * ndep;
-  const double *rp = raypts + ((size_t) col * nlambda + iref) * ndep * RP_NFIELD + RP_CHI;
+  const double *rp = chi_ref + (size_t) col * chi_col_stride;
   double *tau = scratch + (size_t) col * 2 * ndep, *cmass = tau + ndep;
-#define CHI(k) rp[(size_t) (k) * RP_NFIELD]
+#define CHI(k) rp[(size_t) (k) * chi_k_stride]
 #define RHO(k) ((RH_AMU * wght_per_H) * nHtot[k])
   if (atm_scale == 0) {                                  // TAU500, multiatmos.c:140-151; height row holds tau_ref
     double tprev = height[0], hprev = 0.0;
@@ -255,8 +256,22 @@ int rh_launch_scales(rhb200_ctx *c, int ncol, int ndep, int iref, int atm_scale,
 {
   if (atm_scale == 2 && !d_scales_out) return RHB200_OK; // GEOMETRIC: the heights are the input
   ScopedKernelTimer t(c, RHB200_K_PREP);
-  scales_kernel<<<(unsigned) ((ncol + 31) / 32), 32, 0, c->stream>>>(ncol, ndep, c->wav.nlambda, iref, atm_scale, wght_per_H,
-                                                                    total_abund, gravity, d_raypts, d_atmos, d_scratch, d_scales_out);
+  scales_kernel<<<(unsigned) ((ncol + 31) / 32), 32, 0, c->stream>>>(ncol, ndep, atm_scale, wght_per_H, total_abund, gravity,
+      d_raypts + (size_t) iref * ndep * RP_NFIELD + RP_CHI, (size_t) c->wav.nlambda * ndep * RP_NFIELD, (size_t) RP_NFIELD,
+      d_atmos, d_scratch, d_scales_out);
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}
+
+// the same with the reference-wavelength opacity read from a plain [ncol][nlambda][ndep] array (NLTE: spectrum.chi_c_lam)
+int rh_launch_scales_chi(rhb200_ctx *c, int ncol, int ndep, int nlambda, int iref, int atm_scale, double wght_per_H,
+                         double total_abund, double gravity,
+                         const double *d_chi_c, double *d_atmos, double *d_scratch, double *d_scales_out)
+{
+  if (atm_scale == 2 && !d_scales_out) return RHB200_OK;
+  ScopedKernelTimer t(c, RHB200_K_PREP);
+  scales_kernel<<<(unsigned) ((ncol + 31) / 32), 32, 0, c->stream>>>(ncol, ndep, atm_scale, wght_per_H, total_abund, gravity,
+      d_chi_c + (size_t) iref * ndep, (size_t) nlambda * ndep, (size_t) 1, d_atmos, d_scratch, d_scales_out);
   RH_CUDA(cudaGetLastError());
   return RHB200_OK;
 }

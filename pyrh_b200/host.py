@@ -26,6 +26,7 @@ import math
 import os
 import re
 import struct
+from collections import OrderedDict
 from dataclasses import dataclass
 from pathlib import Path
 
@@ -611,16 +612,19 @@ def read_atom_lines(atom_file):
     return a["ID"], [(a["stage"][ln["i"]], ln["lambda0"], ln["qwing"]) for ln in a["lines"]]
 
 
-def passive_line_table(cwd, kw, el: Elements, level_first, path=None):
+def passive_line_table(cwd, kw, el: Elements, level_first, path=None, status="PASSIVE"):
     """Device table of the bound-bound lines of the PASSIVE model atoms (passive_bb, metal.c:174-344) with the
     depth-independent factors of Damping() (broad.c:60-314) evaluated here: rows [nline, PL_NFIELD] in the reference's
     order (atoms, then lines), component shifts and fractions.  ``level_first[a]`` = row of atom a's first level in
-    the population table."""
+    the population table.  ``status`` = "ACTIVE" gives the same table for the lines of the ACTIVE atoms (Damping() of
+    getProfiles, profile.c:112)."""
     atoms_dir = pyrh_path(path) / "rh" / "Atoms"
     rows, cs, cf = [], [], []
     FOURPIEPS0 = 4.0 * PI * EPSILON_0
     H_weight, He_weight, He_abund = el.weight[0], el.weight[1], el.abund[1]
-    for a, (fname, _) in enumerate(_atoms_listed(cwd, kw)):
+    for a, (fname, st) in enumerate(_atoms_listed(cwd, kw)):
+        if (st == "ACTIVE") != (status == "ACTIVE"):
+            continue
         at = read_atom(atoms_dir / fname)
         e = el.ID.index(at["ID"])
         weight, E, stage = el.weight[e], at["E"], at["stage"]
@@ -876,28 +880,29 @@ def molecular_line_table(cwd, kw, el: Elements, path=None):
     return np.array(rows).reshape(-1, ML_NFIELD), np.array(sel).reshape(-1, MS_NFIELD)
 
 
-def read_background_model(cwd, kw, el: Elements, path=None):
+def read_background_model(cwd, kw, el: Elements, path=None, allow_active=False):
     """The flat background model the device continuum / chemistry kernels take (rhb200_continuum_model,
     rhb200_set_chemistry) from the *.atom and *.molecule files of the working directory's lists: level table,
     bound-free edges with their cross-section tables, the Rayleigh lines of H and He, the chemical network.  The
     published opacity tables RH keeps in its source (H-, H2-, H2+, OH, CH) come from data/background_falc11.npz."""
     root = pyrh_path(path) / "rh"
     listed = _atoms_listed(cwd, kw)
-    if any(s != "PASSIVE" for _, s in listed):
-        raise NotImplementedError("ACTIVE atoms: use pyrh_b200.nlte (the NLTE entry points take the parsed problem)")
+    if any(s != "PASSIVE" for _, s in listed) and not allow_active:
+        raise NotImplementedError("ACTIVE atoms: this is the LTE session (host.compute1d routes such directories to NlteSession)")
     tabs = {k: v for k, v in np.load(DATA / "background_falc11.npz").items() if k.startswith("tab_")}
     lev, bf, tl, ta, ray, pt, atoms = [], [], [], [], [], [], []
     l0 = 0
-    for m, (fname, _) in enumerate(listed):
+    for m, (fname, st) in enumerate(listed):
         at = read_atom(root / "Atoms" / fname)
         if m == 0 and at["ID"] != "H ":
             raise ValueError("First atomic model is not hydrogen (readatom.c:845-849)")
         atoms.append(at)
         pt.append(el.ID.index(at["ID"]) + 1)
+        act = float(st == "ACTIVE")                              # Metal_bf / Hydrogen_bf skip ACTIVE atoms (metal.c:105, hydrogen.c:179)
         for i in range(len(at["E"])):
-            lev.append([m, at["E"][i], at["stage"][i], at["g"][i], 0.0])
+            lev.append([m, at["E"][i], at["stage"][i], at["g"][i], act])
         for j, i, alpha0, hyd, lambda0, lam, alp in read_atom_continua(root / "Atoms" / fname, at):
-            bf.append([m, l0 + i, l0 + j, lambda0, lam[0], hyd, alpha0, len(lam), len(tl), 0.0])
+            bf.append([m, l0 + i, l0 + j, lambda0, lam[0], hyd, alpha0, len(lam), len(tl), act])
             tl += lam; ta += alp
         if m < 2:                                                # Rayleigh(): lines from the ground level of H and He
             for ln in at["lines"]:
@@ -924,8 +929,9 @@ def read_background_model(cwd, kw, el: Elements, path=None):
             r[16 + j], r[20 + j] = nuc_elems.index(e), cnt
         r[24], r[25], r[26] = mo["ID"] == "H2", mo["ID"] == "OH", mo["ID"] == "CH"
     ids = [mo["ID"] for mo in mols]
-    hdr = np.array([len(listed), len(lev), len(bf), len(tl), len(ray), 0.0, float(len(pt) > 1 and pt[1] == 2),
-                    float("OH" in ids), float("CH" in ids), float("H2" in ids), 0.0, float(kw["VMICRO_CHAR"]) * 1.0E+03, 0.0,
+    any_active = any(st == "ACTIVE" for _, st in listed)
+    hdr = np.array([len(listed), len(lev), len(bf), len(tl), len(ray), float(listed[0][1] == "ACTIVE"), float(len(pt) > 1 and pt[1] == 2),
+                    float("OH" in ids), float("CH" in ids), float("H2" in ids), float(any_active), float(kw["VMICRO_CHAR"]) * 1.0E+03, 0.0,
                     len(atoms[0]["E"]), 1.0, 1.0])
     out = dict(ct_hdr=hdr, ct_lev=np.array(lev), ct_bf=np.array(bf).reshape(-1, 10), ct_tab_lambda=np.array(tl),
                ct_tab_alpha=np.array(ta), ct_ray=np.array(ray).reshape(-1, 8), ce_nuclei=np.array(nuclei, np.float64),
@@ -1138,38 +1144,104 @@ def get_ne_from_nH(cwd, atm_scale, scale, temperature, nH, device=0):
     return np.array([x * CUBE_CM for x in ne])                                       # pyrh_hse.c:647
 
 
-_SESSIONS: dict = {}
+_SESSIONS: OrderedDict = OrderedDict()   # per-process LRU of resident sessions (bounded: MAX_SESSIONS)
+MAX_SESSIONS = 4
 
 
-def _session_key(cwd, wave, extra):
-    st = []
-    for f in ("keyword.input", "atoms.input", "kurucz.input"):
-        p = Path(cwd) / f
-        st.append((f, p.stat().st_mtime_ns if p.exists() else 0))
-    return (str(Path(cwd).resolve()), tuple(st), np.asarray(wave, np.float64).tobytes(), extra)
+class Populations:
+    """pyrh.pyx:170-176: what compute1d(get_populations=True) returns per ACTIVE atom."""
+
+    def __init__(self, ID, nlevel, nz, n, nstar):
+        self.ID, self.nlevel, self.nz, self.n, self.nstar = ID, nlevel, nz, n, nstar
+
+
+def _input_files(cwd, kw, path=None):
+    """Every file a session reads: a change of any of them (or of PYRH_PATH) must not hit a stale session."""
+    cwd = Path(cwd)
+    files = [cwd / "keyword.input", cwd / kw["ATOMS_FILE"], cwd / kw["MOLECULES_FILE"]]
+    root = pyrh_path(path) / "rh"
+    files += [Path(kw.get("ABUND_FILE") or root / "Atoms" / "abundance.input"),
+              Path(kw.get("KURUCZ_PF_DATA") or root / "Atoms" / "pf_Kurucz.input")]
+    if kw["KURUCZ_DATA"].lower() != "none" and (cwd / kw["KURUCZ_DATA"]).exists():
+        files.append(cwd / kw["KURUCZ_DATA"])
+        for ln in (cwd / kw["KURUCZ_DATA"]).read_text().splitlines():
+            if ln.strip() and ln[0] != "#":
+                files.append(cwd / ln.split()[0])
+    files += [root / "Atoms" / f for f, _ in _atoms_listed(cwd, kw)]
+    if files[2].exists():
+        for ln in files[2].read_text().splitlines():
+            f = ln.split("#", 1)[0].split()
+            if len(f) >= 2 and f[0].endswith(".molecule"):
+                files.append(root / "Molecules" / f[0])
+    return files
+
+
+def _session_key(cwd, wave, extra, path=None):
+    kw = read_keywords(cwd)
+    st = tuple((str(p), p.stat().st_mtime_ns if p.exists() else 0) for p in _input_files(cwd, kw, path))
+    return (str(Path(cwd).resolve()), str(pyrh_path(path)), st, np.asarray(wave, np.float64).tobytes(), extra)
+
+
+def close_sessions():
+    """Release every cached session (GPU context, device tables, page-locked staging)."""
+    for s in _SESSIONS.values():
+        s.close()
+    _SESSIONS.clear()
+
+
+def _get_session(cwd, wave, device, overrides):
+    """LRU lookup; the least recently used session is closed when the cache is full, so a caller that varies log gf or
+    an abundance from call to call holds at most MAX_SESSIONS contexts."""
+    tob = lambda x: None if x is None else np.asarray(x).tobytes()   # noqa: E731
+    key = _session_key(cwd, wave, tuple(tob(overrides[k]) for k in sorted(overrides)) + (device,))
+    s = _SESSIONS.get(key)
+    if s is not None:
+        _SESSIONS.move_to_end(key)
+        return s
+    kw = read_keywords(cwd)
+    if any(st == "ACTIVE" for _, st in _atoms_listed(cwd, kw)):
+        from . import nlte_host
+        s = nlte_host.NlteSession(cwd, wave, device, None, **overrides)
+    else:
+        s = Session(cwd, wave, device, None, **overrides)
+    _SESSIONS[key] = s
+    while len(_SESSIONS) > MAX_SESSIONS:
+        _, old = _SESSIONS.popitem(last=False)
+        old.close()
+    return s
 
 
 def compute1d(cwd, mu, atm_scale, atmosphere, wave, loggf_ids=None, loggf_values=None, lam_ids=None, lam_values=None,
               fudge_wave=None, fudge_value=None, atomic_number=None, atomic_abundance=None, get_atomic_rfs=False,
               get_populations=False, device=0):
-    """Drop-in for ``pyrh.compute1d`` (pyrh.pyx:537-668) in LTE: returns ``(sI, sQ, sU, sV, lam)``.  The parsed
-    working directory stays resident on the GPU between calls (per-process cache keyed on the directory, the input
-    files' mtimes, the wavelength grid and the per-call line / abundance overrides)."""
-    tob = lambda x: None if x is None else np.asarray(x).tobytes()   # noqa: E731
-    key = _session_key(cwd, wave, (tob(loggf_ids), tob(loggf_values), tob(lam_ids), tob(lam_values),
-                                   tob(atomic_number), tob(atomic_abundance), tob(fudge_wave), tob(fudge_value), device))
-    s = _SESSIONS.get(key)
-    if s is None:
-        s = _SESSIONS[key] = Session(cwd, wave, device, None, loggf_ids, loggf_values, lam_ids, lam_values, fudge_wave,
-                                     fudge_value, atomic_number, atomic_abundance)
-    if get_atomic_rfs:                                           # pyrh.pyx:658-660: (output, rf.T); lam_ids columns stay 0
-        st, rf = s.compute_rf(atmosphere, mu=mu, atm_scale=atm_scale)
+    """Drop-in for ``pyrh.compute1d`` (pyrh.pyx:537-668): returns ``(sI, sQ, sU, sV, lam)``; with ACTIVE atoms in
+    ``atoms.input`` the NLTE problem is solved first (initScatter, Iterate, the final pass at ``mu``) and
+    ``get_populations`` adds a tuple of ``Populations`` (one per ACTIVE atom).  The parsed working directory stays
+    resident on the GPU between calls (bounded per-process LRU keyed on the directory, PYRH_PATH, the mtimes of every
+    input file read, the wavelength grid and the per-call line / abundance / fudge overrides)."""
+    s = _get_session(cwd, wave, device, dict(loggf_ids=loggf_ids, loggf_values=loggf_values, lam_ids=lam_ids,
+                                             lam_values=lam_values, fudge_wave=fudge_wave, fudge_value=fudge_value,
+                                             atomic_number=atomic_number, atomic_abundance=atomic_abundance))
+    nlte = not isinstance(s, Session)
+    populations = ()
+    if nlte:
+        if get_atomic_rfs:
+            raise NotImplementedError("get_atomic_rfs with ACTIVE atoms is not ported")
+        res = s.compute(atmosphere, mu=mu, atm_scale=atm_scale)
+        zero = np.zeros_like(res["I"])                              # atmos.Stokes is TRUE, STOKES_MODE NO_STOKES: Q = U = V = 0
+        output = (res["I"], zero, zero.copy(), zero.copy(), s.wavelengths)
+        if get_populations:
+            populations = tuple(Populations(ID, n.shape[0], n.shape[1], n, ns) for ID, n, ns in s.populations(res))
     else:
-        st = s.compute(atmosphere, mu=mu, atm_scale=atm_scale)
-    output = (st[0], None, None, None, s.wavelengths) if s.stokes_mode == "NO_STOKES" else \
-        (st[0], st[1], st[2], st[3], s.wavelengths)                # spec.stokes false: pyrh.pyx:647-652
-    if get_atomic_rfs:
-        output = (output, rf)
-    if get_populations:                                          # populations of the ACTIVE atoms: none in LTE
-        return output, ()                                        # (pyrh.pyx:654-673)
+        if get_atomic_rfs:                                       # pyrh.pyx:658-660: (output, rf.T); lam_ids columns stay 0
+            st, rf = s.compute_rf(atmosphere, mu=mu, atm_scale=atm_scale)
+        else:
+            st = s.compute(atmosphere, mu=mu, atm_scale=atm_scale)
+        # rhf1d() sets atmos.Stokes = TRUE unconditionally (pyrh_compute1dray.c:258), so _solveray always fills sQ/sU/sV
+        # and sets spec->stokes (pyrh_solveray.c:137-142): in NO_STOKES mode they are arrays of zeros, never None
+        output = (st[0], st[1], st[2], st[3], s.wavelengths)
+        if get_atomic_rfs:
+            output = (output, rf)
+    if get_populations:                                          # pyrh.pyx:654-673
+        return output, populations
     return output

@@ -35,6 +35,13 @@ class ColumnsStruct(C.Structure):
                                   "vel", "chi_c", "eta_c", "sca_c", "n", "J")]
 
 
+class FrontStruct(C.Structure):
+    """rhb200_nlte_front (include/rhb200.h)."""
+    _fields_ = [("atom_model", ip), ("ncoll", C.c_int), ("ncolltab", C.c_int), ("coll", dp), ("coll_T", dp),
+                ("coll_coef", dp), ("coll_M", dp), ("line_rows", dp), ("NmaxScatter", C.c_int), ("NmaxIter", C.c_int),
+                ("iterLimit", C.c_double), ("plan1", C.POINTER(PlanStruct))]
+
+
 @dataclass
 class NlteProblem:
     """Flat description of one NLTE problem (layout of include/rhb200.h, rhb200_nlte_plan/_columns).
