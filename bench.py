@@ -223,6 +223,119 @@ def reference_throughput(steps=5, warmup=3, cols_per_proc=2, procs=None, variant
                 cols_per_step=procs * cols_per_proc)
 
 
+# ------------------------------------------------------------------ NLTE records (BASELINE configs 4 and 5)
+NLTE_KW = dict(N_MAX_ITER=100, N_MAX_SCATTER=2, NG_ORDER=2, NG_DELAY=10, NG_PERIOD=3, ITER_LIMIT="1.0E-4", PRD_N_MAX_ITER=0,
+               STOKES_MODE="NO_STOKES")
+NLTE_CASES = {
+    # configs[3]: H (6 levels) + Ca II (5 levels + continuum) ACTIVE, CRD, Ng acceleration, to convergence
+    "config4": dict(kw=dict(NLTE_KW, NRAYS=3, HYDROGEN_LTE="FALSE"), active=("H_6.atom", "CaII.atom"),
+                    wave=(630.25, 630.5, 21), ncol=512),
+    # configs[4] sample: Ca II 8542, ~1000 wavelengths, 5 mu, columns of the synthetic cube (per GPU)
+    "config5_sample": dict(kw=dict(NLTE_KW, NRAYS=5, HYDROGEN_LTE="TRUE"), active=("CaII.atom",),
+                           wave=(853.5, 855.5, 600), ncol=4096),
+}
+
+
+def _pyrh_data_path():
+    """$PYRH_PATH, else the atom / molecule DATA files staged beside the oracle build (files only: nothing is imported)."""
+    if not os.environ.get("PYRH_PATH"):
+        os.environ["PYRH_PATH"] = str(ROOT / "oracle" / "_ref" / "pyrh_path")
+    return os.environ["PYRH_PATH"]
+
+
+def _nlte_workdir(case):
+    import tempfile
+    from pyrh_b200 import workdir
+    c = NLTE_CASES[case]
+    return workdir.stage(tempfile.mkdtemp(prefix=f"rhb200_{case}_"), c["kw"], active=c["active"], extra_atoms=("CaII.atom",))
+
+
+def nlte_records(device, rank, ncol_scale=1.0):
+    """NLTE through the drop-in call (NlteSession.compute = rhb200_nlte_compute1d_batch): host atmosphere rows in,
+    spectra + populations out, everything between on the device.  One record per case: atmospheres/s and formal-solution
+    ray-points/s of a batch of perturbed 70-depth columns (and the latency of one FAL-C atmosphere for config 4)."""
+    from pyrh_b200 import nlte_host, synthetic
+    _pyrh_data_path()
+    base = np.load(ROOT / "tests" / "golden" / "falc_base.npy")
+    out = {}
+    for case, c in NLTE_CASES.items():
+        ncol = max(8, int(c["ncol"] * ncol_scale))
+        s = nlte_host.NlteSession(_nlte_workdir(case), np.linspace(*c["wave"]), device)
+        atm = synthetic.perturbed_batch(base, ncol, ndep=NDEP, first=10000 + rank * ncol)
+        s.compute(atm[:min(64, ncol)])                                  # warm-up: allocations, first launches
+        s.ctx.synchronize()
+        t0 = time.perf_counter()
+        res = s.compute(atm)
+        s.ctx.synchronize()
+        dt = time.perf_counter() - t0
+        conv = res["niter"] < int(c["kw"]["N_MAX_ITER"])
+        rec = {"workload": f"{ncol} perturbed FAL-C columns x {NDEP} depths, {len(s.lam)} wavelengths, NRAYS {s.nrays}, "
+                           f"ACTIVE {'+'.join(a.split('.')[0] for a in c['active'])}, CRD, Ng 2/10/3, ITER_LIMIT 1e-4",
+               "ncol": ncol, "nspect": int(len(s.lam)), "nrays": s.nrays, "seconds": dt, "atmospheres_per_s": ncol / dt,
+               "ray_points_per_s": s.ray_points(res, NDEP) / dt, "ray_points": s.ray_points(res, NDEP),
+               "iterations_median": float(np.median(res["niter"])), "iterations_max": int(res["niter"].max()),
+               "converged_columns": int(conv.sum()), "all_finite": bool(np.isfinite(res["I"][conv]).all()),
+               "h2d_bytes": int(atm.nbytes), "d2h_bytes": int(res["I"].nbytes + res["n"].nbytes + res["nstar"].nbytes)}
+        if case == "config4":                                           # the single FAL-C atmosphere configs[3] names
+            one = base.copy()
+            s.compute(one)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                r1 = s.compute(one)
+            rec["single_falc_atmosphere_ms"] = 1e3 * (time.perf_counter() - t0) / 3
+            rec["single_falc_iterations"] = int(r1["niter"])
+        # per-kernel-family split of one smaller batch (CUDA events around every launch: serialising, separate pass)
+        s.ctx.timing(True)
+        s.compute(atm[:min(256, ncol)])
+        rec["kernel_ms_per_256_columns"] = {n: ms for n, (ms, cnt) in s.ctx.timing_get().items() if cnt}
+        s.ctx.timing(False)
+        s.close()
+        out[case] = rec
+    return out
+
+
+def nlte_ref_worker(case, column):
+    """One column of an NLTE case through the unmodified reference, in a process of its own (bench.py --nlte-ref-worker):
+    prints the seconds rhf1d() took.  The reference exit()s on columns whose statistical equilibrium turns singular."""
+    from oracle import refdriver as rd
+    from pyrh_b200 import synthetic
+    _pyrh_data_path()
+    a = synthetic.perturbed_batch(np.load(ROOT / "tests" / "golden" / "falc_base.npy"), 1, ndep=NDEP, first=column)[0]
+    cwd = _nlte_workdir(case)
+    t0 = time.perf_counter()
+    rd.rhf1d(a, np.linspace(*NLTE_CASES[case]["wave"]), cwd, get_populations=True)
+    print(f"NLTE_REF_SECONDS {time.perf_counter() - t0:.6f}", flush=True)
+
+
+def nlte_reference_baseline(procs=None, limit_s=120.0):
+    """The unmodified reference's rhf1d() on the same NLTE workloads: one process per host core, one column each, all
+    started together (bounded sample).  Every column runs in its OWN process with a time limit: the reference calls
+    exit() from LUdecomp ("Singular matrix") on some perturbed columns and would take a worker pool down with it."""
+    procs = procs or os.cpu_count() or 1
+    out = {}
+    for case in NLTE_CASES:
+        ps = [subprocess.Popen([sys.executable, str(ROOT / "bench.py"), "--nlte-ref-worker", case, str(10000 + p)],
+                               stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for p in range(procs)]
+        t, t_end = [], time.perf_counter() + limit_s
+        for q in ps:
+            try:
+                o, _ = q.communicate(timeout=max(1.0, t_end - time.perf_counter()))
+            except subprocess.TimeoutExpired:
+                q.kill()
+                q.communicate()
+                continue
+            t += [float(ln.split()[1]) for ln in o.splitlines() if ln.startswith("NLTE_REF_SECONDS")]
+        if not t:
+            out[case] = {"atmospheres_per_s": None, "cores": procs, "kind": "reference", "sample": "no column finished"}
+            continue
+        out[case] = {"atmospheres_per_s": len(t) / max(t), "cores": procs, "kind": "reference",
+                     "seconds_per_atmosphere_per_core": float(np.mean(t)), "columns_finished": len(t),
+                     "columns_the_reference_aborted_on": procs - len(t),
+                     "sample": f"{procs} perturbed columns started together, one rhf1d(get_populations) process per core; "
+                               f"{len(t)} finished, slowest {max(t):.1f} s"}
+    return out
+
+
 # ------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -233,7 +346,13 @@ def main():
     ap.add_argument("--ncol", type=int, default=NCOL_DEFAULT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-cols-per-proc", type=int, default=3)
+    ap.add_argument("--nlte-ref-worker", nargs=2, metavar=("CASE", "COLUMN"), help=argparse.SUPPRESS)
+    ap.add_argument("--no-nlte", action="store_true", help="skip the NLTE (configs 4 / 5) records")
+    ap.add_argument("--nlte-scale", type=float, default=1.0, help="scale the NLTE batch sizes (profiling runs)")
     args = ap.parse_args()
+    if args.nlte_ref_worker:
+        nlte_ref_worker(args.nlte_ref_worker[0], int(args.nlte_ref_worker[1]))
+        return
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -378,6 +497,12 @@ def main():
     finite_b = bool(np.isfinite(stokes_b).all())
 
     fma_tf, nofma_tf = ctx.fp64_peak()
+    nlte = None
+    if not args.no_nlte:
+        try:
+            nlte = nlte_records(local_rank, rank, args.nlte_scale)
+        except Exception as e:          # noqa: BLE001  -- the headline must survive a missing data directory
+            nlte = {"unavailable": f"{type(e).__name__}: {e}"}
 
     if rank != 0:
         ctx.close()
@@ -446,7 +571,7 @@ def main():
                     "h2d_bytes_per_step": int(at.nbytes + chi.nbytes + eta.nbytes),
                     "d2h_bytes_per_step": int(stokes.nbytes), "ms_per_step": ms_e2e_bg / args.steps,
                     "bitwise_equal_to_device_resident_run": same},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "nlte": nlte}
     if world == 1 and not args.no_cpu_baseline:
         try:
             probe_cols = [c for c in (0, 1000, 4097, ncol - 1) if c < ncol]
@@ -466,6 +591,14 @@ def main():
         except Exception as e:          # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": "ray-points/s", "cores": 0, "kind": "reference",
                                     "sample": f"unavailable: {e}"}
+        if isinstance(nlte, dict) and "config4" in nlte:
+            try:
+                for case, b in nlte_reference_baseline().items():
+                    nlte[case]["cpu_baseline"] = b
+                    if b["atmospheres_per_s"]:
+                        nlte[case]["speedup_vs_reference_all_cores"] = nlte[case]["atmospheres_per_s"] / b["atmospheres_per_s"]
+            except Exception as e:          # noqa: BLE001
+                nlte["cpu_baseline_unavailable"] = f"{type(e).__name__}: {e}"
     print(json.dumps(line))
     ctx.close()
     if dist is not None:

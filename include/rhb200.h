@@ -573,6 +573,14 @@ int rhb200_nlte_formal(rhb200_ctx *ctx, const rhb200_nlte_plan *plan, int ncol,
 enum { RHB200_REDUCE_SUM = 0, RHB200_REDUCE_MAX = 1 };
 typedef int (*rhb200_allreduce_fn)(void *user, double *device_buf, size_t count, int op);
 int rhb200_nlte_set_shard(rhb200_ctx *ctx, int rank, int nrank, rhb200_allreduce_fn fn, void *user);
+/* Order of the sums in addtoGamma / addtoRates (fillgamma.c:139-196, 375-461).  exact = 1: one thread per (column,
+   transition, depth) adds the contributions of all wavelengths and rays in the reference's order -- Gamma, rates and
+   populations then equal the reference's to the last bit, at the price of a long serial walk.  exact = 0 (default):
+   every transition's wavelengths are cut into fixed segments of 16 (RHB200_NLTE_GAMMA_SEG) that are summed
+   concurrently and then added in segment order: deterministic and independent of batch size, chunking and rank count,
+   populations within ~1e-13 of the exact mode (north_star bar: 1e-6), several times faster.  The environment
+   variable RHB200_NLTE_EXACT overrides. */
+int rhb200_nlte_set_exact_rates(rhb200_ctx *ctx, int exact);
 int rhb200_nlte_shard_range(const rhb200_nlte_plan *plan, int rank, int nrank, int *ns_lo, int *ns_hi);
 /* ---- NLTE through the drop-in call: everything rhf1d() does per column for a working directory with ACTIVE atoms
    (pyrh_compute1dray.c:112-388 with input.solve_NLTE, STOKES_MODE = NO_STOKES, CRD), on the device, for a batch:
@@ -611,11 +619,13 @@ typedef struct {
 } rhb200_nlte_front;
 /* atmosphere [ncol][nrow][ndep] as in rhb200_compute1d_batch.  Out (any may be NULL): spectrum [ncol][Nspect] = spectrum.I[][0]
    of the final pass on plan->lambda (lambda_ref included; _solveray drops it), pops_n / pops_nstar [ncol][sum Nlevel][ndep]
-   = AtomPops.n / .nstar, niter [ncol] iterations Iterate() took, scales [ncol][3][ndep] = height, tau_ref, column mass. */
+   = AtomPops.n / .nstar, niter [ncol] iterations Iterate() took, passes [ncol][2] = solveSpectrum(FALSE, FALSE) passes of
+   initScatter and of the loop after Iterate(), scales [ncol][3][ndep] = height, tau_ref, column mass. */
 int rhb200_nlte_compute1d_batch(rhb200_ctx *ctx, const rhb200_nlte_plan *plan, const rhb200_nlte_front *front,
                                 int ncol, int ndep, int nrow, double mu, int atm_scale, const double *atmosphere,
                                 int iref, double wght_per_H, double vmacro_tresh,
-                                double *spectrum, double *pops_n, double *pops_nstar, int *niter, double *scales);
+                                double *spectrum, double *pops_n, double *pops_nstar, int *niter, int *passes,
+                                double *scales);
 /* test hook: the per-column inputs the front end hands to Iterate() for the columns of the LAST
    rhb200_nlte_compute1d_batch call that fit in one chunk: which = 0 C, 1 nstar, 2 ntotal, 3 adamp, 4 vbroad,
    5 chi_c, 6 eta_c, 7 sca_c, 8 height, 9 J after the last pass, 10..12 chi_c/eta_c/sca_c of the final pass,
@@ -640,9 +650,10 @@ int rhb200_flush_l2(rhb200_ctx *ctx);
 /* ---- instrumentation ------------------------------------------------------
    CUDA-event time (ms) and launch count per kernel family accumulated since the
    last rhb200_timing_reset(); which: 0 prep, 1 line opacity, 2 DELO-Bezier3,
-   3 scalar Bezier3, 4 other.  Mirrors the getCPU() labels the reference stubs
+   3 scalar Bezier3, 4 other, 5 NLTE Gamma/rates, 6 NLTE J, 7 statEquil, 8 Ng.  Mirrors the getCPU() labels the reference stubs
    out (rh/getcpu.c:60). */
 enum { RHB200_K_PREP = 0, RHB200_K_OPACITY, RHB200_K_DELO, RHB200_K_BEZIER, RHB200_K_OTHER,
+       RHB200_K_GAMMA /* addtoGamma/addtoRates/addtoCoupling */, RHB200_K_J, RHB200_K_STATEQ, RHB200_K_NG,
        RHB200_K_COUNT };
 int rhb200_timing_enable(rhb200_ctx *ctx, int on);
 int rhb200_timing_reset(rhb200_ctx *ctx);

@@ -33,7 +33,7 @@ SYMBOLS = [
     ("rhb200_get_line_windows", C.c_int, [vp, ip, ip, ip, C.c_int, ip]),
     ("rhb200_get_wavelength_flags", C.c_int, [vp, ip]),
     ("rhb200_nlte_compute1d_batch", C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, vp, C.c_int,
-                                              C.c_double, C.c_double, vp, vp, vp, vp, vp]),
+                                              C.c_double, C.c_double, vp, vp, vp, vp, vp, vp]),
     ("rhb200_nlte_front_debug", C.c_int, [vp, C.c_int, dp, C.c_size_t]),
     ("rhb200_lte_stokes_batch", C.c_int, [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
                                           vp, vp, vp, vp]),
@@ -51,6 +51,7 @@ SYMBOLS = [
                                     C.c_double, C.c_int, C.c_int, ip, dp, dp]),
     ("rhb200_determinate", C.c_int, [C.c_char_p, C.c_double, ip, dp, ip, dp]),
     ("rhb200_zeeman", C.c_int, [C.c_char_p, C.c_double, C.c_char_p, C.c_double, C.c_double, C.c_int, ip, dp, dp]),
+    ("rhb200_nlte_set_exact_rates", C.c_int, [vp, C.c_int]),
     ("rhb200_nlte_set_shard", C.c_int, [vp, C.c_int, C.c_int, ALLREDUCE_FN, vp]),
     ("rhb200_nlte_shard_range", C.c_int, [vp, C.c_int, C.c_int, ip, ip]),
     ("rhb200_molecular_opacity_batch", C.c_int, [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,

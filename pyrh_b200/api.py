@@ -562,7 +562,8 @@ class Context:
 
     def timing_get(self):
         out = {}
-        for name, k in (("prep", 0), ("opacity", 1), ("delo", 2), ("bezier", 3), ("other", 4)):
+        for name, k in (("prep", 0), ("opacity", 1), ("delo", 2), ("bezier", 3), ("other", 4), ("nlte_gamma", 5),
+                        ("nlte_J", 6), ("statequil", 7), ("ng", 8)):
             ms, n = C.c_double(), C.c_long()
             _lib.check(self.lib.rhb200_timing_get(self.h, k, C.byref(ms), C.byref(n)))
             out[name] = (ms.value, n.value)

@@ -95,6 +95,8 @@ struct rhb200_ctx {
   int lrf_npar = 0; int *d_lrf_lines = nullptr;
   // doubles per depth point of the scalar-ray scratch: chi, S, I (+ dchi, deta, dI[npar] in RF mode)
   int scal_fields() const { return 3 + 3*lrf_npar; }
+  // NLTE rate accumulation: 0 = fixed-partition two-stage reduction (default), 1 = the reference's add order, bit-identical
+  int nlte_exact_rates = 0;
   // wavelength shard of the NLTE solve (rhb200_nlte_set_shard)
   int shard_rank = 0, shard_nrank = 1;
   rhb200_allreduce_fn shard_fn = nullptr; void *shard_user = nullptr;

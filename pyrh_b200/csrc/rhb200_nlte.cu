@@ -49,12 +49,15 @@ struct Plan {            // device copy of the shared problem structure
   const double *lambda, *muz, *wmu, *trans, *tr_lambda, *tr_wlambda, *tr_alpha;
   const int *atom_nlevel, *lev_off, *gam_off, *as_first, *as_trans, *angle_dep, *ray_off,
             *ray_ns, *ray_mu, *ray_dir, *prow_tr, *line_tr;
+  // fixed partition of every transition's wavelengths into segments (deterministic two-stage rate accumulation)
+  int nseg; const int *seg_tr, *seg_lo, *seg_hi, *tr_seg0;   // [nseg] transition, [lo, hi) wavelengths; [Ntrans+1] first segment
 };
 
 struct Cols {            // device per-column arrays
   const double *T, *height, *nstar, *ntotal, *C, *chi_c, *eta_c, *sca_c, *adamp, *vbroad, *vel;
   double *phi, *wphi;
   double *n, *J, *Gamma, *Rij, *Rji, *gw, *chi, *S, *I, *Psi, *scr, *dJ, *Iem;
+  double *part;            // [ncol][nseg][4][Ndep] partial {Gij, Gji, Rij, Rji} of the segments
   const int *active;
 };
 
@@ -347,13 +350,19 @@ nlte_dJmax_kernel(Plan P, Cols C, int ncol, double *dJmax)
 // small per-thread cache: the products are formed in the reference's association order
 // (V*w)*(n_i - g n_j), (thn*g)*V, ((thn*g)*V)*n_j, so hoisting the right-hand factors changes no rounding.
 #define NLTE_MAXACT 12
+// SEG: the thread covers one SEGMENT of its transition's wavelengths and stores partial sums (stage 1 of the
+// fixed-partition reduction, nlte_gamma_sum_kernel adds them in segment order); !SEG: the whole transition in the
+// reference's order, bit-identical to fillgamma.c.
+template <bool SEG>
 __global__ void __launch_bounds__(64, 8)
 nlte_gamma_kernel(Plan P, Cols C, int ncol)
 {
   const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
   const int N = P.Ndep;
   if (t >= (size_t) ncol * N) return;
-  const int k = (int) (t % N), col = (int) (t / N), tid = blockIdx.y;   // heavy transitions (lines) start first
+  const int k = (int) (t % N), col = (int) (t / N);
+  const int seg = SEG ? (int) blockIdx.y : 0;
+  const int tid = SEG ? P.seg_tr[seg] : (int) blockIdx.y;   // heavy transitions (lines) start first
   if (!C.active[col]) return;
   const double *trs = P.trans + (size_t) tid * TR_NFIELD;
   const int a = (int) trs[TR_ATOM], i = (int) trs[TR_I], j = (int) trs[TR_J], Nl = P.atom_nlevel[a];
@@ -362,10 +371,11 @@ nlte_gamma_kernel(Plan P, Cols C, int ncol)
   const size_t gbase = ((size_t) col * P.ngam + P.gam_off[a]) * N;
   const double hc_4PI = (RH_HPLANCK * RH_CLIGHT) / (4.0 * RH_PI);
   double Gij = 0.0, Gji = 0.0;
-  if (P.add_C) { Gij = C.C[gbase + (size_t)(i*Nl + j) * N + k]; Gji = C.C[gbase + (size_t)(j*Nl + i) * N + k]; }   // initGammaAtom
+  if (!SEG && P.add_C) { Gij = C.C[gbase + (size_t)(i*Nl + j) * N + k]; Gji = C.C[gbase + (size_t)(j*Nl + i) * N + k]; }   // initGammaAtom
   double Rij = 0.0, Rji = 0.0;                                                                          // zeroRates
 
-  const int ns_first = Nblue > P.ns_lo ? Nblue : P.ns_lo, ns_last = Nblue + Nla < P.ns_hi ? Nblue + Nla : P.ns_hi;
+  const int w_lo = SEG ? P.seg_lo[seg] : Nblue, w_hi = SEG ? P.seg_hi[seg] : Nblue + Nla;
+  const int ns_first = w_lo > P.ns_lo ? w_lo : P.ns_lo, ns_last = w_hi < P.ns_hi ? w_hi : P.ns_hi;
   for (int ns = ns_first; ns < ns_last; ns++) {
     const int first = P.as_first[ns], nact = P.as_first[ns+1] - first;
     const int ad = P.angle_dep[ns];
@@ -462,10 +472,41 @@ nlte_gamma_kernel(Plan P, Cols C, int ncol)
       }
     }
   }
+  if (SEG) {
+    double *o = C.part + (((size_t) col * P.nseg + seg) * 4) * N + k;
+    o[0] = Gij; o[N] = Gji; o[2*(size_t) N] = Rij; o[3*(size_t) N] = Rji;
+    return;
+  }
   C.Gamma[gbase + (size_t)(i*Nl + j) * N + k] = Gij;
   C.Gamma[gbase + (size_t)(j*Nl + i) * N + k] = Gji;
   C.Rij[((size_t) col * P.Ntrans + tid) * N + k] = Rij;
   C.Rji[((size_t) col * P.Ntrans + tid) * N + k] = Rji;
+}
+
+// stage 2: collisional part + the segments' partial sums in segment (= wavelength) order: the same partition for every
+// batch size, chunking and rank count, so results are run-to-run and layout independent (not the reference's add order:
+// populations agree to ~1e-13 instead of to the bit; north_star asks 1e-6)
+__global__ void __launch_bounds__(128)
+nlte_gamma_sum_kernel(Plan P, Cols C, int ncol)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = P.Ndep;
+  if (t >= (size_t) ncol * P.Ntrans * N) return;
+  const int k = (int) (t % N), tid = (int) ((t / N) % P.Ntrans), col = (int) (t / ((size_t) N * P.Ntrans));
+  if (!C.active[col]) return;
+  const double *trs = P.trans + (size_t) tid * TR_NFIELD;
+  const int a = (int) trs[TR_ATOM], i = (int) trs[TR_I], j = (int) trs[TR_J], Nl = P.atom_nlevel[a];
+  const size_t gbase = ((size_t) col * P.ngam + P.gam_off[a]) * N;
+  double Gij = 0.0, Gji = 0.0, Rij = 0.0, Rji = 0.0;
+  if (P.add_C) { Gij = C.C[gbase + (size_t)(i*Nl + j) * N + k]; Gji = C.C[gbase + (size_t)(j*Nl + i) * N + k]; }
+  for (int sg = P.tr_seg0[tid]; sg < P.tr_seg0[tid+1]; sg++) {
+    const double *p = C.part + (((size_t) col * P.nseg + sg) * 4) * N + k;
+    Gij += p[0]; Gji += p[N]; Rij += p[2*(size_t) N]; Rji += p[3*(size_t) N];
+  }
+  C.Gamma[gbase + (size_t)(i*Nl + j) * N + k] = Gij;
+  C.Gamma[gbase + (size_t)(j*Nl + i) * N + k] = Gji;
+  C.Rij[t] = Rij;
+  C.Rji[t] = Rji;
 }
 
 // Gamma entries that belong to no radiative transition keep the collisional value (initGammaAtom)
@@ -755,6 +796,7 @@ struct NlteEngine {
     P.add_C = (rank == 0);
     DevArena &ar = plan_ar;
     double *dd; int *di;
+#define UPI2(field, src, n) RH_CHECK(ar.upload(&di, src, (size_t) (n))); P.field = di
 #define UPD(field, src, n) RH_CHECK(ar.upload(&dd, src, (size_t) (n))); P.field = dd
 #define UPI(field, src, n) RH_CHECK(ar.upload(&di, src, (size_t) (n))); P.field = di
     UPD(lambda, pl->lambda, Ns); UPD(muz, pl->muz, Nr); UPD(wmu, pl->wmu, Nr);
@@ -783,18 +825,36 @@ struct NlteEngine {
     }
 #undef UPD
 #undef UPI
+    {                                            // segments of the rate accumulation (RHB200_NLTE_GAMMA_SEG wavelengths each)
+      int seglen = 16;
+      if (const char *e = getenv("RHB200_NLTE_GAMMA_SEG")) { const int v = atoi(e); if (v > 0) seglen = v; }
+      exact_rates = c->nlte_exact_rates != 0;
+      if (const char *e = getenv("RHB200_NLTE_EXACT")) exact_rates = atoi(e) != 0;
+      std::vector<int> seg_tr, seg_lo, seg_hi, tr_seg0(Nt + 1, 0);
+      for (int t = 0; t < Nt; t++) {
+        const double *tr = pl->trans + (size_t) t*RHB200_TR_NFIELD;
+        const int b0 = (int) tr[RHB200_TR_NBLUE], b1 = b0 + (int) tr[RHB200_TR_NLAMBDA];
+        tr_seg0[t] = (int) seg_tr.size();
+        for (int lo = b0; lo < b1; lo += seglen) { seg_tr.push_back(t); seg_lo.push_back(lo); seg_hi.push_back(std::min(b1, lo + seglen)); }
+      }
+      tr_seg0[Nt] = (int) seg_tr.size();
+      P.nseg = nseg = (int) seg_tr.size();
+      UPI2(seg_tr, seg_tr.data(), std::max(1, nseg)); UPI2(seg_lo, seg_lo.data(), std::max(1, nseg));
+      UPI2(seg_hi, seg_hi.data(), std::max(1, nseg)); UPI2(tr_seg0, tr_seg0.data(), Nt + 1);
+    }
     Norder = pl->Ngorder; Ndelay = std::max(pl->Ngdelay, Norder + 2); Nperiod = std::max(1, pl->Ngperiod);
     prev_off.assign(Na+1, 0);
     for (int a = 0; a < Na; a++) prev_off[a+1] = prev_off[a] + (size_t)(Norder+2) * pl->atom_nlevel[a] * N;
     RH_CHECK(ar.upload(&d_prev_off, prev_off.data(), Na+1));
     return RHB200_OK;
   }
-  bool profile_maps_ok = false;
+  bool profile_maps_ok = false, exact_rates = false;
+  int nseg = 0;
 
   // doubles of device memory per column that alloc() takes (chunk sizing of the front end)
   size_t doubles_per_column(bool own_inputs) const {
-    size_t d = (size_t) N * ((size_t) ngam + 2*(size_t) Nt + 2*(size_t) nas + 6*(size_t) nray + (size_t) Ns + nphirow + nline) + nray
-             + prev_off[Na] + Na;
+    size_t d = (size_t) N * ((size_t) ngam + 2*(size_t) Nt + 2*(size_t) nas + 6*(size_t) nray + (size_t) Ns + nphirow + nline +
+                             (exact_rates ? 0 : 4*(size_t) nseg)) + nray + prev_off[Na] + Na;
     if (own_inputs) d += (size_t) N * (2 + 2*(size_t) nlev + Na + ngam + nline + Na + 1 + 4*(size_t) Ns);
     return d;
   }
@@ -809,6 +869,7 @@ struct NlteEngine {
     RH_CHECK(ar.alloc(&C.phi, cN*nphirow)); RH_CHECK(ar.alloc(&C.wphi, cN*nline));
     RH_CHECK(ar.alloc(&C.Gamma, cN*ngam)); RH_CHECK(ar.alloc(&C.Rij, cN*Nt, true)); RH_CHECK(ar.alloc(&C.Rji, cN*Nt, true));
     RH_CHECK(ar.alloc(&C.gw, cN*nas*2));
+    if (!exact_rates) RH_CHECK(ar.alloc(&C.part, cN*nseg*4));
     RH_CHECK(ar.alloc(&C.chi, cN*nray)); RH_CHECK(ar.alloc(&C.S, cN*nray)); RH_CHECK(ar.alloc(&C.I, cN*nray));
     RH_CHECK(ar.alloc(&C.Psi, cN*nray)); RH_CHECK(ar.alloc(&C.scr, cN*nray*2)); RH_CHECK(ar.alloc(&C.dJ, cN*Ns, true));
     RH_CHECK(ar.alloc(&C.Iem, (size_t) ncol*nray, true));
@@ -911,7 +972,7 @@ struct NlteEngine {
       { ScopedKernelTimer t(c, RHB200_K_BEZIER);
         launch_rays(0); }
       if (update_J) {
-        { ScopedKernelTimer t(c, RHB200_K_OTHER);
+        { ScopedKernelTimer t(c, RHB200_K_J);
           nlte_J_kernel<<<RH_GRID(cN*Ns, 128), 0, st>>>(P, C, ncol); }
         nlte_dJmax_kernel<<<ncol, 256, 0, st>>>(P, C, ncol, d_dJmax);
         RH_CUDA(cudaGetLastError());
@@ -968,9 +1029,13 @@ struct NlteEngine {
         nlte_opacity_kernel<<<(unsigned) (((cN + 127) / 128) * Ns), 128, 0, st>>>(P, C, ncol); }
       { ScopedKernelTimer t(c, RHB200_K_BEZIER);
         launch_rays(1); }
-      { ScopedKernelTimer t(c, RHB200_K_OTHER);
-        nlte_gamma_kernel<<<dim3((unsigned) ((cN + 63) / 64), (unsigned) Nt), 64, 0, st>>>(P, C, ncol); }
-      { ScopedKernelTimer t(c, RHB200_K_OTHER);
+      { ScopedKernelTimer t(c, RHB200_K_GAMMA);
+        if (exact_rates) nlte_gamma_kernel<false><<<dim3((unsigned) ((cN + 63) / 64), (unsigned) Nt), 64, 0, st>>>(P, C, ncol);
+        else {
+          nlte_gamma_kernel<true><<<dim3((unsigned) ((cN + 63) / 64), (unsigned) nseg), 64, 0, st>>>(P, C, ncol);
+          nlte_gamma_sum_kernel<<<RH_GRID(cN*Nt, 128), 0, st>>>(P, C, ncol);
+        } }
+      { ScopedKernelTimer t(c, RHB200_K_J);
         nlte_J_kernel<<<RH_GRID(cN*Ns, 128), 0, st>>>(P, C, ncol); }
       // the exchange step of a wavelength-sharded atmosphere: radiative rates add up over ranks
       RH_CHECK(allreduce(C.Gamma, cN*ngam, RHB200_REDUCE_SUM));
@@ -984,11 +1049,11 @@ struct NlteEngine {
           RH_CUDA(cudaMemcpy(rates_dump + cN*Nt, C.Rji, cN*Nt*sizeof(double), cudaMemcpyDeviceToHost));
         }
       }
-      { ScopedKernelTimer t(c, RHB200_K_OTHER);
+      { ScopedKernelTimer t(c, RHB200_K_STATEQ);
         if (maxnl <= 8) nlte_statequil_kernel<8><<<RH_GRID(cN*Na, 64), 0, st>>>(P, C, ncol, isum);
         else if (maxnl <= 16) nlte_statequil_kernel<16><<<RH_GRID(cN*Na, 64), 0, st>>>(P, C, ncol, isum);
         else nlte_statequil_kernel<32><<<RH_GRID(cN*Na, 64), 0, st>>>(P, C, ncol, isum); }
-      { ScopedKernelTimer t(c, RHB200_K_OTHER);
+      { ScopedKernelTimer t(c, RHB200_K_NG);
         nlte_ng_kernel<<<ncol*Na, 128, 0, st>>>(P, C, ncol, d_prev, d_prev_off, Norder, Ndelay, Nperiod, it, d_dpops); }
       RH_CUDA(cudaGetLastError());
       RH_CUDA(cudaMemcpyAsync(h_dpops.data(), d_dpops, h_dpops.size()*sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1055,6 +1120,13 @@ void rh_nlte_shard_range(int Nspect, const int *ray_off, int rank, int nrank, in
     return ns;
   };
   *lo = bound(rank); *hi = bound(rank + 1);
+}
+
+extern "C" int rhb200_nlte_set_exact_rates(rhb200_ctx *c, int exact)
+{
+  if (!c) { rhb200_set_error("null context"); return RHB200_EINVAL; }
+  c->nlte_exact_rates = exact != 0;
+  return RHB200_OK;
 }
 
 extern "C" int rhb200_nlte_set_shard(rhb200_ctx *c, int rank, int nrank, rhb200_allreduce_fn fn, void *user)

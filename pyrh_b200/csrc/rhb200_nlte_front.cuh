@@ -202,7 +202,8 @@ extern "C" int rhb200_nlte_front_debug(rhb200_ctx *c, int which, double *out, si
 extern "C" int rhb200_nlte_compute1d_batch(rhb200_ctx *c, const rhb200_nlte_plan *pl, const rhb200_nlte_front *fr,
                                            int ncol, int ndep, int nrow, double mu, int atm_scale, const double *atmosphere,
                                            int iref, double wght_per_H, double vmacro_tresh,
-                                           double *spectrum, double *out_n, double *out_nstar, int *niter_out, double *scales)
+                                           double *spectrum, double *out_n, double *out_nstar, int *niter_out, int *passes_out,
+                                           double *scales)
 {
   if (!c || !pl || !fr || !fr->plan1 || !atmosphere) { rhb200_set_error("null argument"); return RHB200_EINVAL; }
   RH_CUDA(cudaSetDevice(c->device));
@@ -327,7 +328,7 @@ extern "C" int rhb200_nlte_compute1d_batch(rhb200_ctx *c, const rhb200_nlte_plan
     RH_CUDA(cudaMemcpy(g_front_debug.arr[which].data(), d, count * sizeof(double), cudaMemcpyDeviceToHost));
     return RHB200_OK;
   };
-  static const bool debug_keep = getenv("RHB200_NLTE_FRONT_DEBUG") != nullptr;
+  const bool debug_keep = getenv("RHB200_NLTE_FRONT_DEBUG") != nullptr;     // test hook, read per call
 
   for (int c0 = 0; c0 < ncol; c0 += cc) {
     const int n = std::min(cc, ncol - c0);
@@ -369,11 +370,12 @@ extern "C" int rhb200_nlte_compute1d_batch(rhb200_ctx *c, const rhb200_nlte_plan
     }
     // ---- initScatter, Iterate, the scattering passes after it
     RH_CHECK(E.prepare(nullptr, nullptr, true));
-    RH_CHECK(E.scatter(fr->NmaxIter ? fr->NmaxScatter : 0, 1, fr->iterLimit, nullptr, nullptr, nullptr));
-    std::vector<int> niter(n, 0);
+    std::vector<int> niter(n, 0), pass_a(n, 0), pass_b(n, 0);
+    RH_CHECK(E.scatter(fr->NmaxIter ? fr->NmaxScatter : 0, 1, fr->iterLimit, pass_a.data(), nullptr, nullptr));
     RH_CHECK(E.iterate(fr->NmaxIter, fr->iterLimit, niter.data(), nullptr, 0, nullptr, nullptr));
-    RH_CHECK(E.scatter(fr->NmaxScatter, 2, fr->iterLimit, nullptr, nullptr, nullptr));
+    RH_CHECK(E.scatter(fr->NmaxScatter, 2, fr->iterLimit, pass_b.data(), nullptr, nullptr));
     if (niter_out) memcpy(niter_out + c0, niter.data(), n * sizeof(int));
+    if (passes_out) for (int q = 0; q < n; q++) { passes_out[2*(size_t) (c0 + q)] = pass_a[q]; passes_out[2*(size_t) (c0 + q) + 1] = pass_b[q]; }
     // ---- _solveray(): one ray at mu; Background() and getProfiles() again
     RH_CHECK(rh_launch_pyrh_rows(c, n, N, nrow, atm_scale, mu, 0.0, d_in, d_at, nullptr));
     // pyrh_rows rewrote the scale row: put the heights back

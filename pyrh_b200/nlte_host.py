@@ -588,19 +588,33 @@ class NlteSession:
                             self.hdr["iterLimit"], C.pointer(plan1))
         Ns, nlev = len(self.lam), int(np.sum(self.plan["atom_nlevel"]))
         spec = np.zeros((ncol, Ns)); n = np.zeros((ncol, nlev, ndep)); nstar = np.zeros((ncol, nlev, ndep))
-        niter = np.zeros(ncol, np.int32)
+        niter, passes = np.zeros(ncol, np.int32), np.zeros((ncol, 2), np.int32)
         scales = np.zeros((ncol, 3, ndep)) if get_scales else None
         vp = lambda x: None if x is None else C.c_void_p(x.ctypes.data)   # noqa: E731
         lib.check(self.ctx.lib.rhb200_nlte_compute1d_batch(
             self.ctx.h, C.byref(plan), C.byref(fr), ncol, ndep, nrow, float(mu), int(atm_scale), vp(a), self.iref,
-            float(self.el.wght_per_H), self.vmacro_tresh, vp(spec), vp(n), vp(nstar), vp(niter), vp(scales)))
+            float(self.el.wght_per_H), self.vmacro_tresh, vp(spec), vp(n), vp(nstar), vp(niter), vp(passes), vp(scales)))
         I = spec[:, self.lam != self.lambda_ref]
-        out = dict(I=I, n=n, nstar=nstar, niter=niter)
+        out = dict(I=I, n=n, nstar=nstar, niter=niter, passes=passes)
         if get_scales:
             out["scales"] = scales
         if single:
             out = {k: v[0] for k, v in out.items()}
         return out
+
+    def ray_points(self, res, ndep):
+        """Formal-solution ray-points of a ``compute`` result (SURVEY 8(d) unit of work): depth steps of every ray of every
+        solveSpectrum pass -- per wavelength Nrays x 2 where the wavelength is angle dependent (line present: both
+        directions), else Nrays (Feautrier) -- times initScatter passes + iterations + passes after Iterate(), plus the
+        single-mu final pass."""
+        hasline = np.zeros(len(self.lam), bool)
+        hasline[:] = self.plan["bg_hasline"] != 0
+        tr = self.plan["trans"]
+        for t in tr[tr[:, TR_TYPE] == 0]:
+            hasline[int(t[TR_NBLUE]):int(t[TR_NBLUE]) + int(t[TR_NLAMBDA])] = True
+        per_pass = int(np.sum(np.where(hasline, 2, 1)))
+        npass = np.atleast_1d(res["niter"]).astype(np.int64) + np.atleast_2d(res["passes"]).sum(axis=1)
+        return int(np.sum(npass * per_pass * self.nrays + per_pass) * ndep)
 
     def populations(self, res):
         """``res`` of one column -> tuple of (ID, n [Nlevel, ndep], nstar [Nlevel, ndep]) per ACTIVE atom: what

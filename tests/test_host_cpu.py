@@ -171,3 +171,65 @@ def test_barklem_cross_section_of_model_atom_lines():
         assert 0.2 < alpha < 0.35 and 1e-15 < cross < 1e-13          # ABO: sigma ~ 300-700 a0^2, alpha ~ 0.25-0.3
     ca2 = host.read_atom(atoms / "CaII.atom")
     assert all("BARKLEM" not in ln["vdw"] for ln in ca2["lines"])      # ions: readatom.c:313-319 -> UNSOLD
+
+
+@pytest.mark.parametrize("fixture,kw,active", [("nlte_caii", {}, ()), ("nlte_h_caii", {"HYDROGEN_LTE": "FALSE"}, ("H_6.atom",))])
+def test_nlte_plan_equals_reference_parsed_state(fixture, kw, active):
+    """pyrh_b200.nlte_host: readAtom of ACTIVE atoms + getLambda + SortLambda (merged grid, Nblue / Nlambda with Hunt's
+    starting-guess behaviour, active sets in the reference's order, hydrogenic and tabulated bound-free cross-sections,
+    quadrature weights) give the flat plan the probe recorded inside the reference, bit for bit."""
+    import os
+    from oracle import refdriver as rd
+    from oracle.gen_golden_nlte import KW
+    from pyrh_b200 import host, nlte_host as nh
+    os.environ["PYRH_PATH"] = str(PYRH_PATH)
+    g = np.load(GOLD / f"{fixture}.npz")
+    cwd = rd.make_workdir("tests", keywords=dict(KW, **kw), atoms_active=active, atoms_extra=(("CaII.atom", "ACTIVE"),))
+    k = host.read_keywords(cwd)
+    root = PYRH_PATH / "rh" / "Atoms"
+    atoms = [nh.read_active_atom(root / f, k) for f, s in host._atoms_listed(cwd, k) if s == "ACTIVE"]
+    p = nh.build_plan(atoms, np.linspace(630.25, 630.5, 21), float(k["LAMBDA_REF"]), int(k["NRAYS"]), k)
+    for key in ("lam", "muz", "wmu", "atom_nlevel", "tr_lambda", "tr_wlambda", "tr_alpha", "as_first", "as_trans"):
+        assert np.array_equal(p[key], g[key]), key
+    gt = g["trans"].copy()
+    lines = gt[:, nh.TR_TYPE] == 0
+    gt[lines, nh.TR_LAMBDA0] = g["line_lambda0"][gt[lines, nh.TR_LINEIDX].astype(int)]
+    assert np.array_equal(p["trans"], gt)
+    assert p["nphirow"] == g["phi"].shape[0] and p["nline"] == len(g["wphi"])
+    p1 = nh.single_mu_plan(p, 1.0)
+    assert p1["nphirow"] == g["fs_phi"].shape[0] and list(p1["muz"]) == [1.0]
+    coll, T, C, M = nh.collision_table(atoms)
+    assert len(coll) == sum(1 for at in atoms for ln in at["coll"] if ln.split()[0] in ("OMEGA", "CE", "CI"))
+    assert len(T) == len(C) == len(M) == int(coll[:, nh.CO_NT].sum())
+
+
+def test_hunt_reproduces_the_reference_quirk():
+    """Hunt() (hunt.c:17-78) is not Locate(): hunting DOWN onto an exact table value returns the index below it.
+    SortLambda's Nred inherits this, so nlte_host.hunt must too (H 2-4 of H_6.atom loses its last wavelength that way)."""
+    from pyrh_b200 import nlte_host as nh
+    arr = [float(x) for x in range(10)]
+    assert nh.locate(arr, 4.0) == 4 and nh.hunt(arr, 4.0, 0) == 4           # no usable guess: bisection
+    assert nh.hunt(arr, 4.0, 2) == 4                                         # hunting up: exact hit kept
+    assert nh.hunt(arr, 4.0, 6) == 3                                         # hunting down lands ON the value: one below
+    assert nh.hunt(arr, 4.0, 7) == 4                                         # ... steps over it: bracket still contains it
+    assert nh.hunt(arr, 4.5, 7) == 4 and nh.hunt(arr, 9.0, 9) == 9 and nh.hunt(arr, 0.0, 5) == 0
+    rng = np.random.default_rng(3)
+    tab = np.sort(rng.uniform(0, 100, 200))
+    for v, guess in zip(rng.uniform(-5, 105, 500), rng.integers(0, 200, 500)):
+        lo = nh.locate(tab, v)
+        assert nh.hunt(tab, v, int(guess)) == lo                              # generic values: same bracket
+
+
+def test_gauss_legendre_and_spline_helpers():
+    from pyrh_b200 import nlte_host as nh
+    x, w = nh.gauss_leg(0.0, 1.0, 5)
+    xs, ws = np.polynomial.legendre.leggauss(5)
+    assert np.allclose(x, 0.5 * (xs + 1), atol=1e-14) and np.allclose(w, 0.5 * ws, atol=1e-14)
+    t = [3000.0, 5000.0, 7000.0, 15000.0, 50000.0]
+    y = [1.0, 2.0, 1.5, 4.0, 3.0]
+    M = nh.spline_coef(t, y)
+    assert M[0] == 0.0 and M[-1] == 0.0
+    assert nh.spline_eval(t, y, M, [5000.0, 2000.0, 60000.0]) == [2.0, 1.0, 3.0]
+    from scipy.interpolate import CubicSpline
+    cs = CubicSpline(t, y, bc_type="natural")
+    assert np.allclose(nh.spline_eval(t, y, M, [4000.0, 9000.0, 30000.0]), cs([4000.0, 9000.0, 30000.0]), rtol=1e-12)
