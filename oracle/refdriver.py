@@ -63,10 +63,13 @@ _libs: dict[str, C.CDLL] = {}
 def load(variant: str = "scalar") -> C.CDLL:
     if variant in _libs:
         return _libs[variant]
-    path = REFDIR / f"liboracle_{variant}.so"
+    # "bridged": the reference's library with integration/pyrh_b200_bridge.c compiled in (integration/build_bridged.sh):
+    # same rhf1d() prototype, per-column work on the GPU through librhb200
+    path = HERE / "_build" / "libpyrh_bridged.so" if variant == "bridged" else REFDIR / f"liboracle_{variant}.so"
     if not path.exists():
         raise FileNotFoundError(f"{path} missing: run `make -C oracle ref` where /root/reference exists")
     os.environ["PYRH_PATH"] = str(REFDIR / "pyrh_path")
+    os.environ.setdefault("RHB200_DATA", str(HERE.parent / "pyrh_b200" / "data"))
     lib = C.CDLL(str(path), mode=os.RTLD_LOCAL)
     lib.rhf1d.restype = MySpectrum
     lib.rhf1d.argtypes = [
@@ -79,11 +82,17 @@ def load(variant: str = "scalar") -> C.CDLL:
         C.c_int, c_int_p, c_double_p,
         C.c_int, c_int_p, c_double_p,
         C.c_int, C.c_int, C.c_int, C.c_char_p]
-    lib.probe_enable.argtypes = [C.c_uint]
-    lib.probe_reset.argtypes = []
-    lib.probe_count.restype = C.c_long
-    lib.probe_get.restype = C.POINTER(ProbeRec)
-    lib.probe_get.argtypes = [C.c_long]
+    if variant != "bridged":
+        lib.probe_enable.argtypes = [C.c_uint]
+        lib.probe_reset.argtypes = []
+        lib.probe_count.restype = C.c_long
+        lib.probe_get.restype = C.POINTER(ProbeRec)
+        lib.probe_get.argtypes = [C.c_long]
+    else:
+        lib.rhf1d_batch.restype = MySpectrum
+        lib.rhf1d_batch.argtypes = [C.c_char_p, C.c_double, C.c_int, C.c_int, c_double_p, C.c_int, C.c_int, c_double_p,
+                                    C.c_int, c_double_p, c_double_p, C.c_int, c_int_p, c_double_p, C.c_int, c_int_p,
+                                    c_double_p, C.c_int, c_int_p, c_double_p, c_double_p, c_double_p, c_double_p, c_int_p]
     _libs[variant] = lib
     return lib
 
@@ -166,8 +175,9 @@ def rhf1d(atmosphere: np.ndarray, wave: np.ndarray, cwd: str, mu: float = 1.0,
     nf = 0 if fudge_wave is None else len(fudge_wave)
     f_lam = np.ascontiguousarray(fudge_wave if nf else [0.0], dtype=np.float64)
     f_val = np.ascontiguousarray(fudge_value if nf else [0.0], dtype=np.float64)     # [3][nf] row-major
-    lib.probe_reset()
-    lib.probe_enable(probe)
+    if variant != "bridged":
+        lib.probe_reset()
+        lib.probe_enable(probe)
     old = os.getcwd()
     os.chdir(cwd)   # Kurucz list entries are opened relative to the process cwd (kurucz.c:160-165)
     try:
@@ -197,7 +207,36 @@ def rhf1d(atmosphere: np.ndarray, wave: np.ndarray, cwd: str, mu: float = 1.0,
         out["pops"] = pops
     if probe:
         out["records"] = records(lib)
-    lib.probe_enable(0)
+    if variant != "bridged":
+        lib.probe_enable(0)
+    return out
+
+
+def rhf1d_batch(atmospheres: np.ndarray, wave: np.ndarray, cwd: str, mu: float = 1.0, atm_scale: int = 0,
+                get_populations: bool = False, nlev: int = 0):
+    """rhf1d_batch() of the bridged library: [ncol, 9, Ndep] pyrh rows -> dict(lam, stokes [ncol, 4, nlw][, n, nstar, niter])."""
+    lib = load("bridged")
+    atm = np.ascontiguousarray(atmospheres, np.float64)[:, :9].copy()
+    wave = np.ascontiguousarray(wave, np.float64).copy()
+    ncol, _, ndep = atm.shape
+    cap = len(wave) + 4096
+    st = np.zeros((ncol, 4, cap))
+    n = np.zeros((ncol, nlev, ndep)) if get_populations else None
+    ns = np.zeros((ncol, nlev, ndep)) if get_populations else None
+    nit = np.zeros(ncol, np.int32)
+    old = os.getcwd()
+    os.chdir(cwd)
+    try:
+        spec = lib.rhf1d_batch(str(cwd).encode(), float(mu), ndep, ncol, _dp(atm), int(atm_scale), len(wave), _dp(wave),
+                               0, None, None, 0, None, None, 0, None, None, 0, None, None, _dp(st),
+                               _dp(n) if get_populations else None, _dp(ns) if get_populations else None,
+                               nit.ctypes.data_as(c_int_p))
+    finally:
+        os.chdir(old)
+    nlw = spec.nlw
+    out = dict(lam=np.ctypeslib.as_array(spec.lam, shape=(nlw,)).copy(), stokes=st.reshape(-1)[:ncol * 4 * nlw].reshape(ncol, 4, nlw).copy())
+    if get_populations:
+        out.update(n=n, nstar=ns, niter=nit)
     return out
 
 

@@ -1442,3 +1442,73 @@ def test_nlte_fast_rates_default_mode_within_tolerance(case):
     assert np.all(en[conv] <= 1e-6) and np.all(eI[conv] <= 1e-6)
     assert np.array_equal(res["n"], again["n"]) and np.array_equal(res["I"], again["I"])
     assert np.array_equal(res["n"][2:5], part["n"]) and np.array_equal(res["I"][2:5], part["I"])
+
+
+def _bridged():
+    from oracle import refdriver as rd
+    if not (rd.HERE / "_build" / "libpyrh_bridged.so").exists() or not rd.available():
+        pytest.skip("oracle/_build/libpyrh_bridged.so not built (integration/build_bridged.sh where /root/reference exists)")
+    os.environ["RHB200_DATA"] = str(Path(__file__).resolve().parent.parent / "pyrh_b200" / "data")
+    return rd
+
+
+@pytest.mark.gpu
+def test_bridged_reference_library_rhf1d_lte():
+    """Row (b) of the scope table, compiled: the reference's own pyrh C library with integration/pyrh_b200_bridge.c
+    + integration/pyrh_b200.patch built in (integration/build_bridged.sh).  Its `rhf1d()` -- exact prototype and
+    by-value `mySpectrum` of rh/rhf1d/pyrh_compute1dray.h:12-36, called through the same ctypes binding as the
+    unmodified library -- runs the reference's host set-up (readInput ... SortLambda), flattens the parsed structs
+    into the rhb200 tables in C and does the per-column work on the GPU.  Bytes identical to the unmodified rhf1d():
+    config 1 (FULL_STOKES, B = 1 kG), a 70-depth benchmark column, the reference's NO_STOKES test directory at
+    mu = 0.5, and get_atomic_rfs."""
+    rd = _bridged()
+    full = dict(np.load(GOLD / "falc_full.npz"))
+    cwd = rd.make_workdir("benchmark")
+    o = rd.rhf1d(full["atmosphere"], full["wave"], cwd, variant="bridged")
+    got = np.array([o[k] for k in "IQUV"])
+    REPORT["bridged_rhf1d_config1_exact"] = bool(np.array_equal(got, full["stokes"]))
+    assert np.array_equal(o["lam"], full["lam_spect"][full["lam_spect"] != 500.0])
+    assert np.array_equal(got, full["stokes"])
+    g = dict(np.load(GOLD / "synth70_c2.npz"))
+    o = rd.rhf1d(g["atmosphere"], g["wave"], cwd, variant="bridged")           # second call: tables rebuilt on the same context
+    assert np.array_equal(np.array([o[k] for k in "IQUV"]), g["stokes_scalar"])
+    # rhf1d_batch: six columns through one call = six rhf1d() calls
+    gs = [dict(np.load(GOLD / f"synth70_c{c}.npz")) for c in range(3)]
+    atm = np.stack([x["atmosphere"] for x in gs] * 2)
+    b = rd.rhf1d_batch(atm, gs[0]["wave"], cwd)
+    for c in range(6):
+        assert np.array_equal(b["stokes"][c], gs[c % 3]["stokes_scalar"])
+    # (the log gf calls come last: the reference never resets atmos.Nloggf / loggf_ids, so a later call without them
+    #  would read the stale pointers -- its own quirk, pyrh_compute1dray.c:199-204)
+    t = dict(np.load(GOLD / "ref_test_compute1d.npz"))
+    cwd_t = rd.make_workdir("tests")
+    o = rd.rhf1d(t["moving_atmosphere"], t["wave"], cwd_t, mu=0.5, variant="bridged")
+    assert np.array_equal(o["I"], t["moving_I"]) and not o["Q"].any()
+    live = rd.rhf1d(t["atmosphere"], t["wave"], cwd_t, loggf_ids=[1], loggf_values=[-0.969], get_atomic_rfs=True)
+    o = rd.rhf1d(t["atmosphere"], t["wave"], cwd_t, loggf_ids=[1], loggf_values=[-0.969], get_atomic_rfs=True, variant="bridged")
+    assert np.array_equal(o["I"], live["I"]) and np.array_equal(o["rfs"], live["rfs"]) and np.abs(o["rfs"]).max() > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["caii_r3", "caii_r5", "h_caii_r3", "h_caii_r5"])
+def test_bridged_reference_library_rhf1d_nlte(case):
+    """The bridged library with ACTIVE atoms: the reference's readAtom / getLambda / SortLambda state (active sets,
+    line grids, continuum cross-sections) and the collisional sections of the atom files are flattened in C
+    (integration/pyrh_b200_bridge.c) and rhb200_nlte_compute1d_batch does the rest.  rhf1d(get_populations) returns the
+    reference's own AtomPops; spectrum and populations are bit-identical to the unmodified library's on perturbed
+    columns (rate accumulation in the reference's order), also through rhf1d_batch."""
+    import json
+    rd = _bridged()
+    g = np.load(GOLD / "nlte_front.npz")
+    c = json.loads(str(g["cases"]))[case]
+    cwd = rd.make_workdir("tests", keywords=c["kw"], atoms_active=tuple(c["active"]), atoms_extra=(("CaII.atom", "ACTIVE"),))
+    atm, wave, mu = g["atmosphere"], g[f"{case}_wave"], float(g[f"{case}_mu"])
+    o = rd.rhf1d(atm[1], wave, cwd, mu=mu, get_populations=True, variant="bridged")
+    n = np.concatenate([o["pops"][k]["n"] for k in c["keys"]])
+    ns = np.concatenate([o["pops"][k]["nstar"] for k in c["keys"]])
+    REPORT[f"bridged_rhf1d_nlte_{case}_exact"] = bool(np.array_equal(o["I"], g[f"{case}_I"][1]) and np.array_equal(n, g[f"{case}_n"][1]))
+    assert np.array_equal(o["lam"], g[f"{case}_lam"]) and np.array_equal(o["I"], g[f"{case}_I"][1])
+    assert np.array_equal(n, g[f"{case}_n"][1]) and np.array_equal(ns, g[f"{case}_nstar"][1])
+    b = rd.rhf1d_batch(atm[:4], wave, cwd, mu=mu, get_populations=True, nlev=n.shape[0])
+    assert np.array_equal(b["stokes"][:, 0], g[f"{case}_I"][:4]) and np.array_equal(b["n"], g[f"{case}_n"][:4])
+    assert np.array_equal(b["niter"], g[f"{case}_niter"][:4])
