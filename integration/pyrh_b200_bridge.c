@@ -77,6 +77,9 @@ void pyrh_b200_save_inputs(int Ndep, int atm_scale, double *scale, double *temp,
   if (Ndep != g_rows_ndep) { g_rows = (double *) realloc(g_rows, (size_t) 9 * Ndep * sizeof(double)); g_rows_ndep = Ndep; }
   for (r = 0; r < 9; r++) memcpy(g_rows + (size_t) r * Ndep, src[r], Ndep * sizeof(double));
   g_atm_scale = atm_scale;
+  /* rhf1d() only ever SETS atmos.Nloggf / Nlam (pyrh_compute1dray.c:199-211): a call without log gf / wavelength
+     overrides after one with them would make readKuruczLines() read the previous caller's freed arrays */
+  atmos.Nloggf = 0; atmos.Nlam = 0;
 }
 
 /* ---- published opacity tables (pyrh_b200/data/opacity_tables.txt; hydrogen.c / ohchbf.c keep them function-static) */

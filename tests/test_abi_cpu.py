@@ -66,3 +66,22 @@ def test_synthetic_generator_is_deterministic():
     assert np.array_equal(a[1:], b)
     g = np.load(ROOT / "tests" / "golden" / "synth70_c1.npz")
     assert np.array_equal(g["atmosphere"], a[1])
+
+
+def test_bridged_reference_library_exports_the_pyrh_symbols():
+    """oracle/_build/libpyrh_bridged.so (integration/build_bridged.sh): the reference's pyrh C library with the bridge
+    compiled in must export exactly what rh.pxd:140-185 binds -- rhf1d, get_RLK_lines, hse, get_scales, get_ne_from_nH --
+    plus the non-breaking additions rhf1d_batch / pyrh_b200_close, and be linked against librhb200."""
+    import ctypes
+    import subprocess
+    from pathlib import Path
+    import pytest
+    so = Path(__file__).resolve().parent.parent / "oracle" / "_build" / "libpyrh_bridged.so"
+    if not so.exists():
+        pytest.skip("bridged library not built (needs /root/reference: integration/build_bridged.sh)")
+    lib = ctypes.CDLL(str(so))
+    for name in ("rhf1d", "get_RLK_lines", "hse", "get_scales", "get_ne_from_nH", "rhf1d_batch", "pyrh_b200_close",
+                 "pyrh_b200_solve", "pyrh_b200_save_inputs"):
+        assert hasattr(lib, name), name
+    needed = subprocess.run(["readelf", "-d", str(so)], capture_output=True, text=True).stdout
+    assert "librhb200.so" in needed
