@@ -489,6 +489,47 @@ def main():
     barrier()
     ms_e2e = maxreduce(ms_e2e)
     launches_b = sum(v[1] for v in ctx.timing_get().values()) - launches_b0
+    # ---- strong scaling of the same call: the 16 384 columns of configs[1] in TOTAL, column-sharded over the ranks
+    #      (each rank runs its contiguous block; no collective on the data path)
+    lo, cnt = rank * ncol // world, (rank + 1) * ncol // world - rank * ncol // world
+    run_s = lambda: ctx.compute1d_batch(pyrh_atm[lo:lo + cnt], wght_per_H=wght_per_H, out=stokes_b[lo:lo + cnt], keep_lambda_ref=True)
+    run_s()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run_s()
+    ctx.synchronize()
+    ms_strong = 1e3 * (time.perf_counter() - t0)
+    barrier()
+    ms_strong = maxreduce(ms_strong)
+    # ---- the same from ONE process driving every visible GPU (rhb200_compute1d_batch_multi): only when not under torchrun
+    multi = None
+    if world == 1 and args.gpus > 1:
+        import ctypes as C
+        from pyrh_b200 import _lib
+        ctxs = [ctx]
+        for d in range(1, args.gpus):
+            cd = api.Context(d)
+            cd.set_lines(LineTable.from_npz(g0)); cd.set_wavelengths(lam_spect); cd.set_continuum(model, abundance)
+            cd.set_chemistry(full["ce_nuclei"][:, 1].astype(np.int32), full["ce_mol"])
+            ctxs.append(cd)
+        handles = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+        iref = int(np.flatnonzero(lam_spect == 500.0)[0])
+        run_m = lambda: _lib.check(ctx.lib.rhb200_compute1d_batch_multi(
+            len(ctxs), handles, ncol, NDEP, 9, 1.0, 0, C.c_void_p(pyrh_atm.ctypes.data), iref, wght_per_H, 0.0,
+            _lib.BC_ZERO, _lib.BC_THERMALIZED, C.c_void_p(stokes_b.ctypes.data), None))
+        ref_b = stokes_b.copy()
+        run_m(); run_m()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            run_m()
+        ms_multi = 1e3 * (time.perf_counter() - t0)
+        multi = {"devices": args.gpus, "ncol_total": ncol, "ms_per_step": ms_multi / args.steps,
+                 "value": units * args.steps / (ms_multi * 1e-3), "unit": "ray-points/s",
+                 "speedup_vs_one_gpu": (ms_e2e / ms_multi), "bitwise_equal_to_one_gpu": bool(np.array_equal(ref_b, stokes_b)),
+                 "call": "rhb200_compute1d_batch_multi: one process, one host thread per device, contiguous column blocks"}
+        for cd in ctxs[1:]:
+            cd.close()
     ctx.timing(True)
     run_b()
     kt_b = {n: (ms / max(cnt, 1), cnt) for n, (ms, cnt) in ctx.timing_get().items() if cnt}
@@ -571,6 +612,11 @@ def main():
                     "h2d_bytes_per_step": int(at.nbytes + chi.nbytes + eta.nbytes),
                     "d2h_bytes_per_step": int(stokes.nbytes), "ms_per_step": ms_e2e_bg / args.steps,
                     "bitwise_equal_to_device_resident_run": same},
+            "strong_scaling": {"ncol_total": ncol, "n_gpus": world, "ms_per_step": ms_strong / args.steps,
+                               "value": units * args.steps / (ms_strong * 1e-3), "unit": "ray-points/s",
+                               "note": "the SAME 16 384-column batch split over the ranks (e2e call, host buffers); "
+                                       "efficiency = value / (n_gpus x the n_gpus = 1 value)"},
+            "single_process_multi_gpu": multi,
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "nlte": nlte}
     if world == 1 and not args.no_cpu_baseline:
         try:

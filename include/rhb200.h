@@ -374,6 +374,19 @@ int rhb200_compute1d_batch(rhb200_ctx *ctx, int ncol, int ndep, int nrow, double
                            const double *atmosphere, int iref, double wght_per_H, double vmacro_tresh,
                            int bc_top, int bc_bottom, double *stokes, double *scales);
 
+/* One host batch over several GPUs of the box, from one process (BASELINE configs[1]: "column-sharded over 1/2/4/8
+   GPUs"): ctxs[nctx] are contexts opened on different devices and set up with the same tables; the columns are cut into
+   nctx contiguous blocks (rhb200_shard_columns), every block runs rhb200_compute1d_batch on its own context from its own
+   host thread -- copies and kernels of the devices overlap -- and the call returns when all are done.  No data-path
+   collective: columns are independent.  Arguments as rhb200_compute1d_batch; page-locked host buffers
+   (rhb200_host_alloc_pinned) keep the copies of the devices concurrent.  Returns the first error of any block. */
+int rhb200_compute1d_batch_multi(int nctx, rhb200_ctx *const *ctxs, int ncol, int ndep, int nrow, double mu, int atm_scale,
+                                 const double *atmosphere, int iref, double wght_per_H, double vmacro_tresh,
+                                 int bc_top, int bc_bottom, double *stokes, double *scales);
+/* block [*first, *first + *count) of `ncol` columns that shard `rank` of `nrank` takes (contiguous, sizes differ by at
+   most one) */
+int rhb200_shard_columns(int ncol, int rank, int nrank, int *first, int *count);
+
 /* rhb200_compute1d_batch with get_atomic_rfs = 1: additionally rfs [ncol][nlambda][npar] = atmos.atomic_rfs[nspect][0][p]
    (formal.c:278-282, pyrh_solveray.c:144-147; pyrh.compute1d returns its transpose without the lambda_ref entry), the
    response of the emergent intensity to log gf of the lines registered with rhb200_set_loggf_rf.  As in the reference

@@ -66,6 +66,9 @@ SYMBOLS = [
     ("rhb200_lte_stokes_batch_atmos", C.c_int, [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, vp, vp]),
     ("rhb200_compute1d_batch", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, vp, C.c_int, C.c_double,
                                          C.c_double, C.c_int, C.c_int, vp, vp]),
+    ("rhb200_compute1d_batch_multi", C.c_int, [C.c_int, C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, vp,
+                                               C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, vp, vp]),
+    ("rhb200_shard_columns", C.c_int, [C.c_int, C.c_int, C.c_int, ip, ip]),
     ("rhb200_compute1d_rf_batch", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, vp, C.c_int, C.c_double,
                                             C.c_double, C.c_int, C.c_int, vp, vp, vp]),
     ("rhb200_set_loggf_rf", C.c_int, [vp, C.c_int, ip]),

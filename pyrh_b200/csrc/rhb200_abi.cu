@@ -4,6 +4,7 @@
 #include <cmath>
 #include <algorithm>
 #include <mutex>
+#include <thread>
 #include "rhb200_common.cuh"
 
 // ------------------------------------------------------------------ errors
@@ -743,6 +744,50 @@ extern "C" int rhb200_compute1d_batch(rhb200_ctx *c, int ncol, int ndep, int nro
   if (!(wght_per_H > 0.0) && atm_scale == 1) { rhb200_set_error("wght_per_H (abundance.c:220) is needed for the column-mass scale"); return RHB200_EINVAL; }
   PyrhIn py{atmosphere, nrow, atm_scale, iref, wght_per_H, vmacro_tresh, scales};
   return lte_batch_host(c, ncol, ndep, mu, 1, bc_top, bc_bottom, nullptr, nullptr, nullptr, nullptr, stokes, 1, &py);
+}
+
+extern "C" int rhb200_shard_columns(int ncol, int rank, int nrank, int *first, int *count)
+{
+  if (ncol < 0 || nrank < 1 || rank < 0 || rank >= nrank || !first || !count) { rhb200_set_error("rhb200_shard_columns: bad arguments"); return RHB200_EINVAL; }
+  const int base = ncol / nrank, rem = ncol % nrank;
+  *first = rank * base + std::min(rank, rem);
+  *count = base + (rank < rem ? 1 : 0);
+  return RHB200_OK;
+}
+
+// One host batch fanned over the GPUs of the box from one process: a host thread per context, contiguous column blocks,
+// no collective (columns are independent).  The error text of a failing block is copied into the caller's thread.
+extern "C" int rhb200_compute1d_batch_multi(int nctx, rhb200_ctx *const *ctxs, int ncol, int ndep, int nrow, double mu, int atm_scale,
+                                            const double *atmosphere, int iref, double wght_per_H, double vmacro_tresh,
+                                            int bc_top, int bc_bottom, double *stokes, double *scales)
+{
+  if (nctx < 1 || !ctxs) { rhb200_set_error("rhb200_compute1d_batch_multi: no contexts"); return RHB200_EINVAL; }
+  for (int i = 0; i < nctx; i++) {
+    if (!ctxs[i]) { rhb200_set_error("context %d is NULL", i); return RHB200_EINVAL; }
+    if (ctxs[i]->wav.nlambda != ctxs[0]->wav.nlambda) { rhb200_set_error("contexts differ in their wavelength grids"); return RHB200_EINVAL; }
+    for (int j = 0; j < i; j++) if (ctxs[j]->device == ctxs[i]->device) { rhb200_set_error("contexts %d and %d share device %d", j, i, ctxs[i]->device); return RHB200_EINVAL; }
+  }
+  if (nctx == 1) return rhb200_compute1d_batch(ctxs[0], ncol, ndep, nrow, mu, atm_scale, atmosphere, iref, wght_per_H, vmacro_tresh,
+                                               bc_top, bc_bottom, stokes, scales);
+  const int nl = ctxs[0]->wav.nlambda;
+  std::vector<int> rc(nctx, RHB200_OK);
+  std::vector<std::string> err(nctx);
+  std::vector<std::thread> th;
+  for (int i = 0; i < nctx; i++)
+    th.emplace_back([&, i]() {
+      int first = 0, count = 0;
+      rhb200_shard_columns(ncol, i, nctx, &first, &count);
+      if (count == 0) return;
+      rc[i] = rhb200_compute1d_batch(ctxs[i], count, ndep, nrow, mu, atm_scale, atmosphere + (size_t) first * nrow * ndep, iref,
+                                     wght_per_H, vmacro_tresh, bc_top, bc_bottom,
+                                     stokes ? stokes + (size_t) first * 4 * nl : nullptr,
+                                     scales ? scales + (size_t) first * 3 * ndep : nullptr);
+      if (rc[i] != RHB200_OK) err[i] = rhb200_last_error();
+    });
+  for (auto &t : th) t.join();
+  for (int i = 0; i < nctx; i++)
+    if (rc[i] != RHB200_OK) { rhb200_set_error("device %d: %s", ctxs[i]->device, err[i].c_str()); return rc[i]; }
+  return RHB200_OK;
 }
 
 // get_atomic_rfs = 1 (pyrh.pyx:604-606, 658-660): rhb200_compute1d_batch plus mySpectrum.rfs for the log gf parameters

@@ -1038,6 +1038,45 @@ class Session:
         self.ctx.close()
 
 
+class MultiSession:
+    """One host batch over several GPUs of the box from ONE process (BASELINE configs[1]: column-sharded over 1/2/4/8
+    GPUs): a Session per device with the same tables; ``compute`` cuts the columns into contiguous blocks and runs them
+    concurrently (``rhb200_compute1d_batch_multi``: one host thread per device, no collective -- columns are
+    independent).  Results are bit-identical to a single-device run."""
+
+    def __init__(self, cwd, wave, devices, **kwargs):
+        if len(set(devices)) != len(devices) or not devices:
+            raise ValueError("devices must be a non-empty list of distinct CUDA device indices")
+        self.sessions = [Session(cwd, wave, device=d, **kwargs) for d in devices]
+        self.devices = list(devices)
+
+    @property
+    def wavelengths(self):
+        return self.sessions[0].wavelengths
+
+    def compute(self, atmosphere, mu=1.0, atm_scale=0, out=None):
+        """``atmosphere`` [ncol, 9+, ndep] (pyrh units; page-locked memory keeps the devices' copies concurrent) ->
+        Stokes [ncol, 4, nlambda] on ``wavelengths``."""
+        import ctypes as C
+        from . import _lib, api
+        s0 = self.sessions[0]
+        a = np.ascontiguousarray(atmosphere, np.float64)
+        ncol, nrow, ndep = a.shape
+        nl = len(s0.lam)
+        iref = int(np.flatnonzero(s0.lam == s0.lambda_ref)[0])
+        st = np.empty((ncol, 4, nl)) if out is None else out
+        handles = (C.c_void_p * len(self.sessions))(*[s.ctx.h for s in self.sessions])
+        _lib.check(s0.ctx.lib.rhb200_compute1d_batch_multi(
+            len(self.sessions), handles, ncol, ndep, nrow, float(mu), int(atm_scale), C.c_void_p(a.ctypes.data), iref,
+            float(s0.el.wght_per_H), float(s0.vmacro_tresh) * api.KM_TO_M, _lib.BC_ZERO, _lib.BC_THERMALIZED,
+            C.c_void_p(st.ctypes.data), None))
+        return st if out is not None else np.delete(st, iref, axis=2)
+
+    def close(self):
+        for s in self.sessions:
+            s.close()
+
+
 def get_scales(cwd, atm_scale, scale, atmosphere, lam_ref, atomic_number=None, atomic_abundance=None, device=0):
     """Drop-in for ``pyrh.get_scales`` (pyrh.pyx:491-534): ``(tau, height [m], cmass [kg m^-2])`` of one column from
     Background() at ``lam_ref`` and convertScales().  Like the reference it looks at no Kurucz line

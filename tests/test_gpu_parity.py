@@ -1512,3 +1512,92 @@ def test_bridged_reference_library_rhf1d_nlte(case):
     b = rd.rhf1d_batch(atm[:4], wave, cwd, mu=mu, get_populations=True, nlev=n.shape[0])
     assert np.array_equal(b["stokes"][:, 0], g[f"{case}_I"][:4]) and np.array_equal(b["n"], g[f"{case}_n"][:4])
     assert np.array_equal(b["niter"], g[f"{case}_niter"][:4])
+
+
+def _ref_columns(args):
+    """worker: rhf1d() of the unmodified reference for a list of columns of the synthetic batch"""
+    cols, ndep = args
+    from oracle import refdriver as rd
+    from pyrh_b200 import synthetic
+    base = np.load(GOLD / "falc_base.npy")
+    cwd = rd.make_workdir("benchmark")
+    wave = rd.hinode_wave(301)
+    out = []
+    for c in cols:
+        a = synthetic.perturbed_batch(base, 1, ndep=ndep, first=int(c))[0]
+        o = rd.rhf1d(a, wave, cwd)
+        out.append(np.array([o[k] for k in "IQUV"]))
+    return out
+
+
+@pytest.mark.gpu
+def test_full_size_batch_256_random_columns_vs_reference():
+    """BASELINE configs[1] at full size: 16 384 perturbed FAL-C columns x 70 depths x 301 wavelengths through the
+    drop-in call (host.Session.compute = rhb200_compute1d_batch), and 256 columns drawn at random from the batch
+    checked against the unmodified reference's rhf1d() (one process per host core): Stokes I, Q, U, V bit-identical
+    (north_star: I 1e-9 relative, Q/U/V 1e-12 of the continuum)."""
+    import multiprocessing as mp
+    from oracle import refdriver as rd
+    from pyrh_b200 import host, synthetic
+    if not rd.available():
+        pytest.skip("reference not staged (oracle/_ref)")
+    os.environ["PYRH_PATH"] = str(rd.REFDIR / "pyrh_path")
+    ncol, ndep = 16384, 70
+    cwd = rd.make_workdir("benchmark")
+    s = host.Session(cwd, rd.hinode_wave(301))
+    try:
+        atm = synthetic.perturbed_batch(np.load(GOLD / "falc_base.npy"), ncol, ndep=ndep)
+        st = s.compute(atm)
+    finally:
+        s.close()
+    assert st.shape == (ncol, 4, 301) and np.isfinite(st).all()
+    pick = np.sort(np.random.default_rng(7).choice(ncol, 256, replace=False))
+    nproc = min(os.cpu_count() or 1, 32)
+    with mp.get_context("fork").Pool(nproc) as pool:
+        parts = pool.map(_ref_columns, [(pick[p::nproc], ndep) for p in range(nproc)], chunksize=1)
+    ref = np.zeros((256, 4, 301))
+    for p, part in enumerate(parts):
+        ref[p::nproc] = np.array(part)
+    got = st[pick]
+    Ic = ref[:, 0].max(axis=1)[:, None, None]
+    eI = float(np.max(np.abs(got[:, 0] / ref[:, 0] - 1)))
+    eP = float(np.max(np.abs(got[:, 1:] - ref[:, 1:]) / Ic))
+    REPORT["full_size_256_columns"] = dict(I_maxrel=eI, QUV_over_Ic=eP, bitwise=bool(np.array_equal(got, ref)))
+    assert eI <= 1e-9 and eP <= 1e-12
+    assert np.array_equal(got, ref)
+
+
+@pytest.mark.gpu
+def test_single_process_multi_gpu_batch():
+    """host.MultiSession / rhb200_compute1d_batch_multi: one host batch fanned over all visible GPUs from one process
+    (a host thread per device, contiguous column blocks, no collective).  Bit-identical to the single-device call; with
+    one visible GPU the multi entry must still work (one context)."""
+    from oracle import refdriver as rd
+    from pyrh_b200 import _lib, host, synthetic
+    if not rd.available():
+        pytest.skip("reference input files not staged (oracle/_ref)")
+    os.environ["PYRH_PATH"] = str(rd.REFDIR / "pyrh_path")
+    ndev = _lib.load().rhb200_device_count()
+    cwd = rd.make_workdir("benchmark")
+    atm = synthetic.perturbed_batch(np.load(GOLD / "falc_base.npy"), 1001, ndep=70)
+    one = host.Session(cwd, rd.hinode_wave(301))
+    try:
+        ref = one.compute(atm)
+    finally:
+        one.close()
+    ms = host.MultiSession(cwd, rd.hinode_wave(301), devices=list(range(ndev)))
+    try:
+        got = ms.compute(atm)
+    finally:
+        ms.close()
+    REPORT["multi_session_devices"] = ndev
+    assert np.array_equal(got, ref)
+    lib = _lib.load()
+    import ctypes as C
+    tot = 0
+    for r in range(3):
+        f, n = C.c_int(), C.c_int()
+        assert lib.rhb200_shard_columns(1001, r, 3, C.byref(f), C.byref(n)) == 0
+        assert f.value == tot
+        tot += n.value
+    assert tot == 1001
