@@ -4,6 +4,7 @@
 // is IEEE-deterministic (see DESIGN.md "Arithmetic contract").
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -102,6 +103,7 @@ struct rhb200_ctx {
   rhb200_allreduce_fn shard_fn = nullptr; void *shard_user = nullptr;
   void *elements = nullptr;  // all elements + partition functions (rhb200_set_elements), owned by rhb200_hse.cu
   void *cont = nullptr;      // background-continuum state (rhb200_set_continuum), owned by rhb200_continuum.cu
+  void *nlte_front = nullptr;   // plans / engines / work arrays of rhb200_nlte_compute1d_batch, owned by rhb200_nlte.cu
   // workspace (grown on demand)
   void *ws = nullptr; size_t ws_bytes = 0;
   void *flush = nullptr; size_t flush_bytes = 0;
@@ -132,6 +134,7 @@ struct ScopedKernelTimer {
 
 int rh_ws_reserve(rhb200_ctx *ctx, size_t bytes);
 void rh_continuum_free(rhb200_ctx *ctx);
+void rh_nlte_front_free(rhb200_ctx *ctx);
 void rh_elements_free(rhb200_ctx *ctx);
 int rh_continuum_nlev(const rhb200_ctx *ctx);
 int rh_continuum_natom(const rhb200_ctx *ctx);

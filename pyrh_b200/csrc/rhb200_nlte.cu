@@ -26,6 +26,7 @@
 //                   thread in the reference's k-order
 // Columns that reached ITER_LIMIT are frozen (per-column `active` flag), like separate rhf1d calls.
 #include <algorithm>
+#include <chrono>
 #include <vector>
 #include "rhb200_common.cuh"
 #include "rhb200_bezier.cuh"

@@ -181,12 +181,28 @@ nlte_damping_gather_kernel(Plan P, Cols C, int ncol, const double *__restrict__ 
   ((double *) C.vbroad)[((size_t) col * P.Natom + a) * N + k] = p[2*(size_t) N];    // same value from every line of the atom
 }
 
+struct FrontState {                 // kept with the context between calls of rhb200_nlte_compute1d_batch
+  uint64_t key = 0;
+  int cc = 0;
+  NlteEngine E, F;
+  DevArena ar;
+  double *d_in = nullptr, *d_at = nullptr, *d_pops = nullptr, *d_popsn = nullptr, *d_chem = nullptr, *d_ntot = nullptr, *d_tprep = nullptr,
+         *d_sc = nullptr, *d_pc = nullptr, *d_apc = nullptr, *d_elem_n = nullptr, *d_lineprep = nullptr, *d_md = nullptr, *d_mol = nullptr,
+         *d_mchi = nullptr, *d_meta = nullptr, *d_spec = nullptr, *d_abund = nullptr, *d_coll = nullptr, *d_cT = nullptr, *d_cC = nullptr,
+         *d_cM = nullptr, *d_plrows = nullptr, *d_adamp2 = nullptr, *d_chi2 = nullptr, *d_eta2 = nullptr, *d_sca2 = nullptr;
+};
+
 struct FrontDebug {                 // device copies kept for rhb200_nlte_front_debug (test hook)
   std::vector<std::vector<double>> arr;
 };
 FrontDebug g_front_debug;
 
 }  // namespace
+
+void rh_nlte_front_free(rhb200_ctx *c)
+{
+  if (c->nlte_front) { delete (FrontState *) c->nlte_front; c->nlte_front = nullptr; }
+}
 
 extern "C" int rhb200_nlte_front_debug(rhb200_ctx *c, int which, double *out, size_t count)
 {
@@ -241,68 +257,125 @@ extern "C" int rhb200_nlte_compute1d_batch(rhb200_ctx *c, const rhb200_nlte_plan
     }
   }
 
-  // the two engines: Nrays rays for initScatter / Iterate, one ray at `mu` for _solveray()'s pass
+  const bool trace = getenv("RHB200_NLTE_TRACE") != nullptr;
+  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t_prev = now();
+  auto mark = [&](const char *what) {
+    if (!trace) return;
+    cudaStreamSynchronize(c->stream);
+    const double t = now();
+    fprintf(stderr, "[rhb200 nlte] %-28s %9.3f ms\n", what, t - t_prev);
+    t_prev = t;
+  };
+  // ---- state kept with the context between calls (plans, engines, work arrays): rebuilt only when the problem's
+  //      structure, the tables' sizes, the chunk size or mu change -- an inversion calls this thousands of times
   rhb200_nlte_plan p1 = *fr->plan1;
   const double mu1[1] = {mu}, w1[1] = {1.0};
   p1.muz = mu1; p1.wmu = w1; p1.Nrays = 1;
-  NlteEngine E, F;
-  RH_CHECK(E.build(c, pl));
-  RH_CHECK(F.build(c, &p1));
-  if (E.nrank > 1) { rhb200_set_error("wavelength sharding is only available through rhb200_nlte_iterate"); return RHB200_EUNSUPPORTED; }
-
-  // ---- chunk size from the workspace budget
-  size_t budget = (size_t) 48 << 30;
-  if (const char *e = getenv("RHB200_NLTE_WS_GB")) { const double g = atof(e); if (g > 0.01) budget = (size_t) (g * (double) ((size_t) 1 << 30)); }
   const int nline_k = c->tab.nline, nelem = c->tab.nelem;
-  const size_t per_col = sizeof(double) * (E.doubles_per_column(true) + F.doubles_per_column(false) +
-      (size_t) N * ((size_t) nrow + RHB200_AT_NFIELD + 2*(size_t) nlev_model + 2*(size_t) (natom_model + 4) + 8 + 5 +
-                    (size_t) std::max(1, c->wav.npl) * 4 + (size_t) std::max(1, pl->nline) * 4 +
-                    (size_t) std::max(1, nelem) * RHB200_RE_MAXSTAGE + (size_t) std::max(1, nline_k) * LP_NFIELD +
-                    (size_t) c->wav.nmsel * 4 + 2*(size_t) (c->wav.nmw > 0 ? Ns : 0)) + (size_t) Ns);
-  int cc = (int) std::min<size_t>((size_t) ncol, std::max<size_t>(1, budget / per_col));
-  if (const char *e = getenv("RHB200_NLTE_CHUNK_COLS")) { const int v = atoi(e); if (v > 0) cc = std::min(ncol, v); }
-  { const size_t nchunk = ((size_t) ncol + cc - 1) / cc; cc = (int) (((size_t) ncol + nchunk - 1) / nchunk); }
-  if ((size_t) cc * N > (size_t) 65535 * 128) cc = (int) ((size_t) 65535 * 128 / N);      // grid.y limit of the continuum kernel
-
-  RH_CHECK(E.alloc(cc, true, true));
-  RH_CHECK(F.alloc(cc, true, false));
-  // F shares every input with E; only the background of the final pass and the profiles are its own
-  F.C.T = E.C.T; F.C.height = E.C.height; F.C.nstar = E.C.nstar; F.C.ntotal = E.C.ntotal; F.C.C = E.C.C;
-  F.C.vbroad = E.C.vbroad; F.C.vel = E.C.vel; F.C.n = E.C.n; F.C.J = E.C.J;
-  DevArena ar;
-  const size_t cN = (size_t) cc * N;
-  double *d_in, *d_at, *d_pops, *d_popsn, *d_chem, *d_ntot, *d_tprep, *d_sc, *d_pc, *d_apc, *d_elem_n, *d_lineprep,
-         *d_md = nullptr, *d_mol = nullptr, *d_mchi = nullptr, *d_meta = nullptr, *d_spec, *d_abund, *d_coll, *d_cT, *d_cC, *d_cM, *d_plrows,
-         *d_adamp2, *d_chi2, *d_eta2, *d_sca2;
-  RH_CHECK(ar.alloc(&d_in, cN * nrow)); RH_CHECK(ar.alloc(&d_at, cN * RHB200_AT_NFIELD));
-  RH_CHECK(ar.alloc(&d_pops, cN * nlev_model)); RH_CHECK(ar.alloc(&d_popsn, cN * nlev_model));
-  RH_CHECK(ar.alloc(&d_chem, cN * (natom_model + 4))); RH_CHECK(ar.alloc(&d_ntot, cN * natom_model));
-  RH_CHECK(ar.alloc(&d_tprep, cN * 8)); RH_CHECK(ar.alloc(&d_sc, cN * 5));
-  RH_CHECK(ar.alloc(&d_pc, cN * std::max(1, c->wav.npl) * 4)); RH_CHECK(ar.alloc(&d_apc, cN * std::max(1, pl->nline) * 4));
-  RH_CHECK(ar.alloc(&d_elem_n, cN * std::max(1, nelem) * RHB200_RE_MAXSTAGE));
-  RH_CHECK(ar.alloc(&d_lineprep, cN * std::max(1, nline_k) * LP_NFIELD));
   const bool mol_on = c->wav.nmw > 0;
+  uint64_t key = 1469598103934665603ull;
+  auto mix = [&](const void *ptr, size_t bytes) {
+    const unsigned char *q = (const unsigned char *) ptr;
+    for (size_t i = 0; i < bytes; i++) { key ^= q[i]; key *= 1099511628211ull; }
+  };
+  {
+    const int ints[] = {pl->Nspect, pl->Nrays, pl->Ndep, pl->Natom, pl->Ntrans, pl->moving, pl->Ngorder, pl->Ngdelay, pl->Ngperiod,
+                        pl->isum, pl->bc_top, pl->bc_bottom, pl->ntrl, pl->nphirow, pl->nline, fr->ncoll, fr->ncolltab, nrow, ncol,
+                        nline_k, nelem, c->wav.npl, c->wav.nmsel, c->wav.nmw, nlev_model, natom_model, c->s_interpolation,
+                        c->nlte_exact_rates, getenv("RHB200_NLTE_EXACT") ? atoi(getenv("RHB200_NLTE_EXACT")) + 2 : 0,
+                        getenv("RHB200_NLTE_GAMMA_SEG") ? atoi(getenv("RHB200_NLTE_GAMMA_SEG")) : 0,
+                        getenv("RHB200_NLTE_CHUNK_COLS") ? atoi(getenv("RHB200_NLTE_CHUNK_COLS")) : 0};
+    mix(ints, sizeof ints); mix(&mu, sizeof mu);
+    mix(pl->lambda, sizeof(double) * pl->Nspect); mix(pl->muz, sizeof(double) * pl->Nrays); mix(pl->wmu, sizeof(double) * pl->Nrays);
+    mix(pl->atom_nlevel, sizeof(int) * pl->Natom); mix(pl->trans, sizeof(double) * pl->Ntrans * RHB200_TR_NFIELD);
+    mix(fr->plan1->trans, sizeof(double) * pl->Ntrans * RHB200_TR_NFIELD);
+    mix(pl->tr_lambda, sizeof(double) * pl->ntrl); mix(pl->tr_wlambda, sizeof(double) * pl->ntrl); mix(pl->tr_alpha, sizeof(double) * pl->ntrl);
+    mix(pl->as_first, sizeof(int) * (pl->Nspect + 1)); mix(pl->as_trans, sizeof(int) * pl->as_first[pl->Nspect]);
+    mix(pl->bg_hasline, sizeof(int) * pl->Nspect); mix(fr->atom_model, sizeof(int) * pl->Natom);
+    mix(fr->coll, sizeof(double) * fr->ncoll * RHB200_CO_NFIELD); mix(fr->coll_T, sizeof(double) * fr->ncolltab);
+    mix(fr->coll_coef, sizeof(double) * fr->ncolltab); mix(fr->line_rows, sizeof(double) * pl->nline * RHB200_PL_NFIELD);
+    for (int a = 0; a < natom_model; a++) { const double ab = rh_continuum_abundance(c, a); mix(&ab, sizeof ab); }
+  }
+  FrontState *S = (FrontState *) c->nlte_front;
+  const bool reuse = S && S->key == key;
+  mark(reuse ? "state reused (hash)" : "hash");
+  if (!reuse) {
+    delete S;
+    c->nlte_front = nullptr;
+    S = new FrontState();
+    S->key = key;
+    // the two engines: Nrays rays for initScatter / Iterate, one ray at `mu` for _solveray()'s pass
+    int rc = S->E.build(c, pl);
+    if (rc == RHB200_OK) rc = S->F.build(c, &p1);
+    if (rc == RHB200_OK && S->E.nrank > 1) { rhb200_set_error("wavelength sharding is only available through rhb200_nlte_iterate"); rc = RHB200_EUNSUPPORTED; }
+    if (rc != RHB200_OK) { delete S; return rc; }
+    // ---- chunk size from the workspace budget
+    size_t budget = (size_t) 48 << 30;
+    if (const char *e = getenv("RHB200_NLTE_WS_GB")) { const double g = atof(e); if (g > 0.01) budget = (size_t) (g * (double) ((size_t) 1 << 30)); }
+    const size_t per_col = sizeof(double) * (S->E.doubles_per_column(true) + S->F.doubles_per_column(false) +
+        (size_t) N * ((size_t) nrow + RHB200_AT_NFIELD + 2*(size_t) nlev_model + 2*(size_t) (natom_model + 4) + 8 + 5 +
+                      (size_t) std::max(1, c->wav.npl) * 4 + (size_t) std::max(1, pl->nline) * 4 +
+                      (size_t) std::max(1, nelem) * RHB200_RE_MAXSTAGE + (size_t) std::max(1, nline_k) * LP_NFIELD +
+                      (size_t) c->wav.nmsel * 4 + 2*(size_t) (c->wav.nmw > 0 ? Ns : 0)) + (size_t) Ns);
+    int cc = (int) std::min<size_t>((size_t) ncol, std::max<size_t>(1, budget / per_col));
+    if (const char *e = getenv("RHB200_NLTE_CHUNK_COLS")) { const int v = atoi(e); if (v > 0) cc = std::min(ncol, v); }
+    { const size_t nchunk = ((size_t) ncol + cc - 1) / cc; cc = (int) (((size_t) ncol + nchunk - 1) / nchunk); }
+    if ((size_t) cc * N > (size_t) 65535 * 128) cc = (int) ((size_t) 65535 * 128 / N);      // grid.y limit of the continuum kernel
+    S->cc = cc;
+    auto build_state = [&]() -> int {
+      NlteEngine &E = S->E, &F = S->F;
+      DevArena &ar = S->ar;
+      RH_CHECK(E.alloc(cc, true, true));
+      RH_CHECK(F.alloc(cc, true, false));
+      // F shares every input with E; only the background of the final pass and the profiles are its own
+      F.C.T = E.C.T; F.C.height = E.C.height; F.C.nstar = E.C.nstar; F.C.ntotal = E.C.ntotal; F.C.C = E.C.C;
+      F.C.vbroad = E.C.vbroad; F.C.vel = E.C.vel; F.C.n = E.C.n; F.C.J = E.C.J;
+      const size_t cN = (size_t) cc * N;
+      RH_CHECK(ar.alloc(&S->d_in, cN * nrow)); RH_CHECK(ar.alloc(&S->d_at, cN * RHB200_AT_NFIELD));
+      RH_CHECK(ar.alloc(&S->d_pops, cN * nlev_model)); RH_CHECK(ar.alloc(&S->d_popsn, cN * nlev_model));
+      RH_CHECK(ar.alloc(&S->d_chem, cN * (natom_model + 4))); RH_CHECK(ar.alloc(&S->d_ntot, cN * natom_model));
+      RH_CHECK(ar.alloc(&S->d_tprep, cN * 8)); RH_CHECK(ar.alloc(&S->d_sc, cN * 5));
+      RH_CHECK(ar.alloc(&S->d_pc, cN * std::max(1, c->wav.npl) * 4)); RH_CHECK(ar.alloc(&S->d_apc, cN * std::max(1, pl->nline) * 4));
+      RH_CHECK(ar.alloc(&S->d_elem_n, cN * std::max(1, nelem) * RHB200_RE_MAXSTAGE));
+      RH_CHECK(ar.alloc(&S->d_lineprep, cN * std::max(1, nline_k) * LP_NFIELD));
+      if (mol_on) {
+        RH_CHECK(ar.alloc(&S->d_md, cN * c->wav.nmsel)); RH_CHECK(ar.alloc(&S->d_mol, cN * c->wav.nmsel * 3));
+        RH_CHECK(ar.alloc(&S->d_mchi, cN * Ns)); RH_CHECK(ar.alloc(&S->d_meta, cN * Ns));
+      }
+      RH_CHECK(ar.alloc(&S->d_spec, (size_t) cc * Ns));
+      RH_CHECK(ar.alloc(&S->d_adamp2, cN * std::max(1, pl->nline)));
+      RH_CHECK(ar.alloc(&S->d_chi2, cN * Ns)); RH_CHECK(ar.alloc(&S->d_eta2, cN * Ns)); RH_CHECK(ar.alloc(&S->d_sca2, cN * Ns));
+      std::vector<double> ab(natom_model);
+      for (int a = 0; a < natom_model; a++) ab[a] = rh_continuum_abundance(c, a);
+      RH_CHECK(ar.upload(&S->d_abund, ab.data(), ab.size()));
+      // g[j] (OMEGA) / g[i]/g[j] (CE) travel in the spare field of the record: supplied by the host in field 7
+      RH_CHECK(ar.upload(&S->d_coll, fr->coll, (size_t) std::max(1, fr->ncoll) * RHB200_CO_NFIELD));
+      RH_CHECK(ar.upload(&S->d_cT, fr->coll_T, (size_t) std::max(1, fr->ncolltab)));
+      RH_CHECK(ar.upload(&S->d_cC, fr->coll_coef, (size_t) std::max(1, fr->ncolltab)));
+      RH_CHECK(ar.upload(&S->d_cM, fr->coll_M, (size_t) std::max(1, fr->ncolltab)));
+      RH_CHECK(ar.upload(&S->d_plrows, fr->line_rows, (size_t) std::max(1, pl->nline) * RHB200_PL_NFIELD));
+      return RHB200_OK;
+    };
+    rc = build_state();
+    if (rc != RHB200_OK) { delete S; return rc; }
+    c->nlte_front = S;
+    mark("plans, engines, work arrays");
+  }
   if (mol_on) {
     std::vector<int> chem(c->wav.nmsel);
     for (int m = 0; m < c->wav.nmsel; m++) chem[m] = (int) c->h_msel[(size_t) m * 16];
     RH_CHECK(rh_continuum_set_molsel(c, c->wav.nmsel, chem.data()));
-    RH_CHECK(ar.alloc(&d_md, cN * c->wav.nmsel)); RH_CHECK(ar.alloc(&d_mol, cN * c->wav.nmsel * 3));
-    RH_CHECK(ar.alloc(&d_mchi, cN * Ns)); RH_CHECK(ar.alloc(&d_meta, cN * Ns));
   }
-  RH_CHECK(ar.alloc(&d_spec, (size_t) cc * Ns));
-  RH_CHECK(ar.alloc(&d_adamp2, cN * std::max(1, pl->nline)));
-  RH_CHECK(ar.alloc(&d_chi2, cN * Ns)); RH_CHECK(ar.alloc(&d_eta2, cN * Ns)); RH_CHECK(ar.alloc(&d_sca2, cN * Ns));
-  {
-    std::vector<double> ab(natom_model);
-    for (int a = 0; a < natom_model; a++) ab[a] = rh_continuum_abundance(c, a);
-    RH_CHECK(ar.upload(&d_abund, ab.data(), ab.size()));
-    // g[j] (OMEGA) / g[i]/g[j] (CE) travel in the spare field of the record: supplied by the host in field 7
-    RH_CHECK(ar.upload(&d_coll, fr->coll, (size_t) std::max(1, fr->ncoll) * RHB200_CO_NFIELD));
-    RH_CHECK(ar.upload(&d_cT, fr->coll_T, (size_t) std::max(1, fr->ncolltab)));
-    RH_CHECK(ar.upload(&d_cC, fr->coll_coef, (size_t) std::max(1, fr->ncolltab)));
-    RH_CHECK(ar.upload(&d_cM, fr->coll_M, (size_t) std::max(1, fr->ncolltab)));
-    RH_CHECK(ar.upload(&d_plrows, fr->line_rows, (size_t) std::max(1, pl->nline) * RHB200_PL_NFIELD));
-  }
+  NlteEngine &E = S->E, &F = S->F;
+  const int cc = S->cc;
+  const size_t cN = (size_t) cc * N;
+  double *d_in = S->d_in, *d_at = S->d_at, *d_pops = S->d_pops, *d_popsn = S->d_popsn, *d_chem = S->d_chem, *d_ntot = S->d_ntot,
+         *d_tprep = S->d_tprep, *d_sc = S->d_sc, *d_pc = S->d_pc, *d_apc = S->d_apc, *d_elem_n = S->d_elem_n, *d_lineprep = S->d_lineprep,
+         *d_md = S->d_md, *d_mol = S->d_mol, *d_mchi = S->d_mchi, *d_meta = S->d_meta, *d_spec = S->d_spec, *d_abund = S->d_abund,
+         *d_coll = S->d_coll, *d_cT = S->d_cT, *d_cC = S->d_cC, *d_cM = S->d_cM, *d_plrows = S->d_plrows, *d_adamp2 = S->d_adamp2,
+         *d_chi2 = S->d_chi2, *d_eta2 = S->d_eta2, *d_sca2 = S->d_sca2;
+  F.C.adamp = E.C.adamp;
   // collision.c:470-471
   const double C0 = ((2.1798741E-18/sqrt(RH_M_ELECTRON)) * RH_PI*(5.29177349E-11*5.29177349E-11)) * sqrt(8.0/(RH_PI*RH_KBOLTZMANN));
   const double mu_last = pl->muz[pl->Nrays - 1];
@@ -368,12 +441,17 @@ extern "C" int rhb200_nlte_compute1d_batch(rhb200_ctx *c, const rhb200_nlte_plan
       RH_CHECK(keep(5, E.C.chi_c, nN * Ns)); RH_CHECK(keep(6, E.C.eta_c, nN * Ns)); RH_CHECK(keep(7, E.C.sca_c, nN * Ns));
       RH_CHECK(keep(8, E.C.height, nN));
     }
+    mark("background + damping");
     // ---- initScatter, Iterate, the scattering passes after it
     RH_CHECK(E.prepare(nullptr, nullptr, true));
+    mark("profiles + setup");
     std::vector<int> niter(n, 0), pass_a(n, 0), pass_b(n, 0);
     RH_CHECK(E.scatter(fr->NmaxIter ? fr->NmaxScatter : 0, 1, fr->iterLimit, pass_a.data(), nullptr, nullptr));
+    mark("initScatter");
     RH_CHECK(E.iterate(fr->NmaxIter, fr->iterLimit, niter.data(), nullptr, 0, nullptr, nullptr));
+    mark("Iterate");
     RH_CHECK(E.scatter(fr->NmaxScatter, 2, fr->iterLimit, pass_b.data(), nullptr, nullptr));
+    mark("passes after Iterate");
     if (niter_out) memcpy(niter_out + c0, niter.data(), n * sizeof(int));
     if (passes_out) for (int q = 0; q < n; q++) { passes_out[2*(size_t) (c0 + q)] = pass_a[q]; passes_out[2*(size_t) (c0 + q) + 1] = pass_b[q]; }
     // ---- _solveray(): one ray at mu; Background() and getProfiles() again
@@ -400,8 +478,10 @@ extern "C" int rhb200_nlte_compute1d_batch(rhb200_ctx *c, const rhb200_nlte_plan
       nlte_damping_gather_kernel<<<RH_GRID(nN * pl->nline, 128), 0, st>>>(F.P, Ctmp, n, d_apc);    // vbroad: unchanged values
       RH_CUDA(cudaGetLastError());
     }
+    mark("second background + damping");
     RH_CHECK(F.prepare(nullptr, nullptr, false));
     RH_CHECK(F.scatter(1, 0, 0.0, nullptr, nullptr, d_spec));
+    mark("final pass");
     if (debug_keep && c0 == 0) {
       RH_CHECK(keep(9, E.C.J, nN * Ns));
       RH_CHECK(keep(10, d_chi2, nN * Ns)); RH_CHECK(keep(11, d_eta2, nN * Ns)); RH_CHECK(keep(12, d_sca2, nN * Ns));

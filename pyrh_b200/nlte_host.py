@@ -578,14 +578,20 @@ class NlteSession:
         if single:
             a = a[None]
         ncol, nrow, ndep = a.shape
-        keep = []
-        plan = self._plan_struct(self.plan, ndep, keep)
-        plan1 = self._plan_struct(single_mu_plan(self.plan, mu), ndep, keep)
-        model = np.ascontiguousarray(self.active_index, np.int32)
-        fr = nl.FrontStruct(model.ctypes.data_as(lib.ip), len(self.coll), len(self.coll_T),
-                            *[np.ascontiguousarray(x).ctypes.data_as(lib.dp) for x in (self.coll, self.coll_T, self.coll_C, self.coll_M)],
-                            self.line_rows.ctypes.data_as(lib.dp), self.hdr["NmaxScatter"], self.hdr["NmaxIter"],
-                            self.hdr["iterLimit"], C.pointer(plan1))
+        cache = self.__dict__.setdefault("_structs", {})          # the C structs (and the arrays they point into) per (mu, ndep)
+        if (float(mu), ndep) not in cache:
+            keep = []
+            plan = self._plan_struct(self.plan, ndep, keep)
+            plan1 = self._plan_struct(single_mu_plan(self.plan, mu), ndep, keep)
+            model = np.ascontiguousarray(self.active_index, np.int32)
+            tabs = [np.ascontiguousarray(x, np.float64) for x in (self.coll, self.coll_T, self.coll_C, self.coll_M)]
+            fr = nl.FrontStruct(model.ctypes.data_as(lib.ip), len(self.coll), len(self.coll_T),
+                                *[x.ctypes.data_as(lib.dp) for x in tabs],
+                                self.line_rows.ctypes.data_as(lib.dp), self.hdr["NmaxScatter"], self.hdr["NmaxIter"],
+                                self.hdr["iterLimit"], C.pointer(plan1))
+            cache.clear()
+            cache[(float(mu), ndep)] = (plan, plan1, fr, keep, model, tabs)
+        plan, plan1, fr = cache[(float(mu), ndep)][:3]
         Ns, nlev = len(self.lam), int(np.sum(self.plan["atom_nlevel"]))
         spec = np.zeros((ncol, Ns)); n = np.zeros((ncol, nlev, ndep)); nstar = np.zeros((ncol, nlev, ndep))
         niter, passes = np.zeros(ncol, np.int32), np.zeros((ncol, 2), np.int32)
