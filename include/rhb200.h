@@ -106,6 +106,11 @@ int rhb200_set_lines(rhb200_ctx *ctx,
    minus lambda_ref, pyrh_solveray.c:130-150).  Builds the per-wavelength line
    windows of rlk_opacity (kurucz.c:538-566,608) on the host: integer work,
    bit-exact. */
+/* log gf overrides between calls (pyrh.compute1d's loggf_ids / loggf_values, kurucz.c:247-257) without rebuilding
+   anything: rows[n] of the table passed to rhb200_set_lines get new Aji / Bji / Bij; windows, Zeeman patterns, element
+   tables and the device context stay as they are. */
+int rhb200_update_line_strengths(rhb200_ctx *ctx, int n, const int *rows, const double *Aji, const double *Bji, const double *Bij);
+
 int rhb200_set_wavelengths(rhb200_ctx *ctx, int nlambda, const double *lambda);
 
 /* MolecularOpacity in the fused LTE path (opacity.c:711-839, MolProfile :844-916): LTE lines of PASSIVE molecules,

@@ -30,6 +30,7 @@ SYMBOLS = [
     ("rhb200_set_lines", C.c_int, [vp, C.c_int, dp, C.c_int, ip, dp, dp, C.c_int, dp, C.c_int, C.c_int,
                                    dp, dp, C.c_double, C.c_int, C.c_int]),
     ("rhb200_set_wavelengths", C.c_int, [vp, C.c_int, dp]),
+    ("rhb200_update_line_strengths", C.c_int, [vp, C.c_int, ip, dp, dp, dp]),
     ("rhb200_get_line_windows", C.c_int, [vp, ip, ip, ip, C.c_int, ip]),
     ("rhb200_get_wavelength_flags", C.c_int, [vp, ip]),
     ("rhb200_nlte_compute1d_batch", C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, vp, C.c_int,

@@ -174,6 +174,27 @@ extern "C" int rhb200_set_lines(rhb200_ctx *c, int nline, const double *lines, i
   return RHB200_OK;
 }
 
+// In-place update of line strengths (log gf overrides of pyrh.compute1d, kurucz.c:247-257): the windows, Zeeman patterns
+// and every other table stay; only Aji / Bji / Bij of the named rows change, on the host copy and on the device.
+extern "C" int rhb200_update_line_strengths(rhb200_ctx *c, int n, const int *rows, const double *Aji, const double *Bji,
+                                            const double *Bij)
+{
+  RH_NEED_CTX(c);
+  if (n < 0 || (n > 0 && (!rows || !Aji || !Bji || !Bij))) { rhb200_set_error("rhb200_update_line_strengths: bad arguments"); return RHB200_EINVAL; }
+  for (int i = 0; i < n; i++)
+    if (rows[i] < 0 || rows[i] >= c->tab.nline) { rhb200_set_error("line row %d out of range", rows[i]); return RHB200_EINVAL; }
+  RH_CUDA(cudaStreamSynchronize(c->stream));
+  RH_CUDA(cudaStreamSynchronize(c->copy_stream));
+  for (int i = 0; i < n; i++) {
+    double *L = c->h_lines.data() + (size_t) rows[i] * RHB200_RL_NFIELD;
+    L[RHB200_RL_AJI] = Aji[i]; L[RHB200_RL_BJI] = Bji[i]; L[RHB200_RL_BIJ] = Bij[i];
+    // BJI, AJI, BIJ are adjacent fields of the row
+    RH_CUDA(cudaMemcpy(c->tab.lines + (size_t) rows[i] * RHB200_RL_NFIELD + RHB200_RL_BJI, L + RHB200_RL_BJI, 3 * sizeof(double),
+                       cudaMemcpyHostToDevice));
+  }
+  return RHB200_OK;
+}
+
 // MolecularOpacity in the fused LTE path (opacity.c:711-839): LTE lines of PASSIVE molecules, unpolarizable ones only
 // (lines with Hund's-case data need MolZeeman patterns: use rhb200_molecular_opacity_batch with host patterns).
 // mlines [nline][RHB200_ML_NFIELD] grouped by molecule, ascending in lambda0 inside each (RHB200_ML_MOL = row of

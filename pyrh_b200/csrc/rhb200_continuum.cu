@@ -366,58 +366,64 @@ continuum_tile_kernel(int ncol, int nlambda, int ndep, DevModel M,
   const double th_hmff = tp[(size_t) TP_TH_HMFF*ndep], th_h2m = tp[(size_t) TP_TH_H2M*ndep], t_h2p = tp[(size_t) TP_T_H2P*ndep];
   const double ti_oh = tp[(size_t) TP_T_OH*ndep], ti_ch = tp[(size_t) TP_T_CH*ndep];
 
-  double chi_a[CONT_TL], eta_a[CONT_TL], stimB[CONT_TL], explaA[CONT_TL], Bnu[CONT_TL];
-#pragma unroll
-  for (int q = 0; q < CONT_TL; q++) {
-    chi_a[q] = eta_a[q] = 0.0; stimB[q] = explaA[q] = Bnu[q] = 0.0;
-    if (q < nl) {
-      const double *W = shW[q];
-      const int flags = (int) W[WC_FLAGS];
-      Bnu[q] = rhd::planck(Tk, W[WC_LAMBDA]);
-      stimB[q] = rhm::rh_exp(-W[WC_HCKLA_B]/Tk);
-      explaA[q] = rhm::rh_exp(-W[WC_HCKLA_A]/Tk);
-      const double twohnu3_B = W[WC_TWOHNU3_B];
-      if (flags & F_HMBF) {
-        const double alpha_bf = W[WC_ALPHA_HMBF];
-        chi_a[q] += nHm * (1.0 - stimB[q]) * alpha_bf;
-        eta_a[q] += nHm * twohnu3_B * stimB[q] * alpha_bf;
-      }
-      if (flags & F_HMFF) {
-        const double kappa = bilinear_d(M.n_hmff_theta, M.n_hmff_lambda, M.hmff_kappa, th_hmff, W[WC_LI_HMFF]);
-        const double chi = (nH0 * 1.0E-29) * pe * kappa;
-        chi_a[q] += chi; eta_a[q] += chi * Bnu[q];
-      }
-      chi_a[q] *= W[WC_FUDGE_HMIN]; eta_a[q] *= W[WC_FUDGE_HMIN];            // background.c:364-371 (1.0 without fudge)
-      if (flags & F_OH) {
-        double chi = 0.0, eta = 0.0;
-        if (ti_oh >= 0.0) {
-          const double kappa = rhm::rh_exp(RH_LG10 * bilinear_d(M.n_oh_T, M.n_oh_E, M.oh_cross, ti_oh, W[WC_E_OH])) * SQ(RH_CM_TO_M);
-          chi = nOH[ck] * (1.0 - stimB[q]) * kappa;
-          eta = nOH[ck] * twohnu3_B * stimB[q] * kappa;
-        }
-        chi_a[q] += chi; eta_a[q] += eta;
-      }
-      if (flags & F_CH) {
-        double chi = 0.0, eta = 0.0;
-        if (ti_ch >= 0.0) {
-          const double kappa = rhm::rh_exp(RH_LG10 * bilinear_d(M.n_ch_T, M.n_ch_E, M.ch_cross, ti_ch, W[WC_E_CH])) * SQ(RH_CM_TO_M);
-          chi = nCH[ck] * (1.0 - stimB[q]) * kappa;
-          eta = nCH[ck] * twohnu3_B * stimB[q] * kappa;
-        }
-        chi_a[q] += chi; eta_a[q] += eta;
-      }
+  // Per-wavelength state of the thread lives in shared memory ([q][thread]: conflict-free) -- the running sums chi_a /
+  // eta_a, the Planck function and the two exponentials.  Only the accumulators of the bound-free loop stay in
+  // registers, so nothing spills: the previous version kept 20 doubles per thread live across that loop and wrote a
+  // 416-byte stack frame per thread through L2 to DRAM (5x the kernel's algorithmic traffic).
+  __shared__ double sh_chi[CONT_TL][128], sh_eta[CONT_TL][128], sh_Bnu[CONT_TL][128], sh_stimB[CONT_TL][128], sh_expA[CONT_TL][128];
+  const int tx = threadIdx.x;
+#pragma unroll 1
+  for (int q = 0; q < nl; q++) {
+    const double *W = shW[q];
+    const int flags = (int) W[WC_FLAGS];
+    double chi_q = 0.0, eta_q = 0.0;
+    const double Bnu_q = rhd::planck(Tk, W[WC_LAMBDA]);
+    const double stimB_q = rhm::rh_exp(-W[WC_HCKLA_B]/Tk);
+    sh_Bnu[q][tx] = Bnu_q; sh_stimB[q][tx] = stimB_q;
+    sh_expA[q][tx] = rhm::rh_exp(-W[WC_HCKLA_A]/Tk);
+    const double twohnu3_B = W[WC_TWOHNU3_B];
+    if (flags & F_HMBF) {
+      const double alpha_bf = W[WC_ALPHA_HMBF];
+      chi_q += nHm * (1.0 - stimB_q) * alpha_bf;
+      eta_q += nHm * twohnu3_B * stimB_q * alpha_bf;
     }
+    if (flags & F_HMFF) {
+      const double kappa = bilinear_d(M.n_hmff_theta, M.n_hmff_lambda, M.hmff_kappa, th_hmff, W[WC_LI_HMFF]);
+      const double chi = (nH0 * 1.0E-29) * pe * kappa;
+      chi_q += chi; eta_q += chi * Bnu_q;
+    }
+    chi_q *= W[WC_FUDGE_HMIN]; eta_q *= W[WC_FUDGE_HMIN];            // background.c:364-371 (1.0 without fudge)
+    if (flags & F_OH) {
+      double chi = 0.0, eta = 0.0;
+      if (ti_oh >= 0.0) {
+        const double kappa = rhm::rh_exp(RH_LG10 * bilinear_d(M.n_oh_T, M.n_oh_E, M.oh_cross, ti_oh, W[WC_E_OH])) * SQ(RH_CM_TO_M);
+        chi = nOH[ck] * (1.0 - stimB_q) * kappa;
+        eta = nOH[ck] * twohnu3_B * stimB_q * kappa;
+      }
+      chi_q += chi; eta_q += eta;
+    }
+    if (flags & F_CH) {
+      double chi = 0.0, eta = 0.0;
+      if (ti_ch >= 0.0) {
+        const double kappa = rhm::rh_exp(RH_LG10 * bilinear_d(M.n_ch_T, M.n_ch_E, M.ch_cross, ti_ch, W[WC_E_CH])) * SQ(RH_CM_TO_M);
+        chi = nCH[ck] * (1.0 - stimB_q) * kappa;
+        eta = nCH[ck] * twohnu3_B * stimB_q * kappa;
+      }
+      chi_q += chi; eta_q += eta;
+    }
+    sh_chi[q][tx] = chi_q; sh_eta[q][tx] = eta_q;
   }
   // ---- bound-free families: 0 = Hydrogen_bf (ratio to the proton density), 1 = Metal_bf; between them
   //      Hydrogen_ff, H2plus_ff, H2minus_ff enter in Background()'s order
+#pragma unroll 1
   for (int fam = 0; fam < 2; fam++) {
     const int FI = fam ? WC_MBF_FIRST : WC_HBF_FIRST, CI = fam ? WC_MBF_COUNT : WC_HBF_COUNT;
-    double chi_f[CONT_TL], eta_f[CONT_TL];
+    double chi_f[CONT_TL], eta_f[CONT_TL], explaA[CONT_TL];
 #pragma unroll
-    for (int q = 0; q < CONT_TL; q++) chi_f[q] = eta_f[q] = 0.0;
+    for (int q = 0; q < CONT_TL; q++) { chi_f[q] = eta_f[q] = 0.0; explaA[q] = (q < nl) ? sh_expA[q][tx] : 0.0; }
     if (uniform) {
       const int cnt = (int) shW[0][CI];
-#pragma unroll 2       // measured e2e per 2048 columns: 1 -> 14.53 ms (680 B stack), 2 -> 14.49 (416 B), 4 -> 14.57 (336 B)
+#pragma unroll 2
       for (int c = 0; c < cnt; c++) {
         const int i = sh_ij[fam][c][0], j = sh_ij[fam][c][1];
         const double n_i = n_[(size_t) i * ndep];
@@ -455,20 +461,22 @@ continuum_tile_kernel(int ncol, int nlambda, int ndep, DevModel M,
       if (q < nl) {
         const double *W = shW[q];
         const int flags = (int) W[WC_FLAGS];
+        double chi_q = sh_chi[q][tx], eta_q = sh_eta[q][tx];
         if (fam == 0) {
-          if ((int) W[WC_HBF_COUNT] > 0) { chi_a[q] += chi_f[q]; eta_a[q] += eta_f[q]; }
+          const double Bnu_q = sh_Bnu[q][tx];
+          if ((int) W[WC_HBF_COUNT] > 0) { chi_q += chi_f[q]; eta_q += eta_f[q]; }
           {                                                                   // Hydrogen_ff
-            const double stim = 1.0 - stimB[q];
+            const double stim = 1.0 - sh_stimB[q][tx];
             const double y = (W[WC_CY] * Tk) / (RH_HPLANCK*RH_CLIGHT);
             const double gIII = 1.0 + W[WC_GA1] * (1.0 + y) - W[WC_GA2] * (1.0 + (1.0 + y)*0.33333333*y);
             const double g_ff = (gIII > 1.0) ? gIII : 1.0;
             const double chi = M.sigma_ff / sqrt(Tk) * W[WC_NU3] * nek * np * stim * g_ff;
-            chi_a[q] += chi; eta_a[q] += chi * Bnu[q];
+            chi_q += chi; eta_q += chi * Bnu_q;
           }
           if (flags & F_H2P) {
             const double kappa = bilinear_d(M.n_h2p_temp, M.n_h2p_lambda, M.h2p_kappa, t_h2p, W[WC_LI_H2P]);
             const double chi = (nH0 * 1.0E-29) * (np * 1.0E-20) * kappa;
-            chi_a[q] += chi; eta_a[q] += chi * Bnu[q];
+            chi_q += chi; eta_q += chi * Bnu_q;
           }
           if (flags & F_H2M) {
             double chi = 0.0;
@@ -476,11 +484,12 @@ continuum_tile_kernel(int ncol, int nlambda, int ndep, DevModel M,
               const double kappa = bilinear_d(M.n_h2m_theta, M.n_h2m_lambda, M.h2m_kappa, th_h2m, W[WC_LI_H2M]);
               chi = (nH2k * 1.0E-29) * pe * kappa;
             }
-            chi_a[q] += chi; eta_a[q] += chi * Bnu[q];
+            chi_q += chi; eta_q += chi * Bnu_q;
           }
+          sh_chi[q][tx] = chi_q; sh_eta[q][tx] = eta_q;
         } else {
-          if (!M.hse_mode) { chi_a[q] += chi_f[q] * W[WC_FUDGE_METAL]; eta_a[q] += eta_f[q] * W[WC_FUDGE_METAL]; }
-          double chi_out = chi_a[q];
+          if (!M.hse_mode) { chi_q += chi_f[q] * W[WC_FUDGE_METAL]; eta_q += eta_f[q] * W[WC_FUDGE_METAL]; }
+          double chi_out = chi_q;
           const size_t o = ((size_t) col * nlambda + l0 + q) * ndep + k;
           if (M.solve_NLTE || M.hse_mode || sca_ai) {                                       // background.c:456-464
             double sca = nek * M.sigma_T;
@@ -491,7 +500,7 @@ continuum_tile_kernel(int ncol, int nlambda, int ndep, DevModel M,
             if (M.solve_NLTE || M.hse_mode) chi_out += sca;                                 // LTE: sca_c stays separate
             if (sca_ai) sca_ai[o] = sca;
           }
-          chi_ai[o] = chi_out; eta_ai[o] = eta_a[q];
+          chi_ai[o] = chi_out; eta_ai[o] = eta_q;
         }
       }
     }

@@ -409,7 +409,7 @@ def read_kurucz_lines(cwd, kw: dict, el: Elements, loggf_ids=None, loggf_values=
     sorted by lambda0 (background.c:292-294)."""
     C = 2.0 * PI * (Q_ELECTRON / EPSILON_0) * (Q_ELECTRON / M_ELECTRON) / CLIGHT
     LS_Lande = _true(kw["LS_LANDE"])
-    rows, patterns, used, barklem = [], [], {}, {}
+    rows, patterns, used, barklem, si_rows = [], [], {}, {}, []
     if kw["KURUCZ_DATA"].lower() == "none":
         raise NotImplementedError("KURUCZ_DATA = none: the LTE path needs a Kurucz line list")
     for line_index, rec in enumerate(read_kurucz_records(cwd, kw["KURUCZ_DATA"])):
@@ -513,6 +513,7 @@ def read_kurucz_lines(cwd, kw: dict, el: Elements, loggf_ids=None, loggf_values=
             gL_i, gL_j = gL_j, gL_i
         if not LS_Lande and gL_i != -99 * MILLI and gL_j != -99 * MILLI:    # kurucz.c:381-385
             polarizable = True
+        si_rows.append((lambda0, gi, gj, C / (lambda0 * lambda0) * POW10(gf) / gj))
         r = np.zeros(ll.RL_NFIELD)
         r[ll.RL_LAMBDA0] = lambda0 / NM_TO_M
         r[ll.RL_GI], r[ll.RL_GJ], r[ll.RL_EI], r[ll.RL_EJ] = gi, gj, rEi, rEj
@@ -552,6 +553,7 @@ def read_kurucz_lines(cwd, kw: dict, el: Elements, loggf_ids=None, loggf_values=
     lt.validate()
     lt.elem_rows = dict(used)                                    # periodic-table index - 1 -> row of lt.elems
     lt.file_index = np.array(order, np.int64)                    # table row -> line number in the Kurucz files
+    lt.si = [si_rows[i] for i in order]                          # per table row: lambda0 [m], gi, gj, Aji of the file's log gf
     return lt
 
 
@@ -1003,7 +1005,45 @@ class Session:
         ids = [] if loggf_ids is None else [int(i) for i in loggf_ids]
         row_of = {int(f): r for r, f in enumerate(self.lt.file_index)}
         self.loggf_rows = [row_of.get(i, -1) if i not in ids[p + 1:] else -1 for p, i in enumerate(ids)]
-        self.n_atomic_pars = len(ids) + (0 if lam_ids is None else len(lam_ids))
+        self._n_lam_pars = 0 if lam_ids is None else len(lam_ids)
+        self.n_atomic_pars = len(ids) + self._n_lam_pars
+        self._loggf_now = {} if loggf_ids is None else {int(i): float(v) for i, v in zip(loggf_ids, loggf_values)}
+
+    def set_loggf(self, loggf_ids=None, loggf_values=None):
+        """Apply pyrh.compute1d's log gf overrides to the RESIDENT line table (kurucz.c:247-257: the last entry naming a
+        line wins; lines not named get the file's value back): Aji, Bji, Bij of the affected rows are recomputed with
+        readKuruczLines' expressions and patched on the device (rhb200_update_line_strengths) -- no re-parse, no new
+        context."""
+        import ctypes as C_
+        from . import _lib
+        Cc = 2.0 * PI * (Q_ELECTRON / EPSILON_0) * (Q_ELECTRON / M_ELECTRON) / CLIGHT
+        want = {}
+        if loggf_ids is not None:
+            for i, v in zip(loggf_ids, loggf_values):
+                want[int(i)] = float(v)
+        row_of = {int(f): r for r, f in enumerate(self.lt.file_index)}
+        current = self.__dict__.setdefault("_loggf_now", {})
+        rows, A, Bji_, Bij_ = [], [], [], []
+        for fid in set(want) | set(current):
+            r = row_of.get(fid)
+            if r is None or want.get(fid) == current.get(fid):
+                continue
+            lambda0, gi, gj, Aji_file = self.lt.si[r]
+            Aji = Cc / (lambda0 * lambda0) * POW10(want[fid]) / gj if fid in want else Aji_file
+            Bji = (lambda0 * lambda0 * lambda0) / (2.0 * HPLANCK * CLIGHT) * Aji
+            rows.append(r); A.append(Aji); Bji_.append(Bji); Bij_.append((gj / gi) * Bji)
+            self.lt.lines[r, ll.RL_AJI], self.lt.lines[r, ll.RL_BJI], self.lt.lines[r, ll.RL_BIJ] = Aji, Bji, (gj / gi) * Bji
+        if rows:
+            ri = np.ascontiguousarray(rows, np.int32)
+            a, b, c = (np.ascontiguousarray(x, np.float64) for x in (A, Bji_, Bij_))
+            _lib.check(self.ctx.lib.rhb200_update_line_strengths(self.ctx.h, len(rows), ri.ctypes.data_as(_lib.ip),
+                                                                 a.ctypes.data_as(_lib.dp), b.ctypes.data_as(_lib.dp),
+                                                                 c.ctypes.data_as(_lib.dp)))
+        self._loggf_now = dict(want)
+        ids = [] if loggf_ids is None else [int(i) for i in loggf_ids]
+        self.loggf_rows = [row_of.get(i, -1) if i not in ids[p + 1:] else -1 for p, i in enumerate(ids)]
+        self.n_atomic_pars = len(ids) + self._n_lam_pars
+        return len(rows)
 
     def compute_rf(self, atmosphere, mu=1.0, atm_scale=0):
         """``compute`` with ``get_atomic_rfs``: ``(stokes [.., 4, nlambda], rfs [.., n_atomic_pars, nlambda])``."""
@@ -1232,17 +1272,27 @@ def _get_session(cwd, wave, device, overrides):
     """LRU lookup; the least recently used session is closed when the cache is full, so a caller that varies log gf or
     an abundance from call to call holds at most MAX_SESSIONS contexts."""
     tob = lambda x: None if x is None else np.asarray(x).tobytes()   # noqa: E731
-    key = _session_key(cwd, wave, tuple(tob(overrides[k]) for k in sorted(overrides)) + (device,))
+    # log gf overrides are applied IN PLACE to the resident session (Session.set_loggf): not part of the key
+    structural = {k: v for k, v in overrides.items() if k not in ("loggf_ids", "loggf_values")}
+    key = _session_key(cwd, wave, tuple(tob(structural[k]) for k in sorted(structural)) + (device,))
     s = _SESSIONS.get(key)
     if s is not None:
         _SESSIONS.move_to_end(key)
-        return s
+        if isinstance(s, Session):
+            s.set_loggf(overrides.get("loggf_ids"), overrides.get("loggf_values"))
+        elif overrides.get("loggf_ids") is not None and s.loggf_key != (tob(overrides["loggf_ids"]), tob(overrides["loggf_values"])):
+            s = None                                                # NLTE sessions: rebuilt (the LRU bounds them)
+        if s is not None:
+            return s
     kw = read_keywords(cwd)
     if any(st == "ACTIVE" for _, st in _atoms_listed(cwd, kw)):
         from . import nlte_host
         s = nlte_host.NlteSession(cwd, wave, device, None, **overrides)
     else:
         s = Session(cwd, wave, device, None, **overrides)
+    stale = _SESSIONS.pop(key, None)
+    if stale is not None:
+        stale.close()
     _SESSIONS[key] = s
     while len(_SESSIONS) > MAX_SESSIONS:
         _, old = _SESSIONS.popitem(last=False)

@@ -477,6 +477,8 @@ class NlteSession:
         import ctypes as C
         from . import api, continuum, nlte, _lib
         self.cwd = Path(cwd)
+        tob = lambda x: None if x is None else np.asarray(x).tobytes()   # noqa: E731
+        self.loggf_key = (tob(loggf_ids), tob(loggf_values))
         kw = self.kw = H.read_keywords(cwd)
         if kw["STOKES_MODE"].upper() != "NO_STOKES":
             raise NotImplementedError("ACTIVE atoms with STOKES_MODE other than NO_STOKES: the polarised active set "

@@ -1601,3 +1601,42 @@ def test_single_process_multi_gpu_batch():
         assert f.value == tot
         tot += n.value
     assert tot == 1001
+
+
+@pytest.mark.gpu
+def test_session_cache_log_gf_updates_in_place():
+    """An inversion that fits log gf calls compute1d with a different loggf_values every time (globin's use of the
+    argument).  The working directory is parsed once: the overrides patch Aji / Bji / Bij of the resident line table
+    (rhb200_update_line_strengths), so the cache holds ONE session however many values are tried, every result equals
+    the reference's rhf1d() with the same override bit for bit, and taking the override away restores the file's
+    value.  Other overrides (abundances) open further sessions, at most MAX_SESSIONS of them (LRU, closed on eviction)."""
+    import time
+    from oracle import refdriver as rd
+    from pyrh_b200 import host
+    if not rd.available():
+        pytest.skip("reference not staged (oracle/_ref)")
+    os.environ["PYRH_PATH"] = str(rd.REFDIR / "pyrh_path")
+    host.close_sessions()
+    g = dict(np.load(GOLD / "synth70_c1.npz"))
+    cwd = rd.make_workdir("benchmark")
+    base = host.compute1d(cwd, 1.0, 0, g["atmosphere"], g["wave"])
+    assert np.array_equal(np.array(base[:4]), g["stokes_scalar"])
+    vals = np.linspace(-1.2, -0.5, 40)
+    t0 = time.perf_counter()
+    outs = [host.compute1d(cwd, 1.0, 0, g["atmosphere"], g["wave"], loggf_ids=[1], loggf_values=[v]) for v in vals]
+    per_call = (time.perf_counter() - t0) / len(vals)
+    assert len(host._SESSIONS) == 1
+    for v, o in list(zip(vals, outs))[::13]:
+        ref = rd.rhf1d(g["atmosphere"], g["wave"], cwd, loggf_ids=[1], loggf_values=[float(v)])
+        assert np.array_equal(np.array(o[:4]), np.array([ref[k] for k in "IQUV"]))
+    two = host.compute1d(cwd, 1.0, 0, g["atmosphere"], g["wave"], loggf_ids=[0, 1], loggf_values=[-0.9, -1.1])
+    ref = rd.rhf1d(g["atmosphere"], g["wave"], cwd, loggf_ids=[0, 1], loggf_values=[-0.9, -1.1])
+    assert np.array_equal(np.array(two[:4]), np.array([ref[k] for k in "IQUV"]))
+    again = host.compute1d(cwd, 1.0, 0, g["atmosphere"], g["wave"])                      # override gone: the file's log gf again
+    assert np.array_equal(np.array(again[:4]), g["stokes_scalar"]) and len(host._SESSIONS) == 1
+    REPORT["loggf_update_ms_per_call"] = 1e3 * per_call
+    for n in range(host.MAX_SESSIONS + 2):                                              # abundance overrides: bounded LRU
+        host.compute1d(cwd, 1.0, 0, g["atmosphere"], g["wave"], atomic_number=[26], atomic_abundance=[7.40 + 0.01 * n])
+    assert len(host._SESSIONS) == host.MAX_SESSIONS
+    host.close_sessions()
+    assert len(host._SESSIONS) == 0
