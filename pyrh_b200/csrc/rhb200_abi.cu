@@ -591,6 +591,7 @@ static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int mov
                           int chem_on_device = 0, const PyrhIn *py = nullptr)
 {
   RH_NEED_CTX(c);
+  RhRange whole("rhf1d (LTE, batch)");
   RH_CHECK(check_batch_args(c, ncol, ndep, muz, bc_top, bc_bottom));
   if (ncol == 0) return RHB200_OK;
   if ((!atmos && !py) || (!stokes && !(py && (py->rf_out || py->scales_only || py->lrf_out))) || (!chem && !chem_on_device && (!chi_ai || !eta_ai))) { rhb200_set_error("null buffer"); return RHB200_EINVAL; }

@@ -4,6 +4,7 @@
 // is IEEE-deterministic (see DESIGN.md "Arithmetic contract").
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX v3: ranges cost nothing unless a profiler is attached
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -116,12 +117,25 @@ struct rhb200_ctx {
 
 // timed launch helper: records CUDA events around the launch on ctx->stream when
 // instrumentation is on (synchronising: only used for measurement runs)
+// NVTX range names = the labels the reference passes to getCPU() for the same work (rh/getcpu.c is stubbed out in pyrh;
+// examples/time.out shows them): a timeline in Nsight Systems reads like the reference's time.out
+static const char *const RH_NVTX_LABEL[RHB200_K_COUNT] = {
+  "Read Atmosphere / LTE populations / line prep", "Background Opacity", "Spectrum & Operator (Stokes ray)",
+  "Spectrum & Operator (scalar ray)", "Background continuum / scales", "Spectrum & Operator (Gamma, rates)",
+  "Spectrum & Operator (J)", "Populations (statEquil)", "Populations (Ng)"};
+struct RhRange {                     // phase-level range (rhf1d()'s getCPU(1..2, ...) labels)
+  explicit RhRange(const char *label) { nvtxRangePushA(label); }
+  ~RhRange() { nvtxRangePop(); }
+};
+
 struct ScopedKernelTimer {
   rhb200_ctx *c; int which;
   ScopedKernelTimer(rhb200_ctx *ctx, int w) : c(ctx), which(w) {
+    nvtxRangePushA(RH_NVTX_LABEL[w]);
     if (c->timing) cudaEventRecord(c->ev0, c->stream);
   }
   ~ScopedKernelTimer() {
+    nvtxRangePop();
     c->k_launch[which] += 1;
     if (c->timing) {
       cudaEventRecord(c->ev1, c->stream);

@@ -260,7 +260,9 @@ extern "C" int rhb200_nlte_compute1d_batch(rhb200_ctx *c, const rhb200_nlte_plan
   const bool trace = getenv("RHB200_NLTE_TRACE") != nullptr;
   auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   double t_prev = now();
+  RhRange whole("rhf1d (NLTE, batch)");
   auto mark = [&](const char *what) {
+    nvtxMarkA(what);
     if (!trace) return;
     cudaStreamSynchronize(c->stream);
     const double t = now();
