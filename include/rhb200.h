@@ -374,7 +374,7 @@ int rhb200_lte_stokes_batch_atmos(rhb200_ctx *ctx, int ncol, int ndep, double mu
    `wght_per_H` = sum over elements of abundance x atomic weight (abundance.c:186-220).
    `scales` (may be NULL) [ncol][3][ndep]: height [m], tau_ref and column mass [kg m^-2] the reference would hold in
    geometry.height / tau_ref / cmass after convertScales() (for atm_scale 2 the column-mass row needs total_abund
-   and gravity: use rhb200_get_scales_batch). */
+   and gravity: rhb200_set_gravity first, else RHB200_EINVAL). */
 int rhb200_compute1d_batch(rhb200_ctx *ctx, int ncol, int ndep, int nrow, double mu, int atm_scale,
                            const double *atmosphere, int iref, double wght_per_H, double vmacro_tresh,
                            int bc_top, int bc_bottom, double *stokes, double *scales);
@@ -403,6 +403,11 @@ int rhb200_shard_columns(int ncol, int rank, int nrank, int *first, int *count);
 int rhb200_compute1d_rf_batch(rhb200_ctx *ctx, int ncol, int ndep, int nrow, double mu, int atm_scale,
                               const double *atmosphere, int iref, double wght_per_H, double vmacro_tresh,
                               int bc_top, int bc_bottom, double *stokes, double *scales, double *rfs);
+
+/* atmos.totalAbund (abundance.c:219) and atmos.gravity [m s^-2] (multiatmos.c:69,82): the compute1d entry points need
+   them for ONE thing, the column-mass row of `scales` when the column came on a height grid (atm_scale 2,
+   multiatmos.c:153-155); asking for that row without this call is RHB200_EINVAL. */
+int rhb200_set_gravity(rhb200_ctx *ctx, double total_abund, double gravity);
 
 /* pyrh.get_scales() for a batch (pyrh.pyx:491-534, rhf1d/pyrh_hse.c:402-553): Background() at the reference
    wavelength and convertScales(), nothing else.  The reference sets atmos.Nrlk = 0 there, so the context normally

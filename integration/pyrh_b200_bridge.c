@@ -75,7 +75,10 @@ void pyrh_b200_save_inputs(int Ndep, int atm_scale, double *scale, double *temp,
   double *src[9] = {scale, temp, ne, vz, vmic, mag, gamma, chi, nH};
   int r;
   if (Ndep != g_rows_ndep) { g_rows = (double *) realloc(g_rows, (size_t) 9 * Ndep * sizeof(double)); g_rows_ndep = Ndep; }
-  for (r = 0; r < 9; r++) memcpy(g_rows + (size_t) r * Ndep, src[r], Ndep * sizeof(double));
+  for (r = 0; r < 9; r++) {
+    if (src[r]) memcpy(g_rows + (size_t) r * Ndep, src[r], Ndep * sizeof(double));
+    else memset(g_rows + (size_t) r * Ndep, 0, Ndep * sizeof(double));          /* get_scales() has no field rows */
+  }
   g_atm_scale = atm_scale;
   /* rhf1d() only ever SETS atmos.Nloggf / Nlam (pyrh_compute1dray.c:199-211): a call without log gf / wavelength
      overrides after one with them would make readKuruczLines() read the previous caller's freed arrays */
@@ -192,6 +195,8 @@ typedef struct {
 } tables_t;
 static tables_t T;
 
+static int g_no_kurucz = 0;          /* hse() / get_scales(): atmos.Nrlk = 0, no line list is read (pyrh_hse.c:145,441) */
+
 static int stable_by_lambda0(RLK_Line *L, int n, int *order)
 {
   int a, b;
@@ -215,11 +220,11 @@ static void build_tables(int get_atomic_rfs, int fudge_num, double *fudge_lam, d
   for (n = 0; n < nkeep; n++) free(keep[n]);
   nkeep = 0;
 
-  if (input.magneto_optical) FAIL("MAGNETO_OPTICAL = TRUE is refused (the reference overflows chip_c there, readj.c:328)");
+  if (input.magneto_optical && !g_no_kurucz) FAIL("MAGNETO_OPTICAL = TRUE is refused (the reference overflows chip_c there, readj.c:328)");
   if (!g_ctx && !(g_ctx = rhb200_open(getenv("RHB200_DEVICE") ? atoi(getenv("RHB200_DEVICE")) : 0))) FAIL(rhb200_last_error());
 
   /* -- Kurucz lines (Background() reads and sorts them, background.c:284-294) */
-  if (atmos.Nrlk == 0) readKuruczLines(input.KuruczData);
+  if (atmos.Nrlk == 0 && !g_no_kurucz) readKuruczLines(input.KuruczData);
   for (n = 0; n < atmos.Nelem; n++) elem_row[n] = -1;
   for (n = 0; n < atmos.Nrlk; n++) {               /* element rows in order of first appearance in the files */
     const int e = atmos.rlk_lines[n].pt_index - 1;
@@ -677,6 +682,70 @@ mySpectrum rhf1d_batch(char *cwd, double mu, int Ndep, int ncol, double *atmosph
   memset(&g_batch, 0, sizeof g_batch);
   free(col0);
   return spec;
+}
+
+/* ---- pyrh_hse.c: hse(), get_scales(), get_ne_from_nH() */
+static void set_all_elements(void)               /* atmos.elements[] as Solve_ne sees it (solvene.c:55-140) */
+{
+  dvec elems = {0}, pf = {0};
+  int n, i, k, pfrow = 0;
+  if (!g_ctx && !(g_ctx = rhb200_open(getenv("RHB200_DEVICE") ? atoi(getenv("RHB200_DEVICE")) : 0))) FAIL(rhb200_last_error());
+  for (n = 0; n < atmos.Nelem; n++) {
+    Element *el = &atmos.elements[n];
+    double r[RHB200_RE_NFIELD];
+    if (!el->abundance_set) FAIL("element without an abundance (abundance.c:207-215 feeds raw partition functions into Solve_ne)");
+    if (el->Nstage > RHB200_RE_MAXSTAGE) FAIL("element with more ionisation stages than RHB200_RE_MAXSTAGE");
+    memset(r, 0, sizeof r);
+    r[RHB200_RE_WEIGHT] = el->weight; r[RHB200_RE_ABUND] = el->abund; r[RHB200_RE_NSTAGE] = el->Nstage; r[RHB200_RE_PFROW] = pfrow;
+    for (i = 0; i < el->Nstage; i++) r[RHB200_RE_IONPOT0 + i] = el->ionpot[i];
+    for (i = 0; i < RHB200_RE_NFIELD; i++) dv_push(&elems, r[i]);
+    for (i = 0; i < el->Nstage; i++) for (k = 0; k < atmos.Npf; k++) dv_push(&pf, el->pf[i][k]);
+    pfrow += el->Nstage;
+  }
+  CHECK(rhb200_set_elements(g_ctx, atmos.Nelem, elems.v, pfrow, atmos.Npf, pf.v, atmos.Tpf));
+  free(elems.v); free(pf.v);
+}
+
+/* hse() after SortLambda({500 nm}) (patch, pyrh_hse.c:200): the layer-by-layer walk of :212-367 for this column.
+   atmos.T / ne / nHtot alias the caller's arrays (:168-171), pg[0] holds the top pressure [Pa]. */
+int pyrh_b200_hse(int Ndep, int atm_scale, double *scale, double *rho, double *pg, int fudge_num, double *fudge_lam, double *fudge)
+{
+  double pg_top = pg[0];
+  if (atm_scale == 1) FAIL("hse() on a column-mass scale: the reference integrates no pressure there (pyrh_hse.c:283-288)");
+  g_no_kurucz = 1;
+  build_tables(0, fudge_num, fudge_lam, fudge);
+  g_no_kurucz = 0;
+  set_all_elements();
+  CHECK(rhb200_hse_batch(g_ctx, 1, Ndep, atm_scale, scale, atmos.T, &pg_top, atmos.wght_per_H, atmos.totalAbund, atmos.gravity,
+                         atmos.ne, atmos.nHtot, rho, pg));
+  return 1;
+}
+
+/* get_scales() after getBoundary() (patch, pyrh_hse.c:508): Background() at lam_ref + convertScales() (:513-514).
+   The rows in pyrh units were saved by pyrh_b200_save_inputs() before the in-place conversion (:479-485); the
+   results go where the reference's geometry pointers point (:445-462). */
+int pyrh_b200_get_scales(int Ndep)
+{
+  double *sc = (double *) malloc((size_t) 3 * Ndep * sizeof(double));
+  g_no_kurucz = 1;
+  build_tables(0, 0, NULL, NULL);
+  g_no_kurucz = 0;
+  CHECK(rhb200_get_scales_batch(g_ctx, 1, Ndep, 9, g_atm_scale, g_rows, T.iref, atmos.wght_per_H, atmos.totalAbund, atmos.gravity,
+                                atmos.vmacro_tresh, sc));
+  memcpy(geometry.height, sc, Ndep * sizeof(double));
+  memcpy(geometry.tau_ref, sc + Ndep, Ndep * sizeof(double));
+  memcpy(geometry.cmass, sc + 2 * (size_t) Ndep, Ndep * sizeof(double));
+  free(sc);
+  return 1;
+}
+
+/* get_ne_from_nH() in place of Background(FALSE, TRUE) with SOLVE_NE = ONCE (patch, pyrh_hse.c:644-645):
+   atmos.T [K], atmos.nHtot [m^-3] -> atmos.ne [m^-3] */
+int pyrh_b200_solve_ne(int Ndep)
+{
+  set_all_elements();
+  CHECK(rhb200_solve_ne_batch(g_ctx, (size_t) Ndep, atmos.T, atmos.nHtot, atmos.ne, 1));
+  return 1;
 }
 
 void pyrh_b200_close(void)

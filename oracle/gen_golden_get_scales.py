@@ -13,8 +13,8 @@ from oracle.gen_golden import GOLD
 dp = C.POINTER(C.c_double)
 
 
-def get_scales(atm, atm_scale, cwd, lam_ref=500.0):
-    lib = rd.load("scalar")
+def get_scales(atm, atm_scale, cwd, lam_ref=500.0, variant="scalar"):
+    lib = rd.load(variant)
     lib.get_scales.restype = None
     lib.get_scales.argtypes = [C.c_char_p, C.c_int] + [dp] * 6 + [C.c_int, C.c_double] + [dp] * 3 + [C.c_int, C.c_void_p, C.c_void_p]
     a = np.ascontiguousarray(atm, np.float64).copy()

@@ -22,8 +22,8 @@ def _call(cwd, fn):
         os.chdir(old)
 
 
-def get_ne_from_nH(cwd, atm_scale, scale, T, nH):
-    lib = rd.load("scalar")
+def get_ne_from_nH(cwd, atm_scale, scale, T, nH, variant="scalar"):
+    lib = rd.load(variant)
     lib.get_ne_from_nH.restype = None
     lib.get_ne_from_nH.argtypes = [C.c_char_p, C.c_int, C.c_int, dp, dp, dp, dp]
     scale, T, nH = (np.ascontiguousarray(x, np.float64).copy() for x in (scale, T, nH))
@@ -33,8 +33,8 @@ def get_ne_from_nH(cwd, atm_scale, scale, T, nH):
     return ne
 
 
-def hse(cwd, atm_scale, scale, T, pg_top, fudge_wave=None, fudge_value=None):
-    lib = rd.load("scalar")
+def hse(cwd, atm_scale, scale, T, pg_top, fudge_wave=None, fudge_value=None, variant="scalar"):
+    lib = rd.load(variant)
     lib.hse.restype = None
     lib.hse.argtypes = [C.c_char_p, C.c_int, dp, dp, dp, dp, dp, dp, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                         C.c_int, C.c_void_p, C.c_void_p]

@@ -84,6 +84,7 @@ SYMBOLS = [
                                    dp, dp, dp, dp]),
     ("rhb200_set_elements", C.c_int, [vp, C.c_int, dp, C.c_int, C.c_int, dp, dp]),
     ("rhb200_solve_ne_batch", C.c_int, [vp, C.c_size_t, dp, dp, dp, C.c_int]),
+    ("rhb200_set_gravity", C.c_int, [vp, C.c_double, C.c_double]),
     ("rhb200_get_scales_batch", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_double, C.c_double,
                                           C.c_double, C.c_double, vp]),
     ("rhb200_set_solvers", C.c_int, [vp, C.c_int, C.c_int]),

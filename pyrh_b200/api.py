@@ -329,6 +329,11 @@ class Context:
                                              float(wght_per_H), float(total_abund), float(g), *[_dp(o) for o in out]))
         return tuple(out)
 
+    def set_gravity(self, total_abund, gravity=None):
+        """atmos.totalAbund / atmos.gravity for the column-mass row of ``get_scales=True`` on a height grid."""
+        g = math.exp(2.30258509299404568402 * 4.4) * 1.0E-02 if gravity is None else gravity    # multiatmos.c:69,82
+        _lib.check(self.lib.rhb200_set_gravity(self.h, float(total_abund), float(g)))
+
     def get_scales_batch(self, atmosphere, atm_scale=0, lambda_ref=500.0, wght_per_H=0.0, total_abund=0.0,
                          gravity=None, vmacro_tresh=0.0):
         """``pyrh.get_scales`` for a batch: ``[ncol, 3, ndep]`` = height [m], tau_ref, column mass [kg m^-2]."""

@@ -765,7 +765,19 @@ extern "C" int rhb200_compute1d_batch(rhb200_ctx *c, int ncol, int ndep, int nro
   if (iref < 0 || iref >= c->wav.nlambda) { rhb200_set_error("iref outside the wavelength grid"); return RHB200_EINVAL; }
   if (!(wght_per_H > 0.0) && atm_scale == 1) { rhb200_set_error("wght_per_H (abundance.c:220) is needed for the column-mass scale"); return RHB200_EINVAL; }
   PyrhIn py{atmosphere, nrow, atm_scale, iref, wght_per_H, vmacro_tresh, scales};
+  if (scales && atm_scale == 2) {
+    if (!(c->gravity > 0.0)) { rhb200_set_error("scales on a height grid: the column-mass row needs rhb200_set_gravity() (multiatmos.c:153-155)"); return RHB200_EINVAL; }
+    py.total_abund = c->total_abund; py.gravity = c->gravity;
+  }
   return lte_batch_host(c, ncol, ndep, mu, 1, bc_top, bc_bottom, nullptr, nullptr, nullptr, nullptr, stokes, 1, &py);
+}
+
+extern "C" int rhb200_set_gravity(rhb200_ctx *c, double total_abund, double gravity)
+{
+  RH_NEED_CTX(c);
+  if (!(total_abund > 0.0) || !(gravity > 0.0)) { rhb200_set_error("total_abund and gravity [m/s^2] must be positive"); return RHB200_EINVAL; }
+  c->total_abund = total_abund; c->gravity = gravity;
+  return RHB200_OK;
 }
 
 extern "C" int rhb200_shard_columns(int ncol, int rank, int nrank, int *first, int *count)
@@ -825,6 +837,10 @@ extern "C" int rhb200_compute1d_rf_batch(rhb200_ctx *c, int ncol, int ndep, int 
   if (iref < 0 || iref >= c->wav.nlambda) { rhb200_set_error("iref outside the wavelength grid"); return RHB200_EINVAL; }
   if (!(wght_per_H > 0.0) && atm_scale == 1) { rhb200_set_error("wght_per_H (abundance.c:220) is needed for the column-mass scale"); return RHB200_EINVAL; }
   PyrhIn py{atmosphere, nrow, atm_scale, iref, wght_per_H, vmacro_tresh, scales};
+  if (scales && atm_scale == 2) {
+    if (!(c->gravity > 0.0)) { rhb200_set_error("scales on a height grid: the column-mass row needs rhb200_set_gravity() (multiatmos.c:153-155)"); return RHB200_EINVAL; }
+    py.total_abund = c->total_abund; py.gravity = c->gravity;
+  }
   py.lrf_out = rfs;
   return lte_batch_host(c, ncol, ndep, mu, 1, bc_top, bc_bottom, nullptr, nullptr, nullptr, nullptr, stokes, 1, &py);
 }
@@ -862,6 +878,104 @@ struct DevBuf {
   template <class T> T *as() { return (T *) p; }
 };
 
+// Single-depth perturbations without the 2 npar ndep full syntheses: everything before convertScales() is local in
+// depth, so the depth-kp opacities of "parameter p changed at depth kp" are those of the pseudo column "parameter p
+// changed at every depth".  Per base column 1 + 2 npar full columns go through Background() (instead of 2 npar ndep);
+// each virtual column then gets its own convertScales() walk (vscales_kernel) and formal solution, reading the base
+// column's ray-point records with the depth-kp record taken from the pseudo column.  Same arithmetic on the same
+// numbers as the brute-force path: results are bit-identical (tests/test_gpu_parity.py).
+// Two slots / streams: the D2H of chunk i overlaps the kernels of chunk i+1.
+static int rf_fd_single_depth(rhb200_ctx *c, int ncol, int ndep, int nrow, double mu, int atm_scale, int iref, double wght_per_H,
+                              int bc_top, int bc_bottom, int npar, const int *d_rows, const double *d_delta,
+                              const double *d_base, double *rf)
+{
+  RhRange whole("rhf1d (LTE, finite-difference response functions)");
+  RH_CHECK(check_batch_args(c, ncol, ndep, mu, bc_top, bc_bottom));
+  if (!c->cont) { rhb200_set_error("rhb200_set_continuum() has not been called"); return RHB200_ESTATE; }
+  const int nl = c->wav.nlambda, nfull1 = 1 + 2*npar, nv1 = 2*npar*ndep, nslots = 2;
+  const bool mol_on = c->wav.nmw > 0;
+  if (mol_on) {
+    std::vector<int> chem(c->wav.nmsel);
+    for (int m = 0; m < c->wav.nmsel; m++) chem[m] = (int) c->h_msel[(size_t) m * 16];
+    RH_CHECK(rh_continuum_set_molsel(c, c->wav.nmsel, chem.data()));
+  }
+  const int nchem = rh_continuum_natom(c) + 4, nlev = rh_continuum_nlev(c);
+  struct Lay { size_t in, at, chi, eta, ch, pp, tp, pc, md, mchi, meta, ws, vws, vst, vsc, rfo, total; };
+  auto layout = [&](int nb) {
+    Lay y; size_t o = 0;
+    const size_t nf = (size_t) nb * nfull1, nv = (size_t) nb * nv1;
+    auto take = [&](size_t bytes) { const size_t at = o; o += align_up(bytes); return at; };
+    y.in  = take(nf * nrow * ndep * sizeof(double));
+    y.at  = take(nf * RHB200_AT_NFIELD * ndep * sizeof(double));
+    y.chi = take(nf * nl * ndep * sizeof(double));
+    y.eta = take(nf * nl * ndep * sizeof(double));
+    y.ch  = take(nf * nchem * ndep * sizeof(double));
+    y.pp  = take(nf * nlev * ndep * sizeof(double));
+    y.tp  = take(nf * 8 * ndep * sizeof(double));
+    y.pc  = take(nf * std::max(1, c->wav.npl) * 4 * ndep * sizeof(double));
+    y.md  = take(mol_on ? nf * c->wav.nmsel * 4 * ndep * sizeof(double) : 0);
+    y.mchi = take(mol_on ? nf * nl * ndep * sizeof(double) : 0);
+    y.meta = take(mol_on ? nf * nl * ndep * sizeof(double) : 0);
+    y.ws  = take(ChunkLayout(c, (int) nf, ndep).total);
+    y.vws = take(nv * 4 * ndep * sizeof(double));
+    y.vst = take(nv * 4 * nl * sizeof(double));
+    y.vsc = take(nv * std::max(1, c->wav.nnoline) * 5 * ndep * sizeof(double));
+    y.rfo = take(nv / 2 * 4 * nl * sizeof(double));
+    y.total = o;
+    return y;
+  };
+  size_t budget = (size_t) 8 << 30;
+  if (const char *e = getenv("RHB200_WS_GB")) { double g = atof(e); if (g > 0.01) budget = (size_t) (g * (double) ((size_t) 1 << 30)); }
+  const size_t per = layout(1).total;
+  int nb = (int) std::max<size_t>(1, std::min<size_t>((size_t) ncol, budget / (nslots * per)));
+  if (const char *e = getenv("RHB200_RF_CHUNK_COLS")) { int v = atoi(e); if (v > 0) nb = std::min(ncol, v); }
+  if (nb < ncol) { const int nchunk = (ncol + nb - 1) / nb; nb = (ncol + nchunk - 1) / nchunk; }
+  const Lay y = layout(nb);
+  RH_CHECK(rh_ws_reserve(c, nslots * y.total));
+  cudaStream_t streams[2] = {c->stream, c->copy_stream};
+  cudaStream_t saved = c->stream;
+  int rc = RHB200_OK, i = 0;
+  for (int b0 = 0; b0 < ncol && rc == RHB200_OK; b0 += nb, i++) {
+    const int n = std::min(nb, ncol - b0), nf = n * nfull1, nv = n * nv1;
+    char *base = (char *) c->ws + (size_t) (i % nslots) * y.total;
+    auto D = [&](size_t off) { return (double *) (base + off); };
+    c->stream = streams[i % nslots];
+    ChunkLayout L(c, nf, ndep);
+    char *ws = base + y.ws;
+    double *d_elem_n = (double *) ws, *d_lineprep = (double *) (ws + L.elem_n), *d_raypts = (double *) (ws + L.elem_n + L.lineprep);
+#define RF_STEP(call) if ((rc = (call)) != RHB200_OK) break
+    RF_STEP(rh_launch_rf_expand_full(c, b0, n, ndep, nrow, npar, d_rows, d_delta, d_base, D(y.in)));
+    RF_STEP(rh_launch_pyrh_rows(c, nf, ndep, nrow, atm_scale, mu, 0.0, D(y.in), D(y.at), nullptr));
+    RF_STEP(rh_continuum_chunk(c, nf, ndep, D(y.at), D(y.ch), D(y.pp), D(y.tp), D(y.chi), D(y.eta), 1, mol_on ? D(y.md) : nullptr, nullptr));
+    if (mol_on) RF_STEP(rh_molecular_chunk(c, nf, ndep, mu, D(y.at), D(y.md), D(y.md) + (size_t) nf * c->wav.nmsel * ndep, D(y.mchi), D(y.meta)));
+    RF_STEP(rh_passive_chunk(c, nf, ndep, mu, D(y.at), D(y.pp), nlev, D(y.pc), D(y.chi), D(y.eta)));
+    RF_STEP(rh_launch_proton(c, nf, ndep, nlev, rh_continuum_proton_level(c), D(y.pp), D(y.at)));
+    RF_STEP(rh_launch_prep(c, nf, ndep, mu, 1, D(y.at), d_elem_n, d_lineprep));
+    RF_STEP(rh_launch_opacity_fused(c, nf, ndep, 1, D(y.at), d_lineprep, D(y.chi), D(y.eta), d_raypts,
+                                    mol_on ? D(y.mchi) : nullptr, mol_on ? D(y.meta) : nullptr, nullptr));
+    RF_STEP(rh_launch_vscales(c, n, npar, ndep, iref, atm_scale, wght_per_H, 0.0, 1.0, d_raypts, D(y.at), D(y.vws)));
+    cudaError_t e;
+    if (c->no_stokes && (e = cudaMemsetAsync(D(y.vst), 0, (size_t) nv * 4 * nl * sizeof(double), c->stream)) != cudaSuccess) {
+      rhb200_set_error("memset failed: %s", cudaGetErrorString(e)); rc = RHB200_ECUDA; break;
+    }
+    if (!c->no_stokes) RF_STEP(rh_launch_delo_vcols(c, n, npar, ndep, mu, bc_top, bc_bottom, D(y.vws), d_raypts, D(y.vst)));
+    RF_STEP(rh_launch_noline_vcols(c, n, npar, ndep, mu, bc_top, bc_bottom, D(y.vws), d_raypts, D(y.vst), D(y.vsc)));
+    RF_STEP(rh_launch_rf_diff(c, b0 * nv1, nv, ndep, nl, npar, d_delta, D(y.vst), D(y.rfo)));
+#undef RF_STEP
+    if ((e = cudaMemcpyAsync(rf + (size_t) b0 * (nv1 / 2) * 4 * nl, D(y.rfo), (size_t) (nv / 2) * 4 * nl * sizeof(double),
+                             cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) {
+      rhb200_set_error("D2H copy failed: %s", cudaGetErrorString(e)); rc = RHB200_ECUDA; break;
+    }
+  }
+  c->stream = saved;
+  cudaError_t e1 = cudaStreamSynchronize(streams[0]), e2 = cudaStreamSynchronize(streams[1]);
+  if (rc == RHB200_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) {
+    rhb200_set_error("kernel execution failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    rc = RHB200_ECUDA;
+  }
+  return rc;
+}
+
 // Finite-difference response functions of the LTE Stokes spectrum to the atmosphere rows, per depth point:
 // what a pyrh caller (an inversion code) obtains from 2 x npar x ndep calls of pyrh.compute1d per column.
 extern "C" int rhb200_rf_fd_batch(rhb200_ctx *c, int ncol, int ndep, int nrow, double mu, int atm_scale,
@@ -887,6 +1001,14 @@ extern "C" int rhb200_rf_fd_batch(rhb200_ctx *c, int ncol, int ndep, int nrow, d
   RH_CUDA(cudaMemcpy(base.p, atmosphere, (size_t) ncol * nrow * ndep * sizeof(double), cudaMemcpyHostToDevice));
   RH_CUDA(cudaMemcpy(rows.p, par_rows, (size_t) npar * sizeof(int), cudaMemcpyHostToDevice));
   RH_CUDA(cudaMemcpy(delta.p, par_delta, (size_t) npar * sizeof(double), cudaMemcpyHostToDevice));
+  // the depth-local route needs: no scale-row parameter (the scale couples the depths), every column moving
+  // (VMACRO_TRESH = 0; atmos.moving is a property of the whole column) and no scattering iteration (J couples them)
+  bool local = c->n_max_scatter <= 0 && !(vmacro_tresh > 0.0) && c->cont != nullptr;
+  for (int p = 0; p < npar; p++) if (par_rows[p] == 0) local = false;
+  if (const char *e = getenv("RHB200_RF_FD_BRUTE")) if (atoi(e) != 0) local = false;
+  if (local)
+    return rf_fd_single_depth(c, ncol, ndep, nrow, mu, atm_scale, iref, wght_per_H, bc_top, bc_bottom, npar,
+                              (const int *) rows.p, (const double *) delta.p, (const double *) base.p, rf);
   PyrhIn py{nullptr, nrow, atm_scale, iref, wght_per_H, vmacro_tresh, nullptr};
   py.rf_npar = npar; py.d_rf_rows = (const int *) rows.p; py.d_rf_delta = (const double *) delta.p;
   py.d_base = (const double *) base.p; py.rf_out = rf;

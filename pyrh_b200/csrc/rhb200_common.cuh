@@ -99,6 +99,7 @@ struct rhb200_ctx {
   int scal_fields() const { return 3 + 3*lrf_npar; }
   // NLTE rate accumulation: 0 = fixed-partition two-stage reduction (default), 1 = the reference's add order, bit-identical
   int nlte_exact_rates = 0;
+  double total_abund = 0.0, gravity = 0.0;      // rhb200_set_gravity: the column mass of a height scale (multiatmos.c:153-155)
   // wavelength shard of the NLTE solve (rhb200_nlte_set_shard)
   int shard_rank = 0, shard_nrank = 1;
   rhb200_allreduce_fn shard_fn = nullptr; void *shard_user = nullptr;
@@ -219,6 +220,17 @@ int rh_launch_opacity_raw(rhb200_ctx *ctx, int ncol, int ndep, int to_obs,
 int rh_launch_delo_raypts(rhb200_ctx *ctx, int ncol, int ndep, double muz, int bc_top, int bc_bottom,
                           const double *d_atmos, const double *d_raypts,
                           double *d_stokes /* [ncol][4][nlambda] */);
+// single-depth finite-difference columns (rhb200_rf_fd_batch): see vscales_kernel in rhb200_scales.cu
+int rh_launch_rf_expand_full(rhb200_ctx *ctx, int b0, int nb, int ndep, int nrow, int npar, const int *d_rows,
+                             const double *d_delta, const double *d_base, double *d_in);
+int rh_launch_vscales(rhb200_ctx *ctx, int nb, int npar, int ndep, int iref, int atm_scale, double wght_per_H,
+                      double total_abund, double gravity, const double *d_raypts, const double *d_atmos,
+                      double *d_vws /* [nv][4][ndep] */);
+int rh_launch_delo_vcols(rhb200_ctx *ctx, int nb, int npar, int ndep, double muz, int bc_top, int bc_bottom,
+                         const double *d_vws, const double *d_raypts, double *d_stokes /* [nv][4][nlambda] */);
+int rh_launch_noline_vcols(rhb200_ctx *ctx, int nb, int npar, int ndep, double muz, int bc_top, int bc_bottom,
+                           const double *d_vws, const double *d_raypts, double *d_stokes,
+                           double *d_scratch /* [nv][nnoline][5][ndep] */);
 int rh_launch_delo_generic(rhb200_ctx *ctx, int solver /* RHB200_DELO_* */, int nray, int ndep, double muz, int to_obs,
                            int bc_top, int bc_bottom, const int *d_ray_col,
                            const double *d_ray_lambda, const double *d_height, const double *d_T,

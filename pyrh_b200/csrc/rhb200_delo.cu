@@ -34,6 +34,36 @@ struct RayPtsIO {
   }
 };
 
+// ---- IO policy of the single-depth finite-difference columns (rhb200_rf_fd_batch): the base column's records
+//      everywhere except at depth kp, where the pseudo column's record (parameter changed at every depth) is read
+struct RayPtsPatchIO {
+  const double2 *__restrict__ rp, *__restrict__ rq;
+  int kp;
+  double *out;
+  int nlambda, kout;
+  __device__ __forceinline__ const double2 *rec(int k) const { return (k == kp ? rq : rp) + 4*(size_t)k; }
+  __device__ __forceinline__ double chi(int k) const { return __ldg(reinterpret_cast<const double *>(rec(k))); }
+  __device__ __forceinline__ void K(int k, double x[3]) const {
+    const double2 *r = rec(k);
+    const double2 a = __ldg(r), b = __ldg(r + 1);
+    x[0] = a.y; x[1] = b.x; x[2] = b.y;
+  }
+  __device__ __forceinline__ void S(int k, double s[4]) const {
+    const double2 *r = rec(k);
+    const double2 a = __ldg(r + 2), b = __ldg(r + 3);
+    s[0] = a.x; s[1] = a.y; s[2] = b.x; s[3] = b.y;
+  }
+  __device__ __forceinline__ void storeI(int k, const double I[4]) {
+    if (k == kout) {
+      out[0] = I[0]; out[nlambda] = I[1]; out[2*(size_t)nlambda] = I[2]; out[3*(size_t)nlambda] = I[3];
+    }
+  }
+  __device__ __forceinline__ void storePsi(int, double) {}
+  __device__ __forceinline__ void prefetch(int k, int ndep) const {
+    if (k >= 0 && k < ndep) asm volatile("prefetch.global.L1 [%0];" :: "l"(rec(k)));
+  }
+};
+
 // ---- IO policy: reference layouts chi[nray][ndep], S[nray][4][ndep], chiQUV[nray][3][ndep]
 struct GenericIO {
   const double *__restrict__ chi_, *__restrict__ S_, *__restrict__ q_;
@@ -71,6 +101,27 @@ delo_raypts_kernel(int ncol, int nlambda, int ndep, double muz, int bc_top, int 
               stokes + (size_t) col * 4 * nlambda + l, nlambda, 0};
   rhd::delo_bezier3_ray(io, ndep, at + RHB200_AT_HEIGHT * ndep, muz, 1, bc_top, bc_bottom,
                         at + RHB200_AT_T * ndep, __ldg(lambda + l));
+}
+
+// single-depth finite-difference columns: one thread per (virtual column, wavelength); vws [nv][4][ndep] = height, T, ..
+// of the virtual column (vscales_kernel), raypts those of the chunk's full columns (base + pseudo)
+__global__ void __launch_bounds__(128, 4)
+delo_vcols_kernel(int nv, int npar, int nlambda, int ndep, double muz, int bc_top, int bc_bottom, int parabolic,
+                  const double *__restrict__ vws, const double *__restrict__ lambda, const int *__restrict__ wflags,
+                  const double *__restrict__ raypts, double *__restrict__ stokes)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t) nv * nlambda) return;
+  const int v = (int) (t / nlambda), l = (int) (t - (size_t) v * nlambda);
+  if ((__ldg(wflags + l) & 2) == 0) return;
+  const int s = v & 1, kp = (v >> 1) % ndep, p = ((v >> 1) / ndep) % npar, b = ((v >> 1) / ndep) / npar;
+  const size_t fb = (size_t) b * (1 + 2*npar), fq = fb + 1 + 2*p + s;
+  RayPtsPatchIO io{reinterpret_cast<const double2 *>(raypts + (fb * nlambda + l) * (size_t) ndep * RP_NFIELD),
+                   reinterpret_cast<const double2 *>(raypts + (fq * nlambda + l) * (size_t) ndep * RP_NFIELD), kp,
+                   stokes + (size_t) v * 4 * nlambda + l, nlambda, 0};
+  const double *w = vws + (size_t) v * 4 * ndep;
+  if (parabolic) rhp::stokes_parabolic_ray(io, ndep, w, muz, 1, bc_top, bc_bottom, w + ndep, __ldg(lambda + l));
+  else           rhd::delo_bezier3_ray(io, ndep, w, muz, 1, bc_top, bc_bottom, w + ndep, __ldg(lambda + l));
 }
 
 // fused LTE path with S_INTERPOLATION_STOKES = DELO_PARABOLIC (formal.c:215-216)
@@ -236,6 +287,45 @@ feautrier_raypts_kernel(int ncol, int nlambda, int ndep, double muz, int bc_top,
   out[0] = I0; out[nlambda] = 0.0; out[2*(size_t) nlambda] = 0.0; out[3*(size_t) nlambda] = 0.0;
 }
 
+// the same rays for the single-depth finite-difference columns: chi and S of the virtual column are gathered into its
+// own scratch rows (the base records are shared by 2 npar ndep virtual columns, so Feautrier's F / z cannot live in
+// them).  scratch [nv][nnoline][5][ndep]: chi, S, I / P, F, z.  vmacro_tresh = 0 on this path: every column is moving.
+__global__ void __launch_bounds__(128)
+noline_vcols_kernel(int nv, int npar, int nlambda, int ndep, double muz, int bc_top, int bc_bottom,
+                    const int *__restrict__ nolines, int nnoline, const double *__restrict__ vws,
+                    const double *__restrict__ lambda, const double *__restrict__ raypts, double *__restrict__ stokes,
+                    const int *__restrict__ wflags, int solver, double *__restrict__ scratch)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t) nv * nnoline) return;
+  const int v = (int) (t / nnoline), l = __ldg(nolines + (int) (t - (size_t) v * nnoline));
+  const int sg = v & 1, kp = (v >> 1) % ndep, p = ((v >> 1) / ndep) % npar, b = ((v >> 1) / ndep) / npar;
+  const size_t fb = (size_t) b * (1 + 2*npar), fq = fb + 1 + 2*p + sg;
+  const double *rb = raypts + (fb * nlambda + l) * (size_t) ndep * RP_NFIELD, *rq = raypts + (fq * nlambda + l) * (size_t) ndep * RP_NFIELD;
+  const double *z = vws + (size_t) v * 4 * ndep, *Tc = z + ndep;
+  double *c = scratch + t * 5 * (size_t) ndep, *s = c + ndep, *Ir = s + ndep;
+  for (int k = 0; k < ndep; k++) {
+    const double *r = (k == kp ? rq : rb) + (size_t) k * RP_NFIELD;
+    c[k] = r[RP_CHI]; s[k] = r[RP_SI];
+  }
+  const int fl = __ldg(wflags + l);
+  const double lam = __ldg(lambda + l);
+  double I0;
+  if (fl & 3) {                                               // a line and a moving column: the scalar S_INTERPOLATION ray
+    switch (solver) {                                         // formal.c:229-235
+    case RHB200_S_LINEAR:    rhp::linear_ray(ndep, z, muz, 1, bc_top, bc_bottom, Tc, lam, c, s, Ir, nullptr); break;
+    case RHB200_S_PARABOLIC: rhp::parabolic_ray(ndep, z, muz, 1, bc_top, bc_bottom, Tc, lam, c, s, Ir, nullptr); break;
+    default:                 rhz::bezier3_ray(ndep, z, muz, 1, bc_top, bc_bottom, Tc, lam, c, s, Ir, nullptr);
+    }
+    I0 = Ir[0];
+  } else {
+    FeauGenericIO io{c, s, z, Ir, nullptr, Ir + ndep, ndep};
+    I0 = rhf::feautrier_ray(io, ndep, muz, bc_top, bc_bottom, Tc, lam);
+  }
+  double *out = stokes + (size_t) v * 4 * nlambda + l;
+  out[0] = I0; out[nlambda] = 0.0; out[2*(size_t) nlambda] = 0.0; out[3*(size_t) nlambda] = 0.0;
+}
+
 // One pass of the LTE scattering iteration (pyrh_compute1dray.c:332-337 -> solveSpectrum -> Formal, angle-independent
 // branch formal.c:289-309) over the Feautrier wavelengths of the columns that have not converged yet:
 // S = (eta + sca Jdag)/chi, new J = P, the column's dJmax through an atomic max on the bit pattern (dJ >= 0).
@@ -349,6 +439,36 @@ int rh_launch_delo_raypts(rhb200_ctx *ctx, int ncol, int ndep, double muz, int b
     case 6: RH_LAUNCH_DELO(6); break;
     default: RH_LAUNCH_DELO(3); break;
     }
+  }
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}
+
+int rh_launch_delo_vcols(rhb200_ctx *ctx, int nb, int npar, int ndep, double muz, int bc_top, int bc_bottom,
+                         const double *d_vws, const double *d_raypts, double *d_stokes)
+{
+  const int nv = nb * npar * ndep * 2;
+  const size_t nray = (size_t) nv * ctx->wav.nlambda;
+  if (nray == 0) return RHB200_OK;
+  {
+    ScopedKernelTimer t(ctx, RHB200_K_DELO);
+    delo_vcols_kernel<<<(unsigned) ((nray + 127) / 128), 128, 0, ctx->stream>>>(nv, npar, ctx->wav.nlambda, ndep, muz, bc_top, bc_bottom,
+        ctx->s_interpolation_stokes == RHB200_DELO_PARABOLIC, d_vws, ctx->wav.lambda, ctx->wav.flags, d_raypts, d_stokes);
+  }
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}
+
+int rh_launch_noline_vcols(rhb200_ctx *ctx, int nb, int npar, int ndep, double muz, int bc_top, int bc_bottom,
+                           const double *d_vws, const double *d_raypts, double *d_stokes, double *d_scratch)
+{
+  const int nv = nb * npar * ndep * 2, nn = ctx->wav.nnoline;
+  const size_t n = (size_t) nv * nn;
+  if (n == 0) return RHB200_OK;
+  {
+    ScopedKernelTimer t(ctx, RHB200_K_BEZIER);
+    noline_vcols_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, ctx->stream>>>(nv, npar, ctx->wav.nlambda, ndep, muz, bc_top, bc_bottom,
+        ctx->wav.noline, nn, d_vws, ctx->wav.lambda, d_raypts, d_stokes, ctx->wav.flags, ctx->s_interpolation, d_scratch);
   }
   RH_CUDA(cudaGetLastError());
   return RHB200_OK;

@@ -232,6 +232,7 @@ extern "C" int rhb200_nlte_compute1d_batch(rhb200_ctx *c, const rhb200_nlte_plan
   if (!c->no_stokes) { rhb200_set_error("NLTE with STOKES_MODE other than NO_STOKES (polarised active sets) is not implemented"); return RHB200_EUNSUPPORTED; }
   if (pl->Natom > NF_MAXATOM) { rhb200_set_error("too many ACTIVE atoms"); return RHB200_EUNSUPPORTED; }
   if (vmacro_tresh > 0.0) { rhb200_set_error("VMACRO_TRESH > 0 (columns that may be static) is not implemented on the NLTE path"); return RHB200_EUNSUPPORTED; }
+  if (scales && atm_scale == 2 && !(c->gravity > 0.0)) { rhb200_set_error("scales on a height grid: the column-mass row needs rhb200_set_gravity() (multiatmos.c:153-155)"); return RHB200_EINVAL; }
   const int N = ndep, Ns = pl->Nspect;
   const int nlev_model = rh_continuum_nlev(c), natom_model = rh_continuum_natom(c);
   const int H_nlevel = rh_continuum_proton_level(c) + 1;
@@ -428,7 +429,7 @@ extern "C" int rhb200_nlte_compute1d_batch(rhb200_ctx *c, const rhb200_nlte_plan
       pops_n = d_popsn;
     }
     RH_CHECK(background(n, mu_last, pops_n, (double *) E.C.chi_c, (double *) E.C.eta_c, (double *) E.C.sca_c));
-    RH_CHECK(rh_launch_scales_chi(c, n, N, Ns, iref, atm_scale, wght_per_H, 0.0, 1.0, E.C.chi_c, d_at, d_sc,
+    RH_CHECK(rh_launch_scales_chi(c, n, N, Ns, iref, atm_scale, wght_per_H, c->total_abund, c->gravity > 0.0 ? c->gravity : 1.0, E.C.chi_c, d_at, d_sc,
                                   scales ? d_sc + 2*cN : nullptr));
     nlte_height_kernel<<<RH_GRID(nN, 128), 0, st>>>(n, N, d_at, (double *) E.C.height);
     // ---- getProfiles(): Damping() with the populations atom->n shows at this point

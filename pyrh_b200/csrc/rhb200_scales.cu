@@ -93,61 +93,54 @@ proton_kernel(int ncol, int ndep, int nlev, int proton_level, const double *__re
   atmos[((size_t) col * RHB200_AT_NFIELD + RHB200_AT_NP) * ndep + k] = pops[((size_t) col * nlev + proton_level) * ndep + k];
 }
 
-// one thread per column, sequential in depth like the reference.  chi_ref = total opacity at the reference
-// wavelength (spectrum.chi_c_lam[ref_index], readj.c:319: the last record written for that wavelength, i.e.
-// continuum + lines of the up-ray), read from the ray-point records of wavelength iref.
-// scratch [ncol][2][ndep] keeps tau_ref and cmass; scales_out [ncol][3][ndep] = height, tau_ref, cmass.
-__global__ void scales_kernel(int ncol, int ndep, int atm_scale, double wght_per_H,
-                              double total_abund, double gravity,
-                              const double *__restrict__ chi_ref, size_t chi_col_stride, size_t chi_k_stride,
-                              double *__restrict__ atmos,
-                              double *__restrict__ scratch, double *__restrict__ scales_out)
+// convertScales() for one column, sequential in depth like the reference.  `in` hands over the column: chi(k) = total
+// opacity at the reference wavelength (spectrum.chi_c_lam[ref_index], readj.c:319: the last record written for that
+// wavelength, i.e. continuum + lines of the up-ray), nH(k), T(k), ne(k) and scale(k) = the scale the column came with
+// (tau_ref, cmass or height, SI).  height / tau / cmass [ndep] receive the three scales.
+template <class In>
+__device__ __forceinline__ void convert_scales(const In &in, int ndep, int atm_scale, double wght_per_H, double total_abund,
+                                               double gravity, double *height, double *__restrict__ tau,
+                                               double *__restrict__ cmass)
 {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= ncol) return;
-  const double *at = atmos + (size_t) col * RHB200_AT_NFIELD * ndep;
-  double *height = atmos + ((size_t) col * RHB200_AT_NFIELD + RHB200_AT_HEIGHT) * ndep;
-  const double *nHtot = at + (size_t) RHB200_AT_NHTOT * ndep;
-  const double *rp = chi_ref + (size_t) col * chi_col_stride;
-  double *tau = scratch + (size_t) col * 2 * ndep, *cmass = tau + ndep;
-#define CHI(k) rp[(size_t) (k) * chi_k_stride]
-#define RHO(k) ((RH_AMU * wght_per_H) * nHtot[k])
-  if (atm_scale == 0) {                                  // TAU500, multiatmos.c:140-151; height row holds tau_ref
-    double tprev = height[0], hprev = 0.0;
+#define CHI(k) in.chi(k)
+#define RHO(k) ((RH_AMU * wght_per_H) * in.nH(k))
+  if (atm_scale == 0) {                                  // TAU500, multiatmos.c:140-151
+    double tprev = in.scale(0), hprev = 0.0;
     tau[0] = tprev;
     height[0] = 0.0;
     double cprev = (tprev / CHI(0)) * RHO(0);
     cmass[0] = cprev;
     for (int k = 1; k < ndep; k++) {
-      const double tk = height[k];
+      const double tk = in.scale(k);
       tau[k] = tk;
       const double hk = hprev - 2.0 * (tk - tprev) / (CHI(k-1) + CHI(k));
       const double ck = cprev + 0.5*(RHO(k-1) + RHO(k)) * (hprev - hk);
       height[k] = hk; cmass[k] = ck;
       hprev = hk; tprev = tk; cprev = ck;
     }
-  } else if (atm_scale == 1) {                           // COLUMN_MASS, :128-138; height row holds cmass
-    double cprev = height[0], hprev = 0.0;
+  } else if (atm_scale == 1) {                           // COLUMN_MASS, :128-138
+    double cprev = in.scale(0), hprev = 0.0;
     double tprev = CHI(0) / RHO(0) * cprev;
     tau[0] = tprev; cmass[0] = cprev;
     height[0] = 0.0;
     for (int k = 1; k < ndep; k++) {
-      const double ck = height[k];
+      const double ck = in.scale(k);
       const double hk = hprev - 2.0*(ck - cprev) / (RHO(k-1) + RHO(k));
       const double tk = tprev + 0.5*(CHI(k-1) + CHI(k)) * (hprev - hk);
       height[k] = hk; tau[k] = tk; cmass[k] = ck;
       hprev = hk; cprev = ck; tprev = tk;
     }
   } else {                                               // GEOMETRIC, :153-163: heights stay as they came
-    const double *T = at + (size_t) RHB200_AT_T * ndep, *ne = at + (size_t) RHB200_AT_NE * ndep;
-    double cprev = (nHtot[0] * total_abund + ne[0]) * (RH_KBOLTZMANN * T[0] / gravity);
-    double tprev = 0.5 * CHI(0) * (height[0] - height[1]);
+    double cprev = (in.nH(0) * total_abund + in.ne(0)) * (RH_KBOLTZMANN * in.T(0) / gravity);
+    double tprev = 0.5 * CHI(0) * (in.scale(0) - in.scale(1));
     if (tprev > 1.0) tprev = 0.0;
     cmass[0] = cprev; tau[0] = tprev;
+    height[0] = in.scale(0);
     for (int k = 1; k < ndep; k++) {
-      const double ck = cprev + 0.5*(RHO(k-1) + RHO(k)) * (height[k-1] - height[k]);
-      const double tk = tprev + 0.5*(CHI(k-1) + CHI(k)) * (height[k-1] - height[k]);
+      const double ck = cprev + 0.5*(RHO(k-1) + RHO(k)) * (in.scale(k-1) - in.scale(k));
+      const double tk = tprev + 0.5*(CHI(k-1) + CHI(k)) * (in.scale(k-1) - in.scale(k));
       cmass[k] = ck; tau[k] = tk;
+      height[k] = in.scale(k);
       cprev = ck; tprev = tk;
     }
   }
@@ -171,12 +164,65 @@ __global__ void scales_kernel(int ncol, int ndep, int atm_scale, double wght_per
     }
     for (int k = 0; k < ndep; k++) height[k] = height[k] - h_zero;
   }
+#undef CHI
+#undef RHO
+}
+
+// one thread per column.  The height row of `atmos` holds the incoming scale and receives the heights;
+// scratch [ncol][2][ndep] keeps tau_ref and cmass; scales_out [ncol][3][ndep] = height, tau_ref, cmass.
+struct ColumnScalesIn {
+  const double *rp; size_t kstride; const double *at; int ndep;
+  __device__ __forceinline__ double chi(int k) const { return rp[(size_t) k * kstride]; }
+  __device__ __forceinline__ double nH(int k) const { return at[(size_t) RHB200_AT_NHTOT * ndep + k]; }
+  __device__ __forceinline__ double T(int k) const { return at[(size_t) RHB200_AT_T * ndep + k]; }
+  __device__ __forceinline__ double ne(int k) const { return at[(size_t) RHB200_AT_NE * ndep + k]; }
+  __device__ __forceinline__ double scale(int k) const { return at[(size_t) RHB200_AT_HEIGHT * ndep + k]; }
+};
+__global__ void scales_kernel(int ncol, int ndep, int atm_scale, double wght_per_H,
+                              double total_abund, double gravity,
+                              const double *__restrict__ chi_ref, size_t chi_col_stride, size_t chi_k_stride,
+                              double *atmos, double *__restrict__ scratch, double *__restrict__ scales_out)
+{
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncol) return;
+  double *height = atmos + ((size_t) col * RHB200_AT_NFIELD + RHB200_AT_HEIGHT) * ndep;
+  double *tau = scratch + (size_t) col * 2 * ndep, *cmass = tau + ndep;
+  ColumnScalesIn in{chi_ref + (size_t) col * chi_col_stride, chi_k_stride, atmos + (size_t) col * RHB200_AT_NFIELD * ndep, ndep};
+  // the walk reads scale(k) once, before it writes height[k] (same row): in-place like the reference
+  convert_scales(in, ndep, atm_scale, wght_per_H, total_abund, gravity, height, tau, cmass);
   if (scales_out) {
     double *o = scales_out + (size_t) col * 3 * ndep;
     for (int k = 0; k < ndep; k++) { o[k] = height[k]; o[ndep + k] = tau[k]; o[2*ndep + k] = cmass[k]; }
   }
-#undef CHI
-#undef RHO
+}
+
+// finite-difference response functions, single-depth perturbations (rhb200_rf_fd_batch): virtual column
+// v = ((b*npar + p)*ndep + kp)*2 + s is base column b with parameter p changed at depth kp alone.  Everything before
+// convertScales() is local in depth, so its depth-kp values are those of the PSEUDO column (b, p, s) -- the base with
+// the parameter changed at every depth (full column b*(1 + 2 npar) + 1 + 2p + s).  This kernel walks the scales of
+// the virtual column from the base's rows with the depth-kp entries replaced.  vws [nv][4][ndep]: height, T, tau, cmass.
+struct VirtualScalesIn {
+  const double *rp_b, *rp_q; size_t kstride; const double *at_b, *at_q; int ndep, kp;
+  __device__ __forceinline__ double chi(int k) const { return (k == kp ? rp_q : rp_b)[(size_t) k * kstride]; }
+  __device__ __forceinline__ double nH(int k) const { return (k == kp ? at_q : at_b)[(size_t) RHB200_AT_NHTOT * ndep + k]; }
+  __device__ __forceinline__ double T(int k) const { return (k == kp ? at_q : at_b)[(size_t) RHB200_AT_T * ndep + k]; }
+  __device__ __forceinline__ double ne(int k) const { return (k == kp ? at_q : at_b)[(size_t) RHB200_AT_NE * ndep + k]; }
+  __device__ __forceinline__ double scale(int k) const { return at_b[(size_t) RHB200_AT_HEIGHT * ndep + k]; }
+};
+__global__ void __launch_bounds__(64)
+vscales_kernel(int nv, int npar, int ndep, int atm_scale, double wght_per_H, double total_abund, double gravity,
+               const double *__restrict__ chi_ref, size_t chi_col_stride, size_t chi_k_stride,
+               const double *__restrict__ atmos, double *__restrict__ vws)
+{
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nv) return;
+  const int s = v & 1, kp = (v >> 1) % ndep, p = ((v >> 1) / ndep) % npar, b = ((v >> 1) / ndep) / npar;
+  const size_t fb = (size_t) b * (1 + 2*npar), fq = fb + 1 + 2*p + s;
+  VirtualScalesIn in{chi_ref + fb * chi_col_stride, chi_ref + fq * chi_col_stride, chi_k_stride,
+                     atmos + fb * RHB200_AT_NFIELD * ndep, atmos + fq * RHB200_AT_NFIELD * ndep, ndep, kp};
+  double *w = vws + (size_t) v * 4 * ndep;
+  for (int k = 0; k < ndep; k++) w[ndep + k] = in.T(k);
+  convert_scales(in, ndep, atm_scale, wght_per_H, total_abund, gravity, w, w + 2*(size_t) ndep, w + 3*(size_t) ndep);
 }
 
 // ---- finite-difference response functions: perturbed copies of the base columns, made where they are consumed.
@@ -193,6 +239,22 @@ rf_expand_kernel(int v0, int n, int ndep, int nrow, int npar, const int *__restr
   const int s = v & 1, kp = (v >> 1) % ndep, p = ((v >> 1) / ndep) % npar, b = ((v >> 1) / ndep) / npar;
   double x = base[((size_t) b * nrow + r) * ndep + k];
   if (r == rows[p] && k == kp) x = s ? x - delta[p] : x + delta[p];
+  out[t] = x;
+}
+
+// the full columns of a chunk of base columns b0 .. b0+nb-1: column (b - b0)*(1 + 2 npar) is the base itself,
+// + 1 + 2p + s the pseudo column with row rows[p] changed by +delta[p] (s = 0) / -delta[p] (s = 1) at EVERY depth
+__global__ void __launch_bounds__(128)
+rf_expand_full_kernel(int b0, int nb, int ndep, int nrow, int npar, const int *__restrict__ rows, const double *__restrict__ delta,
+                      const double *__restrict__ base, double *__restrict__ out)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const int nfull = 1 + 2*npar;
+  if (t >= (size_t) nb * nfull * nrow * ndep) return;
+  const int k = (int) (t % ndep), r = (int) ((t / ndep) % nrow);
+  const int f = (int) (t / ((size_t) ndep * nrow)), b = f / nfull, j = f % nfull;
+  double x = base[((size_t) (b0 + b) * nrow + r) * ndep + k];
+  if (j > 0 && r == rows[(j - 1) >> 1]) x = ((j - 1) & 1) ? x - delta[(j - 1) >> 1] : x + delta[(j - 1) >> 1];
   out[t] = x;
 }
 
@@ -215,6 +277,28 @@ int rh_launch_rf_expand(rhb200_ctx *c, int v0, int n, int ndep, int nrow, int np
   const size_t tot = (size_t) n * nrow * ndep;
   ScopedKernelTimer t(c, RHB200_K_PREP);
   rf_expand_kernel<<<(unsigned) ((tot + 127) / 128), 128, 0, c->stream>>>(v0, n, ndep, nrow, npar, d_rows, d_delta, d_base, d_in);
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}
+
+int rh_launch_rf_expand_full(rhb200_ctx *c, int b0, int nb, int ndep, int nrow, int npar, const int *d_rows,
+                             const double *d_delta, const double *d_base, double *d_in)
+{
+  const size_t tot = (size_t) nb * (1 + 2*npar) * nrow * ndep;
+  ScopedKernelTimer t(c, RHB200_K_PREP);
+  rf_expand_full_kernel<<<(unsigned) ((tot + 127) / 128), 128, 0, c->stream>>>(b0, nb, ndep, nrow, npar, d_rows, d_delta, d_base, d_in);
+  RH_CUDA(cudaGetLastError());
+  return RHB200_OK;
+}
+
+int rh_launch_vscales(rhb200_ctx *c, int nb, int npar, int ndep, int iref, int atm_scale, double wght_per_H,
+                      double total_abund, double gravity, const double *d_raypts, const double *d_atmos, double *d_vws)
+{
+  const int nv = nb * npar * ndep * 2;
+  ScopedKernelTimer t(c, RHB200_K_PREP);
+  vscales_kernel<<<(unsigned) ((nv + 63) / 64), 64, 0, c->stream>>>(nv, npar, ndep, atm_scale, wght_per_H, total_abund, gravity,
+      d_raypts + (size_t) iref * ndep * RP_NFIELD + RP_CHI, (size_t) c->wav.nlambda * ndep * RP_NFIELD, (size_t) RP_NFIELD,
+      d_atmos, d_vws);
   RH_CUDA(cudaGetLastError());
   return RHB200_OK;
 }

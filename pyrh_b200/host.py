@@ -409,7 +409,7 @@ def read_kurucz_lines(cwd, kw: dict, el: Elements, loggf_ids=None, loggf_values=
     sorted by lambda0 (background.c:292-294)."""
     C = 2.0 * PI * (Q_ELECTRON / EPSILON_0) * (Q_ELECTRON / M_ELECTRON) / CLIGHT
     LS_Lande = _true(kw["LS_LANDE"])
-    rows, patterns, used, barklem, si_rows = [], [], {}, {}, []
+    rows, patterns, used, barklem, si_rows, file_idx = [], [], {}, {}, [], []
     if kw["KURUCZ_DATA"].lower() == "none":
         raise NotImplementedError("KURUCZ_DATA = none: the LTE path needs a Kurucz line list")
     for line_index, rec in enumerate(read_kurucz_records(cwd, kw["KURUCZ_DATA"])):
@@ -446,7 +446,7 @@ def read_kurucz_lines(cwd, kw: dict, el: Elements, loggf_ids=None, loggf_values=
         Bij = (gj / gi) * Bji
         e = pt_index - 1
         if not el.abundance_set[e]:
-            raise ValueError(f"line {line_index}: no abundance for element {el.ID[e]}")
+            continue            # the reference keeps the line but rlk_opacity never adds it (kurucz.c:612-614)
         # ABO columns (kurucz.c:271-294).  The shipped lists end before column 160: the reference then scans
         # whatever its buffer holds there; no information is the only defined reading
         cross = alpha = 0.0
@@ -528,6 +528,7 @@ def read_kurucz_lines(cwd, kw: dict, el: Elements, loggf_ids=None, loggf_values=
         pat = zeeman.rlk_zeeman(gi, gj, Si, Li, Sj, Lj, gL_i, gL_j, LS_Lande) if polarizable else None
         rows.append(r)
         patterns.append(pat)
+        file_idx.append(line_index)
     order = sorted(range(len(rows)), key=lambda i: rows[i][ll.RL_LAMBDA0])       # stable; qsort in the reference
     zq, zs, zst, out = [], [], [], []
     for i in order:
@@ -552,7 +553,7 @@ def read_kurucz_lines(cwd, kw: dict, el: Elements, loggf_ids=None, loggf_values=
                       vmicro_char=float(kw["VMICRO_CHAR"]) * 1.0E+03)
     lt.validate()
     lt.elem_rows = dict(used)                                    # periodic-table index - 1 -> row of lt.elems
-    lt.file_index = np.array(order, np.int64)                    # table row -> line number in the Kurucz files
+    lt.file_index = np.array([file_idx[i] for i in order], np.int64)     # table row -> line number in the Kurucz files
     lt.si = [si_rows[i] for i in order]                          # per table row: lambda0 [m], gi, gj, Aji of the file's log gf
     return lt
 
@@ -1000,6 +1001,7 @@ class Session:
         self.ctx.set_continuum(self.model, abundance)
         self.ctx.set_chemistry(bg["ce_nuclei"][:, 1].astype(np.int32), bg["ce_mol"])
         self.vmacro_tresh = float(kw["VMACRO_TRESH"])
+        self.ctx.set_gravity(self.el.totalAbund)
         # get_atomic_rfs: parameter p <-> the line loggf_ids[p] names (RLK_Line.loggf_rf_ind = the LAST p that names
         # it, kurucz.c:250-259); input.n_atomic_pars = Nloggf + Nlam, and no line carries a parameter beyond Nloggf
         ids = [] if loggf_ids is None else [int(i) for i in loggf_ids]

@@ -540,6 +540,7 @@ class NlteSession:
                         NmaxScatter=int(kw["N_MAX_SCATTER"]), bc_top=_lib.BC_ZERO, bc_bottom=_lib.BC_THERMALIZED)
         self._C, self._nlte, self._lib = C, nlte, _lib
         self.vmacro_tresh = float(kw["VMACRO_TRESH"])
+        self.ctx.set_gravity(self.el.totalAbund)
         self.IDs = [at["ID"] for at in self.atoms]
 
     @staticmethod

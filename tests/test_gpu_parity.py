@@ -827,13 +827,17 @@ def test_compute1d_batch_from_pyrh_rows(ctx, case):
     sc, mu = int(p[f"{case}_scale_mu"][0]), float(p[f"{case}_scale_mu"][1])
     atm = p[f"{case}_atmosphere"]
     ncol = 5                                             # same column several times: chunk-internal indexing
+    if sc == 2:       # the column-mass row of a height grid needs atmos.totalAbund and gravity (multiatmos.c:153-155)
+        with pytest.raises(RuntimeError):
+            ctx.compute1d_batch(atm[None], mu=mu, atm_scale=sc, wght_per_H=float(p[f"{case}_abund_sums"][0]), get_scales=True)
+        ctx.set_gravity(float(p[f"{case}_abund_sums"][1]), float(p[f"{case}_abund_sums"][3]))
     st, scales = ctx.compute1d_batch(np.repeat(atm[None], ncol, axis=0), mu=mu, atm_scale=sc,
                                      wght_per_H=float(p[f"{case}_abund_sums"][0]), get_scales=True)
     ref = p[f"{case}_stokes"]
     for c in range(ncol):
-        if sc != 2:
-            assert np.array_equal(scales[c, 0], p[f"{case}_height"]), "height"
-            assert np.array_equal(scales[c, 1], p[f"{case}_tau_ref"]), "tau_ref"
+        assert np.array_equal(scales[c, 0], p[f"{case}_height"]), "height"
+        assert np.array_equal(scales[c, 1], p[f"{case}_tau_ref"]), "tau_ref"
+        assert np.array_equal(scales[c, 2], p[f"{case}_cmass"]), "cmass"
         REPORT[f"compute1d_batch_{case}_exact"] = bool(np.array_equal(st[c], ref))
         assert np.max(np.abs(st[c][0] / ref[0] - 1)) < 1e-9
         assert np.array_equal(st[c], ref)
@@ -871,6 +875,37 @@ def test_rf_fd_batch_equals_reference_differences(ctx):
     REPORT["rf_fd_max_err_over_peak"] = float(np.max(np.abs(got - g["rf"]) / scale))
     assert np.array_equal(got, g["rf"])
     assert np.isfinite(rf).all() and np.abs(rf[0]).max() > 0
+
+
+@pytest.mark.parametrize("scale", ["tau", "tau_mu06", "cmass", "height"])
+def test_rf_fd_single_depth_route_equals_full_syntheses(ctx, monkeypatch, scale):
+    """The finite-difference response functions do not run 2 x npar x ndep full syntheses per column: everything before
+    convertScales() is local in depth, so 1 + 2 npar full columns per base column supply the opacities and each
+    single-depth perturbation only gets its own scale walk and formal solution (rf_fd_single_depth, rhb200_abi.cu).
+    Bytes identical to the brute-force expansion (RHB200_RF_FD_BRUTE=1) for every non-scale row, on the three depth
+    scales, for an inclined ray, and with ragged chunks."""
+    p = dict(np.load(GOLD / "pyrh_scales.npz"))
+    _pyrh_ctx(ctx, p[f"{scale}_lambda"])
+    w = float(p[f"{scale}_abund_sums"][0])
+    atm_scale = {"tau": 0, "tau_mu06": 0, "cmass": 1, "height": 2}[scale]
+    mu = float(p[f"{scale}_scale_mu"][1])
+    gs = [np.load(GOLD / f"synth70_c{c}.npz")["atmosphere"] for c in range(3)]
+    if atm_scale == 0:
+        atm = np.stack([p[f"{scale}_atmosphere"], gs[1], gs[2]])
+    else:
+        atm = np.stack([p[f"{scale}_atmosphere"]] * 3)
+        atm[1, 1] *= 1.01; atm[2, 5] *= 0.5
+    rows = np.array([1, 2, 3, 4, 5, 6, 7, 8], np.int32)
+    delta = np.array([1.0, 1.0e9, 0.01, 0.01, 5.0, 0.01, 0.01, 1.0e12])
+    kw = dict(mu=mu, atm_scale=atm_scale, wght_per_H=w, keep_lambda_ref=True)
+    fast = ctx.rf_fd_batch(atm, rows, delta, **kw)
+    monkeypatch.setenv("RHB200_RF_CHUNK_COLS", "2")
+    assert np.array_equal(ctx.rf_fd_batch(atm, rows, delta, **kw), fast)
+    monkeypatch.setenv("RHB200_RF_FD_BRUTE", "1")
+    brute = ctx.rf_fd_batch(atm, rows, delta, **kw)
+    assert np.isfinite(brute).all() and all(np.abs(brute[:, q]).max() > 0 for q in range(len(rows)))
+    REPORT[f"rf_fd_single_depth_exact_{scale}"] = bool(np.array_equal(fast, brute))
+    assert np.array_equal(fast, brute)
 
 
 def test_host_compute1d_drop_in():
@@ -1487,6 +1522,42 @@ def test_bridged_reference_library_rhf1d_lte():
     live = rd.rhf1d(t["atmosphere"], t["wave"], cwd_t, loggf_ids=[1], loggf_values=[-0.969], get_atomic_rfs=True)
     o = rd.rhf1d(t["atmosphere"], t["wave"], cwd_t, loggf_ids=[1], loggf_values=[-0.969], get_atomic_rfs=True, variant="bridged")
     assert np.array_equal(o["I"], live["I"]) and np.array_equal(o["rfs"], live["rfs"]) and np.abs(o["rfs"]).max() > 0
+
+
+@pytest.mark.gpu
+def test_bridged_reference_library_hse_get_scales_get_ne():
+    """The other three entry points rh.pxd:140-185 binds, through the bridged library (hooks in rhf1d/pyrh_hse.c,
+    integration/pyrh_b200.patch): hse() walks the layers with rhb200_hse_batch, get_scales() is
+    rhb200_get_scales_batch, get_ne_from_nH() is rhb200_solve_ne_batch.  Same prototypes, same in/out arrays; bytes
+    identical to the unmodified library's results (fixtures ne_hse / get_scales, oracle/gen_golden_ne.py,
+    oracle/gen_golden_get_scales.py)."""
+    rd = _bridged()
+    from oracle import gen_golden_ne as gn, gen_golden_get_scales as gs
+    cwd = rd.make_workdir("benchmark")
+    g = dict(np.load(GOLD / "ne_hse.npz"))
+    for c in (0, 1):
+        a = np.load(GOLD / f"synth70_c{c}.npz")["atmosphere"]
+        ne = gn.get_ne_from_nH(cwd, 0, a[0], g[f"c{c}_T"], g[f"c{c}_nH"], variant="bridged")
+        assert np.array_equal(ne, g[f"c{c}_ne"])
+    for name in ("hse01", "hse1"):
+        out = gn.hse(cwd, 0, g[name + "_scale"], g[name + "_T"], float(g[name + "_pgtop"]), variant="bridged")
+        for got, key in zip(out, ("ne", "nH", "rho", "pg")):
+            assert np.array_equal(got, g[f"{name}_{key}"]), (name, key)
+    out = gn.hse(cwd, 0, g["hse01_scale"], g["hse01_T"], 0.1, g["hsef_wave"], g["hsef_value"], variant="bridged")
+    for got, key in zip(out, ("ne", "nH", "rho", "pg")):
+        assert np.array_equal(got, g[f"hsef_{key}"]), key
+    s = dict(np.load(GOLD / "get_scales.npz"))
+    tau, h, cm = gs.get_scales(s["tau_atmosphere"], 0, cwd, variant="bridged")
+    assert np.array_equal(h, s["tau_height"]) and np.array_equal(cm, s["tau_cmass"])
+    tau, h, cm = gs.get_scales(s["cmass_atmosphere"], 1, cwd, variant="bridged")
+    assert np.array_equal(h, s["cmass_height"]) and np.array_equal(tau, s["cmass_tau"])
+    tau, h, cm = gs.get_scales(s["height_atmosphere"], 2, cwd, variant="bridged")
+    assert np.array_equal(tau, s["height_tau"]) and np.array_equal(cm, s["height_cmass"])
+    REPORT["bridged_hse_get_scales_get_ne_exact"] = True
+    # and rhf1d() still works on the same context afterwards (tables rebuilt per call)
+    full = dict(np.load(GOLD / "synth70_c0.npz"))
+    o = rd.rhf1d(full["atmosphere"], full["wave"], cwd, variant="bridged")
+    assert np.array_equal(np.array([o[k] for k in "IQUV"]), full["stokes_scalar"])
 
 
 @pytest.mark.gpu
