@@ -268,13 +268,17 @@ def nlte_records(device, rank, ncol_scale=1.0):
         res = s.compute(atm)
         s.ctx.synchronize()
         dt = time.perf_counter() - t0
-        conv = res["niter"] < int(c["kw"]["N_MAX_ITER"])
+        finite = np.isfinite(res["I"]).all(axis=tuple(range(1, res["I"].ndim))) & np.isfinite(res["n"]).all(axis=tuple(range(1, res["n"].ndim)))
+        conv = (res["niter"] < int(c["kw"]["N_MAX_ITER"])) & finite
         rec = {"workload": f"{ncol} perturbed FAL-C columns x {NDEP} depths, {len(s.lam)} wavelengths, NRAYS {s.nrays}, "
                            f"ACTIVE {'+'.join(a.split('.')[0] for a in c['active'])}, CRD, Ng 2/10/3, ITER_LIMIT 1e-4",
                "ncol": ncol, "nspect": int(len(s.lam)), "nrays": s.nrays, "seconds": dt, "atmospheres_per_s": ncol / dt,
                "ray_points_per_s": s.ray_points(res, NDEP) / dt, "ray_points": s.ray_points(res, NDEP),
                "iterations_median": float(np.median(res["niter"])), "iterations_max": int(res["niter"].max()),
-               "converged_columns": int(conv.sum()), "all_finite": bool(np.isfinite(res["I"][conv]).all()),
+               "converged_columns": int(conv.sum()), "all_finite": bool(finite.all()),
+               # statistical equilibrium turned singular on these perturbed columns: NaN populations here, exit() from
+               # LUdecomp ("Singular matrix") in the reference (see cpu_baseline.columns_the_reference_aborted_on)
+               "nonfinite_columns": int((~finite).sum()),
                "h2d_bytes": int(atm.nbytes), "d2h_bytes": int(res["I"].nbytes + res["n"].nbytes + res["nstar"].nbytes)}
         if case == "config4":                                           # the single FAL-C atmosphere configs[3] names
             one = base.copy()

@@ -11,6 +11,8 @@
  *   3. hands back the reference's own `mySpectrum` (rh/rhf1d/pyrh_compute1dray.h:12-19): malloc'd lam/sI/sQ/sU/sV,
  *      rfs, atom_pops pointing at the live atom->n / atom->nstar like _solveray() does (pyrh_solveray.c:119-186).
  * `rhf1d()` keeps its exact signature; `rhf1d_batch()` is the non-breaking addition for many columns.
+ * The other entry points rh.pxd binds are hooked the same way in rh/rhf1d/pyrh_hse.c: hse() -> rhb200_hse_batch,
+ * get_scales() -> rhb200_get_scales_batch, get_ne_from_nH() -> rhb200_solve_ne_batch (end of this file).
  *
  * Nothing here is a fallback: when the device library refuses a configuration the call aborts through the reference's
  * Error(ERROR_LEVEL_2) convention.

@@ -1286,7 +1286,7 @@ def test_get_atomic_rfs_whole_call(tmp_path):
     cwd = _stage_cwd(tmp_path / "a", kurucz="fe6300", keywords={"STOKES_MODE": ("FULL_STOKES", "NO_STOKES")})
     (sI, sQ, sU, sV, lam), rf = host.compute1d(cwd, 1.0, 0, g["atmosphere"], g["wave"], loggf_ids=ids, loggf_values=vals,
                                                get_atomic_rfs=True)
-    assert sQ is None and rf.shape == (2, len(g["wave"]))
+    assert not sQ.any() and not sU.any() and not sV.any() and rf.shape == (2, len(g["wave"]))
     REPORT["loggf_rf_ns_exact"] = bool(np.array_equal(rf.T, g["ns_rfs"]))
     assert np.array_equal(sI, g["ns_stokes"][0])
     assert np.max(np.abs(rf.T / g["ns_rfs"] - 1)) < 1e-9
