@@ -276,8 +276,9 @@ def nlte_records(device, rank, ncol_scale=1.0):
                "ray_points_per_s": s.ray_points(res, NDEP) / dt, "ray_points": s.ray_points(res, NDEP),
                "iterations_median": float(np.median(res["niter"])), "iterations_max": int(res["niter"].max()),
                "converged_columns": int(conv.sum()), "all_finite": bool(finite.all()),
-               # statistical equilibrium turned singular on these perturbed columns: NaN populations here, exit() from
-               # LUdecomp ("Singular matrix") in the reference (see cpu_baseline.columns_the_reference_aborted_on)
+               # the MALI/Ng iteration of the reference diverges on these perturbed columns (negative, then NaN
+               # populations; or exit() from LUdecomp, "Singular matrix"): with the reference's summation order
+               # (RHB200_NLTE_EXACT=1) the same columns fail here, bit for bit; see cpu_baseline.columns_the_reference_*
                "nonfinite_columns": int((~finite).sum()),
                "h2d_bytes": int(atm.nbytes), "d2h_bytes": int(res["I"].nbytes + res["n"].nbytes + res["nstar"].nbytes)}
         if case == "config4":                                           # the single FAL-C atmosphere configs[3] names
@@ -307,8 +308,11 @@ def nlte_ref_worker(case, column):
     a = synthetic.perturbed_batch(np.load(ROOT / "tests" / "golden" / "falc_base.npy"), 1, ndep=NDEP, first=column)[0]
     cwd = _nlte_workdir(case)
     t0 = time.perf_counter()
-    rd.rhf1d(a, np.linspace(*NLTE_CASES[case]["wave"]), cwd, get_populations=True)
-    print(f"NLTE_REF_SECONDS {time.perf_counter() - t0:.6f}", flush=True)
+    o = rd.rhf1d(a, np.linspace(*NLTE_CASES[case]["wave"]), cwd, get_populations=True)
+    dt = time.perf_counter() - t0
+    ok = bool(np.isfinite(o["I"]).all() and all(np.isfinite(v["n"]).all() for v in o.get("pops", {}).values()))
+    print(f"NLTE_REF_FINITE {int(ok)}", flush=True)          # the reference also RETURNS NaN populations on some columns
+    print(f"NLTE_REF_SECONDS {dt:.6f}", flush=True)
 
 
 def nlte_reference_baseline(procs=None, limit_s=120.0):
@@ -320,7 +324,7 @@ def nlte_reference_baseline(procs=None, limit_s=120.0):
     for case in NLTE_CASES:
         ps = [subprocess.Popen([sys.executable, str(ROOT / "bench.py"), "--nlte-ref-worker", case, str(10000 + p)],
                                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for p in range(procs)]
-        t, t_end = [], time.perf_counter() + limit_s
+        t, nan_cols, t_end = [], 0, time.perf_counter() + limit_s
         for q in ps:
             try:
                 o, _ = q.communicate(timeout=max(1.0, t_end - time.perf_counter()))
@@ -329,12 +333,14 @@ def nlte_reference_baseline(procs=None, limit_s=120.0):
                 q.communicate()
                 continue
             t += [float(ln.split()[1]) for ln in o.splitlines() if ln.startswith("NLTE_REF_SECONDS")]
+            nan_cols += sum(1 for ln in o.splitlines() if ln.startswith("NLTE_REF_FINITE 0"))
         if not t:
             out[case] = {"atmospheres_per_s": None, "cores": procs, "kind": "reference", "sample": "no column finished"}
             continue
         out[case] = {"atmospheres_per_s": len(t) / max(t), "cores": procs, "kind": "reference",
                      "seconds_per_atmosphere_per_core": float(np.mean(t)), "columns_finished": len(t),
                      "columns_the_reference_aborted_on": procs - len(t),
+                     "columns_the_reference_returned_nan_for": nan_cols,
                      "sample": f"{procs} perturbed columns started together, one rhf1d(get_populations) process per core; "
                                f"{len(t)} finished, slowest {max(t):.1f} s"}
     return out

@@ -70,6 +70,11 @@ void probe_reset(void)
   mol_snapshot_done = 0;
   pbb_nseen = 0;
   cont_snapshot_done = 0;
+  /* rhf1d() only ever SETS atmos.Nloggf / Nlam (pyrh_compute1dray.c:199-211): after a call with log gf overrides a
+     call without them reads the previous caller's (freed) arrays in readKuruczLines().  The driver calls this before
+     every rhf1d(), so each call sees only its own overrides -- what pyrh users get from a fresh process. */
+  atmos.Nloggf = 0;
+  atmos.Nlam = 0;
 }
 long      probe_count(void)       { return nrec; }
 ProbeRec *probe_get(long i)       { return (i >= 0 && i < nrec) ? &recs[i] : NULL; }

@@ -59,7 +59,6 @@ struct Cols {            // device per-column arrays
   double *phi, *wphi;
   double *n, *J, *Gamma, *Rij, *Rji, *gw, *chi, *S, *I, *Psi, *scr, *dJ, *Iem;
   double *part;            // [ncol][nseg][4][Ndep] partial {Gij, Gji, Rij, Rji} of the segments
-  double *eta_at;          // [Natom][ncol][nray][Ndep] atom->rhth.eta of Opacity() (opacity.c:252-260), read by the rate kernel; may be NULL
   const int *active;
 };
 
@@ -208,11 +207,6 @@ nlte_opacity_kernel(Plan P, Cols C, int ncol)
         if (cur_atom >= 0) {
 #pragma unroll
           for (int q = 0; q < NLTE_RB; q++) as_eta[q] += eta_atom[q];
-          if (C.eta_at) {
-            double *ea = C.eta_at + (((size_t) cur_atom * ncol + col) * P.nray + r0) * N + k;
-#pragma unroll
-            for (int q = 0; q < NLTE_RB; q++) if (q < nb) ea[(size_t) q * N] = eta_atom[q];
-          }
         }
 #pragma unroll
         for (int q = 0; q < NLTE_RB; q++) eta_atom[q] = 0.0;
@@ -237,11 +231,6 @@ nlte_opacity_kernel(Plan P, Cols C, int ncol)
 #pragma unroll
         for (int q = 0; q < NLTE_RB; q++) { as_chi[q] += V * diff; eta_atom[q] += tg * V * n_j; }
       }
-    }
-    if (cur_atom >= 0 && C.eta_at) {
-      double *ea = C.eta_at + (((size_t) cur_atom * ncol + col) * P.nray + r0) * N + k;
-#pragma unroll
-      for (int q = 0; q < NLTE_RB; q++) if (q < nb) ea[(size_t) q * N] = eta_atom[q];
     }
 #pragma unroll
     for (int q = 0; q < NLTE_RB; q++) {
@@ -386,8 +375,6 @@ nlte_gamma_kernel(Plan P, Cols C, int ncol)
   if (!SEG && P.add_C) { Gij = C.C[gbase + (size_t)(i*Nl + j) * N + k]; Gji = C.C[gbase + (size_t)(j*Nl + i) * N + k]; }   // initGammaAtom
   double Rij = 0.0, Rji = 0.0;                                                                          // zeroRates
 
-  const bool use_eta = C.eta_at != nullptr;
-  const double *eta_a = use_eta ? C.eta_at + (size_t) a * ncol * P.nray * N : nullptr;
   const int w_lo = SEG ? P.seg_lo[seg] : Nblue, w_hi = SEG ? P.seg_hi[seg] : Nblue + Nla;
   const int ns_first = w_lo > P.ns_lo ? w_lo : P.ns_lo, ns_last = w_hi < P.ns_hi ? w_hi : P.ns_hi;
   for (int ns = ns_first; ns < ns_last; ns++) {
@@ -403,11 +390,8 @@ nlte_gamma_kernel(Plan P, Cols C, int ncol)
       const int tm = P.as_trans[first+n];
       const double *tr = P.trans + (size_t) tm * TR_NFIELD;
       if ((int) tr[TR_ATOM] != a) continue;
-      const int im = (int) tr[TR_I], jm = (int) tr[TR_J], la = ns - (int) tr[TR_NBLUE];
-      // with the atom's emissivity taken from the opacity kernel only the target itself and the transitions that
-      // share a level with it enter the cross-coupling sums (fillgamma.c:139-196, 321-327)
-      if (C.eta_at && tm != tid && im != i && jm != j && jm != i) continue;
       if (m == NLTE_MAXACT) { m++; break; }
+      const int im = (int) tr[TR_I], jm = (int) tr[TR_J], la = ns - (int) tr[TR_NBLUE];
       const double *gw = C.gw + (((size_t) col * P.nas + first + n) * 2) * N + k;
       const double g = gw[0], w = gw[N];
       const double thn = twohnu3_of(P, tr, ns);
@@ -446,7 +430,6 @@ nlte_gamma_kernel(Plan P, Cols C, int ncol)
           const size_t rk = ((size_t) col * P.nray + r) * N + k;
           Iv[q] = __ldg(C.I + rk);
           Pv[q] = __ldg(C.Psi + rk) / __ldg(C.chi + rk);           // formal.c:248 / :301
-          if (use_eta) eta_atom[q] = __ldg(eta_a + rk);
           wmuv[q] = ad ? 0.5 * P.wmu[mu] : P.wmu[mu];
           lamu[q] = 2*mu + P.ray_dir[r];
         }
@@ -464,12 +447,10 @@ nlte_gamma_kernel(Plan P, Cols C, int ncol)
         for (int q = 0; q < NLTE_RB; q++) {
           if (f & 16) {
             const double tgV = tg * V[q];
-            if (!use_eta) eta_atom[q] += tgV * nj;                // opacity.c:257-258
-            if (f & 3) {
-              const double chicc = V[q] * w * diff;               // fillgamma.c:321-327
-              if (f & 1) chi_up_i[q] += chicc;
-              if (f & 2) { chi_down_j[q] += chicc; Uji_down_j[q] += tgV; }
-            }
+            eta_atom[q] += tgV * nj;                              // opacity.c:257-258
+            const double chicc = V[q] * w * diff;                 // fillgamma.c:321-327
+            if (f & 1) chi_up_i[q] += chicc;
+            if (f & 2) { chi_down_j[q] += chicc; Uji_down_j[q] += tgV; }
             if (f & 4) Uji_down_i[q] += tgV;
           }
           if (f & 8) Vs[q] = V[q];
@@ -754,7 +735,6 @@ struct NlteEngine {
   bool device_profiles = false;
   std::vector<int> lev_off, gam_off, angle_dep, ray_off, ray_ns, ray_mu, ray_dir, nlevel;
   std::vector<size_t> prev_off;
-  double *d_eta_at = nullptr; bool use_eta_at = true;      // RHB200_NLTE_ETA_AT=0: the rate kernel re-derives the atom's emissivity (A/B knob)
   int *d_active = nullptr; double *d_prev = nullptr; size_t *d_prev_off = nullptr; double *d_dpops = nullptr, *d_dJmax = nullptr;
   std::vector<int> active;
 
@@ -849,7 +829,6 @@ struct NlteEngine {
     {                                            // segments of the rate accumulation (RHB200_NLTE_GAMMA_SEG wavelengths each)
       int seglen = 16;
       if (const char *e = getenv("RHB200_NLTE_GAMMA_SEG")) { const int v = atoi(e); if (v > 0) seglen = v; }
-      if (const char *e = getenv("RHB200_NLTE_ETA_AT")) use_eta_at = atoi(e) != 0;
       exact_rates = c->nlte_exact_rates != 0;
       if (const char *e = getenv("RHB200_NLTE_EXACT")) exact_rates = atoi(e) != 0;
       std::vector<int> seg_tr, seg_lo, seg_hi, tr_seg0(Nt + 1, 0);
@@ -875,7 +854,7 @@ struct NlteEngine {
 
   // doubles of device memory per column that alloc() takes (chunk sizing of the front end)
   size_t doubles_per_column(bool own_inputs) const {
-    size_t d = (size_t) N * ((size_t) ngam + 2*(size_t) Nt + 2*(size_t) nas + (6 + (size_t) Na)*(size_t) nray + (size_t) Ns + nphirow + nline +
+    size_t d = (size_t) N * ((size_t) ngam + 2*(size_t) Nt + 2*(size_t) nas + 6*(size_t) nray + (size_t) Ns + nphirow + nline +
                              (exact_rates ? 0 : 4*(size_t) nseg)) + nray + prev_off[Na] + Na;
     if (own_inputs) d += (size_t) N * (2 + 2*(size_t) nlev + Na + ngam + nline + Na + 1 + 4*(size_t) Ns);
     return d;
@@ -893,8 +872,7 @@ struct NlteEngine {
     RH_CHECK(ar.alloc(&C.gw, cN*nas*2));
     if (!exact_rates) RH_CHECK(ar.alloc(&C.part, cN*nseg*4));
     RH_CHECK(ar.alloc(&C.chi, cN*nray)); RH_CHECK(ar.alloc(&C.S, cN*nray)); RH_CHECK(ar.alloc(&C.I, cN*nray));
-    RH_CHECK(ar.alloc(&C.Psi, cN*nray)); RH_CHECK(ar.alloc(&d_eta_at, cN*nray*Na)); C.eta_at = nullptr;
-    RH_CHECK(ar.alloc(&C.scr, cN*nray*2)); RH_CHECK(ar.alloc(&C.dJ, cN*Ns, true));
+    RH_CHECK(ar.alloc(&C.Psi, cN*nray)); RH_CHECK(ar.alloc(&C.scr, cN*nray*2)); RH_CHECK(ar.alloc(&C.dJ, cN*Ns, true));
     RH_CHECK(ar.alloc(&C.Iem, (size_t) ncol*nray, true));
     active.assign(ncol, 1);
     RH_CHECK(ar.upload(&d_active, active.data(), ncol));
@@ -1048,7 +1026,6 @@ struct NlteEngine {
     for (int it = 1; it <= NmaxIter && nactive > 0; it++) {
       { ScopedKernelTimer t(c, RHB200_K_OTHER);
         nlte_gamma_init_kernel<<<RH_GRID(cN*ngam, 256), 0, st>>>(P, C, ncol); }
-      C.eta_at = use_eta_at ? d_eta_at : nullptr;   // only the passes that feed the rate kernel keep the atoms' emissivities
       { ScopedKernelTimer t(c, RHB200_K_OPACITY);
         nlte_opacity_kernel<<<(unsigned) (((cN + 127) / 128) * Ns), 128, 0, st>>>(P, C, ncol); }
       { ScopedKernelTimer t(c, RHB200_K_BEZIER);
@@ -1059,7 +1036,6 @@ struct NlteEngine {
           nlte_gamma_kernel<true><<<dim3((unsigned) ((cN + 63) / 64), (unsigned) nseg), 64, 0, st>>>(P, C, ncol);
           nlte_gamma_sum_kernel<<<RH_GRID(cN*Nt, 128), 0, st>>>(P, C, ncol);
         } }
-      C.eta_at = nullptr;
       { ScopedKernelTimer t(c, RHB200_K_J);
         nlte_J_kernel<<<RH_GRID(cN*Ns, 128), 0, st>>>(P, C, ncol); }
       // the exchange step of a wavelength-sharded atmosphere: radiative rates add up over ranks
