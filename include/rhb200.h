@@ -639,6 +639,16 @@ typedef struct {
   int NmaxScatter, NmaxIter;      /* keywords N_MAX_SCATTER, N_MAX_ITER */
   double iterLimit;               /* ITER_LIMIT */
   const rhb200_nlte_plan *plan1;  /* the same plan with Nrays = 1 and the profile rows of one ray (muz/wmu are set by the call) */
+  /* STOKES_MODE (zero-initialise for NO_STOKES).  stokes = 1 is FIELD_FREE: initScatter and Iterate() run with field-free
+     profiles exactly as in NO_STOKES; adjustStokesMode() (zeeman.c:303-345) then recomputes the profiles of the polarizable
+     lines with their Zeeman patterns (Profile(), profile.c:112-305) and the passes after Iterate() and _solveray()'s pass
+     solve all four Stokes parameters where the active set or the background holds a polarised line (formal.c:86-217,
+     opacity.c:262-296, stokesopac.c:28-82).  FULL_STOKES during the MALI iterations is not implemented. */
+  int stokes;
+  const int    *line_pol;         /* [plan->nline] line->polarizable (readatom.c:352-368) */
+  const int    *line_zoff;        /* [plan->nline + 1] slice of each line in the pattern tables (0 components if not polarizable) */
+  const int    *zq;               /* Zeeman(line), zeeman.c:186-281 (rhb200_zeeman): q, shift, strength */
+  const double *zshift, *zstrength;
 } rhb200_nlte_front;
 /* atmosphere [ncol][nrow][ndep] as in rhb200_compute1d_batch.  Out (any may be NULL): spectrum [ncol][Nspect] = spectrum.I[][0]
    of the final pass on plan->lambda (lambda_ref included; _solveray drops it), pops_n / pops_nstar [ncol][sum Nlevel][ndep]
@@ -649,6 +659,13 @@ int rhb200_nlte_compute1d_batch(rhb200_ctx *ctx, const rhb200_nlte_plan *plan, c
                                 int iref, double wght_per_H, double vmacro_tresh,
                                 double *spectrum, double *pops_n, double *pops_nstar, int *niter, int *passes,
                                 double *scales);
+/* The same with the emergent Stokes Q, U, V of the final pass: quv [ncol][3][Nspect] (zeros where Formal() solved for I
+   alone; all zeros unless front->stokes). */
+int rhb200_nlte_compute1d_stokes_batch(rhb200_ctx *ctx, const rhb200_nlte_plan *plan, const rhb200_nlte_front *front,
+                                       int ncol, int ndep, int nrow, double mu, int atm_scale, const double *atmosphere,
+                                       int iref, double wght_per_H, double vmacro_tresh,
+                                       double *spectrum, double *quv, double *pops_n, double *pops_nstar, int *niter, int *passes,
+                                       double *scales);
 /* test hook: the per-column inputs the front end hands to Iterate() for the columns of the LAST
    rhb200_nlte_compute1d_batch call that fit in one chunk: which = 0 C, 1 nstar, 2 ntotal, 3 adamp, 4 vbroad,
    5 chi_c, 6 eta_c, 7 sca_c, 8 height, 9 J after the last pass, 10..12 chi_c/eta_c/sca_c of the final pass,

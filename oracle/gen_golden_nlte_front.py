@@ -6,6 +6,8 @@ get_populations on 8 synthetic perturbed FAL-C columns (70 depths, SURVEY 8(d) r
     h_caii_r3 / h_caii_r5   H (6 levels) + Ca II ACTIVE (BASELINE config 4), NRAYS = 3 / 5, Hinode window
 CRD (PRD_N_MAX_ITER = 0), Ng order 2, ITER_LIMIT 1e-4, NO_STOKES.  Recorded: spectrum, populations n / nstar of the
 ACTIVE atoms, and the number of MALI iterations (counted from the probe's updatePopulations records).
+    caii_r3_ff / h_caii_r5_ff   the same with STOKES_MODE = FIELD_FREE: field-free iterations, then adjustStokesMode()
+                                and the full Stokes solution (I, Q, U, V recorded; the columns carry B up to 2.5 kG)
 
     python -m oracle.gen_golden_nlte_front
 """
@@ -33,6 +35,10 @@ CASES = {
                       keys=("H ", "CA"), mu=1.0),
     "h_caii_r5": dict(kw=dict(KW, NRAYS=5, HYDROGEN_LTE="FALSE"), active=("H_6.atom",), wave=(630.25, 630.5, 21),
                       keys=("H ", "CA"), mu=0.8),
+    "caii_r3_ff": dict(kw=dict(KW, NRAYS=3, HYDROGEN_LTE="TRUE", STOKES_MODE="FIELD_FREE"), active=(), wave=(854.2, 854.7, 41),
+                       keys=("CA",), mu=1.0),
+    "h_caii_r5_ff": dict(kw=dict(KW, NRAYS=5, HYDROGEN_LTE="FALSE", STOKES_MODE="FIELD_FREE"), active=("H_6.atom",),
+                         wave=(630.25, 630.5, 21), keys=("H ", "CA"), mu=0.8),
 }
 # columns of the synthetic batch; column 4 is left out: its MALI iteration does not converge in the reference (100
 # iterations at NRAYS = 3) and ends in "Singular matrix" -> exit() at NRAYS = 5, so there is nothing to be identical to
@@ -49,15 +55,22 @@ def main():
     base = np.load(GOLD / "falc_base.npy")
     atm = synthetic.perturbed_batch(base, max(COLUMNS) + 1, ndep=70)[list(COLUMNS)]
     out = dict(atmosphere=atm)
+    only = [a for a in sys.argv[1:] if a in CASES]
+    if only:                                       # add / refresh the named cases, keep the rest of the fixture
+        out = dict(np.load(GOLD / "nlte_front.npz"))
+        assert np.array_equal(out["atmosphere"], atm)
     for case, c in CASES.items():
+        if only and case not in only:
+            continue
         cwd = workdir(case)
         wave = np.linspace(*c["wave"])
-        I, n, ns, nit = [], [], [], []
+        I, n, ns, nit, quv = [], [], [], [], []
         for col in range(NCOL):
             o = rd.rhf1d(atm[col], wave, cwd, mu=c["mu"], probe=rd.PROBE_NLTE, get_populations=True)
             R = recs_by_tag(o["records"])
             nit.append(len({m[1] for m, _ in R["up_n"]}))
             I.append(o["I"])
+            quv.append(np.array([o["Q"], o["U"], o["V"]]))
             n.append(np.concatenate([o["pops"][k]["n"] for k in c["keys"]]))
             ns.append(np.concatenate([o["pops"][k]["nstar"] for k in c["keys"]]))
             lam = o["lam"]
@@ -65,6 +78,9 @@ def main():
         out.update({f"{case}_wave": wave, f"{case}_lam": lam, f"{case}_I": np.array(I), f"{case}_n": np.array(n),
                     f"{case}_nstar": np.array(ns), f"{case}_niter": np.array(nit, np.int32),
                     f"{case}_mu": np.float64(c["mu"])})
+        if c["kw"]["STOKES_MODE"] != "NO_STOKES":
+            out[f"{case}_QUV"] = np.array(quv)
+            print(f"[golden] {case}: max |Q|, |U|, |V| / max I =", np.abs(np.array(quv)).max(axis=(0, 2)) / np.array(I).max())
     out["cases"] = np.array(json.dumps({k: dict(kw=v["kw"], active=list(v["active"]), keys=list(v["keys"])) for k, v in CASES.items()}))
     np.savez_compressed(GOLD / "nlte_front.npz", **out)
     print(f"[golden] nlte_front.npz: {(GOLD / 'nlte_front.npz').stat().st_size/1e6:.2f} MB")

@@ -35,6 +35,8 @@ SYMBOLS = [
     ("rhb200_get_wavelength_flags", C.c_int, [vp, ip]),
     ("rhb200_nlte_compute1d_batch", C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, vp, C.c_int,
                                               C.c_double, C.c_double, vp, vp, vp, vp, vp, vp]),
+    ("rhb200_nlte_compute1d_stokes_batch", C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, vp, C.c_int,
+                                                     C.c_double, C.c_double, vp, vp, vp, vp, vp, vp, vp]),
     ("rhb200_nlte_front_debug", C.c_int, [vp, C.c_int, dp, C.c_size_t]),
     ("rhb200_lte_stokes_batch", C.c_int, [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
                                           vp, vp, vp, vp]),

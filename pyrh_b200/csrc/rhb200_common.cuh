@@ -209,7 +209,7 @@ int rh_launch_loggf_rf(rhb200_ctx *ctx, int ncol, int ndep, double muz, int bc_t
                        int moving, const int *d_col_moving,
                        double *d_scratch, double *d_rf /* [ncol][nlambda][npar] */);
 int rh_launch_opacity_addI(rhb200_ctx *ctx, int ncol, int ndep, int to_obs, const double *d_atmos, const double *d_lineprep,
-                           double *d_chi_c, double *d_eta_c);
+                           double *d_chi_c, double *d_eta_c, double *d_chi_quv = nullptr, double *d_eta_quv = nullptr);
 int rh_launch_add_molecular(rhb200_ctx *ctx, int ncol, int ndep, const double *d_molchi, const double *d_moleta,
                             double *d_chi_c, double *d_eta_c);
 int rh_launch_line_damping(rhb200_ctx *ctx, int ncol, int ndep, int nline, const double *d_plrows, const double *d_atmos,

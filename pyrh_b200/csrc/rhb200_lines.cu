@@ -319,7 +319,8 @@ opacity_addI_kernel(int ncol, int nlambda, int ndep, int to_obs, int nline,
                     const double *__restrict__ lines, const int *__restrict__ zq,
                     const double *__restrict__ zshift, const double *__restrict__ zstrength,
                     const double *__restrict__ atmos, const double *__restrict__ lineprep,
-                    double *__restrict__ chi_c, double *__restrict__ eta_c)
+                    double *__restrict__ chi_c, double *__restrict__ eta_c,
+                    double *__restrict__ chi_quv, double *__restrict__ eta_quv /* [ncol][nlambda][3][ndep] or NULL */)
 {
   const size_t npts = (size_t) ncol * nlambda * ndep;
   const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -338,6 +339,13 @@ opacity_addI_kernel(int ncol, int nlambda, int ndep, int to_obs, int nline,
             __ldg(at + RHB200_AT_SIN_2CHI*ndep + k));
   chi_c[t] += s.chi[0];
   eta_c[t] += s.eta[0];
+  if (chi_quv) {                                   // the Q, U, V records of a polarised background (readj.c:303-337)
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      chi_quv[(r*3 + i)*ndep + k] = s.chi[i + 1];
+      eta_quv[(r*3 + i)*ndep + k] = s.eta[i + 1];
+    }
+  }
 }
 
 // chi_c += a, eta_c += b where the wavelength has entries in the window list (molecular lines of the NLTE background)
@@ -833,7 +841,7 @@ int rh_launch_loggf_dopac(rhb200_ctx *ctx, int ncol, int ndep, const double *d_a
 }
 
 int rh_launch_opacity_addI(rhb200_ctx *ctx, int ncol, int ndep, int to_obs, const double *d_atmos, const double *d_lineprep,
-                           double *d_chi_c, double *d_eta_c)
+                           double *d_chi_c, double *d_eta_c, double *d_chi_quv, double *d_eta_quv)
 {
   const size_t npts = (size_t) ncol * ctx->wav.nlambda * ndep;
   if (npts == 0 || ctx->tab.nline == 0) return RHB200_OK;
@@ -842,7 +850,8 @@ int rh_launch_opacity_addI(rhb200_ctx *ctx, int ncol, int ndep, int to_obs, cons
     ScopedKernelTimer t(ctx, RHB200_K_OPACITY);
     opacity_addI_kernel<<<(unsigned) ((npts + 127) / 128), 128, 0, ctx->stream>>>(ncol, ctx->wav.nlambda, ndep, to_obs,
         ctx->tab.nline, ctx->wav.lambda, ctx->wav.first, ctx->wav.count, ctx->wav.idx,
-        ctx->tab.lines, ctx->tab.zq, ctx->tab.zshift, ctx->tab.zstrength, d_atmos, d_lineprep, d_chi_c, d_eta_c);
+        ctx->tab.lines, ctx->tab.zq, ctx->tab.zshift, ctx->tab.zstrength, d_atmos, d_lineprep, d_chi_c, d_eta_c,
+        d_chi_quv, d_eta_quv);
   }
   RH_CUDA(cudaGetLastError());
   return RHB200_OK;

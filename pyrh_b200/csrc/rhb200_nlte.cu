@@ -52,6 +52,12 @@ struct Plan {            // device copy of the shared problem structure
             *ray_ns, *ray_mu, *ray_dir, *prow_tr, *line_tr;
   // fixed partition of every transition's wavelengths into segments (deterministic two-stage rate accumulation)
   int nseg; const int *seg_tr, *seg_lo, *seg_hi, *tr_seg0;   // [nseg] transition, [lo, hi) wavelengths; [Ntrans+1] first segment
+  // FULL_STOKES formal solution with polarizable ACTIVE lines (after adjustStokesMode(), zeeman.c:303-345)
+  int stokes;                                   // input.StokesMode == FULL_STOKES for the passes run now
+  int stokes_solver;                            // S_INTERPOLATION_STOKES
+  const int *line_pol, *line_zoff, *zq;         // [nline] line->polarizable, [nline+1] slices of the Zeeman pattern tables
+  const double *zshift, *zstrength;
+  const int *pol_as, *pol_c;                    // [Nspect] containsPolarized(as) (with StokesMode FULL_STOKES), backgrflags.ispolarized
 };
 
 struct Cols {            // device per-column arrays
@@ -59,6 +65,11 @@ struct Cols {            // device per-column arrays
   double *phi, *wphi;
   double *n, *J, *Gamma, *Rij, *Rji, *gw, *chi, *S, *I, *Psi, *scr, *dJ, *Iem;
   double *part;            // [ncol][nseg][4][Ndep] partial {Gij, Gji, Rij, Rji} of the segments
+  // FULL_STOKES passes: atmos.B [ncol][Ndep]; cos_gamma, cos_2chi, sin_2chi [ncol][Nrays][3][Ndep] (Bproject, project.c);
+  // phi_Q/U/V [3][ncol][nphirow][Ndep]; background chi_c / eta_c Q,U,V [ncol][Nspect][3][Ndep];
+  // per ray chi_Q,U,V and S_Q,U,V [ncol][nray][3][Ndep]; emergent Q,U,V [ncol][nray][3]
+  const double *B, *bproj, *chi_cQ, *eta_cQ;
+  double *phiQ, *chiQ, *SQ, *IemQ;
   const int *active;
 };
 
@@ -117,8 +128,72 @@ nlte_profile_kernel(Plan P, Cols C, int ncol)
   const double v_los = (P.muz[mu] * C.vel[(size_t) col * N + k]) / vbroad;               // :188-190
   const double sign = to_obs ? 1.0 : -1.0;
   const double vk = v + sign * v_los;
-  const double H = rhv::voigt_armstrong(C.adamp[((size_t) col * P.nline + li) * N + k], vk);
+  const double adamp = C.adamp[((size_t) col * P.nline + li) * N + k];
+  if (P.stokes && P.line_pol[li]) {
+    // profile.c:112-116, 174-184, 239-305: Zeeman components through Voigt(.., HUMLICEK), one isotope component
+    const double Larmor = (RH_Q_ELECTRON / (4.0*RH_PI*RH_M_ELECTRON)) * (lambda0*RH_NM_TO_M);
+    const double vB = Larmor * C.B[(size_t) col * N + k] / vbroad;
+    const double sv = 1.0 / (RH_SQRTPI * vbroad);
+    const double *bp = C.bproj + (((size_t) col * P.Nrays + mu) * 3) * N + k;
+    const double cos_gamma = bp[0], cos_2chi = bp[N], sin_2chi = bp[2*(size_t) N];
+    const double sin2_gamma = 1.0 - cos_gamma*cos_gamma;
+    double phi_sm = 0.0, phi_pi = 0.0, phi_sp = 0.0;
+    for (int nz = P.line_zoff[li]; nz < P.line_zoff[li+1]; nz++) {
+      const double H = rhv::humlicek_H(adamp, vk - P.zshift[nz]*vB);
+      const int q = P.zq[nz];
+      if (q == -1)     phi_sm += P.zstrength[nz] * H;
+      else if (q == 0) phi_pi += P.zstrength[nz] * H;
+      else if (q == 1) phi_sp += P.zstrength[nz] * H;
+    }
+    const double phi_sigma = (phi_sp + phi_sm) * 1.0;
+    const double phi_delta = 0.5*phi_pi * 1.0 - 0.25*phi_sigma;
+    const size_t plane = (size_t) ncol * P.nphirow * N;
+    C.phi[t]            = 0.0 + (phi_delta*sin2_gamma + 0.5*phi_sigma) * sv;
+    C.phiQ[t]           = 0.0 + sign * phi_delta * sin2_gamma * cos_2chi * sv;
+    C.phiQ[plane + t]   = 0.0 + phi_delta * sin2_gamma * sin_2chi * sv;
+    C.phiQ[2*plane + t] = 0.0 + sign * 0.5*(phi_sp - phi_sm) * cos_gamma * sv;
+    return;
+  }
+  const double H = rhv::voigt_armstrong(adamp, vk);
   C.phi[t] = 0.0 + H * 1.0 / (RH_SQRTPI * vbroad);                                      // :317-318
+}
+
+// Bproject() for every ray of the plan (rhf1d/project.c:38-80, geometry of rhf1d/anglequad.c: mux = sqrt(1 - muz^2),
+// muy = 0) from the pyrh rows B [G], gamma, chi: one thread per (column, depth)
+__global__ void __launch_bounds__(128)
+nlte_bproject_kernel(Plan P, int ncol, int nrow, const double *__restrict__ in, double *__restrict__ B, double *__restrict__ bproj)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = P.Ndep;
+  if (t >= (size_t) ncol * N) return;
+  const int col = (int) (t / N), k = (int) (t % N);
+  const double *a = in + (size_t) col * nrow * N + k;
+  B[t] = a[(size_t) 5 * N] / 1e4;                                                         // pyrh_compute1dray.c:266
+  const double gamma_B = a[(size_t) 6 * N], chi_B = a[(size_t) 7 * N];
+  for (int mu = 0; mu < P.Nrays; mu++) {
+    const double muz = P.muz[mu];
+    double cg, c2, s2;
+    if (muz == 1.0) {                                                                     // project.c:52-58
+      cg = rhm::rh_cos(gamma_B);
+      c2 = rhm::rh_cos(2.0 * chi_B);
+      s2 = rhm::rh_sin(2.0 * chi_B);
+    } else {                                                                              // project.c:60-77
+      const double mux = sqrt(1.0 - muz*muz), muy = 0.0;
+      const double csc_theta = 1.0 / sqrt(1.0 - muz*muz);
+      const double sin_gamma = rhm::rh_sin(gamma_B);
+      const double bx = sin_gamma * rhm::rh_cos(chi_B);
+      const double by = sin_gamma * rhm::rh_sin(chi_B);
+      const double bz = rhm::rh_cos(gamma_B);
+      const double b3 = mux*bx + muy*by + muz*bz;
+      const double b1 = csc_theta * (bz - muz*b3);
+      const double b2 = csc_theta * (muy*bx - mux*by);
+      cg = b3;
+      c2 = (b1*b1 - b2*b2) / (1.0 - b3*b3);
+      s2 = 2.0 * b1*b2 / (1.0 - b3*b3);
+    }
+    double *o = bproj + (((size_t) col * P.Nrays + mu) * 3) * N + k;
+    o[0] = cg; o[N] = c2; o[2*(size_t) N] = s2;
+  }
 }
 
 // wphi[k] = 1 / sum_{la,mu,dir} phi wlambda 0.5 wmu, summed in the reference's order (profile.c:320,358)
@@ -246,6 +321,74 @@ nlte_opacity_kernel(Plan P, Cols C, int ncol)
   }
 }
 
+// ---- (1b) FULL_STOKES passes: Q, U, V of Opacity() (opacity.c:262-296, 375-380) and of Formal()'s source vector and
+//      StokesK numerators (formal.c:184-206, stokesopac.c:49-60) at the wavelengths that hold a polarizable ACTIVE
+//      line or a polarised background line.  One thread per (column, wavelength, depth), after nlte_opacity_kernel
+//      (reads its chi_I).  chiQ [ray][3][N] = K'[0][1..3] numerators, SQ [ray][3][N] = S_Q,U,V.
+__global__ void __launch_bounds__(128)
+nlte_opacity_quv_kernel(Plan P, Cols C, int ncol)
+{
+  const int N = P.Ndep, ns = (int) (blockIdx.x % P.Nspect);
+  const size_t t = (size_t) (blockIdx.x / P.Nspect) * blockDim.x + threadIdx.x;
+  if (t >= (size_t) ncol * N) return;
+  const int k = (int) (t % N), col = (int) (t / N);
+  if (!C.active[col]) return;
+  if (ns < P.ns_lo || ns >= P.ns_hi) return;
+  const int pol_as = P.pol_as[ns], pol_c = P.pol_c[ns];
+  if (!pol_as && !pol_c) return;
+  const int first = P.as_first[ns], nact = P.as_first[ns+1] - first;
+  const double *ncol_ = C.n + (size_t) col * P.nlev * N;
+  const double hc_4PI = (RH_HPLANCK * RH_CLIGHT) / (4.0 * RH_PI);
+  const size_t plane = (size_t) ncol * P.nphirow * N;
+  double cq[3] = {0.0, 0.0, 0.0}, eq[3] = {0.0, 0.0, 0.0};
+  if (pol_c) {
+    const double *bc = C.chi_cQ + (((size_t) col * P.Nspect + ns) * 3) * N + k, *be = C.eta_cQ + (((size_t) col * P.Nspect + ns) * 3) * N + k;
+    for (int s = 0; s < 3; s++) { cq[s] = bc[(size_t) s * N]; eq[s] = be[(size_t) s * N]; }
+  }
+  for (int r = P.ray_off[ns]; r < P.ray_off[ns+1]; r++) {
+    const int lamu = 2*P.ray_mu[r] + P.ray_dir[r];
+    double chi_q[3] = {0.0, 0.0, 0.0}, eta_q[3] = {0.0, 0.0, 0.0}, eta_atom[3] = {0.0, 0.0, 0.0};
+    int cur_atom = -1;
+    if (pol_as)
+      for (int n = 0; n < nact; n++) {
+        const double *tr = P.trans + (size_t) P.as_trans[first+n] * TR_NFIELD;
+        const int a = (int) tr[TR_ATOM];
+        if (a != cur_atom) {                      // as->eta += atom->rhth.eta for all four records, opacity.c:375-380
+          if (cur_atom >= 0) for (int s = 0; s < 3; s++) eta_q[s] += eta_atom[s];
+          for (int s = 0; s < 3; s++) eta_atom[s] = 0.0;
+          cur_atom = a;
+        }
+        if (tr[TR_TYPE] != 0.0 || !P.line_pol[(int) tr[TR_LINEIDX]]) continue;
+        const int la = ns - (int) tr[TR_NBLUE];
+        const double twohnu3_c2 = tr[TR_AJI] / tr[TR_BJI];
+        if (twohnu3_c2 == 0.0) continue;          // opacity.c:252
+        const double g = C.gw[(((size_t) col * P.nas + first + n) * 2) * N + k];
+        const double n_i = ncol_[(size_t)(P.lev_off[a] + (int) tr[TR_I]) * N + k];
+        const double n_j = ncol_[(size_t)(P.lev_off[a] + (int) tr[TR_J]) * N + k];
+        const double Bijxhc_4PI = hc_4PI * tr[TR_BIJ] * tr[TR_ISOFRAC];
+        const double chi_l = Bijxhc_4PI * (n_i - g*n_j);                       // opacity.c:271-272
+        const double eta_l = Bijxhc_4PI * twohnu3_c2 * g * n_j;                // :283-284
+        const double *ph = C.phiQ + ((size_t) col * P.nphirow + (int) tr[TR_PHIROW] + 2*P.Nrays*la + lamu) * N + k;
+        for (int s = 0; s < 3; s++) {
+          const double f = ph[(size_t) s * plane];
+          chi_q[s] += chi_l * f;
+          eta_atom[s] += eta_l * f;
+        }
+      }
+    if (cur_atom >= 0) for (int s = 0; s < 3; s++) eta_q[s] += eta_atom[s];
+    const size_t rk = ((size_t) col * P.nray + r) * N + k;
+    const double chi = C.chi[rk];
+    double *oc = C.chiQ + ((size_t) col * P.nray + r) * 3 * N + k, *os = C.SQ + ((size_t) col * P.nray + r) * 3 * N + k;
+    for (int s = 0; s < 3; s++) {
+      double K = 0.0, S = 0.0;
+      if (pol_as) { K = chi_q[s]; S += eta_q[s]; }          // stokesopac.c:49-52, formal.c:187-189
+      if (pol_c)  { K += cq[s];   S += eq[s]; }             // :60-63, :192-194
+      oc[(size_t) s * N] = K;
+      os[(size_t) s * N] = S / chi;                         // formal.c:204-207
+    }
+  }
+}
+
 // ---- (2) formal solution of every ray: Piecewise_Bezier3_1D for angle-dependent wavelengths,
 //      Feautrier otherwise (formal.c:157-309)
 struct NlteFeauIO {
@@ -263,6 +406,46 @@ struct NlteFeauIO {
   __device__ __forceinline__ bool wantPsi() const { return Psi_ != nullptr; }
 };
 
+// FULL_STOKES rays (formal.c:184-217): Piece_Stokes_Bezier3_1D / Piece_Stokes_1D on chi_I, S[4], K' numerators
+struct NlteStokesIO {
+  const double *__restrict__ chi_, *__restrict__ S_, *__restrict__ SQ_, *__restrict__ q_;
+  double *I_, *Psi_, *IemQ_;
+  int ndep, kem;
+  __device__ __forceinline__ double chi(int k) const { return chi_[k]; }
+  __device__ __forceinline__ void K(int k, double x[3]) const {   // StokesK, stokesopac.c:72-77
+    const double c = chi_[k];
+    x[0] = q_[k] / c; x[1] = q_[ndep + k] / c; x[2] = q_[2*ndep + k] / c;
+  }
+  __device__ __forceinline__ void S(int k, double s[4]) const {
+    s[0] = S_[k]; s[1] = SQ_[k]; s[2] = SQ_[ndep+k]; s[3] = SQ_[2*ndep+k];
+  }
+  __device__ __forceinline__ void storeI(int k, const double I[4]) {
+    I_[k] = I[0];
+    if (k == kem) { IemQ_[0] = I[1]; IemQ_[1] = I[2]; IemQ_[2] = I[3]; }
+  }
+  __device__ __forceinline__ void storePsi(int k, double p) { if (Psi_) Psi_[k] = p; }
+  __device__ __forceinline__ void prefetch(int, int) const {}
+};
+__global__ void __launch_bounds__(128, 4)
+nlte_ray_stokes_kernel(Plan P, Cols C, int ncol, int eval_operator)
+{
+  const size_t cr = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (cr >= (size_t) ncol * P.nray) return;
+  const int r = (int) (cr % P.nray), col = (int) (cr / P.nray), N = P.Ndep;
+  if (!C.active[col]) return;
+  const int ns = P.ray_ns[r], mu = P.ray_mu[r], dir = P.ray_dir[r];
+  if (ns < P.ns_lo || ns >= P.ns_hi) return;
+  if (!(P.pol_as[ns] || P.pol_c[ns])) return;              // solveStokes, formal.c:94-95
+  const double *h = C.height + (size_t) col * N, *T = C.T + (size_t) col * N;
+  NlteStokesIO io{C.chi + cr * N, C.S + cr * N, C.SQ + cr * 3 * N, C.chiQ + cr * 3 * N, C.I + cr * N,
+                  eval_operator ? C.Psi + cr * N : nullptr, C.IemQ + cr * 3, N, 0};
+  if (P.stokes_solver == RHB200_DELO_PARABOLIC)
+    rhp::stokes_parabolic_ray(io, N, h, P.muz[mu], dir, P.bc_top, P.bc_bottom, T, P.lambda[ns]);
+  else
+    rhd::delo_bezier3_ray(io, N, h, P.muz[mu], dir, P.bc_top, P.bc_bottom, T, P.lambda[ns]);
+  C.Iem[cr] = C.I[cr * N];
+}
+
 // SOLVER is a template parameter so that each instantiation carries one solver's registers only
 template <int SOLVER, int MINB>
 __global__ void __launch_bounds__(128, MINB)
@@ -274,6 +457,7 @@ nlte_ray_kernel(Plan P, Cols C, int ncol, int eval_operator)
   if (!C.active[col]) return;
   const int ns = P.ray_ns[r], mu = P.ray_mu[r], dir = P.ray_dir[r];
   if (ns < P.ns_lo || ns >= P.ns_hi) return;
+  if (P.stokes && (P.pol_as[ns] || P.pol_c[ns])) return;   // nlte_ray_stokes_kernel
   const double *h = C.height + (size_t) col * N, *T = C.T + (size_t) col * N;
   double *Psi = eval_operator ? C.Psi + cr * N : nullptr;
   if (P.angle_dep[ns]) {
@@ -669,6 +853,18 @@ nlte_pack_spectrum_kernel(Plan P, Cols C, int ncol, double *__restrict__ spec)
   const int r = P.ray_off[ns] + (P.angle_dep[ns] ? 1 : 0);      // rays of a wavelength: (mu 0, down), (mu 0, up), ...
   spec[t] = C.Iem[(size_t) col * P.nray + r];
 }
+// spectrum.Stokes_Q/U/V[nspect][0] (formal.c:273-277): zero where Formal() did not solve for them (initSolution's calloc)
+__global__ void __launch_bounds__(128)
+nlte_pack_quv_kernel(Plan P, Cols C, int ncol, double *__restrict__ quv /* [ncol][3][Nspect] */)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t) ncol * P.Nspect) return;
+  const int ns = (int) (t % P.Nspect), col = (int) (t / P.Nspect);
+  const bool solved = P.stokes && (P.pol_as[ns] || P.pol_c[ns]);
+  const int r = P.ray_off[ns] + (P.angle_dep[ns] ? 1 : 0);
+  for (int s = 0; s < 3; s++)
+    quv[((size_t) col * 3 + s) * P.Nspect + ns] = solved ? C.IemQ[((size_t) col * P.nray + r) * 3 + s] : 0.0;
+}
 
 template <class T> int up(T **d, const T *h, size_t n)
 {
@@ -850,13 +1046,55 @@ struct NlteEngine {
     return RHB200_OK;
   }
   bool profile_maps_ok = false, exact_rates = false;
+  bool has_zeeman = false;                       // set_zeeman() was called: the FULL_STOKES passes are available
+  double *d_chi_cQ = nullptr, *d_eta_cQ = nullptr;   // background Q, U, V records of this engine [ncol][Ns][3][N]
   int nseg = 0;
 
   // doubles of device memory per column that alloc() takes (chunk sizing of the front end)
+  // Zeeman patterns of the polarizable ACTIVE lines (Zeeman(), zeeman.c:186-281; line->polarizable, readatom.c:352-368)
+  // and the flags Formal() derives from them with StokesMode FULL_STOKES (formal.c:86-95)
+  int set_zeeman(const rhb200_nlte_plan *pl, const int *line_pol, const int *line_zoff, const int *zq, const double *zshift,
+                 const double *zstrength) {
+    if (!line_pol || !line_zoff) { rhb200_set_error("rhb200_nlte: Zeeman tables missing"); return RHB200_EINVAL; }
+    DevArena &ar = plan_ar;
+    int *di; double *dd;
+    const int nz = line_zoff[nline];
+    if (nz > 0 && (!zq || !zshift || !zstrength)) { rhb200_set_error("rhb200_nlte: Zeeman tables missing"); return RHB200_EINVAL; }
+    RH_CHECK(ar.upload(&di, line_pol, (size_t) std::max(1, nline))); P.line_pol = di;
+    RH_CHECK(ar.upload(&di, line_zoff, (size_t) nline + 1)); P.line_zoff = di;
+    RH_CHECK(ar.upload(&di, zq, (size_t) nz)); P.zq = di;
+    RH_CHECK(ar.upload(&dd, zshift, (size_t) nz)); P.zshift = dd;
+    RH_CHECK(ar.upload(&dd, zstrength, (size_t) nz)); P.zstrength = dd;
+    std::vector<int> pol_as(Ns, 0), pol_c(Ns, 0), wflags(Ns, 0);
+    for (int ns = 0; ns < Ns; ns++)
+      for (int e = pl->as_first[ns]; e < pl->as_first[ns+1]; e++) {
+        const double *tr = pl->trans + (size_t) pl->as_trans[e]*RHB200_TR_NFIELD;
+        if (tr[RHB200_TR_TYPE] == 0.0 && line_pol[(int) tr[RHB200_TR_LINEIDX]]) pol_as[ns] = 1;
+      }
+    if (c->wav.nlambda != Ns) { rhb200_set_error("rhb200_set_wavelengths() must hold plan->lambda"); return RHB200_ESTATE; }
+    RH_CUDA(cudaMemcpy(wflags.data(), c->wav.flags, (size_t) Ns * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int ns = 0; ns < Ns; ns++) pol_c[ns] = (wflags[ns] & 2) ? 1 : 0;       // backgrflags.ispolarized
+    RH_CHECK(ar.upload(&di, pol_as.data(), (size_t) Ns)); P.pol_as = di;
+    RH_CHECK(ar.upload(&di, pol_c.data(), (size_t) Ns)); P.pol_c = di;
+    P.stokes = 0; P.stokes_solver = c->s_interpolation_stokes;
+    has_zeeman = true;
+    return RHB200_OK;
+  }
+  void set_stokes(bool on) { P.stokes = (on && has_zeeman) ? 1 : 0; }
+
+  // B, Bproject() of every ray of this engine from the pyrh rows (d_in [ncol][nrow][N])
+  int bproject(const double *d_in, int nrow) {
+    if (!has_zeeman) return RHB200_OK;
+    nlte_bproject_kernel<<<RH_GRID((size_t) ncol * N, 128), 0, c->stream>>>(P, ncol, nrow, d_in, (double *) C.B, (double *) C.bproj);
+    RH_CUDA(cudaGetLastError());
+    return RHB200_OK;
+  }
+
   size_t doubles_per_column(bool own_inputs) const {
     size_t d = (size_t) N * ((size_t) ngam + 2*(size_t) Nt + 2*(size_t) nas + 6*(size_t) nray + (size_t) Ns + nphirow + nline +
                              (exact_rates ? 0 : 4*(size_t) nseg)) + nray + prev_off[Na] + Na;
     if (own_inputs) d += (size_t) N * (2 + 2*(size_t) nlev + Na + ngam + nline + Na + 1 + 4*(size_t) Ns);
+    if (has_zeeman) d += (size_t) N * (1 + 3*(size_t) Nr + 3*(size_t) nphirow + 6*(size_t) Ns + 6*(size_t) nray) + 3*(size_t) nray;
     return d;
   }
 
@@ -874,6 +1112,16 @@ struct NlteEngine {
     RH_CHECK(ar.alloc(&C.chi, cN*nray)); RH_CHECK(ar.alloc(&C.S, cN*nray)); RH_CHECK(ar.alloc(&C.I, cN*nray));
     RH_CHECK(ar.alloc(&C.Psi, cN*nray)); RH_CHECK(ar.alloc(&C.scr, cN*nray*2)); RH_CHECK(ar.alloc(&C.dJ, cN*Ns, true));
     RH_CHECK(ar.alloc(&C.Iem, (size_t) ncol*nray, true));
+    if (has_zeeman) {
+      double *dd;
+      RH_CHECK(ar.alloc(&dd, cN)); C.B = dd;
+      RH_CHECK(ar.alloc(&dd, cN*Nr*3)); C.bproj = dd;
+      RH_CHECK(ar.alloc(&C.phiQ, cN*nphirow*3, true));
+      RH_CHECK(ar.alloc(&d_chi_cQ, cN*Ns*3, true)); RH_CHECK(ar.alloc(&d_eta_cQ, cN*Ns*3, true));
+      C.chi_cQ = d_chi_cQ; C.eta_cQ = d_eta_cQ;
+      RH_CHECK(ar.alloc(&C.chiQ, cN*nray*3)); RH_CHECK(ar.alloc(&C.SQ, cN*nray*3));
+      RH_CHECK(ar.alloc(&C.IemQ, (size_t) ncol*nray*3, true));
+    }
     active.assign(ncol, 1);
     RH_CHECK(ar.upload(&d_active, active.data(), ncol));
     C.active = d_active;
@@ -925,6 +1173,7 @@ struct NlteEngine {
     else RH_RAYS_M(RHB200_S_BEZIER3);
 #undef RH_RAYS_M
 #undef RH_RAYS
+    if (P.stokes) { ScopedKernelTimer t(c, RHB200_K_DELO); nlte_ray_stokes_kernel<<<blocks, 128, 0, c->stream>>>(P, C, ncol, eval_operator); }
   }
 
   // Profile() + wphi (when evaluated here), the per-entry weights, NgInit (accelerate.c:57-59)
@@ -960,7 +1209,8 @@ struct NlteEngine {
 
   // solveSpectrum(FALSE, FALSE) repeated: initScatter (update_J 1), the passes after Iterate() (2), the final formal
   // solution (0).  Iem_host [ncol][Ns][Nr] or NULL; d_Iem_spec: device [ncol][Ns] emergent intensity of ray mu = 0 or NULL
-  int scatter(int NmaxScatter, int update_J, double limit, int *nscat_out, double *Iem_host, double *d_Iem_spec) {
+  int scatter(int NmaxScatter, int update_J, double limit, int *nscat_out, double *Iem_host, double *d_Iem_spec,
+              double *d_quv_spec = nullptr /* device [ncol][3][Ns] emergent Q, U, V of ray mu = 0 */) {
     cudaStream_t st = c->stream;
     const size_t cN = (size_t) ncol * N;
     std::vector<int> nscat(ncol, 0);
@@ -969,7 +1219,8 @@ struct NlteEngine {
     int nact_s = ncol;
     for (int it = 0; it < NmaxScatter && nact_s > 0; it++) {
       { ScopedKernelTimer t(c, RHB200_K_OPACITY);
-        nlte_opacity_kernel<<<(unsigned) (((cN + 127) / 128) * Ns), 128, 0, st>>>(P, C, ncol); }
+        nlte_opacity_kernel<<<(unsigned) (((cN + 127) / 128) * Ns), 128, 0, st>>>(P, C, ncol);
+        if (P.stokes) nlte_opacity_quv_kernel<<<(unsigned) (((cN + 127) / 128) * Ns), 128, 0, st>>>(P, C, ncol); }
       { ScopedKernelTimer t(c, RHB200_K_BEZIER);
         launch_rays(0); }
       if (update_J) {
@@ -1007,6 +1258,8 @@ struct NlteEngine {
       }
       if (d_Iem_spec) {
         nlte_pack_spectrum_kernel<<<RH_GRID((size_t) ncol*Ns, 128), 0, st>>>(P, C, ncol, d_Iem_spec);
+        if (d_quv_spec && has_zeeman) nlte_pack_quv_kernel<<<RH_GRID((size_t) ncol*Ns, 128), 0, st>>>(P, C, ncol, d_quv_spec);
+        else if (d_quv_spec) RH_CUDA(cudaMemsetAsync(d_quv_spec, 0, (size_t) ncol * 3 * Ns * sizeof(double), st));
         RH_CUDA(cudaGetLastError());
       }
     }
@@ -1023,6 +1276,7 @@ struct NlteEngine {
     std::vector<int> niter(ncol, 0);
     active.assign(ncol, 1);
     int nactive = ncol;
+    if (P.stokes && NmaxIter > 0) { rhb200_set_error("MALI iterations with FULL_STOKES radiation (Stokes I_eff, fillgamma.c:106-129) are not implemented: use STOKES_MODE = FIELD_FREE"); return RHB200_EUNSUPPORTED; }
     for (int it = 1; it <= NmaxIter && nactive > 0; it++) {
       { ScopedKernelTimer t(c, RHB200_K_OTHER);
         nlte_gamma_init_kernel<<<RH_GRID(cN*ngam, 256), 0, st>>>(P, C, ncol); }

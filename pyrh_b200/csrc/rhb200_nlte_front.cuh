@@ -181,6 +181,17 @@ nlte_damping_gather_kernel(Plan P, Cols C, int ncol, const double *__restrict__ 
   ((double *) C.vbroad)[((size_t) col * P.Natom + a) * N + k] = p[2*(size_t) N];    // same value from every line of the atom
 }
 
+// adjustStokesMode() runs Profile() -- and with it Damping() -- for the POLARIZABLE lines only (zeeman.c:329-341)
+__global__ void __launch_bounds__(128)
+nlte_adamp_select_kernel(Plan P, int ncol, const double *__restrict__ src, double *__restrict__ dst)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = P.Ndep;
+  if (t >= (size_t) ncol * P.nline * N) return;
+  const int li = (int) ((t / N) % P.nline);
+  if (P.line_pol[li]) dst[t] = src[t];
+}
+
 struct FrontState {                 // kept with the context between calls of rhb200_nlte_compute1d_batch
   uint64_t key = 0;
   int cc = 0;
@@ -189,7 +200,8 @@ struct FrontState {                 // kept with the context between calls of rh
   double *d_in = nullptr, *d_at = nullptr, *d_pops = nullptr, *d_popsn = nullptr, *d_chem = nullptr, *d_ntot = nullptr, *d_tprep = nullptr,
          *d_sc = nullptr, *d_pc = nullptr, *d_apc = nullptr, *d_elem_n = nullptr, *d_lineprep = nullptr, *d_md = nullptr, *d_mol = nullptr,
          *d_mchi = nullptr, *d_meta = nullptr, *d_spec = nullptr, *d_abund = nullptr, *d_coll = nullptr, *d_cT = nullptr, *d_cC = nullptr,
-         *d_cM = nullptr, *d_plrows = nullptr, *d_adamp2 = nullptr, *d_chi2 = nullptr, *d_eta2 = nullptr, *d_sca2 = nullptr;
+         *d_cM = nullptr, *d_plrows = nullptr, *d_adamp2 = nullptr, *d_chi2 = nullptr, *d_eta2 = nullptr, *d_sca2 = nullptr,
+         *d_quv = nullptr;
 };
 
 struct FrontDebug {                 // device copies kept for rhb200_nlte_front_debug (test hook)
@@ -215,11 +227,26 @@ extern "C" int rhb200_nlte_front_debug(rhb200_ctx *c, int which, double *out, si
   return RHB200_OK;
 }
 
+extern "C" int rhb200_nlte_compute1d_stokes_batch(rhb200_ctx *c, const rhb200_nlte_plan *pl, const rhb200_nlte_front *fr,
+                                                  int ncol, int ndep, int nrow, double mu, int atm_scale, const double *atmosphere,
+                                                  int iref, double wght_per_H, double vmacro_tresh,
+                                                  double *spectrum, double *quv, double *out_n, double *out_nstar, int *niter_out,
+                                                  int *passes_out, double *scales);
 extern "C" int rhb200_nlte_compute1d_batch(rhb200_ctx *c, const rhb200_nlte_plan *pl, const rhb200_nlte_front *fr,
                                            int ncol, int ndep, int nrow, double mu, int atm_scale, const double *atmosphere,
                                            int iref, double wght_per_H, double vmacro_tresh,
                                            double *spectrum, double *out_n, double *out_nstar, int *niter_out, int *passes_out,
                                            double *scales)
+{
+  return rhb200_nlte_compute1d_stokes_batch(c, pl, fr, ncol, ndep, nrow, mu, atm_scale, atmosphere, iref, wght_per_H, vmacro_tresh,
+                                            spectrum, nullptr, out_n, out_nstar, niter_out, passes_out, scales);
+}
+
+extern "C" int rhb200_nlte_compute1d_stokes_batch(rhb200_ctx *c, const rhb200_nlte_plan *pl, const rhb200_nlte_front *fr,
+                                                  int ncol, int ndep, int nrow, double mu, int atm_scale, const double *atmosphere,
+                                                  int iref, double wght_per_H, double vmacro_tresh,
+                                                  double *spectrum, double *quv, double *out_n, double *out_nstar, int *niter_out,
+                                                  int *passes_out, double *scales)
 {
   if (!c || !pl || !fr || !fr->plan1 || !atmosphere) { rhb200_set_error("null argument"); return RHB200_EINVAL; }
   RH_CUDA(cudaSetDevice(c->device));
@@ -229,7 +256,10 @@ extern "C" int rhb200_nlte_compute1d_batch(rhb200_ctx *c, const rhb200_nlte_plan
   if (c->wav.nlambda != pl->Nspect) { rhb200_set_error("rhb200_set_wavelengths() must hold plan->lambda (%d vs %d wavelengths)", c->wav.nlambda, pl->Nspect); return RHB200_ESTATE; }
   if (iref < 0 || iref >= pl->Nspect) { rhb200_set_error("iref outside the wavelength grid"); return RHB200_EINVAL; }
   if (!c->cont || !rh_continuum_has_chemistry(c)) { rhb200_set_error("rhb200_set_continuum() / rhb200_set_chemistry() have not been called"); return RHB200_ESTATE; }
-  if (!c->no_stokes) { rhb200_set_error("NLTE with STOKES_MODE other than NO_STOKES (polarised active sets) is not implemented"); return RHB200_EUNSUPPORTED; }
+  if (fr->stokes != 0 && fr->stokes != 1) { rhb200_set_error("front->stokes must be 0 (NO_STOKES) or 1 (FIELD_FREE)"); return RHB200_EUNSUPPORTED; }
+  const bool stokes = fr->stokes == 1;
+  if (!c->no_stokes) { rhb200_set_error("the background of the NLTE path is set up with rhb200_set_stokes_mode(ctx, 0): the FULL_STOKES passes of FIELD_FREE are selected by front->stokes"); return RHB200_EUNSUPPORTED; }
+  if (stokes && (!fr->line_pol || !fr->line_zoff)) { rhb200_set_error("front->stokes needs line_pol / line_zoff and the Zeeman tables"); return RHB200_EINVAL; }
   if (pl->Natom > NF_MAXATOM) { rhb200_set_error("too many ACTIVE atoms"); return RHB200_EUNSUPPORTED; }
   if (vmacro_tresh > 0.0) { rhb200_set_error("VMACRO_TRESH > 0 (columns that may be static) is not implemented on the NLTE path"); return RHB200_EUNSUPPORTED; }
   if (scales && atm_scale == 2 && !(c->gravity > 0.0)) { rhb200_set_error("scales on a height grid: the column-mass row needs rhb200_set_gravity() (multiatmos.c:153-155)"); return RHB200_EINVAL; }
@@ -298,6 +328,12 @@ extern "C" int rhb200_nlte_compute1d_batch(rhb200_ctx *c, const rhb200_nlte_plan
     mix(pl->bg_hasline, sizeof(int) * pl->Nspect); mix(fr->atom_model, sizeof(int) * pl->Natom);
     mix(fr->coll, sizeof(double) * fr->ncoll * RHB200_CO_NFIELD); mix(fr->coll_T, sizeof(double) * fr->ncolltab);
     mix(fr->coll_coef, sizeof(double) * fr->ncolltab); mix(fr->line_rows, sizeof(double) * pl->nline * RHB200_PL_NFIELD);
+    mix(&fr->stokes, sizeof(int)); mix(&c->s_interpolation_stokes, sizeof(int));
+    if (stokes) {
+      const int nz = fr->line_zoff[pl->nline];
+      mix(fr->line_pol, sizeof(int) * pl->nline); mix(fr->line_zoff, sizeof(int) * (pl->nline + 1));
+      if (nz > 0) { mix(fr->zq, sizeof(int) * nz); mix(fr->zshift, sizeof(double) * nz); mix(fr->zstrength, sizeof(double) * nz); }
+    }
     for (int a = 0; a < natom_model; a++) { const double ab = rh_continuum_abundance(c, a); mix(&ab, sizeof ab); }
   }
   FrontState *S = (FrontState *) c->nlte_front;
@@ -311,6 +347,8 @@ extern "C" int rhb200_nlte_compute1d_batch(rhb200_ctx *c, const rhb200_nlte_plan
     // the two engines: Nrays rays for initScatter / Iterate, one ray at `mu` for _solveray()'s pass
     int rc = S->E.build(c, pl);
     if (rc == RHB200_OK) rc = S->F.build(c, &p1);
+    if (rc == RHB200_OK && stokes) rc = S->E.set_zeeman(pl, fr->line_pol, fr->line_zoff, fr->zq, fr->zshift, fr->zstrength);
+    if (rc == RHB200_OK && stokes) rc = S->F.set_zeeman(&p1, fr->line_pol, fr->line_zoff, fr->zq, fr->zshift, fr->zstrength);
     if (rc == RHB200_OK && S->E.nrank > 1) { rhb200_set_error("wavelength sharding is only available through rhb200_nlte_iterate"); rc = RHB200_EUNSUPPORTED; }
     if (rc != RHB200_OK) { delete S; return rc; }
     // ---- chunk size from the workspace budget
@@ -346,7 +384,7 @@ extern "C" int rhb200_nlte_compute1d_batch(rhb200_ctx *c, const rhb200_nlte_plan
         RH_CHECK(ar.alloc(&S->d_md, cN * c->wav.nmsel)); RH_CHECK(ar.alloc(&S->d_mol, cN * c->wav.nmsel * 3));
         RH_CHECK(ar.alloc(&S->d_mchi, cN * Ns)); RH_CHECK(ar.alloc(&S->d_meta, cN * Ns));
       }
-      RH_CHECK(ar.alloc(&S->d_spec, (size_t) cc * Ns));
+      RH_CHECK(ar.alloc(&S->d_spec, (size_t) cc * Ns)); RH_CHECK(ar.alloc(&S->d_quv, (size_t) cc * Ns * 3));
       RH_CHECK(ar.alloc(&S->d_adamp2, cN * std::max(1, pl->nline)));
       RH_CHECK(ar.alloc(&S->d_chi2, cN * Ns)); RH_CHECK(ar.alloc(&S->d_eta2, cN * Ns)); RH_CHECK(ar.alloc(&S->d_sca2, cN * Ns));
       std::vector<double> ab(natom_model);
@@ -387,13 +425,14 @@ extern "C" int rhb200_nlte_compute1d_batch(rhb200_ctx *c, const rhb200_nlte_plan
 
   // background of one chunk for ray direction muz (up): continuum with the populations seen through atom->n, passive_bb,
   // Kurucz lines, molecular lines -> chi_c (scattering included: background.c:462), eta_c, sca_c
-  auto background = [&](int n, double muz, const double *pops_n, double *chi_c, double *eta_c, double *sca_c) -> int {
+  auto background = [&](int n, double muz, const double *pops_n, double *chi_c, double *eta_c, double *sca_c,
+                        double *chi_quv, double *eta_quv) -> int {
     RH_CHECK(rh_continuum_opac(c, n, N, d_at, d_chem, pops_n, d_pops, d_tprep, chi_c, eta_c, sca_c));
     if (mol_on) RH_CHECK(rh_molecular_chunk(c, n, N, muz, d_at, d_md, d_mol, d_mchi, d_meta));
     RH_CHECK(rh_passive_chunk(c, n, N, muz, d_at, pops_n, nlev_model, d_pc, chi_c, eta_c));
     RH_CHECK(rh_launch_proton(c, n, N, nlev_model, rh_continuum_proton_level(c), pops_n, d_at));
     RH_CHECK(rh_launch_prep(c, n, N, muz, 1, d_at, d_elem_n, d_lineprep));
-    RH_CHECK(rh_launch_opacity_addI(c, n, N, 1, d_at, d_lineprep, chi_c, eta_c));
+    RH_CHECK(rh_launch_opacity_addI(c, n, N, 1, d_at, d_lineprep, chi_c, eta_c, chi_quv, eta_quv));
     if (mol_on) RH_CHECK(rh_launch_add_molecular(c, n, N, d_mchi, d_meta, chi_c, eta_c));
     return RHB200_OK;
   };
@@ -428,7 +467,9 @@ extern "C" int rhb200_nlte_compute1d_batch(rhb200_ctx *c, const rhb200_nlte_plan
       RH_CUDA(cudaGetLastError());
       pops_n = d_popsn;
     }
-    RH_CHECK(background(n, mu_last, pops_n, (double *) E.C.chi_c, (double *) E.C.eta_c, (double *) E.C.sca_c));
+    RH_CHECK(background(n, mu_last, pops_n, (double *) E.C.chi_c, (double *) E.C.eta_c, (double *) E.C.sca_c,
+                        stokes ? E.d_chi_cQ : nullptr, stokes ? E.d_eta_cQ : nullptr));
+    if (stokes) RH_CHECK(E.bproject(d_in, nrow));
     RH_CHECK(rh_launch_scales_chi(c, n, N, Ns, iref, atm_scale, wght_per_H, c->total_abund, c->gravity > 0.0 ? c->gravity : 1.0, E.C.chi_c, d_at, d_sc,
                                   scales ? d_sc + 2*cN : nullptr));
     nlte_height_kernel<<<RH_GRID(nN, 128), 0, st>>>(n, N, d_at, (double *) E.C.height);
@@ -453,7 +494,24 @@ extern "C" int rhb200_nlte_compute1d_batch(rhb200_ctx *c, const rhb200_nlte_plan
     mark("initScatter");
     RH_CHECK(E.iterate(fr->NmaxIter, fr->iterLimit, niter.data(), nullptr, 0, nullptr, nullptr));
     mark("Iterate");
+    if (stokes) {                                    // adjustStokesMode(), pyrh_compute1dray.c:332: Profile() of the polarizable lines again
+      if (H_active) {                                // their Damping() now sees hydrogen's NLTE populations
+        nlte_popsn_kernel<<<RH_GRID(nN * nlev_model, 128), 0, st>>>(n, N, nlev_model, H_nlevel, d_pops, E.C.n, E.nlev,
+                                                                    E.lev_off[H_engine_atom], d_popsn);
+        RH_CUDA(cudaGetLastError());
+        RH_CHECK(rh_launch_line_damping(c, n, N, pl->nline, d_plrows, d_at, pops_n, nlev_model, d_apc));
+        Cols Ctmp = E.C;
+        Ctmp.adamp = d_adamp2;
+        nlte_damping_gather_kernel<<<RH_GRID(nN * pl->nline, 128), 0, st>>>(E.P, Ctmp, n, d_apc);
+        nlte_adamp_select_kernel<<<RH_GRID(nN * pl->nline, 128), 0, st>>>(E.P, n, d_adamp2, (double *) E.C.adamp);
+        RH_CUDA(cudaGetLastError());
+      }
+      E.set_stokes(true);
+      RH_CHECK(E.prepare(nullptr, nullptr, false));
+      mark("adjustStokesMode");
+    }
     RH_CHECK(E.scatter(fr->NmaxScatter, 2, fr->iterLimit, pass_b.data(), nullptr, nullptr));
+    E.set_stokes(false);
     mark("passes after Iterate");
     if (niter_out) memcpy(niter_out + c0, niter.data(), n * sizeof(int));
     if (passes_out) for (int q = 0; q < n; q++) { passes_out[2*(size_t) (c0 + q)] = pass_a[q]; passes_out[2*(size_t) (c0 + q) + 1] = pass_b[q]; }
@@ -472,7 +530,8 @@ extern "C" int rhb200_nlte_compute1d_batch(rhb200_ctx *c, const rhb200_nlte_plan
                                                                   E.lev_off[H_engine_atom], d_popsn);
       RH_CUDA(cudaGetLastError());
     }
-    RH_CHECK(background(n, mu, pops_n, d_chi2, d_eta2, d_sca2));
+    RH_CHECK(background(n, mu, pops_n, d_chi2, d_eta2, d_sca2, stokes ? F.d_chi_cQ : nullptr, stokes ? F.d_eta_cQ : nullptr));
+    if (stokes) { RH_CHECK(F.bproject(d_in, nrow)); F.set_stokes(true); }
     F.C.chi_c = d_chi2; F.C.eta_c = d_eta2; F.C.sca_c = d_sca2;
     {                                                // Damping() again: hydrogen's populations changed (NLTE solution if
       RH_CHECK(rh_launch_line_damping(c, n, N, pl->nline, d_plrows, d_at, pops_n, nlev_model, d_apc));   // ACTIVE, else the
@@ -483,7 +542,7 @@ extern "C" int rhb200_nlte_compute1d_batch(rhb200_ctx *c, const rhb200_nlte_plan
     }
     mark("second background + damping");
     RH_CHECK(F.prepare(nullptr, nullptr, false));
-    RH_CHECK(F.scatter(1, 0, 0.0, nullptr, nullptr, d_spec));
+    RH_CHECK(F.scatter(1, 0, 0.0, nullptr, nullptr, d_spec, quv ? S->d_quv : nullptr));
     mark("final pass");
     if (debug_keep && c0 == 0) {
       RH_CHECK(keep(9, E.C.J, nN * Ns));
@@ -492,6 +551,7 @@ extern "C" int rhb200_nlte_compute1d_batch(rhb200_ctx *c, const rhb200_nlte_plan
     }
     RH_CUDA(cudaStreamSynchronize(st));
     if (spectrum) RH_CUDA(cudaMemcpy(spectrum + (size_t) c0 * Ns, d_spec, (size_t) n * Ns * sizeof(double), cudaMemcpyDeviceToHost));
+    if (quv) RH_CUDA(cudaMemcpy(quv + (size_t) c0 * 3 * Ns, S->d_quv, (size_t) n * 3 * Ns * sizeof(double), cudaMemcpyDeviceToHost));
     if (out_n) RH_CUDA(cudaMemcpy(out_n + (size_t) c0 * E.nlev * N, E.C.n, nN * E.nlev * sizeof(double), cudaMemcpyDeviceToHost));
     if (out_nstar) RH_CUDA(cudaMemcpy(out_nstar + (size_t) c0 * E.nlev * N, E.C.nstar, nN * E.nlev * sizeof(double), cudaMemcpyDeviceToHost));
     if (scales) RH_CUDA(cudaMemcpy(scales + (size_t) c0 * 3 * N, d_sc + 2*cN, nN * 3 * sizeof(double), cudaMemcpyDeviceToHost));

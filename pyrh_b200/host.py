@@ -1319,8 +1319,8 @@ def compute1d(cwd, mu, atm_scale, atmosphere, wave, loggf_ids=None, loggf_values
         if get_atomic_rfs:
             raise NotImplementedError("get_atomic_rfs with ACTIVE atoms is not ported")
         res = s.compute(atmosphere, mu=mu, atm_scale=atm_scale)
-        zero = np.zeros_like(res["I"])                              # atmos.Stokes is TRUE, STOKES_MODE NO_STOKES: Q = U = V = 0
-        output = (res["I"], zero, zero.copy(), zero.copy(), s.wavelengths)
+        # atmos.Stokes is TRUE: zeros with STOKES_MODE NO_STOKES, the full Stokes solution after FIELD_FREE iterations
+        output = (res["I"], res["Q"], res["U"], res["V"], s.wavelengths)
         if get_populations:
             populations = tuple(Populations(ID, n.shape[0], n.shape[1], n, ns) for ID, n, ns in s.populations(res))
     else:

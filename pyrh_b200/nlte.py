@@ -39,7 +39,8 @@ class FrontStruct(C.Structure):
     """rhb200_nlte_front (include/rhb200.h)."""
     _fields_ = [("atom_model", ip), ("ncoll", C.c_int), ("ncolltab", C.c_int), ("coll", dp), ("coll_T", dp),
                 ("coll_coef", dp), ("coll_M", dp), ("line_rows", dp), ("NmaxScatter", C.c_int), ("NmaxIter", C.c_int),
-                ("iterLimit", C.c_double), ("plan1", C.POINTER(PlanStruct))]
+                ("iterLimit", C.c_double), ("plan1", C.POINTER(PlanStruct)),
+                ("stokes", C.c_int), ("line_pol", ip), ("line_zoff", ip), ("zq", ip), ("zshift", dp), ("zstrength", dp)]
 
 
 @dataclass

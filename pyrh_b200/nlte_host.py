@@ -480,9 +480,11 @@ class NlteSession:
         tob = lambda x: None if x is None else np.asarray(x).tobytes()   # noqa: E731
         self.loggf_key = (tob(loggf_ids), tob(loggf_values))
         kw = self.kw = H.read_keywords(cwd)
-        if kw["STOKES_MODE"].upper() != "NO_STOKES":
-            raise NotImplementedError("ACTIVE atoms with STOKES_MODE other than NO_STOKES: the polarised active set "
-                                      "(opacity.c:168-296, profile.c:112-191) is not ported")
+        self.stokes_mode = kw["STOKES_MODE"].upper()
+        if self.stokes_mode not in ("NO_STOKES", "FIELD_FREE"):
+            raise NotImplementedError("ACTIVE atoms with STOKES_MODE = %s: MALI iterations on polarised radiation (Stokes "
+                                      "I_eff, fillgamma.c:106-129) are not ported; FIELD_FREE (field-free iterations, then "
+                                      "the full Stokes solution, zeeman.c:303-345) and NO_STOKES are" % self.stokes_mode)
         if H._true(kw["MAGNETO_OPTICAL"]):
             raise NotImplementedError("MAGNETO_OPTICAL = TRUE is refused (the reference overflows chip_c there, readj.c:328)")
         if H._true(kw.get("DO_FUDGE", "FALSE")) and fudge_wave is None:
@@ -542,6 +544,25 @@ class NlteSession:
         self.vmacro_tresh = float(kw["VMACRO_TRESH"])
         self.ctx.set_gravity(self.el.totalAbund)
         self.IDs = [at["ID"] for at in self.atoms]
+        # FIELD_FREE: Zeeman patterns of the polarizable ACTIVE lines (Zeeman(), zeeman.c:186-281), line-index order
+        self.line_pol, self.line_zoff, zq, zs, zt = [], [0], [], [], []
+        for at in self.atoms:
+            for ln in at["lines"]:
+                pol = bool(ln["polarizable"]) and self.stokes_mode == "FIELD_FREE"
+                if pol:
+                    if len(ln["c_shift"]) > 1:
+                        raise ValueError("cannot treat composite line with polarization (readatom.c:355-359)")
+                    q, sh, st = zeeman.zeeman(at["label"][ln["i"]], at["g"][ln["i"]], at["label"][ln["j"]], at["g"][ln["j"]],
+                                              ln["g_Lande_eff"])
+                    zq += list(q); zs += list(sh); zt += list(st)
+                self.line_pol.append(int(pol))
+                self.line_zoff.append(len(zq))
+        assert len(self.line_pol) == self.plan["nline"]
+        self.line_pol = np.ascontiguousarray(self.line_pol, np.int32)
+        self.line_zoff = np.ascontiguousarray(self.line_zoff, np.int32)
+        self.zq = np.ascontiguousarray(zq if zq else [0], np.int32)
+        self.zshift = np.ascontiguousarray(zs if zs else [0.0], np.float64)
+        self.zstrength = np.ascontiguousarray(zt if zt else [0.0], np.float64)
 
     @staticmethod
     def _check_initial_solution(cwd, kw):
@@ -591,7 +612,10 @@ class NlteSession:
             fr = nl.FrontStruct(model.ctypes.data_as(lib.ip), len(self.coll), len(self.coll_T),
                                 *[x.ctypes.data_as(lib.dp) for x in tabs],
                                 self.line_rows.ctypes.data_as(lib.dp), self.hdr["NmaxScatter"], self.hdr["NmaxIter"],
-                                self.hdr["iterLimit"], C.pointer(plan1))
+                                self.hdr["iterLimit"], C.pointer(plan1), int(self.stokes_mode == "FIELD_FREE"),
+                                self.line_pol.ctypes.data_as(lib.ip), self.line_zoff.ctypes.data_as(lib.ip),
+                                self.zq.ctypes.data_as(lib.ip), self.zshift.ctypes.data_as(lib.dp),
+                                self.zstrength.ctypes.data_as(lib.dp))
             cache.clear()
             cache[(float(mu), ndep)] = (plan, plan1, fr, keep, model, tabs)
         plan, plan1, fr = cache[(float(mu), ndep)][:3]
@@ -600,11 +624,13 @@ class NlteSession:
         niter, passes = np.zeros(ncol, np.int32), np.zeros((ncol, 2), np.int32)
         scales = np.zeros((ncol, 3, ndep)) if get_scales else None
         vp = lambda x: None if x is None else C.c_void_p(x.ctypes.data)   # noqa: E731
-        lib.check(self.ctx.lib.rhb200_nlte_compute1d_batch(
+        quv = np.zeros((ncol, 3, Ns))
+        lib.check(self.ctx.lib.rhb200_nlte_compute1d_stokes_batch(
             self.ctx.h, C.byref(plan), C.byref(fr), ncol, ndep, nrow, float(mu), int(atm_scale), vp(a), self.iref,
-            float(self.el.wght_per_H), self.vmacro_tresh, vp(spec), vp(n), vp(nstar), vp(niter), vp(passes), vp(scales)))
-        I = spec[:, self.lam != self.lambda_ref]
-        out = dict(I=I, n=n, nstar=nstar, niter=niter, passes=passes)
+            float(self.el.wght_per_H), self.vmacro_tresh, vp(spec), vp(quv), vp(n), vp(nstar), vp(niter), vp(passes), vp(scales)))
+        user = self.lam != self.lambda_ref
+        I = spec[:, user]
+        out = dict(I=I, Q=quv[:, 0][:, user], U=quv[:, 1][:, user], V=quv[:, 2][:, user], n=n, nstar=nstar, niter=niter, passes=passes)
         if get_scales:
             out["scales"] = scales
         if single:

@@ -1401,6 +1401,43 @@ def test_nlte_through_compute1d_on_perturbed_columns(case):
     host.close_sessions()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["caii_r3_ff", "h_caii_r5_ff"])
+def test_nlte_field_free_full_stokes_solution(case):
+    """STOKES_MODE = FIELD_FREE with ACTIVE atoms: the MALI iterations run field-free, adjustStokesMode() (zeeman.c:303-345)
+    then recomputes the profiles of the polarizable lines with their Zeeman patterns (Profile(), profile.c:112-305) and the
+    passes after Iterate() and _solveray()'s pass solve all four Stokes parameters (Opacity IQUV, opacity.c:262-296;
+    StokesK + Piece_Stokes_Bezier3_1D with an active set, formal.c:184-217).  Ca II 8542 alone (polarizable ACTIVE line) and
+    H + Ca II in the Hinode window at mu = 0.8 (polarised BACKGROUND: Fe I 6301/6302 with the last-ray record).  Eight
+    perturbed columns with B up to 2.5 kG against the reference: iterations identical, populations <= 1e-6, I <= 1e-9,
+    Q, U, V <= 1e-12 of the continuum (north_star); reported: whether every number is bit-identical."""
+    from pyrh_b200 import host, nlte_host
+    g, cwd = _nlte_front_case(case)
+    atm, wave, mu = g["atmosphere"], g[f"{case}_wave"], float(g[f"{case}_mu"])
+    s = nlte_host.NlteSession(cwd, wave)
+    try:
+        res = s.compute(atm, mu=mu)
+    finally:
+        s.close()
+    ref = g[f"{case}_QUV"]
+    got = np.stack([res["Q"], res["U"], res["V"]], axis=1)
+    Ic = g[f"{case}_I"].max(axis=1)[:, None, None]
+    en = float(np.max(np.abs(res["n"] / g[f"{case}_n"] - 1)))
+    eI = float(np.max(np.abs(res["I"] / g[f"{case}_I"] - 1)))
+    eP = float(np.max(np.abs(got - ref) / Ic))
+    REPORT[f"nlte_field_free_{case}"] = dict(niter_equal=bool(np.array_equal(res["niter"], g[f"{case}_niter"])), n_maxrel=en,
+                                             I_maxrel=eI, QUV_over_Ic=eP, I_exact=bool(np.array_equal(res["I"], g[f"{case}_I"])),
+                                             QUV_exact=bool(np.array_equal(got, ref)),
+                                             QUV_max_over_Ic=float(np.max(np.abs(ref) / Ic)))
+    assert np.abs(ref).max() > 0 and np.abs(got).max() > 0
+    assert np.array_equal(res["niter"], g[f"{case}_niter"])
+    assert en <= 1e-6 and eI <= 1e-9 and eP <= 1e-12
+    assert np.array_equal(res["n"], g[f"{case}_n"])            # the iterations are the NO_STOKES ones, to the bit
+    (sI, sQ, sU, sV, lam) = host.compute1d(cwd, mu, 0, atm[2], wave)
+    assert np.array_equal(sI, res["I"][2]) and np.array_equal(sQ, res["Q"][2]) and np.array_equal(sV, res["V"][2])
+    host.close_sessions()
+
+
 def json_keys(g, case):
     import json
     return json.loads(str(g["cases"]))[case]["keys"]
