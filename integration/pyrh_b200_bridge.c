@@ -497,18 +497,22 @@ static void collisions(Atom *atom, int a, dvec *rows, dvec *tT, dvec *tC, dvec *
   free(Tg);
 }
 
-static void solve_nlte(double mu, int ncol, const double *rows9, int nrow, double *spec_out, double *n_out, double *ns_out, int *niter)
+static void solve_nlte(double mu, int ncol, const double *rows9, int nrow, double *spec_out, double *quv_out, double *n_out, double *ns_out, int *niter)
 {
   const int Ns = spectrum.Nspect, Na = atmos.Nactiveatom, N = atmos.Nspace;
   rhb200_nlte_plan P, P1;
   rhb200_nlte_front F;
   dvec trans = {0}, trans1 = {0}, wl = {0}, ww = {0}, wa = {0}, co = {0}, tT = {0}, tC = {0}, tM = {0}, lr = {0};
-  ivec asf = {0}, ast = {0};
+  ivec asf = {0}, ast = {0}, lpol = {0}, lzoff = {0}, zq = {0};
+  dvec zs = {0}, zt = {0};
+  const int field_free = input.StokesMode == FIELD_FREE;
   int *nlevel = (int *) malloc(Na * sizeof(int)), *model = (int *) malloc(Na * sizeof(int)), *hasline = (int *) malloc(Ns * sizeof(int));
   int **lidx = (int **) malloc(Na * sizeof(int *)), **cidx = (int **) malloc(Na * sizeof(int *));
   int a, kr, la, ns, n, phirow = 0, phirow1 = 0, nline = 0, ntr = 0;
   double mu1 = mu, w1 = 1.0;
-  if (input.StokesMode != NO_STOKES) FAIL("ACTIVE atoms with STOKES_MODE other than NO_STOKES are not implemented");
+  if (input.StokesMode != NO_STOKES && !field_free)
+    FAIL("ACTIVE atoms with STOKES_MODE FULL_STOKES / POLARIZATION_FREE (MALI iterations on polarised radiation) are not implemented: use FIELD_FREE");
+  iv_push(&lzoff, 0);
   if (!atmos.moving) FAIL("static atmospheres with ACTIVE atoms are not implemented");
   for (a = 0; a < Na; a++) {
     Atom *atom = atmos.activeatoms[a];
@@ -534,6 +538,13 @@ static void solve_nlte(double mu, int ncol, const double *rows9, int nrow, doubl
       phirow += 2 * atmos.Nrays * L->Nlambda; phirow1 += 2 * L->Nlambda;
       line_row(atom, model[a], T.lev0[model[a]], L, 0, pr);
       for (n = 0; n < NPL; n++) dv_push(&lr, pr[n]);
+      if (field_free && L->polarizable) {                  /* Zeeman(line), zeeman.c:186-281: what Profile() uses (profile.c:115) */
+        ZeemanMultiplet *zm = Zeeman(L);
+        for (n = 0; n < zm->Ncomponent; n++) { iv_push(&zq, zm->q[n]); dv_push(&zs, zm->shift[n]); dv_push(&zt, zm->strength[n]); }
+        freeZeeman(zm); free(zm);
+        iv_push(&lpol, 1);
+      } else iv_push(&lpol, 0);
+      iv_push(&lzoff, zq.n);
       lidx[a][kr] = ntr++; nline++;
     }
     for (kr = 0; kr < atom->Ncont; kr++) {
@@ -574,8 +585,11 @@ static void solve_nlte(double mu, int ncol, const double *rows9, int nrow, doubl
   F.atom_model = model; F.ncoll = co.n / RHB200_CO_NFIELD; F.ncolltab = tT.n; F.coll = co.v; F.coll_T = tT.v; F.coll_coef = tC.v;
   F.coll_M = tM.v; F.line_rows = lr.v; F.NmaxScatter = input.NmaxScatter; F.NmaxIter = input.NmaxIter; F.iterLimit = input.iterLimit;
   F.plan1 = &P1;
-  CHECK(rhb200_nlte_compute1d_batch(g_ctx, &P, &F, ncol, N, nrow, mu, g_atm_scale, rows9, T.iref, atmos.wght_per_H,
-                                    atmos.vmacro_tresh, spec_out, n_out, ns_out, niter, NULL, NULL));
+  if (zq.n == 0) { iv_push(&zq, 0); dv_push(&zs, 0.0); dv_push(&zt, 0.0); }
+  F.stokes = field_free; F.line_pol = lpol.v; F.line_zoff = lzoff.v; F.zq = zq.v; F.zshift = zs.v; F.zstrength = zt.v;
+  CHECK(rhb200_nlte_compute1d_stokes_batch(g_ctx, &P, &F, ncol, N, nrow, mu, g_atm_scale, rows9, T.iref, atmos.wght_per_H,
+                                           atmos.vmacro_tresh, spec_out, quv_out, n_out, ns_out, niter, NULL, NULL));
+  free(lpol.v); free(lzoff.v); free(zq.v); free(zs.v); free(zt.v);
   for (a = 0; a < Na; a++) { free(lidx[a]); free(cidx[a]); }
   free(lidx); free(cidx); free(nlevel); free(model); free(hasline);
   free(trans.v); free(trans1.v); free(wl.v); free(ww.v); free(wa.v); free(co.v); free(tT.v); free(tC.v); free(tM.v); free(lr.v);
@@ -599,14 +613,26 @@ int pyrh_b200_solve(double mu, int get_atomic_rfs, int get_populations, int fudg
   if (input.solve_NLTE) {
     int nlev = 0;
     double *I = (double *) malloc((size_t) ncol * Ns * sizeof(double)), *pn, *ps;
+    double *quv = (double *) calloc((size_t) ncol * 3 * Ns, sizeof(double));
     for (a = 0; a < atmos.Nactiveatom; a++) nlev += atmos.activeatoms[a]->Nlevel;
     pn = (double *) malloc((size_t) ncol * nlev * N * sizeof(double)); ps = (double *) malloc((size_t) ncol * nlev * N * sizeof(double));
-    solve_nlte(mu, ncol, rows, 9, I, pn, ps, g_batch.niter);
-    for (n = 0, index = 0; n < Ns; n++) if (spectrum.lambda[n] != atmos.lambda_ref) { spec->lam[index] = spectrum.lambda[n]; spec->sI[index++] = I[n]; }
+    solve_nlte(mu, ncol, rows, 9, I, quv, pn, ps, g_batch.niter);
+    for (n = 0, index = 0; n < Ns; n++)
+      if (spectrum.lambda[n] != atmos.lambda_ref) {
+        spec->lam[index] = spectrum.lambda[n]; spec->sI[index] = I[n];
+        spec->sQ[index] = quv[n]; spec->sU[index] = quv[Ns + n]; spec->sV[index] = quv[2*(size_t) Ns + n];
+        index++;
+      }
     if (g_batch.ncol > 0) {
       int c;
       for (c = 0; c < ncol; c++)
-        for (n = 0, index = 0; n < Ns; n++) if (spectrum.lambda[n] != atmos.lambda_ref) g_batch.stokes[((size_t) c * 4) * Nlw + index++] = I[(size_t) c * Ns + n];
+        for (n = 0, index = 0; n < Ns; n++)
+          if (spectrum.lambda[n] != atmos.lambda_ref) {
+            int q;
+            g_batch.stokes[((size_t) c * 4) * Nlw + index] = I[(size_t) c * Ns + n];
+            for (q = 0; q < 3; q++) g_batch.stokes[((size_t) c * 4 + q + 1) * Nlw + index] = quv[((size_t) c * 3 + q) * Ns + n];
+            index++;
+          }
       if (g_batch.pops_n) memcpy(g_batch.pops_n, pn, (size_t) ncol * nlev * N * sizeof(double));
       if (g_batch.pops_nstar) memcpy(g_batch.pops_nstar, ps, (size_t) ncol * nlev * N * sizeof(double));
     }
@@ -619,7 +645,7 @@ int pyrh_b200_solve(double mu, int get_atomic_rfs, int get_populations, int fudg
         l0 += atom->Nlevel;
       }
     }
-    free(I); free(pn); free(ps);
+    free(I); free(quv); free(pn); free(ps);
   } else {
     const int nl = Ns, npar = T.lrf_npar;
     double *st = (double *) malloc((size_t) ncol * 4 * nl * sizeof(double)), *rf = NULL;

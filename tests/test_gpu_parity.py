@@ -1598,7 +1598,7 @@ def test_bridged_reference_library_hse_get_scales_get_ne():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", ["caii_r3", "caii_r5", "h_caii_r3", "h_caii_r5"])
+@pytest.mark.parametrize("case", ["caii_r3", "caii_r5", "h_caii_r3", "h_caii_r5", "caii_r3_ff", "h_caii_r5_ff"])
 def test_bridged_reference_library_rhf1d_nlte(case):
     """The bridged library with ACTIVE atoms: the reference's readAtom / getLambda / SortLambda state (active sets,
     line grids, continuum cross-sections) and the collisional sections of the atom files are flattened in C
@@ -1620,6 +1620,12 @@ def test_bridged_reference_library_rhf1d_nlte(case):
     b = rd.rhf1d_batch(atm[:4], wave, cwd, mu=mu, get_populations=True, nlev=n.shape[0])
     assert np.array_equal(b["stokes"][:, 0], g[f"{case}_I"][:4]) and np.array_equal(b["n"], g[f"{case}_n"][:4])
     assert np.array_equal(b["niter"], g[f"{case}_niter"][:4])
+    if case.endswith("_ff"):                        # STOKES_MODE = FIELD_FREE: the full Stokes solution after the iterations
+        quv = g[f"{case}_QUV"]
+        assert np.array_equal(np.array([o["Q"], o["U"], o["V"]]), quv[1]) and np.abs(quv[1]).max() > 0
+        assert np.array_equal(b["stokes"][:, 1:], quv[:4])
+    else:
+        assert not o["Q"].any() and not b["stokes"][:, 1:].any()
 
 
 def _ref_columns(args):
