@@ -643,7 +643,9 @@ typedef struct {
      profiles exactly as in NO_STOKES; adjustStokesMode() (zeeman.c:303-345) then recomputes the profiles of the polarizable
      lines with their Zeeman patterns (Profile(), profile.c:112-305) and the passes after Iterate() and _solveray()'s pass
      solve all four Stokes parameters where the active set or the background holds a polarised line (formal.c:86-217,
-     opacity.c:262-296, stokesopac.c:28-82).  FULL_STOKES during the MALI iterations is not implemented. */
+     opacity.c:262-296, stokesopac.c:28-82).  stokes = 2 is FULL_STOKES: polarised profiles and rays from initScatter on,
+     Gamma from I_eff = I + Q + U + V - Psi (eta + eta_Q + eta_U + eta_V) where the active set holds a polarizable
+     line (fillgamma.c:106-129).  POLARIZATION_FREE is not implemented. */
   int stokes;
   const int    *line_pol;         /* [plan->nline] line->polarizable (readatom.c:352-368) */
   const int    *line_zoff;        /* [plan->nline + 1] slice of each line in the pattern tables (0 components if not polarizable) */

@@ -70,6 +70,7 @@ struct Cols {            // device per-column arrays
   // per ray chi_Q,U,V and S_Q,U,V [ncol][nray][3][Ndep]; emergent Q,U,V [ncol][nray][3]
   const double *B, *bproj, *chi_cQ, *eta_cQ;
   double *phiQ, *chiQ, *SQ, *IemQ;
+  double *IQ;              // Stokes Q, U, V along every FULL_STOKES ray [ncol][nray][3][Ndep] (Stokes I_eff, fillgamma.c:106-129)
   const int *active;
 };
 
@@ -409,7 +410,7 @@ struct NlteFeauIO {
 // FULL_STOKES rays (formal.c:184-217): Piece_Stokes_Bezier3_1D / Piece_Stokes_1D on chi_I, S[4], K' numerators
 struct NlteStokesIO {
   const double *__restrict__ chi_, *__restrict__ S_, *__restrict__ SQ_, *__restrict__ q_;
-  double *I_, *Psi_, *IemQ_;
+  double *I_, *Psi_, *IemQ_, *IQ_;
   int ndep, kem;
   __device__ __forceinline__ double chi(int k) const { return chi_[k]; }
   __device__ __forceinline__ void K(int k, double x[3]) const {   // StokesK, stokesopac.c:72-77
@@ -421,6 +422,7 @@ struct NlteStokesIO {
   }
   __device__ __forceinline__ void storeI(int k, const double I[4]) {
     I_[k] = I[0];
+    if (IQ_) { IQ_[k] = I[1]; IQ_[ndep + k] = I[2]; IQ_[2*ndep + k] = I[3]; }
     if (k == kem) { IemQ_[0] = I[1]; IemQ_[1] = I[2]; IemQ_[2] = I[3]; }
   }
   __device__ __forceinline__ void storePsi(int k, double p) { if (Psi_) Psi_[k] = p; }
@@ -438,7 +440,7 @@ nlte_ray_stokes_kernel(Plan P, Cols C, int ncol, int eval_operator)
   if (!(P.pol_as[ns] || P.pol_c[ns])) return;              // solveStokes, formal.c:94-95
   const double *h = C.height + (size_t) col * N, *T = C.T + (size_t) col * N;
   NlteStokesIO io{C.chi + cr * N, C.S + cr * N, C.SQ + cr * 3 * N, C.chiQ + cr * 3 * N, C.I + cr * N,
-                  eval_operator ? C.Psi + cr * N : nullptr, C.IemQ + cr * 3, N, 0};
+                  eval_operator ? C.Psi + cr * N : nullptr, C.IemQ + cr * 3, eval_operator ? C.IQ + cr * 3 * N : nullptr, N, 0};
   if (P.stokes_solver == RHB200_DELO_PARABOLIC)
     rhp::stokes_parabolic_ray(io, N, h, P.muz[mu], dir, P.bc_top, P.bc_bottom, T, P.lambda[ns]);
   else
@@ -538,7 +540,7 @@ nlte_dJmax_kernel(Plan P, Cols C, int ncol, double *dJmax)
 // SEG: the thread covers one SEGMENT of its transition's wavelengths and stores partial sums (stage 1 of the
 // fixed-partition reduction, nlte_gamma_sum_kernel adds them in segment order); !SEG: the whole transition in the
 // reference's order, bit-identical to fillgamma.c.
-template <bool SEG>
+template <bool SEG, bool STK>
 __global__ void __launch_bounds__(64, 8)
 nlte_gamma_kernel(Plan P, Cols C, int ncol)
 {
@@ -564,6 +566,9 @@ nlte_gamma_kernel(Plan P, Cols C, int ncol)
   for (int ns = ns_first; ns < ns_last; ns++) {
     const int first = P.as_first[ns], nact = P.as_first[ns+1] - first;
     const int ad = P.angle_dep[ns];
+    const bool pol = STK && P.pol_as[ns];        // FULL_STOKES && containsPolarized(as), fillgamma.c:106,122
+    const size_t plane = (size_t) ncol * P.nphirow * N;
+    double e_el[STK ? NLTE_MAXACT : 1];          // Bij hc/4pi (2h nu^3/c^2) g_ij n_j of polarizable lines (opacity.c:283-284)
     // ---- entries of this atom at this wavelength (ray independent part)
     int    e_flag[NLTE_MAXACT];                 // bit0 im==i, bit1 jm==j, bit2 jm==i, bit3 self, bit4 thn != 0, bit5 line
     double e_w[NLTE_MAXACT], e_diff[NLTE_MAXACT], e_tg[NLTE_MAXACT], e_nj[NLTE_MAXACT], e_c[NLTE_MAXACT];
@@ -583,6 +588,10 @@ nlte_gamma_kernel(Plan P, Cols C, int ncol)
       const bool line = tr[TR_TYPE] == 0.0;
       e_flag[m] = (im == i ? 1 : 0) | (jm == j ? 2 : 0) | (jm == i ? 4 : 0) | (tm == tid ? 8 : 0) |
                   (thn != 0.0 ? 16 : 0) | (line ? 32 : 0);
+      if (STK) {
+        const bool lp = pol && line && P.line_pol[(int) tr[TR_LINEIDX]] != 0;
+        if (lp) { e_flag[m] |= 64; e_el[m] = hc_4PI * tr[TR_BIJ] * tr[TR_ISOFRAC] * thn * g * n_j; }
+      }
       e_w[m] = w; e_diff[m] = n_i - g*n_j; e_tg[m] = thn * g; e_nj[m] = n_j;
       if (line) {                                // V = Bij hc/4pi phi(ray), opacity.c:188-193
         e_c[m] = hc_4PI * tr[TR_BIJ] * tr[TR_ISOFRAC];
@@ -604,6 +613,7 @@ nlte_gamma_kernel(Plan P, Cols C, int ncol)
       double Iv[NLTE_RB], Pv[NLTE_RB], wmuv[NLTE_RB];
       int lamu[NLTE_RB];
       double eta_atom[NLTE_RB], chi_up_i[NLTE_RB], Uji_down_j[NLTE_RB], chi_down_j[NLTE_RB], Uji_down_i[NLTE_RB], Vs[NLTE_RB];
+      double eQ[STK ? NLTE_RB : 1], eU[STK ? NLTE_RB : 1], eV[STK ? NLTE_RB : 1], Iq[STK ? NLTE_RB : 1], Iu[STK ? NLTE_RB : 1], Iv4[STK ? NLTE_RB : 1];
       double ws = 0.0;
 #pragma unroll
       for (int q = 0; q < NLTE_RB; q++) {
@@ -616,6 +626,13 @@ nlte_gamma_kernel(Plan P, Cols C, int ncol)
           Pv[q] = __ldg(C.Psi + rk) / __ldg(C.chi + rk);           // formal.c:248 / :301
           wmuv[q] = ad ? 0.5 * P.wmu[mu] : P.wmu[mu];
           lamu[q] = 2*mu + P.ray_dir[r];
+        }
+        if (STK) {
+          eQ[q] = eU[q] = eV[q] = Iq[q] = Iu[q] = Iv4[q] = 0.0;
+          if (pol && q < nb) {
+            const double *iq = C.IQ + (((size_t) col * P.nray + r0 + q) * 3) * N + k;
+            Iq[q] = __ldg(iq); Iu[q] = __ldg(iq + N); Iv4[q] = __ldg(iq + 2*(size_t) N);
+          }
         }
       }
       for (int e = 0; e < m; e++) {               // entries in active-set order: per-ray sums keep their order
@@ -639,12 +656,22 @@ nlte_gamma_kernel(Plan P, Cols C, int ncol)
           }
           if (f & 8) Vs[q] = V[q];
         }
+        if (STK && (f & 64)) {                      // eta_Q,U,V of this atom (opacity.c:283-291)
+          const double el = e_el[e];
+#pragma unroll
+          for (int q = 0; q < NLTE_RB; q++)
+            if (q < nb) {
+              const double *pq = C.phiQ + (size_t) (ph - C.phi) + (size_t) lamu[q] * N;
+              eQ[q] += el * __ldg(pq); eU[q] += el * __ldg(pq + plane); eV[q] += el * __ldg(pq + 2*plane);
+            }
+        }
       }
 #pragma unroll
       for (int q = 0; q < NLTE_RB; q++) {
         if (q < nb) {
           const double I = Iv[q], Psi = Pv[q], wmu = wmuv[q];
-          const double Ieff = I - Psi * eta_atom[q];               // fillgamma.c:130-133
+          const double Ieff = (STK && pol) ? I + Iq[q] + Iu[q] + Iv4[q] - Psi * (eta_atom[q] + eQ[q] + eU[q] + eV[q])   // fillgamma.c:122-128
+                                           : I - Psi * eta_atom[q];               // fillgamma.c:130-133
           const double wlamu = Vs[q] * ws * wmu;
           Gji += Ieff * wlamu;                                     // fillgamma.c:163-168
           Gij += (thns + Ieff) * gs * wlamu;
@@ -1094,7 +1121,7 @@ struct NlteEngine {
     size_t d = (size_t) N * ((size_t) ngam + 2*(size_t) Nt + 2*(size_t) nas + 6*(size_t) nray + (size_t) Ns + nphirow + nline +
                              (exact_rates ? 0 : 4*(size_t) nseg)) + nray + prev_off[Na] + Na;
     if (own_inputs) d += (size_t) N * (2 + 2*(size_t) nlev + Na + ngam + nline + Na + 1 + 4*(size_t) Ns);
-    if (has_zeeman) d += (size_t) N * (1 + 3*(size_t) Nr + 3*(size_t) nphirow + 6*(size_t) Ns + 6*(size_t) nray) + 3*(size_t) nray;
+    if (has_zeeman) d += (size_t) N * (1 + 3*(size_t) Nr + 3*(size_t) nphirow + 6*(size_t) Ns + 9*(size_t) nray) + 3*(size_t) nray;
     return d;
   }
 
@@ -1119,7 +1146,7 @@ struct NlteEngine {
       RH_CHECK(ar.alloc(&C.phiQ, cN*nphirow*3, true));
       RH_CHECK(ar.alloc(&d_chi_cQ, cN*Ns*3, true)); RH_CHECK(ar.alloc(&d_eta_cQ, cN*Ns*3, true));
       C.chi_cQ = d_chi_cQ; C.eta_cQ = d_eta_cQ;
-      RH_CHECK(ar.alloc(&C.chiQ, cN*nray*3)); RH_CHECK(ar.alloc(&C.SQ, cN*nray*3));
+      RH_CHECK(ar.alloc(&C.chiQ, cN*nray*3)); RH_CHECK(ar.alloc(&C.SQ, cN*nray*3)); RH_CHECK(ar.alloc(&C.IQ, cN*nray*3));
       RH_CHECK(ar.alloc(&C.IemQ, (size_t) ncol*nray*3, true));
     }
     active.assign(ncol, 1);
@@ -1276,18 +1303,21 @@ struct NlteEngine {
     std::vector<int> niter(ncol, 0);
     active.assign(ncol, 1);
     int nactive = ncol;
-    if (P.stokes && NmaxIter > 0) { rhb200_set_error("MALI iterations with FULL_STOKES radiation (Stokes I_eff, fillgamma.c:106-129) are not implemented: use STOKES_MODE = FIELD_FREE"); return RHB200_EUNSUPPORTED; }
     for (int it = 1; it <= NmaxIter && nactive > 0; it++) {
       { ScopedKernelTimer t(c, RHB200_K_OTHER);
         nlte_gamma_init_kernel<<<RH_GRID(cN*ngam, 256), 0, st>>>(P, C, ncol); }
       { ScopedKernelTimer t(c, RHB200_K_OPACITY);
-        nlte_opacity_kernel<<<(unsigned) (((cN + 127) / 128) * Ns), 128, 0, st>>>(P, C, ncol); }
+        nlte_opacity_kernel<<<(unsigned) (((cN + 127) / 128) * Ns), 128, 0, st>>>(P, C, ncol);
+        if (P.stokes) nlte_opacity_quv_kernel<<<(unsigned) (((cN + 127) / 128) * Ns), 128, 0, st>>>(P, C, ncol); }
       { ScopedKernelTimer t(c, RHB200_K_BEZIER);
         launch_rays(1); }
       { ScopedKernelTimer t(c, RHB200_K_GAMMA);
-        if (exact_rates) nlte_gamma_kernel<false><<<dim3((unsigned) ((cN + 63) / 64), (unsigned) Nt), 64, 0, st>>>(P, C, ncol);
-        else {
-          nlte_gamma_kernel<true><<<dim3((unsigned) ((cN + 63) / 64), (unsigned) nseg), 64, 0, st>>>(P, C, ncol);
+        if (exact_rates) {
+          if (P.stokes) nlte_gamma_kernel<false, true><<<dim3((unsigned) ((cN + 63) / 64), (unsigned) Nt), 64, 0, st>>>(P, C, ncol);
+          else nlte_gamma_kernel<false, false><<<dim3((unsigned) ((cN + 63) / 64), (unsigned) Nt), 64, 0, st>>>(P, C, ncol);
+        } else {
+          if (P.stokes) nlte_gamma_kernel<true, true><<<dim3((unsigned) ((cN + 63) / 64), (unsigned) nseg), 64, 0, st>>>(P, C, ncol);
+          else nlte_gamma_kernel<true, false><<<dim3((unsigned) ((cN + 63) / 64), (unsigned) nseg), 64, 0, st>>>(P, C, ncol);
           nlte_gamma_sum_kernel<<<RH_GRID(cN*Nt, 128), 0, st>>>(P, C, ncol);
         } }
       { ScopedKernelTimer t(c, RHB200_K_J);

@@ -1438,6 +1438,40 @@ def test_nlte_field_free_full_stokes_solution(case):
     host.close_sessions()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["caii_r3_fs", "h_caii_r3_fs"])
+def test_nlte_full_stokes_iterations(case):
+    """STOKES_MODE = FULL_STOKES with ACTIVE atoms: Zeeman profiles, Stokes rays with the approximate operator and
+    I_eff = I + Q + U + V - Psi (eta + eta_Q + eta_U + eta_V) (fillgamma.c:106-129) in EVERY MALI iteration.  Perturbed
+    columns with B up to 2.5 kG.  On two of the eight columns the reference itself ends in NaN populations after 2 / 7
+    iterations; on the other six: iteration count identical, populations, I, Q, U, V bit-identical (bars: 1e-6 / 1e-9 /
+    1e-12 of the continuum)."""
+    from pyrh_b200 import nlte_host
+    g, cwd = _nlte_front_case(case)
+    atm, wave, mu = g["atmosphere"], g[f"{case}_wave"], float(g[f"{case}_mu"])
+    s = nlte_host.NlteSession(cwd, wave)
+    try:
+        res = s.compute(atm, mu=mu)
+    finally:
+        s.close()
+    ok = np.isfinite(g[f"{case}_n"]).reshape(len(atm), -1).all(axis=1)
+    assert ok.sum() >= 6
+    ref = g[f"{case}_QUV"][ok]
+    got = np.stack([res["Q"], res["U"], res["V"]], axis=1)[ok]
+    Ic = g[f"{case}_I"][ok].max(axis=1)[:, None, None]
+    en = float(np.max(np.abs(res["n"][ok] / g[f"{case}_n"][ok] - 1)))
+    eI = float(np.max(np.abs(res["I"][ok] / g[f"{case}_I"][ok] - 1)))
+    eP = float(np.max(np.abs(got - ref) / Ic))
+    REPORT[f"nlte_full_stokes_{case}"] = dict(niter=res["niter"].tolist(), niter_ref=g[f"{case}_niter"].tolist(), n_maxrel=en,
+                                              I_maxrel=eI, QUV_over_Ic=eP, n_exact=bool(np.array_equal(res["n"][ok], g[f"{case}_n"][ok])),
+                                              IQUV_exact=bool(np.array_equal(got, ref) and np.array_equal(res["I"][ok], g[f"{case}_I"][ok])),
+                                              reference_nan_columns=np.nonzero(~ok)[0].tolist(),
+                                              ours_nan_columns=np.nonzero(~np.isfinite(res["n"]).reshape(len(atm), -1).all(axis=1))[0].tolist())
+    assert np.array_equal(res["niter"][ok], g[f"{case}_niter"][ok])
+    assert en <= 1e-6 and eI <= 1e-9 and eP <= 1e-12
+    assert np.array_equal(res["n"][ok], g[f"{case}_n"][ok]) and np.array_equal(got, ref)
+
+
 def json_keys(g, case):
     import json
     return json.loads(str(g["cases"]))[case]["keys"]
@@ -1598,7 +1632,7 @@ def test_bridged_reference_library_hse_get_scales_get_ne():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", ["caii_r3", "caii_r5", "h_caii_r3", "h_caii_r5", "caii_r3_ff", "h_caii_r5_ff"])
+@pytest.mark.parametrize("case", ["caii_r3", "caii_r5", "h_caii_r3", "h_caii_r5", "caii_r3_ff", "h_caii_r5_ff", "caii_r3_fs"])
 def test_bridged_reference_library_rhf1d_nlte(case):
     """The bridged library with ACTIVE atoms: the reference's readAtom / getLambda / SortLambda state (active sets,
     line grids, continuum cross-sections) and the collisional sections of the atom files are flattened in C
@@ -1620,7 +1654,7 @@ def test_bridged_reference_library_rhf1d_nlte(case):
     b = rd.rhf1d_batch(atm[:4], wave, cwd, mu=mu, get_populations=True, nlev=n.shape[0])
     assert np.array_equal(b["stokes"][:, 0], g[f"{case}_I"][:4]) and np.array_equal(b["n"], g[f"{case}_n"][:4])
     assert np.array_equal(b["niter"], g[f"{case}_niter"][:4])
-    if case.endswith("_ff"):                        # STOKES_MODE = FIELD_FREE: the full Stokes solution after the iterations
+    if case.endswith("_ff") or case.endswith("_fs"):   # FIELD_FREE / FULL_STOKES: the full Stokes solution
         quv = g[f"{case}_QUV"]
         assert np.array_equal(np.array([o["Q"], o["U"], o["V"]]), quv[1]) and np.abs(quv[1]).max() > 0
         assert np.array_equal(b["stokes"][:, 1:], quv[:4])
