@@ -651,6 +651,15 @@ typedef struct {
   const int    *line_zoff;        /* [plan->nline + 1] slice of each line in the pattern tables (0 components if not polarizable) */
   const int    *zq;               /* Zeeman(line), zeeman.c:186-281 (rhb200_zeeman): q, shift, strength */
   const double *zshift, *zstrength;
+  /* angle-averaged partial redistribution (zero-initialise for CRD): line->PRD of every ACTIVE line (readatom.c:255-258:
+     shape PRD and PRD_N_MAX_ITER > 0) and the keywords PRD_N_MAX_ITER, PRD_ITER_LIMIT.  After updatePopulations() of
+     every MALI iteration Redistribute() (redistribute.c:38-106) runs PRDScatter() (scatter.c:51-290: Gouttebroze's GII,
+     linear interpolation of J, no cross redistribution) for each PRD line and solveSpectrum(FALSE, TRUE) over their
+     wavelengths, per column until the profile ratio rho changes by less than the limit.  PRD_NG_ORDER > 0,
+     PRD_ANGLE_DEP and XRD are not implemented. */
+  const int    *line_prd;         /* [plan->nline] or NULL */
+  int PRD_NmaxIter;
+  double PRDiterLimit;
 } rhb200_nlte_front;
 /* atmosphere [ncol][nrow][ndep] as in rhb200_compute1d_batch.  Out (any may be NULL): spectrum [ncol][Nspect] = spectrum.I[][0]
    of the final pass on plan->lambda (lambda_ref included; _solveray drops it), pops_n / pops_nstar [ncol][sum Nlevel][ndep]

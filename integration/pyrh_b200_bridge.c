@@ -504,7 +504,7 @@ static void solve_nlte(double mu, int ncol, const double *rows9, int nrow, doubl
   rhb200_nlte_plan P, P1;
   rhb200_nlte_front F;
   dvec trans = {0}, trans1 = {0}, wl = {0}, ww = {0}, wa = {0}, co = {0}, tT = {0}, tC = {0}, tM = {0}, lr = {0};
-  ivec asf = {0}, ast = {0}, lpol = {0}, lzoff = {0}, zq = {0};
+  ivec asf = {0}, ast = {0}, lpol = {0}, lzoff = {0}, zq = {0}, lprd = {0};
   dvec zs = {0}, zt = {0};
   const int field_free = input.StokesMode == FIELD_FREE || input.StokesMode == FULL_STOKES;    /* polarised passes needed */
   int *nlevel = (int *) malloc(Na * sizeof(int)), *model = (int *) malloc(Na * sizeof(int)), *hasline = (int *) malloc(Ns * sizeof(int));
@@ -523,7 +523,9 @@ static void solve_nlte(double mu, int ncol, const double *rows9, int nrow, doubl
     for (kr = 0; kr < atom->Nline; kr++) {                 /* device order: an atom's lines, then its continua */
       AtomicLine *L = &atom->line[kr];
       double r[RHB200_TR_NFIELD], pr[NPL];
-      if (L->PRD) FAIL("PRD lines are not implemented: set PRD_N_MAX_ITER = 0");
+      if (L->PRD && (input.PRD_angle_dep || input.XRD)) FAIL("PRD_ANGLE_DEP / XRD (angle-dependent and cross redistribution) are not implemented");
+      if (L->PRD && input.PRD_Ngorder > 0) FAIL("PRD_NG_ORDER > 0 is not implemented");
+      iv_push(&lprd, L->PRD ? 1 : 0);
       if (L->Ncomponent > 1) FAIL("multi-component ACTIVE lines are not implemented");
       memset(r, 0, sizeof r);
       r[RHB200_TR_ATOM] = a; r[RHB200_TR_TYPE] = 0; r[RHB200_TR_I] = L->i; r[RHB200_TR_J] = L->j; r[RHB200_TR_NBLUE] = L->Nblue;
@@ -586,10 +588,11 @@ static void solve_nlte(double mu, int ncol, const double *rows9, int nrow, doubl
   F.coll_M = tM.v; F.line_rows = lr.v; F.NmaxScatter = input.NmaxScatter; F.NmaxIter = input.NmaxIter; F.iterLimit = input.iterLimit;
   F.plan1 = &P1;
   if (zq.n == 0) { iv_push(&zq, 0); dv_push(&zs, 0.0); dv_push(&zt, 0.0); }
+  F.line_prd = lprd.v; F.PRD_NmaxIter = input.PRD_NmaxIter; F.PRDiterLimit = input.PRDiterLimit;
   F.stokes = input.StokesMode == FULL_STOKES ? 2 : (input.StokesMode == FIELD_FREE ? 1 : 0); F.line_pol = lpol.v; F.line_zoff = lzoff.v; F.zq = zq.v; F.zshift = zs.v; F.zstrength = zt.v;
   CHECK(rhb200_nlte_compute1d_stokes_batch(g_ctx, &P, &F, ncol, N, nrow, mu, g_atm_scale, rows9, T.iref, atmos.wght_per_H,
                                            atmos.vmacro_tresh, spec_out, quv_out, n_out, ns_out, niter, NULL, NULL));
-  free(lpol.v); free(lzoff.v); free(zq.v); free(zs.v); free(zt.v);
+  free(lprd.v); free(lpol.v); free(lzoff.v); free(zq.v); free(zs.v); free(zt.v);
   for (a = 0; a < Na; a++) { free(lidx[a]); free(cidx[a]); }
   free(lidx); free(cidx); free(nlevel); free(model); free(hasline);
   free(trans.v); free(trans1.v); free(wl.v); free(ww.v); free(wa.v); free(co.v); free(tT.v); free(tC.v); free(tM.v); free(lr.v);

@@ -9,6 +9,8 @@ ACTIVE atoms, and the number of MALI iterations (counted from the probe's update
     caii_r3_ff / h_caii_r5_ff   the same with STOKES_MODE = FIELD_FREE: field-free iterations, then adjustStokesMode()
                                 and the full Stokes solution (I, Q, U, V recorded; the columns carry B up to 2.5 kG)
     caii_r3_fs / h_caii_r3_fs   STOKES_MODE = FULL_STOKES: polarised profiles, rays and I_eff in every MALI iteration
+    caii_r3_prd / caii_r5_prd1  angle-averaged PRD in Ca II H & K: PRD_N_MAX_ITER 3 / 1 (the shipped
+                                keyword.input.NLTE has 1), user grid inside Ca II K for the first
 
     python -m oracle.gen_golden_nlte_front
 """
@@ -42,6 +44,10 @@ CASES = {
                        keys=("CA",), mu=0.9),
     "h_caii_r3_fs": dict(kw=dict(KW, NRAYS=3, HYDROGEN_LTE="FALSE", STOKES_MODE="FULL_STOKES"), active=("H_6.atom",),
                          wave=(630.25, 630.5, 21), keys=("H ", "CA"), mu=1.0),
+    "caii_r3_prd": dict(kw=dict(KW, NRAYS=3, HYDROGEN_LTE="TRUE", PRD_N_MAX_ITER=3, PRD_ITER_LIMIT="1.0E-2"), active=(),
+                        wave=(393.2, 393.5, 31), keys=("CA",), mu=1.0),
+    "caii_r5_prd1": dict(kw=dict(KW, NRAYS=5, HYDROGEN_LTE="TRUE", PRD_N_MAX_ITER=1, PRD_ITER_LIMIT="1.0E-2"), active=(),
+                         wave=(854.2, 854.7, 41), keys=("CA",), mu=0.8),
     "h_caii_r5_ff": dict(kw=dict(KW, NRAYS=5, HYDROGEN_LTE="FALSE", STOKES_MODE="FIELD_FREE"), active=("H_6.atom",),
                          wave=(630.25, 630.5, 21), keys=("H ", "CA"), mu=0.8),
 }
@@ -56,7 +62,22 @@ def workdir(case):
     return rd.make_workdir("tests", keywords=c["kw"], atoms_active=c["active"], atoms_extra=(("CaII.atom", "ACTIVE"),))
 
 
+def one_column(case, col, path):
+    """child process: one column of one case through the reference (it exit()s on some columns: "Singular matrix")"""
+    c = CASES[case]
+    base = np.load(GOLD / "falc_base.npy")
+    atm = synthetic.perturbed_batch(base, max(COLUMNS) + 1, ndep=70)[list(COLUMNS)]
+    o = rd.rhf1d(atm[col], np.linspace(*c["wave"]), workdir(case), mu=c["mu"], probe=rd.PROBE_NLTE, get_populations=True)
+    R = recs_by_tag(o["records"])
+    np.savez(path, nit=len({m[1] for m, _ in R["up_n"]}), I=o["I"], quv=np.array([o["Q"], o["U"], o["V"]]), lam=o["lam"],
+             n=np.concatenate([o["pops"][k]["n"] for k in c["keys"]]), ns=np.concatenate([o["pops"][k]["nstar"] for k in c["keys"]]))
+
+
 def main():
+    import subprocess
+    import tempfile
+    if len(sys.argv) > 1 and sys.argv[1] == "--one":
+        return one_column(sys.argv[2], int(sys.argv[3]), sys.argv[4])
     base = np.load(GOLD / "falc_base.npy")
     atm = synthetic.perturbed_batch(base, max(COLUMNS) + 1, ndep=70)[list(COLUMNS)]
     out = dict(atmosphere=atm)
@@ -67,25 +88,32 @@ def main():
     for case, c in CASES.items():
         if only and case not in only:
             continue
-        cwd = workdir(case)
         wave = np.linspace(*c["wave"])
-        I, n, ns, nit, quv = [], [], [], [], []
+        I, n, ns, nit, quv, ok = [], [], [], [], [], []
         for col in range(NCOL):
-            o = rd.rhf1d(atm[col], wave, cwd, mu=c["mu"], probe=rd.PROBE_NLTE, get_populations=True)
-            R = recs_by_tag(o["records"])
-            nit.append(len({m[1] for m, _ in R["up_n"]}))
-            I.append(o["I"])
-            quv.append(np.array([o["Q"], o["U"], o["V"]]))
-            n.append(np.concatenate([o["pops"][k]["n"] for k in c["keys"]]))
-            ns.append(np.concatenate([o["pops"][k]["nstar"] for k in c["keys"]]))
-            lam = o["lam"]
+            with tempfile.TemporaryDirectory() as td:
+                f = str(Path(td) / "col.npz")
+                r = subprocess.run([sys.executable, "-m", "oracle.gen_golden_nlte_front", "--one", case, str(col), f],
+                                   cwd=str(ROOT), capture_output=True, text=True)
+                if r.returncode != 0 or not Path(f).exists():
+                    ok.append(0)
+                    print(f"[golden] {case} column {col}: the reference exited ({r.stdout.strip()[-60:]!r})", flush=True)
+                    continue
+                o = dict(np.load(f))
+            ok.append(1)
+            nit.append(int(o["nit"])); I.append(o["I"]); quv.append(o["quv"]); n.append(o["n"]); ns.append(o["ns"]); lam = o["lam"]
             print(f"[golden] {case} column {col}: {nit[-1]} iterations, {len(lam)} wavelengths", flush=True)
-        out.update({f"{case}_wave": wave, f"{case}_lam": lam, f"{case}_I": np.array(I), f"{case}_n": np.array(n),
-                    f"{case}_nstar": np.array(ns), f"{case}_niter": np.array(nit, np.int32),
-                    f"{case}_mu": np.float64(c["mu"])})
+        ok = np.array(ok, bool)
+
+        def full(rows):                              # columns the reference aborted on are NaN / -1
+            a = np.full((NCOL,) + rows[0].shape, np.nan)
+            a[ok] = np.array(rows)
+            return a
+        nit_all = np.full(NCOL, -1, np.int32); nit_all[ok] = nit
+        out.update({f"{case}_wave": wave, f"{case}_lam": lam, f"{case}_I": full(I), f"{case}_n": full(n),
+                    f"{case}_nstar": full(ns), f"{case}_niter": nit_all, f"{case}_mu": np.float64(c["mu"])})
         if c["kw"]["STOKES_MODE"] != "NO_STOKES":
-            out[f"{case}_QUV"] = np.array(quv)
-            print(f"[golden] {case}: max |Q|, |U|, |V| / max I =", np.abs(np.array(quv)).max(axis=(0, 2)) / np.array(I).max())
+            out[f"{case}_QUV"] = full(quv)
     out["cases"] = np.array(json.dumps({k: dict(kw=v["kw"], active=list(v["active"]), keys=list(v["keys"])) for k, v in CASES.items()}))
     np.savez_compressed(GOLD / "nlte_front.npz", **out)
     print(f"[golden] nlte_front.npz: {(GOLD / 'nlte_front.npz').stat().st_size/1e6:.2f} MB")

@@ -213,7 +213,7 @@ int rh_launch_opacity_addI(rhb200_ctx *ctx, int ncol, int ndep, int to_obs, cons
 int rh_launch_add_molecular(rhb200_ctx *ctx, int ncol, int ndep, const double *d_molchi, const double *d_moleta,
                             double *d_chi_c, double *d_eta_c);
 int rh_launch_line_damping(rhb200_ctx *ctx, int ncol, int ndep, int nline, const double *d_plrows, const double *d_atmos,
-                           const double *d_pops, int nlev, double *d_pcol);
+                           const double *d_pops, int nlev, double *d_pcol, double *d_qelast = nullptr);
 int rh_launch_opacity_raw(rhb200_ctx *ctx, int ncol, int ndep, int to_obs,
                           const double *d_atmos, const double *d_lineprep,
                           double *d_chi, double *d_eta /* [ncol][nlambda][4][ndep] */);

@@ -589,7 +589,8 @@ passive_bb_kernel(int accumulate, int ncol, int nlambda, int ndep, int nline, do
 // Damping() (broad.c:273-314: van der Waals + quadratic Stark + hydrogen's linear Stark, in that order) -> pcol.
 __global__ void __launch_bounds__(128)
 passive_prep_kernel(int ncol, int ndep, int npl, int nlev, const double *__restrict__ plrows,
-                    const double *__restrict__ atmos, const double *__restrict__ pops, double *__restrict__ pcol)
+                    const double *__restrict__ atmos, const double *__restrict__ pops, double *__restrict__ pcol,
+                    double *__restrict__ qelast_out /* line->Qelast [ncol][npl][ndep] (broad.c:305-308) or NULL */)
 {
   const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t) ncol * npl * ndep) return;
@@ -600,9 +601,8 @@ passive_prep_kernel(int ncol, int ndep, int npl, int nlev, const double *__restr
   const double T = at[RHB200_AT_T*ndep + k], ne = at[RHB200_AT_NE*ndep + k], vturb = at[RHB200_AT_VTURB*ndep + k];
   const double vtherm = 2.0*RH_KBOLTZMANN/(RH_AMU * L[RHB200_PL_WEIGHT]);
   const double vbroad = sqrt(vtherm*T + vturb*vturb);
-  double adamp = 0.0;
+  double adamp = 0.0, Qelast = 0.0;
   if (L[RHB200_PL_VOIGT] != 0.0) {
-    double Qelast = 0.0;
     const int vdw = (int) L[RHB200_PL_VDW_TYPE];
     if (vdw >= 0) {                                                            // VanderWaals, broad.c:60-140
       double GvdW;
@@ -629,6 +629,7 @@ passive_prep_kernel(int ncol, int ndep, int npl, int nlev, const double *__restr
   o[ndep] = P[(size_t) ((int) L[RHB200_PL_LEVEL_J]) * ndep];
   o[2*(size_t) ndep] = vbroad;
   o[3*(size_t) ndep] = adamp;
+  if (qelast_out) qelast_out[t] = Qelast;
 }
 
 __global__ void voigt_kernel(int n, const double *__restrict__ a, const double *__restrict__ v,
@@ -740,7 +741,7 @@ int rh_passive_chunk(rhb200_ctx *ctx, int ncol, int ndep, double muz, const doub
   {
     ScopedKernelTimer t(ctx, RHB200_K_PREP);
     const size_t n = (size_t) ncol * w.npl * ndep;
-    passive_prep_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, ctx->stream>>>(ncol, ndep, w.npl, nlev, w.pl_rows, d_atmos, d_pops, d_pcol);
+    passive_prep_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, ctx->stream>>>(ncol, ndep, w.npl, nlev, w.pl_rows, d_atmos, d_pops, d_pcol, nullptr);
   }
   {
     ScopedKernelTimer t(ctx, RHB200_K_OPACITY);
@@ -871,12 +872,12 @@ int rh_launch_add_molecular(rhb200_ctx *ctx, int ncol, int ndep, const double *d
 // Damping() + Doppler width of an arbitrary line table (rows RHB200_PL_*): the ACTIVE lines of the NLTE front end.
 // d_pcol [ncol][nline][4][ndep] = n_i, n_j, vbroad, adamp
 int rh_launch_line_damping(rhb200_ctx *ctx, int ncol, int ndep, int nline, const double *d_plrows, const double *d_atmos,
-                           const double *d_pops, int nlev, double *d_pcol)
+                           const double *d_pops, int nlev, double *d_pcol, double *d_qelast)
 {
   const size_t n = (size_t) ncol * nline * ndep;
   if (n == 0) return RHB200_OK;
   ScopedKernelTimer t(ctx, RHB200_K_PREP);
-  passive_prep_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, ctx->stream>>>(ncol, ndep, nline, nlev, d_plrows, d_atmos, d_pops, d_pcol);
+  passive_prep_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, ctx->stream>>>(ncol, ndep, nline, nlev, d_plrows, d_atmos, d_pops, d_pcol, d_qelast);
   RH_CUDA(cudaGetLastError());
   return RHB200_OK;
 }

@@ -58,6 +58,10 @@ struct Plan {            // device copy of the shared problem structure
   const int *line_pol, *line_zoff, *zq;         // [nline] line->polarizable, [nline+1] slices of the Zeeman pattern tables
   const double *zshift, *zstrength;
   const int *pol_as, *pol_c;                    // [Nspect] containsPolarized(as) (with StokesMode FULL_STOKES), backgrflags.ispolarized
+  // angle-averaged PRD (scatter.c:51-290, redistribute.c:38-106): the PRD lines, their rows in rho, containsPRDline(as)
+  int nprd, nrho;
+  const int *prd_tr, *prd_roff, *tr_prd, *prd_ns;
+  const int *ns_mask;                           // solveSpectrum(.., redistribute = TRUE): only these wavelengths (or NULL: all)
 };
 
 struct Cols {            // device per-column arrays
@@ -70,6 +74,8 @@ struct Cols {            // device per-column arrays
   // per ray chi_Q,U,V and S_Q,U,V [ncol][nray][3][Ndep]; emergent Q,U,V [ncol][nray][3]
   const double *B, *bproj, *chi_cQ, *eta_cQ;
   double *phiQ, *chiQ, *SQ, *IemQ;
+  double *rho;             // line->rho_prd [ncol][nrho][Ndep] of the PRD lines (profile ratio of emission to absorption)
+  const double *Qelast;    // line->Qelast [ncol][nline][Ndep] (Damping(), broad.c:305-308)
   double *IQ;              // Stokes Q, U, V along every FULL_STOKES ray [ncol][nray][3][Ndep] (Stokes I_eff, fillgamma.c:106-129)
   const int *active;
 };
@@ -95,6 +101,8 @@ nlte_setup_kernel(Plan P, Cols C, int ncol)
   double g, w;
   if (tr[TR_TYPE] == 0.0) {
     g = tr[TR_BJI] / tr[TR_BIJ];
+    if (P.nprd > 0 && P.tr_prd[tr_id] >= 0)      // PRD correction to the emission profile, opacity.c:207-217
+      g *= C.rho[((size_t) col * P.nrho + P.prd_roff[P.tr_prd[tr_id]] + la) * N + k];
     const double wlambda = P.tr_wlambda[(int) tr[TR_WOFF] + la];
     w = wlambda * C.wphi[((size_t) col * P.nline + (int) tr[TR_LINEIDX]) * N + k] / hc_4PI;
   } else {
@@ -259,6 +267,7 @@ nlte_opacity_kernel(Plan P, Cols C, int ncol)
   const int k = (int) (t % N), col = (int) (t / N);
   if (!C.active[col]) return;
   if (ns < P.ns_lo || ns >= P.ns_hi) return;           // another rank's wavelength
+  if (P.ns_mask && !P.ns_mask[ns]) return;
   const int first = P.as_first[ns], nact = P.as_first[ns+1] - first;
   const double *ncol_ = C.n + (size_t) col * P.nlev * N;
   const double hc_4PI = (RH_HPLANCK * RH_CLIGHT) / (4.0 * RH_PI);
@@ -335,6 +344,7 @@ nlte_opacity_quv_kernel(Plan P, Cols C, int ncol)
   const int k = (int) (t % N), col = (int) (t / N);
   if (!C.active[col]) return;
   if (ns < P.ns_lo || ns >= P.ns_hi) return;
+  if (P.ns_mask && !P.ns_mask[ns]) return;
   const int pol_as = P.pol_as[ns], pol_c = P.pol_c[ns];
   if (!pol_as && !pol_c) return;
   const int first = P.as_first[ns], nact = P.as_first[ns+1] - first;
@@ -437,6 +447,7 @@ nlte_ray_stokes_kernel(Plan P, Cols C, int ncol, int eval_operator)
   if (!C.active[col]) return;
   const int ns = P.ray_ns[r], mu = P.ray_mu[r], dir = P.ray_dir[r];
   if (ns < P.ns_lo || ns >= P.ns_hi) return;
+  if (P.ns_mask && !P.ns_mask[ns]) return;
   if (!(P.pol_as[ns] || P.pol_c[ns])) return;              // solveStokes, formal.c:94-95
   const double *h = C.height + (size_t) col * N, *T = C.T + (size_t) col * N;
   NlteStokesIO io{C.chi + cr * N, C.S + cr * N, C.SQ + cr * 3 * N, C.chiQ + cr * 3 * N, C.I + cr * N,
@@ -459,6 +470,7 @@ nlte_ray_kernel(Plan P, Cols C, int ncol, int eval_operator)
   if (!C.active[col]) return;
   const int ns = P.ray_ns[r], mu = P.ray_mu[r], dir = P.ray_dir[r];
   if (ns < P.ns_lo || ns >= P.ns_hi) return;
+  if (P.ns_mask && !P.ns_mask[ns]) return;
   if (P.stokes && (P.pol_as[ns] || P.pol_c[ns])) return;   // nlte_ray_stokes_kernel
   const double *h = C.height + (size_t) col * N, *T = C.T + (size_t) col * N;
   double *Psi = eval_operator ? C.Psi + cr * N : nullptr;
@@ -491,6 +503,7 @@ nlte_J_kernel(Plan P, Cols C, int ncol)
   const int ns = (int) (cl % P.Nspect), col = (int) (cl / P.Nspect);
   if (!C.active[col]) return;
   if (ns < P.ns_lo || ns >= P.ns_hi) return;
+  if (P.ns_mask && !P.ns_mask[ns]) return;
   const int ad = P.angle_dep[ns];
   double J = 0.0;
   const int r_end = P.ray_off[ns+1];
@@ -509,6 +522,169 @@ nlte_J_kernel(Plan P, Cols C, int ncol)
   const double Jdag = C.J[t];
   C.J[t] = J;
   C.dJ[t] = fabs(1.0 - Jdag / J);
+}
+
+// ---- angle-averaged PRD.  GII: Gouttebroze's approximation with Uitenbroek's cross-redistribution form (giigen.c:87-147)
+#define PRD_QCORE   2.0
+#define PRD_QWING   4.0
+#define PRD_QSPREAD 5.0
+#define PRD_DQ      0.25
+__device__ __forceinline__ double prd_gzero(double x) { return 1.0 / (fabs(x) + sqrt(x*x + 1.273239545)); }
+__device__ __forceinline__ double prd_gii(double adamp, double waveratio, double q_emit, double q_abs)
+{
+  if (q_emit < 0.0) { q_emit = -q_emit; q_abs = -q_abs; }
+  double pcore = 0.0, gii = 0.0;
+  if (q_emit < PRD_QWING) {
+    if (q_abs < -PRD_QWING || q_abs > q_emit + waveratio*PRD_QSPREAD) return gii;
+    if (fabs(q_abs) <= q_emit) gii = prd_gzero(q_emit);
+    else gii = rhm::rh_exp(q_emit*q_emit - q_abs*q_abs) * prd_gzero(q_abs);
+    if (q_emit >= PRD_QCORE) {
+      const double phicore = rhm::rh_exp(-(q_emit*q_emit));
+      const double phiwing = adamp / (RH_SQRTPI * (adamp*adamp + q_emit*q_emit));
+      pcore = phicore / (phicore + phiwing);
+    }
+  }
+  if (q_emit >= PRD_QCORE) {
+    const double aq_emit = waveratio * q_emit;
+    if (q_emit >= PRD_QWING) {
+      if (fabs(q_abs - aq_emit) > waveratio*PRD_QSPREAD) return gii;
+      pcore = 0.0;
+    }
+    const double umin = fabs((q_abs - aq_emit) / (1.0 + waveratio));
+    double giiwing = (1.0 + waveratio) * (1.0 - 2.0*umin*prd_gzero(umin)) * rhm::rh_exp(-(umin*umin));
+    if (waveratio == 1.0) {
+      const double epsilon = q_abs / aq_emit;
+      giiwing *= (2.75 - (2.5 - 0.75*epsilon) * epsilon);
+    } else {
+      const double u1 = fabs((q_abs - aq_emit) / (waveratio - 1.0));
+      giiwing -= fabs(1.0 - waveratio) * (1.0 - 2.0*u1*prd_gzero(u1)) * rhm::rh_exp(-(u1*u1));
+    }
+    giiwing = giiwing / (2.0 * waveratio * RH_SQRTPI);
+    gii = pcore*gii + (1.0 - pcore)*giiwing;
+  }
+  return gii;
+}
+
+// PRDScatter() (scatter.c:51-290, LINEAR representation, no cross redistribution): one thread per (column, row of rho,
+// depth).  drho [ncol]: MaxChange of the Ng structure of order 0 (maxchange.c:32-50), as the bit pattern of a double >= 0
+__global__ void __launch_bounds__(128)
+nlte_prd_scatter_kernel(Plan P, Cols C, int ncol, unsigned long long *__restrict__ drho)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = P.Ndep;
+  if (t >= (size_t) ncol * P.nrho * N) return;
+  const int k = (int) (t % N), row = (int) ((t / N) % P.nrho), col = (int) (t / ((size_t) N * P.nrho));
+  if (!C.active[col]) return;
+  int p = 0;
+  while (row >= P.prd_roff[p+1]) p++;
+  const int la = row - P.prd_roff[p], tid = P.prd_tr[p];
+  const double *tr = P.trans + (size_t) tid * TR_NFIELD;
+  const int a = (int) tr[TR_ATOM], i = (int) tr[TR_I], j = (int) tr[TR_J], Nl = P.atom_nlevel[a], li = (int) tr[TR_LINEIDX];
+  const int Nblue = (int) tr[TR_NBLUE], Nla = (int) tr[TR_NLAMBDA];
+  const double lambda0 = tr[TR_LAMBDA0], Bij = tr[TR_BIJ];
+  const double *lam = P.tr_lambda + (int) tr[TR_WOFF];
+  const double vbroad = C.vbroad[((size_t) col * P.Natom + a) * N + k];
+  const double adamp = C.adamp[((size_t) col * P.nline + li) * N + k];      // = (Grad + Qelast) cDop / vbroad, scatter.c:118
+  // total rate out of the upper level, scatter.c:122-137
+  double Pj = C.Qelast[((size_t) col * P.nline + li) * N + k];
+  const size_t gbase = ((size_t) col * P.ngam + P.gam_off[a]) * N;
+  for (int ip = 0; ip < Nl; ip++) Pj += C.C[gbase + (size_t) (ip*Nl + j) * N + k];
+  for (int t2 = 0; t2 < P.Ntrans; t2++) {        // the atom's lines (kr order), then its continua (kr order)
+    const double *q = P.trans + (size_t) t2 * TR_NFIELD;
+    if ((int) q[TR_ATOM] != a) continue;
+    const size_t rk = ((size_t) col * P.Ntrans + t2) * N + k;
+    if ((int) q[TR_J] == j) Pj += C.Rji[rk];
+    if ((int) q[TR_I] == j) Pj += C.Rij[rk];
+  }
+  const double *n = C.n + ((size_t) col * P.nlev + P.lev_off[a]) * N + k;
+  const double gamma = n[(size_t) i * N] / n[(size_t) j * N] * Bij / Pj;
+  const double Jbar = C.Rij[((size_t) col * P.Ntrans + tid) * N + k] / Bij;
+  const double *Jk = C.J + ((size_t) col * P.Nspect + Nblue) * N + k;        // J_k[la'] = Jk[la' * N]
+#define QABS(l) ((lam[l] - lambda0) * RH_CLIGHT / (lambda0 * vbroad))
+  const double q_emit = QABS(la);
+  double q0, qN;                                                                // scatter.c:176-193 with waveratio = 1
+  if (fabs(q_emit) < PRD_QCORE) { q0 = -PRD_QWING; qN = PRD_QWING; }
+  else if (fabs(q_emit) < PRD_QWING) {
+    if (q_emit > 0.0) { q0 = -PRD_QWING; qN = 1.0 * (q_emit + PRD_QSPREAD); }
+    else              { q0 = 1.0 * (q_emit - PRD_QSPREAD); qN = PRD_QWING; }
+  } else { q0 = 1.0 * (q_emit - PRD_QSPREAD); qN = 1.0 * (q_emit + PRD_QSPREAD); }
+  const int Np = (int) ((qN - q0) / PRD_DQ) + 1;
+  const double xmin = QABS(0), xmax = QABS(Nla - 1);
+  int jt = 0;
+  double qa0 = xmin, qa1 = QABS(1);
+  double qp = q0, gnorm = 0.0, scatInt = 0.0;
+  for (int lap = 0; lap < Np; lap++) {
+    if (lap > 0) qp = qp + PRD_DQ;                                              // :195-196
+    double Jv;                                                                  // Linear(.., hunt), linear.c:22-51
+    if (qp <= xmin) Jv = Jk[0];
+    else if (qp >= xmax) Jv = Jk[(size_t) (Nla - 1) * N];
+    else {
+      while (jt < Nla - 2 && qa1 <= qp) { jt++; qa0 = qa1; qa1 = QABS(jt + 1); }
+      const double fx = (qa1 - qp) / (qa1 - qa0);
+      Jv = fx*Jk[(size_t) jt * N] + (1 - fx)*Jk[(size_t) (jt + 1) * N];
+    }
+    double wq = PRD_DQ;                                                         // :231-236 (later assignments win)
+    if (lap == 0) wq = 5.0/12.0 * PRD_DQ;
+    if (lap == 1) wq = 13.0/12.0 * PRD_DQ;
+    if (lap == Np-1) wq = 5.0/12.0 * PRD_DQ;
+    if (lap == Np-2) wq = 13.0/12.0 * PRD_DQ;
+    const double gii = prd_gii(adamp, 1.0, q_emit, qp) * wq;
+    gnorm += gii;
+    scatInt += Jv * gii;
+  }
+#undef QABS
+  const double rho_new = 1.0 + gamma*(scatInt/gnorm - Jbar);                    // :109-113, 281
+  const double rho_old = C.rho[t];
+  C.rho[t] = rho_new;
+  if (rho_new != 0.0) {
+    const double d = fabs((rho_new - rho_old) / rho_new);
+    atomicMax(drho + col, (unsigned long long) __double_as_longlong(d));
+  }
+}
+
+// addtoRates(.., redistribute = TRUE) after zeroRates(TRUE) (fillgamma.c:337-461): the rates of the PRD lines alone,
+// rays in the reference's order.  One thread per (column, PRD line, depth)
+__global__ void __launch_bounds__(64)
+nlte_prd_rates_kernel(Plan P, Cols C, int ncol)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = P.Ndep;
+  if (t >= (size_t) ncol * P.nprd * N) return;
+  const int k = (int) (t % N), p = (int) ((t / N) % P.nprd), col = (int) (t / ((size_t) N * P.nprd));
+  if (!C.active[col]) return;
+  const int tid = P.prd_tr[p];
+  const double *tr = P.trans + (size_t) tid * TR_NFIELD;
+  const int Nblue = (int) tr[TR_NBLUE], Nla = (int) tr[TR_NLAMBDA];
+  const double hc_4PI = (RH_HPLANCK * RH_CLIGHT) / (4.0 * RH_PI);
+  const double c = hc_4PI * tr[TR_BIJ] * tr[TR_ISOFRAC], thn = tr[TR_AJI] / tr[TR_BJI];
+  double Rij = 0.0, Rji = 0.0;
+  for (int ns = Nblue; ns < Nblue + Nla; ns++) {
+    const int first = P.as_first[ns], nact = P.as_first[ns+1] - first;
+    int e = -1;
+    for (int n = 0; n < nact; n++) if (P.as_trans[first+n] == tid) { e = first + n; break; }
+    if (e < 0) continue;
+    const double *gw = C.gw + (((size_t) col * P.nas + e) * 2) * N + k;
+    const double g = gw[0], w = gw[N];
+    const int ad = P.angle_dep[ns], la = ns - Nblue;
+    const double *ph = C.phi + ((size_t) col * P.nphirow + (int) tr[TR_PHIROW] + 2*P.Nrays*la) * N + k;
+    for (int r = P.ray_off[ns]; r < P.ray_off[ns+1]; r++) {
+      const int mu = P.ray_mu[r];
+      const double wmu = ad ? 0.5 * P.wmu[mu] : P.wmu[mu];
+      const double I = C.I[((size_t) col * P.nray + r) * N + k];
+      const double V = c * ph[(size_t) (2*mu + P.ray_dir[r]) * N];
+      const double wlamu = V * w * wmu;
+      Rij += I * wlamu;
+      Rji += g * (thn + I) * wlamu;
+    }
+  }
+  C.Rij[((size_t) col * P.Ntrans + tid) * N + k] = Rij;
+  C.Rji[((size_t) col * P.Ntrans + tid) * N + k] = Rji;
+}
+
+__global__ void nlte_fill_kernel(double *__restrict__ a, size_t n, double v)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) a[t] = v;
 }
 
 // dJmax per column (solveSpectrum's return value, iterate.c:236-244): max is order independent
@@ -1074,6 +1250,8 @@ struct NlteEngine {
   }
   bool profile_maps_ok = false, exact_rates = false;
   bool has_zeeman = false;                       // set_zeeman() was called: the FULL_STOKES passes are available
+  int nprd = 0, nrho = 0, prd_nmax = 0; double prd_limit = 0.0;   // set_prd(): PRD lines, PRD_N_MAX_ITER, PRD_ITER_LIMIT
+  int *d_prd_ns = nullptr; unsigned long long *d_drho = nullptr;
   double *d_chi_cQ = nullptr, *d_eta_cQ = nullptr;   // background Q, U, V records of this engine [ncol][Ns][3][N]
   int nseg = 0;
 
@@ -1109,6 +1287,74 @@ struct NlteEngine {
   }
   void set_stokes(bool on) { P.stokes = (on && has_zeeman) ? 1 : 0; }
 
+  // line->PRD of the ACTIVE lines (readatom.c:255-258) and the keywords of Redistribute() (iterate.c:98-108)
+  int set_prd(const rhb200_nlte_plan *pl, const int *line_prd, int PRD_NmaxIter, double PRDiterLimit) {
+    std::vector<int> prd_tr, roff(1, 0), tr_prd(Nt, -1), prd_ns(Ns, 0);
+    for (int t = 0; t < Nt; t++) {
+      const double *tr = pl->trans + (size_t) t*RHB200_TR_NFIELD;
+      if (tr[RHB200_TR_TYPE] != 0.0 || !line_prd[(int) tr[RHB200_TR_LINEIDX]]) continue;
+      tr_prd[t] = (int) prd_tr.size();
+      prd_tr.push_back(t);
+      roff.push_back(roff.back() + (int) tr[RHB200_TR_NLAMBDA]);
+      for (int ns = (int) tr[RHB200_TR_NBLUE]; ns < (int) tr[RHB200_TR_NBLUE] + (int) tr[RHB200_TR_NLAMBDA]; ns++) prd_ns[ns] = 1;
+    }
+    nprd = (int) prd_tr.size(); nrho = roff.back(); prd_nmax = PRD_NmaxIter; prd_limit = PRDiterLimit;
+    P.nprd = nprd; P.nrho = nrho; P.ns_mask = nullptr;
+    if (nprd == 0) return RHB200_OK;
+    if (nrank > 1) { rhb200_set_error("PRD lines in a wavelength-sharded solve are not implemented"); return RHB200_EUNSUPPORTED; }
+    DevArena &ar = plan_ar;
+    int *di;
+    RH_CHECK(ar.upload(&di, prd_tr.data(), prd_tr.size())); P.prd_tr = di;
+    RH_CHECK(ar.upload(&di, roff.data(), roff.size())); P.prd_roff = di;
+    RH_CHECK(ar.upload(&di, tr_prd.data(), tr_prd.size())); P.tr_prd = di;
+    RH_CHECK(ar.upload(&di, prd_ns.data(), prd_ns.size())); P.prd_ns = di; d_prd_ns = di;
+    return RHB200_OK;
+  }
+
+  // Redistribute(PRD_NmaxIter, PRDiterlimit) (redistribute.c:38-106) with Ng order 0: PRDScatter of every PRD line,
+  // then solveSpectrum(FALSE, TRUE) over the wavelengths that hold one; per column until its rho changes by < limit.
+  // dpops [ncol]: this iteration's dpopsmax (a negative PRD_ITER_LIMIT follows it, iterate.c:103-106)
+  int redistribute(const std::vector<double> &dpops) {
+    if (nprd == 0 || prd_nmax <= 0) return RHB200_OK;
+    cudaStream_t st = c->stream;
+    const size_t cN = (size_t) ncol * N;
+    std::vector<int> act(active);                   // columns still iterating in Iterate()
+    std::vector<unsigned long long> h_drho(ncol);
+    int left = 0;
+    for (int col = 0; col < ncol; col++) left += act[col];
+    bool masked = false;
+    for (int it = 1; it <= prd_nmax && left > 0; it++) {
+      RH_CUDA(cudaMemsetAsync(d_drho, 0, (size_t) ncol * sizeof(unsigned long long), st));
+      { ScopedKernelTimer t(c, RHB200_K_OTHER);
+        nlte_prd_scatter_kernel<<<RH_GRID(cN*nrho, 128), 0, st>>>(P, C, ncol, d_drho);
+        nlte_setup_kernel<<<RH_GRID(cN*nas, 128), 0, st>>>(P, C, ncol); }
+      P.ns_mask = d_prd_ns;
+      { ScopedKernelTimer t(c, RHB200_K_OPACITY);
+        nlte_opacity_kernel<<<(unsigned) (((cN + 127) / 128) * Ns), 128, 0, st>>>(P, C, ncol);
+        if (P.stokes) nlte_opacity_quv_kernel<<<(unsigned) (((cN + 127) / 128) * Ns), 128, 0, st>>>(P, C, ncol); }
+      { ScopedKernelTimer t(c, RHB200_K_BEZIER);
+        launch_rays(0); }
+      { ScopedKernelTimer t(c, RHB200_K_J);
+        nlte_J_kernel<<<RH_GRID(cN*Ns, 128), 0, st>>>(P, C, ncol); }
+      { ScopedKernelTimer t(c, RHB200_K_GAMMA);
+        nlte_prd_rates_kernel<<<RH_GRID(cN*nprd, 64), 0, st>>>(P, C, ncol); }
+      P.ns_mask = nullptr;
+      RH_CUDA(cudaGetLastError());
+      RH_CUDA(cudaMemcpyAsync(h_drho.data(), d_drho, (size_t) ncol * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+      RH_CUDA(cudaStreamSynchronize(st));
+      bool changed = false;
+      for (int col = 0; col < ncol; col++) {
+        if (!act[col]) continue;
+        double d; memcpy(&d, &h_drho[col], sizeof d);
+        const double limit = prd_limit < 0.0 ? std::max(dpops[col], -prd_limit) : prd_limit;
+        if (d < limit) { act[col] = 0; left--; changed = true; }
+      }
+      if (changed && left > 0 && it < prd_nmax) { RH_CUDA(cudaMemcpyAsync(d_active, act.data(), ncol*sizeof(int), cudaMemcpyHostToDevice, st)); masked = true; }
+    }
+    if (masked) RH_CUDA(cudaMemcpyAsync(d_active, active.data(), ncol*sizeof(int), cudaMemcpyHostToDevice, st));
+    return RHB200_OK;
+  }
+
   // B, Bproject() of every ray of this engine from the pyrh rows (d_in [ncol][nrow][N])
   int bproject(const double *d_in, int nrow) {
     if (!has_zeeman) return RHB200_OK;
@@ -1121,6 +1367,7 @@ struct NlteEngine {
     size_t d = (size_t) N * ((size_t) ngam + 2*(size_t) Nt + 2*(size_t) nas + 6*(size_t) nray + (size_t) Ns + nphirow + nline +
                              (exact_rates ? 0 : 4*(size_t) nseg)) + nray + prev_off[Na] + Na;
     if (own_inputs) d += (size_t) N * (2 + 2*(size_t) nlev + Na + ngam + nline + Na + 1 + 4*(size_t) Ns);
+    d += (size_t) N * ((size_t) nrho + nline) + 1;
     if (has_zeeman) d += (size_t) N * (1 + 3*(size_t) Nr + 3*(size_t) nphirow + 6*(size_t) Ns + 9*(size_t) nray) + 3*(size_t) nray;
     return d;
   }
@@ -1139,6 +1386,8 @@ struct NlteEngine {
     RH_CHECK(ar.alloc(&C.chi, cN*nray)); RH_CHECK(ar.alloc(&C.S, cN*nray)); RH_CHECK(ar.alloc(&C.I, cN*nray));
     RH_CHECK(ar.alloc(&C.Psi, cN*nray)); RH_CHECK(ar.alloc(&C.scr, cN*nray*2)); RH_CHECK(ar.alloc(&C.dJ, cN*Ns, true));
     RH_CHECK(ar.alloc(&C.Iem, (size_t) ncol*nray, true));
+    { double *dd; RH_CHECK(ar.alloc(&dd, cN*std::max(1, nline), true)); C.Qelast = dd; }
+    RH_CHECK(ar.alloc(&C.rho, cN*std::max(1, nrho))); RH_CHECK(ar.alloc(&d_drho, (size_t) ncol, true));
     if (has_zeeman) {
       double *dd;
       RH_CHECK(ar.alloc(&dd, cN)); C.B = dd;
@@ -1221,6 +1470,10 @@ struct NlteEngine {
         RH_CUDA(cudaStreamSynchronize(st));
         RH_CUDA(cudaMemcpy(wphi_out, C.wphi, cN*nline*sizeof(double), cudaMemcpyDeviceToHost));
       }
+    }
+    if (nprd > 0 && ng_init) {                       // Profile() of a PRD line starts from rho = 1 (profile.c:83-103)
+      nlte_fill_kernel<<<RH_GRID(cN*nrho, 256), 0, st>>>(C.rho, cN*nrho, 1.0);
+      RH_CUDA(cudaGetLastError());
     }
     { ScopedKernelTimer t(c, RHB200_K_OTHER);
       nlte_setup_kernel<<<RH_GRID(cN*nas, 128), 0, st>>>(P, C, ncol); }
@@ -1343,6 +1596,12 @@ struct NlteEngine {
       RH_CUDA(cudaGetLastError());
       RH_CUDA(cudaMemcpyAsync(h_dpops.data(), d_dpops, h_dpops.size()*sizeof(double), cudaMemcpyDeviceToHost, st));
       RH_CUDA(cudaStreamSynchronize(st));
+      if (nprd > 0) {                               // iterate.c:98-108: before the convergence test of this iteration
+        std::vector<double> dcol(ncol, 0.0);
+        for (int col = 0; col < ncol; col++)
+          for (int a = 0; a < Na; a++) dcol[col] = std::max(dcol[col], h_dpops[(size_t) col*Na + a]);
+        RH_CHECK(redistribute(dcol));
+      }
       bool changed = false;
       for (int col = 0; col < ncol; col++) {
         if (!active[col]) continue;

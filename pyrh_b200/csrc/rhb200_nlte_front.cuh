@@ -258,6 +258,8 @@ extern "C" int rhb200_nlte_compute1d_stokes_batch(rhb200_ctx *c, const rhb200_nl
   if (!c->cont || !rh_continuum_has_chemistry(c)) { rhb200_set_error("rhb200_set_continuum() / rhb200_set_chemistry() have not been called"); return RHB200_ESTATE; }
   if (fr->stokes < 0 || fr->stokes > 2) { rhb200_set_error("front->stokes must be 0 (NO_STOKES), 1 (FIELD_FREE) or 2 (FULL_STOKES)"); return RHB200_EUNSUPPORTED; }
   const bool stokes = fr->stokes != 0, full_stokes = fr->stokes == 2;
+  bool prd = false;
+  if (fr->line_prd && fr->PRD_NmaxIter > 0) for (int l = 0; l < pl->nline; l++) prd = prd || fr->line_prd[l] != 0;
   if (!c->no_stokes) { rhb200_set_error("the background of the NLTE path is set up with rhb200_set_stokes_mode(ctx, 0): the FULL_STOKES passes of FIELD_FREE are selected by front->stokes"); return RHB200_EUNSUPPORTED; }
   if (stokes && (!fr->line_pol || !fr->line_zoff)) { rhb200_set_error("front->stokes needs line_pol / line_zoff and the Zeeman tables"); return RHB200_EINVAL; }
   if (pl->Natom > NF_MAXATOM) { rhb200_set_error("too many ACTIVE atoms"); return RHB200_EUNSUPPORTED; }
@@ -329,6 +331,7 @@ extern "C" int rhb200_nlte_compute1d_stokes_batch(rhb200_ctx *c, const rhb200_nl
     mix(fr->coll, sizeof(double) * fr->ncoll * RHB200_CO_NFIELD); mix(fr->coll_T, sizeof(double) * fr->ncolltab);
     mix(fr->coll_coef, sizeof(double) * fr->ncolltab); mix(fr->line_rows, sizeof(double) * pl->nline * RHB200_PL_NFIELD);
     mix(&fr->stokes, sizeof(int)); mix(&c->s_interpolation_stokes, sizeof(int));
+    if (prd) { mix(fr->line_prd, sizeof(int) * pl->nline); mix(&fr->PRD_NmaxIter, sizeof(int)); mix(&fr->PRDiterLimit, sizeof(double)); }
     if (stokes) {
       const int nz = fr->line_zoff[pl->nline];
       mix(fr->line_pol, sizeof(int) * pl->nline); mix(fr->line_zoff, sizeof(int) * (pl->nline + 1));
@@ -349,6 +352,8 @@ extern "C" int rhb200_nlte_compute1d_stokes_batch(rhb200_ctx *c, const rhb200_nl
     if (rc == RHB200_OK) rc = S->F.build(c, &p1);
     if (rc == RHB200_OK && stokes) rc = S->E.set_zeeman(pl, fr->line_pol, fr->line_zoff, fr->zq, fr->zshift, fr->zstrength);
     if (rc == RHB200_OK && stokes) rc = S->F.set_zeeman(&p1, fr->line_pol, fr->line_zoff, fr->zq, fr->zshift, fr->zstrength);
+    if (rc == RHB200_OK && prd) rc = S->E.set_prd(pl, fr->line_prd, fr->PRD_NmaxIter, fr->PRDiterLimit);
+    if (rc == RHB200_OK && prd) rc = S->F.set_prd(&p1, fr->line_prd, 0, 0.0);
     if (rc == RHB200_OK && S->E.nrank > 1) { rhb200_set_error("wavelength sharding is only available through rhb200_nlte_iterate"); rc = RHB200_EUNSUPPORTED; }
     if (rc != RHB200_OK) { delete S; return rc; }
     // ---- chunk size from the workspace budget
@@ -372,6 +377,7 @@ extern "C" int rhb200_nlte_compute1d_stokes_batch(rhb200_ctx *c, const rhb200_nl
       // F shares every input with E; only the background of the final pass and the profiles are its own
       F.C.T = E.C.T; F.C.height = E.C.height; F.C.nstar = E.C.nstar; F.C.ntotal = E.C.ntotal; F.C.C = E.C.C;
       F.C.vbroad = E.C.vbroad; F.C.vel = E.C.vel; F.C.n = E.C.n; F.C.J = E.C.J;
+      F.C.rho = E.C.rho;                               // the final pass keeps the profile ratio of the PRD lines (profile.c:83-90)
       const size_t cN = (size_t) cc * N;
       RH_CHECK(ar.alloc(&S->d_in, cN * nrow)); RH_CHECK(ar.alloc(&S->d_at, cN * RHB200_AT_NFIELD));
       RH_CHECK(ar.alloc(&S->d_pops, cN * nlev_model)); RH_CHECK(ar.alloc(&S->d_popsn, cN * nlev_model));
@@ -474,8 +480,8 @@ extern "C" int rhb200_nlte_compute1d_stokes_batch(rhb200_ctx *c, const rhb200_nl
     RH_CHECK(rh_launch_scales_chi(c, n, N, Ns, iref, atm_scale, wght_per_H, c->total_abund, c->gravity > 0.0 ? c->gravity : 1.0, E.C.chi_c, d_at, d_sc,
                                   scales ? d_sc + 2*cN : nullptr));
     nlte_height_kernel<<<RH_GRID(nN, 128), 0, st>>>(n, N, d_at, (double *) E.C.height);
-    // ---- getProfiles(): Damping() with the populations atom->n shows at this point
-    RH_CHECK(rh_launch_line_damping(c, n, N, pl->nline, d_plrows, d_at, pops_n, nlev_model, d_apc));
+    // ---- getProfiles(): Damping() with the populations atom->n shows at this point (line->Qelast of PRD lines kept)
+    RH_CHECK(rh_launch_line_damping(c, n, N, pl->nline, d_plrows, d_at, pops_n, nlev_model, d_apc, prd ? (double *) E.C.Qelast : nullptr));
     nlte_damping_gather_kernel<<<RH_GRID(nN * pl->nline, 128), 0, st>>>(E.P, E.C, n, d_apc);
     RH_CUDA(cudaGetLastError());
     RH_CUDA(cudaMemsetAsync(E.C.J, 0, nN * Ns * sizeof(double), st));                  // initSolution: J = 0

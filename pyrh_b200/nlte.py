@@ -40,7 +40,8 @@ class FrontStruct(C.Structure):
     _fields_ = [("atom_model", ip), ("ncoll", C.c_int), ("ncolltab", C.c_int), ("coll", dp), ("coll_T", dp),
                 ("coll_coef", dp), ("coll_M", dp), ("line_rows", dp), ("NmaxScatter", C.c_int), ("NmaxIter", C.c_int),
                 ("iterLimit", C.c_double), ("plan1", C.POINTER(PlanStruct)),
-                ("stokes", C.c_int), ("line_pol", ip), ("line_zoff", ip), ("zq", ip), ("zshift", dp), ("zstrength", dp)]
+                ("stokes", C.c_int), ("line_pol", ip), ("line_zoff", ip), ("zq", ip), ("zshift", dp), ("zstrength", dp),
+                ("line_prd", ip), ("PRD_NmaxIter", C.c_int), ("PRDiterLimit", C.c_double)]
 
 
 @dataclass

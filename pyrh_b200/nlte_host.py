@@ -217,9 +217,7 @@ def read_active_atom(atom_file, kw, moving=True):
         ln.update(kr=kr, Nlambda_in=int(f[4]), symmetric="ASYMM" not in f[5], qcore=float(f[6]),
                   g_Lande_eff=float(f[15]) if len(f) > 15 and H._scan_float(f[15])[0] is not None else 0.0,
                   isotope_frac=1.0)
-        if "PRD" in f[3] and prd_on:
-            raise NotImplementedError(f"{atom_file}: line {ln['j']}->{ln['i']} is a PRD line and PRD_N_MAX_ITER > 0 "
-                                      "(readatom.c:255): partial redistribution is not ported -- set PRD_N_MAX_ITER = 0")
+        ln["PRD"] = bool("PRD" in f[3] and prd_on)                       # readatom.c:255-258
         if "COMPOSIT" in f[3]:
             pos += 1 + int(data[pos].split()[0])
         i, j = ln["i"], ln["j"]
@@ -543,6 +541,14 @@ class NlteSession:
         self.vmacro_tresh = float(kw["VMACRO_TRESH"])
         self.ctx.set_gravity(self.el.totalAbund)
         self.IDs = [at["ID"] for at in self.atoms]
+        # angle-averaged PRD (redistribute.c, scatter.c:51-290): line->PRD in line-index order + the keywords
+        self.line_prd = np.ascontiguousarray([int(ln["PRD"]) for at in self.atoms for ln in at["lines"]], np.int32)
+        self.prd_nmax, self.prd_limit = int(kw.get("PRD_N_MAX_ITER", "3")), float(kw.get("PRD_ITER_LIMIT", "1.0E-2"))
+        if self.line_prd.any():
+            if H._true(kw.get("PRD_ANGLE_DEP", "FALSE")) or H._true(kw.get("XRD", "FALSE")):
+                raise NotImplementedError("PRD_ANGLE_DEP / XRD = TRUE (angle-dependent and cross redistribution) are not ported")
+            if int(kw.get("PRD_NG_ORDER", "0")) > 0:
+                raise NotImplementedError("PRD_NG_ORDER > 0 (Ng acceleration of the PRD profile ratio) is not ported")
         # FIELD_FREE: Zeeman patterns of the polarizable ACTIVE lines (Zeeman(), zeeman.c:186-281), line-index order
         self.line_pol, self.line_zoff, zq, zs, zt = [], [0], [], [], []
         for at in self.atoms:
@@ -614,7 +620,8 @@ class NlteSession:
                                 self.hdr["iterLimit"], C.pointer(plan1), {"NO_STOKES": 0, "FIELD_FREE": 1, "FULL_STOKES": 2}[self.stokes_mode],
                                 self.line_pol.ctypes.data_as(lib.ip), self.line_zoff.ctypes.data_as(lib.ip),
                                 self.zq.ctypes.data_as(lib.ip), self.zshift.ctypes.data_as(lib.dp),
-                                self.zstrength.ctypes.data_as(lib.dp))
+                                self.zstrength.ctypes.data_as(lib.dp), self.line_prd.ctypes.data_as(lib.ip), self.prd_nmax,
+                                self.prd_limit)
             cache.clear()
             cache[(float(mu), ndep)] = (plan, plan1, fr, keep, model, tabs)
         plan, plan1, fr = cache[(float(mu), ndep)][:3]

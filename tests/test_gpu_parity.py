@@ -1472,6 +1472,40 @@ def test_nlte_full_stokes_iterations(case):
     assert np.array_equal(res["n"][ok], g[f"{case}_n"][ok]) and np.array_equal(got, ref)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["caii_r3_prd", "caii_r5_prd1"])
+def test_nlte_partial_redistribution(case):
+    """Angle-averaged PRD in Ca II H & K (readatom.c:255-258, PRD_N_MAX_ITER 3 / 1): after updatePopulations() of every
+    MALI iteration Redistribute() (redistribute.c:38-106) = PRDScatter() per PRD line (scatter.c:51-290: total rate out
+    of the upper level, Gouttebroze's GII on the 0.25-Doppler-width grid, linear interpolation of J, rho = 1 + gamma
+    (scatInt / gnorm - Jbar)) + solveSpectrum(FALSE, TRUE) over the PRD wavelengths (J and the PRD lines' rates), per
+    column until rho changes by < PRD_ITER_LIMIT; rho enters the emission profile (opacity.c:207-217).  Perturbed columns;
+    the reference exit()s ("Singular matrix") on some of them, those are not compared.  Bars: iterations identical,
+    populations <= 1e-6, spectrum <= 1e-9."""
+    from pyrh_b200 import nlte_host
+    g, cwd = _nlte_front_case(case)
+    atm, wave, mu = g["atmosphere"], g[f"{case}_wave"], float(g[f"{case}_mu"])
+    s = nlte_host.NlteSession(cwd, wave)
+    try:
+        res = s.compute(atm, mu=mu)
+    finally:
+        s.close()
+    assert s.line_prd.sum() == 2
+    ok = np.isfinite(g[f"{case}_n"]).reshape(len(atm), -1).all(axis=1) & (g[f"{case}_niter"] > 0)
+    conv = ok & (g[f"{case}_niter"] < 100)
+    assert conv.sum() >= 4
+    en = float(np.max(np.abs(res["n"][conv] / g[f"{case}_n"][conv] - 1)))
+    eI = float(np.max(np.abs(res["I"][conv] / g[f"{case}_I"][conv] - 1)))
+    REPORT[f"nlte_prd_{case}"] = dict(niter=res["niter"].tolist(), niter_ref=g[f"{case}_niter"].tolist(), n_maxrel=en, I_maxrel=eI,
+                                      n_exact=bool(np.array_equal(res["n"][ok], g[f"{case}_n"][ok])),
+                                      I_exact=bool(np.array_equal(res["I"][ok], g[f"{case}_I"][ok])))
+    assert np.array_equal(res["niter"][conv], g[f"{case}_niter"][conv])
+    assert en <= 1e-6 and eI <= 1e-9
+    # reached: every column the reference finishes, the 100-iteration ones included, to the bit
+    assert np.array_equal(res["niter"][ok], g[f"{case}_niter"][ok])
+    assert np.array_equal(res["n"][ok], g[f"{case}_n"][ok]) and np.array_equal(res["I"][ok], g[f"{case}_I"][ok])
+
+
 def json_keys(g, case):
     import json
     return json.loads(str(g["cases"]))[case]["keys"]
@@ -1632,7 +1666,7 @@ def test_bridged_reference_library_hse_get_scales_get_ne():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", ["caii_r3", "caii_r5", "h_caii_r3", "h_caii_r5", "caii_r3_ff", "h_caii_r5_ff", "caii_r3_fs"])
+@pytest.mark.parametrize("case", ["caii_r3", "caii_r5", "h_caii_r3", "h_caii_r5", "caii_r3_ff", "h_caii_r5_ff", "caii_r3_fs", "caii_r5_prd1"])
 def test_bridged_reference_library_rhf1d_nlte(case):
     """The bridged library with ACTIVE atoms: the reference's readAtom / getLambda / SortLambda state (active sets,
     line grids, continuum cross-sections) and the collisional sections of the atom files are flattened in C
