@@ -596,6 +596,15 @@ int rhb200_nlte_formal(rhb200_ctx *ctx, const rhb200_nlte_plan *plan, int ncol,
 enum { RHB200_REDUCE_SUM = 0, RHB200_REDUCE_MAX = 1 };
 typedef int (*rhb200_allreduce_fn)(void *user, double *device_buf, size_t count, int op);
 int rhb200_nlte_set_shard(rhb200_ctx *ctx, int rank, int nrank, rhb200_allreduce_fn fn, void *user);
+/* The same exchange with NCCL called by the library itself: libnccl is loaded at run time (dlopen; RHB200_NCCL_LIB names
+   it, else libnccl.so.2), nothing is linked.  Per MALI iteration Gamma, Rij, Rji go out as ONE ncclGroup of three
+   ncclAllReduce(.., ncclDouble, ncclSum, comm, stream) on the context's compute stream -- no host synchronisation, no
+   callback; dJmax (ncclMax), J and the emergent intensities likewise.  `nccl_comm` is the host's ncclComm_t for this
+   rank's GPU; or let the library create it: rank 0 calls rhb200_nccl_unique_id, ships the 128 bytes to the other
+   ranks by any means (MPI_Bcast, a file, torch.distributed), every rank calls rhb200_nlte_set_shard_nccl_id. */
+int rhb200_nlte_set_shard_nccl(rhb200_ctx *ctx, int rank, int nrank, void *nccl_comm);
+int rhb200_nccl_unique_id(char id[128]);
+int rhb200_nlte_set_shard_nccl_id(rhb200_ctx *ctx, int rank, int nrank, const char id[128]);
 /* Order of the sums in addtoGamma / addtoRates (fillgamma.c:139-196, 375-461).  exact = 1: one thread per (column,
    transition, depth) adds the contributions of all wavelengths and rays in the reference's order -- Gamma, rates and
    populations then equal the reference's to the last bit, at the price of a long serial walk.  exact = 0 (default):

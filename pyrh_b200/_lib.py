@@ -56,6 +56,9 @@ SYMBOLS = [
     ("rhb200_zeeman", C.c_int, [C.c_char_p, C.c_double, C.c_char_p, C.c_double, C.c_double, C.c_int, ip, dp, dp]),
     ("rhb200_nlte_set_exact_rates", C.c_int, [vp, C.c_int]),
     ("rhb200_nlte_set_shard", C.c_int, [vp, C.c_int, C.c_int, ALLREDUCE_FN, vp]),
+    ("rhb200_nlte_set_shard_nccl", C.c_int, [vp, C.c_int, C.c_int, vp]),
+    ("rhb200_nccl_unique_id", C.c_int, [C.c_char_p]),
+    ("rhb200_nlte_set_shard_nccl_id", C.c_int, [vp, C.c_int, C.c_int, C.c_char_p]),
     ("rhb200_nlte_shard_range", C.c_int, [vp, C.c_int, C.c_int, ip, ip]),
     ("rhb200_molecular_opacity_batch", C.c_int, [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
                                                  dp, C.c_int, ip, dp, dp, C.c_double, C.c_int, dp, dp, dp, dp, dp, ip]),

@@ -85,7 +85,7 @@ extern "C" void rhb200_close(rhb200_ctx *c)
   if (!c) return;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
-  free_tables(c); free_wave(c); rh_continuum_free(c); rh_elements_free(c); rh_nlte_front_free(c);
+  free_tables(c); free_wave(c); rh_continuum_free(c); rh_elements_free(c); rh_nlte_front_free(c); rh_nccl_release(c);
   cudaFree(c->ws); cudaFree(c->flush);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);

@@ -103,6 +103,8 @@ struct rhb200_ctx {
   // wavelength shard of the NLTE solve (rhb200_nlte_set_shard)
   int shard_rank = 0, shard_nrank = 1;
   rhb200_allreduce_fn shard_fn = nullptr; void *shard_user = nullptr;
+  bool nccl_owned = false;
+  void *nccl_comm = nullptr;                     // rhb200_nlte_set_shard_nccl: ncclAllReduce on the compute stream, no host sync
   void *elements = nullptr;  // all elements + partition functions (rhb200_set_elements), owned by rhb200_hse.cu
   void *cont = nullptr;      // background-continuum state (rhb200_set_continuum), owned by rhb200_continuum.cu
   void *nlte_front = nullptr;   // plans / engines / work arrays of rhb200_nlte_compute1d_batch, owned by rhb200_nlte.cu
@@ -169,6 +171,9 @@ int rh_launch_scales(rhb200_ctx *ctx, int ncol, int ndep, int iref, int atm_scal
 int rh_continuum_chunk(rhb200_ctx *ctx, int cc, int ndep, const double *d_atmos, const double *d_chem,
                        double *d_pops, double *d_tprep, double *d_chi, double *d_eta, int chem_on_device,
                        double *d_molout = nullptr, double *d_sca = nullptr);
+int rh_nccl_allreduce(rhb200_ctx *ctx, double *buf, size_t count, int op);
+int rh_nccl_group(int end);
+void rh_nccl_release(rhb200_ctx *ctx);
 int rh_continuum_set_molsel(rhb200_ctx *ctx, int nsel, const int *chem_index);
 int rh_continuum_ltepops(rhb200_ctx *ctx, int cc, int ndep, const double *d_atmos, const double *d_chem_host, double *d_pops,
                          const double *d_ntot_in);

@@ -1139,6 +1139,7 @@ struct NlteEngine {
 
   int allreduce(double *buf, size_t count, int op) {
     if (nrank == 1) return RHB200_OK;
+    if (c->nccl_comm) return rh_nccl_allreduce(c, buf, count, op);        // enqueued on the compute stream, no host sync
     RH_CUDA(cudaStreamSynchronize(c->stream));
     if (c->shard_fn(c->shard_user, buf, count, op) != 0) { rhb200_set_error("allreduce callback failed"); return RHB200_ECUDA; }
     return RHB200_OK;
@@ -1576,9 +1577,11 @@ struct NlteEngine {
       { ScopedKernelTimer t(c, RHB200_K_J);
         nlte_J_kernel<<<RH_GRID(cN*Ns, 128), 0, st>>>(P, C, ncol); }
       // the exchange step of a wavelength-sharded atmosphere: radiative rates add up over ranks
+      if (c->nccl_comm && nrank > 1) RH_CHECK(rh_nccl_group(0));           // one fused launch for the three buffers
       RH_CHECK(allreduce(C.Gamma, cN*ngam, RHB200_REDUCE_SUM));
       RH_CHECK(allreduce(C.Rij, cN*Nt, RHB200_REDUCE_SUM));
       RH_CHECK(allreduce(C.Rji, cN*Nt, RHB200_REDUCE_SUM));
+      if (c->nccl_comm && nrank > 1) RH_CHECK(rh_nccl_group(1));
       if (it == dump_iter) {
         RH_CUDA(cudaStreamSynchronize(st));
         if (gamma_dump) RH_CUDA(cudaMemcpy(gamma_dump, C.Gamma, cN*ngam*sizeof(double), cudaMemcpyDeviceToHost));
@@ -1673,10 +1676,86 @@ extern "C" int rhb200_nlte_set_exact_rates(rhb200_ctx *c, int exact)
   return RHB200_OK;
 }
 
+// ---- native NCCL for the wavelength shard: the library loads libnccl at run time (dlopen), nothing is linked
+#include <dlfcn.h>
+namespace {
+struct NcclApi {
+  void *h = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*GetUniqueId)(void *) = nullptr;
+  struct Id { char b[128]; };
+  int (*CommInitRank)(void **, int, Id, int) = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+int nccl_load()
+{
+  if (g_nccl.h) return RHB200_OK;
+  const char *names[] = {getenv("RHB200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  for (const char *n : names) { if (n && (g_nccl.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break; }
+  if (!g_nccl.h) { rhb200_set_error("cannot load libnccl (set RHB200_NCCL_LIB): %s", dlerror()); return RHB200_ESTATE; }
+#define SYM(f, name) *(void **) &g_nccl.f = dlsym(g_nccl.h, name); if (!g_nccl.f) { rhb200_set_error("libnccl lacks %s", name); g_nccl.h = nullptr; return RHB200_ESTATE; }
+  SYM(AllReduce, "ncclAllReduce") SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(GetUniqueId, "ncclGetUniqueId")
+  SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy") SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+  return RHB200_OK;
+}
+}  // namespace
+int rh_nccl_allreduce(rhb200_ctx *c, double *buf, size_t count, int op)
+{
+  const int rc = g_nccl.AllReduce(buf, buf, count, /* ncclDouble */ 8, op == RHB200_REDUCE_MAX ? /* ncclMax */ 2 : /* ncclSum */ 0,
+                                  c->nccl_comm, c->stream);
+  if (rc != 0) { rhb200_set_error("ncclAllReduce: %s", g_nccl.GetErrorString(rc)); return RHB200_ECUDA; }
+  return RHB200_OK;
+}
+int rh_nccl_group(int end)
+{
+  const int rc = end ? g_nccl.GroupEnd() : g_nccl.GroupStart();
+  if (rc != 0) { rhb200_set_error("ncclGroup%s: %s", end ? "End" : "Start", g_nccl.GetErrorString(rc)); return RHB200_ECUDA; }
+  return RHB200_OK;
+}
+extern "C" int rhb200_nccl_unique_id(char id[128])
+{
+  RH_CHECK(nccl_load());
+  const int rc = g_nccl.GetUniqueId(id);
+  if (rc != 0) { rhb200_set_error("ncclGetUniqueId: %s", g_nccl.GetErrorString(rc)); return RHB200_ECUDA; }
+  return RHB200_OK;
+}
+extern "C" int rhb200_nlte_set_shard_nccl_id(rhb200_ctx *c, int rank, int nrank, const char id[128])
+{
+  if (!c || !id || nrank < 1 || rank < 0 || rank >= nrank) { rhb200_set_error("bad shard arguments"); return RHB200_EINVAL; }
+  RH_CHECK(nccl_load());
+  RH_CUDA(cudaSetDevice(c->device));
+  NcclApi::Id uid;
+  memcpy(uid.b, id, sizeof uid.b);
+  void *comm = nullptr;
+  const int rc = g_nccl.CommInitRank(&comm, nrank, uid, rank);
+  if (rc != 0) { rhb200_set_error("ncclCommInitRank: %s", g_nccl.GetErrorString(rc)); return RHB200_ECUDA; }
+  c->nccl_comm = comm; c->nccl_owned = true; c->shard_rank = rank; c->shard_nrank = nrank; c->shard_fn = nullptr; c->shard_user = nullptr;
+  return RHB200_OK;
+}
+extern "C" int rhb200_nlte_set_shard_nccl(rhb200_ctx *c, int rank, int nrank, void *nccl_comm)
+{
+  if (!c || nrank < 1 || rank < 0 || rank >= nrank || (nrank > 1 && !nccl_comm)) { rhb200_set_error("bad shard arguments"); return RHB200_EINVAL; }
+  if (nrank > 1) RH_CHECK(nccl_load());
+  c->nccl_comm = nrank > 1 ? nccl_comm : nullptr; c->nccl_owned = false;
+  c->shard_rank = rank; c->shard_nrank = nrank; c->shard_fn = nullptr; c->shard_user = nullptr;
+  return RHB200_OK;
+}
+void rh_nccl_release(rhb200_ctx *c)
+{
+  if (c->nccl_comm && c->nccl_owned && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
+  c->nccl_comm = nullptr; c->nccl_owned = false;
+}
+
 extern "C" int rhb200_nlte_set_shard(rhb200_ctx *c, int rank, int nrank, rhb200_allreduce_fn fn, void *user)
 {
   if (!c) { rhb200_set_error("null context"); return RHB200_EINVAL; }
   if (nrank < 1 || rank < 0 || rank >= nrank || (nrank > 1 && !fn)) { rhb200_set_error("bad shard arguments"); return RHB200_EINVAL; }
+  rh_nccl_release(c);
   c->shard_rank = rank; c->shard_nrank = nrank; c->shard_fn = fn; c->shard_user = user;
   return RHB200_OK;
 }

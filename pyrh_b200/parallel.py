@@ -100,6 +100,22 @@ def make_allreduce(group=None):
     return _lib.ALLREDUCE_FN(reduce), stats
 
 
+def shard_nlte_native(ctx, group=None):
+    """The same with NCCL called by the library itself (rhb200_nlte_set_shard_nccl_id): torch.distributed only ships the
+    128-byte ncclUniqueId of rank 0; the reductions run on the context's stream without callbacks or host syncs."""
+    import ctypes as C
+    import torch.distributed as dist
+    from . import _lib
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    buf = C.create_string_buffer(128)
+    if rank == 0:
+        _lib.check(ctx.lib.rhb200_nccl_unique_id(buf))
+    box = [buf.raw]
+    dist.broadcast_object_list(box, src=0, group=group)
+    uid = C.create_string_buffer(box[0], 128)
+    _lib.check(ctx.lib.rhb200_nlte_set_shard_nccl_id(ctx.h, rank, world, uid))
+
+
 def shard_nlte(ctx, group=None):
     """Register this rank's wavelength shard with the context: later ``nlte.iterate`` / ``nlte.formal``
     calls formally solve only this rank's wavelengths and all-reduce rates once per iteration."""

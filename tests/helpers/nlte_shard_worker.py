@@ -31,7 +31,12 @@ def main():
     prob = nlte.NlteProblem.from_golden(g, ncol=ncol)
     prob.J0 = np.zeros_like(prob.J0)
     ctx = Context(local)
-    stats = parallel.shard_nlte(ctx)
+    native = os.environ.get("RHB200_SHARD_NATIVE_NCCL", "0") != "0"     # NCCL called by the library (dlopen), no callback
+    if native:
+        parallel.shard_nlte_native(ctx)
+        stats = {"calls": 0, "bytes": 0}
+    else:
+        stats = parallel.shard_nlte(ctx)
     lo, hi = nlte.shard_range(prob, rank, world)
     nscat = int(g["hdr"][11])
     res = nlte.iterate(ctx, prob, nscatter=nscat)             # warm-up + result
@@ -49,7 +54,7 @@ def main():
     if rank == 0:
         rel = float(np.max(np.abs(res["n"][0] / g["n_final"] - 1)))
         relJ = float(np.nanmax(np.abs(res["J"][0] / g["J_final"] - 1)))
-        rep = dict(world=world, ncol=ncol, niter=int(res["niter"][0]), niter_ref=int(g["niter"]),
+        rep = dict(world=world, ncol=ncol, exchange="native ncclAllReduce group on the compute stream" if native else "torch.distributed callback", niter=int(res["niter"][0]), niter_ref=int(g["niter"]),
                    pops_max_rel_vs_reference=rel, J_max_rel_vs_reference=relJ, ranks_identical=same,
                    shard_rank0=[lo, hi], Nspect=int(g["hdr"][0]), seconds=dt,
                    allreduce_calls_per_solve=stats["calls"] - calls0,

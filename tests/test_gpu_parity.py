@@ -535,9 +535,12 @@ def test_nlte_with_other_scalar_solvers(ctx, tag, solver):
     assert not np.array_equal(out["n"][0], g["n_iter"][1])
 
 
-def test_nlte_wavelength_sharded_two_gpus(tmp_path):
+@pytest.mark.parametrize("exchange", ["native_nccl", "callback"])
+def test_nlte_wavelength_sharded_two_gpus(tmp_path, exchange):
     """One atmosphere split by wavelength over 2 GPUs, Gamma/rates all-reduced over NCCL each MALI
-    iteration: same iteration count as the reference, populations within north_star's 1e-6."""
+    iteration: same iteration count as the reference, populations within north_star's 1e-6.
+    native_nccl: the library itself calls ncclAllReduce (dlopen'ed libnccl, one group per iteration on the compute
+    stream, rhb200_nlte_set_shard_nccl_id); callback: the host's reduction (rhb200_nlte_set_shard)."""
     import subprocess
     import sys
     import torch
@@ -545,13 +548,14 @@ def test_nlte_wavelength_sharded_two_gpus(tmp_path):
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     root = Path(__file__).resolve().parent.parent
     out = tmp_path / "shard.json"
+    env = dict(os.environ, RHB200_SHARD_NATIVE_NCCL="1" if exchange == "native_nccl" else "0")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29631",
+                        "--master-addr", "127.0.0.1", "--master-port", "29631" if exchange == "callback" else "29633",
                         str(root / "tests" / "helpers" / "nlte_shard_worker.py"), str(out)],
-                       capture_output=True, text=True, timeout=600)
+                       capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     rep = json.loads(out.read_text())
-    REPORT["nlte_lambda_shard_2gpu"] = rep
+    REPORT[f"nlte_lambda_shard_2gpu_{exchange}"] = rep
     assert rep["niter"] == rep["niter_ref"] and rep["pops_max_rel_vs_reference"] < 1e-6
 
 
