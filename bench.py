@@ -250,7 +250,7 @@ def _nlte_workdir(case):
     return workdir.stage(tempfile.mkdtemp(prefix=f"rhb200_{case}_"), c["kw"], active=c["active"], extra_atoms=("CaII.atom",))
 
 
-def nlte_records(device, rank, ncol_scale=1.0):
+def nlte_records(device, rank, ncol_scale=1.0, world=1, barrier=None, maxreduce=None):
     """NLTE through the drop-in call (NlteSession.compute = rhb200_nlte_compute1d_batch): host atmosphere rows in,
     spectra + populations out, everything between on the device.  One record per case: atmospheres/s and formal-solution
     ray-points/s of a batch of perturbed 70-depth columns (and the latency of one FAL-C atmosphere for config 4)."""
@@ -264,15 +264,20 @@ def nlte_records(device, rank, ncol_scale=1.0):
         atm = synthetic.perturbed_batch(base, ncol, ndep=NDEP, first=10000 + rank * ncol)
         s.compute(atm[:min(64, ncol)])                                  # warm-up: allocations, first launches
         s.ctx.synchronize()
+        if barrier:
+            barrier()
         t0 = time.perf_counter()
         res = s.compute(atm)
         s.ctx.synchronize()
         dt = time.perf_counter() - t0
+        if maxreduce:                                                   # every rank solves its own ncol columns (weak scaling)
+            dt = maxreduce(dt)
         finite = np.isfinite(res["I"]).all(axis=tuple(range(1, res["I"].ndim))) & np.isfinite(res["n"]).all(axis=tuple(range(1, res["n"].ndim)))
         conv = (res["niter"] < int(c["kw"]["N_MAX_ITER"])) & finite
         rec = {"workload": f"{ncol} perturbed FAL-C columns x {NDEP} depths, {len(s.lam)} wavelengths, NRAYS {s.nrays}, "
                            f"ACTIVE {'+'.join(a.split('.')[0] for a in c['active'])}, CRD, Ng 2/10/3, ITER_LIMIT 1e-4",
                "ncol": ncol, "nspect": int(len(s.lam)), "nrays": s.nrays, "seconds": dt, "atmospheres_per_s": ncol / dt,
+               "n_gpus": world, "atmospheres_per_s_all_gpus": world * ncol / dt,        # columns sharded over the ranks, no collective
                "ray_points_per_s": s.ray_points(res, NDEP) / dt, "ray_points": s.ray_points(res, NDEP),
                "iterations_median": float(np.median(res["niter"])), "iterations_max": int(res["niter"].max()),
                "converged_columns": int(conv.sum()), "all_finite": bool(finite.all()),
@@ -551,7 +556,7 @@ def main():
     nlte = None
     if not args.no_nlte:
         try:
-            nlte = nlte_records(local_rank, rank, args.nlte_scale)
+            nlte = nlte_records(local_rank, rank, args.nlte_scale, world, barrier, maxreduce)
         except Exception as e:          # noqa: BLE001  -- the headline must survive a missing data directory
             nlte = {"unavailable": f"{type(e).__name__}: {e}"}
 
