@@ -17,7 +17,8 @@ __device__ __forceinline__ void bezier3_ray_t(const int ndep, const double *__re
                                               const double *__restrict__ chi, const double *__restrict__ S,
                                               double *I, double *__restrict__ Psi,
                                               const int npar, const double *__restrict__ dchi,
-                                              const double *__restrict__ deta, double *__restrict__ dI)
+                                              const double *__restrict__ deta, double *__restrict__ dI,
+                                              const bool psi_over_chi = false /* store Psi[k] / chi[k] (formal.c:247-248) */)
 {
   using namespace rhd;
   const double zmu = 1.0 / muz;
@@ -37,7 +38,7 @@ __device__ __forceinline__ void bezier3_ray_t(const int ndep, const double *__re
     I_upw = B0 - (B1 - B0) / dtau_uw;
   }
   I[ks] = I_upw;
-  if (Psi) Psi[ks] = 0.0;
+  if (Psi) Psi[ks] = psi_over_chi ? 0.0 / chi[ks] : 0.0;
 
   int k = ks + dk;
   double dsup = fabs(z[k] - z[k-dk]) * zmu;
@@ -102,7 +103,7 @@ __device__ __forceinline__ void bezier3_ray_t(const int ndep, const double *__re
           dI[k*npar + p] = dI_upw[p]*eps + alpha*Zk + beta*Zkm1 + gamma*z1 + theta*z2;
         }
       }
-      if (Psi) Psi[k] = alpha + gamma;
+      if (Psi) Psi[k] = psi_over_chi ? (alpha + gamma) / chi[k] : alpha + gamma;
       fchi = fnext;
     } else {
       dtau_uw = 0.5 * zmu * (chi[k] + chi[k-dk]) * fabs(z[k] - z[k-dk]);
@@ -118,7 +119,7 @@ __device__ __forceinline__ void bezier3_ray_t(const int ndep, const double *__re
           dI[k*npar + p] = (1.0 - w0)*dI_upw[p] + w0*Zk + w1*dZk[p];
         }
       }
-      if (Psi) Psi[k] = w0 - w1 / dtau_uw;
+      if (Psi) Psi[k] = psi_over_chi ? (w0 - w1 / dtau_uw) / chi[k] : w0 - w1 / dtau_uw;
     }
     I_upw = I[k];
     dsup = dsdn; dchi_up = dchi_c; dchi_c = dchi_dn; dtau_uw = dtau_dw; dS_up = dS_c;
@@ -130,9 +131,9 @@ __device__ __forceinline__ void bezier3_ray(const int ndep, const double *__rest
                                             const int to_obs, const int bc_top, const int bc_bottom,
                                             const double *__restrict__ T, const double lambda,
                                             const double *__restrict__ chi, const double *__restrict__ S,
-                                            double *__restrict__ I, double *__restrict__ Psi)
+                                            double *__restrict__ I, double *__restrict__ Psi, const bool psi_over_chi = false)
 {
-  bezier3_ray_t<false>(ndep, z, muz, to_obs, bc_top, bc_bottom, T, lambda, chi, S, I, Psi, 0, nullptr, nullptr, nullptr);
+  bezier3_ray_t<false>(ndep, z, muz, to_obs, bc_top, bc_bottom, T, lambda, chi, S, I, Psi, 0, nullptr, nullptr, nullptr, psi_over_chi);
 }
 
 }  // namespace rhz

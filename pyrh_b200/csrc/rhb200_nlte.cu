@@ -52,6 +52,9 @@ struct Plan {            // device copy of the shared problem structure
             *ray_ns, *ray_mu, *ray_dir, *prow_tr, *line_tr;
   // fixed partition of every transition's wavelengths into segments (deterministic two-stage rate accumulation)
   int nseg; const int *seg_tr, *seg_lo, *seg_hi, *tr_seg0;   // [nseg] transition, [lo, hi) wavelengths; [Ntrans+1] first segment
+  // atom-major rate accumulation (default mode): chunks of 16 wavelengths per atom; every transition the atom has in a
+  // chunk owns a slot of partial sums; as_slot maps an active-set entry to its slot
+  int naseg, nslot, aseg_maxslot; const int *aseg_atom, *aseg_lo, *aseg_hi, *aseg_slot0, *as_slot, *tr_slot0, *tr_slots;
   // FULL_STOKES formal solution with polarizable ACTIVE lines (after adjustStokesMode(), zeeman.c:303-345)
   int stokes;                                   // input.StokesMode == FULL_STOKES for the passes run now
   int stokes_solver;                            // S_INTERPOLATION_STOKES
@@ -413,7 +416,7 @@ struct NlteFeauIO {
   __device__ __forceinline__ double getF(int k) const { return scr[k]; }
   __device__ __forceinline__ double getZ(int k) const { return scr[ndep + k]; }
   __device__ __forceinline__ void storeP(int k, double v) { P_[k] = v; }
-  __device__ __forceinline__ void storePsi(int k, double v) { Psi_[k] = v; }
+  __device__ __forceinline__ void storePsi(int k, double v) { Psi_[k] = v / chi_[k]; }     // Psi[k] /= chi[k], formal.c:300-301
   __device__ __forceinline__ bool wantPsi() const { return Psi_ != nullptr; }
 };
 
@@ -435,7 +438,7 @@ struct NlteStokesIO {
     if (IQ_) { IQ_[k] = I[1]; IQ_[ndep + k] = I[2]; IQ_[2*ndep + k] = I[3]; }
     if (k == kem) { IemQ_[0] = I[1]; IemQ_[1] = I[2]; IemQ_[2] = I[3]; }
   }
-  __device__ __forceinline__ void storePsi(int k, double p) { if (Psi_) Psi_[k] = p; }
+  __device__ __forceinline__ void storePsi(int k, double p) { if (Psi_) Psi_[k] = p / chi_[k]; }     // formal.c:247-248
   __device__ __forceinline__ void prefetch(int, int) const {}
 };
 __global__ void __launch_bounds__(128, 4)
@@ -474,16 +477,20 @@ nlte_ray_kernel(Plan P, Cols C, int ncol, int eval_operator)
   if (P.stokes && (P.pol_as[ns] || P.pol_c[ns])) return;   // nlte_ray_stokes_kernel
   const double *h = C.height + (size_t) col * N, *T = C.T + (size_t) col * N;
   double *Psi = eval_operator ? C.Psi + cr * N : nullptr;
+  // every solver hands back Psi / chi (formal.c:247-248, 300-301): the rate kernels would otherwise divide once per
+  // (transition, ray-point) instead of once per ray-point
   if (P.angle_dep[ns]) {
-    if (SOLVER == RHB200_S_LINEAR)                   // S_INTERPOLATION, formal.c:229-235
-      rhp::linear_ray(N, h, P.muz[mu], dir, P.bc_top, P.bc_bottom, T, P.lambda[ns], C.chi + cr * N,
-                      C.S + cr * N, C.I + cr * N, Psi);
-    else if (SOLVER == RHB200_S_PARABOLIC)
-      rhp::parabolic_ray(N, h, P.muz[mu], dir, P.bc_top, P.bc_bottom, T, P.lambda[ns], C.chi + cr * N,
-                         C.S + cr * N, C.I + cr * N, Psi);
-    else
+    if (SOLVER == RHB200_S_LINEAR || SOLVER == RHB200_S_PARABOLIC) {        // S_INTERPOLATION, formal.c:229-235
+      if (SOLVER == RHB200_S_LINEAR)
+        rhp::linear_ray(N, h, P.muz[mu], dir, P.bc_top, P.bc_bottom, T, P.lambda[ns], C.chi + cr * N,
+                        C.S + cr * N, C.I + cr * N, Psi);
+      else
+        rhp::parabolic_ray(N, h, P.muz[mu], dir, P.bc_top, P.bc_bottom, T, P.lambda[ns], C.chi + cr * N,
+                           C.S + cr * N, C.I + cr * N, Psi);
+      if (Psi) { const double *chi = C.chi + cr * N; for (int k = 0; k < N; k++) Psi[k] = Psi[k] / chi[k]; }
+    } else
       rhz::bezier3_ray(N, h, P.muz[mu], dir, P.bc_top, P.bc_bottom, T, P.lambda[ns], C.chi + cr * N,
-                       C.S + cr * N, C.I + cr * N, Psi);
+                       C.S + cr * N, C.I + cr * N, Psi, true);
     C.Iem[cr] = C.I[cr * N];                         // spectrum.I[nspect][mu] = I[0] (formal.c:270)
   } else {
     NlteFeauIO io{C.chi + cr * N, C.S + cr * N, h, C.I + cr * N, Psi, C.scr + cr * 2 * N, N};
@@ -799,7 +806,7 @@ nlte_gamma_kernel(Plan P, Cols C, int ncol)
           const int r = r0 + q, mu = P.ray_mu[r];
           const size_t rk = ((size_t) col * P.nray + r) * N + k;
           Iv[q] = __ldg(C.I + rk);
-          Pv[q] = __ldg(C.Psi + rk) / __ldg(C.chi + rk);           // formal.c:248 / :301
+          Pv[q] = __ldg(C.Psi + rk);                               // Psi / chi (formal.c:248 / :301), divided by the ray kernel
           wmuv[q] = ad ? 0.5 * P.wmu[mu] : P.wmu[mu];
           lamu[q] = 2*mu + P.ray_dir[r];
         }
@@ -869,6 +876,146 @@ nlte_gamma_kernel(Plan P, Cols C, int ncol)
   C.Gamma[gbase + (size_t)(j*Nl + i) * N + k] = Gji;
   C.Rij[((size_t) col * P.Ntrans + tid) * N + k] = Rij;
   C.Rji[((size_t) col * P.Ntrans + tid) * N + k] = Rji;
+}
+
+// ---- (4b) the default rate accumulation, ATOM-major: one thread per (column, depth) x (atom, chunk of wavelengths).
+// The transition-major kernels above load I, Psi, chi once per (transition, wavelength, ray) -- for H + Ca II nine
+// times per ray-point, because the continua overlap every line; here they are loaded once per (atom, wavelength, ray)
+// and addtoCoupling's per-level sums (chi_up[i], chi_down[j], Uji_down[j], fillgamma.c:251-332) are formed once and
+// shared by all transitions of the atom, as in the reference.  Partial {Gij, Gji, Rij, Rji} per (chunk, transition
+// slot) are added by nlte_gamma_slot_sum_kernel in chunk order: a fixed partition, deterministic and independent of
+// batch size and chunking.  Within a chunk every sum keeps the reference's order.
+#define NLTE_MAXSLOT 24
+#define NLTE_MAXLEV 8
+__global__ void __launch_bounds__(64, 8)
+nlte_gamma_atom_kernel(Plan P, Cols C, int ncol)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = P.Ndep;
+  if (t >= (size_t) ncol * N) return;
+  const int k = (int) (t % N), col = (int) (t / N);
+  if (!C.active[col]) return;
+  const int sg = (int) blockIdx.y, a = P.aseg_atom[sg], slot0 = P.aseg_slot0[sg], nslot = P.aseg_slot0[sg+1] - slot0;
+  const double *ncol_ = C.n + (size_t) col * P.nlev * N;
+  const double hc_4PI = (RH_HPLANCK * RH_CLIGHT) / (4.0 * RH_PI);
+  // per-thread accumulators and level sums live in shared memory, [index][thread]: dynamically indexed, conflict free
+  extern __shared__ double sh_gamma[];
+  double *acc = sh_gamma + threadIdx.x;                       // acc[(slot*4 + c)*64]
+  double *lev = sh_gamma + (size_t) P.aseg_maxslot * 4 * 64 + threadIdx.x;     // lev[(x*NLTE_MAXLEV + l)*64], x = 0 chi_up, 1 chi_down, 2 Uji_down
+#define ACC(q, c) acc[((q)*4 + (c))*64]
+#define LEV(x, l) lev[((x)*NLTE_MAXLEV + (l))*64]
+  for (int q = 0; q < nslot; q++) ACC(q, 0) = ACC(q, 1) = ACC(q, 2) = ACC(q, 3) = 0.0;
+  const int ns_first = P.aseg_lo[sg] > P.ns_lo ? P.aseg_lo[sg] : P.ns_lo, ns_last = P.aseg_hi[sg] < P.ns_hi ? P.aseg_hi[sg] : P.ns_hi;
+  for (int ns = ns_first; ns < ns_last; ns++) {
+    const int first = P.as_first[ns], nact = P.as_first[ns+1] - first;
+    const int ad = P.angle_dep[ns];
+    int    e_im[NLTE_MAXACT], e_jm[NLTE_MAXACT], e_slot[NLTE_MAXACT], e_on[NLTE_MAXACT];
+    double e_w[NLTE_MAXACT], e_diff[NLTE_MAXACT], e_tg[NLTE_MAXACT], e_nj[NLTE_MAXACT], e_c[NLTE_MAXACT], e_g[NLTE_MAXACT], e_thn[NLTE_MAXACT];
+    const double *e_phi[NLTE_MAXACT];
+    int cntj[NLTE_MAXLEV];                          // number of entries whose upper level is this level (fillgamma.c:180-196)
+    for (int l = 0; l < NLTE_MAXLEV; l++) cntj[l] = 0;
+    int m = 0;
+    for (int n = 0; n < nact && m < NLTE_MAXACT; n++) {
+      const int tm = P.as_trans[first+n];
+      const double *tr = P.trans + (size_t) tm * TR_NFIELD;
+      if ((int) tr[TR_ATOM] != a) continue;
+      const int im = (int) tr[TR_I], jm = (int) tr[TR_J], la = ns - (int) tr[TR_NBLUE];
+      const double *gw = C.gw + (((size_t) col * P.nas + first + n) * 2) * N + k;
+      const double g = gw[0], w = gw[N];
+      const double thn = twohnu3_of(P, tr, ns);
+      const double n_i = ncol_[(size_t)(P.lev_off[a] + im) * N + k], n_j = ncol_[(size_t)(P.lev_off[a] + jm) * N + k];
+      e_im[m] = im; e_jm[m] = jm; e_slot[m] = P.as_slot[first+n]; e_on[m] = thn != 0.0;
+      e_w[m] = w; e_diff[m] = n_i - g*n_j; e_tg[m] = thn * g; e_nj[m] = n_j; e_g[m] = g; e_thn[m] = thn;
+      if (tr[TR_TYPE] == 0.0) {
+        e_c[m] = hc_4PI * tr[TR_BIJ] * tr[TR_ISOFRAC];
+        e_phi[m] = C.phi + ((size_t) col * P.nphirow + (int) tr[TR_PHIROW] + 2*P.Nrays*la) * N + k;
+      } else {
+        e_c[m] = P.tr_alpha[(int) tr[TR_WOFF] + la];
+        e_phi[m] = nullptr;
+      }
+      cntj[jm]++;
+      m++;
+    }
+    const int r_end = P.ray_off[ns+1];
+    for (int r0 = P.ray_off[ns]; r0 < r_end; r0 += NLTE_RB) {
+      const int nb = r_end - r0 < NLTE_RB ? r_end - r0 : NLTE_RB;
+      double Iv[NLTE_RB], Pv[NLTE_RB], wmuv[NLTE_RB];
+      int lamu[NLTE_RB];
+#pragma unroll
+      for (int q = 0; q < NLTE_RB; q++) {           // the loads of a batch of rays are issued together
+        Iv[q] = Pv[q] = wmuv[q] = 0.0; lamu[q] = 0;
+        if (q < nb) {
+          const int r = r0 + q, mu = P.ray_mu[r];
+          const size_t rk = ((size_t) col * P.nray + r) * N + k;
+          Iv[q] = __ldg(C.I + rk);
+          Pv[q] = __ldg(C.Psi + rk);
+          wmuv[q] = ad ? 0.5 * P.wmu[mu] : P.wmu[mu];
+          lamu[q] = 2*mu + P.ray_dir[r];
+        }
+      }
+      for (int q = 0; q < nb; q++) {
+        double V[NLTE_MAXACT];
+        for (int l = 0; l < NLTE_MAXLEV; l++) LEV(0, l) = LEV(1, l) = LEV(2, l) = 0.0;
+        double eta_atom = 0.0;
+        for (int e = 0; e < m; e++) {               // Opacity() + addtoCoupling(), active-set order
+          const double v = e_phi[e] ? e_c[e] * __ldg(e_phi[e] + (size_t) lamu[q] * N) : e_c[e];
+          V[e] = v;
+          if (e_on[e]) {
+            const double tgV = e_tg[e] * v;
+            eta_atom += tgV * e_nj[e];
+            const double chicc = v * e_w[e] * e_diff[e];
+            LEV(0, e_im[e]) += chicc;
+            LEV(1, e_jm[e]) += chicc;
+            LEV(2, e_jm[e]) += tgV;
+          }
+        }
+        const double I = Iv[q], Psi = Pv[q], wmu = wmuv[q];
+        const double Ieff = I - Psi * eta_atom;
+        for (int e = 0; e < m; e++) {               // addtoGamma() + addtoRates() of every transition of the atom
+          const int i = e_im[e], j = e_jm[e];
+          const double wlamu = V[e] * e_w[e] * wmu;
+          const int sl = e_slot[e];
+          double Gij = ACC(sl, 0), Gji = ACC(sl, 1);
+          Gji += Ieff * wlamu;
+          Gij += (e_thn[e] + Ieff) * e_g[e] * wlamu;
+          Gij -= LEV(0, i) * Psi * LEV(2, j) * wmu;
+          for (int z = 0; z < cntj[i]; z++) Gji += LEV(1, j) * Psi * LEV(2, i) * wmu;
+          ACC(sl, 0) = Gij; ACC(sl, 1) = Gji;
+          ACC(sl, 2) += I * wlamu;
+          ACC(sl, 3) += e_g[e] * (e_thn[e] + I) * wlamu;
+        }
+      }
+    }
+  }
+  for (int q = 0; q < nslot; q++) {
+    double *o = C.part + (((size_t) col * P.nslot + slot0 + q) * 4) * N + k;
+    o[0] = ACC(q, 0); o[N] = ACC(q, 1); o[2*(size_t) N] = ACC(q, 2); o[3*(size_t) N] = ACC(q, 3);
+  }
+#undef ACC
+#undef LEV
+}
+
+__global__ void __launch_bounds__(128)
+nlte_gamma_slot_sum_kernel(Plan P, Cols C, int ncol)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = P.Ndep;
+  if (t >= (size_t) ncol * P.Ntrans * N) return;
+  const int k = (int) (t % N), tid = (int) ((t / N) % P.Ntrans), col = (int) (t / ((size_t) N * P.Ntrans));
+  if (!C.active[col]) return;
+  const double *trs = P.trans + (size_t) tid * TR_NFIELD;
+  const int a = (int) trs[TR_ATOM], i = (int) trs[TR_I], j = (int) trs[TR_J], Nl = P.atom_nlevel[a];
+  const size_t gbase = ((size_t) col * P.ngam + P.gam_off[a]) * N;
+  double Gij = 0.0, Gji = 0.0, Rij = 0.0, Rji = 0.0;
+  if (P.add_C) { Gij = C.C[gbase + (size_t)(i*Nl + j) * N + k]; Gji = C.C[gbase + (size_t)(j*Nl + i) * N + k]; }
+  for (int q = P.tr_slot0[tid]; q < P.tr_slot0[tid+1]; q++) {
+    const double *p = C.part + (((size_t) col * P.nslot + P.tr_slots[q]) * 4) * N + k;
+    Gij += p[0]; Gji += p[N]; Rij += p[2*(size_t) N]; Rji += p[3*(size_t) N];
+  }
+  C.Gamma[gbase + (size_t)(i*Nl + j) * N + k] = Gij;
+  C.Gamma[gbase + (size_t)(j*Nl + i) * N + k] = Gji;
+  C.Rij[t] = Rij;
+  C.Rji[t] = Rji;
 }
 
 // stage 2: collisional part + the segments' partial sums in segment (= wavelength) order: the same partition for every
@@ -1242,6 +1389,59 @@ struct NlteEngine {
       P.nseg = nseg = (int) seg_tr.size();
       UPI2(seg_tr, seg_tr.data(), std::max(1, nseg)); UPI2(seg_lo, seg_lo.data(), std::max(1, nseg));
       UPI2(seg_hi, seg_hi.data(), std::max(1, nseg)); UPI2(tr_seg0, tr_seg0.data(), Nt + 1);
+      // atom-major chunks (nlte_gamma_atom_kernel): per atom, global wavelength chunks of `seglen`
+      std::vector<int> aseg_atom, aseg_lo, aseg_hi, aseg_slot0(1, 0), as_slot(std::max(1, nas), 0), slot_tr;
+      bool ok = true;
+      int maxslot = 1;
+      for (int a = 0; a < Na; a++) if (pl->atom_nlevel[a] > NLTE_MAXLEV) ok = false;
+      for (int a = 0; a < Na && ok; a++)
+        for (int lo = 0; lo < Ns; lo += seglen) {
+          const int hi = std::min(Ns, lo + seglen);
+          std::vector<int> trs;
+          for (int ns = lo; ns < hi; ns++)
+            for (int e = pl->as_first[ns]; e < pl->as_first[ns+1]; e++) {
+              const int t = pl->as_trans[e];
+              if ((int) pl->trans[(size_t) t*RHB200_TR_NFIELD + RHB200_TR_ATOM] != a) continue;
+              size_t q = 0;
+              while (q < trs.size() && trs[q] != t) q++;
+              if (q == trs.size()) trs.push_back(t);
+              as_slot[e] = (int) q;
+            }
+          if (trs.empty()) continue;
+          aseg_atom.push_back(a); aseg_lo.push_back(lo); aseg_hi.push_back(hi);
+          slot_tr.insert(slot_tr.end(), trs.begin(), trs.end());
+          aseg_slot0.push_back((int) slot_tr.size());
+          maxslot = std::max(maxslot, (int) trs.size());
+        }
+      if (maxslot > NLTE_MAXSLOT) ok = false;
+      // measured (profiles/r2_bench_n1.json): the atom-major kernel wins where several transitions of an atom share the
+      // wavelengths (H + Ca II: 313 -> 279 ms per 256 columns) and loses where mostly one does (Ca II alone: 251 -> 406)
+      size_t pairs = 0;
+      for (int ns = 0; ns < Ns; ns++) {
+        std::vector<char> seen(Na, 0);
+        for (int e = pl->as_first[ns]; e < pl->as_first[ns+1]; e++) {
+          const int a = (int) pl->trans[(size_t) pl->as_trans[e]*RHB200_TR_NFIELD + RHB200_TR_ATOM];
+          if (!seen[a]) { seen[a] = 1; pairs++; }
+        }
+      }
+      use_atom_rates = ok && !exact_rates && pairs > 0 && (double) nas / (double) pairs >= 3.0;
+      if (const char *e = getenv("RHB200_NLTE_GAMMA_ATOM")) use_atom_rates = ok && !exact_rates && atoi(e) != 0;
+      if (use_atom_rates) {
+        std::vector<int> tr_slot0(Nt + 1, 0), tr_slots;
+        for (int t = 0; t < Nt; t++) {
+          tr_slot0[t] = (int) tr_slots.size();
+          for (size_t q = 0; q < slot_tr.size(); q++) if (slot_tr[q] == t) tr_slots.push_back((int) q);
+        }
+        tr_slot0[Nt] = (int) tr_slots.size();
+        naseg = (int) aseg_atom.size(); nslot_total = (int) slot_tr.size();
+        P.naseg = naseg; P.nslot = nslot_total; P.aseg_maxslot = maxslot;
+        UPI2(aseg_atom, aseg_atom.data(), std::max(1, naseg)); UPI2(aseg_lo, aseg_lo.data(), std::max(1, naseg));
+        UPI2(aseg_hi, aseg_hi.data(), std::max(1, naseg)); UPI2(aseg_slot0, aseg_slot0.data(), naseg + 1);
+        UPI2(as_slot, as_slot.data(), std::max(1, nas)); UPI2(tr_slot0, tr_slot0.data(), Nt + 1);
+        UPI2(tr_slots, tr_slots.data(), std::max<size_t>(1, tr_slots.size()));
+        gamma_smem = ((size_t) maxslot * 4 + 3 * NLTE_MAXLEV) * 64 * sizeof(double);
+        RH_CUDA(cudaFuncSetAttribute(nlte_gamma_atom_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gamma_smem));
+      }
     }
     Norder = pl->Ngorder; Ndelay = std::max(pl->Ngdelay, Norder + 2); Nperiod = std::max(1, pl->Ngperiod);
     prev_off.assign(Na+1, 0);
@@ -1254,7 +1454,9 @@ struct NlteEngine {
   int nprd = 0, nrho = 0, prd_nmax = 0; double prd_limit = 0.0;   // set_prd(): PRD lines, PRD_N_MAX_ITER, PRD_ITER_LIMIT
   int *d_prd_ns = nullptr; unsigned long long *d_drho = nullptr;
   double *d_chi_cQ = nullptr, *d_eta_cQ = nullptr;   // background Q, U, V records of this engine [ncol][Ns][3][N]
-  int nseg = 0;
+  int nseg = 0, naseg = 0, nslot_total = 0;
+  bool use_atom_rates = false;
+  size_t gamma_smem = 0;
 
   // doubles of device memory per column that alloc() takes (chunk sizing of the front end)
   // Zeeman patterns of the polarizable ACTIVE lines (Zeeman(), zeeman.c:186-281; line->polarizable, readatom.c:352-368)
@@ -1366,7 +1568,7 @@ struct NlteEngine {
 
   size_t doubles_per_column(bool own_inputs) const {
     size_t d = (size_t) N * ((size_t) ngam + 2*(size_t) Nt + 2*(size_t) nas + 6*(size_t) nray + (size_t) Ns + nphirow + nline +
-                             (exact_rates ? 0 : 4*(size_t) nseg)) + nray + prev_off[Na] + Na;
+                             (exact_rates ? 0 : 4*(size_t) std::max(nseg, nslot_total))) + nray + prev_off[Na] + Na;
     if (own_inputs) d += (size_t) N * (2 + 2*(size_t) nlev + Na + ngam + nline + Na + 1 + 4*(size_t) Ns);
     d += (size_t) N * ((size_t) nrho + nline) + 1;
     if (has_zeeman) d += (size_t) N * (1 + 3*(size_t) Nr + 3*(size_t) nphirow + 6*(size_t) Ns + 9*(size_t) nray) + 3*(size_t) nray;
@@ -1383,7 +1585,7 @@ struct NlteEngine {
     RH_CHECK(ar.alloc(&C.phi, cN*nphirow)); RH_CHECK(ar.alloc(&C.wphi, cN*nline));
     RH_CHECK(ar.alloc(&C.Gamma, cN*ngam)); RH_CHECK(ar.alloc(&C.Rij, cN*Nt, true)); RH_CHECK(ar.alloc(&C.Rji, cN*Nt, true));
     RH_CHECK(ar.alloc(&C.gw, cN*nas*2));
-    if (!exact_rates) RH_CHECK(ar.alloc(&C.part, cN*nseg*4));
+    if (!exact_rates) RH_CHECK(ar.alloc(&C.part, cN*std::max(nseg, nslot_total)*4));
     RH_CHECK(ar.alloc(&C.chi, cN*nray)); RH_CHECK(ar.alloc(&C.S, cN*nray)); RH_CHECK(ar.alloc(&C.I, cN*nray));
     RH_CHECK(ar.alloc(&C.Psi, cN*nray)); RH_CHECK(ar.alloc(&C.scr, cN*nray*2)); RH_CHECK(ar.alloc(&C.dJ, cN*Ns, true));
     RH_CHECK(ar.alloc(&C.Iem, (size_t) ncol*nray, true));
@@ -1569,6 +1771,9 @@ struct NlteEngine {
         if (exact_rates) {
           if (P.stokes) nlte_gamma_kernel<false, true><<<dim3((unsigned) ((cN + 63) / 64), (unsigned) Nt), 64, 0, st>>>(P, C, ncol);
           else nlte_gamma_kernel<false, false><<<dim3((unsigned) ((cN + 63) / 64), (unsigned) Nt), 64, 0, st>>>(P, C, ncol);
+        } else if (use_atom_rates && !P.stokes) {
+          nlte_gamma_atom_kernel<<<dim3((unsigned) ((cN + 63) / 64), (unsigned) naseg), 64, gamma_smem, st>>>(P, C, ncol);
+          nlte_gamma_slot_sum_kernel<<<RH_GRID(cN*Nt, 128), 0, st>>>(P, C, ncol);
         } else {
           if (P.stokes) nlte_gamma_kernel<true, true><<<dim3((unsigned) ((cN + 63) / 64), (unsigned) nseg), 64, 0, st>>>(P, C, ncol);
           else nlte_gamma_kernel<true, false><<<dim3((unsigned) ((cN + 63) / 64), (unsigned) nseg), 64, 0, st>>>(P, C, ncol);
