@@ -654,7 +654,8 @@ typedef struct {
      solve all four Stokes parameters where the active set or the background holds a polarised line (formal.c:86-217,
      opacity.c:262-296, stokesopac.c:28-82).  stokes = 2 is FULL_STOKES: polarised profiles and rays from initScatter on,
      Gamma from I_eff = I + Q + U + V - Psi (eta + eta_Q + eta_U + eta_V) where the active set holds a polarizable
-     line (fillgamma.c:106-129).  POLARIZATION_FREE is not implemented. */
+     line (fillgamma.c:106-129).  stokes = 3 is POLARIZATION_FREE: Zeeman-broadened profiles from the start (profile.c:112),
+     scalar transfer during the iterations, the four Stokes parameters afterwards with the same profiles. */
   int stokes;
   const int    *line_pol;         /* [plan->nline] line->polarizable (readatom.c:352-368) */
   const int    *line_zoff;        /* [plan->nline + 1] slice of each line in the pattern tables (0 components if not polarizable) */

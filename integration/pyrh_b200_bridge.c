@@ -506,12 +506,11 @@ static void solve_nlte(double mu, int ncol, const double *rows9, int nrow, doubl
   dvec trans = {0}, trans1 = {0}, wl = {0}, ww = {0}, wa = {0}, co = {0}, tT = {0}, tC = {0}, tM = {0}, lr = {0};
   ivec asf = {0}, ast = {0}, lpol = {0}, lzoff = {0}, zq = {0}, lprd = {0};
   dvec zs = {0}, zt = {0};
-  const int field_free = input.StokesMode == FIELD_FREE || input.StokesMode == FULL_STOKES;    /* polarised passes needed */
+  const int field_free = input.StokesMode != NO_STOKES;                   /* polarised passes needed */
   int *nlevel = (int *) malloc(Na * sizeof(int)), *model = (int *) malloc(Na * sizeof(int)), *hasline = (int *) malloc(Ns * sizeof(int));
   int **lidx = (int **) malloc(Na * sizeof(int *)), **cidx = (int **) malloc(Na * sizeof(int *));
   int a, kr, la, ns, n, phirow = 0, phirow1 = 0, nline = 0, ntr = 0;
   double mu1 = mu, w1 = 1.0;
-  if (input.StokesMode == POLARIZATION_FREE) FAIL("ACTIVE atoms with STOKES_MODE = POLARIZATION_FREE are not implemented");
   iv_push(&lzoff, 0);
   if (!atmos.moving) FAIL("static atmospheres with ACTIVE atoms are not implemented");
   for (a = 0; a < Na; a++) {
@@ -589,7 +588,7 @@ static void solve_nlte(double mu, int ncol, const double *rows9, int nrow, doubl
   F.plan1 = &P1;
   if (zq.n == 0) { iv_push(&zq, 0); dv_push(&zs, 0.0); dv_push(&zt, 0.0); }
   F.line_prd = lprd.v; F.PRD_NmaxIter = input.PRD_NmaxIter; F.PRDiterLimit = input.PRDiterLimit;
-  F.stokes = input.StokesMode == FULL_STOKES ? 2 : (input.StokesMode == FIELD_FREE ? 1 : 0); F.line_pol = lpol.v; F.line_zoff = lzoff.v; F.zq = zq.v; F.zshift = zs.v; F.zstrength = zt.v;
+  F.stokes = input.StokesMode == FULL_STOKES ? 2 : (input.StokesMode == FIELD_FREE ? 1 : (input.StokesMode == POLARIZATION_FREE ? 3 : 0)); F.line_pol = lpol.v; F.line_zoff = lzoff.v; F.zq = zq.v; F.zshift = zs.v; F.zstrength = zt.v;
   CHECK(rhb200_nlte_compute1d_stokes_batch(g_ctx, &P, &F, ncol, N, nrow, mu, g_atm_scale, rows9, T.iref, atmos.wght_per_H,
                                            atmos.vmacro_tresh, spec_out, quv_out, n_out, ns_out, niter, NULL, NULL));
   free(lprd.v); free(lpol.v); free(lzoff.v); free(zq.v); free(zs.v); free(zt.v);

@@ -8,6 +8,7 @@ CRD (PRD_N_MAX_ITER = 0), Ng order 2, ITER_LIMIT 1e-4, NO_STOKES.  Recorded: spe
 ACTIVE atoms, and the number of MALI iterations (counted from the probe's updatePopulations records).
     caii_r3_ff / h_caii_r5_ff   the same with STOKES_MODE = FIELD_FREE: field-free iterations, then adjustStokesMode()
                                 and the full Stokes solution (I, Q, U, V recorded; the columns carry B up to 2.5 kG)
+    caii_r3_pf                  STOKES_MODE = POLARIZATION_FREE: Zeeman-broadened profiles, scalar iterations, then full Stokes
     caii_r3_fs / h_caii_r3_fs   STOKES_MODE = FULL_STOKES: polarised profiles, rays and I_eff in every MALI iteration
     caii_r3_prd / caii_r5_prd1  angle-averaged PRD in Ca II H & K: PRD_N_MAX_ITER 3 / 1 (the shipped
                                 keyword.input.NLTE has 1), user grid inside Ca II K for the first
@@ -48,6 +49,8 @@ CASES = {
                         wave=(393.2, 393.5, 31), keys=("CA",), mu=1.0),
     "caii_r5_prd1": dict(kw=dict(KW, NRAYS=5, HYDROGEN_LTE="TRUE", PRD_N_MAX_ITER=1, PRD_ITER_LIMIT="1.0E-2"), active=(),
                          wave=(854.2, 854.7, 41), keys=("CA",), mu=0.8),
+    "caii_r3_pf": dict(kw=dict(KW, NRAYS=3, HYDROGEN_LTE="TRUE", STOKES_MODE="POLARIZATION_FREE"), active=(), wave=(854.2, 854.7, 41),
+                       keys=("CA",), mu=1.0),
     "h_caii_r5_ff": dict(kw=dict(KW, NRAYS=5, HYDROGEN_LTE="FALSE", STOKES_MODE="FIELD_FREE"), active=("H_6.atom",),
                          wave=(630.25, 630.5, 21), keys=("H ", "CA"), mu=0.8),
 }

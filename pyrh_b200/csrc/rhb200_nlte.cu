@@ -57,6 +57,7 @@ struct Plan {            // device copy of the shared problem structure
   int naseg, nslot, aseg_maxslot; const int *aseg_atom, *aseg_lo, *aseg_hi, *aseg_slot0, *as_slot, *tr_slot0, *tr_slots;
   // FULL_STOKES formal solution with polarizable ACTIVE lines (after adjustStokesMode(), zeeman.c:303-345)
   int stokes;                                   // input.StokesMode == FULL_STOKES for the passes run now
+  int stokes_prof;                              // input.StokesMode > FIELD_FREE when Profile() ran: Zeeman profiles (profile.c:112)
   int stokes_solver;                            // S_INTERPOLATION_STOKES
   const int *line_pol, *line_zoff, *zq;         // [nline] line->polarizable, [nline+1] slices of the Zeeman pattern tables
   const double *zshift, *zstrength;
@@ -141,7 +142,7 @@ nlte_profile_kernel(Plan P, Cols C, int ncol)
   const double sign = to_obs ? 1.0 : -1.0;
   const double vk = v + sign * v_los;
   const double adamp = C.adamp[((size_t) col * P.nline + li) * N + k];
-  if (P.stokes && P.line_pol[li]) {
+  if (P.stokes_prof && P.line_pol[li]) {
     // profile.c:112-116, 174-184, 239-305: Zeeman components through Voigt(.., HUMLICEK), one isotope component
     const double Larmor = (RH_Q_ELECTRON / (4.0*RH_PI*RH_M_ELECTRON)) * (lambda0*RH_NM_TO_M);
     const double vB = Larmor * C.B[(size_t) col * N + k] / vbroad;
@@ -1484,11 +1485,13 @@ struct NlteEngine {
     for (int ns = 0; ns < Ns; ns++) pol_c[ns] = (wflags[ns] & 2) ? 1 : 0;       // backgrflags.ispolarized
     RH_CHECK(ar.upload(&di, pol_as.data(), (size_t) Ns)); P.pol_as = di;
     RH_CHECK(ar.upload(&di, pol_c.data(), (size_t) Ns)); P.pol_c = di;
-    P.stokes = 0; P.stokes_solver = c->s_interpolation_stokes;
+    P.stokes = 0; P.stokes_prof = 0; P.stokes_solver = c->s_interpolation_stokes;
     has_zeeman = true;
     return RHB200_OK;
   }
-  void set_stokes(bool on) { P.stokes = (on && has_zeeman) ? 1 : 0; }
+  void set_stokes(bool on) { P.stokes = P.stokes_prof = (on && has_zeeman) ? 1 : 0; }
+  // POLARIZATION_FREE: Zeeman profiles, scalar transfer
+  void set_stokes_profiles_only(bool on) { P.stokes = 0; P.stokes_prof = (on && has_zeeman) ? 1 : 0; }
 
   // line->PRD of the ACTIVE lines (readatom.c:255-258) and the keywords of Redistribute() (iterate.c:98-108)
   int set_prd(const rhb200_nlte_plan *pl, const int *line_prd, int PRD_NmaxIter, double PRDiterLimit) {

@@ -256,8 +256,8 @@ extern "C" int rhb200_nlte_compute1d_stokes_batch(rhb200_ctx *c, const rhb200_nl
   if (c->wav.nlambda != pl->Nspect) { rhb200_set_error("rhb200_set_wavelengths() must hold plan->lambda (%d vs %d wavelengths)", c->wav.nlambda, pl->Nspect); return RHB200_ESTATE; }
   if (iref < 0 || iref >= pl->Nspect) { rhb200_set_error("iref outside the wavelength grid"); return RHB200_EINVAL; }
   if (!c->cont || !rh_continuum_has_chemistry(c)) { rhb200_set_error("rhb200_set_continuum() / rhb200_set_chemistry() have not been called"); return RHB200_ESTATE; }
-  if (fr->stokes < 0 || fr->stokes > 2) { rhb200_set_error("front->stokes must be 0 (NO_STOKES), 1 (FIELD_FREE) or 2 (FULL_STOKES)"); return RHB200_EUNSUPPORTED; }
-  const bool stokes = fr->stokes != 0, full_stokes = fr->stokes == 2;
+  if (fr->stokes < 0 || fr->stokes > 3) { rhb200_set_error("front->stokes must be 0 (NO_STOKES), 1 (FIELD_FREE), 2 (FULL_STOKES) or 3 (POLARIZATION_FREE)"); return RHB200_EUNSUPPORTED; }
+  const bool stokes = fr->stokes != 0, full_stokes = fr->stokes == 2, pol_free = fr->stokes == 3;
   bool prd = false;
   if (fr->line_prd && fr->PRD_NmaxIter > 0) for (int l = 0; l < pl->nline; l++) prd = prd || fr->line_prd[l] != 0;
   if (!c->no_stokes) { rhb200_set_error("the background of the NLTE path is set up with rhb200_set_stokes_mode(ctx, 0): the FULL_STOKES passes of FIELD_FREE are selected by front->stokes"); return RHB200_EUNSUPPORTED; }
@@ -477,6 +477,7 @@ extern "C" int rhb200_nlte_compute1d_stokes_batch(rhb200_ctx *c, const rhb200_nl
                         stokes ? E.d_chi_cQ : nullptr, stokes ? E.d_eta_cQ : nullptr));
     if (stokes) RH_CHECK(E.bproject(d_in, nrow));
     E.set_stokes(full_stokes);                       // FULL_STOKES: polarised profiles, rays and I_eff from the first pass on
+    if (pol_free) E.set_stokes_profiles_only(true);  // POLARIZATION_FREE: Zeeman-broadened profiles, I alone (opacity.c:97, formal.c:94)
     RH_CHECK(rh_launch_scales_chi(c, n, N, Ns, iref, atm_scale, wght_per_H, c->total_abund, c->gravity > 0.0 ? c->gravity : 1.0, E.C.chi_c, d_at, d_sc,
                                   scales ? d_sc + 2*cN : nullptr));
     nlte_height_kernel<<<RH_GRID(nN, 128), 0, st>>>(n, N, d_at, (double *) E.C.height);
@@ -501,7 +502,8 @@ extern "C" int rhb200_nlte_compute1d_stokes_batch(rhb200_ctx *c, const rhb200_nl
     mark("initScatter");
     RH_CHECK(E.iterate(fr->NmaxIter, fr->iterLimit, niter.data(), nullptr, 0, nullptr, nullptr));
     mark("Iterate");
-    if (stokes && !full_stokes) {                    // adjustStokesMode(), pyrh_compute1dray.c:332: Profile() of the polarizable lines again
+    if (pol_free) E.set_stokes(true);                // adjustStokesMode(): FULL_STOKES from here on, the profiles are kept (zeeman.c:319-321)
+    if (stokes && !full_stokes && !pol_free) {       // adjustStokesMode(), pyrh_compute1dray.c:332: Profile() of the polarizable lines again
       if (H_active) {                                // their Damping() now sees hydrogen's NLTE populations
         nlte_popsn_kernel<<<RH_GRID(nN * nlev_model, 128), 0, st>>>(n, N, nlev_model, H_nlevel, d_pops, E.C.n, E.nlev,
                                                                     E.lev_off[H_engine_atom], d_popsn);
@@ -519,6 +521,7 @@ extern "C" int rhb200_nlte_compute1d_stokes_batch(rhb200_ctx *c, const rhb200_nl
     }
     RH_CHECK(E.scatter(fr->NmaxScatter, 2, fr->iterLimit, pass_b.data(), nullptr, nullptr));
     E.set_stokes(full_stokes);
+    if (pol_free) E.set_stokes_profiles_only(true);
     mark("passes after Iterate");
     if (niter_out) memcpy(niter_out + c0, niter.data(), n * sizeof(int));
     if (passes_out) for (int q = 0; q < n; q++) { passes_out[2*(size_t) (c0 + q)] = pass_a[q]; passes_out[2*(size_t) (c0 + q) + 1] = pass_b[q]; }

@@ -993,7 +993,9 @@ class Session:
         self.ctx.set_model_lines(self.model_lines)
         self.ctx.set_scatter(int(kw["N_MAX_SCATTER"]), float(kw.get("ITER_LIMIT", "1.0E-2")))   # pyrh_compute1dray.c:332-337
         self.stokes_mode = kw["STOKES_MODE"].upper()
-        self.ctx.set_stokes_mode(self.stokes_mode)
+        # without ACTIVE atoms Formal() solves for Q, U, V only when StokesMode == FULL_STOKES (formal.c:94-95) and
+        # adjustStokesMode() leaves the mode alone (zeeman.c:315-317): FIELD_FREE and POLARIZATION_FREE are NO_STOKES here
+        self.ctx.set_stokes_mode("FULL_STOKES" if self.stokes_mode == "FULL_STOKES" else "NO_STOKES")
         self.ctx.set_wavelengths(self.lam)
         self.ctx.set_solvers(kw["S_INTERPOLATION"], kw["S_INTERPOLATION_STOKES"])
         abundance = np.array([self.el.abund[int(p) - 1] for p in bg["atom_pt_index"]])

@@ -479,9 +479,9 @@ class NlteSession:
         self.loggf_key = (tob(loggf_ids), tob(loggf_values))
         kw = self.kw = H.read_keywords(cwd)
         self.stokes_mode = kw["STOKES_MODE"].upper()
-        if self.stokes_mode not in ("NO_STOKES", "FIELD_FREE", "FULL_STOKES"):
-            raise NotImplementedError("ACTIVE atoms with STOKES_MODE = %s are not ported (NO_STOKES, FIELD_FREE, FULL_STOKES are)"
-                                      % self.stokes_mode)
+        if self.stokes_mode not in ("NO_STOKES", "FIELD_FREE", "FULL_STOKES", "POLARIZATION_FREE"):
+            raise ValueError("STOKES_MODE = %s (readvalue.c:262-283 knows NO_STOKES, FIELD_FREE, POLARIZATION_FREE, FULL_STOKES)"
+                             % self.stokes_mode)
         if H._true(kw["MAGNETO_OPTICAL"]):
             raise NotImplementedError("MAGNETO_OPTICAL = TRUE is refused (the reference overflows chip_c there, readj.c:328)")
         if H._true(kw.get("DO_FUDGE", "FALSE")) and fudge_wave is None:
@@ -617,7 +617,7 @@ class NlteSession:
             fr = nl.FrontStruct(model.ctypes.data_as(lib.ip), len(self.coll), len(self.coll_T),
                                 *[x.ctypes.data_as(lib.dp) for x in tabs],
                                 self.line_rows.ctypes.data_as(lib.dp), self.hdr["NmaxScatter"], self.hdr["NmaxIter"],
-                                self.hdr["iterLimit"], C.pointer(plan1), {"NO_STOKES": 0, "FIELD_FREE": 1, "FULL_STOKES": 2}[self.stokes_mode],
+                                self.hdr["iterLimit"], C.pointer(plan1), {"NO_STOKES": 0, "FIELD_FREE": 1, "FULL_STOKES": 2, "POLARIZATION_FREE": 3}[self.stokes_mode],
                                 self.line_pol.ctypes.data_as(lib.ip), self.line_zoff.ctypes.data_as(lib.ip),
                                 self.zq.ctypes.data_as(lib.ip), self.zshift.ctypes.data_as(lib.dp),
                                 self.zstrength.ctypes.data_as(lib.dp), self.line_prd.ctypes.data_as(lib.ip), self.prd_nmax,

@@ -1193,6 +1193,15 @@ def test_reference_own_test_compute1d(tmp_path):
     assert np.array_equal(spec[0], g["I"])
     spec = host.compute1d(cwd, 0.5, atm_scale, g["moving_atmosphere"], g["wave"])
     assert np.array_equal(spec[0], g["moving_I"])
+    # without ACTIVE atoms FIELD_FREE and POLARIZATION_FREE are NO_STOKES (formal.c:94-95, zeeman.c:315-317; the
+    # unmodified reference returns the same bytes for the three keywords)
+    kw = (tmp_path / "keyword.input").read_text()
+    for mode in ("FIELD_FREE", "POLARIZATION_FREE"):
+        (tmp_path / "keyword.input").write_text(kw.replace("STOKES_MODE = NO_STOKES", f"STOKES_MODE = {mode}"))
+        host.close_sessions()
+        spec = host.compute1d(cwd, 1.0, atm_scale, g["atmosphere"], g["wave"])
+        assert np.array_equal(spec[0], g["I"]) and not spec[3].any()
+    host.close_sessions()
 
 
 def test_molecular_lines_in_the_fused_path():
@@ -1406,7 +1415,7 @@ def test_nlte_through_compute1d_on_perturbed_columns(case):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", ["caii_r3_ff", "h_caii_r5_ff"])
+@pytest.mark.parametrize("case", ["caii_r3_ff", "h_caii_r5_ff", "caii_r3_pf"])
 def test_nlte_field_free_full_stokes_solution(case):
     """STOKES_MODE = FIELD_FREE with ACTIVE atoms: the MALI iterations run field-free, adjustStokesMode() (zeeman.c:303-345)
     then recomputes the profiles of the polarizable lines with their Zeeman patterns (Profile(), profile.c:112-305) and the
@@ -1414,7 +1423,9 @@ def test_nlte_field_free_full_stokes_solution(case):
     StokesK + Piece_Stokes_Bezier3_1D with an active set, formal.c:184-217).  Ca II 8542 alone (polarizable ACTIVE line) and
     H + Ca II in the Hinode window at mu = 0.8 (polarised BACKGROUND: Fe I 6301/6302 with the last-ray record).  Eight
     perturbed columns with B up to 2.5 kG against the reference: iterations identical, populations <= 1e-6, I <= 1e-9,
-    Q, U, V <= 1e-12 of the continuum (north_star); reported: whether every number is bit-identical."""
+    Q, U, V <= 1e-12 of the continuum (north_star); reported: whether every number is bit-identical.
+    caii_r3_pf: STOKES_MODE = POLARIZATION_FREE -- Zeeman-broadened profiles from the start (profile.c:112), scalar transfer
+    in the iterations, the Stokes solution afterwards with the same profiles (zeeman.c:319-321)."""
     from pyrh_b200 import host, nlte_host
     g, cwd = _nlte_front_case(case)
     atm, wave, mu = g["atmosphere"], g[f"{case}_wave"], float(g[f"{case}_mu"])
@@ -1436,7 +1447,7 @@ def test_nlte_field_free_full_stokes_solution(case):
     assert np.abs(ref).max() > 0 and np.abs(got).max() > 0
     assert np.array_equal(res["niter"], g[f"{case}_niter"])
     assert en <= 1e-6 and eI <= 1e-9 and eP <= 1e-12
-    assert np.array_equal(res["n"], g[f"{case}_n"])            # the iterations are the NO_STOKES ones, to the bit
+    assert np.array_equal(res["n"], g[f"{case}_n"])            # (FIELD_FREE: the iterations are the NO_STOKES ones, to the bit)
     (sI, sQ, sU, sV, lam) = host.compute1d(cwd, mu, 0, atm[2], wave)
     assert np.array_equal(sI, res["I"][2]) and np.array_equal(sQ, res["Q"][2]) and np.array_equal(sV, res["V"][2])
     host.close_sessions()
@@ -1670,7 +1681,7 @@ def test_bridged_reference_library_hse_get_scales_get_ne():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", ["caii_r3", "caii_r5", "h_caii_r3", "h_caii_r5", "caii_r3_ff", "h_caii_r5_ff", "caii_r3_fs", "caii_r5_prd1"])
+@pytest.mark.parametrize("case", ["caii_r3", "caii_r5", "h_caii_r3", "h_caii_r5", "caii_r3_ff", "h_caii_r5_ff", "caii_r3_fs", "caii_r5_prd1", "caii_r3_pf"])
 def test_bridged_reference_library_rhf1d_nlte(case):
     """The bridged library with ACTIVE atoms: the reference's readAtom / getLambda / SortLambda state (active sets,
     line grids, continuum cross-sections) and the collisional sections of the atom files are flattened in C
@@ -1692,7 +1703,7 @@ def test_bridged_reference_library_rhf1d_nlte(case):
     b = rd.rhf1d_batch(atm[:4], wave, cwd, mu=mu, get_populations=True, nlev=n.shape[0])
     assert np.array_equal(b["stokes"][:, 0], g[f"{case}_I"][:4]) and np.array_equal(b["n"], g[f"{case}_n"][:4])
     assert np.array_equal(b["niter"], g[f"{case}_niter"][:4])
-    if case.endswith("_ff") or case.endswith("_fs"):   # FIELD_FREE / FULL_STOKES: the full Stokes solution
+    if case.endswith(("_ff", "_fs", "_pf")):        # FIELD_FREE / FULL_STOKES / POLARIZATION_FREE: the full Stokes solution
         quv = g[f"{case}_QUV"]
         assert np.array_equal(np.array([o["Q"], o["U"], o["V"]]), quv[1]) and np.abs(quv[1]).max() > 0
         assert np.array_equal(b["stokes"][:, 1:], quv[:4])
