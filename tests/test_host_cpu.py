@@ -233,3 +233,26 @@ def test_gauss_legendre_and_spline_helpers():
     from scipy.interpolate import CubicSpline
     cs = CubicSpline(t, y, bc_type="natural")
     assert np.allclose(nh.spline_eval(t, y, M, [4000.0, 9000.0, 30000.0]), cs([4000.0, 9000.0, 30000.0]), rtol=1e-12)
+
+
+def test_active_atom_prd_and_polarizable_flags():
+    """readAtom for an ACTIVE atom (readatom.c:247-258, 352-368): Ca II H & K carry the shape string PRD and become PRD
+    lines only when PRD_N_MAX_ITER > 0; every Ca II line has term labels determinate() can read (|dJ| <= 1), so all
+    five are polarizable -- their Zeeman patterns (zeeman.c:186-281) have 4 / 6 (J 1/2-1/2, 1/2-3/2) ... components
+    with strengths normalised per q."""
+    from pyrh_b200 import nlte_host, zeeman
+    root = Path(__file__).resolve().parent.parent / "oracle" / "_ref" / "pyrh_path" / "rh" / "Atoms"
+    if not (root / "CaII.atom").exists():
+        pytest.skip("reference atom files not staged (oracle/_ref)")
+    kw = dict(PRD_N_MAX_ITER="3", VMICRO_CHAR="5.0", B_STRENGTH_CHAR="0.0")
+    at = nlte_host.read_active_atom(root / "CaII.atom", kw)
+    prd = {(ln["j"], ln["i"]): ln["PRD"] for ln in at["lines"]}
+    assert prd == {(3, 0): True, (4, 0): True, (3, 1): False, (4, 1): False, (4, 2): False}
+    assert all(ln["polarizable"] for ln in at["lines"])
+    at0 = nlte_host.read_active_atom(root / "CaII.atom", dict(kw, PRD_N_MAX_ITER="0"))
+    assert not any(ln["PRD"] for ln in at0["lines"])
+    for ln in at["lines"]:
+        q, sh, st = zeeman.zeeman(at["label"][ln["i"]], at["g"][ln["i"]], at["label"][ln["j"]], at["g"][ln["j"]], ln["g_Lande_eff"])
+        assert len(q) > 0 and set(q) <= {-1, 0, 1}
+        for comp in (-1, 0, 1):
+            assert abs(sum(s_ for q_, s_ in zip(q, st) if q_ == comp) - 1.0) < 1e-12

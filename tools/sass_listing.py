@@ -10,8 +10,15 @@ WANT = ("opacity_fused_kernelILi10ENS_11ZeemanParamELb0ELb0", "delo_raypts_kerne
         "chemeq_coop_kernelILi16")
 
 
+WANT_R2 = ("nlte_gamma_kernelILb1ELb0", "nlte_gamma_atom_kernel", "nlte_ray_kernelILi2ELi8", "nlte_opacity_kernel", "nlte_prd_scatter_kernel",
+           "nlte_ray_stokes_kernel", "continuum_tile_kernelILi8", "delo_vcols_kernel")
+
+
 def main():
+    global WANT
     out_name = sys.argv[1] if len(sys.argv) > 1 else "r1_sass_hot_kernels.txt"
+    if len(sys.argv) > 2 and sys.argv[2] == "r2":
+        WANT = WANT_R2
     txt = subprocess.run(["cuobjdump", "-sass", str(ROOT / "pyrh_b200" / "csrc" / "librhb200.so")],
                          capture_output=True, text=True).stdout
     blocks = re.split(r"\n\s*Function : ", txt)
