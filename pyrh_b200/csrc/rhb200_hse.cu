@@ -85,6 +85,79 @@ __device__ double solve_ne_point(int nelem, int npf, const double *__restrict__ 
   return ne;
 }
 
+// The same for small batches, one WARP per depth point: a GPU thread needs ~1 ms for the ~500 Saha factors of one
+// Newton step, which is what a single-column pyrh.hse call waits for 125 times.  Lane l evaluates getfjk() of the
+// elements l, l + 32, ... and leaves the terms akj fjk[j], akj dfjk[j] in shared memory; lane 0 then adds them to
+// `error` and `sum` in the reference's (element, stage) order, so the result is the bit pattern of solve_ne_point().
+// sh: 2 * nelem * RHB200_RE_MAXSTAGE doubles per warp.
+__device__ double solve_ne_point_coop(int nelem, int npf, const double *__restrict__ elems, const double *__restrict__ pf,
+                                      const double *__restrict__ Tpf, double T, double nHtot, double ne_in,
+                                      int fromscratch, int uk_zero, double *sh)
+{
+  constexpr int MS = RHB200_RE_MAXSTAGE;
+  const int lane = threadIdx.x & 31;
+  double *sh_e = sh, *sh_s = sh + (size_t) nelem * MS;
+  const double C1 = (RH_HPLANCK/(2.0*RH_PI*RH_M_ELECTRON)) * (RH_HPLANCK/RH_KBOLTZMANN);
+  double ne_old, ne = ne_in;
+  if (fromscratch) {
+    const double Uk = uk_zero ? 0.0 : pf_interp(npf, Tpf, pf + (size_t) ((int) elems[RHB200_RE_PFROW]) * npf, T);
+    const double PhiH = 0.5 * rhm::rh_pow(C1/T, 1.5) * rhm::rh_exp(Uk + elems[RHB200_RE_IONPOT0]/(RH_KBOLTZMANN*T));
+    ne_old = (sqrt(1.0 + 4.0*nHtot*PhiH) - 1.0) / (2.0*PhiH);
+    ne = ne_old;
+  } else ne_old = ne_in;
+  double fjk[MS], dfjk[MS];
+  for (int niter = 0; niter < N_MAX_ELECTRON_ITERATIONS; niter++) {
+    for (int n = lane; n < nelem; n += 32) {
+      const double *e = elems + (size_t) n * RHB200_RE_NFIELD;
+      const int nst = (int) e[RHB200_RE_NSTAGE], row = (int) e[RHB200_RE_PFROW];
+      const double CT_ne = 2.0 * rhm::rh_pow(C1/T, -1.5) / ne_old;
+      double sum1 = 1.0, sum2 = 0.0;
+      fjk[0] = 1.0; dfjk[0] = 0.0;
+      double Uk = pf_interp(npf, Tpf, pf + (size_t) row * npf, T);
+      for (int j = 1; j < nst; j++) {
+        const double Ukp1 = pf_interp(npf, Tpf, pf + (size_t) (row + j) * npf, T);
+        fjk[j]  = fjk[j-1] * CT_ne * rhm::rh_exp(Ukp1 - Uk - e[RHB200_RE_IONPOT0 + j-1]/(RH_KBOLTZMANN*T));
+        dfjk[j] = -j * fjk[j] / ne_old;
+        sum1 += fjk[j];
+        sum2 += dfjk[j];
+        Uk = Ukp1;
+      }
+      for (int j = 0; j < nst; j++) {
+        fjk[j] /= sum1;
+        dfjk[j] = (dfjk[j] - fjk[j] * sum2) / sum1;
+      }
+      if (n == 0) {
+        const double PhiHmin = 0.25*rhm::rh_pow(C1/T, 1.5) * rhm::rh_exp(0.754 * RH_EV / (RH_KBOLTZMANN * T));
+        sh_e[0] = ne_old * fjk[0] * PhiHmin;
+        sh_s[0] = (fjk[0] + ne_old * dfjk[0]) * PhiHmin;
+      }
+      for (int j = 1; j < nst; j++) {
+        const double akj = e[RHB200_RE_ABUND] * j;
+        sh_e[(size_t) n * MS + j] = akj * fjk[j];
+        sh_s[(size_t) n * MS + j] = akj * dfjk[j];
+      }
+    }
+    __syncwarp();
+    double dne = 0.0;
+    if (lane == 0) {
+      double error = ne_old / nHtot, sum = 0.0;
+      for (int n = 0; n < nelem; n++) {
+        const int nst = (int) elems[(size_t) n * RHB200_RE_NFIELD + RHB200_RE_NSTAGE];
+        if (n == 0) { error += sh_e[0]; sum -= sh_s[0]; }
+        for (int j = 1; j < nst; j++) { error -= sh_e[(size_t) n * MS + j]; sum += sh_s[(size_t) n * MS + j]; }
+      }
+      ne = ne_old - nHtot * error / (1.0 - nHtot * sum);
+      dne = fabs((ne - ne_old)/ne_old);
+    }
+    ne = __shfl_sync(0xffffffffu, ne, 0);
+    dne = __shfl_sync(0xffffffffu, dne, 0);
+    __syncwarp();
+    ne_old = ne;
+    if (dne <= MAX_ELECTRON_ERROR) break;
+  }
+  return ne;
+}
+
 __global__ void __launch_bounds__(128)
 solve_ne_kernel(size_t n, int nelem, int npf, const double *__restrict__ elems, const double *__restrict__ pf,
                 const double *__restrict__ Tpf, const double *__restrict__ T, const double *__restrict__ nHtot,
@@ -137,6 +210,25 @@ __global__ void hse_pre_kernel(HseCols H, int k, int nelem, int npf, const doubl
   double *a = atL + (size_t) col * RHB200_AT_NFIELD;
   for (int f = 0; f < RHB200_AT_NFIELD; f++) a[f] = 0.0;
   a[RHB200_AT_T] = H.T[o]; a[RHB200_AT_NE] = ne; a[RHB200_AT_NHTOT] = H.nHtot[o];
+}
+
+// the same with one warp per column (small batches: see solve_ne_point_coop)
+__global__ void __launch_bounds__(32)
+hse_pre_coop_kernel(HseCols H, int k, int nelem, int npf, const double *__restrict__ elems,
+                    const double *__restrict__ pf, const double *__restrict__ Tpf, double *__restrict__ atL)
+{
+  extern __shared__ double hse_sh[];
+  const int col = blockIdx.x;
+  if (col >= H.ncol || H.done[col]) return;
+  const size_t o = (size_t) col * H.ndep + k;
+  const double ne = solve_ne_point_coop(nelem, npf, elems, pf, Tpf, H.T[o], H.nHtot[o], 0.0, 1, 1, hse_sh);
+  if (threadIdx.x == 0) {
+    H.rho[o] = (RH_AMU * H.wght_per_H) * H.nHtot[o];
+    H.ne[o] = ne;
+    double *a = atL + (size_t) col * RHB200_AT_NFIELD;
+    for (int f = 0; f < RHB200_AT_NFIELD; f++) a[f] = 0.0;
+    a[RHB200_AT_T] = H.T[o]; a[RHB200_AT_NE] = ne; a[RHB200_AT_NHTOT] = H.nHtot[o];
+  }
 }
 
 // second half: pressure integration and the new total hydrogen density (pyrh_hse.c:236-254, 308-372)
@@ -215,7 +307,11 @@ extern "C" int rhb200_hse_batch(rhb200_ctx *c, int ncol, int ndep, int atm_scale
     int nactive = ncol;
     if ((e = cudaMemcpyAsync(H.nactive, &nactive, sizeof(int), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) { fail("flag"); break; }
     for (int it = 0; it < 50 && nactive > 0 && rc == RHB200_OK; it++) {
-      hse_pre_kernel<<<gb, 64, 0, c->stream>>>(H, k, t->nelem, t->npf, t->elems, t->pf, t->Tpf, atL);
+      if (ncol <= 2048)                            // few columns: one warp each (a single thread needs ~1 ms per Newton solve)
+        hse_pre_coop_kernel<<<ncol, 32, 2 * (size_t) t->nelem * RHB200_RE_MAXSTAGE * sizeof(double), c->stream>>>(
+            H, k, t->nelem, t->npf, t->elems, t->pf, t->Tpf, atL);
+      else
+        hse_pre_kernel<<<gb, 64, 0, c->stream>>>(H, k, t->nelem, t->npf, t->elems, t->pf, t->Tpf, atL);
       rc = rh_continuum_chunk(c, ncol, 1, atL, chemL, popsL, tprepL, chiL, etaL, 1);
       if (rc != RHB200_OK) break;
       hse_post_kernel<<<gb, 64, 0, c->stream>>>(H, k, chiL);

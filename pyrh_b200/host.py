@@ -1121,29 +1121,77 @@ class MultiSession:
             s.close()
 
 
-def get_scales(cwd, atm_scale, scale, atmosphere, lam_ref, atomic_number=None, atomic_abundance=None, device=0):
-    """Drop-in for ``pyrh.get_scales`` (pyrh.pyx:491-534): ``(tau, height [m], cmass [kg m^-2])`` of one column from
-    Background() at ``lam_ref`` and convertScales().  Like the reference it looks at no Kurucz line
-    (pyrh_hse.c:441) and takes the depth scale from ``scale`` (``atmosphere`` row 0 is ignored)."""
-    from . import api, continuum
-    kw = read_keywords(cwd)
-    el = read_elements(None, kw, atomic_number, atomic_abundance)
-    bg = read_background_model(cwd, kw, el)
-    ctx = api.Context(device)
-    try:
+class ScalesSession:
+    """The parsed working directory of ``get_scales`` resident on one GPU (continuum model at ``lam_ref``, chemistry)."""
+
+    def __init__(self, cwd, lam_ref, device=0, atomic_number=None, atomic_abundance=None):
+        from . import api, continuum
+        kw = read_keywords(cwd)
+        self.el = el = read_elements(None, kw, atomic_number, atomic_abundance)
+        bg = read_background_model(cwd, kw, el)
+        self.lam_ref, self.vmacro_tresh = float(lam_ref), float(kw["VMACRO_TRESH"])
+        self.ctx = ctx = api.Context(device)
         empty = ll.LineTable(lines=np.zeros((0, ll.RL_NFIELD)), zq=np.zeros(0, np.int32), zshift=np.zeros(0),
                              zstrength=np.zeros(0), elems=np.zeros((0, ll.RE_NFIELD)), pf=np.zeros((0, len(el.Tpf))),
                              Tpf=el.Tpf, vmicro_char=float(kw["VMICRO_CHAR"]) * 1.0E+03)
         ctx.set_lines(empty)
-        ctx.set_wavelengths(np.array([float(lam_ref)]))
+        ctx.set_wavelengths(np.array([self.lam_ref]))
         ctx.set_continuum(continuum.ContinuumModel(bg), np.array([el.abund[int(p) - 1] for p in bg["atom_pt_index"]]))
         ctx.set_chemistry(bg["ce_nuclei"][:, 1].astype(np.int32), bg["ce_mol"])
-        a = np.array(atmosphere, np.float64)[None, :9].copy()
-        a[0, 0] = scale
-        sc = ctx.get_scales_batch(a, atm_scale, float(lam_ref), el.wght_per_H, el.totalAbund,
-                                  vmacro_tresh=float(kw["VMACRO_TRESH"]))[0]
-    finally:
-        ctx.close()
+
+    def get_scales(self, atm_scale, atmosphere):
+        """``atmosphere`` [ncol, 9, ndep] (row 0 = the depth scale) -> [ncol, 3, ndep]: height, tau_ref, column mass."""
+        return self.ctx.get_scales_batch(atmosphere, atm_scale, self.lam_ref, self.el.wght_per_H, self.el.totalAbund,
+                                         vmacro_tresh=self.vmacro_tresh)
+
+    def close(self):
+        self.ctx.close()
+
+
+class NeSession:
+    """atmos.elements[] resident on one GPU for ``get_ne_from_nH`` (Solve_ne over all elements)."""
+
+    def __init__(self, cwd, device=0):
+        from . import api
+        kw = read_keywords(cwd)
+        el = read_elements(None, kw)
+        if not el.abundance_set.all():
+            raise NotImplementedError("elements without an abundance: the reference feeds their raw partition functions "
+                                      "into Solve_ne (abundance.c:207-215); not reproduced")
+        self.ctx = api.Context(device)
+        self.ctx.set_elements(*element_table(el), el.Tpf)
+
+    def close(self):
+        self.ctx.close()
+
+
+def _cached(kind, cwd, extra, factory):
+    """The same bounded LRU as compute1d's sessions, for the helpers pyrh users call once per pixel (hse, get_scales,
+    get_ne_from_nH): keyed on the directory, PYRH_PATH, the mtimes of every input file read and the call's overrides."""
+    tob = lambda x: None if x is None else np.asarray(x).tobytes()   # noqa: E731
+    key = _session_key(cwd, np.zeros(0), (kind,) + tuple(tob(x) if not isinstance(x, (int, float, str)) else x for x in extra))
+    s = _SESSIONS.get(key)
+    if s is not None:
+        _SESSIONS.move_to_end(key)
+        return s
+    s = factory()
+    _SESSIONS[key] = s
+    while len(_SESSIONS) > MAX_SESSIONS:
+        _, old = _SESSIONS.popitem(last=False)
+        old.close()
+    return s
+
+
+def get_scales(cwd, atm_scale, scale, atmosphere, lam_ref, atomic_number=None, atomic_abundance=None, device=0):
+    """Drop-in for ``pyrh.get_scales`` (pyrh.pyx:491-534): ``(tau, height [m], cmass [kg m^-2])`` of one column from
+    Background() at ``lam_ref`` and convertScales().  Like the reference it looks at no Kurucz line
+    (pyrh_hse.c:441) and takes the depth scale from ``scale`` (``atmosphere`` row 0 is ignored).  The parsed directory
+    stays resident between calls (``close_sessions()`` releases it)."""
+    s = _cached("get_scales", cwd, (float(lam_ref), atomic_number, atomic_abundance, device),
+                lambda: ScalesSession(cwd, lam_ref, device, atomic_number, atomic_abundance))
+    a = np.array(atmosphere, np.float64)[None, :9].copy()
+    a[0, 0] = scale
+    sc = s.get_scales(atm_scale, a)[0]
     return sc[1], sc[0], sc[2]
 
 
@@ -1198,11 +1246,9 @@ class HseSession:
 def hse(cwd, atm_scale, scale, temp, pg_top=0.1, fudge_wave=None, fudge_value=None, atomic_number=None,
         atomic_abundance=None, full_output=False, device=0):
     """Drop-in for ``pyrh.hse`` (pyrh.pyx:427-489): ``(ne, nHtot)`` or, with ``full_output``, ``(ne, nHtot, rho, pg)``."""
-    s = HseSession(cwd, device, atomic_number, atomic_abundance, fudge_wave, fudge_value)
-    try:
-        ne, nH, rho, pg = s.hse(atm_scale, scale, temp, pg_top)
-    finally:
-        s.close()
+    s = _cached("hse", cwd, (atomic_number, atomic_abundance, fudge_wave, fudge_value, device),
+                lambda: HseSession(cwd, device, atomic_number, atomic_abundance, fudge_wave, fudge_value))
+    ne, nH, rho, pg = s.hse(atm_scale, scale, temp, pg_top)
     return (ne, nH, rho, pg) if full_output else (ne, nH)
 
 
@@ -1210,20 +1256,10 @@ def get_ne_from_nH(cwd, atm_scale, scale, temperature, nH, device=0):
     """Drop-in for ``pyrh.get_ne_from_nH`` (pyrh.pyx:396-425): electron density [cm^-3] from temperature [K] and total
     hydrogen density [cm^-3] by the LTE ionisation equilibrium of all elements (Solve_ne from scratch, hydrogen in
     LTE).  ``atm_scale`` / ``scale`` are accepted like the reference's and, like there, do not enter the result."""
-    from . import api
-    kw = read_keywords(cwd)
-    el = read_elements(None, kw)
-    if not el.abundance_set.all():
-        raise NotImplementedError("elements without an abundance: the reference feeds their raw partition functions "
-                                  "into Solve_ne (abundance.c:207-215); not reproduced")
-    ctx = api.Context(device)
-    try:
-        ctx.set_elements(*element_table(el), el.Tpf)
-        CUBE_CM = 1.0E-02 * 1.0E-02 * 1.0E-02
-        nHtot = np.array([x / CUBE_CM for x in np.asarray(nH, np.float64)])          # pyrh_hse.c:626
-        ne = ctx.solve_ne(np.asarray(temperature, np.float64), nHtot)
-    finally:
-        ctx.close()
+    s = _cached("get_ne_from_nH", cwd, (device,), lambda: NeSession(cwd, device))
+    CUBE_CM = 1.0E-02 * 1.0E-02 * 1.0E-02
+    nHtot = np.array([x / CUBE_CM for x in np.asarray(nH, np.float64)])              # pyrh_hse.c:626
+    ne = s.ctx.solve_ne(np.asarray(temperature, np.float64), nHtot)
     return np.array([x * CUBE_CM for x in ne])                                       # pyrh_hse.c:647
 
 
