@@ -607,6 +607,8 @@ int pyrh_b200_solve(double mu, int get_atomic_rfs, int get_populations, int fudg
   const double *rows = g_batch.ncol > 0 ? g_batch.atm : g_rows;
   int n, index, a;
   memset(spec, 0, sizeof *spec);
+  if (atmos.hydrostatic) FAIL("HYDROSTATIC = TRUE (Hydrostatic() inside Iterate()) is not implemented");
+  if (input.backgr_pol) FAIL("BACKGROUND_POLARIZATION = TRUE (scattering polarisation through J20) is not implemented");
   build_tables(get_atomic_rfs, fudge_num, fudge_lam, fudge);
   spec->nlw = Nlw; spec->Nrays = atmos.Nrays; spec->stokes = 1;
   spec->lam = (double *) malloc(Nlw * sizeof(double));

@@ -110,6 +110,16 @@ class Elements:
     avgMolWght: float
 
 
+def refuse_unported_keywords(kw):
+    """Keywords that change rhf1d()'s result and that this path does not implement: refused, never ignored."""
+    if _true(kw.get("HYDROSTATIC", "FALSE")):
+        raise NotImplementedError("HYDROSTATIC = TRUE (Hydrostatic() inside Iterate(), iterate.c:120-128) is not ported")
+    if _true(kw.get("BACKGROUND_POLARIZATION", "FALSE")):
+        raise NotImplementedError("BACKGROUND_POLARIZATION = TRUE (scattering polarisation through J20, formal.c:143-321) is not ported")
+    if kw.get("ATMOS_ITOP", "none").lower() != "none":
+        raise NotImplementedError("ATMOS_ITOP: an irradiated top boundary (multiatmos.c:63-64, 186-220) is not ported")
+
+
 def pyrh_path(explicit=None) -> Path:
     p = explicit or os.environ.get("PYRH_PATH")
     if not p:
@@ -972,6 +982,7 @@ class Session:
         # reference interpolating in an empty table (undefined) -- refused
         if _true(kw.get("DO_FUDGE", "FALSE")) and fudge_wave is None:
             raise NotImplementedError("DO_FUDGE = TRUE without fudge_wave / fudge_value is undefined in the reference")
+        refuse_unported_keywords(kw)
         if _true(kw["MAGNETO_OPTICAL"]):
             raise NotImplementedError("MAGNETO_OPTICAL = TRUE is refused (the reference overflows chip_c there, readj.c:328)")
         listed = _atoms_listed(cwd, kw)

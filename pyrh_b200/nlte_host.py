@@ -482,6 +482,7 @@ class NlteSession:
         if self.stokes_mode not in ("NO_STOKES", "FIELD_FREE", "FULL_STOKES", "POLARIZATION_FREE"):
             raise ValueError("STOKES_MODE = %s (readvalue.c:262-283 knows NO_STOKES, FIELD_FREE, POLARIZATION_FREE, FULL_STOKES)"
                              % self.stokes_mode)
+        H.refuse_unported_keywords(kw)
         if H._true(kw["MAGNETO_OPTICAL"]):
             raise NotImplementedError("MAGNETO_OPTICAL = TRUE is refused (the reference overflows chip_c there, readj.c:328)")
         if H._true(kw.get("DO_FUDGE", "FALSE")) and fudge_wave is None:

@@ -256,3 +256,12 @@ def test_active_atom_prd_and_polarizable_flags():
         assert len(q) > 0 and set(q) <= {-1, 0, 1}
         for comp in (-1, 0, 1):
             assert abs(sum(s_ for q_, s_ in zip(q, st) if q_ == comp) - 1.0) < 1e-12
+
+
+def test_unported_keywords_are_refused_not_ignored():
+    """Keywords that change rhf1d()'s result and that the device path does not implement raise instead of being ignored."""
+    from pyrh_b200 import host
+    host.refuse_unported_keywords({"HYDROSTATIC": "FALSE", "BACKGROUND_POLARIZATION": "FALSE", "ATMOS_ITOP": "none"})
+    for bad in ({"HYDROSTATIC": "TRUE"}, {"BACKGROUND_POLARIZATION": "TRUE"}, {"ATMOS_ITOP": "itop.dat"}):
+        with pytest.raises(NotImplementedError):
+            host.refuse_unported_keywords(bad)
