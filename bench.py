@@ -260,18 +260,32 @@ def nlte_records(device, rank, ncol_scale=1.0, world=1, barrier=None, maxreduce=
     out = {}
     for case, c in NLTE_CASES.items():
         ncol = max(8, int(c["ncol"] * ncol_scale))
-        s = nlte_host.NlteSession(_nlte_workdir(case), np.linspace(*c["wave"]), device)
-        atm = synthetic.perturbed_batch(base, ncol, ndep=NDEP, first=10000 + rank * ncol)
-        s.compute(atm[:min(64, ncol)])                                  # warm-up: allocations, first launches
-        s.ctx.synchronize()
+        # under N ranks the barrier and the max-reduction are collectives: every rank reaches both whatever happens to it
+        s, res, err, dt = None, None, None, float("inf")
+        try:
+            s = nlte_host.NlteSession(_nlte_workdir(case), np.linspace(*c["wave"]), device)
+            atm = synthetic.perturbed_batch(base, ncol, ndep=NDEP, first=10000 + rank * ncol)
+            s.compute(atm[:min(64, ncol)])                              # warm-up: allocations, first launches
+            s.ctx.synchronize()
+        except Exception as e:          # noqa: BLE001
+            err = e
         if barrier:
             barrier()
-        t0 = time.perf_counter()
-        res = s.compute(atm)
-        s.ctx.synchronize()
-        dt = time.perf_counter() - t0
+        if err is None:
+            try:
+                t0 = time.perf_counter()
+                res = s.compute(atm)
+                s.ctx.synchronize()
+                dt = time.perf_counter() - t0
+            except Exception as e:      # noqa: BLE001
+                err = e
         if maxreduce:                                                   # every rank solves its own ncol columns (weak scaling)
             dt = maxreduce(dt)
+        if err is not None or not np.isfinite(dt):
+            out[case] = {"unavailable": f"{type(err).__name__}: {err}" if err is not None else "another rank failed"}
+            if s is not None:
+                s.close()
+            continue
         finite = np.isfinite(res["I"]).all(axis=tuple(range(1, res["I"].ndim))) & np.isfinite(res["n"]).all(axis=tuple(range(1, res["n"].ndim)))
         conv = (res["niter"] < int(c["kw"]["N_MAX_ITER"])) & finite
         rec = {"workload": f"{ncol} perturbed FAL-C columns x {NDEP} depths, {len(s.lam)} wavelengths, NRAYS {s.nrays}, "
