@@ -887,7 +887,7 @@ struct DevBuf {
 // Two slots / streams: the D2H of chunk i overlaps the kernels of chunk i+1.
 static int rf_fd_single_depth(rhb200_ctx *c, int ncol, int ndep, int nrow, double mu, int atm_scale, int iref, double wght_per_H,
                               int bc_top, int bc_bottom, int npar, const int *d_rows, const double *d_delta,
-                              const double *d_base, double *rf)
+                              const double *d_base, double *rf, const int *h_rows)
 {
   RhRange whole("rhf1d (LTE, finite-difference response functions)");
   RH_CHECK(check_batch_args(c, ncol, ndep, mu, bc_top, bc_bottom));
@@ -900,7 +900,19 @@ static int rf_fd_single_depth(rhb200_ctx *c, int ncol, int ndep, int nrow, doubl
     RH_CHECK(rh_continuum_set_molsel(c, c->wav.nmsel, chem.data()));
   }
   const int nchem = rh_continuum_natom(c) + 4, nlev = rh_continuum_nlev(c);
-  struct Lay { size_t in, at, chi, eta, ch, pp, tp, pc, md, mchi, meta, ws, vws, vst, vsc, rfo, total; };
+  // parameters that leave T, n_e, n_H and the opacity at the reference wavelength alone (v_z, v_mic, B, gamma, chi with a
+  // line-free reference wavelength) leave the depth scales alone: below the perturbed depth their rays are the base
+  // column's, bit for bit, and resume from its saved sweep (delo_base_state_kernel)
+  std::vector<int> neutral(npar, 0);
+  int pn = -1;
+  {
+    int fl = 1;
+    RH_CUDA(cudaMemcpy(&fl, c->wav.flags + iref, sizeof(int), cudaMemcpyDeviceToHost));
+    const bool resume = (fl & 3) == 0 && !c->no_stokes && !(getenv("RHB200_RF_FD_NO_RESUME") && atoi(getenv("RHB200_RF_FD_NO_RESUME")));
+    for (int p = 0; p < npar && resume; p++)
+      if (h_rows[p] >= 3 && h_rows[p] <= 7) { neutral[p] = 1; if (pn < 0) pn = p; }
+  }
+  struct Lay { size_t in, at, chi, eta, ch, pp, tp, pc, md, mchi, meta, ws, vws, vst, vsc, rfo, st, neu, total; };
   auto layout = [&](int nb) {
     Lay y; size_t o = 0;
     const size_t nf = (size_t) nb * nfull1, nv = (size_t) nb * nv1;
@@ -921,6 +933,8 @@ static int rf_fd_single_depth(rhb200_ctx *c, int ncol, int ndep, int nrow, doubl
     y.vst = take(nv * 4 * nl * sizeof(double));
     y.vsc = take(nv * std::max(1, c->wav.nnoline) * 5 * ndep * sizeof(double));
     y.rfo = take(nv / 2 * 4 * nl * sizeof(double));
+    y.st  = take(pn >= 0 ? (size_t) nb * nl * ndep * 44 * sizeof(double) : 0);      // DELO_NSTATE doubles per (ray, depth)
+    y.neu = take((size_t) npar * sizeof(int));
     y.total = o;
     return y;
   };
@@ -958,7 +972,11 @@ static int rf_fd_single_depth(rhb200_ctx *c, int ncol, int ndep, int nrow, doubl
     if (c->no_stokes && (e = cudaMemsetAsync(D(y.vst), 0, (size_t) nv * 4 * nl * sizeof(double), c->stream)) != cudaSuccess) {
       rhb200_set_error("memset failed: %s", cudaGetErrorString(e)); rc = RHB200_ECUDA; break;
     }
-    if (!c->no_stokes) RF_STEP(rh_launch_delo_vcols(c, n, npar, ndep, mu, bc_top, bc_bottom, D(y.vws), d_raypts, D(y.vst)));
+    if ((e = cudaMemcpyAsync(base + y.neu, neutral.data(), (size_t) npar * sizeof(int), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) {
+      rhb200_set_error("H2D copy failed: %s", cudaGetErrorString(e)); rc = RHB200_ECUDA; break;
+    }
+    if (!c->no_stokes) RF_STEP(rh_launch_delo_vcols(c, n, npar, ndep, mu, bc_top, bc_bottom, D(y.vws), d_raypts, D(y.vst),
+                                                    (const int *) (base + y.neu), pn, pn >= 0 ? D(y.st) : nullptr));
     RF_STEP(rh_launch_noline_vcols(c, n, npar, ndep, mu, bc_top, bc_bottom, D(y.vws), d_raypts, D(y.vst), D(y.vsc)));
     RF_STEP(rh_launch_rf_diff(c, b0 * nv1, nv, ndep, nl, npar, d_delta, D(y.vst), D(y.rfo)));
 #undef RF_STEP
@@ -1008,7 +1026,7 @@ extern "C" int rhb200_rf_fd_batch(rhb200_ctx *c, int ncol, int ndep, int nrow, d
   if (const char *e = getenv("RHB200_RF_FD_BRUTE")) if (atoi(e) != 0) local = false;
   if (local)
     return rf_fd_single_depth(c, ncol, ndep, nrow, mu, atm_scale, iref, wght_per_H, bc_top, bc_bottom, npar,
-                              (const int *) rows.p, (const double *) delta.p, (const double *) base.p, rf);
+                              (const int *) rows.p, (const double *) delta.p, (const double *) base.p, rf, par_rows);
   PyrhIn py{nullptr, nrow, atm_scale, iref, wght_per_H, vmacro_tresh, nullptr};
   py.rf_npar = npar; py.d_rf_rows = (const int *) rows.p; py.d_rf_delta = (const double *) delta.p;
   py.d_base = (const double *) base.p; py.rf_out = rf;

@@ -232,7 +232,9 @@ int rh_launch_vscales(rhb200_ctx *ctx, int nb, int npar, int ndep, int iref, int
                       double total_abund, double gravity, const double *d_raypts, const double *d_atmos,
                       double *d_vws /* [nv][4][ndep] */);
 int rh_launch_delo_vcols(rhb200_ctx *ctx, int nb, int npar, int ndep, double muz, int bc_top, int bc_bottom,
-                         const double *d_vws, const double *d_raypts, double *d_stokes /* [nv][4][nlambda] */);
+                         const double *d_vws, const double *d_raypts, double *d_stokes /* [nv][4][nlambda] */,
+                         const int *d_neutral /* [npar] or NULL */, int pn /* a neutral parameter or -1 */,
+                         double *d_state /* [nb][nlambda][ndep][DELO_NSTATE] or NULL */);
 int rh_launch_noline_vcols(rhb200_ctx *ctx, int nb, int npar, int ndep, double muz, int bc_top, int bc_bottom,
                            const double *d_vws, const double *d_raypts, double *d_stokes,
                            double *d_scratch /* [nv][nnoline][5][ndep] */);

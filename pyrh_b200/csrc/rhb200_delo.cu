@@ -103,12 +103,34 @@ delo_raypts_kernel(int ncol, int nlambda, int ndep, double muz, int bc_top, int 
                         at + RHB200_AT_T * ndep, __ldg(lambda + l));
 }
 
+// the BASE column's polarised rays once, saving the state of the sweep at every depth (delo_bezier3_ray MODE 1):
+// perturbations of parameters that leave the depth scales alone (v_z, v_mic, B, gamma, chi) resume from it.
+// Heights / T: those of virtual column (b, pn, 0, 0), pn such a parameter -- bit-identical to the base column's.
+__global__ void __launch_bounds__(128, 4)
+delo_base_state_kernel(int nb, int npar, int pn, int nlambda, int ndep, double muz, int bc_top, int bc_bottom,
+                       const double *__restrict__ vws, const double *__restrict__ lambda, const int *__restrict__ wflags,
+                       const double *__restrict__ raypts, double *__restrict__ state)
+{
+  const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t) nb * nlambda) return;
+  const int b = (int) (t / nlambda), l = (int) (t - (size_t) b * nlambda);
+  if ((__ldg(wflags + l) & 2) == 0) return;
+  const size_t fb = (size_t) b * (1 + 2*npar);
+  double sink[4];
+  RayPtsIO io{reinterpret_cast<const double2 *>(raypts + (fb * nlambda + l) * (size_t) ndep * RP_NFIELD), sink, 1, -1};
+  const double *w = vws + ((((size_t) b * npar + pn) * ndep + 0) * 2 + 0) * 4 * ndep;
+  rhd::delo_bezier3_ray<RayPtsIO, 1>(io, ndep, w, muz, 1, bc_top, bc_bottom, w + ndep, __ldg(lambda + l),
+                                      state + t * (size_t) ndep * DELO_NSTATE);
+}
+
 // single-depth finite-difference columns: one thread per (virtual column, wavelength); vws [nv][4][ndep] = height, T, ..
-// of the virtual column (vscales_kernel), raypts those of the chunk's full columns (base + pseudo)
+// of the virtual column (vscales_kernel), raypts those of the chunk's full columns (base + pseudo).
+// neutral [npar] (or NULL): the parameter leaves heights and T alone -> resume the base sweep at depth kp + 2
 __global__ void __launch_bounds__(128, 4)
 delo_vcols_kernel(int nv, int npar, int nlambda, int ndep, double muz, int bc_top, int bc_bottom, int parabolic,
                   const double *__restrict__ vws, const double *__restrict__ lambda, const int *__restrict__ wflags,
-                  const double *__restrict__ raypts, double *__restrict__ stokes)
+                  const double *__restrict__ raypts, double *__restrict__ stokes,
+                  const int *__restrict__ neutral, double *__restrict__ state)
 {
   const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t) nv * nlambda) return;
@@ -121,6 +143,9 @@ delo_vcols_kernel(int nv, int npar, int nlambda, int ndep, double muz, int bc_to
                    stokes + (size_t) v * 4 * nlambda + l, nlambda, 0};
   const double *w = vws + (size_t) v * 4 * ndep;
   if (parabolic) rhp::stokes_parabolic_ray(io, ndep, w, muz, 1, bc_top, bc_bottom, w + ndep, __ldg(lambda + l));
+  else if (state && neutral[p] && kp + 2 <= ndep - 2)
+    rhd::delo_bezier3_ray<RayPtsPatchIO, 2>(io, ndep, w, muz, 1, bc_top, bc_bottom, w + ndep, __ldg(lambda + l),
+                                            state + ((size_t) b * nlambda + l) * (size_t) ndep * DELO_NSTATE, kp + 2);
   else           rhd::delo_bezier3_ray(io, ndep, w, muz, 1, bc_top, bc_bottom, w + ndep, __ldg(lambda + l));
 }
 
@@ -445,15 +470,21 @@ int rh_launch_delo_raypts(rhb200_ctx *ctx, int ncol, int ndep, double muz, int b
 }
 
 int rh_launch_delo_vcols(rhb200_ctx *ctx, int nb, int npar, int ndep, double muz, int bc_top, int bc_bottom,
-                         const double *d_vws, const double *d_raypts, double *d_stokes)
+                         const double *d_vws, const double *d_raypts, double *d_stokes,
+                         const int *d_neutral, int pn, double *d_state)
 {
   const int nv = nb * npar * ndep * 2;
   const size_t nray = (size_t) nv * ctx->wav.nlambda;
   if (nray == 0) return RHB200_OK;
+  const bool parabolic = ctx->s_interpolation_stokes == RHB200_DELO_PARABOLIC;
+  if (parabolic || pn < 0) d_state = nullptr;
   {
     ScopedKernelTimer t(ctx, RHB200_K_DELO);
+    if (d_state)
+      delo_base_state_kernel<<<(unsigned) (((size_t) nb * ctx->wav.nlambda + 127) / 128), 128, 0, ctx->stream>>>(nb, npar, pn,
+          ctx->wav.nlambda, ndep, muz, bc_top, bc_bottom, d_vws, ctx->wav.lambda, ctx->wav.flags, d_raypts, d_state);
     delo_vcols_kernel<<<(unsigned) ((nray + 127) / 128), 128, 0, ctx->stream>>>(nv, npar, ctx->wav.nlambda, ndep, muz, bc_top, bc_bottom,
-        ctx->s_interpolation_stokes == RHB200_DELO_PARABOLIC, d_vws, ctx->wav.lambda, ctx->wav.flags, d_raypts, d_stokes);
+        parabolic, d_vws, ctx->wav.lambda, ctx->wav.flags, d_raypts, d_stokes, d_neutral, d_state);
   }
   RH_CUDA(cudaGetLastError());
   return RHB200_OK;

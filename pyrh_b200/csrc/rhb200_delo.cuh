@@ -129,11 +129,17 @@ __device__ __forceinline__ void m4v(const float a[16], const double b[4], double
 //   double chi(int k); void K(int k, double x[3]);   K'[0][1..3] at depth k (already / chi_I)
 //   void S(int k, double s[4]);
 //   void storeI(int k, const double I[4]); void storePsi(int k, double psi);
-template <class IO>
+// MODE 1 additionally saves, MODE 2 starts from, the complete state of the sweep on entry to the step that arrives at
+// depth k (DELO_NSTATE doubles at state[k*DELO_NSTATE]): a ray whose records differ from a saved ray's only at depth kp
+// is bit-identical to it up to the step arriving at kp + 2 (to_obs; its stencil reaches chi at k - 2) and can resume there
+// (finite-difference response functions, rhb200_rf_fd_batch).
+#define DELO_NSTATE 44
+template <class IO, int MODE = 0>
 __device__ __forceinline__ void delo_bezier3_ray(IO &io, const int ndep, const double *__restrict__ z,
                                                  const double muz, const int to_obs,
                                                  const int bc_top, const int bc_bottom,
-                                                 const double *__restrict__ T, const double lambda)
+                                                 const double *__restrict__ T, const double lambda,
+                                                 double *state = nullptr, const int kstart = -1)
 {
   const double imu = 1.0 / muz;
   const int dk = to_obs ? -1 : 1;
@@ -181,7 +187,18 @@ __device__ __forceinline__ void delo_bezier3_ray(IO &io, const int ndep, const d
     for (int n = 0; n < 3; n++) { dKu[n] = ruw.div(K0[n] - Ku[n]); fK[n] = dKu[n]; }
   }
 
+#define DELO_STATE(OP) { double *q_ = state + (size_t) k * DELO_NSTATE; int n_ = 0;                                   \
+    for (int m_ = 0; m_ < 4; m_++) { OP(I[m_]); OP(Su[m_]); OP(S0[m_]); OP(dSu[m_]); OP(fS[m_]); }                        \
+    for (int m_ = 0; m_ < 3; m_++) { OP(Ku[m_]); OP(K0[m_]); OP(dKu[m_]); OP(fK[m_]); }                                    \
+    OP(dtau_uw); OP(dsup); OP(dchi_up); OP(dchi_c); OP(fchi); OP(c_m); OP(c_0); OP(c_p); OP(z_m); OP(z_0); OP(z_p); }
+#define DELO_PUT(x) q_[n_++] = (x)
+#define DELO_GET(x) (x) = q_[n_++]
+  if (MODE == 2 && kstart >= 0) {                  // resume: only for to_obs sweeps with k = kstart still inside the loop
+    k = kstart;
+    DELO_STATE(DELO_GET)
+  }
   for (; k != ke; k += dk) {
+    if (MODE == 1) DELO_STATE(DELO_PUT)
     io.prefetch(k + 4*dk, ndep);                   // pull the records of a later depth into L1
     dsdn = fabs(z_p - z_0) * imu;
     double dchi_dn, c_pp = 0.0, z_pp = 0.0, fnext = fchi;
@@ -317,5 +334,9 @@ __device__ __forceinline__ void delo_bezier3_ray(IO &io, const int ndep, const d
     io.storeI(ke, V1);
   }
 }
+
+#undef DELO_STATE
+#undef DELO_PUT
+#undef DELO_GET
 
 }  // namespace rhd
