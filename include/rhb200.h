@@ -451,7 +451,14 @@ int rhb200_hse_batch(rhb200_ctx *ctx, int ncol, int ndep, int atm_scale, const d
    with S exactly what rhb200_compute1d_batch returns for the perturbed column (so the result equals the one
    formed from the reference's own rhf1d() spectra bit for bit).  par_rows[p] = row of `atmosphere` (1 T, 3 v_z,
    4 v_mic, 5 B, 6 gamma, 7 chi, also 2 ne, 8 nH), par_delta[p] > 0 in the row's unit.  Other arguments as in
-   rhb200_compute1d_batch; nlambda includes the reference wavelength. */
+   rhb200_compute1d_batch; nlambda includes the reference wavelength.
+   rhb200_rf_fd_depths_batch restricts the perturbations to the depths an inversion has its nodes at: work and the
+   device-to-host traffic scale with nsel / ndep. */
+int rhb200_rf_fd_depths_batch(rhb200_ctx *ctx, int ncol, int ndep, int nrow, double mu, int atm_scale,
+                              const double *atmosphere, int iref, double wght_per_H, double vmacro_tresh,
+                              int bc_top, int bc_bottom, int npar, const int *par_rows, const double *par_delta,
+                              int nsel, const int *depths /* [nsel] depth indices, or NULL: all */,
+                              double *rf /* [ncol][npar][nsel][4][nlambda] */);
 int rhb200_rf_fd_batch(rhb200_ctx *ctx, int ncol, int ndep, int nrow, double mu, int atm_scale,
                        const double *atmosphere, int iref, double wght_per_H, double vmacro_tresh,
                        int bc_top, int bc_bottom, int npar, const int *par_rows, const double *par_delta,

@@ -80,6 +80,8 @@ SYMBOLS = [
     ("rhb200_set_loggf_rf", C.c_int, [vp, C.c_int, ip]),
     ("rhb200_rf_fd_batch", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, vp, C.c_int, C.c_double,
                                      C.c_double, C.c_int, C.c_int, C.c_int, ip, dp, vp]),
+    ("rhb200_rf_fd_depths_batch", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, vp, C.c_int, C.c_double,
+                                            C.c_double, C.c_int, C.c_int, C.c_int, ip, dp, C.c_int, ip, vp]),
     ("rhb200_set_model_lines", C.c_int, [vp, C.c_int, dp]),
     ("rhb200_set_stokes_mode", C.c_int, [vp, C.c_int]),
     ("rhb200_set_scatter", C.c_int, [vp, C.c_int, C.c_double]),

@@ -354,20 +354,24 @@ class Context:
 
     def rf_fd_batch(self, atmosphere, par_rows, par_delta, mu=1.0, atm_scale=0, lambda_ref=500.0, wght_per_H=0.0,
                     vmacro_tresh=0.0, bc_top=_lib.BC_ZERO, bc_bottom=_lib.BC_THERMALIZED, out=None,
-                    keep_lambda_ref=False):
+                    keep_lambda_ref=False, depths=None):
         """Centred finite-difference response functions ``[ncol, npar, ndep, 4, nlambda]`` of the spectrum
         ``compute1d_batch`` returns, to ``atmosphere`` row ``par_rows[p]`` at every depth (step ``par_delta[p]``).
-        The perturbed columns are generated and differenced on the device."""
+        The perturbed columns are generated and differenced on the device.  ``depths``: only these depth indices (the
+        nodes of an inversion) -> ``[ncol, npar, len(depths), 4, nlambda]``."""
         a = np.ascontiguousarray(atmosphere, np.float64)
         ncol, nrow, ndep = a.shape
         rows = np.ascontiguousarray(par_rows, np.int32)
         delta = np.ascontiguousarray(par_delta, np.float64)
         iref = self._iref(lambda_ref)
-        rf = np.empty((ncol, len(rows), ndep, 4, self.nlambda)) if out is None else out
-        _lib.check(self.lib.rhb200_rf_fd_batch(self.h, ncol, ndep, nrow, float(mu), int(atm_scale), _vp(a), iref,
-                                               float(wght_per_H), float(vmacro_tresh) * KM_TO_M, int(bc_top),
-                                               int(bc_bottom), len(rows), rows.ctypes.data_as(C.POINTER(C.c_int)),
-                                               _dp(delta), _vp(rf)))
+        sel = None if depths is None else np.ascontiguousarray(depths, np.int32)
+        nsel = ndep if sel is None else len(sel)
+        rf = np.empty((ncol, len(rows), nsel, 4, self.nlambda)) if out is None else out
+        _lib.check(self.lib.rhb200_rf_fd_depths_batch(self.h, ncol, ndep, nrow, float(mu), int(atm_scale), _vp(a), iref,
+                                                      float(wght_per_H), float(vmacro_tresh) * KM_TO_M, int(bc_top),
+                                                      int(bc_bottom), len(rows), rows.ctypes.data_as(C.POINTER(C.c_int)),
+                                                      _dp(delta), nsel,
+                                                      None if sel is None else sel.ctypes.data_as(C.POINTER(C.c_int)), _vp(rf)))
         return rf if keep_lambda_ref else np.delete(rf, iref, axis=4)
 
     def lte_stokes_batch_dev(self, ncol, ndep, d_atmos, d_chi_ai, d_eta_ai, d_stokes, mu=1.0,

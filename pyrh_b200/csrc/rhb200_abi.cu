@@ -506,6 +506,7 @@ struct PyrhIn {
   // v = ((base*npar + p)*ndep + k)*2 + s is base column `base` with row rf_rows[p] changed by +delta (s = 0) or
   // -delta (s = 1) at depth k; they are expanded on the device from d_base and only the differences travel back
   int rf_npar = 0; const int *d_rf_rows = nullptr; const double *d_rf_delta = nullptr; const double *d_base = nullptr;
+  int rf_nsel = 0; const int *d_rf_sel = nullptr;         // perturbed depths: sel[0 .. nsel) (NULL: all ndep)
   double *rf_out = nullptr;
   double *lrf_out = nullptr;                     // analytic log gf response functions [ncol][nlambda][lrf_npar] (rhb200_compute1d_rf_batch)
 };
@@ -652,7 +653,8 @@ static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int mov
     cudaError_t e;
     if (py) {
       if (py->rf_npar) {
-        rc = rh_launch_rf_expand(c, c0, n, ndep, py->nrow, py->rf_npar, py->d_rf_rows, py->d_rf_delta, py->d_base, d_in);
+        rc = rh_launch_rf_expand(c, c0, n, ndep, py->nrow, py->rf_npar, py->d_rf_rows, py->d_rf_delta, py->d_base, d_in,
+                                 py->rf_nsel, py->d_rf_sel);
         if (rc != RHB200_OK) break;
       } else
       if ((e = cudaMemcpyAsync(d_in, py->atmosphere + (size_t) c0 * py->nrow * ndep,
@@ -708,7 +710,7 @@ static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int mov
     }
     if (py && py->scales_only) continue;
     if (py && py->rf_npar) {                     // (S+ - S-) / (2 delta); d_chi is free once the opacity kernel has run
-      rc = rh_launch_rf_diff(c, c0, n, ndep, nl, py->rf_npar, py->d_rf_delta, d_st, d_chi);
+      rc = rh_launch_rf_diff(c, c0, n, py->rf_nsel, nl, py->rf_npar, py->d_rf_delta, d_st, d_chi);
       if (rc != RHB200_OK) break;
       if ((e = cudaMemcpyAsync(py->rf_out + (size_t) (c0 / 2) * 4 * nl, d_chi, (size_t) (n / 2) * 4 * nl * sizeof(double),
                                cudaMemcpyDeviceToHost, st)) != cudaSuccess) {
@@ -887,12 +889,12 @@ struct DevBuf {
 // Two slots / streams: the D2H of chunk i overlaps the kernels of chunk i+1.
 static int rf_fd_single_depth(rhb200_ctx *c, int ncol, int ndep, int nrow, double mu, int atm_scale, int iref, double wght_per_H,
                               int bc_top, int bc_bottom, int npar, const int *d_rows, const double *d_delta,
-                              const double *d_base, double *rf, const int *h_rows)
+                              const double *d_base, double *rf, const int *h_rows, int nsel, const int *d_sel)
 {
   RhRange whole("rhf1d (LTE, finite-difference response functions)");
   RH_CHECK(check_batch_args(c, ncol, ndep, mu, bc_top, bc_bottom));
   if (!c->cont) { rhb200_set_error("rhb200_set_continuum() has not been called"); return RHB200_ESTATE; }
-  const int nl = c->wav.nlambda, nfull1 = 1 + 2*npar, nv1 = 2*npar*ndep, nslots = 2;
+  const int nl = c->wav.nlambda, nfull1 = 1 + 2*npar, nv1 = 2*npar*nsel, nslots = 2;
   const bool mol_on = c->wav.nmw > 0;
   if (mol_on) {
     std::vector<int> chem(c->wav.nmsel);
@@ -967,7 +969,7 @@ static int rf_fd_single_depth(rhb200_ctx *c, int ncol, int ndep, int nrow, doubl
     RF_STEP(rh_launch_prep(c, nf, ndep, mu, 1, D(y.at), d_elem_n, d_lineprep));
     RF_STEP(rh_launch_opacity_fused(c, nf, ndep, 1, D(y.at), d_lineprep, D(y.chi), D(y.eta), d_raypts,
                                     mol_on ? D(y.mchi) : nullptr, mol_on ? D(y.meta) : nullptr, nullptr));
-    RF_STEP(rh_launch_vscales(c, n, npar, ndep, iref, atm_scale, wght_per_H, 0.0, 1.0, d_raypts, D(y.at), D(y.vws)));
+    RF_STEP(rh_launch_vscales(c, n, npar, ndep, iref, atm_scale, wght_per_H, 0.0, 1.0, d_raypts, D(y.at), D(y.vws), nsel, d_sel));
     cudaError_t e;
     if (c->no_stokes && (e = cudaMemsetAsync(D(y.vst), 0, (size_t) nv * 4 * nl * sizeof(double), c->stream)) != cudaSuccess) {
       rhb200_set_error("memset failed: %s", cudaGetErrorString(e)); rc = RHB200_ECUDA; break;
@@ -976,9 +978,9 @@ static int rf_fd_single_depth(rhb200_ctx *c, int ncol, int ndep, int nrow, doubl
       rhb200_set_error("H2D copy failed: %s", cudaGetErrorString(e)); rc = RHB200_ECUDA; break;
     }
     if (!c->no_stokes) RF_STEP(rh_launch_delo_vcols(c, n, npar, ndep, mu, bc_top, bc_bottom, D(y.vws), d_raypts, D(y.vst),
-                                                    (const int *) (base + y.neu), pn, pn >= 0 ? D(y.st) : nullptr));
-    RF_STEP(rh_launch_noline_vcols(c, n, npar, ndep, mu, bc_top, bc_bottom, D(y.vws), d_raypts, D(y.vst), D(y.vsc)));
-    RF_STEP(rh_launch_rf_diff(c, b0 * nv1, nv, ndep, nl, npar, d_delta, D(y.vst), D(y.rfo)));
+                                                    (const int *) (base + y.neu), pn, pn >= 0 ? D(y.st) : nullptr, nsel, d_sel));
+    RF_STEP(rh_launch_noline_vcols(c, n, npar, ndep, mu, bc_top, bc_bottom, D(y.vws), d_raypts, D(y.vst), D(y.vsc), nsel, d_sel));
+    RF_STEP(rh_launch_rf_diff(c, b0 * nv1, nv, nsel, nl, npar, d_delta, D(y.vst), D(y.rfo)));
 #undef RF_STEP
     if ((e = cudaMemcpyAsync(rf + (size_t) b0 * (nv1 / 2) * 4 * nl, D(y.rfo), (size_t) (nv / 2) * 4 * nl * sizeof(double),
                              cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) {
@@ -996,23 +998,42 @@ static int rf_fd_single_depth(rhb200_ctx *c, int ncol, int ndep, int nrow, doubl
 
 // Finite-difference response functions of the LTE Stokes spectrum to the atmosphere rows, per depth point:
 // what a pyrh caller (an inversion code) obtains from 2 x npar x ndep calls of pyrh.compute1d per column.
+extern "C" int rhb200_rf_fd_depths_batch(rhb200_ctx *c, int ncol, int ndep, int nrow, double mu, int atm_scale,
+                                         const double *atmosphere, int iref, double wght_per_H, double vmacro_tresh,
+                                         int bc_top, int bc_bottom, int npar, const int *par_rows, const double *par_delta,
+                                         int nsel, const int *depths, double *rf);
 extern "C" int rhb200_rf_fd_batch(rhb200_ctx *c, int ncol, int ndep, int nrow, double mu, int atm_scale,
                                   const double *atmosphere, int iref, double wght_per_H, double vmacro_tresh,
                                   int bc_top, int bc_bottom, int npar, const int *par_rows, const double *par_delta,
                                   double *rf)
 {
+  return rhb200_rf_fd_depths_batch(c, ncol, ndep, nrow, mu, atm_scale, atmosphere, iref, wght_per_H, vmacro_tresh, bc_top, bc_bottom,
+                                   npar, par_rows, par_delta, ndep, nullptr, rf);
+}
+
+// the same at SELECTED depths only (the nodes of an inversion): depths [nsel] ascending indices (NULL: all),
+// rf [ncol][npar][nsel][4][nlambda]; work and D2H traffic scale with nsel / ndep
+extern "C" int rhb200_rf_fd_depths_batch(rhb200_ctx *c, int ncol, int ndep, int nrow, double mu, int atm_scale,
+                                         const double *atmosphere, int iref, double wght_per_H, double vmacro_tresh,
+                                         int bc_top, int bc_bottom, int npar, const int *par_rows, const double *par_delta,
+                                         int nsel, const int *depths, double *rf)
+{
   RH_NEED_CTX(c);
+  if (nsel < 1 || nsel > ndep) { rhb200_set_error("nsel must be 1 .. ndep"); return RHB200_EINVAL; }
+  if (depths) for (int q = 0; q < nsel; q++) if (depths[q] < 0 || depths[q] >= ndep) { rhb200_set_error("depth index %d out of range", depths[q]); return RHB200_EINVAL; }
   if (!atmosphere || !rf || !par_rows || !par_delta) { rhb200_set_error("null buffer"); return RHB200_EINVAL; }
   if (nrow < 9 || atm_scale < 0 || atm_scale > 2 || iref < 0 || iref >= c->wav.nlambda || npar < 1 || ncol < 0) {
     rhb200_set_error("bad arguments"); return RHB200_EINVAL;
   }
   for (int p = 0; p < npar; p++)
     if (par_rows[p] < 0 || par_rows[p] >= nrow || !(par_delta[p] > 0.0)) { rhb200_set_error("parameter %d: row %d / delta %g", p, par_rows[p], par_delta[p]); return RHB200_EINVAL; }
-  const long long nvirt = (long long) ncol * npar * ndep * 2;
+  const long long nvirt = (long long) ncol * npar * nsel * 2;
   if (nvirt > 0x7fffffffLL) { rhb200_set_error("too many perturbed columns in one call (%lld)", nvirt); return RHB200_EINVAL; }
   if (ncol == 0) return RHB200_OK;
   RH_CUDA(cudaSetDevice(c->device));
-  DevBuf base, rows, delta;
+  DevBuf base, rows, delta, sel;
+  if (depths) RH_CHECK(sel.from_host(depths, (size_t) nsel * sizeof(int)));
+  const int *d_sel = depths ? (const int *) sel.p : nullptr;
   RH_CHECK(base.alloc((size_t) ncol * nrow * ndep * sizeof(double)));
   RH_CHECK(rows.alloc((size_t) npar * sizeof(int)));
   RH_CHECK(delta.alloc((size_t) npar * sizeof(double)));
@@ -1026,10 +1047,10 @@ extern "C" int rhb200_rf_fd_batch(rhb200_ctx *c, int ncol, int ndep, int nrow, d
   if (const char *e = getenv("RHB200_RF_FD_BRUTE")) if (atoi(e) != 0) local = false;
   if (local)
     return rf_fd_single_depth(c, ncol, ndep, nrow, mu, atm_scale, iref, wght_per_H, bc_top, bc_bottom, npar,
-                              (const int *) rows.p, (const double *) delta.p, (const double *) base.p, rf, par_rows);
+                              (const int *) rows.p, (const double *) delta.p, (const double *) base.p, rf, par_rows, nsel, d_sel);
   PyrhIn py{nullptr, nrow, atm_scale, iref, wght_per_H, vmacro_tresh, nullptr};
   py.rf_npar = npar; py.d_rf_rows = (const int *) rows.p; py.d_rf_delta = (const double *) delta.p;
-  py.d_base = (const double *) base.p; py.rf_out = rf;
+  py.d_base = (const double *) base.p; py.rf_out = rf; py.rf_nsel = nsel; py.d_rf_sel = d_sel;
   return lte_batch_host(c, (int) nvirt, ndep, mu, 1, bc_top, bc_bottom, nullptr, nullptr, nullptr, nullptr, nullptr, 1, &py);
 }
 static int to_host(void *h, const void *d, size_t bytes)

@@ -162,8 +162,8 @@ int rh_continuum_has_chemistry(const rhb200_ctx *ctx);
 int rh_launch_pyrh_rows(rhb200_ctx *ctx, int ncol, int ndep, int nrow_in, int atm_scale, double muz, double vmacro_tresh,
                         const double *d_in, double *d_atmos, int *d_col_moving);
 int rh_launch_rf_expand(rhb200_ctx *ctx, int v0, int n, int ndep, int nrow, int npar, const int *d_rows,
-                        const double *d_delta, const double *d_base, double *d_in);
-int rh_launch_rf_diff(rhb200_ctx *ctx, int v0, int n, int ndep, int nlambda, int npar, const double *d_delta,
+                        const double *d_delta, const double *d_base, double *d_in, int nsel, const int *d_sel);
+int rh_launch_rf_diff(rhb200_ctx *ctx, int v0, int n, int nsel, int nlambda, int npar, const double *d_delta,
                       const double *d_stokes, double *d_rf);
 int rh_launch_proton(rhb200_ctx *ctx, int ncol, int ndep, int nlev, int proton_level, const double *d_pops, double *d_atmos);
 int rh_launch_scales(rhb200_ctx *ctx, int ncol, int ndep, int iref, int atm_scale, double wght_per_H,
@@ -230,14 +230,14 @@ int rh_launch_rf_expand_full(rhb200_ctx *ctx, int b0, int nb, int ndep, int nrow
                              const double *d_delta, const double *d_base, double *d_in);
 int rh_launch_vscales(rhb200_ctx *ctx, int nb, int npar, int ndep, int iref, int atm_scale, double wght_per_H,
                       double total_abund, double gravity, const double *d_raypts, const double *d_atmos,
-                      double *d_vws /* [nv][4][ndep] */);
+                      double *d_vws /* [nv][4][ndep] */, int nsel, const int *d_sel);
 int rh_launch_delo_vcols(rhb200_ctx *ctx, int nb, int npar, int ndep, double muz, int bc_top, int bc_bottom,
                          const double *d_vws, const double *d_raypts, double *d_stokes /* [nv][4][nlambda] */,
                          const int *d_neutral /* [npar] or NULL */, int pn /* a neutral parameter or -1 */,
-                         double *d_state /* [nb][nlambda][ndep][DELO_NSTATE] or NULL */);
+                         double *d_state /* [nb][nlambda][ndep][DELO_NSTATE] or NULL */, int nsel, const int *d_sel);
 int rh_launch_noline_vcols(rhb200_ctx *ctx, int nb, int npar, int ndep, double muz, int bc_top, int bc_bottom,
                            const double *d_vws, const double *d_raypts, double *d_stokes,
-                           double *d_scratch /* [nv][nnoline][5][ndep] */);
+                           double *d_scratch /* [nv][nnoline][5][ndep] */, int nsel, const int *d_sel);
 int rh_launch_delo_generic(rhb200_ctx *ctx, int solver /* RHB200_DELO_* */, int nray, int ndep, double muz, int to_obs,
                            int bc_top, int bc_bottom, const int *d_ray_col,
                            const double *d_ray_lambda, const double *d_height, const double *d_T,

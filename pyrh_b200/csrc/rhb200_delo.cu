@@ -107,7 +107,7 @@ delo_raypts_kernel(int ncol, int nlambda, int ndep, double muz, int bc_top, int 
 // perturbations of parameters that leave the depth scales alone (v_z, v_mic, B, gamma, chi) resume from it.
 // Heights / T: those of virtual column (b, pn, 0, 0), pn such a parameter -- bit-identical to the base column's.
 __global__ void __launch_bounds__(128, 4)
-delo_base_state_kernel(int nb, int npar, int pn, int nlambda, int ndep, double muz, int bc_top, int bc_bottom,
+delo_base_state_kernel(int nb, int npar, int pn, int nsel, int nlambda, int ndep, double muz, int bc_top, int bc_bottom,
                        const double *__restrict__ vws, const double *__restrict__ lambda, const int *__restrict__ wflags,
                        const double *__restrict__ raypts, double *__restrict__ state)
 {
@@ -118,7 +118,7 @@ delo_base_state_kernel(int nb, int npar, int pn, int nlambda, int ndep, double m
   const size_t fb = (size_t) b * (1 + 2*npar);
   double sink[4];
   RayPtsIO io{reinterpret_cast<const double2 *>(raypts + (fb * nlambda + l) * (size_t) ndep * RP_NFIELD), sink, 1, -1};
-  const double *w = vws + ((((size_t) b * npar + pn) * ndep + 0) * 2 + 0) * 4 * ndep;
+  const double *w = vws + ((((size_t) b * npar + pn) * nsel + 0) * 2 + 0) * 4 * ndep;
   rhd::delo_bezier3_ray<RayPtsIO, 1>(io, ndep, w, muz, 1, bc_top, bc_bottom, w + ndep, __ldg(lambda + l),
                                       state + t * (size_t) ndep * DELO_NSTATE);
 }
@@ -130,13 +130,13 @@ __global__ void __launch_bounds__(128, 4)
 delo_vcols_kernel(int nv, int npar, int nlambda, int ndep, double muz, int bc_top, int bc_bottom, int parabolic,
                   const double *__restrict__ vws, const double *__restrict__ lambda, const int *__restrict__ wflags,
                   const double *__restrict__ raypts, double *__restrict__ stokes,
-                  const int *__restrict__ neutral, double *__restrict__ state)
+                  const int *__restrict__ neutral, double *__restrict__ state, int nsel, const int *__restrict__ sel)
 {
   const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t) nv * nlambda) return;
   const int v = (int) (t / nlambda), l = (int) (t - (size_t) v * nlambda);
   if ((__ldg(wflags + l) & 2) == 0) return;
-  const int s = v & 1, kp = (v >> 1) % ndep, p = ((v >> 1) / ndep) % npar, b = ((v >> 1) / ndep) / npar;
+  const int s = v & 1, kq = (v >> 1) % nsel, kp = sel ? sel[kq] : kq, p = ((v >> 1) / nsel) % npar, b = ((v >> 1) / nsel) / npar;
   const size_t fb = (size_t) b * (1 + 2*npar), fq = fb + 1 + 2*p + s;
   RayPtsPatchIO io{reinterpret_cast<const double2 *>(raypts + (fb * nlambda + l) * (size_t) ndep * RP_NFIELD),
                    reinterpret_cast<const double2 *>(raypts + (fq * nlambda + l) * (size_t) ndep * RP_NFIELD), kp,
@@ -319,12 +319,12 @@ __global__ void __launch_bounds__(128)
 noline_vcols_kernel(int nv, int npar, int nlambda, int ndep, double muz, int bc_top, int bc_bottom,
                     const int *__restrict__ nolines, int nnoline, const double *__restrict__ vws,
                     const double *__restrict__ lambda, const double *__restrict__ raypts, double *__restrict__ stokes,
-                    const int *__restrict__ wflags, int solver, double *__restrict__ scratch)
+                    const int *__restrict__ wflags, int solver, double *__restrict__ scratch, int nsel, const int *__restrict__ sel)
 {
   const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t) nv * nnoline) return;
   const int v = (int) (t / nnoline), l = __ldg(nolines + (int) (t - (size_t) v * nnoline));
-  const int sg = v & 1, kp = (v >> 1) % ndep, p = ((v >> 1) / ndep) % npar, b = ((v >> 1) / ndep) / npar;
+  const int sg = v & 1, kq = (v >> 1) % nsel, kp = sel ? sel[kq] : kq, p = ((v >> 1) / nsel) % npar, b = ((v >> 1) / nsel) / npar;
   const size_t fb = (size_t) b * (1 + 2*npar), fq = fb + 1 + 2*p + sg;
   const double *rb = raypts + (fb * nlambda + l) * (size_t) ndep * RP_NFIELD, *rq = raypts + (fq * nlambda + l) * (size_t) ndep * RP_NFIELD;
   const double *z = vws + (size_t) v * 4 * ndep, *Tc = z + ndep;
@@ -471,9 +471,9 @@ int rh_launch_delo_raypts(rhb200_ctx *ctx, int ncol, int ndep, double muz, int b
 
 int rh_launch_delo_vcols(rhb200_ctx *ctx, int nb, int npar, int ndep, double muz, int bc_top, int bc_bottom,
                          const double *d_vws, const double *d_raypts, double *d_stokes,
-                         const int *d_neutral, int pn, double *d_state)
+                         const int *d_neutral, int pn, double *d_state, int nsel, const int *d_sel)
 {
-  const int nv = nb * npar * ndep * 2;
+  const int nv = nb * npar * nsel * 2;
   const size_t nray = (size_t) nv * ctx->wav.nlambda;
   if (nray == 0) return RHB200_OK;
   const bool parabolic = ctx->s_interpolation_stokes == RHB200_DELO_PARABOLIC;
@@ -481,25 +481,26 @@ int rh_launch_delo_vcols(rhb200_ctx *ctx, int nb, int npar, int ndep, double muz
   {
     ScopedKernelTimer t(ctx, RHB200_K_DELO);
     if (d_state)
-      delo_base_state_kernel<<<(unsigned) (((size_t) nb * ctx->wav.nlambda + 127) / 128), 128, 0, ctx->stream>>>(nb, npar, pn,
+      delo_base_state_kernel<<<(unsigned) (((size_t) nb * ctx->wav.nlambda + 127) / 128), 128, 0, ctx->stream>>>(nb, npar, pn, nsel,
           ctx->wav.nlambda, ndep, muz, bc_top, bc_bottom, d_vws, ctx->wav.lambda, ctx->wav.flags, d_raypts, d_state);
     delo_vcols_kernel<<<(unsigned) ((nray + 127) / 128), 128, 0, ctx->stream>>>(nv, npar, ctx->wav.nlambda, ndep, muz, bc_top, bc_bottom,
-        parabolic, d_vws, ctx->wav.lambda, ctx->wav.flags, d_raypts, d_stokes, d_neutral, d_state);
+        parabolic, d_vws, ctx->wav.lambda, ctx->wav.flags, d_raypts, d_stokes, d_neutral, d_state, nsel, d_sel);
   }
   RH_CUDA(cudaGetLastError());
   return RHB200_OK;
 }
 
 int rh_launch_noline_vcols(rhb200_ctx *ctx, int nb, int npar, int ndep, double muz, int bc_top, int bc_bottom,
-                           const double *d_vws, const double *d_raypts, double *d_stokes, double *d_scratch)
+                           const double *d_vws, const double *d_raypts, double *d_stokes, double *d_scratch,
+                           int nsel, const int *d_sel)
 {
-  const int nv = nb * npar * ndep * 2, nn = ctx->wav.nnoline;
+  const int nv = nb * npar * nsel * 2, nn = ctx->wav.nnoline;
   const size_t n = (size_t) nv * nn;
   if (n == 0) return RHB200_OK;
   {
     ScopedKernelTimer t(ctx, RHB200_K_BEZIER);
     noline_vcols_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, ctx->stream>>>(nv, npar, ctx->wav.nlambda, ndep, muz, bc_top, bc_bottom,
-        ctx->wav.noline, nn, d_vws, ctx->wav.lambda, d_raypts, d_stokes, ctx->wav.flags, ctx->s_interpolation, d_scratch);
+        ctx->wav.noline, nn, d_vws, ctx->wav.lambda, d_raypts, d_stokes, ctx->wav.flags, ctx->s_interpolation, d_scratch, nsel, d_sel);
   }
   RH_CUDA(cudaGetLastError());
   return RHB200_OK;

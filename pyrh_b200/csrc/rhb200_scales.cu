@@ -210,13 +210,13 @@ struct VirtualScalesIn {
   __device__ __forceinline__ double scale(int k) const { return at_b[(size_t) RHB200_AT_HEIGHT * ndep + k]; }
 };
 __global__ void __launch_bounds__(64)
-vscales_kernel(int nv, int npar, int ndep, int atm_scale, double wght_per_H, double total_abund, double gravity,
+vscales_kernel(int nv, int npar, int ndep, int nsel, const int *__restrict__ sel, int atm_scale, double wght_per_H, double total_abund, double gravity,
                const double *__restrict__ chi_ref, size_t chi_col_stride, size_t chi_k_stride,
                const double *__restrict__ atmos, double *__restrict__ vws)
 {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= nv) return;
-  const int s = v & 1, kp = (v >> 1) % ndep, p = ((v >> 1) / ndep) % npar, b = ((v >> 1) / ndep) / npar;
+  const int s = v & 1, kq = (v >> 1) % nsel, kp = sel ? sel[kq] : kq, p = ((v >> 1) / nsel) % npar, b = ((v >> 1) / nsel) / npar;
   const size_t fb = (size_t) b * (1 + 2*npar), fq = fb + 1 + 2*p + s;
   VirtualScalesIn in{chi_ref + fb * chi_col_stride, chi_ref + fq * chi_col_stride, chi_k_stride,
                      atmos + fb * RHB200_AT_NFIELD * ndep, atmos + fq * RHB200_AT_NFIELD * ndep, ndep, kp};
@@ -229,14 +229,14 @@ vscales_kernel(int nv, int npar, int ndep, int atm_scale, double wght_per_H, dou
 // virtual column v = ((base*npar + p)*ndep + kp)*2 + s: row rows[p] of column `base` changed at depth kp by
 // +delta[p] (s = 0) or -delta[p] (s = 1); everything else is copied.  One thread per (virtual column, row, depth).
 __global__ void __launch_bounds__(128)
-rf_expand_kernel(int v0, int n, int ndep, int nrow, int npar, const int *__restrict__ rows, const double *__restrict__ delta,
+rf_expand_kernel(int v0, int n, int ndep, int nsel, const int *__restrict__ sel, int nrow, int npar, const int *__restrict__ rows, const double *__restrict__ delta,
                  const double *__restrict__ base, double *__restrict__ out)
 {
   const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t) n * nrow * ndep) return;
   const int k = (int) (t % ndep), r = (int) ((t / ndep) % nrow);
   const int v = v0 + (int) (t / ((size_t) ndep * nrow));
-  const int s = v & 1, kp = (v >> 1) % ndep, p = ((v >> 1) / ndep) % npar, b = ((v >> 1) / ndep) / npar;
+  const int s = v & 1, kq = (v >> 1) % nsel, kp = sel ? sel[kq] : kq, p = ((v >> 1) / nsel) % npar, b = ((v >> 1) / nsel) / npar;
   double x = base[((size_t) b * nrow + r) * ndep + k];
   if (r == rows[p] && k == kp) x = s ? x - delta[p] : x + delta[p];
   out[t] = x;
@@ -260,23 +260,23 @@ rf_expand_full_kernel(int b0, int nb, int ndep, int nrow, int npar, const int *_
 
 // rf[pair][4][nlambda] = (S(+delta) - S(-delta)) / (2 delta); one thread per element
 __global__ void __launch_bounds__(128)
-rf_diff_kernel(int v0, int npair, int ndep, int n4l, int npar, const double *__restrict__ delta,
+rf_diff_kernel(int v0, int npair, int nsel, int n4l, int npar, const double *__restrict__ delta,
                const double *__restrict__ stokes, double *__restrict__ rf)
 {
   const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t) npair * n4l) return;
   const int pair = (int) (t / n4l), e = (int) (t % n4l);
-  const int p = (((v0 >> 1) + pair) / ndep) % npar;
+  const int p = (((v0 >> 1) + pair) / nsel) % npar;
   const double a = stokes[(size_t) (2*pair) * n4l + e], b = stokes[(size_t) (2*pair + 1) * n4l + e];
   rf[t] = (a - b) / (2.0 * delta[p]);
 }
 
 int rh_launch_rf_expand(rhb200_ctx *c, int v0, int n, int ndep, int nrow, int npar, const int *d_rows,
-                        const double *d_delta, const double *d_base, double *d_in)
+                        const double *d_delta, const double *d_base, double *d_in, int nsel, const int *d_sel)
 {
   const size_t tot = (size_t) n * nrow * ndep;
   ScopedKernelTimer t(c, RHB200_K_PREP);
-  rf_expand_kernel<<<(unsigned) ((tot + 127) / 128), 128, 0, c->stream>>>(v0, n, ndep, nrow, npar, d_rows, d_delta, d_base, d_in);
+  rf_expand_kernel<<<(unsigned) ((tot + 127) / 128), 128, 0, c->stream>>>(v0, n, ndep, nsel, d_sel, nrow, npar, d_rows, d_delta, d_base, d_in);
   RH_CUDA(cudaGetLastError());
   return RHB200_OK;
 }
@@ -292,23 +292,24 @@ int rh_launch_rf_expand_full(rhb200_ctx *c, int b0, int nb, int ndep, int nrow, 
 }
 
 int rh_launch_vscales(rhb200_ctx *c, int nb, int npar, int ndep, int iref, int atm_scale, double wght_per_H,
-                      double total_abund, double gravity, const double *d_raypts, const double *d_atmos, double *d_vws)
+                      double total_abund, double gravity, const double *d_raypts, const double *d_atmos, double *d_vws,
+                      int nsel, const int *d_sel)
 {
-  const int nv = nb * npar * ndep * 2;
+  const int nv = nb * npar * nsel * 2;
   ScopedKernelTimer t(c, RHB200_K_PREP);
-  vscales_kernel<<<(unsigned) ((nv + 63) / 64), 64, 0, c->stream>>>(nv, npar, ndep, atm_scale, wght_per_H, total_abund, gravity,
+  vscales_kernel<<<(unsigned) ((nv + 63) / 64), 64, 0, c->stream>>>(nv, npar, ndep, nsel, d_sel, atm_scale, wght_per_H, total_abund, gravity,
       d_raypts + (size_t) iref * ndep * RP_NFIELD + RP_CHI, (size_t) c->wav.nlambda * ndep * RP_NFIELD, (size_t) RP_NFIELD,
       d_atmos, d_vws);
   RH_CUDA(cudaGetLastError());
   return RHB200_OK;
 }
 
-int rh_launch_rf_diff(rhb200_ctx *c, int v0, int n, int ndep, int nlambda, int npar, const double *d_delta,
+int rh_launch_rf_diff(rhb200_ctx *c, int v0, int n, int nsel, int nlambda, int npar, const double *d_delta,
                       const double *d_stokes, double *d_rf)
 {
   const size_t tot = (size_t) (n / 2) * 4 * nlambda;
   ScopedKernelTimer t(c, RHB200_K_PREP);
-  rf_diff_kernel<<<(unsigned) ((tot + 127) / 128), 128, 0, c->stream>>>(v0, n / 2, ndep, 4 * nlambda, npar, d_delta, d_stokes, d_rf);
+  rf_diff_kernel<<<(unsigned) ((tot + 127) / 128), 128, 0, c->stream>>>(v0, n / 2, nsel, 4 * nlambda, npar, d_delta, d_stokes, d_rf);
   RH_CUDA(cudaGetLastError());
   return RHB200_OK;
 }

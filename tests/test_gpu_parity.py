@@ -910,6 +910,11 @@ def test_rf_fd_single_depth_route_equals_full_syntheses(ctx, monkeypatch, scale)
     assert np.isfinite(brute).all() and all(np.abs(brute[:, q]).max() > 0 for q in range(len(rows)))
     REPORT[f"rf_fd_single_depth_exact_{scale}"] = bool(np.array_equal(fast, brute))
     assert np.array_equal(fast, brute)
+    # selected depths only (rhb200_rf_fd_depths_batch): the same numbers at the nodes, both routes
+    nodes = [0, 7, 33, 34, 68, 69]
+    assert np.array_equal(ctx.rf_fd_batch(atm, rows, delta, depths=nodes, **kw), brute[:, :, nodes])
+    monkeypatch.delenv("RHB200_RF_FD_BRUTE")
+    assert np.array_equal(ctx.rf_fd_batch(atm, rows, delta, depths=nodes, **kw), brute[:, :, nodes])
 
 
 def test_host_compute1d_drop_in():
