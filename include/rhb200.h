@@ -114,14 +114,20 @@ int rhb200_update_line_strengths(rhb200_ctx *ctx, int n, const int *rows, const 
 int rhb200_set_wavelengths(rhb200_ctx *ctx, int nlambda, const double *lambda);
 
 /* MolecularOpacity in the fused LTE path (opacity.c:711-839, MolProfile :844-916): LTE lines of PASSIVE molecules,
-   added to the background after the Kurucz lines like Background() does (background.c:548-566); unpolarizable lines
-   only (lines with Hund's-case data need MolZeeman patterns: rhb200_molecular_opacity_batch takes them from the
-   host).  mlines [nline][RHB200_ML_NFIELD] grouped by molecule, ascending lambda0 inside each, RHB200_ML_MOL = row
+   added to the background after the Kurucz lines like Background() does (background.c:548-566).  mlines [nline][RHB200_ML_NFIELD] grouped by molecule, ascending lambda0 inside each, RHB200_ML_MOL = row
    of `molecules`; molecules [nmol][16] = {index in the chemical network of rhb200_set_chemistry, molecular weight,
    enum fit_type, Tmin, Tmax, Npf, pf_coef[0..7]}.  Densities come from the chemistry kernel, partition functions
    (partfunction, chemequil.c:395-443) and Doppler widths are formed on the device.  Call after rhb200_set_continuum /
    rhb200_set_chemistry and before rhb200_set_wavelengths; rhb200_set_lines clears the table. */
 int rhb200_set_molecular_lines(rhb200_ctx *ctx, int nline, const double *mlines, int nmol, const double *molecules);
+/* The same with polarizable lines (line lists that carry Hund's-case data, readmolecule.c:859-912): rows with
+   RHB200_ML_POLARIZABLE != 0 name their MolZeeman components (molzeeman.c:196-319: q, shift in Larmor units, strength
+   normalised per q) as [RHB200_ML_ZOFF, + RHB200_ML_NCOMP) of zq / zshift / zstrength [ncomp]; their wavelengths are
+   flagged polarised (backgrflags.ispolarized, opacity.c:794-797), the profile is MolProfile's Zeeman sum
+   (opacity.c:866-899) and chi_c / eta_c get the Q, U, V parts after the Kurucz lines' (background.c:548-566).  Without
+   MAGNETO_OPTICAL only.  rhb200_set_molecular_lines() is the ncomp = 0 case and refuses polarizable rows. */
+int rhb200_set_molecular_lines_zeeman(rhb200_ctx *ctx, int nline, const double *mlines, int nmol, const double *molecules,
+                                      int ncomp, const int *zq, const double *zshift, const double *zstrength);
 
 /* get_atomic_rfs (rh/inputs.h:92, pyrh.pyx:604-606): the Kurucz lines whose log gf the analytic response function is
    taken for.  line_rows[p] = row of the table passed to rhb200_set_lines that carries parameter p (the reference's

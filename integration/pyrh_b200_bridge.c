@@ -337,7 +337,8 @@ static void build_tables(int get_atomic_rfs, int fudge_num, double *fudge_lam, d
     else CHECK(rhb200_set_passive_lines(g_ctx, 0, NULL, 0, NULL, NULL));
     CHECK(rhb200_set_model_lines(g_ctx, ml.n / 4, ml.v));
     {                                               /* MolecularOpacity (opacity.c:711-839): line lists of PASSIVE molecules */
-      dvec mrows = {0}, msel = {0};
+      dvec mrows = {0}, msel = {0}, mzs = {0}, mzt = {0};
+      ivec mzq = {0};
       int nsel = 0;
       for (n = 0; n < atmos.Nmolecule; n++) {
         Molecule *mo = &atmos.molecules[n];
@@ -346,8 +347,12 @@ static void build_tables(int get_atomic_rfs, int fudge_num, double *fudge_lam, d
         for (kr = 0; kr < mo->Nrt; kr++) {            /* readMolecule() left them sorted by lambda0 (readmolecule.c:247) */
           MolecularLine *mrt = &mo->mrt[kr];
           double r[RHB200_ML_NFIELD];
-          if (mrt->polarizable) FAIL("polarizable molecular lines (MolZeeman, molzeeman.c) are not ported");
           memset(r, 0, sizeof r);
+          if (mrt->polarizable) {                     /* the reference's own MolZeeman() pattern (opacity.c:796 builds it lazily) */
+            if (mrt->zm == NULL) mrt->zm = MolZeeman(mrt);
+            r[RHB200_ML_POLARIZABLE] = 1.0; r[RHB200_ML_ZOFF] = mzq.n; r[RHB200_ML_NCOMP] = mrt->zm->Ncomponent;
+            for (i = 0; i < mrt->zm->Ncomponent; i++) { iv_push(&mzq, mrt->zm->q[i]); dv_push(&mzs, mrt->zm->shift[i]); dv_push(&mzt, mrt->zm->strength[i]); }
+          }
           r[RHB200_ML_LAMBDA0] = mrt->lambda0; r[RHB200_ML_EI] = mrt->Ei; r[RHB200_ML_GI] = mrt->gi; r[RHB200_ML_BIJ] = mrt->Bij;
           r[RHB200_ML_AJI] = mrt->Aji; r[RHB200_ML_BJI] = mrt->Bji; r[RHB200_ML_ISO_FRAC] = mrt->isotope_frac;
           r[RHB200_ML_QWING] = mrt->qwing; r[RHB200_ML_MOL] = nsel;
@@ -362,8 +367,8 @@ static void build_tables(int get_atomic_rfs, int fudge_num, double *fudge_lam, d
         }
         nsel++;
       }
-      CHECK(rhb200_set_molecular_lines(g_ctx, mrows.n / RHB200_ML_NFIELD, mrows.v, nsel, msel.v));
-      free(mrows.v); free(msel.v);
+      CHECK(rhb200_set_molecular_lines_zeeman(g_ctx, mrows.n / RHB200_ML_NFIELD, mrows.v, nsel, msel.v, mzq.n, mzq.v, mzs.v, mzt.v));
+      free(mrows.v); free(msel.v); free(mzq.v); free(mzs.v); free(mzt.v);
     }
     CHECK(rhb200_set_scatter(g_ctx, input.NmaxScatter, input.iterLimit));
     /* with ACTIVE atoms the polarised passes are selected through rhb200_nlte_front.stokes; the background is set up I-only */

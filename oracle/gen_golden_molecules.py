@@ -53,5 +53,38 @@ def main():
           f"port exact {ok}/{len(out['mol_meta'])} -> {(GOLD / 'falc_molecules.npz').stat().st_size/1e3:.0f} kB")
 
 
+def main_polarizable():
+    """The same window with a polarizable copy of the CN list (refdriver.polarizable_cn_tree): MolZeeman patterns,
+    MolProfile's Zeeman sum, Q/U/V background opacity from molecules.  Output: tests/golden/falc_molecules_pol.npz."""
+    import os
+    import tempfile
+    atm = falc_case_atm()
+    wave = np.linspace(846.9, 847.8, 46)
+    cwd = rd.make_workdir("benchmark")
+    rd.load()
+    keep = os.environ["PYRH_PATH"]
+    os.environ["PYRH_PATH"] = rd.polarizable_cn_tree(tempfile.mkdtemp(prefix="rhref_pyrhpath_"))
+    try:
+        o = rd.rhf1d(atm, wave, cwd, probe=rd.PROBE_RLK | rd.PROBE_SNAP)
+    finally:
+        os.environ["PYRH_PATH"] = keep
+    R = recs_by_tag(o["records"])
+    zq, zs, zt, rows = [], [], [], []
+    for m, d in sorted(R["mol_line"], key=lambda x: (x[0][0], x[0][1])):
+        nc = m[2]
+        rows.append(np.concatenate([d[:9], [len(zq), nc]]))
+        zq += list(d[10:10 + nc].astype(int)); zs += list(d[10 + nc:10 + 2 * nc]); zt += list(d[10 + 2 * nc:10 + 3 * nc])
+    out = dict(atmosphere=atm, wave=wave, stokes=np.array([o["I"], o["Q"], o["U"], o["V"]]), lam_out=o["lam"],
+               mlines=np.array(rows), zq=np.array(zq, np.int32), zshift=np.array(zs), zstrength=np.array(zt))
+    np.savez_compressed(GOLD / "falc_molecules_pol.npz", **out)
+    ref = dict(np.load(GOLD / "falc_molecules.npz"))["stokes"]
+    print(f"[golden] falc_molecules_pol: {len(rows)} lines, {len(zq)} Zeeman components; max |V/I| {np.max(np.abs(out['stokes'][3] / out['stokes'][0])):.3e}; "
+          f"differs from the unpolarizable run: {not np.array_equal(ref, out['stokes'])}")
+
+
 if __name__ == "__main__":
-    main()
+    import sys
+    if "--polarizable" in sys.argv:
+        main_polarizable()
+    else:
+        main()

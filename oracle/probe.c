@@ -749,7 +749,11 @@ flags __wrap_MolecularOpacity(double lambda, int nspect, int mu, bool_t to_obs,
           MolecularLine *l = &m->mrt[kr];
           ZeemanMultiplet *zm = l->zm;
           int own = 0;
-          if (l->polarizable && zm == NULL) { zm = MolZeeman(l); own = 1; }   /* lazily built in the reference too */
+          if (l->polarizable && zm == NULL) {            /* lazily built in the reference too (opacity.c:796) */
+            double keep = l->g_Lande_eff;                /* MolZeeman() stores g_eff in the line (molzeeman.c:308): left there, */
+            zm = MolZeeman(l); own = 1;                  /* the reference's own later call would build a normal triplet instead */
+            l->g_Lande_eff = keep;
+          }
           int nc = zm ? zm->Ncomponent : 0;
           double *r = rec_new("mol_line", 10 + 3*nc, n, kr, nc, l->polarizable, 0, 0);
           r[0] = l->lambda0; r[1] = l->Ei; r[2] = l->gi; r[3] = l->Bij; r[4] = l->Aji; r[5] = l->Bji;

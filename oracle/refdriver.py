@@ -153,6 +153,33 @@ def make_workdir(kind: str = "benchmark", keywords: dict | None = None,
     return d
 
 
+def polarizable_cn_tree(dst: str) -> str:
+    """A $PYRH_PATH whose CN.molecule lists a POLARIZABLE copy of the CN B-X list the reference ships: none of the
+    shipped molecular lists carries the Hund's-case columns readMolecularLines() looks for behind column 71
+    (readmolecule.c:859-912), so MolZeeman() is unreachable with stock data.  The copy appends " B S 0.5 B S 0.5"
+    (B 2Sigma+ - X 2Sigma+: Hund's case b, Lambda = 0, S = 1/2) to every line, labels the list KURUCZ_CD18 and raises log gf by 7.
+    Everything else is symlinked."""
+    src = REFDIR / "pyrh_path" / "rh"
+    d = Path(dst) / "rh"
+    (d / "Molecules" / "CN").mkdir(parents=True)
+    for f in src.iterdir():
+        if f.name != "Molecules":
+            os.symlink(f, d / f.name)
+    for f in (src / "Molecules").iterdir():
+        if f.name not in ("CN", "CN.molecule"):
+            os.symlink(f, d / "Molecules" / f.name)
+    lines = (src / "Molecules" / "CN" / "CN_B-X_SCIP_CH1.asc").read_text().splitlines()
+    # the shipped list has its subbranch digits where KURUCZ_CD18 expects them (columns 56 / 64); under its own
+    # KURUCZ_NEW label sscanf("%1d") at column 57 fails and MolZeeman() would read an uninitialised mrt->subi
+    # log gf + 7: the shipped values (around -10) leave the lines invisible against the continuum
+    out = [ln.replace("KURUCZ_NEW", "KURUCZ_CD18") if i == 0 else ln if (i < 2 or not ln.strip() or ln[0] == "#")
+           else ln[:10] + f"{float(ln[10:17]) + 7.0:7.3f}" + ln[17:].ljust(53) + " B S 0.5 B S 0.5" for i, ln in enumerate(lines)]
+    (d / "Molecules" / "CN" / "CN_B-X_polarizable.asc").write_text("\n".join(out) + "\n")
+    mol = (src / "Molecules" / "CN.molecule").read_text().replace("CN/CN_B-X_SCIP_CH1.asc", "CN/CN_B-X_polarizable.asc")
+    (d / "Molecules" / "CN.molecule").write_text(mol)
+    return str(Path(dst))
+
+
 def _dp(a):
     return a.ctypes.data_as(c_double_p)
 

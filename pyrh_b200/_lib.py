@@ -86,6 +86,7 @@ SYMBOLS = [
     ("rhb200_set_stokes_mode", C.c_int, [vp, C.c_int]),
     ("rhb200_set_scatter", C.c_int, [vp, C.c_int, C.c_double]),
     ("rhb200_set_molecular_lines", C.c_int, [vp, C.c_int, dp, C.c_int, dp]),
+    ("rhb200_set_molecular_lines_zeeman", C.c_int, [vp, C.c_int, dp, C.c_int, dp, C.c_int, ip, dp, dp]),
     ("rhb200_set_passive_lines", C.c_int, [vp, C.c_int, dp, C.c_int, dp, dp]),
     ("rhb200_hse_batch", C.c_int, [vp, C.c_int, C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_double, C.c_double,
                                    dp, dp, dp, dp]),

@@ -136,12 +136,17 @@ class Context:
         rows = np.ascontiguousarray(rows, np.float64).reshape(-1, 4)
         _lib.check(self.lib.rhb200_set_model_lines(self.h, len(rows), _dp(rows)))
 
-    def set_molecular_lines(self, mlines, molecules):
-        """Unpolarizable lines of PASSIVE molecules for the fused path: ``mlines [n, 16]``, ``molecules [nmol, 16]``
-        (after set_continuum / set_chemistry, before set_wavelengths)."""
+    def set_molecular_lines(self, mlines, molecules, zq=None, zshift=None, zstrength=None):
+        """Lines of PASSIVE molecules for the fused path: ``mlines [n, 16]``, ``molecules [nmol, 16]`` (after
+        set_continuum / set_chemistry, before set_wavelengths); polarizable rows index their MolZeeman components in
+        ``zq / zshift / zstrength``."""
         ml = np.ascontiguousarray(mlines, np.float64).reshape(-1, 16)
         ms = np.ascontiguousarray(molecules, np.float64).reshape(-1, 16)
-        _lib.check(self.lib.rhb200_set_molecular_lines(self.h, len(ml), _dp(ml), len(ms), _dp(ms)))
+        zq = np.ascontiguousarray(zq if zq is not None else [], np.int32)
+        zs = np.ascontiguousarray(zshift if zshift is not None else [], np.float64)
+        zt = np.ascontiguousarray(zstrength if zstrength is not None else [], np.float64)
+        _lib.check(self.lib.rhb200_set_molecular_lines_zeeman(self.h, len(ml), _dp(ml), len(ms), _dp(ms), len(zq),
+                                                              zq.ctypes.data_as(_lib.ip), _dp(zs), _dp(zt)))
 
     def set_scatter(self, n_max_scatter=0, iter_limit=1.0e-2):
         """keywords N_MAX_SCATTER / ITER_LIMIT in LTE: scattering passes of the line-free wavelengths."""

@@ -76,6 +76,7 @@ static void free_wave(rhb200_ctx *c)
   DevWave &w = c->wav;
   cudaFree(w.lambda); cudaFree(w.first); cudaFree(w.count); cudaFree(w.idx); cudaFree(w.flags); cudaFree(w.noline); cudaFree(w.unpol_rank);
   cudaFree(w.mw_first); cudaFree(w.mw_count); cudaFree(w.mw_idx); cudaFree(w.ml_rows); cudaFree(w.ml_sel);
+  cudaFree(w.mz_q); cudaFree(w.mz_shift); cudaFree(w.mz_strength);
   cudaFree(w.pw_first); cudaFree(w.pw_count); cudaFree(w.pw_idx); cudaFree(w.pl_rows); cudaFree(w.pl_pb); cudaFree(w.pl_cshift); cudaFree(w.pl_cfrac);
   w = DevWave();
 }
@@ -170,7 +171,7 @@ extern "C" int rhb200_set_lines(rhb200_ctx *c, int nline, const double *lines, i
   free_wave(c);     // windows depend on the line table
   c->h_model_lines.clear();
   c->h_plines.clear(); c->h_pcshift.clear(); c->h_pcfrac.clear();
-  c->h_mlines.clear(); c->h_msel.clear();
+  c->h_mlines.clear(); c->h_msel.clear(); c->h_mzq.clear(); c->h_mzshift.clear(); c->h_mzstrength.clear();
   return RHB200_OK;
 }
 
@@ -195,16 +196,19 @@ extern "C" int rhb200_update_line_strengths(rhb200_ctx *c, int n, const int *row
   return RHB200_OK;
 }
 
-// MolecularOpacity in the fused LTE path (opacity.c:711-839): LTE lines of PASSIVE molecules, unpolarizable ones only
-// (lines with Hund's-case data need MolZeeman patterns: use rhb200_molecular_opacity_batch with host patterns).
+// MolecularOpacity in the fused LTE path (opacity.c:711-839): LTE lines of PASSIVE molecules.
 // mlines [nline][RHB200_ML_NFIELD] grouped by molecule, ascending in lambda0 inside each (RHB200_ML_MOL = row of
 // `molecules`); molecules [nmol][16] = {index in the chemical network of rhb200_set_chemistry, molecular weight,
-// enum fit_type, Tmin, Tmax, Npf, pf_coef[0..7]} (readmolecule.c:199-237).  Needs rhb200_set_continuum and
+// enum fit_type, Tmin, Tmax, Npf, pf_coef[0..7]} (readmolecule.c:199-237).  Polarizable lines (Hund's-case data in the
+// list, readmolecule.c:859-912) carry RHB200_ML_POLARIZABLE != 0 and the range [RHB200_ML_ZOFF, + RHB200_ML_NCOMP) of
+// their MolZeeman components (molzeeman.c:196-319) in zq / zshift / zstrength.  Needs rhb200_set_continuum and
 // rhb200_set_chemistry before the first batch call; call before rhb200_set_wavelengths; rhb200_set_lines clears the table.
-extern "C" int rhb200_set_molecular_lines(rhb200_ctx *c, int nline, const double *mlines, int nmol, const double *molecules)
+extern "C" int rhb200_set_molecular_lines_zeeman(rhb200_ctx *c, int nline, const double *mlines, int nmol, const double *molecules,
+                                                 int ncomp, const int *zq, const double *zshift, const double *zstrength)
 {
   RH_NEED_CTX(c);
-  if (nline < 0 || nmol < 0 || (nline > 0 && (!mlines || !molecules || nmol == 0))) { rhb200_set_error("rhb200_set_molecular_lines: bad arguments"); return RHB200_EINVAL; }
+  if (nline < 0 || nmol < 0 || ncomp < 0 || (nline > 0 && (!mlines || !molecules || nmol == 0)) ||
+      (ncomp > 0 && (!zq || !zshift || !zstrength))) { rhb200_set_error("rhb200_set_molecular_lines: bad arguments"); return RHB200_EINVAL; }
   std::vector<int> chem(nmol);
   for (int m = 0; m < nmol; m++) {
     chem[m] = (int) molecules[(size_t) m * 16];
@@ -215,12 +219,20 @@ extern "C" int rhb200_set_molecular_lines(rhb200_ctx *c, int nline, const double
     const int m = (int) L[RHB200_ML_MOL];
     if (m < 0 || m >= nmol) { rhb200_set_error("molecular line %d: molecule index out of range", n); return RHB200_EINVAL; }
     if (n > 0 && m < (int) L[RHB200_ML_MOL - RHB200_ML_NFIELD]) { rhb200_set_error("molecular lines must be grouped by molecule"); return RHB200_EINVAL; }
-    if (L[RHB200_ML_POLARIZABLE] != 0.0) { rhb200_set_error("molecular line %d is polarizable: MolZeeman patterns are not part of the fused path", n); return RHB200_EUNSUPPORTED; }
+    if (L[RHB200_ML_POLARIZABLE] != 0.0) {
+      const int zoff = (int) L[RHB200_ML_ZOFF], nc = (int) L[RHB200_ML_NCOMP];
+      if (zoff < 0 || nc < 0 || zoff + nc > ncomp) { rhb200_set_error("molecular line %d is polarizable: its MolZeeman components [%d, %d) are outside the tables (%d)", n, zoff, zoff + nc, ncomp); return RHB200_EINVAL; }
+    }
   }
   c->h_mlines.assign(mlines, mlines + (size_t) nline * RHB200_ML_NFIELD);
   c->h_msel.assign(molecules, molecules + (size_t) nmol * 16);
+  c->h_mzq.assign(zq, zq + ncomp); c->h_mzshift.assign(zshift, zshift + ncomp); c->h_mzstrength.assign(zstrength, zstrength + ncomp);
   free_wave(c);
   return RHB200_OK;
+}
+extern "C" int rhb200_set_molecular_lines(rhb200_ctx *c, int nline, const double *mlines, int nmol, const double *molecules)
+{
+  return rhb200_set_molecular_lines_zeeman(c, nline, mlines, nmol, molecules, 0, nullptr, nullptr, nullptr);
 }
 
 // keywords N_MAX_SCATTER / ITER_LIMIT in LTE (pyrh_compute1dray.c:332-337): after the formal solution the reference
@@ -360,6 +372,7 @@ extern "C" int rhb200_set_wavelengths(rhb200_ctx *c, int nlambda, const double *
   // MolecularOpacity windows (opacity.c:774-787), molecule by molecule, lines in table order
   const int NML = (int) (c->h_mlines.size() / RHB200_ML_NFIELD), NMS = (int) (c->h_msel.size() / 16);
   std::vector<int> mw_first(nlambda, 0), mw_count(nlambda, 0), mw_idx, mfirst(NMS, -1), mlast(NMS, -1);
+  int mol_pol = 0;
   for (int n = 0; n < NML; n++) {
     const int m = (int) c->h_mlines[(size_t) n * RHB200_ML_NFIELD + RHB200_ML_MOL];
     if (mfirst[m] < 0) mfirst[m] = n;
@@ -376,7 +389,10 @@ extern "C" int rhb200_set_wavelengths(rhb200_ctx *c, int nlambda, const double *
       for (int n = mfirst[m]; n <= mlast[m]; n++) {
         const double *L = c->h_mlines.data() + (size_t) n * RHB200_ML_NFIELD;
         const double dl = lam * L[RHB200_ML_QWING] * vc;
-        if (std::fabs(L[RHB200_ML_LAMBDA0] - lam) <= dl) { mw_idx.push_back(n); c->h_flags[l] |= 1; }
+        if (std::fabs(L[RHB200_ML_LAMBDA0] - lam) <= dl) {
+          mw_idx.push_back(n); c->h_flags[l] |= 1;
+          if (L[RHB200_ML_POLARIZABLE] != 0.0) { c->h_flags[l] |= 2; mol_pol = 1; }     // backgrflags.ispolarized, opacity.c:794-797
+        }
       }
     }
     mw_count[l] = (int) mw_idx.size() - mw_first[l];
@@ -390,6 +406,12 @@ extern "C" int rhb200_set_wavelengths(rhb200_ctx *c, int nlambda, const double *
     RH_CHECK(upload(&w.mw_first, mw_first.data(), (size_t) nlambda));
     RH_CHECK(upload(&w.mw_count, mw_count.data(), (size_t) nlambda));
     RH_CHECK(upload(&w.mw_idx, mw_idx.data(), mw_idx.size()));
+    w.mol_pol = mol_pol;
+    if (mol_pol) {
+      RH_CHECK(upload(&w.mz_q, c->h_mzq.data(), c->h_mzq.size()));
+      RH_CHECK(upload(&w.mz_shift, c->h_mzshift.data(), c->h_mzshift.size()));
+      RH_CHECK(upload(&w.mz_strength, c->h_mzstrength.data(), c->h_mzstrength.size()));
+    }
   }
   w.npl = (int) pact.size(); w.npw = (int) pw_idx.size();
   if (w.npl) {
@@ -626,7 +648,7 @@ static int lte_batch_host(rhb200_ctx *c, int ncol, int ndep, double muz, int mov
     RH_CHECK(rh_continuum_set_molsel(c, c->wav.nmsel, chem.data()));
   }
   const size_t b_md = mol_on ? align_up((size_t) cc * c->wav.nmsel * 4 * ndep * sizeof(double)) : 0;   // densities + {n, pf, vbroad}
-  const size_t b_mo = mol_on ? b_op : 0;                                                                // chi, eta of the molecular lines
+  const size_t b_mo = mol_on ? (c->wav.mol_pol ? 4 : 1) * b_op : 0;                                     // chi, eta of the molecular lines (I, or I Q U V planes)
   const size_t b_sa = (c->n_max_scatter > 0 && cont_dev) ? b_op : 0;                                  // scattering opacity
   const size_t slot = L.total + b_at + 2*b_op + b_st + b_ch + b_pp + b_tp + b_in + b_sc + b_pc + b_md + 2*b_mo + b_sa;
   RH_CHECK(rh_ws_reserve(c, nslots * slot));
@@ -928,8 +950,8 @@ static int rf_fd_single_depth(rhb200_ctx *c, int ncol, int ndep, int nrow, doubl
     y.tp  = take(nf * 8 * ndep * sizeof(double));
     y.pc  = take(nf * std::max(1, c->wav.npl) * 4 * ndep * sizeof(double));
     y.md  = take(mol_on ? nf * c->wav.nmsel * 4 * ndep * sizeof(double) : 0);
-    y.mchi = take(mol_on ? nf * nl * ndep * sizeof(double) : 0);
-    y.meta = take(mol_on ? nf * nl * ndep * sizeof(double) : 0);
+    y.mchi = take(mol_on ? (c->wav.mol_pol ? 4 : 1) * nf * nl * ndep * sizeof(double) : 0);
+    y.meta = take(mol_on ? (c->wav.mol_pol ? 4 : 1) * nf * nl * ndep * sizeof(double) : 0);
     y.ws  = take(ChunkLayout(c, (int) nf, ndep).total);
     y.vws = take(nv * 4 * ndep * sizeof(double));
     y.vst = take(nv * 4 * nl * sizeof(double));

@@ -70,6 +70,8 @@ struct DevWave {
   int nml = 0, nmsel = 0, nmw = 0;
   int *mw_first = nullptr, *mw_count = nullptr, *mw_idx = nullptr;
   double *ml_rows = nullptr /* [nml][RHB200_ML_NFIELD] */, *ml_sel = nullptr /* [nmsel][16] */;
+  int mol_pol = 0;                                     // a polarizable molecular line (MolZeeman pattern) lies in some window
+  int *mz_q = nullptr; double *mz_shift = nullptr, *mz_strength = nullptr;   // Zeeman components of the molecular lines
   double *pl_rows = nullptr /* [npl][RHB200_PL_NFIELD] */, *pl_pb = nullptr /* [npl][RHB200_PB_NFIELD] */, *pl_cshift = nullptr, *pl_cfrac = nullptr;   // [nlambda] rank among the wavelengths with flags == 1 (line, unpolarised), else -1
 };
 
@@ -88,6 +90,7 @@ struct rhb200_ctx {
   std::vector<int> h_first, h_count, h_idx, h_flags, h_noline;
   std::vector<double> h_model_lines;
   std::vector<double> h_plines, h_pcshift, h_pcfrac;   // rhb200_set_passive_lines
+  std::vector<int> h_mzq; std::vector<double> h_mzshift, h_mzstrength;   // MolZeeman components (rhb200_set_molecular_lines_zeeman)
   std::vector<double> h_mlines, h_msel;                // rhb200_set_molecular_lines     // rhb200_set_model_lines: [n][4] element row, stage, lambda0 [nm], qwing
   // formal solver selection (keyword.input S_INTERPOLATION / S_INTERPOLATION_STOKES, inputs.h:26-27)
   int s_interpolation = RHB200_S_BEZIER3, s_interpolation_stokes = RHB200_DELO_BEZIER3;
@@ -200,7 +203,7 @@ int rh_launch_passive_bb(rhb200_ctx *ctx, int ncol, int nlambda, int ndep, int n
 int rh_passive_chunk(rhb200_ctx *ctx, int ncol, int ndep, double muz, const double *d_atmos, const double *d_pops, int nlev,
                       double *d_pcol /* [ncol][npl][4][ndep] */, double *d_chi_ai, double *d_eta_ai);
 int rh_molecular_chunk(rhb200_ctx *ctx, int ncol, int ndep, double muz, const double *d_atmos, const double *d_molden,
-                        double *d_mol /* [ncol][nmsel][3][ndep] */, double *d_molchi, double *d_moleta /* [ncol][nlambda][ndep] */);
+                        double *d_mol /* [ncol][nmsel][3][ndep] */, double *d_molchi, double *d_moleta /* [ncol][nlambda][ndep], or [4] of those planes (I, Q, U, V) when wav.mol_pol */);
 int rh_launch_prep(rhb200_ctx *ctx, int ncol, int ndep, double muz, int moving,
                    const double *d_atmos, double *d_elem_n, double *d_lineprep);
 int rh_launch_opacity_fused(rhb200_ctx *ctx, int ncol, int ndep, int to_obs,

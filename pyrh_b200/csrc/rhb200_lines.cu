@@ -246,7 +246,7 @@ opacity_fused_kernel(int ncol, int nlambda, int ndep, int to_obs, int nline,
                      const double *__restrict__ chi_ai, const double *__restrict__ eta_ai,
                      double *__restrict__ raypts,
                      const double *__restrict__ mol_chi, const double *__restrict__ mol_eta,
-                     const double *__restrict__ sca_ai, const int *__restrict__ wflags, int all_scalar)
+                     const double *__restrict__ sca_ai, const int *__restrict__ wflags, int all_scalar, int mol_pol)
 {
   const size_t npts = (size_t) ncol * nlambda * ndep;
   const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -267,7 +267,13 @@ opacity_fused_kernel(int ncol, int nlambda, int ndep, int to_obs, int nline,
   // molecular lines come last in Background() (background.c:548-566): chi_c = (chi_ai + Kurucz) + molecules
   double chi = __ldg(chi_ai + t) + s.chi[0], eta = __ldg(eta_ai + t) + s.eta[0];
   if (RLKS) chi += s.scatt;                        // background.c:538-543: sca_c += scatt; chi_c += scatt
-  if (mol_chi) { chi += __ldg(mol_chi + t); eta += __ldg(mol_eta + t); }
+  if (mol_chi) {
+    chi += __ldg(mol_chi + t); eta += __ldg(mol_eta + t);
+    if (mol_pol) {                                 // polarizable molecular lines: chi_c[QUV] = (0 + Kurucz) + molecules
+#pragma unroll
+      for (int i = 1; i < 4; i++) { s.chi[i] += __ldg(mol_chi + i*npts + t); s.eta[i] += __ldg(mol_eta + i*npts + t); }
+    }
+  }
   const rhdiv::Recip rchi(chi);                  // seven IEEE quotients, one reciprocal refinement
   double2 *o = reinterpret_cast<double2 *>(raypts + t * RP_NFIELD);
   o[0] = make_double2(chi, rchi.div(s.chi[1]));
@@ -483,9 +489,13 @@ mol_opacity_raw_kernel(int intensity_only, int ncol, int nlambda, int ndep, int 
       e4[1] += eta_l * phi_Q;  e4[2] += eta_l * phi_U;  e4[3] += eta_l * phi_V;
     }
   }
-  if (intensity_only) {          // fused path (unpolarizable lines): [ncol][nlambda][ndep], zero where there is no line
+  if (intensity_only) {          // fused path: [ncol][nlambda][ndep], zero where there is no line; 2 = I, Q, U, V planes
     chi[t] = c4[0];
     eta[t] = e4[0];
+    if (intensity_only == 2) {
+#pragma unroll
+      for (int i = 1; i < 4; i++) { chi[i*npts + t] = c4[i]; eta[i*npts + t] = e4[i]; }
+    }
     return;
   }
 #pragma unroll
@@ -692,7 +702,7 @@ int rh_launch_mol_opacity_raw(rhb200_ctx *ctx, int ncol, int nlambda, int ndep, 
   return RHB200_OK;
 }
 
-// MolecularOpacity of one chunk in the fused path (unpolarizable lines): densities / partition functions / Doppler
+// MolecularOpacity of one chunk in the fused path: densities / partition functions / Doppler
 // widths of the molecules with line lists, then chi and eta of their lines per ray-point, which the Kurucz-line
 // kernel adds last (background.c:548-566)
 int rh_molecular_chunk(rhb200_ctx *ctx, int ncol, int ndep, double muz, const double *d_atmos, const double *d_molden,
@@ -708,8 +718,8 @@ int rh_molecular_chunk(rhb200_ctx *ctx, int ncol, int ndep, double muz, const do
   {
     ScopedKernelTimer t(ctx, RHB200_K_OPACITY);
     const size_t n = (size_t) ncol * w.nlambda * ndep;
-    mol_opacity_raw_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, ctx->stream>>>(1, ncol, w.nlambda, ndep, w.nmsel, muz, 1, 1,
-        w.lambda, w.mw_first, w.mw_count, w.mw_idx, w.ml_rows, nullptr, nullptr, nullptr, d_atmos, d_mol, d_molchi, d_moleta);
+    mol_opacity_raw_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, ctx->stream>>>(w.mol_pol ? 2 : 1, ncol, w.nlambda, ndep, w.nmsel, muz, 1, 1,
+        w.lambda, w.mw_first, w.mw_count, w.mw_idx, w.ml_rows, w.mz_q, w.mz_shift, w.mz_strength, d_atmos, d_mol, d_molchi, d_moleta);
   }
   RH_CUDA(cudaGetLastError());
   return RHB200_OK;
@@ -789,7 +799,7 @@ int rh_launch_opacity_fused(rhb200_ctx *ctx, int ncol, int ndep, int to_obs,
       arm = arm || (L[RHB200_RL_GRAD] != 0.0 && L[RHB200_RL_POLARIZABLE] == 0.0);
     }
 #define RH_OPF_ARGS(Z) (ncol, ctx->wav.nlambda, ndep, to_obs, ctx->tab.nline, ctx->wav.lambda, ctx->wav.first, \
-        ctx->wav.count, ctx->wav.idx, ctx->tab.lines, Z, d_atmos, d_lineprep, d_chi_ai, d_eta_ai, d_raypts, d_molchi, d_moleta, d_sca, ctx->wav.flags, ctx->no_stokes)
+        ctx->wav.count, ctx->wav.idx, ctx->tab.lines, Z, d_atmos, d_lineprep, d_chi_ai, d_eta_ai, d_raypts, d_molchi, d_moleta, d_sca, ctx->wav.flags, ctx->no_stokes, ctx->wav.mol_pol)
 #define RH_LAUNCH_OPF(M, ZT, Z) do { if (ctx->tab.rlkscatter) opacity_fused_kernel<M, ZT, true, true><<<grid, block, 0, ctx->stream>>>RH_OPF_ARGS(Z); \
         else if (arm) opacity_fused_kernel<M, ZT, true, false><<<grid, block, 0, ctx->stream>>>RH_OPF_ARGS(Z); \
         else opacity_fused_kernel<M, ZT, false, false><<<grid, block, 0, ctx->stream>>>RH_OPF_ARGS(Z); } while (0)

@@ -309,6 +309,7 @@ extern "C" int rhb200_nlte_compute1d_stokes_batch(rhb200_ctx *c, const rhb200_nl
   p1.muz = mu1; p1.wmu = w1; p1.Nrays = 1;
   const int nline_k = c->tab.nline, nelem = c->tab.nelem;
   const bool mol_on = c->wav.nmw > 0;
+  if (c->wav.mol_pol) { rhb200_set_error("polarizable molecular lines with ACTIVE atoms are not implemented"); return RHB200_EUNSUPPORTED; }
   uint64_t key = 1469598103934665603ull;
   auto mix = [&](const void *ptr, size_t bytes) {
     const unsigned char *q = (const unsigned char *) ptr;

@@ -17,7 +17,7 @@ What is parsed here (once per working directory, cached), with the reference's o
 
 Only the published opacity tables RH keeps inside its C sources (H-, H2-, H2+, OH, CH) come from a data file
 (``data/background_falc11.npz``).  A working directory that asks for ACTIVE atoms,
-MAGNETO_OPTICAL, polarizable molecular line lists or anything else this path does not implement is refused loudly
+MAGNETO_OPTICAL or anything else this path does not implement is refused loudly
 (``NotImplementedError``), never approximated.
 """
 from __future__ import annotations
@@ -836,21 +836,79 @@ ML_NFIELD = 16
 MS_NFIELD = 16         # molecule rows of Context.set_molecular_lines: chem index, weight, fit, Tmin, Tmax, Npf, pf_coef[8]
 
 
-def read_molecular_lines(list_file, mol_sel):
+def mol_lande(hund, Lambda, S, sub, J):
+    """Lande factor of a molecular level: Hund's case a (MolLande_a, molzeeman.c:107-115; the reference never sets
+    Omega, so the factor is 0) or case b (MolLande_b, :120-136) with N = J - S + (sub - 1) (:159, :171)."""
+    if hund == "A":
+        Omega = 0.0
+        return (Lambda + 2.0 * S) * Omega / (J * (J + 1.0))
+    N = J - S + (sub - 1)
+    if Lambda == 0:
+        return 1.0 / (J * (J + 1.0)) * (J * (J + 1.0) - N * (N + 1.0) + S * (S + 1.0))
+    return 1.0 / (J * (J + 1.0)) * (Lambda * Lambda / (2 * N * (N + 1.0)) * (J * (J + 1.0) + N * (N + 1.0) - S * (S + 1.0)) +
+                                    J * (J + 1.0) - N * (N + 1.0) + S * (S + 1.0))
+
+
+def mol_zeeman_strength(Ju, Mu, Jl, Ml):
+    """MolZeemanStr (molzeeman.c:36-101): strength of the component (Ju, Mu) -> (Jl, Ml), q = Ml - Mu, dJ = Jl - Ju."""
+    q, dJ = int(Ml - Mu), int(Jl - Ju)
+    if dJ == 1:
+        if q == 1:
+            return (Ju + 1.0 + Mu) * (Ju + 2.0 + Mu) / (2 * (Ju + 1.0) * (2 * Ju + 1.0) * (2 * Ju + 3.0))
+        if q == 0:
+            return (Ju + 1.0 + Mu) * (Ju + 1.0 - Mu) / ((Ju + 1.0) * (2 * Ju + 1.0) * (2 * Ju + 3.0))
+        return (Ju + 1.0 - Mu) * (Ju + 2.0 - Mu) / (2 * (Ju + 1.0) * (2 * Ju + 1.0) * (2 * Ju + 3.0))
+    if dJ == 0:
+        if q == 1:
+            return (Ju - Mu) * (Ju + 1.0 + Mu) / (2 * Ju * (Ju + 1.0) * (2 * Ju + 1.0))
+        if q == 0:
+            return Mu * Mu / (Ju * (Ju + 1.0) * (2 * Ju + 1.0))
+        return (Ju + Mu) * (Ju + 1.0 - Mu) / (2 * Ju * (Ju + 1.0) * (2 * Ju + 1.0))
+    if dJ == -1:
+        if q == 1:
+            return (Ju - Mu) * (Ju - 1.0 - Mu) / (2 * Ju * (2 * Ju - 1.0) * (2 * Ju + 1.0))
+        if q == 0:
+            return (Ju + Mu) * (Ju - Mu) / (Ju * (2 * Ju - 1.0) * (2 * Ju + 1.0))
+        return (Ju + Mu) * (Ju - 1.0 + Mu) / (2 * Ju * (2 * Ju - 1.0) * (2 * Ju + 1.0))
+    raise ValueError(f"MolZeemanStr: invalid dJ {dJ}")
+
+
+def mol_zeeman(gi, gj, hund_i, Lambda_i, S_i, sub_i, hund_j, Lambda_j, S_j, sub_j):
+    """MolZeeman (molzeeman.c:196-319), anomalous splitting: (q, shift, strength) of every component with
+    abs(Ml - Mu) <= 1 in the reference's (Ml outer, Mu inner) order, strengths normalised per q."""
+    Jl, Ju = np.float64((gi - 1.0) / 2.0), np.float64((gj - 1.0) / 2.0)       # numpy scalars: J = 0 divides like C does
+    with np.errstate(all="ignore"):
+        gLl, gLu = mol_lande(hund_i, Lambda_i, S_i, sub_i, Jl), mol_lande(hund_j, Lambda_j, S_j, sub_j, Ju)
+    Jl, Ju, gLl, gLu = float(Jl), float(Ju), float(gLl), float(gLu)
+    q, shift, strength, norm = [], [], [], [0.0, 0.0, 0.0]
+    Ml = -Jl
+    while Ml <= Jl:
+        Mu = -Ju
+        while Mu <= Ju:
+            if abs(Ml - Mu) <= 1.0:
+                q.append(int(Ml - Mu))
+                shift.append(gLl * Ml - gLu * Mu)
+                strength.append(mol_zeeman_strength(Ju, Mu, Jl, Ml))
+                norm[q[-1] + 1] += strength[-1]
+            Mu += 1
+        Ml += 1
+    return q, shift, [s / norm[k + 1] for s, k in zip(strength, q)]
+
+
+def read_molecular_lines(list_file, mol_sel, zq, zshift, zstrength):
     """One line list of a molecule (readMolecularLines, readmolecule.c:437-770, KURUCZ_NEW / KURUCZ_CD18 formats) ->
-    rows [n, ML_NFIELD].  Lines that carry Hund's-case data are polarizable (MolZeeman) and refused."""
+    rows [n, ML_NFIELD].  Lines that carry Hund's-case data behind column 71 (:859-912) are polarizable -- pyrh always
+    sets atmos.Stokes -- and get their MolZeeman components appended to zq / zshift / zstrength."""
     data = [ln for ln in Path(list_file).read_text().splitlines() if ln.strip() and ln[0] != "#"]
     h = data[0].split()
     nrt, fmt = int(h[0]), h[2]
     if not any(f in fmt for f in ("KURUCZ_NEW", "KURUCZ_CD18")):
         raise NotImplementedError(f"{list_file}: molecular line format {fmt} is not ported")
+    sub_col = 56 if "KURUCZ_CD18" in fmt else 57                           # subbranch digit (:790-791, :816-817)
     qwing = float(data[1].split()[1])
     C = 2 * PI * (Q_ELECTRON / EPSILON_0) * (Q_ELECTRON / M_ELECTRON) / CLIGHT
     rows = []
     for ln in data[2:2 + nrt]:
-        if len(ln) > 71:
-            raise NotImplementedError(f"{list_file}: lines with Hund's-case data are polarizable (MolZeeman, "
-                                      "molzeeman.c) -- not ported")
         log_gf, gi, Ei, gj, Ej = float(ln[10:17]), float(ln[17:22]), float(ln[22:32]), float(ln[32:37]), float(ln[37:48])
         Ei = (HPLANCK * CLIGHT) / CM_TO_M * abs(Ei)
         Ej = (HPLANCK * CLIGHT) / CM_TO_M * abs(Ej)
@@ -862,15 +920,32 @@ def read_molecular_lines(list_file, mol_sel):
         r = np.zeros(ML_NFIELD)
         r[ML_LAMBDA0], r[ML_EI], r[ML_GI], r[ML_BIJ], r[ML_AJI], r[ML_BJI] = lambda0 / NM_TO_M, Ei, gi, Bij, Aji, Bji
         r[ML_ISO_FRAC], r[ML_QWING], r[ML_MOL] = 1.0, qwing, mol_sel
+        if len(ln) + 1 > 71:                                                # strlen(inputLine) counts the newline
+            f = ln[71:].split()
+            if len(f) < 6 or f[0][0] not in "AB" or f[3][0] not in "AB" or f[1][0] not in "SPDF" or f[4][0] not in "SPDF":
+                raise ValueError(f"{list_file}: bad Hund's-case data {ln[71:]!r} (the reference exits, readmolecule.c:867-906)")
+            sub = []
+            for c0 in (sub_col, sub_col + 8):                              # sscanf(inputLine + c0, "%1d", ...)
+                t = ln[c0:].lstrip()
+                if not t or not t[0].isdigit():
+                    raise ValueError(f"{list_file}: no subbranch digit at column {c0} of {ln!r}: the reference then feeds an "
+                                     "uninitialised mrt->subi / subj to MolZeeman (readmolecule.c:790-791, 816-817)")
+                sub.append(int(t[0]))
+            q, sh, st = mol_zeeman(gi, gj, f[0][0], "SPDF".index(f[1][0]), float(f[2]), sub[0],
+                                   f[3][0], "SPDF".index(f[4][0]), float(f[5]), sub[1])
+            r[ML_POLARIZABLE], r[ML_ZOFF], r[ML_NCOMP] = 1.0, len(zq), len(q)
+            zq += q; zshift += sh; zstrength += st
         rows.append(r)
     return rows
 
 
 def molecular_line_table(cwd, kw, el: Elements, path=None):
-    """(mlines [n, ML_NFIELD], molecules [nsel, MS_NFIELD]) of the PASSIVE molecules that come with line lists, in the
-    order of molecules.input; each molecule's lines ascending in lambda0 (qsort(mrt_ascend), readmolecule.c:247)."""
+    """(mlines [n, ML_NFIELD], molecules [nsel, MS_NFIELD], (zq, zshift, zstrength)) of the PASSIVE molecules that come
+    with line lists, in the order of molecules.input; each molecule's lines ascending in lambda0 (qsort(mrt_ascend),
+    readmolecule.c:247); the last item holds the MolZeeman components of the polarizable lines."""
     root = pyrh_path(path) / "rh" / "Molecules"
     rows, sel = [], []
+    zq, zshift, zstrength = [], [], []
     k = -1
     for ln in (Path(cwd) / kw["MOLECULES_FILE"]).read_text().splitlines():
         f = ln.split("#", 1)[0].split()
@@ -881,7 +956,7 @@ def molecular_line_table(cwd, kw, el: Elements, path=None):
                 continue
             mine = []
             for lst in mo["line_lists"]:
-                mine += read_molecular_lines(root / lst, len(sel))
+                mine += read_molecular_lines(root / lst, len(sel), zq, zshift, zstrength)
             mine.sort(key=lambda r: r[ML_LAMBDA0])
             rows += mine
             if len(mo["pf_coef"]) > 8:
@@ -890,7 +965,8 @@ def molecular_line_table(cwd, kw, el: Elements, path=None):
             m[0:6] = k, mo["weight"], mo["fit"], mo["Tmin"], mo["Tmax"], len(mo["pf_coef"])
             m[6:6 + len(mo["pf_coef"])] = mo["pf_coef"]
             sel.append(m)
-    return np.array(rows).reshape(-1, ML_NFIELD), np.array(sel).reshape(-1, MS_NFIELD)
+    return (np.array(rows).reshape(-1, ML_NFIELD), np.array(sel).reshape(-1, MS_NFIELD),
+            (np.array(zq, np.int32), np.array(zshift, np.float64), np.array(zstrength, np.float64)))
 
 
 def read_background_model(cwd, kw, el: Elements, path=None, allow_active=False):
@@ -991,11 +1067,11 @@ class Session:
         self.lt = read_kurucz_lines(cwd, kw, self.el, loggf_ids, loggf_values, lam_ids, lam_values, path)
         self.lambda_ref = float(kw["LAMBDA_REF"])
         self.lam = sort_lambda(wave, self.lambda_ref)
-        mlines, msel = molecular_line_table(cwd, kw, self.el, path)      # refuses polarizable lists (MolZeeman)
+        mlines, msel, mzee = molecular_line_table(cwd, kw, self.el, path)      # MolZeeman patterns of polarizable lists included
         self.ctx = api.Context(device)
         self.ctx.set_lines(self.lt, magneto_optical=False, rlkscatter=_true(kw["RLK_SCATTER"]))
         if len(mlines):                                                  # MolecularOpacity, opacity.c:711-839
-            self.ctx.set_molecular_lines(mlines, msel)
+            self.ctx.set_molecular_lines(mlines, msel, *mzee)
         if _true(kw.get("ALLOW_PASSIVE_BB", "TRUE")):                       # passive_bb, metal.c:174-344
             lev = bg["ct_lev"]
             first = [int(np.flatnonzero(lev[:, 0] == a)[0]) for a in range(len(listed))]

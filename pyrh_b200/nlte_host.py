@@ -509,11 +509,11 @@ class NlteSession:
             raise NotImplementedError("LAMBDA_REF = 0: convertScales needs the reference wavelength")
         bg = self.background = H.read_background_model(cwd, kw, el, path, allow_active=True)
         self.lt = H.read_kurucz_lines(cwd, kw, el, loggf_ids, loggf_values, lam_ids, lam_values, path)
-        mlines, msel = H.molecular_line_table(cwd, kw, el, path)
+        mlines, msel, mzee = H.molecular_line_table(cwd, kw, el, path)
         self.ctx = ctx = api.Context(device)
         ctx.set_lines(self.lt, magneto_optical=False, rlkscatter=False)
         if len(mlines):
-            ctx.set_molecular_lines(mlines, msel)
+            ctx.set_molecular_lines(mlines, msel, *mzee)
         lev = bg["ct_lev"]
         first = [int(np.flatnonzero(lev[:, 0] == a)[0]) for a in range(len(listed))]
         if H._true(kw.get("ALLOW_PASSIVE_BB", "TRUE")):

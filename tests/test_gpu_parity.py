@@ -1230,6 +1230,44 @@ def test_molecular_lines_in_the_fused_path():
     assert 1 - ref[0].min() / ref[0].max() > 1e-4          # the lines are there
 
 
+def test_polarizable_molecular_lines_in_the_fused_path(tmp_path):
+    """MolZeeman: a molecular line list with Hund's-case data (a polarizable copy of the shipped CN B-X list with
+    log gf + 7, oracle.refdriver.polarizable_cn_tree).  The host forms the Zeeman patterns, the device evaluates
+    MolProfile's Zeeman sum, flags the wavelengths polarised (DELO solver) and adds the molecules' Q, U, V opacity and
+    emissivity after the Kurucz lines'.  FAL-C, B = 1 kG: I, Q, U, V identical to the reference's rhf1d() (fixture
+    falc_molecules_pol, max |V/I| 8e-6), through pyrh_b200.host.compute1d and through the bridged reference library."""
+    from pyrh_b200 import host
+    from oracle import refdriver as rd
+    root = Path(__file__).resolve().parent.parent
+    cwd = root / "oracle" / "_ref" / "inputs" / "benchmark"
+    if not (cwd / "keyword.input").exists():
+        pytest.skip("reference input files not staged (oracle/_ref)")
+    keep = os.environ.get("PYRH_PATH")
+    os.environ["PYRH_PATH"] = rd.polarizable_cn_tree(str(tmp_path / "pyrh_path"))
+    g = dict(np.load(GOLD / "falc_molecules_pol.npz"))
+    try:
+        host.close_sessions()
+        out = host.compute1d(str(cwd), 1.0, 0, g["atmosphere"], g["wave"])
+        got, ref = np.array(out[:4]), g["stokes"]
+        REPORT["molecular_polarizable_fused_exact"] = bool(np.array_equal(got, ref))
+        assert np.array_equal(out[4], g["lam_out"])
+        assert np.max(np.abs(got[0] / ref[0] - 1)) < 1e-9
+        assert np.array_equal(got, ref)
+        assert np.abs(ref[3]).max() / ref[0].max() > 1e-6        # the molecular lines polarise the spectrum
+        if (root / "oracle" / "_build" / "libpyrh_bridged.so").exists():
+            rd.load("bridged")
+            os.environ["PYRH_PATH"] = str(tmp_path / "pyrh_path")  # load() points it at the stock tree
+            o = rd.rhf1d(g["atmosphere"], g["wave"], rd.make_workdir("benchmark"), variant="bridged")
+            REPORT["molecular_polarizable_bridged_exact"] = bool(np.array_equal(np.array([o[k] for k in "IQUV"]), ref))
+            assert np.array_equal(np.array([o[k] for k in "IQUV"]), ref)
+    finally:
+        host.close_sessions()
+        if keep is None:
+            os.environ.pop("PYRH_PATH", None)
+        else:
+            os.environ["PYRH_PATH"] = keep
+
+
 def test_opacity_fudge_factors():
     """pyrh.compute1d's fudge_wave / fudge_value (H-, scattering and metal bound-free factors interpolated in
     wavelength, background.c:364-371, 438-464) on the device: identical to rhf1d() with the same factors, which also

@@ -101,10 +101,39 @@ def test_molecular_line_list_equals_reference_tables():
     from pyrh_b200 import host
     kw = host.read_keywords(CWD)
     el = host.read_elements(PYRH_PATH, kw)
-    rows, sel = host.molecular_line_table(CWD, kw, el, PYRH_PATH)
+    rows, sel, zee = host.molecular_line_table(CWD, kw, el, PYRH_PATH)
+    assert len(zee[0]) == 0 and not rows[:, host.ML_POLARIZABLE].any()      # the shipped CN list carries no Hund's-case data
     g = np.load(GOLD / "falc_molecules.npz")
     assert rows.shape == (99, host.ML_NFIELD) and np.array_equal(rows[:, :9], g["mlines"][:, :9])
     assert sel.shape == (1, host.MS_NFIELD) and sel[0, 0] == 7 and sel[0, 1] == 12.01 + 14.01       # CN: 8th molecule
+
+
+def test_polarizable_molecular_lines_get_molzeeman_patterns(tmp_path):
+    """Hund's-case columns behind column 71 of a molecular line list (readmolecule.c:859-912) make the lines polarizable;
+    MolZeeman (molzeeman.c:196-319: case-b Lande factors, anomalous pattern, strengths normalised per q) in Python equals
+    the reference's patterns bit for bit -- 99 lines, 9080 components recorded from the reference on a polarizable copy
+    of the shipped CN list (oracle.refdriver.polarizable_cn_tree, fixture falc_molecules_pol).  A list without the
+    subbranch digit where its format expects it is refused (the reference reads uninitialised memory there)."""
+    from pyrh_b200 import host
+    from oracle import refdriver as rd
+    if not rd.available():
+        pytest.skip("reference data files not staged (oracle/_ref)")
+    pp = rd.polarizable_cn_tree(str(tmp_path / "pyrh_path"))
+    kw = host.read_keywords(CWD)
+    el = host.read_elements(pp, kw)
+    rows, sel, (zq, zs, zt) = host.molecular_line_table(CWD, kw, el, pp)
+    g = np.load(GOLD / "falc_molecules_pol.npz")
+    assert rows.shape == (99, host.ML_NFIELD) and rows[:, host.ML_POLARIZABLE].all()
+    assert np.array_equal(rows[:, :9], g["mlines"][:, :9])
+    assert np.array_equal(rows[:, host.ML_ZOFF], g["mlines"][:, 9]) and np.array_equal(rows[:, host.ML_NCOMP], g["mlines"][:, 10])
+    assert np.array_equal(zq, g["zq"]) and np.array_equal(zs, g["zshift"]) and np.array_equal(zt, g["zstrength"])
+    for q in (-1, 0, 1):                                          # normalised per q, line by line
+        o, n = int(rows[0, host.ML_ZOFF]), int(rows[0, host.ML_NCOMP])
+        assert abs(zt[o:o + n][zq[o:o + n] == q].sum() - 1.0) < 1e-14
+    lst = Path(pp) / "rh" / "Molecules" / "CN" / "CN_B-X_polarizable.asc"
+    lst.write_text(lst.read_text().replace("KURUCZ_CD18", "KURUCZ_NEW"))
+    with pytest.raises(ValueError, match="subbranch"):
+        host.molecular_line_table(CWD, kw, el, pp)
 
 
 def test_background_model_from_atom_and_molecule_files():
