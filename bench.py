@@ -608,6 +608,9 @@ def main():
                            "prep": "prep_kernel"}.get(dom, dom),
                 "bound": "fp64", "achieved": achieved_tf, "peak": fma_tf, "unit": "TFLOP/s",
                 "frac": achieved_tf / fma_tf if fma_tf else None, "traffic": traffic,
+                # the arithmetic contract (-fmad=false: every product and sum rounds like the reference's x86-64 build)
+                # caps this code at one flop per FP64 instruction; the headline fraction stays the one against the DFMA peak
+                "frac_of_no_fma_ceiling": achieved_tf / nofma_tf if nofma_tf else None,
                 "algorithmic_bytes": pts_per_launch * (BYTES_DELO if dom == "delo" else 80.0),
                 "peak_source": "rhb200_fp64_peak(): DFMA micro-benchmark run in this process (2 flop/FMA); "
                                f"non-FMA FP64 issue rate {nofma_tf:.1f} Tinst/s",
