@@ -301,13 +301,15 @@ extern "C" int rhb200_hse_batch(rhb200_ctx *c, int ncol, int ndep, int atm_scale
     if ((e = cudaMemcpy(H.pg, h.data(), n * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) fail("upload");
   }
   rh_continuum_set_hse_mode(c, 1);
+  static int coop_max = -1;
+  if (coop_max < 0) { const char *e = getenv("RHB200_HSE_COOP_MAX"); coop_max = e ? atoi(e) : 65536; }   // measured: 4096 columns 0.53 -> 0.17 s, 16 384 columns 0.48 -> 0.40 s against the thread-per-column kernel
   const unsigned gb = (unsigned) ((ncol + 63) / 64);
   for (int k = 0; k < ndep && rc == RHB200_OK; k++) {
     hse_layer_init_kernel<<<gb, 64, 0, c->stream>>>(H, k);
     int nactive = ncol;
     if ((e = cudaMemcpyAsync(H.nactive, &nactive, sizeof(int), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) { fail("flag"); break; }
     for (int it = 0; it < 50 && nactive > 0 && rc == RHB200_OK; it++) {
-      if (ncol <= 2048)                            // few columns: one warp each (a single thread needs ~1 ms per Newton solve)
+      if (ncol <= coop_max)                        // one warp per column (a single thread needs ~1 ms per Newton solve)
         hse_pre_coop_kernel<<<ncol, 32, 2 * (size_t) t->nelem * RHB200_RE_MAXSTAGE * sizeof(double), c->stream>>>(
             H, k, t->nelem, t->npf, t->elems, t->pf, t->Tpf, atL);
       else

@@ -14,6 +14,12 @@ t0 = time.perf_counter()
 ne, nH, rho, pg = s.hse(0, atm[:, 0], atm[:, 1], 0.1)
 dt = time.perf_counter() - t0
 launches = sum(v[1] for v in s.ctx.timing_get().values())
+s.ctx.timing(True)
+t1 = time.perf_counter()
+s.hse(0, atm[:, 0], atm[:, 1], 0.1)
+dt_timed = time.perf_counter() - t1
 print(json.dumps({"workload": f"pyrh.hse: {ncol} columns x 70 depths, log tau500 grid, pg_top = 0.1 Pa", "columns": ncol,
                   "seconds": dt, "columns_per_s": ncol / dt, "finite": bool(np.isfinite(pg).all()),
-                  "pg_bottom_mean": float(pg[:, -1].mean()), "kernel_launch_groups": int(launches)}))
+                  "pg_bottom_mean": float(pg[:, -1].mean()), "kernel_launch_groups": int(launches),
+                  "second_call_with_per_launch_events_s": dt_timed,
+                  "kernel_ms": {k: round(v[0], 2) for k, v in s.ctx.timing_get().items() if v[1]}}))
