@@ -52,6 +52,18 @@ ZeemanMultiplet *RLKZeeman(RLK_Line *rlk);          /* kurucz.c:832 */
 
 /* ---- state kept between calls: one device context, the pyrh-unit copy of the caller's rows, a pending batch */
 static rhb200_ctx *g_ctx = NULL;
+/* PYRH_B200_TRACE=1: FNV-1a hash of every table handed to the library (and the Kurucz line rows themselves), to stderr:
+   two calls that should be identical and are not show which parsed table differs -- the reference's readers have
+   state of their own (e.g. the stale-buffer read of kurucz.c:273) */
+static void trace(const char *name, const void *p, size_t bytes)
+{
+  const unsigned char *q = (const unsigned char *) p;
+  unsigned long long h = 1469598103934665603ull;
+  size_t i;
+  if (!getenv("PYRH_B200_TRACE")) return;
+  for (i = 0; p && i < bytes; i++) { h ^= q[i]; h *= 1099511628211ull; }
+  fprintf(stderr, "pyrh_b200 trace: %-12s %9lu bytes %016llx\n", name, (unsigned long) bytes, h);
+}
 static double *g_rows = NULL;       /* [9][Ndep] pyrh units, saved before rhf1d() converts the caller's arrays in place */
 static int g_rows_ndep = 0, g_atm_scale = 0;
 static struct { int ncol; const double *atm; double *stokes, *pops_n, *pops_nstar; int *niter; } g_batch = {0};
@@ -269,6 +281,10 @@ static void build_tables(int get_atomic_rfs, int fudge_num, double *fudge_lam, d
     }
     if (zq.n == 0) { iv_push(&zq, 0); dv_push(&zs, 0.0); dv_push(&zt, 0.0); zq.n = 0; }
     if (!pf.n) for (k = 0; k < atmos.Npf; k++) dv_push(&pf, 0.0);
+    trace("lines", lines.v, lines.n * sizeof(double));
+    if (getenv("PYRH_B200_TRACE")) for (n = 0; n < lines.n; n++) fprintf(stderr, "pyrh_b200 linefield %d %d %.17g\n", n / RHB200_RL_NFIELD, n % RHB200_RL_NFIELD, lines.v[n]);
+ trace("zs", zs.v, zq.n * sizeof(double)); trace("zt", zt.v, zq.n * sizeof(double));
+    trace("elems", elems.v, elems.n * sizeof(double)); trace("pf", pf.v, pf.n * sizeof(double)); trace("Tpf", atmos.Tpf, atmos.Npf * sizeof(double));
     CHECK(rhb200_set_lines(g_ctx, atmos.Nrlk, lines.v, zq.n, zq.v, zs.v, zt.v, nelem, elems.v, nelem ? pf.n / atmos.Npf : 0,
                            atmos.Npf, pf.v, atmos.Tpf, atmos.vmicro_char, 0, input.rlkscatter ? 1 : 0));
     free(row_elem);
@@ -333,6 +349,7 @@ static void build_tables(int get_atomic_rfs, int fudge_num, double *fudge_lam, d
       l0 += atom->Nlevel;
     }
     T.lev0[atmos.Natom] = T.nlev = l0;
+    trace("passive", pl.v, pl.n * sizeof(double)); trace("pcs", cs.v, cs.n * sizeof(double)); trace("pcf", cf.v, cs.n * sizeof(double)); trace("modellines", ml.v, ml.n * sizeof(double));
     if (input.allow_passive_bb) CHECK(rhb200_set_passive_lines(g_ctx, pl.n / NPL, pl.v, cs.n, cs.v, cf.v));
     else CHECK(rhb200_set_passive_lines(g_ctx, 0, NULL, 0, NULL, NULL));
     CHECK(rhb200_set_model_lines(g_ctx, ml.n / 4, ml.v));
@@ -367,6 +384,7 @@ static void build_tables(int get_atomic_rfs, int fudge_num, double *fudge_lam, d
         }
         nsel++;
       }
+      trace("mollines", mrows.v, mrows.n * sizeof(double)); trace("molsel", msel.v, msel.n * sizeof(double)); trace("molzs", mzs.v, mzq.n * sizeof(double));
       CHECK(rhb200_set_molecular_lines_zeeman(g_ctx, mrows.n / RHB200_ML_NFIELD, mrows.v, nsel, msel.v, mzq.n, mzq.v, mzs.v, mzt.v));
       free(mrows.v); free(msel.v); free(mzq.v); free(mzs.v); free(mzt.v);
     }
@@ -380,6 +398,7 @@ static void build_tables(int get_atomic_rfs, int fudge_num, double *fudge_lam, d
     T.iref = -1;
     for (n = 0; n < T.nlam; n++) if (T.lam[n] == atmos.lambda_ref) T.iref = n;
     if (T.iref < 0) FAIL("LAMBDA_REF = 0: convertScales needs the reference wavelength");
+    trace("lambda", T.lam, T.nlam * sizeof(double));
     CHECK(rhb200_set_wavelengths(g_ctx, T.nlam, T.lam));
     CHECK(rhb200_set_solvers(g_ctx, (int) input.S_interpolation, (int) input.S_interpolation_stokes));
     /* -- continuum model */
@@ -404,6 +423,8 @@ static void build_tables(int get_atomic_rfs, int fudge_num, double *fudge_lam, d
     M.oh_T = tab("oh_T", &M.n_oh_T); M.oh_E = tab("oh_E", &M.n_oh_E); M.oh_cross = tab("oh_cross", NULL);
     M.ch_T = tab("ch_T", &M.n_ch_T); M.ch_E = tab("ch_E", &M.n_ch_E); M.ch_cross = tab("ch_cross", NULL);
     if (fudge_lam != NULL) { M.do_fudge = 1; M.n_fudge = fudge_num; M.fudge_lambda = fudge_lam; M.fudge = fudge; }
+    trace("lev", lev.v, lev.n * sizeof(double)); trace("bf", bf.v, bf.n * sizeof(double)); trace("tab_lambda", tl.v, tl.n * sizeof(double)); trace("tab_alpha", ta.v, ta.n * sizeof(double));
+    trace("ray", ray.v, ray.n * sizeof(double)); trace("abund", ab.v, ab.n * sizeof(double)); trace("vmicro", &M.vmicro_char, sizeof(double));
     CHECK(rhb200_set_continuum(g_ctx, &M, ab.v));
     keep[nkeep++] = lev.v; keep[nkeep++] = bf.v; keep[nkeep++] = tl.v; keep[nkeep++] = ta.v; keep[nkeep++] = ray.v;
     free(pl.v); free(cs.v); free(cf.v); free(ml.v); free(ab.v);
@@ -434,6 +455,7 @@ static void build_tables(int get_atomic_rfs, int fudge_num, double *fudge_lam, d
       r[24] = !strcmp(mo->ID, "H2"); r[25] = !strcmp(mo->ID, "OH"); r[26] = !strcmp(mo->ID, "CH");
     }
     T.nmol = atmos.Nmolecule;
+    trace("chem_mol", mol, (size_t) atmos.Nmolecule * 32 * sizeof(double)); trace("nuc_atom", nuc_atom, nnuc * sizeof(int));
     CHECK(rhb200_set_chemistry(g_ctx, nnuc, nuc_atom, atmos.Nmolecule, mol));
     free(nuc_elem); free(nuc_atom); free(mol);
   }
@@ -665,6 +687,7 @@ int pyrh_b200_solve(double mu, int get_atomic_rfs, int get_populations, int fudg
       CHECK(rhb200_compute1d_rf_batch(g_ctx, ncol, N, 9, mu, g_atm_scale, rows, T.iref, atmos.wght_per_H, atmos.vmacro_tresh,
                                       bc_top, bc_bot, st, NULL, rf));
     } else
+      trace("rows", rows, (size_t) ncol * 9 * N * sizeof(double)); trace("wght_per_H", &atmos.wght_per_H, sizeof(double)); trace("vmacro_tresh", &atmos.vmacro_tresh, sizeof(double));
       CHECK(rhb200_compute1d_batch(g_ctx, ncol, N, 9, mu, g_atm_scale, rows, T.iref, atmos.wght_per_H, atmos.vmacro_tresh,
                                    bc_top, bc_bot, st, NULL));
     if (input.get_atomic_rfs) spec->rfs = matrix_double(Nlw, input.n_atomic_pars);
