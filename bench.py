@@ -271,12 +271,15 @@ def nlte_records(device, rank, ncol_scale=1.0, world=1, barrier=None, maxreduce=
             err = e
         if barrier:
             barrier()
+        times = []
         if err is None:
             try:
-                t0 = time.perf_counter()
-                res = s.compute(atm)
-                s.ctx.synchronize()
-                dt = time.perf_counter() - t0
+                for _ in range(2):      # two timed calls of the same batch, the faster one is reported (both are kept):
+                    t0 = time.perf_counter()    # a call has one host read-back per MALI iteration and is sensitive to host noise
+                    res = s.compute(atm)
+                    s.ctx.synchronize()
+                    times.append(time.perf_counter() - t0)
+                dt = min(times)
             except Exception as e:      # noqa: BLE001
                 err = e
         if maxreduce:                                                   # every rank solves its own ncol columns (weak scaling)
@@ -290,7 +293,8 @@ def nlte_records(device, rank, ncol_scale=1.0, world=1, barrier=None, maxreduce=
         conv = (res["niter"] < int(c["kw"]["N_MAX_ITER"])) & finite
         rec = {"workload": f"{ncol} perturbed FAL-C columns x {NDEP} depths, {len(s.lam)} wavelengths, NRAYS {s.nrays}, "
                            f"ACTIVE {'+'.join(a.split('.')[0] for a in c['active'])}, CRD, Ng 2/10/3, ITER_LIMIT 1e-4",
-               "ncol": ncol, "nspect": int(len(s.lam)), "nrays": s.nrays, "seconds": dt, "atmospheres_per_s": ncol / dt,
+               "ncol": ncol, "nspect": int(len(s.lam)), "nrays": s.nrays, "seconds": dt, "seconds_each_call": times,
+               "atmospheres_per_s": ncol / dt,
                "n_gpus": world, "atmospheres_per_s_all_gpus": world * ncol / dt,        # columns sharded over the ranks, no collective
                "ray_points_per_s": s.ray_points(res, NDEP) / dt, "ray_points": s.ray_points(res, NDEP),
                "iterations_median": float(np.median(res["niter"])), "iterations_max": int(res["niter"].max()),
