@@ -85,3 +85,25 @@ def test_bridged_reference_library_exports_the_pyrh_symbols():
         assert hasattr(lib, name), name
     needed = subprocess.run(["readelf", "-d", str(so)], capture_output=True, text=True).stdout
     assert "librhb200.so" in needed
+
+
+def test_committed_bench_lines_carry_every_contract_key():
+    """The bench lines committed under profiles/ (GPU arm and reference arm of the same round) carry every key the
+    measurement contract names -- a guard against silently dropping one when bench.py is edited."""
+    import json
+    root = Path(__file__).resolve().parent.parent
+    line = json.loads((root / "profiles" / "r2_bench_n1.json").read_text().strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in line, k
+    assert "workload" in line["config"] and "model" not in line["config"]
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(line["clocks"])
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"])
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(line["roofline"])
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(line["cpu_baseline"])
+    assert line["gpu_launches"] > 0 and line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["value"] != line["value"]
+    assert abs(line["roofline"]["frac"] - line["roofline"]["achieved"] / line["roofline"]["peak"]) < 1e-12
+    ref = json.loads((root / "profiles" / "r2_bench_reference_arm.json").read_text().strip().splitlines()[-1])
+    assert ref["impl"] == "reference" and ref["metric"] == line["metric"] and ref["unit"] == line["unit"]
+    assert ref["config"]["workload"] == line["config"]["workload"]
+    assert ref["cpu_baseline"]["kind"] == "reference" and ref["e2e"]["h2d_bytes_per_step"] == 0
