@@ -250,6 +250,9 @@ def _nlte_workdir(case):
     return workdir.stage(tempfile.mkdtemp(prefix=f"rhb200_{case}_"), c["kw"], active=c["active"], extra_atoms=("CaII.atom",))
 
 
+_NLTE_SAMPLE = {}      # case -> first columns of the GPU arm's batch (rank 0), for the parity record of the reference leg
+
+
 def nlte_records(device, rank, ncol_scale=1.0, world=1, barrier=None, maxreduce=None):
     """NLTE through the drop-in call (NlteSession.compute = rhb200_nlte_compute1d_batch): host atmosphere rows in,
     spectra + populations out, everything between on the device.  One record per case: atmospheres/s and formal-solution
@@ -289,6 +292,8 @@ def nlte_records(device, rank, ncol_scale=1.0, world=1, barrier=None, maxreduce=
             if s is not None:
                 s.close()
             continue
+        if rank == 0:                   # the columns the reference leg recomputes (column ids 10000 ...)
+            _NLTE_SAMPLE[case] = {"I": np.array(res["I"][:64]), "n": np.array(res["n"][:64]), "niter": np.array(res["niter"][:64])}
         finite = np.isfinite(res["I"]).all(axis=tuple(range(1, res["I"].ndim))) & np.isfinite(res["n"]).all(axis=tuple(range(1, res["n"].ndim)))
         conv = (res["niter"] < int(c["kw"]["N_MAX_ITER"])) & finite
         rec = {"workload": f"{ncol} perturbed FAL-C columns x {NDEP} depths, {len(s.lam)} wavelengths, NRAYS {s.nrays}, "
@@ -334,6 +339,9 @@ def nlte_ref_worker(case, column):
     o = rd.rhf1d(a, np.linspace(*NLTE_CASES[case]["wave"]), cwd, get_populations=True)
     dt = time.perf_counter() - t0
     ok = bool(np.isfinite(o["I"]).all() and all(np.isfinite(v["n"]).all() for v in o.get("pops", {}).values()))
+    dump = os.environ.get("RHB200_NLTE_REF_DUMP")
+    if dump:                            # spectrum + populations (atoms in the reference's order) for the parity record
+        np.savez(Path(dump) / f"{case}_{column}.npz", I=o["I"], n=np.concatenate([v["n"] for v in o["pops"].values()]))
     print(f"NLTE_REF_FINITE {int(ok)}", flush=True)          # the reference also RETURNS NaN populations on some columns
     print(f"NLTE_REF_SECONDS {dt:.6f}", flush=True)
 
@@ -342,11 +350,14 @@ def nlte_reference_baseline(procs=None, limit_s=120.0):
     """The unmodified reference's rhf1d() on the same NLTE workloads: one process per host core, one column each, all
     started together (bounded sample).  Every column runs in its OWN process with a time limit: the reference calls
     exit() from LUdecomp ("Singular matrix") on some perturbed columns and would take a worker pool down with it."""
+    import tempfile
     procs = procs or os.cpu_count() or 1
     out = {}
+    dump = tempfile.mkdtemp(prefix="rhb200_nlte_ref_")
+    env = dict(os.environ, RHB200_NLTE_REF_DUMP=dump)
     for case in NLTE_CASES:
         ps = [subprocess.Popen([sys.executable, str(ROOT / "bench.py"), "--nlte-ref-worker", case, str(10000 + p)],
-                               stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for p in range(procs)]
+                               stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env) for p in range(procs)]
         t, nan_cols, t_end = [], 0, time.perf_counter() + limit_s
         for q in ps:
             try:
@@ -366,6 +377,35 @@ def nlte_reference_baseline(procs=None, limit_s=120.0):
                      "columns_the_reference_returned_nan_for": nan_cols,
                      "sample": f"{procs} perturbed columns started together, one rhf1d(get_populations) process per core; "
                                f"{len(t)} finished, slowest {max(t):.1f} s"}
+        # parity of the GPU arm on the very same columns (default rate accumulation: fixed-partition sums, so the bar is
+        # north_star's 1e-6 on populations, not bits; RHB200_NLTE_EXACT=1 reproduces the reference's order bit for bit)
+        g = _NLTE_SAMPLE.get(case)
+        if g is not None:
+            errn, errI, ncmp, both_nan, one_nan, per_col = 0.0, 0.0, 0, 0, 0, []
+            for p in range(min(procs, len(g["I"]))):
+                f = Path(dump) / f"{case}_{10000 + p}.npz"
+                if not f.exists():
+                    continue
+                r = np.load(f)
+                fin_r = bool(np.isfinite(r["I"]).all() and np.isfinite(r["n"]).all())
+                fin_g = bool(np.isfinite(g["I"][p]).all() and np.isfinite(g["n"][p]).all())
+                if not fin_r or not fin_g:
+                    both_nan += int(not fin_r and not fin_g)
+                    one_nan += int(fin_r != fin_g)
+                    continue
+                ncmp += 1
+                en = float(np.max(np.abs(g["n"][p].reshape(r["n"].shape) / r["n"] - 1.0)))
+                eI = float(np.max(np.abs(g["I"][p] / r["I"] - 1.0)))
+                per_col.append({"column": 10000 + p, "iterations": int(g["niter"][p]), "max_rel_err_populations": en, "max_rel_err_I": eI})
+                errn, errI = max(errn, en), max(errI, eI)
+            out[case]["parity_vs_reference"] = {"columns_compared": ncmp, "max_rel_err_populations": errn, "max_rel_err_I": errI,
+                                                "columns_nan_in_both": both_nan, "columns_nan_in_one_only": one_nan,
+                                                "tolerance": 1.0e-6, "within_tolerance": bool(ncmp > 0 and errn <= 1.0e-6 and errI <= 1.0e-6),
+                                                "columns_within_tolerance": sum(1 for c in per_col if c["max_rel_err_populations"] <= 1.0e-6),
+                                                "per_column": per_col,
+                                                "note": "columns that converge in the usual ~30 iterations agree to ~1e-9; a column the MALI/Ng "
+                                                        "iteration struggles with (50+ iterations) amplifies the summation-order difference of the "
+                                                        "default fixed-partition rate sums; RHB200_NLTE_EXACT=1 (reference order) is bit-identical"}
     return out
 
 
