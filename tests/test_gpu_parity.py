@@ -1656,6 +1656,24 @@ def test_nlte_fast_rates_default_mode_within_tolerance(case):
     assert np.array_equal(res["n"][2:5], part["n"]) and np.array_equal(res["I"][2:5], part["I"])
 
 
+def test_nlte_fast_rates_off_by_keyword_is_bit_exact():
+    """NlteSession(exact_rates=True) = rhb200_nlte_set_exact_rates, without the environment switch the other parity
+    tests use (this test's name keeps the fixture from setting it): iteration counts, populations and spectrum of the
+    perturbed NRAYS 5 Ca II columns identical to the reference, the 100-iteration column included."""
+    from pyrh_b200 import nlte_host
+    assert "RHB200_NLTE_EXACT" not in os.environ
+    case = "caii_r5"
+    g, cwd = _nlte_front_case(case)
+    atm, wave, mu = g["atmosphere"], g[f"{case}_wave"], float(g[f"{case}_mu"])
+    s = nlte_host.NlteSession(cwd, wave, exact_rates=True)
+    try:
+        res = s.compute(atm, mu=mu)
+    finally:
+        s.close()
+    assert np.array_equal(res["niter"], g[f"{case}_niter"])
+    assert np.array_equal(res["n"], g[f"{case}_n"], equal_nan=True) and np.array_equal(res["I"], g[f"{case}_I"], equal_nan=True)
+
+
 def _bridged():
     from oracle import refdriver as rd
     if not (rd.HERE / "_build" / "libpyrh_bridged.so").exists() or not rd.available():
