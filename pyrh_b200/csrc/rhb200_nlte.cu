@@ -490,8 +490,8 @@ nlte_ray_kernel(Plan P, Cols C, int ncol, int eval_operator)
                            C.S + cr * N, C.I + cr * N, Psi);
       if (Psi) { const double *chi = C.chi + cr * N; for (int k = 0; k < N; k++) Psi[k] = Psi[k] / chi[k]; }
     } else
-      rhz::bezier3_ray(N, h, P.muz[mu], dir, P.bc_top, P.bc_bottom, T, P.lambda[ns], C.chi + cr * N,
-                       C.S + cr * N, C.I + cr * N, Psi, true);
+      rhz::bezier3_ray_w(N, h, P.muz[mu], dir, P.bc_top, P.bc_bottom, T, P.lambda[ns], C.chi + cr * N,
+                         C.S + cr * N, C.I + cr * N, Psi, true);
     C.Iem[cr] = C.I[cr * N];                         // spectrum.I[nspect][mu] = I[0] (formal.c:270)
   } else {
     NlteFeauIO io{C.chi + cr * N, C.S + cr * N, h, C.I + cr * N, Psi, C.scr + cr * 2 * N, N};
@@ -1646,7 +1646,7 @@ struct NlteEngine {
 
   void launch_rays(int eval_operator) {
     static int ray_minb = -1;
-    if (ray_minb < 0) { const char *e = getenv("RHB200_NLTE_RAY_MINB"); ray_minb = e ? atoi(e) : 8; }
+    if (ray_minb < 0) { const char *e = getenv("RHB200_NLTE_RAY_MINB"); ray_minb = e ? atoi(e) : 6; }   // with the register-window solver: 8 -> 5.05 / 2.77 ms, 6 -> 4.30 / 2.45, 4 -> 4.49 / 2.69 (configs[4] sample / configs[3], 256 columns)
     const unsigned blocks = (unsigned) (((size_t) ncol*nray + 127) / 128);
 #define RH_RAYS(S, M) nlte_ray_kernel<S, M><<<blocks, 128, 0, c->stream>>>(P, C, ncol, eval_operator)
 #define RH_RAYS_M(S) do { if (ray_minb >= 8) RH_RAYS(S, 8); else if (ray_minb >= 6) RH_RAYS(S, 6); else RH_RAYS(S, 4); } while (0)
