@@ -259,6 +259,12 @@ __device__ __forceinline__ double twohnu3_of(const Plan &P, const double *tr, in
 // ray-independent factors (n_i - g n_j, thn g, n_j, background, Jdag) are loaded once, and the walk over
 // the active set is uniform across the block.  Products keep the reference's association:
 // V*(n_i - g n_j), ((thn*g)*V)*n_j (opacity.c:252-260).
+// blocks of 64 threads per SM the rate kernels are compiled for.  Measured per launch, 256 columns (configs[4] sample /
+// configs[3]): 12 -> 5.14 / 12.0 ms (80 registers, 850 B of spills), 10 -> 3.88 / 8.97, 8 -> 3.42 / 7.76 (128 registers, still
+// spilling), 6 and 5 -> 2.79 / 6.93 (149 / 126 registers, no spills), 4 -> 5.78 / 12.7
+#ifndef NLTE_GAMMA_MINB
+#define NLTE_GAMMA_MINB 6
+#endif
 #define NLTE_RB 6
 __global__ void __launch_bounds__(128)
 nlte_opacity_kernel(Plan P, Cols C, int ncol)
@@ -725,7 +731,7 @@ nlte_dJmax_kernel(Plan P, Cols C, int ncol, double *dJmax)
 // fixed-partition reduction, nlte_gamma_sum_kernel adds them in segment order); !SEG: the whole transition in the
 // reference's order, bit-identical to fillgamma.c.
 template <bool SEG, bool STK>
-__global__ void __launch_bounds__(64, 8)
+__global__ void __launch_bounds__(64, NLTE_GAMMA_MINB)
 nlte_gamma_kernel(Plan P, Cols C, int ncol)
 {
   const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -888,7 +894,7 @@ nlte_gamma_kernel(Plan P, Cols C, int ncol)
 // batch size and chunking.  Within a chunk every sum keeps the reference's order.
 #define NLTE_MAXSLOT 24
 #define NLTE_MAXLEV 8
-__global__ void __launch_bounds__(64, 8)
+__global__ void __launch_bounds__(64, NLTE_GAMMA_MINB)
 nlte_gamma_atom_kernel(Plan P, Cols C, int ncol)
 {
   const size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
