@@ -266,7 +266,12 @@ __device__ __forceinline__ double twohnu3_of(const Plan &P, const double *tr, in
 #define NLTE_GAMMA_MINB 6
 #endif
 #define NLTE_RB 6
-__global__ void __launch_bounds__(128)
+// blocks/SM of the opacity kernel, measured per launch at 256 columns (configs[4] sample / configs[3]): 3 -> 1.51 / 1.40 ms,
+// 4 -> 1.24 / 1.10, 5 -> 1.13 / 0.97 (96 registers), 6 -> 1.41 / 1.03
+#ifndef NLTE_OPAC_MINB
+#define NLTE_OPAC_MINB 5
+#endif
+__global__ void __launch_bounds__(128, NLTE_OPAC_MINB)
 nlte_opacity_kernel(Plan P, Cols C, int ncol)
 {
   // consecutive blocks take consecutive wavelengths of the same (column, depth) chunk: their rays are
