@@ -265,7 +265,9 @@ __device__ __forceinline__ double twohnu3_of(const Plan &P, const double *tr, in
 #ifndef NLTE_GAMMA_MINB
 #define NLTE_GAMMA_MINB 6
 #endif
+#ifndef NLTE_RB
 #define NLTE_RB 6
+#endif
 // blocks/SM of the opacity kernel, measured per launch at 256 columns (configs[4] sample / configs[3]): 3 -> 1.51 / 1.40 ms,
 // 4 -> 1.24 / 1.10, 5 -> 1.13 / 0.97 (96 registers), 6 -> 1.41 / 1.03
 #ifndef NLTE_OPAC_MINB
