@@ -1662,7 +1662,7 @@ struct NlteEngine {
     if (ray_minb < 0) { const char *e = getenv("RHB200_NLTE_RAY_MINB"); ray_minb = e ? atoi(e) : 6; }   // with the register-window solver: 8 -> 5.05 / 2.77 ms, 6 -> 4.30 / 2.45, 4 -> 4.49 / 2.69 (configs[4] sample / configs[3], 256 columns)
     const unsigned blocks = (unsigned) (((size_t) ncol*nray + 127) / 128);
 #define RH_RAYS(S, M) nlte_ray_kernel<S, M><<<blocks, 128, 0, c->stream>>>(P, C, ncol, eval_operator)
-#define RH_RAYS_M(S) do { if (ray_minb >= 8) RH_RAYS(S, 8); else if (ray_minb >= 6) RH_RAYS(S, 6); else RH_RAYS(S, 4); } while (0)
+#define RH_RAYS_M(S) do { if (ray_minb >= 8) RH_RAYS(S, 8); else if (ray_minb >= 6) RH_RAYS(S, 6); else if (ray_minb == 5) RH_RAYS(S, 5); else RH_RAYS(S, 4); } while (0)
     if (P.solver == RHB200_S_LINEAR) RH_RAYS_M(RHB200_S_LINEAR);
     else if (P.solver == RHB200_S_PARABOLIC) RH_RAYS_M(RHB200_S_PARABOLIC);
     else RH_RAYS_M(RHB200_S_BEZIER3);
